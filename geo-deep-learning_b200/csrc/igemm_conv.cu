@@ -1,0 +1,835 @@
+// igemm_conv.cu — tensor-core implicit-GEMM convolution for sm_100a (forward / dgrad and wgrad).
+//
+// Forward (gdl_conv2d_nhwc_fwd), per CTA tile of 128 output pixels x BN output channels:
+//   D[128 x BN] (fp32, TMEM) = sum over taps (r,s), sources, channel chunks of
+//       A[128 pixels x BK channels]  (TMA 4-D box of the NHWC input shifted by the tap; the
+//                                     padding halo is TMA out-of-bounds zero fill)
+//     x B[BN x BK]                   (TMA 2-D box of the packed weights [Cout][R][S][Ctot])
+//   Both operands are K-major in shared memory with the hardware swizzle that matches BK
+//   (128B / 64B / 32B for BK = 64 / 32 / 16 channels); tcgen05.mma.kind::f16, M = 128, N = BN.
+//   Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (+ TMEM alloc), warps 2..5 = epilogue
+//   (tcgen05.ld -> bias/ReLU -> NHWC store).  Persistent grid, double-buffered accumulators.
+//
+// Wgrad (gdl_conv2d_nhwc_wgrad): D[128 (Cout) x BN (Cin)] += dYᵀ[64 px x 128] · X_tap[64 px x BN]
+//   with BOTH operands MN-major (pixels are the contraction dim, channels are contiguous in
+//   HBM and in the TMA box); split over pixel ranges, partial sums added with red.global.add.
+#include <string.h>
+
+#include <type_traits>
+
+#include "../../include/gdl_b200.h"
+#include "tmap.cuh"
+
+namespace gdl {
+
+constexpr int kMaxStages = 8;
+constexpr int kConvThreads = 192;  // 6 warps
+constexpr int kSmemBudget = 200 * 1024;
+constexpr int kMinSmemRequest = 120 * 1024;  // forces 1 CTA / SM (TMEM is allocated per CTA)
+
+struct ConvFwdKParams {
+  CUtensorMap tmA[GDL_MAX_SRC];
+  CUtensorMap tmB;
+  int num_src;
+  int src_chunks[GDL_MAX_SRC];
+  int src_coff[GDL_MAX_SRC];
+  int Ctot;
+  int R, S, pad_h, pad_w;
+  int Nimg, Ho, Wo;
+  int TH, TW, tiles_w, tiles_h;
+  int Cout, BN, n_tiles, num_tiles;
+  int BK, stages, a_bytes, b_bytes, stage_bytes, tmem_cols;
+  int ab_fmt;
+  void* out;
+  int out_dtype;
+  long long ldo;
+  int vec_ok;
+  const float* bias;
+  int relu;
+};
+
+GDL_DEVINL uint8_t* align_smem_1024(uint8_t* raw) {
+  uint32_t a = smem_u32(raw);
+  uint32_t pad = (1024u - (a & 1023u)) & 1023u;
+  return raw + pad;
+}
+
+template <typename T>
+GDL_DEVINL void store_row16(T* dst, const float (&f)[16], int nvalid, int vec_ok);
+
+template <>
+GDL_DEVINL void store_row16<float>(float* dst, const float (&f)[16], int nvalid, int vec_ok) {
+  if (nvalid == 16 && vec_ok) {
+    float4* d4 = reinterpret_cast<float4*>(dst);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) d4[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
+  } else {
+#pragma unroll
+    for (int i = 0; i < 16; ++i)
+      if (i < nvalid) dst[i] = f[i];
+  }
+}
+template <>
+GDL_DEVINL void store_row16<__nv_bfloat16>(__nv_bfloat16* dst, const float (&f)[16], int nvalid,
+                                           int vec_ok) {
+  if (nvalid == 16 && vec_ok) {
+    uint4* d4 = reinterpret_cast<uint4*>(dst);
+    d4[0] = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]),
+                       pack_bf16x2(f[6], f[7]));
+    d4[1] = make_uint4(pack_bf16x2(f[8], f[9]), pack_bf16x2(f[10], f[11]),
+                       pack_bf16x2(f[12], f[13]), pack_bf16x2(f[14], f[15]));
+  } else {
+#pragma unroll
+    for (int i = 0; i < 16; ++i)
+      if (i < nvalid) dst[i] = __float2bfloat16_rn(f[i]);
+  }
+}
+template <>
+GDL_DEVINL void store_row16<__half>(__half* dst, const float (&f)[16], int nvalid, int vec_ok) {
+  if (nvalid == 16 && vec_ok) {
+    uint4* d4 = reinterpret_cast<uint4*>(dst);
+    d4[0] = make_uint4(pack_f16x2(f[0], f[1]), pack_f16x2(f[2], f[3]), pack_f16x2(f[4], f[5]),
+                       pack_f16x2(f[6], f[7]));
+    d4[1] = make_uint4(pack_f16x2(f[8], f[9]), pack_f16x2(f[10], f[11]), pack_f16x2(f[12], f[13]),
+                       pack_f16x2(f[14], f[15]));
+  } else {
+#pragma unroll
+    for (int i = 0; i < 16; ++i)
+      if (i < nvalid) dst[i] = __float2half_rn(f[i]);
+  }
+}
+
+__global__ void __launch_bounds__(kConvThreads, 1)
+conv_fwd_kernel(const __grid_constant__ ConvFwdKParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = align_smem_1024(smem_raw);
+
+  __shared__ __align__(8) uint64_t full_bar[kMaxStages];
+  __shared__ __align__(8) uint64_t empty_bar[kMaxStages];
+  __shared__ __align__(8) uint64_t tfull_bar[2];
+  __shared__ __align__(8) uint64_t tempty_bar[2];
+  __shared__ uint32_t tmem_base_smem;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int taps = p.R * p.S;
+  const int tiles_per_img = p.tiles_w * p.tiles_h;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < p.num_src; ++s) tma_prefetch_desc(&p.tmA[s]);
+    tma_prefetch_desc(&p.tmB);
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int i = 0; i < p.stages; ++i) {
+        mbar_init(&full_bar[i], 1);
+        mbar_init(&empty_bar[i], 1);
+      }
+      for (int i = 0; i < 2; ++i) {
+        mbar_init(&tfull_bar[i], 1);
+        mbar_init(&tempty_bar[i], 128);
+      }
+      fence_mbar_init();
+    }
+    __syncwarp();
+    tmem_alloc(&tmem_base_smem, (uint32_t)p.tmem_cols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_smem;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      const uint32_t tx = (uint32_t)(p.a_bytes + p.b_bytes);
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        const int n_tile = tile % p.n_tiles;
+        const int m_tile = tile / p.n_tiles;
+        const int img = m_tile / tiles_per_img;
+        const int t_in = m_tile - img * tiles_per_img;
+        const int h0 = (t_in / p.tiles_w) * p.TH;
+        const int w0 = (t_in % p.tiles_w) * p.TW;
+        const int n0 = n_tile * p.BN;
+        for (int tap = 0; tap < taps; ++tap) {
+          const int r = tap / p.S, s = tap - r * p.S;
+          for (int src = 0; src < p.num_src; ++src) {
+            const int kbase = tap * p.Ctot + p.src_coff[src];
+            for (int ch = 0; ch < p.src_chunks[src]; ++ch) {
+              mbar_wait(&empty_bar[stage], phase ^ 1);
+              uint8_t* a_dst = smem + (size_t)stage * p.stage_bytes;
+              uint8_t* b_dst = a_dst + p.a_bytes;
+              mbar_expect_tx(&full_bar[stage], tx);
+              tma_load_4d(a_dst, &p.tmA[src], &full_bar[stage], ch * p.BK, w0 + s - p.pad_w,
+                          h0 + r - p.pad_h, img);
+              tma_load_2d(b_dst, &p.tmB, &full_bar[stage], kbase + ch * p.BK, n0);
+              if (++stage == p.stages) {
+                stage = 0;
+                phase ^= 1;
+              }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (one thread) =====================
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc(128, p.BN, p.ab_fmt, 0, 0);
+      const uint32_t lt = umma_layout_type(p.BK * 2);
+      const uint32_t sbo = 8u * p.BK * 2u;
+      const int ksteps = p.BK / 16;
+      int k_iters = 0;
+      for (int src = 0; src < p.num_src; ++src) k_iters += p.src_chunks[src];
+      k_iters *= taps;
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+        const int acc = it & 1;
+        const uint32_t aphase = (it >> 1) & 1;
+        mbar_wait(&tempty_bar[acc], aphase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.BN);
+        for (int k = 0; k < k_iters; ++k) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem + (size_t)stage * p.stage_bytes);
+          const uint32_t b_addr = a_addr + p.a_bytes;
+          for (int kk = 0; kk < ksteps; ++kk) {
+            const uint64_t da = umma_smem_desc(a_addr + kk * 32, 16, sbo, lt);
+            const uint64_t db = umma_smem_desc(b_addr + kk * 32, 16, sbo, lt);
+            umma_f16(d_tmem, da, db, idesc, (uint32_t)((k | kk) != 0));
+          }
+          umma_commit(&empty_bar[stage]);
+          if (++stage == p.stages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit(&tfull_bar[acc]);
+      }
+    }
+  } else {
+    // ===================== epilogue: TMEM -> registers -> HBM =====================
+    const int q = warp & 3;  // TMEM lane quadrant this warp may access
+    const int row = q * 32 + lane;
+    const int th = row / p.TW, tw = row - th * p.TW;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const uint32_t aphase = (it >> 1) & 1;
+      const int n_tile = tile % p.n_tiles;
+      const int m_tile = tile / p.n_tiles;
+      const int img = m_tile / tiles_per_img;
+      const int t_in = m_tile - img * tiles_per_img;
+      const int h = (t_in / p.tiles_w) * p.TH + th;
+      const int w = (t_in % p.tiles_w) * p.TW + tw;
+      const int n0 = n_tile * p.BN;
+      const bool valid = (h < p.Ho) && (w < p.Wo);
+      const long long pix = ((long long)img * p.Ho + h) * p.Wo + w;
+      mbar_wait(&tfull_bar[acc], aphase);
+      tc_fence_after();
+      const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.BN);
+      for (int j = 0; j < p.BN / 16; ++j) {
+        uint32_t v[16];
+        tmem_ld_32x32b_x16(t_addr + j * 16, v);
+        tmem_ld_wait();
+        const int c0 = n0 + j * 16;
+        const int nvalid = min(16, p.Cout - c0);
+        if (valid && nvalid > 0) {
+          float f[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]);
+          if (p.bias != nullptr) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+              if (i < nvalid) f[i] += __ldg(p.bias + c0 + i);
+          }
+          if (p.relu) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) f[i] = fmaxf(f[i], 0.f);
+          }
+          const long long off = pix * p.ldo + c0;
+          if (p.out_dtype == GDL_F32)
+            store_row16<float>(reinterpret_cast<float*>(p.out) + off, f, nvalid, p.vec_ok);
+          else if (p.out_dtype == GDL_BF16)
+            store_row16<__nv_bfloat16>(reinterpret_cast<__nv_bfloat16*>(p.out) + off, f, nvalid,
+                                       p.vec_ok);
+          else
+            store_row16<__half>(reinterpret_cast<__half*>(p.out) + off, f, nvalid, p.vec_ok);
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&tempty_bar[acc]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// host helpers
+// ------------------------------------------------------------------------------------------
+static int pow2_ge(int v) {
+  int p = 32;
+  while (p < v) p <<= 1;
+  return p;
+}
+
+// choose TH x TW = npix (power of two) minimising the padded area of an H x W image
+static void choose_tile(int H, int W, int npix, int* TH, int* TW) {
+  long long best = -1;
+  int bth = 1, btw = npix;
+  for (int tw = npix; tw >= 1; tw >>= 1) {
+    int th = npix / tw;
+    long long cost = (long long)((W + tw - 1) / tw) * tw * ((H + th - 1) / th) * th;
+    if (best < 0 || cost < best) {
+      best = cost;
+      bth = th;
+      btw = tw;
+    }
+  }
+  *TH = bth;
+  *TW = btw;
+}
+
+static int chunk_width(const gdl_src_t* src, int n) {
+  int bk = 64;
+  for (int i = 0; i < n; ++i) {
+    while (bk > 16 && (src[i].channels % bk) != 0) bk >>= 1;
+  }
+  return bk;
+}
+
+static int sm_count() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess ||
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+      n = kNumSMsB200;
+  }
+  return n;
+}
+
+static int validate_srcs(int num_src, const gdl_src_t* src, int* ctot) {
+  GDL_REQUIRE(num_src >= 1 && num_src <= GDL_MAX_SRC, GDL_ERR_INVALID,
+              "num_src must be in [1,%d] (got %d)", GDL_MAX_SRC, num_src);
+  int c = 0;
+  for (int i = 0; i < num_src; ++i) {
+    GDL_REQUIRE(src[i].ptr != nullptr, GDL_ERR_INVALID, "source %d: null pointer", i);
+    GDL_REQUIRE(src[i].channels > 0 && src[i].channels % 16 == 0, GDL_ERR_INVALID,
+                "source %d: channels must be a positive multiple of 16 (got %d)", i, src[i].channels);
+    GDL_REQUIRE(src[i].ld >= src[i].channels && src[i].ld % 8 == 0, GDL_ERR_INVALID,
+                "source %d: pixel stride %d invalid for %d channels", i, src[i].ld, src[i].channels);
+    c += src[i].channels;
+  }
+  *ctot = c;
+  return 0;
+}
+
+}  // namespace gdl
+
+using namespace gdl;
+
+extern "C" int gdl_conv2d_nhwc_fwd(const gdl_conv_fwd_t* d, void* stream_) {
+  GDL_REQUIRE(d != nullptr, GDL_ERR_INVALID, "null descriptor");
+  cudaStream_t stream = (cudaStream_t)stream_;
+  int Ctot = 0;
+  int st = validate_srcs(d->num_src, d->src, &Ctot);
+  if (st) return st;
+  GDL_REQUIRE(d->N > 0 && d->H > 0 && d->W > 0 && d->Cout > 0, GDL_ERR_INVALID,
+              "bad conv shape N=%d H=%d W=%d Cout=%d", d->N, d->H, d->W, d->Cout);
+  GDL_REQUIRE(d->R >= 1 && d->S >= 1 && d->R <= 15 && d->S <= 15 && d->pad_h >= 0 && d->pad_w >= 0,
+              GDL_ERR_INVALID, "bad filter R=%d S=%d pad=%d,%d", d->R, d->S, d->pad_h, d->pad_w);
+  GDL_REQUIRE(d->dtype == GDL_BF16 || d->dtype == GDL_F16, GDL_ERR_INVALID, "operand dtype must be bf16/f16");
+  GDL_REQUIRE(d->out_dtype == GDL_BF16 || d->out_dtype == GDL_F16 || d->out_dtype == GDL_F32,
+              GDL_ERR_INVALID, "bad out_dtype %d", d->out_dtype);
+  GDL_REQUIRE(d->weight && d->out, GDL_ERR_INVALID, "null weight/out");
+  const int Ho = d->H + 2 * d->pad_h - d->R + 1;
+  const int Wo = d->W + 2 * d->pad_w - d->S + 1;
+  GDL_REQUIRE(Ho > 0 && Wo > 0, GDL_ERR_INVALID, "empty output %dx%d", Ho, Wo);
+  GDL_REQUIRE(d->ldo >= d->Cout, GDL_ERR_INVALID, "ldo %d < Cout %d", d->ldo, d->Cout);
+
+  ConvFwdKParams p;
+  memset(&p, 0, sizeof(p));
+  p.num_src = d->num_src;
+  p.Ctot = Ctot;
+  p.R = d->R;
+  p.S = d->S;
+  p.pad_h = d->pad_h;
+  p.pad_w = d->pad_w;
+  p.BK = chunk_width(d->src, d->num_src);
+  // geometry: a pointwise conv over NHWC is a flat GEMM over N*H*W pixels
+  int N = d->N, H = d->H, W = d->W, oH = Ho, oW = Wo;
+  if (d->R == 1 && d->S == 1 && d->pad_h == 0 && d->pad_w == 0) {
+    long long M = (long long)N * H * W;
+    GDL_REQUIRE(M < (1ll << 31), GDL_ERR_UNSUPPORTED, "too many pixels");
+    W = (int)M;
+    H = 1;
+    N = 1;
+    oH = 1;
+    oW = W;
+  }
+  p.Nimg = N;
+  p.Ho = oH;
+  p.Wo = oW;
+  choose_tile(oH, oW, 128, &p.TH, &p.TW);
+  p.tiles_w = (oW + p.TW - 1) / p.TW;
+  p.tiles_h = (oH + p.TH - 1) / p.TH;
+  p.Cout = d->Cout;
+  p.n_tiles = (d->Cout + 255) / 256;
+  p.BN = (((d->Cout + p.n_tiles - 1) / p.n_tiles) + 15) / 16 * 16;
+  long long num_tiles = (long long)N * p.tiles_w * p.tiles_h * p.n_tiles;
+  GDL_REQUIRE(num_tiles < (1ll << 31), GDL_ERR_UNSUPPORTED, "too many tiles");
+  p.num_tiles = (int)num_tiles;
+  p.a_bytes = 128 * p.BK * 2;
+  p.b_bytes = p.BN * p.BK * 2;
+  p.stage_bytes = p.a_bytes + ((p.b_bytes + 1023) / 1024) * 1024;
+  p.stages = kSmemBudget / p.stage_bytes;
+  if (p.stages > kMaxStages) p.stages = kMaxStages;
+  GDL_REQUIRE(p.stages >= 2, GDL_ERR_UNSUPPORTED, "tile does not fit shared memory");
+  p.tmem_cols = pow2_ge(2 * p.BN);
+  p.ab_fmt = d->dtype == GDL_BF16 ? 1 : 0;
+  p.out = d->out;
+  p.out_dtype = d->out_dtype;
+  p.ldo = d->ldo;
+  const int esz = d->out_dtype == GDL_F32 ? 4 : 2;
+  p.vec_ok = ((reinterpret_cast<uintptr_t>(d->out) & 15) == 0) && ((d->ldo * esz) % 16 == 0);
+  p.bias = d->bias;
+  p.relu = d->relu;
+
+  int coff = 0;
+  for (int i = 0; i < d->num_src; ++i) {
+    p.src_chunks[i] = d->src[i].channels / p.BK;
+    p.src_coff[i] = coff;
+    coff += d->src[i].channels;
+    st = make_tmap_nhwc(&p.tmA[i], d->src[i].ptr, d->dtype, d->src[i].channels, W, H, N, d->src[i].ld,
+                        p.BK, p.TW, p.TH, p.BK * 2);
+    if (st) return st;
+  }
+  const long long Ktot = (long long)d->R * d->S * Ctot;
+  st = make_tmap_2d(&p.tmB, d->weight, d->dtype, Ktot, d->Cout, Ktot, p.BK, p.BN, p.BK * 2);
+  if (st) return st;
+
+  int smem = p.stages * p.stage_bytes + 1024;
+  if (smem < kMinSmemRequest) smem = kMinSmemRequest;
+  static bool attr_set = false;
+  if (!attr_set) {
+    GDL_CHECK_CUDA(cudaFuncSetAttribute(conv_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        kSmemBudget + 4096));
+    attr_set = true;
+  }
+  int grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();
+  conv_fwd_kernel<<<grid, kConvThreads, smem, stream>>>(p);
+  GDL_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ==========================================================================================
+// wgrad
+// ==========================================================================================
+namespace gdl {
+
+constexpr int kMaxNTiles = 48;
+constexpr int kWgPix = 64;  // pixels (contraction length) per pipeline stage
+
+struct ConvWgradKParams {
+  CUtensorMap tmDY;
+  CUtensorMap tmX[GDL_MAX_SRC];
+  int Ctot, Cout;
+  int R, S, pad_h, pad_w;
+  int TH, TW, tiles_w, tiles_h;
+  int pix_blocks;  // N * tiles_h * tiles_w
+  int ksplit, pb_per_split;
+  int m_tiles, n_ntiles, num_units;
+  int caA, caB;  // channel atom widths (elements) of dY and X boxes: 16/32/64
+  int nt_src[kMaxNTiles], nt_c0[kMaxNTiles], nt_w[kMaxNTiles], nt_coff[kMaxNTiles];
+  int stages, a_bytes, stage_bytes, tmem_cols, bn_max;
+  int ab_fmt;
+  float* dw;
+};
+
+__global__ void __launch_bounds__(kConvThreads, 1)
+conv_wgrad_kernel(const __grid_constant__ ConvWgradKParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = align_smem_1024(smem_raw);
+
+  __shared__ __align__(8) uint64_t full_bar[kMaxStages];
+  __shared__ __align__(8) uint64_t empty_bar[kMaxStages];
+  __shared__ __align__(8) uint64_t tfull_bar[2];
+  __shared__ __align__(8) uint64_t tempty_bar[2];
+  __shared__ uint32_t tmem_base_smem;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int taps = p.R * p.S;
+  const int tiles_per_img = p.tiles_w * p.tiles_h;
+
+  // A-operand atoms beyond Cout are never loaded: they must read as zero.
+  {
+    uint4* z = reinterpret_cast<uint4*>(smem);
+    const int n16 = p.stages * p.stage_bytes / 16;
+    for (int i = threadIdx.x; i < n16; i += blockDim.x) z[i] = make_uint4(0, 0, 0, 0);
+    fence_proxy_async_smem();
+  }
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.tmDY);
+    tma_prefetch_desc(&p.tmX[0]);
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int i = 0; i < p.stages; ++i) {
+        mbar_init(&full_bar[i], 1);
+        mbar_init(&empty_bar[i], 1);
+      }
+      for (int i = 0; i < 2; ++i) {
+        mbar_init(&tfull_bar[i], 1);
+        mbar_init(&tempty_bar[i], 128);
+      }
+      fence_mbar_init();
+    }
+    __syncwarp();
+    tmem_alloc(&tmem_base_smem, (uint32_t)p.tmem_cols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_smem;
+
+  const int atomA_bytes = kWgPix * p.caA * 2;  // one MN atom (caA channels) x 64 pixels
+  const int atomB_bytes = kWgPix * p.caB * 2;
+
+  // unit -> (tap, n-tile, m-tile, k-split); tap fastest so co-resident CTAs share dY / X in L2
+  auto decode = [&](int u, int& tap, int& nt, int& mt, int& ks) {
+    tap = u % taps;
+    u /= taps;
+    nt = u % p.n_ntiles;
+    u /= p.n_ntiles;
+    mt = u % p.m_tiles;
+    ks = u / p.m_tiles;
+  };
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int u = blockIdx.x; u < p.num_units; u += gridDim.x) {
+        int tap, nt, mt, ks;
+        decode(u, tap, nt, mt, ks);
+        const int r = tap / p.S, s = tap - r * p.S;
+        const int m0 = mt * 128;
+        const int a_atoms = min(128, p.Cout - m0) / p.caA;  // Cout % caA == 0
+        const int b_atoms = p.nt_w[nt] / p.caB;
+        const int src = p.nt_src[nt];
+        const int c0 = p.nt_c0[nt];
+        const uint32_t tx = (uint32_t)(a_atoms * atomA_bytes + b_atoms * atomB_bytes);
+        const int pb0 = ks * p.pb_per_split;
+        const int pb1 = min(p.pix_blocks, pb0 + p.pb_per_split);
+        for (int pb = pb0; pb < pb1; ++pb) {
+          const int img = pb / tiles_per_img;
+          const int t_in = pb - img * tiles_per_img;
+          const int h0 = (t_in / p.tiles_w) * p.TH;
+          const int w0 = (t_in % p.tiles_w) * p.TW;
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* a_dst = smem + (size_t)stage * p.stage_bytes;
+          uint8_t* b_dst = a_dst + p.a_bytes;
+          mbar_expect_tx(&full_bar[stage], tx);
+          for (int a = 0; a < a_atoms; ++a)
+            tma_load_4d(a_dst + a * atomA_bytes, &p.tmDY, &full_bar[stage], m0 + a * p.caA, w0, h0, img);
+          for (int b = 0; b < b_atoms; ++b)
+            tma_load_4d(b_dst + b * atomB_bytes, &p.tmX[src], &full_bar[stage], c0 + b * p.caB,
+                        w0 + s - p.pad_w, h0 + r - p.pad_h, img);
+          if (++stage == p.stages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t ltA = umma_layout_type(p.caA * 2), ltB = umma_layout_type(p.caB * 2);
+      const uint32_t sboA = 8u * p.caA * 2u, sboB = 8u * p.caB * 2u;  // 8 pixel rows
+      const uint32_t kstepA = 16u * p.caA * 2u, kstepB = 16u * p.caB * 2u;  // 16 pixel rows
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int u = blockIdx.x; u < p.num_units; u += gridDim.x, ++it) {
+        int tap, nt, mt, ks;
+        decode(u, tap, nt, mt, ks);
+        const int bn = p.nt_w[nt];
+        const uint32_t idesc = umma_idesc(128, bn, p.ab_fmt, 1, 1);
+        const int acc = it & 1;
+        const uint32_t aphase = (it >> 1) & 1;
+        mbar_wait(&tempty_bar[acc], aphase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.bn_max);
+        const int pb0 = ks * p.pb_per_split;
+        const int pb1 = min(p.pix_blocks, pb0 + p.pb_per_split);
+        for (int pb = pb0; pb < pb1; ++pb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem + (size_t)stage * p.stage_bytes);
+          const uint32_t b_addr = a_addr + p.a_bytes;
+          for (int kk = 0; kk < kWgPix / 16; ++kk) {
+            const uint64_t da = umma_smem_desc(a_addr + kk * kstepA, atomA_bytes, sboA, ltA);
+            const uint64_t db = umma_smem_desc(b_addr + kk * kstepB, atomB_bytes, sboB, ltB);
+            umma_f16(d_tmem, da, db, idesc, (uint32_t)((pb > pb0) | (kk != 0)));
+          }
+          umma_commit(&empty_bar[stage]);
+          if (++stage == p.stages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit(&tfull_bar[acc]);
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const long long Ktot = (long long)taps * p.Ctot;
+    int it = 0;
+    for (int u = blockIdx.x; u < p.num_units; u += gridDim.x, ++it) {
+      int tap, nt, mt, ks;
+      decode(u, tap, nt, mt, ks);
+      const int acc = it & 1;
+      const uint32_t aphase = (it >> 1) & 1;
+      const int m = mt * 128 + row;
+      const int bn = p.nt_w[nt];
+      const int pb0 = ks * p.pb_per_split;
+      const bool nonempty = pb0 < p.pix_blocks;
+      float* dst = p.dw + (long long)m * Ktot + (long long)tap * p.Ctot + p.nt_coff[nt];
+      mbar_wait(&tfull_bar[acc], aphase);
+      tc_fence_after();
+      const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.bn_max);
+      for (int j = 0; j < bn / 16; ++j) {
+        uint32_t v[16];
+        tmem_ld_32x32b_x16(t_addr + j * 16, v);
+        tmem_ld_wait();
+        if (m < p.Cout && nonempty) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) atomicAdd(dst + j * 16 + i, __uint_as_float(v[i]));
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&tempty_bar[acc]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+  }
+}
+
+}  // namespace gdl
+
+extern "C" int gdl_conv2d_nhwc_wgrad(const gdl_conv_wgrad_t* d, void* stream_) {
+  GDL_REQUIRE(d != nullptr, GDL_ERR_INVALID, "null descriptor");
+  cudaStream_t stream = (cudaStream_t)stream_;
+  int Ctot = 0;
+  int st = validate_srcs(d->num_src, d->src, &Ctot);
+  if (st) return st;
+  GDL_REQUIRE(d->N > 0 && d->H > 0 && d->W > 0 && d->Cout > 0 && d->Cout % 16 == 0, GDL_ERR_INVALID,
+              "wgrad: bad shape N=%d H=%d W=%d Cout=%d (Cout must be a multiple of 16)", d->N, d->H,
+              d->W, d->Cout);
+  GDL_REQUIRE(d->R >= 1 && d->S >= 1 && d->R <= 15 && d->S <= 15, GDL_ERR_INVALID, "bad filter");
+  GDL_REQUIRE(d->dtype == GDL_BF16 || d->dtype == GDL_F16, GDL_ERR_INVALID, "operand dtype must be bf16/f16");
+  GDL_REQUIRE(d->dy && d->dw, GDL_ERR_INVALID, "null dy/dw");
+  GDL_REQUIRE(d->ld_dy >= d->Cout && d->ld_dy % 8 == 0, GDL_ERR_INVALID, "bad ld_dy %d", d->ld_dy);
+  const int Ho = d->H + 2 * d->pad_h - d->R + 1;
+  const int Wo = d->W + 2 * d->pad_w - d->S + 1;
+  GDL_REQUIRE(Ho > 0 && Wo > 0, GDL_ERR_INVALID, "empty output");
+
+  ConvWgradKParams p;
+  memset(&p, 0, sizeof(p));
+  p.Ctot = Ctot;
+  p.Cout = d->Cout;
+  p.R = d->R;
+  p.S = d->S;
+  p.pad_h = d->pad_h;
+  p.pad_w = d->pad_w;
+  p.caB = chunk_width(d->src, d->num_src);
+  p.caA = 64;
+  while (p.caA > 16 && (d->Cout % p.caA) != 0) p.caA >>= 1;
+
+  int N = d->N, H = d->H, W = d->W, oH = Ho, oW = Wo;
+  if (d->R == 1 && d->S == 1 && d->pad_h == 0 && d->pad_w == 0) {
+    long long M = (long long)N * H * W;
+    GDL_REQUIRE(M < (1ll << 31), GDL_ERR_UNSUPPORTED, "too many pixels");
+    W = (int)M;
+    H = 1;
+    N = 1;
+    oH = 1;
+    oW = W;
+  }
+  choose_tile(oH, oW, kWgPix, &p.TH, &p.TW);
+  p.tiles_w = (oW + p.TW - 1) / p.TW;
+  p.tiles_h = (oH + p.TH - 1) / p.TH;
+  long long pbs = (long long)N * p.tiles_w * p.tiles_h;
+  GDL_REQUIRE(pbs < (1ll << 31), GDL_ERR_UNSUPPORTED, "too many pixel blocks");
+  p.pix_blocks = (int)pbs;
+  p.m_tiles = (d->Cout + 127) / 128;
+
+  // n-tiles: chunks of <= 256 channels that never straddle two sources
+  int nn = 0, coff = 0, bn_max = 16;
+  for (int i = 0; i < d->num_src; ++i) {
+    int c = d->src[i].channels;
+    int parts = (c + 255) / 256;
+    int w = ((c + parts - 1) / parts + p.caB - 1) / p.caB * p.caB;
+    for (int c0 = 0; c0 < c; c0 += w) {
+      GDL_REQUIRE(nn < kMaxNTiles, GDL_ERR_UNSUPPORTED, "too many channel tiles");
+      p.nt_src[nn] = i;
+      p.nt_c0[nn] = c0;
+      p.nt_w[nn] = (c - c0) < w ? (c - c0) : w;
+      p.nt_coff[nn] = coff + c0;
+      if (p.nt_w[nn] > bn_max) bn_max = p.nt_w[nn];
+      ++nn;
+    }
+    coff += c;
+    st = make_tmap_nhwc(&p.tmX[i], d->src[i].ptr, d->dtype, c, W, H, N, d->src[i].ld, p.caB, p.TW, p.TH,
+                        p.caB * 2);
+    if (st) return st;
+  }
+  p.n_ntiles = nn;
+  p.bn_max = bn_max;
+  st = make_tmap_nhwc(&p.tmDY, d->dy, d->dtype, d->Cout, oW, oH, N, d->ld_dy, p.caA, p.TW, p.TH, p.caA * 2);
+  if (st) return st;
+
+  const int taps = d->R * d->S;
+  long long base_units = (long long)p.m_tiles * nn * taps;
+  // split the pixel range so that the grid sees >= ~3 waves, but keep >= 8 stages of work per unit
+  int ks = (int)((3ll * sm_count() + base_units - 1) / base_units);
+  int max_ks = p.pix_blocks / 8;
+  if (max_ks < 1) max_ks = 1;
+  if (ks > max_ks) ks = max_ks;
+  if (ks < 1) ks = 1;
+  p.pb_per_split = (p.pix_blocks + ks - 1) / ks;
+  p.ksplit = (p.pix_blocks + p.pb_per_split - 1) / p.pb_per_split;
+  long long units = base_units * p.ksplit;
+  GDL_REQUIRE(units < (1ll << 31), GDL_ERR_UNSUPPORTED, "too many work units");
+  p.num_units = (int)units;
+
+  p.a_bytes = kWgPix * 128 * 2;
+  const int b_bytes = kWgPix * bn_max * 2;
+  p.stage_bytes = p.a_bytes + ((b_bytes + 1023) / 1024) * 1024;
+  p.stages = kSmemBudget / p.stage_bytes;
+  if (p.stages > kMaxStages) p.stages = kMaxStages;
+  GDL_REQUIRE(p.stages >= 2, GDL_ERR_UNSUPPORTED, "tile does not fit shared memory");
+  p.tmem_cols = pow2_ge(2 * bn_max);
+  p.ab_fmt = d->dtype == GDL_BF16 ? 1 : 0;
+  p.dw = d->dw;
+
+  int smem = p.stages * p.stage_bytes + 1024;
+  if (smem < kMinSmemRequest) smem = kMinSmemRequest;
+  static bool attr_set = false;
+  if (!attr_set) {
+    GDL_CHECK_CUDA(cudaFuncSetAttribute(conv_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        kSmemBudget + 4096));
+    attr_set = true;
+  }
+  int grid = p.num_units < sm_count() ? p.num_units : sm_count();
+  conv_wgrad_kernel<<<grid, kConvThreads, smem, stream>>>(p);
+  GDL_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ==========================================================================================
+// weight layout transforms (tiny, HBM-bound; run once per optimizer step)
+// ==========================================================================================
+namespace gdl {
+
+template <typename T>
+__global__ void pack_weight_kernel(const float* __restrict__ src, T* __restrict__ dst, int Cout, int Cin,
+                                   int R, int S, int transpose) {
+  const long long total = (long long)Cout * Cin * R * S;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    // i indexes dst
+    long long t = i;
+    float v;
+    if (!transpose) {
+      const int c = t % Cin;
+      t /= Cin;
+      const int s = t % S;
+      t /= S;
+      const int r = t % R;
+      const int k = t / R;
+      v = src[(((long long)k * Cin + c) * R + r) * S + s];
+    } else {
+      const int k = t % Cout;
+      t /= Cout;
+      const int s2 = t % S;
+      t /= S;
+      const int r2 = t % R;
+      const int c = t / R;
+      v = src[(((long long)k * Cin + c) * R + (R - 1 - r2)) * S + (S - 1 - s2)];
+    }
+    if constexpr (sizeof(T) == 2 && std::is_same<T, __nv_bfloat16>::value)
+      dst[i] = __float2bfloat16_rn(v);
+    else
+      dst[i] = __float2half_rn(v);
+  }
+}
+
+__global__ void unpack_wgrad_kernel(const float* __restrict__ src, float* __restrict__ dst, int Cout,
+                                    int Cin, int R, int S, int accumulate) {
+  const long long total = (long long)Cout * Cin * R * S;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    // i indexes dst (OIHW)
+    long long t = i;
+    const int s = t % S;
+    t /= S;
+    const int r = t % R;
+    t /= R;
+    const int c = t % Cin;
+    const int k = t / Cin;
+    const float v = src[(((long long)k * R + r) * S + s) * Cin + c];
+    dst[i] = accumulate ? dst[i] + v : v;
+  }
+}
+
+}  // namespace gdl
+
+extern "C" int gdl_pack_conv_weight(const float* src, void* dst, int Cout, int Cin, int R, int S,
+                                    int transpose, int dtype, void* stream) {
+  GDL_REQUIRE(src && dst && Cout > 0 && Cin > 0 && R > 0 && S > 0, GDL_ERR_INVALID, "pack_weight: bad args");
+  GDL_REQUIRE(dtype == GDL_BF16 || dtype == GDL_F16, GDL_ERR_INVALID, "pack_weight: dtype");
+  const long long total = (long long)Cout * Cin * R * S;
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  if (dtype == GDL_BF16)
+    pack_weight_kernel<__nv_bfloat16><<<blocks, 256, 0, (cudaStream_t)stream>>>(
+        src, (__nv_bfloat16*)dst, Cout, Cin, R, S, transpose);
+  else
+    pack_weight_kernel<__half><<<blocks, 256, 0, (cudaStream_t)stream>>>(src, (__half*)dst, Cout, Cin, R,
+                                                                        S, transpose);
+  GDL_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int gdl_unpack_conv_wgrad(const float* src, float* dst, int Cout, int Cin, int R, int S,
+                                     int accumulate, void* stream) {
+  GDL_REQUIRE(src && dst && Cout > 0 && Cin > 0 && R > 0 && S > 0, GDL_ERR_INVALID, "unpack_wgrad: bad args");
+  const long long total = (long long)Cout * Cin * R * S;
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  unpack_wgrad_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(src, dst, Cout, Cin, R, S, accumulate);
+  GDL_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
