@@ -1,0 +1,840 @@
+// elementwise.cu — the HBM-bound kernels around the tensor-core convs: input normalisation,
+// im2col/col2im for strided convs, BatchNorm (train/eval) statistics / apply / backward,
+// gradient gather (+ReLU mask, +2x2 sum-pool of an upsampled consumer), max-pool.
+//
+// All activations are NHWC 16-bit with C % 8 == 0 so every thread moves 128-bit vectors
+// (8 channels); rows are addressed as x[row * ld + c].  Grids are sized in multiples of the
+// SM count and grid-stride over rows.
+#include <string.h>
+
+#include "../../include/gdl_b200.h"
+#include "common.cuh"
+
+namespace gdl {
+
+// ------------------------------------------------------------------------------------------
+// 8-wide 16-bit vector helpers
+// ------------------------------------------------------------------------------------------
+template <typename T>
+struct Vec8;
+
+template <>
+struct Vec8<__nv_bfloat16> {
+  static GDL_DEVINL void unpack(const uint4& u, float (&f)[8]) {
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      f[2 * i] = bf16_lo(w[i]);
+      f[2 * i + 1] = bf16_hi(w[i]);
+    }
+  }
+  static GDL_DEVINL uint4 pack(const float (&f)[8]) {
+    return make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]),
+                      pack_bf16x2(f[6], f[7]));
+  }
+  static GDL_DEVINL float to_float(__nv_bfloat16 v) { return __bfloat162float(v); }
+  static GDL_DEVINL __nv_bfloat16 from_float(float v) { return __float2bfloat16_rn(v); }
+};
+template <>
+struct Vec8<__half> {
+  static GDL_DEVINL void unpack(const uint4& u, float (&f)[8]) {
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      __half2 h = *reinterpret_cast<const __half2*>(&w[i]);
+      float2 t = __half22float2(h);
+      f[2 * i] = t.x;
+      f[2 * i + 1] = t.y;
+    }
+  }
+  static GDL_DEVINL uint4 pack(const float (&f)[8]) {
+    return make_uint4(pack_f16x2(f[0], f[1]), pack_f16x2(f[2], f[3]), pack_f16x2(f[4], f[5]),
+                      pack_f16x2(f[6], f[7]));
+  }
+  static GDL_DEVINL float to_float(__half v) { return __half2float(v); }
+  static GDL_DEVINL __half from_float(float v) { return __float2half_rn(v); }
+};
+
+template <typename T>
+GDL_DEVINL void load8(const T* p, float (&f)[8]) {
+  uint4 u = *reinterpret_cast<const uint4*>(p);
+  Vec8<T>::unpack(u, f);
+}
+template <typename T>
+GDL_DEVINL void store8(T* p, const float (&f)[8]) {
+  *reinterpret_cast<uint4*>(p) = Vec8<T>::pack(f);
+}
+
+static int ew_blocks(long long work_items, int threads, int max_waves = 8) {
+  long long b = (work_items + threads - 1) / threads;
+  long long cap = (long long)kNumSMsB200 * max_waves;
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return (int)b;
+}
+
+#define GDL_DISPATCH_16(dtype, ...)                                  \
+  do {                                                               \
+    if ((dtype) == GDL_BF16) {                                       \
+      using T = __nv_bfloat16;                                       \
+      __VA_ARGS__;                                                   \
+    } else if ((dtype) == GDL_F16) {                                 \
+      using T = __half;                                              \
+      __VA_ARGS__;                                                   \
+    } else {                                                         \
+      ::gdl::set_last_error("16-bit dtype expected, got %d", dtype); \
+      return GDL_ERR_INVALID;                                        \
+    }                                                                \
+  } while (0)
+
+// ------------------------------------------------------------------------------------------
+// input normalisation: y = ((x / 255) - mean_c) / std_c, uint8 (or f32) HWC -> 16-bit NHWC.
+// Arithmetic order follows utils/tensors.py:10-35 (true divisions, fp32).
+// ------------------------------------------------------------------------------------------
+template <typename T, typename TIn>
+__global__ void normalize_kernel(const TIn* __restrict__ x, T* __restrict__ y, long long npix, int C,
+                                 int ld, const float* __restrict__ mean, const float* __restrict__ stdv,
+                                 float image_max, int in_is_chw, long long hw) {
+  const long long total = npix * ld;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long pix = i / ld;
+    const int c = (int)(i - pix * ld);
+    float v = 0.f;
+    if (c < C) {
+      float raw;
+      if (in_is_chw) {
+        const long long n = pix / hw, p = pix - n * hw;
+        raw = (float)x[(n * C + c) * hw + p];
+      } else {
+        raw = (float)x[pix * C + c];
+      }
+      v = raw;
+      if (image_max > 0.f) v = __fdiv_rn(raw, image_max);
+      if (mean != nullptr) v = __fdiv_rn(v - mean[c], stdv[c]);
+    }
+    y[i] = Vec8<T>::from_float(v);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// im2col (for strided convs and the C_in = 3/4/6 stem): col[(n,ho,wo)][(r,s,c)], zero padded
+// to Kpad columns.  One thread moves one 16-byte (8 element) chunk.
+// ------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void im2col_vec8_kernel(const T* __restrict__ x, T* __restrict__ col, int N, int H, int W,
+                                   int C, int ld, int R, int S, int stride, int pad, int Ho, int Wo,
+                                   int Kpad) {
+  const int cv = C / 8;
+  const int kchunks = Kpad / 8;
+  const long long total = (long long)N * Ho * Wo * kchunks;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long row = i / kchunks;
+    const int kc = (int)(i - row * kchunks);
+    const int tap = kc / cv, c8 = kc - tap * cv;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (tap < R * S) {
+      const int r = tap / S, s = tap - r * S;
+      const int wo = (int)(row % Wo);
+      const long long t = row / Wo;
+      const int ho = (int)(t % Ho);
+      const int n = (int)(t / Ho);
+      const int h = ho * stride - pad + r, w = wo * stride - pad + s;
+      if (h >= 0 && h < H && w >= 0 && w < W)
+        v = *reinterpret_cast<const uint4*>(x + (((long long)n * H + h) * W + w) * ld + c8 * 8);
+    }
+    *reinterpret_cast<uint4*>(col + row * Kpad + kc * 8) = v;
+  }
+}
+
+// generic (any C): one thread per output element
+template <typename T>
+__global__ void im2col_scalar_kernel(const T* __restrict__ x, T* __restrict__ col, int N, int H, int W,
+                                     int C, int ld, int R, int S, int stride, int pad, int Ho, int Wo,
+                                     int Kpad) {
+  const long long total = (long long)N * Ho * Wo * Kpad;
+  const int K = R * S * C;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long row = i / Kpad;
+    const int k = (int)(i - row * Kpad);
+    T v = Vec8<T>::from_float(0.f);
+    if (k < K) {
+      const int tap = k / C, c = k - tap * C;
+      const int r = tap / S, s = tap - r * S;
+      const int wo = (int)(row % Wo);
+      const long long t = row / Wo;
+      const int ho = (int)(t % Ho);
+      const int n = (int)(t / Ho);
+      const int h = ho * stride - pad + r, w = wo * stride - pad + s;
+      if (h >= 0 && h < H && w >= 0 && w < W) v = x[(((long long)n * H + h) * W + w) * ld + c];
+    }
+    col[i] = v;
+  }
+}
+
+// col2im (gather form): dx[n,h,w,c] = sum over taps of dcol[(n,ho,wo)][(r,s,c)]
+template <typename T>
+__global__ void col2im_vec8_kernel(const T* __restrict__ dcol, T* __restrict__ dx, int N, int H, int W,
+                                   int C, int ld, int R, int S, int stride, int pad, int Ho, int Wo,
+                                   int Kpad) {
+  const int cv = C / 8;
+  const long long total = (long long)N * H * W * cv;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long pix = i / cv;
+    const int c8 = (int)(i - pix * cv);
+    const int w = (int)(pix % W);
+    const long long t = pix / W;
+    const int h = (int)(t % H);
+    const int n = (int)(t / H);
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int r = 0; r < R; ++r) {
+      const int hn = h + pad - r;
+      if (hn < 0 || hn % stride) continue;
+      const int ho = hn / stride;
+      if (ho >= Ho) continue;
+      for (int s = 0; s < S; ++s) {
+        const int wn = w + pad - s;
+        if (wn < 0 || wn % stride) continue;
+        const int wo = wn / stride;
+        if (wo >= Wo) continue;
+        float f[8];
+        load8(dcol + (((long long)n * Ho + ho) * Wo + wo) * Kpad + (r * S + s) * C + c8 * 8, f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] += f[j];
+      }
+    }
+    store8(dx + pix * ld + c8 * 8, acc);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// BatchNorm statistics.  x: [M][C] (ld).  Per channel: pivot p_c (caller supplied, e.g. the
+// running mean: identical on every rank so partial sums can be all-reduced for SyncBN),
+//   S1 = sum(x - p), S2 = sum((x - p)^2)   (pivoting keeps S2/M - (S1/M)^2 well conditioned)
+// Block = 256 threads = (C/8 channel-vectors) x (rows in flight); each thread strides rows.
+// ------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void bn_stats_kernel(const T* __restrict__ x, long long M, int C, int ld,
+                                float* __restrict__ sums /* [2][C], pre-zeroed */,
+                                const float* __restrict__ pivot /* [C] or null */) {
+  const int cv = C / 8;
+  const int tpr = cv < (int)blockDim.x ? cv : blockDim.x;  // threads spanning the channel dim
+  const int rows_per_block = blockDim.x / tpr;
+  const int tc = threadIdx.x % tpr;
+  const int tr = threadIdx.x / tpr;
+  extern __shared__ float red[];  // [rows_per_block][tpr*8][2] reduced at the end
+  for (int cbase = 0; cbase < cv; cbase += tpr) {  // uniform trip count (barriers inside)
+    const int c8 = cbase + tc;
+    const bool active = (c8 < cv) && (tr < rows_per_block);
+    float piv[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (active && pivot != nullptr) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) piv[j] = pivot[c8 * 8 + j];
+    }
+    float s1[8] = {0, 0, 0, 0, 0, 0, 0, 0}, s2[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (active) {
+      for (long long row = (long long)blockIdx.x * rows_per_block + tr; row < M;
+           row += (long long)gridDim.x * rows_per_block) {
+        float f[8];
+        load8(x + row * ld + c8 * 8, f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float d = f[j] - piv[j];
+          s1[j] += d;
+          s2[j] = fmaf(d, d, s2[j]);
+        }
+      }
+    }
+    // reduce across the rows_per_block threads that share this channel vector
+    __syncthreads();
+    if (tr < rows_per_block) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        red[((tr * tpr + tc) * 8 + j) * 2 + 0] = s1[j];
+        red[((tr * tpr + tc) * 8 + j) * 2 + 1] = s2[j];
+      }
+    }
+    __syncthreads();
+    if (tr == 0 && c8 < cv) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float a = 0.f, b = 0.f;
+        for (int r = 0; r < rows_per_block; ++r) {
+          a += red[((r * tpr + tc) * 8 + j) * 2 + 0];
+          b += red[((r * tpr + tc) * 8 + j) * 2 + 1];
+        }
+        atomicAdd(&sums[c8 * 8 + j], a);
+        atomicAdd(&sums[C + c8 * 8 + j], b);
+      }
+    }
+  }
+}
+
+// finalize: mean/var -> (scale, shift) for the apply kernel, saved (mean, invstd) for backward,
+// running statistics update with momentum and unbiased variance (nn.BatchNorm2d semantics).
+__global__ void bn_finalize_kernel(const float* pivot /* may alias running_mean */, const float* __restrict__ sums, long long M,
+                                   int C, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                   float eps, float momentum, float* running_mean,
+                                   float* __restrict__ running_var, float* __restrict__ scale,
+                                   float* __restrict__ shift, float* __restrict__ save_mean,
+                                   float* __restrict__ save_invstd) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const float piv = pivot ? pivot[c] : 0.f;
+  const float invM = 1.0f / (float)M;
+  const float m1 = sums[c] * invM;
+  float var = sums[C + c] * invM - m1 * m1;
+  var = fmaxf(var, 0.f);
+  const float mean = piv + m1;
+  const float invstd = rsqrtf(var + eps);
+  const float g = gamma ? gamma[c] : 1.f, b = beta ? beta[c] : 0.f;
+  scale[c] = g * invstd;
+  shift[c] = b - mean * g * invstd;
+  save_mean[c] = mean;
+  save_invstd[c] = invstd;
+  if (running_mean) {
+    const float unb = M > 1 ? var * ((float)M / (float)(M - 1)) : var;
+    running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mean;
+    running_var[c] = (1.f - momentum) * running_var[c] + momentum * unb;
+  }
+}
+
+// eval-mode: scale/shift from running statistics
+__global__ void bn_eval_coeffs_kernel(int C, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                      const float* __restrict__ rm, const float* __restrict__ rv, float eps,
+                                      float* __restrict__ scale, float* __restrict__ shift) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const float invstd = rsqrtf(rv[c] + eps);
+  const float g = gamma ? gamma[c] : 1.f, b = beta ? beta[c] : 0.f;
+  scale[c] = g * invstd;
+  shift[c] = b - rm[c] * g * invstd;
+}
+
+// ------------------------------------------------------------------------------------------
+// BN apply (+ residual, + ReLU, + optional nearest x2 upsampled second output)
+//   y = act( x*scale + shift + [ res*rscale + rshift | res ] )
+// ------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void bn_apply_kernel(const T* __restrict__ x, int ldx, const float* __restrict__ scale,
+                                const float* __restrict__ shift, const T* __restrict__ res, int ldr,
+                                const float* __restrict__ rscale, const float* __restrict__ rshift,
+                                int relu, T* __restrict__ y, int ldy, T* __restrict__ y_up, int ldu,
+                                int N, int H, int W, int C) {
+  const int cv = C / 8;
+  const long long total = (long long)N * H * W * cv;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long pix = i / cv;
+    const int c0 = (int)(i - pix * cv) * 8;
+    float f[8];
+    load8(x + pix * ldx + c0, f);
+    const float4 sa = *reinterpret_cast<const float4*>(scale + c0);
+    const float4 sb = *reinterpret_cast<const float4*>(scale + c0 + 4);
+    const float4 ha = *reinterpret_cast<const float4*>(shift + c0);
+    const float4 hb = *reinterpret_cast<const float4*>(shift + c0 + 4);
+    const float sc[8] = {sa.x, sa.y, sa.z, sa.w, sb.x, sb.y, sb.z, sb.w};
+    const float sh[8] = {ha.x, ha.y, ha.z, ha.w, hb.x, hb.y, hb.z, hb.w};
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f[j] = fmaf(f[j], sc[j], sh[j]);
+    if (res != nullptr) {
+      float g[8];
+      load8(res + pix * ldr + c0, g);
+      if (rscale != nullptr) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) g[j] = fmaf(g[j], rscale[c0 + j], rshift[c0 + j]);
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] += g[j];
+    }
+    if (relu) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], 0.f);
+    }
+    const uint4 packed = Vec8<T>::pack(f);
+    if (y != nullptr) *reinterpret_cast<uint4*>(y + pix * ldy + c0) = packed;
+    if (y_up != nullptr) {
+      const int w = (int)(pix % W);
+      const long long t = pix / W;
+      const int h = (int)(t % H);
+      const long long n = t / H;
+      const long long W2 = 2ll * W;
+      const long long base = ((n * 2 * H + 2 * h) * W2 + 2 * w);
+      T* u = y_up + base * ldu + c0;
+      *reinterpret_cast<uint4*>(u) = packed;
+      *reinterpret_cast<uint4*>(u + ldu) = packed;
+      *reinterpret_cast<uint4*>(u + W2 * ldu) = packed;
+      *reinterpret_cast<uint4*>(u + (W2 + 1) * ldu) = packed;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// gradient gather: g = (sum_k src_k) [* (y > 0)], optionally accumulating the BN-backward sums
+//   sum_g[c] and sum_gxhat[c] = sum g * (x - mean) * invstd  in the same pass.
+// A source with mode 1 is the gradient of a nearest-x2-upsampled copy (shape 2H x 2W): its
+// contribution is the 2x2 sum.
+// ------------------------------------------------------------------------------------------
+struct GatherSrcs {
+  const void* ptr[GDL_MAX_SRC];
+  int ld[GDL_MAX_SRC];
+  int mode[GDL_MAX_SRC];
+  int n;
+};
+
+template <typename T>
+__global__ void grad_gather_kernel(GatherSrcs srcs, const T* __restrict__ y, int ldy, const T* __restrict__ x,
+                                   int ldx, const float* __restrict__ mean, const float* __restrict__ invstd,
+                                   T* __restrict__ g, int ldg, float* __restrict__ sums /* [2][C] or null */,
+                                   int N, int H, int W, int C) {
+  const int cv = C / 8;
+  const int tpr = cv < (int)blockDim.x ? cv : blockDim.x;
+  const int rows_per_block = blockDim.x / tpr;
+  const int tc = threadIdx.x % tpr;
+  const int tr = threadIdx.x / tpr;
+  const long long M = (long long)N * H * W;
+  extern __shared__ float red[];
+  for (int cbase = 0; cbase < cv; cbase += tpr) {  // uniform trip count (barriers inside)
+    const int c8 = cbase + tc;
+    const bool active = (c8 < cv) && (tr < rows_per_block);
+    const int c0 = c8 * 8;
+    float s1[8] = {0, 0, 0, 0, 0, 0, 0, 0}, s2[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    float mu[8] = {0, 0, 0, 0, 0, 0, 0, 0}, is[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (sums != nullptr && active) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        mu[j] = mean[c0 + j];
+        is[j] = invstd[c0 + j];
+      }
+    }
+    if (active) {
+      for (long long pix = (long long)blockIdx.x * rows_per_block + tr; pix < M;
+           pix += (long long)gridDim.x * rows_per_block) {
+        float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        for (int k = 0; k < srcs.n; ++k) {
+          const T* sp = reinterpret_cast<const T*>(srcs.ptr[k]);
+          float f[8];
+          if (srcs.mode[k] == 0) {
+            load8(sp + pix * srcs.ld[k] + c0, f);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[j] += f[j];
+          } else {
+            const int w = (int)(pix % W);
+            const long long t = pix / W;
+            const int h = (int)(t % H);
+            const long long n = t / H;
+            const long long W2 = 2ll * W;
+            const T* b = sp + ((n * 2 * H + 2 * h) * W2 + 2 * w) * srcs.ld[k] + c0;
+            float s4[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+            load8(b, f);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) s4[j] += f[j];
+            load8(b + srcs.ld[k], f);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) s4[j] += f[j];
+            load8(b + W2 * srcs.ld[k], f);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) s4[j] += f[j];
+            load8(b + (W2 + 1) * srcs.ld[k], f);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[j] += s4[j] + f[j];
+          }
+        }
+        if (y != nullptr) {
+          float yy[8];
+          load8(y + pix * ldy + c0, yy);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[j] = yy[j] > 0.f ? acc[j] : 0.f;
+        }
+        // the gradient that flows on is the 16-bit rounded one: use it for the sums too
+        const uint4 packed = Vec8<T>::pack(acc);
+        if (g != nullptr) *reinterpret_cast<uint4*>(g + pix * ldg + c0) = packed;
+        if (sums != nullptr) {
+          float gr[8], xx[8];
+          Vec8<T>::unpack(packed, gr);
+          load8(x + pix * ldx + c0, xx);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            s1[j] += gr[j];
+            s2[j] = fmaf(gr[j], (xx[j] - mu[j]) * is[j], s2[j]);
+          }
+        }
+      }
+    }
+    if (sums != nullptr) {
+      __syncthreads();
+      if (tr < rows_per_block) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          red[((tr * tpr + tc) * 8 + j) * 2 + 0] = s1[j];
+          red[((tr * tpr + tc) * 8 + j) * 2 + 1] = s2[j];
+        }
+      }
+      __syncthreads();
+      if (tr == 0 && c8 < cv) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float a = 0.f, b = 0.f;
+          for (int r = 0; r < rows_per_block; ++r) {
+            a += red[((r * tpr + tc) * 8 + j) * 2 + 0];
+            b += red[((r * tpr + tc) * 8 + j) * 2 + 1];
+          }
+          atomicAdd(&sums[c0 + j], a);
+          atomicAdd(&sums[C + c0 + j], b);
+        }
+      }
+    }
+  }
+}
+
+// BN backward, elementwise part:  dx = gamma*invstd * (g - sum_g/M - xhat * sum_gxhat/M)
+// (in place on g allowed); also emits dgamma = sum_gxhat, dbeta = sum_g (accumulated).
+template <typename T>
+__global__ void bn_bwd_apply_kernel(const T* __restrict__ g, int ldg, const T* __restrict__ x, int ldx,
+                                    const float* __restrict__ mean, const float* __restrict__ invstd,
+                                    const float* __restrict__ gamma, const float* __restrict__ sums,
+                                    T* __restrict__ dx, int ldd, long long M, long long count, int C) {
+  const int cv = C / 8;
+  const long long total = M * cv;
+  const float invM = 1.0f / (float)count;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long pix = i / cv;
+    const int c0 = (int)(i - pix * cv) * 8;
+    float gg[8], xx[8], o[8];
+    load8(g + pix * ldg + c0, gg);
+    load8(x + pix * ldx + c0, xx);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = c0 + j;
+      const float is = invstd[c];
+      const float xhat = (xx[j] - mean[c]) * is;
+      const float ga = gamma ? gamma[c] : 1.f;
+      o[j] = ga * is * (gg[j] - sums[c] * invM - xhat * sums[C + c] * invM);
+    }
+    store8(dx + pix * ldd + c0, o);
+  }
+}
+
+__global__ void bn_param_grads_kernel(const float* __restrict__ sums, int C, float* __restrict__ dgamma,
+                                      float* __restrict__ dbeta, int accumulate) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  if (dgamma) dgamma[c] = (accumulate ? dgamma[c] : 0.f) + sums[C + c];
+  if (dbeta) dbeta[c] = (accumulate ? dbeta[c] : 0.f) + sums[c];
+}
+
+// ------------------------------------------------------------------------------------------
+// max-pool 3x3 / stride 2 / pad 1 (ResNet stem), NHWC.  The argmax tap (first maximum in
+// (r,s) scan order, as ATen) is saved as one byte per output element for the backward.
+// ------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void maxpool3x3s2_fwd_kernel(const T* __restrict__ x, int ldx, T* __restrict__ y, int ldy,
+                                        uint8_t* __restrict__ idx, int N, int H, int W, int C, int Ho, int Wo) {
+  const int cv = C / 8;
+  const long long total = (long long)N * Ho * Wo * cv;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long opix = i / cv;
+    const int c0 = (int)(i - opix * cv) * 8;
+    const int wo = (int)(opix % Wo);
+    const long long t = opix / Wo;
+    const int ho = (int)(t % Ho);
+    const int n = (int)(t / Ho);
+    float best[8];
+    int bi[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      best[j] = -INFINITY;
+      bi[j] = 0;
+    }
+    bool first = true;
+    for (int r = 0; r < 3; ++r) {
+      const int h = 2 * ho - 1 + r;
+      if (h < 0 || h >= H) continue;
+      for (int s = 0; s < 3; ++s) {
+        const int w = 2 * wo - 1 + s;
+        if (w < 0 || w >= W) continue;
+        float f[8];
+        load8(x + (((long long)n * H + h) * W + w) * ldx + c0, f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          if (first || f[j] > best[j]) {
+            best[j] = f[j];
+            bi[j] = r * 3 + s;
+          }
+        }
+        first = false;
+      }
+    }
+    store8(y + opix * ldy + c0, best);
+    if (idx != nullptr) {
+      uint2 p;
+      p.x = (uint32_t)bi[0] | ((uint32_t)bi[1] << 8) | ((uint32_t)bi[2] << 16) | ((uint32_t)bi[3] << 24);
+      p.y = (uint32_t)bi[4] | ((uint32_t)bi[5] << 8) | ((uint32_t)bi[6] << 16) | ((uint32_t)bi[7] << 24);
+      *reinterpret_cast<uint2*>(idx + opix * C + c0) = p;
+    }
+  }
+}
+
+template <typename T>
+__global__ void maxpool3x3s2_bwd_kernel(const T* __restrict__ dy, int ldy, const uint8_t* __restrict__ idx,
+                                        T* __restrict__ dx, int ldx, int N, int H, int W, int C, int Ho,
+                                        int Wo) {
+  const int cv = C / 8;
+  const long long total = (long long)N * H * W * cv;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long pix = i / cv;
+    const int c0 = (int)(i - pix * cv) * 8;
+    const int w = (int)(pix % W);
+    const long long t = pix / W;
+    const int h = (int)(t % H);
+    const int n = (int)(t / H);
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int r = 0; r < 3; ++r) {
+      const int hn = h + 1 - r;
+      if (hn < 0 || (hn & 1)) continue;
+      const int ho = hn >> 1;
+      if (ho >= Ho) continue;
+      for (int s = 0; s < 3; ++s) {
+        const int wn = w + 1 - s;
+        if (wn < 0 || (wn & 1)) continue;
+        const int wo = wn >> 1;
+        if (wo >= Wo) continue;
+        const long long opix = ((long long)n * Ho + ho) * Wo + wo;
+        const uint2 p = *reinterpret_cast<const uint2*>(idx + opix * C + c0);
+        float f[8];
+        load8(dy + opix * ldy + c0, f);
+        const int tap = r * 3 + s;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const uint32_t word = j < 4 ? p.x : p.y;
+          const int sel = (word >> ((j & 3) * 8)) & 0xff;
+          if (sel == tap) acc[j] += f[j];
+        }
+      }
+    }
+    store8(dx + pix * ldx + c0, acc);
+  }
+}
+
+}  // namespace gdl
+
+using namespace gdl;
+
+// ==========================================================================================
+// C ABI
+// ==========================================================================================
+extern "C" int gdl_normalize_to_nhwc(const void* x, int in_kind, void* y, int out_dtype, long long N,
+                                     long long H, long long W, int C, int ld, const float* mean,
+                                     const float* stdv, float image_max, void* stream) {
+  GDL_REQUIRE(x && y && N > 0 && H > 0 && W > 0 && C > 0 && ld >= C, GDL_ERR_INVALID, "normalize: bad args");
+  GDL_REQUIRE((mean == nullptr) == (stdv == nullptr), GDL_ERR_INVALID, "normalize: mean and std go together");
+  const long long npix = N * H * W;
+  const int blocks = ew_blocks(npix * ld, 256, 16);
+  cudaStream_t st = (cudaStream_t)stream;
+  // in_kind: 0 = uint8 NHWC, 1 = f32 NHWC, 2 = f32 NCHW, 3 = uint8 NCHW
+  GDL_DISPATCH_16(out_dtype, {
+    if (in_kind == 0)
+      normalize_kernel<T, uint8_t><<<blocks, 256, 0, st>>>((const uint8_t*)x, (T*)y, npix, C, ld, mean, stdv, image_max, 0, H * W);
+    else if (in_kind == 1)
+      normalize_kernel<T, float><<<blocks, 256, 0, st>>>((const float*)x, (T*)y, npix, C, ld, mean, stdv, image_max, 0, H * W);
+    else if (in_kind == 2)
+      normalize_kernel<T, float><<<blocks, 256, 0, st>>>((const float*)x, (T*)y, npix, C, ld, mean, stdv, image_max, 1, H * W);
+    else if (in_kind == 3)
+      normalize_kernel<T, uint8_t><<<blocks, 256, 0, st>>>((const uint8_t*)x, (T*)y, npix, C, ld, mean, stdv, image_max, 1, H * W);
+    else {
+      set_last_error("normalize: unknown in_kind %d", in_kind);
+      return GDL_ERR_INVALID;
+    }
+  });
+  GDL_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int gdl_im2col_nhwc(const void* x, void* col, int dtype, int N, int H, int W, int C, int ld,
+                               int R, int S, int stride, int pad, int Kpad, void* stream) {
+  GDL_REQUIRE(x && col && N > 0 && H > 0 && W > 0 && C > 0 && ld >= C && R > 0 && S > 0 && stride > 0 && pad >= 0,
+              GDL_ERR_INVALID, "im2col: bad args");
+  GDL_REQUIRE(Kpad >= R * S * C && Kpad % 8 == 0, GDL_ERR_INVALID, "im2col: Kpad %d too small or not a multiple of 8", Kpad);
+  const int Ho = (H + 2 * pad - R) / stride + 1, Wo = (W + 2 * pad - S) / stride + 1;
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool vec = (C % 8 == 0) && (ld % 8 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
+  GDL_DISPATCH_16(dtype, {
+    if (vec) {
+      const long long total = (long long)N * Ho * Wo * (Kpad / 8);
+      im2col_vec8_kernel<T><<<ew_blocks(total, 256, 16), 256, 0, st>>>((const T*)x, (T*)col, N, H, W, C, ld, R, S, stride, pad, Ho, Wo, Kpad);
+    } else {
+      const long long total = (long long)N * Ho * Wo * Kpad;
+      im2col_scalar_kernel<T><<<ew_blocks(total, 256, 32), 256, 0, st>>>((const T*)x, (T*)col, N, H, W, C, ld, R, S, stride, pad, Ho, Wo, Kpad);
+    }
+  });
+  GDL_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int gdl_col2im_nhwc(const void* dcol, void* dx, int dtype, int N, int H, int W, int C, int ld,
+                               int R, int S, int stride, int pad, int Kpad, void* stream) {
+  GDL_REQUIRE(dcol && dx && N > 0 && H > 0 && W > 0 && C > 0 && C % 8 == 0 && ld >= C && ld % 8 == 0,
+              GDL_ERR_INVALID, "col2im: bad args (C must be a multiple of 8)");
+  GDL_REQUIRE(Kpad >= R * S * C && Kpad % 8 == 0, GDL_ERR_INVALID, "col2im: bad Kpad");
+  const int Ho = (H + 2 * pad - R) / stride + 1, Wo = (W + 2 * pad - S) / stride + 1;
+  const long long total = (long long)N * H * W * (C / 8);
+  cudaStream_t st = (cudaStream_t)stream;
+  GDL_DISPATCH_16(dtype, {
+    col2im_vec8_kernel<T><<<ew_blocks(total, 256, 16), 256, 0, st>>>((const T*)dcol, (T*)dx, N, H, W, C, ld, R, S, stride, pad, Ho, Wo, Kpad);
+  });
+  GDL_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+static int stats_launch_geometry(int C, int* threads, int* smem_bytes) {
+  const int cv = C / 8;
+  const int t = 256;
+  const int tpr = cv < t ? cv : t;
+  const int rpb = t / tpr;
+  *threads = t;
+  *smem_bytes = rpb * tpr * 8 * 2 * (int)sizeof(float);
+  return rpb;
+}
+
+extern "C" int gdl_bn_stats(const void* x, int dtype, long long M, int C, int ld, float* sums,
+                            const float* pivot, void* stream) {
+  GDL_REQUIRE(x && sums && M > 0 && C > 0 && C % 8 == 0 && ld >= C && ld % 8 == 0, GDL_ERR_INVALID,
+              "bn_stats: bad args (C=%d must be a multiple of 8)", C);
+  cudaStream_t st = (cudaStream_t)stream;
+  GDL_CHECK_CUDA(cudaMemsetAsync(sums, 0, 2 * (size_t)C * sizeof(float), st));
+  int threads, smem;
+  const int rpb = stats_launch_geometry(C, &threads, &smem);
+  long long blocks = (M + rpb * 16 - 1) / (rpb * 16);  // >= 16 rows per thread
+  if (blocks > 2 * kNumSMsB200) blocks = 2 * kNumSMsB200;
+  if (blocks < 1) blocks = 1;
+  GDL_DISPATCH_16(dtype, { bn_stats_kernel<T><<<(int)blocks, threads, smem, st>>>((const T*)x, M, C, ld, sums, pivot); });
+  GDL_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int gdl_bn_finalize(const float* pivot, const float* sums, long long M, int C, const float* gamma,
+                               const float* beta, float eps, float momentum, float* running_mean,
+                               float* running_var, float* scale, float* shift, float* save_mean,
+                               float* save_invstd, void* stream) {
+  GDL_REQUIRE(sums && scale && shift && save_mean && save_invstd && M > 0 && C > 0, GDL_ERR_INVALID,
+              "bn_finalize: bad args");
+  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, (cudaStream_t)stream>>>(pivot, sums, M, C, gamma, beta, eps,
+                                                                       momentum, running_mean, running_var, scale,
+                                                                       shift, save_mean, save_invstd);
+  GDL_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int gdl_bn_eval_coeffs(int C, const float* gamma, const float* beta, const float* running_mean,
+                                  const float* running_var, float eps, float* scale, float* shift, void* stream) {
+  GDL_REQUIRE(C > 0 && running_mean && running_var && scale && shift, GDL_ERR_INVALID, "bn_eval_coeffs: bad args");
+  bn_eval_coeffs_kernel<<<(C + 127) / 128, 128, 0, (cudaStream_t)stream>>>(C, gamma, beta, running_mean,
+                                                                          running_var, eps, scale, shift);
+  GDL_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int gdl_bn_apply(const void* x, int ldx, const float* scale, const float* shift, const void* res,
+                            int ldr, const float* rscale, const float* rshift, int relu, void* y, int ldy,
+                            void* y_up, int ldu, int dtype, int N, int H, int W, int C, void* stream) {
+  GDL_REQUIRE(x && scale && shift && (y || y_up) && N > 0 && H > 0 && W > 0 && C > 0 && C % 8 == 0,
+              GDL_ERR_INVALID, "bn_apply: bad args (C=%d must be a multiple of 8)", C);
+  GDL_REQUIRE(ldx % 8 == 0 && (!y || ldy % 8 == 0) && (!y_up || ldu % 8 == 0) && (!res || ldr % 8 == 0),
+              GDL_ERR_INVALID, "bn_apply: strides must be multiples of 8");
+  GDL_REQUIRE((rscale == nullptr) == (rshift == nullptr), GDL_ERR_INVALID, "bn_apply: rscale/rshift go together");
+  const long long total = (long long)N * H * W * (C / 8);
+  cudaStream_t st = (cudaStream_t)stream;
+  GDL_DISPATCH_16(dtype, {
+    bn_apply_kernel<T><<<ew_blocks(total, 256, 16), 256, 0, st>>>((const T*)x, ldx, scale, shift, (const T*)res, ldr,
+                                                                  rscale, rshift, relu, (T*)y, ldy, (T*)y_up, ldu,
+                                                                  N, H, W, C);
+  });
+  GDL_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int gdl_grad_gather(int num_src, const void* const* src_ptr, const int* src_ld, const int* src_mode,
+                               const void* y, int ldy, const void* x, int ldx, const float* mean,
+                               const float* invstd, void* g, int ldg, float* sums, int dtype, int N, int H,
+                               int W, int C, void* stream) {
+  GDL_REQUIRE(num_src >= 1 && num_src <= GDL_MAX_SRC && src_ptr && src_ld && src_mode, GDL_ERR_INVALID,
+              "grad_gather: between 1 and %d sources", GDL_MAX_SRC);
+  GDL_REQUIRE(N > 0 && H > 0 && W > 0 && C > 0 && C % 8 == 0, GDL_ERR_INVALID, "grad_gather: bad shape");
+  GDL_REQUIRE(g || sums, GDL_ERR_INVALID, "grad_gather: nothing to produce");
+  GDL_REQUIRE(!sums || (x && mean && invstd), GDL_ERR_INVALID, "grad_gather: sums need x, mean, invstd");
+  GatherSrcs gs;
+  memset(&gs, 0, sizeof(gs));
+  gs.n = num_src;
+  for (int i = 0; i < num_src; ++i) {
+    GDL_REQUIRE(src_ptr[i] && src_ld[i] % 8 == 0, GDL_ERR_INVALID, "grad_gather: bad source %d", i);
+    gs.ptr[i] = src_ptr[i];
+    gs.ld[i] = src_ld[i];
+    gs.mode[i] = src_mode[i];
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  if (sums) GDL_CHECK_CUDA(cudaMemsetAsync(sums, 0, 2 * (size_t)C * sizeof(float), st));
+  int threads, smem;
+  const int rpb = stats_launch_geometry(C, &threads, &smem);
+  const long long M = (long long)N * H * W;
+  long long blocks = (M + rpb * 8 - 1) / (rpb * 8);
+  if (blocks > 4 * kNumSMsB200) blocks = 4 * kNumSMsB200;
+  if (blocks < 1) blocks = 1;
+  GDL_DISPATCH_16(dtype, {
+    grad_gather_kernel<T><<<(int)blocks, threads, smem, st>>>(gs, (const T*)y, ldy, (const T*)x, ldx, mean, invstd,
+                                                             (T*)g, ldg, sums, N, H, W, C);
+  });
+  GDL_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int gdl_bn_bwd_apply(const void* g, int ldg, const void* x, int ldx, const float* mean,
+                                const float* invstd, const float* gamma, const float* sums, void* dx, int ldd,
+                                float* dgamma, float* dbeta, int accumulate_param_grads, int dtype, long long M,
+                                long long count, int C, void* stream) {
+  GDL_REQUIRE(g && x && mean && invstd && sums && dx && M > 0 && C > 0 && C % 8 == 0, GDL_ERR_INVALID,
+              "bn_bwd_apply: bad args");
+  cudaStream_t st = (cudaStream_t)stream;
+  GDL_DISPATCH_16(dtype, {
+    bn_bwd_apply_kernel<T><<<ew_blocks(M * (C / 8), 256, 16), 256, 0, st>>>((const T*)g, ldg, (const T*)x, ldx, mean,
+                                                                           invstd, gamma, sums, (T*)dx, ldd, M, count > 0 ? count : M, C);
+  });
+  GDL_CHECK_CUDA(cudaGetLastError());
+  if (dgamma || dbeta) {
+    bn_param_grads_kernel<<<(C + 127) / 128, 128, 0, st>>>(sums, C, dgamma, dbeta, accumulate_param_grads);
+    GDL_CHECK_CUDA(cudaGetLastError());
+  }
+  return 0;
+}
+
+extern "C" int gdl_maxpool3x3s2_fwd(const void* x, int ldx, void* y, int ldy, unsigned char* idx, int dtype, int N,
+                                    int H, int W, int C, void* stream) {
+  GDL_REQUIRE(x && y && N > 0 && H > 0 && W > 0 && C > 0 && C % 8 == 0 && ldx % 8 == 0 && ldy % 8 == 0,
+              GDL_ERR_INVALID, "maxpool: bad args");
+  const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
+  const long long total = (long long)N * Ho * Wo * (C / 8);
+  cudaStream_t st = (cudaStream_t)stream;
+  GDL_DISPATCH_16(dtype, {
+    maxpool3x3s2_fwd_kernel<T><<<ew_blocks(total, 256, 16), 256, 0, st>>>((const T*)x, ldx, (T*)y, ldy, idx, N, H, W, C, Ho, Wo);
+  });
+  GDL_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int gdl_maxpool3x3s2_bwd(const void* dy, int ldy, const unsigned char* idx, void* dx, int ldx, int dtype,
+                                    int N, int H, int W, int C, void* stream) {
+  GDL_REQUIRE(dy && idx && dx && N > 0 && H > 0 && W > 0 && C > 0 && C % 8 == 0, GDL_ERR_INVALID, "maxpool bwd: bad args");
+  const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
+  const long long total = (long long)N * H * W * (C / 8);
+  cudaStream_t st = (cudaStream_t)stream;
+  GDL_DISPATCH_16(dtype, {
+    maxpool3x3s2_bwd_kernel<T><<<ew_blocks(total, 256, 16), 256, 0, st>>>((const T*)dy, ldy, idx, (T*)dx, ldx, N, H, W, C, Ho, Wo);
+  });
+  GDL_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}

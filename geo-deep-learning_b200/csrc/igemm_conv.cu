@@ -753,45 +753,55 @@ extern "C" int gdl_conv2d_nhwc_wgrad(const gdl_conv_wgrad_t* d, void* stream_) {
 // ==========================================================================================
 namespace gdl {
 
+// dst row r (of `rows` rows, `cols` valid columns, row stride dst_ld, zero padded):
+//   mode 0: rows = Cout, cols = (r,s,c)        dst[k][(r,s,c)]           = src[k][c][r][s]
+//   mode 1: rows = Cin,  cols = (r',s',k)      dst[c][(R-1-r,S-1-s,k)]   = src[k][c][r][s]   (dgrad)
+//   mode 2: rows = (r,s,c), cols = k           dst[(r,s,c)][k]           = src[k][c][r][s]   (im2col dgrad)
 template <typename T>
 __global__ void pack_weight_kernel(const float* __restrict__ src, T* __restrict__ dst, int Cout, int Cin,
-                                   int R, int S, int transpose) {
-  const long long total = (long long)Cout * Cin * R * S;
+                                   int R, int S, int mode, int rows, int cols, int dst_ld) {
+  const long long total = (long long)rows * dst_ld;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
-    // i indexes dst
-    long long t = i;
-    float v;
-    if (!transpose) {
-      const int c = t % Cin;
-      t /= Cin;
-      const int s = t % S;
-      t /= S;
-      const int r = t % R;
-      const int k = t / R;
+    const int row = (int)(i / dst_ld);
+    const int col = (int)(i - (long long)row * dst_ld);
+    float v = 0.f;
+    if (col < cols) {
+      int k, c, r, s;
+      if (mode == 0) {
+        k = row;
+        c = col % Cin;
+        const int t = col / Cin;
+        s = t % S;
+        r = t / S;
+      } else if (mode == 1) {
+        c = row;
+        k = col % Cout;
+        const int t = col / Cout;
+        s = S - 1 - (t % S);
+        r = R - 1 - (t / S);
+      } else {
+        k = col;
+        c = row % Cin;
+        const int t = row / Cin;
+        s = t % S;
+        r = t / S;
+      }
       v = src[(((long long)k * Cin + c) * R + r) * S + s];
-    } else {
-      const int k = t % Cout;
-      t /= Cout;
-      const int s2 = t % S;
-      t /= S;
-      const int r2 = t % R;
-      const int c = t / R;
-      v = src[(((long long)k * Cin + c) * R + (R - 1 - r2)) * S + (S - 1 - s2)];
     }
-    if constexpr (sizeof(T) == 2 && std::is_same<T, __nv_bfloat16>::value)
+    if constexpr (std::is_same<T, __nv_bfloat16>::value)
       dst[i] = __float2bfloat16_rn(v);
     else
       dst[i] = __float2half_rn(v);
   }
 }
 
+// grad fp32 [Cout][src_ld] with columns (r,s,c) -> fp32 OIHW
 __global__ void unpack_wgrad_kernel(const float* __restrict__ src, float* __restrict__ dst, int Cout,
-                                    int Cin, int R, int S, int accumulate) {
+                                    int Cin, int R, int S, int src_ld, int accumulate) {
   const long long total = (long long)Cout * Cin * R * S;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
-    // i indexes dst (OIHW)
     long long t = i;
     const int s = t % S;
     t /= S;
@@ -799,7 +809,7 @@ __global__ void unpack_wgrad_kernel(const float* __restrict__ src, float* __rest
     t /= R;
     const int c = t % Cin;
     const int k = t / Cin;
-    const float v = src[(((long long)k * R + r) * S + s) * Cin + c];
+    const float v = src[(long long)k * src_ld + ((long long)r * S + s) * Cin + c];
     dst[i] = accumulate ? dst[i] + v : v;
   }
 }
@@ -807,29 +817,36 @@ __global__ void unpack_wgrad_kernel(const float* __restrict__ src, float* __rest
 }  // namespace gdl
 
 extern "C" int gdl_pack_conv_weight(const float* src, void* dst, int Cout, int Cin, int R, int S,
-                                    int transpose, int dtype, void* stream) {
+                                    int mode, int dst_ld, int dtype, void* stream) {
   GDL_REQUIRE(src && dst && Cout > 0 && Cin > 0 && R > 0 && S > 0, GDL_ERR_INVALID, "pack_weight: bad args");
   GDL_REQUIRE(dtype == GDL_BF16 || dtype == GDL_F16, GDL_ERR_INVALID, "pack_weight: dtype");
-  const long long total = (long long)Cout * Cin * R * S;
+  GDL_REQUIRE(mode >= 0 && mode <= 2, GDL_ERR_INVALID, "pack_weight: mode %d", mode);
+  const int rows = mode == 0 ? Cout : (mode == 1 ? Cin : R * S * Cin);
+  const int cols = mode == 0 ? R * S * Cin : (mode == 1 ? R * S * Cout : Cout);
+  if (dst_ld <= 0) dst_ld = cols;
+  GDL_REQUIRE(dst_ld >= cols, GDL_ERR_INVALID, "pack_weight: dst_ld %d < %d", dst_ld, cols);
+  const long long total = (long long)rows * dst_ld;
   int blocks = (int)((total + 255) / 256);
   if (blocks > 148 * 16) blocks = 148 * 16;
   if (dtype == GDL_BF16)
     pack_weight_kernel<__nv_bfloat16><<<blocks, 256, 0, (cudaStream_t)stream>>>(
-        src, (__nv_bfloat16*)dst, Cout, Cin, R, S, transpose);
+        src, (__nv_bfloat16*)dst, Cout, Cin, R, S, mode, rows, cols, dst_ld);
   else
-    pack_weight_kernel<__half><<<blocks, 256, 0, (cudaStream_t)stream>>>(src, (__half*)dst, Cout, Cin, R,
-                                                                        S, transpose);
+    pack_weight_kernel<__half><<<blocks, 256, 0, (cudaStream_t)stream>>>(src, (__half*)dst, Cout, Cin, R, S,
+                                                                        mode, rows, cols, dst_ld);
   GDL_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
 
 extern "C" int gdl_unpack_conv_wgrad(const float* src, float* dst, int Cout, int Cin, int R, int S,
-                                     int accumulate, void* stream) {
+                                     int src_ld, int accumulate, void* stream) {
   GDL_REQUIRE(src && dst && Cout > 0 && Cin > 0 && R > 0 && S > 0, GDL_ERR_INVALID, "unpack_wgrad: bad args");
+  if (src_ld <= 0) src_ld = R * S * Cin;
+  GDL_REQUIRE(src_ld >= R * S * Cin, GDL_ERR_INVALID, "unpack_wgrad: src_ld too small");
   const long long total = (long long)Cout * Cin * R * S;
   int blocks = (int)((total + 255) / 256);
   if (blocks > 148 * 16) blocks = 148 * 16;
-  unpack_wgrad_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(src, dst, Cout, Cin, R, S, accumulate);
+  unpack_wgrad_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(src, dst, Cout, Cin, R, S, src_ld, accumulate);
   GDL_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -73,8 +73,49 @@ def load():
     lib = C.CDLL(str(_LIB_PATH))
     lib.gdl_last_error.restype = C.c_char_p
     lib.gdl_version.restype = C.c_int
+    _declare(lib)
     _lib = lib
     return lib
+
+
+_VP, _I, _LL, _F = C.c_void_p, C.c_int, C.c_longlong, C.c_float
+
+# argument types of every entry point in include/gdl_b200.h (explicit: long long / float args
+# would otherwise be passed as 32-bit ints by ctypes)
+_SIGS = {
+    "gdl_conv2d_nhwc_fwd": [_VP, _VP],
+    "gdl_conv2d_nhwc_wgrad": [_VP, _VP],
+    "gdl_pack_conv_weight": [_VP, _VP, _I, _I, _I, _I, _I, _I, _I, _VP],
+    "gdl_unpack_conv_wgrad": [_VP, _VP, _I, _I, _I, _I, _I, _I, _VP],
+    "gdl_normalize_to_nhwc": [_VP, _I, _VP, _I, _LL, _LL, _LL, _I, _I, _VP, _VP, _F, _VP],
+    "gdl_im2col_nhwc": [_VP, _VP, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _VP],
+    "gdl_col2im_nhwc": [_VP, _VP, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _VP],
+    "gdl_bn_stats": [_VP, _I, _LL, _I, _I, _VP, _VP, _VP],
+    "gdl_bn_finalize": [_VP, _VP, _LL, _I, _VP, _VP, _F, _F, _VP, _VP, _VP, _VP, _VP, _VP, _VP],
+    "gdl_bn_eval_coeffs": [_I, _VP, _VP, _VP, _VP, _F, _VP, _VP, _VP],
+    "gdl_bn_apply": [_VP, _I, _VP, _VP, _VP, _I, _VP, _VP, _I, _VP, _I, _VP, _I, _I, _I, _I, _I, _I, _VP],
+    "gdl_grad_gather": [_I, _VP, _VP, _VP, _VP, _I, _VP, _I, _VP, _VP, _VP, _I, _VP, _I, _I, _I, _I, _I, _VP],
+    "gdl_bn_bwd_apply": [_VP, _I, _VP, _I, _VP, _VP, _VP, _VP, _VP, _I, _VP, _VP, _I, _I, _LL, _LL, _I, _VP],
+    "gdl_maxpool3x3s2_fwd": [_VP, _I, _VP, _I, _VP, _I, _I, _I, _I, _I, _VP],
+    "gdl_maxpool3x3s2_bwd": [_VP, _I, _VP, _VP, _I, _I, _I, _I, _I, _I, _VP],
+    "gdl_seg_loss_fwd": [_VP, _I, _VP, _I, _LL, _I, _LL, _I, _F, _F, _F, _I, _F, _F, _VP, _VP, _VP],
+    "gdl_seg_loss_bwd": [_VP, _I, _VP, _I, _LL, _I, _LL, _I, _F, _F, _F, _I, _F, _F, _VP, _VP, _VP, _I, _I, _VP],
+    "gdl_argmax_classes": [_VP, _I, _LL, _I, _F, _VP, _VP],
+    "gdl_adam_step": [_VP, _VP, _VP, _VP, _LL, _F, _F, _F, _F, _F, _I, _VP, _VP],
+    "gdl_grad_clip_coef": [_VP, _LL, _F, _VP, _VP, _VP],
+    "gdl_device_info": [_VP, _VP, _VP, _VP],
+}
+
+
+def exported_symbols() -> list[str]:
+    return ["gdl_last_error", "gdl_version", *_SIGS.keys()]
+
+
+def _declare(lib) -> None:
+    for name, args in _SIGS.items():
+        fn = getattr(lib, name)  # AttributeError if the .so lacks a declared symbol: fail loudly
+        fn.argtypes = args
+        fn.restype = C.c_int
 
 
 def check(status: int) -> None:

@@ -1,0 +1,323 @@
+"""Static-graph execution engine: forward ops that record hand-written backward closures.
+
+torch.autograd never differentiates through the hot path: every op below launches the sm_100a
+kernels of libgdlb200.so for its forward AND registers a closure that launches the matching
+backward kernels.  Gradients w.r.t. an activation are not summed eagerly: each consumer
+registers a *gradient source* (a channel slice of its dgrad output, or the gradient of the
+nearest-x2-upsampled copy) on the activation, and the producer's backward reads them all in
+one fused `grad_gather` pass (sum + ReLU mask + BatchNorm-backward reductions).
+
+Layout: NHWC 16-bit activations (bf16 or fp16), fp32 parameters / statistics / gradients.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Callable
+
+import torch
+
+from . import ops
+
+
+class Act:
+    """An activation (N,H,W,C) + the gradient sources registered by its consumers."""
+
+    __slots__ = ("t", "gsrcs", "needs_grad", "up")
+
+    def __init__(self, t: torch.Tensor, needs_grad: bool = True) -> None:
+        self.t = t
+        self.gsrcs: list[tuple[torch.Tensor, int]] = []
+        self.needs_grad = needs_grad
+        self.up: Act | None = None  # nearest-x2 upsampled copy written by the producer
+
+    @property
+    def shape(self):
+        return self.t.shape
+
+    def all_gsrcs(self) -> list[tuple[torch.Tensor, int]]:
+        s = list(self.gsrcs)
+        if self.up is not None:
+            s += [(t, 1) for t, _ in self.up.gsrcs]
+        return s
+
+
+@dataclass
+class BNParams:
+    weight: torch.Tensor
+    bias: torch.Tensor
+    running_mean: torch.Tensor
+    running_var: torch.Tensor
+    num_batches_tracked: torch.Tensor | None
+    eps: float = 1e-5
+    momentum: float = 0.1
+
+
+@dataclass
+class RawConv:
+    """Raw (pre-normalisation) conv output + what its backward needs."""
+    x: torch.Tensor
+    srcs: list[Act]
+    weight: torch.nn.Parameter
+    stride: int
+    pad: int
+    col: torch.Tensor | None = None  # im2col matrix (strided / narrow-input convs)
+    kpad: int = 0
+    cin_store: int = 0  # channels per pixel as stored (>= weight.shape[1] when the input is padded)
+
+
+@dataclass
+class BNState:
+    p: BNParams
+    scale: torch.Tensor
+    shift: torch.Tensor
+    mean: torch.Tensor | None = None
+    invstd: torch.Tensor | None = None
+    count: int = 0
+
+
+class Engine:
+    def __init__(self, dtype: torch.dtype = torch.bfloat16, training: bool = True, wcache: dict | None = None,
+                 grad_dst: dict[int, torch.Tensor] | None = None, sync_bn_group=None) -> None:
+        """wcache: persistent dict for packed 16-bit weights (owner clears it when it updates parameters
+        behind torch's back); grad_dst: id(param) -> pre-zeroed fp32 tensor the gradient is written into
+        (e.g. a view of a flat gradient buffer); sync_bn_group: torch.distributed process group for
+        SyncBatchNorm statistics (None = per-rank statistics)."""
+        self.dtype = dtype
+        self.training = training
+        self.tape: list[Callable[[], None]] = []
+        self._wcache: dict = wcache if wcache is not None else {}
+        self.grad_dst = grad_dst or {}
+        self.sync_bn_group = sync_bn_group
+        self.param_grads: dict[int, torch.Tensor] = {}
+        self._head = None
+
+    # ------------------------------------------------------------------ parameters
+    def packed(self, w: torch.Tensor, mode: int, ld: int = 0) -> torch.Tensor:
+        """16-bit operand of a weight, cached until the parameter is modified in place."""
+        key = (w.data_ptr(), mode, ld, self.dtype)
+        ver = w._version
+        hit = self._wcache.get(key)
+        if hit is not None and hit[0] == ver:
+            return hit[1]
+        out = ops.pack_conv_weight(w.detach(), self.dtype, mode, ld)
+        self._wcache[key] = (ver, out)
+        return out
+
+    def grad_buffer(self, p: torch.Tensor, zero: bool) -> torch.Tensor:
+        """Destination for d(loss)/d(p): the registered (pre-zeroed) view, else a fresh tensor."""
+        k = id(p)
+        if k in self.param_grads:
+            raise NotImplementedError("parameter used twice in one graph")
+        dst = self.grad_dst.get(k)
+        if dst is None:
+            dst = torch.zeros_like(p, memory_format=torch.contiguous_format) if zero else torch.empty_like(
+                p, memory_format=torch.contiguous_format)
+        self.param_grads[k] = dst
+        return dst
+
+    # ------------------------------------------------------------------ convolution
+    def conv_raw(self, srcs: list[Act], weight: torch.nn.Parameter, stride: int, pad: int,
+                 bias: torch.Tensor | None = None, out_dtype: torch.dtype | None = None,
+                 relu: bool = False) -> RawConv:
+        cout, cin, r, s = weight.shape
+        stored = sum(a.t.shape[3] for a in srcs)
+        direct = stride == 1 and all(a.t.shape[3] % 16 == 0 for a in srcs) and stored == cin
+        if direct:
+            wp = self.packed(weight, 0)
+            x = ops.conv2d_fwd([a.t for a in srcs], wp, cout, r, s, pad, pad, out_dtype=out_dtype, bias=bias,
+                               relu=relu)
+            return RawConv(x, srcs, weight, stride, pad, cin_store=stored)
+        if len(srcs) != 1:
+            raise NotImplementedError("strided / narrow-input convs take a single source")
+        a = srcs[0]
+        k = r * s * cin
+        kpad = (k + 63) // 64 * 64
+        if stored != cin:  # zero-padded input channels: gather only the real ones
+            col = ops.im2col(a.t, cin, r, s, stride, pad, kpad)
+        else:
+            col = ops.im2col(a.t, cin, r, s, stride, pad, kpad)
+        wp = self.packed(weight, 0, kpad)
+        x = ops.conv2d_fwd([col], wp, cout, 1, 1, 0, 0, out_dtype=out_dtype, bias=bias, relu=relu)
+        return RawConv(x, srcs, weight, stride, pad, col=col if self.training else None, kpad=kpad, cin_store=stored)
+
+    def conv_backward(self, rc: RawConv, dx: torch.Tensor) -> None:
+        """dx = gradient w.r.t. the raw conv output (N,Ho,Wo,Cout'), Cout' >= Cout zero padded."""
+        w = rc.weight
+        cout, cin, r, s = w.shape
+        coutp = dx.shape[3]
+        dev = dx.device
+        if rc.col is None:
+            if w.requires_grad:
+                if r == 1 and s == 1 and coutp == cout:
+                    # OIHW == [Cout][(r,s,c)] for a pointwise conv: accumulate straight into the gradient
+                    ops.conv2d_wgrad([a.t for a in rc.srcs], dx, 1, 1, 0, 0, self.grad_buffer(w, True).view(cout, cin))
+                else:
+                    dw = torch.zeros((coutp, r * s * cin), dtype=torch.float32, device=dev)
+                    ops.conv2d_wgrad([a.t for a in rc.srcs], dx, r, s, rc.pad, rc.pad, dw)
+                    ops.unpack_conv_wgrad(dw, self.grad_buffer(w, False), r * s * cin)
+            if any(a.needs_grad for a in rc.srcs):
+                wt = self._dgrad_weight(w, coutp)
+                dcat = ops.conv2d_fwd([dx], wt, cin, r, s, r - 1 - rc.pad, s - 1 - rc.pad)
+                off = 0
+                for a in rc.srcs:
+                    c = a.t.shape[3]
+                    if a.needs_grad:
+                        a.gsrcs.append((dcat[..., off:off + c], 0))
+                    off += c
+        else:
+            a = rc.srcs[0]
+            if w.requires_grad:
+                dw = torch.zeros((coutp, rc.kpad), dtype=torch.float32, device=dev)
+                ops.conv2d_wgrad([rc.col], dx, 1, 1, 0, 0, dw)
+                ops.unpack_conv_wgrad(dw, self.grad_buffer(w, False), rc.kpad)
+            if a.needs_grad:
+                if coutp != cout:
+                    raise NotImplementedError("padded-output dgrad through im2col")
+                wt = self.packed(w, 2)  # [(r,s,c)][Cout]
+                dcol = ops.conv2d_fwd([dx], wt, r * s * cin, 1, 1, 0, 0)
+                n, h, wd, c = a.t.shape
+                a.gsrcs.append((ops.col2im(dcol, n, h, wd, c, r, s, rc.stride, rc.pad), 0))
+
+    def _dgrad_weight(self, w: torch.Tensor, coutp: int) -> torch.Tensor:
+        cout = w.shape[0]
+        if coutp == cout:
+            return self.packed(w, 1)
+        key = (w.data_ptr(), "dgrad_pad", coutp, self.dtype)
+        hit = self._wcache.get(key)
+        if hit is not None and hit[0] == w._version:
+            return hit[1]
+        wpad = torch.zeros((coutp, *w.shape[1:]), dtype=torch.float32, device=w.device)
+        wpad[:cout] = w.detach()
+        out = ops.pack_conv_weight(wpad, self.dtype, 1)
+        self._wcache[key] = (w._version, out)
+        return out
+
+    # ------------------------------------------------------------------ batch norm
+    def _allreduce(self, t: torch.Tensor) -> None:
+        import torch.distributed as dist
+        dist.all_reduce(t, group=self.sync_bn_group)
+
+    def bn_prepare(self, rc: RawConv, p: BNParams) -> BNState:
+        c = rc.x.shape[3]
+        dev = rc.x.device
+        buf = torch.empty((4, c), dtype=torch.float32, device=dev)
+        scale, shift, mean, invstd = buf[0], buf[1], buf[2], buf[3]
+        if self.training:
+            sums = torch.empty(2 * c, dtype=torch.float32, device=dev)
+            # pivot = running mean: the same on every rank, so partial sums add up across ranks
+            ops.bn_stats(rc.x, sums, p.running_mean)
+            count = ops._rows(rc.x)
+            if self.sync_bn_group is not None:
+                self._allreduce(sums)
+                count *= self.sync_bn_group.size()
+            ops.bn_finalize(p.running_mean, sums, count, p.weight, p.bias, p.eps, p.momentum, p.running_mean,
+                            p.running_var, scale, shift, mean, invstd)
+            if p.num_batches_tracked is not None:
+                p.num_batches_tracked += 1
+            st = BNState(p, scale, shift, mean, invstd)
+            st.count = count
+            return st
+        ops.bn_eval_coeffs(p.weight, p.bias, p.running_mean, p.running_var, p.eps, scale, shift)
+        return BNState(p, scale, shift)
+
+    def bn_act(self, rc: RawConv, bn: BNState, *, relu: bool = True, residual: Act | None = None,
+               res_branch: tuple[RawConv, BNState] | None = None, want_up: bool = False,
+               want_plain: bool = True) -> Act:
+        """y = act(bn(x) [+ residual | + bn_d(x_d)]); optionally also the nearest-x2 upsampled copy."""
+        n, h, w, c = rc.x.shape
+        dev = rc.x.device
+        y = torch.empty((n, h, w, c), dtype=self.dtype, device=dev) if (want_plain or self.training) else None
+        yu = torch.empty((n, 2 * h, 2 * w, c), dtype=self.dtype, device=dev) if want_up else None
+        res = rscale = rshift = None
+        if residual is not None:
+            res = residual.t
+        elif res_branch is not None:
+            res, rscale, rshift = res_branch[0].x, res_branch[1].scale, res_branch[1].shift
+        ops.bn_apply(rc.x, bn.scale, bn.shift, res=res, rscale=rscale, rshift=rshift, relu=relu, y=y, y_up=yu)
+        out = Act(y)
+        if want_up:
+            out.up = Act(yu)
+        if self.training:
+            self.tape.append(lambda: self._bn_act_backward(out, rc, bn, relu, residual, res_branch))
+        return out
+
+    def _bn_act_backward(self, out: Act, rc: RawConv, bn: BNState, relu: bool, residual: Act | None,
+                         res_branch: tuple[RawConv, BNState] | None) -> None:
+        srcs = out.all_gsrcs()
+        if not srcs:
+            return
+        x = rc.x
+        c = x.shape[3]
+        dev = x.device
+        g = torch.empty(x.shape, dtype=self.dtype, device=dev)
+        sums = torch.empty(2 * c, dtype=torch.float32, device=dev)
+        ops.grad_gather(srcs, x.shape, self.dtype, y=out.t if relu else None, x=x, mean=bn.mean, invstd=bn.invstd,
+                        g=g, sums=sums)
+        out.gsrcs.clear()
+        if out.up is not None:
+            out.up.gsrcs.clear()
+        dx = torch.empty(x.shape, dtype=self.dtype, device=dev)
+        self._bn_param_bwd(g, x, bn, sums, dx)
+        self.conv_backward(rc, dx)
+        if residual is not None and residual.needs_grad:
+            residual.gsrcs.append((g, 0))
+        elif res_branch is not None:
+            rcd, bnd = res_branch
+            sums_d = torch.empty(2 * c, dtype=torch.float32, device=dev)
+            ops.grad_gather([(g, 0)], x.shape, self.dtype, x=rcd.x, mean=bnd.mean, invstd=bnd.invstd, sums=sums_d)
+            dxd = torch.empty(x.shape, dtype=self.dtype, device=dev)
+            self._bn_param_bwd(g, rcd.x, bnd, sums_d, dxd)
+            self.conv_backward(rcd, dxd)
+
+    def _bn_param_bwd(self, g, x, bn: BNState, sums, dx) -> None:
+        p = bn.p
+        if self.sync_bn_group is not None:
+            self._allreduce(sums)
+        dgamma = self.grad_buffer(p.weight, False) if p.weight.requires_grad else None
+        dbeta = self.grad_buffer(p.bias, False) if p.bias.requires_grad else None
+        ops.bn_bwd_apply(g, x, bn.mean, bn.invstd, p.weight, sums, dx, dgamma, dbeta, False, bn.count)
+
+    # ------------------------------------------------------------------ pooling
+    def maxpool3x3s2(self, a: Act) -> Act:
+        y, idx = ops.maxpool3x3s2_fwd(a.t, self.training and a.needs_grad)
+        out = Act(y)
+        if self.training and a.needs_grad:
+            n, h, w, c = a.t.shape
+
+            def bwd() -> None:
+                srcs = out.all_gsrcs()
+                if not srcs:
+                    return
+                if len(srcs) == 1 and srcs[0][1] == 0 and srcs[0][0].stride(2) == c:
+                    dy = srcs[0][0]
+                else:
+                    dy = torch.empty(y.shape, dtype=self.dtype, device=y.device)
+                    ops.grad_gather(srcs, y.shape, self.dtype, g=dy)
+                out.gsrcs.clear()
+                a.gsrcs.append((ops.maxpool3x3s2_bwd(dy, idx, h, w), 0))
+
+            self.tape.append(bwd)
+        return out
+
+    # ------------------------------------------------------------------ head
+    def conv_head(self, a: Act, weight: torch.nn.Parameter, bias: torch.nn.Parameter | None, pad: int) -> torch.Tensor:
+        """Conv (+bias) producing fp32 logits (N,H,W,K); its backward takes d(logits) padded to 16 channels."""
+        rc = self.conv_raw([a], weight, 1, pad, bias=bias, out_dtype=torch.float32)
+        self._head = (rc, bias)
+        return rc.x
+
+    def head_backward(self, dlogits16: torch.Tensor) -> None:
+        """dlogits16: (N,H,W,16k) 16-bit, channels >= K zero."""
+        rc, bias = self._head
+        if bias is not None and bias.requires_grad:
+            k = bias.numel()
+            sums = torch.empty(2 * dlogits16.shape[3], dtype=torch.float32, device=dlogits16.device)
+            ops.bn_stats(dlogits16, sums)  # column sums (no pivot)
+            self.grad_buffer(bias, False).copy_(sums[:k])
+        self.conv_backward(rc, dlogits16)
+
+    # ------------------------------------------------------------------ driver
+    def backward(self) -> None:
+        for fn in reversed(self.tape):
+            fn()
+        self.tape.clear()

@@ -83,22 +83,204 @@ def conv2d_wgrad(srcs: Sequence[torch.Tensor], dy: torch.Tensor, r: int, s: int,
     return dw
 
 
-def pack_conv_weight(w_oihw: torch.Tensor, dtype: torch.dtype, transpose: bool = False,
+def pack_conv_weight(w_oihw: torch.Tensor, dtype: torch.dtype, mode: int = 0, ld: int = 0,
                      out: torch.Tensor | None = None) -> torch.Tensor:
-    """fp32 OIHW -> 16-bit [Cout][R][S][Cin] (or the dgrad operand [Cin][R][S][Cout], taps flipped)."""
+    """fp32 OIHW -> 16-bit operand. mode 0: [Cout][(r,s,c)]; 1: [Cin][(R-1-r,S-1-s,k)] (dgrad);
+    2: [(r,s,c)][Cout] (dgrad of an im2col'd conv). `ld` pads the row stride with zeros."""
     k, c, r, s = w_oihw.shape
     if w_oihw.dtype != torch.float32 or not w_oihw.is_contiguous():
         raise ValueError("weight must be contiguous fp32 OIHW")
+    rows = k if mode == 0 else (c if mode == 1 else r * s * c)
+    cols = r * s * c if mode == 0 else (r * s * k if mode == 1 else k)
+    ld = ld or cols
     if out is None:
-        shape = (c, r, s, k) if transpose else (k, r, s, c)
-        out = torch.empty(shape, dtype=dtype, device=w_oihw.device)
-    L.check(L.load().gdl_pack_conv_weight(L.ptr(w_oihw), L.ptr(out), k, c, r, s, int(transpose),
+        out = torch.empty((rows, ld), dtype=dtype, device=w_oihw.device)
+    L.check(L.load().gdl_pack_conv_weight(L.ptr(w_oihw), L.ptr(out), k, c, r, s, mode, ld,
                                           L.dt_code(dtype), L.stream_ptr()))
     return out
 
 
-def unpack_conv_wgrad(dw_krsc: torch.Tensor, out_oihw: torch.Tensor, accumulate: bool = False) -> torch.Tensor:
+def unpack_conv_wgrad(dw: torch.Tensor, out_oihw: torch.Tensor, src_ld: int = 0,
+                      accumulate: bool = False) -> torch.Tensor:
     k, c, r, s = out_oihw.shape
-    L.check(L.load().gdl_unpack_conv_wgrad(L.ptr(dw_krsc), L.ptr(out_oihw), k, c, r, s,
+    L.check(L.load().gdl_unpack_conv_wgrad(L.ptr(dw), L.ptr(out_oihw), k, c, r, s, src_ld,
                                            int(accumulate), L.stream_ptr()))
     return out_oihw
+
+
+# ---------------------------------------------------------------------------------------------
+# HBM-bound kernels (elementwise.cu)
+# ---------------------------------------------------------------------------------------------
+_IN_KIND = {(torch.uint8, False): 0, (torch.float32, False): 1, (torch.float32, True): 2, (torch.uint8, True): 3}
+
+
+def normalize_to_nhwc(x: torch.Tensor, chw: bool, out_dtype: torch.dtype, ld: int,
+                      mean: torch.Tensor | None = None, std: torch.Tensor | None = None,
+                      image_max: float = 0.0) -> torch.Tensor:
+    """uint8/f32 image batch (NHWC if chw=False else NCHW) -> 16-bit NHWC (N,H,W,ld), channels >= C zero.
+    y = ((x / image_max) - mean) / std   (utils/tensors.py:10-35); image_max=0 and mean=None skip a step."""
+    if not x.is_contiguous():
+        raise ValueError("normalize: contiguous input expected")
+    if chw:
+        n, c, h, w = x.shape
+    else:
+        n, h, w, c = x.shape
+    out = torch.empty((n, h, w, ld), dtype=out_dtype, device=x.device)
+    L.check(L.load().gdl_normalize_to_nhwc(L.ptr(x), _IN_KIND[(x.dtype, chw)], L.ptr(out), L.dt_code(out_dtype),
+                                           n, h, w, c, ld, L.ptr(mean), L.ptr(std), float(image_max),
+                                           L.stream_ptr()))
+    return out
+
+
+def im2col(x: torch.Tensor, c: int, r: int, s: int, stride: int, pad: int, kpad: int) -> torch.Tensor:
+    n, h, w, _ = x.shape
+    ho, wo = (h + 2 * pad - r) // stride + 1, (w + 2 * pad - s) // stride + 1
+    col = torch.empty((n, ho, wo, kpad), dtype=x.dtype, device=x.device)
+    L.check(L.load().gdl_im2col_nhwc(L.ptr(x), L.ptr(col), L.dt_code(x.dtype), n, h, w, c, x.stride(2), r, s,
+                                     stride, pad, kpad, L.stream_ptr()))
+    return col
+
+
+def col2im(dcol: torch.Tensor, n: int, h: int, w: int, c: int, r: int, s: int, stride: int, pad: int) -> torch.Tensor:
+    dx = torch.empty((n, h, w, c), dtype=dcol.dtype, device=dcol.device)
+    L.check(L.load().gdl_col2im_nhwc(L.ptr(dcol), L.ptr(dx), L.dt_code(dcol.dtype), n, h, w, c, c, r, s, stride,
+                                     pad, dcol.stride(2), L.stream_ptr()))
+    return dx
+
+
+def _rows(x: torch.Tensor) -> int:
+    return x.shape[0] * x.shape[1] * x.shape[2]
+
+
+def bn_stats(x: torch.Tensor, sums: torch.Tensor, pivot: torch.Tensor | None = None) -> torch.Tensor:
+    """sums[0:C] = sum(x - p), sums[C:2C] = sum((x-p)^2); p = per-channel pivot (fp32 [C]) or 0."""
+    L.check(L.load().gdl_bn_stats(L.ptr(x), L.dt_code(x.dtype), _rows(x), x.shape[3], x.stride(2), L.ptr(sums),
+                                  L.ptr(pivot), L.stream_ptr()))
+    return sums
+
+
+def bn_finalize(pivot, sums, count, gamma, beta, eps, momentum, running_mean, running_var, scale, shift, save_mean,
+                save_invstd) -> None:
+    L.check(L.load().gdl_bn_finalize(L.ptr(pivot), L.ptr(sums), int(count), scale.numel(), L.ptr(gamma),
+                                     L.ptr(beta), float(eps), float(momentum), L.ptr(running_mean),
+                                     L.ptr(running_var), L.ptr(scale), L.ptr(shift), L.ptr(save_mean),
+                                     L.ptr(save_invstd), L.stream_ptr()))
+
+
+def bn_eval_coeffs(gamma, beta, running_mean, running_var, eps, scale, shift) -> None:
+    L.check(L.load().gdl_bn_eval_coeffs(running_mean.numel(), L.ptr(gamma), L.ptr(beta), L.ptr(running_mean),
+                                        L.ptr(running_var), float(eps), L.ptr(scale), L.ptr(shift), L.stream_ptr()))
+
+
+def bn_apply(x, scale, shift, *, res=None, rscale=None, rshift=None, relu=True, y=None, y_up=None) -> None:
+    n, h, w, c = x.shape
+    L.check(L.load().gdl_bn_apply(L.ptr(x), x.stride(2), L.ptr(scale), L.ptr(shift), L.ptr(res),
+                                  res.stride(2) if res is not None else 0, L.ptr(rscale), L.ptr(rshift), int(relu),
+                                  L.ptr(y), y.stride(2) if y is not None else 0, L.ptr(y_up),
+                                  y_up.stride(2) if y_up is not None else 0, L.dt_code(x.dtype), n, h, w, c,
+                                  L.stream_ptr()))
+
+
+def grad_gather(srcs, shape, dtype, *, y=None, x=None, mean=None, invstd=None, g=None, sums=None) -> None:
+    """g = (sum of gradient sources) [* (y > 0)]; srcs = [(tensor, mode)], mode 1 = 2x2 sum of a 2H x 2W tensor.
+    With sums/x/mean/invstd also reduces the BatchNorm-backward sums in the same pass."""
+    n, h, w, c = shape
+    k = len(srcs)
+    ptrs = (C.c_void_p * k)(*[t.data_ptr() for t, _ in srcs])
+    lds = (C.c_int * k)(*[t.stride(2) for t, _ in srcs])
+    modes = (C.c_int * k)(*[m for _, m in srcs])
+    L.check(L.load().gdl_grad_gather(k, ptrs, lds, modes, L.ptr(y), y.stride(2) if y is not None else 0, L.ptr(x),
+                                     x.stride(2) if x is not None else 0, L.ptr(mean), L.ptr(invstd), L.ptr(g),
+                                     g.stride(2) if g is not None else 0, L.ptr(sums), L.dt_code(dtype), n, h, w, c,
+                                     L.stream_ptr()))
+
+
+def bn_bwd_apply(g, x, mean, invstd, gamma, sums, dx, dgamma, dbeta, accumulate: bool, count: int = 0) -> None:
+    """count = number of elements per channel the (possibly all-reduced) sums cover (0 = local rows)."""
+    L.check(L.load().gdl_bn_bwd_apply(L.ptr(g), g.stride(2), L.ptr(x), x.stride(2), L.ptr(mean), L.ptr(invstd),
+                                      L.ptr(gamma), L.ptr(sums), L.ptr(dx), dx.stride(2), L.ptr(dgamma),
+                                      L.ptr(dbeta), int(accumulate), L.dt_code(x.dtype), _rows(x),
+                                      int(count) or _rows(x), x.shape[3], L.stream_ptr()))
+
+
+def maxpool3x3s2_fwd(x: torch.Tensor, want_idx: bool):
+    n, h, w, c = x.shape
+    ho, wo = (h - 1) // 2 + 1, (w - 1) // 2 + 1
+    y = torch.empty((n, ho, wo, c), dtype=x.dtype, device=x.device)
+    idx = torch.empty((n, ho, wo, c), dtype=torch.uint8, device=x.device) if want_idx else None
+    L.check(L.load().gdl_maxpool3x3s2_fwd(L.ptr(x), x.stride(2), L.ptr(y), c, L.ptr(idx), L.dt_code(x.dtype), n, h, w,
+                                          c, L.stream_ptr()))
+    return y, idx
+
+
+def maxpool3x3s2_bwd(dy: torch.Tensor, idx: torch.Tensor, h: int, w: int) -> torch.Tensor:
+    n, _, _, c = dy.shape
+    dx = torch.empty((n, h, w, c), dtype=dy.dtype, device=dy.device)
+    L.check(L.load().gdl_maxpool3x3s2_bwd(L.ptr(dy), dy.stride(2), L.ptr(idx), L.ptr(dx), c, L.dt_code(dy.dtype), n,
+                                          h, w, c, L.stream_ptr()))
+    return dx
+
+
+# ---------------------------------------------------------------------------------------------
+# losses / optimizer (loss_optim.cu)
+# ---------------------------------------------------------------------------------------------
+class LossSpec:
+    """weights of the CE and Dice terms + their options (see csrc/loss_optim.cu)."""
+
+    def __init__(self, w_ce=1.0, w_dice=0.0, label_smoothing=0.0, ce_mean_over_all=False, ignore_index=None,
+                 dice_smooth=0.0, dice_eps=1e-7):
+        self.w_ce, self.w_dice = float(w_ce), float(w_dice)
+        self.label_smoothing = float(label_smoothing)
+        self.ce_mean_over_all = bool(ce_mean_over_all)
+        self.ignore_index = ignore_index
+        self.dice_smooth, self.dice_eps = float(dice_smooth), float(dice_eps)
+
+    def args(self):
+        ign = self.ignore_index
+        return (int(ign) if ign is not None else 0, int(ign is not None), self.w_ce, self.w_dice,
+                self.label_smoothing, int(self.ce_mean_over_all), self.dice_smooth, self.dice_eps)
+
+
+def _target_kind(t: torch.Tensor) -> int:
+    if t.dtype == torch.int64:
+        return 0
+    if t.dtype == torch.uint8:
+        return 1
+    raise ValueError(f"target dtype must be int64 or uint8, got {t.dtype}")
+
+
+def seg_loss_fwd(logits: torch.Tensor, target: torch.Tensor, spec: LossSpec):
+    """logits fp32 (N,H,W,K) NHWC (pixel stride = stride(2)); returns (coeff, stats); coeff[0] is the loss."""
+    k = logits.shape[3]
+    m = _rows(logits)
+    stats = torch.empty(4 + 3 * k, dtype=torch.float32, device=logits.device)
+    coeff = torch.empty(2 + 2 * k, dtype=torch.float32, device=logits.device)
+    L.check(L.load().gdl_seg_loss_fwd(L.ptr(logits), logits.stride(2), L.ptr(target), _target_kind(target), m, k,
+                                      *spec.args(), L.ptr(stats), L.ptr(coeff), L.stream_ptr()))
+    return coeff, stats
+
+
+def seg_loss_bwd(logits, target, spec: LossSpec, coeff, grad_scale, dlogits) -> None:
+    k = logits.shape[3]
+    L.check(L.load().gdl_seg_loss_bwd(L.ptr(logits), logits.stride(2), L.ptr(target), _target_kind(target),
+                                      _rows(logits), k, *spec.args(), L.ptr(coeff), L.ptr(grad_scale), L.ptr(dlogits),
+                                      dlogits.stride(2), L.dt_code(dlogits.dtype), L.stream_ptr()))
+
+
+def argmax_classes(logits: torch.Tensor, threshold: float = 0.5) -> torch.Tensor:
+    n, h, w, k = logits.shape
+    out = torch.empty((n, h, w), dtype=torch.int64, device=logits.device)
+    L.check(L.load().gdl_argmax_classes(L.ptr(logits), logits.stride(2), n * h * w, k, float(threshold), L.ptr(out),
+                                        L.stream_ptr()))
+    return out
+
+
+def adam_step(p, g, m, v, lr, beta1, beta2, eps, weight_decay, step, grad_scale=None) -> None:
+    L.check(L.load().gdl_adam_step(L.ptr(p), L.ptr(g), L.ptr(m), L.ptr(v), p.numel(), float(lr), float(beta1),
+                                   float(beta2), float(eps), float(weight_decay), int(step), L.ptr(grad_scale),
+                                   L.stream_ptr()))
+
+
+def grad_clip_coef(g, max_norm, scratch, scale) -> None:
+    L.check(L.load().gdl_grad_clip_coef(L.ptr(g), g.numel(), float(max_norm), L.ptr(scratch), L.ptr(scale),
+                                        L.stream_ptr()))

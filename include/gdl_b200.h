@@ -99,13 +99,14 @@ int gdl_conv2d_nhwc_wgrad(const gdl_conv_wgrad_t* d, void* stream);
 
 /* ---- weight layout transforms ---------------------------------------------------------------
  * src: fp32 OIHW [Cout][Cin][R][S] (the nn.Parameter / state_dict layout of the reference).
- * transpose=0: dst[k][r][s][c]           = src[k][c][r][s]           (forward operand)
- * transpose=1: dst[c][R-1-r][S-1-s][k]   = src[k][c][r][s]           (dgrad operand)
- * dst is 16-bit (dtype). */
-int gdl_pack_conv_weight(const float* src, void* dst, int Cout, int Cin, int R, int S, int transpose,
-                         int dtype, void* stream);
-/* grad (fp32 [Cout][R][S][Cin], from wgrad) -> fp32 OIHW, dst = (accumulate? dst:0) + src */
-int gdl_unpack_conv_wgrad(const float* src, float* dst, int Cout, int Cin, int R, int S,
+ * mode 0: dst[k][(r,s,c)]          = src[k][c][r][s]   forward operand  (rows Cout)
+ * mode 1: dst[c][(R-1-r,S-1-s,k)]  = src[k][c][r][s]   dgrad operand    (rows Cin, taps flipped)
+ * mode 2: dst[(r,s,c)][k]          = src[k][c][r][s]   dgrad operand of an im2col'd conv
+ * dst is 16-bit (dtype); dst_ld = row stride in elements (0 = dense), pad columns are zeroed. */
+int gdl_pack_conv_weight(const float* src, void* dst, int Cout, int Cin, int R, int S, int mode,
+                         int dst_ld, int dtype, void* stream);
+/* grad fp32 [Cout][src_ld] (columns (r,s,c), from wgrad) -> fp32 OIHW; dst = (accumulate? dst:0)+src */
+int gdl_unpack_conv_wgrad(const float* src, float* dst, int Cout, int Cin, int R, int S, int src_ld,
                           int accumulate, void* stream);
 
 #ifdef __cplusplus
