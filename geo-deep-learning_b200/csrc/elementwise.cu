@@ -812,6 +812,16 @@ extern "C" int gdl_bn_bwd_apply(const void* g, int ldg, const void* x, int ldx, 
   return 0;
 }
 
+extern "C" int gdl_bn_param_grads(const float* sums, int C, float* dgamma, float* dbeta, int accumulate,
+                                  void* stream) {
+  GDL_REQUIRE(sums && C > 0, GDL_ERR_INVALID, "bn_param_grads: bad args");
+  if (dgamma || dbeta) {
+    bn_param_grads_kernel<<<(C + 127) / 128, 128, 0, (cudaStream_t)stream>>>(sums, C, dgamma, dbeta, accumulate);
+    GDL_CHECK_CUDA(cudaGetLastError());
+  }
+  return 0;
+}
+
 extern "C" int gdl_maxpool3x3s2_fwd(const void* x, int ldx, void* y, int ldy, unsigned char* idx, int dtype, int N,
                                     int H, int W, int C, void* stream) {
   GDL_REQUIRE(x && y && N > 0 && H > 0 && W > 0 && C > 0 && C % 8 == 0 && ldx % 8 == 0 && ldy % 8 == 0,

@@ -96,6 +96,7 @@ _SIGS = {
     "gdl_bn_apply": [_VP, _I, _VP, _VP, _VP, _I, _VP, _VP, _I, _VP, _I, _VP, _I, _I, _I, _I, _I, _I, _VP],
     "gdl_grad_gather": [_I, _VP, _VP, _VP, _VP, _I, _VP, _I, _VP, _VP, _VP, _I, _VP, _I, _I, _I, _I, _I, _VP],
     "gdl_bn_bwd_apply": [_VP, _I, _VP, _I, _VP, _VP, _VP, _VP, _VP, _I, _VP, _VP, _I, _I, _LL, _LL, _I, _VP],
+    "gdl_bn_param_grads": [_VP, _I, _VP, _VP, _I, _VP],
     "gdl_maxpool3x3s2_fwd": [_VP, _I, _VP, _I, _VP, _I, _I, _I, _I, _I, _VP],
     "gdl_maxpool3x3s2_bwd": [_VP, _I, _VP, _VP, _I, _I, _I, _I, _I, _I, _VP],
     "gdl_seg_loss_fwd": [_VP, _I, _VP, _I, _LL, _I, _LL, _I, _F, _F, _F, _I, _F, _F, _VP, _VP, _VP],

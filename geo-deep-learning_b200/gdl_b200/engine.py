@@ -77,12 +77,14 @@ class BNState:
 
 class Engine:
     def __init__(self, dtype: torch.dtype = torch.bfloat16, training: bool = True, wcache: dict | None = None,
-                 grad_dst: dict[int, torch.Tensor] | None = None, sync_bn_group=None) -> None:
+                 grad_dst: dict[int, torch.Tensor] | None = None, sync_bn_group=None,
+                 acc_dtype: torch.dtype = torch.float32) -> None:
         """wcache: persistent dict for packed 16-bit weights (owner clears it when it updates parameters
         behind torch's back); grad_dst: id(param) -> pre-zeroed fp32 tensor the gradient is written into
         (e.g. a view of a flat gradient buffer); sync_bn_group: torch.distributed process group for
         SyncBatchNorm statistics (None = per-rank statistics)."""
         self.dtype = dtype
+        self.acc_dtype = acc_dtype  # statistics / gradients / logits (fp32; float64 only in CPU host-logic tests)
         self.training = training
         self.tape: list[Callable[[], None]] = []
         self._wcache: dict = wcache if wcache is not None else {}
@@ -152,7 +154,7 @@ class Engine:
                     # OIHW == [Cout][(r,s,c)] for a pointwise conv: accumulate straight into the gradient
                     ops.conv2d_wgrad([a.t for a in rc.srcs], dx, 1, 1, 0, 0, self.grad_buffer(w, True).view(cout, cin))
                 else:
-                    dw = torch.zeros((coutp, r * s * cin), dtype=torch.float32, device=dev)
+                    dw = torch.zeros((coutp, r * s * cin), dtype=self.acc_dtype, device=dev)
                     ops.conv2d_wgrad([a.t for a in rc.srcs], dx, r, s, rc.pad, rc.pad, dw)
                     ops.unpack_conv_wgrad(dw, self.grad_buffer(w, False), r * s * cin)
             if any(a.needs_grad for a in rc.srcs):
@@ -167,7 +169,7 @@ class Engine:
         else:
             a = rc.srcs[0]
             if w.requires_grad:
-                dw = torch.zeros((coutp, rc.kpad), dtype=torch.float32, device=dev)
+                dw = torch.zeros((coutp, rc.kpad), dtype=self.acc_dtype, device=dev)
                 ops.conv2d_wgrad([rc.col], dx, 1, 1, 0, 0, dw)
                 ops.unpack_conv_wgrad(dw, self.grad_buffer(w, False), rc.kpad)
             if a.needs_grad:
@@ -186,7 +188,7 @@ class Engine:
         hit = self._wcache.get(key)
         if hit is not None and hit[0] == w._version:
             return hit[1]
-        wpad = torch.zeros((coutp, *w.shape[1:]), dtype=torch.float32, device=w.device)
+        wpad = torch.zeros((coutp, *w.shape[1:]), dtype=self.acc_dtype, device=w.device)
         wpad[:cout] = w.detach()
         out = ops.pack_conv_weight(wpad, self.dtype, 1)
         self._wcache[key] = (w._version, out)
@@ -200,10 +202,10 @@ class Engine:
     def bn_prepare(self, rc: RawConv, p: BNParams) -> BNState:
         c = rc.x.shape[3]
         dev = rc.x.device
-        buf = torch.empty((4, c), dtype=torch.float32, device=dev)
+        buf = torch.empty((4, c), dtype=self.acc_dtype, device=dev)
         scale, shift, mean, invstd = buf[0], buf[1], buf[2], buf[3]
         if self.training:
-            sums = torch.empty(2 * c, dtype=torch.float32, device=dev)
+            sums = torch.empty(2 * c, dtype=self.acc_dtype, device=dev)
             # pivot = running mean: the same on every rank, so partial sums add up across ranks
             ops.bn_stats(rc.x, sums, p.running_mean)
             count = ops._rows(rc.x)
@@ -250,7 +252,7 @@ class Engine:
         c = x.shape[3]
         dev = x.device
         g = torch.empty(x.shape, dtype=self.dtype, device=dev)
-        sums = torch.empty(2 * c, dtype=torch.float32, device=dev)
+        sums = torch.empty(2 * c, dtype=self.acc_dtype, device=dev)
         ops.grad_gather(srcs, x.shape, self.dtype, y=out.t if relu else None, x=x, mean=bn.mean, invstd=bn.invstd,
                         g=g, sums=sums)
         out.gsrcs.clear()
@@ -263,7 +265,7 @@ class Engine:
             residual.gsrcs.append((g, 0))
         elif res_branch is not None:
             rcd, bnd = res_branch
-            sums_d = torch.empty(2 * c, dtype=torch.float32, device=dev)
+            sums_d = torch.empty(2 * c, dtype=self.acc_dtype, device=dev)
             ops.grad_gather([(g, 0)], x.shape, self.dtype, x=rcd.x, mean=bnd.mean, invstd=bnd.invstd, sums=sums_d)
             dxd = torch.empty(x.shape, dtype=self.dtype, device=dev)
             self._bn_param_bwd(g, rcd.x, bnd, sums_d, dxd)
@@ -271,10 +273,14 @@ class Engine:
 
     def _bn_param_bwd(self, g, x, bn: BNState, sums, dx) -> None:
         p = bn.p
-        if self.sync_bn_group is not None:
-            self._allreduce(sums)
         dgamma = self.grad_buffer(p.weight, False) if p.weight.requires_grad else None
         dbeta = self.grad_buffer(p.bias, False) if p.bias.requires_grad else None
+        if self.sync_bn_group is not None:
+            # parameter gradients come from the LOCAL sums (DDP averages them afterwards, as
+            # torch SyncBatchNorm does); dx needs the global ones.
+            ops.bn_param_grads(sums, dgamma, dbeta)
+            self._allreduce(sums)
+            dgamma = dbeta = None
         ops.bn_bwd_apply(g, x, bn.mean, bn.invstd, p.weight, sums, dx, dgamma, dbeta, False, bn.count)
 
     # ------------------------------------------------------------------ pooling
@@ -302,7 +308,7 @@ class Engine:
     # ------------------------------------------------------------------ head
     def conv_head(self, a: Act, weight: torch.nn.Parameter, bias: torch.nn.Parameter | None, pad: int) -> torch.Tensor:
         """Conv (+bias) producing fp32 logits (N,H,W,K); its backward takes d(logits) padded to 16 channels."""
-        rc = self.conv_raw([a], weight, 1, pad, bias=bias, out_dtype=torch.float32)
+        rc = self.conv_raw([a], weight, 1, pad, bias=bias, out_dtype=self.acc_dtype)
         self._head = (rc, bias)
         return rc.x
 
@@ -311,13 +317,14 @@ class Engine:
         rc, bias = self._head
         if bias is not None and bias.requires_grad:
             k = bias.numel()
-            sums = torch.empty(2 * dlogits16.shape[3], dtype=torch.float32, device=dlogits16.device)
+            sums = torch.empty(2 * dlogits16.shape[3], dtype=self.acc_dtype, device=dlogits16.device)
             ops.bn_stats(dlogits16, sums)  # column sums (no pivot)
             self.grad_buffer(bias, False).copy_(sums[:k])
         self.conv_backward(rc, dlogits16)
 
     # ------------------------------------------------------------------ driver
     def backward(self) -> None:
-        for fn in reversed(self.tape):
-            fn()
-        self.tape.clear()
+        # pop as we go so each layer's saved activations are released as soon as it is done
+        while self.tape:
+            self.tape.pop()()
+        self._head = None

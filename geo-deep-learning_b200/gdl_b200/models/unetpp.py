@@ -153,6 +153,8 @@ class UnetPlusPlus(nn.Module):
         self.classes = classes
         self.compute_dtype = compute_dtype
         self.last_engine: Engine | None = None
+        self._wcache: dict = {}
+        self.sync_bn_group = None  # set to a torch.distributed group for SyncBatchNorm statistics
 
     # ------------------------------------------------------------------ engine graph
     def _block(self, eng: Engine, blk: nn.Module, x: Act, want_up: bool) -> Act:
@@ -208,15 +210,19 @@ class UnetPlusPlus(nn.Module):
         n = len(feats) - 1
         for layer in range(n):
             for depth in range(n - layer):
+                dl = depth + layer
+                # x_{depth}_{dl} is upsampled by x_{depth}_{dl+1} (exists while dl < n-1) or by x_0_n
+                up = dl < n - 1 or depth == 0
                 if layer == 0:
                     dense[f"x_{depth}_{depth}"] = self._decoder_block(eng, f"x_{depth}_{depth}", feats[depth],
-                                                                      [feats[depth + 1]], True)
+                                                                      [feats[depth + 1]], up)
                 else:
-                    dl = depth + layer
                     skips = [dense[f"x_{i}_{dl}"] for i in range(depth + 1, dl + 1)] + [feats[dl + 1]]
                     dense[f"x_{depth}_{dl}"] = self._decoder_block(eng, f"x_{depth}_{dl}", dense[f"x_{depth}_{dl - 1}"],
-                                                                   skips, depth == 0)
+                                                                   skips, up)
         last = self._decoder_block(eng, f"x_0_{n}", dense[f"x_0_{n - 1}"], [], False)
+        dense[f"x_0_{n}"] = last
+        eng.named = {"e1": e1, "e2": e2, "e3": e3, "e4": e4, "e5": e5, **dense}  # for tests / debugging
         head = self.segmentation_head[0]
         return eng.conv_head(last, head.weight, head.bias, 1)
 
@@ -234,7 +240,7 @@ class UnetPlusPlus(nn.Module):
         if torch.is_grad_enabled() and self.training and any(p.requires_grad for p in params):
             return _UnetPPFn.apply(self, image, *params)
         with torch.no_grad():
-            eng = Engine(self.compute_dtype, training=False)
+            eng = Engine(self.compute_dtype, training=False, wcache=self._wcache)
             logits = self.run(eng, self._input(image))
         return logits.permute(0, 3, 1, 2)
 
@@ -242,7 +248,7 @@ class UnetPlusPlus(nn.Module):
 class _UnetPPFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, model: UnetPlusPlus, image: torch.Tensor, *params: torch.Tensor) -> torch.Tensor:
-        eng = Engine(model.compute_dtype, training=True)
+        eng = Engine(model.compute_dtype, training=True, wcache=model._wcache, sync_bn_group=model.sync_bn_group)
         logits = model.run(eng, model._input(image))
         ctx.eng = eng
         ctx.params = params

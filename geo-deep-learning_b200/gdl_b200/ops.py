@@ -13,6 +13,72 @@ import torch
 from . import _lib as L
 
 
+def _ck(status: int) -> None:
+    """check the status of a C-ABI call that launched (at least) one kernel"""
+    L.check(status)
+    _count()
+
+
+# ---------------------------------------------------------------------------------------------
+# instrumentation: launch counter (bench.py's gpu_launches) and per-launch conv timing (roofline)
+# ---------------------------------------------------------------------------------------------
+_LAUNCHES = 0
+_PROFILER = None
+
+
+def _count(n: int = 1) -> None:
+    global _LAUNCHES
+    _LAUNCHES += n
+
+
+def launch_count() -> int:
+    return _LAUNCHES
+
+
+def reset_launch_count() -> None:
+    global _LAUNCHES
+    _LAUNCHES = 0
+
+
+class ConvProfiler:
+    """CUDA-event pair around every tensor-core conv launch on the launching stream."""
+
+    def __init__(self) -> None:
+        self.records: list[tuple[str, float, torch.cuda.Event, torch.cuda.Event]] = []
+
+    def begin(self) -> torch.cuda.Event:
+        e = torch.cuda.Event(enable_timing=True)
+        e.record()
+        return e
+
+    def end(self, kernel: str, flops: float, e0: torch.cuda.Event) -> None:
+        e1 = torch.cuda.Event(enable_timing=True)
+        e1.record()
+        self.records.append((kernel, flops, e0, e1))
+
+    def summary(self, steps: int = 1) -> dict:
+        torch.cuda.synchronize()
+        out: dict[str, dict] = {}
+        for kernel, flops, e0, e1 in self.records:
+            d = out.setdefault(kernel, {"ms": 0.0, "flops": 0.0, "launches": 0})
+            d["ms"] += e0.elapsed_time(e1)
+            d["flops"] += flops
+            d["launches"] += 1
+        for d in out.values():
+            d["tflops"] = d["flops"] / (d["ms"] * 1e-3) / 1e12 if d["ms"] > 0 else 0.0
+            d["ms_per_step"] = d["ms"] / steps
+            d["launches_per_step"] = d["launches"] / steps
+        for k in ("conv_fwd_kernel", "conv_wgrad_kernel"):
+            out.setdefault(k, {"ms": 0.0, "flops": 0.0, "launches": 0, "tflops": 0.0, "ms_per_step": 0.0,
+                               "launches_per_step": 0.0})
+        return out
+
+
+def set_conv_profiler(p: ConvProfiler | None) -> None:
+    global _PROFILER
+    _PROFILER = p
+
+
 def _nhwc_src(t: torch.Tensor) -> tuple[int, int, int, int, int]:
     if t.dim() != 4:
         raise ValueError(f"NHWC activation expected 4 dims, got {tuple(t.shape)}")
@@ -62,7 +128,12 @@ def conv2d_fwd(srcs: Sequence[torch.Tensor], weight: torch.Tensor, cout: int, r:
     d.ldo = out.stride(2)
     d.bias = bias.data_ptr() if bias is not None else None
     d.relu = int(relu)
+    e0 = _PROFILER.begin() if _PROFILER is not None else None
     L.check(L.load().gdl_conv2d_nhwc_fwd(C.byref(d), L.stream_ptr()))
+    _count()
+    if e0 is not None:
+        ctot = sum(t.shape[3] for t in srcs)
+        _PROFILER.end("conv_fwd_kernel", 2.0 * n * ho * wo * cout * r * s * ctot, e0)
     return out
 
 
@@ -79,7 +150,12 @@ def conv2d_wgrad(srcs: Sequence[torch.Tensor], dy: torch.Tensor, r: int, s: int,
     if dw.dtype != torch.float32 or not dw.is_contiguous():
         raise ValueError("dw must be contiguous fp32")
     d.dw = dw.data_ptr()
+    e0 = _PROFILER.begin() if _PROFILER is not None else None
     L.check(L.load().gdl_conv2d_nhwc_wgrad(C.byref(d), L.stream_ptr()))
+    _count()
+    if e0 is not None:
+        ctot = sum(t.shape[3] for t in srcs)
+        _PROFILER.end("conv_wgrad_kernel", 2.0 * dy.shape[0] * dy.shape[1] * dy.shape[2] * dy.shape[3] * r * s * ctot, e0)
     return dw
 
 
@@ -95,7 +171,7 @@ def pack_conv_weight(w_oihw: torch.Tensor, dtype: torch.dtype, mode: int = 0, ld
     ld = ld or cols
     if out is None:
         out = torch.empty((rows, ld), dtype=dtype, device=w_oihw.device)
-    L.check(L.load().gdl_pack_conv_weight(L.ptr(w_oihw), L.ptr(out), k, c, r, s, mode, ld,
+    _ck(L.load().gdl_pack_conv_weight(L.ptr(w_oihw), L.ptr(out), k, c, r, s, mode, ld,
                                           L.dt_code(dtype), L.stream_ptr()))
     return out
 
@@ -103,7 +179,7 @@ def pack_conv_weight(w_oihw: torch.Tensor, dtype: torch.dtype, mode: int = 0, ld
 def unpack_conv_wgrad(dw: torch.Tensor, out_oihw: torch.Tensor, src_ld: int = 0,
                       accumulate: bool = False) -> torch.Tensor:
     k, c, r, s = out_oihw.shape
-    L.check(L.load().gdl_unpack_conv_wgrad(L.ptr(dw), L.ptr(out_oihw), k, c, r, s, src_ld,
+    _ck(L.load().gdl_unpack_conv_wgrad(L.ptr(dw), L.ptr(out_oihw), k, c, r, s, src_ld,
                                            int(accumulate), L.stream_ptr()))
     return out_oihw
 
@@ -126,7 +202,7 @@ def normalize_to_nhwc(x: torch.Tensor, chw: bool, out_dtype: torch.dtype, ld: in
     else:
         n, h, w, c = x.shape
     out = torch.empty((n, h, w, ld), dtype=out_dtype, device=x.device)
-    L.check(L.load().gdl_normalize_to_nhwc(L.ptr(x), _IN_KIND[(x.dtype, chw)], L.ptr(out), L.dt_code(out_dtype),
+    _ck(L.load().gdl_normalize_to_nhwc(L.ptr(x), _IN_KIND[(x.dtype, chw)], L.ptr(out), L.dt_code(out_dtype),
                                            n, h, w, c, ld, L.ptr(mean), L.ptr(std), float(image_max),
                                            L.stream_ptr()))
     return out
@@ -136,14 +212,14 @@ def im2col(x: torch.Tensor, c: int, r: int, s: int, stride: int, pad: int, kpad:
     n, h, w, _ = x.shape
     ho, wo = (h + 2 * pad - r) // stride + 1, (w + 2 * pad - s) // stride + 1
     col = torch.empty((n, ho, wo, kpad), dtype=x.dtype, device=x.device)
-    L.check(L.load().gdl_im2col_nhwc(L.ptr(x), L.ptr(col), L.dt_code(x.dtype), n, h, w, c, x.stride(2), r, s,
+    _ck(L.load().gdl_im2col_nhwc(L.ptr(x), L.ptr(col), L.dt_code(x.dtype), n, h, w, c, x.stride(2), r, s,
                                      stride, pad, kpad, L.stream_ptr()))
     return col
 
 
 def col2im(dcol: torch.Tensor, n: int, h: int, w: int, c: int, r: int, s: int, stride: int, pad: int) -> torch.Tensor:
     dx = torch.empty((n, h, w, c), dtype=dcol.dtype, device=dcol.device)
-    L.check(L.load().gdl_col2im_nhwc(L.ptr(dcol), L.ptr(dx), L.dt_code(dcol.dtype), n, h, w, c, c, r, s, stride,
+    _ck(L.load().gdl_col2im_nhwc(L.ptr(dcol), L.ptr(dx), L.dt_code(dcol.dtype), n, h, w, c, c, r, s, stride,
                                      pad, dcol.stride(2), L.stream_ptr()))
     return dx
 
@@ -154,27 +230,27 @@ def _rows(x: torch.Tensor) -> int:
 
 def bn_stats(x: torch.Tensor, sums: torch.Tensor, pivot: torch.Tensor | None = None) -> torch.Tensor:
     """sums[0:C] = sum(x - p), sums[C:2C] = sum((x-p)^2); p = per-channel pivot (fp32 [C]) or 0."""
-    L.check(L.load().gdl_bn_stats(L.ptr(x), L.dt_code(x.dtype), _rows(x), x.shape[3], x.stride(2), L.ptr(sums),
+    _ck(L.load().gdl_bn_stats(L.ptr(x), L.dt_code(x.dtype), _rows(x), x.shape[3], x.stride(2), L.ptr(sums),
                                   L.ptr(pivot), L.stream_ptr()))
     return sums
 
 
 def bn_finalize(pivot, sums, count, gamma, beta, eps, momentum, running_mean, running_var, scale, shift, save_mean,
                 save_invstd) -> None:
-    L.check(L.load().gdl_bn_finalize(L.ptr(pivot), L.ptr(sums), int(count), scale.numel(), L.ptr(gamma),
+    _ck(L.load().gdl_bn_finalize(L.ptr(pivot), L.ptr(sums), int(count), scale.numel(), L.ptr(gamma),
                                      L.ptr(beta), float(eps), float(momentum), L.ptr(running_mean),
                                      L.ptr(running_var), L.ptr(scale), L.ptr(shift), L.ptr(save_mean),
                                      L.ptr(save_invstd), L.stream_ptr()))
 
 
 def bn_eval_coeffs(gamma, beta, running_mean, running_var, eps, scale, shift) -> None:
-    L.check(L.load().gdl_bn_eval_coeffs(running_mean.numel(), L.ptr(gamma), L.ptr(beta), L.ptr(running_mean),
+    _ck(L.load().gdl_bn_eval_coeffs(running_mean.numel(), L.ptr(gamma), L.ptr(beta), L.ptr(running_mean),
                                         L.ptr(running_var), float(eps), L.ptr(scale), L.ptr(shift), L.stream_ptr()))
 
 
 def bn_apply(x, scale, shift, *, res=None, rscale=None, rshift=None, relu=True, y=None, y_up=None) -> None:
     n, h, w, c = x.shape
-    L.check(L.load().gdl_bn_apply(L.ptr(x), x.stride(2), L.ptr(scale), L.ptr(shift), L.ptr(res),
+    _ck(L.load().gdl_bn_apply(L.ptr(x), x.stride(2), L.ptr(scale), L.ptr(shift), L.ptr(res),
                                   res.stride(2) if res is not None else 0, L.ptr(rscale), L.ptr(rshift), int(relu),
                                   L.ptr(y), y.stride(2) if y is not None else 0, L.ptr(y_up),
                                   y_up.stride(2) if y_up is not None else 0, L.dt_code(x.dtype), n, h, w, c,
@@ -189,7 +265,7 @@ def grad_gather(srcs, shape, dtype, *, y=None, x=None, mean=None, invstd=None, g
     ptrs = (C.c_void_p * k)(*[t.data_ptr() for t, _ in srcs])
     lds = (C.c_int * k)(*[t.stride(2) for t, _ in srcs])
     modes = (C.c_int * k)(*[m for _, m in srcs])
-    L.check(L.load().gdl_grad_gather(k, ptrs, lds, modes, L.ptr(y), y.stride(2) if y is not None else 0, L.ptr(x),
+    _ck(L.load().gdl_grad_gather(k, ptrs, lds, modes, L.ptr(y), y.stride(2) if y is not None else 0, L.ptr(x),
                                      x.stride(2) if x is not None else 0, L.ptr(mean), L.ptr(invstd), L.ptr(g),
                                      g.stride(2) if g is not None else 0, L.ptr(sums), L.dt_code(dtype), n, h, w, c,
                                      L.stream_ptr()))
@@ -197,10 +273,16 @@ def grad_gather(srcs, shape, dtype, *, y=None, x=None, mean=None, invstd=None, g
 
 def bn_bwd_apply(g, x, mean, invstd, gamma, sums, dx, dgamma, dbeta, accumulate: bool, count: int = 0) -> None:
     """count = number of elements per channel the (possibly all-reduced) sums cover (0 = local rows)."""
-    L.check(L.load().gdl_bn_bwd_apply(L.ptr(g), g.stride(2), L.ptr(x), x.stride(2), L.ptr(mean), L.ptr(invstd),
+    _ck(L.load().gdl_bn_bwd_apply(L.ptr(g), g.stride(2), L.ptr(x), x.stride(2), L.ptr(mean), L.ptr(invstd),
                                       L.ptr(gamma), L.ptr(sums), L.ptr(dx), dx.stride(2), L.ptr(dgamma),
                                       L.ptr(dbeta), int(accumulate), L.dt_code(x.dtype), _rows(x),
                                       int(count) or _rows(x), x.shape[3], L.stream_ptr()))
+
+
+def bn_param_grads(sums, dgamma, dbeta, accumulate: bool = False) -> None:
+    """dgamma = sums[C:2C] (sum g*xhat), dbeta = sums[0:C] (sum g)."""
+    _ck(L.load().gdl_bn_param_grads(L.ptr(sums), sums.numel() // 2, L.ptr(dgamma), L.ptr(dbeta),
+                                        int(accumulate), L.stream_ptr()))
 
 
 def maxpool3x3s2_fwd(x: torch.Tensor, want_idx: bool):
@@ -208,7 +290,7 @@ def maxpool3x3s2_fwd(x: torch.Tensor, want_idx: bool):
     ho, wo = (h - 1) // 2 + 1, (w - 1) // 2 + 1
     y = torch.empty((n, ho, wo, c), dtype=x.dtype, device=x.device)
     idx = torch.empty((n, ho, wo, c), dtype=torch.uint8, device=x.device) if want_idx else None
-    L.check(L.load().gdl_maxpool3x3s2_fwd(L.ptr(x), x.stride(2), L.ptr(y), c, L.ptr(idx), L.dt_code(x.dtype), n, h, w,
+    _ck(L.load().gdl_maxpool3x3s2_fwd(L.ptr(x), x.stride(2), L.ptr(y), c, L.ptr(idx), L.dt_code(x.dtype), n, h, w,
                                           c, L.stream_ptr()))
     return y, idx
 
@@ -216,7 +298,7 @@ def maxpool3x3s2_fwd(x: torch.Tensor, want_idx: bool):
 def maxpool3x3s2_bwd(dy: torch.Tensor, idx: torch.Tensor, h: int, w: int) -> torch.Tensor:
     n, _, _, c = dy.shape
     dx = torch.empty((n, h, w, c), dtype=dy.dtype, device=dy.device)
-    L.check(L.load().gdl_maxpool3x3s2_bwd(L.ptr(dy), dy.stride(2), L.ptr(idx), L.ptr(dx), c, L.dt_code(dy.dtype), n,
+    _ck(L.load().gdl_maxpool3x3s2_bwd(L.ptr(dy), dy.stride(2), L.ptr(idx), L.ptr(dx), c, L.dt_code(dy.dtype), n,
                                           h, w, c, L.stream_ptr()))
     return dx
 
@@ -255,14 +337,14 @@ def seg_loss_fwd(logits: torch.Tensor, target: torch.Tensor, spec: LossSpec):
     m = _rows(logits)
     stats = torch.empty(4 + 3 * k, dtype=torch.float32, device=logits.device)
     coeff = torch.empty(2 + 2 * k, dtype=torch.float32, device=logits.device)
-    L.check(L.load().gdl_seg_loss_fwd(L.ptr(logits), logits.stride(2), L.ptr(target), _target_kind(target), m, k,
+    _ck(L.load().gdl_seg_loss_fwd(L.ptr(logits), logits.stride(2), L.ptr(target), _target_kind(target), m, k,
                                       *spec.args(), L.ptr(stats), L.ptr(coeff), L.stream_ptr()))
     return coeff, stats
 
 
 def seg_loss_bwd(logits, target, spec: LossSpec, coeff, grad_scale, dlogits) -> None:
     k = logits.shape[3]
-    L.check(L.load().gdl_seg_loss_bwd(L.ptr(logits), logits.stride(2), L.ptr(target), _target_kind(target),
+    _ck(L.load().gdl_seg_loss_bwd(L.ptr(logits), logits.stride(2), L.ptr(target), _target_kind(target),
                                       _rows(logits), k, *spec.args(), L.ptr(coeff), L.ptr(grad_scale), L.ptr(dlogits),
                                       dlogits.stride(2), L.dt_code(dlogits.dtype), L.stream_ptr()))
 
@@ -270,17 +352,17 @@ def seg_loss_bwd(logits, target, spec: LossSpec, coeff, grad_scale, dlogits) -> 
 def argmax_classes(logits: torch.Tensor, threshold: float = 0.5) -> torch.Tensor:
     n, h, w, k = logits.shape
     out = torch.empty((n, h, w), dtype=torch.int64, device=logits.device)
-    L.check(L.load().gdl_argmax_classes(L.ptr(logits), logits.stride(2), n * h * w, k, float(threshold), L.ptr(out),
+    _ck(L.load().gdl_argmax_classes(L.ptr(logits), logits.stride(2), n * h * w, k, float(threshold), L.ptr(out),
                                         L.stream_ptr()))
     return out
 
 
 def adam_step(p, g, m, v, lr, beta1, beta2, eps, weight_decay, step, grad_scale=None) -> None:
-    L.check(L.load().gdl_adam_step(L.ptr(p), L.ptr(g), L.ptr(m), L.ptr(v), p.numel(), float(lr), float(beta1),
+    _ck(L.load().gdl_adam_step(L.ptr(p), L.ptr(g), L.ptr(m), L.ptr(v), p.numel(), float(lr), float(beta1),
                                    float(beta2), float(eps), float(weight_decay), int(step), L.ptr(grad_scale),
                                    L.stream_ptr()))
 
 
 def grad_clip_coef(g, max_norm, scratch, scale) -> None:
-    L.check(L.load().gdl_grad_clip_coef(L.ptr(g), g.numel(), float(max_norm), L.ptr(scratch), L.ptr(scale),
+    _ck(L.load().gdl_grad_clip_coef(L.ptr(g), g.numel(), float(max_norm), L.ptr(scratch), L.ptr(scale),
                                         L.stream_ptr()))

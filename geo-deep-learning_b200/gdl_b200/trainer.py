@@ -1,0 +1,102 @@
+"""Fused training step: uint8 tiles in, updated parameters out, no autograd in between.
+
+normalise (uint8 HWC -> 16-bit NHWC) -> engine forward -> loss kernels -> engine backward ->
+(NCCL all-reduce of the flat gradient) -> (clip) -> fused Adam on flat fp32 buffers.
+This is the path bench.py times; the autograd.Function route in models/ is the Lightning
+drop-in and runs the same kernels.
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+from . import ops
+from .engine import Act, Engine
+from .ops import LossSpec
+
+
+class FusedTrainer:
+    def __init__(self, model: torch.nn.Module, loss: LossSpec, *, lr: float = 1e-4, betas=(0.9, 0.999),
+                 eps: float = 1e-8, weight_decay: float = 0.0, mean=None, std=None, image_max: float = 255.0,
+                 clip_grad_norm: float | None = None, process_group=None, sync_bn: bool = False) -> None:
+        self.model = model
+        self.loss = loss
+        self.lr, self.betas, self.eps, self.weight_decay = lr, betas, eps, weight_decay
+        self.image_max = image_max
+        self.clip = clip_grad_norm
+        self.group = process_group
+        self.world = dist.get_world_size(process_group) if (process_group is not None or dist.is_initialized()) else 1
+        if self.world > 1 and self.group is None:
+            self.group = dist.group.WORLD
+        self.sync_bn = sync_bn and self.world > 1
+        self.step_count = 0
+        dev = next(model.parameters()).device
+        self.dev = dev
+        self.params = [p for p in model.parameters() if p.requires_grad]
+        total = sum(p.numel() for p in self.params)
+        self.flat = torch.empty(total, dtype=torch.float32, device=dev)
+        self.gflat = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.m = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.v = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.grad_dst: dict[int, torch.Tensor] = {}
+        off = 0
+        with torch.no_grad():
+            for p in self.params:
+                n = p.numel()
+                self.flat[off:off + n].copy_(p.detach().reshape(-1))
+                p.data = self.flat[off:off + n].view(p.shape)
+                g = self.gflat[off:off + n].view(p.shape)
+                p.grad = g
+                self.grad_dst[id(p)] = g
+                off += n
+        self.mean = torch.as_tensor(mean, dtype=torch.float32, device=dev) if mean is not None else None
+        self.std = torch.as_tensor(std, dtype=torch.float32, device=dev) if std is not None else None
+        self.scratch = torch.zeros(2, dtype=torch.float32, device=dev)
+        self.last_engine: Engine | None = None
+
+    @torch.no_grad()
+    def forward_backward(self, image_u8: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
+        """image_u8: (N,H,W,C) uint8 on the device; target: (N,H,W) int64/uint8. Returns the loss (device scalar)
+        with d(loss)/d(params) left in the flat gradient buffer."""
+        model = self.model
+        self.gflat.zero_()
+        eng = Engine(model.compute_dtype, training=True, wcache=model._wcache, grad_dst=self.grad_dst,
+                     sync_bn_group=self.group if self.sync_bn else None)
+        c = image_u8.shape[3]
+        x = ops.normalize_to_nhwc(image_u8, False, model.compute_dtype, (c + 7) // 8 * 8, self.mean, self.std,
+                                  self.image_max)
+        logits = model.run(eng, Act(x, needs_grad=False))
+        coeff, _ = ops.seg_loss_fwd(logits, target, self.loss)
+        n, h, w, k = logits.shape
+        d16 = torch.zeros((n, h, w, (k + 15) // 16 * 16), dtype=model.compute_dtype, device=logits.device)
+        ops.seg_loss_bwd(logits, target, self.loss, coeff, None, d16)
+        eng.head_backward(d16)
+        eng.backward()
+        self.last_engine = eng
+        return coeff[0]
+
+    @torch.no_grad()
+    def optimizer_step(self) -> None:
+        if self.world > 1:
+            dist.all_reduce(self.gflat, group=self.group)
+            scale_by = 1.0 / self.world
+        else:
+            scale_by = None
+        gs = None
+        if self.clip is not None or scale_by is not None:
+            gs = self.scratch[1:2]
+            if self.clip is not None:
+                if scale_by is not None:
+                    self.gflat.mul_(scale_by)
+                ops.grad_clip_coef(self.gflat, self.clip, self.scratch[0:1], gs)
+            else:
+                gs.fill_(scale_by)
+        self.step_count += 1
+        ops.adam_step(self.flat, self.gflat, self.m, self.v, self.lr, self.betas[0], self.betas[1], self.eps,
+                      self.weight_decay, self.step_count, gs)
+        self.model._wcache.clear()  # parameters changed behind torch's version counters
+
+    def step(self, image_u8: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
+        loss = self.forward_backward(image_u8, target)
+        self.optimizer_step()
+        return loss

@@ -109,6 +109,100 @@ int gdl_pack_conv_weight(const float* src, void* dst, int Cout, int Cin, int R, 
 int gdl_unpack_conv_wgrad(const float* src, float* dst, int Cout, int Cin, int R, int S, int src_ld,
                           int accumulate, void* stream);
 
+/* =============================================================================================
+ * HBM-bound kernels (csrc/elementwise.cu).  16-bit NHWC activations, C % 8 == 0 unless noted;
+ * `dtype` = GDL_BF16 / GDL_F16.
+ * ============================================================================================= */
+
+/* Patch normalise + layout change: y = ((x / image_max) - mean[c]) / std[c] written as 16-bit NHWC
+ * with pixel stride ld (channels >= C are zero).  Replaces utils/tensors.py:10-35
+ * (`normalization`, `standardization`) and their call sites datasets/wds_dataset.py:230-236,
+ * datasets/csv_dataset.py:149-153 (true fp32 divisions, same order).  image_max <= 0 skips the
+ * first step, mean == NULL the second (then it is a pure cast/transposition of batch["image"]).
+ * in_kind: 0 = uint8 NHWC, 1 = f32 NHWC, 2 = f32 NCHW, 3 = uint8 NCHW. */
+int gdl_normalize_to_nhwc(const void* x, int in_kind, void* y, int out_dtype, long long N, long long H,
+                          long long W, int C, int ld, const float* mean, const float* stdv, float image_max,
+                          void* stream);
+
+/* im2col / col2im for strided convs and the 3/4/6-band stem (torchvision ResNet conv1 7x7/2, the
+ * 3x3/2 and 1x1/2 convs of layer2-4): col[(n,ho,wo)][(r,s,c)] zero padded to Kpad columns; the conv
+ * itself is then gdl_conv2d_nhwc_fwd with R=S=1.  col2im is the gather-form adjoint (C % 8 == 0). */
+int gdl_im2col_nhwc(const void* x, void* col, int dtype, int N, int H, int W, int C, int ld, int R, int S,
+                    int stride, int pad, int Kpad, void* stream);
+int gdl_col2im_nhwc(const void* dcol, void* dx, int dtype, int N, int H, int W, int C, int ld, int R, int S,
+                    int stride, int pad, int Kpad, void* stream);
+
+/* BatchNorm2d, training mode (nn.BatchNorm2d inside models/utils.py:10-52 ConvModule,
+ * segformer_mlp.py:63-72, smp Conv2dReLU, torchvision ResNet): split into
+ *   stats    sums[0:C] = sum(x - pivot), sums[C:2C] = sum((x - pivot)^2)   (fp32, zeroed inside)
+ *   finalize mean/biased var -> scale = gamma*invstd, shift = beta - mean*scale, saved mean/invstd,
+ *            running stats update (momentum, unbiased var); `count` = elements per channel the sums
+ *            cover (after an optional cross-rank all-reduce of `sums` = SyncBatchNorm)
+ *   apply    y = act(x*scale + shift [+ res | + res*rscale + rshift]); optional second output y_up =
+ *            nearest x2 upsample of y (smp DecoderBlock's F.interpolate(scale_factor=2, "nearest"))
+ * pivot (fp32 [C], may be NULL, may alias running_mean) only conditions the variance formula. */
+int gdl_bn_stats(const void* x, int dtype, long long M, int C, int ld, float* sums, const float* pivot,
+                 void* stream);
+int gdl_bn_finalize(const float* pivot, const float* sums, long long count, int C, const float* gamma,
+                    const float* beta, float eps, float momentum, float* running_mean, float* running_var,
+                    float* scale, float* shift, float* save_mean, float* save_invstd, void* stream);
+int gdl_bn_eval_coeffs(int C, const float* gamma, const float* beta, const float* running_mean,
+                       const float* running_var, float eps, float* scale, float* shift, void* stream);
+int gdl_bn_apply(const void* x, int ldx, const float* scale, const float* shift, const void* res, int ldr,
+                 const float* rscale, const float* rshift, int relu, void* y, int ldy, void* y_up, int ldu,
+                 int dtype, int N, int H, int W, int C, void* stream);
+
+/* Backward of [concat-consumers] -> ReLU -> BatchNorm in two passes (autograd of the above, a20):
+ *   grad_gather  g = (sum_k src_k) * (y > 0); src mode 1 = gradient of the x2-upsampled copy
+ *                (2H x 2W), contributes its 2x2 sum.  With sums != NULL also reduces
+ *                sums[0:C] = sum g, sums[C:2C] = sum g*(x-mean)*invstd in the same pass.
+ *   bn_bwd_apply dx = gamma*invstd*(g - sums[0:C]/count - xhat*sums[C:2C]/count); optional
+ *                dgamma = sums[C:2C], dbeta = sums[0:C]. */
+int gdl_grad_gather(int num_src, const void* const* src_ptr, const int* src_ld, const int* src_mode,
+                    const void* y, int ldy, const void* x, int ldx, const float* mean, const float* invstd,
+                    void* g, int ldg, float* sums, int dtype, int N, int H, int W, int C, void* stream);
+int gdl_bn_bwd_apply(const void* g, int ldg, const void* x, int ldx, const float* mean, const float* invstd,
+                     const float* gamma, const float* sums, void* dx, int ldd, float* dgamma, float* dbeta,
+                     int accumulate_param_grads, int dtype, long long M, long long count, int C, void* stream);
+int gdl_bn_param_grads(const float* sums, int C, float* dgamma, float* dbeta, int accumulate, void* stream);
+
+/* MaxPool2d(kernel 3, stride 2, pad 1) of the ResNet stem; idx (1 byte/element, may be NULL) holds
+ * the winning tap (first maximum in scan order, as ATen) for the backward. */
+int gdl_maxpool3x3s2_fwd(const void* x, int ldx, void* y, int ldy, unsigned char* idx, int dtype, int N, int H,
+                         int W, int C, void* stream);
+int gdl_maxpool3x3s2_bwd(const void* dy, int ldy, const unsigned char* idx, void* dx, int ldx, int dtype, int N,
+                         int H, int W, int C, void* stream);
+
+/* =============================================================================================
+ * losses, eval post-processing, optimizer (csrc/loss_optim.cu).  logits: fp32 [M][ld], K classes.
+ * ============================================================================================= */
+
+/* loss = w_ce * CE + w_dice * Dice over M pixels (training_step's `self.loss(y_hat, y)`,
+ * segmentation_segformer.py:226-229; torch.nn.CrossEntropyLoss / smp SoftCrossEntropyLoss /
+ * smp DiceLoss semantics, see csrc/loss_optim.cu).  K == 1 is the binary (sigmoid) mode.
+ * target_kind: 0 = int64, 1 = uint8.  stats: 4+3K floats, coeff: 2+2K floats, coeff[0] = loss.
+ * bwd writes d(loss)/d(logits) * grad_scale[0] as [M][ldd] of out_dtype (columns >= K untouched). */
+int gdl_seg_loss_fwd(const float* logits, int ld, const void* target, int target_kind, long long M, int K,
+                     long long ignore_index, int has_ignore, float w_ce, float w_dice, float label_smoothing,
+                     int ce_mean_over_all, float dice_smooth, float dice_eps, float* stats, float* coeff,
+                     void* stream);
+int gdl_seg_loss_bwd(const float* logits, int ld, const void* target, int target_kind, long long M, int K,
+                     long long ignore_index, int has_ignore, float w_ce, float w_dice, float label_smoothing,
+                     int ce_mean_over_all, float dice_smooth, float dice_eps, const float* coeff,
+                     const float* grad_scale, void* dlogits, int ldd, int out_dtype, void* stream);
+
+/* softmax(dim=1).argmax(dim=1) (K > 1) or sigmoid > threshold (K == 1):
+ * segmentation_segformer.py:268-271, segmentation_unetplus.py test/validation steps. */
+int gdl_argmax_classes(const float* logits, int ld, long long M, int K, float threshold, long long* out,
+                       void* stream);
+
+/* torch.optim.Adam step on flat fp32 buffers; g is multiplied by grad_scale[0] first (may be NULL).
+ * gdl_grad_clip_coef: scale[0] = min(1, max_norm / (||g||_2 + 1e-6))  (clip_grad_norm_). */
+int gdl_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
+                  float eps, float weight_decay, int step, const float* grad_scale, void* stream);
+int gdl_grad_clip_coef(const float* g, long long n, float max_norm, float* sumsq_scratch, float* scale,
+                       void* stream);
+
 #ifdef __cplusplus
 }
 #endif

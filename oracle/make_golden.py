@@ -1,0 +1,94 @@
+"""Generate tests/golden/*.pt (run in the BUILD container, where /root/reference exists).
+
+  python oracle/make_golden.py
+
+* tensors_golden.pt   — outputs of the REFERENCE's own geo_deep_learning/utils/tensors.py
+                        (`normalization`, `standardization`) on seeded inputs: pins oracle/tensors.py
+                        and the CUDA normalise kernel to the reference itself.
+* unetpp_r18_golden.pt — seeded input / state_dict / logits / loss / selected gradients of
+                        oracle/unetpp.py (resnet18, 3 bands, 5 classes, 64x64): a regression pin of
+                        the oracle restatement (smp itself is not installable here, so its values
+                        cannot be generated; see oracle/unetpp.py header).
+"""
+from __future__ import annotations
+
+import importlib.util
+import sys
+from pathlib import Path
+
+import torch
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+REF = Path("/root/reference")
+OUT = ROOT / "tests" / "golden"
+
+
+def _load_ref_tensors():
+    spec = importlib.util.spec_from_file_location("ref_tensors", REF / "geo_deep_learning" / "utils" / "tensors.py")
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def tensors_golden() -> None:
+    ref = _load_ref_tensors()
+    g = torch.Generator().manual_seed(20260925)
+    cases = {}
+    for c in (3, 4, 6):
+        raw = torch.randint(0, 256, (2, c, 16, 16), generator=g, dtype=torch.uint8)
+        mean = torch.rand(c, generator=g) * 0.5 + 0.2
+        std = torch.rand(c, generator=g) * 0.3 + 0.1
+        x = ref.normalization(raw.float())
+        y = ref.standardization(x, mean.view(c, 1), std.view(c, 1))
+        cases[f"c{c}"] = {"raw": raw, "mean": mean, "std": std, "normalized": x, "standardized": y}
+    cases["norm_custom"] = {"in": torch.tensor([0.0, 255.0]),
+                            "out": ref.normalization(torch.tensor([0.0, 255.0]), 0, 255, -1.0, 1.0)}
+    torch.save(cases, OUT / "tensors_golden.pt")
+    print("wrote tensors_golden.pt")
+
+
+def build_seeded_r18():
+    """Deterministic oracle weights (CPU RNG stream of this torch build) used by the golden file."""
+    from oracle.unetpp import UnetPlusPlusOracle
+    torch.manual_seed(7)
+    m = UnetPlusPlusOracle("resnet18", 3, 5).train()
+    # non-trivial BN affine parameters so their gradients are exercised
+    with torch.no_grad():
+        for mod in m.modules():
+            if isinstance(mod, torch.nn.BatchNorm2d):
+                mod.weight.uniform_(0.5, 1.5)
+                mod.bias.uniform_(-0.2, 0.2)
+    return m
+
+
+def unetpp_golden() -> None:
+    m = build_seeded_r18()
+    sd0 = {k: v.clone() for k, v in m.state_dict().items()}
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(2, 3, 64, 64, generator=g)
+    t = torch.randint(0, 5, (2, 64, 64), generator=g)
+    logits = m(x)
+    loss = torch.nn.functional.cross_entropy(logits, t)
+    loss.backward()
+    grads = {n: p.grad.clone() for n, p in m.named_parameters()
+             if n in ("encoder.conv1.weight", "encoder.layer1.0.conv1.weight", "encoder.layer4.1.bn2.weight",
+                      "decoder.blocks.x_0_0.conv1.0.weight", "decoder.blocks.x_0_3.conv2.1.bias",
+                      "segmentation_head.0.weight", "segmentation_head.0.bias")}
+    m.eval()
+    with torch.no_grad():
+        logits_eval = m(x)
+    # weights are NOT stored (64 MB): they are regenerated from the seed by build_seeded_r18() below
+    torch.save({"weight_checksum": sum(v.double().sum() for v in sd0.values() if v.is_floating_point()),
+                "x": x, "target": t, "logits_train_sum": logits.detach().double().sum(),
+                "logits_train_slice": logits.detach()[:, :, ::8, ::8].clone(), "loss": loss.detach(),
+                "grad_norms": {k: v.norm() for k, v in grads.items()},
+                "logits_eval_slice": logits_eval[:, :, ::8, ::8].clone()}, OUT / "unetpp_r18_golden.pt")
+    print("wrote unetpp_r18_golden.pt")
+
+
+if __name__ == "__main__":
+    OUT.mkdir(parents=True, exist_ok=True)
+    tensors_golden()
+    if "--all" in sys.argv:
+        unetpp_golden()

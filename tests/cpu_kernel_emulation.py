@@ -1,0 +1,279 @@
+"""TEST INFRASTRUCTURE ONLY — torch/CPU emulation of the gdl_b200.ops kernel wrappers.
+
+It lets the `-m "not gpu"` suite exercise the HOST logic (engine graph wiring, gradient-source
+bookkeeping, virtual concat, im2col routing, trainer buffers) without a GPU, in fp32, against the
+oracle's autograd.  It is installed by monkeypatching `gdl_b200.ops` inside a test and is never
+imported by the product (which has no CPU path and raises without the CUDA library).
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn.functional as F
+
+
+_WORK = torch.float32  # arithmetic dtype of the emulation (tests may switch to float64)
+
+
+def set_work_dtype(dt):
+    global _WORK
+    _WORK = dt
+
+
+def _nchw(t):
+    return t.permute(0, 3, 1, 2)
+
+
+def _nhwc(t):
+    return t.permute(0, 2, 3, 1)
+
+
+def pack_conv_weight(w, dtype, mode=0, ld=0, out=None):
+    k, c, r, s = w.shape
+    if mode == 0:
+        m = w.permute(0, 2, 3, 1).reshape(k, r * s * c)
+    elif mode == 1:
+        m = w.flip(2, 3).permute(1, 2, 3, 0).reshape(c, r * s * k)
+    else:
+        m = w.permute(2, 3, 1, 0).reshape(r * s * c, k)
+    ld = ld or m.shape[1]
+    o = torch.zeros(m.shape[0], ld, dtype=dtype)
+    o[:, :m.shape[1]] = m.to(dtype)
+    return o
+
+
+def conv2d_fwd(srcs, weight, cout, r, s, pad_h, pad_w, *, out=None, out_dtype=None, bias=None, relu=False):
+    x = torch.cat(list(srcs), 3).to(_WORK)
+    ctot = x.shape[3]
+    w = weight[:cout, :r * s * ctot].to(_WORK).reshape(cout, r, s, ctot).permute(0, 3, 1, 2)
+    y = F.conv2d(_nchw(x), w, bias, padding=(pad_h, pad_w))
+    if relu:
+        y = F.relu(y)
+    y = _nhwc(y).to(out_dtype or srcs[0].dtype)
+    if out is not None:
+        out.copy_(y)
+        return out
+    return y.contiguous()
+
+
+def conv2d_wgrad(srcs, dy, r, s, pad_h, pad_w, dw):
+    x = _nchw(torch.cat(list(srcs), 3).to(_WORK))
+    cout, ctot = dy.shape[3], x.shape[1]
+    g = torch.nn.grad.conv2d_weight(x, (cout, ctot, r, s), _nchw(dy.to(_WORK)).contiguous(), padding=(pad_h, pad_w))
+    dw[:, :r * s * ctot] += g.permute(0, 2, 3, 1).reshape(cout, r * s * ctot)
+    return dw
+
+
+def unpack_conv_wgrad(dw, out_oihw, src_ld=0, accumulate=False):
+    k, c, r, s = out_oihw.shape
+    v = dw[:k, :r * s * c].reshape(k, r, s, c).permute(0, 3, 1, 2)
+    if accumulate:
+        out_oihw += v
+    else:
+        out_oihw.copy_(v)
+    return out_oihw
+
+
+def normalize_to_nhwc(x, chw, out_dtype, ld, mean=None, std=None, image_max=0.0):
+    v = x.to(_WORK)
+    if chw:
+        v = v.permute(0, 2, 3, 1)
+    if image_max > 0:
+        v = v / image_max
+    if mean is not None:
+        v = (v - mean) / std
+    n, h, w, c = v.shape
+    out = torch.zeros(n, h, w, ld, dtype=out_dtype)
+    out[..., :c] = v.to(out_dtype)
+    return out
+
+
+def im2col(x, c, r, s, stride, pad, kpad):
+    n, h, w, _ = x.shape
+    unf = F.unfold(_nchw(x[..., :c].to(_WORK)), (r, s), padding=pad, stride=stride)
+    ho, wo = (h + 2 * pad - r) // stride + 1, (w + 2 * pad - s) // stride + 1
+    m = unf.view(n, c, r * s, ho, wo).permute(0, 3, 4, 2, 1).reshape(n, ho, wo, r * s * c)
+    col = torch.zeros(n, ho, wo, kpad, dtype=x.dtype)
+    col[..., :r * s * c] = m.to(x.dtype)
+    return col
+
+
+def col2im(dcol, n, h, w, c, r, s, stride, pad):
+    ho, wo = dcol.shape[1], dcol.shape[2]
+    d = dcol[..., :r * s * c].to(_WORK).view(n, ho, wo, r * s, c).permute(0, 4, 3, 1, 2).reshape(n, c * r * s, ho * wo)
+    return _nhwc(F.fold(d, (h, w), (r, s), padding=pad, stride=stride)).to(dcol.dtype).contiguous()
+
+
+def _rows(x):
+    return x.shape[0] * x.shape[1] * x.shape[2]
+
+
+def bn_stats(x, sums, pivot=None):
+    c = x.shape[3]
+    v = x.to(_WORK).reshape(-1, c)
+    if pivot is not None:
+        v = v - pivot
+    sums[:c] = v.sum(0)
+    sums[c:] = (v * v).sum(0)
+    return sums
+
+
+def bn_finalize(pivot, sums, count, gamma, beta, eps, momentum, running_mean, running_var, scale, shift, save_mean,
+                save_invstd):
+    c = scale.numel()
+    m1 = sums[:c] / count
+    var = (sums[c:] / count - m1 * m1).clamp_min(0)
+    mean = m1 + (pivot if pivot is not None else 0)
+    invstd = (var + eps).rsqrt()
+    scale.copy_(gamma * invstd)
+    shift.copy_(beta - mean * gamma * invstd)
+    save_mean.copy_(mean)
+    save_invstd.copy_(invstd)
+    if running_mean is not None:
+        unb = var * (count / (count - 1)) if count > 1 else var
+        running_mean.mul_(1 - momentum).add_(momentum * mean)
+        running_var.mul_(1 - momentum).add_(momentum * unb)
+
+
+def bn_eval_coeffs(gamma, beta, running_mean, running_var, eps, scale, shift):
+    invstd = (running_var + eps).rsqrt()
+    scale.copy_(gamma * invstd)
+    shift.copy_(beta - running_mean * gamma * invstd)
+
+
+def bn_apply(x, scale, shift, *, res=None, rscale=None, rshift=None, relu=True, y=None, y_up=None):
+    v = x.to(_WORK) * scale + shift
+    if res is not None:
+        r = res.to(_WORK)
+        if rscale is not None:
+            r = r * rscale + rshift
+        v = v + r
+    if relu:
+        v = F.relu(v)
+    v = v.to(x.dtype)
+    if y is not None:
+        y.copy_(v)
+    if y_up is not None:
+        y_up.copy_(v.repeat_interleave(2, 1).repeat_interleave(2, 2))
+
+
+def grad_gather(srcs, shape, dtype, *, y=None, x=None, mean=None, invstd=None, g=None, sums=None):
+    acc = torch.zeros(shape, dtype=_WORK)
+    for t, mode in srcs:
+        t = t.to(_WORK)
+        if mode == 1:
+            n, h2, w2, c = t.shape
+            t = t.view(n, h2 // 2, 2, w2 // 2, 2, c).sum((2, 4))
+        acc = acc + t
+    if y is not None:
+        acc = acc * (y.to(_WORK) > 0)
+    acc16 = acc.to(dtype)
+    if g is not None:
+        g.copy_(acc16)
+    if sums is not None:
+        c = shape[3]
+        gr = acc16.to(_WORK).reshape(-1, c)
+        xh = (x.to(_WORK).reshape(-1, c) - mean) * invstd
+        sums[:c] = gr.sum(0)
+        sums[c:] = (gr * xh).sum(0)
+
+
+def bn_bwd_apply(g, x, mean, invstd, gamma, sums, dx, dgamma, dbeta, accumulate, count=0):
+    c = x.shape[3]
+    m = count or _rows(x)
+    xh = (x.to(_WORK) - mean) * invstd
+    dx.copy_((gamma * invstd * (g.to(_WORK) - sums[:c] / m - xh * sums[c:] / m)).to(dx.dtype))
+    bn_param_grads(sums, dgamma, dbeta, accumulate)
+
+
+def bn_param_grads(sums, dgamma, dbeta, accumulate=False):
+    c = sums.numel() // 2
+    if dgamma is not None:
+        dgamma.copy_(sums[c:] + (dgamma if accumulate else 0))
+    if dbeta is not None:
+        dbeta.copy_(sums[:c] + (dbeta if accumulate else 0))
+
+
+def maxpool3x3s2_fwd(x, want_idx):
+    y, idx = F.max_pool2d(_nchw(x.to(_WORK)), 3, 2, 1, return_indices=True)
+    return _nhwc(y).to(x.dtype).contiguous(), (idx if want_idx else None)
+
+
+def maxpool3x3s2_bwd(dy, idx, h, w):
+    n, ho, wo, c = dy.shape
+    dx = torch.zeros(n, c, h * w, dtype=_WORK)
+    dx.scatter_add_(2, idx.reshape(n, c, -1), _nchw(dy.to(_WORK)).reshape(n, c, -1))
+    return _nhwc(dx.view(n, c, h, w)).to(dy.dtype).contiguous()
+
+
+class LossSpec:
+    def __init__(self, w_ce=1.0, w_dice=0.0, label_smoothing=0.0, ce_mean_over_all=False, ignore_index=None,
+                 dice_smooth=0.0, dice_eps=1e-7):
+        self.w_ce, self.w_dice = w_ce, w_dice
+        self.label_smoothing, self.ce_mean_over_all, self.ignore_index = label_smoothing, ce_mean_over_all, ignore_index
+        self.dice_smooth, self.dice_eps = dice_smooth, dice_eps
+
+
+_LOSS_GRADS: dict = {}
+
+
+def _loss_value(logits_nchw, target, spec):
+    from oracle import losses as ol
+    loss = 0.0
+    if spec.w_ce:
+        if spec.ce_mean_over_all:
+            loss = loss + spec.w_ce * ol.soft_ce_loss(logits_nchw, target, spec.label_smoothing, spec.ignore_index)
+        else:
+            loss = loss + spec.w_ce * F.cross_entropy(logits_nchw, target.long(), label_smoothing=spec.label_smoothing,
+                                                      ignore_index=spec.ignore_index if spec.ignore_index is not None else -100)
+    if spec.w_dice:
+        mode = "binary" if logits_nchw.shape[1] == 1 else "multiclass"
+        loss = loss + spec.w_dice * ol.dice_loss(logits_nchw, target, mode, spec.dice_smooth, spec.dice_eps, spec.ignore_index)
+    return loss
+
+
+def seg_loss_fwd(logits, target, spec):
+    x = _nchw(logits).detach().clone().requires_grad_(True)
+    with torch.enable_grad():
+        loss = _loss_value(x, target, spec)
+        loss.backward()
+    coeff = torch.zeros(2 + 2 * logits.shape[3], dtype=_WORK)
+    coeff[0] = loss.detach()
+    _LOSS_GRADS[id(coeff)] = _nhwc(x.grad).contiguous()
+    return coeff, None
+
+
+def seg_loss_bwd(logits, target, spec, coeff, grad_scale, dlogits):
+    grad = _LOSS_GRADS.pop(id(coeff))
+    k = logits.shape[3]
+    s = grad_scale[0] if grad_scale is not None else 1.0
+    dlogits[..., :k] = (grad * s).to(dlogits.dtype)
+
+
+def argmax_classes(logits, threshold=0.5):
+    return logits.argmax(3) if logits.shape[3] > 1 else (logits[..., 0].sigmoid() > threshold).long()
+
+
+def adam_step(p, g, m, v, lr, beta1, beta2, eps, weight_decay, step, grad_scale=None):
+    gi = g * (grad_scale[0] if grad_scale is not None else 1.0)
+    if weight_decay:
+        gi = gi + weight_decay * p
+    m.mul_(beta1).add_((1 - beta1) * gi)
+    v.mul_(beta2).add_((1 - beta2) * gi * gi)
+    bc1, bc2 = 1 - beta1 ** step, 1 - beta2 ** step
+    p.sub_((lr / bc1) * m / (v.sqrt() / bc2 ** 0.5 + eps))
+
+
+def grad_clip_coef(g, max_norm, scratch, scale):
+    scale[0] = min(1.0, max_norm / (g.norm().item() + 1e-6))
+
+
+def install(monkeypatch):
+    """Replace every kernel wrapper of gdl_b200.ops by its emulation (and in modules that did
+    `from .ops import X`)."""
+    import gdl_b200.ops as ops
+    import gdl_b200.trainer as trainer
+    names = [n for n, v in globals().items() if callable(v) and not n.startswith("_") and n not in ("install",)]
+    for n in names:
+        if hasattr(ops, n):
+            monkeypatch.setattr(ops, n, globals()[n])
+    monkeypatch.setattr(trainer, "LossSpec", LossSpec, raising=False)

@@ -1,0 +1,94 @@
+"""CPU: host logic of the engine / model graph / trainer, with the CUDA kernels replaced by the fp32
+torch emulation in tests/cpu_kernel_emulation.py.  With fp32 "kernels" the engine's hand-written
+backward must reproduce the oracle's autograd to float accuracy — this pins the graph wiring
+(virtual concat order, gradient-source bookkeeping, residual / downsample branches, im2col routing)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+import cpu_kernel_emulation as emu
+
+
+def _pair(enc, cin, k):
+    from gdl_b200.models.unetpp import UnetPlusPlus
+    from oracle.unetpp import UnetPlusPlusOracle
+    torch.manual_seed(0)
+    ora = UnetPlusPlusOracle(enc, cin, k)
+    with torch.no_grad():
+        for m in ora.modules():
+            if isinstance(m, torch.nn.BatchNorm2d):
+                m.weight.uniform_(0.5, 1.5)
+                m.bias.uniform_(-0.2, 0.2)
+    prod = UnetPlusPlus(enc, in_channels=cin, classes=k, compute_dtype=torch.float32)
+    prod.load_state_dict(ora.state_dict())
+    return ora, prod
+
+
+@pytest.fixture
+def f64(monkeypatch):
+    """float64 everywhere: in fp32 a single pre-activation within 1e-5 of zero flips its ReLU mask
+    between two summation orders and moves a BN-bias gradient by percents (observed), which would
+    hide real wiring bugs behind a loose tolerance."""
+    emu.set_work_dtype(torch.float64)
+    yield torch.float64
+    emu.set_work_dtype(torch.float32)
+
+
+@pytest.mark.parametrize("enc,cin,k", [("resnet18", 3, 5), ("resnet50", 4, 3)])
+def test_engine_backward_equals_oracle_autograd(monkeypatch, f64, enc, cin, k):
+    from gdl_b200.engine import Act, Engine
+    emu.install(monkeypatch)
+    ora, prod = _pair(enc, cin, k)
+    ora, prod = ora.double(), prod.double()
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(2, cin, 64, 64, generator=g).double()
+    t = torch.randint(0, k, (2, 64, 64), generator=g)
+    ora.train()
+    ref = ora(x)
+    F.cross_entropy(ref, t).backward()
+
+    eng = Engine(torch.float64, training=True, acc_dtype=torch.float64)
+    xin = emu.normalize_to_nhwc(x, True, torch.float64, (cin + 7) // 8 * 8)
+    with torch.no_grad():  # the product runs inside autograd.Function.forward / FusedTrainer (no autograd)
+        logits = prod.run(eng, Act(xin, needs_grad=False))
+    assert torch.allclose(logits.permute(0, 3, 1, 2), ref, atol=1e-9, rtol=1e-9)
+    d = logits.detach().permute(0, 3, 1, 2).clone().requires_grad_(True)
+    F.cross_entropy(d, t).backward()
+    d16 = torch.zeros(2, 64, 64, 16, dtype=torch.float64)
+    d16[..., :k] = d.grad.permute(0, 2, 3, 1)
+    with torch.no_grad():
+        eng.head_backward(d16)
+        eng.backward()
+    refg = dict(ora.named_parameters())
+    for n, p in prod.named_parameters():
+        got = eng.param_grads[id(p)]
+        want = refg[n].grad
+        err = (got - want).norm() / (want.norm() + 1e-12)
+        assert err < 1e-8, f"{n}: {err}"
+    # running statistics were updated exactly once
+    for (n, a), (_, b) in zip(prod.named_buffers(), ora.named_buffers()):
+        if "running" in n:
+            assert torch.allclose(a, b, atol=1e-9, rtol=1e-9), n
+    assert not eng.tape
+
+
+def test_trainer_flat_buffers_and_step(monkeypatch):
+    from gdl_b200.trainer import FusedTrainer
+    emu.install(monkeypatch)
+    _, prod = _pair("resnet18", 3, 4)
+    prod.train()
+    tr = FusedTrainer(prod, emu.LossSpec(1.0, 0.0, ignore_index=-100), lr=1e-2, mean=[0.5] * 3, std=[0.25] * 3,
+                      clip_grad_norm=1.0)
+    assert tr.flat.numel() == sum(p.numel() for p in prod.parameters())
+    # parameters are views of the flat buffer, gradients views of the flat gradient buffer
+    p0 = next(prod.parameters())
+    assert p0.data_ptr() == tr.flat.data_ptr() and p0.grad.data_ptr() == tr.gflat.data_ptr()
+    g = torch.Generator().manual_seed(3)
+    t = torch.randint(0, 4, (2, 2, 2), generator=g).repeat_interleave(16, 1).repeat_interleave(16, 2)
+    raw = (t.unsqueeze(-1) * 60 + torch.randint(0, 20, (2, 32, 32, 3), generator=g)).to(torch.uint8)
+    losses = [float(tr.step(raw, t)) for _ in range(6)]
+    assert all(torch.isfinite(torch.tensor(losses)))
+    assert losses[-1] < losses[0]
+    # state_dict still exposes the (updated) parameters under the reference's key names
+    sd = prod.state_dict()
+    assert "decoder.blocks.x_0_0.conv1.0.weight" in sd and sd["encoder.conv1.weight"].data_ptr() == p0.data_ptr()

@@ -1,0 +1,186 @@
+"""GPU: whole-model parity of the B200 UNet++ against the oracle (fp32, CPU-equivalent math run in
+torch fp32 on the same weights and inputs).
+
+The product computes in bf16 (or fp16) with fp32 accumulation; a 16-bit pipeline cannot match an
+fp32 oracle to 1e-5.  The bar used here (SURVEY.md §7 "hard parts"): the product's deviation from
+the fp32 oracle must be no worse than ~2.5x the deviation of the REFERENCE STACK itself run under
+torch.autocast(same 16-bit dtype) on the same inputs, and the argmax masks must agree with the
+fp32 oracle at least as often as the autocast reference does (minus 0.5 %).
+"""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def _models(enc, cin, k, seed=0, dtype=torch.bfloat16):
+    from gdl_b200.models.unetpp import UnetPlusPlus
+    from oracle.unetpp import UnetPlusPlusOracle
+    torch.manual_seed(seed)
+    ora = UnetPlusPlusOracle(enc, cin, k)
+    with torch.no_grad():
+        for m in ora.modules():
+            if isinstance(m, torch.nn.BatchNorm2d):
+                m.weight.uniform_(0.5, 1.5)
+                m.bias.uniform_(-0.2, 0.2)
+    ora = ora.cuda()
+    prod = UnetPlusPlus(enc, in_channels=cin, classes=k, compute_dtype=dtype).cuda()
+    prod.load_state_dict(ora.state_dict())  # identical keys: the drop-in contract
+    return ora, prod
+
+
+def _rel(a, b):
+    return ((a.float() - b.float()).norm() / (b.float().norm() + 1e-20)).item()
+
+
+@pytest.mark.parametrize("enc,cin,k,hw,dtype", [
+    ("resnet18", 3, 5, 64, torch.bfloat16),
+    ("resnet18", 3, 5, 64, torch.float16),
+    ("resnet50", 4, 5, 64, torch.bfloat16),
+    ("resnet34", 6, 2, 96, torch.bfloat16),
+])
+def test_train_step_parity(cuda, enc, cin, k, hw, dtype):
+    ora, prod = _models(enc, cin, k, dtype=dtype)
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(4, cin, hw, hw, generator=g).cuda()
+    t = torch.randint(0, k, (4, hw, hw), generator=g).cuda()
+
+    ora.train()
+    ref_logits = ora(x)
+    ref_loss = F.cross_entropy(ref_logits, t)
+    ref_loss.backward()
+    ref_grads = {n: p.grad.clone() for n, p in ora.named_parameters()}
+    ref_rm = {n: b.clone() for n, b in ora.named_buffers() if "running" in n}
+
+    # the reference stack under autocast: how far does 16-bit compute move things on its own?
+    ora2, _ = _models(enc, cin, k, dtype=dtype)
+    ora2.train()
+    with torch.autocast("cuda", dtype=dtype):
+        ac_logits = ora2(x)
+    ac_loss = F.cross_entropy(ac_logits.float(), t)
+    ac_loss.backward()
+    ac_grads = {n: p.grad.clone() for n, p in ora2.named_parameters()}
+
+    prod.train()
+    logits = prod(x)
+    assert logits.shape == ref_logits.shape and logits.dtype == torch.float32
+    loss = F.cross_entropy(logits, t)
+    loss.backward()
+
+    e_prod, e_ac = _rel(logits, ref_logits), _rel(ac_logits, ref_logits)
+    print(f"[{enc} {dtype}] logits rel err: product {e_prod:.4f}, autocast reference {e_ac:.4f}")
+    assert e_prod < max(2.5 * e_ac, 5e-3)
+    assert abs(loss.item() - ref_loss.item()) < max(2.5 * abs(ac_loss.item() - ref_loss.item()), 5e-3)
+
+    worst = 0.0
+    for n, p in prod.named_parameters():
+        assert p.grad is not None, n
+        assert p.grad.shape == ref_grads[n].shape
+        ep, ea = _rel(p.grad, ref_grads[n]), _rel(ac_grads[n], ref_grads[n])
+        worst = max(worst, ep / max(ea, 2e-3))
+        assert ep < max(3.0 * ea, 2e-2), f"{n}: product {ep:.4f} vs autocast {ea:.4f}"
+    print(f"[{enc} {dtype}] worst grad err ratio vs autocast: {worst:.2f}")
+
+    for n, b in prod.named_buffers():
+        if "running" in n:
+            assert torch.allclose(b, ref_rm[n], atol=2e-2, rtol=2e-2), n
+        if n.endswith("num_batches_tracked"):
+            assert int(b) == 1
+
+
+def test_intermediate_features_track_oracle(cuda):
+    from oracle.unetpp import encoder_features
+    ora, prod = _models("resnet18", 3, 5)
+    g = torch.Generator().manual_seed(2)
+    x = torch.randn(2, 3, 64, 64, generator=g).cuda()
+    ora.train()
+    prod.train()
+    with torch.no_grad():
+        feats = encoder_features(ora.encoder, x)
+    logits = prod(x)
+    eng = prod.last_engine
+    for i, name in enumerate(["e1", "e2", "e3", "e4", "e5"]):
+        got = eng.named[name].t.float().permute(0, 3, 1, 2)
+        err = _rel(got, feats[i + 1])
+        print(name, err)
+        assert err < 0.03, name
+    assert torch.isfinite(logits).all()
+
+
+def test_eval_forward_and_argmax(cuda):
+    from gdl_b200 import ops
+    ora, prod = _models("resnet18", 4, 5)
+    g = torch.Generator().manual_seed(3)
+    # a few training steps' worth of running statistics so eval-mode BN is non-trivial
+    with torch.no_grad():
+        for m in ora.modules():
+            if isinstance(m, torch.nn.BatchNorm2d):
+                m.running_mean.normal_(0, 0.1)
+                m.running_var.uniform_(0.5, 1.5)
+    prod.load_state_dict(ora.state_dict())
+    x = torch.randn(2, 4, 128, 128, generator=g).cuda()
+    ora.eval()
+    prod.eval()
+    with torch.no_grad():
+        ref = ora(x)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            ac = ora(x).float()
+        out = prod(x)
+    assert _rel(out, ref) < max(2.5 * _rel(ac, ref), 5e-3)
+    agree_prod = (out.argmax(1) == ref.argmax(1)).float().mean().item()
+    agree_ac = (ac.argmax(1) == ref.argmax(1)).float().mean().item()
+    print(f"argmax agreement with fp32 oracle: product {agree_prod:.4f}, autocast reference {agree_ac:.4f}")
+    assert agree_prod >= agree_ac - 0.005
+    # the argmax kernel itself is bit-exact on the product's own logits
+    nhwc = out.permute(0, 2, 3, 1)
+    assert torch.equal(ops.argmax_classes(nhwc), out.argmax(1))
+
+
+def test_loss_modules_and_fused_trainer_agree_with_autograd_route(cuda):
+    from gdl_b200.losses import CrossEntropyLoss, DiceLoss
+    from gdl_b200.ops import LossSpec
+    from gdl_b200.trainer import FusedTrainer
+    ora, prod = _models("resnet18", 3, 5)
+    _, prod2 = _models("resnet18", 3, 5)
+    g = torch.Generator().manual_seed(4)
+    raw = torch.randint(0, 256, (2, 64, 64, 3), generator=g, dtype=torch.uint8).cuda()
+    t = torch.randint(0, 5, (2, 64, 64), generator=g).cuda()
+    mean, std = [0.4, 0.5, 0.6], [0.2, 0.25, 0.3]
+    # route A: reference-style batch (float NCHW standardised) -> module forward -> loss module -> autograd
+    from oracle import tensors as ot
+    img = ot.standardization(ot.normalization(raw.permute(0, 3, 1, 2).float()), torch.tensor(mean).view(3, 1).cuda(),
+                             torch.tensor(std).view(3, 1).cuda())
+    prod.train()
+    loss_a = CrossEntropyLoss()(prod(img), t)
+    loss_a.backward()
+    # route B: fused trainer from the raw uint8 tile
+    prod2.train()
+    tr = FusedTrainer(prod2, LossSpec(1.0, 0.0, ignore_index=-100), lr=1e-3, mean=mean, std=std)
+    loss_b = tr.forward_backward(raw, t)
+    assert abs(loss_a.item() - loss_b.item()) < 1e-3
+    for (n, pa), (_, pb) in zip(prod.named_parameters(), prod2.named_parameters()):
+        assert _rel(pb.grad, pa.grad) < 2e-2, n
+    before = tr.flat.clone()
+    tr.optimizer_step()
+    assert (tr.flat - before).abs().max() > 0
+    # dice through the module API runs and is differentiable
+    prod.zero_grad()
+    ld = DiceLoss("multiclass")(prod(img), t)
+    ld.backward()
+    assert torch.isfinite(ld) and prod.segmentation_head[0].weight.grad.abs().sum() > 0
+
+
+def test_training_reduces_loss(cuda):
+    """A few fused steps on a fixed synthetic batch must drive the loss down (end-to-end sanity)."""
+    from gdl_b200.ops import LossSpec
+    from gdl_b200.trainer import FusedTrainer
+    _, prod = _models("resnet18", 3, 5, seed=5)
+    g = torch.Generator().manual_seed(6)
+    t = torch.randint(0, 5, (4, 2, 2), generator=g).repeat_interleave(32, 1).repeat_interleave(32, 2).cuda()
+    raw = (t.unsqueeze(-1) * 50 + torch.randint(0, 30, (4, 64, 64, 3), generator=g).cuda()).to(torch.uint8)
+    prod.train()
+    tr = FusedTrainer(prod, LossSpec(1.0, 0.0, ignore_index=-100), lr=2e-3, mean=[0.5] * 3, std=[0.2] * 3)
+    losses = [tr.step(raw, t).item() for _ in range(12)]
+    print("losses", [round(v, 4) for v in losses])
+    assert losses[-1] < 0.7 * losses[0]
