@@ -18,7 +18,8 @@ from .ops import LossSpec
 class FusedTrainer:
     def __init__(self, model: torch.nn.Module, loss: LossSpec, *, lr: float = 1e-4, betas=(0.9, 0.999),
                  eps: float = 1e-8, weight_decay: float = 0.0, mean=None, std=None, image_max: float = 255.0,
-                 clip_grad_norm: float | None = None, process_group=None, sync_bn: bool = False) -> None:
+                 clip_grad_norm: float | None = None, process_group=None, sync_bn: bool = False,
+                 acc_dtype: torch.dtype = torch.float32) -> None:
         self.model = model
         self.loss = loss
         self.lr, self.betas, self.eps, self.weight_decay = lr, betas, eps, weight_decay
@@ -29,15 +30,16 @@ class FusedTrainer:
         if self.world > 1 and self.group is None:
             self.group = dist.group.WORLD
         self.sync_bn = sync_bn and self.world > 1
+        self.acc_dtype = acc_dtype  # fp32 on the GPU; float64 only in CPU host-logic tests
         self.step_count = 0
         dev = next(model.parameters()).device
         self.dev = dev
         self.params = [p for p in model.parameters() if p.requires_grad]
         total = sum(p.numel() for p in self.params)
-        self.flat = torch.empty(total, dtype=torch.float32, device=dev)
-        self.gflat = torch.zeros(total, dtype=torch.float32, device=dev)
-        self.m = torch.zeros(total, dtype=torch.float32, device=dev)
-        self.v = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.flat = torch.empty(total, dtype=acc_dtype, device=dev)
+        self.gflat = torch.zeros(total, dtype=acc_dtype, device=dev)
+        self.m = torch.zeros(total, dtype=acc_dtype, device=dev)
+        self.v = torch.zeros(total, dtype=acc_dtype, device=dev)
         self.grad_dst: dict[int, torch.Tensor] = {}
         off = 0
         with torch.no_grad():
@@ -49,9 +51,9 @@ class FusedTrainer:
                 p.grad = g
                 self.grad_dst[id(p)] = g
                 off += n
-        self.mean = torch.as_tensor(mean, dtype=torch.float32, device=dev) if mean is not None else None
-        self.std = torch.as_tensor(std, dtype=torch.float32, device=dev) if std is not None else None
-        self.scratch = torch.zeros(2, dtype=torch.float32, device=dev)
+        self.mean = torch.as_tensor(mean, dtype=acc_dtype, device=dev) if mean is not None else None
+        self.std = torch.as_tensor(std, dtype=acc_dtype, device=dev) if std is not None else None
+        self.scratch = torch.zeros(2, dtype=acc_dtype, device=dev)
         self.last_engine: Engine | None = None
 
     @torch.no_grad()
@@ -61,7 +63,7 @@ class FusedTrainer:
         model = self.model
         self.gflat.zero_()
         eng = Engine(model.compute_dtype, training=True, wcache=model._wcache, grad_dst=self.grad_dst,
-                     sync_bn_group=self.group if self.sync_bn else None)
+                     sync_bn_group=self.group if self.sync_bn else None, acc_dtype=self.acc_dtype)
         c = image_u8.shape[3]
         x = ops.normalize_to_nhwc(image_u8, False, model.compute_dtype, (c + 7) // 8 * 8, self.mean, self.std,
                                   self.image_max)

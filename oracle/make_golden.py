@@ -87,8 +87,44 @@ def unetpp_golden() -> None:
     print("wrote unetpp_r18_golden.pt")
 
 
+def segformer_golden() -> None:
+    """Outputs of the REFERENCE's SegFormerSegmentationModel (mit_b0, 3 bands, 5 classes, 64x64) loaded
+    with oracle.segformer.init_state_dict(seed=0): pins oracle/segformer.py to the reference itself."""
+    import torch.nn.functional as F
+    from oracle import ref_shims
+    from oracle import segformer as osf
+    sd = osf.init_state_dict("mit_b0", 3, 5, seed=0)
+    ref = ref_shims.reference_segformer("mit_b0", 3, 5)
+    ref.load_state_dict(sd)
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(2, 3, 64, 64, generator=g)
+    t = torch.randint(0, 5, (2, 64, 64), generator=g)
+    ref.eval()
+    with torch.no_grad():
+        logits_eval = ref(x)
+    ref.train()
+    for m in ref.modules():  # stochastic layers off: parity is defined without dropout / drop-path
+        if m.__class__.__name__ in ("DropPath", "Dropout2d", "Dropout"):
+            m.eval()
+    logits = ref(x)
+    loss = F.cross_entropy(logits, t)
+    loss.backward()
+    names = ["encoder.patch_embed1.proj.weight", "encoder.block1.0.attn.q.weight", "encoder.block1.0.attn.sr.weight",
+             "encoder.block2.1.mlp.dwconv.dwconv.weight", "encoder.block4.1.attn.kv.weight", "encoder.norm3.weight",
+             "decoder.linear_c2.proj.weight", "decoder.linear_fuse.0.weight", "decoder.linear_fuse.1.bias",
+             "decoder.linear_pred.weight"]
+    params = dict(ref.named_parameters())
+    torch.save({"x": x, "target": t, "logits_eval_slice": logits_eval[:, :, ::8, ::8].clone(),
+                "logits_train_slice": logits.detach()[:, :, ::8, ::8].clone(), "loss": loss.detach(),
+                "grad_norms": {n: params[n].grad.norm() for n in names},
+                "grad_slices": {n: params[n].grad.flatten()[:64].clone() for n in names}},
+               OUT / "segformer_b0_golden.pt")
+    print("wrote segformer_b0_golden.pt")
+
+
 if __name__ == "__main__":
     OUT.mkdir(parents=True, exist_ok=True)
     tensors_golden()
     if "--all" in sys.argv:
         unetpp_golden()
+        segformer_golden()

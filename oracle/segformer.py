@@ -1,0 +1,171 @@
+"""ORACLE (test infrastructure — never imported by the product path).
+
+Functional CPU/fp32 restatement of the reference's SegFormer path:
+  encoder  geo_deep_learning/models/encoders/mix_transformer.py  (OverlapPatchEmbed :224-276,
+           Attention :66-157, Mlp/DWConv :17-63,533-546, Block :160-221, stage loop :489-526)
+  decoder  geo_deep_learning/models/decoders/segformer_mlp.py:8-130
+  model    geo_deep_learning/models/segmentation/segformer.py:47-57 (final bilinear x4)
+
+It is written over a plain `state_dict` (same keys as `SegFormerSegmentationModel`) instead of
+nn.Modules, so it travels to the GPU box where /root/reference does not exist.
+
+PARITY STATUS: **pinned** — tests/test_oracle_cpu.py compares it with the reference's own modules
+(imported from /root/reference through a 20-line timm shim, oracle/ref_shims.py) when that tree is
+present, and tests/golden/segformer_b0_golden.pt holds the reference's outputs (logits slice, loss,
+gradient norms for seeded weights/inputs) produced by oracle/make_golden.py for where it is not.
+
+Stochastic parts (DropPath, Dropout2d) are identity here: parity runs use eval mode or drop rates 0,
+as SURVEY.md §5 prescribes; BatchNorm in `linear_fuse` follows `training`.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn.functional as F
+
+# name: (embed_dims, heads, depths, decoder embedding dim)   [mix_transformer.py:599-708, segformer_mlp.py:40-44]
+MIT_CFG = {
+    "mit_b0": ((32, 64, 160, 256), (1, 2, 5, 8), (2, 2, 2, 2), 256),
+    "mit_b1": ((64, 128, 320, 512), (1, 2, 5, 8), (2, 2, 2, 2), 256),
+    "mit_b2": ((64, 128, 320, 512), (1, 2, 5, 8), (3, 4, 6, 3), 768),
+    "mit_b3": ((64, 128, 320, 512), (1, 2, 5, 8), (3, 4, 18, 3), 768),
+    "mit_b4": ((64, 128, 320, 512), (1, 2, 5, 8), (3, 8, 27, 3), 768),
+    "mit_b5": ((64, 128, 320, 512), (1, 2, 5, 8), (3, 6, 40, 3), 768),
+}
+SR_RATIOS = (8, 4, 2, 1)
+EPS_BLOCK = 1e-6  # norm_layer=partial(LayerNorm, eps=1e-6): block norm1/norm2 and the stage norms
+EPS_PLAIN = 1e-5  # plain nn.LayerNorm: OverlapPatchEmbed.norm (:251) and Attention.norm (:100)
+
+
+def _ln(x, sd, prefix, eps):
+    return F.layer_norm(x, (x.shape[-1],), sd[prefix + ".weight"], sd[prefix + ".bias"], eps)
+
+
+def _linear(x, sd, prefix):
+    return F.linear(x, sd[prefix + ".weight"], sd.get(prefix + ".bias"))
+
+
+def attention(x, h, w, sd, p, heads, sr):
+    b, n, c = x.shape
+    d = c // heads
+    q = _linear(x, sd, p + ".q").view(b, n, heads, d).transpose(1, 2)
+    if sr > 1:
+        xm = x.transpose(1, 2).reshape(b, c, h, w)
+        xm = F.conv2d(xm, sd[p + ".sr.weight"], sd[p + ".sr.bias"], stride=sr)
+        xr = _ln(xm.flatten(2).transpose(1, 2), sd, p + ".norm", EPS_PLAIN)
+    else:
+        xr = x
+    kv = _linear(xr, sd, p + ".kv").view(b, -1, 2, heads, d).permute(2, 0, 3, 1, 4)
+    k, v = kv[0], kv[1]
+    a = torch.softmax((q @ k.transpose(-2, -1)) * d ** -0.5, dim=-1)
+    o = (a @ v).transpose(1, 2).reshape(b, n, c)
+    return _linear(o, sd, p + ".proj")
+
+
+def mix_ffn(x, h, w, sd, p):
+    b, n, _ = x.shape
+    y = _linear(x, sd, p + ".fc1")
+    ch = y.shape[-1]
+    ym = y.transpose(1, 2).reshape(b, ch, h, w)
+    ym = F.conv2d(ym, sd[p + ".dwconv.dwconv.weight"], sd[p + ".dwconv.dwconv.bias"], padding=1, groups=ch)
+    y = F.gelu(ym.flatten(2).transpose(1, 2))
+    return _linear(y, sd, p + ".fc2")
+
+
+def encoder(sd, img, name, prefix="encoder."):
+    dims, heads, depths, _ = MIT_CFG[name]
+    x = img
+    feats = []
+    for s in range(4):
+        pe = f"{prefix}patch_embed{s + 1}"
+        k, stride = (7, 4) if s == 0 else (3, 2)
+        x = F.conv2d(x, sd[pe + ".proj.weight"], sd[pe + ".proj.bias"], stride=stride, padding=k // 2)
+        b, c, h, w = x.shape
+        t = _ln(x.flatten(2).transpose(1, 2), sd, pe + ".norm", EPS_PLAIN)
+        for i in range(depths[s]):
+            bp = f"{prefix}block{s + 1}.{i}"
+            t = t + attention(_ln(t, sd, bp + ".norm1", EPS_BLOCK), h, w, sd, bp + ".attn", heads[s], SR_RATIOS[s])
+            t = t + mix_ffn(_ln(t, sd, bp + ".norm2", EPS_BLOCK), h, w, sd, bp + ".mlp")
+        t = _ln(t, sd, f"{prefix}norm{s + 1}", EPS_BLOCK)
+        x = t.reshape(b, h, w, c).permute(0, 3, 1, 2).contiguous()
+        feats.append(x)
+    return feats
+
+
+def decoder(sd, feats, training, prefix="decoder.", bn_momentum=0.1):
+    c1 = feats[0]
+    size = c1.shape[2:]
+    ups = []
+    for lvl in (4, 3, 2, 1):
+        f = feats[lvl - 1]
+        b, c, h, w = f.shape
+        y = _linear(f.flatten(2).transpose(1, 2), sd, f"{prefix}linear_c{lvl}.proj")
+        y = y.transpose(1, 2).reshape(b, -1, h, w)
+        if lvl != 1:
+            y = F.interpolate(y, size=size, mode="bilinear", align_corners=False)
+        ups.append(y)
+    x = F.conv2d(torch.cat(ups, 1), sd[prefix + "linear_fuse.0.weight"])
+    x = F.batch_norm(x, sd[prefix + "linear_fuse.1.running_mean"], sd[prefix + "linear_fuse.1.running_var"],
+                     sd[prefix + "linear_fuse.1.weight"], sd[prefix + "linear_fuse.1.bias"], training, bn_momentum, 1e-5)
+    x = F.relu(x)
+    return F.conv2d(x, sd[prefix + "linear_pred.weight"], sd[prefix + "linear_pred.bias"])
+
+
+def segformer_forward(sd, img, name="mit_b2", training=False):
+    """logits (B, K, H, W). `sd` holds tensors (optionally requiring grad) under the reference's keys."""
+    y = decoder(sd, encoder(sd, img, name), training)
+    return F.interpolate(y, size=img.shape[2:], mode="bilinear", align_corners=False)
+
+
+def init_state_dict(name="mit_b2", in_channels=3, num_classes=5, seed=0):
+    """Seeded weights with the reference's shapes/keys (values follow its init distributions loosely;
+    parity tests copy the SAME tensors into the product, so only shapes/keys matter here)."""
+    g = torch.Generator().manual_seed(seed)
+    dims, heads, depths, emb = MIT_CFG[name]
+    sd: dict[str, torch.Tensor] = {}
+
+    def lin(p, cin, cout, bias=True):
+        sd[p + ".weight"] = torch.randn(cout, cin, generator=g) * 0.02 * 2.5
+        if bias:
+            sd[p + ".bias"] = torch.randn(cout, generator=g) * 0.02
+
+    def ln(p, c):
+        sd[p + ".weight"] = 1 + 0.1 * torch.randn(c, generator=g)
+        sd[p + ".bias"] = 0.05 * torch.randn(c, generator=g)
+
+    def conv(p, cin, cout, k, groups=1, bias=True):
+        fan_out = k * k * cout // groups
+        sd[p + ".weight"] = torch.randn(cout, cin // groups, k, k, generator=g) * (2.0 / fan_out) ** 0.5
+        if bias:
+            sd[p + ".bias"] = torch.randn(cout, generator=g) * 0.02
+
+    cin = in_channels
+    for s in range(4):
+        c = dims[s]
+        pe = f"encoder.patch_embed{s + 1}"
+        conv(pe + ".proj", cin, c, 7 if s == 0 else 3)
+        ln(pe + ".norm", c)
+        for i in range(depths[s]):
+            bp = f"encoder.block{s + 1}.{i}"
+            ln(bp + ".norm1", c)
+            lin(bp + ".attn.q", c, c)
+            lin(bp + ".attn.kv", c, 2 * c)
+            lin(bp + ".attn.proj", c, c)
+            if SR_RATIOS[s] > 1:
+                conv(bp + ".attn.sr", c, c, SR_RATIOS[s])
+                ln(bp + ".attn.norm", c)
+            ln(bp + ".norm2", c)
+            lin(bp + ".mlp.fc1", c, 4 * c)
+            conv(bp + ".mlp.dwconv.dwconv", 4 * c, 4 * c, 3, groups=4 * c)
+            lin(bp + ".mlp.fc2", 4 * c, c)
+        ln(f"encoder.norm{s + 1}", c)
+        cin = c
+    for lvl in (4, 3, 2, 1):
+        lin(f"decoder.linear_c{lvl}.proj", dims[lvl - 1], emb)
+    sd["decoder.linear_fuse.0.weight"] = torch.randn(emb, 4 * emb, 1, 1, generator=g) * (1.0 / (4 * emb)) ** 0.5
+    sd["decoder.linear_fuse.1.weight"] = 1 + 0.1 * torch.randn(emb, generator=g)
+    sd["decoder.linear_fuse.1.bias"] = 0.05 * torch.randn(emb, generator=g)
+    sd["decoder.linear_fuse.1.running_mean"] = torch.zeros(emb)
+    sd["decoder.linear_fuse.1.running_var"] = torch.ones(emb)
+    sd["decoder.linear_fuse.1.num_batches_tracked"] = torch.tensor(0)
+    conv("decoder.linear_pred", emb, num_classes, 1)
+    return sd

@@ -277,3 +277,13 @@ def install(monkeypatch):
         if hasattr(ops, n):
             monkeypatch.setattr(ops, n, globals()[n])
     monkeypatch.setattr(trainer, "LossSpec", LossSpec, raising=False)
+
+
+def install_global():
+    """Same as install() but without pytest's monkeypatch (for spawned worker processes)."""
+    import gdl_b200.ops as ops
+    import gdl_b200.trainer as trainer
+    for n, v in list(globals().items()):
+        if callable(v) and not n.startswith("_") and n not in ("install", "install_global", "set_work_dtype") and hasattr(ops, n):
+            setattr(ops, n, v)
+    trainer.LossSpec = LossSpec

@@ -1,0 +1,72 @@
+"""CPU, world_size = 2 over gloo: the N>1 host logic of the fused trainer (flat-gradient all-reduce,
+SyncBatchNorm statistics exchange, identical updates on every rank).  Kernels are the float64 torch
+emulation (tests/cpu_kernel_emulation.py); the property checked is the one DDP + SyncBN guarantee:
+two ranks with B tiles each end up with exactly the parameters of one process training on the 2B tiles."""
+import os
+import socket
+import sys
+from pathlib import Path
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def _free_port() -> int:
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _data(k=4):
+    g = torch.Generator().manual_seed(3)
+    t = torch.randint(0, k, (4, 2, 2), generator=g).repeat_interleave(16, 1).repeat_interleave(16, 2)
+    raw = (t.unsqueeze(-1) * 60 + torch.randint(0, 20, (4, 32, 32, 3), generator=g)).to(torch.uint8)
+    return raw, t
+
+
+def _make_trainer(sync_bn):
+    import cpu_kernel_emulation as emu
+    from gdl_b200.models.unetpp import UnetPlusPlus
+    from gdl_b200.trainer import FusedTrainer
+    emu.install_global()
+    emu.set_work_dtype(torch.float64)
+    torch.manual_seed(0)
+    model = UnetPlusPlus("resnet18", in_channels=3, classes=4, compute_dtype=torch.float64).double().train()
+    return FusedTrainer(model, emu.LossSpec(1.0, 0.0, ignore_index=-100), lr=1e-2, mean=[0.5] * 3, std=[0.25] * 3,
+                        sync_bn=sync_bn, acc_dtype=torch.float64)
+
+
+def _worker(rank, world, port, out):
+    for p in (ROOT, ROOT / "geo-deep-learning_b200", ROOT / "tests"):
+        sys.path.insert(0, str(p))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    tr = _make_trainer(sync_bn=True)
+    assert tr.world == 2 and tr.sync_bn
+    raw, t = _data()
+    lo, hi = rank * 2, rank * 2 + 2  # rank-sharded tiles (weak scaling: 2 tiles per rank)
+    losses = [float(tr.step(raw[lo:hi], t[lo:hi])) for _ in range(2)]
+    torch.save({"flat": tr.flat.clone(), "losses": losses,
+                "rm": tr.model.encoder.bn1.running_mean.clone()}, f"{out}/rank{rank}.pt")
+    dist.destroy_process_group()
+
+
+def test_two_ranks_equal_one_process_on_the_union(tmp_path):
+    port = _free_port()
+    mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    r0, r1 = torch.load(tmp_path / "rank0.pt"), torch.load(tmp_path / "rank1.pt")
+    assert torch.equal(r0["flat"], r1["flat"])  # every rank applies the same update
+    assert torch.equal(r0["rm"], r1["rm"])
+    # single process, all 4 tiles
+    sys.path.insert(0, str(ROOT / "tests"))
+    tr = _make_trainer(sync_bn=False)
+    raw, t = _data()
+    losses = [float(tr.step(raw, t)) for _ in range(2)]
+    assert torch.allclose(tr.flat, r0["flat"], atol=1e-9, rtol=1e-7)
+    assert torch.allclose(tr.model.encoder.bn1.running_mean, r0["rm"], atol=1e-10)
+    # the global loss is the mean of the per-rank losses
+    for i in range(2):
+        assert abs(losses[i] - 0.5 * (r0["losses"][i] + r1["losses"][i])) < 1e-9

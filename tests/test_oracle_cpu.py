@@ -104,3 +104,51 @@ def test_soft_ce_reduces_to_ce_without_smoothing():
     # torch's label_smoothing formula is the same one
     assert torch.allclose(olosses.soft_ce_loss(x, t, 0.1, None),
                           torch.nn.functional.cross_entropy(x, t, label_smoothing=0.1), atol=1e-6)
+
+
+# --- SegFormer restatement: pinned to the reference's own modules ------------------------------------
+def _close(a, b, rel=5e-6):
+    """max |a-b| <= rel * max |b|  (fp32 re-association noise between two summation orders)"""
+    return (a - b).abs().max().item() <= rel * b.abs().max().item() + 1e-12
+
+
+def _segformer_train_outputs(sd, g):
+    from oracle import segformer as osf
+    sd = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and "running" not in k else v.clone())
+          for k, v in sd.items()}
+    logits = osf.segformer_forward(sd, g["x"], "mit_b0", training=True)
+    loss = torch.nn.functional.cross_entropy(logits, g["target"])
+    loss.backward()
+    return sd, logits, loss
+
+
+def test_segformer_oracle_matches_reference_golden():
+    """tests/golden/segformer_b0_golden.pt was produced by the REFERENCE's SegFormerSegmentationModel."""
+    from oracle import segformer as osf
+    g = torch.load(GOLD / "segformer_b0_golden.pt")
+    sd0 = osf.init_state_dict("mit_b0", 3, 5, seed=0)
+    with torch.no_grad():
+        ev = osf.segformer_forward(sd0, g["x"], "mit_b0", training=False)
+    assert _close(ev[:, :, ::8, ::8], g["logits_eval_slice"])
+    sd, logits, loss = _segformer_train_outputs(sd0, g)
+    assert _close(logits[:, :, ::8, ::8], g["logits_train_slice"])
+    assert torch.allclose(loss, g["loss"], atol=1e-6)
+    for n, want in g["grad_slices"].items():
+        assert _close(sd[n].grad.flatten()[:64], want, 1e-4), n
+
+
+def test_segformer_oracle_matches_reference_import():
+    """When /root/reference is mounted (build container), compare with the live reference modules."""
+    from oracle import ref_shims
+    from oracle import segformer as osf
+    if not ref_shims.available():
+        pytest.skip("/root/reference not present (GPU box): covered by the golden file")
+    sd0 = osf.init_state_dict("mit_b2", 4, 5, seed=3)
+    ref = ref_shims.reference_segformer("mit_b2", 4, 5)
+    assert set(ref.state_dict().keys()) == set(sd0.keys())
+    ref.load_state_dict(sd0)
+    assert sum(p.numel() for p in ref.parameters()) == 27_350_469 + 3136  # SURVEY §8c: +3 136 per extra band
+    ref.eval()
+    x = torch.randn(1, 4, 64, 64, generator=torch.Generator().manual_seed(0))
+    with torch.no_grad():
+        assert _close(osf.segformer_forward(sd0, x, "mit_b2"), ref(x))
