@@ -241,6 +241,8 @@ def main_product(args) -> None:
     torch.cuda.synchronize()
     ops.set_conv_profiler(None)
     roof = prof.summary(nprof)
+    if args.table and rank == 0:
+        prof.dump_table(args.table, nprof)
 
     cpu = None
     if rank == 0 and not args.no_cpu_baseline:
@@ -289,6 +291,7 @@ def main() -> None:
     ap.add_argument("--batch", type=int, default=0, help="tiles per GPU (default: the workload's 32)")
     ap.add_argument("--sync-bn", type=int, default=1, help="SyncBatchNorm statistics when N > 1 (reference YAMLs: true)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--table", default="", help="write the per-launch conv profile (shape, ms, TFLOP/s) to this JSON file")
     args = ap.parse_args()
     if args.impl == "reference":
         main_reference(args)

@@ -73,6 +73,17 @@ static int ew_blocks(long long work_items, int threads, int max_waves = 8) {
   return (int)b;
 }
 
+// grid for the "one 8-channel vector per thread, stride over rows" kernels (256 threads / block)
+static int row_grid(long long rows, int C) {
+  const int cv = C / 8;
+  const int tpr = cv < 256 ? cv : 256;
+  const int rpb = 256 / tpr;
+  long long b = (rows + (long long)rpb * 4 - 1) / ((long long)rpb * 4);  // >= 4 rows per thread
+  const long long cap = (long long)kNumSMsB200 * 8;
+  if (b > cap) b = cap;
+  return (int)(b < 1 ? 1 : b);
+}
+
 #define GDL_DISPATCH_16(dtype, ...)                                  \
   do {                                                               \
     if ((dtype) == GDL_BF16) {                                       \
@@ -324,50 +335,54 @@ __global__ void bn_apply_kernel(const T* __restrict__ x, int ldx, const float* _
                                 const float* __restrict__ rscale, const float* __restrict__ rshift,
                                 int relu, T* __restrict__ y, int ldy, T* __restrict__ y_up, int ldu,
                                 int N, int H, int W, int C) {
+  // each thread owns one 8-channel vector (coefficients live in registers) and strides over pixels
   const int cv = C / 8;
-  const long long total = (long long)N * H * W * cv;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const long long pix = i / cv;
-    const int c0 = (int)(i - pix * cv) * 8;
-    float f[8];
-    load8(x + pix * ldx + c0, f);
-    const float4 sa = *reinterpret_cast<const float4*>(scale + c0);
-    const float4 sb = *reinterpret_cast<const float4*>(scale + c0 + 4);
-    const float4 ha = *reinterpret_cast<const float4*>(shift + c0);
-    const float4 hb = *reinterpret_cast<const float4*>(shift + c0 + 4);
-    const float sc[8] = {sa.x, sa.y, sa.z, sa.w, sb.x, sb.y, sb.z, sb.w};
-    const float sh[8] = {ha.x, ha.y, ha.z, ha.w, hb.x, hb.y, hb.z, hb.w};
+  const int tpr = cv < (int)blockDim.x ? cv : blockDim.x;
+  const int rows_per_block = blockDim.x / tpr;
+  const int tc = threadIdx.x % tpr;
+  const int tr = threadIdx.x / tpr;
+  if (tr >= rows_per_block) return;
+  const long long M = (long long)N * H * W;
+  const long long W2 = 2ll * W;
+  for (int c8 = tc; c8 < cv; c8 += tpr) {
+    const int c0 = c8 * 8;
+    float sc[8], sh[8], rs[8], rh[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) f[j] = fmaf(f[j], sc[j], sh[j]);
-    if (res != nullptr) {
-      float g[8];
-      load8(res + pix * ldr + c0, g);
-      if (rscale != nullptr) {
+    for (int j = 0; j < 8; ++j) {
+      sc[j] = scale[c0 + j];
+      sh[j] = shift[c0 + j];
+      rs[j] = rscale ? rscale[c0 + j] : 1.f;
+      rh[j] = rshift ? rshift[c0 + j] : 0.f;
+    }
+    for (long long pix = (long long)blockIdx.x * rows_per_block + tr; pix < M;
+         pix += (long long)gridDim.x * rows_per_block) {
+      float f[8];
+      load8(x + pix * ldx + c0, f);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) g[j] = fmaf(g[j], rscale[c0 + j], rshift[c0 + j]);
+      for (int j = 0; j < 8; ++j) f[j] = fmaf(f[j], sc[j], sh[j]);
+      if (res != nullptr) {
+        float g[8];
+        load8(res + pix * ldr + c0, g);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] += fmaf(g[j], rs[j], rh[j]);
       }
+      if (relu) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) f[j] += g[j];
-    }
-    if (relu) {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], 0.f);
-    }
-    const uint4 packed = Vec8<T>::pack(f);
-    if (y != nullptr) *reinterpret_cast<uint4*>(y + pix * ldy + c0) = packed;
-    if (y_up != nullptr) {
-      const int w = (int)(pix % W);
-      const long long t = pix / W;
-      const int h = (int)(t % H);
-      const long long n = t / H;
-      const long long W2 = 2ll * W;
-      const long long base = ((n * 2 * H + 2 * h) * W2 + 2 * w);
-      T* u = y_up + base * ldu + c0;
-      *reinterpret_cast<uint4*>(u) = packed;
-      *reinterpret_cast<uint4*>(u + ldu) = packed;
-      *reinterpret_cast<uint4*>(u + W2 * ldu) = packed;
-      *reinterpret_cast<uint4*>(u + (W2 + 1) * ldu) = packed;
+        for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], 0.f);
+      }
+      const uint4 packed = Vec8<T>::pack(f);
+      if (y != nullptr) *reinterpret_cast<uint4*>(y + pix * ldy + c0) = packed;
+      if (y_up != nullptr) {
+        const int w = (int)(pix % W);
+        const long long t = pix / W;
+        const int h = (int)(t % H);
+        const long long n = t / H;
+        T* u = y_up + ((n * 2 * H + 2 * h) * W2 + 2 * w) * ldu + c0;
+        *reinterpret_cast<uint4*>(u) = packed;
+        *reinterpret_cast<uint4*>(u + ldu) = packed;
+        *reinterpret_cast<uint4*>(u + W2 * ldu) = packed;
+        *reinterpret_cast<uint4*>(u + (W2 + 1) * ldu) = packed;
+      }
     }
   }
 }
@@ -497,25 +512,51 @@ __global__ void bn_bwd_apply_kernel(const T* __restrict__ g, int ldg, const T* _
                                     const float* __restrict__ mean, const float* __restrict__ invstd,
                                     const float* __restrict__ gamma, const float* __restrict__ sums,
                                     T* __restrict__ dx, int ldd, long long M, long long count, int C) {
+  // dx = a*g + b*x + c with per-channel a = gamma*invstd, b = -a*invstd*s2/M, c = a*(mean*invstd*s2/M - s1/M)
   const int cv = C / 8;
-  const long long total = M * cv;
+  const int tpr = cv < (int)blockDim.x ? cv : blockDim.x;
+  const int rows_per_block = blockDim.x / tpr;
+  const int tc = threadIdx.x % tpr;
+  const int tr = threadIdx.x / tpr;
+  if (tr >= rows_per_block) return;
   const float invM = 1.0f / (float)count;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const long long pix = i / cv;
-    const int c0 = (int)(i - pix * cv) * 8;
-    float gg[8], xx[8], o[8];
-    load8(g + pix * ldg + c0, gg);
-    load8(x + pix * ldx + c0, xx);
+  for (int c8 = tc; c8 < cv; c8 += tpr) {
+    const int c0 = c8 * 8;
+    float ca[8], cb[8], cc[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const int c = c0 + j;
       const float is = invstd[c];
-      const float xhat = (xx[j] - mean[c]) * is;
-      const float ga = gamma ? gamma[c] : 1.f;
-      o[j] = ga * is * (gg[j] - sums[c] * invM - xhat * sums[C + c] * invM);
+      const float a = (gamma ? gamma[c] : 1.f) * is;
+      const float s1 = sums[c] * invM, s2 = sums[C + c] * invM;
+      ca[j] = a;
+      cb[j] = -a * is * s2;
+      cc[j] = a * (mean[c] * is * s2 - s1);
     }
-    store8(dx + pix * ldd + c0, o);
+    const long long stride = (long long)gridDim.x * rows_per_block;
+    long long pix = (long long)blockIdx.x * rows_per_block + tr;
+    for (; pix + stride < M; pix += 2 * stride) {  // two rows in flight per thread
+      float g0[8], x0[8], g1[8], x1[8], o0[8], o1[8];
+      load8(g + pix * ldg + c0, g0);
+      load8(x + pix * ldx + c0, x0);
+      load8(g + (pix + stride) * ldg + c0, g1);
+      load8(x + (pix + stride) * ldx + c0, x1);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        o0[j] = fmaf(ca[j], g0[j], fmaf(cb[j], x0[j], cc[j]));
+        o1[j] = fmaf(ca[j], g1[j], fmaf(cb[j], x1[j], cc[j]));
+      }
+      store8(dx + pix * ldd + c0, o0);
+      store8(dx + (pix + stride) * ldd + c0, o1);
+    }
+    if (pix < M) {
+      float g0[8], x0[8], o0[8];
+      load8(g + pix * ldg + c0, g0);
+      load8(x + pix * ldx + c0, x0);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o0[j] = fmaf(ca[j], g0[j], fmaf(cb[j], x0[j], cc[j]));
+      store8(dx + pix * ldd + c0, o0);
+    }
   }
 }
 
@@ -751,7 +792,7 @@ extern "C" int gdl_bn_apply(const void* x, int ldx, const float* scale, const fl
   const long long total = (long long)N * H * W * (C / 8);
   cudaStream_t st = (cudaStream_t)stream;
   GDL_DISPATCH_16(dtype, {
-    bn_apply_kernel<T><<<ew_blocks(total, 256, 16), 256, 0, st>>>((const T*)x, ldx, scale, shift, (const T*)res, ldr,
+    bn_apply_kernel<T><<<row_grid(total / (C / 8), C), 256, 0, st>>>((const T*)x, ldx, scale, shift, (const T*)res, ldr,
                                                                   rscale, rshift, relu, (T*)y, ldy, (T*)y_up, ldu,
                                                                   N, H, W, C);
   });
@@ -782,8 +823,8 @@ extern "C" int gdl_grad_gather(int num_src, const void* const* src_ptr, const in
   int threads, smem;
   const int rpb = stats_launch_geometry(C, &threads, &smem);
   const long long M = (long long)N * H * W;
-  long long blocks = (M + rpb * 8 - 1) / (rpb * 8);
-  if (blocks > 4 * kNumSMsB200) blocks = 4 * kNumSMsB200;
+  long long blocks = (M + rpb * 4 - 1) / (rpb * 4);
+  if (blocks > 8 * kNumSMsB200) blocks = 8 * kNumSMsB200;
   if (blocks < 1) blocks = 1;
   GDL_DISPATCH_16(dtype, {
     grad_gather_kernel<T><<<(int)blocks, threads, smem, st>>>(gs, (const T*)y, ldy, (const T*)x, ldx, mean, invstd,
@@ -801,7 +842,7 @@ extern "C" int gdl_bn_bwd_apply(const void* g, int ldg, const void* x, int ldx, 
               "bn_bwd_apply: bad args");
   cudaStream_t st = (cudaStream_t)stream;
   GDL_DISPATCH_16(dtype, {
-    bn_bwd_apply_kernel<T><<<ew_blocks(M * (C / 8), 256, 16), 256, 0, st>>>((const T*)g, ldg, (const T*)x, ldx, mean,
+    bn_bwd_apply_kernel<T><<<row_grid(M, C), 256, 0, st>>>((const T*)g, ldg, (const T*)x, ldx, mean,
                                                                            invstd, gamma, sums, (T*)dx, ldd, M, count > 0 ? count : M, C);
   });
   GDL_CHECK_CUDA(cudaGetLastError());

@@ -13,6 +13,7 @@
 // Wgrad (gdl_conv2d_nhwc_wgrad): D[128 (Cout) x BN (Cin)] += dYᵀ[64 px x 128] · X_tap[64 px x BN]
 //   with BOTH operands MN-major (pixels are the contraction dim, channels are contiguous in
 //   HBM and in the TMA box); split over pixel ranges, partial sums added with red.global.add.
+#include <stdlib.h>
 #include <string.h>
 
 #include <type_traits>
@@ -619,8 +620,14 @@ conv_wgrad_kernel(const __grid_constant__ ConvWgradKParams p) {
         tmem_ld_32x32b_x16(t_addr + j * 16, v);
         tmem_ld_wait();
         if (m < p.Cout && nonempty) {
+          // 4 x red.global.add.v4.f32 (16-byte aligned: Ctot, channel offsets and j*16 are multiples of 16)
+          float* d = dst + j * 16;
 #pragma unroll
-          for (int i = 0; i < 16; ++i) atomicAdd(dst + j * 16 + i, __uint_as_float(v[i]));
+          for (int i = 0; i < 4; ++i)
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(d + 4 * i),
+                         "f"(__uint_as_float(v[4 * i])), "f"(__uint_as_float(v[4 * i + 1])),
+                         "f"(__uint_as_float(v[4 * i + 2])), "f"(__uint_as_float(v[4 * i + 3]))
+                         : "memory");
         }
       }
       tc_fence_before();
@@ -712,9 +719,24 @@ extern "C" int gdl_conv2d_nhwc_wgrad(const gdl_conv_wgrad_t* d, void* stream_) {
 
   const int taps = d->R * d->S;
   long long base_units = (long long)p.m_tiles * nn * taps;
-  // split the pixel range so that the grid sees >= ~3 waves, but keep >= 8 stages of work per unit
+  // Split the pixel range: (a) the grid should see >= ~3 waves; (b) the pixels one wave of co-resident
+  // units streams (dY + X rows of one split) should stay L2-resident so the 9 taps / channel tiles that
+  // share them hit in L2 (budget GDL_WGRAD_L2_MB, default 24 MB); (c) keep >= 32 stages of MMA work per
+  // unit so the red.global epilogue stays a small fraction.
   int ks = (int)((3ll * sm_count() + base_units - 1) / base_units);
-  int max_ks = p.pix_blocks / 8;
+  {
+    static long long budget = -1;
+    if (budget < 0) {
+      const char* e = getenv("GDL_WGRAD_L2_MB");
+      budget = (e ? atoll(e) : 24) * (1ll << 20);
+    }
+    const long long bytes_per_pb = (long long)kWgPix * (Ctot + d->Cout) * 2;
+    long long pb_budget = budget / bytes_per_pb;
+    if (pb_budget < 32) pb_budget = 32;
+    int ks_l2 = (int)((p.pix_blocks + pb_budget - 1) / pb_budget);
+    if (ks_l2 > ks) ks = ks_l2;
+  }
+  int max_ks = p.pix_blocks / 32;
   if (max_ks < 1) max_ks = 1;
   if (ks > max_ks) ks = max_ks;
   if (ks < 1) ks = 1;

@@ -1,0 +1,663 @@
+// transformer.cu — the HBM-bound kernels of the MixTransformer / SegFormer path:
+// LayerNorm (fwd/bwd, fp32 residual stream in, 16-bit normalised tokens out), row softmax for the
+// spatial-reduction attention scores (fwd/bwd), depthwise 3x3 conv + bias + exact-erf GELU of the
+// Mix-FFN (fwd/bwd, NHWC so no NLC<->NCHW transposes exist), bilinear resize with
+// align_corners=False (fwd/bwd, 16-bit features and fp32 logits).
+//
+// Tokens (B, N, C) and maps (B, h, w, C) are the same memory (NHWC), which is why the reference's
+// reshape/permute/contiguous copies (mix_transformer.py:499,541-546; segformer_mlp.py:78-121) vanish.
+#include <math.h>
+#include <string.h>
+
+#include <type_traits>
+
+#include "../../include/gdl_b200.h"
+#include "common.cuh"
+
+namespace gdl {
+
+template <typename T>
+GDL_DEVINL float to_f(T v);
+template <>
+GDL_DEVINL float to_f<float>(float v) { return v; }
+template <>
+GDL_DEVINL float to_f<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+template <>
+GDL_DEVINL float to_f<__half>(__half v) { return __half2float(v); }
+template <typename T>
+GDL_DEVINL T from_f(float v);
+template <>
+GDL_DEVINL float from_f<float>(float v) { return v; }
+template <>
+GDL_DEVINL __nv_bfloat16 from_f<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+template <>
+GDL_DEVINL __half from_f<__half>(float v) { return __float2half_rn(v); }
+
+static int row_blocks(long long rows, int rows_per_block, int max_waves = 8) {
+  long long b = (rows + rows_per_block - 1) / rows_per_block;
+  long long cap = (long long)kNumSMsB200 * max_waves;
+  if (b > cap) b = cap;
+  return (int)(b < 1 ? 1 : b);
+}
+
+// ------------------------------------------------------------------------------------------
+// LayerNorm over the last dim.  One warp per row; C <= 32 * kLnMaxPerLane.
+// x: TI (fp32 residual stream or 16-bit), y: TO (16-bit operand of the next GEMM, or fp32).
+// ------------------------------------------------------------------------------------------
+constexpr int kLnMaxPerLane = 32;  // C <= 1024
+
+template <typename TI, typename TO>
+__global__ void layernorm_fwd_kernel(const TI* __restrict__ x, long long ldx, const float* __restrict__ gamma,
+                                     const float* __restrict__ beta, float eps, TO* __restrict__ y, long long ldy,
+                                     float* __restrict__ mean_out, float* __restrict__ rstd_out, long long M, int C) {
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  const int per = (C + 31) / 32;
+  for (long long row = (long long)blockIdx.x * wpb + (threadIdx.x >> 5); row < M; row += (long long)gridDim.x * wpb) {
+    float v[kLnMaxPerLane];
+    float s = 0.f;
+#pragma unroll 4
+    for (int i = 0; i < per; ++i) {
+      const int c = lane + 32 * i;
+      v[i] = c < C ? to_f<TI>(x[row * ldx + c]) : 0.f;
+      s += v[i];
+    }
+    const float mean = warp_sum(s) / (float)C;
+    float q = 0.f;
+#pragma unroll 4
+    for (int i = 0; i < per; ++i) {
+      const int c = lane + 32 * i;
+      const float d = c < C ? v[i] - mean : 0.f;
+      q = fmaf(d, d, q);
+    }
+    const float rstd = rsqrtf(warp_sum(q) / (float)C + eps);
+#pragma unroll 4
+    for (int i = 0; i < per; ++i) {
+      const int c = lane + 32 * i;
+      if (c < C) y[row * ldy + c] = from_f<TO>((v[i] - mean) * rstd * gamma[c] + beta[c]);
+    }
+    if (lane == 0) {
+      if (mean_out) mean_out[row] = mean;
+      if (rstd_out) rstd_out[row] = rstd;
+    }
+  }
+}
+
+// backward: dx = rstd * (g*gamma - mean_c(g*gamma) - xhat * mean_c(g*gamma*xhat)) [+ add]
+//   written as fp32 (residual-stream gradient) and/or as a 16-bit copy (operand of the previous GEMM's
+//   dgrad/wgrad).  dgamma/dbeta partial sums per block -> atomics (pre-zeroed [2][C]: dgamma then dbeta).
+template <typename TI, typename TG>
+__global__ void layernorm_bwd_kernel(const TG* __restrict__ g, long long ldg, const TI* __restrict__ x, long long ldx,
+                                     const float* __restrict__ mean, const float* __restrict__ rstd,
+                                     const float* __restrict__ gamma, const float* __restrict__ add, long long lda,
+                                     float* __restrict__ dx32, long long ld32, void* __restrict__ dx16, long long ld16,
+                                     int dx16_is_half, float* __restrict__ pgrads, long long M, int C) {
+  extern __shared__ float sh[];  // [2][C]
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sh[i] = 0.f;
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  const int per = (C + 31) / 32;
+  float dga[kLnMaxPerLane], dbe[kLnMaxPerLane];
+#pragma unroll 4
+  for (int i = 0; i < per; ++i) dga[i] = dbe[i] = 0.f;
+  for (long long row = (long long)blockIdx.x * wpb + (threadIdx.x >> 5); row < M; row += (long long)gridDim.x * wpb) {
+    const float mu = mean[row], rs = rstd[row];
+    float gg[kLnMaxPerLane], xh[kLnMaxPerLane];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll 4
+    for (int i = 0; i < per; ++i) {
+      const int c = lane + 32 * i;
+      if (c < C) {
+        const float gv = to_f<TG>(g[row * ldg + c]);
+        xh[i] = (to_f<TI>(x[row * ldx + c]) - mu) * rs;
+        dga[i] = fmaf(gv, xh[i], dga[i]);
+        dbe[i] += gv;
+        gg[i] = gv * gamma[c];
+        s1 += gg[i];
+        s2 = fmaf(gg[i], xh[i], s2);
+      } else {
+        gg[i] = xh[i] = 0.f;
+      }
+    }
+    s1 = warp_sum(s1) / (float)C;
+    s2 = warp_sum(s2) / (float)C;
+#pragma unroll 4
+    for (int i = 0; i < per; ++i) {
+      const int c = lane + 32 * i;
+      if (c < C) {
+        float d = rs * (gg[i] - s1 - xh[i] * s2);
+        if (add) d += add[row * lda + c];
+        if (dx32) dx32[row * ld32 + c] = d;
+        if (dx16) {
+          if (dx16_is_half)
+            reinterpret_cast<__half*>(dx16)[row * ld16 + c] = __float2half_rn(d);
+          else
+            reinterpret_cast<__nv_bfloat16*>(dx16)[row * ld16 + c] = __float2bfloat16_rn(d);
+        }
+      }
+    }
+  }
+  if (pgrads != nullptr) {
+#pragma unroll 4
+    for (int i = 0; i < per; ++i) {
+      const int c = lane + 32 * i;
+      if (c < C) {
+        atomicAdd(&sh[c], dga[i]);
+        atomicAdd(&sh[C + c], dbe[i]);
+      }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) atomicAdd(&pgrads[i], sh[i]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// softmax over rows of length L (attention scores, mix_transformer.py:151-152):
+//   p = softmax(scale * s); rows are stored with stride ld >= L, pad columns of p are written 0.
+// backward: ds = scale * p * (dp - sum_j dp_j p_j)
+// ------------------------------------------------------------------------------------------
+constexpr int kSmMaxPerLane = 32;  // L <= 1024
+
+template <typename T>
+__global__ void softmax_fwd_kernel(const T* __restrict__ s, long long lds, float scale, T* __restrict__ p,
+                                   long long ldp, long long M, int L, int Lpad) {
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  const int per = (Lpad + 31) / 32;
+  for (long long row = (long long)blockIdx.x * wpb + (threadIdx.x >> 5); row < M; row += (long long)gridDim.x * wpb) {
+    float v[kSmMaxPerLane];
+    float mx = -INFINITY;
+#pragma unroll 4
+    for (int i = 0; i < per; ++i) {
+      const int c = lane + 32 * i;
+      v[i] = c < L ? to_f<T>(s[row * lds + c]) * scale : -INFINITY;
+      mx = fmaxf(mx, v[i]);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    float sum = 0.f;
+#pragma unroll 4
+    for (int i = 0; i < per; ++i) {
+      const int c = lane + 32 * i;
+      v[i] = c < L ? expf(v[i] - mx) : 0.f;
+      sum += v[i];
+    }
+    const float inv = 1.f / warp_sum(sum);
+#pragma unroll 4
+    for (int i = 0; i < per; ++i) {
+      const int c = lane + 32 * i;
+      if (c < Lpad) p[row * ldp + c] = from_f<T>(v[i] * inv);
+    }
+  }
+}
+
+template <typename T>
+__global__ void softmax_bwd_kernel(const T* __restrict__ p, long long ldp, const T* __restrict__ dp, long long lddp,
+                                   float scale, T* __restrict__ ds, long long ldds, long long M, int L, int Lpad) {
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  const int per = (Lpad + 31) / 32;
+  for (long long row = (long long)blockIdx.x * wpb + (threadIdx.x >> 5); row < M; row += (long long)gridDim.x * wpb) {
+    float pv[kSmMaxPerLane], dv[kSmMaxPerLane];
+    float dot = 0.f;
+#pragma unroll 4
+    for (int i = 0; i < per; ++i) {
+      const int c = lane + 32 * i;
+      pv[i] = c < L ? to_f<T>(p[row * ldp + c]) : 0.f;
+      dv[i] = c < L ? to_f<T>(dp[row * lddp + c]) : 0.f;
+      dot = fmaf(pv[i], dv[i], dot);
+    }
+    dot = warp_sum(dot);
+#pragma unroll 4
+    for (int i = 0; i < per; ++i) {
+      const int c = lane + 32 * i;
+      if (c < Lpad) ds[row * ldds + c] = from_f<T>(c < L ? scale * pv[i] * (dv[i] - dot) : 0.f);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// depthwise 3x3 (pad 1, stride 1, bias) + exact GELU, NHWC 16-bit, C % 8 == 0  (Mlp.dwconv + act,
+// mix_transformer.py:56-63,533-546).  Weights fp32 [C][3][3] (the nn.Conv2d(groups=C) layout squeezed).
+// fwd stores the pre-activation (16-bit, as the autocast reference does) for the backward.
+// ------------------------------------------------------------------------------------------
+GDL_DEVINL float gelu_f(float v) { return 0.5f * v * (1.f + erff(v * 0.70710678118654752f)); }
+GDL_DEVINL float gelu_grad_f(float v) {
+  return 0.5f * (1.f + erff(v * 0.70710678118654752f)) + v * 0.39894228040143268f * expf(-0.5f * v * v);
+}
+
+template <typename T>
+GDL_DEVINL void ld8(const T* p, float (&f)[8]);
+template <>
+GDL_DEVINL void ld8<__nv_bfloat16>(const __nv_bfloat16* p, float (&f)[8]) {
+  const uint4 u = *reinterpret_cast<const uint4*>(p);
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    f[2 * i] = bf16_lo(w[i]);
+    f[2 * i + 1] = bf16_hi(w[i]);
+  }
+}
+template <>
+GDL_DEVINL void ld8<__half>(const __half* p, float (&f)[8]) {
+  const uint4 u = *reinterpret_cast<const uint4*>(p);
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 t = __half22float2(*reinterpret_cast<const __half2*>(&w[i]));
+    f[2 * i] = t.x;
+    f[2 * i + 1] = t.y;
+  }
+}
+template <typename T>
+GDL_DEVINL void st8(T* p, const float (&f)[8]);
+template <>
+GDL_DEVINL void st8<__nv_bfloat16>(__nv_bfloat16* p, const float (&f)[8]) {
+  *reinterpret_cast<uint4*>(p) = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]),
+                                            pack_bf16x2(f[6], f[7]));
+}
+template <>
+GDL_DEVINL void st8<__half>(__half* p, const float (&f)[8]) {
+  *reinterpret_cast<uint4*>(p) = make_uint4(pack_f16x2(f[0], f[1]), pack_f16x2(f[2], f[3]), pack_f16x2(f[4], f[5]),
+                                            pack_f16x2(f[6], f[7]));
+}
+
+template <typename T>
+__global__ void dwconv_gelu_fwd_kernel(const T* __restrict__ x, int ldx, const float* __restrict__ w,
+                                       const float* __restrict__ bias, T* __restrict__ pre, T* __restrict__ y, int N,
+                                       int H, int W, int C) {
+  const int cv = C / 8;
+  const long long total = (long long)N * H * W * cv;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long pix = i / cv;
+    const int c0 = (int)(i - pix * cv) * 8;
+    const int wq = (int)(pix % W);
+    const long long t = pix / W;
+    const int hq = (int)(t % H);
+    const long long n = t / H;
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = bias ? bias[c0 + j] : 0.f;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      const int hh = hq + r - 1;
+      if (hh < 0 || hh >= H) continue;
+#pragma unroll
+      for (int s = 0; s < 3; ++s) {
+        const int ww = wq + s - 1;
+        if (ww < 0 || ww >= W) continue;
+        float f[8];
+        ld8(x + ((n * H + hh) * W + ww) * ldx + c0, f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = fmaf(f[j], w[(c0 + j) * 9 + r * 3 + s], acc[j]);
+      }
+    }
+    // the autocast reference rounds the conv output to 16 bits before GELU: do the same
+    st8(pre + pix * C + c0, acc);
+    float pr[8], out[8];
+    ld8(pre + pix * C + c0, pr);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) out[j] = gelu_f(pr[j]);
+    st8(y + pix * C + c0, out);
+  }
+}
+
+// dpre = dy * gelu'(pre)   (in place on dy allowed)
+template <typename T>
+__global__ void gelu_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ pre, T* __restrict__ dpre,
+                                long long n8) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n8;
+       i += (long long)gridDim.x * blockDim.x) {
+    float a[8], b[8], o[8];
+    ld8(dy + i * 8, a);
+    ld8(pre + i * 8, b);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = a[j] * gelu_grad_f(b[j]);
+    st8(dpre + i * 8, o);
+  }
+}
+
+// dx = depthwise-conv-transpose(dpre); dw[c][tap] += sum dpre * x_shifted; db[c] += sum dpre
+// pgrads: fp32 [C][10] (9 taps + bias), pre-zeroed, accumulated with atomics (block partials in smem)
+template <typename T>
+__global__ void dwconv_bwd_kernel(const T* __restrict__ dpre, const T* __restrict__ x, int ldx,
+                                  const float* __restrict__ w, T* __restrict__ dx, int lddx,
+                                  float* __restrict__ pgrads, int N, int H, int W, int C) {
+  // block: blockDim.x = cvb (channel vectors handled by this block) * rows; each thread owns one channel vector
+  const int cv = C / 8;
+  const int tpr = cv < (int)blockDim.x ? cv : blockDim.x;
+  const int rows_per_block = blockDim.x / tpr;
+  const int tc = threadIdx.x % tpr;
+  const int tr = threadIdx.x / tpr;
+  const long long M = (long long)N * H * W;
+  for (int cbase = 0; cbase < cv; cbase += tpr) {
+    const int c8 = cbase + tc;
+    const bool active = c8 < cv && tr < rows_per_block;
+    const int c0 = c8 * 8;
+    float wg[8][10];
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+#pragma unroll
+      for (int k = 0; k < 10; ++k) wg[j][k] = 0.f;
+    if (active) {
+      for (long long pix = (long long)blockIdx.x * rows_per_block + tr; pix < M;
+           pix += (long long)gridDim.x * rows_per_block) {
+        const int wq = (int)(pix % W);
+        const long long t = pix / W;
+        const int hq = (int)(t % H);
+        const long long n = t / H;
+        float g0[8];
+        ld8(dpre + pix * C + c0, g0);
+        float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+#pragma unroll
+          for (int s = 0; s < 3; ++s) {
+            // weight gradient: dpre[p] * x[p + (r-1, s-1)]
+            const int hx = hq + r - 1, wx = wq + s - 1;
+            if (hx >= 0 && hx < H && wx >= 0 && wx < W) {
+              float f[8];
+              ld8(x + ((n * H + hx) * W + wx) * ldx + c0, f);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) wg[j][r * 3 + s] = fmaf(g0[j], f[j], wg[j][r * 3 + s]);
+            }
+            // input gradient: dx[p] = sum dpre[p - (r-1, s-1)] * w[r][s]
+            const int hg = hq - (r - 1), wgx = wq - (s - 1);
+            if (hg >= 0 && hg < H && wgx >= 0 && wgx < W) {
+              float f[8];
+              ld8(dpre + ((n * H + hg) * W + wgx) * C + c0, f);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) acc[j] = fmaf(f[j], w[(c0 + j) * 9 + r * 3 + s], acc[j]);
+            }
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) wg[j][9] += g0[j];
+        st8(dx + pix * lddx + c0, acc);
+      }
+      if (pgrads != nullptr) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+#pragma unroll
+          for (int k = 0; k < 10; ++k) atomicAdd(&pgrads[(long long)(c0 + j) * 10 + k], wg[j][k]);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// bilinear resize, align_corners=False (F.interpolate(mode="bilinear"), segformer.py:51-57,
+// segformer_mlp.py:88-119).  Source index rule of ATen: src = scale*(dst+0.5)-0.5, clamped at 0.
+// ------------------------------------------------------------------------------------------
+GDL_DEVINL void bil_src(int dst, float scale, int in_size, int& i0, int& i1, float& l0, float& l1) {
+  float src = scale * ((float)dst + 0.5f) - 0.5f;
+  if (src < 0.f) src = 0.f;
+  i0 = (int)src;
+  if (i0 > in_size - 1) i0 = in_size - 1;
+  i1 = i0 < in_size - 1 ? i0 + 1 : i0;
+  l1 = src - (float)i0;
+  l0 = 1.f - l1;
+}
+
+template <typename T>
+__global__ void bilinear_fwd_kernel(const T* __restrict__ x, long long ldx, T* __restrict__ y, long long ldy, int N,
+                                    int Hi, int Wi, int Ho, int Wo, int C, float sh, float sw) {
+  const long long total = (long long)N * Ho * Wo * C;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    long long t = i / C;
+    const int wo = (int)(t % Wo);
+    t /= Wo;
+    const int ho = (int)(t % Ho);
+    const long long n = t / Ho;
+    int h0, h1, w0, w1;
+    float a0, a1, b0, b1;
+    bil_src(ho, sh, Hi, h0, h1, a0, a1);
+    bil_src(wo, sw, Wi, w0, w1, b0, b1);
+    const T* base = x + n * Hi * Wi * ldx + c;
+    const float v = a0 * (b0 * to_f<T>(base[((long long)h0 * Wi + w0) * ldx]) + b1 * to_f<T>(base[((long long)h0 * Wi + w1) * ldx])) +
+                    a1 * (b0 * to_f<T>(base[((long long)h1 * Wi + w0) * ldx]) + b1 * to_f<T>(base[((long long)h1 * Wi + w1) * ldx]));
+    y[((n * Ho + ho) * Wo + wo) * ldy + c] = from_f<T>(v);
+  }
+}
+
+// gather-form adjoint: dx[n,hi,wi,c] = sum over output pixels whose taps touch (hi,wi)
+GDL_DEVINL void bil_range(int i, float scale, int out_size, int& lo, int& hi) {
+  // outputs d with floor(src(d)) in {i-1, i}: src(d) in [i-1, i+1)  ->  d in [(i-0.5)/scale-0.5, (i+1.5)/scale-0.5)
+  float a = ((float)i - 0.5f) / scale - 0.5f, b = ((float)i + 1.5f) / scale - 0.5f;
+  lo = (int)floorf(a) - 1;
+  hi = (int)ceilf(b) + 1;
+  if (lo < 0) lo = 0;
+  if (hi > out_size - 1) hi = out_size - 1;
+}
+
+template <typename T>
+__global__ void bilinear_bwd_kernel(const T* __restrict__ dy, long long ldy, T* __restrict__ dx, long long ldx, int N,
+                                    int Hi, int Wi, int Ho, int Wo, int C, float sh, float sw) {
+  const long long total = (long long)N * Hi * Wi * C;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    long long t = i / C;
+    const int wi = (int)(t % Wi);
+    t /= Wi;
+    const int hi = (int)(t % Hi);
+    const long long n = t / Hi;
+    int hlo, hhi, wlo, whi;
+    bil_range(hi, sh, Ho, hlo, hhi);
+    bil_range(wi, sw, Wo, wlo, whi);
+    float acc = 0.f;
+    for (int ho = hlo; ho <= hhi; ++ho) {
+      int h0, h1;
+      float a0, a1;
+      bil_src(ho, sh, Hi, h0, h1, a0, a1);
+      float wh = (h0 == hi ? a0 : 0.f) + (h1 == hi ? a1 : 0.f);
+      if (wh == 0.f) continue;
+      for (int wo = wlo; wo <= whi; ++wo) {
+        int w0, w1;
+        float b0, b1;
+        bil_src(wo, sw, Wi, w0, w1, b0, b1);
+        const float ww = (w0 == wi ? b0 : 0.f) + (w1 == wi ? b1 : 0.f);
+        if (ww == 0.f) continue;
+        acc = fmaf(wh * ww, to_f<T>(dy[((n * Ho + ho) * Wo + wo) * ldy + c]), acc);
+      }
+    }
+    dx[((n * Hi + hi) * Wi + wi) * ldx + c] = from_f<T>(acc);
+  }
+}
+
+// elementwise helpers for the fp32 residual stream
+template <typename T>
+__global__ void cast_f32_kernel(const float* __restrict__ x, T* __restrict__ y, long long n) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    y[i] = from_f<T>(x[i]);
+}
+
+}  // namespace gdl
+
+using namespace gdl;
+
+#define GDL_DISPATCH_T(dtype, ...)                                     \
+  do {                                                                 \
+    if ((dtype) == GDL_BF16) {                                         \
+      using T = __nv_bfloat16;                                         \
+      __VA_ARGS__;                                                     \
+    } else if ((dtype) == GDL_F16) {                                   \
+      using T = __half;                                                \
+      __VA_ARGS__;                                                     \
+    } else if ((dtype) == GDL_F32) {                                   \
+      using T = float;                                                 \
+      __VA_ARGS__;                                                     \
+    } else {                                                           \
+      ::gdl::set_last_error("unknown dtype %d", dtype);                \
+      return GDL_ERR_INVALID;                                          \
+    }                                                                  \
+  } while (0)
+
+extern "C" int gdl_layernorm_fwd(const void* x, int x_dtype, long long ldx, const float* gamma, const float* beta,
+                                 float eps, void* y, int y_dtype, long long ldy, float* mean, float* rstd,
+                                 long long M, int C, void* stream) {
+  GDL_REQUIRE(x && y && gamma && beta && M > 0 && C > 0 && C <= 32 * kLnMaxPerLane, GDL_ERR_INVALID,
+              "layernorm: bad args (C=%d must be <= %d)", C, 32 * kLnMaxPerLane);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int blocks = row_blocks(M, 8);
+#define LN_FWD(TI, TO) \
+  layernorm_fwd_kernel<TI, TO><<<blocks, 256, 0, st>>>((const TI*)x, ldx, gamma, beta, eps, (TO*)y, ldy, mean, rstd, M, C)
+  if (x_dtype == GDL_F32) {
+    if (y_dtype == GDL_F32) LN_FWD(float, float);
+    else if (y_dtype == GDL_BF16) LN_FWD(float, __nv_bfloat16);
+    else LN_FWD(float, __half);
+  } else if (x_dtype == GDL_BF16) {
+    if (y_dtype == GDL_F32) LN_FWD(__nv_bfloat16, float);
+    else if (y_dtype == GDL_BF16) LN_FWD(__nv_bfloat16, __nv_bfloat16);
+    else LN_FWD(__nv_bfloat16, __half);
+  } else {
+    if (y_dtype == GDL_F32) LN_FWD(__half, float);
+    else if (y_dtype == GDL_BF16) LN_FWD(__half, __nv_bfloat16);
+    else LN_FWD(__half, __half);
+  }
+#undef LN_FWD
+  GDL_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int gdl_layernorm_bwd(const void* g, int g_dtype, long long ldg, const void* x, int x_dtype, long long ldx,
+                                 const float* mean, const float* rstd, const float* gamma, const float* add,
+                                 long long lda, float* dx32, long long ld32, void* dx16, int dx16_dtype, long long ld16,
+                                 float* pgrads /* [2][C] dgamma, dbeta: accumulated */, long long M, int C,
+                                 void* stream) {
+  GDL_REQUIRE(g && x && mean && rstd && gamma && (dx32 || dx16) && M > 0 && C > 0 && C <= 32 * kLnMaxPerLane,
+              GDL_ERR_INVALID, "layernorm_bwd: bad args");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int blocks = row_blocks(M, 8, 4);
+  const int smem = 2 * C * (int)sizeof(float);
+  const int is_half = dx16_dtype == GDL_F16;
+#define LN_BWD(TI, TG)                                                                                          \
+  layernorm_bwd_kernel<TI, TG><<<blocks, 256, smem, st>>>((const TG*)g, ldg, (const TI*)x, ldx, mean, rstd, gamma, add, \
+                                                         lda, dx32, ld32, dx16, ld16, is_half, pgrads, M, C)
+  if (x_dtype == GDL_F32) {
+    if (g_dtype == GDL_F32) LN_BWD(float, float);
+    else if (g_dtype == GDL_BF16) LN_BWD(float, __nv_bfloat16);
+    else LN_BWD(float, __half);
+  } else if (x_dtype == GDL_BF16) {
+    if (g_dtype == GDL_F32) LN_BWD(__nv_bfloat16, float);
+    else if (g_dtype == GDL_BF16) LN_BWD(__nv_bfloat16, __nv_bfloat16);
+    else LN_BWD(__nv_bfloat16, __half);
+  } else {
+    if (g_dtype == GDL_F32) LN_BWD(__half, float);
+    else if (g_dtype == GDL_BF16) LN_BWD(__half, __nv_bfloat16);
+    else LN_BWD(__half, __half);
+  }
+#undef LN_BWD
+  GDL_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int gdl_softmax_fwd(const void* s, long long lds, float scale, void* p, long long ldp, int dtype,
+                               long long M, int L, int Lpad, void* stream) {
+  GDL_REQUIRE(s && p && M > 0 && L > 0 && Lpad >= L && Lpad <= 32 * kSmMaxPerLane && ldp >= Lpad && lds >= L,
+              GDL_ERR_INVALID, "softmax: bad args (L=%d Lpad=%d)", L, Lpad);
+  cudaStream_t st = (cudaStream_t)stream;
+  GDL_DISPATCH_T(dtype, { softmax_fwd_kernel<T><<<row_blocks(M, 8), 256, 0, st>>>((const T*)s, lds, scale, (T*)p, ldp, M, L, Lpad); });
+  GDL_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int gdl_softmax_bwd(const void* p, long long ldp, const void* dp, long long lddp, float scale, void* ds,
+                               long long ldds, int dtype, long long M, int L, int Lpad, void* stream) {
+  GDL_REQUIRE(p && dp && ds && M > 0 && L > 0 && Lpad >= L && Lpad <= 32 * kSmMaxPerLane, GDL_ERR_INVALID,
+              "softmax_bwd: bad args");
+  cudaStream_t st = (cudaStream_t)stream;
+  GDL_DISPATCH_T(dtype, {
+    softmax_bwd_kernel<T><<<row_blocks(M, 8), 256, 0, st>>>((const T*)p, ldp, (const T*)dp, lddp, scale, (T*)ds, ldds, M, L, Lpad);
+  });
+  GDL_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int gdl_dwconv3x3_gelu_fwd(const void* x, int ldx, const float* w, const float* bias, void* pre, void* y,
+                                      int dtype, int N, int H, int W, int C, void* stream) {
+  GDL_REQUIRE(x && w && pre && y && N > 0 && H > 0 && W > 0 && C > 0 && C % 8 == 0 && ldx % 8 == 0, GDL_ERR_INVALID,
+              "dwconv_gelu: bad args");
+  GDL_REQUIRE(dtype == GDL_BF16 || dtype == GDL_F16, GDL_ERR_INVALID, "dwconv_gelu: 16-bit dtype expected");
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long total = (long long)N * H * W * (C / 8);
+  long long b = (total + 255) / 256;
+  if (b > 16 * kNumSMsB200) b = 16 * kNumSMsB200;
+  if (dtype == GDL_BF16)
+    dwconv_gelu_fwd_kernel<__nv_bfloat16><<<(int)b, 256, 0, st>>>((const __nv_bfloat16*)x, ldx, w, bias, (__nv_bfloat16*)pre, (__nv_bfloat16*)y, N, H, W, C);
+  else
+    dwconv_gelu_fwd_kernel<__half><<<(int)b, 256, 0, st>>>((const __half*)x, ldx, w, bias, (__half*)pre, (__half*)y, N, H, W, C);
+  GDL_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int gdl_dwconv3x3_gelu_bwd(const void* dy, const void* pre, const void* x, int ldx, const float* w,
+                                      void* dpre_scratch, void* dx, int lddx, float* pgrads /* [C][10] accumulated */,
+                                      int dtype, int N, int H, int W, int C, void* stream) {
+  GDL_REQUIRE(dy && pre && x && w && dpre_scratch && dx && N > 0 && H > 0 && W > 0 && C > 0 && C % 8 == 0,
+              GDL_ERR_INVALID, "dwconv_gelu_bwd: bad args");
+  GDL_REQUIRE(dtype == GDL_BF16 || dtype == GDL_F16, GDL_ERR_INVALID, "dwconv_gelu_bwd: 16-bit dtype expected");
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long M = (long long)N * H * W;
+  const long long n8 = M * (C / 8);
+  long long b1 = (n8 + 255) / 256;
+  if (b1 > 16 * kNumSMsB200) b1 = 16 * kNumSMsB200;
+  const int cv = C / 8;
+  const int tpr = cv < 256 ? cv : 256;
+  const int rpb = 256 / tpr;
+  long long b2 = (M + rpb * 8 - 1) / (rpb * 8);
+  if (b2 > 4 * kNumSMsB200) b2 = 4 * kNumSMsB200;
+  if (b2 < 1) b2 = 1;
+  if (dtype == GDL_BF16) {
+    using T = __nv_bfloat16;
+    gelu_bwd_kernel<T><<<(int)b1, 256, 0, st>>>((const T*)dy, (const T*)pre, (T*)dpre_scratch, n8);
+    dwconv_bwd_kernel<T><<<(int)b2, 256, 0, st>>>((const T*)dpre_scratch, (const T*)x, ldx, w, (T*)dx, lddx, pgrads, N, H, W, C);
+  } else {
+    using T = __half;
+    gelu_bwd_kernel<T><<<(int)b1, 256, 0, st>>>((const T*)dy, (const T*)pre, (T*)dpre_scratch, n8);
+    dwconv_bwd_kernel<T><<<(int)b2, 256, 0, st>>>((const T*)dpre_scratch, (const T*)x, ldx, w, (T*)dx, lddx, pgrads, N, H, W, C);
+  }
+  GDL_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int gdl_bilinear_fwd(const void* x, long long ldx, void* y, long long ldy, int dtype, int N, int Hi, int Wi,
+                                int Ho, int Wo, int C, void* stream) {
+  GDL_REQUIRE(x && y && N > 0 && Hi > 0 && Wi > 0 && Ho > 0 && Wo > 0 && C > 0 && ldx >= C && ldy >= C, GDL_ERR_INVALID,
+              "bilinear: bad args");
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long total = (long long)N * Ho * Wo * C;
+  long long b = (total + 255) / 256;
+  if (b > 16 * kNumSMsB200) b = 16 * kNumSMsB200;
+  const float sh = (float)Hi / (float)Ho, sw = (float)Wi / (float)Wo;
+  GDL_DISPATCH_T(dtype, { bilinear_fwd_kernel<T><<<(int)b, 256, 0, st>>>((const T*)x, ldx, (T*)y, ldy, N, Hi, Wi, Ho, Wo, C, sh, sw); });
+  GDL_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int gdl_bilinear_bwd(const void* dy, long long ldy, void* dx, long long ldx, int dtype, int N, int Hi, int Wi,
+                                int Ho, int Wo, int C, void* stream) {
+  GDL_REQUIRE(dy && dx && N > 0 && Hi > 0 && Wi > 0 && Ho > 0 && Wo > 0 && C > 0, GDL_ERR_INVALID, "bilinear_bwd: bad args");
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long total = (long long)N * Hi * Wi * C;
+  long long b = (total + 255) / 256;
+  if (b > 16 * kNumSMsB200) b = 16 * kNumSMsB200;
+  const float sh = (float)Hi / (float)Ho, sw = (float)Wi / (float)Wo;
+  GDL_DISPATCH_T(dtype, { bilinear_bwd_kernel<T><<<(int)b, 256, 0, st>>>((const T*)dy, ldy, (T*)dx, ldx, N, Hi, Wi, Ho, Wo, C, sh, sw); });
+  GDL_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int gdl_cast_f32(const float* x, void* y, int dtype, long long n, void* stream) {
+  GDL_REQUIRE(x && y && n > 0, GDL_ERR_INVALID, "cast: bad args");
+  cudaStream_t st = (cudaStream_t)stream;
+  long long b = (n + 255) / 256;
+  if (b > 16 * kNumSMsB200) b = 16 * kNumSMsB200;
+  GDL_DISPATCH_T(dtype, { cast_f32_kernel<T><<<(int)b, 256, 0, st>>>(x, (T*)y, n); });
+  GDL_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}

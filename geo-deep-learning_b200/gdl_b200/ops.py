@@ -45,16 +45,32 @@ class ConvProfiler:
 
     def __init__(self) -> None:
         self.records: list[tuple[str, float, torch.cuda.Event, torch.cuda.Event]] = []
+        self.descs: list[str] = []
 
     def begin(self) -> torch.cuda.Event:
         e = torch.cuda.Event(enable_timing=True)
         e.record()
         return e
 
-    def end(self, kernel: str, flops: float, e0: torch.cuda.Event) -> None:
+    def end(self, kernel: str, flops: float, e0: torch.cuda.Event, desc: str = "") -> None:
         e1 = torch.cuda.Event(enable_timing=True)
         e1.record()
         self.records.append((kernel, flops, e0, e1))
+        self.descs.append(desc)
+
+    def dump_table(self, path: str, steps: int) -> None:
+        """per-launch table of the LAST profiled step: kernel, shape, ms, TFLOP/s (sorted by time)."""
+        import json
+        torch.cuda.synchronize()
+        n = len(self.records) // steps
+        rows = []
+        for (kernel, flops, e0, e1), desc in zip(self.records[-n:], self.descs[-n:]):
+            ms = e0.elapsed_time(e1)
+            rows.append({"kernel": kernel, "shape": desc, "ms": round(ms, 4), "gflop": round(flops / 1e9, 2),
+                         "tflops": round(flops / ms / 1e9, 1) if ms > 0 else 0})
+        rows.sort(key=lambda r: -r["ms"])
+        with open(path, "w") as f:
+            json.dump(rows, f, indent=0)
 
     def summary(self, steps: int = 1) -> dict:
         torch.cuda.synchronize()
@@ -133,7 +149,8 @@ def conv2d_fwd(srcs: Sequence[torch.Tensor], weight: torch.Tensor, cout: int, r:
     _count()
     if e0 is not None:
         ctot = sum(t.shape[3] for t in srcs)
-        _PROFILER.end("conv_fwd_kernel", 2.0 * n * ho * wo * cout * r * s * ctot, e0)
+        _PROFILER.end("conv_fwd_kernel", 2.0 * n * ho * wo * cout * r * s * ctot, e0,
+                      f"N{n} {ho}x{wo} src{[t.shape[3] for t in srcs]} -> {cout} k{r}")
     return out
 
 
@@ -155,7 +172,8 @@ def conv2d_wgrad(srcs: Sequence[torch.Tensor], dy: torch.Tensor, r: int, s: int,
     _count()
     if e0 is not None:
         ctot = sum(t.shape[3] for t in srcs)
-        _PROFILER.end("conv_wgrad_kernel", 2.0 * dy.shape[0] * dy.shape[1] * dy.shape[2] * dy.shape[3] * r * s * ctot, e0)
+        _PROFILER.end("conv_wgrad_kernel", 2.0 * dy.shape[0] * dy.shape[1] * dy.shape[2] * dy.shape[3] * r * s * ctot, e0,
+                      f"N{dy.shape[0]} {dy.shape[1]}x{dy.shape[2]} src{[t.shape[3] for t in srcs]} -> {dy.shape[3]} k{r}")
     return dw
 
 
@@ -366,3 +384,96 @@ def adam_step(p, g, m, v, lr, beta1, beta2, eps, weight_decay, step, grad_scale=
 def grad_clip_coef(g, max_norm, scratch, scale) -> None:
     _ck(L.load().gdl_grad_clip_coef(L.ptr(g), g.numel(), float(max_norm), L.ptr(scratch), L.ptr(scale),
                                         L.stream_ptr()))
+
+
+# ---------------------------------------------------------------------------------------------
+# MixTransformer / SegFormer kernels (transformer.cu).  Token tensors are (..., C) with a uniform row
+# stride stride(-2); M = number of rows.
+# ---------------------------------------------------------------------------------------------
+def _rows2(t: torch.Tensor) -> int:
+    return t.numel() // t.shape[-1]
+
+
+def layernorm_fwd(x, gamma, beta, eps, out_dtype, want_stats: bool = True):
+    m, c = _rows2(x), x.shape[-1]
+    y = torch.empty(x.shape, dtype=out_dtype, device=x.device)
+    stats = torch.empty((2, m), dtype=torch.float32, device=x.device) if want_stats else None
+    _ck(L.load().gdl_layernorm_fwd(L.ptr(x), L.dt_code(x.dtype), x.stride(-2), L.ptr(gamma), L.ptr(beta), float(eps),
+                                   L.ptr(y), L.dt_code(out_dtype), c, L.ptr(stats[0]) if want_stats else None,
+                                   L.ptr(stats[1]) if want_stats else None, m, c, L.stream_ptr()))
+    return y, stats
+
+
+def layernorm_bwd(g, x, stats, gamma, *, add=None, want32: bool = True, dtype16=None, pgrads=None):
+    """returns (dx32 | None, dx16 | None); pgrads [2][C] (dgamma, dbeta) is accumulated into."""
+    m, c = _rows2(x), x.shape[-1]
+    dx32 = torch.empty(x.shape, dtype=torch.float32, device=x.device) if want32 else None
+    dx16 = torch.empty(x.shape, dtype=dtype16, device=x.device) if dtype16 is not None else None
+    _ck(L.load().gdl_layernorm_bwd(L.ptr(g), L.dt_code(g.dtype), g.stride(-2), L.ptr(x), L.dt_code(x.dtype),
+                                   x.stride(-2), L.ptr(stats[0]), L.ptr(stats[1]), L.ptr(gamma), L.ptr(add),
+                                   add.stride(-2) if add is not None else 0, L.ptr(dx32), c, L.ptr(dx16),
+                                   L.dt_code(dtype16) if dtype16 is not None else 0, c, L.ptr(pgrads), m, c,
+                                   L.stream_ptr()))
+    return dx32, dx16
+
+
+def softmax_fwd(s, scale, length, p=None):
+    """s: (..., Lpad) rows; p = softmax(scale * s[..., :length]) with zeros in the pad columns."""
+    lpad = s.shape[-1]
+    if p is None:
+        p = torch.empty_like(s)
+    _ck(L.load().gdl_softmax_fwd(L.ptr(s), s.stride(-2), float(scale), L.ptr(p), p.stride(-2), L.dt_code(s.dtype),
+                                 _rows2(s), length, lpad, L.stream_ptr()))
+    return p
+
+
+def softmax_bwd(p, dp, scale, length, ds=None):
+    lpad = p.shape[-1]
+    if ds is None:
+        ds = torch.empty_like(p)
+    _ck(L.load().gdl_softmax_bwd(L.ptr(p), p.stride(-2), L.ptr(dp), dp.stride(-2), float(scale), L.ptr(ds),
+                                 ds.stride(-2), L.dt_code(p.dtype), _rows2(p), length, lpad, L.stream_ptr()))
+    return ds
+
+
+def dwconv3x3_gelu_fwd(x, w, bias):
+    """x (N,H,W,C) 16-bit; w fp32 [C][3][3] (nn.Conv2d(groups=C).weight squeezed); returns (y, pre)."""
+    n, h, wd, c = x.shape
+    pre = torch.empty((n, h, wd, c), dtype=x.dtype, device=x.device)
+    y = torch.empty_like(pre)
+    _ck(L.load().gdl_dwconv3x3_gelu_fwd(L.ptr(x), x.stride(2), L.ptr(w), L.ptr(bias), L.ptr(pre), L.ptr(y),
+                                        L.dt_code(x.dtype), n, h, wd, c, L.stream_ptr()))
+    return y, pre
+
+
+def dwconv3x3_gelu_bwd(dy, pre, x, w, pgrads):
+    """returns dx; pgrads fp32 [C][10] (9 taps + bias) accumulated into."""
+    n, h, wd, c = x.shape
+    scratch = torch.empty((n, h, wd, c), dtype=x.dtype, device=x.device)
+    dx = torch.empty((n, h, wd, c), dtype=x.dtype, device=x.device)
+    _ck(L.load().gdl_dwconv3x3_gelu_bwd(L.ptr(dy), L.ptr(pre), L.ptr(x), x.stride(2), L.ptr(w), L.ptr(scratch),
+                                        L.ptr(dx), c, L.ptr(pgrads), L.dt_code(x.dtype), n, h, wd, c, L.stream_ptr()), )
+    return dx
+
+
+def bilinear_fwd(x, ho, wo, out=None):
+    n, hi, wi, c = x.shape
+    if out is None:
+        out = torch.empty((n, ho, wo, c), dtype=x.dtype, device=x.device)
+    _ck(L.load().gdl_bilinear_fwd(L.ptr(x), x.stride(2), L.ptr(out), out.stride(2), L.dt_code(x.dtype), n, hi, wi, ho,
+                                  wo, c, L.stream_ptr()))
+    return out
+
+
+def bilinear_bwd(dy, hi, wi):
+    n, ho, wo, c = dy.shape
+    dx = torch.empty((n, hi, wi, c), dtype=dy.dtype, device=dy.device)
+    _ck(L.load().gdl_bilinear_bwd(L.ptr(dy), dy.stride(2), L.ptr(dx), c, L.dt_code(dy.dtype), n, hi, wi, ho, wo, c,
+                                  L.stream_ptr()))
+    return dx
+
+
+def cast_f32(x, dtype):
+    y = torch.empty(x.shape, dtype=dtype, device=x.device)
+    _ck(L.load().gdl_cast_f32(L.ptr(x), L.ptr(y), L.dt_code(dtype), x.numel(), L.stream_ptr()))
+    return y

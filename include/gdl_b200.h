@@ -203,6 +203,51 @@ int gdl_adam_step(float* p, const float* g, float* m, float* v, long long n, flo
 int gdl_grad_clip_coef(const float* g, long long n, float max_norm, float* sumsq_scratch, float* scale,
                        void* stream);
 
+/* =============================================================================================
+ * MixTransformer / SegFormer HBM-bound kernels (csrc/transformer.cu).  Tokens (B,N,C) and maps
+ * (B,h,w,C) are the same NHWC memory, so the reference's reshape/permute/contiguous copies
+ * (mix_transformer.py:499,541-546; segformer_mlp.py:78-121) do not exist here.
+ * ============================================================================================= */
+
+/* nn.LayerNorm over the last dim (eps 1e-6 for block/stage norms, 1e-5 for OverlapPatchEmbed.norm and
+ * Attention.norm: mix_transformer.py:100,251,611).  x: fp32 (residual stream) or 16-bit, y: 16-bit or
+ * fp32; mean/rstd [M] saved for the backward.  bwd: dx (+ add) as fp32 and/or a 16-bit copy; pgrads
+ * [2][C] = (dgamma, dbeta) accumulated (zero first). */
+int gdl_layernorm_fwd(const void* x, int x_dtype, long long ldx, const float* gamma, const float* beta, float eps,
+                      void* y, int y_dtype, long long ldy, float* mean, float* rstd, long long M, int C,
+                      void* stream);
+int gdl_layernorm_bwd(const void* g, int g_dtype, long long ldg, const void* x, int x_dtype, long long ldx,
+                      const float* mean, const float* rstd, const float* gamma, const float* add, long long lda,
+                      float* dx32, long long ld32, void* dx16, int dx16_dtype, long long ld16, float* pgrads,
+                      long long M, int C, void* stream);
+
+/* attention scores: p = softmax(scale * s) over rows of length L (mix_transformer.py:151-152); columns
+ * [L, Lpad) of p are written as zeros so p can be the K-padded operand of the P.V GEMM.
+ * bwd: ds = scale * p * (dp - sum_j dp_j p_j). */
+int gdl_softmax_fwd(const void* s, long long lds, float scale, void* p, long long ldp, int dtype, long long M,
+                    int L, int Lpad, void* stream);
+int gdl_softmax_bwd(const void* p, long long ldp, const void* dp, long long lddp, float scale, void* ds,
+                    long long ldds, int dtype, long long M, int L, int Lpad, void* stream);
+
+/* Mix-FFN middle: y = GELU(depthwise3x3(x) + b) (Mlp.dwconv + act, mix_transformer.py:56-63,533-546), exact
+ * erf GELU; `pre` keeps the 16-bit pre-activation for the backward.  w: fp32 [C][3][3].
+ * bwd: dx and pgrads [C][10] (9 taps + bias, accumulated; zero first); dpre_scratch: [M][C] 16-bit. */
+int gdl_dwconv3x3_gelu_fwd(const void* x, int ldx, const float* w, const float* bias, void* pre, void* y, int dtype,
+                           int N, int H, int W, int C, void* stream);
+int gdl_dwconv3x3_gelu_bwd(const void* dy, const void* pre, const void* x, int ldx, const float* w,
+                           void* dpre_scratch, void* dx, int lddx, float* pgrads, int dtype, int N, int H, int W,
+                           int C, void* stream);
+
+/* F.interpolate(mode="bilinear", align_corners=False) on NHWC (segformer.py:51-57, segformer_mlp.py:88-119,
+ * dofa.py:90-105) for 16-bit features or fp32 logits, and its adjoint in gather form. */
+int gdl_bilinear_fwd(const void* x, long long ldx, void* y, long long ldy, int dtype, int N, int Hi, int Wi, int Ho,
+                     int Wo, int C, void* stream);
+int gdl_bilinear_bwd(const void* dy, long long ldy, void* dx, long long ldx, int dtype, int N, int Hi, int Wi,
+                     int Ho, int Wo, int C, void* stream);
+
+/* fp32 -> dtype cast of a flat buffer (residual-stream gradient -> 16-bit GEMM operand) */
+int gdl_cast_f32(const float* x, void* y, int dtype, long long n, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
