@@ -47,6 +47,11 @@ struct ConvFwdKParams {
   int vec_ok;
   const float* bias;
   int relu;
+  const void* residual;  // optional, added in the epilogue (fp32 residual stream or 16-bit)
+  int res_dtype;
+  long long ldr;
+  int w_rows_per_img;    // batched B operand: weight row offset per image (attention GEMMs), 0 = shared
+  int w_mn_major;        // B operand stored [K rows][N cols] (N contiguous): P.V and dS.K of the attention
 };
 
 GDL_DEVINL uint8_t* align_smem_1024(uint8_t* raw) {
@@ -166,7 +171,10 @@ conv_fwd_kernel(const __grid_constant__ ConvFwdKParams p) {
               mbar_expect_tx(&full_bar[stage], tx);
               tma_load_4d(a_dst, &p.tmA[src], &full_bar[stage], ch * p.BK, w0 + s - p.pad_w,
                           h0 + r - p.pad_h, img);
-              tma_load_2d(b_dst, &p.tmB, &full_bar[stage], kbase + ch * p.BK, n0);
+              if (p.w_mn_major)
+                tma_load_2d(b_dst, &p.tmB, &full_bar[stage], n0, kbase + ch * p.BK + img * p.w_rows_per_img);
+              else
+                tma_load_2d(b_dst, &p.tmB, &full_bar[stage], kbase + ch * p.BK, n0 + img * p.w_rows_per_img);
               if (++stage == p.stages) {
                 stage = 0;
                 phase ^= 1;
@@ -179,10 +187,14 @@ conv_fwd_kernel(const __grid_constant__ ConvFwdKParams p) {
   } else if (warp == 1) {
     // ===================== MMA issuer (one thread) =====================
     if (lane == 0) {
-      const uint32_t idesc = umma_idesc(128, p.BN, p.ab_fmt, 0, 0);
+      const uint32_t idesc = umma_idesc(128, p.BN, p.ab_fmt, 0, p.w_mn_major);
       const uint32_t lt = umma_layout_type(p.BK * 2);
       const uint32_t sbo = 8u * p.BK * 2u;
       const int ksteps = p.BK / 16;
+      // MN-major B: one atom of BN (<= 64) contiguous channels per K row; 8 K-rows per swizzle group
+      const uint32_t ltB = p.w_mn_major ? umma_layout_type(p.BN * 2) : lt;
+      const uint32_t sboB = p.w_mn_major ? 8u * p.BN * 2u : sbo;
+      const uint32_t kstepB = p.w_mn_major ? 16u * p.BN * 2u : 32u;
       int k_iters = 0;
       for (int src = 0; src < p.num_src; ++src) k_iters += p.src_chunks[src];
       k_iters *= taps;
@@ -202,7 +214,7 @@ conv_fwd_kernel(const __grid_constant__ ConvFwdKParams p) {
           const uint32_t b_addr = a_addr + p.a_bytes;
           for (int kk = 0; kk < ksteps; ++kk) {
             const uint64_t da = umma_smem_desc(a_addr + kk * 32, 16, sbo, lt);
-            const uint64_t db = umma_smem_desc(b_addr + kk * 32, 16, sbo, lt);
+            const uint64_t db = umma_smem_desc(b_addr + kk * kstepB, 16, sboB, ltB);
             umma_f16(d_tmem, da, db, idesc, (uint32_t)((k | kk) != 0));
           }
           umma_commit(&empty_bar[stage]);
@@ -249,6 +261,25 @@ conv_fwd_kernel(const __grid_constant__ ConvFwdKParams p) {
 #pragma unroll
             for (int i = 0; i < 16; ++i)
               if (i < nvalid) f[i] += __ldg(p.bias + c0 + i);
+          }
+          if (p.residual != nullptr) {
+            const long long roff = pix * p.ldr + c0;
+            if (p.res_dtype == GDL_F32) {
+              const float* r = reinterpret_cast<const float*>(p.residual) + roff;
+#pragma unroll
+              for (int i = 0; i < 16; ++i)
+                if (i < nvalid) f[i] += r[i];
+            } else if (p.res_dtype == GDL_BF16) {
+              const __nv_bfloat16* r = reinterpret_cast<const __nv_bfloat16*>(p.residual) + roff;
+#pragma unroll
+              for (int i = 0; i < 16; ++i)
+                if (i < nvalid) f[i] += __bfloat162float(r[i]);
+            } else {
+              const __half* r = reinterpret_cast<const __half*>(p.residual) + roff;
+#pragma unroll
+              for (int i = 0; i < 16; ++i)
+                if (i < nvalid) f[i] += __half2float(r[i]);
+            }
           }
           if (p.relu) {
 #pragma unroll
@@ -372,7 +403,7 @@ extern "C" int gdl_conv2d_nhwc_fwd(const gdl_conv_fwd_t* d, void* stream_) {
   p.BK = chunk_width(d->src, d->num_src);
   // geometry: a pointwise conv over NHWC is a flat GEMM over N*H*W pixels
   int N = d->N, H = d->H, W = d->W, oH = Ho, oW = Wo;
-  if (d->R == 1 && d->S == 1 && d->pad_h == 0 && d->pad_w == 0) {
+  if (d->R == 1 && d->S == 1 && d->pad_h == 0 && d->pad_w == 0 && d->w_rows_per_img == 0) {
     long long M = (long long)N * H * W;
     GDL_REQUIRE(M < (1ll << 31), GDL_ERR_UNSUPPORTED, "too many pixels");
     W = (int)M;
@@ -380,6 +411,11 @@ extern "C" int gdl_conv2d_nhwc_fwd(const gdl_conv_fwd_t* d, void* stream_) {
     N = 1;
     oH = 1;
     oW = W;
+  }
+  if (d->w_mn_major) {
+    GDL_REQUIRE(d->R == 1 && d->S == 1 && d->num_src == 1, GDL_ERR_INVALID, "w_mn_major: pointwise, single source only");
+    GDL_REQUIRE((d->Cout == 16 || d->Cout == 32 || d->Cout == 64), GDL_ERR_UNSUPPORTED,
+                "w_mn_major: Cout must be 16, 32 or 64 (got %d)", d->Cout);
   }
   p.Nimg = N;
   p.Ho = oH;
@@ -408,6 +444,12 @@ extern "C" int gdl_conv2d_nhwc_fwd(const gdl_conv_fwd_t* d, void* stream_) {
   p.vec_ok = ((reinterpret_cast<uintptr_t>(d->out) & 15) == 0) && ((d->ldo * esz) % 16 == 0);
   p.bias = d->bias;
   p.relu = d->relu;
+  p.residual = d->residual;
+  p.res_dtype = d->res_dtype;
+  p.ldr = d->ldr;
+  p.w_rows_per_img = d->w_rows_per_img;
+  p.w_mn_major = d->w_mn_major;
+  GDL_REQUIRE(d->residual == nullptr || d->ldr >= d->Cout, GDL_ERR_INVALID, "residual stride %d < Cout", d->ldr);
 
   int coff = 0;
   for (int i = 0; i < d->num_src; ++i) {
@@ -419,7 +461,15 @@ extern "C" int gdl_conv2d_nhwc_fwd(const gdl_conv_fwd_t* d, void* stream_) {
     if (st) return st;
   }
   const long long Ktot = (long long)d->R * d->S * Ctot;
-  st = make_tmap_2d(&p.tmB, d->weight, d->dtype, Ktot, d->Cout, Ktot, p.BK, p.BN, p.BK * 2);
+  const long long w_ld = d->w_ld > 0 ? d->w_ld : (d->w_mn_major ? d->Cout : Ktot);
+  if (d->w_mn_major) {
+    // weight matrix [w_rows (K index, all images)][Cout] with row stride w_ld: box = (Cout cols, BK rows)
+    const long long w_rows = d->w_rows > 0 ? d->w_rows : Ktot;
+    st = make_tmap_2d(&p.tmB, d->weight, d->dtype, d->Cout, w_rows, w_ld, p.BN, p.BK, p.BN * 2);
+  } else {
+    const long long w_rows = d->w_rows > 0 ? d->w_rows : d->Cout;
+    st = make_tmap_2d(&p.tmB, d->weight, d->dtype, Ktot, w_rows, w_ld, p.BK, p.BN, p.BK * 2);
+  }
   if (st) return st;
 
   int smem = p.stages * p.stage_bytes + 1024;
@@ -458,6 +508,10 @@ struct ConvWgradKParams {
   int stages, a_bytes, stage_bytes, tmem_cols, bn_max;
   int ab_fmt;
   float* dw;
+  long long dw_ld;          // row stride of dw (elements)
+  long long dw_img_stride;  // batched: dw of image i starts at dw + i * dw_img_stride
+  int batched;              // one independent dW per image (attention: dV = P^T dO, dK = dS^T Q)
+  int pb_per_img;
 };
 
 __global__ void __launch_bounds__(kConvThreads, 1)
@@ -520,6 +574,19 @@ conv_wgrad_kernel(const __grid_constant__ ConvWgradKParams p) {
     mt = u % p.m_tiles;
     ks = u / p.m_tiles;
   };
+  // pixel-block range of split `ks`; in batched mode ks = img * ksplit + split-within-image
+  auto pb_range = [&](int ks, int& pb0, int& pb1, int& img) {
+    if (p.batched) {
+      img = ks / p.ksplit;
+      const int sp = ks - img * p.ksplit;
+      pb0 = img * p.pb_per_img + sp * p.pb_per_split;
+      pb1 = min((img + 1) * p.pb_per_img, pb0 + p.pb_per_split);
+    } else {
+      img = 0;
+      pb0 = ks * p.pb_per_split;
+      pb1 = min(p.pix_blocks, pb0 + p.pb_per_split);
+    }
+  };
 
   if (warp == 0) {
     if (lane == 0) {
@@ -535,8 +602,8 @@ conv_wgrad_kernel(const __grid_constant__ ConvWgradKParams p) {
         const int src = p.nt_src[nt];
         const int c0 = p.nt_c0[nt];
         const uint32_t tx = (uint32_t)(a_atoms * atomA_bytes + b_atoms * atomB_bytes);
-        const int pb0 = ks * p.pb_per_split;
-        const int pb1 = min(p.pix_blocks, pb0 + p.pb_per_split);
+        int pb0, pb1, uimg;
+        pb_range(ks, pb0, pb1, uimg);
         for (int pb = pb0; pb < pb1; ++pb) {
           const int img = pb / tiles_per_img;
           const int t_in = pb - img * tiles_per_img;
@@ -576,8 +643,8 @@ conv_wgrad_kernel(const __grid_constant__ ConvWgradKParams p) {
         mbar_wait(&tempty_bar[acc], aphase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.bn_max);
-        const int pb0 = ks * p.pb_per_split;
-        const int pb1 = min(p.pix_blocks, pb0 + p.pb_per_split);
+        int pb0, pb1, uimg;
+        pb_range(ks, pb0, pb1, uimg);
         for (int pb = pb0; pb < pb1; ++pb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
@@ -600,7 +667,6 @@ conv_wgrad_kernel(const __grid_constant__ ConvWgradKParams p) {
   } else {
     const int q = warp & 3;
     const int row = q * 32 + lane;
-    const long long Ktot = (long long)taps * p.Ctot;
     int it = 0;
     for (int u = blockIdx.x; u < p.num_units; u += gridDim.x, ++it) {
       int tap, nt, mt, ks;
@@ -609,9 +675,11 @@ conv_wgrad_kernel(const __grid_constant__ ConvWgradKParams p) {
       const uint32_t aphase = (it >> 1) & 1;
       const int m = mt * 128 + row;
       const int bn = p.nt_w[nt];
-      const int pb0 = ks * p.pb_per_split;
-      const bool nonempty = pb0 < p.pix_blocks;
-      float* dst = p.dw + (long long)m * Ktot + (long long)tap * p.Ctot + p.nt_coff[nt];
+      int pb0, pb1, uimg;
+      pb_range(ks, pb0, pb1, uimg);
+      const bool nonempty = pb0 < pb1;
+      float* dst = p.dw + (long long)uimg * p.dw_img_stride + (long long)m * p.dw_ld + (long long)tap * p.Ctot +
+                   p.nt_coff[nt];
       mbar_wait(&tfull_bar[acc], aphase);
       tc_fence_after();
       const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.bn_max);
@@ -675,7 +743,7 @@ extern "C" int gdl_conv2d_nhwc_wgrad(const gdl_conv_wgrad_t* d, void* stream_) {
   while (p.caA > 16 && (d->Cout % p.caA) != 0) p.caA >>= 1;
 
   int N = d->N, H = d->H, W = d->W, oH = Ho, oW = Wo;
-  if (d->R == 1 && d->S == 1 && d->pad_h == 0 && d->pad_w == 0) {
+  if (d->R == 1 && d->S == 1 && d->pad_h == 0 && d->pad_w == 0 && !d->batched) {
     long long M = (long long)N * H * W;
     GDL_REQUIRE(M < (1ll << 31), GDL_ERR_UNSUPPORTED, "too many pixels");
     W = (int)M;
@@ -718,6 +786,25 @@ extern "C" int gdl_conv2d_nhwc_wgrad(const gdl_conv_wgrad_t* d, void* stream_) {
   if (st) return st;
 
   const int taps = d->R * d->S;
+  p.batched = d->batched;
+  p.pb_per_img = p.tiles_w * p.tiles_h;
+  p.dw_ld = d->dw_ld > 0 ? d->dw_ld : (long long)taps * Ctot;
+  p.dw_img_stride = d->dw_img_stride;
+  if (d->batched) {
+    // one independent product per image: split each image's pixel blocks on its own
+    GDL_REQUIRE(!(d->R == 1 && d->S == 1 && d->pad_h == 0 && d->pad_w == 0) || N == d->N, GDL_ERR_INVALID, "batched wgrad");
+    long long bu = (long long)p.m_tiles * nn * taps * N;
+    int ks = (int)((2ll * sm_count() + bu - 1) / bu);
+    int max_ks = p.pb_per_img / 8;
+    if (max_ks < 1) max_ks = 1;
+    if (ks > max_ks) ks = max_ks;
+    if (ks < 1) ks = 1;
+    p.pb_per_split = (p.pb_per_img + ks - 1) / ks;
+    p.ksplit = (p.pb_per_img + p.pb_per_split - 1) / p.pb_per_split;
+    long long units = bu * p.ksplit;
+    GDL_REQUIRE(units < (1ll << 31), GDL_ERR_UNSUPPORTED, "too many work units");
+    p.num_units = (int)units;
+  }
   long long base_units = (long long)p.m_tiles * nn * taps;
   // Split the pixel range: (a) the grid should see >= ~3 waves; (b) the pixels one wave of co-resident
   // units streams (dY + X rows of one split) should stay L2-resident so the 9 taps / channel tiles that
@@ -740,11 +827,13 @@ extern "C" int gdl_conv2d_nhwc_wgrad(const gdl_conv_wgrad_t* d, void* stream_) {
   if (max_ks < 1) max_ks = 1;
   if (ks > max_ks) ks = max_ks;
   if (ks < 1) ks = 1;
-  p.pb_per_split = (p.pix_blocks + ks - 1) / ks;
-  p.ksplit = (p.pix_blocks + p.pb_per_split - 1) / p.pb_per_split;
-  long long units = base_units * p.ksplit;
-  GDL_REQUIRE(units < (1ll << 31), GDL_ERR_UNSUPPORTED, "too many work units");
-  p.num_units = (int)units;
+  if (!d->batched) {
+    p.pb_per_split = (p.pix_blocks + ks - 1) / ks;
+    p.ksplit = (p.pix_blocks + p.pb_per_split - 1) / p.pb_per_split;
+    long long units = base_units * p.ksplit;
+    GDL_REQUIRE(units < (1ll << 31), GDL_ERR_UNSUPPORTED, "too many work units");
+    p.num_units = (int)units;
+  }
 
   p.a_bytes = kWgPix * 128 * 2;
   const int b_bytes = kWgPix * bn_max * 2;

@@ -40,6 +40,13 @@ class ConvFwd(C.Structure):
         ("ldo", C.c_int),
         ("bias", C.c_void_p),
         ("relu", C.c_int),
+        ("residual", C.c_void_p),
+        ("res_dtype", C.c_int),
+        ("ldr", C.c_int),
+        ("w_ld", C.c_int),
+        ("w_rows", C.c_int),
+        ("w_rows_per_img", C.c_int),
+        ("w_mn_major", C.c_int),
     ]
 
 
@@ -54,6 +61,9 @@ class ConvWgrad(C.Structure):
         ("ld_dy", C.c_int),
         ("dtype", C.c_int),
         ("dw", C.c_void_p),
+        ("dw_ld", C.c_int),
+        ("dw_img_stride", C.c_longlong),
+        ("batched", C.c_int),
     ]
 
 

@@ -63,6 +63,8 @@ class RawConv:
     col: torch.Tensor | None = None  # im2col matrix (strided / narrow-input convs)
     kpad: int = 0
     cin_store: int = 0  # channels per pixel as stored (>= weight.shape[1] when the input is padded)
+    wshape: tuple | None = None  # (Cout, Cin, R, S) view of the parameter (nn.Linear weights are (Cout, Cin))
+    bias: torch.Tensor | None = None
 
 
 @dataclass
@@ -94,14 +96,17 @@ class Engine:
         self._head = None
 
     # ------------------------------------------------------------------ parameters
-    def packed(self, w: torch.Tensor, mode: int, ld: int = 0) -> torch.Tensor:
+    def packed(self, w: torch.Tensor, mode: int, ld: int = 0, wshape: tuple | None = None) -> torch.Tensor:
         """16-bit operand of a weight, cached until the parameter is modified in place."""
         key = (w.data_ptr(), mode, ld, self.dtype)
         ver = w._version
         hit = self._wcache.get(key)
         if hit is not None and hit[0] == ver:
             return hit[1]
-        out = ops.pack_conv_weight(w.detach(), self.dtype, mode, ld)
+        wv = w.detach()
+        if wshape is not None:
+            wv = wv.view(wshape)
+        out = ops.pack_conv_weight(wv, self.dtype, mode, ld)
         self._wcache[key] = (ver, out)
         return out
 
@@ -120,34 +125,42 @@ class Engine:
     # ------------------------------------------------------------------ convolution
     def conv_raw(self, srcs: list[Act], weight: torch.nn.Parameter, stride: int, pad: int,
                  bias: torch.Tensor | None = None, out_dtype: torch.dtype | None = None,
-                 relu: bool = False) -> RawConv:
-        cout, cin, r, s = weight.shape
+                 relu: bool = False, wshape: tuple | None = None, residual: torch.Tensor | None = None) -> RawConv:
+        """Convolution / linear layer.  `wshape` views the parameter as (Cout, Cin, R, S) (nn.Linear);
+        `residual` (N,H,W,Cout) is added in the GEMM epilogue (fp32 residual stream)."""
+        wshape = tuple(wshape) if wshape is not None else tuple(weight.shape)
+        cout, cin, r, s = wshape
         stored = sum(a.t.shape[3] for a in srcs)
         direct = stride == 1 and all(a.t.shape[3] % 16 == 0 for a in srcs) and stored == cin
         if direct:
-            wp = self.packed(weight, 0)
+            wp = self.packed(weight, 0, 0, wshape)
             x = ops.conv2d_fwd([a.t for a in srcs], wp, cout, r, s, pad, pad, out_dtype=out_dtype, bias=bias,
-                               relu=relu)
-            return RawConv(x, srcs, weight, stride, pad, cin_store=stored)
+                               relu=relu, residual=residual)
+            return RawConv(x, srcs, weight, stride, pad, cin_store=stored, wshape=wshape, bias=bias)
         if len(srcs) != 1:
             raise NotImplementedError("strided / narrow-input convs take a single source")
         a = srcs[0]
         k = r * s * cin
         kpad = (k + 63) // 64 * 64
-        if stored != cin:  # zero-padded input channels: gather only the real ones
-            col = ops.im2col(a.t, cin, r, s, stride, pad, kpad)
-        else:
-            col = ops.im2col(a.t, cin, r, s, stride, pad, kpad)
-        wp = self.packed(weight, 0, kpad)
-        x = ops.conv2d_fwd([col], wp, cout, 1, 1, 0, 0, out_dtype=out_dtype, bias=bias, relu=relu)
-        return RawConv(x, srcs, weight, stride, pad, col=col if self.training else None, kpad=kpad, cin_store=stored)
+        col = ops.im2col(a.t, cin, r, s, stride, pad, kpad)
+        wp = self.packed(weight, 0, kpad, wshape)
+        x = ops.conv2d_fwd([col], wp, cout, 1, 1, 0, 0, out_dtype=out_dtype, bias=bias, relu=relu, residual=residual)
+        return RawConv(x, srcs, weight, stride, pad, col=col if self.training else None, kpad=kpad, cin_store=stored,
+                       wshape=wshape, bias=bias)
 
-    def conv_backward(self, rc: RawConv, dx: torch.Tensor) -> None:
-        """dx = gradient w.r.t. the raw conv output (N,Ho,Wo,Cout'), Cout' >= Cout zero padded."""
+    def conv_backward(self, rc: RawConv, dx: torch.Tensor, dgrad_residual: torch.Tensor | None = None) -> None:
+        """dx = gradient w.r.t. the raw conv output (N,Ho,Wo,Cout'), Cout' >= Cout zero padded.
+        Weight (and bias) gradients go to grad_buffer; input gradients are registered as gradient sources on
+        the source activations.  `dgrad_residual` is added to the (single-source) input gradient in the dgrad
+        GEMM epilogue (sum of two gradient paths without an extra pass)."""
         w = rc.weight
-        cout, cin, r, s = w.shape
+        cout, cin, r, s = rc.wshape
         coutp = dx.shape[3]
         dev = dx.device
+        if rc.bias is not None and rc.bias.requires_grad:
+            sums = torch.empty(2 * coutp, dtype=self.acc_dtype, device=dev)
+            ops.bn_stats(dx, sums)  # column sums (no pivot)
+            self.grad_buffer(rc.bias, False).copy_(sums[:cout])
         if rc.col is None:
             if w.requires_grad:
                 if r == 1 and s == 1 and coutp == cout:
@@ -156,10 +169,10 @@ class Engine:
                 else:
                     dw = torch.zeros((coutp, r * s * cin), dtype=self.acc_dtype, device=dev)
                     ops.conv2d_wgrad([a.t for a in rc.srcs], dx, r, s, rc.pad, rc.pad, dw)
-                    ops.unpack_conv_wgrad(dw, self.grad_buffer(w, False), r * s * cin)
+                    ops.unpack_conv_wgrad(dw, self.grad_buffer(w, False).view(cout, cin, r, s), r * s * cin)
             if any(a.needs_grad for a in rc.srcs):
-                wt = self._dgrad_weight(w, coutp)
-                dcat = ops.conv2d_fwd([dx], wt, cin, r, s, r - 1 - rc.pad, s - 1 - rc.pad)
+                wt = self._dgrad_weight(w, coutp, rc.wshape)
+                dcat = ops.conv2d_fwd([dx], wt, cin, r, s, r - 1 - rc.pad, s - 1 - rc.pad, residual=dgrad_residual)
                 off = 0
                 for a in rc.srcs:
                     c = a.t.shape[3]
@@ -171,25 +184,25 @@ class Engine:
             if w.requires_grad:
                 dw = torch.zeros((coutp, rc.kpad), dtype=self.acc_dtype, device=dev)
                 ops.conv2d_wgrad([rc.col], dx, 1, 1, 0, 0, dw)
-                ops.unpack_conv_wgrad(dw, self.grad_buffer(w, False), rc.kpad)
+                ops.unpack_conv_wgrad(dw, self.grad_buffer(w, False).view(cout, cin, r, s), rc.kpad)
             if a.needs_grad:
                 if coutp != cout:
                     raise NotImplementedError("padded-output dgrad through im2col")
-                wt = self.packed(w, 2)  # [(r,s,c)][Cout]
+                wt = self.packed(w, 2, 0, rc.wshape)  # [(r,s,c)][Cout]
                 dcol = ops.conv2d_fwd([dx], wt, r * s * cin, 1, 1, 0, 0)
                 n, h, wd, c = a.t.shape
                 a.gsrcs.append((ops.col2im(dcol, n, h, wd, c, r, s, rc.stride, rc.pad), 0))
 
-    def _dgrad_weight(self, w: torch.Tensor, coutp: int) -> torch.Tensor:
-        cout = w.shape[0]
+    def _dgrad_weight(self, w: torch.Tensor, coutp: int, wshape: tuple) -> torch.Tensor:
+        cout = wshape[0]
         if coutp == cout:
-            return self.packed(w, 1)
+            return self.packed(w, 1, 0, wshape)
         key = (w.data_ptr(), "dgrad_pad", coutp, self.dtype)
         hit = self._wcache.get(key)
         if hit is not None and hit[0] == w._version:
             return hit[1]
-        wpad = torch.zeros((coutp, *w.shape[1:]), dtype=self.acc_dtype, device=w.device)
-        wpad[:cout] = w.detach()
+        wpad = torch.zeros((coutp, *wshape[1:]), dtype=self.acc_dtype, device=w.device)
+        wpad[:cout] = w.detach().view(wshape)
         out = ops.pack_conv_weight(wpad, self.dtype, 1)
         self._wcache[key] = (w._version, out)
         return out
@@ -314,13 +327,8 @@ class Engine:
 
     def head_backward(self, dlogits16: torch.Tensor) -> None:
         """dlogits16: (N,H,W,16k) 16-bit, channels >= K zero."""
-        rc, bias = self._head
-        if bias is not None and bias.requires_grad:
-            k = bias.numel()
-            sums = torch.empty(2 * dlogits16.shape[3], dtype=self.acc_dtype, device=dlogits16.device)
-            ops.bn_stats(dlogits16, sums)  # column sums (no pivot)
-            self.grad_buffer(bias, False).copy_(sums[:k])
-        self.conv_backward(rc, dlogits16)
+        rc, _ = self._head
+        self.conv_backward(rc, dlogits16)  # weight, bias and input gradients
 
     # ------------------------------------------------------------------ driver
     def backward(self) -> None:

@@ -1,0 +1,427 @@
+"""B200-native SegFormer (MixTransformer encoder + all-MLP decoder + bilinear x4 head).
+
+Drop-in for `SegFormerSegmentationModel(encoder, in_channels, weights, freeze_layers, num_classes)`
+(geo_deep_learning/models/segmentation/segformer.py:15-57): same constructor keywords, same
+`state_dict` keys/shapes (`encoder.patch_embed1.proj.weight`, `encoder.block1.0.attn.q.weight`,
+`decoder.linear_fuse.0.weight`, ...), same forward contract (float NCHW image -> (N, K, H, W) logits).
+The nn.* sub-modules only hold parameters; arithmetic runs on libgdlb200.so:
+
+  * tokens stay NHWC == (B, N, C) end to end (no NLC<->NCHW copies, mix_transformer.py:499,541-546);
+  * every Linear / 1x1 conv / patch-embed / sr conv is the tcgen05 implicit-GEMM kernel (bias and the
+    residual add fused in its epilogue); attention is q.k^T -> softmax kernel -> P.V with the k/v slices
+    of the kv tensor used in place as batched GEMM operands (no per-head transposes or copies);
+  * the residual stream is kept in fp32 (what torch.autocast does), LayerNorm emits the 16-bit operand
+    of the next GEMM;
+  * the decoder reads its 4 upsampled projections as a virtual concat (the 3072-channel torch.cat of
+    segformer_mlp.py:127 is never materialised).
+
+Stochastic layers (DropPath, Dropout2d) are identity: parity is defined without them and
+they are not implemented yet (drop_path_rate / dropout_ratio must be 0 for training-time equivalence).
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+import torch.nn as nn
+
+from .. import ops
+from ..engine import Act, BNParams, Engine
+
+MIT_CFG = {
+    # name: (embed_dims, heads, depths, decoder embedding dim)
+    "mit_b0": ((32, 64, 160, 256), (1, 2, 5, 8), (2, 2, 2, 2), 256),
+    "mit_b1": ((64, 128, 320, 512), (1, 2, 5, 8), (2, 2, 2, 2), 256),
+    "mit_b2": ((64, 128, 320, 512), (1, 2, 5, 8), (3, 4, 6, 3), 768),
+    "mit_b3": ((64, 128, 320, 512), (1, 2, 5, 8), (3, 4, 18, 3), 768),
+    "mit_b4": ((64, 128, 320, 512), (1, 2, 5, 8), (3, 8, 27, 3), 768),
+    "mit_b5": ((64, 128, 320, 512), (1, 2, 5, 8), (3, 6, 40, 3), 768),
+}
+SR_RATIOS = (8, 4, 2, 1)
+
+
+def _init(m: nn.Module) -> None:  # MixVisionTransformer._init_weights (mix_transformer.py:425-439)
+    if isinstance(m, nn.Linear):
+        nn.init.trunc_normal_(m.weight, std=0.02, a=-2.0, b=2.0)
+        if m.bias is not None:
+            nn.init.constant_(m.bias, 0)
+    elif isinstance(m, nn.LayerNorm):
+        nn.init.constant_(m.bias, 0)
+        nn.init.constant_(m.weight, 1.0)
+    elif isinstance(m, nn.Conv2d):
+        fan_out = m.kernel_size[0] * m.kernel_size[1] * m.out_channels // m.groups
+        m.weight.data.normal_(0, math.sqrt(2.0 / fan_out))
+        if m.bias is not None:
+            m.bias.data.zero_()
+
+
+class _PatchEmbed(nn.Module):
+    def __init__(self, k: int, stride: int, cin: int, dim: int) -> None:
+        super().__init__()
+        self.proj = nn.Conv2d(cin, dim, k, stride=stride, padding=k // 2)
+        self.norm = nn.LayerNorm(dim)  # eps 1e-5 (plain nn.LayerNorm, mix_transformer.py:251)
+
+
+class _Attention(nn.Module):
+    def __init__(self, dim: int, heads: int, sr: int) -> None:
+        super().__init__()
+        self.q = nn.Linear(dim, dim)
+        self.kv = nn.Linear(dim, 2 * dim)
+        self.proj = nn.Linear(dim, dim)
+        self.sr_ratio, self.num_heads = sr, heads
+        if sr > 1:
+            self.sr = nn.Conv2d(dim, dim, sr, stride=sr)
+            self.norm = nn.LayerNorm(dim)  # eps 1e-5 (mix_transformer.py:100)
+
+
+class _DWConv(nn.Module):
+    def __init__(self, dim: int) -> None:
+        super().__init__()
+        self.dwconv = nn.Conv2d(dim, dim, 3, 1, 1, bias=True, groups=dim)
+
+
+class _Mlp(nn.Module):
+    def __init__(self, dim: int) -> None:
+        super().__init__()
+        self.fc1 = nn.Linear(dim, 4 * dim)
+        self.dwconv = _DWConv(4 * dim)
+        self.fc2 = nn.Linear(4 * dim, dim)
+
+
+class _Block(nn.Module):
+    def __init__(self, dim: int, heads: int, sr: int) -> None:
+        super().__init__()
+        self.norm1 = nn.LayerNorm(dim, eps=1e-6)
+        self.attn = _Attention(dim, heads, sr)
+        self.norm2 = nn.LayerNorm(dim, eps=1e-6)
+        self.mlp = _Mlp(dim)
+
+
+class MixTransformerEncoder(nn.Module):
+    def __init__(self, name: str, in_channels: int) -> None:
+        super().__init__()
+        if name not in MIT_CFG:
+            raise KeyError(f"Wrong encoder name `{name}`, supported encoders: {list(MIT_CFG)}")
+        self.name = name
+        dims, heads, depths, _ = MIT_CFG[name]
+        cin = in_channels
+        for s in range(4):
+            setattr(self, f"patch_embed{s + 1}", _PatchEmbed(7 if s == 0 else 3, 4 if s == 0 else 2, cin, dims[s]))
+            cin = dims[s]
+        for s in range(4):
+            setattr(self, f"block{s + 1}", nn.ModuleList(_Block(dims[s], heads[s], SR_RATIOS[s]) for _ in range(depths[s])))
+            setattr(self, f"norm{s + 1}", nn.LayerNorm(dims[s], eps=1e-6))
+        self.apply(_init)
+        self.out_channels = dims
+
+
+class _MLPProj(nn.Module):
+    def __init__(self, cin: int, emb: int) -> None:
+        super().__init__()
+        self.proj = nn.Linear(cin, emb)
+
+
+class SegFormerDecoder(nn.Module):
+    def __init__(self, name: str, num_classes: int) -> None:
+        super().__init__()
+        dims, _, _, emb = MIT_CFG[name]
+        for lvl in (4, 3, 2, 1):
+            setattr(self, f"linear_c{lvl}", _MLPProj(dims[lvl - 1], emb))
+        self.linear_fuse = nn.Sequential(nn.Conv2d(4 * emb, emb, 1, bias=False), nn.BatchNorm2d(emb), nn.ReLU(inplace=True))
+        self.linear_pred = nn.Conv2d(emb, num_classes, 1)
+        self.embedding_dim = emb
+
+
+class _Saved:
+    """per-op saved tensors for the hand-written backward"""
+
+    def __init__(self, **kw) -> None:
+        self.__dict__.update(kw)
+
+
+def _lin_shape(w: torch.Tensor) -> tuple:
+    return (w.shape[0], w.shape[1], 1, 1)
+
+
+class SegFormer(nn.Module):
+    def __init__(self, encoder: str = "mit_b0", in_channels: int = 3, weights: str | None = None,
+                 freeze_layers: list[str] | None = None, num_classes: int = 1, *, use_dynamic_encoder: bool = False,
+                 compute_dtype: torch.dtype = torch.bfloat16) -> None:
+        super().__init__()
+        if use_dynamic_encoder:
+            raise NotImplementedError("DynamicMixTransformer (SURVEY §8f rank 4) is not implemented")
+        if weights is not None:
+            raise ValueError("weights must be None: load pretrained tensors through load_state_dict")
+        self.encoder = MixTransformerEncoder(encoder, in_channels)
+        self.decoder = SegFormerDecoder(encoder, num_classes)
+        self.name = encoder
+        self.num_classes = num_classes
+        self.compute_dtype = compute_dtype
+        self._wcache: dict = {}
+        self.sync_bn_group = None
+        self.last_engine: Engine | None = None
+        if freeze_layers:  # BaseSegmentationModel._freeze_layers (models/segmentation/base.py:29-44)
+            for n, p in self.named_parameters():
+                if any(layer in n for layer in freeze_layers):
+                    p.requires_grad = False
+
+    # ====================================================================================== forward
+    def _linear(self, eng: Engine, x: torch.Tensor, lin: nn.Linear, *, residual=None, out_dtype=None, needs_grad=True):
+        a = Act(x, needs_grad=needs_grad)
+        rc = eng.conv_raw([a], lin.weight, 1, 0, bias=lin.bias, out_dtype=out_dtype, wshape=_lin_shape(lin.weight),
+                          residual=residual)
+        return rc, a
+
+    def _attention_fwd(self, eng: Engine, a16: torch.Tensor, attn: _Attention, stream: torch.Tensor):
+        """returns (new fp32 stream, saved).  a16 = LN1(stream) as 16-bit tokens (B,h,w,C)."""
+        b, h, w, c = a16.shape
+        heads = attn.num_heads
+        d = c // heads
+        n = h * w
+        dt = eng.dtype
+        rc_q, act_a = self._linear(eng, a16, attn.q)
+        q = rc_q.x
+        sv = _Saved(act_a=act_a, rc_q=rc_q, heads=heads, d=d)
+        if attn.sr_ratio > 1:
+            rc_sr = eng.conv_raw([act_a], attn.sr.weight, attn.sr_ratio, 0, bias=attn.sr.bias)
+            kvin, st_sr = ops.layernorm_fwd(rc_sr.x, attn.norm.weight, attn.norm.bias, attn.norm.eps, dt, eng.training)
+            sv.rc_sr, sv.st_sr = rc_sr, st_sr
+        else:
+            kvin = a16
+        rc_kv, act_kvin = self._linear(eng, kvin, attn.kv)
+        kv = rc_kv.x
+        nk = kv.shape[1] * kv.shape[2]
+        lp = (nk + 15) // 16 * 16
+        kv2 = kv.view(b * nk, 2 * c)
+        q4 = q.view(b, 1, n, c)
+        scores = torch.empty((b, 1, n, heads * lp), dtype=dt, device=q.device)
+        for hd in range(heads):
+            ops.conv2d_fwd([q4[..., hd * d:(hd + 1) * d]], kv2[:, hd * d:(hd + 1) * d], nk, 1, 1, 0, 0,
+                           out=scores[..., hd * lp:hd * lp + nk], w_rows_per_img=nk)
+        p = ops.softmax_fwd(scores.view(b, n, heads, lp), d ** -0.5, nk)
+        p4 = p.view(b, 1, n, heads * lp)
+        o = torch.empty((b, 1, n, c), dtype=dt, device=q.device)
+        for hd in range(heads):
+            ops.conv2d_fwd([p4[..., hd * lp:(hd + 1) * lp]], kv2[:, c + hd * d:c + (hd + 1) * d], d, 1, 1, 0, 0,
+                           out=o[..., hd * d:(hd + 1) * d], w_rows_per_img=nk, w_mn_major=True)
+        rc_proj, act_o = self._linear(eng, o.view(b, h, w, c), attn.proj, residual=stream, out_dtype=stream.dtype)
+        sv.__dict__.update(rc_kv=rc_kv, act_kvin=act_kvin, kv2=kv2, q4=q4, p4=p4, nk=nk, lp=lp, rc_proj=rc_proj,
+                           act_o=act_o)
+        return rc_proj.x, sv
+
+    def _mlp_fwd(self, eng: Engine, a16: torch.Tensor, mlp: _Mlp, stream: torch.Tensor):
+        rc1, act_a = self._linear(eng, a16, mlp.fc1)
+        dw = mlp.dwconv.dwconv
+        y, pre = ops.dwconv3x3_gelu_fwd(rc1.x, dw.weight.detach().view(dw.weight.shape[0], 9), dw.bias)
+        rc2, act_y = self._linear(eng, y, mlp.fc2, residual=stream, out_dtype=stream.dtype)
+        return rc2.x, _Saved(rc1=rc1, act_a=act_a, pre=pre, rc2=rc2, act_y=act_y)
+
+    def run(self, eng: Engine, x: Act) -> torch.Tensor:
+        """x: NHWC 16-bit image (channels possibly zero padded).  Returns fp32 logits (N,H,W,K)."""
+        enc, dec = self.encoder, self.decoder
+        dims, heads, depths, emb = MIT_CFG[self.name]
+        dt = eng.dtype
+        acc = eng.acc_dtype
+        _, hh, ww, _ = x.t.shape
+        if hh % 32 or ww % 32:
+            raise ValueError(f"input height/width ({hh},{ww}) must be divisible by 32")
+        stages = []
+        cur = x
+        for s in range(4):
+            pe: _PatchEmbed = getattr(enc, f"patch_embed{s + 1}")
+            k, stride = pe.proj.kernel_size[0], pe.proj.stride[0]
+            rc_pe = eng.conv_raw([cur], pe.proj.weight, stride, k // 2, bias=pe.proj.bias)
+            stream, st_pe = ops.layernorm_fwd(rc_pe.x, pe.norm.weight, pe.norm.bias, pe.norm.eps, acc, eng.training)
+            blocks = []
+            for blk in getattr(enc, f"block{s + 1}"):
+                a1, st1 = ops.layernorm_fwd(stream, blk.norm1.weight, blk.norm1.bias, blk.norm1.eps, dt, eng.training)
+                x_in = stream
+                stream, sv_attn = self._attention_fwd(eng, a1, blk.attn, stream)
+                a2, st2 = ops.layernorm_fwd(stream, blk.norm2.weight, blk.norm2.bias, blk.norm2.eps, dt, eng.training)
+                x_mid = stream
+                stream, sv_mlp = self._mlp_fwd(eng, a2, blk.mlp, stream)
+                blocks.append(_Saved(blk=blk, x_in=x_in, st1=st1, attn=sv_attn, x_mid=x_mid, st2=st2, mlp=sv_mlp))
+            nrm = getattr(enc, f"norm{s + 1}")
+            feat, st_out = ops.layernorm_fwd(stream, nrm.weight, nrm.bias, nrm.eps, dt, eng.training)
+            feat_act = Act(feat)
+            stages.append(_Saved(pe=pe, rc_pe=rc_pe, st_pe=st_pe, blocks=blocks, norm=nrm, x_out=stream, st_out=st_out,
+                                 feat=feat_act, src=cur))
+            cur = feat_act
+        # ---- decoder (segformer_mlp.py:77-130)
+        h1, w1 = stages[0].feat.t.shape[1:3]
+        projs = []
+        for lvl in (4, 3, 2, 1):
+            f = stages[lvl - 1].feat
+            lin = getattr(dec, f"linear_c{lvl}").proj
+            rc = eng.conv_raw([f], lin.weight, 1, 0, bias=lin.bias, wshape=_lin_shape(lin.weight))
+            up = Act(ops.bilinear_fwd(rc.x, h1, w1)) if lvl != 1 else Act(rc.x)
+            projs.append(_Saved(lvl=lvl, rc=rc, up=up))
+        rc_fuse = eng.conv_raw([p.up for p in projs], dec.linear_fuse[0].weight, 1, 0)
+        bn = dec.linear_fuse[1]
+        bn_state = eng.bn_prepare(rc_fuse, BNParams(bn.weight, bn.bias, bn.running_mean, bn.running_var,
+                                                    bn.num_batches_tracked, bn.eps, bn.momentum or 0.1))
+        z = eng.bn_act(rc_fuse, bn_state, relu=True)  # registers its own backward on the tape
+        rc_pred = eng.conv_raw([z], dec.linear_pred.weight, 1, 0, bias=dec.linear_pred.bias, out_dtype=acc)
+        logits = ops.bilinear_fwd(rc_pred.x, hh, ww)
+        eng.named = {f"c{s + 1}": stages[s].feat for s in range(4)}
+        self._saved = _Saved(stages=stages, projs=projs, rc_pred=rc_pred, z=z, h1=h1, w1=w1, hh=hh, ww=ww)
+        return logits
+
+    # ====================================================================================== backward
+    def _pgrads_ln(self, eng: Engine, ln: nn.LayerNorm):
+        need = ln.weight.requires_grad or ln.bias.requires_grad
+        return torch.zeros((2, ln.weight.numel()), dtype=eng.acc_dtype, device=ln.weight.device) if need else None
+
+    def _store_ln_grads(self, eng: Engine, ln: nn.LayerNorm, pg) -> None:
+        if pg is None:
+            return
+        if ln.weight.requires_grad:
+            eng.grad_buffer(ln.weight, False).copy_(pg[0])
+        if ln.bias.requires_grad:
+            eng.grad_buffer(ln.bias, False).copy_(pg[1])
+
+    @staticmethod
+    def _take(act: Act) -> torch.Tensor:
+        """the single registered gradient source of an activation (contiguous rows or a channel slice)"""
+        assert len(act.gsrcs) == 1 and act.gsrcs[0][1] == 0
+        g = act.gsrcs[0][0]
+        act.gsrcs.clear()
+        return g
+
+    def _mlp_bwd(self, eng: Engine, blk: _Block, sv, g16: torch.Tensor) -> torch.Tensor:
+        """g16: stream gradient (16-bit copy).  Returns d(LN2 output) as 16-bit."""
+        eng.conv_backward(sv.rc2, g16)
+        dy = self._take(sv.act_y)
+        dw = blk.mlp.dwconv.dwconv
+        c4 = dw.weight.shape[0]
+        pg = torch.zeros((c4, 10), dtype=eng.acc_dtype, device=dy.device)
+        df1 = ops.dwconv3x3_gelu_bwd(dy, sv.pre, sv.rc1.x, dw.weight.detach().view(c4, 9), pg)
+        if dw.weight.requires_grad:
+            eng.grad_buffer(dw.weight, False).view(c4, 9).copy_(pg[:, :9])
+        if dw.bias is not None and dw.bias.requires_grad:
+            eng.grad_buffer(dw.bias, False).copy_(pg[:, 9])
+        eng.conv_backward(sv.rc1, df1)
+        return self._take(sv.act_a)
+
+    def _attention_bwd(self, eng: Engine, blk: _Block, sv, g16: torch.Tensor) -> torch.Tensor:
+        """g16: stream gradient (16-bit).  Returns d(LN1 output) as 16-bit (sum of the q and k/v paths)."""
+        attn = blk.attn
+        heads, d, nk, lp = sv.heads, sv.d, sv.nk, sv.lp
+        eng.conv_backward(sv.rc_proj, g16)
+        do = self._take(sv.act_o)  # (B,h,w,C)
+        b, h, w, c = do.shape
+        n = h * w
+        dt = eng.dtype
+        do4 = do.view(b, 1, n, c)
+        dp = torch.empty((b, 1, n, heads * lp), dtype=dt, device=do.device)
+        for hd in range(heads):
+            ops.conv2d_fwd([do4[..., hd * d:(hd + 1) * d]], sv.kv2[:, c + hd * d:c + (hd + 1) * d], nk, 1, 1, 0, 0,
+                           out=dp[..., hd * lp:hd * lp + nk], w_rows_per_img=nk)
+        ds = ops.softmax_bwd(sv.p4.view(b, n, heads, lp), dp.view(b, n, heads, lp), d ** -0.5, nk)
+        ds4 = ds.view(b, 1, n, heads * lp)
+        dq = torch.empty((b, 1, n, c), dtype=dt, device=do.device)
+        dkv32 = torch.zeros((b, lp, 2 * c), dtype=eng.acc_dtype, device=do.device)
+        for hd in range(heads):
+            ops.conv2d_fwd([ds4[..., hd * lp:(hd + 1) * lp]], sv.kv2[:, hd * d:(hd + 1) * d], d, 1, 1, 0, 0,
+                           out=dq[..., hd * d:(hd + 1) * d], w_rows_per_img=nk, w_mn_major=True)
+            # dV[b] = P^T dO,  dK[b] = dS^T q   (one independent product per image)
+            ops.conv2d_wgrad([do4[..., hd * d:(hd + 1) * d]], sv.p4[..., hd * lp:(hd + 1) * lp], 1, 1, 0, 0,
+                             dkv32[:, :, c + hd * d:c + (hd + 1) * d])
+            ops.conv2d_wgrad([sv.q4[..., hd * d:(hd + 1) * d]], ds4[..., hd * lp:(hd + 1) * lp], 1, 1, 0, 0,
+                             dkv32[:, :, hd * d:(hd + 1) * d])
+        dkv = ops.cast_f32(dkv32 if lp == nk else dkv32[:, :nk].contiguous(), dt)
+        eng.conv_backward(sv.rc_kv, dkv.view(sv.rc_kv.x.shape))
+        dkvin = self._take(sv.act_kvin)
+        if attn.sr_ratio > 1:
+            pg = self._pgrads_ln(eng, attn.norm)
+            _, dsr = ops.layernorm_bwd(dkvin, sv.rc_sr.x, sv.st_sr, attn.norm.weight, want32=False, dtype16=dt, pgrads=pg)
+            self._store_ln_grads(eng, attn.norm, pg)
+            eng.conv_backward(sv.rc_sr, dsr)
+            other = self._take(sv.act_a)  # gradient that reached LN1's output through sr -> kv
+        else:
+            other = dkvin
+        eng.conv_backward(sv.rc_q, dq.view(b, h, w, c), dgrad_residual=other)
+        return self._take(sv.act_a)
+
+    def backward(self, eng: Engine, dlogits: torch.Tensor) -> None:
+        """dlogits: fp32 (N,H,W,K) gradient of the loss w.r.t. the logits returned by run()."""
+        S = self._saved
+        dt = eng.dtype
+        k = dlogits.shape[3]
+        d128 = ops.bilinear_bwd(dlogits, S.h1, S.w1)
+        d16 = ops.normalize_to_nhwc(d128, False, dt, (k + 15) // 16 * 16)
+        eng.conv_backward(S.rc_pred, d16)
+        eng.backward()  # linear_fuse BN/ReLU + the fuse GEMM: registers gradients on the 4 projections
+        feat_grads: list[list[torch.Tensor]] = [[] for _ in range(4)]
+        for p in S.projs:
+            g = self._take(p.up)
+            if p.lvl != 1:
+                g = ops.bilinear_bwd(g, p.rc.x.shape[1], p.rc.x.shape[2])
+            eng.conv_backward(p.rc, g)
+            feat_grads[p.lvl - 1].append(self._take(S.stages[p.lvl - 1].feat))
+        for s in (3, 2, 1, 0):
+            st = S.stages[s]
+            gs = feat_grads[s]
+            if len(gs) == 2:
+                g = torch.empty(st.feat.t.shape, dtype=dt, device=st.feat.t.device)
+                ops.grad_gather([(gs[0], 0), (gs[1], 0)], st.feat.t.shape, dt, g=g)
+            else:
+                g = gs[0]
+            pg = self._pgrads_ln(eng, st.norm)
+            gstream, g16 = ops.layernorm_bwd(g, st.x_out, st.st_out, st.norm.weight, want32=True, dtype16=dt, pgrads=pg)
+            self._store_ln_grads(eng, st.norm, pg)
+            for bs in reversed(st.blocks):
+                blk = bs.blk
+                da2 = self._mlp_bwd(eng, blk, bs.mlp, g16)
+                pg = self._pgrads_ln(eng, blk.norm2)
+                gstream, g16 = ops.layernorm_bwd(da2, bs.x_mid, bs.st2, blk.norm2.weight, add=gstream, want32=True,
+                                                 dtype16=dt, pgrads=pg)
+                self._store_ln_grads(eng, blk.norm2, pg)
+                da1 = self._attention_bwd(eng, blk, bs.attn, g16)
+                pg = self._pgrads_ln(eng, blk.norm1)
+                gstream, g16 = ops.layernorm_bwd(da1, bs.x_in, bs.st1, blk.norm1.weight, add=gstream, want32=True,
+                                                 dtype16=dt, pgrads=pg)
+                self._store_ln_grads(eng, blk.norm1, pg)
+            pg = self._pgrads_ln(eng, st.pe.norm)
+            _, dpe = ops.layernorm_bwd(gstream, st.rc_pe.x, st.st_pe, st.pe.norm.weight, want32=False, dtype16=dt, pgrads=pg)
+            self._store_ln_grads(eng, st.pe.norm, pg)
+            eng.conv_backward(st.rc_pe, dpe)
+            if s > 0:
+                feat_grads[s - 1].append(self._take(S.stages[s - 1].feat))
+        self._saved = None
+
+    # ====================================================================================== nn.Module surface
+    def _input(self, image: torch.Tensor) -> Act:
+        c = image.shape[1]
+        x = ops.normalize_to_nhwc(image.contiguous().float(), True, self.compute_dtype, (c + 7) // 8 * 8)
+        return Act(x, needs_grad=False)
+
+    def forward(self, img: torch.Tensor) -> torch.Tensor:
+        if not img.is_cuda:
+            raise RuntimeError("gdl_b200.SegFormer runs on CUDA (sm_100a) only; there is no CPU fallback")
+        params = list(self.parameters())
+        if torch.is_grad_enabled() and self.training and any(p.requires_grad for p in params):
+            return _SegFormerFn.apply(self, img, *params)
+        with torch.no_grad():
+            eng = Engine(self.compute_dtype, training=False, wcache=self._wcache)
+            logits = self.run(eng, self._input(img))
+            self._saved = None
+        return logits.permute(0, 3, 1, 2)
+
+
+class _SegFormerFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, model: SegFormer, image: torch.Tensor, *params: torch.Tensor) -> torch.Tensor:
+        eng = Engine(model.compute_dtype, training=True, wcache=model._wcache, sync_bn_group=model.sync_bn_group)
+        logits = model.run(eng, model._input(image))
+        ctx.eng, ctx.model, ctx.params = eng, model, params
+        model.last_engine = eng
+        return logits.permute(0, 3, 1, 2)
+
+    @staticmethod
+    def backward(ctx, dlogits: torch.Tensor):
+        eng: Engine = ctx.eng
+        ctx.model.backward(eng, dlogits.permute(0, 2, 3, 1).contiguous().float())
+        grads = tuple(eng.param_grads.get(id(p)) if p.requires_grad else None for p in ctx.params)
+        ctx.eng = None
+        return (None, None, *grads)

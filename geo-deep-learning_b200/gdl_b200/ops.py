@@ -128,8 +128,10 @@ def _fill_srcs(desc, srcs: Sequence[torch.Tensor]):
 def conv2d_fwd(srcs: Sequence[torch.Tensor], weight: torch.Tensor, cout: int, r: int, s: int,
                pad_h: int, pad_w: int, *, out: torch.Tensor | None = None,
                out_dtype: torch.dtype | None = None, bias: torch.Tensor | None = None,
-               relu: bool = False) -> torch.Tensor:
-    """gdl_conv2d_nhwc_fwd. `weight` is the packed [Cout][R][S][Ctot] 16-bit operand."""
+               relu: bool = False, residual: torch.Tensor | None = None, w_ld: int = 0, w_rows: int = 0,
+               w_rows_per_img: int = 0, w_mn_major: bool = False) -> torch.Tensor:
+    """gdl_conv2d_nhwc_fwd. `weight` is the packed [Cout][R][S][Ctot] 16-bit operand (or, with the w_*
+    options, a slice of an activation tensor used as the B operand of an attention GEMM)."""
     d = L.ConvFwd()
     n, h, w = _fill_srcs(d, srcs)
     dt = srcs[0].dtype
@@ -144,6 +146,13 @@ def conv2d_fwd(srcs: Sequence[torch.Tensor], weight: torch.Tensor, cout: int, r:
     d.ldo = out.stride(2)
     d.bias = bias.data_ptr() if bias is not None else None
     d.relu = int(relu)
+    if residual is not None:
+        d.residual = residual.data_ptr()
+        d.res_dtype = L.dt_code(residual.dtype)
+        d.ldr = residual.stride(2)
+    if w_rows_per_img or w_mn_major:  # `weight` is a 2-D view [rows][cols] of an activation tensor
+        w_ld, w_rows = weight.stride(0), weight.shape[0]
+    d.w_ld, d.w_rows, d.w_rows_per_img, d.w_mn_major = w_ld, w_rows, w_rows_per_img, int(w_mn_major)
     e0 = _PROFILER.begin() if _PROFILER is not None else None
     L.check(L.load().gdl_conv2d_nhwc_fwd(C.byref(d), L.stream_ptr()))
     _count()
@@ -156,7 +165,8 @@ def conv2d_fwd(srcs: Sequence[torch.Tensor], weight: torch.Tensor, cout: int, r:
 
 def conv2d_wgrad(srcs: Sequence[torch.Tensor], dy: torch.Tensor, r: int, s: int, pad_h: int,
                  pad_w: int, dw: torch.Tensor) -> torch.Tensor:
-    """gdl_conv2d_nhwc_wgrad: accumulates into fp32 dw [Cout][R][S][Ctot]."""
+    """gdl_conv2d_nhwc_wgrad: accumulates into fp32 dw.  dw 2-D [Cout][R*S*Ctot] (row stride = stride(0)), or
+    3-D [N][Cout][Ctot] = batched: one independent product per image (attention dV = P^T dO, dK = dS^T q)."""
     d = L.ConvWgrad()
     _fill_srcs(d, srcs)
     d.Cout = dy.shape[3]
@@ -164,9 +174,13 @@ def conv2d_wgrad(srcs: Sequence[torch.Tensor], dy: torch.Tensor, r: int, s: int,
     d.dy = dy.data_ptr()
     d.ld_dy = dy.stride(2)
     d.dtype = L.dt_code(srcs[0].dtype)
-    if dw.dtype != torch.float32 or not dw.is_contiguous():
-        raise ValueError("dw must be contiguous fp32")
+    if dw.dtype != torch.float32 or dw.stride(-1) != 1:
+        raise ValueError("dw must be fp32 with a contiguous last dim")
     d.dw = dw.data_ptr()
+    if dw.dim() == 3:
+        d.batched, d.dw_img_stride, d.dw_ld = 1, dw.stride(0), dw.stride(1)
+    else:
+        d.batched, d.dw_img_stride, d.dw_ld = 0, 0, dw.stride(0)
     e0 = _PROFILER.begin() if _PROFILER is not None else None
     L.check(L.load().gdl_conv2d_nhwc_wgrad(C.byref(d), L.stream_ptr()))
     _count()

@@ -74,6 +74,22 @@ typedef struct {
   int ldo;
   const float* bias; /* optional [Cout] fp32                   */
   int relu;
+  /* --- optional extensions (zero = off) ---------------------------------------------------------
+   * residual: added in the epilogue before the activation (x + proj(...) / x + fc2(...) of
+   *   mix_transformer.py:218-221); res_dtype GDL_F32 (fp32 residual stream) or 16-bit, stride ldr.
+   * w_ld / w_rows: row stride (elements) and row count of the weight matrix when it is a slice of a
+   *   wider tensor (default: dense [Cout][R*S*Ctot]).
+   * w_rows_per_img: batched B operand — image n uses weight rows [n*w_rows_per_img, ...): one GEMM per
+   *   (image, head) for q.k^T and dP = dO.v^T (mix_transformer.py:151-155).
+   * w_mn_major: the weight matrix is stored [K rows][Cout cols] (Cout = 16/32/64 contiguous), i.e. the
+   *   B operand is used transposed without a copy: P.V and dS.K of the attention. */
+  const void* residual;
+  int res_dtype;
+  int ldr;
+  int w_ld;
+  int w_rows;
+  int w_rows_per_img;
+  int w_mn_major;
 } gdl_conv_fwd_t;
 int gdl_conv2d_nhwc_fwd(const gdl_conv_fwd_t* d, void* stream);
 
@@ -91,6 +107,11 @@ typedef struct {
   int ld_dy;
   int dtype;
   float* dw;
+  /* optional (zero = dense / not batched): dw row stride in elements; batched = one independent
+   * dw per image at dw + n*dw_img_stride (attention: dV = P^T dO, dK = dS^T q per image and head). */
+  int dw_ld;
+  long long dw_img_stride;
+  int batched;
 } gdl_conv_wgrad_t;
 int gdl_conv2d_nhwc_wgrad(const gdl_conv_wgrad_t* d, void* stream);
 

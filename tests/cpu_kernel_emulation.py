@@ -41,14 +41,35 @@ def pack_conv_weight(w, dtype, mode=0, ld=0, out=None):
     return o
 
 
-def conv2d_fwd(srcs, weight, cout, r, s, pad_h, pad_w, *, out=None, out_dtype=None, bias=None, relu=False):
+def conv2d_fwd(srcs, weight, cout, r, s, pad_h, pad_w, *, out=None, out_dtype=None, bias=None, relu=False,
+               residual=None, w_ld=0, w_rows=0, w_rows_per_img=0, w_mn_major=False):
     x = torch.cat(list(srcs), 3).to(_WORK)
     ctot = x.shape[3]
-    w = weight[:cout, :r * s * ctot].to(_WORK).reshape(cout, r, s, ctot).permute(0, 3, 1, 2)
-    y = F.conv2d(_nchw(x), w, bias, padding=(pad_h, pad_w))
+    if w_rows_per_img or w_mn_major:
+        # attention GEMMs: `weight` is a 2-D view [rows][cols]; image n uses rows [n*rpi, ...)
+        n = x.shape[0]
+        ys = []
+        wf = weight.to(_WORK)
+        for i in range(n):
+            r0 = i * w_rows_per_img
+            if w_mn_major:  # rows = contraction index (zero beyond the matrix), cols = Cout
+                blk = torch.zeros(ctot, cout, dtype=_WORK)
+                avail = max(0, min(ctot, wf.shape[0] - r0))
+                blk[:avail] = wf[r0:r0 + avail, :cout]
+                ys.append(x[i] @ blk)
+            else:  # rows = Cout, cols = contraction index
+                ys.append(x[i] @ wf[r0:r0 + cout, :ctot].t())
+        y = torch.stack(ys)
+        if bias is not None:
+            y = y + bias
+    else:
+        w = weight[:cout, :r * s * ctot].to(_WORK).reshape(cout, r, s, ctot).permute(0, 3, 1, 2)
+        y = _nhwc(F.conv2d(_nchw(x), w, bias, padding=(pad_h, pad_w)))
+    if residual is not None:
+        y = y + residual.to(_WORK)
     if relu:
         y = F.relu(y)
-    y = _nhwc(y).to(out_dtype or srcs[0].dtype)
+    y = y.to(out_dtype or (out.dtype if out is not None else srcs[0].dtype))
     if out is not None:
         out.copy_(y)
         return out
@@ -56,9 +77,13 @@ def conv2d_fwd(srcs, weight, cout, r, s, pad_h, pad_w, *, out=None, out_dtype=No
 
 
 def conv2d_wgrad(srcs, dy, r, s, pad_h, pad_w, dw):
-    x = _nchw(torch.cat(list(srcs), 3).to(_WORK))
-    cout, ctot = dy.shape[3], x.shape[1]
-    g = torch.nn.grad.conv2d_weight(x, (cout, ctot, r, s), _nchw(dy.to(_WORK)).contiguous(), padding=(pad_h, pad_w))
+    x = torch.cat(list(srcs), 3).to(_WORK)
+    cout, ctot = dy.shape[3], x.shape[3]
+    if dw.dim() == 3:  # batched: dw[n] += dy[n]^T x[n]
+        for i in range(x.shape[0]):
+            dw[i, :, :ctot] += dy[i].to(_WORK).reshape(-1, cout).t() @ x[i].reshape(-1, ctot)
+        return dw
+    g = torch.nn.grad.conv2d_weight(_nchw(x), (cout, ctot, r, s), _nchw(dy.to(_WORK)).contiguous(), padding=(pad_h, pad_w))
     dw[:, :r * s * ctot] += g.permute(0, 2, 3, 1).reshape(cout, r * s * ctot)
     return dw
 
@@ -265,6 +290,88 @@ def adam_step(p, g, m, v, lr, beta1, beta2, eps, weight_decay, step, grad_scale=
 
 def grad_clip_coef(g, max_norm, scratch, scale):
     scale[0] = min(1.0, max_norm / (g.norm().item() + 1e-6))
+
+
+# ---- MixTransformer / SegFormer kernels -------------------------------------------------------
+def layernorm_fwd(x, gamma, beta, eps, out_dtype, want_stats=True):
+    v = x.to(_WORK)
+    mean = v.mean(-1)
+    var = v.var(-1, unbiased=False)
+    rstd = (var + eps).rsqrt()
+    y = ((v - mean.unsqueeze(-1)) * rstd.unsqueeze(-1) * gamma + beta).to(out_dtype)
+    return y, (torch.stack([mean.reshape(-1), rstd.reshape(-1)]) if want_stats else None)
+
+
+def layernorm_bwd(g, x, stats, gamma, *, add=None, want32=True, dtype16=None, pgrads=None):
+    c = x.shape[-1]
+    mean, rstd = stats[0].reshape(x.shape[:-1] + (1,)), stats[1].reshape(x.shape[:-1] + (1,))
+    xh = (x.to(_WORK) - mean) * rstd
+    gf = g.to(_WORK)
+    gg = gf * gamma
+    dx = rstd * (gg - gg.mean(-1, keepdim=True) - xh * (gg * xh).mean(-1, keepdim=True))
+    if add is not None:
+        dx = dx + add
+    if pgrads is not None:
+        pgrads[0] += (gf * xh).reshape(-1, c).sum(0)
+        pgrads[1] += gf.reshape(-1, c).sum(0)
+    return (dx.clone() if want32 else None), (dx.to(dtype16) if dtype16 is not None else None)
+
+
+def softmax_fwd(s, scale, length, p=None):
+    out = torch.zeros_like(s) if p is None else p
+    out.zero_()
+    out[..., :length] = torch.softmax(s[..., :length].to(_WORK) * scale, -1).to(s.dtype)
+    return out
+
+
+def softmax_bwd(p, dp, scale, length, ds=None):
+    out = torch.zeros_like(p) if ds is None else ds
+    out.zero_()
+    pf, df = p[..., :length].to(_WORK), dp[..., :length].to(_WORK)
+    out[..., :length] = (scale * pf * (df - (df * pf).sum(-1, keepdim=True))).to(p.dtype)
+    return out
+
+
+def dwconv3x3_gelu_fwd(x, w, bias):
+    c = x.shape[3]
+    pre = _nhwc(F.conv2d(_nchw(x.to(_WORK)), w.reshape(c, 1, 3, 3).to(_WORK), bias, padding=1, groups=c)).to(x.dtype)
+    return F.gelu(pre.to(_WORK)).to(x.dtype).contiguous(), pre.contiguous()
+
+
+def dwconv3x3_gelu_bwd(dy, pre, x, w, pgrads):
+    c = x.shape[3]
+    pr = pre.to(_WORK).detach().requires_grad_(True)
+    with torch.enable_grad():
+        F.gelu(pr).backward(dy.to(_WORK))
+    dpre = pr.grad.to(x.dtype).to(_WORK)
+    xr = _nchw(x.to(_WORK)).detach().requires_grad_(True)
+    wr = w.reshape(c, 1, 3, 3).to(_WORK).detach().requires_grad_(True)
+    br = torch.zeros(c, dtype=_WORK, requires_grad=True)
+    with torch.enable_grad():
+        F.conv2d(xr, wr, br, padding=1, groups=c).backward(_nchw(dpre))
+    pgrads[:, :9] += wr.grad.reshape(c, 9)
+    pgrads[:, 9] += br.grad
+    return _nhwc(xr.grad).to(x.dtype).contiguous()
+
+
+def bilinear_fwd(x, ho, wo, out=None):
+    y = _nhwc(F.interpolate(_nchw(x.to(_WORK)), size=(ho, wo), mode="bilinear", align_corners=False)).to(x.dtype)
+    if out is not None:
+        out.copy_(y)
+        return out
+    return y.contiguous()
+
+
+def bilinear_bwd(dy, hi, wi):
+    n, ho, wo, c = dy.shape
+    xr = torch.zeros(n, c, hi, wi, dtype=_WORK, requires_grad=True)
+    with torch.enable_grad():
+        F.interpolate(xr, size=(ho, wo), mode="bilinear", align_corners=False).backward(_nchw(dy.to(_WORK)))
+    return _nhwc(xr.grad).to(dy.dtype).contiguous()
+
+
+def cast_f32(x, dtype):
+    return x.to(dtype)
 
 
 def install(monkeypatch):

@@ -92,3 +92,43 @@ def test_trainer_flat_buffers_and_step(monkeypatch):
     # state_dict still exposes the (updated) parameters under the reference's key names
     sd = prod.state_dict()
     assert "decoder.blocks.x_0_0.conv1.0.weight" in sd and sd["encoder.conv1.weight"].data_ptr() == p0.data_ptr()
+
+
+@pytest.mark.parametrize("name,cin,hw", [("mit_b0", 3, 64), ("mit_b1", 4, 128)])
+def test_segformer_backward_equals_oracle_autograd(monkeypatch, f64, name, cin, hw):
+    """SegFormer graph wiring (attention GEMM operand slicing, fp32 residual stream, LayerNorm chain,
+    virtual-concat decoder, bilinear heads) against the reference-pinned functional oracle, in float64."""
+    from gdl_b200.engine import Act, Engine
+    from gdl_b200.models.segformer import SegFormer
+    from oracle import segformer as osf
+    emu.install(monkeypatch)
+    k = 5
+    torch.manual_seed(0)
+    prod = SegFormer(name, in_channels=cin, num_classes=k, compute_dtype=torch.float64).double().train()
+    with torch.no_grad():  # make every affine parameter / bias non-trivial
+        for n_, p in prod.named_parameters():
+            if p.dim() == 1:
+                p.add_(0.1 * torch.randn_like(p))
+    sd = {n_: (v.detach().clone().requires_grad_(True) if v.is_floating_point() and "running" not in n_ else v.clone())
+          for n_, v in prod.state_dict().items()}
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(2, cin, hw, hw, generator=g).double()
+    t = torch.randint(0, k, (2, hw, hw), generator=g)
+    ref = osf.segformer_forward(sd, x, name, training=True)
+    F.cross_entropy(ref, t).backward()
+
+    eng = Engine(torch.float64, training=True, acc_dtype=torch.float64)
+    with torch.no_grad():
+        xin = emu.normalize_to_nhwc(x, True, torch.float64, 8)
+        logits = prod.run(eng, Act(xin, needs_grad=False))
+    assert torch.allclose(logits.permute(0, 3, 1, 2), ref, atol=1e-9, rtol=1e-9)
+    d = logits.detach().permute(0, 3, 1, 2).clone().requires_grad_(True)
+    F.cross_entropy(d, t).backward()
+    with torch.no_grad():
+        prod.backward(eng, d.grad.permute(0, 2, 3, 1).contiguous())
+    for n_, p in prod.named_parameters():
+        got, want = eng.param_grads[id(p)], sd[n_].grad
+        err = (got - want).abs().max() / (want.abs().max() + 1e-30)
+        # parameters whose true gradient is ~0 (biases in front of a train-mode BatchNorm) only carry noise
+        assert err < 1e-7 or want.abs().max() < 1e-12, f"{n_}: {err}"
+    assert torch.allclose(prod.decoder.linear_fuse[1].running_mean, sd["decoder.linear_fuse.1.running_mean"], atol=1e-12)
