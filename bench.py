@@ -91,7 +91,13 @@ def cpu_reference_steps(steps: int, warmup: int, tiles_per_step: int = 1, budget
     from oracle import tensors as ot
     from oracle.unetpp import UnetPlusPlusOracle
 
-    cores = os.cpu_count() or 1
+    # all the threads torch will use on this box: its default = the cores this process may run on
+    # (sched affinity / cgroup aware); forcing os.cpu_count() oversubscribes shared hosts and runs slower
+    try:
+        avail = len(os.sched_getaffinity(0))
+    except AttributeError:
+        avail = os.cpu_count() or 1
+    cores = max(1, min(avail, torch.get_num_threads() if torch.get_num_threads() > 1 else avail))
     torch.set_num_threads(cores)
     torch.manual_seed(0)
     w = WORKLOAD

@@ -808,14 +808,14 @@ extern "C" int gdl_conv2d_nhwc_wgrad(const gdl_conv_wgrad_t* d, void* stream_) {
   long long base_units = (long long)p.m_tiles * nn * taps;
   // Split the pixel range: (a) the grid should see >= ~3 waves; (b) the pixels one wave of co-resident
   // units streams (dY + X rows of one split) should stay L2-resident so the 9 taps / channel tiles that
-  // share them hit in L2 (budget GDL_WGRAD_L2_MB, default 24 MB); (c) keep >= 32 stages of MMA work per
+  // share them hit in L2 (budget GDL_WGRAD_L2_MB, default 8 MB: measured best of 8/24/64 on B200); (c) keep >= 32 stages of MMA work per
   // unit so the red.global epilogue stays a small fraction.
   int ks = (int)((3ll * sm_count() + base_units - 1) / base_units);
   {
     static long long budget = -1;
     if (budget < 0) {
       const char* e = getenv("GDL_WGRAD_L2_MB");
-      budget = (e ? atoll(e) : 24) * (1ll << 20);
+      budget = (e ? atoll(e) : 8) * (1ll << 20);
     }
     const long long bytes_per_pb = (long long)kWgPix * (Ctot + d->Cout) * 2;
     long long pb_budget = budget / bytes_per_pb;

@@ -70,10 +70,17 @@ class FusedTrainer:
         logits = model.run(eng, Act(x, needs_grad=False))
         coeff, _ = ops.seg_loss_fwd(logits, target, self.loss)
         n, h, w, k = logits.shape
-        d16 = torch.zeros((n, h, w, (k + 15) // 16 * 16), dtype=model.compute_dtype, device=logits.device)
-        ops.seg_loss_bwd(logits, target, self.loss, coeff, None, d16)
-        eng.head_backward(d16)
-        eng.backward()
+        if hasattr(model, "backward"):
+            # models that own their backward (SegFormer: the logits pass through a bilinear x4 first)
+            d = torch.empty_like(logits)
+            ops.seg_loss_bwd(logits, target, self.loss, coeff, None, d)
+            model.backward(eng, d)
+        else:
+            # UNet++: the loss kernel writes the 16-bit, 16-channel-padded operand of the head's dgrad/wgrad
+            d16 = torch.zeros((n, h, w, (k + 15) // 16 * 16), dtype=model.compute_dtype, device=logits.device)
+            ops.seg_loss_bwd(logits, target, self.loss, coeff, None, d16)
+            eng.head_backward(d16)
+            eng.backward()
         self.last_engine = eng
         return coeff[0]
 

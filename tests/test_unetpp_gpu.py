@@ -55,6 +55,7 @@ def test_train_step_parity(cuda, enc, cin, k, hw, dtype):
     ref_loss.backward()
     ref_grads = {n: p.grad.clone() for n, p in ora.named_parameters()}
     ref_rm = {n: b.clone() for n, b in ora.named_buffers() if "running" in n}
+    ac_rm = None
 
     # the reference stack under autocast: how far does 16-bit compute move things on its own?
     ora2, _ = _models(enc, cin, k, dtype=dtype)
@@ -64,6 +65,7 @@ def test_train_step_parity(cuda, enc, cin, k, hw, dtype):
     ac_loss = F.cross_entropy(ac_logits.float(), t)
     ac_loss.backward()
     ac_grads = {n: p.grad.clone() for n, p in ora2.named_parameters()}
+    ac_rm = {n: b.clone() for n, b in ora2.named_buffers() if "running" in n}
 
     prod.train()
     logits = prod(x)
@@ -90,8 +92,9 @@ def test_train_step_parity(cuda, enc, cin, k, hw, dtype):
         assert ep < max(3.0 * ea, 2e-2), f"{n}: product {ep:.4f} vs autocast {ea:.4f}"
 
     for n, b in prod.named_buffers():
-        if "running" in n:
-            assert torch.allclose(b, ref_rm[n], atol=2e-2, rtol=2e-2), n
+        if "running" in n:  # running statistics: as close to the fp32 oracle as the autocast reference is
+            dev_ac = (ac_rm[n] - ref_rm[n]).abs().max().item()
+            assert (b - ref_rm[n]).abs().max().item() < max(3.0 * dev_ac, 2e-2), n
         if n.endswith("num_batches_tracked"):
             assert int(b) == 1
 
