@@ -24,12 +24,23 @@ ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 sys.path.insert(0, str(ROOT / "geo-deep-learning_b200"))
 
-WORKLOAD = {
-    "name": "unetpp_resnet50_4band_512_k5_b32",
-    "encoder": "resnet50", "bands": 4, "tile": 512, "classes": 5, "batch_per_gpu": 32,
+WORKLOADS = {
+    # BASELINE.json configs[1] — the configuration the single-GPU metric is quoted on (default)
+    "unetpp_r50": {"name": "unetpp_resnet50_4band_512_k5_b32", "family": "unetpp", "encoder": "resnet50", "bands": 4,
+                   "tile": 512, "classes": 5, "batch_per_gpu": 32, "train_gflop_per_tile": 1380.7},
+    # BASELINE.json configs[2] — SegFormer-B2, 3-band 512x512, batch 16 / GPU
+    "segformer_b2": {"name": "segformer_b2_3band_512_k5_b16", "family": "segformer", "encoder": "mit_b2", "bands": 3,
+                     "tile": 512, "classes": 5, "batch_per_gpu": 16, "train_gflop_per_tile": 363.1},
 }
-TRAIN_GFLOP_PER_TILE = 1380.7  # 3 x 460.24 GFLOP forward (2 FLOP / MAC)
-MEAN, STD = [0.5] * 4, [0.2] * 4
+WORKLOAD = WORKLOADS["unetpp_r50"]
+TRAIN_GFLOP_PER_TILE = WORKLOAD["train_gflop_per_tile"]  # 3 x forward GFLOP (2 FLOP / MAC)
+MEAN, STD = [0.5] * 6, [0.2] * 6
+
+
+def _select_workload(key: str) -> None:
+    global WORKLOAD, TRAIN_GFLOP_PER_TILE
+    WORKLOAD = WORKLOADS[key]
+    TRAIN_GFLOP_PER_TILE = WORKLOAD["train_gflop_per_tile"]
 
 
 def _peaks() -> dict:
@@ -89,7 +100,6 @@ def cpu_reference_steps(steps: int, warmup: int, tiles_per_step: int = 1, budget
     import torch
     import torch.nn.functional as F
     from oracle import tensors as ot
-    from oracle.unetpp import UnetPlusPlusOracle
 
     # all the threads torch will use on this box: its default = the cores this process may run on
     # (sched affinity / cgroup aware); forcing os.cpu_count() oversubscribes shared hosts and runs slower
@@ -101,18 +111,35 @@ def cpu_reference_steps(steps: int, warmup: int, tiles_per_step: int = 1, budget
     torch.set_num_threads(cores)
     torch.manual_seed(0)
     w = WORKLOAD
-    model = UnetPlusPlusOracle(w["encoder"], w["bands"], w["classes"]).train()
-    opt = torch.optim.Adam(model.parameters(), lr=1e-4)
+    nb = w["bands"]
     g = torch.Generator().manual_seed(1234)
-    raw = torch.randint(0, 256, (tiles_per_step, w["bands"], w["tile"], w["tile"]), generator=g, dtype=torch.uint8)
+    raw = torch.randint(0, 256, (tiles_per_step, nb, w["tile"], w["tile"]), generator=g, dtype=torch.uint8)
     mask = torch.randint(0, w["classes"], (tiles_per_step, w["tile"] // 32, w["tile"] // 32), generator=g)
     mask = mask.repeat_interleave(32, 1).repeat_interleave(32, 2)
-    mean, std = torch.tensor(MEAN).view(-1, 1), torch.tensor(STD).view(-1, 1)
+    mean, std = torch.tensor(MEAN[:nb]).view(-1, 1), torch.tensor(STD[:nb]).view(-1, 1)
+    if w["family"] == "unetpp":
+        from oracle.unetpp import UnetPlusPlusOracle
+        model = UnetPlusPlusOracle(w["encoder"], nb, w["classes"]).train()
+        params = list(model.parameters())
+
+        def fwd(x):
+            return model(x)
+        what = "oracle port of smp.UnetPlusPlus: smp itself is not installable offline"
+    else:
+        from oracle import segformer as osf
+        sd = osf.init_state_dict(w["encoder"], nb, w["classes"])
+        sd = {k: (v.requires_grad_(True) if v.is_floating_point() and "running" not in k else v) for k, v in sd.items()}
+        params = [v for v in sd.values() if v.requires_grad]
+
+        def fwd(x):
+            return osf.segformer_forward(sd, x, w["encoder"], training=True)
+        what = "functional restatement of the reference's SegFormerSegmentationModel, pinned to it by golden vectors"
+    opt = torch.optim.Adam(params, lr=1e-4)
 
     def step() -> float:
         x = ot.standardization(ot.normalization(raw.float()), mean, std)
         opt.zero_grad(set_to_none=True)
-        loss = F.cross_entropy(model(x), mask)
+        loss = F.cross_entropy(fwd(x), mask)
         loss.backward()
         opt.step()
         return float(loss.detach())
@@ -130,7 +157,7 @@ def cpu_reference_steps(steps: int, warmup: int, tiles_per_step: int = 1, budget
     total = sum(times)
     return {"value": tiles_per_step * len(times) / total, "unit": "tiles/s", "cores": cores, "kind": "port",
             "sample": f"{len(times)} step(s) x {tiles_per_step} tile(s) of {w['name']} (fwd+CE+bwd+Adam, fp32, "
-                      f"{cores} threads, oracle port of smp.UnetPlusPlus: smp itself is not installable offline)",
+                      f"{cores} threads, {what})",
             "ms_per_step": 1e3 * total / len(times), "steps_timed": len(times)}
 
 
@@ -177,9 +204,14 @@ def main_product(args) -> None:
     w = WORKLOAD
     B, C, T, K = args.batch or w["batch_per_gpu"], w["bands"], w["tile"], w["classes"]
     torch.manual_seed(0)  # identical initial weights on every rank (what DDP's broadcast gives)
-    model = UnetPlusPlus(w["encoder"], in_channels=C, classes=K, compute_dtype=torch.bfloat16).to(dev).train()
-    trainer = FusedTrainer(model, ops.LossSpec(1.0, 0.0, ignore_index=-100), lr=1e-4, mean=MEAN, std=STD,
-                           image_max=255.0, sync_bn=bool(args.sync_bn))
+    if w["family"] == "unetpp":
+        model = UnetPlusPlus(w["encoder"], in_channels=C, classes=K, compute_dtype=torch.bfloat16).to(dev).train()
+    else:
+        from gdl_b200.models.segformer import SegFormer
+        model = SegFormer(w["encoder"], in_channels=C, num_classes=K, compute_dtype=torch.bfloat16).to(dev).train()
+    trainer = FusedTrainer(model, ops.LossSpec(1.0, 0.0, ignore_index=-100), lr=1e-4, mean=MEAN[:C], std=STD[:C],
+                           image_max=255.0, sync_bn=bool(args.sync_bn),
+                           clip_grad_norm=1.0 if w["family"] == "segformer" else None)
 
     # synthetic tiles: NBUF distinct batches so consecutive steps never re-read the same input (and the
     # per-step working set, tens of GB of activations, is far larger than the 126 MB L2 anyway)
@@ -298,7 +330,9 @@ def main() -> None:
     ap.add_argument("--sync-bn", type=int, default=1, help="SyncBatchNorm statistics when N > 1 (reference YAMLs: true)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--table", default="", help="write the per-launch conv profile (shape, ms, TFLOP/s) to this JSON file")
+    ap.add_argument("--workload", default="unetpp_r50", choices=sorted(WORKLOADS))
     args = ap.parse_args()
+    _select_workload(args.workload)
     if args.impl == "reference":
         main_reference(args)
     else:

@@ -23,6 +23,17 @@
 
 namespace gdl {
 
+// runtime options (gdl_set_option); env vars GDL_CONV_HALO / GDL_WGRAD_HALO / GDL_WGRAD_L2_MB seed them
+static int g_opt_conv_halo = -1, g_opt_wgrad_halo = -1;
+static long long g_opt_wgrad_l2_mb = -1;
+static int opt_int(int& slot, const char* env, int dflt) {
+  if (slot < 0) {
+    const char* e = getenv(env);
+    slot = e ? atoi(e) : dflt;
+  }
+  return slot;
+}
+
 constexpr int kMaxStages = 8;
 constexpr int kConvThreads = 192;  // 6 warps
 constexpr int kSmemBudget = 200 * 1024;
@@ -52,6 +63,12 @@ struct ConvFwdKParams {
   long long ldr;
   int w_rows_per_img;    // batched B operand: weight row offset per image (attention GEMMs), 0 = shared
   int w_mn_major;        // B operand stored [K rows][N cols] (N contiguous): P.V and dS.K of the attention
+  // halo mode (3x3, pad 1, 128x1-pixel tiles, BK = 64): one k-iteration loads ONE input row segment with
+  // its 2 halo pixels (130 px) and the weights of the 3 horizontal taps; the 3 taps are 3 MMAs whose A
+  // descriptor start is shifted by 0/1/2 rows (128 B) inside the swizzled tile -> A traffic / 3.
+  int halo;
+  int halo_bo;           // set the descriptor base_offset field for the shifted start (probe-determined)
+  int b_slot;            // bytes between the 3 per-tap weight tiles of a stage
 };
 
 GDL_DEVINL uint8_t* align_smem_1024(uint8_t* raw) {
@@ -160,6 +177,28 @@ conv_fwd_kernel(const __grid_constant__ ConvFwdKParams p) {
         const int h0 = (t_in / p.tiles_w) * p.TH;
         const int w0 = (t_in % p.tiles_w) * p.TW;
         const int n0 = n_tile * p.BN;
+        if (p.halo) {
+          const uint32_t txh = (uint32_t)(130 * p.BK * 2 + 3 * p.b_bytes);
+          for (int r = 0; r < 3; ++r) {
+            for (int src = 0; src < p.num_src; ++src) {
+              for (int ch = 0; ch < p.src_chunks[src]; ++ch) {
+                mbar_wait(&empty_bar[stage], phase ^ 1);
+                uint8_t* a_dst = smem + (size_t)stage * p.stage_bytes;
+                uint8_t* b_dst = a_dst + p.a_bytes;
+                mbar_expect_tx(&full_bar[stage], txh);
+                tma_load_4d(a_dst, &p.tmA[src], &full_bar[stage], ch * p.BK, w0 - 1, h0 + r - 1, img);
+                for (int s = 0; s < 3; ++s)
+                  tma_load_2d(b_dst + s * p.b_slot, &p.tmB, &full_bar[stage],
+                              (r * 3 + s) * p.Ctot + p.src_coff[src] + ch * p.BK, n0);
+                if (++stage == p.stages) {
+                  stage = 0;
+                  phase ^= 1;
+                }
+              }
+            }
+          }
+          continue;
+        }
         for (int tap = 0; tap < taps; ++tap) {
           const int r = tap / p.S, s = tap - r * p.S;
           for (int src = 0; src < p.num_src; ++src) {
@@ -197,7 +236,7 @@ conv_fwd_kernel(const __grid_constant__ ConvFwdKParams p) {
       const uint32_t kstepB = p.w_mn_major ? 16u * p.BN * 2u : 32u;
       int k_iters = 0;
       for (int src = 0; src < p.num_src; ++src) k_iters += p.src_chunks[src];
-      k_iters *= taps;
+      k_iters *= p.halo ? 3 : taps;
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
@@ -212,10 +251,22 @@ conv_fwd_kernel(const __grid_constant__ ConvFwdKParams p) {
           tc_fence_after();
           const uint32_t a_addr = smem_u32(smem + (size_t)stage * p.stage_bytes);
           const uint32_t b_addr = a_addr + p.a_bytes;
-          for (int kk = 0; kk < ksteps; ++kk) {
-            const uint64_t da = umma_smem_desc(a_addr + kk * 32, 16, sbo, lt);
-            const uint64_t db = umma_smem_desc(b_addr + kk * kstepB, 16, sboB, ltB);
-            umma_f16(d_tmem, da, db, idesc, (uint32_t)((k | kk) != 0));
+          if (p.halo) {
+            for (int s3 = 0; s3 < 3; ++s3) {
+              const uint32_t a_s = a_addr + s3 * 128;  // shift by one pixel row (BK = 64 -> 128 B rows)
+              const uint64_t bo = p.halo_bo ? ((uint64_t)((a_s >> 7) & 7) << 49) : 0;
+              for (int kk = 0; kk < ksteps; ++kk) {
+                const uint64_t da = umma_smem_desc(a_s + kk * 32, 16, sbo, lt) | bo;
+                const uint64_t db = umma_smem_desc(b_addr + s3 * p.b_slot + kk * 32, 16, sbo, lt);
+                umma_f16(d_tmem, da, db, idesc, (uint32_t)((k | kk | s3) != 0));
+              }
+            }
+          } else {
+            for (int kk = 0; kk < ksteps; ++kk) {
+              const uint64_t da = umma_smem_desc(a_addr + kk * 32, 16, sbo, lt);
+              const uint64_t db = umma_smem_desc(b_addr + kk * kstepB, 16, sboB, ltB);
+              umma_f16(d_tmem, da, db, idesc, (uint32_t)((k | kk) != 0));
+            }
           }
           umma_commit(&empty_bar[stage]);
           if (++stage == p.stages) {
@@ -373,6 +424,18 @@ static int validate_srcs(int num_src, const gdl_src_t* src, int* ctot) {
 
 using namespace gdl;
 
+extern "C" int gdl_set_option(const char* name, long long value) {
+  GDL_REQUIRE(name != nullptr, GDL_ERR_INVALID, "set_option: null name");
+  if (!strcmp(name, "conv_halo")) g_opt_conv_halo = (int)value;
+  else if (!strcmp(name, "wgrad_halo")) g_opt_wgrad_halo = (int)value;
+  else if (!strcmp(name, "wgrad_l2_mb")) g_opt_wgrad_l2_mb = value;
+  else {
+    set_last_error("set_option: unknown option '%s'", name);
+    return GDL_ERR_INVALID;
+  }
+  return 0;
+}
+
 extern "C" int gdl_conv2d_nhwc_fwd(const gdl_conv_fwd_t* d, void* stream_) {
   GDL_REQUIRE(d != nullptr, GDL_ERR_INVALID, "null descriptor");
   cudaStream_t stream = (cudaStream_t)stream_;
@@ -432,6 +495,19 @@ extern "C" int gdl_conv2d_nhwc_fwd(const gdl_conv_fwd_t* d, void* stream_) {
   p.a_bytes = 128 * p.BK * 2;
   p.b_bytes = p.BN * p.BK * 2;
   p.stage_bytes = p.a_bytes + ((p.b_bytes + 1023) / 1024) * 1024;
+  {
+    // conv_halo: 0 = off, 1 = on.  (The tools/probe_shift.py probe showed that a descriptor start shifted
+    // by whole rows inside the 1024-byte swizzle repeat addresses the expected rows with base_offset = 0.)
+    const int halo_cfg = opt_int(g_opt_conv_halo, "GDL_CONV_HALO", 1);
+    if (halo_cfg > 0 && d->R == 3 && d->S == 3 && d->pad_h == 1 && d->pad_w == 1 && p.TH == 1 && p.TW == 128 &&
+        p.BK == 64 && p.BN <= 128 && !d->w_mn_major && d->w_rows_per_img == 0) {
+      p.halo = 1;
+      p.halo_bo = 0;
+      p.a_bytes = ((130 * p.BK * 2 + 1023) / 1024) * 1024;
+      p.b_slot = ((p.b_bytes + 1023) / 1024) * 1024;
+      p.stage_bytes = p.a_bytes + 3 * p.b_slot;
+    }
+  }
   p.stages = kSmemBudget / p.stage_bytes;
   if (p.stages > kMaxStages) p.stages = kMaxStages;
   GDL_REQUIRE(p.stages >= 2, GDL_ERR_UNSUPPORTED, "tile does not fit shared memory");
@@ -457,7 +533,7 @@ extern "C" int gdl_conv2d_nhwc_fwd(const gdl_conv_fwd_t* d, void* stream_) {
     p.src_coff[i] = coff;
     coff += d->src[i].channels;
     st = make_tmap_nhwc(&p.tmA[i], d->src[i].ptr, d->dtype, d->src[i].channels, W, H, N, d->src[i].ld,
-                        p.BK, p.TW, p.TH, p.BK * 2);
+                        p.BK, p.halo ? 130 : p.TW, p.TH, p.BK * 2);
     if (st) return st;
   }
   const long long Ktot = (long long)d->R * d->S * Ctot;
@@ -512,6 +588,14 @@ struct ConvWgradKParams {
   long long dw_img_stride;  // batched: dw of image i starts at dw + i * dw_img_stride
   int batched;              // one independent dW per image (attention: dV = P^T dO, dK = dS^T Q)
   int pb_per_img;
+  // halo mode (3x3, pad 1, 64x1-pixel blocks, 64-channel X atoms): a unit owns one filter ROW r and keeps
+  // 3 accumulators (s = 0,1,2); each k-iteration loads the X row segment once with its 2 halo pixels
+  // (66 px) and the 3 horizontal taps are MMAs whose B descriptor start is shifted by s rows (128 B).
+  int halo;
+  int nsub;        // accumulators per unit (1, or 3 in halo mode)
+  int nacc;        // TMEM accumulator sets in flight (2 = double buffered, 1 = single)
+  int unit_taps;   // units along the tap axis (R*S, or 3 filter rows in halo mode)
+  int b_atom_bytes;  // bytes of one X atom in a stage (64 px, or 66 px padded to 9 KiB in halo mode)
 };
 
 __global__ void __launch_bounds__(kConvThreads, 1)
@@ -527,7 +611,7 @@ conv_wgrad_kernel(const __grid_constant__ ConvWgradKParams p) {
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int taps = p.R * p.S;
+  const int taps = p.unit_taps;
   const int tiles_per_img = p.tiles_w * p.tiles_h;
 
   // A-operand atoms beyond Cout are never loaded: they must read as zero.
@@ -563,7 +647,9 @@ conv_wgrad_kernel(const __grid_constant__ ConvWgradKParams p) {
   const uint32_t tmem_base = tmem_base_smem;
 
   const int atomA_bytes = kWgPix * p.caA * 2;  // one MN atom (caA channels) x 64 pixels
-  const int atomB_bytes = kWgPix * p.caB * 2;
+  const int atomB_bytes = p.b_atom_bytes;
+  const uint32_t atomB_tx = p.halo ? 66u * 128u : (uint32_t)(kWgPix * p.caB * 2);
+  const uint32_t acc_stride = (uint32_t)(p.nsub * p.bn_max);
 
   // unit -> (tap, n-tile, m-tile, k-split); tap fastest so co-resident CTAs share dY / X in L2
   auto decode = [&](int u, int& tap, int& nt, int& mt, int& ks) {
@@ -595,13 +681,14 @@ conv_wgrad_kernel(const __grid_constant__ ConvWgradKParams p) {
       for (int u = blockIdx.x; u < p.num_units; u += gridDim.x) {
         int tap, nt, mt, ks;
         decode(u, tap, nt, mt, ks);
-        const int r = tap / p.S, s = tap - r * p.S;
+        const int r = p.halo ? tap : tap / p.S;
+        const int s = p.halo ? 0 : tap - r * p.S;  // halo: the box starts one pixel left (s = 0) and is 66 wide
         const int m0 = mt * 128;
         const int a_atoms = min(128, p.Cout - m0) / p.caA;  // Cout % caA == 0
         const int b_atoms = p.nt_w[nt] / p.caB;
         const int src = p.nt_src[nt];
         const int c0 = p.nt_c0[nt];
-        const uint32_t tx = (uint32_t)(a_atoms * atomA_bytes + b_atoms * atomB_bytes);
+        const uint32_t tx = (uint32_t)(a_atoms * atomA_bytes) + (uint32_t)b_atoms * atomB_tx;
         int pb0, pb1, uimg;
         pb_range(ks, pb0, pb1, uimg);
         for (int pb = pb0; pb < pb1; ++pb) {
@@ -638,11 +725,11 @@ conv_wgrad_kernel(const __grid_constant__ ConvWgradKParams p) {
         decode(u, tap, nt, mt, ks);
         const int bn = p.nt_w[nt];
         const uint32_t idesc = umma_idesc(128, bn, p.ab_fmt, 1, 1);
-        const int acc = it & 1;
-        const uint32_t aphase = (it >> 1) & 1;
+        const int acc = it % p.nacc;
+        const uint32_t aphase = (it / p.nacc) & 1;
         mbar_wait(&tempty_bar[acc], aphase ^ 1);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.bn_max);
+        const uint32_t d_tmem = tmem_base + (uint32_t)acc * acc_stride;
         int pb0, pb1, uimg;
         pb_range(ks, pb0, pb1, uimg);
         for (int pb = pb0; pb < pb1; ++pb) {
@@ -650,10 +737,12 @@ conv_wgrad_kernel(const __grid_constant__ ConvWgradKParams p) {
           tc_fence_after();
           const uint32_t a_addr = smem_u32(smem + (size_t)stage * p.stage_bytes);
           const uint32_t b_addr = a_addr + p.a_bytes;
-          for (int kk = 0; kk < kWgPix / 16; ++kk) {
-            const uint64_t da = umma_smem_desc(a_addr + kk * kstepA, atomA_bytes, sboA, ltA);
-            const uint64_t db = umma_smem_desc(b_addr + kk * kstepB, atomB_bytes, sboB, ltB);
-            umma_f16(d_tmem, da, db, idesc, (uint32_t)((pb > pb0) | (kk != 0)));
+          for (int s3 = 0; s3 < p.nsub; ++s3) {
+            for (int kk = 0; kk < kWgPix / 16; ++kk) {
+              const uint64_t da = umma_smem_desc(a_addr + kk * kstepA, atomA_bytes, sboA, ltA);
+              const uint64_t db = umma_smem_desc(b_addr + s3 * 128 + kk * kstepB, atomB_bytes, sboB, ltB);
+              umma_f16(d_tmem + (uint32_t)(s3 * p.bn_max), da, db, idesc, (uint32_t)((pb > pb0) | (kk != 0)));
+            }
           }
           umma_commit(&empty_bar[stage]);
           if (++stage == p.stages) {
@@ -671,31 +760,35 @@ conv_wgrad_kernel(const __grid_constant__ ConvWgradKParams p) {
     for (int u = blockIdx.x; u < p.num_units; u += gridDim.x, ++it) {
       int tap, nt, mt, ks;
       decode(u, tap, nt, mt, ks);
-      const int acc = it & 1;
-      const uint32_t aphase = (it >> 1) & 1;
+      const int acc = it % p.nacc;
+      const uint32_t aphase = (it / p.nacc) & 1;
       const int m = mt * 128 + row;
       const int bn = p.nt_w[nt];
       int pb0, pb1, uimg;
       pb_range(ks, pb0, pb1, uimg);
       const bool nonempty = pb0 < pb1;
-      float* dst = p.dw + (long long)uimg * p.dw_img_stride + (long long)m * p.dw_ld + (long long)tap * p.Ctot +
-                   p.nt_coff[nt];
       mbar_wait(&tfull_bar[acc], aphase);
       tc_fence_after();
-      const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.bn_max);
-      for (int j = 0; j < bn / 16; ++j) {
-        uint32_t v[16];
-        tmem_ld_32x32b_x16(t_addr + j * 16, v);
-        tmem_ld_wait();
-        if (m < p.Cout && nonempty) {
-          // 4 x red.global.add.v4.f32 (16-byte aligned: Ctot, channel offsets and j*16 are multiples of 16)
-          float* d = dst + j * 16;
+      for (int s3 = 0; s3 < p.nsub; ++s3) {
+        const int tap_idx = p.halo ? tap * 3 + s3 : tap;
+        float* dst = p.dw + (long long)uimg * p.dw_img_stride + (long long)m * p.dw_ld + (long long)tap_idx * p.Ctot +
+                     p.nt_coff[nt];
+        const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * acc_stride +
+                                (uint32_t)(s3 * p.bn_max);
+        for (int j = 0; j < bn / 16; ++j) {
+          uint32_t v[16];
+          tmem_ld_32x32b_x16(t_addr + j * 16, v);
+          tmem_ld_wait();
+          if (m < p.Cout && nonempty) {
+            // 4 x red.global.add.v4.f32 (16-byte aligned: Ctot, channel offsets and j*16 are multiples of 16)
+            float* d = dst + j * 16;
 #pragma unroll
-          for (int i = 0; i < 4; ++i)
-            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(d + 4 * i),
-                         "f"(__uint_as_float(v[4 * i])), "f"(__uint_as_float(v[4 * i + 1])),
-                         "f"(__uint_as_float(v[4 * i + 2])), "f"(__uint_as_float(v[4 * i + 3]))
-                         : "memory");
+            for (int i = 0; i < 4; ++i)
+              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(d + 4 * i),
+                           "f"(__uint_as_float(v[4 * i])), "f"(__uint_as_float(v[4 * i + 1])),
+                           "f"(__uint_as_float(v[4 * i + 2])), "f"(__uint_as_float(v[4 * i + 3]))
+                           : "memory");
+          }
         }
       }
       tc_fence_before();
@@ -753,6 +846,14 @@ extern "C" int gdl_conv2d_nhwc_wgrad(const gdl_conv_wgrad_t* d, void* stream_) {
     oW = W;
   }
   choose_tile(oH, oW, kWgPix, &p.TH, &p.TW);
+  {
+    const int halo_cfg = opt_int(g_opt_wgrad_halo, "GDL_WGRAD_HALO", 1);
+    p.halo = halo_cfg > 0 && d->R == 3 && d->S == 3 && d->pad_h == 1 && d->pad_w == 1 && p.TH == 1 &&
+             p.TW == kWgPix && p.caB == 64 && !d->batched;
+  }
+  p.nsub = p.halo ? 3 : 1;
+  p.unit_taps = p.halo ? 3 : d->R * d->S;
+  p.b_atom_bytes = p.halo ? 9216 : kWgPix * p.caB * 2;
   p.tiles_w = (oW + p.TW - 1) / p.TW;
   p.tiles_h = (oH + p.TH - 1) / p.TH;
   long long pbs = (long long)N * p.tiles_w * p.tiles_h;
@@ -764,7 +865,8 @@ extern "C" int gdl_conv2d_nhwc_wgrad(const gdl_conv_wgrad_t* d, void* stream_) {
   int nn = 0, coff = 0, bn_max = 16;
   for (int i = 0; i < d->num_src; ++i) {
     int c = d->src[i].channels;
-    int parts = (c + 255) / 256;
+    const int cap = p.halo ? 128 : 256;  // halo: 3 accumulators of <= 128 columns fit TMEM (single-buffered)
+    int parts = (c + cap - 1) / cap;
     int w = ((c + parts - 1) / parts + p.caB - 1) / p.caB * p.caB;
     for (int c0 = 0; c0 < c; c0 += w) {
       GDL_REQUIRE(nn < kMaxNTiles, GDL_ERR_UNSUPPORTED, "too many channel tiles");
@@ -776,8 +878,8 @@ extern "C" int gdl_conv2d_nhwc_wgrad(const gdl_conv_wgrad_t* d, void* stream_) {
       ++nn;
     }
     coff += c;
-    st = make_tmap_nhwc(&p.tmX[i], d->src[i].ptr, d->dtype, c, W, H, N, d->src[i].ld, p.caB, p.TW, p.TH,
-                        p.caB * 2);
+    st = make_tmap_nhwc(&p.tmX[i], d->src[i].ptr, d->dtype, c, W, H, N, d->src[i].ld, p.caB,
+                        p.halo ? p.TW + 2 : p.TW, p.TH, p.caB * 2);
     if (st) return st;
   }
   p.n_ntiles = nn;
@@ -785,10 +887,10 @@ extern "C" int gdl_conv2d_nhwc_wgrad(const gdl_conv_wgrad_t* d, void* stream_) {
   st = make_tmap_nhwc(&p.tmDY, d->dy, d->dtype, d->Cout, oW, oH, N, d->ld_dy, p.caA, p.TW, p.TH, p.caA * 2);
   if (st) return st;
 
-  const int taps = d->R * d->S;
+  const int taps = p.unit_taps;
   p.batched = d->batched;
   p.pb_per_img = p.tiles_w * p.tiles_h;
-  p.dw_ld = d->dw_ld > 0 ? d->dw_ld : (long long)taps * Ctot;
+  p.dw_ld = d->dw_ld > 0 ? d->dw_ld : (long long)d->R * d->S * Ctot;
   p.dw_img_stride = d->dw_img_stride;
   if (d->batched) {
     // one independent product per image: split each image's pixel blocks on its own
@@ -812,11 +914,11 @@ extern "C" int gdl_conv2d_nhwc_wgrad(const gdl_conv_wgrad_t* d, void* stream_) {
   // unit so the red.global epilogue stays a small fraction.
   int ks = (int)((3ll * sm_count() + base_units - 1) / base_units);
   {
-    static long long budget = -1;
-    if (budget < 0) {
+    if (g_opt_wgrad_l2_mb < 0) {
       const char* e = getenv("GDL_WGRAD_L2_MB");
-      budget = (e ? atoll(e) : 8) * (1ll << 20);
+      g_opt_wgrad_l2_mb = e ? atoll(e) : 8;
     }
+    const long long budget = g_opt_wgrad_l2_mb * (1ll << 20);
     const long long bytes_per_pb = (long long)kWgPix * (Ctot + d->Cout) * 2;
     long long pb_budget = budget / bytes_per_pb;
     if (pb_budget < 32) pb_budget = 32;
@@ -836,12 +938,14 @@ extern "C" int gdl_conv2d_nhwc_wgrad(const gdl_conv_wgrad_t* d, void* stream_) {
   }
 
   p.a_bytes = kWgPix * 128 * 2;
-  const int b_bytes = kWgPix * bn_max * 2;
+  const int b_bytes = p.halo ? (bn_max / 64) * p.b_atom_bytes : kWgPix * bn_max * 2;
   p.stage_bytes = p.a_bytes + ((b_bytes + 1023) / 1024) * 1024;
   p.stages = kSmemBudget / p.stage_bytes;
   if (p.stages > kMaxStages) p.stages = kMaxStages;
   GDL_REQUIRE(p.stages >= 2, GDL_ERR_UNSUPPORTED, "tile does not fit shared memory");
-  p.tmem_cols = pow2_ge(2 * bn_max);
+  p.nacc = (2 * p.nsub * bn_max <= 512) ? 2 : 1;
+  p.tmem_cols = pow2_ge(p.nacc * p.nsub * bn_max);
+  GDL_REQUIRE(p.tmem_cols <= 512, GDL_ERR_UNSUPPORTED, "accumulators do not fit TMEM");
   p.ab_fmt = d->dtype == GDL_BF16 ? 1 : 0;
   p.dw = d->dw;
 

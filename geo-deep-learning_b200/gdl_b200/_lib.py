@@ -115,6 +115,7 @@ _SIGS = {
     "gdl_adam_step": [_VP, _VP, _VP, _VP, _LL, _F, _F, _F, _F, _F, _I, _VP, _VP],
     "gdl_grad_clip_coef": [_VP, _LL, _F, _VP, _VP, _VP],
     "gdl_device_info": [_VP, _VP, _VP, _VP],
+    "gdl_set_option": [C.c_char_p, _LL],
     "gdl_layernorm_fwd": [_VP, _I, _LL, _VP, _VP, _F, _VP, _I, _LL, _VP, _VP, _LL, _I, _VP],
     "gdl_layernorm_bwd": [_VP, _I, _LL, _VP, _I, _LL, _VP, _VP, _VP, _VP, _LL, _VP, _LL, _VP, _I, _LL, _VP, _LL, _I, _VP],
     "gdl_softmax_fwd": [_VP, _LL, _F, _VP, _LL, _I, _LL, _I, _I, _VP],

@@ -95,6 +95,11 @@ def set_conv_profiler(p: ConvProfiler | None) -> None:
     _PROFILER = p
 
 
+def set_option(name: str, value: int) -> None:
+    """runtime tuning switch of the library (see gdl_set_option in include/gdl_b200.h)"""
+    L.check(L.load().gdl_set_option(name.encode(), int(value)))
+
+
 def _nhwc_src(t: torch.Tensor) -> tuple[int, int, int, int, int]:
     if t.dim() != 4:
         raise ValueError(f"NHWC activation expected 4 dims, got {tuple(t.shape)}")
