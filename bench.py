@@ -211,7 +211,8 @@ def main_product(args) -> None:
         model = SegFormer(w["encoder"], in_channels=C, num_classes=K, compute_dtype=torch.bfloat16).to(dev).train()
     trainer = FusedTrainer(model, ops.LossSpec(1.0, 0.0, ignore_index=-100), lr=1e-4, mean=MEAN[:C], std=STD[:C],
                            image_max=255.0, sync_bn=bool(args.sync_bn),
-                           clip_grad_norm=1.0 if w["family"] == "segformer" else None)
+                           clip_grad_norm=1.0 if w["family"] == "segformer" else None,
+                           cuda_graph=bool(args.cuda_graph) and world == 1)
 
     # synthetic tiles: NBUF distinct batches so consecutive steps never re-read the same input (and the
     # per-step working set, tens of GB of activations, is far larger than the 126 MB L2 anyway)
@@ -261,9 +262,8 @@ def main_product(args) -> None:
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
-    ops.reset_launch_count()
     ms = timed(step_resident, args.steps)
-    launches = ops.launch_count()
+    launches = trainer.launches_per_step * args.steps  # kernels of libgdlb200.so per step (counted at capture)
     clk = clocks.stop() if rank == 0 else None
 
     for i in range(2):
@@ -271,6 +271,8 @@ def main_product(args) -> None:
     ms_e2e = timed(step_e2e, args.steps)
 
     # ---- roofline of the dominant kernels: per-launch CUDA events around every tensor-core conv launch
+    # (eager launches: events cannot be read back from inside a replayed graph)
+    trainer.cuda_graph = False
     prof = ops.ConvProfiler()
     ops.set_conv_profiler(prof)
     nprof = max(1, min(3, args.steps))
@@ -297,7 +299,7 @@ def main_product(args) -> None:
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": w["name"], "global_batch": B * world, "parallelism": f"dp{world}",
-                       "loss": "cross_entropy", "optimizer": "adam", "sync_bn": bool(args.sync_bn and world > 1),
+                       "loss": "cross_entropy", "optimizer": "adam", "sync_bn": bool(args.sync_bn and world > 1), "cuda_graph": bool(args.cuda_graph) and world == 1,
                        "l2": f"{NBUF} rotating input batches; per-step working set >> 126 MB L2"},
             "clocks": clk,
             "e2e": {"value": tiles / (ms_e2e / 1e3), "unit": "tiles/s",
@@ -329,6 +331,7 @@ def main() -> None:
     ap.add_argument("--batch", type=int, default=0, help="tiles per GPU (default: the workload's 32)")
     ap.add_argument("--sync-bn", type=int, default=1, help="SyncBatchNorm statistics when N > 1 (reference YAMLs: true)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cuda-graph", type=int, default=1, help="capture the whole step in a CUDA graph (N=1)")
     ap.add_argument("--table", default="", help="write the per-launch conv profile (shape, ms, TFLOP/s) to this JSON file")
     ap.add_argument("--workload", default="unetpp_r50", choices=sorted(WORKLOADS))
     args = ap.parse_args()

@@ -159,6 +159,37 @@ __global__ void im2col_vec8_kernel(const T* __restrict__ x, T* __restrict__ col,
   }
 }
 
+// 4-channel input stored with pixel stride 4 or 8 (the 4-band stem): one thread moves two taps (2 x 8 B)
+template <typename T>
+__global__ void im2col_c4_kernel(const T* __restrict__ x, T* __restrict__ col, int N, int H, int W, int ld, int R,
+                                 int S, int stride, int pad, int Ho, int Wo, int Kpad) {
+  const int pairs = Kpad / 8;  // 8 elements = 2 taps per thread
+  const int taps = R * S;
+  const long long total = (long long)N * Ho * Wo * pairs;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long row = i / pairs;
+    const int pr = (int)(i - row * pairs);
+    const int wo = (int)(row % Wo);
+    const long long t = row / Wo;
+    const int ho = (int)(t % Ho);
+    const int n = (int)(t / Ho);
+    uint2 v[2];
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int tap = pr * 2 + j;
+      v[j] = make_uint2(0, 0);
+      if (tap < taps) {
+        const int r = tap / S, s2 = tap - r * S;
+        const int h = ho * stride - pad + r, w = wo * stride - pad + s2;
+        if (h >= 0 && h < H && w >= 0 && w < W)
+          v[j] = *reinterpret_cast<const uint2*>(x + (((long long)n * H + h) * W + w) * ld);
+      }
+    }
+    *reinterpret_cast<uint4*>(col + row * Kpad + pr * 8) = make_uint4(v[0].x, v[0].y, v[1].x, v[1].y);
+  }
+}
+
 // generic (any C): one thread per output element
 template <typename T>
 __global__ void im2col_scalar_kernel(const T* __restrict__ x, T* __restrict__ col, int N, int H, int W,
@@ -706,7 +737,10 @@ extern "C" int gdl_im2col_nhwc(const void* x, void* col, int dtype, int N, int H
   cudaStream_t st = (cudaStream_t)stream;
   const bool vec = (C % 8 == 0) && (ld % 8 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
   GDL_DISPATCH_16(dtype, {
-    if (vec) {
+    if (C == 4 && ld % 4 == 0 && ((reinterpret_cast<uintptr_t>(x) & 7) == 0)) {
+      const long long total = (long long)N * Ho * Wo * (Kpad / 8);
+      im2col_c4_kernel<T><<<ew_blocks(total, 256, 16), 256, 0, st>>>((const T*)x, (T*)col, N, H, W, ld, R, S, stride, pad, Ho, Wo, Kpad);
+    } else if (vec) {
       const long long total = (long long)N * Ho * Wo * (Kpad / 8);
       im2col_vec8_kernel<T><<<ew_blocks(total, 256, 16), 256, 0, st>>>((const T*)x, (T*)col, N, H, W, C, ld, R, S, stride, pad, Ho, Wo, Kpad);
     } else {

@@ -36,7 +36,7 @@ static int opt_int(int& slot, const char* env, int dflt) {
 
 constexpr int kMaxStages = 8;
 constexpr int kConvThreads = 192;  // 6 warps
-constexpr int kSmemBudget = 200 * 1024;
+constexpr int kSmemBudget = 196 * 1024;  // + 16.5 KB static epilogue staging + barriers < 227 KB
 constexpr int kMinSmemRequest = 120 * 1024;  // forces 1 CTA / SM (TMEM is allocated per CTA)
 
 struct ConvFwdKParams {
@@ -56,6 +56,7 @@ struct ConvFwdKParams {
   int out_dtype;
   long long ldo;
   int vec_ok;
+  int pair_ok;  // 16-bit outputs: (pixel, even channel) addresses are 4-byte aligned -> packed 2-channel stores
   const float* bias;
   int relu;
   const void* residual;  // optional, added in the epilogue (fp32 residual stream or 16-bit)
@@ -132,6 +133,7 @@ conv_fwd_kernel(const __grid_constant__ ConvFwdKParams p) {
   __shared__ __align__(8) uint64_t tfull_bar[2];
   __shared__ __align__(8) uint64_t tempty_bar[2];
   __shared__ uint32_t tmem_base_smem;
+  __shared__ float stage_buf[4][32 * 33];  // per-epilogue-warp transpose tile (padded: conflict free)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -253,7 +255,7 @@ conv_fwd_kernel(const __grid_constant__ ConvFwdKParams p) {
           const uint32_t b_addr = a_addr + p.a_bytes;
           if (p.halo) {
             for (int s3 = 0; s3 < 3; ++s3) {
-              const uint32_t a_s = a_addr + s3 * 128;  // shift by one pixel row (BK = 64 -> 128 B rows)
+              const uint32_t a_s = a_addr + s3 * p.BK * 2;  // shift by one pixel row (BK*2 bytes)
               const uint64_t bo = p.halo_bo ? ((uint64_t)((a_s >> 7) & 7) << 49) : 0;
               for (int kk = 0; kk < ksteps; ++kk) {
                 const uint64_t da = umma_smem_desc(a_s + kk * 32, 16, sbo, lt) | bo;
@@ -278,10 +280,16 @@ conv_fwd_kernel(const __grid_constant__ ConvFwdKParams p) {
       }
     }
   } else {
-    // ===================== epilogue: TMEM -> registers -> HBM =====================
+    // ===================== epilogue: TMEM -> registers -> smem transpose -> coalesced HBM =====================
+    // tcgen05.ld hands every thread one accumulator ROW; storing rows from registers makes each warp store hit
+    // 32 different lines.  Each warp therefore transposes 32x32 blocks through a private padded smem tile so
+    // that consecutive lanes write consecutive channels of one pixel (128-byte segments), and applies bias /
+    // residual / ReLU / conversion on the way out with equally coalesced residual loads.
     const int q = warp & 3;  // TMEM lane quadrant this warp may access
     const int row = q * 32 + lane;
     const int th = row / p.TW, tw = row - th * p.TW;
+    float* stg = &stage_buf[q][0];
+    const bool out16 = p.out_dtype != GDL_F32;
     int it = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
       const int acc = it & 1;
@@ -294,56 +302,92 @@ conv_fwd_kernel(const __grid_constant__ ConvFwdKParams p) {
       const int w = (t_in % p.tiles_w) * p.TW + tw;
       const int n0 = n_tile * p.BN;
       const bool valid = (h < p.Ho) && (w < p.Wo);
-      const long long pix = ((long long)img * p.Ho + h) * p.Wo + w;
+      // pixel index of this lane's row; -1 marks rows outside the image
+      const long long my_pix = valid ? ((long long)img * p.Ho + h) * p.Wo + w : -1;
       mbar_wait(&tfull_bar[acc], aphase);
       tc_fence_after();
       const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.BN);
-      for (int j = 0; j < p.BN / 16; ++j) {
-        uint32_t v[16];
-        tmem_ld_32x32b_x16(t_addr + j * 16, v);
+      for (int cb = 0; cb < p.BN; cb += 32) {
+        const int ccols = min(32, p.BN - cb);  // 16 or 32
+        uint32_t v0[16], v1[16];
+        tmem_ld_32x32b_x16(t_addr + cb, v0);
+        if (ccols > 16) tmem_ld_32x32b_x16(t_addr + cb + 16, v1);
         tmem_ld_wait();
-        const int c0 = n0 + j * 16;
-        const int nvalid = min(16, p.Cout - c0);
-        if (valid && nvalid > 0) {
-          float f[16];
+        __syncwarp();
 #pragma unroll
-          for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]);
-          if (p.bias != nullptr) {
+        for (int i = 0; i < 16; ++i) stg[lane * 33 + i] = __uint_as_float(v0[i]);
+        if (ccols > 16) {
 #pragma unroll
-            for (int i = 0; i < 16; ++i)
-              if (i < nvalid) f[i] += __ldg(p.bias + c0 + i);
+          for (int i = 0; i < 16; ++i) stg[lane * 33 + 16 + i] = __uint_as_float(v1[i]);
+        }
+        __syncwarp();
+        const int c0 = n0 + cb;
+        if (!out16) {
+          // fp32 output: lane = column, one pixel row (<= 128 B) per store instruction
+          const int col = c0 + lane;
+          const bool cok = lane < ccols && col < p.Cout;
+          const float bv = (cok && p.bias) ? __ldg(p.bias + col) : 0.f;
+          float* outp = reinterpret_cast<float*>(p.out);
+          for (int rr = 0; rr < 32; ++rr) {
+            const long long pix = __shfl_sync(0xffffffffu, my_pix, rr);
+            if (pix < 0 || !cok) continue;
+            float f = stg[rr * 33 + lane] + bv;
+            if (p.residual != nullptr) {
+              const long long ro = pix * p.ldr + col;
+              if (p.res_dtype == GDL_F32) f += reinterpret_cast<const float*>(p.residual)[ro];
+              else if (p.res_dtype == GDL_BF16) f += __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p.residual)[ro]);
+              else f += __half2float(reinterpret_cast<const __half*>(p.residual)[ro]);
+            }
+            if (p.relu) f = fmaxf(f, 0.f);
+            outp[pix * p.ldo + col] = f;
           }
-          if (p.residual != nullptr) {
-            const long long roff = pix * p.ldr + c0;
-            if (p.res_dtype == GDL_F32) {
-              const float* r = reinterpret_cast<const float*>(p.residual) + roff;
-#pragma unroll
-              for (int i = 0; i < 16; ++i)
-                if (i < nvalid) f[i] += r[i];
-            } else if (p.res_dtype == GDL_BF16) {
-              const __nv_bfloat16* r = reinterpret_cast<const __nv_bfloat16*>(p.residual) + roff;
-#pragma unroll
-              for (int i = 0; i < 16; ++i)
-                if (i < nvalid) f[i] += __bfloat162float(r[i]);
+        } else {
+          // 16-bit output: lanes 0..15 write pixel rr, lanes 16..31 pixel rr+1; each lane two adjacent channels
+          const int hl = lane >> 4, l2 = (lane & 15) * 2;
+          const int col = c0 + l2;
+          const bool c0ok = l2 < ccols && col < p.Cout;
+          const bool c1ok = l2 + 1 < ccols && col + 1 < p.Cout;
+          const float b0 = (c0ok && p.bias) ? __ldg(p.bias + col) : 0.f;
+          const float b1 = (c1ok && p.bias) ? __ldg(p.bias + col + 1) : 0.f;
+          for (int rr = 0; rr < 32; rr += 2) {
+            const long long pix = __shfl_sync(0xffffffffu, my_pix, rr + hl);
+            if (pix < 0 || !c0ok) continue;
+            float f0 = stg[(rr + hl) * 33 + l2] + b0;
+            float f1 = stg[(rr + hl) * 33 + l2 + 1] + b1;
+            if (p.residual != nullptr) {
+              const long long ro = pix * p.ldr + col;
+              if (p.res_dtype == GDL_F32) {
+                f0 += reinterpret_cast<const float*>(p.residual)[ro];
+                if (c1ok) f1 += reinterpret_cast<const float*>(p.residual)[ro + 1];
+              } else if (p.res_dtype == GDL_BF16) {
+                f0 += __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p.residual)[ro]);
+                if (c1ok) f1 += __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p.residual)[ro + 1]);
+              } else {
+                f0 += __half2float(reinterpret_cast<const __half*>(p.residual)[ro]);
+                if (c1ok) f1 += __half2float(reinterpret_cast<const __half*>(p.residual)[ro + 1]);
+              }
+            }
+            if (p.relu) {
+              f0 = fmaxf(f0, 0.f);
+              f1 = fmaxf(f1, 0.f);
+            }
+            const long long off = pix * p.ldo + col;
+            if (p.out_dtype == GDL_BF16) {
+              __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + off;
+              if (c1ok && p.pair_ok) *reinterpret_cast<uint32_t*>(o) = pack_bf16x2(f0, f1);
+              else {
+                o[0] = __float2bfloat16_rn(f0);
+                if (c1ok) o[1] = __float2bfloat16_rn(f1);
+              }
             } else {
-              const __half* r = reinterpret_cast<const __half*>(p.residual) + roff;
-#pragma unroll
-              for (int i = 0; i < 16; ++i)
-                if (i < nvalid) f[i] += __half2float(r[i]);
+              __half* o = reinterpret_cast<__half*>(p.out) + off;
+              if (c1ok && p.pair_ok) *reinterpret_cast<uint32_t*>(o) = pack_f16x2(f0, f1);
+              else {
+                o[0] = __float2half_rn(f0);
+                if (c1ok) o[1] = __float2half_rn(f1);
+              }
             }
           }
-          if (p.relu) {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) f[i] = fmaxf(f[i], 0.f);
-          }
-          const long long off = pix * p.ldo + c0;
-          if (p.out_dtype == GDL_F32)
-            store_row16<float>(reinterpret_cast<float*>(p.out) + off, f, nvalid, p.vec_ok);
-          else if (p.out_dtype == GDL_BF16)
-            store_row16<__nv_bfloat16>(reinterpret_cast<__nv_bfloat16*>(p.out) + off, f, nvalid,
-                                       p.vec_ok);
-          else
-            store_row16<__half>(reinterpret_cast<__half*>(p.out) + off, f, nvalid, p.vec_ok);
         }
       }
       tc_fence_before();
@@ -500,7 +544,7 @@ extern "C" int gdl_conv2d_nhwc_fwd(const gdl_conv_fwd_t* d, void* stream_) {
     // by whole rows inside the 1024-byte swizzle repeat addresses the expected rows with base_offset = 0.)
     const int halo_cfg = opt_int(g_opt_conv_halo, "GDL_CONV_HALO", 1);
     if (halo_cfg > 0 && d->R == 3 && d->S == 3 && d->pad_h == 1 && d->pad_w == 1 && p.TH == 1 && p.TW == 128 &&
-        p.BK == 64 && p.BN <= 128 && !d->w_mn_major && d->w_rows_per_img == 0) {
+        p.BN <= 128 && !d->w_mn_major && d->w_rows_per_img == 0) {
       p.halo = 1;
       p.halo_bo = 0;
       p.a_bytes = ((130 * p.BK * 2 + 1023) / 1024) * 1024;
@@ -518,6 +562,7 @@ extern "C" int gdl_conv2d_nhwc_fwd(const gdl_conv_fwd_t* d, void* stream_) {
   p.ldo = d->ldo;
   const int esz = d->out_dtype == GDL_F32 ? 4 : 2;
   p.vec_ok = ((reinterpret_cast<uintptr_t>(d->out) & 15) == 0) && ((d->ldo * esz) % 16 == 0);
+  p.pair_ok = ((reinterpret_cast<uintptr_t>(d->out) & 3) == 0) && (d->ldo % 2 == 0);
   p.bias = d->bias;
   p.relu = d->relu;
   p.residual = d->residual;
@@ -648,7 +693,7 @@ conv_wgrad_kernel(const __grid_constant__ ConvWgradKParams p) {
 
   const int atomA_bytes = kWgPix * p.caA * 2;  // one MN atom (caA channels) x 64 pixels
   const int atomB_bytes = p.b_atom_bytes;
-  const uint32_t atomB_tx = p.halo ? 66u * 128u : (uint32_t)(kWgPix * p.caB * 2);
+  const uint32_t atomB_tx = (uint32_t)((p.halo ? kWgPix + 2 : kWgPix) * p.caB * 2);
   const uint32_t acc_stride = (uint32_t)(p.nsub * p.bn_max);
 
   // unit -> (tap, n-tile, m-tile, k-split); tap fastest so co-resident CTAs share dY / X in L2
@@ -740,7 +785,7 @@ conv_wgrad_kernel(const __grid_constant__ ConvWgradKParams p) {
           for (int s3 = 0; s3 < p.nsub; ++s3) {
             for (int kk = 0; kk < kWgPix / 16; ++kk) {
               const uint64_t da = umma_smem_desc(a_addr + kk * kstepA, atomA_bytes, sboA, ltA);
-              const uint64_t db = umma_smem_desc(b_addr + s3 * 128 + kk * kstepB, atomB_bytes, sboB, ltB);
+              const uint64_t db = umma_smem_desc(b_addr + s3 * p.caB * 2 + kk * kstepB, atomB_bytes, sboB, ltB);
               umma_f16(d_tmem + (uint32_t)(s3 * p.bn_max), da, db, idesc, (uint32_t)((pb > pb0) | (kk != 0)));
             }
           }
@@ -849,11 +894,11 @@ extern "C" int gdl_conv2d_nhwc_wgrad(const gdl_conv_wgrad_t* d, void* stream_) {
   {
     const int halo_cfg = opt_int(g_opt_wgrad_halo, "GDL_WGRAD_HALO", 1);
     p.halo = halo_cfg > 0 && d->R == 3 && d->S == 3 && d->pad_h == 1 && d->pad_w == 1 && p.TH == 1 &&
-             p.TW == kWgPix && p.caB == 64 && !d->batched;
+             p.TW == kWgPix && !d->batched;
   }
   p.nsub = p.halo ? 3 : 1;
   p.unit_taps = p.halo ? 3 : d->R * d->S;
-  p.b_atom_bytes = p.halo ? 9216 : kWgPix * p.caB * 2;
+  p.b_atom_bytes = p.halo ? (((kWgPix + 2) * p.caB * 2 + 1023) / 1024) * 1024 : kWgPix * p.caB * 2;
   p.tiles_w = (oW + p.TW - 1) / p.TW;
   p.tiles_h = (oH + p.TH - 1) / p.TH;
   long long pbs = (long long)N * p.tiles_w * p.tiles_h;
@@ -938,7 +983,7 @@ extern "C" int gdl_conv2d_nhwc_wgrad(const gdl_conv_wgrad_t* d, void* stream_) {
   }
 
   p.a_bytes = kWgPix * 128 * 2;
-  const int b_bytes = p.halo ? (bn_max / 64) * p.b_atom_bytes : kWgPix * bn_max * 2;
+  const int b_bytes = p.halo ? ((bn_max + p.caB - 1) / p.caB) * p.b_atom_bytes : kWgPix * bn_max * 2;
   p.stage_bytes = p.a_bytes + ((b_bytes + 1023) / 1024) * 1024;
   p.stages = kSmemBudget / p.stage_bytes;
   if (p.stages > kMaxStages) p.stages = kMaxStages;

@@ -280,6 +280,35 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
   }
 }
 
+// device-side step counter variant (CUDA-graph friendly: nothing step-dependent is baked into kernel
+// parameters).  state[0] = step (as float), state[1] = 1 - beta1^step, state[2] = sqrt(1 - beta2^step)
+__global__ void adam_advance_kernel(float* __restrict__ state, float beta1, float beta2) {
+  const float step = state[0] + 1.f;
+  state[0] = step;
+  state[1] = 1.f - powf(beta1, step);
+  state[2] = sqrtf(1.f - powf(beta2, step));
+}
+
+__global__ void adam_dev_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                float* __restrict__ v, long long n, float lr, float beta1, float beta2, float eps,
+                                float weight_decay, const float* __restrict__ state,
+                                const float* __restrict__ grad_scale) {
+  const float gsc = grad_scale ? grad_scale[0] : 1.f;
+  const float bc1 = state[1], bc2_sqrt = state[2];
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    float gi = g[i] * gsc;
+    const float pi = p[i];
+    if (weight_decay != 0.f) gi = fmaf(weight_decay, pi, gi);
+    const float mi = m[i] + (gi - m[i]) * (1.f - beta1);
+    const float vi = v[i] * beta2 + (1.f - beta2) * gi * gi;
+    m[i] = mi;
+    v[i] = vi;
+    const float denom = sqrtf(vi) / bc2_sqrt + eps;
+    p[i] = pi - (lr / bc1) * (mi / denom);
+  }
+}
+
 // sum of squares of a flat fp32 buffer (for clip_grad_norm_); result accumulated into out[0]
 __global__ void sumsq_kernel(const float* __restrict__ g, long long n, float* __restrict__ out) {
   float s = 0.f;
@@ -412,6 +441,19 @@ extern "C" int gdl_adam_step(float* p, const float* g, float* m, float* v, long 
   if (b > 8 * kNumSMsB200) b = 8 * kNumSMsB200;
   adam_kernel<<<(int)b, 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay,
                                                        (float)bc1, (float)sqrt(bc2), grad_scale);
+  GDL_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int gdl_adam_step_dev(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1,
+                                 float beta2, float eps, float weight_decay, float* state /* 3 floats */,
+                                 const float* grad_scale, void* stream) {
+  GDL_REQUIRE(p && g && m && v && state && n > 0, GDL_ERR_INVALID, "adam_dev: bad args");
+  cudaStream_t st = (cudaStream_t)stream;
+  adam_advance_kernel<<<1, 1, 0, st>>>(state, beta1, beta2);
+  long long b = (n + 255) / 256;
+  if (b > 8 * kNumSMsB200) b = 8 * kNumSMsB200;
+  adam_dev_kernel<<<(int)b, 256, 0, st>>>(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, state, grad_scale);
   GDL_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -267,40 +267,54 @@ template <typename T>
 __global__ void dwconv_gelu_fwd_kernel(const T* __restrict__ x, int ldx, const float* __restrict__ w,
                                        const float* __restrict__ bias, T* __restrict__ pre, T* __restrict__ y, int N,
                                        int H, int W, int C) {
+  // each thread owns one 8-channel vector: its 72 filter taps + 8 biases live in registers; it strides over pixels
   const int cv = C / 8;
-  const long long total = (long long)N * H * W * cv;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const long long pix = i / cv;
-    const int c0 = (int)(i - pix * cv) * 8;
-    const int wq = (int)(pix % W);
-    const long long t = pix / W;
-    const int hq = (int)(t % H);
-    const long long n = t / H;
-    float acc[8];
+  const int tpr = cv < (int)blockDim.x ? cv : blockDim.x;
+  const int rows_per_block = blockDim.x / tpr;
+  const int tc = threadIdx.x % tpr;
+  const int tr = threadIdx.x / tpr;
+  if (tr >= rows_per_block) return;
+  const long long M = (long long)N * H * W;
+  for (int c8 = tc; c8 < cv; c8 += tpr) {
+    const int c0 = c8 * 8;
+    float wr[8][9], bz[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] = bias ? bias[c0 + j] : 0.f;
+    for (int j = 0; j < 8; ++j) {
+      bz[j] = bias ? bias[c0 + j] : 0.f;
 #pragma unroll
-    for (int r = 0; r < 3; ++r) {
-      const int hh = hq + r - 1;
-      if (hh < 0 || hh >= H) continue;
-#pragma unroll
-      for (int s = 0; s < 3; ++s) {
-        const int ww = wq + s - 1;
-        if (ww < 0 || ww >= W) continue;
-        float f[8];
-        ld8(x + ((n * H + hh) * W + ww) * ldx + c0, f);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) acc[j] = fmaf(f[j], w[(c0 + j) * 9 + r * 3 + s], acc[j]);
-      }
+      for (int k = 0; k < 9; ++k) wr[j][k] = w[(c0 + j) * 9 + k];
     }
-    // the autocast reference rounds the conv output to 16 bits before GELU: do the same
-    st8(pre + pix * C + c0, acc);
-    float pr[8], out[8];
-    ld8(pre + pix * C + c0, pr);
+    for (long long pix = (long long)blockIdx.x * rows_per_block + tr; pix < M;
+         pix += (long long)gridDim.x * rows_per_block) {
+      const int wq = (int)(pix % W);
+      const long long t = pix / W;
+      const int hq = (int)(t % H);
+      const long long n = t / H;
+      float acc[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) out[j] = gelu_f(pr[j]);
-    st8(y + pix * C + c0, out);
+      for (int j = 0; j < 8; ++j) acc[j] = bz[j];
+#pragma unroll
+      for (int r = 0; r < 3; ++r) {
+        const int hh = hq + r - 1;
+        if (hh < 0 || hh >= H) continue;
+#pragma unroll
+        for (int s2 = 0; s2 < 3; ++s2) {
+          const int ww = wq + s2 - 1;
+          if (ww < 0 || ww >= W) continue;
+          float f[8];
+          ld8(x + ((n * H + hh) * W + ww) * ldx + c0, f);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[j] = fmaf(f[j], wr[j][r * 3 + s2], acc[j]);
+        }
+      }
+      // the autocast reference rounds the conv output to 16 bits before GELU: do the same
+      const float (&a)[8] = acc;
+      st8(pre + pix * C + c0, a);
+      float out[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) out[j] = gelu_f(to_f<T>(from_f<T>(acc[j])));
+      st8(y + pix * C + c0, out);
+    }
   }
 }
 
@@ -319,71 +333,97 @@ __global__ void gelu_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ 
   }
 }
 
-// dx = depthwise-conv-transpose(dpre); dw[c][tap] += sum dpre * x_shifted; db[c] += sum dpre
-// pgrads: fp32 [C][10] (9 taps + bias), pre-zeroed, accumulated with atomics (block partials in smem)
+// dx = depthwise-conv-transpose(dpre)   (filter taps in registers, thread strides over pixels)
 template <typename T>
-__global__ void dwconv_bwd_kernel(const T* __restrict__ dpre, const T* __restrict__ x, int ldx,
-                                  const float* __restrict__ w, T* __restrict__ dx, int lddx,
-                                  float* __restrict__ pgrads, int N, int H, int W, int C) {
-  // block: blockDim.x = cvb (channel vectors handled by this block) * rows; each thread owns one channel vector
+__global__ void dwconv_bwd_dx_kernel(const T* __restrict__ dpre, const float* __restrict__ w, T* __restrict__ dx,
+                                     int lddx, int N, int H, int W, int C) {
   const int cv = C / 8;
   const int tpr = cv < (int)blockDim.x ? cv : blockDim.x;
   const int rows_per_block = blockDim.x / tpr;
   const int tc = threadIdx.x % tpr;
   const int tr = threadIdx.x / tpr;
+  if (tr >= rows_per_block) return;
   const long long M = (long long)N * H * W;
-  for (int cbase = 0; cbase < cv; cbase += tpr) {
-    const int c8 = cbase + tc;
-    const bool active = c8 < cv && tr < rows_per_block;
+  for (int c8 = tc; c8 < cv; c8 += tpr) {
+    const int c0 = c8 * 8;
+    float wr[8][9];
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+#pragma unroll
+      for (int k = 0; k < 9; ++k) wr[j][k] = w[(c0 + j) * 9 + k];
+    for (long long pix = (long long)blockIdx.x * rows_per_block + tr; pix < M;
+         pix += (long long)gridDim.x * rows_per_block) {
+      const int wq = (int)(pix % W);
+      const long long t = pix / W;
+      const int hq = (int)(t % H);
+      const long long n = t / H;
+      float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+      for (int r = 0; r < 3; ++r) {
+        const int hg = hq - (r - 1);
+        if (hg < 0 || hg >= H) continue;
+#pragma unroll
+        for (int s2 = 0; s2 < 3; ++s2) {
+          const int wg = wq - (s2 - 1);
+          if (wg < 0 || wg >= W) continue;
+          float f[8];
+          ld8(dpre + ((n * H + hg) * W + wg) * C + c0, f);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[j] = fmaf(f[j], wr[j][r * 3 + s2], acc[j]);
+        }
+      }
+      st8(dx + pix * lddx + c0, acc);
+    }
+  }
+}
+
+// dw[c][tap] += sum_p dpre[p] * x[p + tap], db[c] += sum_p dpre[p]; pgrads fp32 [C][10], accumulated
+template <typename T>
+__global__ void dwconv_bwd_dw_kernel(const T* __restrict__ dpre, const T* __restrict__ x, int ldx,
+                                     float* __restrict__ pgrads, int N, int H, int W, int C) {
+  const int cv = C / 8;
+  const int tpr = cv < (int)blockDim.x ? cv : blockDim.x;
+  const int rows_per_block = blockDim.x / tpr;
+  const int tc = threadIdx.x % tpr;
+  const int tr = threadIdx.x / tpr;
+  if (tr >= rows_per_block) return;
+  const long long M = (long long)N * H * W;
+  for (int c8 = tc; c8 < cv; c8 += tpr) {
     const int c0 = c8 * 8;
     float wg[8][10];
 #pragma unroll
     for (int j = 0; j < 8; ++j)
 #pragma unroll
       for (int k = 0; k < 10; ++k) wg[j][k] = 0.f;
-    if (active) {
-      for (long long pix = (long long)blockIdx.x * rows_per_block + tr; pix < M;
-           pix += (long long)gridDim.x * rows_per_block) {
-        const int wq = (int)(pix % W);
-        const long long t = pix / W;
-        const int hq = (int)(t % H);
-        const long long n = t / H;
-        float g0[8];
-        ld8(dpre + pix * C + c0, g0);
-        float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (long long pix = (long long)blockIdx.x * rows_per_block + tr; pix < M;
+         pix += (long long)gridDim.x * rows_per_block) {
+      const int wq = (int)(pix % W);
+      const long long t = pix / W;
+      const int hq = (int)(t % H);
+      const long long n = t / H;
+      float g0[8];
+      ld8(dpre + pix * C + c0, g0);
 #pragma unroll
-        for (int r = 0; r < 3; ++r) {
+      for (int j = 0; j < 8; ++j) wg[j][9] += g0[j];
 #pragma unroll
-          for (int s = 0; s < 3; ++s) {
-            // weight gradient: dpre[p] * x[p + (r-1, s-1)]
-            const int hx = hq + r - 1, wx = wq + s - 1;
-            if (hx >= 0 && hx < H && wx >= 0 && wx < W) {
-              float f[8];
-              ld8(x + ((n * H + hx) * W + wx) * ldx + c0, f);
+      for (int r = 0; r < 3; ++r) {
+        const int hx = hq + r - 1;
+        if (hx < 0 || hx >= H) continue;
 #pragma unroll
-              for (int j = 0; j < 8; ++j) wg[j][r * 3 + s] = fmaf(g0[j], f[j], wg[j][r * 3 + s]);
-            }
-            // input gradient: dx[p] = sum dpre[p - (r-1, s-1)] * w[r][s]
-            const int hg = hq - (r - 1), wgx = wq - (s - 1);
-            if (hg >= 0 && hg < H && wgx >= 0 && wgx < W) {
-              float f[8];
-              ld8(dpre + ((n * H + hg) * W + wgx) * C + c0, f);
+        for (int s2 = 0; s2 < 3; ++s2) {
+          const int wx = wq + s2 - 1;
+          if (wx < 0 || wx >= W) continue;
+          float f[8];
+          ld8(x + ((n * H + hx) * W + wx) * ldx + c0, f);
 #pragma unroll
-              for (int j = 0; j < 8; ++j) acc[j] = fmaf(f[j], w[(c0 + j) * 9 + r * 3 + s], acc[j]);
-            }
-          }
+          for (int j = 0; j < 8; ++j) wg[j][r * 3 + s2] = fmaf(g0[j], f[j], wg[j][r * 3 + s2]);
         }
-#pragma unroll
-        for (int j = 0; j < 8; ++j) wg[j][9] += g0[j];
-        st8(dx + pix * lddx + c0, acc);
-      }
-      if (pgrads != nullptr) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j)
-#pragma unroll
-          for (int k = 0; k < 10; ++k) atomicAdd(&pgrads[(long long)(c0 + j) * 10 + k], wg[j][k]);
       }
     }
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+#pragma unroll
+      for (int k = 0; k < 10; ++k) atomicAdd(&pgrads[(long long)(c0 + j) * 10 + k], wg[j][k]);
   }
 }
 
@@ -421,6 +461,36 @@ __global__ void bilinear_fwd_kernel(const T* __restrict__ x, long long ldx, T* _
     const float v = a0 * (b0 * to_f<T>(base[((long long)h0 * Wi + w0) * ldx]) + b1 * to_f<T>(base[((long long)h0 * Wi + w1) * ldx])) +
                     a1 * (b0 * to_f<T>(base[((long long)h1 * Wi + w0) * ldx]) + b1 * to_f<T>(base[((long long)h1 * Wi + w1) * ldx]));
     y[((n * Ho + ho) * Wo + wo) * ldy + c] = from_f<T>(v);
+  }
+}
+
+// 8 channels per thread (16-bit features, C % 8 == 0)
+template <typename T>
+__global__ void bilinear_fwd_vec8_kernel(const T* __restrict__ x, long long ldx, T* __restrict__ y, long long ldy, int N,
+                                         int Hi, int Wi, int Ho, int Wo, int C, float sh, float sw) {
+  const int cv = C / 8;
+  const long long total = (long long)N * Ho * Wo * cv;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c0 = (int)(i % cv) * 8;
+    long long t = i / cv;
+    const int wo = (int)(t % Wo);
+    t /= Wo;
+    const int ho = (int)(t % Ho);
+    const long long n = t / Ho;
+    int h0, h1, w0, w1;
+    float a0, a1, b0, b1;
+    bil_src(ho, sh, Hi, h0, h1, a0, a1);
+    bil_src(wo, sw, Wi, w0, w1, b0, b1);
+    const T* base = x + n * Hi * Wi * ldx + c0;
+    float f00[8], f01[8], f10[8], f11[8], o[8];
+    ld8(base + ((long long)h0 * Wi + w0) * ldx, f00);
+    ld8(base + ((long long)h0 * Wi + w1) * ldx, f01);
+    ld8(base + ((long long)h1 * Wi + w0) * ldx, f10);
+    ld8(base + ((long long)h1 * Wi + w1) * ldx, f11);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = a0 * (b0 * f00[j] + b1 * f01[j]) + a1 * (b0 * f10[j] + b1 * f11[j]);
+    st8(y + ((n * Ho + ho) * Wo + wo) * ldy + c0, o);
   }
 }
 
@@ -466,6 +536,46 @@ __global__ void bilinear_bwd_kernel(const T* __restrict__ dy, long long ldy, T* 
       }
     }
     dx[((n * Hi + hi) * Wi + wi) * ldx + c] = from_f<T>(acc);
+  }
+}
+
+template <typename T>
+__global__ void bilinear_bwd_vec8_kernel(const T* __restrict__ dy, long long ldy, T* __restrict__ dx, long long ldx,
+                                         int N, int Hi, int Wi, int Ho, int Wo, int C, float sh, float sw) {
+  const int cv = C / 8;
+  const long long total = (long long)N * Hi * Wi * cv;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c0 = (int)(i % cv) * 8;
+    long long t = i / cv;
+    const int wi = (int)(t % Wi);
+    t /= Wi;
+    const int hi = (int)(t % Hi);
+    const long long n = t / Hi;
+    int hlo, hhi, wlo, whi;
+    bil_range(hi, sh, Ho, hlo, hhi);
+    bil_range(wi, sw, Wo, wlo, whi);
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int ho = hlo; ho <= hhi; ++ho) {
+      int h0, h1;
+      float a0, a1;
+      bil_src(ho, sh, Hi, h0, h1, a0, a1);
+      const float wh = (h0 == hi ? a0 : 0.f) + (h1 == hi ? a1 : 0.f);
+      if (wh == 0.f) continue;
+      for (int wo = wlo; wo <= whi; ++wo) {
+        int w0, w1;
+        float b0, b1;
+        bil_src(wo, sw, Wi, w0, w1, b0, b1);
+        const float ww = (w0 == wi ? b0 : 0.f) + (w1 == wi ? b1 : 0.f);
+        if (ww == 0.f) continue;
+        float f[8];
+        ld8(dy + ((n * Ho + ho) * Wo + wo) * ldy + c0, f);
+        const float k = wh * ww;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = fmaf(k, f[j], acc[j]);
+      }
+    }
+    st8(dx + ((n * Hi + hi) * Wi + wi) * ldx + c0, acc);
   }
 }
 
@@ -578,19 +688,27 @@ extern "C" int gdl_softmax_bwd(const void* p, long long ldp, const void* dp, lon
   return 0;
 }
 
+static int chan_row_grid(long long rows, int C, int rows_per_thread) {
+  const int cv = C / 8;
+  const int tpr = cv < 256 ? cv : 256;
+  const int rpb = 256 / tpr;
+  long long b = (rows + (long long)rpb * rows_per_thread - 1) / ((long long)rpb * rows_per_thread);
+  const long long cap = (long long)kNumSMsB200 * 8;
+  if (b > cap) b = cap;
+  return (int)(b < 1 ? 1 : b);
+}
+
 extern "C" int gdl_dwconv3x3_gelu_fwd(const void* x, int ldx, const float* w, const float* bias, void* pre, void* y,
                                       int dtype, int N, int H, int W, int C, void* stream) {
   GDL_REQUIRE(x && w && pre && y && N > 0 && H > 0 && W > 0 && C > 0 && C % 8 == 0 && ldx % 8 == 0, GDL_ERR_INVALID,
               "dwconv_gelu: bad args");
   GDL_REQUIRE(dtype == GDL_BF16 || dtype == GDL_F16, GDL_ERR_INVALID, "dwconv_gelu: 16-bit dtype expected");
   cudaStream_t st = (cudaStream_t)stream;
-  const long long total = (long long)N * H * W * (C / 8);
-  long long b = (total + 255) / 256;
-  if (b > 16 * kNumSMsB200) b = 16 * kNumSMsB200;
+  const int grid = chan_row_grid((long long)N * H * W, C, 8);
   if (dtype == GDL_BF16)
-    dwconv_gelu_fwd_kernel<__nv_bfloat16><<<(int)b, 256, 0, st>>>((const __nv_bfloat16*)x, ldx, w, bias, (__nv_bfloat16*)pre, (__nv_bfloat16*)y, N, H, W, C);
+    dwconv_gelu_fwd_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)x, ldx, w, bias, (__nv_bfloat16*)pre, (__nv_bfloat16*)y, N, H, W, C);
   else
-    dwconv_gelu_fwd_kernel<__half><<<(int)b, 256, 0, st>>>((const __half*)x, ldx, w, bias, (__half*)pre, (__half*)y, N, H, W, C);
+    dwconv_gelu_fwd_kernel<__half><<<grid, 256, 0, st>>>((const __half*)x, ldx, w, bias, (__half*)pre, (__half*)y, N, H, W, C);
   GDL_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -606,20 +724,18 @@ extern "C" int gdl_dwconv3x3_gelu_bwd(const void* dy, const void* pre, const voi
   const long long n8 = M * (C / 8);
   long long b1 = (n8 + 255) / 256;
   if (b1 > 16 * kNumSMsB200) b1 = 16 * kNumSMsB200;
-  const int cv = C / 8;
-  const int tpr = cv < 256 ? cv : 256;
-  const int rpb = 256 / tpr;
-  long long b2 = (M + rpb * 8 - 1) / (rpb * 8);
-  if (b2 > 4 * kNumSMsB200) b2 = 4 * kNumSMsB200;
-  if (b2 < 1) b2 = 1;
+  const int g_dx = chan_row_grid(M, C, 8);
+  const int g_dw = chan_row_grid(M, C, 64);  // fewer, longer threads: 80 atomics per thread at the end
   if (dtype == GDL_BF16) {
     using T = __nv_bfloat16;
     gelu_bwd_kernel<T><<<(int)b1, 256, 0, st>>>((const T*)dy, (const T*)pre, (T*)dpre_scratch, n8);
-    dwconv_bwd_kernel<T><<<(int)b2, 256, 0, st>>>((const T*)dpre_scratch, (const T*)x, ldx, w, (T*)dx, lddx, pgrads, N, H, W, C);
+    dwconv_bwd_dx_kernel<T><<<g_dx, 256, 0, st>>>((const T*)dpre_scratch, w, (T*)dx, lddx, N, H, W, C);
+    if (pgrads) dwconv_bwd_dw_kernel<T><<<g_dw, 256, 0, st>>>((const T*)dpre_scratch, (const T*)x, ldx, pgrads, N, H, W, C);
   } else {
     using T = __half;
     gelu_bwd_kernel<T><<<(int)b1, 256, 0, st>>>((const T*)dy, (const T*)pre, (T*)dpre_scratch, n8);
-    dwconv_bwd_kernel<T><<<(int)b2, 256, 0, st>>>((const T*)dpre_scratch, (const T*)x, ldx, w, (T*)dx, lddx, pgrads, N, H, W, C);
+    dwconv_bwd_dx_kernel<T><<<g_dx, 256, 0, st>>>((const T*)dpre_scratch, w, (T*)dx, lddx, N, H, W, C);
+    if (pgrads) dwconv_bwd_dw_kernel<T><<<g_dw, 256, 0, st>>>((const T*)dpre_scratch, (const T*)x, ldx, pgrads, N, H, W, C);
   }
   GDL_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -634,6 +750,17 @@ extern "C" int gdl_bilinear_fwd(const void* x, long long ldx, void* y, long long
   long long b = (total + 255) / 256;
   if (b > 16 * kNumSMsB200) b = 16 * kNumSMsB200;
   const float sh = (float)Hi / (float)Ho, sw = (float)Wi / (float)Wo;
+  if (dtype != GDL_F32 && C % 8 == 0 && ldx % 8 == 0 && ldy % 8 == 0 && ((uintptr_t)x & 15) == 0 && ((uintptr_t)y & 15) == 0) {
+    long long bv = (total / 8 + 255) / 256;
+    if (bv > 16 * kNumSMsB200) bv = 16 * kNumSMsB200;
+    if (bv < 1) bv = 1;
+    if (dtype == GDL_BF16)
+      bilinear_fwd_vec8_kernel<__nv_bfloat16><<<(int)bv, 256, 0, st>>>((const __nv_bfloat16*)x, ldx, (__nv_bfloat16*)y, ldy, N, Hi, Wi, Ho, Wo, C, sh, sw);
+    else
+      bilinear_fwd_vec8_kernel<__half><<<(int)bv, 256, 0, st>>>((const __half*)x, ldx, (__half*)y, ldy, N, Hi, Wi, Ho, Wo, C, sh, sw);
+    GDL_CHECK_CUDA(cudaGetLastError());
+    return 0;
+  }
   GDL_DISPATCH_T(dtype, { bilinear_fwd_kernel<T><<<(int)b, 256, 0, st>>>((const T*)x, ldx, (T*)y, ldy, N, Hi, Wi, Ho, Wo, C, sh, sw); });
   GDL_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -647,6 +774,17 @@ extern "C" int gdl_bilinear_bwd(const void* dy, long long ldy, void* dx, long lo
   long long b = (total + 255) / 256;
   if (b > 16 * kNumSMsB200) b = 16 * kNumSMsB200;
   const float sh = (float)Hi / (float)Ho, sw = (float)Wi / (float)Wo;
+  if (dtype != GDL_F32 && C % 8 == 0 && ldx % 8 == 0 && ldy % 8 == 0 && ((uintptr_t)dx & 15) == 0 && ((uintptr_t)dy & 15) == 0) {
+    long long bv = (total / 8 + 127) / 128;
+    if (bv > 16 * kNumSMsB200) bv = 16 * kNumSMsB200;
+    if (bv < 1) bv = 1;
+    if (dtype == GDL_BF16)
+      bilinear_bwd_vec8_kernel<__nv_bfloat16><<<(int)bv, 128, 0, st>>>((const __nv_bfloat16*)dy, ldy, (__nv_bfloat16*)dx, ldx, N, Hi, Wi, Ho, Wo, C, sh, sw);
+    else
+      bilinear_bwd_vec8_kernel<__half><<<(int)bv, 128, 0, st>>>((const __half*)dy, ldy, (__half*)dx, ldx, N, Hi, Wi, Ho, Wo, C, sh, sw);
+    GDL_CHECK_CUDA(cudaGetLastError());
+    return 0;
+  }
   GDL_DISPATCH_T(dtype, { bilinear_bwd_kernel<T><<<(int)b, 256, 0, st>>>((const T*)dy, ldy, (T*)dx, ldx, N, Hi, Wi, Ho, Wo, C, sh, sw); });
   GDL_CHECK_CUDA(cudaGetLastError());
   return 0;

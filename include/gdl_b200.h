@@ -224,6 +224,10 @@ int gdl_argmax_classes(const float* logits, int ld, long long M, int K, float th
  * gdl_grad_clip_coef: scale[0] = min(1, max_norm / (||g||_2 + 1e-6))  (clip_grad_norm_). */
 int gdl_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
                   float eps, float weight_decay, int step, const float* grad_scale, void* stream);
+/* same update with the step counter on the device: state[0] = step, state[1..2] = bias corrections, advanced
+ * by the call itself (nothing step-dependent in kernel parameters: the step can live in a CUDA graph). */
+int gdl_adam_step_dev(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
+                      float eps, float weight_decay, float* state, const float* grad_scale, void* stream);
 int gdl_grad_clip_coef(const float* g, long long n, float max_norm, float* sumsq_scratch, float* scale,
                        void* stream);
 

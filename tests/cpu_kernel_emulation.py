@@ -288,6 +288,14 @@ def adam_step(p, g, m, v, lr, beta1, beta2, eps, weight_decay, step, grad_scale=
     p.sub_((lr / bc1) * m / (v.sqrt() / bc2 ** 0.5 + eps))
 
 
+def adam_step_dev(p, g, m, v, lr, beta1, beta2, eps, weight_decay, state, grad_scale=None):
+    state[0] += 1
+    step = int(state[0].item())
+    state[1] = 1 - beta1 ** step
+    state[2] = (1 - beta2 ** step) ** 0.5
+    adam_step(p, g, m, v, lr, beta1, beta2, eps, weight_decay, step, grad_scale)
+
+
 def grad_clip_coef(g, max_norm, scratch, scale):
     scale[0] = min(1.0, max_norm / (g.norm().item() + 1e-6))
 

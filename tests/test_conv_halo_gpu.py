@@ -22,7 +22,7 @@ def halo_switch():
 
 @pytest.mark.parametrize("n,h,w,chans,cout", [
     (2, 4, 128, [64], 64), (1, 6, 256, [64, 128], 32), (2, 3, 384, [256, 64, 64], 128), (1, 2, 128, [64], 16),
-    (1, 5, 512, [128], 64),
+    (1, 5, 512, [128], 64), (1, 4, 256, [16], 16), (2, 3, 128, [32], 16), (1, 3, 128, [32, 32], 32), (1, 2, 128, [16], 5),
 ])
 def test_fwd_halo_equals_per_tap_and_fp32(cuda, halo_switch, n, h, w, chans, cout):
     from gdl_b200 import ops
@@ -44,7 +44,7 @@ def test_fwd_halo_equals_per_tap_and_fp32(cuda, halo_switch, n, h, w, chans, cou
 
 @pytest.mark.parametrize("n,h,w,chans,cout", [
     (2, 4, 64, [64], 64), (1, 6, 128, [64, 128], 32), (2, 3, 256, [256, 64, 64], 128), (1, 2, 128, [64], 16),
-    (1, 5, 192, [128], 256),
+    (1, 5, 192, [128], 256), (1, 4, 256, [16], 16), (2, 3, 128, [32], 16), (1, 3, 64, [32, 32], 32),
 ])
 def test_wgrad_halo_equals_per_tap_and_autograd(cuda, halo_switch, n, h, w, chans, cout):
     from gdl_b200 import ops

@@ -375,3 +375,22 @@ def test_adam_and_clip_match_torch(cuda):
         ops.grad_clip_coef(grad, 1.0, scratch[0:1], scratch[1:2])
         ops.adam_step(p, grad, m, v, 1e-3, 0.9, 0.999, 1e-8, 0.01, step, scratch[1:2])
         assert torch.allclose(p, ref.detach(), atol=1e-6, rtol=1e-5)
+
+
+def test_adam_device_step_counter_matches_torch(cuda):
+    from gdl_b200 import ops
+    g = torch.Generator().manual_seed(11)
+    n = 50_001
+    p0 = torch.randn(n, generator=g).cuda()
+    p = p0.clone()
+    ref = torch.nn.Parameter(p0.clone())
+    opt = torch.optim.Adam([ref], lr=2e-3, betas=(0.9, 0.999), eps=1e-8)
+    m, v = torch.zeros(n, device="cuda"), torch.zeros(n, device="cuda")
+    state = torch.zeros(3, device="cuda")
+    for _ in range(4):
+        grad = torch.randn(n, generator=g).cuda()
+        ref.grad = grad.clone()
+        opt.step()
+        ops.adam_step_dev(p, grad, m, v, 2e-3, 0.9, 0.999, 1e-8, 0.0, state)
+        assert torch.allclose(p, ref.detach(), atol=1e-6, rtol=1e-5)
+    assert state[0].item() == 4
