@@ -579,6 +579,69 @@ __global__ void bilinear_bwd_vec8_kernel(const T* __restrict__ dy, long long ldy
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// nn.AdaptiveAvgPool2d(s) on NHWC (PPM, models/utils.py:55-93): bin [floor(i*H/s), ceil((i+1)*H/s))
+// ------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void adaptive_avgpool_fwd_kernel(const T* __restrict__ x, long long ldx, T* __restrict__ y, int N, int H,
+                                            int W, int C, int S) {
+  const long long total = (long long)N * S * S * C;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    long long t = i / C;
+    const int ow = (int)(t % S);
+    t /= S;
+    const int oh = (int)(t % S);
+    const long long n = t / S;
+    const int h0 = (oh * H) / S, h1 = ((oh + 1) * H + S - 1) / S;
+    const int w0 = (ow * W) / S, w1 = ((ow + 1) * W + S - 1) / S;
+    float acc = 0.f;
+    for (int h = h0; h < h1; ++h)
+      for (int w = w0; w < w1; ++w) acc += to_f<T>(x[((n * H + h) * W + w) * ldx + c]);
+    y[i] = from_f<T>(acc / (float)((h1 - h0) * (w1 - w0)));
+  }
+}
+
+template <typename T>
+__global__ void adaptive_avgpool_bwd_kernel(const T* __restrict__ dy, T* __restrict__ dx, int N, int H, int W, int C,
+                                            int S) {
+  const long long total = (long long)N * H * W * C;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    long long t = i / C;
+    const int w = (int)(t % W);
+    t /= W;
+    const int h = (int)(t % H);
+    const long long n = t / H;
+    float acc = 0.f;
+    for (int oh = 0; oh < S; ++oh) {
+      const int h0 = (oh * H) / S, h1 = ((oh + 1) * H + S - 1) / S;
+      if (h < h0 || h >= h1) continue;
+      for (int ow = 0; ow < S; ++ow) {
+        const int w0 = (ow * W) / S, w1 = ((ow + 1) * W + S - 1) / S;
+        if (w < w0 || w >= w1) continue;
+        acc += to_f<T>(dy[((n * S + oh) * S + ow) * C + c]) / (float)((h1 - h0) * (w1 - w0));
+      }
+    }
+    dx[i] = from_f<T>(acc);
+  }
+}
+
+// y = a + b (16-bit NHWC with strides) — UperNet top-down path  laterals[i-1] + up(laterals[i])
+template <typename T>
+__global__ void add_kernel(const T* __restrict__ a, long long lda, const T* __restrict__ b, long long ldb,
+                           T* __restrict__ y, long long ldy, long long M, int C) {
+  const long long total = M * C;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / C;
+    const int c = (int)(i - r * C);
+    y[r * ldy + c] = from_f<T>(to_f<T>(a[r * lda + c]) + to_f<T>(b[r * ldb + c]));
+  }
+}
+
 // elementwise helpers for the fp32 residual stream
 template <typename T>
 __global__ void cast_f32_kernel(const float* __restrict__ x, T* __restrict__ y, long long n) {
@@ -786,6 +849,42 @@ extern "C" int gdl_bilinear_bwd(const void* dy, long long ldy, void* dx, long lo
     return 0;
   }
   GDL_DISPATCH_T(dtype, { bilinear_bwd_kernel<T><<<(int)b, 256, 0, st>>>((const T*)dy, ldy, (T*)dx, ldx, N, Hi, Wi, Ho, Wo, C, sh, sw); });
+  GDL_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int gdl_adaptive_avgpool_fwd(const void* x, long long ldx, void* y, int dtype, int N, int H, int W, int C,
+                                        int S, void* stream) {
+  GDL_REQUIRE(x && y && N > 0 && H > 0 && W > 0 && C > 0 && S > 0 && S <= H && S <= W, GDL_ERR_INVALID,
+              "adaptive_avgpool: bad args");
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long total = (long long)N * S * S * C;
+  long long b = (total + 255) / 256;
+  if (b > 8 * kNumSMsB200) b = 8 * kNumSMsB200;
+  GDL_DISPATCH_T(dtype, { adaptive_avgpool_fwd_kernel<T><<<(int)b, 256, 0, st>>>((const T*)x, ldx, (T*)y, N, H, W, C, S); });
+  GDL_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int gdl_adaptive_avgpool_bwd(const void* dy, void* dx, int dtype, int N, int H, int W, int C, int S,
+                                        void* stream) {
+  GDL_REQUIRE(dy && dx && N > 0 && H > 0 && W > 0 && C > 0 && S > 0, GDL_ERR_INVALID, "adaptive_avgpool_bwd: bad args");
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long total = (long long)N * H * W * C;
+  long long b = (total + 255) / 256;
+  if (b > 8 * kNumSMsB200) b = 8 * kNumSMsB200;
+  GDL_DISPATCH_T(dtype, { adaptive_avgpool_bwd_kernel<T><<<(int)b, 256, 0, st>>>((const T*)dy, (T*)dx, N, H, W, C, S); });
+  GDL_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int gdl_add_nhwc(const void* a, long long lda, const void* b, long long ldb, void* y, long long ldy, int dtype,
+                            long long M, int C, void* stream) {
+  GDL_REQUIRE(a && b && y && M > 0 && C > 0, GDL_ERR_INVALID, "add: bad args");
+  cudaStream_t st = (cudaStream_t)stream;
+  long long blk = (M * C + 255) / 256;
+  if (blk > 16 * kNumSMsB200) blk = 16 * kNumSMsB200;
+  GDL_DISPATCH_T(dtype, { add_kernel<T><<<(int)blk, 256, 0, st>>>((const T*)a, lda, (const T*)b, ldb, (T*)y, ldy, M, C); });
   GDL_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -126,6 +126,9 @@ _SIGS = {
     "gdl_bilinear_fwd": [_VP, _LL, _VP, _LL, _I, _I, _I, _I, _I, _I, _I, _VP],
     "gdl_bilinear_bwd": [_VP, _LL, _VP, _LL, _I, _I, _I, _I, _I, _I, _I, _VP],
     "gdl_cast_f32": [_VP, _VP, _I, _LL, _VP],
+    "gdl_adaptive_avgpool_fwd": [_VP, _LL, _VP, _I, _I, _I, _I, _I, _I, _VP],
+    "gdl_adaptive_avgpool_bwd": [_VP, _VP, _I, _I, _I, _I, _I, _I, _VP],
+    "gdl_add_nhwc": [_VP, _LL, _VP, _LL, _VP, _LL, _I, _LL, _I, _VP],
     "gdl_debug_shift_probe": [_VP, _VP, _VP, _I, _I, _I, _VP],
 }
 

@@ -318,6 +318,69 @@ class Engine:
             self.tape.append(bwd)
         return out
 
+    # ------------------------------------------------------------------ generic tape ops
+    def collect_grad(self, a: Act) -> torch.Tensor | None:
+        """Sum of the gradient sources registered on `a` as one dense 16-bit tensor (None if there are none)."""
+        srcs = a.all_gsrcs()
+        if not srcs:
+            return None
+        n, h, w, c = a.t.shape
+        if len(srcs) == 1 and srcs[0][1] == 0 and srcs[0][0].stride(2) == c:
+            g = srcs[0][0]
+        else:
+            g = torch.empty((n, h, w, c), dtype=self.dtype, device=a.t.device)
+            ops.grad_gather(srcs, a.t.shape, self.dtype, g=g)
+        a.gsrcs.clear()
+        if a.up is not None:
+            a.up.gsrcs.clear()
+        return g
+
+    def bilinear(self, a: Act, ho: int, wo: int) -> Act:
+        """F.interpolate(mode="bilinear", align_corners=False) to (ho, wo); identity sizes are passed through."""
+        n, h, w, c = a.t.shape
+        if (h, w) == (ho, wo):
+            return a
+        out = Act(ops.bilinear_fwd(a.t, ho, wo))
+        if self.training and a.needs_grad:
+            def bwd() -> None:
+                g = self.collect_grad(out)
+                if g is not None:
+                    a.gsrcs.append((ops.bilinear_bwd(g, h, w), 0))
+            self.tape.append(bwd)
+        return out
+
+    def add(self, a: Act, b: Act) -> Act:
+        out = Act(ops.add_nhwc(a.t, b.t))
+        if self.training:
+            def bwd() -> None:
+                g = self.collect_grad(out)
+                if g is not None:
+                    if a.needs_grad:
+                        a.gsrcs.append((g, 0))
+                    if b.needs_grad:
+                        b.gsrcs.append((g, 0))
+            self.tape.append(bwd)
+        return out
+
+    def adaptive_avgpool(self, a: Act, s: int) -> Act:
+        n, h, w, c = a.t.shape
+        out = Act(ops.adaptive_avgpool_fwd(a.t, s))
+        if self.training and a.needs_grad:
+            def bwd() -> None:
+                g = self.collect_grad(out)
+                if g is not None:
+                    a.gsrcs.append((ops.adaptive_avgpool_bwd(g.contiguous(), h, w), 0))
+            self.tape.append(bwd)
+        return out
+
+    def conv_bn_relu(self, srcs: list[Act], conv: torch.nn.Conv2d, bn: torch.nn.BatchNorm2d, *, want_up: bool = False) -> Act:
+        """ConvModule: conv (stride 1, optional bias) + BatchNorm2d + ReLU"""
+        pad = conv.padding[0]
+        rc = self.conv_raw(srcs, conv.weight, conv.stride[0], pad, bias=conv.bias)
+        st = self.bn_prepare(rc, BNParams(bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.num_batches_tracked,
+                                          bn.eps, bn.momentum if bn.momentum is not None else 0.1))
+        return self.bn_act(rc, st, relu=True, want_up=want_up)
+
     # ------------------------------------------------------------------ head
     def conv_head(self, a: Act, weight: torch.nn.Parameter, bias: torch.nn.Parameter | None, pad: int) -> torch.Tensor:
         """Conv (+bias) producing fp32 logits (N,H,W,K); its backward takes d(logits) padded to 16 channels."""

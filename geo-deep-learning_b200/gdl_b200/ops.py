@@ -503,3 +503,27 @@ def cast_f32(x, dtype):
     y = torch.empty(x.shape, dtype=dtype, device=x.device)
     _ck(L.load().gdl_cast_f32(L.ptr(x), L.ptr(y), L.dt_code(dtype), x.numel(), L.stream_ptr()))
     return y
+
+
+def adaptive_avgpool_fwd(x, s):
+    n, h, w, c = x.shape
+    y = torch.empty((n, s, s, c), dtype=x.dtype, device=x.device)
+    _ck(L.load().gdl_adaptive_avgpool_fwd(L.ptr(x), x.stride(2), L.ptr(y), L.dt_code(x.dtype), n, h, w, c, s, L.stream_ptr()))
+    return y
+
+
+def adaptive_avgpool_bwd(dy, h, w):
+    n, s, _, c = dy.shape
+    if not dy.is_contiguous():
+        raise ValueError("adaptive_avgpool_bwd: dense dy expected")
+    dx = torch.empty((n, h, w, c), dtype=dy.dtype, device=dy.device)
+    _ck(L.load().gdl_adaptive_avgpool_bwd(L.ptr(dy), L.ptr(dx), L.dt_code(dy.dtype), n, h, w, c, s, L.stream_ptr()))
+    return dx
+
+
+def add_nhwc(a, b):
+    n, h, w, c = a.shape
+    y = torch.empty((n, h, w, c), dtype=a.dtype, device=a.device)
+    _ck(L.load().gdl_add_nhwc(L.ptr(a), a.stride(2), L.ptr(b), b.stride(2), L.ptr(y), c, L.dt_code(a.dtype), n * h * w, c,
+                              L.stream_ptr()))
+    return y

@@ -273,6 +273,15 @@ int gdl_bilinear_fwd(const void* x, long long ldx, void* y, long long ldy, int d
 int gdl_bilinear_bwd(const void* dy, long long ldy, void* dx, long long ldx, int dtype, int N, int Hi, int Wi,
                      int Ho, int Wo, int C, void* stream);
 
+/* nn.AdaptiveAvgPool2d(S) of the UperNet pyramid pooling module (models/utils.py:55-93) and its adjoint;
+ * y/dy are dense [N][S][S][C]. */
+int gdl_adaptive_avgpool_fwd(const void* x, long long ldx, void* y, int dtype, int N, int H, int W, int C, int S,
+                             void* stream);
+int gdl_adaptive_avgpool_bwd(const void* dy, void* dx, int dtype, int N, int H, int W, int C, int S, void* stream);
+/* y = a + b on NHWC rows (UperNet top-down path, upernet.py:128-135) */
+int gdl_add_nhwc(const void* a, long long lda, const void* b, long long ldb, void* y, long long ldy, int dtype,
+                 long long M, int C, void* stream);
+
 /* fp32 -> dtype cast of a flat buffer (residual-stream gradient -> 16-bit GEMM operand) */
 int gdl_cast_f32(const float* x, void* y, int dtype, long long n, void* stream);
 

@@ -122,9 +122,48 @@ def segformer_golden() -> None:
     print("wrote segformer_b0_golden.pt")
 
 
+def upernet_golden() -> None:
+    """Outputs of the REFERENCE's MultiLevelNeck + UperNetDecoder + FCNHead + SegmentationHead (all torch-only,
+    imported from /root/reference) loaded with oracle.upernet.init_state_dict(96, 64, 5, seed=1)."""
+    import torch.nn as nn
+    import torch.nn.functional as F
+    if str(REF) not in sys.path:
+        sys.path.insert(0, str(REF))
+    from geo_deep_learning.models.decoders.upernet import UperNetDecoder
+    from geo_deep_learning.models.heads.fcn_head import FCNHead
+    from geo_deep_learning.models.heads.segmentation_head import SegmentationHead
+    from geo_deep_learning.models.necks.multilevel_neck import MultiLevelNeck
+    from oracle import upernet as ou
+    e, ch, k = 96, 64, 5
+    m = nn.Module()
+    m.neck = MultiLevelNeck([e] * 4, [e] * 4, scales=[4, 2, 1, 0.5], norm_cfg={"type": "BN"}, act_cfg={"type": "ReLU"})
+    m.decoder = UperNetDecoder([e] * 4, (1, 2, 3, 6), ch, align_corners=False, scale_modules=False)
+    m.aux_head = FCNHead(e, ch, num_convs=1, num_classes=k, dropout_ratio=0.0)
+    m.head = SegmentationHead(ch, k)
+    m.load_state_dict(ou.init_state_dict(e, ch, k, seed=1))
+    g = torch.Generator().manual_seed(2)
+    feats = [torch.randn(2, e, 12, 12, generator=g) for _ in range(4)]
+    t = torch.randint(0, k, (2, 168, 168), generator=g)
+    m.train()
+    f = m.neck(feats)
+    out = F.interpolate(m.head(m.decoder(f)), size=(168, 168), mode="bilinear", align_corners=False)
+    aux = F.interpolate(m.aux_head(f[-1]), size=(168, 168), mode="bilinear", align_corners=False)
+    loss = F.cross_entropy(out, t) + 0.4 * F.cross_entropy(aux, t)
+    loss.backward()
+    names = ["neck.lateral_convs.0.conv.weight", "neck.convs.3.conv.bias", "decoder.psp_modules.2.1.conv.weight",
+             "decoder.bottleneck.conv.weight", "decoder.fpn_convs.1.norm.weight", "decoder.fpn_bottleneck.conv.weight",
+             "aux_head.cls_seg.weight", "head.conv.bias"]
+    params = dict(m.named_parameters())
+    torch.save({"feats": feats, "target": t, "out_slice": out.detach()[:, :, ::8, ::8].clone(),
+                "aux_slice": aux.detach()[:, :, ::8, ::8].clone(), "loss": loss.detach(),
+                "grad_slices": {n: params[n].grad.flatten()[:64].clone() for n in names}}, OUT / "upernet_golden.pt")
+    print("wrote upernet_golden.pt")
+
+
 if __name__ == "__main__":
     OUT.mkdir(parents=True, exist_ok=True)
     tensors_golden()
     if "--all" in sys.argv:
         unetpp_golden()
         segformer_golden()
+        upernet_golden()

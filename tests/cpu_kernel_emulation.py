@@ -378,6 +378,22 @@ def bilinear_bwd(dy, hi, wi):
     return _nhwc(xr.grad).to(dy.dtype).contiguous()
 
 
+def adaptive_avgpool_fwd(x, s):
+    return _nhwc(F.adaptive_avg_pool2d(_nchw(x.to(_WORK)), s)).to(x.dtype).contiguous()
+
+
+def adaptive_avgpool_bwd(dy, h, w):
+    n, s, _, c = dy.shape
+    xr = torch.zeros(n, c, h, w, dtype=_WORK, requires_grad=True)
+    with torch.enable_grad():
+        F.adaptive_avg_pool2d(xr, s).backward(_nchw(dy.to(_WORK)))
+    return _nhwc(xr.grad).to(dy.dtype).contiguous()
+
+
+def add_nhwc(a, b):
+    return (a.to(_WORK) + b.to(_WORK)).to(a.dtype).contiguous()
+
+
 def cast_f32(x, dtype):
     return x.to(dtype)
 

@@ -132,3 +132,44 @@ def test_segformer_backward_equals_oracle_autograd(monkeypatch, f64, name, cin, 
         # parameters whose true gradient is ~0 (biases in front of a train-mode BatchNorm) only carry noise
         assert err < 1e-7 or want.abs().max() < 1e-12, f"{n_}: {err}"
     assert torch.allclose(prod.decoder.linear_fuse[1].running_mean, sd["decoder.linear_fuse.1.running_mean"], atol=1e-12)
+
+
+def test_upernet_backward_equals_oracle_autograd(monkeypatch, f64):
+    """MultiLevelNeck + UperNet + heads wiring (PPM pooling, top-down adds, virtual concats, two logit maps)."""
+    from gdl_b200.engine import Act, Engine
+    from gdl_b200.models.upernet import UperNetSegmentor
+    from oracle import upernet as ou
+    emu.install(monkeypatch)
+    e, ch, k = 96, 64, 5
+    torch.manual_seed(0)
+    prod = UperNetSegmentor(e, ch, k, compute_dtype=torch.float64).double().train()
+    with torch.no_grad():
+        for _, p in prod.named_parameters():
+            if p.dim() == 1:
+                p.add_(0.1 * torch.randn_like(p))
+    sd = {n_: (v.detach().clone().requires_grad_(True) if v.is_floating_point() and "running" not in n_ else v.clone())
+          for n_, v in prod.state_dict().items()}
+    assert set(sd) == set(ou.init_state_dict(e, ch, k))
+    g = torch.Generator().manual_seed(1)
+    feats = [torch.randn(2, e, 12, 12, generator=g).double().requires_grad_(True) for _ in range(4)]
+    t = torch.randint(0, k, (2, 168, 168), generator=g)
+    ro, ra = ou.upernet_forward(sd, feats, (168, 168), training=True)
+    (F.cross_entropy(ro, t) + 0.4 * F.cross_entropy(ra, t)).backward()
+
+    eng = Engine(torch.float64, training=True, acc_dtype=torch.float64)
+    with torch.no_grad():
+        acts = [Act(f.detach().permute(0, 2, 3, 1).contiguous(), needs_grad=True) for f in feats]
+        o, a = prod.run(eng, acts, (168, 168))
+    assert torch.allclose(o.permute(0, 3, 1, 2), ro, atol=1e-9) and torch.allclose(a.permute(0, 3, 1, 2), ra, atol=1e-9)
+    do = o.detach().permute(0, 3, 1, 2).clone().requires_grad_(True)
+    da = a.detach().permute(0, 3, 1, 2).clone().requires_grad_(True)
+    (F.cross_entropy(do, t) + 0.4 * F.cross_entropy(da, t)).backward()
+    with torch.no_grad():
+        prod.backward(eng, do.grad.permute(0, 2, 3, 1).contiguous(), da.grad.permute(0, 2, 3, 1).contiguous())
+        fg = [eng.collect_grad(x) for x in acts]
+    for n_, p in prod.named_parameters():
+        got, want = eng.param_grads[id(p)], sd[n_].grad
+        err = (got - want).abs().max() / (want.abs().max() + 1e-30)
+        assert err < 1e-7 or want.abs().max() < 1e-12, f"{n_}: {err}"
+    for f, gf in zip(feats, fg):  # gradients reach the encoder maps too (un-frozen encoder case)
+        assert torch.allclose(gf.permute(0, 3, 1, 2), f.grad, atol=1e-10)

@@ -152,3 +152,18 @@ def test_segformer_oracle_matches_reference_import():
     x = torch.randn(1, 4, 64, 64, generator=torch.Generator().manual_seed(0))
     with torch.no_grad():
         assert _close(osf.segformer_forward(sd0, x, "mit_b2"), ref(x))
+
+
+# --- MultiLevelNeck + UperNet + heads restatement: pinned to the reference's own modules -----------------
+def test_upernet_oracle_matches_reference_golden():
+    from oracle import upernet as ou
+    g = torch.load(GOLD / "upernet_golden.pt")
+    sd = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and "running" not in k else v.clone())
+          for k, v in ou.init_state_dict(96, 64, 5, seed=1).items()}
+    out, aux = ou.upernet_forward(sd, g["feats"], (168, 168), training=True)
+    loss = torch.nn.functional.cross_entropy(out, g["target"]) + 0.4 * torch.nn.functional.cross_entropy(aux, g["target"])
+    loss.backward()
+    assert _close(out[:, :, ::8, ::8], g["out_slice"]) and _close(aux[:, :, ::8, ::8], g["aux_slice"])
+    assert torch.allclose(loss, g["loss"], atol=1e-6)
+    for n, want in g["grad_slices"].items():
+        assert _close(sd[n].grad.flatten()[:64], want, 1e-4), n
