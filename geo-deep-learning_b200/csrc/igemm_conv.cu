@@ -24,7 +24,7 @@
 namespace gdl {
 
 // runtime options (gdl_set_option); env vars GDL_CONV_HALO / GDL_WGRAD_HALO / GDL_WGRAD_L2_MB seed them
-static int g_opt_conv_halo = -1, g_opt_wgrad_halo = -1;
+static int g_opt_conv_halo = -1, g_opt_wgrad_halo = -1, g_opt_conv_epilogue = -1;
 static long long g_opt_wgrad_l2_mb = -1;
 static int opt_int(int& slot, const char* env, int dflt) {
   if (slot < 0) {
@@ -56,7 +56,9 @@ struct ConvFwdKParams {
   int out_dtype;
   long long ldo;
   int vec_ok;
-  int pair_ok;  // 16-bit outputs: (pixel, even channel) addresses are 4-byte aligned -> packed 2-channel stores
+  int pair_ok;  // (unused)
+  int res_vec_ok;  // fp32 residual rows are 16-byte aligned -> float4 loads
+  int epi_mode;    // 0 = direct row stores, 1 = smem-transposed coalesced stores
   const float* bias;
   int relu;
   const void* residual;  // optional, added in the epilogue (fp32 residual stream or 16-bit)
@@ -133,7 +135,8 @@ conv_fwd_kernel(const __grid_constant__ ConvFwdKParams p) {
   __shared__ __align__(8) uint64_t tfull_bar[2];
   __shared__ __align__(8) uint64_t tempty_bar[2];
   __shared__ uint32_t tmem_base_smem;
-  __shared__ float stage_buf[4][32 * 33];  // per-epilogue-warp transpose tile (padded: conflict free)
+  __shared__ __align__(16) float stage_buf[4][32 * 36];  // per-epilogue-warp transpose tile (stride 36: 128-bit conflict free)
+  __shared__ long long stage_pix[4][32];                  // pixel index of each accumulator row of the current tile
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -282,14 +285,90 @@ conv_fwd_kernel(const __grid_constant__ ConvFwdKParams p) {
   } else {
     // ===================== epilogue: TMEM -> registers -> smem transpose -> coalesced HBM =====================
     // tcgen05.ld hands every thread one accumulator ROW; storing rows from registers makes each warp store hit
-    // 32 different lines.  Each warp therefore transposes 32x32 blocks through a private padded smem tile so
-    // that consecutive lanes write consecutive channels of one pixel (128-byte segments), and applies bias /
-    // residual / ReLU / conversion on the way out with equally coalesced residual loads.
+    // 32 different lines (measured: ~4 cycles per 16-byte store, the bound of every tile with K < ~2300).
+    // Each warp transposes 32x32 blocks through a private smem tile (row stride 36 floats: 128-bit writes and
+    // reads are bank-conflict free) and writes 16-byte vectors such that 4 (16-bit) / 8 (fp32) consecutive lanes
+    // cover one pixel's 64 / 128 contiguous bytes; bias / residual / activation are applied on the way out.
     const int q = warp & 3;  // TMEM lane quadrant this warp may access
     const int row = q * 32 + lane;
     const int th = row / p.TW, tw = row - th * p.TW;
     float* stg = &stage_buf[q][0];
+    long long* spix = &stage_pix[q][0];
     const bool out16 = p.out_dtype != GDL_F32;
+    const int vw = out16 ? 8 : 4;           // channels per 16-byte output vector
+    const int lpr = 32 / vw;                // lanes per pixel row (4 or 8)
+    const int rpi = 32 / lpr;               // pixel rows per iteration (8 or 4)
+    const int my_r = lane / lpr, my_seg = lane % lpr;
+    if (p.epi_mode == 0) {
+      // direct variant: every thread stores its own accumulator row (16-byte vectors, 32 lines per warp store)
+      int it = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+        const int acc = it & 1;
+        const uint32_t aphase = (it >> 1) & 1;
+        const int n_tile = tile % p.n_tiles;
+        const int m_tile = tile / p.n_tiles;
+        const int img = m_tile / tiles_per_img;
+        const int t_in = m_tile - img * tiles_per_img;
+        const int h = (t_in / p.tiles_w) * p.TH + th;
+        const int w = (t_in % p.tiles_w) * p.TW + tw;
+        const int n0 = n_tile * p.BN;
+        const bool valid = (h < p.Ho) && (w < p.Wo);
+        const long long pix = ((long long)img * p.Ho + h) * p.Wo + w;
+        mbar_wait(&tfull_bar[acc], aphase);
+        tc_fence_after();
+        const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.BN);
+        for (int j = 0; j < p.BN / 16; ++j) {
+          uint32_t v[16];
+          tmem_ld_32x32b_x16(t_addr + j * 16, v);
+          tmem_ld_wait();
+          const int c0 = n0 + j * 16;
+          const int nvalid = min(16, p.Cout - c0);
+          if (valid && nvalid > 0) {
+            float f[16];
+  #pragma unroll
+            for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]);
+            if (p.bias != nullptr) {
+  #pragma unroll
+              for (int i = 0; i < 16; ++i)
+                if (i < nvalid) f[i] += __ldg(p.bias + c0 + i);
+            }
+            if (p.residual != nullptr) {
+              const long long roff = pix * p.ldr + c0;
+              if (p.res_dtype == GDL_F32) {
+                const float* r = reinterpret_cast<const float*>(p.residual) + roff;
+  #pragma unroll
+                for (int i = 0; i < 16; ++i)
+                  if (i < nvalid) f[i] += r[i];
+              } else if (p.res_dtype == GDL_BF16) {
+                const __nv_bfloat16* r = reinterpret_cast<const __nv_bfloat16*>(p.residual) + roff;
+  #pragma unroll
+                for (int i = 0; i < 16; ++i)
+                  if (i < nvalid) f[i] += __bfloat162float(r[i]);
+              } else {
+                const __half* r = reinterpret_cast<const __half*>(p.residual) + roff;
+  #pragma unroll
+                for (int i = 0; i < 16; ++i)
+                  if (i < nvalid) f[i] += __half2float(r[i]);
+              }
+            }
+            if (p.relu) {
+  #pragma unroll
+              for (int i = 0; i < 16; ++i) f[i] = fmaxf(f[i], 0.f);
+            }
+            const long long off = pix * p.ldo + c0;
+            if (p.out_dtype == GDL_F32)
+              store_row16<float>(reinterpret_cast<float*>(p.out) + off, f, nvalid, p.vec_ok);
+            else if (p.out_dtype == GDL_BF16)
+              store_row16<__nv_bfloat16>(reinterpret_cast<__nv_bfloat16*>(p.out) + off, f, nvalid,
+                                         p.vec_ok);
+            else
+              store_row16<__half>(reinterpret_cast<__half*>(p.out) + off, f, nvalid, p.vec_ok);
+          }
+        }
+        tc_fence_before();
+        mbar_arrive(&tempty_bar[acc]);
+      }
+    } else {
     int it = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
       const int acc = it & 1;
@@ -302,8 +381,8 @@ conv_fwd_kernel(const __grid_constant__ ConvFwdKParams p) {
       const int w = (t_in % p.tiles_w) * p.TW + tw;
       const int n0 = n_tile * p.BN;
       const bool valid = (h < p.Ho) && (w < p.Wo);
-      // pixel index of this lane's row; -1 marks rows outside the image
-      const long long my_pix = valid ? ((long long)img * p.Ho + h) * p.Wo + w : -1;
+      __syncwarp();
+      spix[lane] = valid ? ((long long)img * p.Ho + h) * p.Wo + w : -1;  // pixel index of row `lane`, -1 = outside
       mbar_wait(&tfull_bar[acc], aphase);
       tc_fence_after();
       const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.BN);
@@ -314,78 +393,103 @@ conv_fwd_kernel(const __grid_constant__ ConvFwdKParams p) {
         if (ccols > 16) tmem_ld_32x32b_x16(t_addr + cb + 16, v1);
         tmem_ld_wait();
         __syncwarp();
+        float4* srow = reinterpret_cast<float4*>(stg + lane * 36);
 #pragma unroll
-        for (int i = 0; i < 16; ++i) stg[lane * 33 + i] = __uint_as_float(v0[i]);
+        for (int i = 0; i < 4; ++i)
+          srow[i] = make_float4(__uint_as_float(v0[4 * i]), __uint_as_float(v0[4 * i + 1]),
+                                __uint_as_float(v0[4 * i + 2]), __uint_as_float(v0[4 * i + 3]));
         if (ccols > 16) {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) stg[lane * 33 + 16 + i] = __uint_as_float(v1[i]);
+          for (int i = 0; i < 4; ++i)
+            srow[4 + i] = make_float4(__uint_as_float(v1[4 * i]), __uint_as_float(v1[4 * i + 1]),
+                                      __uint_as_float(v1[4 * i + 2]), __uint_as_float(v1[4 * i + 3]));
         }
         __syncwarp();
         const int c0 = n0 + cb;
-        if (!out16) {
-          // fp32 output: lane = column, one pixel row (<= 128 B) per store instruction
-          const int col = c0 + lane;
-          const bool cok = lane < ccols && col < p.Cout;
-          const float bv = (cok && p.bias) ? __ldg(p.bias + col) : 0.f;
-          float* outp = reinterpret_cast<float*>(p.out);
-          for (int rr = 0; rr < 32; ++rr) {
-            const long long pix = __shfl_sync(0xffffffffu, my_pix, rr);
-            if (pix < 0 || !cok) continue;
-            float f = stg[rr * 33 + lane] + bv;
-            if (p.residual != nullptr) {
-              const long long ro = pix * p.ldr + col;
-              if (p.res_dtype == GDL_F32) f += reinterpret_cast<const float*>(p.residual)[ro];
-              else if (p.res_dtype == GDL_BF16) f += __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p.residual)[ro]);
-              else f += __half2float(reinterpret_cast<const __half*>(p.residual)[ro]);
-            }
-            if (p.relu) f = fmaxf(f, 0.f);
-            outp[pix * p.ldo + col] = f;
+        const int cseg = my_seg * vw;            // first channel of this lane's vector inside the chunk
+        const int col = c0 + cseg;
+        const bool seg_in = cseg < ccols;
+        const int nval = seg_in ? min(vw, p.Cout - col) : 0;  // valid channels of this lane's vector
+        float bv[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) bv[j] = (p.bias != nullptr && j < nval) ? __ldg(p.bias + col + j) : 0.f;
+#pragma unroll 4
+        for (int r0 = 0; r0 < 32; r0 += rpi) {
+          const int rr = r0 + my_r;
+          const long long pix = spix[rr];
+          if (pix < 0 || nval <= 0) continue;
+          float f[8];
+          const float4* sp = reinterpret_cast<const float4*>(stg + rr * 36 + cseg);
+          const float4 a4 = sp[0];
+          f[0] = a4.x; f[1] = a4.y; f[2] = a4.z; f[3] = a4.w;
+          if (out16) {
+            const float4 b4 = sp[1];
+            f[4] = b4.x; f[5] = b4.y; f[6] = b4.z; f[7] = b4.w;
+          } else {
+            f[4] = f[5] = f[6] = f[7] = 0.f;
           }
-        } else {
-          // 16-bit output: lanes 0..15 write pixel rr, lanes 16..31 pixel rr+1; each lane two adjacent channels
-          const int hl = lane >> 4, l2 = (lane & 15) * 2;
-          const int col = c0 + l2;
-          const bool c0ok = l2 < ccols && col < p.Cout;
-          const bool c1ok = l2 + 1 < ccols && col + 1 < p.Cout;
-          const float b0 = (c0ok && p.bias) ? __ldg(p.bias + col) : 0.f;
-          const float b1 = (c1ok && p.bias) ? __ldg(p.bias + col + 1) : 0.f;
-          for (int rr = 0; rr < 32; rr += 2) {
-            const long long pix = __shfl_sync(0xffffffffu, my_pix, rr + hl);
-            if (pix < 0 || !c0ok) continue;
-            float f0 = stg[(rr + hl) * 33 + l2] + b0;
-            float f1 = stg[(rr + hl) * 33 + l2 + 1] + b1;
-            if (p.residual != nullptr) {
-              const long long ro = pix * p.ldr + col;
-              if (p.res_dtype == GDL_F32) {
-                f0 += reinterpret_cast<const float*>(p.residual)[ro];
-                if (c1ok) f1 += reinterpret_cast<const float*>(p.residual)[ro + 1];
-              } else if (p.res_dtype == GDL_BF16) {
-                f0 += __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p.residual)[ro]);
-                if (c1ok) f1 += __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p.residual)[ro + 1]);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) f[j] += bv[j];
+          if (p.residual != nullptr) {
+            const long long ro = pix * p.ldr + col;
+            if (p.res_dtype == GDL_F32) {
+              const float* rp = reinterpret_cast<const float*>(p.residual) + ro;
+              if (p.res_vec_ok && nval == vw) {
+                const float4 r4 = *reinterpret_cast<const float4*>(rp);
+                f[0] += r4.x; f[1] += r4.y; f[2] += r4.z; f[3] += r4.w;
+                if (out16) {
+                  const float4 s4 = *reinterpret_cast<const float4*>(rp + 4);
+                  f[4] += s4.x; f[5] += s4.y; f[6] += s4.z; f[7] += s4.w;
+                }
               } else {
-                f0 += __half2float(reinterpret_cast<const __half*>(p.residual)[ro]);
-                if (c1ok) f1 += __half2float(reinterpret_cast<const __half*>(p.residual)[ro + 1]);
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                  if (j < nval) f[j] += rp[j];
               }
-            }
-            if (p.relu) {
-              f0 = fmaxf(f0, 0.f);
-              f1 = fmaxf(f1, 0.f);
-            }
-            const long long off = pix * p.ldo + col;
-            if (p.out_dtype == GDL_BF16) {
-              __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + off;
-              if (c1ok && p.pair_ok) *reinterpret_cast<uint32_t*>(o) = pack_bf16x2(f0, f1);
-              else {
-                o[0] = __float2bfloat16_rn(f0);
-                if (c1ok) o[1] = __float2bfloat16_rn(f1);
-              }
+            } else if (p.res_dtype == GDL_BF16) {
+              const __nv_bfloat16* rp = reinterpret_cast<const __nv_bfloat16*>(p.residual) + ro;
+#pragma unroll
+              for (int j = 0; j < 8; ++j)
+                if (j < nval) f[j] += __bfloat162float(rp[j]);
             } else {
-              __half* o = reinterpret_cast<__half*>(p.out) + off;
-              if (c1ok && p.pair_ok) *reinterpret_cast<uint32_t*>(o) = pack_f16x2(f0, f1);
-              else {
-                o[0] = __float2half_rn(f0);
-                if (c1ok) o[1] = __float2half_rn(f1);
-              }
+              const __half* rp = reinterpret_cast<const __half*>(p.residual) + ro;
+#pragma unroll
+              for (int j = 0; j < 8; ++j)
+                if (j < nval) f[j] += __half2float(rp[j]);
+            }
+          }
+          if (p.relu) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], 0.f);
+          }
+          const long long off = pix * p.ldo + col;
+          if (p.out_dtype == GDL_F32) {
+            float* o = reinterpret_cast<float*>(p.out) + off;
+            if (p.vec_ok && nval == 4) *reinterpret_cast<float4*>(o) = make_float4(f[0], f[1], f[2], f[3]);
+            else {
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                if (j < nval) o[j] = f[j];
+            }
+          } else if (p.out_dtype == GDL_BF16) {
+            __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + off;
+            if (p.vec_ok && nval == 8)
+              *reinterpret_cast<uint4*>(o) = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]),
+                                                        pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+            else {
+#pragma unroll
+              for (int j = 0; j < 8; ++j)
+                if (j < nval) o[j] = __float2bfloat16_rn(f[j]);
+            }
+          } else {
+            __half* o = reinterpret_cast<__half*>(p.out) + off;
+            if (p.vec_ok && nval == 8)
+              *reinterpret_cast<uint4*>(o) = make_uint4(pack_f16x2(f[0], f[1]), pack_f16x2(f[2], f[3]),
+                                                        pack_f16x2(f[4], f[5]), pack_f16x2(f[6], f[7]));
+            else {
+#pragma unroll
+              for (int j = 0; j < 8; ++j)
+                if (j < nval) o[j] = __float2half_rn(f[j]);
             }
           }
         }
@@ -393,6 +497,7 @@ conv_fwd_kernel(const __grid_constant__ ConvFwdKParams p) {
       tc_fence_before();
       mbar_arrive(&tempty_bar[acc]);
     }
+    }  // epi_mode
   }
 
   tc_fence_before();
@@ -472,6 +577,7 @@ extern "C" int gdl_set_option(const char* name, long long value) {
   GDL_REQUIRE(name != nullptr, GDL_ERR_INVALID, "set_option: null name");
   if (!strcmp(name, "conv_halo")) g_opt_conv_halo = (int)value;
   else if (!strcmp(name, "wgrad_halo")) g_opt_wgrad_halo = (int)value;
+  else if (!strcmp(name, "conv_epilogue")) g_opt_conv_epilogue = (int)value;
   else if (!strcmp(name, "wgrad_l2_mb")) g_opt_wgrad_l2_mb = value;
   else {
     set_last_error("set_option: unknown option '%s'", name);
@@ -562,7 +668,10 @@ extern "C" int gdl_conv2d_nhwc_fwd(const gdl_conv_fwd_t* d, void* stream_) {
   p.ldo = d->ldo;
   const int esz = d->out_dtype == GDL_F32 ? 4 : 2;
   p.vec_ok = ((reinterpret_cast<uintptr_t>(d->out) & 15) == 0) && ((d->ldo * esz) % 16 == 0);
-  p.pair_ok = ((reinterpret_cast<uintptr_t>(d->out) & 3) == 0) && (d->ldo % 2 == 0);
+  p.pair_ok = 0;
+  p.epi_mode = opt_int(g_opt_conv_epilogue, "GDL_CONV_EPILOGUE", 1);
+  p.res_vec_ok = d->residual != nullptr && d->res_dtype == GDL_F32 &&
+                 ((reinterpret_cast<uintptr_t>(d->residual) & 15) == 0) && (d->ldr % 4 == 0);
   p.bias = d->bias;
   p.relu = d->relu;
   p.residual = d->residual;
