@@ -456,7 +456,57 @@ __global__ void grad_gather_kernel(GatherSrcs srcs, const T* __restrict__ y, int
         is[j] = invstd[c0 + j];
       }
     }
-    if (active) {
+    const bool fast = srcs.n == 1 && srcs.mode[0] == 0 && y != nullptr && x != nullptr && g != nullptr && sums != nullptr;
+    if (active && fast) {
+      // common case (one consumer, ReLU + BatchNorm producer): two pixel rows per iteration, 6 loads in flight
+      const T* sp = reinterpret_cast<const T*>(srcs.ptr[0]);
+      const long long lds0 = srcs.ld[0];
+      const long long stride = (long long)gridDim.x * rows_per_block;
+      long long pix = (long long)blockIdx.x * rows_per_block + tr;
+      for (; pix + stride < M; pix += 2 * stride) {
+        const long long p1 = pix + stride;
+        float a0[8], y0[8], x0[8], a1[8], y1[8], x1[8];
+        load8(sp + pix * lds0 + c0, a0);
+        load8(y + pix * ldy + c0, y0);
+        load8(x + pix * ldx + c0, x0);
+        load8(sp + p1 * lds0 + c0, a1);
+        load8(y + p1 * ldy + c0, y1);
+        load8(x + p1 * ldx + c0, x1);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          a0[j] = y0[j] > 0.f ? a0[j] : 0.f;
+          a1[j] = y1[j] > 0.f ? a1[j] : 0.f;
+        }
+        const uint4 pk0 = Vec8<T>::pack(a0), pk1 = Vec8<T>::pack(a1);
+        *reinterpret_cast<uint4*>(g + pix * ldg + c0) = pk0;
+        *reinterpret_cast<uint4*>(g + p1 * ldg + c0) = pk1;
+        float g0[8], g1[8];
+        Vec8<T>::unpack(pk0, g0);
+        Vec8<T>::unpack(pk1, g1);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          s1[j] += g0[j] + g1[j];
+          s2[j] = fmaf(g0[j], (x0[j] - mu[j]) * is[j], s2[j]);
+          s2[j] = fmaf(g1[j], (x1[j] - mu[j]) * is[j], s2[j]);
+        }
+      }
+      if (pix < M) {
+        float a0[8], y0[8], x0[8], g0[8];
+        load8(sp + pix * lds0 + c0, a0);
+        load8(y + pix * ldy + c0, y0);
+        load8(x + pix * ldx + c0, x0);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) a0[j] = y0[j] > 0.f ? a0[j] : 0.f;
+        const uint4 pk0 = Vec8<T>::pack(a0);
+        *reinterpret_cast<uint4*>(g + pix * ldg + c0) = pk0;
+        Vec8<T>::unpack(pk0, g0);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          s1[j] += g0[j];
+          s2[j] = fmaf(g0[j], (x0[j] - mu[j]) * is[j], s2[j]);
+        }
+      }
+    } else if (active) {
       for (long long pix = (long long)blockIdx.x * rows_per_block + tr; pix < M;
            pix += (long long)gridDim.x * rows_per_block) {
         float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};

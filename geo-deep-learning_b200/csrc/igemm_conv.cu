@@ -61,6 +61,7 @@ struct ConvFwdKParams {
   int epi_mode;    // 0 = direct row stores, 1 = smem-transposed coalesced stores
   const float* bias;
   int relu;
+  const float* oscale;   // optional per-channel multiplier applied to (acc + bias) before the residual (LayerScale)
   const void* residual;  // optional, added in the epilogue (fp32 residual stream or 16-bit)
   int res_dtype;
   long long ldr;
@@ -410,9 +411,12 @@ conv_fwd_kernel(const __grid_constant__ ConvFwdKParams p) {
         const int col = c0 + cseg;
         const bool seg_in = cseg < ccols;
         const int nval = seg_in ? min(vw, p.Cout - col) : 0;  // valid channels of this lane's vector
-        float bv[8];
+        float bv[8], sv[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) bv[j] = (p.bias != nullptr && j < nval) ? __ldg(p.bias + col + j) : 0.f;
+        for (int j = 0; j < 8; ++j) {
+          bv[j] = (p.bias != nullptr && j < nval) ? __ldg(p.bias + col + j) : 0.f;
+          sv[j] = (p.oscale != nullptr && j < nval) ? __ldg(p.oscale + col + j) : 1.f;
+        }
 #pragma unroll 4
         for (int r0 = 0; r0 < 32; r0 += rpi) {
           const int rr = r0 + my_r;
@@ -429,7 +433,7 @@ conv_fwd_kernel(const __grid_constant__ ConvFwdKParams p) {
             f[4] = f[5] = f[6] = f[7] = 0.f;
           }
 #pragma unroll
-          for (int j = 0; j < 8; ++j) f[j] += bv[j];
+          for (int j = 0; j < 8; ++j) f[j] = (f[j] + bv[j]) * sv[j];
           if (p.residual != nullptr) {
             const long long ro = pix * p.ldr + col;
             if (p.res_dtype == GDL_F32) {
@@ -458,9 +462,12 @@ conv_fwd_kernel(const __grid_constant__ ConvFwdKParams p) {
                 if (j < nval) f[j] += __half2float(rp[j]);
             }
           }
-          if (p.relu) {
+          if (p.relu == 1) {
 #pragma unroll
             for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], 0.f);
+          } else if (p.relu == 2) {  // exact (erf) GELU, nn.GELU default
+#pragma unroll
+            for (int j = 0; j < 8; ++j) f[j] = 0.5f * f[j] * (1.f + erff(f[j] * 0.70710678118654752f));
           }
           const long long off = pix * p.ldo + col;
           if (p.out_dtype == GDL_F32) {
@@ -669,11 +676,12 @@ extern "C" int gdl_conv2d_nhwc_fwd(const gdl_conv_fwd_t* d, void* stream_) {
   const int esz = d->out_dtype == GDL_F32 ? 4 : 2;
   p.vec_ok = ((reinterpret_cast<uintptr_t>(d->out) & 15) == 0) && ((d->ldo * esz) % 16 == 0);
   p.pair_ok = 0;
-  p.epi_mode = opt_int(g_opt_conv_epilogue, "GDL_CONV_EPILOGUE", 1);
+  p.epi_mode = opt_int(g_opt_conv_epilogue, "GDL_CONV_EPILOGUE", 0);  // direct row stores: faster in-model (run 7 A/B)
   p.res_vec_ok = d->residual != nullptr && d->res_dtype == GDL_F32 &&
                  ((reinterpret_cast<uintptr_t>(d->residual) & 15) == 0) && (d->ldr % 4 == 0);
   p.bias = d->bias;
   p.relu = d->relu;
+  p.oscale = d->oscale;
   p.residual = d->residual;
   p.res_dtype = d->res_dtype;
   p.ldr = d->ldr;

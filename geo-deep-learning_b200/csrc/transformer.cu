@@ -157,7 +157,7 @@ __global__ void layernorm_bwd_kernel(const TG* __restrict__ g, long long ldg, co
 //   p = softmax(scale * s); rows are stored with stride ld >= L, pad columns of p are written 0.
 // backward: ds = scale * p * (dp - sum_j dp_j p_j)
 // ------------------------------------------------------------------------------------------
-constexpr int kSmMaxPerLane = 32;  // L <= 1024
+constexpr int kSmMaxPerLane = 48;  // L <= 1536 (DOFA: 1297 tokens)
 
 template <typename T>
 __global__ void softmax_fwd_kernel(const T* __restrict__ s, long long lds, float scale, T* __restrict__ p,
@@ -642,6 +642,37 @@ __global__ void add_kernel(const T* __restrict__ a, long long lda, const T* __re
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// ViT token glue (dofa_v2.py:445-468): tokens[b][0] = cls, tokens[b][1+p] = patch[b][p] + pos[1+p];
+// feature tap: feat[b][p] = cast(tokens[b][1+p])  (drop the cls token, NHWC map = token rows)
+// ------------------------------------------------------------------------------------------
+template <typename TP>
+__global__ void vit_assemble_tokens_kernel(const TP* __restrict__ patch, const float* __restrict__ pos,
+                                           const float* __restrict__ cls, float* __restrict__ tokens, int B, int P, int C) {
+  const long long total = (long long)B * (P + 1) * C;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    const long long t = i / C;
+    const int tok = (int)(t % (P + 1));
+    const long long b = t / (P + 1);
+    tokens[i] = tok == 0 ? cls[c] : to_f<TP>(patch[(b * P + tok - 1) * C + c]) + pos[(long long)tok * C + c];
+  }
+}
+
+template <typename TO>
+__global__ void vit_extract_feature_kernel(const float* __restrict__ tokens, TO* __restrict__ feat, int B, int P, int C) {
+  const long long total = (long long)B * P * C;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    const long long t = i / C;
+    const int p = (int)(t % P);
+    const long long b = t / P;
+    feat[i] = from_f<TO>(tokens[(b * (P + 1) + p + 1) * C + c]);
+  }
+}
+
 // elementwise helpers for the fp32 residual stream
 template <typename T>
 __global__ void cast_f32_kernel(const float* __restrict__ x, T* __restrict__ y, long long n) {
@@ -885,6 +916,27 @@ extern "C" int gdl_add_nhwc(const void* a, long long lda, const void* b, long lo
   long long blk = (M * C + 255) / 256;
   if (blk > 16 * kNumSMsB200) blk = 16 * kNumSMsB200;
   GDL_DISPATCH_T(dtype, { add_kernel<T><<<(int)blk, 256, 0, st>>>((const T*)a, lda, (const T*)b, ldb, (T*)y, ldy, M, C); });
+  GDL_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int gdl_vit_assemble_tokens(const void* patch, int patch_dtype, const float* pos, const float* cls,
+                                       float* tokens, int B, int P, int C, void* stream) {
+  GDL_REQUIRE(patch && pos && cls && tokens && B > 0 && P > 0 && C > 0, GDL_ERR_INVALID, "vit_assemble_tokens: bad args");
+  cudaStream_t st = (cudaStream_t)stream;
+  long long b = ((long long)B * (P + 1) * C + 255) / 256;
+  if (b > 16 * kNumSMsB200) b = 16 * kNumSMsB200;
+  GDL_DISPATCH_T(patch_dtype, { vit_assemble_tokens_kernel<T><<<(int)b, 256, 0, st>>>((const T*)patch, pos, cls, tokens, B, P, C); });
+  GDL_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int gdl_vit_extract_feature(const float* tokens, void* feat, int feat_dtype, int B, int P, int C, void* stream) {
+  GDL_REQUIRE(tokens && feat && B > 0 && P > 0 && C > 0, GDL_ERR_INVALID, "vit_extract_feature: bad args");
+  cudaStream_t st = (cudaStream_t)stream;
+  long long b = ((long long)B * P * C + 255) / 256;
+  if (b > 16 * kNumSMsB200) b = 16 * kNumSMsB200;
+  GDL_DISPATCH_T(feat_dtype, { vit_extract_feature_kernel<T><<<(int)b, 256, 0, st>>>(tokens, (T*)feat, B, P, C); });
   GDL_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -43,6 +43,7 @@ class ConvFwd(C.Structure):
         ("residual", C.c_void_p),
         ("res_dtype", C.c_int),
         ("ldr", C.c_int),
+        ("oscale", C.c_void_p),
         ("w_ld", C.c_int),
         ("w_rows", C.c_int),
         ("w_rows_per_img", C.c_int),
@@ -126,6 +127,8 @@ _SIGS = {
     "gdl_bilinear_fwd": [_VP, _LL, _VP, _LL, _I, _I, _I, _I, _I, _I, _I, _VP],
     "gdl_bilinear_bwd": [_VP, _LL, _VP, _LL, _I, _I, _I, _I, _I, _I, _I, _VP],
     "gdl_cast_f32": [_VP, _VP, _I, _LL, _VP],
+    "gdl_vit_assemble_tokens": [_VP, _I, _VP, _VP, _VP, _I, _I, _I, _VP],
+    "gdl_vit_extract_feature": [_VP, _VP, _I, _I, _I, _I, _VP],
     "gdl_adaptive_avgpool_fwd": [_VP, _LL, _VP, _I, _I, _I, _I, _I, _I, _VP],
     "gdl_adaptive_avgpool_bwd": [_VP, _VP, _I, _I, _I, _I, _I, _I, _VP],
     "gdl_add_nhwc": [_VP, _LL, _VP, _LL, _VP, _LL, _I, _LL, _I, _VP],

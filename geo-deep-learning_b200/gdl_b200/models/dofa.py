@@ -1,0 +1,298 @@
+"""B200-native DOFA-v2 encoder (forward) + the DOFA segmentation model.
+
+`DOFAv2` mirrors geo_deep_learning/models/encoders/dofa_v2.py (constructor keywords, `state_dict` keys
+`patch_embed.weight_generator.transformer_encoder.layers.0.self_attn.in_proj_weight`, `blocks.3.attn.qkv.weight`,
+`blocks.3.ls1.gamma`, `pos_embed`, `cls_token`, ...; `create_dofa_base/large`), `DOFASegmentationModel` mirrors
+models/segmentation/dofa.py:24-107 (encoder + MultiLevelNeck + UperNetDecoder + SegmentationHead + FCNHead,
+`forward(x, wavelengths) -> SegmentationOutput(out, aux)`).
+
+The encoder is FORWARD-ONLY: the shipped configuration freezes it (`freeze_layers: ["encoder"]`,
+configs/dofa_config_RGB.yaml:57), so its backward is never needed there; training with an un-frozen encoder raises
+NotImplementedError.  Every matmul (weight-generator transformer layer, dynamic patch embedding, qkv / proj / MLP of
+the 12 ViT blocks, q.k^T and P.V) is the tcgen05 GEMM kernel; LayerNorm / softmax / GELU / LayerScale / residual are
+the fused epilogues and row kernels of libgdlb200.so.  Host-side torch is used only for glue on tiny tensors: the
+sin/cos of <= 12 wavelengths, concatenating the 128+C+1 generator tokens, and re-laying the generated (C, 14*14*D)
+weights as OIHW (x 0.01) before the packing kernel.
+"""
+from __future__ import annotations
+
+from typing import NamedTuple
+
+import torch
+import torch.nn as nn
+
+from .. import ops
+from ..engine import Act, Engine
+from .upernet import FCNHead, MultiLevelNeck, SegmentationHead, UperNetDecoder, UperNetSegmentor, _UperNetFn
+
+
+class SegmentationOutput(NamedTuple):
+    out: torch.Tensor
+    aux: torch.Tensor | None
+
+
+def _sincos_1d(embed_dim: int, pos: torch.Tensor) -> torch.Tensor:
+    omega = torch.arange(embed_dim // 2, dtype=torch.float32, device=pos.device) / (embed_dim / 2.0)
+    omega = 1.0 / 10000 ** omega
+    out = torch.einsum("m,d->md", pos.reshape(-1).float(), omega)
+    return torch.cat([torch.sin(out), torch.cos(out)], dim=1)
+
+
+def _sincos_2d(embed_dim: int, grid: int) -> torch.Tensor:
+    gh, gw = torch.meshgrid(torch.arange(grid), torch.arange(grid), indexing="ij")
+    pe = torch.cat([_sincos_1d(embed_dim // 2, gh), _sincos_1d(embed_dim // 2, gw)], dim=1)
+    return torch.cat([torch.zeros(1, embed_dim), pe], dim=0)
+
+
+class _FCRes(nn.Module):
+    def __init__(self, n: int = 128) -> None:
+        super().__init__()
+        self.w1, self.w2 = nn.Linear(n, n), nn.Linear(n, n)
+
+
+class _WeightGenerator(nn.Module):
+    def __init__(self, input_dim: int, output_dim: int, embed_dim: int) -> None:
+        super().__init__()
+        layer = nn.TransformerEncoderLayer(d_model=input_dim, nhead=4, activation="gelu", norm_first=False,
+                                           batch_first=False, dropout=0.0)
+        self.transformer_encoder = nn.TransformerEncoder(layer, num_layers=1, enable_nested_tensor=False)
+        self.fc_weight = nn.Linear(input_dim, output_dim)
+        self.fc_bias = nn.Linear(input_dim, embed_dim)
+        self.weight_tokens = nn.Parameter(torch.empty(128, input_dim))
+        self.bias_token = nn.Parameter(torch.empty(1, input_dim))
+        nn.init.normal_(self.weight_tokens, std=0.02)
+        nn.init.normal_(self.bias_token, std=0.02)
+
+
+class _Embedding(nn.Module):
+    def __init__(self, kernel_size: int, embed_dim: int) -> None:
+        super().__init__()
+        self.weight_generator = _WeightGenerator(128, kernel_size * kernel_size * embed_dim, embed_dim)
+        self.fclayer = _FCRes(128)
+        for m in self.modules():  # DOFAv2Embedding._init_weights
+            if isinstance(m, nn.Linear):
+                nn.init.xavier_uniform_(m.weight)
+                m.bias.data.fill_(0.01)
+
+
+class _LayerScale(nn.Module):
+    def __init__(self, dim: int, init: float) -> None:
+        super().__init__()
+        self.gamma = nn.Parameter(init * torch.ones(dim))
+
+
+class _Attn(nn.Module):
+    def __init__(self, dim: int) -> None:
+        super().__init__()
+        self.qkv, self.proj = nn.Linear(dim, 3 * dim), nn.Linear(dim, dim)
+
+
+class _Mlp(nn.Module):
+    def __init__(self, dim: int, ratio: float) -> None:
+        super().__init__()
+        self.fc1, self.fc2 = nn.Linear(dim, int(dim * ratio)), nn.Linear(int(dim * ratio), dim)
+
+
+class _ViTBlock(nn.Module):
+    def __init__(self, dim: int, ratio: float, init_values: float) -> None:
+        super().__init__()
+        self.norm1, self.attn, self.ls1 = nn.LayerNorm(dim), _Attn(dim), _LayerScale(dim, init_values)
+        self.norm2, self.mlp, self.ls2 = nn.LayerNorm(dim), _Mlp(dim, ratio), _LayerScale(dim, init_values)
+
+
+_PACKED: dict = {}  # id(weight) -> (version, dtype, packed 16-bit operand): frozen encoder weights are packed once
+
+
+def _packed(w: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
+    key = id(w)
+    hit = _PACKED.get(key)
+    if hit is not None and hit[0] == w._version and hit[1] == dtype and hit[2].device == w.device and hit[3]() is w:
+        return hit[2]
+    n, k = w.shape
+    wp = ops.pack_conv_weight(w.detach().float().contiguous().view(n, k, 1, 1), dtype)
+    import weakref
+    _PACKED[key] = (w._version, dtype, wp, weakref.ref(w))
+    return wp
+
+
+def _lin(x2d: torch.Tensor, lin, *, out_dtype=None, relu=False, gelu=False, residual=None, oscale=None, w=None, b=None):
+    """rows (M, K) 16-bit -> (M, N): the tcgen05 GEMM with bias / activation / LayerScale / residual epilogue"""
+    w = lin.weight if w is None else w
+    b = (lin.bias if lin is not None else None) if b is None else b
+    m, k = x2d.shape
+    n = w.shape[0]
+    wp = _packed(w, x2d.dtype)
+    res4 = residual.view(1, 1, m, n) if residual is not None else None
+    y = ops.conv2d_fwd([x2d.view(1, 1, m, k)], wp, n, 1, 1, 0, 0, out_dtype=out_dtype or x2d.dtype,
+                       bias=b.detach().float() if b is not None else None, relu=relu, gelu=gelu, residual=res4,
+                       oscale=oscale.detach().float() if oscale is not None else None)
+    return y.view(m, n)
+
+
+def _mha(qkv: torch.Tensor, b: int, n: int, heads: int, c: int, dt) -> torch.Tensor:
+    """qkv (b*n, 3c) 16-bit with columns [q | k | v] -> softmax(q k^T d^-1/2) v as (b*n, c)"""
+    d = c // heads
+    lp = (n + 15) // 16 * 16
+    q4 = qkv.view(b, 1, n, 3 * c)
+    scores = torch.empty((b, 1, n, heads * lp), dtype=dt, device=qkv.device)
+    for hd in range(heads):
+        ops.conv2d_fwd([q4[..., hd * d:(hd + 1) * d]], qkv[:, c + hd * d:c + (hd + 1) * d], n, 1, 1, 0, 0,
+                       out=scores[..., hd * lp:hd * lp + n], w_rows_per_img=n)
+    p = ops.softmax_fwd(scores.view(b, n, heads, lp), d ** -0.5, n)
+    p4 = p.view(b, 1, n, heads * lp)
+    o = torch.empty((b, 1, n, c), dtype=dt, device=qkv.device)
+    for hd in range(heads):
+        ops.conv2d_fwd([p4[..., hd * lp:(hd + 1) * lp]], qkv[:, 2 * c + hd * d:2 * c + (hd + 1) * d], d, 1, 1, 0, 0,
+                       out=o[..., hd * d:(hd + 1) * d], w_rows_per_img=n, w_mn_major=True)
+    return o.view(b * n, c)
+
+
+class DOFAv2(nn.Module):
+    def __init__(self, encoder_name: str = "dofa_base", img_size=224, patch_size: int = 14, embed_dim: int = 768,
+                 depth: int = 12, num_heads: int = 12, mlp_ratio: float = 4.0, drop_rate: float = 0.0,
+                 drop_path_rate: float = 0.1, out_indices: list[int] | None = None, init_values: float = 1e-5, *,
+                 convert_patch_to_16: bool = False, pretrained: bool = False,
+                 compute_dtype: torch.dtype = torch.bfloat16) -> None:
+        super().__init__()
+        if convert_patch_to_16:
+            raise NotImplementedError("convert_patch_to_16 (bicubic re-sampling of the generated kernels)")
+        if pretrained:
+            raise ValueError("pretrained=True downloads from HuggingFace; load the tensors with load_state_dict")
+        img_size = (img_size, img_size) if isinstance(img_size, int) else tuple(img_size)
+        self.encoder_name, self.img_size, self.patch_size = encoder_name, img_size, patch_size
+        self.embed_dim, self.depth, self.num_heads = embed_dim, depth, num_heads
+        self.num_patches = (img_size[0] // patch_size) * (img_size[1] // patch_size)
+        self.out_indices = list(out_indices) if out_indices is not None else [depth - 1]
+        self.patch_embed = _Embedding(patch_size, embed_dim)
+        self.pos_embed = nn.Parameter(_sincos_2d(embed_dim, int(self.num_patches ** 0.5)).unsqueeze(0), requires_grad=False)
+        self.cls_token = nn.Parameter(torch.zeros(1, 1, embed_dim))
+        nn.init.normal_(self.cls_token, std=0.02)
+        self.blocks = nn.ModuleList(_ViTBlock(embed_dim, mlp_ratio, init_values) for _ in range(depth))
+        self.norm = nn.LayerNorm(embed_dim)
+        self.compute_dtype = compute_dtype
+
+    # ---------------------------------------------------------------------------------- weight generator
+    @torch.no_grad()
+    def _dynamic_weights(self, wavelengths: torch.Tensor, c: int):
+        """wavelengths (C,) in um -> (OIHW fp32 weights (D, C, k, k) * 0.01, bias (D,) * 0.01)   (dofa_v2.py:148-166)"""
+        dt = self.compute_dtype
+        pe, wg = self.patch_embed, self.patch_embed.weight_generator
+        waves = _sincos_1d(128, wavelengths.float() * 1000).contiguous()                       # (C,128) fp32
+        h1 = _lin(ops.cast_f32(waves, dt), pe.fclayer.w1, relu=True)
+        h2 = _lin(h1, pe.fclayer.w2, relu=True, out_dtype=torch.float32)
+        waves = ops.add_nhwc(waves.view(1, 1, c, 128), h2.view(1, 1, c, 128)).view(c, 128)     # x + relu(w2 relu(w1 x))
+        x = torch.cat([wg.weight_tokens.detach().float(), waves, wg.bias_token.detach().float()], 0).contiguous()
+        n = x.shape[0]
+        layer = wg.transformer_encoder.layers[0]
+        sa = layer.self_attn
+        qkv = _lin(ops.cast_f32(x, dt), None, w=sa.in_proj_weight, b=sa.in_proj_bias)          # (n, 384)
+        att = _mha(qkv, 1, n, 4, 128, dt)
+        y = _lin(att, sa.out_proj, residual=x, out_dtype=torch.float32)                        # x + SA(x)
+        x1, _ = ops.layernorm_fwd(y, layer.norm1.weight, layer.norm1.bias, layer.norm1.eps, torch.float32, False)
+        f = _lin(ops.cast_f32(x1, dt), layer.linear1, gelu=True)
+        y = _lin(f, layer.linear2, residual=x1, out_dtype=torch.float32)
+        x2, _ = ops.layernorm_fwd(y, layer.norm2.weight, layer.norm2.bias, layer.norm2.eps, torch.float32, False)
+        wt = 128
+        wsrc = ops.add_nhwc(x2[wt:wt + c].contiguous().view(1, 1, c, 128), waves.view(1, 1, c, 128)).view(c, 128)
+        weights = _lin(ops.cast_f32(wsrc, dt), wg.fc_weight, out_dtype=torch.float32)          # (C, k*k*D)
+        bias = _lin(ops.cast_f32(x2[n - 1:n].contiguous(), dt), wg.fc_bias, out_dtype=torch.float32)
+        k = self.patch_size
+        w_oihw = (weights.view(c, k, k, self.embed_dim).permute(3, 0, 1, 2) * 0.01).contiguous()
+        return w_oihw, (bias.view(self.embed_dim) * 0.01).contiguous()
+
+    # ---------------------------------------------------------------------------------- forward
+    def forward_features(self, x: torch.Tensor, wavelengths: torch.Tensor) -> list[torch.Tensor]:
+        """x (B,C,H,W) float, wavelengths (C,) or (B,C) -> NHWC 16-bit maps (B, h, w, D) at out_indices"""
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            raise NotImplementedError("DOFAv2 is forward-only here: freeze the encoder (freeze_layers=['encoder']) "
+                                      "or call it under torch.no_grad()")
+        with torch.no_grad():
+            return self._features(x, wavelengths)
+
+    def _features(self, x: torch.Tensor, wavelengths: torch.Tensor) -> list[torch.Tensor]:
+        if wavelengths.dim() == 2:
+            if not torch.allclose(wavelengths, wavelengths[0:1].expand_as(wavelengths)):
+                raise ValueError("DOFA cannot handle different wavelengths within a batch")
+            wavelengths = wavelengths[0]
+        dt = self.compute_dtype
+        b, c, hh, ww = x.shape
+        d, k = self.embed_dim, self.patch_size
+        w_oihw, bias = self._dynamic_weights(wavelengths, c)
+        img = ops.normalize_to_nhwc(x.contiguous().float(), True, dt, (c + 7) // 8 * 8)
+        kk = k * k * c
+        kpad = (kk + 63) // 64 * 64
+        col = ops.im2col(img, c, k, k, k, 1, kpad)
+        wp = ops.pack_conv_weight(w_oihw, dt, 0, kpad)
+        patch = ops.conv2d_fwd([col], wp, d, 1, 1, 0, 0, bias=bias)                           # (B, h, w, D)
+        hp, wpx = patch.shape[1:3]
+        p_tok = hp * wpx
+        if p_tok + 1 != self.pos_embed.shape[1]:
+            raise ValueError(f"image {hh}x{ww} gives {p_tok} patches but pos_embed has {self.pos_embed.shape[1] - 1}")
+        tokens = ops.vit_assemble_tokens(patch.view(b, p_tok, d), self.pos_embed[0].contiguous(),
+                                         self.cls_token.detach().float().view(d).contiguous())
+        n = p_tok + 1
+        feats = []
+        for i, blk in enumerate(self.blocks):
+            t2 = tokens.view(b * n, d)
+            a, _ = ops.layernorm_fwd(t2, blk.norm1.weight, blk.norm1.bias, blk.norm1.eps, dt, False)
+            qkv = _lin(a, blk.attn.qkv)
+            o = _mha(qkv, b, n, self.num_heads, d, dt)
+            t2 = _lin(o, blk.attn.proj, residual=t2, oscale=blk.ls1.gamma, out_dtype=torch.float32)
+            a, _ = ops.layernorm_fwd(t2, blk.norm2.weight, blk.norm2.bias, blk.norm2.eps, dt, False)
+            f = _lin(a, blk.mlp.fc1, gelu=True)
+            t2 = _lin(f, blk.mlp.fc2, residual=t2, oscale=blk.ls2.gamma, out_dtype=torch.float32)
+            tokens = t2.view(b, n, d)
+            if i in self.out_indices:
+                feats.append(ops.vit_extract_feature(tokens, dt).view(b, hp, wpx, d))
+        # reference quirk kept: the final norm is only applied when depth-1 was requested but not tapped (never)
+        return feats
+
+    def forward(self, x: torch.Tensor, wavelengths: torch.Tensor) -> list[torch.Tensor]:
+        """returns the reference's format: list of (B, D, h, w) tensors (channels-last memory)"""
+        return [f.permute(0, 3, 1, 2) for f in self.forward_features(x, wavelengths)]
+
+
+def create_dofa_base(img_size=512, out_indices=(4, 6, 10, 11), *, pretrained: bool = False, **kw) -> DOFAv2:
+    return DOFAv2("dofa_base", img_size, 14, 768, 12, 12, out_indices=list(out_indices), pretrained=pretrained, **kw)
+
+
+def create_dofa_large(img_size=512, out_indices=(5, 11, 17, 23), *, pretrained: bool = False, **kw) -> DOFAv2:
+    return DOFAv2("dofa_large", img_size, 14, 1024, 24, 16, out_indices=list(out_indices), pretrained=pretrained, **kw)
+
+
+class DOFASegmentationModel(UperNetSegmentor):
+    """encoder (frozen DOFA ViT) + MultiLevelNeck + UperNetDecoder + SegmentationHead + FCNHead aux head."""
+
+    def __init__(self, encoder: str = "dofa_base", image_size=(512, 512), freeze_layers: list[str] | None = None,
+                 num_classes: int = 1, *, pretrained: bool = False, compute_dtype: torch.dtype = torch.bfloat16) -> None:
+        if encoder not in ("dofa_base", "dofa_large"):
+            raise ValueError(f"Invalid encoder: {encoder}")
+        dim = 768 if encoder == "dofa_base" else 1024
+        super().__init__(dim, 256, num_classes, compute_dtype)
+        make = create_dofa_base if encoder == "dofa_base" else create_dofa_large
+        self.encoder = make(img_size=image_size, pretrained=pretrained, compute_dtype=compute_dtype)
+        if freeze_layers:
+            for n_, p in self.named_parameters():
+                if any(layer in n_ for layer in freeze_layers):
+                    p.requires_grad = False
+
+    def forward(self, x: torch.Tensor, wavelengths: torch.Tensor) -> SegmentationOutput:  # type: ignore[override]
+        image_size = tuple(x.shape[2:])
+        feats = self.encoder.forward_features(x, wavelengths)  # NHWC 16-bit, no gradient (frozen encoder)
+        head_params = [p for n_, p in self.named_parameters() if not n_.startswith("encoder.")]
+        if torch.is_grad_enabled() and self.training and any(p.requires_grad for p in head_params):
+            nchw = [f.permute(0, 3, 1, 2) for f in feats]
+            out, aux = _UperNetFn.apply(self, image_size, len(nchw), *nchw, *head_params)
+            return SegmentationOutput(out, aux)
+        with torch.no_grad():
+            eng = Engine(self.compute_dtype, training=False, wcache=self._wcache)
+            o, a = self.run(eng, [Act(f, needs_grad=False) for f in feats], image_size)
+            self._saved = None
+        return SegmentationOutput(o.permute(0, 3, 1, 2), a.permute(0, 3, 1, 2))
+
+    def _feat(self, f: torch.Tensor, needs_grad: bool) -> Act:
+        # features coming from the B200 encoder are already NHWC 16-bit (logical NCHW view): no copy
+        nhwc = f.permute(0, 2, 3, 1)
+        if nhwc.dtype == self.compute_dtype and nhwc.is_contiguous():
+            return Act(nhwc, needs_grad=needs_grad)
+        return super()._feat(f, needs_grad)

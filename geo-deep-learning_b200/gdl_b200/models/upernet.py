@@ -161,7 +161,8 @@ class _UperNetFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, model: UperNetSegmentor, image_size, nfeat: int, *args: torch.Tensor):
         feats, params = args[:nfeat], args[nfeat:]
-        eng = Engine(model.compute_dtype, training=True, wcache=model._wcache, sync_bn_group=model.sync_bn_group)
+        eng = Engine(model.compute_dtype, training=True, wcache=model._wcache, sync_bn_group=model.sync_bn_group,
+                     acc_dtype=getattr(model, "acc_dtype", torch.float32))
         acts = [model._feat(f, f.requires_grad) for f in feats]
         o, a = model.run(eng, acts, image_size)
         ctx.eng, ctx.model, ctx.params, ctx.acts = eng, model, params, acts
@@ -172,12 +173,12 @@ class _UperNetFn(torch.autograd.Function):
         eng: Engine = ctx.eng
 
         def nhwc(d):
-            return None if d is None else d.permute(0, 2, 3, 1).contiguous().float()
+            return None if d is None else d.permute(0, 2, 3, 1).contiguous().to(eng.acc_dtype)
         ctx.model.backward(eng, nhwc(d_out), nhwc(d_aux))
         fgrads = []
         for a in ctx.acts:  # gradients w.r.t. the encoder maps (None when the encoder is frozen)
             g = eng.collect_grad(a) if a.needs_grad else None
-            fgrads.append(None if g is None else g.float().permute(0, 3, 1, 2))
+            fgrads.append(None if g is None else g.to(eng.acc_dtype).permute(0, 3, 1, 2))
         grads = tuple(eng.param_grads.get(id(p)) if p.requires_grad else None for p in ctx.params)
         ctx.eng = None
         return (None, None, None, *fgrads, *grads)

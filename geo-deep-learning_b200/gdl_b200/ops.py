@@ -134,7 +134,8 @@ def conv2d_fwd(srcs: Sequence[torch.Tensor], weight: torch.Tensor, cout: int, r:
                pad_h: int, pad_w: int, *, out: torch.Tensor | None = None,
                out_dtype: torch.dtype | None = None, bias: torch.Tensor | None = None,
                relu: bool = False, residual: torch.Tensor | None = None, w_ld: int = 0, w_rows: int = 0,
-               w_rows_per_img: int = 0, w_mn_major: bool = False) -> torch.Tensor:
+               w_rows_per_img: int = 0, w_mn_major: bool = False, gelu: bool = False,
+               oscale: torch.Tensor | None = None) -> torch.Tensor:
     """gdl_conv2d_nhwc_fwd. `weight` is the packed [Cout][R][S][Ctot] 16-bit operand (or, with the w_*
     options, a slice of an activation tensor used as the B operand of an attention GEMM)."""
     d = L.ConvFwd()
@@ -150,7 +151,8 @@ def conv2d_fwd(srcs: Sequence[torch.Tensor], weight: torch.Tensor, cout: int, r:
     d.out_dtype = L.dt_code(out.dtype)
     d.ldo = out.stride(2)
     d.bias = bias.data_ptr() if bias is not None else None
-    d.relu = int(relu)
+    d.relu = 2 if gelu else int(relu)
+    d.oscale = oscale.data_ptr() if oscale is not None else None
     if residual is not None:
         d.residual = residual.data_ptr()
         d.res_dtype = L.dt_code(residual.dtype)
@@ -527,3 +529,20 @@ def add_nhwc(a, b):
     _ck(L.load().gdl_add_nhwc(L.ptr(a), a.stride(2), L.ptr(b), b.stride(2), L.ptr(y), c, L.dt_code(a.dtype), n * h * w, c,
                               L.stream_ptr()))
     return y
+
+
+def vit_assemble_tokens(patch, pos, cls):
+    """patch (B,P,C) 16-bit/fp32, pos fp32 (P+1,C), cls fp32 (C,) -> fp32 tokens (B,P+1,C) = [cls ; patch + pos[1:]]"""
+    b, p_, c = patch.shape
+    tokens = torch.empty((b, p_ + 1, c), dtype=torch.float32, device=patch.device)
+    _ck(L.load().gdl_vit_assemble_tokens(L.ptr(patch), L.dt_code(patch.dtype), L.ptr(pos), L.ptr(cls), L.ptr(tokens), b, p_, c,
+                                         L.stream_ptr()))
+    return tokens
+
+
+def vit_extract_feature(tokens, dtype):
+    """fp32 tokens (B,P+1,C) -> (B,P,C) in `dtype` without the cls token"""
+    b, p1, c = tokens.shape
+    feat = torch.empty((b, p1 - 1, c), dtype=dtype, device=tokens.device)
+    _ck(L.load().gdl_vit_extract_feature(L.ptr(tokens), L.ptr(feat), L.dt_code(dtype), b, p1 - 1, c, L.stream_ptr()))
+    return feat

@@ -76,7 +76,7 @@ typedef struct {
   int out_dtype;   /* GDL_BF16 / GDL_F16 / GDL_F32             */
   int ldo;
   const float* bias; /* optional [Cout] fp32                   */
-  int relu;
+  int relu;          /* activation: 0 none, 1 ReLU, 2 exact-erf GELU (timm Mlp / nn.GELU) */
   /* --- optional extensions (zero = off) ---------------------------------------------------------
    * residual: added in the epilogue before the activation (x + proj(...) / x + fc2(...) of
    *   mix_transformer.py:218-221); res_dtype GDL_F32 (fp32 residual stream) or 16-bit, stride ldr.
@@ -89,6 +89,7 @@ typedef struct {
   const void* residual;
   int res_dtype;
   int ldr;
+  const float* oscale; /* optional fp32 [Cout]: out = act((acc + bias) * oscale + residual) — timm LayerScale gamma */
   int w_ld;
   int w_rows;
   int w_rows_per_img;
@@ -281,6 +282,12 @@ int gdl_adaptive_avgpool_bwd(const void* dy, void* dx, int dtype, int N, int H, 
 /* y = a + b on NHWC rows (UperNet top-down path, upernet.py:128-135) */
 int gdl_add_nhwc(const void* a, long long lda, const void* b, long long ldb, void* y, long long ldy, int dtype,
                  long long M, int C, void* stream);
+
+/* DOFA ViT token glue (dofa_v2.py:445-468): tokens[b] = [cls ; patch[b] + pos_embed[1:]] (fp32 stream), and the
+ * feature tap tokens[:, 1:, :] -> dense (B, P, C) map in `feat_dtype`. */
+int gdl_vit_assemble_tokens(const void* patch, int patch_dtype, const float* pos, const float* cls, float* tokens,
+                            int B, int P, int C, void* stream);
+int gdl_vit_extract_feature(const float* tokens, void* feat, int feat_dtype, int B, int P, int C, void* stream);
 
 /* fp32 -> dtype cast of a flat buffer (residual-stream gradient -> 16-bit GEMM operand) */
 int gdl_cast_f32(const float* x, void* y, int dtype, long long n, void* stream);

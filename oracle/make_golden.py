@@ -160,6 +160,25 @@ def upernet_golden() -> None:
     print("wrote upernet_golden.pt")
 
 
+def dofa_golden() -> None:
+    """Feature maps of the REFERENCE's DOFAv2 encoder (imported from /root/reference on top of oracle/ref_shims.py's
+    timm shim) loaded with oracle.dofa.init_state_dict(192, 4, 112, seed=2, ls_init=0.5); out_indices (1, 2, 3)."""
+    from oracle import dofa as od, ref_shims
+    e, depth, heads, img = 192, 4, 3, 112
+    ref = ref_shims.reference_dofa(img, e, depth, heads, (1, 2, 3))
+    sd = od.init_state_dict(e, depth, img, seed=2, ls_init=0.5)
+    assert set(ref.state_dict()) == set(sd)
+    ref.load_state_dict(sd)
+    ref.eval()
+    g = torch.Generator().manual_seed(4)
+    x = torch.randn(2, 5, img, img, generator=g)
+    wl = torch.tensor([0.49, 0.56, 0.665, 0.842, 1.61])
+    with torch.no_grad():
+        feats = ref(x, wl)
+    torch.save({"x": x, "wavelengths": wl, "feats": [f.clone() for f in feats]}, OUT / "dofa_golden.pt")
+    print("wrote dofa_golden.pt")
+
+
 if __name__ == "__main__":
     OUT.mkdir(parents=True, exist_ok=True)
     tensors_golden()
@@ -167,3 +186,4 @@ if __name__ == "__main__":
         unetpp_golden()
         segformer_golden()
         upernet_golden()
+        dofa_golden()

@@ -42,7 +42,7 @@ def pack_conv_weight(w, dtype, mode=0, ld=0, out=None):
 
 
 def conv2d_fwd(srcs, weight, cout, r, s, pad_h, pad_w, *, out=None, out_dtype=None, bias=None, relu=False,
-               residual=None, w_ld=0, w_rows=0, w_rows_per_img=0, w_mn_major=False):
+               residual=None, w_ld=0, w_rows=0, w_rows_per_img=0, w_mn_major=False, gelu=False, oscale=None):
     x = torch.cat(list(srcs), 3).to(_WORK)
     ctot = x.shape[3]
     if w_rows_per_img or w_mn_major:
@@ -64,11 +64,15 @@ def conv2d_fwd(srcs, weight, cout, r, s, pad_h, pad_w, *, out=None, out_dtype=No
             y = y + bias
     else:
         w = weight[:cout, :r * s * ctot].to(_WORK).reshape(cout, r, s, ctot).permute(0, 3, 1, 2)
-        y = _nhwc(F.conv2d(_nchw(x), w, bias, padding=(pad_h, pad_w)))
+        y = _nhwc(F.conv2d(_nchw(x), w, bias.to(_WORK) if bias is not None else None, padding=(pad_h, pad_w)))
+    if oscale is not None:
+        y = y * oscale
     if residual is not None:
         y = y + residual.to(_WORK)
     if relu:
         y = F.relu(y)
+    if gelu:
+        y = F.gelu(y)
     y = y.to(out_dtype or (out.dtype if out is not None else srcs[0].dtype))
     if out is not None:
         out.copy_(y)
@@ -392,6 +396,18 @@ def adaptive_avgpool_bwd(dy, h, w):
 
 def add_nhwc(a, b):
     return (a.to(_WORK) + b.to(_WORK)).to(a.dtype).contiguous()
+
+
+def vit_assemble_tokens(patch, pos, cls):
+    b, p_, c = patch.shape
+    tok = torch.empty(b, p_ + 1, c, dtype=_WORK)
+    tok[:, 0] = cls
+    tok[:, 1:] = patch.to(_WORK) + pos[1:]
+    return tok
+
+
+def vit_extract_feature(tokens, dtype):
+    return tokens[:, 1:].to(dtype).contiguous()
 
 
 def cast_f32(x, dtype):

@@ -167,3 +167,31 @@ def test_upernet_oracle_matches_reference_golden():
     assert torch.allclose(loss, g["loss"], atol=1e-6)
     for n, want in g["grad_slices"].items():
         assert _close(sd[n].grad.flatten()[:64], want, 1e-4), n
+
+
+# --- DOFA-v2 encoder restatement: pinned to the reference's DOFAv2 (timm Block restated, see oracle/dofa.py) ----
+def test_dofa_oracle_matches_reference_golden():
+    from oracle import dofa as od
+    g = torch.load(GOLD / "dofa_golden.pt")
+    sd = od.init_state_dict(192, 4, 112, seed=2, ls_init=0.5)
+    feats = od.dofa_forward(sd, g["x"], g["wavelengths"], 192, 4, 3, out_indices=(1, 2, 3))
+    assert len(feats) == 3
+    for a, b in zip(feats, g["feats"]):
+        assert a.shape == b.shape == (2, 192, 8, 8) and _close(a, b, 2e-5)
+
+
+def test_dofa_oracle_matches_reference_import():
+    from oracle import dofa as od, ref_shims
+    if not ref_shims.available():
+        pytest.skip("/root/reference not present (GPU box): covered by the golden file")
+    sd = od.init_state_dict(96, 2, 56, seed=7, ls_init=1.0)
+    ref = ref_shims.reference_dofa(56, 96, 2, 3, (0, 1))
+    assert set(ref.state_dict()) == set(sd)
+    ref.load_state_dict(sd)
+    ref.eval()
+    x = torch.randn(1, 3, 56, 56, generator=torch.Generator().manual_seed(0))
+    wl = torch.tensor([0.665, 0.56, 0.49])
+    with torch.no_grad():
+        want = ref(x, wl)
+    for a, b in zip(od.dofa_forward(sd, x, wl, 96, 2, 3, out_indices=(0, 1)), want):
+        assert _close(a, b, 2e-5)
