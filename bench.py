@@ -31,6 +31,11 @@ WORKLOADS = {
     # BASELINE.json configs[2] — SegFormer-B2, 3-band 512x512, batch 16 / GPU
     "segformer_b2": {"name": "segformer_b2_3band_512_k5_b16", "family": "segformer", "encoder": "mit_b2", "bands": 3,
                      "tile": 512, "classes": 5, "batch_per_gpu": 16, "train_gflop_per_tile": 363.1},
+    # BASELINE.json configs[3] — DOFA-base (frozen, configs/dofa_config_RGB.yaml:57) + UperNet, 6-band 512x512.
+    # GFLOP/tile = encoder forward 284.7 (12 ViT-B blocks at 1297 tokens + patch embed) + 3 x 443.05 (neck/UperNet/heads)
+    "dofa_base": {"name": "dofa_base_upernet_6band_512_k5_b16", "family": "dofa", "encoder": "dofa_base", "bands": 6,
+                  "tile": 512, "classes": 5, "batch_per_gpu": 16, "train_gflop_per_tile": 1613.8,
+                  "wavelengths": [0.49, 0.56, 0.665, 0.842, 1.61, 2.19]},
 }
 WORKLOAD = WORKLOADS["unetpp_r50"]
 TRAIN_GFLOP_PER_TILE = WORKLOAD["train_gflop_per_tile"]  # 3 x forward GFLOP (2 FLOP / MAC)
@@ -112,6 +117,8 @@ def cpu_reference_steps(steps: int, warmup: int, tiles_per_step: int = 1, budget
     torch.manual_seed(0)
     w = WORKLOAD
     nb = w["bands"]
+    if w["family"] == "dofa":
+        tiles_per_step = max(2, tiles_per_step)  # the PPM's 1x1 bin needs > 1 value per channel for train-mode BN
     g = torch.Generator().manual_seed(1234)
     raw = torch.randint(0, 256, (tiles_per_step, nb, w["tile"], w["tile"]), generator=g, dtype=torch.uint8)
     mask = torch.randint(0, w["classes"], (tiles_per_step, w["tile"] // 32, w["tile"] // 32), generator=g)
@@ -125,6 +132,20 @@ def cpu_reference_steps(steps: int, warmup: int, tiles_per_step: int = 1, budget
         def fwd(x):
             return model(x)
         what = "oracle port of smp.UnetPlusPlus: smp itself is not installable offline"
+    elif w["family"] == "dofa":
+        from oracle import dofa as od, upernet as ou
+        enc_sd = od.init_state_dict(768, 12, w["tile"])
+        sd = ou.init_state_dict(768, 256, w["classes"])
+        sd = {k: (v.requires_grad_(True) if v.is_floating_point() and "running" not in k else v) for k, v in sd.items()}
+        params = [v for v in sd.values() if v.requires_grad]
+        wl = torch.tensor(w["wavelengths"])
+
+        def fwd(x):
+            with torch.no_grad():  # frozen encoder (freeze_layers: ["encoder"])
+                feats = od.dofa_forward(enc_sd, x, wl)
+            return ou.upernet_forward(sd, feats, (w["tile"], w["tile"]), training=True)
+        what = ("functional restatement of the reference's DOFASegmentationModel (frozen DOFAv2 + UperNet), pinned to it "
+                "by golden vectors")
     else:
         from oracle import segformer as osf
         sd = osf.init_state_dict(w["encoder"], nb, w["classes"])
@@ -139,7 +160,9 @@ def cpu_reference_steps(steps: int, warmup: int, tiles_per_step: int = 1, budget
     def step() -> float:
         x = ot.standardization(ot.normalization(raw.float()), mean, std)
         opt.zero_grad(set_to_none=True)
-        loss = F.cross_entropy(fwd(x), mask)
+        out = fwd(x)
+        loss = (F.cross_entropy(out[0], mask) + 0.4 * F.cross_entropy(out[1], mask)) if isinstance(out, tuple) \
+            else F.cross_entropy(out, mask)
         loss.backward()
         opt.step()
         return float(loss.detach())
@@ -158,7 +181,7 @@ def cpu_reference_steps(steps: int, warmup: int, tiles_per_step: int = 1, budget
     return {"value": tiles_per_step * len(times) / total, "unit": "tiles/s", "cores": cores, "kind": "port",
             "sample": f"{len(times)} step(s) x {tiles_per_step} tile(s) of {w['name']} (fwd+CE+bwd+Adam, fp32, "
                       f"{cores} threads, {what})",
-            "ms_per_step": 1e3 * total / len(times), "steps_timed": len(times)}
+            "ms_per_step": 1e3 * total / len(times), "steps_timed": len(times), "tiles_per_step": tiles_per_step}
 
 
 def main_reference(args) -> None:
@@ -171,7 +194,8 @@ def main_reference(args) -> None:
         "unit": "tiles/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD["name"], "tiles_per_step": 1, "note": "reference CPU path, bounded sample"},
+        "config": {"workload": WORKLOAD["name"], "tiles_per_step": r["tiles_per_step"],
+                   "note": "reference CPU path, bounded sample"},
         "cpu_baseline": {"value": r["value"], "unit": "tiles/s", "cores": r["cores"], "kind": r["kind"],
                          "sample": r["sample"]},
         "e2e": {"value": r["value"], "unit": "tiles/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -206,12 +230,16 @@ def main_product(args) -> None:
     torch.manual_seed(0)  # identical initial weights on every rank (what DDP's broadcast gives)
     if w["family"] == "unetpp":
         model = UnetPlusPlus(w["encoder"], in_channels=C, classes=K, compute_dtype=torch.bfloat16).to(dev).train()
+    elif w["family"] == "dofa":
+        from gdl_b200.models.dofa import DOFASegmentationModel
+        model = DOFASegmentationModel(w["encoder"], (T, T), ["encoder"], K, compute_dtype=torch.bfloat16).to(dev).train()
+        model.wavelengths = torch.tensor(w["wavelengths"], device=dev)
     else:
         from gdl_b200.models.segformer import SegFormer
         model = SegFormer(w["encoder"], in_channels=C, num_classes=K, compute_dtype=torch.bfloat16).to(dev).train()
     trainer = FusedTrainer(model, ops.LossSpec(1.0, 0.0, ignore_index=-100), lr=1e-4, mean=MEAN[:C], std=STD[:C],
                            image_max=255.0, sync_bn=bool(args.sync_bn),
-                           clip_grad_norm=1.0 if w["family"] == "segformer" else None,
+                           clip_grad_norm=1.0 if w["family"] in ("segformer", "dofa") else None,
                            cuda_graph=bool(args.cuda_graph) and world == 1)
 
     # synthetic tiles: NBUF distinct batches so consecutive steps never re-read the same input (and the

@@ -1191,7 +1191,90 @@ __global__ void unpack_wgrad_kernel(const float* __restrict__ src, float* __rest
   }
 }
 
+// ---- pixel-packed form of a narrow 3-wide conv ---------------------------------------------------------------
+// A 3x3 / pad-1 conv over Ci in {16, 32} channels wastes the tensor-core tile (32/64-byte TMA rows, N = 16).  Viewing
+// f = 64/Ci horizontally adjacent pixels as ONE pixel of f*Ci channels turns it into a 3x3 conv (N,H,W/f,f*Ci) ->
+// (N,H,W/f,f*Co) with the block-Toeplitz weights below: same memory, 128-byte rows, N = f*Co.
+//   dst[(j,o)][ky][sx][(j',c)] = src[o][ky][kx][c],  kx = f*(sx-1) + j' - j + 1  (zero when kx is outside 0..2)
+template <typename T>
+__global__ void widen_weight_kernel(const T* __restrict__ src, T* __restrict__ dst, int Co, int Ci, int R, int f) {
+  const long long total = (long long)f * Co * R * 3 * f * Ci;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    long long t = i;
+    const int cc = (int)(t % (f * Ci));
+    t /= f * Ci;
+    const int sx = (int)(t % 3);
+    t /= 3;
+    const int ky = (int)(t % R);
+    const int row = (int)(t / R);
+    const int jp = cc / Ci, c = cc - jp * Ci;
+    const int j = row / Co, o = row - j * Co;
+    const int kx = f * (sx - 1) + jp - j + 1;
+    T v = T(0.f);
+    if (kx >= 0 && kx < 3) v = src[(((long long)o * R + ky) * 3 + kx) * Ci + c];
+    dst[i] = v;
+  }
+}
+
+// fp32 gradient of the widened weights [f*Co][src_ld] (columns (ky,sx,(j',c))) -> fp32 OIHW of the real conv
+__global__ void fold_widened_wgrad_kernel(const float* __restrict__ src, int src_ld, int src_co,
+                                          float* __restrict__ dst, int Co, int Ci, int R, int f, int accumulate) {
+  const long long total = (long long)Co * Ci * R * 3;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    long long t = i;
+    const int kx = (int)(t % 3);
+    t /= 3;
+    const int ky = (int)(t % R);
+    t /= R;
+    const int c = (int)(t % Ci);
+    const int o = (int)(t / Ci);
+    float v = 0.f;
+    for (int j = 0; j < f; ++j) {
+      const int d = j + kx - 1;  // input pixel relative to the packed pixel's first column
+      const int sx = d < 0 ? 0 : (d >= f ? 2 : 1);
+      const int jp = d - f * (sx - 1);
+      v += src[(long long)(j * src_co + o) * src_ld + ((long long)(ky * 3 + sx) * f + jp) * Ci + c];
+    }
+    dst[i] = accumulate ? dst[i] + v : v;
+  }
+}
+
 }  // namespace gdl
+
+extern "C" int gdl_widen_conv_weight(const void* src, void* dst, int Co, int Ci, int R, int f, int dtype,
+                                     void* stream) {
+  GDL_REQUIRE(src && dst && Co > 0 && Ci > 0 && R > 0 && f >= 2, GDL_ERR_INVALID, "widen_conv_weight: bad args");
+  GDL_REQUIRE(dtype == GDL_BF16 || dtype == GDL_F16, GDL_ERR_INVALID, "widen_conv_weight: dtype");
+  const long long total = (long long)f * Co * R * 3 * f * Ci;
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  if (dtype == GDL_BF16)
+    gdl::widen_weight_kernel<__nv_bfloat16><<<blocks, 256, 0, (cudaStream_t)stream>>>(
+        (const __nv_bfloat16*)src, (__nv_bfloat16*)dst, Co, Ci, R, f);
+  else
+    gdl::widen_weight_kernel<__half><<<blocks, 256, 0, (cudaStream_t)stream>>>((const __half*)src, (__half*)dst, Co, Ci,
+                                                                            R, f);
+  GDL_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int gdl_fold_widened_wgrad(const float* src, int src_ld, int src_co, float* dst, int Co, int Ci, int R,
+                                      int f, int accumulate, void* stream) {
+  GDL_REQUIRE(src && dst && Co > 0 && Ci > 0 && R > 0 && f >= 2, GDL_ERR_INVALID, "fold_widened_wgrad: bad args");
+  if (src_co <= 0) src_co = Co;
+  GDL_REQUIRE(src_co >= Co, GDL_ERR_INVALID, "fold_widened_wgrad: src_co < Co");
+  if (src_ld <= 0) src_ld = R * 3 * f * Ci;
+  GDL_REQUIRE(src_ld >= R * 3 * f * Ci, GDL_ERR_INVALID, "fold_widened_wgrad: src_ld too small");
+  const long long total = (long long)Co * Ci * R * 3;
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  gdl::fold_widened_wgrad_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(src, src_ld, src_co, dst, Co, Ci, R, f,
+                                                                           accumulate);
+  GDL_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
 
 extern "C" int gdl_pack_conv_weight(const float* src, void* dst, int Cout, int Cin, int R, int S,
                                     int mode, int dst_ld, int dtype, void* stream) {

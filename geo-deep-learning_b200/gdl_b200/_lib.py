@@ -98,6 +98,8 @@ _SIGS = {
     "gdl_conv2d_nhwc_wgrad": [_VP, _VP],
     "gdl_pack_conv_weight": [_VP, _VP, _I, _I, _I, _I, _I, _I, _I, _VP],
     "gdl_unpack_conv_wgrad": [_VP, _VP, _I, _I, _I, _I, _I, _I, _VP],
+    "gdl_widen_conv_weight": [_VP, _VP, _I, _I, _I, _I, _I, _VP],
+    "gdl_fold_widened_wgrad": [_VP, _I, _I, _VP, _I, _I, _I, _I, _I, _VP],
     "gdl_normalize_to_nhwc": [_VP, _I, _VP, _I, _LL, _LL, _LL, _I, _I, _VP, _VP, _F, _VP],
     "gdl_im2col_nhwc": [_VP, _VP, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _VP],
     "gdl_col2im_nhwc": [_VP, _VP, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _VP],

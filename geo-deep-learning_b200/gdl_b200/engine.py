@@ -65,6 +65,7 @@ class RawConv:
     cin_store: int = 0  # channels per pixel as stored (>= weight.shape[1] when the input is padded)
     wshape: tuple | None = None  # (Cout, Cin, R, S) view of the parameter (nn.Linear weights are (Cout, Cin))
     bias: torch.Tensor | None = None
+    pixel_packed: bool = False  # narrow 3x3 conv run as its pixel-packed (block-Toeplitz) equivalent
 
 
 @dataclass
@@ -110,6 +111,42 @@ class Engine:
         self._wcache[key] = (ver, out)
         return out
 
+    def packed_wide(self, w: torch.Tensor, mode: int, f: int, wshape: tuple, coutp: int = 0) -> torch.Tensor:
+        """Block-Toeplitz operand of a narrow Rx3 conv run on f-pixel packed pixels (ops.widen_conv_weight);
+        mode 1 = the dgrad operand, whose `coutp` input channels may be zero-padded beyond Cout."""
+        key = (w.data_ptr(), "wide", mode, f, coutp, self.dtype)
+        hit = self._wcache.get(key)
+        if hit is not None and hit[0] == w._version:
+            return hit[1]
+        cout, cin, r, _ = wshape
+        if mode == 0:
+            out = ops.widen_conv_weight(self.packed(w, 0, 0, wshape), cout, cin, r, f)
+        else:
+            out = ops.widen_conv_weight(self._dgrad_weight(w, coutp or cout, wshape), cin, coutp or cout, r, f)
+        self._wcache[key] = (w._version, out)
+        return out
+
+    def _tiled_bias(self, bias: torch.Tensor, f: int) -> torch.Tensor:
+        key = (bias.data_ptr(), "tiled_bias", f)
+        hit = self._wcache.get(key)
+        if hit is not None and hit[0] == bias._version:
+            return hit[1]
+        out = bias.detach().to(self.acc_dtype).repeat(f)
+        self._wcache[key] = (bias._version, out)
+        return out
+
+    @staticmethod
+    def _pixel_packable(srcs: list[Act], wshape: tuple, stride: int, pad: int) -> bool:
+        """Single dense source, 3x3 / stride 1 / pad 1, 16 or 32 channels in and out, width divisible by 4: run the
+        conv on 64-channel packed pixels (128-byte rows, N >= 32) instead of 32/64-byte rows with N = 16."""
+        cout, cin, r, s = wshape
+        if len(srcs) != 1 or stride != 1 or pad != 1 or r != 3 or s != 3:
+            return False
+        if cin not in (16, 32) or cout > 32:
+            return False
+        t = srcs[0].t
+        return t.is_contiguous() and t.shape[3] == cin and t.shape[2] % 4 == 0 and ops.option("pixel_pack") != 0
+
     def grad_buffer(self, p: torch.Tensor, zero: bool) -> torch.Tensor:
         """Destination for d(loss)/d(p): the registered (pre-zeroed) view, else a fresh tensor."""
         k = id(p)
@@ -132,6 +169,15 @@ class Engine:
         cout, cin, r, s = wshape
         stored = sum(a.t.shape[3] for a in srcs)
         direct = stride == 1 and all(a.t.shape[3] % 16 == 0 for a in srcs) and stored == cin
+        if direct and residual is None and self._pixel_packable(srcs, wshape, stride, pad):
+            a = srcs[0]
+            n, h, wd, _ = a.t.shape
+            f = 64 // cin
+            x = ops.conv2d_fwd([a.t.view(n, h, wd // f, f * cin)], self.packed_wide(weight, 0, f, wshape), f * cout,
+                               r, s, pad, pad, out_dtype=out_dtype, relu=relu,
+                               bias=self._tiled_bias(bias, f) if bias is not None else None)
+            return RawConv(x.view(n, h, wd, cout), srcs, weight, stride, pad, cin_store=stored, wshape=wshape, bias=bias,
+                           pixel_packed=True)
         if direct:
             wp = self.packed(weight, 0, 0, wshape)
             x = ops.conv2d_fwd([a.t for a in srcs], wp, cout, r, s, pad, pad, out_dtype=out_dtype, bias=bias,
@@ -161,6 +207,21 @@ class Engine:
             sums = torch.empty(2 * coutp, dtype=self.acc_dtype, device=dev)
             ops.bn_stats(dx, sums)  # column sums (no pivot)
             self.grad_buffer(rc.bias, False).copy_(sums[:cout])
+        if rc.pixel_packed and coutp in (16, 32) and dgrad_residual is None and dx.is_contiguous():
+            a = rc.srcs[0]
+            n, h, wd, _ = a.t.shape
+            if w.requires_grad:
+                f = 64 // max(cin, coutp)
+                dw = torch.zeros((f * coutp, r * s * f * cin), dtype=self.acc_dtype, device=dev)
+                ops.conv2d_wgrad([a.t.view(n, h, wd // f, f * cin)], dx.view(n, h, wd // f, f * coutp), r, s, rc.pad,
+                                 rc.pad, dw)
+                ops.fold_widened_wgrad(dw, self.grad_buffer(w, False).view(cout, cin, r, s), f)
+            if a.needs_grad:
+                f = 64 // coutp
+                dcat = ops.conv2d_fwd([dx.view(n, h, wd // f, f * coutp)], self.packed_wide(w, 1, f, rc.wshape, coutp),
+                                      f * cin, r, s, r - 1 - rc.pad, s - 1 - rc.pad)
+                a.gsrcs.append((dcat.view(n, h, wd, cin), 0))
+            return
         if rc.col is None:
             if w.requires_grad:
                 if r == 1 and s == 1 and coutp == cout:

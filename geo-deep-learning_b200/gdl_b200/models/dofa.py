@@ -214,11 +214,16 @@ class DOFAv2(nn.Module):
             if not torch.allclose(wavelengths, wavelengths[0:1].expand_as(wavelengths)):
                 raise ValueError("DOFA cannot handle different wavelengths within a batch")
             wavelengths = wavelengths[0]
+        c = x.shape[1]
+        img = ops.normalize_to_nhwc(x.contiguous().float(), True, self.compute_dtype, (c + 7) // 8 * 8)
+        return self._features_nhwc(img, c, wavelengths)
+
+    def _features_nhwc(self, img: torch.Tensor, c: int, wavelengths: torch.Tensor) -> list[torch.Tensor]:
+        """img: NHWC 16-bit tile batch (B, H, W, ld >= c) as produced by the normalise kernel"""
         dt = self.compute_dtype
-        b, c, hh, ww = x.shape
+        b, hh, ww = img.shape[:3]
         d, k = self.embed_dim, self.patch_size
         w_oihw, bias = self._dynamic_weights(wavelengths, c)
-        img = ops.normalize_to_nhwc(x.contiguous().float(), True, dt, (c + 7) // 8 * 8)
         kk = k * k * c
         kpad = (kk + 63) // 64 * 64
         col = ops.im2col(img, c, k, k, k, 1, kpad)
@@ -289,6 +294,24 @@ class DOFASegmentationModel(UperNetSegmentor):
             o, a = self.run(eng, [Act(f, needs_grad=False) for f in feats], image_size)
             self._saved = None
         return SegmentationOutput(o.permute(0, 3, 1, 2), a.permute(0, 3, 1, 2))
+
+    def fused_train(self, eng: Engine, x16: torch.Tensor, c: int, target: torch.Tensor, spec) -> torch.Tensor:
+        """FusedTrainer hook: normalised NHWC tiles -> loss = L(out) + 0.4 L(aux) (segmentation_dofa.py:226-228) with
+        the gradients of the trainable half left in the engine's destination buffers.  Needs `self.wavelengths`."""
+        if any(p.requires_grad for p in self.encoder.parameters()):
+            raise NotImplementedError("DOFA encoder backward: freeze the encoder (freeze_layers=['encoder'])")
+        feats = self.encoder._features_nhwc(x16, c, self.wavelengths)
+        image_size = tuple(x16.shape[1:3])
+        o, a = self.run(eng, [Act(f, needs_grad=False) for f in feats], image_size)
+        if getattr(self, "_aux_w", None) is None or self._aux_w.device != o.device:
+            self._aux_w = torch.full((1,), 0.4, dtype=torch.float32, device=o.device)
+        co, _ = ops.seg_loss_fwd(o, target, spec)
+        ca, _ = ops.seg_loss_fwd(a, target, spec)
+        d_o, d_a = torch.empty_like(o), torch.empty_like(a)
+        ops.seg_loss_bwd(o, target, spec, co, None, d_o)
+        ops.seg_loss_bwd(a, target, spec, ca, self._aux_w, d_a)
+        self.backward(eng, d_o, d_a)
+        return co[0] + 0.4 * ca[0]
 
     def _feat(self, f: torch.Tensor, needs_grad: bool) -> Act:
         # features coming from the B200 encoder are already NHWC 16-bit (logical NCHW view): no copy

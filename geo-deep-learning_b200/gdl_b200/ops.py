@@ -5,6 +5,8 @@ contiguous and whose pixel stride `stride(2)` may exceed C (channel slice of a w
 """
 from __future__ import annotations
 
+import os
+
 import ctypes as C
 from typing import Sequence
 
@@ -95,8 +97,19 @@ def set_conv_profiler(p: ConvProfiler | None) -> None:
     _PROFILER = p
 
 
+# host-side switches (the library's own are in gdl_set_option); pixel_pack: run 16/32-channel 3x3 convs pixel-packed
+_HOST_OPTS = {"pixel_pack": int(os.environ.get("GDL_PIXEL_PACK", "1"))}
+
+
+def option(name: str) -> int:
+    return _HOST_OPTS[name]
+
+
 def set_option(name: str, value: int) -> None:
-    """runtime tuning switch of the library (see gdl_set_option in include/gdl_b200.h)"""
+    """runtime tuning switch of the library (see gdl_set_option in include/gdl_b200.h) or of the host engine"""
+    if name in _HOST_OPTS:
+        _HOST_OPTS[name] = int(value)
+        return
     L.check(L.load().gdl_set_option(name.encode(), int(value)))
 
 
@@ -220,6 +233,26 @@ def unpack_conv_wgrad(dw: torch.Tensor, out_oihw: torch.Tensor, src_ld: int = 0,
     k, c, r, s = out_oihw.shape
     _ck(L.load().gdl_unpack_conv_wgrad(L.ptr(dw), L.ptr(out_oihw), k, c, r, s, src_ld,
                                            int(accumulate), L.stream_ptr()))
+    return out_oihw
+
+
+def widen_conv_weight(wp: torch.Tensor, co: int, ci: int, r: int, f: int) -> torch.Tensor:
+    """packed 16-bit [Co][R][3][Ci] -> block-Toeplitz [f*Co][R][3][f*Ci]: the same conv on (N,H,W/f,f*Ci) pixels"""
+    if wp.shape != (co, r * 3 * ci) or not wp.is_contiguous():
+        raise ValueError("widen_conv_weight: dense packed [Co][R*3*Ci] operand expected")
+    out = torch.empty((f * co, r * 3 * f * ci), dtype=wp.dtype, device=wp.device)
+    _ck(L.load().gdl_widen_conv_weight(L.ptr(wp), L.ptr(out), co, ci, r, f, L.dt_code(wp.dtype), L.stream_ptr()))
+    return out
+
+
+def fold_widened_wgrad(dw: torch.Tensor, out_oihw: torch.Tensor, f: int, accumulate: bool = False) -> torch.Tensor:
+    """fp32 gradient of widened weights [f*Co][R*3*f*Ci] -> fp32 OIHW gradient of the real Rx3 conv"""
+    co, ci, r, s = out_oihw.shape
+    src_co = dw.shape[0] // f  # >= co when the conv's output channels were zero-padded
+    if s != 3 or dw.shape[0] != f * src_co or src_co < co:
+        raise ValueError("fold_widened_wgrad: shape mismatch")
+    _ck(L.load().gdl_fold_widened_wgrad(L.ptr(dw), dw.stride(0), src_co, L.ptr(out_oihw), co, ci, r, f, int(accumulate),
+                                        L.stream_ptr()))
     return out_oihw
 
 

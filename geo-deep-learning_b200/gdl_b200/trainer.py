@@ -74,6 +74,11 @@ class FusedTrainer:
         c = image_u8.shape[3]
         x = ops.normalize_to_nhwc(image_u8, False, model.compute_dtype, (c + 7) // 8 * 8, self.mean, self.std,
                                   self.image_max)
+        if hasattr(model, "fused_train"):
+            # models with several logit maps / a frozen front half (DOFA + UperNet) own the whole step
+            loss = model.fused_train(eng, x, c, target, self.loss)
+            self.last_engine = eng
+            return loss
         logits = model.run(eng, Act(x, needs_grad=False))
         coeff, _ = ops.seg_loss_fwd(logits, target, self.loss)
         n, h, w, k = logits.shape

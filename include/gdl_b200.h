@@ -134,6 +134,17 @@ int gdl_pack_conv_weight(const float* src, void* dst, int Cout, int Cin, int R, 
 int gdl_unpack_conv_wgrad(const float* src, float* dst, int Cout, int Cin, int R, int S, int src_ld,
                           int accumulate, void* stream);
 
+/* ---- pixel-packed form of a narrow conv (engine-internal re-layout; no reference counterpart: the reference calls
+ * cuDNN through torch.nn.Conv2d, segmentation_models_pytorch decoder blocks with 16/32 channels) ----
+ * A Rx3 / pad-1 conv over Ci channels on (N,H,W,Ci) is the same memory as an Rx3 conv over f*Ci channels on
+ * (N,H,W/f,f*Ci) with block-Toeplitz weights.  src: 16-bit packed weights [Co][R][3][Ci] (mode 0 or mode 1 output of
+ * gdl_pack_conv_weight); dst: [f*Co][R][3][f*Ci], dst[(j,o)][ky][sx][(j',c)] = src[o][ky][f*(sx-1)+j'-j+1][c] or 0. */
+int gdl_widen_conv_weight(const void* src, void* dst, int Co, int Ci, int R, int f, int dtype, void* stream);
+/* fp32 gradient of widened weights [f*src_co][src_ld] (rows (j,o), o < src_co; columns (ky,sx,(j',c))) -> fp32 OIHW
+ * [Co][Ci][R][3] of the conv; src_co >= Co when the output channels were zero-padded (0 = Co) */
+int gdl_fold_widened_wgrad(const float* src, int src_ld, int src_co, float* dst, int Co, int Ci, int R, int f,
+                           int accumulate, void* stream);
+
 /* =============================================================================================
  * HBM-bound kernels (csrc/elementwise.cu).  16-bit NHWC activations, C % 8 == 0 unless noted;
  * `dtype` = GDL_BF16 / GDL_F16.

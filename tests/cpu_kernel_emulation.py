@@ -102,6 +102,37 @@ def unpack_conv_wgrad(dw, out_oihw, src_ld=0, accumulate=False):
     return out_oihw
 
 
+def widen_conv_weight(wp, co, ci, r, f):
+    w = wp.reshape(co, r, 3, ci)
+    out = torch.zeros(f, co, r, 3, f, ci, dtype=wp.dtype)
+    for j in range(f):
+        for sx in range(3):
+            for jp in range(f):
+                kx = f * (sx - 1) + jp - j + 1
+                if 0 <= kx < 3:
+                    out[j, :, :, sx, jp, :] = w[:, :, kx, :]
+    return out.reshape(f * co, r * 3 * f * ci)
+
+
+def fold_widened_wgrad(dw, out_oihw, f, accumulate=False):
+    co, ci, r, _ = out_oihw.shape
+    src_co = dw.shape[0] // f
+    d = dw[:, :r * 3 * f * ci].reshape(f, src_co, r, 3, f, ci)[:, :co]
+    acc = torch.zeros(co, r, 3, ci, dtype=dw.dtype)
+    for j in range(f):
+        for sx in range(3):
+            for jp in range(f):
+                kx = f * (sx - 1) + jp - j + 1
+                if 0 <= kx < 3:
+                    acc[:, :, kx, :] += d[j, :, :, sx, jp, :]
+    v = acc.permute(0, 3, 1, 2).to(out_oihw.dtype)
+    if accumulate:
+        out_oihw += v
+    else:
+        out_oihw.copy_(v)
+    return out_oihw
+
+
 def normalize_to_nhwc(x, chw, out_dtype, ld, mean=None, std=None, image_max=0.0):
     v = x.to(_WORK)
     if chw:

@@ -251,3 +251,35 @@ def test_dofa_segmentation_model_train_step_equals_oracle(monkeypatch, f64):
         want = sd[n_].grad
         err = (p.grad - want).abs().max() / (want.abs().max() + 1e-30)
         assert err < 1e-6 or want.abs().max() < 1e-12, f"{n_}: {err}"
+
+
+def test_dofa_fused_trainer_matches_autograd_route(monkeypatch, f64):
+    """FusedTrainer's `fused_train` hook (frozen encoder, two logit maps, 0.4 aux weight) leaves the same gradients
+    in the flat buffer as the autograd route checked above, and only the trainable half is in the Adam buffers."""
+    from gdl_b200.models.dofa import DOFASegmentationModel
+    from gdl_b200.trainer import FusedTrainer
+    emu.install(monkeypatch)
+    torch.manual_seed(0)
+    m = DOFASegmentationModel("dofa_base", (56, 56), ["encoder"], 4, compute_dtype=torch.float64).double().train()
+    m.acc_dtype = torch.float64
+    m.wavelengths = torch.tensor([0.665, 0.56, 0.49]).double()
+    g = torch.Generator().manual_seed(1)
+    raw = torch.randint(0, 256, (2, 56, 56, 3), generator=g, dtype=torch.uint8)
+    t = torch.randint(0, 4, (2, 56, 56), generator=g)
+    mean, std = [0.5] * 3, [0.25] * 3
+    x = ((raw.double() / 255.0).permute(0, 3, 1, 2) - 0.5) / 0.25
+    out = m(x, m.wavelengths)
+    (F.cross_entropy(out.out, t) + 0.4 * F.cross_entropy(out.aux, t)).backward()
+    want = {n_: p.grad.clone() for n_, p in m.named_parameters() if p.requires_grad}
+    for mod in m.modules():  # the autograd route above already advanced the running statistics once
+        if isinstance(mod, torch.nn.BatchNorm2d):
+            mod.reset_running_stats()
+    tr = FusedTrainer(m, emu.LossSpec(1.0, 0.0, ignore_index=-100), lr=1e-3, mean=mean, std=std, acc_dtype=torch.float64)
+    assert tr.flat.numel() == sum(p.numel() for n_, p in m.named_parameters() if not n_.startswith("encoder."))
+    loss = tr.forward_backward(raw, t)
+    # (the autograd route rounds the image to fp32 before the normalise kernel: ~1e-8 relative input difference)
+    assert abs(float(loss) - float(F.cross_entropy(out.out, t) + 0.4 * F.cross_entropy(out.aux, t))) < 1e-7
+    for n_, p in m.named_parameters():
+        if p.requires_grad:
+            err = (p.grad - want[n_]).abs().max() / (want[n_].abs().max() + 1e-30)
+            assert err < 1e-4 or want[n_].abs().max() < 1e-12, f"{n_}: {err}"
