@@ -245,4 +245,58 @@ GDL_DEVINL float warp_sum(float v) {
   return v;
 }
 
+// ----------------------------------------------------------------------------------------
+// epilogue helpers shared by the tensor-core conv kernels
+// ----------------------------------------------------------------------------------------
+GDL_DEVINL uint8_t* align_smem_1024(uint8_t* raw) {
+  uint32_t a = smem_u32(raw);
+  uint32_t pad = (1024u - (a & 1023u)) & 1023u;
+  return raw + pad;
+}
+
+template <typename T>
+GDL_DEVINL void store_row16(T* dst, const float (&f)[16], int nvalid, int vec_ok);
+
+template <>
+GDL_DEVINL void store_row16<float>(float* dst, const float (&f)[16], int nvalid, int vec_ok) {
+  if (nvalid == 16 && vec_ok) {
+    float4* d4 = reinterpret_cast<float4*>(dst);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) d4[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
+  } else {
+#pragma unroll
+    for (int i = 0; i < 16; ++i)
+      if (i < nvalid) dst[i] = f[i];
+  }
+}
+template <>
+GDL_DEVINL void store_row16<__nv_bfloat16>(__nv_bfloat16* dst, const float (&f)[16], int nvalid,
+                                           int vec_ok) {
+  if (nvalid == 16 && vec_ok) {
+    uint4* d4 = reinterpret_cast<uint4*>(dst);
+    d4[0] = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]),
+                       pack_bf16x2(f[6], f[7]));
+    d4[1] = make_uint4(pack_bf16x2(f[8], f[9]), pack_bf16x2(f[10], f[11]),
+                       pack_bf16x2(f[12], f[13]), pack_bf16x2(f[14], f[15]));
+  } else {
+#pragma unroll
+    for (int i = 0; i < 16; ++i)
+      if (i < nvalid) dst[i] = __float2bfloat16_rn(f[i]);
+  }
+}
+template <>
+GDL_DEVINL void store_row16<__half>(__half* dst, const float (&f)[16], int nvalid, int vec_ok) {
+  if (nvalid == 16 && vec_ok) {
+    uint4* d4 = reinterpret_cast<uint4*>(dst);
+    d4[0] = make_uint4(pack_f16x2(f[0], f[1]), pack_f16x2(f[2], f[3]), pack_f16x2(f[4], f[5]),
+                       pack_f16x2(f[6], f[7]));
+    d4[1] = make_uint4(pack_f16x2(f[8], f[9]), pack_f16x2(f[10], f[11]), pack_f16x2(f[12], f[13]),
+                       pack_f16x2(f[14], f[15]));
+  } else {
+#pragma unroll
+    for (int i = 0; i < 16; ++i)
+      if (i < nvalid) dst[i] = __float2half_rn(f[i]);
+  }
+}
+
 }  // namespace gdl

@@ -1,0 +1,403 @@
+// conv3x3_rows.cu — weight-stationary, row-rolling 3x3 / pad-1 / stride-1 implicit GEMM for narrow outputs.
+//
+// Why: for Cout <= 64 the per-tile kernel in igemm_conv.cu is bound by L2->SM bandwidth, not by the tensor pipe
+// (profiles/: 64-channel layers at 256^2 run at ~490 of ~1230 TFLOP/s).  Per 128-pixel tile and 64-channel k-chunk it
+// pulls 3 input rows (3 x 16.6 KB) AND the 9 weight taps (9 x 8 KB = 73 KB): the weights are the larger stream.
+//
+// Here one CTA owns a column block of G vertically adjacent 128-pixel row tiles (G x BN <= 256 TMEM columns, double
+// buffered), and per k-chunk
+//   * loads the 9 weight taps ONCE (three filter-row stages of a weight ring) for all G tiles,
+//   * streams the G + 2 input rows ONCE (instead of 3 G): input row i feeds the filter rows r = 0,1,2 of the output
+//     tiles g = i+1, i, i-1 — up to 9 MMAs chains per loaded row, each into a different TMEM accumulator,
+//   * keeps the 3 horizontal taps as row-shifted UMMA descriptors inside the 130-pixel halo tile (as the halo mode of
+//     igemm_conv.cu, probe: profiles/r01_probe_shifted_umma_descriptor.json).
+// L2->SM bytes per tile and k-chunk: 16.6 KB x (G+2)/G + 73 KB / G  (G = 4: 43 KB instead of 123 KB).
+//
+// Roles: warp 0 = TMA producer (two rings: input rows, weight filter rows), warp 1 = MMA issuer (one thread),
+// warps 2..5 = epilogue (tcgen05.ld -> bias / ReLU / GELU / LayerScale / residual -> NHWC row stores).
+#include <string.h>
+
+#include "../../include/gdl_b200.h"
+#include "common.cuh"
+#include "tmap.cuh"
+
+namespace gdl {
+
+constexpr int kRowsThreads = 192;
+constexpr int kRowsBK = 64;                      // channels per k-chunk (128-byte swizzled rows)
+constexpr int kRowsAStage = 17 * 1024;           // 130 px x 64 ch x 2 B = 16 640 B, padded to the 1024-B swizzle repeat
+constexpr int kRowsMaxAStages = 6;
+constexpr int kRowsMaxBStages = 6;
+constexpr int kRowsSmemBudget = 200 * 1024;
+
+struct ConvRowsKParams {
+  CUtensorMap tmA[GDL_MAX_SRC];
+  CUtensorMap tmB;
+  int num_src;
+  int src_chunks[GDL_MAX_SRC];
+  int src_coff[GDL_MAX_SRC];
+  int Ctot;
+  int Nimg, Ho, Wo;
+  int tiles_w, hblocks, G;
+  int Cout, BN, n_tiles;
+  long long num_jobs;
+  int a_stages, b_stages, b_tap_bytes, b_stage_bytes;
+  int ab_fmt;
+  void* out;
+  int out_dtype;
+  long long ldo;
+  int vec_ok;
+  const float* bias;
+  int relu;
+  const float* oscale;
+  const void* residual;
+  int res_dtype;
+  long long ldr;
+};
+
+struct RowsJob {
+  int n0, img, w0, h0;
+};
+
+GDL_DEVINL RowsJob rows_job(const ConvRowsKParams& p, long long job) {
+  // consecutive jobs walk down an image column block by block, then across, then images, then Cout tiles
+  RowsJob j;
+  const int hb = (int)(job % p.hblocks);
+  long long t = job / p.hblocks;
+  const int wt = (int)(t % p.tiles_w);
+  t /= p.tiles_w;
+  j.img = (int)(t % p.Nimg);
+  j.n0 = (int)(t / p.Nimg) * p.BN;
+  j.w0 = wt * 128;
+  j.h0 = hb * p.G;
+  return j;
+}
+
+__global__ void __launch_bounds__(kRowsThreads, 1) conv3x3_rows_kernel(const __grid_constant__ ConvRowsKParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = align_smem_1024(smem_raw);
+  uint8_t* smem_b = smem + (size_t)p.a_stages * kRowsAStage;
+
+  __shared__ __align__(8) uint64_t a_full[kRowsMaxAStages];
+  __shared__ __align__(8) uint64_t a_empty[kRowsMaxAStages];
+  __shared__ __align__(8) uint64_t b_full[kRowsMaxBStages];
+  __shared__ __align__(8) uint64_t b_empty[kRowsMaxBStages];
+  __shared__ __align__(8) uint64_t tfull_bar[2];
+  __shared__ __align__(8) uint64_t tempty_bar[2];
+  __shared__ uint32_t tmem_base_smem;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int G = p.G;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < p.num_src; ++s) tma_prefetch_desc(&p.tmA[s]);
+    tma_prefetch_desc(&p.tmB);
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int i = 0; i < p.a_stages; ++i) {
+        mbar_init(&a_full[i], 1);
+        mbar_init(&a_empty[i], 1);
+      }
+      for (int i = 0; i < p.b_stages; ++i) {
+        mbar_init(&b_full[i], 1);
+        mbar_init(&b_empty[i], 1);
+      }
+      for (int i = 0; i < 2; ++i) {
+        mbar_init(&tfull_bar[i], 1);
+        mbar_init(&tempty_bar[i], 128);
+      }
+      fence_mbar_init();
+    }
+    __syncwarp();
+    tmem_alloc(&tmem_base_smem, 512u);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_smem;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int as = 0, bs = 0;
+      uint32_t aph = 0, bph = 0;
+      for (long long job = blockIdx.x; job < p.num_jobs; job += gridDim.x) {
+        const RowsJob j = rows_job(p, job);
+        for (int src = 0; src < p.num_src; ++src) {
+          for (int ch = 0; ch < p.src_chunks[src]; ++ch) {
+            const int kcol = p.src_coff[src] + ch * kRowsBK;
+            for (int i = -1; i <= G; ++i) {
+              if (i <= 1) {  // weights of filter row r = i + 1 (3 taps), first needed by input row i
+                const int r = i + 1;
+                mbar_wait(&b_empty[bs], bph ^ 1);
+                uint8_t* b_dst = smem_b + (size_t)bs * p.b_stage_bytes;
+                mbar_expect_tx(&b_full[bs], (uint32_t)(3 * p.BN * kRowsBK * 2));
+                for (int s = 0; s < 3; ++s)
+                  tma_load_2d(b_dst + s * p.b_tap_bytes, &p.tmB, &b_full[bs], (r * 3 + s) * p.Ctot + kcol, j.n0);
+                if (++bs == p.b_stages) {
+                  bs = 0;
+                  bph ^= 1;
+                }
+              }
+              mbar_wait(&a_empty[as], aph ^ 1);
+              mbar_expect_tx(&a_full[as], (uint32_t)(130 * kRowsBK * 2));
+              tma_load_4d(smem + (size_t)as * kRowsAStage, &p.tmA[src], &a_full[as], ch * kRowsBK, j.w0 - 1, j.h0 + i,
+                          j.img);
+              if (++as == p.a_stages) {
+                as = 0;
+                aph ^= 1;
+              }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (one thread) =====================
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc(128, p.BN, p.ab_fmt, 0, 0);
+      const uint32_t lt = umma_layout_type(kRowsBK * 2);
+      const uint32_t sbo = 8u * kRowsBK * 2u;
+      int as = 0, bs = 0;
+      uint32_t aph = 0, bph = 0;
+      int it = 0;
+      for (long long job = blockIdx.x; job < p.num_jobs; job += gridDim.x, ++it) {
+        const int buf = it & 1;
+        mbar_wait(&tempty_bar[buf], ((it >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t d_base = tmem_base + (uint32_t)(buf * 256);
+        bool first_chunk = true;
+        for (int src = 0; src < p.num_src; ++src) {
+          for (int ch = 0; ch < p.src_chunks[src]; ++ch) {
+            uint32_t b_addr[3] = {0, 0, 0};
+            int b_slot[3] = {0, 0, 0};
+            for (int i = -1; i <= G; ++i) {
+              if (i <= 1) {
+                const int r = i + 1;
+                mbar_wait(&b_full[bs], bph);
+                b_slot[r] = bs;
+                b_addr[r] = smem_u32(smem_b + (size_t)bs * p.b_stage_bytes);
+                if (++bs == p.b_stages) {
+                  bs = 0;
+                  bph ^= 1;
+                }
+              }
+              mbar_wait(&a_full[as], aph);
+              tc_fence_after();
+              const uint32_t a_addr = smem_u32(smem + (size_t)as * kRowsAStage);
+#pragma unroll
+              for (int r = 0; r < 3; ++r) {
+                const int g = i - r + 1;  // output row tile fed by (input row i, filter row r)
+                if (g < 0 || g >= G) continue;
+                const uint32_t d_tmem = d_base + (uint32_t)(g * p.BN);
+#pragma unroll
+                for (int s3 = 0; s3 < 3; ++s3) {
+                  const uint32_t a_s = a_addr + s3 * kRowsBK * 2;  // start shifted by s3 pixels (rows of 128 B)
+                  const uint32_t b_s = b_addr[r] + s3 * p.b_tap_bytes;
+#pragma unroll
+                  for (int kk = 0; kk < kRowsBK / 16; ++kk) {
+                    const uint64_t da = umma_smem_desc(a_s + kk * 32, 16, sbo, lt);
+                    const uint64_t db = umma_smem_desc(b_s + kk * 32, 16, sbo, lt);
+                    umma_f16(d_tmem, da, db, idesc, (uint32_t)(!(first_chunk && r == 0 && s3 == 0 && kk == 0)));
+                  }
+                }
+              }
+              umma_commit(&a_empty[as]);
+              if (++as == p.a_stages) {
+                as = 0;
+                aph ^= 1;
+              }
+              // a filter row's weights are last used by input row G - 2 + r
+              if (i >= G - 2) umma_commit(&b_empty[b_slot[i - (G - 2)]]);
+            }
+            first_chunk = false;
+          }
+        }
+        umma_commit(&tfull_bar[buf]);
+      }
+    }
+  } else {
+    // ===================== epilogue: every thread owns one accumulator row (pixel) =====================
+    const int q = warp & 3;  // TMEM lane quadrant this warp may access
+    const int row = q * 32 + lane;
+    int it = 0;
+    for (long long job = blockIdx.x; job < p.num_jobs; job += gridDim.x, ++it) {
+      const int buf = it & 1;
+      const RowsJob j = rows_job(p, job);
+      const int w = j.w0 + row;
+      mbar_wait(&tfull_bar[buf], (it >> 1) & 1);
+      tc_fence_after();
+      for (int g = 0; g < G; ++g) {
+        const int h = j.h0 + g;
+        const bool valid = (h < p.Ho) && (w < p.Wo);
+        const long long pix = ((long long)j.img * p.Ho + h) * p.Wo + w;
+        const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 256 + g * p.BN);
+        for (int cb = 0; cb < p.BN; cb += 16) {
+          uint32_t v[16];
+          tmem_ld_32x32b_x16(t_addr + cb, v);
+          tmem_ld_wait();
+          const int c0 = j.n0 + cb;
+          const int nvalid = min(16, p.Cout - c0);
+          if (!valid || nvalid <= 0) continue;
+          float f[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]);
+          if (p.bias != nullptr) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+              if (i < nvalid) f[i] += __ldg(p.bias + c0 + i);
+          }
+          if (p.oscale != nullptr) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+              if (i < nvalid) f[i] *= __ldg(p.oscale + c0 + i);
+          }
+          if (p.residual != nullptr) {
+            const long long roff = pix * p.ldr + c0;
+            if (p.res_dtype == GDL_F32) {
+              const float* rp = reinterpret_cast<const float*>(p.residual) + roff;
+#pragma unroll
+              for (int i = 0; i < 16; ++i)
+                if (i < nvalid) f[i] += rp[i];
+            } else if (p.res_dtype == GDL_BF16) {
+              const __nv_bfloat16* rp = reinterpret_cast<const __nv_bfloat16*>(p.residual) + roff;
+#pragma unroll
+              for (int i = 0; i < 16; ++i)
+                if (i < nvalid) f[i] += __bfloat162float(rp[i]);
+            } else {
+              const __half* rp = reinterpret_cast<const __half*>(p.residual) + roff;
+#pragma unroll
+              for (int i = 0; i < 16; ++i)
+                if (i < nvalid) f[i] += __half2float(rp[i]);
+            }
+          }
+          if (p.relu == 1) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) f[i] = fmaxf(f[i], 0.f);
+          } else if (p.relu == 2) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) f[i] = 0.5f * f[i] * (1.f + erff(f[i] * 0.70710678118654752f));
+          }
+          const long long off = pix * p.ldo + c0;
+          if (p.out_dtype == GDL_F32)
+            store_row16<float>(reinterpret_cast<float*>(p.out) + off, f, nvalid, p.vec_ok);
+          else if (p.out_dtype == GDL_BF16)
+            store_row16<__nv_bfloat16>(reinterpret_cast<__nv_bfloat16*>(p.out) + off, f, nvalid, p.vec_ok);
+          else
+            store_row16<__half>(reinterpret_cast<__half*>(p.out) + off, f, nvalid, p.vec_ok);
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&tempty_bar[buf]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tmem_dealloc(tmem_base, 512u);
+  }
+}
+
+static int rows_sm_count() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess ||
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+      n = kNumSMsB200;
+  }
+  return n;
+}
+
+// Returns 1 when the descriptor is a case this kernel covers (then *status holds the launch status), 0 otherwise.
+// Called by gdl_conv2d_nhwc_fwd after it validated the descriptor.
+int conv3x3_rows_try(const gdl_conv_fwd_t* d, cudaStream_t stream, int* status) {
+  *status = 0;
+  if (d->R != 3 || d->S != 3 || d->pad_h != 1 || d->pad_w != 1 || d->w_mn_major || d->w_rows_per_img) return 0;
+  if (d->Cout > 64 || d->W < 64) return 0;
+  int Ctot = 0;
+  for (int i = 0; i < d->num_src; ++i) {
+    if (d->src[i].channels % kRowsBK) return 0;
+    Ctot += d->src[i].channels;
+  }
+  const int BN = (d->Cout + 15) / 16 * 16;
+  int G = 256 / BN;
+  if (G > 8) G = 8;
+  while (G >= 2 && d->H % G) G >>= 1;
+  if (G < 2) return 0;
+
+  ConvRowsKParams p;
+  memset(&p, 0, sizeof(p));
+  p.num_src = d->num_src;
+  p.Ctot = Ctot;
+  p.Nimg = d->N;
+  p.Ho = d->H;
+  p.Wo = d->W;
+  p.tiles_w = (d->W + 127) / 128;
+  p.hblocks = d->H / G;
+  p.G = G;
+  p.Cout = d->Cout;
+  p.BN = BN;
+  p.n_tiles = 1;
+  p.num_jobs = (long long)p.n_tiles * d->N * p.tiles_w * p.hblocks;
+  p.b_tap_bytes = BN * kRowsBK * 2;              // 2 / 4 / 6 / 8 KB: multiples of the 1024-B swizzle repeat
+  p.b_stage_bytes = 3 * p.b_tap_bytes;
+  p.a_stages = 4;
+  p.b_stages = (kRowsSmemBudget - 1024 - p.a_stages * kRowsAStage) / p.b_stage_bytes;
+  if (p.b_stages > kRowsMaxBStages) p.b_stages = kRowsMaxBStages;
+  if (p.b_stages < 4) return 0;
+  {
+    const int left = kRowsSmemBudget - 1024 - p.b_stages * p.b_stage_bytes;
+    p.a_stages = left / kRowsAStage;
+    if (p.a_stages > kRowsMaxAStages) p.a_stages = kRowsMaxAStages;
+  }
+  p.ab_fmt = d->dtype == GDL_BF16 ? 1 : 0;
+  p.out = d->out;
+  p.out_dtype = d->out_dtype;
+  p.ldo = d->ldo;
+  const int esz = d->out_dtype == GDL_F32 ? 4 : 2;
+  p.vec_ok = ((reinterpret_cast<uintptr_t>(d->out) & 15) == 0) && ((d->ldo * esz) % 16 == 0);
+  p.bias = d->bias;
+  p.relu = d->relu;
+  p.oscale = d->oscale;
+  p.residual = d->residual;
+  p.res_dtype = d->res_dtype;
+  p.ldr = d->ldr;
+
+  int coff = 0;
+  for (int i = 0; i < d->num_src; ++i) {
+    p.src_chunks[i] = d->src[i].channels / kRowsBK;
+    p.src_coff[i] = coff;
+    coff += d->src[i].channels;
+    *status = make_tmap_nhwc(&p.tmA[i], d->src[i].ptr, d->dtype, d->src[i].channels, d->W, d->H, d->N, d->src[i].ld,
+                             kRowsBK, 130, 1, kRowsBK * 2);
+    if (*status) return 1;
+  }
+  const long long Ktot = 9ll * Ctot;
+  const long long w_ld = d->w_ld > 0 ? d->w_ld : Ktot;
+  const long long w_rows = d->w_rows > 0 ? d->w_rows : d->Cout;
+  *status = make_tmap_2d(&p.tmB, d->weight, d->dtype, Ktot, w_rows, w_ld, kRowsBK, BN, kRowsBK * 2);
+  if (*status) return 1;
+
+  const int smem = p.a_stages * kRowsAStage + p.b_stages * p.b_stage_bytes + 1024;
+  static bool attr_set = false;
+  if (!attr_set) {
+    *status = check_cuda(cudaFuncSetAttribute(conv3x3_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                              kRowsSmemBudget + 2048),
+                         "cudaFuncSetAttribute(conv3x3_rows_kernel)");
+    if (*status) return 1;
+    attr_set = true;
+  }
+  const int sms = rows_sm_count();
+  const int grid = p.num_jobs < sms ? (int)p.num_jobs : sms;
+  conv3x3_rows_kernel<<<grid, kRowsThreads, smem, stream>>>(p);
+  *status = check_cuda(cudaGetLastError(), "conv3x3_rows_kernel launch");
+  return 1;
+}
+
+}  // namespace gdl

@@ -24,7 +24,8 @@
 namespace gdl {
 
 // runtime options (gdl_set_option); env vars GDL_CONV_HALO / GDL_WGRAD_HALO / GDL_WGRAD_L2_MB seed them
-static int g_opt_conv_halo = -1, g_opt_wgrad_halo = -1, g_opt_conv_epilogue = -1;
+static int g_opt_conv_halo = -1, g_opt_wgrad_halo = -1, g_opt_conv_epilogue = -1, g_opt_conv_rows = -1;
+int conv3x3_rows_try(const gdl_conv_fwd_t* d, cudaStream_t stream, int* status);  // conv3x3_rows.cu
 static long long g_opt_wgrad_l2_mb = -1;
 static int opt_int(int& slot, const char* env, int dflt) {
   if (slot < 0) {
@@ -74,57 +75,6 @@ struct ConvFwdKParams {
   int halo_bo;           // set the descriptor base_offset field for the shifted start (probe-determined)
   int b_slot;            // bytes between the 3 per-tap weight tiles of a stage
 };
-
-GDL_DEVINL uint8_t* align_smem_1024(uint8_t* raw) {
-  uint32_t a = smem_u32(raw);
-  uint32_t pad = (1024u - (a & 1023u)) & 1023u;
-  return raw + pad;
-}
-
-template <typename T>
-GDL_DEVINL void store_row16(T* dst, const float (&f)[16], int nvalid, int vec_ok);
-
-template <>
-GDL_DEVINL void store_row16<float>(float* dst, const float (&f)[16], int nvalid, int vec_ok) {
-  if (nvalid == 16 && vec_ok) {
-    float4* d4 = reinterpret_cast<float4*>(dst);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) d4[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
-  } else {
-#pragma unroll
-    for (int i = 0; i < 16; ++i)
-      if (i < nvalid) dst[i] = f[i];
-  }
-}
-template <>
-GDL_DEVINL void store_row16<__nv_bfloat16>(__nv_bfloat16* dst, const float (&f)[16], int nvalid,
-                                           int vec_ok) {
-  if (nvalid == 16 && vec_ok) {
-    uint4* d4 = reinterpret_cast<uint4*>(dst);
-    d4[0] = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]),
-                       pack_bf16x2(f[6], f[7]));
-    d4[1] = make_uint4(pack_bf16x2(f[8], f[9]), pack_bf16x2(f[10], f[11]),
-                       pack_bf16x2(f[12], f[13]), pack_bf16x2(f[14], f[15]));
-  } else {
-#pragma unroll
-    for (int i = 0; i < 16; ++i)
-      if (i < nvalid) dst[i] = __float2bfloat16_rn(f[i]);
-  }
-}
-template <>
-GDL_DEVINL void store_row16<__half>(__half* dst, const float (&f)[16], int nvalid, int vec_ok) {
-  if (nvalid == 16 && vec_ok) {
-    uint4* d4 = reinterpret_cast<uint4*>(dst);
-    d4[0] = make_uint4(pack_f16x2(f[0], f[1]), pack_f16x2(f[2], f[3]), pack_f16x2(f[4], f[5]),
-                       pack_f16x2(f[6], f[7]));
-    d4[1] = make_uint4(pack_f16x2(f[8], f[9]), pack_f16x2(f[10], f[11]), pack_f16x2(f[12], f[13]),
-                       pack_f16x2(f[14], f[15]));
-  } else {
-#pragma unroll
-    for (int i = 0; i < 16; ++i)
-      if (i < nvalid) dst[i] = __float2half_rn(f[i]);
-  }
-}
 
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv_fwd_kernel(const __grid_constant__ ConvFwdKParams p) {
@@ -333,6 +283,11 @@ conv_fwd_kernel(const __grid_constant__ ConvFwdKParams p) {
               for (int i = 0; i < 16; ++i)
                 if (i < nvalid) f[i] += __ldg(p.bias + c0 + i);
             }
+            if (p.oscale != nullptr) {
+  #pragma unroll
+              for (int i = 0; i < 16; ++i)
+                if (i < nvalid) f[i] *= __ldg(p.oscale + c0 + i);
+            }
             if (p.residual != nullptr) {
               const long long roff = pix * p.ldr + c0;
               if (p.res_dtype == GDL_F32) {
@@ -352,9 +307,12 @@ conv_fwd_kernel(const __grid_constant__ ConvFwdKParams p) {
                   if (i < nvalid) f[i] += __half2float(r[i]);
               }
             }
-            if (p.relu) {
+            if (p.relu == 1) {
   #pragma unroll
               for (int i = 0; i < 16; ++i) f[i] = fmaxf(f[i], 0.f);
+            } else if (p.relu == 2) {  // exact (erf) GELU, nn.GELU default
+  #pragma unroll
+              for (int i = 0; i < 16; ++i) f[i] = 0.5f * f[i] * (1.f + erff(f[i] * 0.70710678118654752f));
             }
             const long long off = pix * p.ldo + c0;
             if (p.out_dtype == GDL_F32)
@@ -586,6 +544,7 @@ extern "C" int gdl_set_option(const char* name, long long value) {
   else if (!strcmp(name, "wgrad_halo")) g_opt_wgrad_halo = (int)value;
   else if (!strcmp(name, "conv_epilogue")) g_opt_conv_epilogue = (int)value;
   else if (!strcmp(name, "wgrad_l2_mb")) g_opt_wgrad_l2_mb = value;
+  else if (!strcmp(name, "conv_rows")) g_opt_conv_rows = (int)value;
   else {
     set_last_error("set_option: unknown option '%s'", name);
     return GDL_ERR_INVALID;
@@ -611,6 +570,13 @@ extern "C" int gdl_conv2d_nhwc_fwd(const gdl_conv_fwd_t* d, void* stream_) {
   const int Wo = d->W + 2 * d->pad_w - d->S + 1;
   GDL_REQUIRE(Ho > 0 && Wo > 0, GDL_ERR_INVALID, "empty output %dx%d", Ho, Wo);
   GDL_REQUIRE(d->ldo >= d->Cout, GDL_ERR_INVALID, "ldo %d < Cout %d", d->ldo, d->Cout);
+
+  GDL_REQUIRE(d->residual == nullptr || d->ldr >= d->Cout, GDL_ERR_INVALID, "residual stride %d < Cout", d->ldr);
+  if (opt_int(g_opt_conv_rows, "GDL_CONV_ROWS", 1) > 0) {
+    // narrow 3x3 convs: weight-stationary row-rolling kernel (conv3x3_rows.cu)
+    int st_rows = 0;
+    if (conv3x3_rows_try(d, stream, &st_rows)) return st_rows;
+  }
 
   ConvFwdKParams p;
   memset(&p, 0, sizeof(p));
