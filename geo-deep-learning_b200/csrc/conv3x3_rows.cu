@@ -15,6 +15,7 @@
 //
 // Roles: warp 0 = TMA producer (two rings: input rows, weight filter rows), warp 1 = MMA issuer (one thread),
 // warps 2..5 = epilogue (tcgen05.ld -> bias / ReLU / GELU / LayerScale / residual -> NHWC row stores).
+#include <stdlib.h>
 #include <string.h>
 
 #include "../../include/gdl_b200.h"
@@ -28,11 +29,15 @@ constexpr int kRowsBK = 64;                      // channels per k-chunk (128-by
 constexpr int kRowsAStage = 17 * 1024;           // 130 px x 64 ch x 2 B = 16 640 B, padded to the 1024-B swizzle repeat
 constexpr int kRowsMaxAStages = 6;
 constexpr int kRowsMaxBStages = 6;
-constexpr int kRowsSmemBudget = 200 * 1024;
+constexpr int kRowsSmemBudget = 224 * 1024;     // + ~300 B static < 227 KB
 
 struct ConvRowsKParams {
   CUtensorMap tmA[GDL_MAX_SRC];
   CUtensorMap tmB;
+  CUtensorMap tmO;       // output tile store (TMA) when tma_store != 0
+  int tma_store;         // 16-bit output, 16-byte aligned rows, no residual: the epilogue stages tiles in smem
+  int o_stage_bytes;     // 128 px x BN x 2 B
+  int o_swz_mask;        // 16-byte-chunk XOR mask of the staging tile's hardware swizzle (7 / 3 / 1 / 0)
   int num_src;
   int src_chunks[GDL_MAX_SRC];
   int src_coff[GDL_MAX_SRC];
@@ -77,6 +82,7 @@ __global__ void __launch_bounds__(kRowsThreads, 1) conv3x3_rows_kernel(const __g
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = align_smem_1024(smem_raw);
   uint8_t* smem_b = smem + (size_t)p.a_stages * kRowsAStage;
+  uint8_t* smem_o = smem_b + (size_t)p.b_stages * p.b_stage_bytes;  // 2 output staging tiles (1024-B aligned)
 
   __shared__ __align__(8) uint64_t a_full[kRowsMaxAStages];
   __shared__ __align__(8) uint64_t a_empty[kRowsMaxAStages];
@@ -223,6 +229,83 @@ __global__ void __launch_bounds__(kRowsThreads, 1) conv3x3_rows_kernel(const __g
     // ===================== epilogue: every thread owns one accumulator row (pixel) =====================
     const int q = warp & 3;  // TMEM lane quadrant this warp may access
     const int row = q * 32 + lane;
+    if (p.tma_store) {
+      // Row stores from registers cost ~4 SM-cycles per 16-byte store (every lane hits another line): 16 k cycles for
+      // the 4 x 16 KB tiles of a job, 3.5x its MMA time (run 9: tensor pipe 28 % active).  Instead each thread writes
+      // its pixel row into a swizzled smem tile and one thread hands the tile to the TMA store engine.
+      const bool issuer = (warp == 2 && lane == 0);
+      const int pitch = p.BN * 2;
+      int st = 0;
+      int it = 0;
+      for (long long job = blockIdx.x; job < p.num_jobs; job += gridDim.x, ++it) {
+        const int buf = it & 1;
+        const RowsJob j = rows_job(p, job);
+        mbar_wait(&tfull_bar[buf], (it >> 1) & 1);
+        tc_fence_after();
+        for (int g = 0; g < G; ++g) {
+          if (issuer) bulk_wait_group_read<1>();  // the store issued two tiles ago no longer reads staging[st]
+          named_bar_sync(1, 128);
+          uint8_t* stg = smem_o + (size_t)st * p.o_stage_bytes;
+          const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 256 + g * p.BN);
+          for (int cb = 0; cb < p.BN; cb += 16) {
+            uint32_t v[16];
+            tmem_ld_32x32b_x16(t_addr + cb, v);
+            tmem_ld_wait();
+            const int c0 = j.n0 + cb;
+            float f[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]);
+            if (p.bias != nullptr) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i)
+                if (c0 + i < p.Cout) f[i] += __ldg(p.bias + c0 + i);
+            }
+            if (p.oscale != nullptr) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i)
+                if (c0 + i < p.Cout) f[i] *= __ldg(p.oscale + c0 + i);
+            }
+            if (p.relu == 1) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) f[i] = fmaxf(f[i], 0.f);
+            } else if (p.relu == 2) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) f[i] = 0.5f * f[i] * (1.f + erff(f[i] * 0.70710678118654752f));
+            }
+            uint4 lo, hi;
+            if (p.out_dtype == GDL_BF16) {
+              lo = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]),
+                              pack_bf16x2(f[6], f[7]));
+              hi = make_uint4(pack_bf16x2(f[8], f[9]), pack_bf16x2(f[10], f[11]), pack_bf16x2(f[12], f[13]),
+                              pack_bf16x2(f[14], f[15]));
+            } else {
+              lo = make_uint4(pack_f16x2(f[0], f[1]), pack_f16x2(f[2], f[3]), pack_f16x2(f[4], f[5]),
+                              pack_f16x2(f[6], f[7]));
+              hi = make_uint4(pack_f16x2(f[8], f[9]), pack_f16x2(f[10], f[11]), pack_f16x2(f[12], f[13]),
+                              pack_f16x2(f[14], f[15]));
+            }
+            uint32_t off = (uint32_t)(row * pitch + cb * 2);
+            uint32_t o0 = off ^ (((off >> 7) & (uint32_t)p.o_swz_mask) << 4);
+            off += 16;
+            uint32_t o1 = off ^ (((off >> 7) & (uint32_t)p.o_swz_mask) << 4);
+            *reinterpret_cast<uint4*>(stg + o0) = lo;
+            *reinterpret_cast<uint4*>(stg + o1) = hi;
+          }
+          if (g == G - 1) {  // every TMEM read of this job is done: hand the accumulators back to the MMA warp
+            tc_fence_before();
+            mbar_arrive(&tempty_bar[buf]);
+          }
+          fence_proxy_async_smem();
+          named_bar_sync(1, 128);
+          if (issuer) {
+            tma_store_4d(&p.tmO, stg, j.n0, j.w0, j.h0 + g, j.img);
+            bulk_commit_group();
+          }
+          st ^= 1;
+        }
+      }
+      if (issuer) bulk_wait_group<0>();
+    } else {
     int it = 0;
     for (long long job = blockIdx.x; job < p.num_jobs; job += gridDim.x, ++it) {
       const int buf = it & 1;
@@ -293,6 +376,7 @@ __global__ void __launch_bounds__(kRowsThreads, 1) conv3x3_rows_kernel(const __g
       tc_fence_before();
       mbar_arrive(&tempty_bar[buf]);
     }
+    }  // tma_store
   }
 
   tc_fence_before();
@@ -347,21 +431,30 @@ int conv3x3_rows_try(const gdl_conv_fwd_t* d, cudaStream_t stream, int* status) 
   p.num_jobs = (long long)p.n_tiles * d->N * p.tiles_w * p.hblocks;
   p.b_tap_bytes = BN * kRowsBK * 2;              // 2 / 4 / 6 / 8 KB: multiples of the 1024-B swizzle repeat
   p.b_stage_bytes = 3 * p.b_tap_bytes;
-  p.a_stages = 4;
-  p.b_stages = (kRowsSmemBudget - 1024 - p.a_stages * kRowsAStage) / p.b_stage_bytes;
-  if (p.b_stages > kRowsMaxBStages) p.b_stages = kRowsMaxBStages;
-  if (p.b_stages < 4) return 0;
-  {
-    const int left = kRowsSmemBudget - 1024 - p.b_stages * p.b_stage_bytes;
-    p.a_stages = left / kRowsAStage;
-    if (p.a_stages > kRowsMaxAStages) p.a_stages = kRowsMaxAStages;
-  }
   p.ab_fmt = d->dtype == GDL_BF16 ? 1 : 0;
   p.out = d->out;
   p.out_dtype = d->out_dtype;
   p.ldo = d->ldo;
   const int esz = d->out_dtype == GDL_F32 ? 4 : 2;
   p.vec_ok = ((reinterpret_cast<uintptr_t>(d->out) & 15) == 0) && ((d->ldo * esz) % 16 == 0);
+  static int opt_tma_store = -1;
+  if (opt_tma_store < 0) {
+    const char* e = getenv("GDL_ROWS_TMA_STORE");
+    opt_tma_store = e ? atoi(e) : 1;
+  }
+  p.tma_store = opt_tma_store && d->out_dtype != GDL_F32 && p.vec_ok && d->residual == nullptr && d->Cout % 8 == 0;
+  p.o_stage_bytes = p.tma_store ? 128 * BN * 2 : 0;  // 4 / 8 / 12 / 16 KB
+  p.o_swz_mask = BN == 64 ? 7 : (BN == 32 ? 3 : (BN == 16 ? 1 : 0));
+  const int fixed = 1024 + 2 * p.o_stage_bytes;
+  p.a_stages = 4;
+  p.b_stages = (kRowsSmemBudget - fixed - p.a_stages * kRowsAStage) / p.b_stage_bytes;
+  if (p.b_stages > kRowsMaxBStages) p.b_stages = kRowsMaxBStages;
+  if (p.b_stages < 4) return 0;
+  {
+    const int left = kRowsSmemBudget - fixed - p.b_stages * p.b_stage_bytes;
+    p.a_stages = left / kRowsAStage;
+    if (p.a_stages > kRowsMaxAStages) p.a_stages = kRowsMaxAStages;
+  }
   p.bias = d->bias;
   p.relu = d->relu;
   p.oscale = d->oscale;
@@ -384,11 +477,16 @@ int conv3x3_rows_try(const gdl_conv_fwd_t* d, cudaStream_t stream, int* status) 
   *status = make_tmap_2d(&p.tmB, d->weight, d->dtype, Ktot, w_rows, w_ld, kRowsBK, BN, kRowsBK * 2);
   if (*status) return 1;
 
-  const int smem = p.a_stages * kRowsAStage + p.b_stages * p.b_stage_bytes + 1024;
+  if (p.tma_store) {
+    const int swz = BN == 64 ? 128 : (BN == 32 ? 64 : (BN == 16 ? 32 : 0));
+    *status = make_tmap_nhwc(&p.tmO, d->out, d->out_dtype, d->Cout, d->W, d->H, d->N, d->ldo, BN, 128, 1, swz);
+    if (*status) return 1;
+  }
+  const int smem = p.a_stages * kRowsAStage + p.b_stages * p.b_stage_bytes + 2 * p.o_stage_bytes + 1024;
   static bool attr_set = false;
   if (!attr_set) {
     *status = check_cuda(cudaFuncSetAttribute(conv3x3_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                              kRowsSmemBudget + 2048),
+                                              kRowsSmemBudget + 1024),
                          "cudaFuncSetAttribute(conv3x3_rows_kernel)");
     if (*status) return 1;
     attr_set = true;

@@ -278,13 +278,16 @@ __global__ void bn_stats_kernel(const T* __restrict__ x, long long M, int C, int
     }
     float s1[8] = {0, 0, 0, 0, 0, 0, 0, 0}, s2[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     if (active) {
-      // 4 independent 16-byte loads in flight per thread (a single one measured 3.6 TB/s in run 8)
-      const long long stride = (long long)gridDim.x * rows_per_block;
-      long long row = (long long)blockIdx.x * rows_per_block + tr;
-      for (; row + 3 * stride < M; row += 4 * stride) {
+      // 4 independent 16-byte loads in flight per thread (a single one measured 3.6 TB/s in run 8); the 4 rows of a
+      // thread are rows_per_block apart, so a block reads one contiguous 4*rows_per_block-row chunk per iteration
+      // (4 distant fronts per thread measured slower than the single load: run 9)
+      const long long chunk = 4ll * rows_per_block;
+      long long base = (long long)blockIdx.x * chunk;
+      for (; base + chunk <= M; base += (long long)gridDim.x * chunk) {
         uint4 u[4];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) u[q] = *reinterpret_cast<const uint4*>(x + (row + q * stride) * ld + c8 * 8);
+        for (int q = 0; q < 4; ++q)
+          u[q] = *reinterpret_cast<const uint4*>(x + (base + q * rows_per_block + tr) * ld + c8 * 8);
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           float f[8];
@@ -297,14 +300,16 @@ __global__ void bn_stats_kernel(const T* __restrict__ x, long long M, int C, int
           }
         }
       }
-      for (; row < M; row += stride) {
-        float f[8];
-        load8(x + row * ld + c8 * 8, f);
+      if (base < M) {  // ragged last chunk (at most one block sees it)
+        for (long long row = base + tr; row < M; row += rows_per_block) {
+          float f[8];
+          load8(x + row * ld + c8 * 8, f);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float d = f[j] - piv[j];
-          s1[j] += d;
-          s2[j] = fmaf(d, d, s2[j]);
+          for (int j = 0; j < 8; ++j) {
+            const float d = f[j] - piv[j];
+            s1[j] += d;
+            s2[j] = fmaf(d, d, s2[j]);
+          }
         }
       }
     }
@@ -484,8 +489,10 @@ __global__ void __launch_bounds__(256) grad_gather_kernel(GatherSrcs srcs, const
       }
     }
     if (active) {
-      const long long stride = (long long)gridDim.x * rows_per_block;
-      for (long long pix0 = (long long)blockIdx.x * rows_per_block + tr; pix0 < M; pix0 += PIX * stride) {
+      // the PIX pixels of a thread are rows_per_block apart: a block covers one contiguous PIX*rows_per_block chunk
+      const long long stride = rows_per_block;
+      for (long long pix0 = (long long)blockIdx.x * PIX * rows_per_block + tr; pix0 < M;
+           pix0 += (long long)gridDim.x * PIX * rows_per_block) {
         uint4 raw[PIX][NS][4];
         uint4 yv[PIX], xv[PIX];
         // ---- issue every load of this iteration ----
@@ -837,7 +844,7 @@ extern "C" int gdl_bn_stats(const void* x, int dtype, long long M, int C, int ld
   int threads, smem;
   const int rpb = stats_launch_geometry(C, &threads, &smem);
   long long blocks = (M + rpb * 16 - 1) / (rpb * 16);  // >= 16 rows per thread
-  if (blocks > 4 * kNumSMsB200) blocks = 4 * kNumSMsB200;
+  if (blocks > 2 * kNumSMsB200) blocks = 2 * kNumSMsB200;
   if (blocks < 1) blocks = 1;
   GDL_DISPATCH_16(dtype, { bn_stats_kernel<T><<<(int)blocks, threads, smem, st>>>((const T*)x, M, C, ld, sums, pivot); });
   GDL_CHECK_CUDA(cudaGetLastError());

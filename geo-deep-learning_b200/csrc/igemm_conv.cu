@@ -59,7 +59,10 @@ struct ConvFwdKParams {
   int vec_ok;
   int pair_ok;  // (unused)
   int res_vec_ok;  // fp32 residual rows are 16-byte aligned -> float4 loads
-  int epi_mode;    // 0 = direct row stores, 1 = smem-transposed coalesced stores
+  int epi_mode;    // 0 = direct row stores, 1 = smem-transposed coalesced stores, 2 = smem-staged TMA tile stores
+  CUtensorMap tmO; // epi_mode 2: output map, box = (o_slab channels, TW, TH)
+  int o_slab;      // channels per staged slab (16 / 32 / 64)
+  int o_stage_bytes, o_swz_mask, o_smem_off;  // staging tile bytes, swizzle chunk mask, offset in dynamic smem
   const float* bias;
   int relu;
   const float* oscale;   // optional per-channel multiplier applied to (acc + bias) before the residual (LayerScale)
@@ -250,7 +253,91 @@ conv_fwd_kernel(const __grid_constant__ ConvFwdKParams p) {
     const int lpr = 32 / vw;                // lanes per pixel row (4 or 8)
     const int rpi = 32 / lpr;               // pixel rows per iteration (8 or 4)
     const int my_r = lane / lpr, my_seg = lane % lpr;
-    if (p.epi_mode == 0) {
+    if (p.epi_mode == 2) {
+      // TMA-store variant: each thread writes its pixel row (16-bit) into a swizzled smem slab of 128 px x o_slab
+      // channels; one thread hands the slab to the TMA store engine (full-line writes, asynchronous).  Row stores from
+      // registers cost ~4 SM-cycles per 16-byte store (32 lines per warp store) and bound every tile with K < ~2300.
+      const bool issuer = (warp == 2 && lane == 0);
+      uint8_t* smem_o = smem + p.o_smem_off;
+      const int pitch = p.o_slab * 2;
+      int st = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+        const int acc = it & 1;
+        const uint32_t aphase = (it >> 1) & 1;
+        const int n_tile = tile % p.n_tiles;
+        const int m_tile = tile / p.n_tiles;
+        const int img = m_tile / tiles_per_img;
+        const int t_in = m_tile - img * tiles_per_img;
+        const int h0 = (t_in / p.tiles_w) * p.TH;
+        const int w0 = (t_in % p.tiles_w) * p.TW;
+        const int n0 = n_tile * p.BN;
+        mbar_wait(&tfull_bar[acc], aphase);
+        tc_fence_after();
+        const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.BN);
+        for (int cb0 = 0; cb0 < p.BN; cb0 += p.o_slab) {
+          if (issuer) bulk_wait_group_read<1>();  // the store issued two slabs ago no longer reads staging[st]
+          named_bar_sync(1, 128);
+          uint8_t* stg = smem_o + (size_t)st * p.o_stage_bytes;
+          for (int cb = cb0; cb < cb0 + p.o_slab; cb += 16) {
+            uint32_t v[16];
+            tmem_ld_32x32b_x16(t_addr + cb, v);
+            tmem_ld_wait();
+            const int c0 = n0 + cb;
+            float f[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]);
+            if (p.bias != nullptr) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i)
+                if (c0 + i < p.Cout) f[i] += __ldg(p.bias + c0 + i);
+            }
+            if (p.oscale != nullptr) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i)
+                if (c0 + i < p.Cout) f[i] *= __ldg(p.oscale + c0 + i);
+            }
+            if (p.relu == 1) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) f[i] = fmaxf(f[i], 0.f);
+            } else if (p.relu == 2) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) f[i] = 0.5f * f[i] * (1.f + erff(f[i] * 0.70710678118654752f));
+            }
+            uint4 lo, hi;
+            if (p.out_dtype == GDL_BF16) {
+              lo = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]),
+                              pack_bf16x2(f[6], f[7]));
+              hi = make_uint4(pack_bf16x2(f[8], f[9]), pack_bf16x2(f[10], f[11]), pack_bf16x2(f[12], f[13]),
+                              pack_bf16x2(f[14], f[15]));
+            } else {
+              lo = make_uint4(pack_f16x2(f[0], f[1]), pack_f16x2(f[2], f[3]), pack_f16x2(f[4], f[5]),
+                              pack_f16x2(f[6], f[7]));
+              hi = make_uint4(pack_f16x2(f[8], f[9]), pack_f16x2(f[10], f[11]), pack_f16x2(f[12], f[13]),
+                              pack_f16x2(f[14], f[15]));
+            }
+            uint32_t off = (uint32_t)(row * pitch + (cb - cb0) * 2);
+            const uint32_t o0 = off ^ (((off >> 7) & (uint32_t)p.o_swz_mask) << 4);
+            off += 16;
+            const uint32_t o1 = off ^ (((off >> 7) & (uint32_t)p.o_swz_mask) << 4);
+            *reinterpret_cast<uint4*>(stg + o0) = lo;
+            *reinterpret_cast<uint4*>(stg + o1) = hi;
+          }
+          if (cb0 + p.o_slab >= p.BN) {  // all TMEM reads of this tile done: release the accumulator
+            tc_fence_before();
+            mbar_arrive(&tempty_bar[acc]);
+          }
+          fence_proxy_async_smem();
+          named_bar_sync(1, 128);
+          if (issuer && n0 + cb0 < p.Cout) {
+            tma_store_4d(&p.tmO, stg, n0 + cb0, w0, h0, img);
+            bulk_commit_group();
+          }
+          st ^= 1;
+        }
+      }
+      if (issuer) bulk_wait_group<0>();
+    } else if (p.epi_mode == 0) {
       // direct variant: every thread stores its own accumulator row (16-byte vectors, 32 lines per warp store)
       int it = 0;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
@@ -631,9 +718,25 @@ extern "C" int gdl_conv2d_nhwc_fwd(const gdl_conv_fwd_t* d, void* stream_) {
       p.stage_bytes = p.a_bytes + 3 * p.b_slot;
     }
   }
-  p.stages = kSmemBudget / p.stage_bytes;
+  p.epi_mode = opt_int(g_opt_conv_epilogue, "GDL_CONV_EPILOGUE", 0);  // 0 direct (default), 1 smem transpose, 2 TMA store
+  int smem_budget = kSmemBudget;
+  if (p.epi_mode == 2) {
+    const int esz_o = d->out_dtype == GDL_F32 ? 4 : 2;
+    const bool aligned = ((reinterpret_cast<uintptr_t>(d->out) & 15) == 0) && ((d->ldo * esz_o) % 16 == 0);
+    const int slab = p.BN % 64 == 0 ? 64 : (p.BN % 32 == 0 ? 32 : 16);
+    if (slab && aligned && d->out_dtype != GDL_F32 && d->residual == nullptr && d->Cout % 8 == 0) {
+      p.o_slab = slab;
+      p.o_stage_bytes = 128 * slab * 2;
+      p.o_swz_mask = slab == 64 ? 7 : (slab == 32 ? 3 : 1);
+      smem_budget -= 2 * p.o_stage_bytes;
+    } else {
+      p.epi_mode = 0;
+    }
+  }
+  p.stages = smem_budget / p.stage_bytes;
   if (p.stages > kMaxStages) p.stages = kMaxStages;
   GDL_REQUIRE(p.stages >= 2, GDL_ERR_UNSUPPORTED, "tile does not fit shared memory");
+  p.o_smem_off = p.stages * p.stage_bytes;  // 1024-aligned: stage_bytes is a multiple of 1024
   p.tmem_cols = pow2_ge(2 * p.BN);
   p.ab_fmt = d->dtype == GDL_BF16 ? 1 : 0;
   p.out = d->out;
@@ -642,7 +745,6 @@ extern "C" int gdl_conv2d_nhwc_fwd(const gdl_conv_fwd_t* d, void* stream_) {
   const int esz = d->out_dtype == GDL_F32 ? 4 : 2;
   p.vec_ok = ((reinterpret_cast<uintptr_t>(d->out) & 15) == 0) && ((d->ldo * esz) % 16 == 0);
   p.pair_ok = 0;
-  p.epi_mode = opt_int(g_opt_conv_epilogue, "GDL_CONV_EPILOGUE", 0);  // direct row stores: faster in-model (run 7 A/B)
   p.res_vec_ok = d->residual != nullptr && d->res_dtype == GDL_F32 &&
                  ((reinterpret_cast<uintptr_t>(d->residual) & 15) == 0) && (d->ldr % 4 == 0);
   p.bias = d->bias;
@@ -676,7 +778,11 @@ extern "C" int gdl_conv2d_nhwc_fwd(const gdl_conv_fwd_t* d, void* stream_) {
   }
   if (st) return st;
 
-  int smem = p.stages * p.stage_bytes + 1024;
+  if (p.epi_mode == 2) {
+    st = make_tmap_nhwc(&p.tmO, d->out, d->out_dtype, d->Cout, oW, oH, N, d->ldo, p.o_slab, p.TW, p.TH, p.o_slab * 2);
+    if (st) return st;
+  }
+  int smem = p.stages * p.stage_bytes + 2 * p.o_stage_bytes + 1024;
   if (smem < kMinSmemRequest) smem = kMinSmemRequest;
   static bool attr_set = false;
   if (!attr_set) {
