@@ -48,6 +48,27 @@ def _select_workload(key: str) -> None:
     TRAIN_GFLOP_PER_TILE = WORKLOAD["train_gflop_per_tile"]
 
 
+def _dram_traffic(family: str) -> tuple[float | None, str | None]:
+    """DRAM bytes per launch of the forward/dgrad conv kernels (conv_fwd_kernel + conv3x3_rows_kernel), from the
+    newest committed ncu pass (dram__bytes_read.sum + dram__bytes_write.sum per launch, tools/summarize_ncu_launches.py)."""
+    import re
+    best = None
+    for f in sorted((ROOT / "profiles").glob(f"r*_dram_traffic_{family}.json")):
+        m = re.search(r"r(\d+)_run(\d+)_", f.name)
+        key = (int(m.group(1)), int(m.group(2))) if m else (0, 0)
+        if best is None or key > best[0]:
+            best = (key, f)
+    if best is None:
+        return None, None
+    k = json.loads(best[1].read_text())["kernels"]
+    rows = [k[n] for n in ("conv_fwd_kernel", "conv3x3_rows_kernel") if n in k]
+    launches = sum(r["launches"] for r in rows)
+    if not launches:
+        return None, None
+    total = sum((r["dram_read_GB"] + r["dram_write_GB"]) * 1e9 for r in rows)
+    return total / launches, f"profiles/{best[1].name}"
+
+
 def _peaks() -> dict:
     p = ROOT / "MEASURED_PEAKS.json"
     if p.exists():
@@ -322,6 +343,7 @@ def main_product(args) -> None:
         tiles = B * world * args.steps
         value = tiles / (ms / 1e3)
         fwd = roof["conv_fwd_kernel"]
+        traffic, traffic_src = _dram_traffic({"unetpp": "unetpp", "segformer": "segformer", "dofa": "dofa"}[w["family"]])
         line = {
             "metric": "512x512 multi-band tiles/sec (train fwd+bwd)", "value": value, "unit": "tiles/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
@@ -335,9 +357,10 @@ def main_product(args) -> None:
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches,
             "model_tflops": TRAIN_GFLOP_PER_TILE * value / world / 1e3,
-            "roofline": {"bound": "tensor", "kernel": "conv_fwd_kernel (forward + dgrad launches)",
+            "roofline": {"bound": "tensor", "kernel": "conv_fwd_kernel + conv3x3_rows_kernel (forward + dgrad launches)",
                          "achieved": fwd["tflops"], "peak": peak_tf, "unit": "TFLOP/s",
-                         "frac": fwd["tflops"] / peak_tf, "traffic": None, "peak_source":
+                         "frac": fwd["tflops"] / peak_tf, "traffic": traffic, "traffic_unit": "DRAM bytes per launch",
+                         "traffic_source": traffic_src, "peak_source":
                          f"{peaks['source']} bf16_tflops_sustained", "launches_per_step": fwd["launches_per_step"],
                          "share_of_step": fwd["ms_per_step"] / (ms / args.steps),
                          "wgrad": {"kernel": "conv_wgrad_kernel", "achieved": roof["conv_wgrad_kernel"]["tflops"],

@@ -26,6 +26,8 @@ namespace gdl {
 // runtime options (gdl_set_option); env vars GDL_CONV_HALO / GDL_WGRAD_HALO / GDL_WGRAD_L2_MB seed them
 static int g_opt_conv_halo = -1, g_opt_wgrad_halo = -1, g_opt_conv_epilogue = -1, g_opt_conv_rows = -1;
 int conv3x3_rows_try(const gdl_conv_fwd_t* d, cudaStream_t stream, int* status);  // conv3x3_rows.cu
+int wgrad3x3_rows_try(const gdl_conv_wgrad_t* d, cudaStream_t stream, int* status);  // wgrad3x3_rows.cu
+static int g_opt_wgrad_rows = -1;
 static long long g_opt_wgrad_l2_mb = -1;
 static int opt_int(int& slot, const char* env, int dflt) {
   if (slot < 0) {
@@ -632,6 +634,7 @@ extern "C" int gdl_set_option(const char* name, long long value) {
   else if (!strcmp(name, "conv_epilogue")) g_opt_conv_epilogue = (int)value;
   else if (!strcmp(name, "wgrad_l2_mb")) g_opt_wgrad_l2_mb = value;
   else if (!strcmp(name, "conv_rows")) g_opt_conv_rows = (int)value;
+  else if (!strcmp(name, "wgrad_rows")) g_opt_wgrad_rows = (int)value;
   else {
     set_last_error("set_option: unknown option '%s'", name);
     return GDL_ERR_INVALID;
@@ -1056,6 +1059,12 @@ extern "C" int gdl_conv2d_nhwc_wgrad(const gdl_conv_wgrad_t* d, void* stream_) {
   const int Ho = d->H + 2 * d->pad_h - d->R + 1;
   const int Wo = d->W + 2 * d->pad_w - d->S + 1;
   GDL_REQUIRE(Ho > 0 && Wo > 0, GDL_ERR_INVALID, "empty output");
+
+  if (opt_int(g_opt_wgrad_rows, "GDL_WGRAD_ROWS", 1) > 0) {
+    // narrow outputs (Cout 16/32/64), 3x3: paired-tap row-streaming kernel (wgrad3x3_rows.cu)
+    int st_rows = 0;
+    if (wgrad3x3_rows_try(d, stream, &st_rows)) return st_rows;
+  }
 
   ConvWgradKParams p;
   memset(&p, 0, sizeof(p));

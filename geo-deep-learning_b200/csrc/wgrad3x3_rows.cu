@@ -1,0 +1,305 @@
+// wgrad3x3_rows.cu — weight gradient of a 3x3 / pad-1 / stride-1 conv with a narrow output (Cout = 16 / 32 / 64).
+//
+// Why: conv_wgrad_kernel (igemm_conv.cu) puts Cout on the MMA's M dimension; with Cout <= 64 at least half of every
+// 128-row MMA is empty, each of its units re-reads dY and X once per filter row, and its epilogue is not overlapped
+// (run 8/9: 135-430 TFLOP/s on these layers, tensor pipe 38 % active with half of that wasted).
+//
+// Here  dW^T[cin][tap][cout] = sum_pixels X_tap^T . dY  with
+//   A = X   (MN-major, M = 128 = [64 input channels at horizontal shift s | the same 64 channels at shift s+1]),
+//   B = dY  (MN-major, N = Cout), K = the 128 pixels of one image-row segment,
+// so one MMA chain produces TWO horizontal taps (rows 0-63 / 64-127 of the accumulator) and a second chain the third
+// tap: 3 useful half-tiles out of 4 instead of 1 out of 2.  A unit = (one 64-channel slab of one source, one block of
+// Hb image rows of one 128-pixel column): it streams the Hb + 2 input rows ONCE (each against the dY rows above, at and
+// below it: filter rows 2, 1, 0), keeps the 3 dY rows it needs in a ring, and owns 6 TMEM accumulators
+// (3 filter rows x {taps 0|1, tap 2}) that are added to the fp32 gradient with coalesced red.global.add at the end.
+//
+// The two 64-channel MN atoms of the paired A operand are two TMA boxes of the same input row (130 pixels starting at
+// w0-1 and at w0) placed kXAtomBytes apart, addressed through the descriptor's leading-dimension byte offset.
+#include <stdlib.h>
+#include <string.h>
+
+#include "../../include/gdl_b200.h"
+#include "common.cuh"
+#include "tmap.cuh"
+
+namespace gdl {
+
+constexpr int kWrThreads = 192;
+constexpr int kWrXAtomBytes = 17 * 1024;  // 130 px x 64 ch x 2 B = 16 640 B, padded to the 1024-B swizzle repeat
+constexpr int kWrXStages = 3;             // input-row stages (2 atoms each)
+constexpr int kWrDYStages = 4;            // dY rows: 3 in use + 1 in flight
+
+struct WgradRowsKParams {
+  CUtensorMap tmX[GDL_MAX_SRC];
+  CUtensorMap tmDY;
+  int num_slabs;
+  int slab_src[64], slab_c0[64], slab_coff[64];  // source index, channel offset inside it, offset in the virtual concat
+  int Ctot, Cout;
+  int Nimg, H, W;
+  int tiles_w, Hb, hblocks;
+  long long num_units;
+  int dy_stage_bytes, dy_row_bytes;  // 128 px x Cout x 2 B (1024-aligned), Cout x 2 B
+  int ab_fmt;
+  float* dw;
+  long long dw_ld;
+};
+
+__global__ void __launch_bounds__(kWrThreads, 1) wgrad3x3_rows_kernel(const __grid_constant__ WgradRowsKParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = align_smem_1024(smem_raw);
+  uint8_t* smem_dy = smem + (size_t)kWrXStages * 2 * kWrXAtomBytes;
+
+  __shared__ __align__(8) uint64_t x_full[kWrXStages];
+  __shared__ __align__(8) uint64_t x_empty[kWrXStages];
+  __shared__ __align__(8) uint64_t dy_full[kWrDYStages];
+  __shared__ __align__(8) uint64_t dy_empty[kWrDYStages];
+  __shared__ __align__(8) uint64_t tfull_bar;
+  __shared__ __align__(8) uint64_t tempty_bar;
+  __shared__ uint32_t tmem_base_smem;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.tmX[0]);
+    tma_prefetch_desc(&p.tmDY);
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int i = 0; i < kWrXStages; ++i) {
+        mbar_init(&x_full[i], 1);
+        mbar_init(&x_empty[i], 1);
+      }
+      for (int i = 0; i < kWrDYStages; ++i) {
+        mbar_init(&dy_full[i], 1);
+        mbar_init(&dy_empty[i], 1);
+      }
+      mbar_init(&tfull_bar, 1);
+      mbar_init(&tempty_bar, 128);
+      fence_mbar_init();
+    }
+    __syncwarp();
+    tmem_alloc(&tmem_base_smem, 512u);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_smem;
+
+  // unit -> (slab fastest: co-resident CTAs share the dY rows of one pixel range in L2; then row block, column, image)
+  auto decode = [&](long long u, int& slab, int& img, int& w0, int& h0, int& rows) {
+    slab = (int)(u % p.num_slabs);
+    long long t = u / p.num_slabs;
+    const int hb = (int)(t % p.hblocks);
+    t /= p.hblocks;
+    const int wt = (int)(t % p.tiles_w);
+    img = (int)(t / p.tiles_w);
+    w0 = wt * 128;
+    h0 = hb * p.Hb;
+    rows = min(p.Hb, p.H - h0);
+  };
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int xs = 0, ds = 0;
+      uint32_t xph = 0, dph = 0;
+      for (long long u = blockIdx.x; u < p.num_units; u += gridDim.x) {
+        int slab, img, w0, h0, rows;
+        decode(u, slab, img, w0, h0, rows);
+        const int src = p.slab_src[slab], c0 = p.slab_c0[slab];
+        for (int i = h0 - 1; i <= h0 + rows; ++i) {
+          if (i + 1 < h0 + rows) {  // dY row i+1 (filter row 0 of input row i) — first use of that row
+            mbar_wait(&dy_empty[ds], dph ^ 1);
+            mbar_expect_tx(&dy_full[ds], (uint32_t)(128 * p.dy_row_bytes));
+            tma_load_4d(smem_dy + (size_t)ds * p.dy_stage_bytes, &p.tmDY, &dy_full[ds], 0, w0, i + 1, img);
+            if (++ds == kWrDYStages) {
+              ds = 0;
+              dph ^= 1;
+            }
+          }
+          mbar_wait(&x_empty[xs], xph ^ 1);
+          mbar_expect_tx(&x_full[xs], (uint32_t)(2 * 130 * 64 * 2));
+          uint8_t* x_dst = smem + (size_t)xs * 2 * kWrXAtomBytes;
+          tma_load_4d(x_dst, &p.tmX[src], &x_full[xs], c0, w0 - 1, i, img);                  // shifts 0 and 2
+          tma_load_4d(x_dst + kWrXAtomBytes, &p.tmX[src], &x_full[xs], c0, w0, i, img);      // shift 1 (second atom)
+          if (++xs == kWrXStages) {
+            xs = 0;
+            xph ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (one thread) =====================
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc(128, p.Cout, p.ab_fmt, 1, 1);
+      const uint32_t ltA = umma_layout_type(128), ltB = umma_layout_type(p.dy_row_bytes);
+      const uint32_t sboA = 8u * 128u, sboB = 8u * (uint32_t)p.dy_row_bytes;      // 8 pixel rows
+      const uint32_t kstepA = 16u * 128u, kstepB = 16u * (uint32_t)p.dy_row_bytes;  // 16 pixel rows
+      int xs = 0, ds = 0;
+      uint32_t xph = 0, dph = 0;
+      int it = 0;
+      for (long long u = blockIdx.x; u < p.num_units; u += gridDim.x, ++it) {
+        int slab, img, w0, h0, rows;
+        decode(u, slab, img, w0, h0, rows);
+        mbar_wait(&tempty_bar, (it & 1) ^ 1);
+        tc_fence_after();
+        const int ds_first = ds;  // ring slot of dY row h0; row h lives in (ds_first + h - h0) % kWrDYStages
+        uint32_t started = 0;     // bit ky: accumulators of filter row ky already hold data
+        for (int i = h0 - 1; i <= h0 + rows; ++i) {
+          if (i + 1 < h0 + rows) {
+            mbar_wait(&dy_full[ds], dph);
+            if (++ds == kWrDYStages) {
+              ds = 0;
+              dph ^= 1;
+            }
+          }
+          mbar_wait(&x_full[xs], xph);
+          tc_fence_after();
+          const uint32_t x_addr = smem_u32(smem + (size_t)xs * 2 * kWrXAtomBytes);
+#pragma unroll
+          for (int ky = 0; ky < 3; ++ky) {
+            const int h = i - ky + 1;  // output row whose gradient meets input row i under filter row ky
+            if (h < h0 || h >= h0 + rows) continue;
+            const uint32_t b_addr = smem_u32(smem_dy + (size_t)((ds_first + h - h0) % kWrDYStages) * p.dy_stage_bytes);
+            const uint32_t d_pair = tmem_base + (uint32_t)(ky * 128);
+            const uint32_t d_single = d_pair + 64u;
+            const uint32_t fresh = ((started >> ky) & 1u) ^ 1u;
+#pragma unroll
+            for (int kk = 0; kk < 8; ++kk) {
+              const uint64_t db = umma_smem_desc(b_addr + kk * kstepB, 128 * p.dy_row_bytes, sboB, ltB);
+              // taps kx = 0 | 1: atoms = the row at shift 0 (box starting at w0-1) | at shift 1 (box starting at w0)
+              const uint64_t da = umma_smem_desc(x_addr + kk * kstepA, kWrXAtomBytes, sboA, ltA);
+              umma_f16(d_pair, da, db, idesc, (uint32_t)!(fresh && kk == 0));
+              // tap kx = 2: first box shifted by two pixel rows (256 B); the second atom's rows are never read back
+              const uint64_t da2 = umma_smem_desc(x_addr + 256 + kk * kstepA, kWrXAtomBytes, sboA, ltA);
+              umma_f16(d_single, da2, db, idesc, (uint32_t)!(fresh && kk == 0));
+            }
+            started |= 1u << ky;
+          }
+          umma_commit(&x_empty[xs]);
+          if (++xs == kWrXStages) {
+            xs = 0;
+            xph ^= 1;
+          }
+          // dY row i-1 was last used by this input row (filter row 2)
+          if (i - 1 >= h0) umma_commit(&dy_empty[(ds_first + i - 1 - h0) % kWrDYStages]);
+        }
+        umma_commit(&tfull_bar);
+      }
+    }
+  } else {
+    // ===================== epilogue: thread = one accumulator row = one input channel (two taps) =====================
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const int cin_row = row & 63;      // channel inside the slab
+    const int kx_pair = row >> 6;      // rows 0-63: tap kx = 0, rows 64-127: tap kx = 1
+    int it = 0;
+    for (long long u = blockIdx.x; u < p.num_units; u += gridDim.x, ++it) {
+      int slab, img, w0, h0, rows;
+      decode(u, slab, img, w0, h0, rows);
+      const long long col0 = p.slab_coff[slab] + cin_row;
+      mbar_wait(&tfull_bar, it & 1);
+      tc_fence_after();
+      for (int ky = 0; ky < 3; ++ky) {
+        const uint32_t t_pair = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ky * 128);
+        for (int sel = 0; sel < 2; ++sel) {  // 0: paired accumulator (taps 0|1), 1: tap 2 (rows 0-63 only)
+          const int kx = sel == 0 ? kx_pair : 2;
+          float* dst = p.dw + (long long)((ky * 3 + kx) * p.Ctot) + col0;
+          for (int j = 0; j < p.Cout; j += 16) {
+            uint32_t v[16];
+            tmem_ld_32x32b_x16(t_pair + (uint32_t)(sel * 64 + j), v);
+            tmem_ld_wait();
+            if (sel == 1 && row >= 64) continue;
+            // lanes = consecutive input channels: every red below is one coalesced 128-byte request per warp
+#pragma unroll
+            for (int o = 0; o < 16; ++o)
+              asm volatile("red.global.add.f32 [%0], %1;" ::"l"(dst + (long long)(j + o) * p.dw_ld),
+                           "f"(__uint_as_float(v[o]))
+                           : "memory");
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&tempty_bar);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tmem_dealloc(tmem_base, 512u);
+  }
+}
+
+// Returns 1 when the descriptor is a case this kernel covers (then *status holds the launch status), 0 otherwise.
+int wgrad3x3_rows_try(const gdl_conv_wgrad_t* d, cudaStream_t stream, int* status) {
+  *status = 0;
+  if (d->R != 3 || d->S != 3 || d->pad_h != 1 || d->pad_w != 1 || d->batched) return 0;
+  if (d->Cout != 16 && d->Cout != 32 && d->Cout != 64) return 0;
+  if (d->W < 64 || d->H < 4) return 0;
+  WgradRowsKParams p;
+  memset(&p, 0, sizeof(p));
+  int coff = 0;
+  for (int i = 0; i < d->num_src; ++i) {
+    if (d->src[i].channels % 64) return 0;
+    for (int c = 0; c < d->src[i].channels; c += 64) {
+      if (p.num_slabs >= 64) return 0;
+      p.slab_src[p.num_slabs] = i;
+      p.slab_c0[p.num_slabs] = c;
+      p.slab_coff[p.num_slabs] = coff + c;
+      ++p.num_slabs;
+    }
+    coff += d->src[i].channels;
+  }
+  p.Ctot = coff;
+  p.Cout = d->Cout;
+  p.Nimg = d->N;
+  p.H = d->H;
+  p.W = d->W;
+  p.tiles_w = (d->W + 127) / 128;
+  // rows per unit: long units amortise the halo rows (2 per block) and the epilogue, but keep >= ~4 waves of units
+  int sms = 0, dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess ||
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0)
+    sms = kNumSMsB200;
+  int Hb = 32;
+  while (Hb > 8 && (long long)p.num_slabs * d->N * p.tiles_w * ((d->H + Hb - 1) / Hb) < 4ll * sms) Hb >>= 1;
+  if (Hb > d->H) Hb = d->H;
+  p.Hb = Hb;
+  p.hblocks = (d->H + Hb - 1) / Hb;
+  p.num_units = (long long)p.num_slabs * d->N * p.tiles_w * p.hblocks;
+  p.dy_row_bytes = d->Cout * 2;
+  p.dy_stage_bytes = 128 * p.dy_row_bytes;  // 4 / 8 / 16 KB
+  p.ab_fmt = d->dtype == GDL_BF16 ? 1 : 0;
+  p.dw = d->dw;
+  p.dw_ld = d->dw_ld > 0 ? d->dw_ld : 9ll * p.Ctot;
+
+  for (int i = 0; i < d->num_src; ++i) {
+    *status = make_tmap_nhwc(&p.tmX[i], d->src[i].ptr, d->dtype, d->src[i].channels, d->W, d->H, d->N, d->src[i].ld, 64,
+                             130, 1, 128);
+    if (*status) return 1;
+  }
+  *status = make_tmap_nhwc(&p.tmDY, d->dy, d->dtype, d->Cout, d->W, d->H, d->N, d->ld_dy, d->Cout, 128, 1,
+                           p.dy_row_bytes);
+  if (*status) return 1;
+
+  const int smem = kWrXStages * 2 * kWrXAtomBytes + kWrDYStages * p.dy_stage_bytes + 1024;
+  static bool attr_set = false;
+  if (!attr_set) {
+    *status = check_cuda(cudaFuncSetAttribute(wgrad3x3_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                              kWrXStages * 2 * kWrXAtomBytes + kWrDYStages * 16 * 1024 + 1024),
+                         "cudaFuncSetAttribute(wgrad3x3_rows_kernel)");
+    if (*status) return 1;
+    attr_set = true;
+  }
+  const int grid = p.num_units < sms ? (int)p.num_units : sms;
+  wgrad3x3_rows_kernel<<<grid, kWrThreads, smem, stream>>>(p);
+  *status = check_cuda(cudaGetLastError(), "wgrad3x3_rows_kernel launch");
+  return 1;
+}
+
+}  // namespace gdl

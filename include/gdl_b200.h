@@ -45,7 +45,8 @@ int gdl_version(void);
 int gdl_device_info(int* sm_count, int* cc_major, int* cc_minor, unsigned long long* total_mem);
 /* tuning switches: "conv_halo" / "wgrad_halo" (0/1: 3x3 convs reuse one halo row tile for the 3 horizontal
  * taps), "wgrad_l2_mb" (L2 budget of the wgrad pixel split), "conv_epilogue" (0 direct row stores / 1 smem-transposed),
- * "conv_rows" (0/1: 3x3 convs with Cout <= 64 use the weight-stationary row-rolling kernel). */
+ * "conv_rows" / "wgrad_rows" (0/1: 3x3 convs with Cout <= 64 use the weight-stationary row-rolling forward kernel / the
+ * paired-tap row-streaming weight-gradient kernel). */
 int gdl_set_option(const char* name, long long value);
 
 /* One member of a "virtual concat": a conv reads its input channels from up to GDL_MAX_SRC
