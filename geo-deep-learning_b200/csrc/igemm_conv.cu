@@ -721,7 +721,7 @@ extern "C" int gdl_conv2d_nhwc_fwd(const gdl_conv_fwd_t* d, void* stream_) {
       p.stage_bytes = p.a_bytes + 3 * p.b_slot;
     }
   }
-  p.epi_mode = opt_int(g_opt_conv_epilogue, "GDL_CONV_EPILOGUE", 0);  // 0 direct (default), 1 smem transpose, 2 TMA store
+  p.epi_mode = opt_int(g_opt_conv_epilogue, "GDL_CONV_EPILOGUE", 2);  // 0 direct, 1 smem transpose, 2 TMA store (default; falls back to 0 when not applicable)
   int smem_budget = kSmemBudget;
   if (p.epi_mode == 2) {
     const int esz_o = d->out_dtype == GDL_F32 ? 4 : 2;

@@ -13,7 +13,7 @@ def opts():
     ops.set_option("conv_rows", 0)  # keep every case on conv_fwd_kernel
     yield ops.set_option
     ops.set_option("conv_rows", 1)
-    ops.set_option("conv_epilogue", 0)
+    ops.set_option("conv_epilogue", 2)
 
 
 @pytest.mark.parametrize("n,h,w,chans,cout,k,dtype,kw", [

@@ -90,7 +90,7 @@ def test_gelu_and_layerscale_epilogues(cuda):
     res = torch.randn(1, 1, 300, 200, generator=g).cuda()
     acc = x.float().view(300, 128) @ w.float().t() + bias
     try:
-        for mode in (0, 1):  # both epilogue variants of the GEMM kernel
+        for mode in (0, 1, 2):  # every epilogue variant of the GEMM kernel
             ops.set_option("conv_epilogue", mode)
             y = ops.conv2d_fwd([x], w, 200, 1, 1, 0, 0, bias=bias, gelu=True, out_dtype=torch.float32)
             assert _rel(y.view(300, 200), F.gelu(acc)) < 1e-5, mode
@@ -99,7 +99,7 @@ def test_gelu_and_layerscale_epilogues(cuda):
             y = ops.conv2d_fwd([x], w, 200, 1, 1, 0, 0, bias=bias, gelu=True)
             assert _rel(y.view(300, 200), F.gelu(acc)) < 2 ** -8, mode
     finally:
-        ops.set_option("conv_epilogue", 0)
+        ops.set_option("conv_epilogue", 2)
 
 
 def test_vit_token_kernels(cuda):
