@@ -133,7 +133,16 @@ def cpu_reference_steps(steps: int, warmup: int, tiles_per_step: int = 1, budget
         avail = len(os.sched_getaffinity(0))
     except AttributeError:
         avail = os.cpu_count() or 1
-    cores = max(1, min(avail, torch.get_num_threads() if torch.get_num_threads() > 1 else avail))
+    # torchrun exports OMP_NUM_THREADS=1 (torch then reports 1 thread): use the physical core count instead — one
+    # thread per LOGICAL cpu oversubscribes the SMT siblings and ran 30x slower on the GPU box (run 12)
+    want = torch.get_num_threads()
+    if want <= 1 or "OMP_NUM_THREADS" in os.environ:
+        try:
+            import psutil
+            want = psutil.cpu_count(logical=False) or avail
+        except Exception:  # noqa: BLE001
+            want = max(1, avail // 2)
+    cores = max(1, min(avail, want))
     torch.set_num_threads(cores)
     torch.manual_seed(0)
     w = WORKLOAD
@@ -261,7 +270,7 @@ def main_product(args) -> None:
     trainer = FusedTrainer(model, ops.LossSpec(1.0, 0.0, ignore_index=-100), lr=1e-4, mean=MEAN[:C], std=STD[:C],
                            image_max=255.0, sync_bn=bool(args.sync_bn),
                            clip_grad_norm=1.0 if w["family"] in ("segformer", "dofa") else None,
-                           cuda_graph=bool(args.cuda_graph) and world == 1)
+                           cuda_graph=bool(args.cuda_graph) and (world == 1 or args.cuda_graph >= 2))
 
     # synthetic tiles: NBUF distinct batches so consecutive steps never re-read the same input (and the
     # per-step working set, tens of GB of activations, is far larger than the 126 MB L2 anyway)
@@ -349,7 +358,7 @@ def main_product(args) -> None:
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": w["name"], "global_batch": B * world, "parallelism": f"dp{world}",
-                       "loss": "cross_entropy", "optimizer": "adam", "sync_bn": bool(args.sync_bn and world > 1), "cuda_graph": bool(args.cuda_graph) and world == 1,
+                       "loss": "cross_entropy", "optimizer": "adam", "sync_bn": bool(args.sync_bn and world > 1), "cuda_graph": bool(args.cuda_graph) and (world == 1 or args.cuda_graph >= 2),
                        "l2": f"{NBUF} rotating input batches; per-step working set >> 126 MB L2"},
             "clocks": clk,
             "e2e": {"value": tiles / (ms_e2e / 1e3), "unit": "tiles/s",
@@ -382,7 +391,7 @@ def main() -> None:
     ap.add_argument("--batch", type=int, default=0, help="tiles per GPU (default: the workload's 32)")
     ap.add_argument("--sync-bn", type=int, default=1, help="SyncBatchNorm statistics when N > 1 (reference YAMLs: true)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cuda-graph", type=int, default=1, help="capture the whole step in a CUDA graph (N=1)")
+    ap.add_argument("--cuda-graph", type=int, default=1, help="1: capture the whole step in a CUDA graph at N=1; 2: also at N>1 (NCCL collectives captured)")
     ap.add_argument("--table", default="", help="write the per-launch conv profile (shape, ms, TFLOP/s) to this JSON file")
     ap.add_argument("--workload", default="unetpp_r50", choices=sorted(WORKLOADS))
     args = ap.parse_args()

@@ -126,7 +126,7 @@ class FusedTrainer:
     def step(self, image_u8: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
         """One training step.  With cuda_graph=True the first call runs eagerly (lazy CUDA init, function
         attributes), the second captures, later calls copy the inputs into the static buffers and replay."""
-        if not self.cuda_graph or self.world > 1:
+        if not self.cuda_graph:
             n0 = ops.launch_count()
             loss = self._eager_step(image_u8, target)
             self.launches_per_step = ops.launch_count() - n0
@@ -146,6 +146,10 @@ class FusedTrainer:
             torch.cuda.synchronize()
             graph = torch.cuda.CUDAGraph()
             n0 = ops.launch_count()
+            if self.world > 1:
+                # the NCCL collectives (flat-gradient all-reduce, SyncBN sums) are captured with the kernels; every rank
+                # captures the same sequence.  Ranks must agree on capture vs eager, so a failure here is fatal.
+                dist.barrier(group=self.group)
             with torch.cuda.graph(graph):
                 self._graph_loss = self._eager_step(s_img, s_tgt)
             self.launches_per_step = ops.launch_count() - n0
