@@ -261,7 +261,9 @@ conv_fwd_kernel(const __grid_constant__ ConvFwdKParams p) {
       // registers cost ~4 SM-cycles per 16-byte store (32 lines per warp store) and bound every tile with K < ~2300.
       const bool issuer = (warp == 2 && lane == 0);
       uint8_t* smem_o = smem + p.o_smem_off;
-      const int pitch = p.o_slab * 2;
+      const int esz = p.out_dtype == GDL_F32 ? 4 : 2;
+      const int pitch = p.o_slab * esz;
+      const int th = row / p.TW, tw = row - th * p.TW;
       int st = 0;
       int it = 0;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
@@ -274,6 +276,8 @@ conv_fwd_kernel(const __grid_constant__ ConvFwdKParams p) {
         const int h0 = (t_in / p.tiles_w) * p.TH;
         const int w0 = (t_in % p.tiles_w) * p.TW;
         const int n0 = n_tile * p.BN;
+        const bool valid = (h0 + th < p.Ho) && (w0 + tw < p.Wo);  // residual rows outside the image are not read
+        const long long pix = ((long long)img * p.Ho + h0 + th) * p.Wo + w0 + tw;
         mbar_wait(&tfull_bar[acc], aphase);
         tc_fence_after();
         const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.BN);
@@ -299,6 +303,30 @@ conv_fwd_kernel(const __grid_constant__ ConvFwdKParams p) {
               for (int i = 0; i < 16; ++i)
                 if (c0 + i < p.Cout) f[i] *= __ldg(p.oscale + c0 + i);
             }
+            if (p.residual != nullptr && valid && c0 < p.Cout) {
+              // every thread reads its own (contiguous) residual row segment; Cout % 4 == 0 and 16-byte aligned rows
+              const long long roff = pix * p.ldr + c0;
+              const int nv = min(16, p.Cout - c0);
+              if (p.res_dtype == GDL_F32) {
+                const float4* rp = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.residual) + roff);
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                  if (4 * i < nv) {
+                    const float4 r4 = rp[i];
+                    f[4 * i] += r4.x; f[4 * i + 1] += r4.y; f[4 * i + 2] += r4.z; f[4 * i + 3] += r4.w;
+                  }
+              } else if (p.res_dtype == GDL_BF16) {
+                const __nv_bfloat16* rp = reinterpret_cast<const __nv_bfloat16*>(p.residual) + roff;
+#pragma unroll
+                for (int i = 0; i < 16; ++i)
+                  if (i < nv) f[i] += __bfloat162float(rp[i]);
+              } else {
+                const __half* rp = reinterpret_cast<const __half*>(p.residual) + roff;
+#pragma unroll
+                for (int i = 0; i < 16; ++i)
+                  if (i < nv) f[i] += __half2float(rp[i]);
+              }
+            }
             if (p.relu == 1) {
 #pragma unroll
               for (int i = 0; i < 16; ++i) f[i] = fmaxf(f[i], 0.f);
@@ -306,24 +334,33 @@ conv_fwd_kernel(const __grid_constant__ ConvFwdKParams p) {
 #pragma unroll
               for (int i = 0; i < 16; ++i) f[i] = 0.5f * f[i] * (1.f + erff(f[i] * 0.70710678118654752f));
             }
-            uint4 lo, hi;
-            if (p.out_dtype == GDL_BF16) {
-              lo = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]),
-                              pack_bf16x2(f[6], f[7]));
-              hi = make_uint4(pack_bf16x2(f[8], f[9]), pack_bf16x2(f[10], f[11]), pack_bf16x2(f[12], f[13]),
-                              pack_bf16x2(f[14], f[15]));
+            uint32_t off = (uint32_t)(row * pitch + (cb - cb0) * esz);
+            if (p.out_dtype == GDL_F32) {
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const uint32_t o = off ^ (((off >> 7) & (uint32_t)p.o_swz_mask) << 4);
+                *reinterpret_cast<float4*>(stg + o) = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
+                off += 16;
+              }
             } else {
-              lo = make_uint4(pack_f16x2(f[0], f[1]), pack_f16x2(f[2], f[3]), pack_f16x2(f[4], f[5]),
-                              pack_f16x2(f[6], f[7]));
-              hi = make_uint4(pack_f16x2(f[8], f[9]), pack_f16x2(f[10], f[11]), pack_f16x2(f[12], f[13]),
-                              pack_f16x2(f[14], f[15]));
+              uint4 lo, hi;
+              if (p.out_dtype == GDL_BF16) {
+                lo = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]),
+                                pack_bf16x2(f[6], f[7]));
+                hi = make_uint4(pack_bf16x2(f[8], f[9]), pack_bf16x2(f[10], f[11]), pack_bf16x2(f[12], f[13]),
+                                pack_bf16x2(f[14], f[15]));
+              } else {
+                lo = make_uint4(pack_f16x2(f[0], f[1]), pack_f16x2(f[2], f[3]), pack_f16x2(f[4], f[5]),
+                                pack_f16x2(f[6], f[7]));
+                hi = make_uint4(pack_f16x2(f[8], f[9]), pack_f16x2(f[10], f[11]), pack_f16x2(f[12], f[13]),
+                                pack_f16x2(f[14], f[15]));
+              }
+              const uint32_t o0 = off ^ (((off >> 7) & (uint32_t)p.o_swz_mask) << 4);
+              off += 16;
+              const uint32_t o1 = off ^ (((off >> 7) & (uint32_t)p.o_swz_mask) << 4);
+              *reinterpret_cast<uint4*>(stg + o0) = lo;
+              *reinterpret_cast<uint4*>(stg + o1) = hi;
             }
-            uint32_t off = (uint32_t)(row * pitch + (cb - cb0) * 2);
-            const uint32_t o0 = off ^ (((off >> 7) & (uint32_t)p.o_swz_mask) << 4);
-            off += 16;
-            const uint32_t o1 = off ^ (((off >> 7) & (uint32_t)p.o_swz_mask) << 4);
-            *reinterpret_cast<uint4*>(stg + o0) = lo;
-            *reinterpret_cast<uint4*>(stg + o1) = hi;
           }
           if (cb0 + p.o_slab >= p.BN) {  // all TMEM reads of this tile done: release the accumulator
             tc_fence_before();
@@ -726,11 +763,19 @@ extern "C" int gdl_conv2d_nhwc_fwd(const gdl_conv_fwd_t* d, void* stream_) {
   if (p.epi_mode == 2) {
     const int esz_o = d->out_dtype == GDL_F32 ? 4 : 2;
     const bool aligned = ((reinterpret_cast<uintptr_t>(d->out) & 15) == 0) && ((d->ldo * esz_o) % 16 == 0);
-    const int slab = p.BN % 64 == 0 ? 64 : (p.BN % 32 == 0 ? 32 : 16);
-    if (slab && aligned && d->out_dtype != GDL_F32 && d->residual == nullptr && d->Cout % 8 == 0) {
+    bool res_ok = true;
+    if (d->residual != nullptr) {  // rows are read as float4 / 16-bit scalars by the thread that owns the pixel
+      const int esz_r = d->res_dtype == GDL_F32 ? 4 : 2;
+      res_ok = ((reinterpret_cast<uintptr_t>(d->residual) & 15) == 0) && ((d->ldr * esz_r) % 16 == 0);
+    }
+    // staged slab rows are 128 / 64 / 32 bytes (hardware swizzle span): 64 / 32 / 16 channels at 2 B, 32 / 16 at 4 B
+    int slab = p.BN % 64 == 0 ? 64 : (p.BN % 32 == 0 ? 32 : 16);
+    if (esz_o == 4 && slab == 64) slab = 32;
+    const int row_bytes = slab * esz_o;
+    if (aligned && res_ok && d->Cout % (16 / esz_o) == 0 && d->Cout % 4 == 0) {
       p.o_slab = slab;
-      p.o_stage_bytes = 128 * slab * 2;
-      p.o_swz_mask = slab == 64 ? 7 : (slab == 32 ? 3 : 1);
+      p.o_stage_bytes = 128 * row_bytes;
+      p.o_swz_mask = row_bytes == 128 ? 7 : (row_bytes == 64 ? 3 : 1);
       smem_budget -= 2 * p.o_stage_bytes;
     } else {
       p.epi_mode = 0;
@@ -782,7 +827,8 @@ extern "C" int gdl_conv2d_nhwc_fwd(const gdl_conv_fwd_t* d, void* stream_) {
   if (st) return st;
 
   if (p.epi_mode == 2) {
-    st = make_tmap_nhwc(&p.tmO, d->out, d->out_dtype, d->Cout, oW, oH, N, d->ldo, p.o_slab, p.TW, p.TH, p.o_slab * 2);
+    st = make_tmap_nhwc(&p.tmO, d->out, d->out_dtype, d->Cout, oW, oH, N, d->ldo, p.o_slab, p.TW, p.TH,
+                        p.o_slab * (d->out_dtype == GDL_F32 ? 4 : 2));
     if (st) return st;
   }
   int smem = p.stages * p.stage_bytes + 2 * p.o_stage_bytes + 1024;

@@ -55,13 +55,13 @@ static int encode(CUtensorMap* out, const void* base, int dtype, int rank, const
                   const cuuint64_t* strides_bytes, const cuuint32_t* box, int swizzle_bytes) {
   PFN_encodeTiled fn = get_encode();
   GDL_REQUIRE(fn != nullptr, GDL_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
-  GDL_REQUIRE(dtype == kDtBF16 || dtype == kDtF16, GDL_ERR_INVALID,
-              "tensor map: 16-bit operand expected");
+  GDL_REQUIRE(dtype == kDtBF16 || dtype == kDtF16 || dtype == kDtF32, GDL_ERR_INVALID, "tensor map: bad dtype %d", dtype);
   GDL_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, GDL_ERR_INVALID,
               "tensor map: base address must be 16-byte aligned");
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
   CUresult r = fn(out,
-                  dtype == kDtBF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16,
+                  dtype == kDtBF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16
+                                   : (dtype == kDtF16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32),
                   (cuuint32_t)rank, const_cast<void*>(base), dims, strides_bytes, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, swz(swizzle_bytes), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -81,11 +81,12 @@ static int encode(CUtensorMap* out, const void* base, int dtype, int rank, const
 int make_tmap_nhwc(CUtensorMap* out, const void* base, int dtype, long long C, long long W,
                    long long H, long long N, long long ld, int boxC, int boxW, int boxH,
                    int swizzle_bytes) {
-  GDL_REQUIRE((ld * 2) % 16 == 0, GDL_ERR_INVALID, "NHWC pixel stride must be a multiple of 8 elements (got %lld)", ld);
-  GDL_REQUIRE(boxC * 2 <= swizzle_bytes || swizzle_bytes == 0, GDL_ERR_INVALID,
-              "tensor map: inner box (%d B) exceeds swizzle span %d", boxC * 2, swizzle_bytes);
+  const long long esz = dtype == kDtF32 ? 4 : 2;
+  GDL_REQUIRE((ld * esz) % 16 == 0, GDL_ERR_INVALID, "NHWC pixel stride must be a multiple of 16 bytes (got %lld elements)", ld);
+  GDL_REQUIRE(boxC * esz <= swizzle_bytes || swizzle_bytes == 0, GDL_ERR_INVALID,
+              "tensor map: inner box (%d B) exceeds swizzle span %d", (int)(boxC * esz), swizzle_bytes);
   cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
-  cuuint64_t str[3] = {(cuuint64_t)(ld * 2), (cuuint64_t)(W * ld * 2), (cuuint64_t)(H * W * ld * 2)};
+  cuuint64_t str[3] = {(cuuint64_t)(ld * esz), (cuuint64_t)(W * ld * esz), (cuuint64_t)(H * W * ld * esz)};
   cuuint32_t box[4] = {(cuuint32_t)boxC, (cuuint32_t)boxW, (cuuint32_t)boxH, 1};
   return encode(out, base, dtype, 4, dims, str, box, swizzle_bytes);
 }

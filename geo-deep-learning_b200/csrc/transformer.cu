@@ -159,17 +159,18 @@ __global__ void layernorm_bwd_kernel(const TG* __restrict__ g, long long ldg, co
 // ------------------------------------------------------------------------------------------
 constexpr int kSmMaxPerLane = 48;  // L <= 1536 (DOFA: 1297 tokens)
 
-template <typename T>
+// PER = compile-time bound of the per-lane element count: the row lives in registers (a runtime trip count put the
+// array in local memory)
+template <typename T, int PER>
 __global__ void softmax_fwd_kernel(const T* __restrict__ s, long long lds, float scale, T* __restrict__ p,
                                    long long ldp, long long M, int L, int Lpad) {
   const int lane = threadIdx.x & 31;
   const int wpb = blockDim.x >> 5;
-  const int per = (Lpad + 31) / 32;
   for (long long row = (long long)blockIdx.x * wpb + (threadIdx.x >> 5); row < M; row += (long long)gridDim.x * wpb) {
-    float v[kSmMaxPerLane];
+    float v[PER];
     float mx = -INFINITY;
-#pragma unroll 4
-    for (int i = 0; i < per; ++i) {
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
       const int c = lane + 32 * i;
       v[i] = c < L ? to_f<T>(s[row * lds + c]) * scale : -INFINITY;
       mx = fmaxf(mx, v[i]);
@@ -177,40 +178,39 @@ __global__ void softmax_fwd_kernel(const T* __restrict__ s, long long lds, float
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
     float sum = 0.f;
-#pragma unroll 4
-    for (int i = 0; i < per; ++i) {
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
       const int c = lane + 32 * i;
       v[i] = c < L ? expf(v[i] - mx) : 0.f;
       sum += v[i];
     }
     const float inv = 1.f / warp_sum(sum);
-#pragma unroll 4
-    for (int i = 0; i < per; ++i) {
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
       const int c = lane + 32 * i;
       if (c < Lpad) p[row * ldp + c] = from_f<T>(v[i] * inv);
     }
   }
 }
 
-template <typename T>
+template <typename T, int PER>
 __global__ void softmax_bwd_kernel(const T* __restrict__ p, long long ldp, const T* __restrict__ dp, long long lddp,
                                    float scale, T* __restrict__ ds, long long ldds, long long M, int L, int Lpad) {
   const int lane = threadIdx.x & 31;
   const int wpb = blockDim.x >> 5;
-  const int per = (Lpad + 31) / 32;
   for (long long row = (long long)blockIdx.x * wpb + (threadIdx.x >> 5); row < M; row += (long long)gridDim.x * wpb) {
-    float pv[kSmMaxPerLane], dv[kSmMaxPerLane];
+    float pv[PER], dv[PER];
     float dot = 0.f;
-#pragma unroll 4
-    for (int i = 0; i < per; ++i) {
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
       const int c = lane + 32 * i;
       pv[i] = c < L ? to_f<T>(p[row * ldp + c]) : 0.f;
       dv[i] = c < L ? to_f<T>(dp[row * lddp + c]) : 0.f;
       dot = fmaf(pv[i], dv[i], dot);
     }
     dot = warp_sum(dot);
-#pragma unroll 4
-    for (int i = 0; i < per; ++i) {
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
       const int c = lane + 32 * i;
       if (c < Lpad) ds[row * ldds + c] = from_f<T>(c < L ? scale * pv[i] * (dv[i] - dot) : 0.f);
     }
@@ -830,7 +830,14 @@ extern "C" int gdl_softmax_fwd(const void* s, long long lds, float scale, void* 
   GDL_REQUIRE(s && p && M > 0 && L > 0 && Lpad >= L && Lpad <= 32 * kSmMaxPerLane && ldp >= Lpad && lds >= L,
               GDL_ERR_INVALID, "softmax: bad args (L=%d Lpad=%d)", L, Lpad);
   cudaStream_t st = (cudaStream_t)stream;
-  GDL_DISPATCH_T(dtype, { softmax_fwd_kernel<T><<<row_blocks(M, 8), 256, 0, st>>>((const T*)s, lds, scale, (T*)p, ldp, M, L, Lpad); });
+  const int per = (Lpad + 31) / 32;
+#define GDL_SM_FWD(PERV) \
+  GDL_DISPATCH_T(dtype, { softmax_fwd_kernel<T, PERV><<<row_blocks(M, 8), 256, 0, st>>>((const T*)s, lds, scale, (T*)p, ldp, M, L, Lpad); })
+  if (per <= 8) GDL_SM_FWD(8);
+  else if (per <= 16) GDL_SM_FWD(16);
+  else if (per <= 32) GDL_SM_FWD(32);
+  else GDL_SM_FWD(kSmMaxPerLane);
+#undef GDL_SM_FWD
   GDL_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -841,7 +848,15 @@ extern "C" int gdl_softmax_bwd(const void* p, long long ldp, const void* dp, lon
               "softmax_bwd: bad args");
   cudaStream_t st = (cudaStream_t)stream;
   GDL_DISPATCH_T(dtype, {
-    softmax_bwd_kernel<T><<<row_blocks(M, 8), 256, 0, st>>>((const T*)p, ldp, (const T*)dp, lddp, scale, (T*)ds, ldds, M, L, Lpad);
+    const int per = (Lpad + 31) / 32;
+    if (per <= 8)
+      softmax_bwd_kernel<T, 8><<<row_blocks(M, 8), 256, 0, st>>>((const T*)p, ldp, (const T*)dp, lddp, scale, (T*)ds, ldds, M, L, Lpad);
+    else if (per <= 16)
+      softmax_bwd_kernel<T, 16><<<row_blocks(M, 8), 256, 0, st>>>((const T*)p, ldp, (const T*)dp, lddp, scale, (T*)ds, ldds, M, L, Lpad);
+    else if (per <= 32)
+      softmax_bwd_kernel<T, 32><<<row_blocks(M, 8), 256, 0, st>>>((const T*)p, ldp, (const T*)dp, lddp, scale, (T*)ds, ldds, M, L, Lpad);
+    else
+      softmax_bwd_kernel<T, kSmMaxPerLane><<<row_blocks(M, 8), 256, 0, st>>>((const T*)p, ldp, (const T*)dp, lddp, scale, (T*)ds, ldds, M, L, Lpad);
   });
   GDL_CHECK_CUDA(cudaGetLastError());
   return 0;

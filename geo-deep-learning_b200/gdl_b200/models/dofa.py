@@ -132,12 +132,15 @@ def _lin(x2d: torch.Tensor, lin, *, out_dtype=None, relu=False, gelu=False, resi
 def _mha(qkv: torch.Tensor, b: int, n: int, heads: int, c: int, dt) -> torch.Tensor:
     """qkv (b*n, 3c) 16-bit with columns [q | k | v] -> softmax(q k^T d^-1/2) v as (b*n, c)"""
     d = c // heads
-    lp = (n + 15) // 16 * 16
+    # key rows padded to a multiple of 64: the P.V GEMM then contracts over 128-byte (64-key) swizzled rows and the
+    # q.k^T GEMM writes whole lp-wide score rows through the TMA-store epilogue.  Score columns >= n hold products with
+    # the next image's keys (or TMA zero fill): the softmax kernel ignores them and writes zeros there.
+    lp = (n + 63) // 64 * 64
     q4 = qkv.view(b, 1, n, 3 * c)
     scores = torch.empty((b, 1, n, heads * lp), dtype=dt, device=qkv.device)
     for hd in range(heads):
-        ops.conv2d_fwd([q4[..., hd * d:(hd + 1) * d]], qkv[:, c + hd * d:c + (hd + 1) * d], n, 1, 1, 0, 0,
-                       out=scores[..., hd * lp:hd * lp + n], w_rows_per_img=n)
+        ops.conv2d_fwd([q4[..., hd * d:(hd + 1) * d]], qkv[:, c + hd * d:c + (hd + 1) * d], lp, 1, 1, 0, 0,
+                       out=scores[..., hd * lp:(hd + 1) * lp], w_rows_per_img=n)
     p = ops.softmax_fwd(scores.view(b, n, heads, lp), d ** -0.5, n)
     p4 = p.view(b, 1, n, heads * lp)
     o = torch.empty((b, 1, n, c), dtype=dt, device=qkv.device)

@@ -57,8 +57,11 @@ def conv2d_fwd(srcs, weight, cout, r, s, pad_h, pad_w, *, out=None, out_dtype=No
                 avail = max(0, min(ctot, wf.shape[0] - r0))
                 blk[:avail] = wf[r0:r0 + avail, :cout]
                 ys.append(x[i] @ blk)
-            else:  # rows = Cout, cols = contraction index
-                ys.append(x[i] @ wf[r0:r0 + cout, :ctot].t())
+            else:  # rows = Cout (zero beyond the matrix, as the TMA zero fill), cols = contraction index
+                blk = torch.zeros(cout, ctot, dtype=_WORK)
+                avail = max(0, min(cout, wf.shape[0] - r0))
+                blk[:avail] = wf[r0:r0 + avail, :ctot]
+                ys.append(x[i] @ blk.t())
         y = torch.stack(ys)
         if bias is not None:
             y = y + bias

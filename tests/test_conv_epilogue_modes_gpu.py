@@ -24,6 +24,10 @@ def opts():
     (3, 9, 130, [32], 32, 3, torch.float16, {"gelu": True, "bias": True}),
     (1, 1, 777, [256], 1024, 1, torch.float16, {"oscale": True, "bias": True}),
     (2, 8, 128, [64], 64, 3, torch.bfloat16, {"bias": True, "relu": True}),        # halo mode of conv_fwd_kernel
+    (1, 1, 3000, [64], 64, 1, torch.bfloat16, {"bias": True, "out32": True, "res": "f32"}),   # fp32 residual stream
+    (2, 17, 33, [128], 320, 1, torch.bfloat16, {"out32": True, "res": "f32", "oscale": True}),  # 2 n-tiles of 160: fp32 slabs of 32
+    (1, 12, 128, [64], 20, 3, torch.bfloat16, {"bias": True, "out32": True}),                 # fp32 logits, Cout = 20
+    (2, 10, 96, [256], 128, 3, torch.float16, {"res": "16", "relu": True}),                   # 16-bit residual (dgrad + skip)
 ])
 def test_epilogue_variants_identical(cuda, opts, n, h, w, chans, cout, k, dtype, kw):
     from gdl_b200 import ops
@@ -37,6 +41,13 @@ def test_epilogue_variants_identical(cuda, opts, n, h, w, chans, cout, k, dtype,
         args["bias"] = torch.randn(cout, generator=g).cuda()
     if kw.get("oscale"):
         args["oscale"] = torch.randn(cout, generator=g).cuda()
+    res = None
+    if kw.get("res"):
+        res = torch.randn(n, h, w, cout, generator=g).cuda()
+        res = res if kw["res"] == "f32" else res.to(dtype)
+        args["residual"] = res
+    if kw.get("out32"):
+        args["out_dtype"] = torch.float32
     outs = {}
     for mode in (0, 1, 2):
         opts("conv_epilogue", mode)
@@ -46,9 +57,11 @@ def test_epilogue_variants_identical(cuda, opts, n, h, w, chans, cout, k, dtype,
     ref = F.conv2d(x, wp.view(cout, k, k, ctot).float().permute(0, 3, 1, 2), args.get("bias"), padding=k // 2)
     if "oscale" in args:
         ref = ref * args["oscale"].view(1, -1, 1, 1)
+    if res is not None:
+        ref = ref + res.float().permute(0, 3, 1, 2)
     ref = F.relu(ref) if args["relu"] else (F.gelu(ref) if args["gelu"] else ref)
     err = ((outs[2].float() - ref.permute(0, 2, 3, 1)).abs().max() / ref.abs().max()).item()
-    assert err < 6e-3
+    assert err < (1e-4 if kw.get("out32") else 6e-3)
 
 
 def test_tma_store_epilogue_respects_channel_slices(cuda, opts):

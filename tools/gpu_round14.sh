@@ -1,0 +1,17 @@
+#!/bin/bash
+# run 14: TMA-store epilogue for fp32 outputs / residuals, templated softmax, DOFA 64-padded keys
+mkdir -p gpurun_out
+echo "=== epilogue + transformer + dofa tests (own process)"
+timeout 900 python -m pytest tests/test_conv_epilogue_modes_gpu.py tests/test_transformer_kernels_gpu.py tests/test_dofa_gpu.py -m gpu -q --no-header -rA -p no:cacheprovider > gpurun_out/pytest_new.log 2>&1; rc=$?
+grep -E "passed|failed|error" gpurun_out/pytest_new.log | tail -3; grep -E "^(FAILED|ERROR)|Error|assert " gpurun_out/pytest_new.log | head -20
+echo "=== pytest -m gpu"
+timeout 1500 python -m pytest tests -m gpu -q --no-header -rA -p no:cacheprovider > gpurun_out/pytest_gpu_full.log 2>&1
+grep -E "passed|failed" gpurun_out/pytest_gpu_full.log | tail -3
+grep -E "^(FAILED|ERROR)" gpurun_out/pytest_gpu_full.log | head -30
+show='import json,sys; d=json.loads(sys.stdin.read()); print(d["value"], d["ms_per_step"], d["e2e"]["value"], d["roofline"]["achieved"], d["roofline"]["wgrad"]["achieved"], d["gpu_launches"])'
+echo "=== bench segformer"; timeout 600 python bench.py --workload segformer_b2 --steps 8 --warmup 3 --table gpurun_out/conv_table_sf.json 2>gpurun_out/bench.err | tee gpurun_out/bench_sf.json | python -c "$show"
+echo "=== bench dofa"; timeout 900 python bench.py --workload dofa_base --steps 6 --warmup 3 --table gpurun_out/conv_table_dofa.json 2>>gpurun_out/bench.err | tee gpurun_out/bench_dofa.json | python -c "$show"
+echo "=== bench unetpp"; timeout 600 python bench.py --steps 8 --warmup 3 --no-cpu-baseline 2>>gpurun_out/bench.err | tee gpurun_out/bench_unetpp.json | python -c "$show"
+tail -5 gpurun_out/bench.err
+echo "=== ncu launch list (dofa, eager)"
+timeout 600 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -s 3000 -c 1500 --csv --log-file gpurun_out/launches_dram_dofa.csv python bench.py --workload dofa_base --steps 1 --warmup 1 --no-cpu-baseline --cuda-graph 0 > gpurun_out/ncu_launch_bench_dofa.log 2>&1; tail -1 gpurun_out/ncu_launch_bench_dofa.log | cut -c1-160
