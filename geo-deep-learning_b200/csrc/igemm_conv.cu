@@ -71,6 +71,8 @@ struct ConvFwdKParams {
   const void* residual;  // optional, added in the epilogue (fp32 residual stream or 16-bit)
   int res_dtype;
   long long ldr;
+  int groups, tiles_per_group;  // grouped launch (all attention heads): tile = group * tiles_per_group + tile-in-group
+  int g_a, g_b, g_o;     // per-group offsets: A channel, B contiguous-dimension element, output channel
   int w_rows_per_img;    // batched B operand: weight row offset per image (attention GEMMs), 0 = shared
   int w_mn_major;        // B operand stored [K rows][N cols] (N contiguous): P.V and dS.K of the attention
   // halo mode (3x3, pad 1, 128x1-pixel tiles, BK = 64): one k-iteration loads ONE input row segment with
@@ -130,7 +132,9 @@ conv_fwd_kernel(const __grid_constant__ ConvFwdKParams p) {
       int stage = 0;
       uint32_t phase = 0;
       const uint32_t tx = (uint32_t)(p.a_bytes + p.b_bytes);
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      for (int tile_g = blockIdx.x; tile_g < p.num_tiles; tile_g += gridDim.x) {
+        const int grp = tile_g / p.tiles_per_group;
+        const int tile = tile_g - grp * p.tiles_per_group;
         const int n_tile = tile % p.n_tiles;
         const int m_tile = tile / p.n_tiles;
         const int img = m_tile / tiles_per_img;
@@ -138,6 +142,7 @@ conv_fwd_kernel(const __grid_constant__ ConvFwdKParams p) {
         const int h0 = (t_in / p.tiles_w) * p.TH;
         const int w0 = (t_in % p.tiles_w) * p.TW;
         const int n0 = n_tile * p.BN;
+        const int ga = grp * p.g_a, gb = grp * p.g_b;
         if (p.halo) {
           const uint32_t txh = (uint32_t)(130 * p.BK * 2 + 3 * p.b_bytes);
           for (int r = 0; r < 3; ++r) {
@@ -169,12 +174,12 @@ conv_fwd_kernel(const __grid_constant__ ConvFwdKParams p) {
               uint8_t* a_dst = smem + (size_t)stage * p.stage_bytes;
               uint8_t* b_dst = a_dst + p.a_bytes;
               mbar_expect_tx(&full_bar[stage], tx);
-              tma_load_4d(a_dst, &p.tmA[src], &full_bar[stage], ch * p.BK, w0 + s - p.pad_w,
+              tma_load_4d(a_dst, &p.tmA[src], &full_bar[stage], ch * p.BK + ga, w0 + s - p.pad_w,
                           h0 + r - p.pad_h, img);
               if (p.w_mn_major)
-                tma_load_2d(b_dst, &p.tmB, &full_bar[stage], n0, kbase + ch * p.BK + img * p.w_rows_per_img);
+                tma_load_2d(b_dst, &p.tmB, &full_bar[stage], n0 + gb, kbase + ch * p.BK + img * p.w_rows_per_img);
               else
-                tma_load_2d(b_dst, &p.tmB, &full_bar[stage], kbase + ch * p.BK, n0 + img * p.w_rows_per_img);
+                tma_load_2d(b_dst, &p.tmB, &full_bar[stage], kbase + ch * p.BK + gb, n0 + img * p.w_rows_per_img);
               if (++stage == p.stages) {
                 stage = 0;
                 phase ^= 1;
@@ -266,9 +271,12 @@ conv_fwd_kernel(const __grid_constant__ ConvFwdKParams p) {
       const int th = row / p.TW, tw = row - th * p.TW;
       int st = 0;
       int it = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+      for (int tile_g = blockIdx.x; tile_g < p.num_tiles; tile_g += gridDim.x, ++it) {
         const int acc = it & 1;
         const uint32_t aphase = (it >> 1) & 1;
+        const int grp = tile_g / p.tiles_per_group;
+        const int tile = tile_g - grp * p.tiles_per_group;
+        const int go = grp * p.g_o;
         const int n_tile = tile % p.n_tiles;
         const int m_tile = tile / p.n_tiles;
         const int img = m_tile / tiles_per_img;
@@ -369,7 +377,7 @@ conv_fwd_kernel(const __grid_constant__ ConvFwdKParams p) {
           fence_proxy_async_smem();
           named_bar_sync(1, 128);
           if (issuer && n0 + cb0 < p.Cout) {
-            tma_store_4d(&p.tmO, stg, n0 + cb0, w0, h0, img);
+            tma_store_4d(&p.tmO, stg, n0 + cb0 + go, w0, h0, img);
             bulk_commit_group();
           }
           st ^= 1;
@@ -379,9 +387,12 @@ conv_fwd_kernel(const __grid_constant__ ConvFwdKParams p) {
     } else if (p.epi_mode == 0) {
       // direct variant: every thread stores its own accumulator row (16-byte vectors, 32 lines per warp store)
       int it = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+      for (int tile_g = blockIdx.x; tile_g < p.num_tiles; tile_g += gridDim.x, ++it) {
         const int acc = it & 1;
         const uint32_t aphase = (it >> 1) & 1;
+        const int grp = tile_g / p.tiles_per_group;
+        const int tile = tile_g - grp * p.tiles_per_group;
+        const int go = grp * p.g_o;
         const int n_tile = tile % p.n_tiles;
         const int m_tile = tile / p.n_tiles;
         const int img = m_tile / tiles_per_img;
@@ -440,7 +451,7 @@ conv_fwd_kernel(const __grid_constant__ ConvFwdKParams p) {
   #pragma unroll
               for (int i = 0; i < 16; ++i) f[i] = 0.5f * f[i] * (1.f + erff(f[i] * 0.70710678118654752f));
             }
-            const long long off = pix * p.ldo + c0;
+            const long long off = pix * p.ldo + c0 + go;
             if (p.out_dtype == GDL_F32)
               store_row16<float>(reinterpret_cast<float*>(p.out) + off, f, nvalid, p.vec_ok);
             else if (p.out_dtype == GDL_BF16)
@@ -455,9 +466,12 @@ conv_fwd_kernel(const __grid_constant__ ConvFwdKParams p) {
       }
     } else {
     int it = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+    for (int tile_g = blockIdx.x; tile_g < p.num_tiles; tile_g += gridDim.x, ++it) {
       const int acc = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
+      const int grp = tile_g / p.tiles_per_group;
+      const int tile = tile_g - grp * p.tiles_per_group;
+      const int go = grp * p.g_o;
       const int n_tile = tile % p.n_tiles;
       const int m_tile = tile / p.n_tiles;
       const int img = m_tile / tiles_per_img;
@@ -553,7 +567,7 @@ conv_fwd_kernel(const __grid_constant__ ConvFwdKParams p) {
 #pragma unroll
             for (int j = 0; j < 8; ++j) f[j] = 0.5f * f[j] * (1.f + erff(f[j] * 0.70710678118654752f));
           }
-          const long long off = pix * p.ldo + col;
+          const long long off = pix * p.ldo + col + go;
           if (p.out_dtype == GDL_F32) {
             float* o = reinterpret_cast<float*>(p.out) + off;
             if (p.vec_ok && nval == 4) *reinterpret_cast<float4*>(o) = make_float4(f[0], f[1], f[2], f[3]);
@@ -740,6 +754,19 @@ extern "C" int gdl_conv2d_nhwc_fwd(const gdl_conv_fwd_t* d, void* stream_) {
   p.n_tiles = (d->Cout + 255) / 256;
   p.BN = (((d->Cout + p.n_tiles - 1) / p.n_tiles) + 15) / 16 * 16;
   long long num_tiles = (long long)N * p.tiles_w * p.tiles_h * p.n_tiles;
+  const int G = d->groups > 1 ? d->groups : 1;
+  if (G > 1) {
+    GDL_REQUIRE(d->R == 1 && d->S == 1 && d->num_src == 1 && !d->bias && !d->oscale && !d->residual, GDL_ERR_INVALID,
+                "grouped launch: pointwise, one source, no bias / oscale / residual");
+    GDL_REQUIRE(d->g_src_stride % 8 == 0 && d->g_w_stride % 8 == 0 && d->g_out_stride > 0, GDL_ERR_INVALID,
+                "grouped launch: strides must be multiples of 8 elements");
+  }
+  p.groups = G;
+  p.tiles_per_group = (int)num_tiles;
+  p.g_a = G > 1 ? d->g_src_stride : 0;
+  p.g_b = G > 1 ? d->g_w_stride : 0;
+  p.g_o = G > 1 ? d->g_out_stride : 0;
+  num_tiles *= G;
   GDL_REQUIRE(num_tiles < (1ll << 31), GDL_ERR_UNSUPPORTED, "too many tiles");
   p.num_tiles = (int)num_tiles;
   p.a_bytes = 128 * p.BK * 2;
@@ -772,7 +799,9 @@ extern "C" int gdl_conv2d_nhwc_fwd(const gdl_conv_fwd_t* d, void* stream_) {
     int slab = p.BN % 64 == 0 ? 64 : (p.BN % 32 == 0 ? 32 : 16);
     if (esz_o == 4 && slab == 64) slab = 32;
     const int row_bytes = slab * esz_o;
-    if (aligned && res_ok && d->Cout % (16 / esz_o) == 0 && d->Cout % 4 == 0) {
+    // grouped: the output map spans all groups, so a slab must not overhang its group's Cout channels
+    const bool grp_ok = G == 1 || ((d->g_out_stride * esz_o) % 16 == 0 && d->Cout % slab == 0);
+    if (aligned && res_ok && grp_ok && d->Cout % (16 / esz_o) == 0 && d->Cout % 4 == 0) {
       p.o_slab = slab;
       p.o_stage_bytes = 128 * row_bytes;
       p.o_swz_mask = row_bytes == 128 ? 7 : (row_bytes == 64 ? 3 : 1);
@@ -791,7 +820,8 @@ extern "C" int gdl_conv2d_nhwc_fwd(const gdl_conv_fwd_t* d, void* stream_) {
   p.out_dtype = d->out_dtype;
   p.ldo = d->ldo;
   const int esz = d->out_dtype == GDL_F32 ? 4 : 2;
-  p.vec_ok = ((reinterpret_cast<uintptr_t>(d->out) & 15) == 0) && ((d->ldo * esz) % 16 == 0);
+  p.vec_ok = ((reinterpret_cast<uintptr_t>(d->out) & 15) == 0) && ((d->ldo * esz) % 16 == 0) &&
+             (G == 1 || (d->g_out_stride * esz) % 16 == 0);
   p.pair_ok = 0;
   p.res_vec_ok = d->residual != nullptr && d->res_dtype == GDL_F32 &&
                  ((reinterpret_cast<uintptr_t>(d->residual) & 15) == 0) && (d->ldr % 4 == 0);
@@ -810,8 +840,8 @@ extern "C" int gdl_conv2d_nhwc_fwd(const gdl_conv_fwd_t* d, void* stream_) {
     p.src_chunks[i] = d->src[i].channels / p.BK;
     p.src_coff[i] = coff;
     coff += d->src[i].channels;
-    st = make_tmap_nhwc(&p.tmA[i], d->src[i].ptr, d->dtype, d->src[i].channels, W, H, N, d->src[i].ld,
-                        p.BK, p.halo ? 130 : p.TW, p.TH, p.BK * 2);
+    st = make_tmap_nhwc(&p.tmA[i], d->src[i].ptr, d->dtype, d->src[i].channels + (long long)(G - 1) * p.g_a, W, H, N,
+                        d->src[i].ld, p.BK, p.halo ? 130 : p.TW, p.TH, p.BK * 2);
     if (st) return st;
   }
   const long long Ktot = (long long)d->R * d->S * Ctot;
@@ -819,15 +849,18 @@ extern "C" int gdl_conv2d_nhwc_fwd(const gdl_conv_fwd_t* d, void* stream_) {
   if (d->w_mn_major) {
     // weight matrix [w_rows (K index, all images)][Cout] with row stride w_ld: box = (Cout cols, BK rows)
     const long long w_rows = d->w_rows > 0 ? d->w_rows : Ktot;
-    st = make_tmap_2d(&p.tmB, d->weight, d->dtype, d->Cout, w_rows, w_ld, p.BN, p.BK, p.BN * 2);
+    st = make_tmap_2d(&p.tmB, d->weight, d->dtype, d->Cout + (long long)(G - 1) * p.g_b, w_rows, w_ld, p.BN, p.BK,
+                      p.BN * 2);
   } else {
     const long long w_rows = d->w_rows > 0 ? d->w_rows : d->Cout;
-    st = make_tmap_2d(&p.tmB, d->weight, d->dtype, Ktot, w_rows, w_ld, p.BK, p.BN, p.BK * 2);
+    st = make_tmap_2d(&p.tmB, d->weight, d->dtype, Ktot + (long long)(G - 1) * p.g_b, w_rows, w_ld, p.BK, p.BN,
+                      p.BK * 2);
   }
   if (st) return st;
 
   if (p.epi_mode == 2) {
-    st = make_tmap_nhwc(&p.tmO, d->out, d->out_dtype, d->Cout, oW, oH, N, d->ldo, p.o_slab, p.TW, p.TH,
+    st = make_tmap_nhwc(&p.tmO, d->out, d->out_dtype, d->Cout + (long long)(G - 1) * p.g_o, oW, oH, N, d->ldo, p.o_slab,
+                        p.TW, p.TH,
                         p.o_slab * (d->out_dtype == GDL_F32 ? 4 : 2));
     if (st) return st;
   }

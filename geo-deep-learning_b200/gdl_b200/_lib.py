@@ -48,6 +48,10 @@ class ConvFwd(C.Structure):
         ("w_rows", C.c_int),
         ("w_rows_per_img", C.c_int),
         ("w_mn_major", C.c_int),
+        ("groups", C.c_int),
+        ("g_src_stride", C.c_int),
+        ("g_w_stride", C.c_int),
+        ("g_out_stride", C.c_int),
     ]
 
 

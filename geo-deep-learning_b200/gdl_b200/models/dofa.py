@@ -138,15 +138,14 @@ def _mha(qkv: torch.Tensor, b: int, n: int, heads: int, c: int, dt) -> torch.Ten
     lp = (n + 63) // 64 * 64
     q4 = qkv.view(b, 1, n, 3 * c)
     scores = torch.empty((b, 1, n, heads * lp), dtype=dt, device=qkv.device)
-    for hd in range(heads):
-        ops.conv2d_fwd([q4[..., hd * d:(hd + 1) * d]], qkv[:, c + hd * d:c + (hd + 1) * d], lp, 1, 1, 0, 0,
-                       out=scores[..., hd * lp:(hd + 1) * lp], w_rows_per_img=n)
+    # one grouped launch per product: head g reads q / k / v columns shifted by g*d and writes scores / P columns by g*lp
+    ops.conv2d_fwd([q4[..., 0:d]], qkv[:, c:c + d], lp, 1, 1, 0, 0, out=scores[..., 0:lp], w_rows_per_img=n,
+                   groups=(heads, d, d, lp))
     p = ops.softmax_fwd(scores.view(b, n, heads, lp), d ** -0.5, n)
     p4 = p.view(b, 1, n, heads * lp)
     o = torch.empty((b, 1, n, c), dtype=dt, device=qkv.device)
-    for hd in range(heads):
-        ops.conv2d_fwd([p4[..., hd * lp:(hd + 1) * lp]], qkv[:, 2 * c + hd * d:2 * c + (hd + 1) * d], d, 1, 1, 0, 0,
-                       out=o[..., hd * d:(hd + 1) * d], w_rows_per_img=n, w_mn_major=True)
+    ops.conv2d_fwd([p4[..., 0:lp]], qkv[:, 2 * c:2 * c + d], d, 1, 1, 0, 0, out=o[..., 0:d], w_rows_per_img=n,
+                   w_mn_major=True, groups=(heads, lp, d, d))
     return o.view(b * n, c)
 
 

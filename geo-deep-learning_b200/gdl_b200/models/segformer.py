@@ -195,15 +195,14 @@ class SegFormer(nn.Module):
         kv2 = kv.view(b * nk, 2 * c)
         q4 = q.view(b, 1, n, c)
         scores = torch.empty((b, 1, n, heads * lp), dtype=dt, device=q.device)
-        for hd in range(heads):
-            ops.conv2d_fwd([q4[..., hd * d:(hd + 1) * d]], kv2[:, hd * d:(hd + 1) * d], nk, 1, 1, 0, 0,
-                           out=scores[..., hd * lp:hd * lp + nk], w_rows_per_img=nk)
+        # all heads in one grouped launch: head g reads q / k / v columns shifted by g*d, writes score columns by g*lp
+        ops.conv2d_fwd([q4[..., 0:d]], kv2[:, 0:d], nk, 1, 1, 0, 0, out=scores[..., 0:nk], w_rows_per_img=nk,
+                       groups=(heads, d, d, lp))
         p = ops.softmax_fwd(scores.view(b, n, heads, lp), d ** -0.5, nk)
         p4 = p.view(b, 1, n, heads * lp)
         o = torch.empty((b, 1, n, c), dtype=dt, device=q.device)
-        for hd in range(heads):
-            ops.conv2d_fwd([p4[..., hd * lp:(hd + 1) * lp]], kv2[:, c + hd * d:c + (hd + 1) * d], d, 1, 1, 0, 0,
-                           out=o[..., hd * d:(hd + 1) * d], w_rows_per_img=nk, w_mn_major=True)
+        ops.conv2d_fwd([p4[..., 0:lp]], kv2[:, c:c + d], d, 1, 1, 0, 0, out=o[..., 0:d], w_rows_per_img=nk,
+                       w_mn_major=True, groups=(heads, lp, d, d))
         rc_proj, act_o = self._linear(eng, o.view(b, h, w, c), attn.proj, residual=stream, out_dtype=stream.dtype)
         sv.__dict__.update(rc_kv=rc_kv, act_kvin=act_kvin, kv2=kv2, q4=q4, p4=p4, nk=nk, lp=lp, rc_proj=rc_proj,
                            act_o=act_o)
@@ -314,16 +313,15 @@ class SegFormer(nn.Module):
         dt = eng.dtype
         do4 = do.view(b, 1, n, c)
         dp = torch.empty((b, 1, n, heads * lp), dtype=dt, device=do.device)
-        for hd in range(heads):
-            ops.conv2d_fwd([do4[..., hd * d:(hd + 1) * d]], sv.kv2[:, c + hd * d:c + (hd + 1) * d], nk, 1, 1, 0, 0,
-                           out=dp[..., hd * lp:hd * lp + nk], w_rows_per_img=nk)
+        ops.conv2d_fwd([do4[..., 0:d]], sv.kv2[:, c:c + d], nk, 1, 1, 0, 0, out=dp[..., 0:nk], w_rows_per_img=nk,
+                       groups=(heads, d, d, lp))
         ds = ops.softmax_bwd(sv.p4.view(b, n, heads, lp), dp.view(b, n, heads, lp), d ** -0.5, nk)
         ds4 = ds.view(b, 1, n, heads * lp)
         dq = torch.empty((b, 1, n, c), dtype=dt, device=do.device)
         dkv32 = torch.zeros((b, lp, 2 * c), dtype=eng.acc_dtype, device=do.device)
+        ops.conv2d_fwd([ds4[..., 0:lp]], sv.kv2[:, 0:d], d, 1, 1, 0, 0, out=dq[..., 0:d], w_rows_per_img=nk,
+                       w_mn_major=True, groups=(heads, lp, d, d))
         for hd in range(heads):
-            ops.conv2d_fwd([ds4[..., hd * lp:(hd + 1) * lp]], sv.kv2[:, hd * d:(hd + 1) * d], d, 1, 1, 0, 0,
-                           out=dq[..., hd * d:(hd + 1) * d], w_rows_per_img=nk, w_mn_major=True)
             # dV[b] = P^T dO,  dK[b] = dS^T q   (one independent product per image)
             ops.conv2d_wgrad([do4[..., hd * d:(hd + 1) * d]], sv.p4[..., hd * lp:(hd + 1) * lp], 1, 1, 0, 0,
                              dkv32[:, :, c + hd * d:c + (hd + 1) * d])

@@ -148,7 +148,7 @@ def conv2d_fwd(srcs: Sequence[torch.Tensor], weight: torch.Tensor, cout: int, r:
                out_dtype: torch.dtype | None = None, bias: torch.Tensor | None = None,
                relu: bool = False, residual: torch.Tensor | None = None, w_ld: int = 0, w_rows: int = 0,
                w_rows_per_img: int = 0, w_mn_major: bool = False, gelu: bool = False,
-               oscale: torch.Tensor | None = None) -> torch.Tensor:
+               oscale: torch.Tensor | None = None, groups: tuple[int, int, int, int] | None = None) -> torch.Tensor:
     """gdl_conv2d_nhwc_fwd. `weight` is the packed [Cout][R][S][Ctot] 16-bit operand (or, with the w_*
     options, a slice of an activation tensor used as the B operand of an attention GEMM)."""
     d = L.ConvFwd()
@@ -173,13 +173,19 @@ def conv2d_fwd(srcs: Sequence[torch.Tensor], weight: torch.Tensor, cout: int, r:
     if w_rows_per_img or w_mn_major:  # `weight` is a 2-D view [rows][cols] of an activation tensor
         w_ld, w_rows = weight.stride(0), weight.shape[0]
     d.w_ld, d.w_rows, d.w_rows_per_img, d.w_mn_major = w_ld, w_rows, w_rows_per_img, int(w_mn_major)
+    ng = 1
+    if groups is not None:
+        # (G, source channel stride, weight stride along its contiguous dim, output channel stride): all heads at once;
+        # srcs[0] / weight / out are the views of group 0
+        ng, d.g_src_stride, d.g_w_stride, d.g_out_stride = groups
+        d.groups = ng
     e0 = _PROFILER.begin() if _PROFILER is not None else None
     L.check(L.load().gdl_conv2d_nhwc_fwd(C.byref(d), L.stream_ptr()))
     _count()
     if e0 is not None:
         ctot = sum(t.shape[3] for t in srcs)
-        _PROFILER.end("conv_fwd_kernel", 2.0 * n * ho * wo * cout * r * s * ctot, e0,
-                      f"N{n} {ho}x{wo} src{[t.shape[3] for t in srcs]} -> {cout} k{r}")
+        _PROFILER.end("conv_fwd_kernel", 2.0 * ng * n * ho * wo * cout * r * s * ctot, e0,
+                      f"N{n} {ho}x{wo} src{[t.shape[3] for t in srcs]} -> {cout} k{r}" + (f" x{ng} groups" if ng > 1 else ""))
     return out
 
 

@@ -96,6 +96,15 @@ typedef struct {
   int w_rows;
   int w_rows_per_img;
   int w_mn_major;
+  /* grouped (multi-head) launch of a pointwise GEMM: `groups` independent products in ONE launch, group g reading the
+   * source channels [g*g_src_stride, +src[0].channels), the weight matrix shifted by g*g_w_stride elements along its
+   * contiguous dimension, and writing the output channels [g*g_out_stride, +Cout).  All attention heads of
+   * mix_transformer.py:139-160 / timm Attention in one launch.  0 or 1 = not grouped; needs R = S = 1, one source, no
+   * bias / oscale / residual. */
+  int groups;
+  int g_src_stride;
+  int g_w_stride;
+  int g_out_stride;
 } gdl_conv_fwd_t;
 int gdl_conv2d_nhwc_fwd(const gdl_conv_fwd_t* d, void* stream);
 

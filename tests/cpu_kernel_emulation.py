@@ -42,7 +42,19 @@ def pack_conv_weight(w, dtype, mode=0, ld=0, out=None):
 
 
 def conv2d_fwd(srcs, weight, cout, r, s, pad_h, pad_w, *, out=None, out_dtype=None, bias=None, relu=False,
-               residual=None, w_ld=0, w_rows=0, w_rows_per_img=0, w_mn_major=False, gelu=False, oscale=None):
+               residual=None, w_ld=0, w_rows=0, w_rows_per_img=0, w_mn_major=False, gelu=False, oscale=None, groups=None):
+    if groups is not None and groups[0] > 1:
+        # all heads in one launch: group g = the same call on views shifted by the per-group strides
+        ng, sa, sw, so = groups
+        x0, c0 = srcs[0], srcs[0].shape[3]
+        xfull = torch.as_strided(x0, x0.shape[:3] + (c0 + (ng - 1) * sa,), x0.stride(), x0.storage_offset())
+        wcols = weight.shape[1] + (ng - 1) * sw
+        wfull = torch.as_strided(weight, (weight.shape[0], wcols), weight.stride(), weight.storage_offset())
+        ofull = torch.as_strided(out, out.shape[:3] + (cout + (ng - 1) * so,), out.stride(), out.storage_offset())
+        for g in range(ng):
+            conv2d_fwd([xfull[..., g * sa:g * sa + c0]], wfull[:, g * sw:g * sw + weight.shape[1]], cout, r, s, pad_h, pad_w,
+                       out=ofull[..., g * so:g * so + cout], w_rows_per_img=w_rows_per_img, w_mn_major=w_mn_major)
+        return out
     x = torch.cat(list(srcs), 3).to(_WORK)
     ctot = x.shape[3]
     if w_rows_per_img or w_mn_major:
