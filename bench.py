@@ -36,6 +36,10 @@ WORKLOADS = {
     "dofa_base": {"name": "dofa_base_upernet_6band_512_k5_b16", "family": "dofa", "encoder": "dofa_base", "bands": 6,
                   "tile": 512, "classes": 5, "batch_per_gpu": 16, "train_gflop_per_tile": 1613.8,
                   "wavelengths": [0.49, 0.56, 0.665, 0.842, 1.61, 2.19]},
+    # BASELINE.json configs[4] — inference only: SegFormer-B5, 4-band raster, 512-pixel windows at stride 256, windows dealt
+    # round-robin to the ranks (strong scaling).  219.5 GFLOP per window (torch flop counter on the oracle's forward).
+    "segformer_b5_infer": {"name": "segformer_b5_4band_sliding512_s256", "family": "infer", "encoder": "mit_b5", "bands": 4,
+                           "tile": 512, "classes": 5, "batch_per_gpu": 16, "train_gflop_per_tile": 219.5, "raster": 10000},
 }
 WORKLOAD = WORKLOADS["unetpp_r50"]
 TRAIN_GFLOP_PER_TILE = WORKLOAD["train_gflop_per_tile"]  # 3 x forward GFLOP (2 FLOP / MAC)
@@ -162,6 +166,8 @@ def cpu_reference_steps(steps: int, warmup: int, tiles_per_step: int = 1, budget
         def fwd(x):
             return model(x)
         what = "oracle port of smp.UnetPlusPlus: smp itself is not installable offline"
+    elif w["family"] == "infer":
+        return cpu_reference_infer(steps, warmup, budget_s, cores)
     elif w["family"] == "dofa":
         from oracle import dofa as od, upernet as ou
         enc_sd = od.init_state_dict(768, 12, w["tile"])
@@ -214,16 +220,52 @@ def cpu_reference_steps(steps: int, warmup: int, tiles_per_step: int = 1, budget
             "ms_per_step": 1e3 * total / len(times), "steps_timed": len(times), "tiles_per_step": tiles_per_step}
 
 
+def cpu_reference_infer(steps: int, warmup: int, budget_s: float | None, cores: int) -> dict:
+    """Reference eval path of one window on the host: normalise -> SegFormer forward -> softmax/argmax."""
+    import torch
+    from oracle import segformer as osf
+    from oracle import tensors as ot
+    w = WORKLOAD
+    nb = w["bands"]
+    sd = osf.init_state_dict(w["encoder"], nb, w["classes"])
+    g = torch.Generator().manual_seed(1234)
+    raw = torch.randint(0, 256, (1, nb, w["tile"], w["tile"]), generator=g, dtype=torch.uint8)
+    mean, std = torch.tensor(MEAN[:nb]).view(-1, 1), torch.tensor(STD[:nb]).view(-1, 1)
+
+    def step() -> None:
+        with torch.no_grad():
+            x = ot.standardization(ot.normalization(raw.float()), mean, std)
+            osf.segformer_forward(sd, x, w["encoder"], training=False).softmax(dim=1).argmax(dim=1)
+
+    for _ in range(warmup):
+        step()
+    times = []
+    t_begin = time.perf_counter()
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        step()
+        times.append(time.perf_counter() - t0)
+        if budget_s is not None and time.perf_counter() - t_begin > budget_s:
+            break
+    total = sum(times)
+    return {"value": len(times) / total, "unit": "tiles/s", "cores": cores, "kind": "port",
+            "sample": f"{len(times)} window(s) of {w['name']} (normalise + forward + softmax/argmax, fp32, {cores} threads, "
+                      "functional restatement of the reference's SegFormerSegmentationModel, pinned to it by golden vectors)",
+            "ms_per_step": 1e3 * total / len(times), "steps_timed": len(times), "tiles_per_step": 1}
+
+
 def main_reference(args) -> None:
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     r = cpu_reference_steps(args.steps, args.warmup, 1)
+    infer = WORKLOAD["family"] == "infer"
     line = {
-        "impl": "reference", "metric": "512x512 multi-band tiles/sec (train fwd+bwd)", "value": r["value"],
+        "impl": "reference", "metric": "512x512 multi-band tiles/sec (inference fwd, sliding window)" if infer
+        else "512x512 multi-band tiles/sec (train fwd+bwd)", "value": r["value"],
         "unit": "tiles/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic",
+        "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "strong" if infer else "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD["name"], "tiles_per_step": r["tiles_per_step"],
                    "note": "reference CPU path, bounded sample"},
         "cpu_baseline": {"value": r["value"], "unit": "tiles/s", "cores": r["cores"], "kind": r["kind"],
@@ -258,6 +300,8 @@ def main_product(args) -> None:
     w = WORKLOAD
     B, C, T, K = args.batch or w["batch_per_gpu"], w["bands"], w["tile"], w["classes"]
     torch.manual_seed(0)  # identical initial weights on every rank (what DDP's broadcast gives)
+    if w["family"] == "infer":
+        return main_infer(args, world, rank, local, dev)
     if w["family"] == "unetpp":
         model = UnetPlusPlus(w["encoder"], in_channels=C, classes=K, compute_dtype=torch.bfloat16).to(dev).train()
     elif w["family"] == "dofa":
@@ -382,6 +426,100 @@ def main_product(args) -> None:
         dist.destroy_process_group()
 
 
+def main_infer(args, world: int, rank: int, local: int, dev) -> None:
+    """Sliding-window inference over one synthetic raster, windows dealt round-robin to the ranks (strong scaling)."""
+    import torch
+    import torch.distributed as dist
+
+    from gdl_b200 import ops
+    from gdl_b200.inference import SlidingWindowSegmenter, window_origins
+    from gdl_b200.models.segformer import SegFormer
+
+    w = WORKLOAD
+    B, C, T, K = args.batch or w["batch_per_gpu"], w["bands"], w["tile"], w["classes"]
+    R = args.raster or w["raster"]
+    model = SegFormer(w["encoder"], in_channels=C, num_classes=K, compute_dtype=torch.bfloat16).to(dev).eval()
+    seg = SlidingWindowSegmenter(model, tile=T, stride=T // 2, batch=B, mean=MEAN[:C], std=STD[:C])
+    nwin = len(window_origins(R, T, T // 2)) ** 2
+    g = torch.Generator().manual_seed(1234)  # the same raster on every rank
+    host = torch.randint(0, 256, (R, R, C), generator=g, dtype=torch.uint8).pin_memory()
+    resident = host.to(dev)
+    out_host = torch.empty((R, R), dtype=torch.uint8).pin_memory()
+
+    def barrier() -> None:
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps: int) -> float:
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            fn(i)
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms)
+
+    def step_resident(i: int):
+        return seg.predict(resident)
+
+    def step_e2e(i: int):
+        out_host.copy_(seg.predict(host), non_blocking=True)  # raster H2D and class map D2H inside the timed region
+        torch.cuda.current_stream().synchronize()
+
+    n0 = ops.launch_count()
+    for i in range(max(1, args.warmup)):
+        step_resident(i)
+    launches_per_step = (ops.launch_count() - n0) // max(1, args.warmup)
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    ms = timed(step_resident, args.steps)
+    clk = clocks.stop() if rank == 0 else None
+    step_e2e(0)
+    ms_e2e = timed(step_e2e, args.steps)
+    prof = ops.ConvProfiler()
+    ops.set_conv_profiler(prof)
+    step_resident(0)
+    torch.cuda.synchronize()
+    ops.set_conv_profiler(None)
+    roof = prof.summary(1)
+    cpu = None
+    if rank == 0 and not args.no_cpu_baseline:
+        cpu = cpu_reference_steps(steps=3, warmup=1, tiles_per_step=1, budget_s=20.0)
+    if rank == 0:
+        peaks = _peaks()
+        peak_tf = float(peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"]))
+        value = nwin * args.steps / (ms / 1e3)
+        fwd = roof["conv_fwd_kernel"]
+        line = {
+            "metric": "512x512 multi-band tiles/sec (inference fwd, sliding window)", "value": value, "unit": "tiles/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": w["name"], "raster": [R, R, C], "windows": nwin, "window_batch": B,
+                       "parallelism": f"windows round-robin over {world} rank(s) + one all-reduce of the logit sums",
+                       "l2": f"raster {R * R * C / 1e6:.0f} MB and activations >> 126 MB L2"},
+            "clocks": clk,
+            "e2e": {"value": nwin * args.steps / (ms_e2e / 1e3), "unit": "tiles/s", "h2d_bytes_per_step": R * R * C,
+                    "d2h_bytes_per_step": R * R, "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": launches_per_step * args.steps,
+            "model_tflops": w["train_gflop_per_tile"] * value / world / 1e3,
+            "roofline": {"bound": "tensor", "kernel": "conv_fwd_kernel (every GEMM / conv of the forward)",
+                         "achieved": fwd["tflops"], "peak": peak_tf, "unit": "TFLOP/s", "frac": fwd["tflops"] / peak_tf,
+                         "traffic": None, "peak_source": f"{peaks['source']} bf16_tflops_sustained",
+                         "launches_per_step": fwd["launches_per_step"],
+                         "share_of_step": fwd["ms_per_step"] / (ms / args.steps)},
+            "cpu_baseline": ({k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")} if cpu else None),
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main() -> None:
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -392,6 +530,7 @@ def main() -> None:
     ap.add_argument("--sync-bn", type=int, default=1, help="SyncBatchNorm statistics when N > 1 (reference YAMLs: true)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cuda-graph", type=int, default=1, help="1: capture the whole step in a CUDA graph at N=1; 2: also at N>1 (NCCL collectives captured)")
+    ap.add_argument("--raster", type=int, default=0, help="segformer_b5_infer: raster side in pixels (default 10000)")
     ap.add_argument("--table", default="", help="write the per-launch conv profile (shape, ms, TFLOP/s) to this JSON file")
     ap.add_argument("--workload", default="unetpp_r50", choices=sorted(WORKLOADS))
     args = ap.parse_args()

@@ -283,3 +283,39 @@ def test_dofa_fused_trainer_matches_autograd_route(monkeypatch, f64):
         if p.requires_grad:
             err = (p.grad - want[n_]).abs().max() / (want[n_].abs().max() + 1e-30)
             assert err < 1e-4 or want[n_].abs().max() < 1e-12, f"{n_}: {err}"
+
+
+def test_sliding_window_inference_equals_window_sum_of_oracle(monkeypatch, f64):
+    """SlidingWindowSegmenter host logic (window grid incl. the border-flush windows, zero padding of small rasters,
+    overlap blending by logit sum, argmax) against a direct restatement on the oracle model."""
+    from gdl_b200.inference import SlidingWindowSegmenter, window_origins
+    emu.install(monkeypatch)
+    assert window_origins(100, 64, 32) == [0, 32, 36] and window_origins(64, 64, 32) == [0] and window_origins(40, 64, 32) == [0]
+    ora, prod = _pair("resnet18", 3, 4)
+    ora, prod = ora.double().eval(), prod.double().eval()
+    prod.compute_dtype = torch.float64
+    mean, std = [0.4, 0.5, 0.6], [0.2, 0.25, 0.3]
+    g = torch.Generator().manual_seed(9)
+    for (h, w) in ((100, 150), (40, 64)):
+        raster = torch.randint(0, 256, (h, w, 3), generator=g, dtype=torch.uint8)
+        seg = SlidingWindowSegmenter(prod, tile=64, stride=32, batch=3, mean=mean, std=std)
+        got = seg.logits(raster)
+        hp, wp = max(h, 64), max(w, 64)
+        padded = torch.zeros(hp, wp, 3, dtype=torch.uint8)
+        padded[:h, :w] = raster
+        x = ((padded.double() / 255.0) - torch.tensor(mean).double()) / torch.tensor(std).double()
+        want = torch.zeros(hp, wp, 4, dtype=torch.float64)
+        n = 0
+        with torch.no_grad():
+            for y in window_origins(hp, 64, 32):
+                for xx in window_origins(wp, 64, 32):
+                    lo = ora(x[y:y + 64, xx:xx + 64].permute(2, 0, 1).unsqueeze(0))[0]
+                    want[y:y + 64, xx:xx + 64] += lo.permute(1, 2, 0)
+                    n += 1
+        assert seg.windows_done == n
+        assert torch.allclose(got.double(), want[:h, :w], atol=1e-5, rtol=1e-5)  # the logit accumulator is fp32
+        cls = seg.predict(raster)
+        assert cls.dtype == torch.uint8 and cls.shape == (h, w)
+        margin = want[:h, :w].topk(2, dim=2).values
+        sure = (margin[..., 0] - margin[..., 1]) > 1e-4
+        assert torch.equal(cls[sure].long(), want[:h, :w].argmax(2)[sure])
