@@ -38,6 +38,39 @@ int check_cuda(cudaError_t e, const char* what);
   } while (0)
 
 // ----------------------------------------------------------------------------------------
+// host: one-time, PER-DEVICE opt-in to > 48 KB of dynamic shared memory (the attribute belongs to the
+// device's context, not to the process: a process that drives several GPUs must set it on each)
+// ----------------------------------------------------------------------------------------
+struct PerDeviceOnce {
+  unsigned long long mask = 0;  // bit d = done on device d (benign race: setting the attribute twice is harmless)
+};
+template <typename K>
+inline cudaError_t set_max_dyn_smem_once(PerDeviceOnce& once, K kernel, int bytes) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  const unsigned long long bit = 1ull << (dev & 63);
+  if (__atomic_load_n(&once.mask, __ATOMIC_ACQUIRE) & bit) return cudaSuccess;
+  e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e == cudaSuccess) __atomic_fetch_or(&once.mask, bit, __ATOMIC_RELEASE);
+  return e;
+}
+
+// SM count of the CURRENT device (persistent kernels launch min(work, #SM) CTAs), cached per device
+inline int device_sm_count() {
+  static int cache[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return kNumSMsB200;
+  int& n = cache[dev & 63];
+  if (n == 0) {
+    int v = 0;
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = kNumSMsB200;
+    n = v;
+  }
+  return n;
+}
+
+// ----------------------------------------------------------------------------------------
 // shared-memory address helpers
 // ----------------------------------------------------------------------------------------
 GDL_DEVINL uint32_t smem_u32(const void* p) {

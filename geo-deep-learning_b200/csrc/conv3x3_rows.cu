@@ -387,16 +387,7 @@ __global__ void __launch_bounds__(kRowsThreads, 1) conv3x3_rows_kernel(const __g
   }
 }
 
-static int rows_sm_count() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess ||
-        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
-      n = kNumSMsB200;
-  }
-  return n;
-}
+static int rows_sm_count() { return device_sm_count(); }
 
 // Returns 1 when the descriptor is a case this kernel covers (then *status holds the launch status), 0 otherwise.
 // Called by gdl_conv2d_nhwc_fwd after it validated the descriptor.
@@ -483,14 +474,10 @@ int conv3x3_rows_try(const gdl_conv_fwd_t* d, cudaStream_t stream, int* status) 
     if (*status) return 1;
   }
   const int smem = p.a_stages * kRowsAStage + p.b_stages * p.b_stage_bytes + 2 * p.o_stage_bytes + 1024;
-  static bool attr_set = false;
-  if (!attr_set) {
-    *status = check_cuda(cudaFuncSetAttribute(conv3x3_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                              kRowsSmemBudget + 1024),
-                         "cudaFuncSetAttribute(conv3x3_rows_kernel)");
-    if (*status) return 1;
-    attr_set = true;
-  }
+  static PerDeviceOnce attr_once;
+  *status = check_cuda(set_max_dyn_smem_once(attr_once, conv3x3_rows_kernel, kRowsSmemBudget + 1024),
+                       "cudaFuncSetAttribute(conv3x3_rows_kernel)");
+  if (*status) return 1;
   const int sms = rows_sm_count();
   const int grid = p.num_jobs < sms ? (int)p.num_jobs : sms;
   conv3x3_rows_kernel<<<grid, kRowsThreads, smem, stream>>>(p);

@@ -111,11 +111,8 @@ extern "C" int gdl_debug_shift_probe(const void* a, const void* b, float* out, i
     st = make_tmap_2d(&p.tmB, b, kDtBF16, 64, 80, 64, 64, 80, 128);
   }
   if (st) return st;
-  static bool attr = false;
-  if (!attr) {
-    GDL_CHECK_CUDA(cudaFuncSetAttribute(probe_shift_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
-    attr = true;
-  }
+  static PerDeviceOnce attr_once;
+  GDL_CHECK_CUDA(set_max_dyn_smem_once(attr_once, probe_shift_kernel, 65536));
   probe_shift_kernel<<<1, 128, 49152 + 1024, (cudaStream_t)stream>>>(p);
   GDL_CHECK_CUDA(cudaGetLastError());
   return 0;

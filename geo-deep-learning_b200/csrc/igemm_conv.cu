@@ -647,16 +647,7 @@ static int chunk_width(const gdl_src_t* src, int n) {
   return bk;
 }
 
-static int sm_count() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess ||
-        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
-      n = kNumSMsB200;
-  }
-  return n;
-}
+static int sm_count() { return device_sm_count(); }
 
 static int validate_srcs(int num_src, const gdl_src_t* src, int* ctot) {
   GDL_REQUIRE(num_src >= 1 && num_src <= GDL_MAX_SRC, GDL_ERR_INVALID,
@@ -866,12 +857,8 @@ extern "C" int gdl_conv2d_nhwc_fwd(const gdl_conv_fwd_t* d, void* stream_) {
   }
   int smem = p.stages * p.stage_bytes + 2 * p.o_stage_bytes + 1024;
   if (smem < kMinSmemRequest) smem = kMinSmemRequest;
-  static bool attr_set = false;
-  if (!attr_set) {
-    GDL_CHECK_CUDA(cudaFuncSetAttribute(conv_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        kSmemBudget + 4096));
-    attr_set = true;
-  }
+  static PerDeviceOnce attr_once;
+  GDL_CHECK_CUDA(set_max_dyn_smem_once(attr_once, conv_fwd_kernel, kSmemBudget + 4096));
   int grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();
   conv_fwd_kernel<<<grid, kConvThreads, smem, stream>>>(p);
   GDL_CHECK_CUDA(cudaGetLastError());
@@ -1273,12 +1260,8 @@ extern "C" int gdl_conv2d_nhwc_wgrad(const gdl_conv_wgrad_t* d, void* stream_) {
 
   int smem = p.stages * p.stage_bytes + 1024;
   if (smem < kMinSmemRequest) smem = kMinSmemRequest;
-  static bool attr_set = false;
-  if (!attr_set) {
-    GDL_CHECK_CUDA(cudaFuncSetAttribute(conv_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        kSmemBudget + 4096));
-    attr_set = true;
-  }
+  static PerDeviceOnce attr_once;
+  GDL_CHECK_CUDA(set_max_dyn_smem_once(attr_once, conv_wgrad_kernel, kSmemBudget + 4096));
   int grid = p.num_units < sm_count() ? p.num_units : sm_count();
   conv_wgrad_kernel<<<grid, kConvThreads, smem, stream>>>(p);
   GDL_CHECK_CUDA(cudaGetLastError());

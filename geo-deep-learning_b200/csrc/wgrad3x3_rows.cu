@@ -288,14 +288,11 @@ int wgrad3x3_rows_try(const gdl_conv_wgrad_t* d, cudaStream_t stream, int* statu
   if (*status) return 1;
 
   const int smem = kWrXStages * 2 * kWrXAtomBytes + kWrDYStages * p.dy_stage_bytes + 1024;
-  static bool attr_set = false;
-  if (!attr_set) {
-    *status = check_cuda(cudaFuncSetAttribute(wgrad3x3_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                              kWrXStages * 2 * kWrXAtomBytes + kWrDYStages * 16 * 1024 + 1024),
-                         "cudaFuncSetAttribute(wgrad3x3_rows_kernel)");
-    if (*status) return 1;
-    attr_set = true;
-  }
+  static PerDeviceOnce attr_once;
+  *status = check_cuda(set_max_dyn_smem_once(attr_once, wgrad3x3_rows_kernel,
+                                             kWrXStages * 2 * kWrXAtomBytes + kWrDYStages * 16 * 1024 + 1024),
+                       "cudaFuncSetAttribute(wgrad3x3_rows_kernel)");
+  if (*status) return 1;
   const int grid = p.num_units < sms ? (int)p.num_units : sms;
   wgrad3x3_rows_kernel<<<grid, kWrThreads, smem, stream>>>(p);
   *status = check_cuda(cudaGetLastError(), "wgrad3x3_rows_kernel launch");

@@ -105,6 +105,7 @@ _SIGS = {
     "gdl_widen_conv_weight": [_VP, _VP, _I, _I, _I, _I, _I, _VP],
     "gdl_fold_widened_wgrad": [_VP, _I, _I, _VP, _I, _I, _I, _I, _I, _VP],
     "gdl_normalize_to_nhwc": [_VP, _I, _VP, _I, _LL, _LL, _LL, _I, _I, _VP, _VP, _F, _VP],
+    "gdl_augment_normalize": [_VP, _I, _VP, _I, _VP, _VP, _I, _VP, _LL, _LL, _LL, _I, _I, _VP, _VP, _F, _VP],
     "gdl_im2col_nhwc": [_VP, _VP, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _VP],
     "gdl_col2im_nhwc": [_VP, _VP, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _VP],
     "gdl_bn_stats": [_VP, _I, _LL, _I, _I, _VP, _VP, _VP],
@@ -119,6 +120,7 @@ _SIGS = {
     "gdl_seg_loss_fwd": [_VP, _I, _VP, _I, _LL, _I, _LL, _I, _F, _F, _F, _I, _F, _F, _VP, _VP, _VP],
     "gdl_seg_loss_bwd": [_VP, _I, _VP, _I, _LL, _I, _LL, _I, _F, _F, _F, _I, _F, _F, _VP, _VP, _VP, _I, _I, _VP],
     "gdl_argmax_classes": [_VP, _I, _LL, _I, _F, _VP, _VP],
+    "gdl_argmax_confusion": [_VP, _I, _LL, _LL, _I, _F, _VP, _I, _LL, _I, _VP, _VP, _VP],
     "gdl_adam_step": [_VP, _VP, _VP, _VP, _LL, _F, _F, _F, _F, _F, _I, _VP, _VP],
     "gdl_adam_step_dev": [_VP, _VP, _VP, _VP, _LL, _F, _F, _F, _F, _F, _VP, _VP, _VP],
     "gdl_grad_clip_coef": [_VP, _LL, _F, _VP, _VP, _VP],

@@ -395,8 +395,7 @@ class SegFormer(nn.Module):
         return Act(x, needs_grad=False)
 
     def forward(self, img: torch.Tensor) -> torch.Tensor:
-        if not img.is_cuda:
-            raise RuntimeError("gdl_b200.SegFormer runs on CUDA (sm_100a) only; there is no CPU fallback")
+        ops.require_cuda(img, "gdl_b200.SegFormer")
         params = list(self.parameters())
         if torch.is_grad_enabled() and self.training and any(p.requires_grad for p in params):
             return _SegFormerFn.apply(self, img, *params)

@@ -234,8 +234,7 @@ class UnetPlusPlus(nn.Module):
         return Act(x, needs_grad=False)
 
     def forward(self, image: torch.Tensor) -> torch.Tensor:
-        if not image.is_cuda:
-            raise RuntimeError("gdl_b200.UnetPlusPlus runs on CUDA (sm_100a) only; there is no CPU fallback")
+        ops.require_cuda(image, "gdl_b200.UnetPlusPlus")
         params = [p for p in self.parameters()]
         if torch.is_grad_enabled() and self.training and any(p.requires_grad for p in params):
             return _UnetPPFn.apply(self, image, *params)

@@ -140,8 +140,7 @@ class UperNetSegmentor(nn.Module):
 
     def forward(self, enc_feats: list[torch.Tensor], image_size: tuple[int, int]):
         """enc_feats: 4 x (N, C, h, w) float tensors (what DOFAv2.forward returns)."""
-        if not enc_feats[0].is_cuda:
-            raise RuntimeError("gdl_b200.UperNetSegmentor runs on CUDA (sm_100a) only; there is no CPU fallback")
+        ops.require_cuda(enc_feats[0], "gdl_b200.UperNetSegmentor")
         params = list(self.parameters())
         if torch.is_grad_enabled() and self.training and any(p.requires_grad for p in params):
             out = _UperNetFn.apply(self, tuple(image_size), len(enc_feats), *enc_feats, *params)

@@ -113,6 +113,12 @@ def set_option(name: str, value: int) -> None:
     L.check(L.load().gdl_set_option(name.encode(), int(value)))
 
 
+def require_cuda(t: torch.Tensor, what: str) -> None:
+    """the hot path has no CPU implementation: refuse host tensors loudly, before any kernel wrapper is reached"""
+    if not t.is_cuda:
+        raise RuntimeError(f"{what} runs on CUDA (sm_100a) only; there is no CPU fallback")
+
+
 def _nhwc_src(t: torch.Tensor) -> tuple[int, int, int, int, int]:
     if t.dim() != 4:
         raise ValueError(f"NHWC activation expected 4 dims, got {tuple(t.shape)}")
@@ -286,6 +292,38 @@ def normalize_to_nhwc(x: torch.Tensor, chw: bool, out_dtype: torch.dtype, ld: in
     return out
 
 
+AUG_IDENTITY, AUG_HFLIP, AUG_VFLIP, AUG_ROT90, AUG_CROP = range(5)
+
+
+def augment_normalize(x: torch.Tensor, chw: bool, mask: torch.Tensor | None, params: torch.Tensor,
+                      out_dtype: torch.dtype, ld: int = 0, mean: torch.Tensor | None = None,
+                      std: torch.Tensor | None = None, image_max: float = 0.0):
+    """Batch augmentation fused with the patch normalisation (gdl_augment_normalize): x uint8/f32 image batch (NHWC if
+    chw=False else NCHW), mask (N,H,W) int64/uint8 or None, params int32 (N,6) = {op, k, y0, x0, ch, cw} on the device.
+    Returns (image, mask'): image = 16-bit NHWC (N,H,W,ld) for a 16-bit out_dtype, f32 NCHW for torch.float32."""
+    if not x.is_contiguous() or (mask is not None and not mask.is_contiguous()):
+        raise ValueError("augment: contiguous inputs expected")
+    if chw:
+        n, c, h, w = x.shape
+    else:
+        n, h, w, c = x.shape
+    if params.dtype != torch.int32 or tuple(params.shape) != (n, 6) or not params.is_contiguous():
+        raise ValueError(f"augment: params must be a contiguous int32 ({n}, 6) tensor")
+    if mask is not None and tuple(mask.shape) != (n, h, w):
+        raise ValueError(f"augment: mask shape {tuple(mask.shape)} does not match the image batch {(n, h, w)}")
+    if out_dtype == torch.float32:
+        out = torch.empty((n, c, h, w), dtype=torch.float32, device=x.device)
+    else:
+        ld = ld or (c + 7) // 8 * 8
+        out = torch.empty((n, h, w, ld), dtype=out_dtype, device=x.device)
+    mask_out = torch.empty_like(mask) if mask is not None else None
+    _ck(L.load().gdl_augment_normalize(L.ptr(x), _IN_KIND[(x.dtype, chw)], L.ptr(mask),
+                                           _target_kind(mask) if mask is not None else 0, L.ptr(params), L.ptr(out),
+                                           L.dt_code(out_dtype), L.ptr(mask_out), n, h, w, c, ld, L.ptr(mean), L.ptr(std),
+                                           float(image_max), L.stream_ptr()))
+    return out, mask_out
+
+
 def im2col(x: torch.Tensor, c: int, r: int, s: int, stride: int, pad: int, kpad: int) -> torch.Tensor:
     n, h, w, _ = x.shape
     ho, wo = (h + 2 * pad - r) // stride + 1, (w + 2 * pad - s) // stride + 1
@@ -433,6 +471,25 @@ def argmax_classes(logits: torch.Tensor, threshold: float = 0.5) -> torch.Tensor
     _ck(L.load().gdl_argmax_classes(L.ptr(logits), logits.stride(2), n * h * w, k, float(threshold), L.ptr(out),
                                         L.stream_ptr()))
     return out
+
+
+def argmax_confusion(logits: torch.Tensor, target: torch.Tensor | None, threshold: float = 0.5,
+                     ignore_index: int | None = None, want_classes: bool = True):
+    """logits fp32 (N,H,W,K) -> (classes int64 (N,H,W) | None, conf int64 (N,Kc,Kc) | None): the eval post-processing
+    (softmax.argmax / sigmoid > threshold) fused with the per-sample confusion counts conf[n][target][prediction]."""
+    n, h, w, k = logits.shape
+    kc = 2 if k == 1 else k
+    classes = torch.empty((n, h, w), dtype=torch.int64, device=logits.device) if want_classes else None
+    conf = None
+    if target is not None:
+        if tuple(target.shape) != (n, h, w) or not target.is_contiguous():
+            raise ValueError(f"argmax_confusion: target must be a contiguous {(n, h, w)} tensor")
+        conf = torch.zeros((n, kc, kc), dtype=torch.int64, device=logits.device)
+    _ck(L.load().gdl_argmax_confusion(L.ptr(logits), logits.stride(2), n, h * w, k, float(threshold), L.ptr(target),
+                                          _target_kind(target) if target is not None else 0,
+                                          int(ignore_index) if ignore_index is not None else 0,
+                                          int(ignore_index is not None), L.ptr(classes), L.ptr(conf), L.stream_ptr()))
+    return classes, conf
 
 
 def adam_step(p, g, m, v, lr, beta1, beta2, eps, weight_decay, step, grad_scale=None) -> None:

@@ -11,11 +11,12 @@ import torch
 from torch import Tensor
 
 from ..models.dofa import DOFASegmentationModel, SegmentationOutput
+from ._hooks import GpuSideHooks
 from .segmentation_segformer import SegmentationSegformer
 from .segmentation_unetplus import _Base, _strip_model_prefix
 
 
-class SegmentationDOFA(_Base):
+class SegmentationDOFA(GpuSideHooks, _Base):
     def __init__(self, encoder: str, *, pretrained: bool, image_size: tuple[int, int], num_classes: int,
                  max_samples: int, loss: Callable, optimizer: Callable = torch.optim.Adam,
                  scheduler: Callable | None = None, scheduler_config: dict[str, Any] | None = None,
@@ -67,3 +68,10 @@ class SegmentationDOFA(_Base):
         self.log("val_loss", loss, batch_size=bs, prog_bar=True, logger=True, on_step=False, on_epoch=True,
                  sync_dist=True, rank_zero_only=True)
         return self._predict(outputs.out)
+
+    def test_step(self, batch: dict[str, Any], batch_idx: int) -> None:  # noqa: ARG002
+        outputs, loss, bs = self._loss(batch)
+        metrics: dict[str, Any] = {"test_loss": loss}
+        _, iou = self._predict_and_score(outputs.out, batch["mask"].squeeze(1).long())
+        metrics.update(iou)
+        self.log_dict(metrics, batch_size=bs, prog_bar=False, logger=True, on_step=False, rank_zero_only=True)

@@ -12,10 +12,11 @@ from torch import Tensor
 
 from .. import ops
 from ..models.segformer import SegFormer
+from ._hooks import GpuSideHooks
 from .segmentation_unetplus import _Base, _strip_model_prefix
 
 
-class SegmentationSegformer(_Base):
+class SegmentationSegformer(GpuSideHooks, _Base):
     def __init__(self, encoder: str, *, image_size: tuple[int, int], in_channels: int, num_classes: int,
                  max_samples: int, loss: Callable, optimizer: Callable = torch.optim.Adam,
                  scheduler: Callable | None = None, scheduler_config: dict[str, Any] | None = None,
@@ -74,3 +75,12 @@ class SegmentationSegformer(_Base):
         self.log("val_loss", self.loss(y_hat, y), batch_size=x.shape[0], prog_bar=True, logger=True,
                  on_step=False, on_epoch=True, sync_dist=True, rank_zero_only=True)
         return self._predict(y_hat)
+
+    def test_step(self, batch: dict[str, Any], batch_idx: int) -> None:  # noqa: ARG002
+        x, y = batch["image"], batch["mask"].squeeze(1).long()
+        y_hat = self(x)
+        metrics: dict[str, Any] = {"test_loss": self.loss(y_hat, y)}
+        _, iou = self._predict_and_score(y_hat, y)  # MeanIoU per class on the argmax kernel (:283-287)
+        metrics.update(iou)
+        self.log_dict(metrics, batch_size=x.shape[0], prog_bar=False, logger=True, on_step=False,
+                      rank_zero_only=True)

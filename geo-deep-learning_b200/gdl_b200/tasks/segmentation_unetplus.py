@@ -3,8 +3,8 @@ as geo_deep_learning/tasks_with_models/segmentation_unetplus.py:34-248, so the Y
 `class_path: tasks_with_models.segmentation_unetplus.SegmentationUnetPlus` can be pointed here.
 
 What changes underneath: `configure_model` builds gdl_b200.models.unetpp.UnetPlusPlus instead of
-smp.UnetPlusPlus (identical state_dict), eval post-processing uses the argmax kernel, and the CPU
-kornia augmentation hook is left to the caller (out of the hot-path scope).
+smp.UnetPlusPlus (identical state_dict), eval post-processing and the MeanIoU counts use the argmax kernel, and the
+kornia augmentation of `on_before_batch_transfer` runs on the device in `on_after_batch_transfer` (tasks/_hooks.py).
 Lightning is optional at import time: without it the class derives from a minimal stand-in that
 offers `log`/`log_dict`/`save_hyperparameters` no-ops so the step methods stay callable.
 """
@@ -43,7 +43,10 @@ def _strip_model_prefix(sd: dict[str, Tensor]) -> dict[str, Tensor]:
     return {(k[len("model."):] if k.startswith("model.") else k): v for k, v in sd.items()}
 
 
-class SegmentationUnetPlus(_Base):
+from ._hooks import GpuSideHooks  # noqa: E402  (after _Base: the stand-in must exist first)
+
+
+class SegmentationUnetPlus(GpuSideHooks, _Base):
     def __init__(self, encoder: str, image_size: tuple[int, int], in_channels: int, num_classes: int,
                  max_samples: int, loss: Callable, optimizer: Callable = torch.optim.Adam,
                  scheduler: Callable | None = None, scheduler_config: dict[str, Any] | None = None,
@@ -117,13 +120,8 @@ class SegmentationUnetPlus(_Base):
         x, y = batch["image"], batch["mask"]
         y_hat = self(x)
         metrics: dict[str, Any] = {"test_loss": self.loss(y_hat, y)}
-        pred = self._predict(y_hat)
-        target = (y[:, 0] if y.dim() == 4 else y).long()
-        k = len(self.labels)
-        conf = torch.bincount((target.reshape(-1) * k + pred.reshape(-1)), minlength=k * k).view(k, k).float()
-        inter = conf.diag()
-        union = conf.sum(0) + conf.sum(1) - inter
-        for i, name in enumerate(self.labels):
-            metrics[f"meaniou_{name}"] = inter[i] / union[i].clamp_min(1)
+        target = y[:, 0] if y.dim() == 4 else y  # the reference squeezes only for the metric (:290)
+        _, iou = self._predict_and_score(y_hat, target if target.dtype in (torch.int64, torch.uint8) else target.long())
+        metrics.update(iou)
         self.log_dict(metrics, batch_size=x.shape[0], prog_bar=False, logger=True, on_step=False,
                       rank_zero_only=True)

@@ -61,19 +61,26 @@ class FusedTrainer:
         self.cuda_graph = cuda_graph
         self._graph = None
         self._static = None
+        self._static_aug = None
         self.launches_per_step = 0
 
     @torch.no_grad()
-    def forward_backward(self, image_u8: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
+    def forward_backward(self, image_u8: torch.Tensor, target: torch.Tensor,
+                         aug_params: torch.Tensor | None = None) -> torch.Tensor:
         """image_u8: (N,H,W,C) uint8 on the device; target: (N,H,W) int64/uint8. Returns the loss (device scalar)
-        with d(loss)/d(params) left in the flat gradient buffer."""
+        with d(loss)/d(params) left in the flat gradient buffer.  aug_params: optional int32 (N,6) device table of
+        gdl_b200.augment.BatchAugmenter.sample(): the augmentation is then applied by the normalisation pass itself."""
         model = self.model
         self.gflat.zero_()
         eng = Engine(model.compute_dtype, training=True, wcache=model._wcache, grad_dst=self.grad_dst,
                      sync_bn_group=self.group if self.sync_bn else None, acc_dtype=self.acc_dtype)
         c = image_u8.shape[3]
-        x = ops.normalize_to_nhwc(image_u8, False, model.compute_dtype, (c + 7) // 8 * 8, self.mean, self.std,
-                                  self.image_max)
+        if aug_params is not None:
+            x, target = ops.augment_normalize(image_u8, False, target, aug_params, model.compute_dtype,
+                                              (c + 7) // 8 * 8, self.mean, self.std, self.image_max)
+        else:
+            x = ops.normalize_to_nhwc(image_u8, False, model.compute_dtype, (c + 7) // 8 * 8, self.mean, self.std,
+                                      self.image_max)
         if hasattr(model, "fused_train"):
             # models with several logit maps / a frozen front half (DOFA + UperNet) own the whole step
             loss = model.fused_train(eng, x, c, target, self.loss)
@@ -117,30 +124,37 @@ class FusedTrainer:
                           self.weight_decay, self.adam_state, gs)
         self.model._wcache.clear()  # parameters changed behind torch's version counters
 
-    def _eager_step(self, image_u8: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
-        loss = self.forward_backward(image_u8, target)
+    def _eager_step(self, image_u8: torch.Tensor, target: torch.Tensor,
+                    aug_params: torch.Tensor | None = None) -> torch.Tensor:
+        loss = self.forward_backward(image_u8, target, aug_params)
         self.optimizer_step()
         return loss
 
     @torch.no_grad()
-    def step(self, image_u8: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
+    def step(self, image_u8: torch.Tensor, target: torch.Tensor, aug_params: torch.Tensor | None = None) -> torch.Tensor:
         """One training step.  With cuda_graph=True the first call runs eagerly (lazy CUDA init, function
-        attributes), the second captures, later calls copy the inputs into the static buffers and replay."""
+        attributes), the second captures, later calls copy the inputs into the static buffers and replay.
+        aug_params (optional, int32 (N,6) on the device) turns the normalisation pass into augment + normalise; a
+        trainer that captured its graph with / without it re-captures when that changes."""
         if not self.cuda_graph:
             n0 = ops.launch_count()
-            loss = self._eager_step(image_u8, target)
+            loss = self._eager_step(image_u8, target, aug_params)
             self.launches_per_step = ops.launch_count() - n0
             return loss
-        key = (tuple(image_u8.shape), image_u8.dtype, tuple(target.shape), target.dtype)
+        key = (tuple(image_u8.shape), image_u8.dtype, tuple(target.shape), target.dtype, aug_params is not None)
         if self._static is None or self._static[0] != key:
             self._static = (key, torch.empty_like(image_u8), torch.empty_like(target), 0)
+            self._static_aug = torch.empty_like(aug_params) if aug_params is not None else None
             self._graph = None
         _, s_img, s_tgt, seen = self._static
         s_img.copy_(image_u8, non_blocking=True)
         s_tgt.copy_(target, non_blocking=True)
+        s_aug = self._static_aug
+        if s_aug is not None:
+            s_aug.copy_(aug_params, non_blocking=True)
         if seen == 0:
             self._static = (key, s_img, s_tgt, 1)
-            return self._eager_step(s_img, s_tgt).clone()
+            return self._eager_step(s_img, s_tgt, s_aug).clone()
         if self._graph is None:
             self.last_engine = None
             torch.cuda.synchronize()
@@ -151,7 +165,7 @@ class FusedTrainer:
                 # captures the same sequence.  Ranks must agree on capture vs eager, so a failure here is fatal.
                 dist.barrier(group=self.group)
             with torch.cuda.graph(graph):
-                self._graph_loss = self._eager_step(s_img, s_tgt)
+                self._graph_loss = self._eager_step(s_img, s_tgt, s_aug)
             self.launches_per_step = ops.launch_count() - n0
             self.last_engine = None  # activations live in the graph's private pool
             self._graph = graph

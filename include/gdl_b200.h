@@ -171,6 +171,22 @@ int gdl_normalize_to_nhwc(const void* x, int in_kind, void* y, int out_dtype, lo
                           long long W, int C, int ld, const float* mean, const float* stdv, float image_max,
                           void* stream);
 
+/* GPU-side batch augmentation fused with the patch normalisation.  Replaces the kornia pipeline every task builds in
+ * `_apply_aug` and runs on the HOST in `on_before_batch_transfer` (segmentation_segformer.py:95-125,206-216;
+ * segmentation_unetplus.py:92-122; segmentation_dofa.py:91-121): RandomHorizontalFlip / RandomVerticalFlip /
+ * RandomRotation90(times 1..3) / RandomResizedCrop (image: bilinear, align_corners=False; mask: nearest), one of them
+ * per batch (`random_apply=1`), each applied per sample with its own p.  The random draws stay on the host
+ * (gdl_b200/augment.py); the kernel applies them:  params = int32 [N][6] = {op, k, y0, x0, ch, cw} per sample,
+ *   op 0 identity | 1 horizontal flip | 2 vertical flip | 3 torch.rot90 by k quarter turns (H == W) |
+ *   4 crop rows y0..y0+ch-1, columns x0..x0+cw-1, resized back to (H, W) with ATen's interpolate index arithmetic.
+ * x: in_kind as gdl_normalize_to_nhwc (0 uint8 NHWC, 1 f32 NHWC, 2 f32 NCHW, 3 uint8 NCHW); y: out_dtype GDL_BF16/GDL_F16 ->
+ * 16-bit NHWC with pixel stride ld (channels >= C zero, same arithmetic as gdl_normalize_to_nhwc: op 0 is bit-identical
+ * to it); GDL_F32 -> f32 NCHW (ld unused).  mask / mask_out: (N,H,W) int64 (mask_kind 0) or uint8 (1), both or neither.
+ * Not in place. */
+int gdl_augment_normalize(const void* x, int in_kind, const void* mask, int mask_kind, const int* params, void* y,
+                          int out_dtype, void* mask_out, long long N, long long H, long long W, int C, int ld,
+                          const float* mean, const float* stdv, float image_max, void* stream);
+
 /* im2col / col2im for strided convs and the 3/4/6-band stem (torchvision ResNet conv1 7x7/2, the
  * 3x3/2 and 1x1/2 convs of layer2-4): col[(n,ho,wo)][(r,s,c)] zero padded to Kpad columns; the conv
  * itself is then gdl_conv2d_nhwc_fwd with R=S=1.  col2im is the gather-form adjoint (C % 8 == 0). */
@@ -242,6 +258,16 @@ int gdl_seg_loss_bwd(const float* logits, int ld, const void* target, int target
  * segmentation_segformer.py:268-271, segmentation_unetplus.py test/validation steps. */
 int gdl_argmax_classes(const float* logits, int ld, long long M, int K, float threshold, long long* out,
                        void* stream);
+
+/* The same post-processing fused with the confusion counts of the evaluation metric: torchmetrics
+ * `MeanIoU(num_classes, per_class=True, input_format="index")` as used by the three tasks' test_step
+ * (segmentation_segformer.py:78-92,283-296) reduces per-SAMPLE intersection / union counts, so the counts are kept per
+ * sample: conf[n][t][p] (int64, Kc x Kc with Kc = max(K, 2)) += #pixels of sample n with target t predicted p; targets
+ * equal to ignore_index (when has_ignore) or outside [0, Kc) are skipped.  logits: fp32 [N*HW][ld]; target_kind 0 = int64,
+ * 1 = uint8 (as gdl_seg_loss_fwd); classes (int64 [N*HW]) and (target, conf) are each optional.  conf must be zeroed by the caller. */
+int gdl_argmax_confusion(const float* logits, int ld, long long N, long long HW, int K, float threshold,
+                         const void* target, int target_kind, long long ignore_index, int has_ignore,
+                         long long* classes, long long* conf, void* stream);
 
 /* torch.optim.Adam step on flat fp32 buffers; g is multiplied by grad_scale[0] first (may be NULL).
  * gdl_grad_clip_coef: scale[0] = min(1, max_norm / (||g||_2 + 1e-6))  (clip_grad_norm_). */

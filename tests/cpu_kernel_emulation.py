@@ -162,6 +162,74 @@ def normalize_to_nhwc(x, chw, out_dtype, ld, mean=None, std=None, image_max=0.0)
     return out
 
 
+def augment_normalize(x, chw, mask, params, out_dtype, ld=0, mean=None, std=None, image_max=0.0):
+    """Line-by-line torch transcription of augment_kernel / aug_taps (csrc/augment_metrics.cu): the same index and
+    weight arithmetic in fp32, vectorised over pixels — so the CPU suite checks the kernel's formulas against torch's
+    flip / rot90 / F.interpolate (oracle/augment.py)."""
+    f32 = torch.float32
+    xin = x if chw else x.permute(0, 3, 1, 2)
+    n, c, h, w = xin.shape
+    xin = xin.to(f32)
+    oy = torch.arange(h).view(1, h, 1).expand(n, h, w)
+    ox = torch.arange(w).view(1, 1, w).expand(n, h, w)
+    q = params.long().cpu()
+    op = q[:, 0].view(n, 1, 1)
+    k = (q[:, 1] & 3).view(n, 1, 1)
+    sy, sx = oy.clone(), ox.clone()
+    sx = torch.where(op == 1, w - 1 - ox, sx)
+    sy = torch.where(op == 2, h - 1 - oy, sy)
+    if h == w:
+        r = op == 3
+        sy = torch.where(r & (k == 1), ox, sy)
+        sx = torch.where(r & (k == 1), w - 1 - oy, sx)
+        sy = torch.where(r & (k == 2), h - 1 - oy, sy)
+        sx = torch.where(r & (k == 2), w - 1 - ox, sx)
+        sy = torch.where(r & (k == 3), h - 1 - ox, sy)
+        sx = torch.where(r & (k == 3), oy, sx)
+    crop = op == 4
+    cy0 = q[:, 2].clamp(0, h - 1).view(n, 1, 1)
+    cx0 = q[:, 3].clamp(0, w - 1).view(n, 1, 1)
+    ch = torch.minimum(q[:, 4].clamp(min=1).view(n, 1, 1), h - cy0)
+    cw = torch.minimum(q[:, 5].clamp(min=1).view(n, 1, 1), w - cx0)
+    scy = ch.to(f32) / torch.tensor(float(h), dtype=f32)
+    scx = cw.to(f32) / torch.tensor(float(w), dtype=f32)
+    fy = (scy * (oy.to(f32) + 0.5) - 0.5).clamp(min=0)
+    fx = (scx * (ox.to(f32) + 0.5) - 0.5).clamp(min=0)
+    iy = torch.minimum(fy.floor().long(), ch - 1)
+    ix = torch.minimum(fx.floor().long(), cw - 1)
+    ly = (fy - iy.to(f32)).clamp(0, 1)
+    lx = (fx - ix.to(f32)).clamp(0, 1)
+    y0 = torch.where(crop, cy0 + iy, sy)
+    y1 = torch.where(crop, cy0 + torch.minimum(iy + 1, ch - 1), sy)
+    x0 = torch.where(crop, cx0 + ix, sx)
+    x1 = torch.where(crop, cx0 + torch.minimum(ix + 1, cw - 1), sx)
+    my = torch.where(crop, cy0 + torch.minimum((oy.to(f32) * scy).floor().long(), ch - 1), sy)
+    mx = torch.where(crop, cx0 + torch.minimum((ox.to(f32) * scx).floor().long(), cw - 1), sx)
+    ly = torch.where(crop, ly, torch.zeros_like(ly))
+    lx = torch.where(crop, lx, torch.zeros_like(lx))
+    flat = xin.reshape(n, c, h * w)
+
+    def tap(yy, xx):
+        return torch.gather(flat, 2, (yy * w + xx).view(n, 1, h * w).expand(n, c, h * w)).view(n, c, h, w)
+    a, b, c2, d = tap(y0, x0), tap(y0, x1), tap(y1, x0), tap(y1, x1)
+    lyb, lxb = ly.unsqueeze(1), lx.unsqueeze(1)
+    interp = (1 - lyb) * ((1 - lxb) * a + lxb * b) + lyb * ((1 - lxb) * c2 + lxb * d)
+    r_ = torch.where(crop.unsqueeze(1), interp, a)
+    if image_max > 0:
+        r_ = r_ / torch.tensor(image_max, dtype=f32)
+    if mean is not None:
+        r_ = (r_ - mean.to(f32).view(1, c, 1, 1)) / std.to(f32).view(1, c, 1, 1)
+    mask_out = None
+    if mask is not None:
+        mask_out = torch.gather(mask.reshape(n, h * w), 1, (my * w + mx).view(n, h * w)).view(n, h, w)
+    if out_dtype == torch.float32:
+        return r_.contiguous(), mask_out
+    ld = ld or (c + 7) // 8 * 8
+    out = torch.zeros(n, h, w, ld, dtype=out_dtype)
+    out[..., :c] = r_.permute(0, 2, 3, 1).to(out_dtype)
+    return out, mask_out
+
+
 def im2col(x, c, r, s, stride, pad, kpad):
     n, h, w, _ = x.shape
     unf = F.unfold(_nchw(x[..., :c].to(_WORK)), (r, s), padding=pad, stride=stride)
@@ -328,6 +396,23 @@ def argmax_classes(logits, threshold=0.5):
     return logits.argmax(3) if logits.shape[3] > 1 else (logits[..., 0].sigmoid() > threshold).long()
 
 
+def argmax_confusion(logits, target, threshold=0.5, ignore_index=None, want_classes=True):
+    n, h, w, k = logits.shape
+    kc = 2 if k == 1 else k
+    cls = argmax_classes(logits, threshold)
+    conf = None
+    if target is not None:
+        t = target.long()
+        keep = (t >= 0) & (t < kc)
+        if ignore_index is not None:
+            keep &= t != ignore_index
+        conf = torch.zeros(n, kc, kc, dtype=torch.int64)
+        for i in range(n):
+            idx = (t[i][keep[i]] * kc + cls[i][keep[i]]).reshape(-1)
+            conf[i] = torch.bincount(idx, minlength=kc * kc).view(kc, kc)
+    return (cls if want_classes else None), conf
+
+
 def adam_step(p, g, m, v, lr, beta1, beta2, eps, weight_decay, step, grad_scale=None):
     gi = g * (grad_scale[0] if grad_scale is not None else 1.0)
     if weight_decay:
@@ -458,6 +543,10 @@ def vit_extract_feature(tokens, dtype):
 
 def cast_f32(x, dtype):
     return x.to(dtype)
+
+
+def require_cuda(t, what):
+    return None  # the emulation runs the host logic on CPU tensors
 
 
 def install(monkeypatch):

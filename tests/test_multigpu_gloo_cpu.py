@@ -7,6 +7,7 @@ import socket
 import sys
 from pathlib import Path
 
+import pytest
 import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
@@ -27,11 +28,14 @@ def _data(k=4):
     return raw, t
 
 
-def _make_trainer(sync_bn):
+def _make_trainer(sync_bn, monkeypatch=None):
     import cpu_kernel_emulation as emu
     from gdl_b200.models.unetpp import UnetPlusPlus
     from gdl_b200.trainer import FusedTrainer
-    emu.install_global()
+    if monkeypatch is None:
+        emu.install_global()  # spawned worker: the process ends with the test
+    else:
+        emu.install(monkeypatch)  # pytest's own process: undone at teardown
     emu.set_work_dtype(torch.float64)
     torch.manual_seed(0)
     model = UnetPlusPlus("resnet18", in_channels=3, classes=4, compute_dtype=torch.float64).double().train()
@@ -54,7 +58,14 @@ def _worker(rank, world, port, out):
     dist.destroy_process_group()
 
 
-def test_two_ranks_equal_one_process_on_the_union(tmp_path):
+@pytest.fixture
+def f64_work_dtype():
+    import cpu_kernel_emulation as emu
+    yield
+    emu.set_work_dtype(torch.float32)
+
+
+def test_two_ranks_equal_one_process_on_the_union(tmp_path, monkeypatch, f64_work_dtype):
     port = _free_port()
     mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
     r0, r1 = torch.load(tmp_path / "rank0.pt"), torch.load(tmp_path / "rank1.pt")
@@ -62,7 +73,7 @@ def test_two_ranks_equal_one_process_on_the_union(tmp_path):
     assert torch.equal(r0["rm"], r1["rm"])
     # single process, all 4 tiles
     sys.path.insert(0, str(ROOT / "tests"))
-    tr = _make_trainer(sync_bn=False)
+    tr = _make_trainer(sync_bn=False, monkeypatch=monkeypatch)
     raw, t = _data()
     losses = [float(tr.step(raw, t)) for _ in range(2)]
     assert torch.allclose(tr.flat, r0["flat"], atol=1e-9, rtol=1e-7)

@@ -1,0 +1,113 @@
+"""CPU: the Lightning-facing task mirrors (gdl_b200/tasks) with the kernels emulated — constructor keywords, the
+training / validation / test step contracts of the reference tasks
+(geo_deep_learning/tasks_with_models/segmentation_{unetplus,segformer,dofa}.py), the device-side augmentation hook
+and the MeanIoU of test_step against the oracle restatements."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+import cpu_kernel_emulation as emu
+from oracle import augment as oaug
+from oracle import metrics as omet
+
+
+def _batch(n, c, hw, k, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    return {"image": torch.randn(n, c, hw, hw, generator=g),
+            "mask": torch.randint(0, k, (n, 1, hw, hw), generator=g)}
+
+
+def _check_iou(logged, logits, target, labels):
+    pred = logits.argmax(1)
+    s, c = omet.mean_iou_update(pred, target, len(labels))
+    want = omet.mean_iou_compute(s, c)
+    for i, name in enumerate(labels):
+        assert abs(float(logged[f"meaniou_{name}"]) - float(want[i])) < 1e-6
+
+
+def test_unetplus_task_steps(monkeypatch):
+    from gdl_b200.tasks.segmentation_unetplus import SegmentationUnetPlus
+    emu.install(monkeypatch)
+    torch.manual_seed(0)
+    task = SegmentationUnetPlus("resnet18", (64, 64), 3, 4, max_samples=2, loss=torch.nn.CrossEntropyLoss(),
+                                class_labels=["bg", "a", "b", "c"], compute_dtype=torch.float32)
+    task.configure_model()
+    task.configure_model()  # idempotent, as Lightning may call it twice
+    assert sorted(task.state_dict())[0].startswith("model.")
+    batch = _batch(2, 3, 64, 4)
+    # the reference's UNet++ task hands the mask to the loss as is (:229-234): CrossEntropyLoss wants (N,H,W) int64
+    batch["mask"] = batch["mask"][:, 0]
+    task.train()
+    loss = task.training_step(batch, 0)
+    loss.backward()
+    assert torch.isfinite(loss) and task.logged["train_loss"] is loss
+    assert all(p.grad is not None for p in task.model.parameters() if p.requires_grad)
+    task.eval()
+    with torch.no_grad():
+        pred = task.validation_step(batch, 0)
+        logits = task(batch["image"])
+        assert pred.dtype == torch.int64 and torch.equal(pred, logits.argmax(1))
+        task.test_step(batch, 0)
+    assert abs(float(task.logged["test_loss"]) - float(F.cross_entropy(logits, batch["mask"]))) < 1e-6
+    _check_iou(task.logged, logits, batch["mask"], task.labels)
+    opt = task.configure_optimizers()
+    assert isinstance(opt[0], torch.optim.Adam)
+
+
+def test_segformer_task_steps_and_device_side_augmentation(monkeypatch):
+    from gdl_b200.tasks.segmentation_segformer import SegmentationSegformer
+    emu.install(monkeypatch)
+    torch.manual_seed(0)
+    task = SegmentationSegformer("mit_b0", image_size=(64, 64), in_channels=4, num_classes=3, max_samples=2,
+                                 loss=torch.nn.CrossEntropyLoss(), compute_dtype=torch.float32)
+    task.configure_model()
+    batch = _batch(3, 4, 64, 3, seed=2)
+    # eval: the hook leaves the batch alone (the reference only augments when trainer.training)
+    task.eval()
+    same = task.on_after_batch_transfer(dict(batch), 0)
+    assert same["image"] is batch["image"] and same["mask"] is batch["mask"]
+    # train: one drawn operation applied per sample; image and mask move together, shapes / dtypes are kept
+    task.train()
+    torch.manual_seed(5)
+    out = task.on_after_batch_transfer(dict(batch), 0)
+    assert out["image"].shape == batch["image"].shape and out["mask"].shape == batch["mask"].shape
+    assert out["mask"].dtype == torch.int64 and out["image"].dtype == torch.float32
+    torch.manual_seed(5)
+    params = task._augmenter.__class__((64, 64)).sample(3)  # the same draws from the same global RNG state
+    want_i, want_m = oaug.apply_params(batch["image"], batch["mask"][:, 0], params)
+    assert torch.equal(out["mask"][:, 0], want_m) and (out["image"] - want_i).abs().max() < 1e-5
+    loss = task.training_step(out, 0)
+    loss.backward()
+    assert torch.isfinite(loss)
+    task.eval()
+    with torch.no_grad():
+        task.test_step(batch, 0)
+        logits = task(batch["image"])
+    _check_iou(task.logged, logits, batch["mask"][:, 0], task.labels)
+    task.gpu_augment = False
+    task.train()
+    assert task.on_after_batch_transfer(dict(batch), 0)["image"] is batch["image"]
+
+
+def test_dofa_task_steps(monkeypatch):
+    from gdl_b200.tasks.segmentation_dofa import SegmentationDOFA
+    emu.install(monkeypatch)
+    torch.manual_seed(0)
+    task = SegmentationDOFA("dofa_base", pretrained=False, image_size=(56, 56), num_classes=3, max_samples=2,
+                            loss=torch.nn.CrossEntropyLoss(), freeze_layers=["encoder"], compute_dtype=torch.float32)
+    task.configure_model()
+    batch = _batch(2, 3, 56, 3, seed=4)
+    batch["wavelengths"] = torch.tensor([0.665, 0.56, 0.49])
+    task.train()
+    loss = task.training_step(batch, 0)
+    loss.backward()
+    assert torch.isfinite(loss)
+    assert all(p.grad is None for n, p in task.model.named_parameters() if n.startswith("encoder."))
+    task.eval()
+    with torch.no_grad():
+        out = task(batch["image"], batch["wavelengths"])
+        task.test_step(batch, 0)
+    y = batch["mask"][:, 0]
+    want = F.cross_entropy(out.out, y) + 0.4 * F.cross_entropy(out.aux, y)
+    assert abs(float(task.logged["test_loss"]) - float(want)) < 1e-5
+    _check_iou(task.logged, out.out, y, task.labels)

@@ -1,0 +1,167 @@
+"""GPU: `gdl_augment_normalize` and `gdl_argmax_confusion` (csrc/augment_metrics.cu) through the C ABI against the
+oracle (torch flip / rot90 / F.interpolate on the normalised float batch; bincount confusion; torchmetrics-1.8 MeanIoU
+restatement).  Integer outputs (masks, classes, counts) are bit-exact; the identity operation is bit-identical to
+gdl_normalize_to_nhwc; resized crops agree to one rounding of the 16-bit output.
+(The file sorts last on purpose: it was written after the round's GPU budget was spent and has not run on a B200 yet.)"""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _inputs(n, c, h, w, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    raw = torch.randint(0, 256, (n, h, w, c), generator=g, dtype=torch.uint8)
+    mask = torch.randint(0, 5, (n, h, w), generator=g, dtype=torch.uint8)
+    return raw, mask
+
+
+def _random_params(n, h, w, seed):
+    from oracle import augment as oaug
+    g = torch.Generator().manual_seed(seed)
+    p = torch.zeros(n, 6, dtype=torch.int32)
+    for i in range(n):
+        op = i % 5
+        p[i, 0] = op
+        if op == oaug.ROT90:
+            p[i, 1] = 1 + (i // 5) % 3
+        if op == oaug.CROP:
+            ch = int(torch.randint(1, h + 1, (1,), generator=g))
+            cw = int(torch.randint(1, w + 1, (1,), generator=g))
+            p[i, 2] = int(torch.randint(0, h - ch + 1, (1,), generator=g))
+            p[i, 3] = int(torch.randint(0, w - cw + 1, (1,), generator=g))
+            p[i, 4], p[i, 5] = ch, cw
+    return p
+
+
+@pytest.mark.parametrize("c,dtype", [(3, torch.bfloat16), (4, torch.bfloat16), (6, torch.float16), (12, torch.bfloat16)])
+def test_augment_normalize_matches_oracle(cuda, c, dtype):
+    from gdl_b200 import ops
+    from oracle import augment as oaug
+    from oracle import tensors as ot
+    n, h, w = 20, 96, 96
+    raw, mask = _inputs(n, c, h, w, seed=c)
+    mean = torch.linspace(0.3, 0.6, c)
+    std = torch.linspace(0.15, 0.3, c)
+    params = _random_params(n, h, w, seed=1)
+    x = ot.standardization(ot.normalization(raw.permute(0, 3, 1, 2).float()), mean.view(-1, 1), std.view(-1, 1))
+    want_i, want_m = oaug.apply_params(x, mask, params)
+    ld = (c + 7) // 8 * 8
+    got, got_m = ops.augment_normalize(raw.cuda(), False, mask.cuda(), params.cuda(), dtype, ld, mean.cuda(), std.cuda(), 255.0)
+    assert got.shape == (n, h, w, ld) and got.dtype == dtype
+    assert torch.equal(got_m.cpu(), want_m)                          # masks: bit exact (permutations and nearest)
+    assert not got[..., c:].any()                                    # channel padding is zero
+    want16 = want_i.permute(0, 2, 3, 1).to(dtype)
+    exact = params[:, 0] != oaug.CROP
+    assert torch.equal(got[..., :c].cpu()[exact], want16[exact])     # flips / rotations: bit exact
+    # resized crops: the kernel interpolates raw values then normalises, the oracle normalises then interpolates — fp32
+    # rounding apart, so at most one unit in the last place of the 16-bit result
+    ulp = 2.0 ** -7 if dtype == torch.bfloat16 else 2.0 ** -10
+    d = (got[..., :c].cpu().float() - want_i.permute(0, 2, 3, 1)).abs()
+    tol = ulp * want_i.permute(0, 2, 3, 1).abs().clamp_min(1.0)
+    assert (d <= tol).all(), float((d / tol).max())
+    # the identity rows are bit-identical to the plain normalise kernel
+    plain = ops.normalize_to_nhwc(raw.cuda(), False, dtype, ld, mean.cuda(), std.cuda(), 255.0)
+    ident = params[:, 0] == oaug.IDENTITY
+    assert torch.equal(got.cpu()[ident], plain.cpu()[ident])
+    # int64 masks and the f32 NCHW route of the Lightning hook (float NCHW in, float NCHW out, no normalisation)
+    got_f, got_m64 = ops.augment_normalize(x.cuda().contiguous(), True, mask.long().cuda(), params.cuda(), torch.float32)
+    assert got_m64.dtype == torch.int64 and torch.equal(got_m64.cpu(), want_m.long())
+    assert torch.equal(got_f.cpu()[exact], want_i[exact])
+    assert (got_f.cpu() - want_i).abs().max() < 1e-5
+
+
+def test_augment_full_tile_batch_and_errors(cuda):
+    from gdl_b200 import ops
+    from gdl_b200.augment import BatchAugmenter
+    from oracle import augment as oaug
+    n, c, t = 8, 4, 512
+    raw, mask = _inputs(n, c, t, t, seed=9)
+    aug = BatchAugmenter((t, t), generator=torch.Generator().manual_seed(3))
+    for _ in range(6):  # a few batches so every operation is drawn at full tile size
+        params = aug.sample(n)
+        got, got_m = aug(raw.cuda(), mask.cuda(), chw=False, out_dtype=torch.bfloat16, image_max=255.0, params=params)
+        want_i, want_m = oaug.apply_params(raw.permute(0, 3, 1, 2).float() / 255.0, mask, params)
+        assert torch.equal(got_m.cpu(), want_m)
+        assert (got[..., :c].cpu().float() - want_i.permute(0, 2, 3, 1)).abs().max() <= 2.0 ** -8
+    with pytest.raises(ValueError):
+        ops.augment_normalize(raw.cuda(), False, mask.cuda(), torch.zeros(n, 5, dtype=torch.int32, device="cuda"),
+                              torch.bfloat16)
+    with pytest.raises(ValueError):
+        ops.augment_normalize(raw.cuda(), False, mask[:4].cuda(), torch.zeros(n, 6, dtype=torch.int32, device="cuda"),
+                              torch.bfloat16)
+
+
+def test_trainer_step_with_augmentation_equals_step_on_augmented_batch(cuda):
+    """FusedTrainer.forward_backward(raw, mask, aug_params) == forward_backward on the batch augmented beforehand
+    (exact operations only, so both runs see bit-identical inputs)."""
+    from gdl_b200 import ops
+    from gdl_b200.models.unetpp import UnetPlusPlus
+    from gdl_b200.trainer import FusedTrainer
+    from oracle import augment as oaug
+    torch.manual_seed(0)
+    n, c, t, k = 4, 4, 64, 5
+    raw, mask = _inputs(n, c, t, t, seed=2)
+    params = torch.tensor([[1, 0, 0, 0, 0, 0], [2, 0, 0, 0, 0, 0], [3, 1, 0, 0, 0, 0], [3, 3, 0, 0, 0, 0]], dtype=torch.int32)
+    pre_i, pre_m = oaug.apply_params(raw.permute(0, 3, 1, 2), mask, params)
+    pre_i = pre_i.permute(0, 2, 3, 1).contiguous()
+    losses = []
+    for use_aug in (True, False):
+        torch.manual_seed(1)
+        model = UnetPlusPlus("resnet18", in_channels=c, classes=k).cuda().train()
+        tr = FusedTrainer(model, ops.LossSpec(1.0, 0.0, ignore_index=-100), mean=[0.5] * c, std=[0.2] * c)
+        if use_aug:
+            losses.append(float(tr.forward_backward(raw.cuda(), mask.cuda(), params.cuda())))
+        else:
+            losses.append(float(tr.forward_backward(pre_i.cuda(), pre_m.cuda())))
+    assert abs(losses[0] - losses[1]) < 2e-3 * abs(losses[1])  # same inputs; fp32 atomics order differs between runs
+
+
+@pytest.mark.parametrize("k,tdtype", [(1, torch.int64), (5, torch.uint8), (5, torch.int64), (19, torch.int64)])
+def test_argmax_confusion_bit_exact(cuda, k, tdtype):
+    from gdl_b200 import ops
+    from oracle import metrics as omet
+    n, h, w = 6, 160, 96
+    kc = 2 if k == 1 else k
+    g = torch.Generator().manual_seed(k)
+    ld = k + 3                                        # logits as a channel slice of a wider buffer
+    buf = torch.randn(n, h, w, ld, generator=g)
+    logits = buf[..., :k]
+    target = torch.randint(0, kc, (n, h, w), generator=g).to(tdtype)
+    want_cls = logits.argmax(3) if k > 1 else (logits[..., 0].sigmoid() > 0.5).long()
+    cls, conf = ops.argmax_confusion(buf.cuda()[..., :k], target.cuda())
+    assert torch.equal(cls.cpu(), want_cls)
+    assert torch.equal(cls.cpu(), ops.argmax_classes(buf.cuda()[..., :k]).cpu())
+    assert torch.equal(conf.cpu(), omet.confusion_per_sample(want_cls, target, kc))
+    # ignore_index and out-of-range targets are skipped
+    t2 = target.clone()
+    t2[:, :7] = 255 if tdtype == torch.uint8 else -100
+    _, conf2 = ops.argmax_confusion(buf.cuda()[..., :k], t2.cuda(), ignore_index=255 if tdtype == torch.uint8 else -100)
+    keep = torch.ones_like(target, dtype=torch.bool)
+    keep[:, :7] = False
+    want2 = torch.stack([torch.bincount((target[i][keep[i]].long() * kc + want_cls[i][keep[i]]), minlength=kc * kc).view(kc, kc)
+                         for i in range(n)])
+    assert torch.equal(conf2.cpu(), want2)
+    # classes only / counts only
+    c_only, none = ops.argmax_confusion(buf.cuda()[..., :k], None)
+    assert none is None and torch.equal(c_only.cpu(), want_cls)
+    none, f_only = ops.argmax_confusion(buf.cuda()[..., :k], target.cuda(), want_classes=False)
+    assert none is None and torch.equal(f_only, conf)
+
+
+def test_mean_iou_metric_on_device(cuda):
+    from gdl_b200.metrics import MeanIoU
+    from oracle import metrics as omet
+    k = 5
+    g = torch.Generator().manual_seed(0)
+    metric = MeanIoU(k)
+    s_tot, c_tot = torch.zeros(k, dtype=torch.float64), torch.zeros(k, dtype=torch.int64)
+    for _ in range(3):
+        logits = torch.randn(4, 128, 128, k, generator=g)
+        target = torch.randint(0, k, (4, 128, 128), generator=g)
+        metric.update(logits.cuda(), target.cuda())
+        s, c = omet.mean_iou_update(logits.argmax(3), target, k)
+        s_tot += s
+        c_tot += c
+    got = torch.stack(list(metric.compute().values())).cpu().double()
+    assert torch.allclose(got, omet.mean_iou_compute(s_tot, c_tot), atol=1e-6)
