@@ -19,11 +19,12 @@ class FusedTrainer:
     def __init__(self, model: torch.nn.Module, loss: LossSpec, *, lr: float = 1e-4, betas=(0.9, 0.999),
                  eps: float = 1e-8, weight_decay: float = 0.0, mean=None, std=None, image_max: float = 255.0,
                  clip_grad_norm: float | None = None, process_group=None, sync_bn: bool = False,
-                 acc_dtype: torch.dtype = torch.float32, cuda_graph: bool = False) -> None:
+                 acc_dtype: torch.dtype = torch.float32, cuda_graph: bool = False, input_chw: bool = False) -> None:
         self.model = model
         self.loss = loss
         self.lr, self.betas, self.eps, self.weight_decay = lr, betas, eps, weight_decay
         self.image_max = image_max
+        self.input_chw = input_chw  # tiles arrive (N,C,H,W) — the layout of the WebDataset shards — instead of (N,H,W,C)
         self.clip = clip_grad_norm
         self.group = process_group
         self.world = dist.get_world_size(process_group) if (process_group is not None or dist.is_initialized()) else 1
@@ -67,19 +68,20 @@ class FusedTrainer:
     @torch.no_grad()
     def forward_backward(self, image_u8: torch.Tensor, target: torch.Tensor,
                          aug_params: torch.Tensor | None = None) -> torch.Tensor:
-        """image_u8: (N,H,W,C) uint8 on the device; target: (N,H,W) int64/uint8. Returns the loss (device scalar)
+        """image_u8: (N,H,W,C) uint8 on the device ((N,C,H,W) with input_chw); target: (N,H,W) int64/uint8. Returns the loss (device scalar)
         with d(loss)/d(params) left in the flat gradient buffer.  aug_params: optional int32 (N,6) device table of
         gdl_b200.augment.BatchAugmenter.sample(): the augmentation is then applied by the normalisation pass itself."""
         model = self.model
         self.gflat.zero_()
         eng = Engine(model.compute_dtype, training=True, wcache=model._wcache, grad_dst=self.grad_dst,
                      sync_bn_group=self.group if self.sync_bn else None, acc_dtype=self.acc_dtype)
-        c = image_u8.shape[3]
+        chw = self.input_chw
+        c = image_u8.shape[1 if chw else 3]
         if aug_params is not None:
-            x, target = ops.augment_normalize(image_u8, False, target, aug_params, model.compute_dtype,
+            x, target = ops.augment_normalize(image_u8, chw, target, aug_params, model.compute_dtype,
                                               (c + 7) // 8 * 8, self.mean, self.std, self.image_max)
         else:
-            x = ops.normalize_to_nhwc(image_u8, False, model.compute_dtype, (c + 7) // 8 * 8, self.mean, self.std,
+            x = ops.normalize_to_nhwc(image_u8, chw, model.compute_dtype, (c + 7) // 8 * 8, self.mean, self.std,
                                       self.image_max)
         if hasattr(model, "fused_train"):
             # models with several logit maps / a frozen front half (DOFA + UperNet) own the whole step

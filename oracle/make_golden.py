@@ -5,6 +5,8 @@
 * tensors_golden.pt   — outputs of the REFERENCE's own geo_deep_learning/utils/tensors.py
                         (`normalization`, `standardization`) on seeded inputs: pins oracle/tensors.py
                         and the CUDA normalise kernel to the reference itself.
+* wds_golden.pt       — outputs of the REFERENCE's `ShardedDataset._process_sample` (datasets/wds_dataset.py) for seeded
+                        samples: pins oracle/wds.py and gdl_b200/wds_feeder.py to the reference itself (`--wds`).
 * unetpp_r18_golden.pt — seeded input / state_dict / logits / loss / selected gradients of
                         oracle/unetpp.py (resnet18, 3 bands, 5 classes, 64x64): a regression pin of
                         the oracle restatement (smp itself is not installable here, so its values
@@ -179,6 +181,51 @@ def dofa_golden() -> None:
     print("wrote dofa_golden.pt")
 
 
+def wds_golden() -> None:
+    """Outputs of the REFERENCE's own `ShardedDataset._process_sample` (datasets/wds_dataset.py:217-303) for seeded
+    samples in the dofa / clay / unified formats.  `webdataset` and `pytorch_lightning` (imported at the top of that
+    module, not installed here) are satisfied by empty stand-ins: `_process_sample` touches neither."""
+    import json
+    import tempfile
+    import types
+
+    import numpy as np
+    for name in ("webdataset", "pytorch_lightning", "pytorch_lightning.utilities"):
+        if name not in sys.modules:
+            sys.modules[name] = types.ModuleType(name)
+    sys.modules["pytorch_lightning.utilities"].rank_zero_only = lambda f: f
+    sys.modules["webdataset"].WebDataset = object  # only named in a return annotation (:393)
+    sys.modules["pytorch_lightning"].utilities = sys.modules["pytorch_lightning.utilities"]
+    sys.path.insert(0, str(REF))
+    from geo_deep_learning.datasets.wds_dataset import ShardedDataset
+
+    sensor = "worldview-3-ortho_test"
+    stats = {"statistics": {sensor: {"mean": [88.5, 97.25, 71.0, 120.75], "std": [41.0, 39.5, 37.25, 55.0],
+                                     "band_count": 4, "patch_count": 3, "dtype": "uint8"}}}
+    rng = np.random.default_rng(20261017)
+    samples = []
+    for i in range(3):
+        meta = {"metadata": {"datetime": ["2021-07-04T15:30:00Z", "2019-12-30T03:05:00+00:00", "not a date"][i],
+                             "coordinates_lat": [45.4215, -33.9, 0.0][i], "coordinates_lon": [-75.6972, 151.2, 180.0][i],
+                             "red_wavelength": 0.66, "green_wavelength": 0.545, "blue_wavelength": 0.48,
+                             "nir_wavelength": 0.8325}}
+        samples.append({"__key__": f"patch_{i:04d}",
+                        "image_patch.npy": rng.integers(0, 256, (4, 16, 16), dtype=np.uint8),
+                        "label_patch.npy": rng.integers(0, 5, (1, 16, 16), dtype=np.uint8),
+                        "metadata.json": meta})
+    out = {"sensor": sensor, "stats": stats, "samples": samples, "outputs": {}}
+    with tempfile.TemporaryDirectory() as td:
+        sp = Path(td) / "stats.json"
+        sp.write_text(json.dumps(stats))
+        for mt in ("dofa", "clay", "unified"):
+            ds = ShardedDataset(sensor, ["unused.tar"], 3, str(sp), model_type=mt, split="trn",
+                                wavelength_keys=None if mt != "dofa" else ["red_wavelength", "green_wavelength",
+                                                                           "blue_wavelength", "nir_wavelength"])
+            out["outputs"][mt] = [ds._process_sample(dict(s)) for s in samples]
+    torch.save(out, OUT / "wds_golden.pt")
+    print("wrote wds_golden.pt")
+
+
 if __name__ == "__main__":
     OUT.mkdir(parents=True, exist_ok=True)
     tensors_golden()
@@ -187,3 +234,5 @@ if __name__ == "__main__":
         segformer_golden()
         upernet_golden()
         dofa_golden()
+    if "--all" in sys.argv or "--wds" in sys.argv:
+        wds_golden()
