@@ -36,6 +36,11 @@ WORKLOADS = {
     "dofa_base": {"name": "dofa_base_upernet_6band_512_k5_b16", "family": "dofa", "encoder": "dofa_base", "bands": 6,
                   "tile": 512, "classes": 5, "batch_per_gpu": 16, "train_gflop_per_tile": 1613.8,
                   "wavelengths": [0.49, 0.56, 0.665, 0.842, 1.61, 2.19]},
+    # the same model with the encoder trained too (3 x 666.1 = 1998.3 GFLOP / tile); eager launches: the weight
+    # generator's backward is torch autograd, which a CUDA-graph capture cannot include
+    "dofa_base_unfrozen": {"name": "dofa_base_upernet_6band_512_k5_b16_encoder_trained", "family": "dofa", "encoder": "dofa_base",
+                           "bands": 6, "tile": 512, "classes": 5, "batch_per_gpu": 16, "train_gflop_per_tile": 1998.3,
+                           "wavelengths": [0.49, 0.56, 0.665, 0.842, 1.61, 2.19], "unfrozen": True},
     # BASELINE.json configs[4] — inference only: SegFormer-B5, 4-band raster, 512-pixel windows at stride 256, windows dealt
     # round-robin to the ranks (strong scaling).  219.5 GFLOP per window (torch flop counter on the oracle's forward).
     "segformer_b5_infer": {"name": "segformer_b5_4band_sliding512_s256", "family": "infer", "encoder": "mit_b5", "bands": 4,
@@ -175,9 +180,13 @@ def cpu_reference_steps(steps: int, warmup: int, tiles_per_step: int = 1, budget
         sd = {k: (v.requires_grad_(True) if v.is_floating_point() and "running" not in k else v) for k, v in sd.items()}
         params = [v for v in sd.values() if v.requires_grad]
         wl = torch.tensor(w["wavelengths"])
+        unfrozen = bool(w.get("unfrozen"))
+        if unfrozen:
+            enc_sd = {k: (v.requires_grad_(True) if v.is_floating_point() and k != "pos_embed" else v) for k, v in enc_sd.items()}
+            params += [v for v in enc_sd.values() if v.requires_grad]
 
         def fwd(x):
-            with torch.no_grad():  # frozen encoder (freeze_layers: ["encoder"])
+            with torch.set_grad_enabled(unfrozen):  # frozen encoder (freeze_layers: ["encoder"]) unless the workload trains it
                 feats = od.dofa_forward(enc_sd, x, wl)
             return ou.upernet_forward(sd, feats, (w["tile"], w["tile"]), training=True)
         what = ("functional restatement of the reference's DOFASegmentationModel (frozen DOFAv2 + UperNet), pinned to it "
@@ -306,7 +315,10 @@ def main_product(args) -> None:
         model = UnetPlusPlus(w["encoder"], in_channels=C, classes=K, compute_dtype=torch.bfloat16).to(dev).train()
     elif w["family"] == "dofa":
         from gdl_b200.models.dofa import DOFASegmentationModel
-        model = DOFASegmentationModel(w["encoder"], (T, T), ["encoder"], K, compute_dtype=torch.bfloat16).to(dev).train()
+        model = DOFASegmentationModel(w["encoder"], (T, T), None if w.get("unfrozen") else ["encoder"], K,
+                                      compute_dtype=torch.bfloat16).to(dev).train()
+        if w.get("unfrozen"):
+            args.cuda_graph = 0
         model.wavelengths = torch.tensor(w["wavelengths"], device=dev)
     else:
         from gdl_b200.models.segformer import SegFormer

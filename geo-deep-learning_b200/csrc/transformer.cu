@@ -835,6 +835,113 @@ __global__ void cast_f32_kernel(const float* __restrict__ x, T* __restrict__ y, 
     y[i] = from_f<T>(x[i]);
 }
 
+// ------------------------------------------------------------------------------------------
+// ViT block glue for TRAINING the DOFA encoder (timm Block: x = x + drop_path(ls(branch(norm(x))))), where the
+// GEMM-epilogue fusions of the forward-only path (GELU, LayerScale + residual) cannot be used because the backward
+// needs the pre-activation / the un-scaled branch output.
+// ------------------------------------------------------------------------------------------
+// y = gelu(x), exact (erf) as nn.GELU
+template <typename T>
+__global__ void gelu_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, long long n8) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n8;
+       i += (long long)gridDim.x * blockDim.x) {
+    float a[8], o[8];
+    ld8(x + i * 8, a);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = gelu_f(a[j]);
+    st8(y + i * 8, o);
+  }
+}
+
+// out[r][c] = res[r][c] + s(r) * gamma[c] * u[r][c]  on the fp32 residual stream; s(r) = sscale[r / rows_per_sample]
+// (DropPath: per-sample keep mask / keep probability) or 1.  One thread per 8 channels.
+template <typename T>
+__global__ void layerscale_add_kernel(const float* __restrict__ res, const T* __restrict__ u,
+                                      const float* __restrict__ gamma, const float* __restrict__ sscale,
+                                      long long rows_per_sample, float* __restrict__ out, long long M, int C) {
+  const int cv = C / 8;
+  const long long total = M * cv;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / cv;
+    const int c = (int)(i - r * cv) * 8;
+    const float s = sscale != nullptr ? sscale[r / rows_per_sample] : 1.f;
+    float uu[8];
+    ld8(u + r * C + c, uu);
+    const float4 r0 = *reinterpret_cast<const float4*>(res + r * C + c), r1 = *reinterpret_cast<const float4*>(res + r * C + c + 4);
+    const float4 g0 = *reinterpret_cast<const float4*>(gamma + c), g1 = *reinterpret_cast<const float4*>(gamma + c + 4);
+    float4 o0, o1;
+    o0.x = r0.x + s * g0.x * uu[0];
+    o0.y = r0.y + s * g0.y * uu[1];
+    o0.z = r0.z + s * g0.z * uu[2];
+    o0.w = r0.w + s * g0.w * uu[3];
+    o1.x = r1.x + s * g1.x * uu[4];
+    o1.y = r1.y + s * g1.y * uu[5];
+    o1.z = r1.z + s * g1.z * uu[6];
+    o1.w = r1.w + s * g1.w * uu[7];
+    *reinterpret_cast<float4*>(out + r * C + c) = o0;
+    *reinterpret_cast<float4*>(out + r * C + c + 4) = o1;
+  }
+}
+
+// backward of the above w.r.t. u and gamma:  du[r][c] = s(r) * gamma[c] * g[r][c] (16-bit operand of the branch's last
+// GEMM backward);  dgamma[c] += sum_r s(r) * g[r][c] * u[r][c]  (fp32 atomics, one per thread and channel at the end).
+// blockDim.x = 256 = rpb rows x tpr channel vectors (tpr = C/8 <= 256).
+template <typename T>
+__global__ void layerscale_bwd_kernel(const float* __restrict__ g, const T* __restrict__ u, const float* __restrict__ gamma,
+                                      const float* __restrict__ sscale, long long rows_per_sample, T* __restrict__ du,
+                                      float* __restrict__ dgamma, long long M, int C) {
+  const int tpr = C / 8;
+  const int rpb = blockDim.x / tpr;
+  const int rl = threadIdx.x / tpr, v = threadIdx.x - rl * tpr;
+  if (rl >= rpb) return;
+  const int c = v * 8;
+  float gm[8], acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    gm[j] = gamma[c + j];
+    acc[j] = 0.f;
+  }
+  for (long long r = (long long)blockIdx.x * rpb + rl; r < M; r += (long long)gridDim.x * rpb) {
+    const float s = sscale != nullptr ? sscale[r / rows_per_sample] : 1.f;
+    float uu[8], o[8];
+    ld8(u + r * C + c, uu);
+    const float4 g0 = *reinterpret_cast<const float4*>(g + r * C + c), g1 = *reinterpret_cast<const float4*>(g + r * C + c + 4);
+    const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      o[j] = s * gm[j] * gg[j];
+      acc[j] += s * gg[j] * uu[j];
+    }
+    st8(du + r * C + c, o);
+  }
+  if (dgamma != nullptr) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) atomicAdd(dgamma + c + j, acc[j]);
+  }
+}
+
+// gradient of a feature tap (feat[b][p] = tokens[b][1+p]) into the fp32 stream gradient (B, P+1, C):
+// init != 0: g[b][0] = 0, g[b][1+p] = dfeat[b][p]   (the deepest tap starts the stream gradient)
+// init == 0: g[b][1+p] += dfeat[b][p]
+template <typename T>
+__global__ void vit_feature_grad_kernel(const T* __restrict__ dfeat, float* __restrict__ g, int B, int P, int C, int init) {
+  const long long total = (long long)B * (P + 1) * C;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    const long long t = i / C;
+    const int tok = (int)(t % (P + 1));
+    const long long b = t / (P + 1);
+    if (tok == 0) {
+      if (init) g[i] = 0.f;
+      continue;
+    }
+    const float d = to_f<T>(dfeat[(b * P + tok - 1) * C + c]);
+    g[i] = init ? d : g[i] + d;
+  }
+}
+
 }  // namespace gdl
 
 using namespace gdl;
@@ -1159,6 +1266,86 @@ extern "C" int gdl_cast_f32(const float* x, void* y, int dtype, long long n, voi
   long long b = (n + 255) / 256;
   if (b > 16 * kNumSMsB200) b = 16 * kNumSMsB200;
   GDL_DISPATCH_T(dtype, { cast_f32_kernel<T><<<(int)b, 256, 0, st>>>(x, (T*)y, n); });
+  GDL_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+#define GDL_DISPATCH_T16(dtype, ...)                                   \
+  do {                                                                 \
+    if ((dtype) == GDL_BF16) {                                         \
+      using T = __nv_bfloat16;                                         \
+      __VA_ARGS__;                                                     \
+    } else if ((dtype) == GDL_F16) {                                   \
+      using T = __half;                                                \
+      __VA_ARGS__;                                                     \
+    } else {                                                           \
+      ::gdl::set_last_error("16-bit dtype expected, got %d", dtype);   \
+      return GDL_ERR_INVALID;                                          \
+    }                                                                  \
+  } while (0)
+
+extern "C" int gdl_gelu_fwd(const void* x, void* y, int dtype, long long n, void* stream) {
+  GDL_REQUIRE(x && y && n > 0 && n % 8 == 0, GDL_ERR_INVALID, "gelu_fwd: bad args (n %% 8 == 0 required)");
+  GDL_REQUIRE(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) == 0, GDL_ERR_INVALID,
+              "gelu_fwd: 16-byte aligned buffers expected");
+  long long b = (n / 8 + 255) / 256;
+  if (b > 16 * kNumSMsB200) b = 16 * kNumSMsB200;
+  GDL_DISPATCH_T16(dtype, { gelu_fwd_kernel<T><<<(int)b, 256, 0, (cudaStream_t)stream>>>((const T*)x, (T*)y, n / 8); });
+  GDL_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int gdl_gelu_bwd(const void* dy, const void* pre, void* dpre, int dtype, long long n, void* stream) {
+  GDL_REQUIRE(dy && pre && dpre && n > 0 && n % 8 == 0, GDL_ERR_INVALID, "gelu_bwd: bad args (n %% 8 == 0 required)");
+  GDL_REQUIRE(((reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(pre) | reinterpret_cast<uintptr_t>(dpre)) & 15) == 0,
+              GDL_ERR_INVALID, "gelu_bwd: 16-byte aligned buffers expected");
+  long long b = (n / 8 + 255) / 256;
+  if (b > 16 * kNumSMsB200) b = 16 * kNumSMsB200;
+  GDL_DISPATCH_T16(dtype, { gelu_bwd_kernel<T><<<(int)b, 256, 0, (cudaStream_t)stream>>>((const T*)dy, (const T*)pre, (T*)dpre, n / 8); });
+  GDL_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int gdl_layerscale_add(const float* res, const void* u, int dtype, const float* gamma, const float* sscale,
+                                  long long rows_per_sample, float* out, long long M, int C, void* stream) {
+  GDL_REQUIRE(res && u && gamma && out && M > 0 && C > 0 && C % 8 == 0, GDL_ERR_INVALID, "layerscale_add: bad args (C %% 8 == 0)");
+  GDL_REQUIRE(sscale == nullptr || rows_per_sample > 0, GDL_ERR_INVALID, "layerscale_add: rows_per_sample must be positive");
+  GDL_REQUIRE(((reinterpret_cast<uintptr_t>(res) | reinterpret_cast<uintptr_t>(u) | reinterpret_cast<uintptr_t>(out) |
+                reinterpret_cast<uintptr_t>(gamma)) & 15) == 0, GDL_ERR_INVALID, "layerscale_add: 16-byte aligned buffers expected");
+  long long b = (M * (C / 8) + 255) / 256;
+  if (b > 16 * kNumSMsB200) b = 16 * kNumSMsB200;
+  GDL_DISPATCH_T16(dtype, {
+    layerscale_add_kernel<T><<<(int)b, 256, 0, (cudaStream_t)stream>>>(res, (const T*)u, gamma, sscale,
+                                                                      rows_per_sample > 0 ? rows_per_sample : 1, out, M, C);
+  });
+  GDL_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int gdl_layerscale_bwd(const float* g, const void* u, int dtype, const float* gamma, const float* sscale,
+                                  long long rows_per_sample, void* du, float* dgamma, long long M, int C, void* stream) {
+  GDL_REQUIRE(g && u && gamma && du && M > 0 && C > 0 && C % 8 == 0 && C <= 2048, GDL_ERR_INVALID,
+              "layerscale_bwd: bad args (C %% 8 == 0, C <= 2048)");
+  GDL_REQUIRE(sscale == nullptr || rows_per_sample > 0, GDL_ERR_INVALID, "layerscale_bwd: rows_per_sample must be positive");
+  GDL_REQUIRE(((reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(u) | reinterpret_cast<uintptr_t>(du)) & 15) == 0,
+              GDL_ERR_INVALID, "layerscale_bwd: 16-byte aligned buffers expected");
+  const int rpb = 256 / (C / 8);
+  long long b = (M + (long long)rpb * 8 - 1) / ((long long)rpb * 8);  // >= 8 rows per thread: few atomics per channel
+  if (b > 2 * kNumSMsB200) b = 2 * kNumSMsB200;
+  if (b < 1) b = 1;
+  GDL_DISPATCH_T16(dtype, {
+    layerscale_bwd_kernel<T><<<(int)b, 256, 0, (cudaStream_t)stream>>>(g, (const T*)u, gamma, sscale,
+                                                                      rows_per_sample > 0 ? rows_per_sample : 1, (T*)du, dgamma, M, C);
+  });
+  GDL_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int gdl_vit_feature_grad(const void* dfeat, int dtype, float* g, int B, int P, int C, int init, void* stream) {
+  GDL_REQUIRE(dfeat && g && B > 0 && P > 0 && C > 0, GDL_ERR_INVALID, "vit_feature_grad: bad args");
+  long long b = ((long long)B * (P + 1) * C + 255) / 256;
+  if (b > 16 * kNumSMsB200) b = 16 * kNumSMsB200;
+  GDL_DISPATCH_T(dtype, { vit_feature_grad_kernel<T><<<(int)b, 256, 0, (cudaStream_t)stream>>>((const T*)dfeat, g, B, P, C, init); });
   GDL_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -137,6 +137,11 @@ _SIGS = {
     "gdl_cast_f32": [_VP, _VP, _I, _LL, _VP],
     "gdl_vit_assemble_tokens": [_VP, _I, _VP, _VP, _VP, _I, _I, _I, _VP],
     "gdl_vit_extract_feature": [_VP, _VP, _I, _I, _I, _I, _VP],
+    "gdl_vit_feature_grad": [_VP, _I, _VP, _I, _I, _I, _I, _VP],
+    "gdl_gelu_fwd": [_VP, _VP, _I, _LL, _VP],
+    "gdl_gelu_bwd": [_VP, _VP, _VP, _I, _LL, _VP],
+    "gdl_layerscale_add": [_VP, _VP, _I, _VP, _VP, _LL, _VP, _LL, _I, _VP],
+    "gdl_layerscale_bwd": [_VP, _VP, _I, _VP, _VP, _LL, _VP, _VP, _LL, _I, _VP],
     "gdl_adaptive_avgpool_fwd": [_VP, _LL, _VP, _I, _I, _I, _I, _I, _I, _VP],
     "gdl_adaptive_avgpool_bwd": [_VP, _VP, _I, _I, _I, _I, _I, _I, _VP],
     "gdl_add_nhwc": [_VP, _LL, _VP, _LL, _VP, _LL, _I, _LL, _I, _VP],

@@ -6,13 +6,21 @@
 models/segmentation/dofa.py:24-107 (encoder + MultiLevelNeck + UperNetDecoder + SegmentationHead + FCNHead,
 `forward(x, wavelengths) -> SegmentationOutput(out, aux)`).
 
-The encoder is FORWARD-ONLY: the shipped configuration freezes it (`freeze_layers: ["encoder"]`,
-configs/dofa_config_RGB.yaml:57), so its backward is never needed there; training with an un-frozen encoder raises
-NotImplementedError.  Every matmul (weight-generator transformer layer, dynamic patch embedding, qkv / proj / MLP of
-the 12 ViT blocks, q.k^T and P.V) is the tcgen05 GEMM kernel; LayerNorm / softmax / GELU / LayerScale / residual are
-the fused epilogues and row kernels of libgdlb200.so.  Host-side torch is used only for glue on tiny tensors: the
-sin/cos of <= 12 wavelengths, concatenating the 128+C+1 generator tokens, and re-laying the generated (C, 14*14*D)
-weights as OIHW (x 0.01) before the packing kernel.
+Two routes through the encoder:
+
+* FROZEN (the shipped configuration: `freeze_layers: ["encoder"]`, configs/dofa_config_RGB.yaml:57) — forward only,
+  `_features_nhwc`.  Every matmul (weight-generator transformer layer, dynamic patch embedding, qkv / proj / MLP of the
+  12 ViT blocks, q.k^T and P.V) is the tcgen05 GEMM kernel; LayerNorm / softmax / GELU / LayerScale / residual are the
+  fused epilogues and row kernels of libgdlb200.so.  Host-side torch is used only for glue on tiny tensors: the sin/cos
+  of <= 12 wavelengths, concatenating the 128+C+1 generator tokens, and re-laying the generated (C, 14*14*D) weights as
+  OIHW (x 0.01) before the packing kernel.
+* TRAINABLE — `run_train` / `backward` (hand-written backward on the engine, like SegFormer): the linears go through
+  `Engine.conv_raw` / `conv_backward` (dgrad + wgrad GEMMs), attention backward is `dP = dO.V^T`, softmax backward,
+  `dQ = dS.K`, `dV = P^T dO`, `dK = dS^T q`; GELU and LayerScale (+ timm's DropPath as a per-sample factor) run as their
+  own kernels so the pre-activation and the un-scaled branch output survive for the backward.  The weight GENERATOR
+  (130 tokens x 128 channels, < 0.01 % of the step's FLOPs) is differentiated by torch autograd in fp32: its output —
+  the patch-embedding weights — gets its gradient from the wgrad kernel, and `torch.autograd.grad` carries it to the
+  generator's parameters.
 """
 from __future__ import annotations
 
@@ -20,6 +28,7 @@ from typing import NamedTuple
 
 import torch
 import torch.nn as nn
+import torch.nn.functional as F
 
 from .. import ops
 from ..engine import Act, Engine
@@ -31,10 +40,10 @@ class SegmentationOutput(NamedTuple):
     aux: torch.Tensor | None
 
 
-def _sincos_1d(embed_dim: int, pos: torch.Tensor) -> torch.Tensor:
+def _sincos_1d(embed_dim: int, pos: torch.Tensor, dtype: torch.dtype = torch.float32) -> torch.Tensor:
     omega = torch.arange(embed_dim // 2, dtype=torch.float32, device=pos.device) / (embed_dim / 2.0)
-    omega = 1.0 / 10000 ** omega
-    out = torch.einsum("m,d->md", pos.reshape(-1).float(), omega)
+    omega = (1.0 / 10000 ** omega).to(dtype)
+    out = torch.einsum("m,d->md", pos.reshape(-1).to(dtype), omega)
     return torch.cat([torch.sin(out), torch.cos(out)], dim=1)
 
 
@@ -98,6 +107,13 @@ class _ViTBlock(nn.Module):
         super().__init__()
         self.norm1, self.attn, self.ls1 = nn.LayerNorm(dim), _Attn(dim), _LayerScale(dim, init_values)
         self.norm2, self.mlp, self.ls2 = nn.LayerNorm(dim), _Mlp(dim, ratio), _LayerScale(dim, init_values)
+
+
+class _SavedBlock:
+    """tensors one ViT block (or the whole encoder) keeps for the hand-written backward"""
+
+    def __init__(self, **kw) -> None:
+        self.__dict__.update(kw)
 
 
 _PACKED: dict = {}  # id(weight) -> (version, dtype, packed 16-bit operand): frozen encoder weights are packed once
@@ -172,6 +188,11 @@ class DOFAv2(nn.Module):
         self.blocks = nn.ModuleList(_ViTBlock(embed_dim, mlp_ratio, init_values) for _ in range(depth))
         self.norm = nn.LayerNorm(embed_dim)
         self.compute_dtype = compute_dtype
+        # timm DropPath rates of the blocks (dofa_v2.py:248: linspace(0, drop_path_rate, depth)); only the TRAINING route
+        # draws masks.  `drop_path_masks` (list of (B,) keep/keep_prob factors per block, or None) overrides the draw.
+        self.drop_path_rates = [float(v) for v in torch.linspace(0, drop_path_rate, depth)]
+        self.drop_path_masks: list | None = None
+        self._saved = None
 
     # ---------------------------------------------------------------------------------- weight generator
     @torch.no_grad()
@@ -254,6 +275,220 @@ class DOFAv2(nn.Module):
         # reference quirk kept: the final norm is only applied when depth-1 was requested but not tapped (never)
         return feats
 
+    # ---------------------------------------------------------------------------------- training route
+    def trainable(self) -> bool:
+        return any(p.requires_grad for p in self.parameters())
+
+    def _generator_params(self) -> list[torch.Tensor]:
+        return [p for p in self.patch_embed.parameters() if p.requires_grad]
+
+    def _dynamic_weights_autograd(self, wavelengths: torch.Tensor, c: int):
+        """dofa_v2.py:148-166 in torch (parameter dtype) under autograd: (D,C,k,k) weights * 0.01, (D,) bias * 0.01."""
+        pe, wg = self.patch_embed, self.patch_embed.weight_generator
+        pdt = wg.weight_tokens.dtype
+        with torch.enable_grad():
+            waves = _sincos_1d(128, wavelengths.to(pdt) * 1000, pdt)  # fp32 parameters: the reference's arithmetic
+            y = F.relu(F.linear(waves, pe.fclayer.w1.weight, pe.fclayer.w1.bias))
+            waves = waves + F.relu(F.linear(y, pe.fclayer.w2.weight, pe.fclayer.w2.bias))
+            x = torch.cat([wg.weight_tokens, waves, wg.bias_token], 0)
+            layer = wg.transformer_encoder.layers[0]  # post-norm encoder layer, dropout 0 (written out: no fast path)
+            sa = layer.self_attn
+            n = x.shape[0]
+            q, k_, v = F.linear(x, sa.in_proj_weight, sa.in_proj_bias).view(n, 3, sa.num_heads, -1).unbind(1)
+            att = torch.softmax(torch.einsum("nhd,mhd->hnm", q, k_) * q.shape[-1] ** -0.5, -1)
+            o = torch.einsum("hnm,mhd->nhd", att, v).reshape(n, -1)
+            x = layer.norm1(x + sa.out_proj(o))
+            x = layer.norm2(x + layer.linear2(F.gelu(layer.linear1(x))))
+            weights = wg.fc_weight(x[128:-1] + waves)
+            bias = wg.fc_bias(x[-1])
+            kk = self.patch_size
+            w_oihw = weights.view(c, kk, kk, self.embed_dim).permute(3, 0, 1, 2) * 0.01
+            return w_oihw, bias.view(self.embed_dim) * 0.01
+
+    def _drop_path_factors(self, i: int, b: int, dev, training: bool):
+        """(B,) fp32 keep-mask / keep-probability of block i (both branches draw their own), or None."""
+        if self.drop_path_masks is not None:
+            return self.drop_path_masks[i]
+        rate = self.drop_path_rates[i]
+        if not training or rate <= 0.0:
+            return None, None
+        keep = 1.0 - rate
+        draw = torch.bernoulli(torch.full((2, b), keep, dtype=torch.float32, device=dev)) / keep
+        return draw[0].contiguous(), draw[1].contiguous()
+
+    def _lin_train(self, eng: Engine, x2d: torch.Tensor, lin: nn.Linear, out_dtype=None):
+        m, k = x2d.shape
+        a = Act(x2d.view(1, 1, m, k))
+        rc = eng.conv_raw([a], lin.weight, 1, 0, bias=lin.bias, out_dtype=out_dtype,
+                          wshape=(lin.weight.shape[0], lin.weight.shape[1], 1, 1))
+        return rc, a
+
+    def run_train(self, eng: Engine, img: torch.Tensor, c: int, wavelengths: torch.Tensor) -> list[Act]:
+        """img: NHWC 16-bit tiles (B,H,W,ld >= c).  Returns the tapped maps as gradient-carrying activations; call
+        `backward(eng)` after their consumers have registered their gradients."""
+        if wavelengths.dim() == 2:
+            if not torch.allclose(wavelengths, wavelengths[0:1].expand_as(wavelengths)):
+                raise ValueError("DOFA cannot handle different wavelengths within a batch")
+            wavelengths = wavelengths[0]
+        dt, acc = eng.dtype, eng.acc_dtype
+        b, hh, ww = img.shape[:3]
+        d, k = self.embed_dim, self.patch_size
+        w_oihw, bias = self._dynamic_weights_autograd(wavelengths, c)
+        kk = k * k * c
+        kpad = (kk + 63) // 64 * 64
+        col = ops.im2col(img, c, k, k, k, 1, kpad)
+        wp = ops.pack_conv_weight(w_oihw.detach().to(acc).contiguous(), dt, 0, kpad)
+        patch = ops.conv2d_fwd([col], wp, d, 1, 1, 0, 0, bias=bias.detach().to(acc).contiguous())
+        hp, wpx = patch.shape[1:3]
+        p_tok = hp * wpx
+        if p_tok + 1 != self.pos_embed.shape[1]:
+            raise ValueError(f"image {hh}x{ww} gives {p_tok} patches but pos_embed has {self.pos_embed.shape[1] - 1}")
+        tokens = ops.vit_assemble_tokens(patch.view(b, p_tok, d), self.pos_embed[0].detach().to(acc).contiguous(),
+                                         self.cls_token.detach().to(acc).view(d).contiguous())
+        n = p_tok + 1
+        m = b * n
+        heads = self.num_heads
+        hd = d // heads
+        lp = (n + 63) // 64 * 64
+        stream = tokens.view(m, d)
+        last = max(self.out_indices)
+        blocks, feats = [], []
+        for i, blk in enumerate(self.blocks[:last + 1]):
+            s1, s2 = self._drop_path_factors(i, b, img.device, eng.training)
+            x_in = stream
+            a1, st1 = ops.layernorm_fwd(stream, blk.norm1.weight, blk.norm1.bias, blk.norm1.eps, dt, True)
+            rc_qkv, act_a1 = self._lin_train(eng, a1, blk.attn.qkv)
+            qkv = rc_qkv.x.view(m, 3 * d)
+            q4 = qkv.view(b, 1, n, 3 * d)
+            scores = torch.empty((b, 1, n, heads * lp), dtype=dt, device=img.device)
+            ops.conv2d_fwd([q4[..., 0:hd]], qkv[:, d:d + hd], lp, 1, 1, 0, 0, out=scores[..., 0:lp], w_rows_per_img=n,
+                           groups=(heads, hd, hd, lp))
+            p4 = ops.softmax_fwd(scores.view(b, n, heads, lp), hd ** -0.5, n).view(b, 1, n, heads * lp)
+            o = torch.empty((b, 1, n, d), dtype=dt, device=img.device)
+            ops.conv2d_fwd([p4[..., 0:lp]], qkv[:, 2 * d:2 * d + hd], hd, 1, 1, 0, 0, out=o[..., 0:hd], w_rows_per_img=n,
+                           w_mn_major=True, groups=(heads, lp, hd, hd))
+            rc_proj, act_o = self._lin_train(eng, o.view(m, d), blk.attn.proj)
+            stream = ops.layerscale_add(stream, rc_proj.x.view(m, d), blk.ls1.gamma.detach().to(acc), s1, n)
+            x_mid = stream
+            a2, st2 = ops.layernorm_fwd(stream, blk.norm2.weight, blk.norm2.bias, blk.norm2.eps, dt, True)
+            rc_fc1, act_a2 = self._lin_train(eng, a2, blk.mlp.fc1)
+            f = ops.gelu_fwd(rc_fc1.x)
+            rc_fc2, act_f = self._lin_train(eng, f.view(m, -1), blk.mlp.fc2)
+            stream = ops.layerscale_add(stream, rc_fc2.x.view(m, d), blk.ls2.gamma.detach().to(acc), s2, n)
+            blocks.append(_SavedBlock(blk=blk, x_in=x_in, st1=st1, rc_qkv=rc_qkv, act_a1=act_a1, p4=p4, rc_proj=rc_proj,
+                                      act_o=act_o, s1=s1, x_mid=x_mid, st2=st2, rc_fc1=rc_fc1, act_a2=act_a2,
+                                      rc_fc2=rc_fc2, act_f=act_f, s2=s2))
+            if i in self.out_indices:
+                feats.append(Act(ops.vit_extract_feature(stream.view(b, n, d), dt).view(b, hp, wpx, d)))
+        self._saved = _SavedBlock(blocks=blocks, feats=feats, col=col, kpad=kpad, w_oihw=w_oihw, bias=bias, b=b, n=n, c=c,
+                                  lp=lp, hp=hp, wpx=wpx)
+        return feats
+
+    @staticmethod
+    def _take(act: Act) -> torch.Tensor:
+        assert len(act.gsrcs) == 1 and act.gsrcs[0][1] == 0
+        g = act.gsrcs[0][0]
+        act.gsrcs.clear()
+        return g
+
+    def _ln_grads(self, eng: Engine, ln: nn.LayerNorm):
+        need = ln.weight.requires_grad or ln.bias.requires_grad
+        return torch.zeros((2, ln.weight.numel()), dtype=eng.acc_dtype, device=ln.weight.device) if need else None
+
+    def _store_ln(self, eng: Engine, ln: nn.LayerNorm, pg) -> None:
+        if pg is None:
+            return
+        if ln.weight.requires_grad:
+            eng.grad_buffer(ln.weight, False).copy_(pg[0])
+        if ln.bias.requires_grad:
+            eng.grad_buffer(ln.bias, False).copy_(pg[1])
+
+    def _layerscale_bwd(self, eng: Engine, ls: _LayerScale, g: torch.Tensor, u: torch.Tensor, sscale, n: int):
+        dg = torch.zeros(ls.gamma.numel(), dtype=eng.acc_dtype, device=g.device) if ls.gamma.requires_grad else None
+        du = ops.layerscale_bwd(g, u, ls.gamma.detach().to(eng.acc_dtype), dg, sscale, n)
+        if dg is not None:
+            eng.grad_buffer(ls.gamma, False).copy_(dg)
+        return du
+
+    def backward(self, eng: Engine) -> None:
+        """Back-propagates the gradients registered on the maps returned by `run_train` through the blocks, the token
+        glue, the dynamic patch embedding and (torch autograd) the weight generator; parameter gradients go to the
+        engine's gradient buffers."""
+        S = self._saved
+        dt, acc = eng.dtype, eng.acc_dtype
+        b, n, d, lp = S.b, S.n, self.embed_dim, S.lp
+        m, heads = b * n, self.num_heads
+        hd = d // heads
+        taps = {idx: f for idx, f in zip(sorted(self.out_indices), S.feats)}
+        g = None  # fp32 gradient of the residual stream, (m, d)
+        for i in range(len(S.blocks) - 1, -1, -1):
+            sv = S.blocks[i]
+            blk = sv.blk
+            if i in taps and taps[i].gsrcs:
+                dfeat = eng.collect_grad(taps[i])
+                g3 = ops.vit_feature_grad(dfeat.reshape(b, n - 1, d), g.view(b, n, d) if g is not None else None)
+                g = g3.view(m, d)
+            if g is None:
+                continue
+            # ---- x = x_mid + drop_path(ls2(fc2(gelu(fc1(norm2(x_mid))))))
+            du2 = self._layerscale_bwd(eng, blk.ls2, g, sv.rc_fc2.x.view(m, d), sv.s2, n)
+            eng.conv_backward(sv.rc_fc2, du2.view(1, 1, m, d))
+            dpre = ops.gelu_bwd(self._take(sv.act_f), sv.rc_fc1.x)
+            eng.conv_backward(sv.rc_fc1, dpre)
+            pg = self._ln_grads(eng, blk.norm2)
+            g, _ = ops.layernorm_bwd(self._take(sv.act_a2).view(m, d), sv.x_mid, sv.st2, blk.norm2.weight, add=g, want32=True,
+                                     pgrads=pg)
+            self._store_ln(eng, blk.norm2, pg)
+            # ---- x_mid = x_in + drop_path(ls1(proj(softmax(q k^T / sqrt(hd)) v)))
+            du1 = self._layerscale_bwd(eng, blk.ls1, g, sv.rc_proj.x.view(m, d), sv.s1, n)
+            eng.conv_backward(sv.rc_proj, du1.view(1, 1, m, d))
+            do4 = self._take(sv.act_o).view(b, 1, n, d)
+            qkv = sv.rc_qkv.x.view(m, 3 * d)
+            q4 = qkv.view(b, 1, n, 3 * d)
+            dp = torch.empty((b, 1, n, heads * lp), dtype=dt, device=g.device)
+            ops.conv2d_fwd([do4[..., 0:hd]], qkv[:, 2 * d:2 * d + hd], lp, 1, 1, 0, 0, out=dp[..., 0:lp], w_rows_per_img=n,
+                           groups=(heads, hd, hd, lp))
+            ds4 = ops.softmax_bwd(sv.p4.view(b, n, heads, lp), dp.view(b, n, heads, lp), hd ** -0.5, n).view(b, 1, n, heads * lp)
+            dqkv = torch.empty((b, 1, n, 3 * d), dtype=dt, device=g.device)
+            ops.conv2d_fwd([ds4[..., 0:lp]], qkv[:, d:d + hd], hd, 1, 1, 0, 0, out=dqkv[..., 0:hd], w_rows_per_img=n,
+                           w_mn_major=True, groups=(heads, lp, hd, hd))
+            dkv32 = torch.zeros((b, lp, 2 * d), dtype=acc, device=g.device)
+            for h_ in range(heads):
+                # dK[b] = dS^T q,  dV[b] = P^T dO   (one independent product per image; key rows >= n stay zero)
+                ops.conv2d_wgrad([q4[..., h_ * hd:(h_ + 1) * hd]], ds4[..., h_ * lp:(h_ + 1) * lp], 1, 1, 0, 0,
+                                 dkv32[:, :, h_ * hd:(h_ + 1) * hd])
+                ops.conv2d_wgrad([do4[..., h_ * hd:(h_ + 1) * hd]], sv.p4[..., h_ * lp:(h_ + 1) * lp], 1, 1, 0, 0,
+                                 dkv32[:, :, d + h_ * hd:d + (h_ + 1) * hd])
+            dqkv.view(b, n, 3 * d)[:, :, d:].copy_(dkv32[:, :n])  # cast + column placement (host-side glue)
+            eng.conv_backward(sv.rc_qkv, dqkv.view(1, 1, m, 3 * d))
+            pg = self._ln_grads(eng, blk.norm1)
+            g, _ = ops.layernorm_bwd(self._take(sv.act_a1).view(m, d), sv.x_in, sv.st1, blk.norm1.weight, add=g, want32=True,
+                                     pgrads=pg)
+            self._store_ln(eng, blk.norm1, pg)
+        self._saved = None
+        if g is None:
+            return
+        # ---- tokens = [cls ; patch + pos]: d(cls) = sum_b g[b][0]; d(patch) = g[:, 1:]
+        g3 = g.view(b, n, d)
+        if self.cls_token.requires_grad:
+            eng.grad_buffer(self.cls_token, False).copy_(g3[:, 0].sum(0).view(1, 1, d))
+        gen = self._generator_params()
+        if not gen:
+            return
+        dpatch = ops.vit_extract_feature(g3, dt).view(b, S.hp, S.wpx, d)
+        dw = torch.zeros((d, S.kpad), dtype=acc, device=g.device)
+        ops.conv2d_wgrad([S.col], dpatch, 1, 1, 0, 0, dw)
+        k = self.patch_size
+        dw_oihw = torch.empty((d, S.c, k, k), dtype=acc, device=g.device)
+        ops.unpack_conv_wgrad(dw, dw_oihw, S.kpad)
+        sums = torch.empty(2 * d, dtype=acc, device=g.device)
+        ops.bn_stats(dpatch, sums)  # column sums: the bias gradient
+        grads = torch.autograd.grad([S.w_oihw, S.bias], gen, [dw_oihw.to(S.w_oihw.dtype), sums[:d].to(S.bias.dtype)],
+                                    allow_unused=True)
+        for p_, gp in zip(gen, grads):
+            if gp is not None:
+                eng.grad_buffer(p_, False).copy_(gp)
+
     def forward(self, x: torch.Tensor, wavelengths: torch.Tensor) -> list[torch.Tensor]:
         """returns the reference's format: list of (B, D, h, w) tensors (channels-last memory)"""
         return [f.permute(0, 3, 1, 2) for f in self.forward_features(x, wavelengths)]
@@ -285,6 +520,11 @@ class DOFASegmentationModel(UperNetSegmentor):
 
     def forward(self, x: torch.Tensor, wavelengths: torch.Tensor) -> SegmentationOutput:  # type: ignore[override]
         image_size = tuple(x.shape[2:])
+        if torch.is_grad_enabled() and self.training and self.encoder.trainable():
+            ops.require_cuda(x, "gdl_b200.DOFASegmentationModel")
+            params = [p for p in self.parameters() if p.requires_grad]
+            out, aux = _DofaSegFn.apply(self, x, wavelengths, *params)
+            return SegmentationOutput(out, aux)
         feats = self.encoder.forward_features(x, wavelengths)  # NHWC 16-bit, no gradient (frozen encoder)
         head_params = [p for n_, p in self.named_parameters() if not n_.startswith("encoder.")]
         if torch.is_grad_enabled() and self.training and any(p.requires_grad for p in head_params):
@@ -300,11 +540,16 @@ class DOFASegmentationModel(UperNetSegmentor):
     def fused_train(self, eng: Engine, x16: torch.Tensor, c: int, target: torch.Tensor, spec) -> torch.Tensor:
         """FusedTrainer hook: normalised NHWC tiles -> loss = L(out) + 0.4 L(aux) (segmentation_dofa.py:226-228) with
         the gradients of the trainable half left in the engine's destination buffers.  Needs `self.wavelengths`."""
-        if any(p.requires_grad for p in self.encoder.parameters()):
-            raise NotImplementedError("DOFA encoder backward: freeze the encoder (freeze_layers=['encoder'])")
-        feats = self.encoder._features_nhwc(x16, c, self.wavelengths)
+        train_enc = self.encoder.trainable()
+        if train_enc:
+            if x16.is_cuda and torch.cuda.is_current_stream_capturing():
+                raise NotImplementedError("CUDA-graph capture of a step with a trainable DOFA encoder: the weight generator is "
+                                          "differentiated by torch autograd (another thread); use cuda_graph=False")
+            feats = self.encoder.run_train(eng, x16, c, self.wavelengths)
+        else:
+            feats = [Act(f, needs_grad=False) for f in self.encoder._features_nhwc(x16, c, self.wavelengths)]
         image_size = tuple(x16.shape[1:3])
-        o, a = self.run(eng, [Act(f, needs_grad=False) for f in feats], image_size)
+        o, a = self.run(eng, feats, image_size)
         if getattr(self, "_aux_w", None) is None or self._aux_w.device != o.device:
             self._aux_w = torch.full((1,), 0.4, dtype=torch.float32, device=o.device)
         co, _ = ops.seg_loss_fwd(o, target, spec)
@@ -313,6 +558,8 @@ class DOFASegmentationModel(UperNetSegmentor):
         ops.seg_loss_bwd(o, target, spec, co, None, d_o)
         ops.seg_loss_bwd(a, target, spec, ca, self._aux_w, d_a)
         self.backward(eng, d_o, d_a)
+        if train_enc:
+            self.encoder.backward(eng)
         return co[0] + 0.4 * ca[0]
 
     def _feat(self, f: torch.Tensor, needs_grad: bool) -> Act:
@@ -321,3 +568,31 @@ class DOFASegmentationModel(UperNetSegmentor):
         if nhwc.dtype == self.compute_dtype and nhwc.is_contiguous():
             return Act(nhwc, needs_grad=needs_grad)
         return super()._feat(f, needs_grad)
+
+
+class _DofaSegFn(torch.autograd.Function):
+    """encoder (trainable) + neck + UperNet + heads as ONE autograd node: the hand-written backward of both halves runs
+    on one engine, the map gradients never leave the 16-bit NHWC layout."""
+
+    @staticmethod
+    def forward(ctx, model: DOFASegmentationModel, x: torch.Tensor, wavelengths: torch.Tensor, *params: torch.Tensor):
+        eng = Engine(model.compute_dtype, training=True, wcache=model._wcache, sync_bn_group=model.sync_bn_group,
+                     acc_dtype=getattr(model, "acc_dtype", torch.float32))
+        c = x.shape[1]
+        img = ops.normalize_to_nhwc(x.contiguous().to(eng.acc_dtype), True, model.compute_dtype, (c + 7) // 8 * 8)
+        feats = model.encoder.run_train(eng, img, c, wavelengths)
+        o, a = model.run(eng, feats, tuple(x.shape[2:]))
+        ctx.eng, ctx.model, ctx.params = eng, model, params
+        return o.permute(0, 3, 1, 2), a.permute(0, 3, 1, 2)
+
+    @staticmethod
+    def backward(ctx, d_out: torch.Tensor, d_aux: torch.Tensor):
+        eng: Engine = ctx.eng
+
+        def nhwc(dd):
+            return None if dd is None else dd.permute(0, 2, 3, 1).contiguous().to(eng.acc_dtype)
+        ctx.model.backward(eng, nhwc(d_out), nhwc(d_aux))
+        ctx.model.encoder.backward(eng)
+        grads = tuple(eng.param_grads.get(id(p)) for p in ctx.params)
+        ctx.eng = None
+        return (None, None, None, *grads)

@@ -642,3 +642,57 @@ def vit_extract_feature(tokens, dtype):
     feat = torch.empty((b, p1 - 1, c), dtype=dtype, device=tokens.device)
     _ck(L.load().gdl_vit_extract_feature(L.ptr(tokens), L.ptr(feat), L.dt_code(dtype), b, p1 - 1, c, L.stream_ptr()))
     return feat
+
+
+def vit_feature_grad(dfeat: torch.Tensor, g: torch.Tensor | None) -> torch.Tensor:
+    """backward of vit_extract_feature: dfeat (B,P,C) is added to rows 1.. of the fp32 stream gradient g (B,P+1,C);
+    g=None starts it (cls row zero)."""
+    b, p, c = dfeat.shape
+    init = g is None
+    if init:
+        g = torch.empty((b, p + 1, c), dtype=torch.float32, device=dfeat.device)
+    if not dfeat.is_contiguous() or not g.is_contiguous() or tuple(g.shape) != (b, p + 1, c):
+        raise ValueError("vit_feature_grad: contiguous (B,P,C) / (B,P+1,C) tensors expected")
+    _ck(L.load().gdl_vit_feature_grad(L.ptr(dfeat), L.dt_code(dfeat.dtype), L.ptr(g), b, p, c, int(init), L.stream_ptr()))
+    return g
+
+
+def gelu_fwd(x: torch.Tensor) -> torch.Tensor:
+    """exact GELU of a contiguous 16-bit tensor (the pre-activation stays with the caller for gelu_bwd)"""
+    if not x.is_contiguous():
+        raise ValueError("gelu_fwd: contiguous input expected")
+    y = torch.empty_like(x)
+    _ck(L.load().gdl_gelu_fwd(L.ptr(x), L.ptr(y), L.dt_code(x.dtype), x.numel(), L.stream_ptr()))
+    return y
+
+
+def gelu_bwd(dy: torch.Tensor, pre: torch.Tensor) -> torch.Tensor:
+    if not dy.is_contiguous() or not pre.is_contiguous() or dy.shape != pre.shape:
+        raise ValueError("gelu_bwd: contiguous tensors of one shape expected")
+    dpre = torch.empty_like(pre)
+    _ck(L.load().gdl_gelu_bwd(L.ptr(dy), L.ptr(pre), L.ptr(dpre), L.dt_code(pre.dtype), pre.numel(), L.stream_ptr()))
+    return dpre
+
+
+def layerscale_add(res: torch.Tensor, u: torch.Tensor, gamma: torch.Tensor, sscale: torch.Tensor | None = None,
+                   rows_per_sample: int = 0) -> torch.Tensor:
+    """fp32 stream (M,C) + s(row) * gamma * u (16-bit (M,C)) -> new fp32 stream; sscale (B,) = DropPath factors."""
+    m, c = u.shape
+    if tuple(res.shape) != (m, c) or not res.is_contiguous() or not u.is_contiguous():
+        raise ValueError("layerscale_add: contiguous (M,C) tensors expected")
+    out = torch.empty_like(res)
+    _ck(L.load().gdl_layerscale_add(L.ptr(res), L.ptr(u), L.dt_code(u.dtype), L.ptr(gamma), L.ptr(sscale),
+                                        int(rows_per_sample), L.ptr(out), m, c, L.stream_ptr()))
+    return out
+
+
+def layerscale_bwd(g: torch.Tensor, u: torch.Tensor, gamma: torch.Tensor, dgamma: torch.Tensor | None,
+                   sscale: torch.Tensor | None = None, rows_per_sample: int = 0) -> torch.Tensor:
+    """g fp32 (M,C) stream gradient -> du (16-bit) = s * gamma * g; dgamma (fp32 (C,), pre-zeroed) += sum_r s * g * u."""
+    m, c = u.shape
+    if tuple(g.shape) != (m, c) or not g.is_contiguous() or not u.is_contiguous():
+        raise ValueError("layerscale_bwd: contiguous (M,C) tensors expected")
+    du = torch.empty_like(u)
+    _ck(L.load().gdl_layerscale_bwd(L.ptr(g), L.ptr(u), L.dt_code(u.dtype), L.ptr(gamma), L.ptr(sscale),
+                                        int(rows_per_sample), L.ptr(du), L.ptr(dgamma), m, c, L.stream_ptr()))
+    return du

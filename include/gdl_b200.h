@@ -337,6 +337,26 @@ int gdl_vit_assemble_tokens(const void* patch, int patch_dtype, const float* pos
                             int B, int P, int C, void* stream);
 int gdl_vit_extract_feature(const float* tokens, void* feat, int feat_dtype, int B, int P, int C, void* stream);
 
+/* Gradient of a feature tap into the fp32 stream gradient g (B, P+1, C): init != 0 starts it (g[b][0] = 0,
+ * g[b][1+p] = dfeat[b][p]), init == 0 accumulates (g[b][1+p] += dfeat[b][p]).  Backward of gdl_vit_extract_feature. */
+int gdl_vit_feature_grad(const void* dfeat, int dtype, float* g, int B, int P, int C, int init, void* stream);
+
+/* ViT block pieces needed when the DOFA encoder is TRAINED (timm.models.vision_transformer.Block as used by
+ * dofa_v2.py:249-263: x = x + drop_path(ls(attn(norm1(x)))); x = x + drop_path(ls(mlp(norm2(x))))).  The forward-only
+ * path fuses GELU and LayerScale + residual into the GEMM epilogues; the training path keeps the pre-activation and the
+ * un-scaled branch output for the backward:
+ *   gelu_fwd / gelu_bwd:  y = gelu(x) exact (erf);  dpre = dy * gelu'(pre)            (16-bit, n % 8 == 0)
+ *   layerscale_add:       out[r][c] = res[r][c] + s(r) * gamma[c] * u[r][c]           (fp32 stream, u 16-bit [M][C])
+ *   layerscale_bwd:       du[r][c] = s(r) * gamma[c] * g[r][c] (16-bit);  dgamma[c] += sum_r s(r) * g[r][c] * u[r][c]
+ * s(r) = sscale[r / rows_per_sample] is timm's DropPath (per-sample keep mask / keep probability); sscale == NULL -> 1.
+ * dgamma (fp32 [C], may be NULL) is accumulated with atomics: zero it first. */
+int gdl_gelu_fwd(const void* x, void* y, int dtype, long long n, void* stream);
+int gdl_gelu_bwd(const void* dy, const void* pre, void* dpre, int dtype, long long n, void* stream);
+int gdl_layerscale_add(const float* res, const void* u, int dtype, const float* gamma, const float* sscale,
+                       long long rows_per_sample, float* out, long long M, int C, void* stream);
+int gdl_layerscale_bwd(const float* g, const void* u, int dtype, const float* gamma, const float* sscale,
+                       long long rows_per_sample, void* du, float* dgamma, long long M, int C, void* stream);
+
 /* fp32 -> dtype cast of a flat buffer (residual-stream gradient -> 16-bit GEMM operand) */
 int gdl_cast_f32(const float* x, void* y, int dtype, long long n, void* stream);
 

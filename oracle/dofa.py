@@ -75,26 +75,31 @@ def patch_embed(sd, img, wavelengths, embed_dim, k=14):
     return x.flatten(2).transpose(1, 2)
 
 
-def vit_block(sd, x, p, heads):
+def vit_block(sd, x, p, heads, drop_path=None):
+    """timm Block; `drop_path` = ((B,), (B,)) per-sample factors keep_mask / keep_prob of the two branches (timm's
+    DropPath in train mode, with the random draw supplied by the caller) or None (eval / rate 0)."""
     b, n, c = x.shape
     d = c // heads
     h = F.layer_norm(x, (c,), sd[p + "norm1.weight"], sd[p + "norm1.bias"], 1e-5)
     qkv = _lin(h, sd, p + "attn.qkv").view(b, n, 3, heads, d).permute(2, 0, 3, 1, 4)
     a = torch.softmax((qkv[0] @ qkv[1].transpose(-2, -1)) * d ** -0.5, dim=-1) @ qkv[2]
     a = _lin(a.transpose(1, 2).reshape(b, n, c), sd, p + "attn.proj")
-    x = x + a * sd[p + "ls1.gamma"]
+    s1 = s2 = 1.0
+    if drop_path is not None and drop_path[0] is not None:
+        s1, s2 = drop_path[0].to(x.dtype).view(b, 1, 1), drop_path[1].to(x.dtype).view(b, 1, 1)
+    x = x + s1 * (a * sd[p + "ls1.gamma"])
     h = F.layer_norm(x, (c,), sd[p + "norm2.weight"], sd[p + "norm2.bias"], 1e-5)
     m = _lin(F.gelu(_lin(h, sd, p + "mlp.fc1")), sd, p + "mlp.fc2")
-    return x + m * sd[p + "ls2.gamma"]
+    return x + s2 * (m * sd[p + "ls2.gamma"])
 
 
-def dofa_forward(sd, img, wavelengths, embed_dim=768, depth=12, heads=12, out_indices=OUT_INDICES_BASE):
+def dofa_forward(sd, img, wavelengths, embed_dim=768, depth=12, heads=12, out_indices=OUT_INDICES_BASE, drop_path=None):
     """img (B,C,H,W), wavelengths (C,) in micrometres -> list of (B, D, H/14', W/14') maps"""
     x = patch_embed(sd, img, wavelengths, embed_dim) + sd["pos_embed"][:, 1:, :]
     x = torch.cat([sd["cls_token"].expand(x.shape[0], -1, -1), x], dim=1)
     feats = []
     for i in range(depth):
-        x = vit_block(sd, x, f"blocks.{i}.", heads)
+        x = vit_block(sd, x, f"blocks.{i}.", heads, None if drop_path is None else drop_path[i])
         if i in out_indices:
             f = x[:, 1:, :]
             b, n, c = f.shape

@@ -541,6 +541,43 @@ def vit_extract_feature(tokens, dtype):
     return tokens[:, 1:].to(dtype).contiguous()
 
 
+def vit_feature_grad(dfeat, g):
+    b, p_, c = dfeat.shape
+    if g is None:
+        g = torch.zeros(b, p_ + 1, c, dtype=_WORK)
+    g[:, 1:] += dfeat.to(g.dtype)
+    return g
+
+
+def gelu_fwd(x):
+    return F.gelu(x.to(_WORK)).to(x.dtype)
+
+
+def gelu_bwd(dy, pre):
+    p_ = pre.detach().to(_WORK).requires_grad_(True)
+    with torch.enable_grad():
+        F.gelu(p_).backward(dy.to(_WORK))
+    return p_.grad.to(pre.dtype)
+
+
+def _sample_scale(sscale, rows_per_sample, m):
+    if sscale is None:
+        return 1.0
+    return sscale.to(_WORK).repeat_interleave(rows_per_sample)[:m].view(m, 1)
+
+
+def layerscale_add(res, u, gamma, sscale=None, rows_per_sample=0):
+    s = _sample_scale(sscale, rows_per_sample, u.shape[0])
+    return (res.to(_WORK) + s * gamma.to(_WORK) * u.to(_WORK)).to(res.dtype)
+
+
+def layerscale_bwd(g, u, gamma, dgamma, sscale=None, rows_per_sample=0):
+    s = _sample_scale(sscale, rows_per_sample, u.shape[0])
+    if dgamma is not None:
+        dgamma += (s * g.to(_WORK) * u.to(_WORK)).sum(0).to(dgamma.dtype)
+    return (s * gamma.to(_WORK) * g.to(_WORK)).to(u.dtype)
+
+
 def cast_f32(x, dtype):
     return x.to(dtype)
 

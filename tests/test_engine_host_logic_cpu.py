@@ -253,6 +253,61 @@ def test_dofa_segmentation_model_train_step_equals_oracle(monkeypatch, f64):
         assert err < 1e-6 or want.abs().max() < 1e-12, f"{n_}: {err}"
 
 
+@pytest.mark.parametrize("drop_path", [False, True])
+def test_dofa_trainable_encoder_backward_equals_oracle_autograd(monkeypatch, f64, drop_path):
+    """Un-frozen DOFA encoder: hand-written backward of the ViT blocks (LayerScale / DropPath factors, GELU, attention,
+    LayerNorm), the token glue, the dynamic patch embedding and — through torch autograd — the weight generator, against
+    the oracle's autograd for every parameter of the model."""
+    from gdl_b200.models.dofa import DOFASegmentationModel
+    from oracle import dofa as od, upernet as ou
+    emu.install(monkeypatch)
+    torch.manual_seed(0)
+    m = DOFASegmentationModel("dofa_base", (56, 56), None, 4, compute_dtype=torch.float64).double().train()
+    m.acc_dtype = torch.float64
+    with torch.no_grad():
+        for n_, p in m.named_parameters():
+            if "ls1" in n_ or "ls2" in n_:
+                p.copy_(0.3 + 0.1 * torch.rand_like(p))
+    assert m.encoder.trainable()
+    g = torch.Generator().manual_seed(1)
+    b = 2
+    if drop_path:  # timm DropPath with the draw supplied: some samples dropped, the others scaled by 1 / keep
+        masks = []
+        for i in range(12):
+            keep = 1.0 - 0.05 * i
+            masks.append(tuple((torch.rand(b, generator=g) < keep).double() / keep for _ in range(2)))
+        masks[11] = (torch.tensor([0.0, 1.25]).double(), torch.tensor([1.25, 0.0]).double())
+        m.encoder.drop_path_masks = masks
+    else:
+        masks = None
+        m.encoder.drop_path_rates = [0.0] * 12
+    sd = {n_: (v.detach().clone().requires_grad_(True) if v.is_floating_point() and "running" not in n_ and n_ != "encoder.pos_embed"
+               else v.clone()) for n_, v in m.state_dict().items()}
+    x = torch.randn(b, 3, 56, 56, generator=g).double()
+    wl = torch.tensor([0.665, 0.56, 0.49]).double()
+    t = torch.randint(0, 4, (b, 56, 56), generator=g)
+    enc_sd = {k[len("encoder."):]: v for k, v in sd.items() if k.startswith("encoder.")}
+    feats = od.dofa_forward(enc_sd, x, wl, drop_path=masks)
+    ro, ra = ou.upernet_forward({k: v for k, v in sd.items() if not k.startswith("encoder.")}, feats, (56, 56), training=True)
+    (F.cross_entropy(ro, t) + 0.4 * F.cross_entropy(ra, t)).backward()
+    out = m(x, wl)
+    assert (out.out - ro).abs().max() < 1e-7 * ro.abs().max() and (out.aux - ra).abs().max() < 1e-7 * ra.abs().max()
+    (F.cross_entropy(out.out, t) + 0.4 * F.cross_entropy(out.aux, t)).backward()
+    checked = 0
+    for n_, p in m.named_parameters():
+        if not p.requires_grad:
+            continue
+        want = sd[n_].grad
+        if want is None:  # encoder.norm is never applied (reference quirk) and has no gradient on either side
+            assert p.grad is None, n_
+            continue
+        assert p.grad is not None, n_
+        err = (p.grad - want).abs().max() / (want.abs().max() + 1e-30)
+        assert err < 1e-5 or want.abs().max() < 1e-12, f"{n_}: {err}"
+        checked += 1
+    assert checked > 200
+
+
 def test_dofa_fused_trainer_matches_autograd_route(monkeypatch, f64):
     """FusedTrainer's `fused_train` hook (frozen encoder, two logit maps, 0.4 aux weight) leaves the same gradients
     in the flat buffer as the autograd route checked above, and only the trainable half is in the Adam buffers."""
@@ -283,6 +338,45 @@ def test_dofa_fused_trainer_matches_autograd_route(monkeypatch, f64):
         if p.requires_grad:
             err = (p.grad - want[n_]).abs().max() / (want[n_].abs().max() + 1e-30)
             assert err < 1e-4 or want[n_].abs().max() < 1e-12, f"{n_}: {err}"
+
+
+def test_dofa_fused_trainer_with_trainable_encoder(monkeypatch, f64):
+    """FusedTrainer on an un-frozen DOFA model: every parameter (encoder included) lives in the flat buffers and gets
+    the gradient of the autograd route; one Adam step moves encoder weights."""
+    from gdl_b200.models.dofa import DOFASegmentationModel
+    from gdl_b200.trainer import FusedTrainer
+    emu.install(monkeypatch)
+    torch.manual_seed(0)
+    m = DOFASegmentationModel("dofa_base", (56, 56), None, 4, compute_dtype=torch.float64).double().train()
+    m.acc_dtype = torch.float64
+    m.encoder.drop_path_rates = [0.0] * 12
+    with torch.no_grad():
+        for n_, p in m.named_parameters():
+            if "ls1" in n_ or "ls2" in n_:
+                p.fill_(0.3)
+    m.wavelengths = torch.tensor([0.665, 0.56, 0.49]).double()
+    g = torch.Generator().manual_seed(1)
+    raw = torch.randint(0, 256, (2, 56, 56, 3), generator=g, dtype=torch.uint8)
+    t = torch.randint(0, 4, (2, 56, 56), generator=g)
+    x = ((raw.double() / 255.0).permute(0, 3, 1, 2) - 0.5) / 0.25
+    out = m(x, m.wavelengths)
+    (F.cross_entropy(out.out, t) + 0.4 * F.cross_entropy(out.aux, t)).backward()
+    want = {n_: p.grad.clone() for n_, p in m.named_parameters() if p.grad is not None}
+    assert any(n_.startswith("encoder.blocks.") for n_ in want) and any("weight_generator" in n_ for n_ in want)
+    for mod in m.modules():
+        if isinstance(mod, torch.nn.BatchNorm2d):
+            mod.reset_running_stats()
+    tr = FusedTrainer(m, emu.LossSpec(1.0, 0.0, ignore_index=-100), lr=1e-3, mean=[0.5] * 3, std=[0.25] * 3,
+                      acc_dtype=torch.float64)
+    assert tr.flat.numel() == sum(p.numel() for p in m.parameters() if p.requires_grad)
+    before = m.encoder.blocks[3].attn.qkv.weight.detach().clone()
+    tr.forward_backward(raw, t)
+    for n_, p in m.named_parameters():
+        if n_ in want:
+            err = (p.grad - want[n_]).abs().max() / (want[n_].abs().max() + 1e-30)
+            assert err < 1e-4 or want[n_].abs().max() < 1e-12, f"{n_}: {err}"
+    tr.optimizer_step()
+    assert not torch.equal(m.encoder.blocks[3].attn.qkv.weight, before)
 
 
 def test_sliding_window_inference_equals_window_sum_of_oracle(monkeypatch, f64):
