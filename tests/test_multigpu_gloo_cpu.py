@@ -81,3 +81,56 @@ def test_two_ranks_equal_one_process_on_the_union(tmp_path, monkeypatch, f64_wor
     # the global loss is the mean of the per-rank losses
     for i in range(2):
         assert abs(losses[i] - 0.5 * (r0["losses"][i] + r1["losses"][i])) < 1e-9
+
+
+# ---------------------------------------------------------------------------------------------
+# tile-sharded sliding-window inference (BASELINE configs[4]): windows dealt round-robin to the ranks, one all-reduce
+# ---------------------------------------------------------------------------------------------
+def _infer_model():
+    import cpu_kernel_emulation as emu
+    from gdl_b200.models.unetpp import UnetPlusPlus
+    emu.set_work_dtype(torch.float64)
+    torch.manual_seed(3)
+    m = UnetPlusPlus("resnet18", in_channels=3, classes=4, compute_dtype=torch.float64).double().eval()
+    with torch.no_grad():
+        for mod in m.modules():
+            if isinstance(mod, torch.nn.BatchNorm2d):
+                mod.running_mean.normal_(0, 0.1)
+                mod.running_var.uniform_(0.5, 1.5)
+    return m
+
+
+def _raster():
+    return torch.randint(0, 256, (100, 150, 3), generator=torch.Generator().manual_seed(8), dtype=torch.uint8)
+
+
+def _infer_worker(rank, world, port, out):
+    for p in (ROOT, ROOT / "geo-deep-learning_b200", ROOT / "tests"):
+        sys.path.insert(0, str(p))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import cpu_kernel_emulation as emu
+    from gdl_b200.inference import SlidingWindowSegmenter
+    emu.install_global()
+    seg = SlidingWindowSegmenter(_infer_model(), tile=64, stride=32, batch=2, mean=[0.4, 0.5, 0.6], std=[0.2, 0.25, 0.3])
+    assert seg.world == world and seg.rank == rank
+    logits = seg.logits(_raster())
+    torch.save({"logits": logits, "windows": seg.windows_done}, f"{out}/infer{rank}.pt")
+    dist.destroy_process_group()
+
+
+def test_sliding_window_sharded_over_two_ranks(tmp_path, monkeypatch, f64_work_dtype):
+    import cpu_kernel_emulation as emu
+    from gdl_b200.inference import SlidingWindowSegmenter, window_origins
+    port = _free_port()
+    mp.spawn(_infer_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    r0, r1 = torch.load(tmp_path / "infer0.pt"), torch.load(tmp_path / "infer1.pt")
+    nwin = len(window_origins(100, 64, 32)) * len(window_origins(150, 64, 32))
+    assert r0["windows"] + r1["windows"] == nwin and abs(r0["windows"] - r1["windows"]) <= 1  # dealt round-robin
+    assert torch.equal(r0["logits"], r1["logits"])  # every rank holds the full sum after the all-reduce
+    sys.path.insert(0, str(ROOT / "tests"))
+    emu.install(monkeypatch)
+    single = SlidingWindowSegmenter(_infer_model(), tile=64, stride=32, batch=2, mean=[0.4, 0.5, 0.6], std=[0.2, 0.25, 0.3])
+    want = single.logits(_raster())
+    assert single.windows_done == nwin
+    assert torch.allclose(r0["logits"], want, atol=1e-5, rtol=1e-5)  # fp32 accumulator, different summation order

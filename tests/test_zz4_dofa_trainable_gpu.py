@@ -23,7 +23,10 @@ def test_vit_training_kernels(cuda, dtype):
     m = b * n
     x = (torch.randn(m, 4 * c, generator=g, device="cuda") * 1.5).to(dtype)
     y = ops.gelu_fwd(x)
-    assert torch.equal(y, F.gelu(x.float()).to(dtype))
+    ref = F.gelu(x.float())
+    ulp = 2.0 ** -7 if dtype == torch.bfloat16 else 2.0 ** -10
+    assert (y.float() - ref).abs().max() <= ulp * ref.abs().max().clamp_min(1.0)
+    assert (y != ref.to(dtype)).float().mean() < 1e-3  # same erf, same rounding: at most rare last-bit differences
     dy = torch.randn(m, 4 * c, generator=g, device="cuda").to(dtype)
     xr = x.float().requires_grad_(True)
     F.gelu(xr).backward(dy.float())
@@ -42,7 +45,7 @@ def test_vit_training_kernels(cuda, dtype):
         gs = torch.randn(m, c, generator=g, device="cuda")
         dgam = torch.zeros(c, device="cuda")
         du = ops.layerscale_bwd(gs, u, gamma, dgam, ss, n)
-        assert torch.equal(du, (srow * gamma * gs).to(dtype)) or (du.float() - srow * gamma * gs).abs().max() <= 2.0 ** -7 * gs.abs().max() * 1.5
+        assert (du.float() - srow * gamma * gs).abs().max() <= 2.0 ** -7 * (gamma.max() * gs.abs().max()) * 1.5
         wg = (srow * gs * u.float()).sum(0)
         assert (dgam - wg).abs().max() <= 1e-4 * wg.abs().max()
     # feature-tap gradient into the stream gradient
