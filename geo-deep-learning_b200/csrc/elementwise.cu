@@ -752,6 +752,30 @@ __global__ void maxpool3x3s2_bwd_kernel(const T* __restrict__ dy, int ldy, const
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// nn.Dropout2d in training mode (segformer_mlp.py:73,129; fcn_head.py:69-83): whole channels of a sample are zeroed,
+// the rest scaled by 1 / (1 - p).  The draw m[n][c] (0 or 1 / (1 - p)) is made by the caller; y = x * m[n][c] is
+// also its own backward (dx = dy * m).
+// ------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void scale_nc_kernel(const T* __restrict__ x, long long ldx, const float* __restrict__ m, T* __restrict__ y,
+                                long long ldy, long long N, long long HW, int C) {
+  const int cv = C / 8;
+  const long long total = N * HW * cv;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long row = i / cv;
+    const int c = (int)(i - row * cv) * 8;
+    const long long n = row / HW;
+    float f[8];
+    load8(x + row * ldx + c, f);
+    const float* mm = m + n * C + c;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f[j] *= mm[j];
+    store8(y + row * ldy + c, f);
+  }
+}
+
 }  // namespace gdl
 
 using namespace gdl;
@@ -988,6 +1012,20 @@ extern "C" int gdl_maxpool3x3s2_bwd(const void* dy, int ldy, const unsigned char
   cudaStream_t st = (cudaStream_t)stream;
   GDL_DISPATCH_16(dtype, {
     maxpool3x3s2_bwd_kernel<T><<<ew_blocks(total, 256, 16), 256, 0, st>>>((const T*)dy, ldy, idx, (T*)dx, ldx, N, H, W, C, Ho, Wo);
+  });
+  GDL_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int gdl_dropout2d_apply(const void* x, long long ldx, const float* mask, void* y, long long ldy, int dtype,
+                                   long long N, long long HW, int C, void* stream) {
+  GDL_REQUIRE(x && mask && y && N > 0 && HW > 0 && C > 0 && C % 8 == 0 && ldx >= C && ldy >= C && ldx % 8 == 0 && ldy % 8 == 0,
+              GDL_ERR_INVALID, "dropout2d: bad args (C, ldx, ldy multiples of 8)");
+  GDL_REQUIRE(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) == 0, GDL_ERR_INVALID,
+              "dropout2d: 16-byte aligned buffers expected");
+  const int blocks = ew_blocks(N * HW * (C / 8), 256, 16);
+  GDL_DISPATCH_16(dtype, {
+    scale_nc_kernel<T><<<blocks, 256, 0, (cudaStream_t)stream>>>((const T*)x, ldx, mask, (T*)y, ldy, N, HW, C);
   });
   GDL_CHECK_CUDA(cudaGetLastError());
   return 0;

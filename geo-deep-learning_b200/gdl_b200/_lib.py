@@ -106,6 +106,7 @@ _SIGS = {
     "gdl_fold_widened_wgrad": [_VP, _I, _I, _VP, _I, _I, _I, _I, _I, _VP],
     "gdl_normalize_to_nhwc": [_VP, _I, _VP, _I, _LL, _LL, _LL, _I, _I, _VP, _VP, _F, _VP],
     "gdl_augment_normalize": [_VP, _I, _VP, _I, _VP, _VP, _I, _VP, _LL, _LL, _LL, _I, _I, _VP, _VP, _F, _VP],
+    "gdl_dropout2d_apply": [_VP, _LL, _VP, _VP, _LL, _I, _LL, _LL, _I, _VP],
     "gdl_im2col_nhwc": [_VP, _VP, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _VP],
     "gdl_col2im_nhwc": [_VP, _VP, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _VP],
     "gdl_bn_stats": [_VP, _I, _LL, _I, _I, _VP, _VP, _VP],

@@ -423,6 +423,24 @@ class Engine:
             self.tape.append(bwd)
         return out
 
+    def dropout2d(self, a: Act, p: float, mask: torch.Tensor | None = None) -> Act:
+        """nn.Dropout2d(p): identity in eval mode or for p == 0; in training whole (sample, channel) planes are zeroed
+        and the rest scaled by 1 / (1 - p).  `mask` (N, C) overrides the draw (tests)."""
+        if not self.training or (p <= 0.0 and mask is None):
+            return a
+        n, _, _, c = a.t.shape
+        if mask is None:
+            mask = torch.bernoulli(torch.full((n, c), 1.0 - p, dtype=torch.float32, device=a.t.device)) / (1.0 - p)
+        mask = mask.to(self.acc_dtype).contiguous()  # fp32 on the GPU
+        out = Act(ops.dropout2d_apply(a.t, mask))
+        if a.needs_grad:
+            def bwd() -> None:
+                g = self.collect_grad(out)
+                if g is not None:
+                    a.gsrcs.append((ops.dropout2d_apply(g, mask), 0))
+            self.tape.append(bwd)
+        return out
+
     def adaptive_avgpool(self, a: Act, s: int) -> Act:
         n, h, w, c = a.t.shape
         out = Act(ops.adaptive_avgpool_fwd(a.t, s))

@@ -506,13 +506,15 @@ class DOFASegmentationModel(UperNetSegmentor):
     """encoder (frozen DOFA ViT) + MultiLevelNeck + UperNetDecoder + SegmentationHead + FCNHead aux head."""
 
     def __init__(self, encoder: str = "dofa_base", image_size=(512, 512), freeze_layers: list[str] | None = None,
-                 num_classes: int = 1, *, pretrained: bool = False, compute_dtype: torch.dtype = torch.bfloat16) -> None:
+                 num_classes: int = 1, *, pretrained: bool = False, compute_dtype: torch.dtype = torch.bfloat16,
+                 aux_dropout_ratio: float = 0.0, drop_path_rate: float = 0.1) -> None:
         if encoder not in ("dofa_base", "dofa_large"):
             raise ValueError(f"Invalid encoder: {encoder}")
         dim = 768 if encoder == "dofa_base" else 1024
-        super().__init__(dim, 256, num_classes, compute_dtype)
+        super().__init__(dim, 256, num_classes, compute_dtype, aux_dropout_ratio)
         make = create_dofa_base if encoder == "dofa_base" else create_dofa_large
-        self.encoder = make(img_size=image_size, pretrained=pretrained, compute_dtype=compute_dtype)
+        self.encoder = make(img_size=image_size, pretrained=pretrained, compute_dtype=compute_dtype,
+                            drop_path_rate=drop_path_rate)
         if freeze_layers:
             for n_, p in self.named_parameters():
                 if any(layer in n_ for layer in freeze_layers):

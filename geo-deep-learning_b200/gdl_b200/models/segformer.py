@@ -15,8 +15,11 @@ The nn.* sub-modules only hold parameters; arithmetic runs on libgdlb200.so:
   * the decoder reads its 4 upsampled projections as a virtual concat (the 3072-channel torch.cat of
     segformer_mlp.py:127 is never materialised).
 
-Stochastic layers (DropPath, Dropout2d) are identity: parity is defined without them and
-they are not implemented yet (drop_path_rate / dropout_ratio must be 0 for training-time equivalence).
+Stochastic layers: the reference trains MiT with DropPath (`drop_path_rate` 0.1, linearly increasing over the blocks,
+mix_transformer.py:341-343,614-705) and the decoder with `nn.Dropout2d(0.1)` before `linear_pred` (segformer_mlp.py:73,129).
+Both are constructor arguments here and default to 0 — the deterministic model parity is defined on; the
+Lightning task mirror passes the reference's values.  With a non-zero rate the residual add of a block leaves the GEMM
+epilogue: the branch output is scaled per sample (timm DropPath = keep mask / keep probability) by `layerscale_add`.
 """
 from __future__ import annotations
 
@@ -146,8 +149,17 @@ def _lin_shape(w: torch.Tensor) -> tuple:
 class SegFormer(nn.Module):
     def __init__(self, encoder: str = "mit_b0", in_channels: int = 3, weights: str | None = None,
                  freeze_layers: list[str] | None = None, num_classes: int = 1, *, use_dynamic_encoder: bool = False,
-                 compute_dtype: torch.dtype = torch.bfloat16) -> None:
+                 compute_dtype: torch.dtype = torch.bfloat16, drop_path_rate: float = 0.0,
+                 dropout_ratio: float = 0.0) -> None:
         super().__init__()
+        if encoder in MIT_CFG:
+            nblk = sum(MIT_CFG[encoder][2])
+            self.drop_path_rates = [float(v) for v in torch.linspace(0, drop_path_rate, nblk)]
+        self.dropout_ratio = dropout_ratio
+        # test hooks: the draws supplied from outside — list over blocks of ((B,), (B,)) factors; (N, emb) Dropout2d mask
+        self.drop_path_masks: list | None = None
+        self.dropout_mask: torch.Tensor | None = None
+        self._ones: dict = {}
         if use_dynamic_encoder:
             raise NotImplementedError("DynamicMixTransformer (SURVEY §8f rank 4) is not implemented")
         if weights is not None:
@@ -172,7 +184,44 @@ class SegFormer(nn.Module):
                           residual=residual)
         return rc, a
 
-    def _attention_fwd(self, eng: Engine, a16: torch.Tensor, attn: _Attention, stream: torch.Tensor):
+    def _drop_path_factors(self, eng: Engine, i: int, b: int, dev):
+        """per-sample factors keep_mask / keep_prob of block i's two branches, or (None, None)"""
+        if not eng.training:
+            return None, None
+        if self.drop_path_masks is not None:
+            return self.drop_path_masks[i]
+        rate = self.drop_path_rates[i]
+        if rate <= 0.0:
+            return None, None
+        keep = 1.0 - rate
+        draw = torch.bernoulli(torch.full((2, b), keep, dtype=torch.float32, device=dev)) / keep
+        return draw[0].contiguous(), draw[1].contiguous()
+
+    def _unit_gamma(self, c: int, like: torch.Tensor) -> torch.Tensor:
+        key = (c, like.dtype, like.device)
+        if key not in self._ones:
+            self._ones[key] = torch.ones(c, dtype=like.dtype, device=like.device)
+        return self._ones[key]
+
+    def _branch_out(self, eng: Engine, y: torch.Tensor, lin: nn.Linear, stream: torch.Tensor, s):
+        """stream + drop_path(lin(y)): fused in the GEMM epilogue when there is no DropPath factor"""
+        if s is None:
+            rc, act = self._linear(eng, y, lin, residual=stream, out_dtype=stream.dtype)
+            return rc.x, rc, act
+        rc, act = self._linear(eng, y, lin)
+        b, h, w, c = stream.shape
+        out = ops.layerscale_add(stream.view(-1, c), rc.x.view(-1, c), self._unit_gamma(c, stream), s, h * w)
+        return out.view(stream.shape), rc, act
+
+    def _branch_grad(self, rc, s, g16: torch.Tensor, g32: torch.Tensor) -> torch.Tensor:
+        """gradient w.r.t. the branch output: the stream gradient, scaled per sample under DropPath"""
+        if s is None:
+            return g16
+        b, h, w, c = g32.shape
+        du = ops.layerscale_bwd(g32.view(-1, c), rc.x.view(-1, c), self._unit_gamma(c, g32), None, s, h * w)
+        return du.view(g16.shape)
+
+    def _attention_fwd(self, eng: Engine, a16: torch.Tensor, attn: _Attention, stream: torch.Tensor, s=None):
         """returns (new fp32 stream, saved).  a16 = LN1(stream) as 16-bit tokens (B,h,w,C)."""
         b, h, w, c = a16.shape
         heads = attn.num_heads
@@ -203,17 +252,17 @@ class SegFormer(nn.Module):
         o = torch.empty((b, 1, n, c), dtype=dt, device=q.device)
         ops.conv2d_fwd([p4[..., 0:lp]], kv2[:, c:c + d], d, 1, 1, 0, 0, out=o[..., 0:d], w_rows_per_img=nk,
                        w_mn_major=True, groups=(heads, lp, d, d))
-        rc_proj, act_o = self._linear(eng, o.view(b, h, w, c), attn.proj, residual=stream, out_dtype=stream.dtype)
+        new_stream, rc_proj, act_o = self._branch_out(eng, o.view(b, h, w, c), attn.proj, stream, s)
         sv.__dict__.update(rc_kv=rc_kv, act_kvin=act_kvin, kv2=kv2, q4=q4, p4=p4, nk=nk, lp=lp, rc_proj=rc_proj,
-                           act_o=act_o)
-        return rc_proj.x, sv
+                           act_o=act_o, s=s)
+        return new_stream, sv
 
-    def _mlp_fwd(self, eng: Engine, a16: torch.Tensor, mlp: _Mlp, stream: torch.Tensor):
+    def _mlp_fwd(self, eng: Engine, a16: torch.Tensor, mlp: _Mlp, stream: torch.Tensor, s=None):
         rc1, act_a = self._linear(eng, a16, mlp.fc1)
         dw = mlp.dwconv.dwconv
         y, pre = ops.dwconv3x3_gelu_fwd(rc1.x, dw.weight.detach().view(dw.weight.shape[0], 9), dw.bias)
-        rc2, act_y = self._linear(eng, y, mlp.fc2, residual=stream, out_dtype=stream.dtype)
-        return rc2.x, _Saved(rc1=rc1, act_a=act_a, pre=pre, rc2=rc2, act_y=act_y)
+        new_stream, rc2, act_y = self._branch_out(eng, y, mlp.fc2, stream, s)
+        return new_stream, _Saved(rc1=rc1, act_a=act_a, pre=pre, rc2=rc2, act_y=act_y, s=s)
 
     def run(self, eng: Engine, x: Act) -> torch.Tensor:
         """x: NHWC 16-bit image (channels possibly zero padded).  Returns fp32 logits (N,H,W,K)."""
@@ -226,6 +275,7 @@ class SegFormer(nn.Module):
             raise ValueError(f"input height/width ({hh},{ww}) must be divisible by 32")
         stages = []
         cur = x
+        blk_index = 0
         for s in range(4):
             pe: _PatchEmbed = getattr(enc, f"patch_embed{s + 1}")
             k, stride = pe.proj.kernel_size[0], pe.proj.stride[0]
@@ -233,12 +283,14 @@ class SegFormer(nn.Module):
             stream, st_pe = ops.layernorm_fwd(rc_pe.x, pe.norm.weight, pe.norm.bias, pe.norm.eps, acc, eng.training)
             blocks = []
             for blk in getattr(enc, f"block{s + 1}"):
+                dp1, dp2 = self._drop_path_factors(eng, blk_index, stream.shape[0], stream.device)
+                blk_index += 1
                 a1, st1 = ops.layernorm_fwd(stream, blk.norm1.weight, blk.norm1.bias, blk.norm1.eps, dt, eng.training)
                 x_in = stream
-                stream, sv_attn = self._attention_fwd(eng, a1, blk.attn, stream)
+                stream, sv_attn = self._attention_fwd(eng, a1, blk.attn, stream, dp1)
                 a2, st2 = ops.layernorm_fwd(stream, blk.norm2.weight, blk.norm2.bias, blk.norm2.eps, dt, eng.training)
                 x_mid = stream
-                stream, sv_mlp = self._mlp_fwd(eng, a2, blk.mlp, stream)
+                stream, sv_mlp = self._mlp_fwd(eng, a2, blk.mlp, stream, dp2)
                 blocks.append(_Saved(blk=blk, x_in=x_in, st1=st1, attn=sv_attn, x_mid=x_mid, st2=st2, mlp=sv_mlp))
             nrm = getattr(enc, f"norm{s + 1}")
             feat, st_out = ops.layernorm_fwd(stream, nrm.weight, nrm.bias, nrm.eps, dt, eng.training)
@@ -260,6 +312,7 @@ class SegFormer(nn.Module):
         bn_state = eng.bn_prepare(rc_fuse, BNParams(bn.weight, bn.bias, bn.running_mean, bn.running_var,
                                                     bn.num_batches_tracked, bn.eps, bn.momentum or 0.1))
         z = eng.bn_act(rc_fuse, bn_state, relu=True)  # registers its own backward on the tape
+        z = eng.dropout2d(z, self.dropout_ratio, self.dropout_mask)  # nn.Dropout2d before linear_pred (train mode only)
         rc_pred = eng.conv_raw([z], dec.linear_pred.weight, 1, 0, bias=dec.linear_pred.bias, out_dtype=acc)
         logits = ops.bilinear_fwd(rc_pred.x, hh, ww)
         eng.named = {f"c{s + 1}": stages[s].feat for s in range(4)}
@@ -287,9 +340,9 @@ class SegFormer(nn.Module):
         act.gsrcs.clear()
         return g
 
-    def _mlp_bwd(self, eng: Engine, blk: _Block, sv, g16: torch.Tensor) -> torch.Tensor:
-        """g16: stream gradient (16-bit copy).  Returns d(LN2 output) as 16-bit."""
-        eng.conv_backward(sv.rc2, g16)
+    def _mlp_bwd(self, eng: Engine, blk: _Block, sv, g16: torch.Tensor, g32: torch.Tensor) -> torch.Tensor:
+        """g16 / g32: stream gradient (16-bit copy / fp32).  Returns d(LN2 output) as 16-bit."""
+        eng.conv_backward(sv.rc2, self._branch_grad(sv.rc2, sv.s, g16, g32))
         dy = self._take(sv.act_y)
         dw = blk.mlp.dwconv.dwconv
         c4 = dw.weight.shape[0]
@@ -302,11 +355,11 @@ class SegFormer(nn.Module):
         eng.conv_backward(sv.rc1, df1)
         return self._take(sv.act_a)
 
-    def _attention_bwd(self, eng: Engine, blk: _Block, sv, g16: torch.Tensor) -> torch.Tensor:
-        """g16: stream gradient (16-bit).  Returns d(LN1 output) as 16-bit (sum of the q and k/v paths)."""
+    def _attention_bwd(self, eng: Engine, blk: _Block, sv, g16: torch.Tensor, g32: torch.Tensor) -> torch.Tensor:
+        """g16 / g32: stream gradient (16-bit / fp32).  Returns d(LN1 output) as 16-bit (sum of the q and k/v paths)."""
         attn = blk.attn
         heads, d, nk, lp = sv.heads, sv.d, sv.nk, sv.lp
-        eng.conv_backward(sv.rc_proj, g16)
+        eng.conv_backward(sv.rc_proj, self._branch_grad(sv.rc_proj, sv.s, g16, g32))
         do = self._take(sv.act_o)  # (B,h,w,C)
         b, h, w, c = do.shape
         n = h * w
@@ -370,12 +423,12 @@ class SegFormer(nn.Module):
             self._store_ln_grads(eng, st.norm, pg)
             for bs in reversed(st.blocks):
                 blk = bs.blk
-                da2 = self._mlp_bwd(eng, blk, bs.mlp, g16)
+                da2 = self._mlp_bwd(eng, blk, bs.mlp, g16, gstream)
                 pg = self._pgrads_ln(eng, blk.norm2)
                 gstream, g16 = ops.layernorm_bwd(da2, bs.x_mid, bs.st2, blk.norm2.weight, add=gstream, want32=True,
                                                  dtype16=dt, pgrads=pg)
                 self._store_ln_grads(eng, blk.norm2, pg)
-                da1 = self._attention_bwd(eng, blk, bs.attn, g16)
+                da1 = self._attention_bwd(eng, blk, bs.attn, g16, gstream)
                 pg = self._pgrads_ln(eng, blk.norm1)
                 gstream, g16 = ops.layernorm_bwd(da1, bs.x_in, bs.st1, blk.norm1.weight, add=gstream, want32=True,
                                                  dtype16=dt, pgrads=pg)

@@ -78,8 +78,12 @@ class UperNetSegmentor(nn.Module):
     """neck + decoder + head + aux_head.  forward(enc_feats, image_size) -> (out, aux) logits (N,K,H,W)."""
 
     def __init__(self, embed_dim: int = 768, channels: int = 256, num_classes: int = 1,
-                 compute_dtype: torch.dtype = torch.bfloat16) -> None:
+                 compute_dtype: torch.dtype = torch.bfloat16, aux_dropout_ratio: float = 0.0) -> None:
         super().__init__()
+        # FCNHead's nn.Dropout2d before cls_seg (fcn_head.py:69-83; the reference default is 0.1, active in train mode).
+        # 0 keeps the deterministic behaviour parity is defined on; the task mirror passes the reference's value.
+        self.aux_dropout_ratio = aux_dropout_ratio
+        self.aux_dropout_mask: torch.Tensor | None = None  # (N, channels) override of the draw (tests)
         self.neck = MultiLevelNeck([embed_dim] * 4, [embed_dim] * 4, scales=list(SCALES))
         self.decoder = UperNetDecoder([embed_dim] * 4, POOL_SCALES, channels)
         self.aux_head = FCNHead(embed_dim, channels, num_classes)
@@ -121,6 +125,7 @@ class UperNetSegmentor(nn.Module):
         acc = eng.acc_dtype
         rc_out = eng.conv_raw([y], self.head.conv.weight, 1, 0, bias=self.head.conv.bias, out_dtype=acc)
         a = cb([nf[-1]], self.aux_head.convs[0].conv, self.aux_head.convs[0].norm)
+        a = eng.dropout2d(a, self.aux_dropout_ratio, self.aux_dropout_mask)
         rc_aux = eng.conv_raw([a], self.aux_head.cls_seg.weight, 1, 0, bias=self.aux_head.cls_seg.bias, out_dtype=acc)
         self._saved = (rc_out, rc_aux)
         eng.named = {f"neck{i}": nf[i] for i in range(4)} | {"fpn": y}

@@ -696,3 +696,14 @@ def layerscale_bwd(g: torch.Tensor, u: torch.Tensor, gamma: torch.Tensor, dgamma
     _ck(L.load().gdl_layerscale_bwd(L.ptr(g), L.ptr(u), L.dt_code(u.dtype), L.ptr(gamma), L.ptr(sscale),
                                         int(rows_per_sample), L.ptr(du), L.ptr(dgamma), m, c, L.stream_ptr()))
     return du
+
+
+def dropout2d_apply(x: torch.Tensor, mask: torch.Tensor) -> torch.Tensor:
+    """x 16-bit NHWC (N,H,W,C), mask fp32 (N,C) = keep / (1 - p): y = x * mask[n][c] (forward and backward of Dropout2d)"""
+    n, h, w, c, ld = _nhwc_src(x)
+    if tuple(mask.shape) != (n, c) or mask.dtype != torch.float32 or not mask.is_contiguous():
+        raise ValueError(f"dropout2d: mask must be a contiguous fp32 ({n}, {c}) tensor")
+    y = torch.empty((n, h, w, c), dtype=x.dtype, device=x.device)
+    _ck(L.load().gdl_dropout2d_apply(L.ptr(x), ld, L.ptr(mask), L.ptr(y), c, L.dt_code(x.dtype), n, h * w, c,
+                                         L.stream_ptr()))
+    return y

@@ -41,7 +41,8 @@ class SegmentationDOFA(GpuSideHooks, _Base):
         if self.model is not None:
             return
         self.model = DOFASegmentationModel(self.encoder, self.image_size, self.freeze_layers, self.num_classes,
-                                           pretrained=self.pretrained, compute_dtype=self.compute_dtype)
+                                           pretrained=self.pretrained, compute_dtype=self.compute_dtype,
+                                           aux_dropout_ratio=0.1)  # FCNHead's Dropout2d default (fcn_head.py:24)
         if self.weights_from_checkpoint_path:
             ckpt = torch.load(self.weights_from_checkpoint_path, map_location="cpu", weights_only=False)
             self.model.load_state_dict(_strip_model_prefix(ckpt.get("state_dict", ckpt)))

@@ -42,8 +42,11 @@ class SegmentationSegformer(GpuSideHooks, _Base):
     def configure_model(self) -> None:
         if self.model is not None:
             return
+        # the reference's train-mode regularisation: DropPath 0.1 in every MiT variant (mix_transformer.py:614-705) and
+        # Dropout2d(0.1) in the MLP decoder (segformer_mlp.py:32,73)
         self.model = SegFormer(self.encoder, self.in_channels, None, self.freeze_layers, self.num_classes,
-                               use_dynamic_encoder=self.use_dynamic_encoder, compute_dtype=self.compute_dtype)
+                               use_dynamic_encoder=self.use_dynamic_encoder, compute_dtype=self.compute_dtype,
+                               drop_path_rate=0.1, dropout_ratio=0.1)
         if self.weights_from_checkpoint_path:
             ckpt = torch.load(self.weights_from_checkpoint_path, map_location="cpu", weights_only=False)
             self.model.load_state_dict(_strip_model_prefix(ckpt.get("state_dict", ckpt)))

@@ -187,6 +187,12 @@ int gdl_augment_normalize(const void* x, int in_kind, const void* mask, int mask
                           int out_dtype, void* mask_out, long long N, long long H, long long W, int C, int ld,
                           const float* mean, const float* stdv, float image_max, void* stream);
 
+/* nn.Dropout2d in training mode (models/decoders/segformer_mlp.py:73,129 before linear_pred; models/heads/fcn_head.py:69-83
+ * before cls_seg): y[n][p][c] = x[n][p][c] * mask[n][c], mask (fp32 [N][C]) = 0 or 1 / (1 - p) drawn by the caller.  The same
+ * call is the backward (dx = dy * mask).  16-bit NHWC with pixel strides ldx / ldy; may run in place. */
+int gdl_dropout2d_apply(const void* x, long long ldx, const float* mask, void* y, long long ldy, int dtype, long long N,
+                        long long HW, int C, void* stream);
+
 /* im2col / col2im for strided convs and the 3/4/6-band stem (torchvision ResNet conv1 7x7/2, the
  * 3x3/2 and 1x1/2 convs of layer2-4): col[(n,ho,wo)][(r,s,c)] zero padded to Kpad columns; the conv
  * itself is then gdl_conv2d_nhwc_fwd with R=S=1.  col2im is the gather-form adjoint (C % 8 == 0). */

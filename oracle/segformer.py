@@ -71,10 +71,14 @@ def mix_ffn(x, h, w, sd, p):
     return _linear(y, sd, p + ".fc2")
 
 
-def encoder(sd, img, name, prefix="encoder."):
+def encoder(sd, img, name, prefix="encoder.", drop_path=None):
+    """`drop_path`: list over all blocks (stage-major, as mix_transformer.py:341-343 numbers its rates) of
+    ((B,), (B,)) factors keep_mask / keep_prob for the attention and Mix-FFN branches — timm's DropPath in train mode with
+    the random draw supplied by the caller — or None (eval / rate 0)."""
     dims, heads, depths, _ = MIT_CFG[name]
     x = img
     feats = []
+    bi = 0
     for s in range(4):
         pe = f"{prefix}patch_embed{s + 1}"
         k, stride = (7, 4) if s == 0 else (3, 2)
@@ -83,15 +87,20 @@ def encoder(sd, img, name, prefix="encoder."):
         t = _ln(x.flatten(2).transpose(1, 2), sd, pe + ".norm", EPS_PLAIN)
         for i in range(depths[s]):
             bp = f"{prefix}block{s + 1}.{i}"
-            t = t + attention(_ln(t, sd, bp + ".norm1", EPS_BLOCK), h, w, sd, bp + ".attn", heads[s], SR_RATIOS[s])
-            t = t + mix_ffn(_ln(t, sd, bp + ".norm2", EPS_BLOCK), h, w, sd, bp + ".mlp")
+            s1 = s2 = 1.0
+            if drop_path is not None and drop_path[bi][0] is not None:
+                s1, s2 = (d.to(t.dtype).view(-1, 1, 1) for d in drop_path[bi])
+            bi += 1
+            t = t + s1 * attention(_ln(t, sd, bp + ".norm1", EPS_BLOCK), h, w, sd, bp + ".attn", heads[s], SR_RATIOS[s])
+            t = t + s2 * mix_ffn(_ln(t, sd, bp + ".norm2", EPS_BLOCK), h, w, sd, bp + ".mlp")
         t = _ln(t, sd, f"{prefix}norm{s + 1}", EPS_BLOCK)
         x = t.reshape(b, h, w, c).permute(0, 3, 1, 2).contiguous()
         feats.append(x)
     return feats
 
 
-def decoder(sd, feats, training, prefix="decoder.", bn_momentum=0.1):
+def decoder(sd, feats, training, prefix="decoder.", bn_momentum=0.1, dropout_mask=None):
+    """`dropout_mask` (B, emb) = keep / (1 - p): the draw of nn.Dropout2d before linear_pred (segformer_mlp.py:129)"""
     c1 = feats[0]
     size = c1.shape[2:]
     ups = []
@@ -107,12 +116,14 @@ def decoder(sd, feats, training, prefix="decoder.", bn_momentum=0.1):
     x = F.batch_norm(x, sd[prefix + "linear_fuse.1.running_mean"], sd[prefix + "linear_fuse.1.running_var"],
                      sd[prefix + "linear_fuse.1.weight"], sd[prefix + "linear_fuse.1.bias"], training, bn_momentum, 1e-5)
     x = F.relu(x)
+    if dropout_mask is not None:
+        x = x * dropout_mask.to(x.dtype)[:, :, None, None]
     return F.conv2d(x, sd[prefix + "linear_pred.weight"], sd[prefix + "linear_pred.bias"])
 
 
-def segformer_forward(sd, img, name="mit_b2", training=False):
+def segformer_forward(sd, img, name="mit_b2", training=False, drop_path=None, dropout_mask=None):
     """logits (B, K, H, W). `sd` holds tensors (optionally requiring grad) under the reference's keys."""
-    y = decoder(sd, encoder(sd, img, name), training)
+    y = decoder(sd, encoder(sd, img, name, drop_path=drop_path), training, dropout_mask=dropout_mask)
     return F.interpolate(y, size=img.shape[2:], mode="bilinear", align_corners=False)
 
 

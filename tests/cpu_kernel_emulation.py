@@ -578,6 +578,10 @@ def layerscale_bwd(g, u, gamma, dgamma, sscale=None, rows_per_sample=0):
     return (s * gamma.to(_WORK) * g.to(_WORK)).to(u.dtype)
 
 
+def dropout2d_apply(x, mask):
+    return (x.to(_WORK) * mask.to(_WORK).view(mask.shape[0], 1, 1, mask.shape[1])).to(x.dtype).contiguous()
+
+
 def cast_f32(x, dtype):
     return x.to(dtype)
 

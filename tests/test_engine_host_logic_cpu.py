@@ -134,6 +134,85 @@ def test_segformer_backward_equals_oracle_autograd(monkeypatch, f64, name, cin, 
     assert torch.allclose(prod.decoder.linear_fuse[1].running_mean, sd["decoder.linear_fuse.1.running_mean"], atol=1e-12)
 
 
+def test_segformer_stochastic_layers_with_supplied_draws(monkeypatch, f64):
+    """DropPath (per-sample factors on both branches of every block) and the decoder's Dropout2d, with the random
+    draws supplied to product and oracle alike: forward and every parameter gradient agree in float64; in eval mode the
+    layers are identities; with rates set and no supplied draws the training forward is stochastic."""
+    from gdl_b200.engine import Act, Engine
+    from gdl_b200.models.segformer import MIT_CFG, SegFormer
+    from oracle import segformer as osf
+    emu.install(monkeypatch)
+    name, cin, hw, k, b = "mit_b0", 3, 64, 4, 3
+    torch.manual_seed(0)
+    prod = SegFormer(name, in_channels=cin, num_classes=k, compute_dtype=torch.float64, drop_path_rate=0.1,
+                     dropout_ratio=0.1).double().train()
+    nblk = sum(MIT_CFG[name][2])
+    assert len(prod.drop_path_rates) == nblk and prod.drop_path_rates[0] == 0.0 and abs(prod.drop_path_rates[-1] - 0.1) < 1e-7
+    g = torch.Generator().manual_seed(1)
+    masks = []
+    for i in range(nblk):
+        keep = 1.0 - 0.1 * i / (nblk - 1)
+        masks.append(tuple((torch.rand(b, generator=g) < keep).double() / keep for _ in range(2)))
+    masks[3] = (torch.tensor([0.0, 1.0, 2.0]).double(), torch.tensor([1.5, 0.0, 0.0]).double())
+    emb = MIT_CFG[name][3]
+    dmask = (torch.rand(b, emb, generator=g) < 0.8).double() / 0.8
+    prod.drop_path_masks, prod.dropout_mask = masks, dmask
+    sd = {n_: (v.detach().clone().requires_grad_(True) if v.is_floating_point() and "running" not in n_ else v.clone())
+          for n_, v in prod.state_dict().items()}
+    x = torch.randn(b, cin, hw, hw, generator=g).double()
+    t = torch.randint(0, k, (b, hw, hw), generator=g)
+    ref = osf.segformer_forward(sd, x, name, training=True, drop_path=masks, dropout_mask=dmask)
+    F.cross_entropy(ref, t).backward()
+    eng = Engine(torch.float64, training=True, acc_dtype=torch.float64)
+    with torch.no_grad():
+        xin = emu.normalize_to_nhwc(x, True, torch.float64, 8)
+        logits = prod.run(eng, Act(xin, needs_grad=False))
+    assert torch.allclose(logits.permute(0, 3, 1, 2), ref, atol=1e-9, rtol=1e-9)
+    d = logits.detach().permute(0, 3, 1, 2).clone().requires_grad_(True)
+    F.cross_entropy(d, t).backward()
+    with torch.no_grad():
+        prod.backward(eng, d.grad.permute(0, 2, 3, 1).contiguous())
+    for n_, p in prod.named_parameters():
+        got, want = eng.param_grads[id(p)], sd[n_].grad
+        err = (got - want).abs().max() / (want.abs().max() + 1e-30)
+        assert err < 1e-7 or want.abs().max() < 1e-12, f"{n_}: {err}"
+    # eval: identities, whatever the rates
+    prod.drop_path_masks = prod.dropout_mask = None
+    with torch.no_grad():
+        e1 = prod.run(Engine(torch.float64, training=False, acc_dtype=torch.float64), Act(xin, needs_grad=False))
+        plain = osf.segformer_forward({n_: v.detach() for n_, v in sd.items()}, x, name, training=False)
+    assert torch.allclose(e1.permute(0, 3, 1, 2), plain, atol=1e-9, rtol=1e-9)
+    # training with rates set and no supplied draws: two passes differ (the layers really draw)
+    with torch.no_grad():
+        torch.manual_seed(1)
+        a = prod.run(Engine(torch.float64, training=True, acc_dtype=torch.float64), Act(xin, needs_grad=False))
+        torch.manual_seed(2)
+        c = prod.run(Engine(torch.float64, training=True, acc_dtype=torch.float64), Act(xin, needs_grad=False))
+    assert not torch.allclose(a, c)
+
+
+def test_upernet_aux_head_dropout_with_supplied_draw(monkeypatch, f64):
+    """FCNHead's Dropout2d (fcn_head.py:69-83) on the engine tape: y = x * m[n][c] forward, the same scaling backward."""
+    from gdl_b200.engine import Act, Engine
+    emu.install(monkeypatch)
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(3, 5, 6, 16, generator=g).double()
+    m = (torch.rand(3, 16, generator=g) < 0.7).double() / 0.7
+    eng = Engine(torch.float64, training=True, acc_dtype=torch.float64)
+    a = Act(x)
+    y = eng.dropout2d(a, 0.3, m)
+    assert torch.equal(y.t, x * m.view(3, 1, 1, 16))
+    gy = torch.randn(3, 5, 6, 16, generator=g).double()
+    y.gsrcs.append((gy, 0))
+    eng.backward()
+    assert torch.equal(eng.collect_grad(a), gy * m.view(3, 1, 1, 16))
+    ev = Engine(torch.float64, training=False, acc_dtype=torch.float64)
+    assert ev.dropout2d(a, 0.3) is a and eng.dropout2d(a, 0.0) is a
+    drawn = eng.dropout2d(Act(torch.ones(4, 2, 2, 64).double()), 0.5).t
+    vals = set(drawn.unique().tolist())
+    assert vals <= {0.0, 2.0} and len(vals) == 2 and torch.equal(drawn[:, 0, 0], drawn[:, 1, 1])  # whole planes
+
+
 def test_upernet_backward_equals_oracle_autograd(monkeypatch, f64):
     """MultiLevelNeck + UperNet + heads wiring (PPM pooling, top-down adds, virtual concats, two logit maps)."""
     from gdl_b200.engine import Act, Engine
