@@ -101,7 +101,7 @@ def _infer_model():
 
 
 def _raster():
-    return torch.randint(0, 256, (100, 150, 3), generator=torch.Generator().manual_seed(8), dtype=torch.uint8)
+    return torch.randint(0, 256, (100, 70, 3), generator=torch.Generator().manual_seed(8), dtype=torch.uint8)
 
 
 def _infer_worker(rank, world, port, out):
@@ -125,7 +125,7 @@ def test_sliding_window_sharded_over_two_ranks(tmp_path, monkeypatch, f64_work_d
     port = _free_port()
     mp.spawn(_infer_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
     r0, r1 = torch.load(tmp_path / "infer0.pt"), torch.load(tmp_path / "infer1.pt")
-    nwin = len(window_origins(100, 64, 32)) * len(window_origins(150, 64, 32))
+    nwin = len(window_origins(100, 64, 32)) * len(window_origins(70, 64, 32))
     assert r0["windows"] + r1["windows"] == nwin and abs(r0["windows"] - r1["windows"]) <= 1  # dealt round-robin
     assert torch.equal(r0["logits"], r1["logits"])  # every rank holds the full sum after the all-reduce
     sys.path.insert(0, str(ROOT / "tests"))

@@ -29,12 +29,12 @@ def test_unetplus_task_steps(monkeypatch):
     from gdl_b200.tasks.segmentation_unetplus import SegmentationUnetPlus
     emu.install(monkeypatch)
     torch.manual_seed(0)
-    task = SegmentationUnetPlus("resnet18", (64, 64), 3, 4, max_samples=2, loss=torch.nn.CrossEntropyLoss(),
+    task = SegmentationUnetPlus("resnet18", (32, 32), 3, 4, max_samples=2, loss=torch.nn.CrossEntropyLoss(),
                                 class_labels=["bg", "a", "b", "c"], compute_dtype=torch.float32)
     task.configure_model()
     task.configure_model()  # idempotent, as Lightning may call it twice
     assert sorted(task.state_dict())[0].startswith("model.")
-    batch = _batch(2, 3, 64, 4)
+    batch = _batch(2, 3, 32, 4)
     # the reference's UNet++ task hands the mask to the loss as is (:229-234): CrossEntropyLoss wants (N,H,W) int64
     batch["mask"] = batch["mask"][:, 0]
     task.train()
