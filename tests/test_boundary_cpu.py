@@ -72,3 +72,48 @@ def test_model_refuses_cpu_input():
     m = UnetPlusPlus("resnet18", in_channels=3, classes=2)
     with pytest.raises(RuntimeError):
         m(torch.zeros(1, 3, 32, 32))
+
+
+def test_checkpoints_round_trip_through_the_reference_loader(tmp_path):
+    """`state_dict` drop-in, against the reference's OWN classes and loader (build container only): a Lightning-style
+    checkpoint of the reference's SegFormerSegmentationModel loads strictly into gdl_b200's SegFormer through the
+    reference's `load_weights_from_checkpoint` (utils/models.py:10-66, full and `load_parts` modes), and the product's
+    state_dict loads strictly back into the reference model."""
+    import importlib.util
+
+    from oracle import ref_shims
+    if not ref_shims.available():
+        pytest.skip("/root/reference not present (GPU box)")
+    from gdl_b200.models.segformer import SegFormer
+    ref = ref_shims.reference_segformer("mit_b1", 4, 3)
+    spec = importlib.util.spec_from_file_location("ref_models_util", ref_shims.REF / "geo_deep_learning" / "utils" / "models.py")
+    util = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(util)
+    with torch.no_grad():
+        for p in ref.parameters():
+            p.normal_(0, 0.05)
+    ckpt = tmp_path / "ref.ckpt"
+    torch.save({"state_dict": {f"model.{k}": v for k, v in ref.state_dict().items()}, "epoch": 3}, ckpt)
+    prod = SegFormer("mit_b1", in_channels=4, num_classes=3)
+    assert util.load_weights_from_checkpoint(prod, str(ckpt)) is None  # strict load: every key and shape matches
+    for k, v in ref.state_dict().items():
+        assert torch.equal(prod.state_dict()[k], v), k
+    prod2 = SegFormer("mit_b1", in_channels=4, num_classes=3)
+    res = util.load_weights_from_checkpoint(prod2, str(ckpt), load_parts=["encoder"])
+    assert not res.unexpected_keys and all(k.startswith("decoder.") for k in res.missing_keys)
+    assert torch.equal(prod2.encoder.block2[1].attn.kv.weight, ref.state_dict()["encoder.block2.1.attn.kv.weight"])
+    ref.load_state_dict(prod.state_dict())  # and back, strictly
+
+
+def test_dofa_encoder_state_dict_matches_the_reference_class():
+    from oracle import ref_shims
+    if not ref_shims.available():
+        pytest.skip("/root/reference not present (GPU box)")
+    from gdl_b200.models.dofa import DOFAv2
+    ref = ref_shims.reference_dofa(56, 64, 2, 4, out_indices=(0, 1))
+    prod = DOFAv2("dofa_base", 56, 14, 64, 2, 4, out_indices=[0, 1])
+    rs, ps = ref.state_dict(), prod.state_dict()
+    assert set(rs) == set(ps)
+    assert all(rs[k].shape == ps[k].shape for k in rs)
+    prod.load_state_dict(rs)
+    ref.load_state_dict(ps)
