@@ -117,3 +117,41 @@ def test_dofa_encoder_state_dict_matches_the_reference_class():
     assert all(rs[k].shape == ps[k].shape for k in rs)
     prod.load_state_dict(rs)
     ref.load_state_dict(ps)
+
+
+def test_reference_patch_first_conv_works_on_the_product_models(monkeypatch):
+    """The reference adapts a 3-band (pretrained) stem to N bands with `patch_first_conv` (models/utils.py:140-181:
+    weights cycled over the bands and scaled by 3/N).  The product models keep the stem as an ordinary nn.Conv2d, so the
+    reference's own function applies unchanged, and the patched model computes what the oracle computes with the same
+    patched tensors."""
+    import importlib.util
+
+    import cpu_kernel_emulation as emu
+    from oracle import ref_shims
+    if not ref_shims.available():
+        pytest.skip("/root/reference not present (GPU box)")
+    from gdl_b200.models.segformer import SegFormer
+    from gdl_b200.models.unetpp import UnetPlusPlus
+    from oracle import segformer as osf
+    from oracle.unetpp import UnetPlusPlusOracle
+    spec = importlib.util.spec_from_file_location("ref_model_utils", ref_shims.REF / "geo_deep_learning" / "models" / "utils.py")
+    util = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(util)
+    emu.install(monkeypatch)
+    torch.manual_seed(0)
+    m = UnetPlusPlus("resnet18", in_channels=3, classes=2, compute_dtype=torch.float32).eval()
+    w3 = m.encoder.conv1.weight.detach().clone()
+    util.patch_first_conv(m, 4, pretrained=True)
+    assert m.encoder.conv1.weight.shape == (64, 4, 7, 7)
+    assert torch.allclose(m.encoder.conv1.weight[:, 3], w3[:, 0] * 0.75) and torch.allclose(m.encoder.conv1.weight[:, 1], w3[:, 1] * 0.75)
+    ora = UnetPlusPlusOracle("resnet18", 4, 2).eval()
+    ora.load_state_dict(m.state_dict())
+    x = torch.randn(1, 4, 32, 32)
+    with torch.no_grad():
+        assert torch.allclose(m(x), ora(x), atol=1e-4, rtol=1e-4)
+    s = SegFormer("mit_b0", in_channels=3, num_classes=2, compute_dtype=torch.float32).eval()
+    util.patch_first_conv(s, 6, pretrained=True)
+    assert s.encoder.patch_embed1.proj.weight.shape[1] == 6
+    x6 = torch.randn(1, 6, 32, 32)
+    with torch.no_grad():
+        assert torch.allclose(s(x6), osf.segformer_forward(s.state_dict(), x6, "mit_b0"), atol=1e-4, rtol=1e-4)
