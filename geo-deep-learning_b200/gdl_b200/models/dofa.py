@@ -539,7 +539,8 @@ class DOFASegmentationModel(UperNetSegmentor):
             self._saved = None
         return SegmentationOutput(o.permute(0, 3, 1, 2), a.permute(0, 3, 1, 2))
 
-    def fused_train(self, eng: Engine, x16: torch.Tensor, c: int, target: torch.Tensor, spec) -> torch.Tensor:
+    def fused_train(self, eng: Engine, x16: torch.Tensor, c: int, target: torch.Tensor, spec,
+                    grad_scale: torch.Tensor | None = None) -> torch.Tensor:
         """FusedTrainer hook: normalised NHWC tiles -> loss = L(out) + 0.4 L(aux) (segmentation_dofa.py:226-228) with
         the gradients of the trainable half left in the engine's destination buffers.  Needs `self.wavelengths`."""
         train_enc = self.encoder.trainable()
@@ -557,8 +558,10 @@ class DOFASegmentationModel(UperNetSegmentor):
         co, _ = ops.seg_loss_fwd(o, target, spec)
         ca, _ = ops.seg_loss_fwd(a, target, spec)
         d_o, d_a = torch.empty_like(o), torch.empty_like(a)
-        ops.seg_loss_bwd(o, target, spec, co, None, d_o)
-        ops.seg_loss_bwd(a, target, spec, ca, self._aux_w, d_a)
+        # grad_scale: the trainer's fp16 loss scale S (device scalar): d(out) *= S, d(aux) *= 0.4 S
+        ops.seg_loss_bwd(o, target, spec, co, grad_scale, d_o)
+        aux_scale = self._aux_w if grad_scale is None else self._aux_w * grad_scale.to(self._aux_w.dtype)
+        ops.seg_loss_bwd(a, target, spec, ca, aux_scale, d_a)
         self.backward(eng, d_o, d_a)
         if train_enc:
             self.encoder.backward(eng)

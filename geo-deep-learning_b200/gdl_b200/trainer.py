@@ -19,12 +19,23 @@ class FusedTrainer:
     def __init__(self, model: torch.nn.Module, loss: LossSpec, *, lr: float = 1e-4, betas=(0.9, 0.999),
                  eps: float = 1e-8, weight_decay: float = 0.0, mean=None, std=None, image_max: float = 255.0,
                  clip_grad_norm: float | None = None, process_group=None, sync_bn: bool = False,
-                 acc_dtype: torch.dtype = torch.float32, cuda_graph: bool = False, input_chw: bool = False) -> None:
+                 acc_dtype: torch.dtype = torch.float32, cuda_graph: bool = False, input_chw: bool = False,
+                 loss_scale: float | str | None = None, growth_interval: int = 2000) -> None:
         self.model = model
         self.loss = loss
         self.lr, self.betas, self.eps, self.weight_decay = lr, betas, eps, weight_decay
         self.image_max = image_max
         self.input_chw = input_chw  # tiles arrive (N,C,H,W) — the layout of the WebDataset shards — instead of (N,H,W,C)
+        # fp16 loss scaling — what Lightning's `precision: 16-mixed` GradScaler does around the reference's backward
+        # (SURVEY §8 a20): d(loss) is multiplied by S before the backward, the flat gradient by 1/S before clip / Adam.
+        # None = off (bf16 needs none); a float = static S; "dynamic" = torch.amp.GradScaler's rule (S0 = 65536, a step with
+        # a non-finite gradient is skipped and halves S, `growth_interval` clean steps double it).
+        if isinstance(loss_scale, str) and loss_scale != "dynamic":
+            raise ValueError("loss_scale must be None, a number or 'dynamic'")
+        if loss_scale == "dynamic" and cuda_graph:
+            raise NotImplementedError("dynamic loss scaling skips steps on the host: use a static scale with cuda_graph=True")
+        self.loss_scale_mode = loss_scale
+        self.growth_interval, self._good_steps, self.skipped_steps = growth_interval, 0, 0
         self.clip = clip_grad_norm
         self.group = process_group
         self.world = dist.get_world_size(process_group) if (process_group is not None or dist.is_initialized()) else 1
@@ -54,6 +65,8 @@ class FusedTrainer:
                 off += n
         self.mean = torch.as_tensor(mean, dtype=acc_dtype, device=dev) if mean is not None else None
         self.std = torch.as_tensor(std, dtype=acc_dtype, device=dev) if std is not None else None
+        self.loss_scale = (None if loss_scale is None else
+                           torch.full((1,), 65536.0 if loss_scale == "dynamic" else float(loss_scale), dtype=acc_dtype, device=dev))
         self.scratch = torch.zeros(2, dtype=acc_dtype, device=dev)
         self.adam_state = torch.zeros(3, dtype=acc_dtype, device=dev)  # step, 1-b1^t, sqrt(1-b2^t) (device side)
         self.last_engine: Engine | None = None
@@ -85,7 +98,8 @@ class FusedTrainer:
                                       self.image_max)
         if hasattr(model, "fused_train"):
             # models with several logit maps / a frozen front half (DOFA + UperNet) own the whole step
-            loss = model.fused_train(eng, x, c, target, self.loss)
+            loss = (model.fused_train(eng, x, c, target, self.loss) if self.loss_scale is None
+                    else model.fused_train(eng, x, c, target, self.loss, grad_scale=self.loss_scale))
             self.last_engine = eng
             return loss
         logits = model.run(eng, Act(x, needs_grad=False))
@@ -94,12 +108,12 @@ class FusedTrainer:
         if hasattr(model, "backward"):
             # models that own their backward (SegFormer: the logits pass through a bilinear x4 first)
             d = torch.empty_like(logits)
-            ops.seg_loss_bwd(logits, target, self.loss, coeff, None, d)
+            ops.seg_loss_bwd(logits, target, self.loss, coeff, self.loss_scale, d)
             model.backward(eng, d)
         else:
             # UNet++: the loss kernel writes the 16-bit, 16-channel-padded operand of the head's dgrad/wgrad
             d16 = torch.zeros((n, h, w, (k + 15) // 16 * 16), dtype=model.compute_dtype, device=logits.device)
-            ops.seg_loss_bwd(logits, target, self.loss, coeff, None, d16)
+            ops.seg_loss_bwd(logits, target, self.loss, coeff, self.loss_scale, d16)
             eng.head_backward(d16)
             eng.backward()
         self.last_engine = eng
@@ -112,6 +126,19 @@ class FusedTrainer:
             scale_by = 1.0 / self.world
         else:
             scale_by = None
+        if self.loss_scale is not None:
+            # unscale first: the clip threshold and Adam see true gradients
+            self.gflat.mul_((1.0 / self.loss_scale).to(self.gflat.dtype))
+            if self.loss_scale_mode == "dynamic":
+                if not bool(torch.isfinite(self.gflat).all()):  # host decision, as GradScaler.step()
+                    self.loss_scale.mul_(0.5)
+                    self._good_steps = 0
+                    self.skipped_steps += 1
+                    return
+                self._good_steps += 1
+                if self._good_steps >= self.growth_interval:
+                    self.loss_scale.mul_(2.0)
+                    self._good_steps = 0
         gs = None
         if self.clip is not None or scale_by is not None:
             gs = self.scratch[1:2]

@@ -94,6 +94,46 @@ def test_trainer_flat_buffers_and_step(monkeypatch):
     assert "decoder.blocks.x_0_0.conv1.0.weight" in sd and sd["encoder.conv1.weight"].data_ptr() == p0.data_ptr()
 
 
+def test_trainer_loss_scaling(monkeypatch, f64):
+    """fp16 loss scaling of the fused trainer (what Lightning's GradScaler does around the reference's backward): a static
+    scale leaves the update unchanged (exact powers of two), the dynamic rule skips a step with a non-finite gradient and
+    halves the scale, and doubles it after `growth_interval` clean steps."""
+    from gdl_b200.trainer import FusedTrainer
+    emu.install(monkeypatch)
+    g = torch.Generator().manual_seed(0)
+    raw = torch.randint(0, 256, (2, 32, 32, 3), generator=g, dtype=torch.uint8)
+    t = torch.randint(0, 4, (2, 32, 32), generator=g)
+
+    def trainer(**kw):
+        _, prod = _pair("resnet18", 3, 4)
+        prod = prod.double().train()
+        prod.compute_dtype = torch.float64
+        return FusedTrainer(prod, emu.LossSpec(1.0, 0.0, ignore_index=-100), lr=1e-3, mean=[0.5] * 3, std=[0.25] * 3,
+                            acc_dtype=torch.float64, clip_grad_norm=1.0, **kw)
+    plain, scaled = trainer(), trainer(loss_scale=1024.0)
+    l0, l1 = plain.step(raw, t), scaled.step(raw, t)
+    assert float(l0) == float(l1)  # the reported loss is never scaled
+    assert torch.allclose(plain.flat, scaled.flat, atol=1e-12, rtol=1e-9)
+    scaled.forward_backward(raw, t)
+    plain.forward_backward(raw, t)
+    assert torch.allclose(scaled.gflat, 1024.0 * plain.gflat, atol=1e-9, rtol=1e-9)  # gradients carry S until the step
+    dyn = trainer(loss_scale="dynamic", growth_interval=2)
+    assert float(dyn.loss_scale) == 65536.0
+    dyn.forward_backward(raw, t)
+    dyn.gflat[7] = float("inf")
+    before = dyn.flat.clone()
+    dyn.optimizer_step()
+    assert torch.equal(dyn.flat, before) and float(dyn.loss_scale) == 32768.0 and dyn.skipped_steps == 1
+    dyn.step(raw, t)
+    assert not torch.equal(dyn.flat, before) and float(dyn.loss_scale) == 32768.0
+    dyn.step(raw, t)
+    assert float(dyn.loss_scale) == 65536.0  # two clean steps: the scale grows back
+    with pytest.raises(NotImplementedError):
+        trainer(loss_scale="dynamic", cuda_graph=True)
+    with pytest.raises(ValueError):
+        trainer(loss_scale="auto")
+
+
 @pytest.mark.parametrize("name,cin,hw", [("mit_b0", 3, 64), ("mit_b1", 4, 128)])
 def test_segformer_backward_equals_oracle_autograd(monkeypatch, f64, name, cin, hw):
     """SegFormer graph wiring (attention GEMM operand slicing, fp32 residual stream, LayerNorm chain,
