@@ -451,7 +451,9 @@ def main_infer(args, world: int, rank: int, local: int, dev) -> None:
     B, C, T, K = args.batch or w["batch_per_gpu"], w["bands"], w["tile"], w["classes"]
     R = args.raster or w["raster"]
     model = SegFormer(w["encoder"], in_channels=C, num_classes=K, compute_dtype=torch.bfloat16).to(dev).eval()
-    seg = SlidingWindowSegmenter(model, tile=T, stride=T // 2, batch=B, mean=MEAN[:C], std=STD[:C])
+    # --cuda-graph 2 replays the window-batch forward from a CUDA graph (default: eager launches, as validated)
+    seg = SlidingWindowSegmenter(model, tile=T, stride=T // 2, batch=B, mean=MEAN[:C], std=STD[:C],
+                                 cuda_graph=args.cuda_graph >= 2)
     nwin = len(window_origins(R, T, T // 2)) ** 2
     g = torch.Generator().manual_seed(1234)  # the same raster on every rank
     host = torch.randint(0, 256, (R, R, C), generator=g, dtype=torch.uint8).pin_memory()
@@ -514,6 +516,7 @@ def main_infer(args, world: int, rank: int, local: int, dev) -> None:
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": w["name"], "raster": [R, R, C], "windows": nwin, "window_batch": B,
                        "parallelism": f"windows round-robin over {world} rank(s) + one all-reduce of the logit sums",
+                       "cuda_graph": args.cuda_graph >= 2,
                        "l2": f"raster {R * R * C / 1e6:.0f} MB and activations >> 126 MB L2"},
             "clocks": clk,
             "e2e": {"value": nwin * args.steps / (ms_e2e / 1e3), "unit": "tiles/s", "h2d_bytes_per_step": R * R * C,

@@ -30,7 +30,8 @@ def window_origins(size: int, tile: int, stride: int) -> list[int]:
 
 class SlidingWindowSegmenter:
     def __init__(self, model: torch.nn.Module, *, tile: int = 512, stride: int = 256, batch: int = 16, mean=None,
-                 std=None, image_max: float = 255.0, threshold: float = 0.5, process_group=None) -> None:
+                 std=None, image_max: float = 255.0, threshold: float = 0.5, process_group=None,
+                 cuda_graph: bool = False) -> None:
         if tile % 32:
             raise ValueError("tile must be divisible by 32")
         if not 0 < stride <= tile:
@@ -45,6 +46,40 @@ class SlidingWindowSegmenter:
         self.mean = torch.as_tensor(mean, dtype=torch.float32, device=dev) if mean is not None else None
         self.std = torch.as_tensor(std, dtype=torch.float32, device=dev) if std is not None else None
         self.windows_done = 0
+        # A window batch is ~1300 launches of 5-50 us kernels (SegFormer-B5): issued from Python they are launch-bound.
+        # cuda_graph=True captures normalise + forward for full batches once (after one eager batch) and replays it; the
+        # ragged last batch runs eagerly.  Same kernels either way.
+        self.cuda_graph = cuda_graph
+        self._graph = None
+        self._static_in: torch.Tensor | None = None
+        self._static_out: torch.Tensor | None = None
+        self._eager_batches = 0
+
+    def _forward_eager(self, crops: torch.Tensor) -> torch.Tensor:
+        model = self.model
+        c = crops.shape[3]
+        x16 = ops.normalize_to_nhwc(crops, False, model.compute_dtype, (c + 7) // 8 * 8, self.mean, self.std, self.image_max)
+        eng = Engine(model.compute_dtype, training=False, wcache=model._wcache)
+        return model.run(eng, Act(x16, needs_grad=False))                                 # fp32 (B, t, t, K)
+
+    def _forward(self, crops: torch.Tensor) -> torch.Tensor:
+        """(B, t, t, C) uint8 window batch -> fp32 logits (B, t, t, K); the result is only valid until the next call"""
+        if not (self.cuda_graph and crops.is_cuda and crops.shape[0] == self.batch):
+            return self._forward_eager(crops)
+        if self._static_in is None or self._static_in.shape != crops.shape:
+            self._static_in, self._graph, self._eager_batches = torch.empty_like(crops), None, 0
+        self._static_in.copy_(crops)
+        if self._graph is None:
+            if self._eager_batches == 0:  # lazy CUDA init, function attributes, packed weights: not inside a capture
+                self._eager_batches = 1
+                return self._forward_eager(self._static_in)
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                self._static_out = self._forward_eager(self._static_in)
+            self._graph = graph
+        self._graph.replay()
+        return self._static_out
 
     @torch.no_grad()
     def logits(self, raster: torch.Tensor) -> torch.Tensor:
@@ -62,14 +97,10 @@ class SlidingWindowSegmenter:
         wins = [(y, x) for y in window_origins(hp, t, self.stride) for x in window_origins(wp, t, self.stride)]
         mine = wins[self.rank::self.world]
         acc = None
-        dtype = model.compute_dtype
-        ld = (c + 7) // 8 * 8
         for i in range(0, len(mine), self.batch):
             chunk = mine[i:i + self.batch]
             crops = torch.stack([raster[y:y + t, x:x + t] for y, x in chunk])            # (B, t, t, C) uint8
-            x16 = ops.normalize_to_nhwc(crops, False, dtype, ld, self.mean, self.std, self.image_max)
-            eng = Engine(dtype, training=False, wcache=model._wcache)
-            out = model.run(eng, Act(x16, needs_grad=False))                              # fp32 (B, t, t, K)
+            out = self._forward(crops)                                                    # fp32 (B, t, t, K)
             if acc is None:
                 acc = torch.zeros((hp, wp, out.shape[3]), dtype=torch.float32, device=self.dev)
             for j, (y, x) in enumerate(chunk):

@@ -51,3 +51,22 @@ def test_sliding_window_segformer_b0(cuda):
     agree_ac = (want_ac.argmax(2) == want.argmax(2)).float().mean().item()
     print(f"class agreement with the fp32 oracle: product {agree:.4f}, autocast oracle {agree_ac:.4f}")
     assert agree >= agree_ac - 0.01 and cls.dtype == torch.uint8 and cls.shape == (h, w)
+
+
+def test_sliding_window_cuda_graph_replay_equals_eager(cuda):
+    """cuda_graph=True (window-batch forward captured once, replayed per full batch; ragged last batch eager) returns
+    the same logit sums as the eager driver."""
+    from gdl_b200.inference import SlidingWindowSegmenter
+    from gdl_b200.models.segformer import SegFormer
+    torch.manual_seed(0)
+    prod = SegFormer("mit_b0", in_channels=3, num_classes=4, compute_dtype=torch.bfloat16).cuda().eval()
+    raster = torch.randint(0, 256, (448, 320, 3), generator=torch.Generator().manual_seed(2), dtype=torch.uint8).cuda()
+    kw = dict(tile=128, stride=64, batch=4, mean=[0.45] * 3, std=[0.22] * 3)
+    eager = SlidingWindowSegmenter(prod, **kw)
+    graph = SlidingWindowSegmenter(prod, cuda_graph=True, **kw)
+    want = eager.logits(raster)
+    got = graph.logits(raster)          # 6 x 4 = 24 windows: 1 eager batch, 1 capture, 4 replays
+    assert graph._graph is not None and graph.windows_done == eager.windows_done == 24
+    assert torch.allclose(got, want, atol=1e-5, rtol=1e-5)
+    again = graph.logits(raster)        # all replays
+    assert torch.allclose(again, want, atol=1e-5, rtol=1e-5)
