@@ -85,11 +85,34 @@ class SegmentationUnetPlus(GpuSideHooks, _Base):
                 self.model.load_state_dict(sd)
 
     def configure_optimizers(self):
+        """segmentation_unetplus.py:146-205.  Without a LightningCLI scheduler dictionary in the hyper-parameters the
+        scheduler callable is applied as is; with one, OneCycleLR gets its horizon from the trainer (estimated stepping
+        batches, else the datamodule's epoch_size / batch_size, else the configured total_steps) and any other class is
+        built by the callable."""
+        import math
         opt = self.optimizer(self.parameters())
-        sched = self.scheduler(opt) if callable(self.scheduler) else None
-        if sched is None:
-            return [opt]
-        return [opt], [{"scheduler": sched, **self.scheduler_config}]
+        hp = self.hparams if isinstance(self.hparams, dict) else dict(self.hparams)
+        cfg = hp.get("scheduler")
+        if not cfg or not isinstance(cfg, dict):
+            sched = self.scheduler(opt) if callable(self.scheduler) else None
+            return ([opt], [{"scheduler": sched, **self.scheduler_config}]) if sched else [opt]
+        if cfg.get("class_path", "") == "torch.optim.lr_scheduler.OneCycleLR":
+            init = cfg.get("init_args", {})
+            max_lr = init.get("max_lr")
+            stepping = self.trainer.estimated_stepping_batches
+            dm = getattr(self.trainer, "datamodule", None)
+            if stepping > -1:
+                sched = torch.optim.lr_scheduler.OneCycleLR(opt, max_lr=max_lr, total_steps=stepping)
+            elif getattr(dm, "epoch_size", None) is not None:
+                accum = self.trainer.accumulate_grad_batches
+                per_epoch = math.ceil(dm.epoch_size / (dm.batch_size * accum))
+                sched = torch.optim.lr_scheduler.OneCycleLR(opt, max_lr=max_lr, steps_per_epoch=per_epoch + int(per_epoch * accum),
+                                                            epochs=self.trainer.max_epochs)
+            else:
+                sched = torch.optim.lr_scheduler.OneCycleLR(opt, max_lr=max_lr, total_steps=init.get("total_steps"))
+        else:
+            sched = self.scheduler(opt)
+        return ([opt], [{"scheduler": sched, **self.scheduler_config}]) if sched else [opt]
 
     def forward(self, image: Tensor) -> Tensor:
         return self.model(image)

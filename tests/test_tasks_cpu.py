@@ -111,3 +111,73 @@ def test_dofa_task_steps(monkeypatch):
     want = F.cross_entropy(out.out, y) + 0.4 * F.cross_entropy(out.aux, y)
     assert abs(float(task.logged["test_loss"]) - float(want)) < 1e-5
     _check_iou(task.logged, out.out, y, task.labels)
+
+
+def test_quickstart_construction_and_one_batch_each(monkeypatch):
+    """The reference's own integration tests (tests/test_notebooks_00quickstart.py:52-71,101-118) against the task mirror:
+    the same constructor arguments, and — Lightning is not installed here — a hand-rolled `fast_dev_run`: one batch of
+    train (step + backward + optimizer + scheduler), validation and test from the reference's RandomDataset recipe."""
+    from torch.utils.data import DataLoader, Dataset
+
+    from gdl_b200.tasks.segmentation_unetplus import SegmentationUnetPlus
+    emu.install(monkeypatch)
+
+    class RandomDataset(Dataset):
+        def __len__(self):
+            return 4
+
+        def __getitem__(self, idx):
+            return {"image": torch.rand(3, 32, 32), "mask": torch.zeros(32, 32, dtype=torch.long)}
+
+    model = SegmentationUnetPlus(encoder="resnet34", in_channels=3, num_classes=2, image_size=(64, 64), max_samples=1,
+                                 loss=torch.nn.CrossEntropyLoss(), optimizer=lambda params: torch.optim.Adam(params, lr=1e-3),
+                                 scheduler=torch.optim.lr_scheduler.StepLR, scheduler_config={"step_size": 1, "gamma": 0.1},
+                                 class_labels=["background", "buildings"], class_colors=["#000000", "#FF0000"])
+    assert hasattr(model, "training_step") and isinstance(model, torch.nn.Module)
+    torch.manual_seed(0)
+    model = SegmentationUnetPlus(encoder="resnet34", in_channels=3, num_classes=2, image_size=(32, 32), max_samples=1,
+                                 loss=torch.nn.CrossEntropyLoss(), optimizer=lambda params: torch.optim.Adam(params, lr=1e-3),
+                                 scheduler=lambda opt: torch.optim.lr_scheduler.StepLR(opt, step_size=1), scheduler_config={},
+                                 class_labels=["background", "buildings"], class_colors=["#000000", "#FF0000"],
+                                 compute_dtype=torch.float32)
+    model.configure_model()
+    (opt,), (sched_cfg,) = model.configure_optimizers()
+    assert sched_cfg["interval"] == "epoch" and isinstance(sched_cfg["scheduler"], torch.optim.lr_scheduler.StepLR)
+    loader = DataLoader(RandomDataset(), batch_size=2)
+    model.train()
+    batch = model.on_after_batch_transfer(next(iter(loader)), 0)
+    w0 = model.model.segmentation_head[0].weight.detach().clone()
+    loss = model.training_step(batch, 0)
+    opt.zero_grad()
+    loss.backward()
+    opt.step()
+    sched_cfg["scheduler"].step()
+    assert torch.isfinite(loss) and not torch.equal(model.model.segmentation_head[0].weight, w0)
+    assert abs(opt.param_groups[0]["lr"] - 1e-4) < 1e-12
+    model.eval()
+    with torch.no_grad():
+        pred = model.validation_step(next(iter(loader)), 0)
+        model.test_step(next(iter(loader)), 0)
+    assert pred.shape == (2, 32, 32) and {"test_loss", "meaniou_background", "meaniou_buildings"} <= set(model.logged)
+
+
+def test_unetplus_onecycle_from_cli_hyperparameters(monkeypatch):
+    """The LightningCLI branch of configure_optimizers (segmentation_unetplus.py:160-200): OneCycleLR sized from the trainer."""
+    from types import SimpleNamespace
+
+    from gdl_b200.tasks.segmentation_unetplus import SegmentationUnetPlus
+    task = SegmentationUnetPlus("resnet18", (32, 32), 3, 2, max_samples=1, loss=torch.nn.CrossEntropyLoss(),
+                                optimizer=lambda p: torch.optim.Adam(p, lr=1e-3), compute_dtype=torch.float32)
+    task.configure_model()
+    cfg = {"class_path": "torch.optim.lr_scheduler.OneCycleLR", "init_args": {"max_lr": 0.01, "total_steps": 77}}
+    task.hparams = {"scheduler": cfg}
+    task.trainer = SimpleNamespace(estimated_stepping_batches=120, datamodule=None, accumulate_grad_batches=1, max_epochs=3)
+    _, (s1,) = task.configure_optimizers()
+    assert isinstance(s1["scheduler"], torch.optim.lr_scheduler.OneCycleLR) and s1["scheduler"].total_steps == 120
+    task.trainer = SimpleNamespace(estimated_stepping_batches=-1, datamodule=SimpleNamespace(epoch_size=100, batch_size=8),
+                                   accumulate_grad_batches=2, max_epochs=3)
+    _, (s2,) = task.configure_optimizers()
+    assert s2["scheduler"].total_steps == (7 + 14) * 3  # ceil(100 / 16) = 7 steps + 7 * 2 buffer, 3 epochs
+    task.trainer = SimpleNamespace(estimated_stepping_batches=-1, datamodule=None, accumulate_grad_batches=1, max_epochs=3)
+    _, (s3,) = task.configure_optimizers()
+    assert s3["scheduler"].total_steps == 77
