@@ -869,16 +869,17 @@ __global__ void layerscale_add_kernel(const float* __restrict__ res, const T* __
     float uu[8];
     ld8(u + r * C + c, uu);
     const float4 r0 = *reinterpret_cast<const float4*>(res + r * C + c), r1 = *reinterpret_cast<const float4*>(res + r * C + c + 4);
-    const float4 g0 = *reinterpret_cast<const float4*>(gamma + c), g1 = *reinterpret_cast<const float4*>(gamma + c + 4);
+    // gamma is a parameter: inside a flat parameter buffer it is only 4-byte aligned, so no vector loads on it
+    const float* gm = gamma + c;
     float4 o0, o1;
-    o0.x = r0.x + s * g0.x * uu[0];
-    o0.y = r0.y + s * g0.y * uu[1];
-    o0.z = r0.z + s * g0.z * uu[2];
-    o0.w = r0.w + s * g0.w * uu[3];
-    o1.x = r1.x + s * g1.x * uu[4];
-    o1.y = r1.y + s * g1.y * uu[5];
-    o1.z = r1.z + s * g1.z * uu[6];
-    o1.w = r1.w + s * g1.w * uu[7];
+    o0.x = r0.x + s * gm[0] * uu[0];
+    o0.y = r0.y + s * gm[1] * uu[1];
+    o0.z = r0.z + s * gm[2] * uu[2];
+    o0.w = r0.w + s * gm[3] * uu[3];
+    o1.x = r1.x + s * gm[4] * uu[4];
+    o1.y = r1.y + s * gm[5] * uu[5];
+    o1.z = r1.z + s * gm[6] * uu[6];
+    o1.w = r1.w + s * gm[7] * uu[7];
     *reinterpret_cast<float4*>(out + r * C + c) = o0;
     *reinterpret_cast<float4*>(out + r * C + c + 4) = o1;
   }
@@ -1310,8 +1311,8 @@ extern "C" int gdl_layerscale_add(const float* res, const void* u, int dtype, co
                                   long long rows_per_sample, float* out, long long M, int C, void* stream) {
   GDL_REQUIRE(res && u && gamma && out && M > 0 && C > 0 && C % 8 == 0, GDL_ERR_INVALID, "layerscale_add: bad args (C %% 8 == 0)");
   GDL_REQUIRE(sscale == nullptr || rows_per_sample > 0, GDL_ERR_INVALID, "layerscale_add: rows_per_sample must be positive");
-  GDL_REQUIRE(((reinterpret_cast<uintptr_t>(res) | reinterpret_cast<uintptr_t>(u) | reinterpret_cast<uintptr_t>(out) |
-                reinterpret_cast<uintptr_t>(gamma)) & 15) == 0, GDL_ERR_INVALID, "layerscale_add: 16-byte aligned buffers expected");
+  GDL_REQUIRE(((reinterpret_cast<uintptr_t>(res) | reinterpret_cast<uintptr_t>(u) | reinterpret_cast<uintptr_t>(out)) & 15) == 0,
+              GDL_ERR_INVALID, "layerscale_add: 16-byte aligned buffers expected");
   long long b = (M * (C / 8) + 255) / 256;
   if (b > 16 * kNumSMsB200) b = 16 * kNumSMsB200;
   GDL_DISPATCH_T16(dtype, {

@@ -47,22 +47,25 @@ class FusedTrainer:
         dev = next(model.parameters()).device
         self.dev = dev
         self.params = [p for p in model.parameters() if p.requires_grad]
-        total = sum(p.numel() for p in self.params)
-        self.flat = torch.empty(total, dtype=acc_dtype, device=dev)
+        # every parameter starts on a 16-byte boundary of the flat buffers: the wgrad kernel accumulates pointwise-conv
+        # gradients straight into them with 128-bit reductions (the gaps stay zero: Adam leaves them at zero)
+        offsets, total = [], 0
+        for p in self.params:
+            offsets.append(total)
+            total += (p.numel() + 3) // 4 * 4
+        self.flat = torch.zeros(total, dtype=acc_dtype, device=dev)
         self.gflat = torch.zeros(total, dtype=acc_dtype, device=dev)
         self.m = torch.zeros(total, dtype=acc_dtype, device=dev)
         self.v = torch.zeros(total, dtype=acc_dtype, device=dev)
         self.grad_dst: dict[int, torch.Tensor] = {}
-        off = 0
         with torch.no_grad():
-            for p in self.params:
+            for p, off in zip(self.params, offsets):
                 n = p.numel()
                 self.flat[off:off + n].copy_(p.detach().reshape(-1))
                 p.data = self.flat[off:off + n].view(p.shape)
                 g = self.gflat[off:off + n].view(p.shape)
                 p.grad = g
                 self.grad_dst[id(p)] = g
-                off += n
         self.mean = torch.as_tensor(mean, dtype=acc_dtype, device=dev) if mean is not None else None
         self.std = torch.as_tensor(std, dtype=acc_dtype, device=dev) if std is not None else None
         self.loss_scale = (None if loss_scale is None else

@@ -79,7 +79,7 @@ def test_trainer_flat_buffers_and_step(monkeypatch):
     prod.train()
     tr = FusedTrainer(prod, emu.LossSpec(1.0, 0.0, ignore_index=-100), lr=1e-2, mean=[0.5] * 3, std=[0.25] * 3,
                       clip_grad_norm=1.0)
-    assert tr.flat.numel() == sum(p.numel() for p in prod.parameters())
+    assert tr.flat.numel() == sum((p.numel() + 3) // 4 * 4 for p in prod.parameters())  # 16-byte aligned slots
     # parameters are views of the flat buffer, gradients views of the flat gradient buffer
     p0 = next(prod.parameters())
     assert p0.data_ptr() == tr.flat.data_ptr() and p0.grad.data_ptr() == tr.gflat.data_ptr()
@@ -92,6 +92,28 @@ def test_trainer_flat_buffers_and_step(monkeypatch):
     # state_dict still exposes the (updated) parameters under the reference's key names
     sd = prod.state_dict()
     assert "decoder.blocks.x_0_0.conv1.0.weight" in sd and sd["encoder.conv1.weight"].data_ptr() == p0.data_ptr()
+
+
+def test_trainer_flat_buffer_slots_are_16_byte_aligned(monkeypatch):
+    """Parameters whose element count is not a multiple of 4 (a 5-class bias) must not misalign what follows them: the
+    wgrad kernel accumulates into the flat gradient buffer with 128-bit reductions."""
+    from gdl_b200.trainer import FusedTrainer
+    emu.install(monkeypatch)
+    _, prod = _pair("resnet18", 3, 5)
+    extra = torch.nn.Parameter(torch.ones(7))
+    prod.register_parameter("odd_sized_first", extra)
+    prod._parameters.move_to_end("odd_sized_first", last=False) if hasattr(prod._parameters, "move_to_end") else None
+    tr = FusedTrainer(prod.train(), emu.LossSpec(1.0, 0.0, ignore_index=-100), mean=[0.5] * 3, std=[0.25] * 3)
+    base = tr.flat.data_ptr()
+    for p in tr.params:
+        assert (p.data_ptr() - base) % 16 == 0 and (p.grad.data_ptr() - tr.gflat.data_ptr()) % 16 == 0
+    assert torch.equal(extra.detach(), torch.ones(7))  # values survive the move into the flat buffer
+    used = sum(p.numel() for p in tr.params)
+    covered = torch.zeros(tr.flat.numel(), dtype=torch.bool)
+    for p in tr.params:
+        off = (p.data_ptr() - base) // tr.flat.element_size()
+        covered[off:off + p.numel()] = True
+    assert tr.flat.numel() > used and int(covered.sum()) == used and not tr.flat[~covered].any()  # gaps are zero
 
 
 def test_trainer_loss_scaling(monkeypatch, f64):
@@ -449,7 +471,7 @@ def test_dofa_fused_trainer_matches_autograd_route(monkeypatch, f64):
         if isinstance(mod, torch.nn.BatchNorm2d):
             mod.reset_running_stats()
     tr = FusedTrainer(m, emu.LossSpec(1.0, 0.0, ignore_index=-100), lr=1e-3, mean=mean, std=std, acc_dtype=torch.float64)
-    assert tr.flat.numel() == sum(p.numel() for n_, p in m.named_parameters() if not n_.startswith("encoder."))
+    assert tr.flat.numel() == sum((p.numel() + 3) // 4 * 4 for n_, p in m.named_parameters() if not n_.startswith("encoder."))
     loss = tr.forward_backward(raw, t)
     # (the autograd route rounds the image to fp32 before the normalise kernel: ~1e-8 relative input difference)
     assert abs(float(loss) - float(F.cross_entropy(out.out, t) + 0.4 * F.cross_entropy(out.aux, t))) < 1e-7
@@ -487,7 +509,7 @@ def test_dofa_fused_trainer_with_trainable_encoder(monkeypatch, f64):
             mod.reset_running_stats()
     tr = FusedTrainer(m, emu.LossSpec(1.0, 0.0, ignore_index=-100), lr=1e-3, mean=[0.5] * 3, std=[0.25] * 3,
                       acc_dtype=torch.float64)
-    assert tr.flat.numel() == sum(p.numel() for p in m.parameters() if p.requires_grad)
+    assert tr.flat.numel() == sum((p.numel() + 3) // 4 * 4 for p in m.parameters() if p.requires_grad)
     before = m.encoder.blocks[3].attn.qkv.weight.detach().clone()
     tr.forward_backward(raw, t)
     for n_, p in m.named_parameters():
