@@ -68,7 +68,10 @@ def test_augment_normalize_matches_oracle(cuda, c, dtype):
     got_f, got_m64 = ops.augment_normalize(x.cuda().contiguous(), True, mask.long().cuda(), params.cuda(), torch.float32)
     assert got_m64.dtype == torch.int64 and torch.equal(got_m64.cpu(), want_m.long())
     assert torch.equal(got_f.cpu()[exact], want_i[exact])
-    assert (got_f.cpu() - want_i).abs().max() < 1e-5
+    # crops: the interpolation weight is the fractional part of an fp32 coordinate of magnitude <= 96 (ulp 8e-6), so two
+    # correct fp32 implementations differ by ~1e-5 x the local contrast (measured 2.2e-5 between ATen and the kernel's
+    # arithmetic transcribed to torch)
+    assert (got_f.cpu() - want_i).abs().max() < 1e-4
 
 
 def test_augment_full_tile_batch_and_errors(cuda):
