@@ -943,6 +943,115 @@ __global__ void vit_feature_grad_kernel(const T* __restrict__ dfeat, float* __re
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// DynamicChannelEmbed (mix_transformer.py:762-865) — the per-band pieces that are not GEMMs.
+//   xw     [P][C*E]  16-bit: band-weighted spatial-conv outputs, band c in columns c*E .. c*E+E-1
+//   scores [P][16]   fp32:   channel-attention logits of the C <= 16 bands (columns >= C unused)
+// channel_pool_fwd:  a = softmax_c(scores);  out[p][e] = sum_c a[c] * xw[p][c*E + e];  attn[p][c] = a[c] (kept for bwd)
+// channel_pool_bwd:  dxw[p][c*E+e] = a[c] * dout[p][e];  dattn[c] = sum_e dout[p][e] * xw[p][c*E+e];
+//                    dscores[c] = a[c] * (dattn[c] - sum_k a[k] dattn[k])   (16-bit, columns >= C zero)
+// One thread per (pixel, 8 channels of E); the E/8 threads of a pixel are adjacent lanes of one warp (E/8 in {1,2,4,8,16,32}).
+// ------------------------------------------------------------------------------------------
+constexpr int kMaxBands = 16;
+
+template <typename T>
+__global__ void channel_pool_fwd_kernel(const T* __restrict__ xw, const float* __restrict__ scores, T* __restrict__ out,
+                                        float* __restrict__ attn, long long P, int C, int E) {
+  const int tpp = E / 8;
+  const long long total = P * tpp;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long p = i / tpp;
+    const int v = (int)(i - p * tpp);
+    float a[kMaxBands];
+    float mx = -INFINITY;
+    for (int c = 0; c < C; ++c) {
+      a[c] = scores[p * 16 + c];
+      mx = fmaxf(mx, a[c]);
+    }
+    float sum = 0.f;
+    for (int c = 0; c < C; ++c) {
+      a[c] = expf(a[c] - mx);
+      sum += a[c];
+    }
+    const float inv = 1.f / sum;
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int c = 0; c < C; ++c) {
+      a[c] *= inv;
+      float x[8];
+      ld8(xw + p * (long long)C * E + (long long)c * E + v * 8, x);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] = fmaf(a[c], x[j], acc[j]);
+    }
+    st8(out + p * E + v * 8, acc);
+    if (v == 0 && attn != nullptr) {
+      for (int c = 0; c < 16; ++c) attn[p * 16 + c] = c < C ? a[c] : 0.f;
+    }
+  }
+}
+
+template <typename T>
+__global__ void channel_pool_bwd_kernel(const T* __restrict__ dout, const T* __restrict__ xw, const float* __restrict__ attn,
+                                        T* __restrict__ dxw, T* __restrict__ dscores, long long P, int C, int E) {
+  const int tpp = E / 8;
+  // whole pixels per block iteration so that the lanes of a pixel stay together and every lane of a warp takes the same
+  // number of trips through the loop (the shuffles below need all 32 lanes)
+  const long long total = P * tpp;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const long long trips = (total + stride - 1) / stride;
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  for (long long t = 0; t < trips; ++t, i += stride) {
+    const bool live = i < total;
+    const long long p = live ? i / tpp : 0;
+    const int v = live ? (int)(i - p * tpp) : 0;
+    float a[kMaxBands], da[kMaxBands];
+    float d[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (live) ld8(dout + p * E + v * 8, d);
+    for (int c = 0; c < C; ++c) {
+      a[c] = live ? attn[p * 16 + c] : 0.f;
+      float part = 0.f;
+      if (live) {
+        float x[8], o[8];
+        ld8(xw + p * (long long)C * E + (long long)c * E + v * 8, x);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          part = fmaf(d[j], x[j], part);
+          o[j] = a[c] * d[j];
+        }
+        st8(dxw + p * (long long)C * E + (long long)c * E + v * 8, o);
+      }
+      for (int off = tpp >> 1; off > 0; off >>= 1) part += __shfl_xor_sync(0xffffffffu, part, off);
+      da[c] = part;
+    }
+    if (live && v == 0) {
+      float dot = 0.f;
+      for (int c = 0; c < C; ++c) dot = fmaf(a[c], da[c], dot);
+      float o0[8], o1[8];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        o0[c] = c < C ? a[c] * (da[c] - dot) : 0.f;
+        o1[c] = c + 8 < C ? a[c + 8] * (da[c + 8] - dot) : 0.f;
+      }
+      st8(dscores + p * 16, o0);
+      st8(dscores + p * 16 + 8, o1);
+    }
+  }
+}
+
+// dx = dy * (y > 0)  (ReLU backward from the activation; 16-bit, n % 8 == 0)
+template <typename T>
+__global__ void relu_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ y, T* __restrict__ dx, long long n8) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n8;
+       i += (long long)gridDim.x * blockDim.x) {
+    float a[8], b[8], o[8];
+    ld8(dy + i * 8, a);
+    ld8(y + i * 8, b);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = b[j] > 0.f ? a[j] : 0.f;
+    st8(dx + i * 8, o);
+  }
+}
+
 }  // namespace gdl
 
 using namespace gdl;
@@ -1347,6 +1456,50 @@ extern "C" int gdl_vit_feature_grad(const void* dfeat, int dtype, float* g, int 
   long long b = ((long long)B * (P + 1) * C + 255) / 256;
   if (b > 16 * kNumSMsB200) b = 16 * kNumSMsB200;
   GDL_DISPATCH_T(dtype, { vit_feature_grad_kernel<T><<<(int)b, 256, 0, (cudaStream_t)stream>>>((const T*)dfeat, g, B, P, C, init); });
+  GDL_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+static bool pow2_le32(int v) { return v >= 1 && v <= 32 && (v & (v - 1)) == 0; }
+
+extern "C" int gdl_channel_pool_fwd(const void* xw, const float* scores, void* out, float* attn, int dtype, long long P,
+                                    int C, int E, void* stream) {
+  GDL_REQUIRE(xw && scores && out && P > 0 && C >= 1 && C <= kMaxBands && E >= 8 && E % 8 == 0 && pow2_le32(E / 8),
+              GDL_ERR_INVALID, "channel_pool_fwd: bad args (1 <= C <= 16 bands, E/8 a power of two <= 32)");
+  GDL_REQUIRE(((reinterpret_cast<uintptr_t>(xw) | reinterpret_cast<uintptr_t>(out)) & 15) == 0, GDL_ERR_INVALID,
+              "channel_pool_fwd: 16-byte aligned buffers expected");
+  long long b = (P * (E / 8) + 255) / 256;
+  if (b > 16 * kNumSMsB200) b = 16 * kNumSMsB200;
+  GDL_DISPATCH_T16(dtype, {
+    channel_pool_fwd_kernel<T><<<(int)b, 256, 0, (cudaStream_t)stream>>>((const T*)xw, scores, (T*)out, attn, P, C, E);
+  });
+  GDL_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int gdl_channel_pool_bwd(const void* dout, const void* xw, const float* attn, void* dxw, void* dscores, int dtype,
+                                    long long P, int C, int E, void* stream) {
+  GDL_REQUIRE(dout && xw && attn && dxw && dscores && P > 0 && C >= 1 && C <= kMaxBands && E >= 8 && E % 8 == 0 &&
+              pow2_le32(E / 8), GDL_ERR_INVALID, "channel_pool_bwd: bad args (1 <= C <= 16 bands, E/8 a power of two <= 32)");
+  GDL_REQUIRE(((reinterpret_cast<uintptr_t>(dout) | reinterpret_cast<uintptr_t>(xw) | reinterpret_cast<uintptr_t>(dxw) |
+                reinterpret_cast<uintptr_t>(dscores)) & 15) == 0, GDL_ERR_INVALID, "channel_pool_bwd: 16-byte aligned buffers expected");
+  long long b = (P * (E / 8) + 255) / 256;
+  if (b > 16 * kNumSMsB200) b = 16 * kNumSMsB200;
+  GDL_DISPATCH_T16(dtype, {
+    channel_pool_bwd_kernel<T><<<(int)b, 256, 0, (cudaStream_t)stream>>>((const T*)dout, (const T*)xw, attn, (T*)dxw,
+                                                                        (T*)dscores, P, C, E);
+  });
+  GDL_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int gdl_relu_bwd(const void* dy, const void* y, void* dx, int dtype, long long n, void* stream) {
+  GDL_REQUIRE(dy && y && dx && n > 0 && n % 8 == 0, GDL_ERR_INVALID, "relu_bwd: bad args (n %% 8 == 0 required)");
+  GDL_REQUIRE(((reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(dx)) & 15) == 0,
+              GDL_ERR_INVALID, "relu_bwd: 16-byte aligned buffers expected");
+  long long b = (n / 8 + 255) / 256;
+  if (b > 16 * kNumSMsB200) b = 16 * kNumSMsB200;
+  GDL_DISPATCH_T16(dtype, { relu_bwd_kernel<T><<<(int)b, 256, 0, (cudaStream_t)stream>>>((const T*)dy, (const T*)y, (T*)dx, n / 8); });
   GDL_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

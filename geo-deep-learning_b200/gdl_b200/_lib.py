@@ -143,6 +143,9 @@ _SIGS = {
     "gdl_gelu_bwd": [_VP, _VP, _VP, _I, _LL, _VP],
     "gdl_layerscale_add": [_VP, _VP, _I, _VP, _VP, _LL, _VP, _LL, _I, _VP],
     "gdl_layerscale_bwd": [_VP, _VP, _I, _VP, _VP, _LL, _VP, _VP, _LL, _I, _VP],
+    "gdl_channel_pool_fwd": [_VP, _VP, _VP, _VP, _I, _LL, _I, _I, _VP],
+    "gdl_channel_pool_bwd": [_VP, _VP, _VP, _VP, _VP, _I, _LL, _I, _I, _VP],
+    "gdl_relu_bwd": [_VP, _VP, _VP, _I, _LL, _VP],
     "gdl_adaptive_avgpool_fwd": [_VP, _LL, _VP, _I, _I, _I, _I, _I, _I, _VP],
     "gdl_adaptive_avgpool_bwd": [_VP, _VP, _I, _I, _I, _I, _I, _I, _VP],
     "gdl_add_nhwc": [_VP, _LL, _VP, _LL, _VP, _LL, _I, _LL, _I, _VP],

@@ -60,7 +60,8 @@ class SlidingWindowSegmenter:
         c = crops.shape[3]
         x16 = ops.normalize_to_nhwc(crops, False, model.compute_dtype, (c + 7) // 8 * 8, self.mean, self.std, self.image_max)
         eng = Engine(model.compute_dtype, training=False, wcache=model._wcache)
-        return model.run(eng, Act(x16, needs_grad=False))                                 # fp32 (B, t, t, K)
+        x = Act(x16, needs_grad=False)
+        return model.run(eng, x, c) if getattr(model, "needs_bands", False) else model.run(eng, x)   # fp32 (B, t, t, K)
 
     def _forward(self, crops: torch.Tensor) -> torch.Tensor:
         """(B, t, t, C) uint8 window batch -> fp32 logits (B, t, t, K); the result is only valid until the next call"""

@@ -100,8 +100,22 @@ class _Block(nn.Module):
         self.mlp = _Mlp(dim)
 
 
+class _DynamicChannelEmbed(nn.Module):
+    """parameter holder of DynamicChannelEmbed (mix_transformer.py:762-811): same sub-module names / shapes"""
+
+    def __init__(self, embed_dim: int, hidden_dim: int = 128) -> None:
+        super().__init__()
+        self.pos_dim = hidden_dim
+        self.weight_gen = nn.Sequential(nn.Linear(hidden_dim, hidden_dim), nn.ReLU(), nn.Linear(hidden_dim, embed_dim), nn.Tanh())
+        self.spatial_conv = nn.Conv2d(1, embed_dim, kernel_size=7, stride=4, padding=3)
+        self.channel_attention = nn.Sequential(nn.Conv1d(embed_dim + hidden_dim, embed_dim // 2, 1), nn.ReLU(),
+                                               nn.Conv1d(embed_dim // 2, 1, 1))
+        self.proj = nn.Linear(embed_dim, embed_dim)
+        self.norm = nn.LayerNorm(embed_dim)  # eps 1e-5
+
+
 class MixTransformerEncoder(nn.Module):
-    def __init__(self, name: str, in_channels: int) -> None:
+    def __init__(self, name: str, in_channels: int, dynamic: bool = False) -> None:
         super().__init__()
         if name not in MIT_CFG:
             raise KeyError(f"Wrong encoder name `{name}`, supported encoders: {list(MIT_CFG)}")
@@ -109,12 +123,16 @@ class MixTransformerEncoder(nn.Module):
         dims, heads, depths, _ = MIT_CFG[name]
         cin = in_channels
         for s in range(4):
-            setattr(self, f"patch_embed{s + 1}", _PatchEmbed(7 if s == 0 else 3, 4 if s == 0 else 2, cin, dims[s]))
+            if not (dynamic and s == 0):  # DynamicMixTransformer drops patch_embed1 (mix_transformer.py:886-893)
+                setattr(self, f"patch_embed{s + 1}", _PatchEmbed(7 if s == 0 else 3, 4 if s == 0 else 2, cin, dims[s]))
             cin = dims[s]
         for s in range(4):
             setattr(self, f"block{s + 1}", nn.ModuleList(_Block(dims[s], heads[s], SR_RATIOS[s]) for _ in range(depths[s])))
             setattr(self, f"norm{s + 1}", nn.LayerNorm(dims[s], eps=1e-6))
         self.apply(_init)
+        if dynamic:  # built outside MixVisionTransformer in the reference: torch's default initialisation
+            self.dynamic_patch_embed1 = _DynamicChannelEmbed(dims[0])
+        self.dynamic = dynamic
         self.out_channels = dims
 
 
@@ -147,6 +165,8 @@ def _lin_shape(w: torch.Tensor) -> tuple:
 
 
 class SegFormer(nn.Module):
+    needs_bands = True  # run() takes the real band count (the image arrives channel-padded to 8)
+
     def __init__(self, encoder: str = "mit_b0", in_channels: int = 3, weights: str | None = None,
                  freeze_layers: list[str] | None = None, num_classes: int = 1, *, use_dynamic_encoder: bool = False,
                  compute_dtype: torch.dtype = torch.bfloat16, drop_path_rate: float = 0.0,
@@ -160,11 +180,12 @@ class SegFormer(nn.Module):
         self.drop_path_masks: list | None = None
         self.dropout_mask: torch.Tensor | None = None
         self._ones: dict = {}
-        if use_dynamic_encoder:
-            raise NotImplementedError("DynamicMixTransformer (SURVEY §8f rank 4) is not implemented")
         if weights is not None:
             raise ValueError("weights must be None: load pretrained tensors through load_state_dict")
-        self.encoder = MixTransformerEncoder(encoder, in_channels)
+        # use_dynamic_encoder: DynamicMixTransformer (mix_transformer.py:868-934) — stage 1's patch embedding is replaced by
+        # the band-count-agnostic DynamicChannelEmbed; `in_channels` is then ignored, as in the reference
+        self.encoder = MixTransformerEncoder(encoder, in_channels, dynamic=use_dynamic_encoder)
+        self._dyn_buf: dict = {}
         self.decoder = SegFormerDecoder(encoder, num_classes)
         self.name = encoder
         self.num_classes = num_classes
@@ -264,8 +285,96 @@ class SegFormer(nn.Module):
         new_stream, rc2, act_y = self._branch_out(eng, y, mlp.fc2, stream, s)
         return new_stream, _Saved(rc1=rc1, act_a=act_a, pre=pre, rc2=rc2, act_y=act_y, s=s)
 
-    def run(self, eng: Engine, x: Act) -> torch.Tensor:
-        """x: NHWC 16-bit image (channels possibly zero padded).  Returns fp32 logits (N,H,W,K)."""
+    # ====================================================================================== DynamicChannelEmbed
+    def _dyn_dense(self, dyn: _DynamicChannelEmbed, c: int):
+        """The three band-wise layers of DynamicChannelEmbed written as ordinary dense convolutions over the bands
+        concatenated along the channel dim (block-diagonal weights), built from the parameters under autograd so that the
+        gradients the wgrad kernels produce for the dense tensors flow back to the parameters (tiny tensors):
+          Wd (C*E, C, 7, 7): band c -> its E maps, spatial_conv.weight * tanh-bounded channel weight cw[c]   (:826-835)
+          W1 (C*E/2, C*E), b1: channel_attention[0] on [xw_c ; pos_enc_c] — the position half is a per-band bias (:836-851)
+          W2 (16, C*E/2), b2: channel_attention[2], one logit per band (rows >= C zero)"""
+        pdt = dyn.proj.weight.dtype
+        dev = dyn.proj.weight.device
+        e = dyn.proj.in_features
+        with torch.enable_grad():
+            pos = torch.arange(c, device=dev).float()
+            inv = 1.0 / (10000 ** (torch.arange(0, dyn.pos_dim, 2, device=dev).float() / dyn.pos_dim))
+            pe = torch.zeros(c, dyn.pos_dim, device=dev)
+            pe[:, 0::2] = torch.sin(pos.unsqueeze(1) * inv)
+            pe[:, 1::2] = torch.cos(pos.unsqueeze(1) * inv)
+            pe = pe.to(pdt)
+            cw = dyn.weight_gen(pe)                                                    # (C, E), tanh-bounded
+            eye = torch.eye(c, dtype=pdt, device=dev)
+            w7 = dyn.spatial_conv.weight[:, 0]                                          # (E, 7, 7)
+            wd = torch.einsum("ce,ekl,cd->cedkl", cw, w7, eye).reshape(c * e, c, 7, 7)
+            bd = (cw * dyn.spatial_conv.bias.unsqueeze(0)).reshape(c * e)
+            ca0, ca2 = dyn.channel_attention[0], dyn.channel_attention[2]
+            w1a, w1b = ca0.weight[:, :e, 0], ca0.weight[:, e:, 0]                       # (E/2, E), (E/2, pos_dim)
+            w1 = torch.einsum("je,cd->cjde", w1a, eye).reshape(c * (e // 2), c * e)
+            b1 = (pe @ w1b.t() + ca0.bias.unsqueeze(0)).reshape(c * (e // 2))
+            w2 = torch.zeros(16, c * (e // 2), dtype=pdt, device=dev)
+            w2 = torch.cat([torch.einsum("j,cd->cdj", ca2.weight[0, :, 0], eye).reshape(c, c * (e // 2)), w2[c:]], 0)
+            b2 = torch.cat([ca2.bias.expand(c), torch.zeros(16 - c, dtype=pdt, device=dev)], 0)
+            return {"wd": wd, "bd": bd, "w1": w1.view(c * (e // 2), c * e, 1, 1), "b1": b1,
+                    "w2": w2.view(16, c * (e // 2), 1, 1), "b2": b2}
+
+    def _dyn_embed_fwd(self, eng: Engine, x: Act, c: int):
+        """x: NHWC 16-bit image, c real bands.  Returns (fp32 token stream (B,h,w,E), saved)."""
+        dyn = self.encoder.dynamic_patch_embed1
+        if c > 16:
+            raise ValueError("DynamicChannelEmbed on the B200 kernels handles at most 16 bands")
+        dt, acc = eng.dtype, eng.acc_dtype
+        graph = self._dyn_dense(dyn, c)
+        key = (c, graph["wd"].device, acc)
+        buf = self._dyn_buf.get(key)
+        if buf is None:  # persistent leaves: in-place refreshed each step, so the engine's packed-weight cache stays valid
+            buf = self._dyn_buf[key] = {k: torch.empty(v.shape, dtype=acc, device=v.device).requires_grad_(True)
+                                        for k, v in graph.items()}
+        with torch.no_grad():
+            for k, v in graph.items():
+                buf[k].copy_(v.detach())
+        e = dyn.proj.in_features
+        rc_xw = eng.conv_raw([x], buf["wd"], 4, 3, bias=buf["bd"], wshape=(c * e, c, 7, 7))
+        act_xw = Act(rc_xw.x)
+        rc_hid = eng.conv_raw([act_xw], buf["w1"], 1, 0, bias=buf["b1"], relu=True)
+        act_hid = Act(rc_hid.x)
+        rc_sc = eng.conv_raw([act_hid], buf["w2"], 1, 0, bias=buf["b2"], out_dtype=acc)
+        pooled, attn = ops.channel_pool_fwd(rc_xw.x, rc_sc.x, c, eng.training)
+        rc_proj, act_pool = self._linear(eng, pooled, dyn.proj)
+        stream, st = ops.layernorm_fwd(rc_proj.x, dyn.norm.weight, dyn.norm.bias, dyn.norm.eps, acc, eng.training)
+        return stream, _Saved(dyn=dyn, c=c, graph=graph, buf=buf, rc_xw=rc_xw, act_xw=act_xw, rc_hid=rc_hid, act_hid=act_hid,
+                              rc_sc=rc_sc, attn=attn, rc_proj=rc_proj, act_pool=act_pool, st=st)
+
+    def _dyn_embed_bwd(self, eng: Engine, sv, gstream: torch.Tensor) -> None:
+        dyn, c, dt = sv.dyn, sv.c, eng.dtype
+        if gstream.is_cuda and torch.cuda.is_current_stream_capturing():
+            raise NotImplementedError("CUDA-graph capture of a step through DynamicChannelEmbed: its band-weight generator is "
+                                      "differentiated by torch autograd; use cuda_graph=False")
+        pg = self._pgrads_ln(eng, dyn.norm)
+        _, dproj = ops.layernorm_bwd(gstream, sv.rc_proj.x, sv.st, dyn.norm.weight, want32=False, dtype16=dt, pgrads=pg)
+        self._store_ln_grads(eng, dyn.norm, pg)
+        eng.conv_backward(sv.rc_proj, dproj)
+        dxw1, dsc = ops.channel_pool_bwd(self._take(sv.act_pool).contiguous(), sv.rc_xw.x, sv.attn, c)
+        eng.conv_backward(sv.rc_sc, dsc)
+        dpre = ops.relu_bwd(self._take(sv.act_hid).contiguous(), sv.rc_hid.x)
+        eng.conv_backward(sv.rc_hid, dpre)
+        dxw2 = self._take(sv.act_xw)
+        dxw = torch.empty(sv.rc_xw.x.shape, dtype=dt, device=dxw1.device)
+        ops.grad_gather([(dxw1, 0), (dxw2, 0)], sv.rc_xw.x.shape, dt, g=dxw)
+        eng.conv_backward(sv.rc_xw, dxw)
+        names = [k for k in sv.graph if id(sv.buf[k]) in eng.param_grads]
+        params = [p_ for n_, p_ in dyn.named_parameters() if p_.requires_grad and not n_.startswith(("proj.", "norm."))]
+        if params and names:
+            grads = torch.autograd.grad([sv.graph[k] for k in names], params,
+                                        [eng.param_grads.pop(id(sv.buf[k])).view(sv.graph[k].shape).to(sv.graph[k].dtype)
+                                         for k in names], allow_unused=True)
+            for p_, g_ in zip(params, grads):
+                if g_ is not None:
+                    eng.grad_buffer(p_, False).copy_(g_)
+
+    def run(self, eng: Engine, x: Act, bands: int | None = None) -> torch.Tensor:
+        """x: NHWC 16-bit image (channels possibly zero padded; `bands` = the real channel count, needed by the dynamic
+        encoder).  Returns fp32 logits (N,H,W,K)."""
         enc, dec = self.encoder, self.decoder
         dims, heads, depths, emb = MIT_CFG[self.name]
         dt = eng.dtype
@@ -277,10 +386,16 @@ class SegFormer(nn.Module):
         cur = x
         blk_index = 0
         for s in range(4):
-            pe: _PatchEmbed = getattr(enc, f"patch_embed{s + 1}")
-            k, stride = pe.proj.kernel_size[0], pe.proj.stride[0]
-            rc_pe = eng.conv_raw([cur], pe.proj.weight, stride, k // 2, bias=pe.proj.bias)
-            stream, st_pe = ops.layernorm_fwd(rc_pe.x, pe.norm.weight, pe.norm.bias, pe.norm.eps, acc, eng.training)
+            sv_dyn = pe = rc_pe = st_pe = None
+            if s == 0 and enc.dynamic:
+                if bands is None:
+                    raise ValueError("the dynamic encoder needs the real band count of the (channel-padded) image")
+                stream, sv_dyn = self._dyn_embed_fwd(eng, cur, bands)
+            else:
+                pe = getattr(enc, f"patch_embed{s + 1}")
+                k, stride = pe.proj.kernel_size[0], pe.proj.stride[0]
+                rc_pe = eng.conv_raw([cur], pe.proj.weight, stride, k // 2, bias=pe.proj.bias)
+                stream, st_pe = ops.layernorm_fwd(rc_pe.x, pe.norm.weight, pe.norm.bias, pe.norm.eps, acc, eng.training)
             blocks = []
             for blk in getattr(enc, f"block{s + 1}"):
                 dp1, dp2 = self._drop_path_factors(eng, blk_index, stream.shape[0], stream.device)
@@ -296,7 +411,7 @@ class SegFormer(nn.Module):
             feat, st_out = ops.layernorm_fwd(stream, nrm.weight, nrm.bias, nrm.eps, dt, eng.training)
             feat_act = Act(feat)
             stages.append(_Saved(pe=pe, rc_pe=rc_pe, st_pe=st_pe, blocks=blocks, norm=nrm, x_out=stream, st_out=st_out,
-                                 feat=feat_act, src=cur))
+                                 feat=feat_act, src=cur, dyn=sv_dyn))
             cur = feat_act
         # ---- decoder (segformer_mlp.py:77-130)
         h1, w1 = stages[0].feat.t.shape[1:3]
@@ -433,6 +548,9 @@ class SegFormer(nn.Module):
                 gstream, g16 = ops.layernorm_bwd(da1, bs.x_in, bs.st1, blk.norm1.weight, add=gstream, want32=True,
                                                  dtype16=dt, pgrads=pg)
                 self._store_ln_grads(eng, blk.norm1, pg)
+            if st.dyn is not None:
+                self._dyn_embed_bwd(eng, st.dyn, gstream)
+                continue
             pg = self._pgrads_ln(eng, st.pe.norm)
             _, dpe = ops.layernorm_bwd(gstream, st.rc_pe.x, st.st_pe, st.pe.norm.weight, want32=False, dtype16=dt, pgrads=pg)
             self._store_ln_grads(eng, st.pe.norm, pg)
@@ -454,7 +572,7 @@ class SegFormer(nn.Module):
             return _SegFormerFn.apply(self, img, *params)
         with torch.no_grad():
             eng = Engine(self.compute_dtype, training=False, wcache=self._wcache)
-            logits = self.run(eng, self._input(img))
+            logits = self.run(eng, self._input(img), img.shape[1])
             self._saved = None
         return logits.permute(0, 3, 1, 2)
 
@@ -463,7 +581,7 @@ class _SegFormerFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, model: SegFormer, image: torch.Tensor, *params: torch.Tensor) -> torch.Tensor:
         eng = Engine(model.compute_dtype, training=True, wcache=model._wcache, sync_bn_group=model.sync_bn_group)
-        logits = model.run(eng, model._input(image))
+        logits = model.run(eng, model._input(image), image.shape[1])
         ctx.eng, ctx.model, ctx.params = eng, model, params
         model.last_engine = eng
         return logits.permute(0, 3, 1, 2)

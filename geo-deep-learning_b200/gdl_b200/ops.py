@@ -707,3 +707,39 @@ def dropout2d_apply(x: torch.Tensor, mask: torch.Tensor) -> torch.Tensor:
     _ck(L.load().gdl_dropout2d_apply(L.ptr(x), ld, L.ptr(mask), L.ptr(y), c, L.dt_code(x.dtype), n, h * w, c,
                                          L.stream_ptr()))
     return y
+
+
+def channel_pool_fwd(xw: torch.Tensor, scores: torch.Tensor, bands: int, want_attn: bool = True):
+    """xw 16-bit (N,H,W,bands*E), scores fp32 (N,H,W,16) -> (out 16-bit (N,H,W,E), attn fp32 (N,H,W,16) | None):
+    softmax over the bands of the channel-attention logits and the weighted sum of the per-band maps."""
+    n, h, w, ce = xw.shape
+    e = ce // bands
+    if not xw.is_contiguous() or not scores.is_contiguous() or tuple(scores.shape) != (n, h, w, 16) or \
+            scores.dtype != torch.float32 or e * bands != ce:
+        raise ValueError("channel_pool_fwd: contiguous xw (N,H,W,bands*E) and fp32 scores (N,H,W,16) expected")
+    out = torch.empty((n, h, w, e), dtype=xw.dtype, device=xw.device)
+    attn = torch.empty((n, h, w, 16), dtype=torch.float32, device=xw.device) if want_attn else None
+    _ck(L.load().gdl_channel_pool_fwd(L.ptr(xw), L.ptr(scores), L.ptr(out), L.ptr(attn), L.dt_code(xw.dtype), n * h * w, bands,
+                                          e, L.stream_ptr()))
+    return out, attn
+
+
+def channel_pool_bwd(dout: torch.Tensor, xw: torch.Tensor, attn: torch.Tensor, bands: int):
+    """-> (dxw 16-bit like xw, dscores 16-bit (N,H,W,16))"""
+    n, h, w, ce = xw.shape
+    e = ce // bands
+    if not dout.is_contiguous() or not xw.is_contiguous() or not attn.is_contiguous() or tuple(dout.shape) != (n, h, w, e):
+        raise ValueError("channel_pool_bwd: contiguous dout (N,H,W,E), xw (N,H,W,bands*E), attn (N,H,W,16) expected")
+    dxw = torch.empty_like(xw)
+    ds = torch.empty((n, h, w, 16), dtype=xw.dtype, device=xw.device)
+    _ck(L.load().gdl_channel_pool_bwd(L.ptr(dout), L.ptr(xw), L.ptr(attn), L.ptr(dxw), L.ptr(ds), L.dt_code(xw.dtype), n * h * w,
+                                          bands, e, L.stream_ptr()))
+    return dxw, ds
+
+
+def relu_bwd(dy: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
+    if not dy.is_contiguous() or not y.is_contiguous() or dy.shape != y.shape:
+        raise ValueError("relu_bwd: contiguous tensors of one shape expected")
+    dx = torch.empty_like(y)
+    _ck(L.load().gdl_relu_bwd(L.ptr(dy), L.ptr(y), L.ptr(dx), L.dt_code(y.dtype), y.numel(), L.stream_ptr()))
+    return dx

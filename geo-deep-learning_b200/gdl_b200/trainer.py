@@ -105,7 +105,8 @@ class FusedTrainer:
                     else model.fused_train(eng, x, c, target, self.loss, grad_scale=self.loss_scale))
             self.last_engine = eng
             return loss
-        logits = model.run(eng, Act(x, needs_grad=False))
+        logits = (model.run(eng, Act(x, needs_grad=False), c) if getattr(model, "needs_bands", False)
+                  else model.run(eng, Act(x, needs_grad=False)))
         coeff, _ = ops.seg_loss_fwd(logits, target, self.loss)
         n, h, w, k = logits.shape
         if hasattr(model, "backward"):

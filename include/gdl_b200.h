@@ -363,6 +363,20 @@ int gdl_layerscale_add(const float* res, const void* u, int dtype, const float* 
 int gdl_layerscale_bwd(const float* g, const void* u, int dtype, const float* gamma, const float* sscale,
                        long long rows_per_sample, void* du, float* dgamma, long long M, int C, void* stream);
 
+/* DynamicChannelEmbed of DynamicMixTransformer (models/encoders/mix_transformer.py:762-865), the parts that are not GEMMs:
+ * the softmax over the C <= 16 input bands of the channel-attention logits and the attention-weighted sum of the per-band
+ * feature maps (:843-848).  xw: 16-bit [P][C*E] (band c in columns c*E..c*E+E-1), scores: fp32 [P][16] (columns >= C
+ * unused), out: 16-bit [P][E], attn: fp32 [P][16] (kept for the backward, may be NULL at inference).
+ *   fwd: a = softmax_c(scores); out[p][e] = sum_c a[c] xw[p][c*E+e]
+ *   bwd: dxw[p][c*E+e] = a[c] dout[p][e]; dscores[p][c] = a[c] (dattn[c] - sum_k a[k] dattn[k]), dattn[c] = sum_e dout[p][e] xw[p][c*E+e]
+ *        (dscores 16-bit [P][16], columns >= C zero: the dY operand of the score conv's backward)
+ * E % 8 == 0 and E / 8 a power of two <= 32 (MiT stage-1 widths 32 / 64).  relu_bwd: dx = dy * (y > 0), n % 8 == 0. */
+int gdl_channel_pool_fwd(const void* xw, const float* scores, void* out, float* attn, int dtype, long long P, int C, int E,
+                         void* stream);
+int gdl_channel_pool_bwd(const void* dout, const void* xw, const float* attn, void* dxw, void* dscores, int dtype, long long P,
+                         int C, int E, void* stream);
+int gdl_relu_bwd(const void* dy, const void* y, void* dx, int dtype, long long n, void* stream);
+
 /* fp32 -> dtype cast of a flat buffer (residual-stream gradient -> 16-bit GEMM operand) */
 int gdl_cast_f32(const float* x, void* y, int dtype, long long n, void* stream);
 

@@ -7,6 +7,7 @@
                         and the CUDA normalise kernel to the reference itself.
 * wds_golden.pt       — outputs of the REFERENCE's `ShardedDataset._process_sample` (datasets/wds_dataset.py) for seeded
                         samples: pins oracle/wds.py and gdl_b200/wds_feeder.py to the reference itself (`--wds`).
+* dynamic_mit_b0_golden.pt — logits of the REFERENCE's SegFormer with its DynamicMixTransformer encoder (`--dynamic`).
 * unetpp_r18_golden.pt — seeded input / state_dict / logits / loss / selected gradients of
                         oracle/unetpp.py (resnet18, 3 bands, 5 classes, 64x64): a regression pin of
                         the oracle restatement (smp itself is not installable here, so its values
@@ -181,6 +182,27 @@ def dofa_golden() -> None:
     print("wrote dofa_golden.pt")
 
 
+def dynamic_mit_golden() -> None:
+    """Logits of the REFERENCE's SegFormerSegmentationModel(use_dynamic_encoder=True) (DynamicMixTransformer /
+    DynamicChannelEmbed, mix_transformer.py:762-934; mit_b0, 5 classes, 64x64) for 3- and 6-band inputs, loaded with
+    oracle.segformer.init_dynamic_state_dict(seed=4): pins oracle.segformer.dynamic_channel_embed to the reference."""
+    from oracle import ref_shims
+    from oracle import segformer as osf
+    ref = ref_shims.reference_segformer("mit_b0", 3, 5, dynamic=True).eval()
+    sd = osf.init_dynamic_state_dict("mit_b0", 5, seed=4)
+    assert set(sd) == set(ref.state_dict())
+    ref.load_state_dict(sd)
+    g = torch.Generator().manual_seed(21)
+    out = {}
+    for c in (3, 6):
+        x = torch.randn(2, c, 64, 64, generator=g)
+        with torch.no_grad():
+            y = ref(x)
+        out[c] = {"x": x, "logits_slice": y[:, :, ::4, ::4].clone()}
+    torch.save(out, OUT / "dynamic_mit_b0_golden.pt")
+    print("wrote dynamic_mit_b0_golden.pt")
+
+
 def wds_golden() -> None:
     """Outputs of the REFERENCE's own `ShardedDataset._process_sample` (datasets/wds_dataset.py:217-303) for seeded
     samples in the dofa / clay / unified formats.  `webdataset` and `pytorch_lightning` (imported at the top of that
@@ -236,3 +258,5 @@ if __name__ == "__main__":
         dofa_golden()
     if "--all" in sys.argv or "--wds" in sys.argv:
         wds_golden()
+    if "--all" in sys.argv or "--dynamic" in sys.argv:
+        dynamic_mit_golden()

@@ -99,13 +99,14 @@ def install_timm_shim() -> None:
     sys.modules["timm.models"], sys.modules["timm.models.vision_transformer"] = models, vt
 
 
-def reference_segformer(name: str, in_channels: int, num_classes: int):
-    """The reference's SegFormerSegmentationModel (weights=None)."""
+def reference_segformer(name: str, in_channels: int, num_classes: int, dynamic: bool = False):
+    """The reference's SegFormerSegmentationModel (weights=None); dynamic=True -> its DynamicMixTransformer encoder."""
     install_timm_shim()
     if str(REF) not in sys.path:
         sys.path.insert(0, str(REF))
     from geo_deep_learning.models.segmentation.segformer import SegFormerSegmentationModel
-    return SegFormerSegmentationModel(encoder=name, in_channels=in_channels, weights=None, num_classes=num_classes)
+    return SegFormerSegmentationModel(encoder=name, in_channels=in_channels, weights=None, num_classes=num_classes,
+                                      use_dynamic_encoder=dynamic)
 
 
 def reference_dofa(img_size: int, embed_dim: int = 768, depth: int = 12, heads: int = 12, out_indices=(4, 6, 10, 11)):

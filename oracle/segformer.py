@@ -71,6 +71,39 @@ def mix_ffn(x, h, w, sd, p):
     return _linear(y, sd, p + ".fc2")
 
 
+def channel_position_encoding(n_channels, pos_dim, dtype=torch.float32):
+    """DynamicChannelEmbed.get_position_encoding (mix_transformer.py:813-824): sinusoidal code of the band index"""
+    positions = torch.arange(n_channels).float()
+    dim_t = torch.arange(0, pos_dim, 2).float()
+    inv_freq = 1.0 / (10000 ** (dim_t / pos_dim))
+    pe = torch.zeros(n_channels, pos_dim)
+    pe[:, 0::2] = torch.sin(positions.unsqueeze(1) * inv_freq)
+    pe[:, 1::2] = torch.cos(positions.unsqueeze(1) * inv_freq)
+    return pe.to(dtype)
+
+
+def dynamic_channel_embed(sd, x, p="encoder.dynamic_patch_embed1"):
+    """DynamicChannelEmbed.forward (mix_transformer.py:826-865): per-band 7x7/4 conv shared by all bands, bounded
+    per-band channel weights from the band's position code, channel attention over the bands, projection + LayerNorm."""
+    b, c, hh, ww = x.shape
+    pos_dim = sd[p + ".weight_gen.0.weight"].shape[1]
+    pe = channel_position_encoding(c, pos_dim, x.dtype)
+    cw = torch.tanh(F.linear(F.relu(F.linear(pe, sd[p + ".weight_gen.0.weight"], sd[p + ".weight_gen.0.bias"])),
+                             sd[p + ".weight_gen.2.weight"], sd[p + ".weight_gen.2.bias"]))            # (C, E)
+    xc = F.conv2d(x.reshape(b * c, 1, hh, ww), sd[p + ".spatial_conv.weight"], sd[p + ".spatial_conv.bias"], stride=4, padding=3)
+    e, h, w = xc.shape[1:]
+    xw = xc.view(b, c, e, h * w) * cw.unsqueeze(0).unsqueeze(-1)
+    cat = torch.cat([xw, pe.unsqueeze(0).unsqueeze(-1).expand(b, -1, -1, h * w)], dim=2)
+    xa = cat.permute(0, 3, 1, 2).reshape(b * h * w, c, e + pos_dim).transpose(1, 2)
+    sc = F.conv1d(F.relu(F.conv1d(xa, sd[p + ".channel_attention.0.weight"], sd[p + ".channel_attention.0.bias"])),
+                  sd[p + ".channel_attention.2.weight"], sd[p + ".channel_attention.2.bias"])
+    sc = sc.transpose(1, 2).reshape(b, h * w, c).permute(0, 2, 1)
+    a = torch.softmax(sc, dim=1).unsqueeze(2)
+    agg = (xw * a).sum(dim=1).transpose(1, 2)                                                          # (B, hw, E)
+    out = _ln(_linear(agg, sd, p + ".proj"), sd, p + ".norm", EPS_PLAIN)
+    return out, h, w
+
+
 def encoder(sd, img, name, prefix="encoder.", drop_path=None):
     """`drop_path`: list over all blocks (stage-major, as mix_transformer.py:341-343 numbers its rates) of
     ((B,), (B,)) factors keep_mask / keep_prob for the attention and Mix-FFN branches — timm's DropPath in train mode with
@@ -79,12 +112,17 @@ def encoder(sd, img, name, prefix="encoder.", drop_path=None):
     x = img
     feats = []
     bi = 0
+    dynamic = f"{prefix}dynamic_patch_embed1.proj.weight" in sd  # DynamicMixTransformer (mix_transformer.py:868-934)
     for s in range(4):
         pe = f"{prefix}patch_embed{s + 1}"
         k, stride = (7, 4) if s == 0 else (3, 2)
-        x = F.conv2d(x, sd[pe + ".proj.weight"], sd[pe + ".proj.bias"], stride=stride, padding=k // 2)
-        b, c, h, w = x.shape
-        t = _ln(x.flatten(2).transpose(1, 2), sd, pe + ".norm", EPS_PLAIN)
+        if s == 0 and dynamic:
+            t, h, w = dynamic_channel_embed(sd, x, f"{prefix}dynamic_patch_embed1")
+            b, c = t.shape[0], t.shape[2]
+        else:
+            x = F.conv2d(x, sd[pe + ".proj.weight"], sd[pe + ".proj.bias"], stride=stride, padding=k // 2)
+            b, c, h, w = x.shape
+            t = _ln(x.flatten(2).transpose(1, 2), sd, pe + ".norm", EPS_PLAIN)
         for i in range(depths[s]):
             bp = f"{prefix}block{s + 1}.{i}"
             s1 = s2 = 1.0
@@ -179,4 +217,23 @@ def init_state_dict(name="mit_b2", in_channels=3, num_classes=5, seed=0):
     sd["decoder.linear_fuse.1.running_var"] = torch.ones(emb)
     sd["decoder.linear_fuse.1.num_batches_tracked"] = torch.tensor(0)
     conv("decoder.linear_pred", emb, num_classes, 1)
+    return sd
+
+
+def init_dynamic_state_dict(name="mit_b0", num_classes=5, seed=0):
+    """init_state_dict with stage 1's patch embedding replaced by seeded DynamicChannelEmbed tensors (reference keys)"""
+    sd = init_state_dict(name, 3, num_classes, seed)
+    sd = {k: v for k, v in sd.items() if not k.startswith("encoder.patch_embed1.")}
+    e = MIT_CFG[name][0][0]
+    g = torch.Generator().manual_seed(seed + 1000)
+    p = "encoder.dynamic_patch_embed1."
+    shapes = {"weight_gen.0.weight": (128, 128), "weight_gen.0.bias": (128,), "weight_gen.2.weight": (e, 128),
+              "weight_gen.2.bias": (e,), "spatial_conv.weight": (e, 1, 7, 7), "spatial_conv.bias": (e,),
+              "channel_attention.0.weight": (e // 2, e + 128, 1), "channel_attention.0.bias": (e // 2,),
+              "channel_attention.2.weight": (1, e // 2, 1), "channel_attention.2.bias": (1,),
+              "proj.weight": (e, e), "proj.bias": (e,), "norm.bias": (e,)}
+    for k, shp in shapes.items():
+        fan_in = shp[1] * (shp[2] if len(shp) > 2 else 1) * (shp[3] if len(shp) > 3 else 1) if len(shp) > 1 else 16
+        sd[p + k] = torch.randn(shp, generator=g) * (1.0 / fan_in) ** 0.5
+    sd[p + "norm.weight"] = 1 + 0.1 * torch.randn(e, generator=g)
     return sd

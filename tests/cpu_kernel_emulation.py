@@ -582,6 +582,32 @@ def dropout2d_apply(x, mask):
     return (x.to(_WORK) * mask.to(_WORK).view(mask.shape[0], 1, 1, mask.shape[1])).to(x.dtype).contiguous()
 
 
+def channel_pool_fwd(xw, scores, bands, want_attn=True):
+    n, h, w, ce = xw.shape
+    e = ce // bands
+    a = torch.softmax(scores[..., :bands].to(_WORK), -1)
+    out = (xw.to(_WORK).view(n, h, w, bands, e) * a.unsqueeze(-1)).sum(3).to(xw.dtype)
+    attn = torch.zeros(n, h, w, 16, dtype=scores.dtype)
+    attn[..., :bands] = a.to(scores.dtype)
+    return out, (attn if want_attn else None)
+
+
+def channel_pool_bwd(dout, xw, attn, bands):
+    n, h, w, ce = xw.shape
+    e = ce // bands
+    a = attn[..., :bands].to(_WORK)
+    d = dout.to(_WORK)
+    dxw = (a.unsqueeze(-1) * d.unsqueeze(3)).reshape(n, h, w, ce).to(xw.dtype)
+    da = (xw.to(_WORK).view(n, h, w, bands, e) * d.unsqueeze(3)).sum(-1)
+    ds = torch.zeros(n, h, w, 16, dtype=xw.dtype)
+    ds[..., :bands] = (a * (da - (a * da).sum(-1, keepdim=True))).to(xw.dtype)
+    return dxw, ds
+
+
+def relu_bwd(dy, y):
+    return torch.where(y > 0, dy, torch.zeros_like(dy))
+
+
 def cast_f32(x, dtype):
     return x.to(dtype)
 

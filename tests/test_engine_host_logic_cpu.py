@@ -253,6 +253,51 @@ def test_segformer_stochastic_layers_with_supplied_draws(monkeypatch, f64):
     assert not torch.allclose(a, c)
 
 
+@pytest.mark.parametrize("name,cin", [("mit_b0", 3), ("mit_b1", 6)])
+def test_dynamic_mix_transformer_backward_equals_oracle_autograd(monkeypatch, f64, name, cin):
+    """`use_dynamic_encoder=True` (DynamicMixTransformer / DynamicChannelEmbed, mix_transformer.py:762-934): the band-wise
+    layers as block-diagonal dense convolutions + the channel-pool kernels + torch autograd for the tiny weight
+    construction, against the oracle (pinned to the reference's own module) — forward and every parameter gradient."""
+    from gdl_b200.engine import Act, Engine
+    from gdl_b200.models.segformer import SegFormer
+    from oracle import segformer as osf
+    emu.install(monkeypatch)
+    k, hw = 4, 64
+    torch.manual_seed(0)
+    prod = SegFormer(name, in_channels=3, num_classes=k, use_dynamic_encoder=True, compute_dtype=torch.float64).double().train()
+    assert not hasattr(prod.encoder, "patch_embed1") and "encoder.dynamic_patch_embed1.spatial_conv.weight" in prod.state_dict()
+    with torch.no_grad():
+        for n_, p in prod.named_parameters():
+            if p.dim() == 1:
+                p.add_(0.1 * torch.randn_like(p))
+    sd = {n_: (v.detach().clone().requires_grad_(True) if v.is_floating_point() and "running" not in n_ else v.clone())
+          for n_, v in prod.state_dict().items()}
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(2, cin, hw, hw, generator=g).double()
+    t = torch.randint(0, k, (2, hw, hw), generator=g)
+    ref = osf.segformer_forward(sd, x, name, training=True)
+    F.cross_entropy(ref, t).backward()
+    eng = Engine(torch.float64, training=True, acc_dtype=torch.float64)
+    with torch.no_grad():
+        xin = emu.normalize_to_nhwc(x, True, torch.float64, 8)
+        logits = prod.run(eng, Act(xin, needs_grad=False), cin)
+    assert torch.allclose(logits.permute(0, 3, 1, 2), ref, atol=1e-9, rtol=1e-9)
+    d = logits.detach().permute(0, 3, 1, 2).clone().requires_grad_(True)
+    F.cross_entropy(d, t).backward()
+    with torch.no_grad():
+        prod.backward(eng, d.grad.permute(0, 2, 3, 1).contiguous())
+    for n_, p in prod.named_parameters():
+        got, want = eng.param_grads[id(p)], sd[n_].grad
+        err = (got - want).abs().max() / (want.abs().max() + 1e-30)
+        assert err < 1e-7 or want.abs().max() < 1e-12, f"{n_}: {err}"
+    # the same model accepts another band count without any change (what "dynamic" means) through the public forward
+    prod.eval()
+    x5 = torch.randn(1, 5, hw, hw, generator=g).double()
+    with torch.no_grad():
+        want5 = osf.segformer_forward({n_: v.detach() for n_, v in sd.items()}, x5, name)
+        assert torch.allclose(prod(x5).double(), want5, atol=1e-5, rtol=1e-5)  # the public forward takes the image as fp32
+
+
 def test_upernet_aux_head_dropout_with_supplied_draw(monkeypatch, f64):
     """FCNHead's Dropout2d (fcn_head.py:69-83) on the engine tape: y = x * m[n][c] forward, the same scaling backward."""
     from gdl_b200.engine import Act, Engine

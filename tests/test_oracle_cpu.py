@@ -154,6 +154,32 @@ def test_segformer_oracle_matches_reference_import():
         assert _close(osf.segformer_forward(sd0, x, "mit_b2"), ref(x))
 
 
+def test_dynamic_mix_transformer_oracle_matches_reference_golden():
+    """tests/golden/dynamic_mit_b0_golden.pt: outputs of the REFERENCE's SegFormer with its DynamicMixTransformer encoder."""
+    from oracle import segformer as osf
+    g = torch.load(GOLD / "dynamic_mit_b0_golden.pt")
+    sd = osf.init_dynamic_state_dict("mit_b0", 5, seed=4)
+    for c, case in g.items():
+        with torch.no_grad():
+            y = osf.segformer_forward(sd, case["x"], "mit_b0")
+        assert _close(y[:, :, ::4, ::4], case["logits_slice"]), c
+
+
+def test_dynamic_mix_transformer_oracle_matches_reference_import():
+    from oracle import ref_shims
+    from oracle import segformer as osf
+    if not ref_shims.available():
+        pytest.skip("/root/reference not present (GPU box): covered by the golden file")
+    ref = ref_shims.reference_segformer("mit_b1", 3, 4, dynamic=True).eval()
+    sd = osf.init_dynamic_state_dict("mit_b1", 4, seed=9)
+    assert set(ref.state_dict().keys()) == set(sd.keys())
+    ref.load_state_dict(sd)
+    for c in (1, 4, 8):
+        x = torch.randn(1, c, 64, 64, generator=torch.Generator().manual_seed(c))
+        with torch.no_grad():
+            assert _close(osf.segformer_forward(sd, x, "mit_b1"), ref(x)), c
+
+
 # --- MultiLevelNeck + UperNet + heads restatement: pinned to the reference's own modules -----------------
 def test_upernet_oracle_matches_reference_golden():
     from oracle import upernet as ou

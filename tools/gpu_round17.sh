@@ -4,7 +4,7 @@
 mkdir -p gpurun_out
 echo "=== new GPU tests (written blind): inference, augment/metrics, feeder, trainable DOFA, stochastic layers"
 for f in tests/test_zz1_inference_gpu.py tests/test_zz2_augment_metrics_gpu.py tests/test_zz3_wds_feeder_gpu.py \
-         tests/test_zz4_dofa_trainable_gpu.py tests/test_zz5_stochastic_layers_gpu.py; do
+         tests/test_zz4_dofa_trainable_gpu.py tests/test_zz5_stochastic_layers_gpu.py tests/test_zz6_dynamic_encoder_gpu.py; do
   timeout 900 python -m pytest "$f" -m gpu -q --no-header -rA -p no:cacheprovider > "gpurun_out/$(basename "$f" .py).log" 2>&1
   echo "$f: $(grep -E 'passed|failed|error' "gpurun_out/$(basename "$f" .py).log" | tail -1)"
   grep -E "^(FAILED|ERROR)|Error|assert " "gpurun_out/$(basename "$f" .py).log" | head -8
