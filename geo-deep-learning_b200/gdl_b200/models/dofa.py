@@ -172,14 +172,16 @@ class DOFAv2(nn.Module):
                  convert_patch_to_16: bool = False, pretrained: bool = False,
                  compute_dtype: torch.dtype = torch.bfloat16) -> None:
         super().__init__()
-        if convert_patch_to_16:
-            raise NotImplementedError("convert_patch_to_16 (bicubic re-sampling of the generated kernels)")
         if pretrained:
             raise ValueError("pretrained=True downloads from HuggingFace; load the tensors with load_state_dict")
         img_size = (img_size, img_size) if isinstance(img_size, int) else tuple(img_size)
         self.encoder_name, self.img_size, self.patch_size = encoder_name, img_size, patch_size
         self.embed_dim, self.depth, self.num_heads = embed_dim, depth, num_heads
-        self.num_patches = (img_size[0] // patch_size) * (img_size[1] // patch_size)
+        # convert_patch_to_16 (dofa_v2.py:168-176,220): the generated 14x14 kernels are resampled to 16x16 (bicubic,
+        # align_corners=False) and applied with stride 16 — the kernels are (D, C, 14, 14), a sub-MB tensor: torch glue
+        self.convert_patch_to_16 = convert_patch_to_16
+        self.conv_kernel = 16 if convert_patch_to_16 else patch_size
+        self.num_patches = (img_size[0] // self.conv_kernel) * (img_size[1] // self.conv_kernel)
         self.out_indices = list(out_indices) if out_indices is not None else [depth - 1]
         self.patch_embed = _Embedding(patch_size, embed_dim)
         self.pos_embed = nn.Parameter(_sincos_2d(embed_dim, int(self.num_patches ** 0.5)).unsqueeze(0), requires_grad=False)
@@ -221,6 +223,8 @@ class DOFAv2(nn.Module):
         bias = _lin(ops.cast_f32(x2[n - 1:n].contiguous(), dt), wg.fc_bias, out_dtype=torch.float32)
         k = self.patch_size
         w_oihw = (weights.view(c, k, k, self.embed_dim).permute(3, 0, 1, 2) * 0.01).contiguous()
+        if self.convert_patch_to_16:
+            w_oihw = F.interpolate(w_oihw, size=(16, 16), mode="bicubic", align_corners=False).contiguous()
         return w_oihw, (bias.view(self.embed_dim) * 0.01).contiguous()
 
     # ---------------------------------------------------------------------------------- forward
@@ -245,7 +249,7 @@ class DOFAv2(nn.Module):
         """img: NHWC 16-bit tile batch (B, H, W, ld >= c) as produced by the normalise kernel"""
         dt = self.compute_dtype
         b, hh, ww = img.shape[:3]
-        d, k = self.embed_dim, self.patch_size
+        d, k = self.embed_dim, self.conv_kernel
         w_oihw, bias = self._dynamic_weights(wavelengths, c)
         kk = k * k * c
         kpad = (kk + 63) // 64 * 64
@@ -303,6 +307,8 @@ class DOFAv2(nn.Module):
             bias = wg.fc_bias(x[-1])
             kk = self.patch_size
             w_oihw = weights.view(c, kk, kk, self.embed_dim).permute(3, 0, 1, 2) * 0.01
+            if self.convert_patch_to_16:
+                w_oihw = F.interpolate(w_oihw, size=(16, 16), mode="bicubic", align_corners=False)
             return w_oihw, bias.view(self.embed_dim) * 0.01
 
     def _drop_path_factors(self, i: int, b: int, dev, training: bool):
@@ -332,7 +338,7 @@ class DOFAv2(nn.Module):
             wavelengths = wavelengths[0]
         dt, acc = eng.dtype, eng.acc_dtype
         b, hh, ww = img.shape[:3]
-        d, k = self.embed_dim, self.patch_size
+        d, k = self.embed_dim, self.conv_kernel
         w_oihw, bias = self._dynamic_weights_autograd(wavelengths, c)
         kk = k * k * c
         kpad = (kk + 63) // 64 * 64
@@ -478,7 +484,7 @@ class DOFAv2(nn.Module):
         dpatch = ops.vit_extract_feature(g3, dt).view(b, S.hp, S.wpx, d)
         dw = torch.zeros((d, S.kpad), dtype=acc, device=g.device)
         ops.conv2d_wgrad([S.col], dpatch, 1, 1, 0, 0, dw)
-        k = self.patch_size
+        k = self.conv_kernel
         dw_oihw = torch.empty((d, S.c, k, k), dtype=acc, device=g.device)
         ops.unpack_conv_wgrad(dw, dw_oihw, S.kpad)
         sums = torch.empty(2 * d, dtype=acc, device=g.device)

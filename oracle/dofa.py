@@ -64,13 +64,16 @@ def weight_generator(sd, waves, p="patch_embed.weight_generator."):
     return _lin(x[wt:-1] + waves, sd, p + "fc_weight"), _lin(x[-1], sd, p + "fc_bias")
 
 
-def patch_embed(sd, img, wavelengths, embed_dim, k=14):
+def patch_embed(sd, img, wavelengths, embed_dim, k=14, convert_to_16=False):
     c = img.shape[1]
     waves = position_embedding(128, wavelengths * 1000)
     y = F.relu(_lin(F.relu(_lin(waves, sd, "patch_embed.fclayer.w1")), sd, "patch_embed.fclayer.w2"))
     waves = waves + y
     w, b = weight_generator(sd, waves)
     w = w.view(c, k, k, embed_dim).permute(3, 0, 1, 2) * 0.01
+    if convert_to_16:  # dofa_v2.py:168-176
+        w = F.interpolate(w, size=(16, 16), mode="bicubic", align_corners=False)
+        k = 16
     x = F.conv2d(img, w, b.view(embed_dim) * 0.01, stride=k, padding=1)
     return x.flatten(2).transpose(1, 2)
 
@@ -93,9 +96,10 @@ def vit_block(sd, x, p, heads, drop_path=None):
     return x + s2 * (m * sd[p + "ls2.gamma"])
 
 
-def dofa_forward(sd, img, wavelengths, embed_dim=768, depth=12, heads=12, out_indices=OUT_INDICES_BASE, drop_path=None):
+def dofa_forward(sd, img, wavelengths, embed_dim=768, depth=12, heads=12, out_indices=OUT_INDICES_BASE, drop_path=None,
+                 convert_to_16=False):
     """img (B,C,H,W), wavelengths (C,) in micrometres -> list of (B, D, H/14', W/14') maps"""
-    x = patch_embed(sd, img, wavelengths, embed_dim) + sd["pos_embed"][:, 1:, :]
+    x = patch_embed(sd, img, wavelengths, embed_dim, convert_to_16=convert_to_16) + sd["pos_embed"][:, 1:, :]
     x = torch.cat([sd["cls_token"].expand(x.shape[0], -1, -1), x], dim=1)
     feats = []
     for i in range(depth):

@@ -109,11 +109,13 @@ def reference_segformer(name: str, in_channels: int, num_classes: int, dynamic: 
                                       use_dynamic_encoder=dynamic)
 
 
-def reference_dofa(img_size: int, embed_dim: int = 768, depth: int = 12, heads: int = 12, out_indices=(4, 6, 10, 11)):
+def reference_dofa(img_size: int, embed_dim: int = 768, depth: int = 12, heads: int = 12, out_indices=(4, 6, 10, 11),
+                   convert_patch_to_16: bool = False):
     """The reference's DOFAv2 encoder (pretrained=False) on top of the timm Block restatement above."""
     install_timm_shim()
     if str(REF) not in sys.path:
         sys.path.insert(0, str(REF))
     from geo_deep_learning.models.encoders.dofa_v2 import DOFAv2
     return DOFAv2(img_size=img_size, patch_size=14, embed_dim=embed_dim, depth=depth, num_heads=heads,
-                  out_indices=list(out_indices), pretrained=False, drop_path_rate=0.0)
+                  out_indices=list(out_indices), pretrained=False, drop_path_rate=0.0,
+                  convert_patch_to_16=convert_patch_to_16)

@@ -388,6 +388,45 @@ def test_dofa_encoder_forward_equals_oracle(monkeypatch, f64):
         prod(x, torch.stack([wl, wl * 1.1]))
 
 
+def test_dofa_convert_patch_to_16(monkeypatch, f64):
+    """DOFAv2(convert_patch_to_16=True): bicubic 14 -> 16 resampling of the generated kernels, stride-16 embedding; frozen
+    route (kernels) and trainable route (autograd through the resampling) against the oracle."""
+    from gdl_b200.engine import Engine
+    from gdl_b200.models.dofa import DOFAv2
+    from oracle import dofa as od
+    emu.install(monkeypatch)
+    torch.manual_seed(0)
+    enc = DOFAv2("dofa_base", 64, 14, 32, 2, 2, out_indices=[0, 1], convert_patch_to_16=True, drop_path_rate=0.0,
+                 compute_dtype=torch.float64).double()
+    assert enc.num_patches == 16 and enc.pos_embed.shape == (1, 17, 32)
+    with torch.no_grad():
+        for n_, p in enc.named_parameters():
+            if "ls1" in n_ or "ls2" in n_:
+                p.fill_(0.5)
+    sd = {n_: v.detach().clone().requires_grad_(v.is_floating_point() and n_ != "pos_embed") for n_, v in enc.state_dict().items()}
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(2, 3, 64, 64, generator=g).double()
+    wl = torch.tensor([0.665, 0.56, 0.49]).double()
+    want = od.dofa_forward(sd, x, wl, 32, 2, 2, out_indices=(0, 1), convert_to_16=True)
+    with torch.no_grad():
+        got = enc(x, wl)
+    for a, b in zip(got, want):
+        # (the frozen route evaluates the wavelength sin/cos in fp32 like the reference; the float64 oracle does not)
+        assert a.shape == b.shape == (2, 32, 4, 4) and (a - b).abs().max() < 1e-5 * b.abs().max()
+    # trainable route: gradients through the resampled kernels reach the weight generator
+    (want[0].sum() + 2 * want[1].sum()).backward()
+    eng = Engine(torch.float64, training=True, acc_dtype=torch.float64)
+    with torch.no_grad():
+        feats = enc.run_train(eng, emu.normalize_to_nhwc(x, True, torch.float64, 8), 3, wl)
+        for f, wgt in zip(feats, (1.0, 2.0)):
+            f.gsrcs.append((torch.full_like(f.t, wgt), 0))
+        enc.backward(eng)
+    for n_ in ("patch_embed.weight_generator.fc_weight.weight", "patch_embed.fclayer.w1.weight", "blocks.0.attn.qkv.weight"):
+        p = dict(enc.named_parameters())[n_]
+        err = (eng.param_grads[id(p)] - sd[n_].grad).abs().max() / sd[n_].grad.abs().max()
+        assert err < 1e-6, (n_, err)
+
+
 def test_dofa_unfrozen_encoder_is_rejected(monkeypatch):
     from gdl_b200.models.dofa import DOFAv2
     emu.install(monkeypatch)

@@ -221,3 +221,22 @@ def test_dofa_oracle_matches_reference_import():
         want = ref(x, wl)
     for a, b in zip(od.dofa_forward(sd, x, wl, 96, 2, 3, out_indices=(0, 1)), want):
         assert _close(a, b, 2e-5)
+
+
+def test_dofa_convert_patch_to_16_matches_reference_import():
+    """`convert_patch_to_16=True` (dofa_v2.py:168-176,220): generated 14x14 kernels resampled to 16x16, stride 16."""
+    from oracle import dofa as od, ref_shims
+    if not ref_shims.available():
+        pytest.skip("/root/reference not present (GPU box)")
+    sd = od.init_state_dict(96, 2, 64, seed=7, ls_init=1.0)
+    sd["pos_embed"] = od.sincos_2d(96, 4).unsqueeze(0)  # (64 // 16)^2 patches
+    ref = ref_shims.reference_dofa(64, 96, 2, 3, (0, 1), convert_patch_to_16=True)
+    assert ref.pos_embed.shape == sd["pos_embed"].shape
+    ref.load_state_dict(sd)
+    ref.eval()
+    x = torch.randn(1, 3, 64, 64, generator=torch.Generator().manual_seed(0))
+    wl = torch.tensor([0.665, 0.56, 0.49])
+    with torch.no_grad():
+        want = ref(x, wl)
+    for a, b in zip(od.dofa_forward(sd, x, wl, 96, 2, 3, out_indices=(0, 1), convert_to_16=True), want):
+        assert a.shape == b.shape == (1, 96, 4, 4) and _close(a, b, 2e-5)
