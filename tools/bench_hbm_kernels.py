@@ -97,6 +97,15 @@ def main() -> None:
     df = torch.randn(b, ntok - 1, d, device=dev, generator=g).bfloat16()
     gs = torch.randn(b, ntok, d, device=dev, generator=g)
     report("vit_feature_grad (accumulate)", b * ntok * d * (2 + 4 + 4), lambda: ops.vit_feature_grad(df, gs))
+    bands, e = 4, 64
+    xw = torch.randn(16, 128, 128, bands * e, device=dev, generator=g).bfloat16()
+    sc = torch.randn(16, 128, 128, 16, device=dev, generator=g)
+    pooled, attn = ops.channel_pool_fwd(xw, sc, bands)
+    px = 16 * 128 * 128
+    report("channel_pool_fwd (4 bands x 64)", px * (bands * e * 2 + 64 + e * 2 + 64), lambda: ops.channel_pool_fwd(xw, sc, bands))
+    report("channel_pool_bwd (4 bands x 64)", px * (e * 2 + bands * e * 2 + 64 + bands * e * 2 + 32),
+           lambda: ops.channel_pool_bwd(pooled, xw, attn, bands))
+    report("relu_bwd (bf16)", xw.numel() * 6, lambda: ops.relu_bwd(xw, xw))
     if args.out:
         Path(args.out).write_text(json.dumps({"hbm_peak_GBps": peak, "rows": rows}, indent=1))
 
