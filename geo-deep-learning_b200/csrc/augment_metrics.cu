@@ -169,7 +169,7 @@ __global__ void argmax_confusion_kernel(const float* __restrict__ logits, int ld
                                         long long* __restrict__ classes, unsigned long long* __restrict__ conf) {
   extern __shared__ unsigned int hist[];
   const int Kc = K == 1 ? 2 : K;
-  const int bins = Kc * Kc;
+  const int bins = target != nullptr ? Kc * Kc : 0;  // no histogram (and no shared memory) for a classes-only call
   for (int b = threadIdx.x; b < bins; b += blockDim.x) hist[b] = 0u;
   __syncthreads();
   const long long n = blockIdx.y;
@@ -261,7 +261,7 @@ extern "C" int gdl_argmax_confusion(const float* logits, int ld, long long N, lo
   if (per > cap) per = cap;
   if (per < 1) per = 1;
   dim3 grid((unsigned)per, (unsigned)N);
-  const size_t smem = (size_t)Kc * Kc * sizeof(unsigned int);
+  const size_t smem = conf != nullptr ? (size_t)Kc * Kc * sizeof(unsigned int) : 0;
   cudaStream_t st = (cudaStream_t)stream;
   if (target_kind == 0)
     argmax_confusion_kernel<long long><<<grid, 256, smem, st>>>(logits, ld, HW, K, threshold, (const long long*)target,
