@@ -26,7 +26,10 @@ def test_vit_training_kernels(cuda, dtype):
     ref = F.gelu(x.float())
     ulp = 2.0 ** -7 if dtype == torch.bfloat16 else 2.0 ** -10
     assert (y.float() - ref).abs().max() <= ulp * ref.abs().max().clamp_min(1.0)
-    assert (y != ref.to(dtype)).float().mean() < 1e-3  # same erf, same rounding: at most rare last-bit differences
+    # same erf, same rounding: at most rare last-bit differences (outside the x < -2 tail, where 1 + erf cancels and two erf
+    # implementations — CUDA's, glibc's under tests/hostemu — may legitimately round differently)
+    body = x.float() > -2.0
+    assert (y != ref.to(dtype))[body].float().mean() < 1e-3
     dy = torch.randn(m, 4 * c, generator=g, device="cuda").to(dtype)
     xr = x.float().requires_grad_(True)
     F.gelu(xr).backward(dy.float())
