@@ -43,7 +43,9 @@ def load_lib():
     return _lib
 
 
-def install(monkeypatch) -> None:
+def install(monkeypatch, torch_convs: bool = False) -> None:
+    """torch_convs: take the tensor-core entry points from the torch emulation instead of running the tcgen05 / TMA kernels on
+    the functional model of hostemu_tc.cpp (faster for whole-model steps)."""
     import cpu_kernel_emulation as emu
     from gdl_b200 import _lib as L
     from gdl_b200 import ops
@@ -53,8 +55,9 @@ def install(monkeypatch) -> None:
     monkeypatch.setattr(L, "ptr", lambda t: C.c_void_p(0 if t is None else t.data_ptr()))
     monkeypatch.setattr(ops, "require_cuda", lambda t, what: None)
     monkeypatch.setattr(torch.cuda, "synchronize", lambda *a, **k: None)
-    for n in TENSOR_CORE_OPS:
-        monkeypatch.setattr(ops, n, getattr(emu, n))
+    if torch_convs:
+        for n in TENSOR_CORE_OPS:
+            monkeypatch.setattr(ops, n, getattr(emu, n))
     emu.set_work_dtype(torch.float32)
 
 
@@ -111,4 +114,24 @@ def run_case(name: str, fname: str, kw: dict, tmp_path=None) -> None:
         kwargs["cuda"] = torch.device("cpu")
     if "tmp_path" in sig.parameters:
         kwargs["tmp_path"] = tmp_path
-    fn(**kwargs)
+    # module-level pytest fixtures (option switches with a teardown) are driven by hand
+    mod, teardown = load_test_module(name), []
+    for pname in sig.parameters:
+        if pname in kwargs:
+            continue
+        fx = getattr(mod, pname, None)
+        raw = getattr(fx, "_get_wrapped_function", None)
+        raw = raw() if raw else getattr(fx, "__wrapped__", None)
+        if raw is None:
+            raise TypeError(f"{fname}: no value for parameter {pname}")
+        val = raw()
+        if inspect.isgenerator(val):
+            teardown.append(val)
+            val = next(val)
+        kwargs[pname] = val
+    try:
+        fn(**kwargs)
+    finally:
+        for gen in teardown:
+            for _ in gen:
+                pass

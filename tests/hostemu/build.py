@@ -9,6 +9,7 @@ shared-memory / shuffle reductions, argument checks) before it meets a B200.  Ne
 from __future__ import annotations
 
 import hashlib
+import os
 import re
 import subprocess
 from pathlib import Path
@@ -17,7 +18,13 @@ HERE = Path(__file__).resolve().parent
 ROOT = HERE.parent.parent
 CSRC = ROOT / "geo-deep-learning_b200" / "csrc"
 OUT = HERE / "_build"
-SOURCES = ["runtime.cu", "elementwise.cu", "transformer.cu", "loss_optim.cu", "augment_metrics.cu"]
+SOURCES = ["runtime.cu", "elementwise.cu", "transformer.cu", "loss_optim.cu", "augment_metrics.cu",
+           "igemm_conv.cu", "conv3x3_rows.cu", "wgrad3x3_rows.cu", "debug_probe.cu"]
+# PTX wrappers of common.cuh whose bodies are forwarded to the functional model in hostemu_tc.cpp
+TC_FORWARD = ["smem_u32", "elect_one", "mbar_init", "mbar_expect_tx", "mbar_arrive", "mbar_try_wait", "tma_load_2d", "tma_load_4d",
+              "tma_store_4d", "named_bar_sync", "tmem_alloc", "tmem_dealloc", "umma_f16", "umma_commit", "tmem_ld_32x32b_x16"]
+TC_NOP = ["fence_mbar_init", "fence_proxy_async_smem", "tma_prefetch_desc", "bulk_commit_group", "bulk_wait_group_read",
+          "bulk_wait_group", "tmem_relinquish", "tc_fence_before", "tc_fence_after", "tmem_ld_wait"]
 HEADERS = ["common.cuh", "tmap.cuh"]
 CUDA_INC = "/usr/local/cuda/include"
 
@@ -91,16 +98,54 @@ def rewrite_launches(src: str) -> str:
         src = src[:j + 1] + call + src[p1 + 1:]
 
 
+def _asm_inputs(body: str) -> list[str]:
+    """expressions of the input operands `"c"(expr)` of an asm statement with no outputs (`:: inputs : clobbers`)"""
+    ins = body.split("::", 1)[1]
+    out, i = [], 0
+    while True:
+        m = re.compile(r'"[a-z]"\s*\(').search(ins, i)
+        if not m:
+            return out
+        e = _match_fwd(ins, m.end() - 1, "(", ")")
+        out.append(ins[m.end():e])
+        i = e + 1
+
+
 def rewrite_asm(src: str) -> str:
     while True:
         m = re.search(r"\basm\s+volatile\s*\(", src)
         if not m:
             return src
         p1 = _match_fwd(src, m.end() - 1, "(", ")")
-        src = src[:m.start()] + "hostemu::unsupported_asm()" + src[p1 + 1:]
+        body = src[m.end():p1]
+        if body.lstrip().startswith('"red.global.add'):
+            ops = _asm_inputs(body)  # [address, value...]: fp32 reduction(s) into global memory
+            new = "do { float* _p = (float*)(" + ops[0] + "); " + " ".join(
+                f"hostemu::tc::red_add_f32(_p + {i}, {v});" for i, v in enumerate(ops[1:])) + " } while (0)"
+        else:
+            new = "hostemu::unsupported_asm()"
+        src = src[:m.start()] + new + src[p1 + 1:]
 
 
-def rewrite(src: str) -> str:
+def forward_wrappers(src: str) -> str:
+    """common.cuh: replace the inline-PTX body of each wrapper by a call into the functional model"""
+    for name in TC_FORWARD + TC_NOP:
+        m = re.search(rf"GDL_DEVINL\s+[\w \*&:]+?\b{name}\s*\(", src)
+        if not m:
+            raise RuntimeError(f"wrapper {name} not found in common.cuh")
+        p1 = _match_fwd(src, m.end() - 1, "(", ")")
+        params = [q for q in _split_top(src[m.end():p1]) if q]
+        names = [re.findall(r"[A-Za-z_]\w*", re.sub(r"\[[^\]]*\]", "", q))[-1] for q in params]
+        b0 = src.index("{", p1)
+        b1 = _match_fwd(src, b0, "{", "}")
+        call = f"hostemu::tc::{name}({', '.join(names)})" if name in TC_FORWARD else "hostemu::tc::nop()"
+        src = src[:b0] + "{ return " + call + "; }" + src[b1 + 1:]
+    return src
+
+
+def rewrite(src: str, common: bool = False) -> str:
+    if common:
+        src = forward_wrappers(src)
     src = rewrite_launches(src)
     src = rewrite_asm(src)
     src = re.sub(r"extern\s+__shared__\s+([\w\s]+?)\s+(\w+)\s*\[\s*\]\s*;", r"\1* \2 = reinterpret_cast<\1*>(hostemu::dyn_smem());", src)
@@ -109,18 +154,22 @@ def rewrite(src: str) -> str:
     return src
 
 
+ASAN = os.environ.get("GDL_HOSTEMU_ASAN", "0") == "1"  # + AddressSanitizer: run python under LD_PRELOAD=libasan.so (tools/hostemu_asan.sh)
+
+
 def lib_path() -> Path:
-    return OUT / "libgdlb200_hostemu.so"
+    return OUT / ("libgdlb200_hostemu_asan.so" if ASAN else "libgdlb200_hostemu.so")
 
 
 def build(verbose: bool = False) -> Path:
     OUT.mkdir(exist_ok=True)
     h = hashlib.sha256()
-    inputs = [CSRC / f for f in SOURCES + HEADERS] + [HERE / "cuda_hostemu.h", HERE / "hostemu_runtime.cpp", Path(__file__),
+    inputs = [CSRC / f for f in SOURCES + HEADERS] + [HERE / "cuda_hostemu.h", HERE / "hostemu_runtime.cpp", HERE / "hostemu_tc.h", HERE / "hostemu_tc.cpp", Path(__file__),
                                                      ROOT / "include" / "gdl_b200.h"]
     for p in inputs:
         h.update(p.read_bytes())
-    stamp = OUT / "stamp"
+    h.update(b"asan" if ASAN else b"plain")
+    stamp = OUT / ("stamp_asan" if ASAN else "stamp")
     if lib_path().exists() and stamp.exists() and stamp.read_text() == h.hexdigest():
         return lib_path()
     gen = OUT / "gen" / "csrc"
@@ -130,7 +179,7 @@ def build(verbose: bool = False) -> Path:
     inc.mkdir(exist_ok=True)
     (inc / "gdl_b200.h").write_bytes((ROOT / "include" / "gdl_b200.h").read_bytes())
     for f in HEADERS:
-        (gen / f).write_text(rewrite((CSRC / f).read_text()))
+        (gen / f).write_text(rewrite((CSRC / f).read_text(), common=f == "common.cuh"))
     cpps = []
     for f in SOURCES:
         text = rewrite((CSRC / f).read_text())
@@ -140,8 +189,8 @@ def build(verbose: bool = False) -> Path:
         dst = gen / (Path(f).stem + ".cpp")
         dst.write_text(text)
         cpps.append(dst)
-    cmd = ["g++", "-std=c++20", "-O1", "-g", "-fPIC", "-shared", "-Wl,-Bsymbolic", "-Wno-unknown-pragmas", "-Wno-attributes", "-fno-strict-aliasing",
-           f"-I{HERE}", f"-I{CUDA_INC}", *map(str, cpps), str(HERE / "hostemu_runtime.cpp"), "-o", str(lib_path())]
+    cmd = ["g++", "-std=c++20", "-O1", "-g", "-fPIC", "-shared", "-Wl,-Bsymbolic", "-Wno-unknown-pragmas", "-Wno-attributes", "-fno-strict-aliasing", "-fsanitize=alignment", "-fno-sanitize-recover=alignment", *(["-fsanitize=address"] if ASAN else []),
+           f"-I{HERE}", f"-I{CUDA_INC}", *map(str, cpps), str(HERE / "hostemu_runtime.cpp"), str(HERE / "hostemu_tc.cpp"), "-o", str(lib_path())]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0 or verbose:
         print(r.stdout[-4000:], r.stderr[-12000:])

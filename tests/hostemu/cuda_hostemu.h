@@ -27,6 +27,12 @@
 #include <algorithm>
 #include <functional>
 
+#include "hostemu_tc.h"
+
+#ifndef __grid_constant__
+#define __grid_constant__
+#endif
+
 // ---- built-in variables ------------------------------------------------------------------------------------------
 inline uint3 threadIdx, blockIdx;
 inline dim3 blockDim, gridDim;
@@ -35,10 +41,16 @@ constexpr int warpSize = 32;
 namespace hostemu {
 void launch(dim3 grid, dim3 block, size_t smem, const std::function<void()>& body);
 void* dyn_smem();
+size_t dyn_smem_offset();
 void sync_block();
 void sync_warp();
 uint64_t* warp_slots();  // 32 x 8-byte exchange slots of the calling fiber's warp
+void sync_named(int id, int nthreads);
+void yield_spin();      // a failed mbarrier poll: stay runnable, let the other fibers run
+void note_progress();   // deadlock detection: something observable changed
 int lane();
+int warp_index();
+int thread_linear();
 [[noreturn]] void unsupported_asm();
 }  // namespace hostemu
 
@@ -53,6 +65,12 @@ int lane();
 #define __host__
 #define __forceinline__ inline
 #define __launch_bounds__(...)
+
+// cuda_runtime.h offers the kernel-pointer overload only under nvcc
+template <typename K>
+inline cudaError_t cudaFuncSetAttribute(K* kernel, cudaFuncAttribute, int) {
+  return kernel != nullptr ? cudaSuccess : cudaErrorInvalidDeviceFunction;
+}
 
 inline void __syncthreads() { hostemu::sync_block(); }
 inline void __syncwarp(unsigned = 0xffffffffu) { hostemu::sync_warp(); }

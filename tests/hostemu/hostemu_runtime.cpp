@@ -8,7 +8,7 @@
 
 namespace hostemu {
 
-enum { kRun = 0, kWaitBlock = 1, kWaitWarp = 2, kDone = 3 };
+enum { kRun = 0, kWaitBlock = 1, kWaitWarp = 2, kDone = 3, kWaitNamed = 4 };
 constexpr size_t kStackBytes = 256 * 1024;
 
 struct Fiber {
@@ -16,6 +16,8 @@ struct Fiber {
   int state;
   uint3 tid;
   int warp, lane;
+  int bar_id, bar_n;  // named barrier (bar.sync id, n) the fiber waits at
+  bool spun;          // last yield was a failed mbarrier poll
 };
 
 static std::vector<Fiber> g_fibers;
@@ -26,7 +28,10 @@ static Fiber* g_cur = nullptr;
 static const std::function<void()>* g_body = nullptr;
 alignas(1024) static unsigned char g_smem[256 * 1024];
 
-void* dyn_smem() { return g_smem; }
+// dynamic shared memory starts 16-byte (not 1024-byte) aligned, a little above shared address 0, as behind static allocations
+constexpr size_t kDynOffset = 1040;
+void* dyn_smem() { return g_smem + kDynOffset; }
+size_t dyn_smem_offset() { return kDynOffset; }
 int lane() { return g_cur->lane; }
 uint64_t* warp_slots() { return g_slots.data() + (size_t)g_cur->warp * 32; }
 
@@ -37,6 +42,24 @@ static void yield_as(int state) {
 }
 void sync_block() { yield_as(kWaitBlock); }
 void sync_warp() { yield_as(kWaitWarp); }
+void sync_named(int id, int n) {
+  g_cur->bar_id = id;
+  g_cur->bar_n = n;
+  yield_as(kWaitNamed);
+}
+static unsigned long long g_progress = 0;
+void note_progress() { ++g_progress; }
+void yield_spin() {
+  g_cur->spun = true;
+  yield_as(kRun);
+}
+int warp_index() { return g_cur->warp; }
+int thread_linear() { return g_cur->warp * 32 + g_cur->lane; }
+namespace tc {
+void* encode_entry_point();
+void block_begin();
+void block_end(unsigned bx, unsigned by, unsigned bz);
+}
 
 [[noreturn]] void unsupported_asm() {
   fprintf(stderr, "hostemu: inline PTX reached (tensor-core / TMA code is not emulated)\n");
@@ -51,7 +74,7 @@ static void fiber_entry() {
 
 void launch(dim3 grid, dim3 block, size_t smem, const std::function<void()>& body) {
   const int nthreads = (int)(block.x * block.y * block.z);
-  if (nthreads <= 0 || nthreads > 1024 || smem > sizeof(g_smem)) {
+  if (nthreads <= 0 || nthreads > 1024 || smem + kDynOffset > sizeof(g_smem)) {
     fprintf(stderr, "hostemu: bad launch (%d threads, %zu B shared)\n", nthreads, smem);
     abort();
   }
@@ -69,6 +92,7 @@ void launch(dim3 grid, dim3 block, size_t smem, const std::function<void()>& bod
         for (int t = 0; t < nthreads; ++t) {
           Fiber& f = g_fibers[t];
           f.state = kRun;
+          f.spun = false;
           f.tid = make_uint3(t % block.x, (t / block.x) % block.y, t / (block.x * block.y));
           f.warp = t / 32;
           f.lane = t % 32;
@@ -78,15 +102,22 @@ void launch(dim3 grid, dim3 block, size_t smem, const std::function<void()>& bod
           f.ctx.uc_link = nullptr;
           makecontext(&f.ctx, fiber_entry, 0);
         }
+        tc::block_begin();
+        int idle_passes = 0;
         for (;;) {
           bool ran = false;
+          const unsigned long long progress0 = g_progress;
+          int spinning = 0;
           for (int t = 0; t < nthreads; ++t) {
             Fiber& f = g_fibers[t];
             if (f.state != kRun) continue;
             g_cur = &f;
             threadIdx = f.tid;
+            f.spun = false;
             swapcontext(&g_main, &f.ctx);
             ran = true;
+            if (f.state == kDone) ++g_progress;
+            if (f.state == kRun && f.spun) ++spinning;
           }
           // every fiber is now waiting or done: open the barriers whose live participants have all arrived
           int live = 0, at_block = 0;
@@ -112,12 +143,32 @@ void launch(dim3 grid, dim3 block, size_t smem, const std::function<void()>& bod
               released = true;
             }
           }
-          if (!released) {
-            fprintf(stderr, "hostemu: block (%u,%u,%u) stuck (%s): %d live fibers, %d at __syncthreads, the rest in a partial warp barrier\n",
-                    bx, by, bz, ran ? "divergent barrier" : "nothing runnable", live, at_block);
+          for (int id = 0; id < 16; ++id) {  // bar.sync id, n
+            int cnt = 0, need = 0;
+            for (int t = 0; t < nthreads; ++t)
+              if (g_fibers[t].state == kWaitNamed && g_fibers[t].bar_id == id) {
+                ++cnt;
+                need = g_fibers[t].bar_n;
+              }
+            if (cnt > 0 && cnt >= need) {
+              for (int t = 0; t < nthreads; ++t)
+                if (g_fibers[t].state == kWaitNamed && g_fibers[t].bar_id == id) g_fibers[t].state = kRun;
+              released = true;
+            }
+          }
+          if (released) ++g_progress;
+          idle_passes = (g_progress == progress0) ? idle_passes + 1 : 0;
+          if ((!released && spinning == 0) || idle_passes > 4) {
+            fprintf(stderr, "hostemu: block (%u,%u,%u) stuck (%s): %d live fibers, %d at __syncthreads, %d polling an mbarrier\n",
+                    bx, by, bz, spinning ? "mbarrier deadlock" : (ran ? "divergent barrier" : "nothing runnable"), live, at_block, spinning);
+            for (int t = 0; t < nthreads; ++t)
+              if (g_fibers[t].state != kDone)
+                fprintf(stderr, "  thread %d: %s\n", t, g_fibers[t].state == kRun ? "polling" : g_fibers[t].state == kWaitBlock ? "__syncthreads"
+                        : g_fibers[t].state == kWaitWarp ? "warp barrier" : "named barrier");
             abort();
           }
         }
+        tc::block_end(bx, by, bz);
       }
   g_body = nullptr;
   g_cur = nullptr;
@@ -150,8 +201,8 @@ cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, enum cudaMemcpyKin
 }
 cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
 cudaError_t cudaGetDriverEntryPoint(const char*, void** fn, unsigned long long, enum cudaDriverEntryPointQueryResult* q) {
-  *fn = nullptr;  // no driver: tensor maps (TMA kernels) are not emulated
-  if (q) *q = cudaDriverEntryPointSymbolNotFound;
+  *fn = hostemu::tc::encode_entry_point();  // cuTensorMapEncodeTiled stand-in of the functional model
+  if (q) *q = cudaDriverEntryPointSuccess;
   return cudaSuccess;
 }
 cudaError_t cudaDeviceSynchronize(void) { return cudaSuccess; }

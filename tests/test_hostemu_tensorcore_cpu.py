@@ -1,0 +1,52 @@
+"""The tensor-core kernels (tcgen05.mma / TMEM / TMA / mbarrier pipelines) EXECUTED on the CPU on a functional model of the
+sm_100a features they use (tests/hostemu/hostemu_tc.cpp): the product's kernel sources, unmodified, with the inline-PTX wrappers
+of csrc/common.cuh forwarded to the model — warp-specialised producer / MMA-issuer / epilogue roles as fibers, mbarrier phases,
+swizzled TMA boxes with zero fill, UMMA shared-memory descriptors (K-major, MN-major, row-shifted starts), TMEM lanes / columns,
+TMA-store epilogues.  The GPU tests of these kernels are the test bodies.
+
+What this proves and what it does not: the model encodes the semantics the code base relies on and reproduces every result the
+B200 produced for these tests (all green on hardware in runs 5-15), so host-side descriptor / pipeline / indexing changes and
+new kernels built from the same primitives can be checked without a GPU.  It says nothing about speed, and hardware behaviour
+outside the modelled subset (e.g. an illegal descriptor the model accepts) is still only found on a B200.
+
+Default: a fast subset.  GDL_HOSTEMU_FULL=1: every parametrisation of every tensor-core test file.
+"""
+import os
+
+import pytest
+
+import hostemu
+
+FULL = os.environ.get("GDL_HOSTEMU_FULL", "0") == "1"
+
+FILES = {
+    "test_kernels_gpu": dict(include=("test_conv_fwd_matches_fp32_conv", "test_conv_reads_channel_slices_and_writes_strided",
+                                      "test_conv_wgrad_matches_autograd", "test_conv_dgrad_through_transposed_weights")),
+    "test_conv_epilogue_modes_gpu": {},
+    "test_conv_halo_gpu": {},
+    "test_conv_rows_gpu": {},
+    "test_wgrad_rows_gpu": {},
+    "test_grouped_gemm_gpu": {},
+    "test_pixel_pack_gpu": {},
+}
+# ids (substring match) that make up the default subset: one or two small cases per kernel / layout family
+FAST = ("(2, 32, 32, [64], 64, 3, 1)", "(1, 16, 16, [16], 5, 1, 0)", "(1, 64, 64, [16], 16, 3, 1)", "(1, 32, 32, [64], 32, 7, 3)",
+        "test_conv_reads_channel_slices", "test_rows_kernel_equals_tile_kernel_and_fp32[2-8-128-[64]-64",
+        "test_rows_kernel_equals_tile_kernel_and_fp32[2-8-128-[64]-5", "test_wgrad_rows_equals_generic_and_fp32[1-4-64",
+        "test_fwd_halo_equals_per_tap_and_fp32[1-3-128-[32, 32]-32", "test_wgrad_halo_equals_per_tap_and_autograd[1-3-64")
+
+
+def _params():
+    out = []
+    for f, sel in FILES.items():
+        for fn, kw, ident in hostemu.cases(f, **sel):
+            fast = any(s in ident for s in FAST)
+            marks = [] if fast else [pytest.mark.skipif(not FULL, reason="set GDL_HOSTEMU_FULL=1 for every tensor-core case")]
+            out.append(pytest.param(f, fn, kw, id=ident, marks=marks))
+    return out
+
+
+@pytest.mark.parametrize("file,fname,kw", _params())
+def test_tensor_core_kernel_on_functional_model(monkeypatch, tmp_path, file, fname, kw):
+    hostemu.install(monkeypatch, torch_convs=False)
+    hostemu.run_case(file, fname, kw, tmp_path)

@@ -80,5 +80,14 @@ def test_adaptive_pool_and_add_kernels(cuda):
         dy = torch.randn(2, s, s, 64, generator=g).bfloat16().cuda()
         ref.backward(dy.float().permute(0, 3, 1, 2))
         assert _rel(ops.adaptive_avgpool_bwd(dy, 18, 18), xr.grad.permute(0, 2, 3, 1)) < 2 ** -7
+    # more bins than pixels (PPM scale 6 on the 3x3 map of a 112-pixel DOFA tile), non-square ratios
+    for hw, s in ((3, 6), (5, 6), (7, 3)):
+        xs = torch.randn(2, hw, hw, 64, generator=g).bfloat16().cuda()
+        xr = xs.float().permute(0, 3, 1, 2).requires_grad_(True)
+        ref = F.adaptive_avg_pool2d(xr, s)
+        assert _rel(ops.adaptive_avgpool_fwd(xs, s), ref.permute(0, 2, 3, 1)) < 2 ** -8
+        dy = torch.randn(2, s, s, 64, generator=g).bfloat16().cuda()
+        ref.backward(dy.float().permute(0, 3, 1, 2))
+        assert _rel(ops.adaptive_avgpool_bwd(dy, hw, hw), xr.grad.permute(0, 2, 3, 1)) < 2 ** -7
     b = torch.randn(2, 18, 18, 64, generator=g).bfloat16().cuda()
     assert torch.equal(ops.add_nhwc(x, b), (x.float() + b.float()).bfloat16())
