@@ -415,6 +415,7 @@ def main_product(args) -> None:
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": w["name"], "global_batch": B * world, "parallelism": f"dp{world}",
                        "loss": "cross_entropy", "optimizer": "adam", "sync_bn": bool(args.sync_bn and world > 1), "cuda_graph": bool(args.cuda_graph) and (world == 1 or args.cuda_graph >= 2),
+                       "sra_fused": bool(ops.option("sra_fused")),
                        "l2": f"{NBUF} rotating input batches; per-step working set >> 126 MB L2"},
             "clocks": clk,
             "e2e": {"value": tiles / (ms_e2e / 1e3), "unit": "tiles/s",
@@ -516,7 +517,7 @@ def main_infer(args, world: int, rank: int, local: int, dev) -> None:
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": w["name"], "raster": [R, R, C], "windows": nwin, "window_batch": B,
                        "parallelism": f"windows round-robin over {world} rank(s) + one all-reduce of the logit sums",
-                       "cuda_graph": args.cuda_graph >= 2,
+                       "cuda_graph": args.cuda_graph >= 2, "sra_fused": bool(ops.option("sra_fused")),
                        "l2": f"raster {R * R * C / 1e6:.0f} MB and activations >> 126 MB L2"},
             "clocks": clk,
             "e2e": {"value": nwin * args.steps / (ms_e2e / 1e3), "unit": "tiles/s", "h2d_bytes_per_step": R * R * C,

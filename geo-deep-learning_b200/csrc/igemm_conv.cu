@@ -665,6 +665,7 @@ static int validate_srcs(int num_src, const gdl_src_t* src, int* ctot) {
   return 0;
 }
 
+extern int g_opt_sra_max_ctas;  // sra_attention.cu
 }  // namespace gdl
 
 using namespace gdl;
@@ -677,6 +678,7 @@ extern "C" int gdl_set_option(const char* name, long long value) {
   else if (!strcmp(name, "wgrad_l2_mb")) g_opt_wgrad_l2_mb = value;
   else if (!strcmp(name, "conv_rows")) g_opt_conv_rows = (int)value;
   else if (!strcmp(name, "wgrad_rows")) g_opt_wgrad_rows = (int)value;
+  else if (!strcmp(name, "sra_max_ctas")) g_opt_sra_max_ctas = (int)value;  // 0 = one CTA per SM (tests: fewer, longer CTAs)
   else {
     set_last_error("set_option: unknown option '%s'", name);
     return GDL_ERR_INVALID;

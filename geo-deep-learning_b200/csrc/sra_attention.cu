@@ -1,0 +1,318 @@
+// sra_attention.cu — fused spatial-reduction attention forward (reference: Attention.forward, mix_transformer.py:131-159):
+//   o = softmax(scale * q.k^T) . v   per (image, head), head dim 64 (MiT-B1 .. B5), at most 256 reduced keys (a 512x512 tile has exactly 256
+//   keys at every MiT stage: N / sr^2), without the score tensor ever reaching HBM.
+//
+// One CTA works on 128-query tiles of one (image, head) at a time:
+//   warp 0      TMA producer: K and V (nk x 64, once per (image, head)), Q tiles (128 x 64, double buffered)
+//   warp 1      MMA issuer:   S = Q.K^T  (M 128, N nk, K 64)  -> TMEM columns [0, nk)
+//                             O = P~.V   (M 128, N 64, K nk)  -> TMEM columns [256, 320); V is the MN-major B operand
+//   warps 2-5   one query row per thread: row max and exp straight from tcgen05.ld, un-normalised P~ (16-bit) into the
+//               swizzled shared-memory A operand of the second MMA, O scaled by 1 / rowsum on the way out (TMA store);
+//               for training the normalised P is written too (the backward's dV = P^T.dO and dS use it) from the same
+//               shared-memory tile.
+// The 128 x 256 fp32 score tile is exactly 256 TMEM columns.  Per tile the exponentials bound the time (MUFU), not the tensor
+// pipe — the point of the kernel is the HBM traffic it removes: scores written / read / re-written / read (8 B per score)
+// become 0 (inference) or one 2-byte write (training).
+#include <stdint.h>
+
+#include "../../include/gdl_b200.h"
+#include "tmap.cuh"
+
+namespace gdl {
+
+constexpr int kSraThreads = 192;
+constexpr int kSraD = 64;           // head dim of MiT-B1 .. B5 (C / heads = 64; B0 has 32 and takes the three-kernel path)
+constexpr int kSraMaxKeys = 256;
+constexpr int kSraTileBytes = 128 * 128;                 // 128 rows x 64 16-bit values, SWIZZLE_128B
+constexpr int kSraOffK = 0, kSraOffV = 32768, kSraOffQ = 65536, kSraOffP = 98304, kSraOffO = 163840;
+constexpr int kSraSmem = kSraOffO + kSraTileBytes;       // 176 KB (+1 KB alignment slack)
+constexpr uint32_t kSraColO = 256;                        // TMEM column of the O accumulator
+
+int g_opt_sra_max_ctas = 0;  // gdl_set_option("sra_max_ctas", n): cap the persistent grid (0 = SM count)
+
+struct SraParams {
+  CUtensorMap tmQ, tmK, tmV, tmO, tmP;
+  int B, heads, qtiles, nk, lp, c;  // c = channels of q (V sits c columns right of K in the kv tensor)
+  int ab_fmt;                       // 1 = bf16, 0 = f16
+  int save_p;
+  float scale_log2e;                // scale * log2(e): p = exp2(scale_log2e * (s - max))
+  int items, per_cta;
+};
+
+template <int FMT>
+GDL_DEVINL uint32_t sra_pack2(float a, float b) {
+  return FMT == 1 ? pack_bf16x2(a, b) : pack_f16x2(a, b);
+}
+template <int FMT>
+GDL_DEVINL float2 sra_unpack2(uint32_t u) {
+  if (FMT == 1) return make_float2(bf16_lo(u), bf16_hi(u));
+  return __half22float2(*reinterpret_cast<__half2*>(&u));
+}
+
+template <int FMT>
+__global__ void __launch_bounds__(kSraThreads, 1) sra_attention_fwd_kernel(const __grid_constant__ SraParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = align_smem_1024(smem_raw);
+
+  __shared__ __align__(8) uint64_t kv_full, kv_empty;
+  __shared__ __align__(8) uint64_t q_full[2], q_empty[2];
+  __shared__ __align__(8) uint64_t s_full, p_full, o_full;
+  __shared__ uint32_t tmem_base_smem;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int item0 = blockIdx.x * p.per_cta;
+  const int item1 = min(p.items, item0 + p.per_cta);
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.tmQ);
+    tma_prefetch_desc(&p.tmK);
+    tma_prefetch_desc(&p.tmV);
+    tma_prefetch_desc(&p.tmO);
+    if (p.save_p) tma_prefetch_desc(&p.tmP);
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      mbar_init(&kv_full, 1);
+      mbar_init(&kv_empty, 1);
+      for (int i = 0; i < 2; ++i) {
+        mbar_init(&q_full[i], 1);
+        mbar_init(&q_empty[i], 1);
+      }
+      mbar_init(&s_full, 1);
+      mbar_init(&p_full, 128);
+      mbar_init(&o_full, 1);
+      fence_mbar_init();
+    }
+    __syncwarp();
+    tmem_alloc(&tmem_base_smem, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_smem;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int cur_bg = -1;
+      uint32_t kv_phase = 0;
+      for (int item = item0, it = 0; item < item1; ++item, ++it) {
+        const int bg = item / p.qtiles, qt = item - bg * p.qtiles;
+        const int b = bg / p.heads, g = bg - b * p.heads;
+        if (bg != cur_bg) {
+          mbar_wait(&kv_empty, kv_phase ^ 1);  // every MMA that read the previous K / V has completed
+          mbar_expect_tx(&kv_full, (uint32_t)(2 * p.nk * 128));
+          tma_load_2d(smem + kSraOffK, &p.tmK, &kv_full, g * kSraD, b * p.nk);
+          tma_load_2d(smem + kSraOffV, &p.tmV, &kv_full, p.c + g * kSraD, b * p.nk);
+          kv_phase ^= 1;
+          cur_bg = bg;
+        }
+        const int s = it & 1;
+        mbar_wait(&q_empty[s], ((it >> 1) & 1) ^ 1);
+        mbar_expect_tx(&q_full[s], (uint32_t)kSraTileBytes);
+        tma_load_4d(smem + kSraOffQ + s * kSraTileBytes, &p.tmQ, &q_full[s], g * kSraD, qt * 128, 0, b);
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (one thread) =====================
+    if (lane == 0) {
+      const uint32_t idesc_s = umma_idesc(128, p.nk, FMT, 0, 0);
+      const uint32_t idesc_o = umma_idesc(128, kSraD, FMT, 0, 1);  // B = V: [key][d], d contiguous (MN-major)
+      const uint32_t lt = umma_layout_type(128);
+      const uint32_t k_addr = smem_u32(smem + kSraOffK), v_addr = smem_u32(smem + kSraOffV);
+      const uint32_t p_addr = smem_u32(smem + kSraOffP);
+      int cur_bg = -1;
+      uint32_t kv_phase = 0;
+      for (int item = item0, it = 0; item < item1; ++item, ++it) {
+        const int bg = item / p.qtiles;
+        if (bg != cur_bg) {
+          mbar_wait(&kv_full, kv_phase);
+          kv_phase ^= 1;
+          cur_bg = bg;
+        }
+        const int s = it & 1;
+        mbar_wait(&q_full[s], (it >> 1) & 1);
+        tc_fence_after();
+        // S may be overwritten: p_full of the previous tile (awaited below) was signalled after its last read of S
+        const uint32_t q_addr = smem_u32(smem + kSraOffQ + s * kSraTileBytes);
+        for (int kk = 0; kk < kSraD / 16; ++kk)
+          umma_f16(tmem_base, umma_smem_desc(q_addr + kk * 32, 16, 1024, lt), umma_smem_desc(k_addr + kk * 32, 16, 1024, lt),
+                   idesc_s, (uint32_t)(kk != 0));
+        umma_commit(&q_empty[s]);
+        umma_commit(&s_full);
+        mbar_wait(&p_full, it & 1);  // P~ of this tile is in shared memory (and O of the previous tile has been read)
+        tc_fence_after();
+        for (int ks = 0; ks < p.nk / 16; ++ks)
+          umma_f16(tmem_base + kSraColO,
+                   umma_smem_desc(p_addr + (ks >> 2) * kSraTileBytes + (ks & 3) * 32, 16, 1024, lt),
+                   umma_smem_desc(v_addr + ks * 2048, 16, 1024, lt), idesc_o, (uint32_t)(ks != 0));
+        umma_commit(&o_full);
+        const bool last_of_bg = item + 1 == item1 || (item + 1) / p.qtiles != bg;
+        if (last_of_bg) umma_commit(&kv_empty);
+      }
+    }
+  } else {
+    // ===================== softmax + epilogue: one query row per thread =====================
+    const int q = warp & 3;           // TMEM lane quadrant of this warp
+    const int row = q * 32 + lane;
+    const bool issuer = (warp == 2 && lane == 0);
+    const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16);
+    uint8_t* p_smem = smem + kSraOffP;
+    uint8_t* o_smem = smem + kSraOffO;
+    const uint32_t rsw = (uint32_t)(row & 7);
+    for (int item = item0, it = 0; item < item1; ++item, ++it) {
+      const int bg = item / p.qtiles, qt = item - bg * p.qtiles;
+      const int b = bg / p.heads, g = bg - b * p.heads;
+      mbar_wait(&s_full, it & 1);
+      tc_fence_after();
+      // pass 1: row maximum
+      float mx = -INFINITY;
+      for (int cb = 0; cb < p.nk; cb += 16) {
+        uint32_t v[16];
+        tmem_ld_32x32b_x16(t_row + cb, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 16; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
+      }
+      // the TMA stores of the previous tile must have finished reading the P / O staging tiles before they are rewritten
+      if (issuer) bulk_wait_group_read<0>();
+      named_bar_sync(1, 128);
+      // pass 2: p~ = exp2(scale_log2e * (s - max)), row sum, 16-bit P~ into the swizzled A operand of the second MMA
+      float sum = 0.f;
+      const float moff = mx * p.scale_log2e;
+      for (int cb = 0; cb < p.nk; cb += 16) {
+        uint32_t v[16];
+        tmem_ld_32x32b_x16(t_row + cb, v);
+        tmem_ld_wait();
+        float e[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          e[i] = exp2f(fmaf(__uint_as_float(v[i]), p.scale_log2e, -moff));
+          sum += e[i];
+        }
+        uint8_t* chunk = p_smem + (cb >> 6) * kSraTileBytes + row * 128;
+        const uint32_t u0 = (uint32_t)((cb & 63) >> 3);
+        *reinterpret_cast<uint4*>(chunk + ((u0 ^ rsw) << 4)) =
+            make_uint4(sra_pack2<FMT>(e[0], e[1]), sra_pack2<FMT>(e[2], e[3]), sra_pack2<FMT>(e[4], e[5]), sra_pack2<FMT>(e[6], e[7]));
+        *reinterpret_cast<uint4*>(chunk + (((u0 + 1) ^ rsw) << 4)) =
+            make_uint4(sra_pack2<FMT>(e[8], e[9]), sra_pack2<FMT>(e[10], e[11]), sra_pack2<FMT>(e[12], e[13]), sra_pack2<FMT>(e[14], e[15]));
+      }
+      tc_fence_before();          // S reads of this thread are complete before the arrive
+      fence_proxy_async_smem();   // generic-proxy writes of P~ visible to the tensor core (async proxy)
+      mbar_arrive(&p_full);
+      const float inv = 1.f / sum;
+      // O epilogue
+      mbar_wait(&o_full, it & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int cb = 0; cb < kSraD; cb += 16) {
+        uint32_t v[16];
+        tmem_ld_32x32b_x16(t_row + kSraColO + cb, v);
+        tmem_ld_wait();
+        float f[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]) * inv;
+        uint8_t* orow = o_smem + row * 128;
+        const uint32_t u0 = (uint32_t)(cb >> 3);
+        *reinterpret_cast<uint4*>(orow + ((u0 ^ rsw) << 4)) =
+            make_uint4(sra_pack2<FMT>(f[0], f[1]), sra_pack2<FMT>(f[2], f[3]), sra_pack2<FMT>(f[4], f[5]), sra_pack2<FMT>(f[6], f[7]));
+        *reinterpret_cast<uint4*>(orow + (((u0 + 1) ^ rsw) << 4)) =
+            make_uint4(sra_pack2<FMT>(f[8], f[9]), sra_pack2<FMT>(f[10], f[11]), sra_pack2<FMT>(f[12], f[13]), sra_pack2<FMT>(f[14], f[15]));
+      }
+      tc_fence_before();  // O has been read: the next tile's second MMA (issued after the next p_full) may overwrite it
+      if (p.save_p) {
+        // normalise this thread's own row of P~ in place (the second MMA has completed: o_full): the saved probabilities
+        for (int ch = 0; ch < p.nk; ch += 64) {
+          uint8_t* chunk = p_smem + (ch >> 6) * kSraTileBytes + row * 128;
+#pragma unroll
+          for (uint32_t u = 0; u < 8; ++u) {
+            uint4* ptr = reinterpret_cast<uint4*>(chunk + ((u ^ rsw) << 4));
+            uint4 w = *ptr;
+            float2 a = sra_unpack2<FMT>(w.x), bb = sra_unpack2<FMT>(w.y), cc = sra_unpack2<FMT>(w.z), dd = sra_unpack2<FMT>(w.w);
+            w.x = sra_pack2<FMT>(a.x * inv, a.y * inv);
+            w.y = sra_pack2<FMT>(bb.x * inv, bb.y * inv);
+            w.z = sra_pack2<FMT>(cc.x * inv, cc.y * inv);
+            w.w = sra_pack2<FMT>(dd.x * inv, dd.y * inv);
+            *ptr = w;
+          }
+        }
+      }
+      fence_proxy_async_smem();
+      named_bar_sync(1, 128);
+      if (issuer) {
+        tma_store_4d(&p.tmO, o_smem, g * kSraD, qt * 128, 0, b);
+        if (p.save_p)
+          for (int ch = 0; ch < p.nk; ch += 64)
+            tma_store_4d(&p.tmP, p_smem + (ch >> 6) * kSraTileBytes, g * p.lp + ch, qt * 128, 0, b);
+        bulk_commit_group();
+      }
+    }
+    if (issuer) bulk_wait_group<0>();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+}  // namespace gdl
+
+using namespace gdl;
+
+extern "C" int gdl_sra_attention_fwd(const void* q, long long ldq, const void* kv, long long ldkv, void* o, long long ldo,
+                                     void* p_out, long long ldp, int B, int N, int heads, int nk, int c, float scale,
+                                     int dtype, void* stream) {
+  GDL_REQUIRE(q && kv && o && B > 0 && N > 0 && heads > 0 && nk > 0, GDL_ERR_INVALID, "sra_attention: bad args");
+  GDL_REQUIRE(dtype == GDL_BF16 || dtype == GDL_F16, GDL_ERR_INVALID, "sra_attention: 16-bit dtype expected");
+  GDL_REQUIRE(c == heads * kSraD, GDL_ERR_UNSUPPORTED, "sra_attention: head dim %d (64 expected)", heads ? c / heads : 0);
+  GDL_REQUIRE(nk % 64 == 0 && nk <= kSraMaxKeys, GDL_ERR_UNSUPPORTED,
+              "sra_attention: %d keys (a multiple of 64, at most %d: use the three-kernel path otherwise)", nk, kSraMaxKeys);
+  GDL_REQUIRE(N % 128 == 0, GDL_ERR_UNSUPPORTED, "sra_attention: %d queries per image (a multiple of 128 expected)", N);
+  GDL_REQUIRE(ldq >= c && ldo >= c && ldkv >= 2 * c && (p_out == nullptr || ldp >= (long long)heads * nk), GDL_ERR_INVALID,
+              "sra_attention: leading dimensions too small");
+  SraParams p;
+  memset(&p, 0, sizeof(p));
+  p.B = B;
+  p.heads = heads;
+  p.qtiles = N / 128;
+  p.nk = nk;
+  p.lp = nk;
+  p.c = c;
+  p.ab_fmt = dtype == GDL_BF16 ? 1 : 0;
+  p.save_p = p_out != nullptr;
+  p.scale_log2e = scale * 1.4426950408889634f;
+  p.items = B * heads * p.qtiles;
+  const int sms = g_opt_sra_max_ctas > 0 ? g_opt_sra_max_ctas : device_sm_count();
+  const int grid = p.items < sms ? p.items : sms;
+  p.per_cta = (p.items + grid - 1) / grid;
+  int st = make_tmap_nhwc(&p.tmQ, q, dtype, c, N, 1, B, ldq, kSraD, 128, 1, 128);
+  if (st) return st;
+  st = make_tmap_2d(&p.tmK, kv, dtype, 2 * c, (long long)B * nk, ldkv, kSraD, nk, 128);
+  if (st) return st;
+  p.tmV = p.tmK;
+  st = make_tmap_nhwc(&p.tmO, o, dtype, c, N, 1, B, ldo, kSraD, 128, 1, 128);
+  if (st) return st;
+  if (p.save_p) {
+    st = make_tmap_nhwc(&p.tmP, p_out, dtype, (long long)heads * nk, N, 1, B, ldp, 64, 128, 1, 128);
+    if (st) return st;
+  }
+  const int smem = kSraSmem + 1024;
+  cudaStream_t s = (cudaStream_t)stream;
+  // the last CTAs may have no item (per_cta rounding): they still take part in nothing but the TMEM allocation
+  if (dtype == GDL_BF16) {
+    static PerDeviceOnce once;
+    GDL_CHECK_CUDA(set_max_dyn_smem_once(once, sra_attention_fwd_kernel<1>, smem));
+    sra_attention_fwd_kernel<1><<<grid, kSraThreads, smem, s>>>(p);
+  } else {
+    static PerDeviceOnce once;
+    GDL_CHECK_CUDA(set_max_dyn_smem_once(once, sra_attention_fwd_kernel<0>, smem));
+    sra_attention_fwd_kernel<0><<<grid, kSraThreads, smem, s>>>(p);
+  }
+  GDL_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}

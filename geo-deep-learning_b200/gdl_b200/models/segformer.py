@@ -264,15 +264,22 @@ class SegFormer(nn.Module):
         lp = (nk + 15) // 16 * 16
         kv2 = kv.view(b * nk, 2 * c)
         q4 = q.view(b, 1, n, c)
-        scores = torch.empty((b, 1, n, heads * lp), dtype=dt, device=q.device)
-        # all heads in one grouped launch: head g reads q / k / v columns shifted by g*d, writes score columns by g*lp
-        ops.conv2d_fwd([q4[..., 0:d]], kv2[:, 0:d], nk, 1, 1, 0, 0, out=scores[..., 0:nk], w_rows_per_img=nk,
-                       groups=(heads, d, d, lp))
-        p = ops.softmax_fwd(scores.view(b, n, heads, lp), d ** -0.5, nk)
-        p4 = p.view(b, 1, n, heads * lp)
-        o = torch.empty((b, 1, n, c), dtype=dt, device=q.device)
-        ops.conv2d_fwd([p4[..., 0:lp]], kv2[:, c:c + d], d, 1, 1, 0, 0, out=o[..., 0:d], w_rows_per_img=nk,
-                       w_mn_major=True, groups=(heads, lp, d, d))
+        if ops.option("sra_fused") and ops.sra_attention_supported(n, nk, d):
+            # ONE kernel: q.k^T in TMEM -> softmax in registers -> P~ through shared memory -> P.V (csrc/sra_attention.cu); the
+            # normalised probabilities are written only when a backward will read them
+            o3, p3 = ops.sra_attention_fwd(q.view(b, n, c), kv2, heads, nk, d ** -0.5, save_p=eng.training)
+            o = o3.view(b, 1, n, c)
+            p4 = p3.view(b, 1, n, heads * lp) if p3 is not None else None
+        else:
+            scores = torch.empty((b, 1, n, heads * lp), dtype=dt, device=q.device)
+            # all heads in one grouped launch: head g reads q / k / v columns shifted by g*d, writes score columns by g*lp
+            ops.conv2d_fwd([q4[..., 0:d]], kv2[:, 0:d], nk, 1, 1, 0, 0, out=scores[..., 0:nk], w_rows_per_img=nk,
+                           groups=(heads, d, d, lp))
+            p = ops.softmax_fwd(scores.view(b, n, heads, lp), d ** -0.5, nk)
+            p4 = p.view(b, 1, n, heads * lp)
+            o = torch.empty((b, 1, n, c), dtype=dt, device=q.device)
+            ops.conv2d_fwd([p4[..., 0:lp]], kv2[:, c:c + d], d, 1, 1, 0, 0, out=o[..., 0:d], w_rows_per_img=nk,
+                           w_mn_major=True, groups=(heads, lp, d, d))
         new_stream, rc_proj, act_o = self._branch_out(eng, o.view(b, h, w, c), attn.proj, stream, s)
         sv.__dict__.update(rc_kv=rc_kv, act_kvin=act_kvin, kv2=kv2, q4=q4, p4=p4, nk=nk, lp=lp, rc_proj=rc_proj,
                            act_o=act_o, s=s)

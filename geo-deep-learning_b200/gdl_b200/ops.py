@@ -98,7 +98,8 @@ def set_conv_profiler(p: ConvProfiler | None) -> None:
 
 
 # host-side switches (the library's own are in gdl_set_option); pixel_pack: run 16/32-channel 3x3 convs pixel-packed
-_HOST_OPTS = {"pixel_pack": int(os.environ.get("GDL_PIXEL_PACK", "1"))}
+# sra_fused: SegFormer attention forward as ONE kernel (gdl_sra_attention_fwd) where its shape limits allow
+_HOST_OPTS = {"pixel_pack": int(os.environ.get("GDL_PIXEL_PACK", "1")), "sra_fused": int(os.environ.get("GDL_SRA_FUSED", "0"))}
 
 
 def option(name: str) -> int:
@@ -549,6 +550,25 @@ def softmax_fwd(s, scale, length, p=None):
     _ck(L.load().gdl_softmax_fwd(L.ptr(s), s.stride(-2), float(scale), L.ptr(p), p.stride(-2), L.dt_code(s.dtype),
                                  _rows2(s), length, lpad, L.stream_ptr()))
     return p
+
+
+def sra_attention_supported(n: int, nk: int, d: int) -> bool:
+    """shapes gdl_sra_attention_fwd covers (one 128-query tile x all keys in TMEM): every MiT stage of a 512x512 tile"""
+    return d == 64 and nk % 64 == 0 and 0 < nk <= 256 and n % 128 == 0
+
+
+def sra_attention_fwd(q, kv2, heads, nk, scale, save_p=True):
+    """Fused attention forward.  q: (B, N, c) 16-bit tokens; kv2: (B*nk, 2c) reduced tokens (K | V).
+    Returns (o (B, N, c), p (B, N, heads*nk) or None)."""
+    b, n, c = q.shape
+    if q.stride(2) != 1 or kv2.stride(1) != 1 or q.stride(0) != n * q.stride(1):
+        raise ValueError("sra_attention_fwd: token rows with a contiguous channel dim expected")
+    o = torch.empty((b, n, c), dtype=q.dtype, device=q.device)
+    p = torch.empty((b, n, heads * nk), dtype=q.dtype, device=q.device) if save_p else None
+    _ck(L.load().gdl_sra_attention_fwd(L.ptr(q), q.stride(1), L.ptr(kv2), kv2.stride(0), L.ptr(o), o.stride(1), L.ptr(p),
+                                       p.stride(1) if p is not None else 0, b, n, heads, nk, c, float(scale),
+                                       L.dt_code(q.dtype), L.stream_ptr()))
+    return o, p
 
 
 def softmax_bwd(p, dp, scale, length, ds=None):

@@ -312,6 +312,17 @@ int gdl_softmax_fwd(const void* s, long long lds, float scale, void* p, long lon
 int gdl_softmax_bwd(const void* p, long long ldp, const void* dp, long long lddp, float scale, void* ds,
                     long long ldds, int dtype, long long M, int L, int Lpad, void* stream);
 
+/* Fused spatial-reduction attention forward (Attention.forward, mix_transformer.py:131-159): for every image b and head g
+ *   o[b, :, g*64:(g+1)*64] = softmax(scale * q_g . k_g^T) . v_g
+ * in ONE kernel (scores stay in TMEM / shared memory).  q: (B, N, c) tokens, row stride ldq; kv: (B*nk, 2c) rows = reduced
+ * tokens, K in columns [0, c), V in [c, 2c), row stride ldkv; o: (B, N, c), row stride ldo.  p_out (optional, training):
+ * (B, N, heads*nk) normalised probabilities of head g in columns [g*nk, (g+1)*nk) — what the backward's dV = P^T.dO and
+ * softmax_bwd read.  Covers head dim 64 (c == 64*heads), nk a multiple of 64 up to 256, N a multiple of 128; anything else
+ * returns GDL_ERR_UNSUPPORTED and the caller uses gdl_conv2d_nhwc_fwd + gdl_softmax_fwd + gdl_conv2d_nhwc_fwd. */
+int gdl_sra_attention_fwd(const void* q, long long ldq, const void* kv, long long ldkv, void* o, long long ldo,
+                          void* p_out, long long ldp, int B, int N, int heads, int nk, int c, float scale, int dtype,
+                          void* stream);
+
 /* Mix-FFN middle: y = GELU(depthwise3x3(x) + b) (Mlp.dwconv + act, mix_transformer.py:56-63,533-546), exact
  * erf GELU; `pre` keeps the 16-bit pre-activation for the backward.  w: fp32 [C][3][3].
  * bwd: dx and pgrads [C][10] (9 taps + bias, accumulated; zero first); dpre_scratch: [M][C] 16-bit. */

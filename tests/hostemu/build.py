@@ -19,7 +19,7 @@ ROOT = HERE.parent.parent
 CSRC = ROOT / "geo-deep-learning_b200" / "csrc"
 OUT = HERE / "_build"
 SOURCES = ["runtime.cu", "elementwise.cu", "transformer.cu", "loss_optim.cu", "augment_metrics.cu",
-           "igemm_conv.cu", "conv3x3_rows.cu", "wgrad3x3_rows.cu", "debug_probe.cu"]
+           "igemm_conv.cu", "conv3x3_rows.cu", "wgrad3x3_rows.cu", "debug_probe.cu", "sra_attention.cu"]
 # PTX wrappers of common.cuh whose bodies are forwarded to the functional model in hostemu_tc.cpp
 TC_FORWARD = ["smem_u32", "elect_one", "mbar_init", "mbar_expect_tx", "mbar_arrive", "mbar_try_wait", "tma_load_2d", "tma_load_4d",
               "tma_store_4d", "named_bar_sync", "tmem_alloc", "tmem_dealloc", "umma_f16", "umma_commit", "tmem_ld_32x32b_x16"]
@@ -120,7 +120,8 @@ def rewrite_asm(src: str) -> str:
         body = src[m.end():p1]
         if body.lstrip().startswith('"red.global.add'):
             ops = _asm_inputs(body)  # [address, value...]: fp32 reduction(s) into global memory
-            new = "do { float* _p = (float*)(" + ops[0] + "); " + " ".join(
+            align = 'hostemu::tc::check_align(_p, 16, "red.global.add.v4.f32"); ' if ".v4." in body else ""
+            new = "do { float* _p = (float*)(" + ops[0] + "); " + align + " ".join(
                 f"hostemu::tc::red_add_f32(_p + {i}, {v});" for i, v in enumerate(ops[1:])) + " } while (0)"
         else:
             new = "hostemu::unsupported_asm()"

@@ -331,6 +331,9 @@ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
 void umma_commit(uint64_t* bar) { mbar_arrive(bar); }  // every MMA issued so far has completed (they complete at issue)
 
 void red_add_f32(float* dst, float v) { *dst += v; }
+void check_align(const void* p, unsigned bytes, const char* what) {
+  if (reinterpret_cast<uintptr_t>(p) % bytes) TC_FAIL("%s: address %p is not %u-byte aligned (misaligned address fault on the GPU)", what, p, bytes);
+}
 
 }  // namespace tc
 }  // namespace hostemu

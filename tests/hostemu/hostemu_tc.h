@@ -31,6 +31,7 @@ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
 void umma_commit(uint64_t* bar);
 void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t (&v)[16]);
 void red_add_f32(float* dst, float v);
+void check_align(const void* p, unsigned bytes, const char* what);
 inline void nop() {}
 }  // namespace tc
 }  // namespace hostemu
