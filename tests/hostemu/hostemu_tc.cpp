@@ -44,6 +44,12 @@ static inline uint32_t swizzle(uint32_t addr, int span) {  // Swizzle<B,4,3> on 
 bool elect_one() { return hostemu::lane() == 0; }
 
 // ---------------------------------------------------------------------------------------------------------------------
+// static counters of the modelled units (tools/hostemu_counters.py): what one launch asks of TMA, the tensor core and TMEM
+// ---------------------------------------------------------------------------------------------------------------------
+enum { kCtrTmaLoadBytes, kCtrTmaStoreBytes, kCtrTmaLoads, kCtrMmaIssued, kCtrMmaMacs, kCtrTmemLd, kCtrMbarWaitsFailed, kCtrRedAdds, kNumCtr };
+static unsigned long long g_ctr[kNumCtr];
+
+// ---------------------------------------------------------------------------------------------------------------------
 // mbarrier: the 8-byte object itself holds the state
 // ---------------------------------------------------------------------------------------------------------------------
 struct MBar {
@@ -90,6 +96,7 @@ uint32_t mbar_try_wait(uint64_t* bar, uint32_t parity) {
   MBar* b = mb(bar);
   const uint32_t phase = (b->init_phase >> 15) & 1u;
   if (phase != (parity & 1u)) return 1;  // the phase with this parity has completed
+  ++g_ctr[kCtrMbarWaitsFailed];
   hostemu::yield_spin();
   return 0;
 }
@@ -191,6 +198,8 @@ void tma_load_2d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, in
   if (t.rank != 2) TC_FAIL("tma_load_2d with a rank-%u map", t.rank);
   const int c[5] = {c0, c1, 0, 0, 0};
   tma_copy(t, smem_u32(smem_dst), c, true);
+  g_ctr[kCtrTmaLoadBytes] += t.box[0] * t.box[1] * t.esz;
+  ++g_ctr[kCtrTmaLoads];
   mbar_complete_tx(bar, t.box[0] * t.box[1] * t.esz);
 }
 void tma_load_4d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2, int c3) {
@@ -198,6 +207,8 @@ void tma_load_4d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, in
   if (t.rank != 4) TC_FAIL("tma_load_4d with a rank-%u map", t.rank);
   const int c[5] = {c0, c1, c2, c3, 0};
   tma_copy(t, smem_u32(smem_dst), c, true);
+  g_ctr[kCtrTmaLoadBytes] += t.box[0] * t.box[1] * t.box[2] * t.box[3] * t.esz;
+  ++g_ctr[kCtrTmaLoads];
   mbar_complete_tx(bar, t.box[0] * t.box[1] * t.box[2] * t.box[3] * t.esz);
 }
 void tma_store_4d(const CUtensorMap* m, const void* smem_src, int c0, int c1, int c2, int c3) {
@@ -205,6 +216,7 @@ void tma_store_4d(const CUtensorMap* m, const void* smem_src, int c0, int c1, in
   if (t.rank != 4) TC_FAIL("tma_store_4d with a rank-%u map", t.rank);
   const int c[5] = {c0, c1, c2, c3, 0};
   tma_copy(t, smem_u32(smem_src), c, false);
+  g_ctr[kCtrTmaStoreBytes] += t.box[0] * t.box[1] * t.box[2] * t.box[3] * t.esz;
   hostemu::note_progress();
 }
 
@@ -250,6 +262,7 @@ void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t (&v)[16]) {
   if (lane_base != 32u * (uint32_t)(hostemu::warp_index() & 3))
     TC_FAIL("tcgen05.ld: warp %d addresses TMEM lanes %u.. (allowed: %d..)", hostemu::warp_index(), lane_base, 32 * (hostemu::warp_index() & 3));
   if (col + 16 > 512) TC_FAIL("tcgen05.ld: columns %u..%u", col, col + 15);
+  if (hostemu::lane() == 0) ++g_ctr[kCtrTmemLd];
   const float* row = g_tmem[lane_base + (uint32_t)hostemu::lane()];
   for (int i = 0; i < 16; ++i) memcpy(&v[i], &row[col + i], 4);
 }
@@ -304,6 +317,8 @@ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
   if (M != 128) TC_FAIL("tcgen05.mma: M = %d accumulator layout not modelled", M);
   const uint32_t lane0 = tmem_d >> 16, col0 = tmem_d & 0xffff;
   if (lane0 != 0 || col0 + (uint32_t)N > 512) TC_FAIL("tcgen05.mma: accumulator at lane %u, columns %u..%u", lane0, col0, col0 + N - 1);
+  ++g_ctr[kCtrMmaIssued];
+  g_ctr[kCtrMmaMacs] += (unsigned long long)M * N * 16;
   const Desc da = decode_desc(desc_a, "A"), db = decode_desc(desc_b, "B");
   static float A[128][16], B[256][16];
   for (int m = 0; m < M; ++m)
@@ -330,10 +345,18 @@ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
 }
 void umma_commit(uint64_t* bar) { mbar_arrive(bar); }  // every MMA issued so far has completed (they complete at issue)
 
-void red_add_f32(float* dst, float v) { *dst += v; }
+void red_add_f32(float* dst, float v) {
+  ++g_ctr[kCtrRedAdds];
+  *dst += v;
+}
 void check_align(const void* p, unsigned bytes, const char* what) {
   if (reinterpret_cast<uintptr_t>(p) % bytes) TC_FAIL("%s: address %p is not %u-byte aligned (misaligned address fault on the GPU)", what, p, bytes);
 }
 
 }  // namespace tc
 }  // namespace hostemu
+
+extern "C" void hostemu_counters_reset(void) { memset(hostemu::tc::g_ctr, 0, sizeof(hostemu::tc::g_ctr)); }
+// out[8]: TMA load bytes, TMA store bytes, TMA load instructions, tcgen05.mma issued, MACs, tcgen05.ld (per warp), failed mbarrier polls,
+// fp32 global reductions
+extern "C" void hostemu_counters_get(unsigned long long* out) { memcpy(out, hostemu::tc::g_ctr, sizeof(hostemu::tc::g_ctr)); }
