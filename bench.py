@@ -415,7 +415,7 @@ def main_product(args) -> None:
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": w["name"], "global_batch": B * world, "parallelism": f"dp{world}",
                        "loss": "cross_entropy", "optimizer": "adam", "sync_bn": bool(args.sync_bn and world > 1), "cuda_graph": bool(args.cuda_graph) and (world == 1 or args.cuda_graph >= 2),
-                       "sra_fused": bool(ops.option("sra_fused")),
+                       "sra_fused": bool(ops.option("sra_fused")), "mha_flash": bool(ops.option("mha_flash")),
                        "l2": f"{NBUF} rotating input batches; per-step working set >> 126 MB L2"},
             "clocks": clk,
             "e2e": {"value": tiles / (ms_e2e / 1e3), "unit": "tiles/s",

@@ -148,6 +148,8 @@ def _lin(x2d: torch.Tensor, lin, *, out_dtype=None, relu=False, gelu=False, resi
 def _mha(qkv: torch.Tensor, b: int, n: int, heads: int, c: int, dt) -> torch.Tensor:
     """qkv (b*n, 3c) 16-bit with columns [q | k | v] -> softmax(q k^T d^-1/2) v as (b*n, c)"""
     d = c // heads
+    if ops.option("mha_flash") and d == 64:
+        return ops.mha_flash_fwd(qkv, b, n, heads, d ** -0.5)  # one kernel, no score / probability tensors (csrc/sra_attention.cu)
     # key rows padded to a multiple of 64: the P.V GEMM then contracts over 128-byte (64-key) swizzled rows and the
     # q.k^T GEMM writes whole lp-wide score rows through the TMA-store epilogue.  Score columns >= n hold products with
     # the next image's keys (or TMA zero fill): the softmax kernel ignores them and writes zeros there.

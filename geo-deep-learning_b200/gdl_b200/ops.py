@@ -99,7 +99,9 @@ def set_conv_profiler(p: ConvProfiler | None) -> None:
 
 # host-side switches (the library's own are in gdl_set_option); pixel_pack: run 16/32-channel 3x3 convs pixel-packed
 # sra_fused: SegFormer attention forward as ONE kernel (gdl_sra_attention_fwd) where its shape limits allow
-_HOST_OPTS = {"pixel_pack": int(os.environ.get("GDL_PIXEL_PACK", "1")), "sra_fused": int(os.environ.get("GDL_SRA_FUSED", "0"))}
+# mha_flash: the DOFA encoder's (forward-only) self-attention as ONE kernel (gdl_mha_flash_fwd, keys streamed)
+_HOST_OPTS = {"pixel_pack": int(os.environ.get("GDL_PIXEL_PACK", "1")), "sra_fused": int(os.environ.get("GDL_SRA_FUSED", "0")),
+              "mha_flash": int(os.environ.get("GDL_MHA_FLASH", "0"))}
 
 
 def option(name: str) -> int:
@@ -569,6 +571,18 @@ def sra_attention_fwd(q, kv2, heads, nk, scale, save_p=True):
                                        p.stride(1) if p is not None else 0, b, n, heads, nk, c, float(scale),
                                        L.dt_code(q.dtype), L.stream_ptr()))
     return o, p
+
+
+def mha_flash_fwd(qkv, b, n, heads, scale):
+    """Self-attention forward of a fused projection qkv (b*n, 3c) = [q | k | v], head dim 64, any token count: one kernel, keys
+    streamed in blocks with the online softmax.  Returns o (b*n, c)."""
+    c = qkv.shape[1] // 3
+    if qkv.dim() != 2 or qkv.stride(1) != 1 or qkv.shape[0] != b * n or c != 64 * heads:
+        raise ValueError("mha_flash_fwd: (b*n, 3*64*heads) projection with a contiguous channel dim expected")
+    o = torch.empty((b * n, c), dtype=qkv.dtype, device=qkv.device)
+    _ck(L.load().gdl_mha_flash_fwd(L.ptr(qkv), qkv.stride(0), L.ptr(qkv[:, c:]), qkv.stride(0), L.ptr(qkv[:, 2 * c:]), qkv.stride(0),
+                                   L.ptr(o), o.stride(0), b, n, heads, float(scale), L.dt_code(qkv.dtype), L.stream_ptr()))
+    return o
 
 
 def softmax_bwd(p, dp, scale, length, ds=None):

@@ -323,6 +323,15 @@ int gdl_sra_attention_fwd(const void* q, long long ldq, const void* kv, long lon
                           void* p_out, long long ldp, int B, int N, int heads, int nk, int c, float scale, int dtype,
                           void* stream);
 
+/* The same kernel for plain multi-head self-attention with many keys (timm's Attention inside the DOFA ViT blocks,
+ * dofa_v2.py:445-487 -> timm vision_transformer.Block): keys are streamed in blocks of 128 with the online-softmax recurrence, so
+ * neither scores nor probabilities exist in HBM.  Forward only (no probabilities are saved).  q / k / v / o point at head 0's 64
+ * columns of token 0 of image 0 (e.g. qkv, qkv + c, qkv + 2c of a fused (B*N, 3c) projection with ld = 3c); head g sits 64*g
+ * columns to the right; images are N rows apart.  Head dim 64; any N (ragged query tiles and key blocks are zero-filled / clipped
+ * by the TMA unit and masked in the softmax). */
+int gdl_mha_flash_fwd(const void* q, long long ldq, const void* k, long long ldk, const void* v, long long ldv, void* o,
+                      long long ldo, int B, int N, int heads, float scale, int dtype, void* stream);
+
 /* Mix-FFN middle: y = GELU(depthwise3x3(x) + b) (Mlp.dwconv + act, mix_transformer.py:56-63,533-546), exact
  * erf GELU; `pre` keeps the 16-bit pre-activation for the backward.  w: fp32 [C][3][3].
  * bwd: dx and pgrads [C][10] (9 taps + bias, accumulated; zero first); dpre_scratch: [M][C] 16-bit. */

@@ -25,7 +25,8 @@ SLOW = {
     "test_zz4_dofa_trainable_gpu": ("test_dofa_unfrozen_train_step_parity", "test_dofa_unfrozen_fused_trainer_reduces_loss"),
     "test_zz5_stochastic_layers_gpu": ("test_segformer_train_step_with_supplied_draws",),
     "test_zz6_dynamic_encoder_gpu": ("test_dynamic_segformer_train_step_parity",),
-    "test_zz7_sra_attention_gpu": ("test_segformer_with_fused_attention_equals_three_kernel_model",),
+    "test_zz7_sra_attention_gpu": ("test_segformer_with_fused_attention_equals_three_kernel_model",
+                                   "test_dofa_encoder_with_flash_attention_equals_three_kernel_encoder"),
 }
 
 

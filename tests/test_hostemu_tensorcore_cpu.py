@@ -29,7 +29,8 @@ FILES = {
     "test_grouped_gemm_gpu": {},
     "test_pixel_pack_gpu": {},
     # written after the GPU budget was spent: the fused attention kernel has only ever run here
-    "test_zz7_sra_attention_gpu": dict(exclude=("test_segformer_with_fused_attention_equals_three_kernel_model",)),
+    "test_zz7_sra_attention_gpu": dict(exclude=("test_segformer_with_fused_attention_equals_three_kernel_model",
+                                                "test_dofa_encoder_with_flash_attention_equals_three_kernel_encoder")),
 }
 # ids (substring match) that make up the default subset: one or two small cases per kernel / layout family
 FAST = ("(2, 32, 32, [64], 64, 3, 1)", "(1, 16, 16, [16], 5, 1, 0)", "(1, 64, 64, [16], 16, 3, 1)", "(1, 32, 32, [64], 32, 7, 3)",

@@ -70,6 +70,59 @@ def test_persistent_ctas_walk_tiles_heads_and_images(cuda, ctas):
     assert (p.float() - p_ref).abs().max() <= 3 * 2.0 ** -8 * p_ref.abs().max()
 
 
+@pytest.mark.parametrize("b,n,heads,dtype,ctas", [
+    (2, 197, 3, torch.bfloat16, 0),     # ViT-B/16 at 224: 196 patches + cls — ragged query tile and ragged second key block
+    (1, 1297, 2, torch.bfloat16, 0),    # DOFA-base on a 512 tile: 36 x 36 patches + cls, 11 key blocks (the last holds 17 keys)
+    (2, 300, 2, torch.float16, 2),      # two long CTAs: the K / V ring wraps across tiles, heads and images
+    (1, 256, 1, torch.bfloat16, 0),     # exactly one resident block through the same entry point
+    (1, 130, 1, torch.bfloat16, 0),     # 2 keys in the last block
+])
+def test_flash_self_attention_matches_fp32(cuda, b, n, heads, dtype, ctas):
+    """gdl_mha_flash_fwd: self-attention of a fused qkv projection with the keys streamed in blocks of 128 (online softmax)"""
+    from gdl_b200 import ops
+    g = torch.Generator().manual_seed(11)
+    c = 64 * heads
+    qkv = torch.randn(b * n, 3 * c, generator=g).to(dtype).cuda()
+    qkv[:, :c] *= 2.0  # wider score range: the running maximum really moves between key blocks
+    ops.set_option("sra_max_ctas", ctas)
+    try:
+        o = ops.mha_flash_fwd(qkv, b, n, heads, 0.125)
+        torch.cuda.synchronize()
+    finally:
+        ops.set_option("sra_max_ctas", 0)
+    q, k, v = (qkv[:, i * c:(i + 1) * c].float().view(b, n, heads, 64) for i in range(3))
+    p = (torch.einsum("bnhd,bkhd->bhnk", q, k) * 0.125).softmax(-1)
+    ref = torch.einsum("bhnk,bkhd->bnhd", p, v).reshape(b * n, c)
+    ulp = 2.0 ** -8 if dtype == torch.bfloat16 else 2.0 ** -11
+    assert (o.float() - ref).abs().max() <= 3 * ulp * ref.abs().max()
+
+
+def test_dofa_encoder_with_flash_attention_equals_three_kernel_encoder(cuda):
+    """the frozen-encoder route of the DOFA model (configs[3]) with the option on and off: same features up to 16-bit rounding"""
+    from gdl_b200 import ops
+    from gdl_b200.models.dofa import DOFAv2
+    torch.manual_seed(0)
+    enc = DOFAv2("dofa_base", img_size=112, depth=2, out_indices=[0, 1]).cuda().eval()
+    with torch.no_grad():
+        for name, prm in enc.named_parameters():
+            if "ls1" in name or "ls2" in name:
+                prm.fill_(0.5)  # LayerScale starts at 1e-5: give the attention branch weight in the features
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(2, 4, 112, 112, generator=g).cuda()
+    wl = torch.tensor([0.665, 0.56, 0.49, 0.842]).cuda()
+    feats = {}
+    try:
+        for flash in (0, 1):
+            ops.set_option("mha_flash", flash)
+            with torch.no_grad():
+                feats[flash] = [f.float().clone() for f in enc(x, wl)]
+    finally:
+        ops.set_option("mha_flash", 0)
+    torch.cuda.synchronize()
+    for f0, f1 in zip(feats[0], feats[1]):
+        assert ((f1 - f0).norm() / f0.norm()).item() < 1e-2
+
+
 def test_fused_attention_equals_three_kernel_path_and_rejects_other_shapes(cuda):
     from gdl_b200 import ops
     g = torch.Generator().manual_seed(8)

@@ -24,6 +24,9 @@ for f in 0 1; do
   GDL_SRA_FUSED=$f timeout 600 python bench.py --workload segformer_b2 --steps 8 --warmup 3 --no-cpu-baseline 2>>gpurun_out/bench.err | tee gpurun_out/bench_sf_b2_fused$f.json | python -c "$show"
   GDL_SRA_FUSED=$f timeout 600 python bench.py --workload segformer_b5_infer --raster 4096 --steps 3 --warmup 1 --no-cpu-baseline 2>>gpurun_out/bench.err | tee gpurun_out/bench_infer_4096_fused$f.json | cut -c1-300
 done
+for f in 0 1; do
+  GDL_MHA_FLASH=$f timeout 600 python bench.py --workload dofa_base --steps 8 --warmup 3 --no-cpu-baseline 2>>gpurun_out/bench.err | tee gpurun_out/bench_dofa_flash$f.json | python -c "$show"
+done
 GDL_SRA_FUSED=1 timeout 900 ncu --set full --clock-control none --import-source on -k regex:sra_attention -c 2 -o gpurun_out/sra_attention_full \
   python bench.py --workload segformer_b2 --steps 1 --warmup 1 --cuda-graph 0 --no-cpu-baseline > /dev/null 2>&1
 echo "=== ncu: new kernels (time + dram bytes per launch)"
