@@ -893,6 +893,10 @@ struct ConvWgradKParams {
   long long dw_img_stride;  // batched: dw of image i starts at dw + i * dw_img_stride
   int batched;              // one independent dW per image (attention: dV = P^T dO, dK = dS^T Q)
   int pb_per_img;
+  // grouped (all attention heads in one launch): unit = group * upg + unit-in-group; group g reads dY / X channels shifted by
+  // g * g_dy / g * g_x and adds into dw + g * g_dw
+  int upg, g_x, g_dy;
+  long long g_dw;
   // halo mode (3x3, pad 1, 64x1-pixel blocks, 64-channel X atoms): a unit owns one filter ROW r and keeps
   // 3 accumulators (s = 0,1,2); each k-iteration loads the X row segment once with its 2 halo pixels
   // (66 px) and the 3 horizontal taps are MMAs whose B descriptor start is shifted by s rows (128 B).
@@ -957,7 +961,9 @@ conv_wgrad_kernel(const __grid_constant__ ConvWgradKParams p) {
   const uint32_t acc_stride = (uint32_t)(p.nsub * p.bn_max);
 
   // unit -> (tap, n-tile, m-tile, k-split); tap fastest so co-resident CTAs share dY / X in L2
-  auto decode = [&](int u, int& tap, int& nt, int& mt, int& ks) {
+  auto decode = [&](int u, int& tap, int& nt, int& mt, int& ks, int& grp) {
+    grp = u / p.upg;
+    u -= grp * p.upg;
     tap = u % taps;
     u /= taps;
     nt = u % p.n_ntiles;
@@ -984,8 +990,8 @@ conv_wgrad_kernel(const __grid_constant__ ConvWgradKParams p) {
       int stage = 0;
       uint32_t phase = 0;
       for (int u = blockIdx.x; u < p.num_units; u += gridDim.x) {
-        int tap, nt, mt, ks;
-        decode(u, tap, nt, mt, ks);
+        int tap, nt, mt, ks, grp;
+        decode(u, tap, nt, mt, ks, grp);
         const int r = p.halo ? tap : tap / p.S;
         const int s = p.halo ? 0 : tap - r * p.S;  // halo: the box starts one pixel left (s = 0) and is 66 wide
         const int m0 = mt * 128;
@@ -1006,9 +1012,9 @@ conv_wgrad_kernel(const __grid_constant__ ConvWgradKParams p) {
           uint8_t* b_dst = a_dst + p.a_bytes;
           mbar_expect_tx(&full_bar[stage], tx);
           for (int a = 0; a < a_atoms; ++a)
-            tma_load_4d(a_dst + a * atomA_bytes, &p.tmDY, &full_bar[stage], m0 + a * p.caA, w0, h0, img);
+            tma_load_4d(a_dst + a * atomA_bytes, &p.tmDY, &full_bar[stage], m0 + a * p.caA + grp * p.g_dy, w0, h0, img);
           for (int b = 0; b < b_atoms; ++b)
-            tma_load_4d(b_dst + b * atomB_bytes, &p.tmX[src], &full_bar[stage], c0 + b * p.caB,
+            tma_load_4d(b_dst + b * atomB_bytes, &p.tmX[src], &full_bar[stage], c0 + b * p.caB + grp * p.g_x,
                         w0 + s - p.pad_w, h0 + r - p.pad_h, img);
           if (++stage == p.stages) {
             stage = 0;
@@ -1026,8 +1032,8 @@ conv_wgrad_kernel(const __grid_constant__ ConvWgradKParams p) {
       uint32_t phase = 0;
       int it = 0;
       for (int u = blockIdx.x; u < p.num_units; u += gridDim.x, ++it) {
-        int tap, nt, mt, ks;
-        decode(u, tap, nt, mt, ks);
+        int tap, nt, mt, ks, grp;
+        decode(u, tap, nt, mt, ks, grp);
         const int bn = p.nt_w[nt];
         const uint32_t idesc = umma_idesc(128, bn, p.ab_fmt, 1, 1);
         const int acc = it % p.nacc;
@@ -1063,8 +1069,8 @@ conv_wgrad_kernel(const __grid_constant__ ConvWgradKParams p) {
     const int row = q * 32 + lane;
     int it = 0;
     for (int u = blockIdx.x; u < p.num_units; u += gridDim.x, ++it) {
-      int tap, nt, mt, ks;
-      decode(u, tap, nt, mt, ks);
+      int tap, nt, mt, ks, grp;
+      decode(u, tap, nt, mt, ks, grp);
       const int acc = it % p.nacc;
       const uint32_t aphase = (it / p.nacc) & 1;
       const int m = mt * 128 + row;
@@ -1077,7 +1083,7 @@ conv_wgrad_kernel(const __grid_constant__ ConvWgradKParams p) {
       for (int s3 = 0; s3 < p.nsub; ++s3) {
         const int tap_idx = p.halo ? tap * 3 + s3 : tap;
         float* dst = p.dw + (long long)uimg * p.dw_img_stride + (long long)m * p.dw_ld + (long long)tap_idx * p.Ctot +
-                     p.nt_coff[nt];
+                     p.nt_coff[nt] + grp * p.g_dw;
         const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * acc_stride +
                                 (uint32_t)(s3 * p.bn_max);
         for (int j = 0; j < bn / 16; ++j) {
@@ -1142,6 +1148,20 @@ extern "C" int gdl_conv2d_nhwc_wgrad(const gdl_conv_wgrad_t* d, void* stream_) {
   p.S = d->S;
   p.pad_h = d->pad_h;
   p.pad_w = d->pad_w;
+  const int G = d->groups > 1 ? d->groups : 1;
+  if (G > 1) {
+    // all heads of dV = P^T.dO / dK = dS^T.q in one launch
+    GDL_REQUIRE(d->batched && d->num_src == 1 && d->R == 1 && d->S == 1 && d->pad_h == 0 && d->pad_w == 0, GDL_ERR_INVALID,
+                "grouped wgrad: batched 1x1 products of one source only");
+    GDL_REQUIRE(d->g_src_stride % 8 == 0 && d->g_dy_stride % 8 == 0 && d->g_dw_stride % 4 == 0 && d->g_src_stride > 0 &&
+                    d->g_dy_stride > 0,
+                GDL_ERR_INVALID, "grouped wgrad: group strides must keep 16-byte alignment");
+    GDL_REQUIRE(d->ld_dy >= d->Cout + (G - 1) * d->g_dy_stride && d->src[0].ld >= d->src[0].channels + (G - 1) * d->g_src_stride,
+                GDL_ERR_INVALID, "grouped wgrad: groups exceed the leading dimensions");
+  }
+  p.g_x = G > 1 ? d->g_src_stride : 0;
+  p.g_dy = G > 1 ? d->g_dy_stride : 0;
+  p.g_dw = G > 1 ? d->g_dw_stride : 0;
   p.caB = chunk_width(d->src, d->num_src);
   p.caA = 64;
   while (p.caA > 16 && (d->Cout % p.caA) != 0) p.caA >>= 1;
@@ -1189,13 +1209,14 @@ extern "C" int gdl_conv2d_nhwc_wgrad(const gdl_conv_wgrad_t* d, void* stream_) {
       ++nn;
     }
     coff += c;
-    st = make_tmap_nhwc(&p.tmX[i], d->src[i].ptr, d->dtype, c, W, H, N, d->src[i].ld, p.caB,
+    st = make_tmap_nhwc(&p.tmX[i], d->src[i].ptr, d->dtype, c + (long long)(G - 1) * d->g_src_stride, W, H, N, d->src[i].ld, p.caB,
                         p.halo ? p.TW + 2 : p.TW, p.TH, p.caB * 2);
     if (st) return st;
   }
   p.n_ntiles = nn;
   p.bn_max = bn_max;
-  st = make_tmap_nhwc(&p.tmDY, d->dy, d->dtype, d->Cout, oW, oH, N, d->ld_dy, p.caA, p.TW, p.TH, p.caA * 2);
+  st = make_tmap_nhwc(&p.tmDY, d->dy, d->dtype, d->Cout + (long long)(G - 1) * d->g_dy_stride, oW, oH, N, d->ld_dy, p.caA, p.TW, p.TH,
+                      p.caA * 2);
   if (st) return st;
 
   const int taps = p.unit_taps;
@@ -1247,6 +1268,10 @@ extern "C" int gdl_conv2d_nhwc_wgrad(const gdl_conv_wgrad_t* d, void* stream_) {
     GDL_REQUIRE(units < (1ll << 31), GDL_ERR_UNSUPPORTED, "too many work units");
     p.num_units = (int)units;
   }
+
+  p.upg = p.num_units;
+  GDL_REQUIRE((long long)p.num_units * G < (1ll << 31), GDL_ERR_UNSUPPORTED, "too many work units");
+  p.num_units *= G;
 
   p.a_bytes = kWgPix * 128 * 2;
   const int b_bytes = p.halo ? ((bn_max + p.caB - 1) / p.caB) * p.b_atom_bytes : kWgPix * bn_max * 2;

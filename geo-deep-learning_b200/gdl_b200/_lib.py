@@ -69,6 +69,10 @@ class ConvWgrad(C.Structure):
         ("dw_ld", C.c_int),
         ("dw_img_stride", C.c_longlong),
         ("batched", C.c_int),
+        ("groups", C.c_int),
+        ("g_src_stride", C.c_int),
+        ("g_dy_stride", C.c_int),
+        ("g_dw_stride", C.c_int),
     ]
 
 

@@ -461,12 +461,16 @@ class DOFAv2(nn.Module):
             ops.conv2d_fwd([ds4[..., 0:lp]], qkv[:, d:d + hd], hd, 1, 1, 0, 0, out=dqkv[..., 0:hd], w_rows_per_img=n,
                            w_mn_major=True, groups=(heads, lp, hd, hd))
             dkv32 = torch.zeros((b, lp, 2 * d), dtype=acc, device=g.device)
-            for h_ in range(heads):
-                # dK[b] = dS^T q,  dV[b] = P^T dO   (one independent product per image; key rows >= n stay zero)
-                ops.conv2d_wgrad([q4[..., h_ * hd:(h_ + 1) * hd]], ds4[..., h_ * lp:(h_ + 1) * lp], 1, 1, 0, 0,
-                                 dkv32[:, :, h_ * hd:(h_ + 1) * hd])
-                ops.conv2d_wgrad([do4[..., h_ * hd:(h_ + 1) * hd]], sv.p4[..., h_ * lp:(h_ + 1) * lp], 1, 1, 0, 0,
-                                 dkv32[:, :, d + h_ * hd:d + (h_ + 1) * hd])
+            # dK[b] = dS^T q,  dV[b] = P^T dO   (one independent product per image and head; key rows >= n stay zero)
+            if ops.option("attn_wgrad_grouped"):
+                ops.conv2d_wgrad([q4[..., 0:hd]], ds4[..., 0:lp], 1, 1, 0, 0, dkv32[:, :, 0:hd], groups=(heads, hd, lp, hd))
+                ops.conv2d_wgrad([do4[..., 0:hd]], sv.p4[..., 0:lp], 1, 1, 0, 0, dkv32[:, :, d:d + hd], groups=(heads, hd, lp, hd))
+            else:
+                for h_ in range(heads):
+                    ops.conv2d_wgrad([q4[..., h_ * hd:(h_ + 1) * hd]], ds4[..., h_ * lp:(h_ + 1) * lp], 1, 1, 0, 0,
+                                     dkv32[:, :, h_ * hd:(h_ + 1) * hd])
+                    ops.conv2d_wgrad([do4[..., h_ * hd:(h_ + 1) * hd]], sv.p4[..., h_ * lp:(h_ + 1) * lp], 1, 1, 0, 0,
+                                     dkv32[:, :, d + h_ * hd:d + (h_ + 1) * hd])
             dqkv.view(b, n, 3 * d)[:, :, d:].copy_(dkv32[:, :n])  # cast + column placement (host-side glue)
             eng.conv_backward(sv.rc_qkv, dqkv.view(1, 1, m, 3 * d))
             pg = self._ln_grads(eng, blk.norm1)

@@ -496,12 +496,17 @@ class SegFormer(nn.Module):
         dkv32 = torch.zeros((b, lp, 2 * c), dtype=eng.acc_dtype, device=do.device)
         ops.conv2d_fwd([ds4[..., 0:lp]], sv.kv2[:, 0:d], d, 1, 1, 0, 0, out=dq[..., 0:d], w_rows_per_img=nk,
                        w_mn_major=True, groups=(heads, lp, d, d))
-        for hd in range(heads):
-            # dV[b] = P^T dO,  dK[b] = dS^T q   (one independent product per image)
-            ops.conv2d_wgrad([do4[..., hd * d:(hd + 1) * d]], sv.p4[..., hd * lp:(hd + 1) * lp], 1, 1, 0, 0,
-                             dkv32[:, :, c + hd * d:c + (hd + 1) * d])
-            ops.conv2d_wgrad([sv.q4[..., hd * d:(hd + 1) * d]], ds4[..., hd * lp:(hd + 1) * lp], 1, 1, 0, 0,
-                             dkv32[:, :, hd * d:(hd + 1) * d])
+        # dV[b] = P^T dO,  dK[b] = dS^T q   (one independent product per image and head)
+        if ops.option("attn_wgrad_grouped") and heads > 1:
+            # all heads in one launch each: head g reads the dO / q columns shifted by g*d, the P / dS columns by g*lp
+            ops.conv2d_wgrad([do4[..., 0:d]], sv.p4[..., 0:lp], 1, 1, 0, 0, dkv32[:, :, c:c + d], groups=(heads, d, lp, d))
+            ops.conv2d_wgrad([sv.q4[..., 0:d]], ds4[..., 0:lp], 1, 1, 0, 0, dkv32[:, :, 0:d], groups=(heads, d, lp, d))
+        else:
+            for hd in range(heads):
+                ops.conv2d_wgrad([do4[..., hd * d:(hd + 1) * d]], sv.p4[..., hd * lp:(hd + 1) * lp], 1, 1, 0, 0,
+                                 dkv32[:, :, c + hd * d:c + (hd + 1) * d])
+                ops.conv2d_wgrad([sv.q4[..., hd * d:(hd + 1) * d]], ds4[..., hd * lp:(hd + 1) * lp], 1, 1, 0, 0,
+                                 dkv32[:, :, hd * d:(hd + 1) * d])
         dkv = ops.cast_f32(dkv32 if lp == nk else dkv32[:, :nk].contiguous(), dt)
         eng.conv_backward(sv.rc_kv, dkv.view(sv.rc_kv.x.shape))
         dkvin = self._take(sv.act_kvin)

@@ -101,7 +101,9 @@ def set_conv_profiler(p: ConvProfiler | None) -> None:
 # sra_fused: SegFormer attention forward as ONE kernel (gdl_sra_attention_fwd) where its shape limits allow
 # mha_flash: the DOFA encoder's (forward-only) self-attention as ONE kernel (gdl_mha_flash_fwd, keys streamed)
 _HOST_OPTS = {"pixel_pack": int(os.environ.get("GDL_PIXEL_PACK", "1")), "sra_fused": int(os.environ.get("GDL_SRA_FUSED", "0")),
-              "mha_flash": int(os.environ.get("GDL_MHA_FLASH", "0"))}
+              "mha_flash": int(os.environ.get("GDL_MHA_FLASH", "0")),
+              # attn_wgrad_grouped: dV / dK of all attention heads as one grouped wgrad launch each (instead of 2 x heads launches)
+              "attn_wgrad_grouped": int(os.environ.get("GDL_ATTN_WGRAD_GROUPED", "0"))}
 
 
 def option(name: str) -> int:
@@ -199,9 +201,11 @@ def conv2d_fwd(srcs: Sequence[torch.Tensor], weight: torch.Tensor, cout: int, r:
 
 
 def conv2d_wgrad(srcs: Sequence[torch.Tensor], dy: torch.Tensor, r: int, s: int, pad_h: int,
-                 pad_w: int, dw: torch.Tensor) -> torch.Tensor:
+                 pad_w: int, dw: torch.Tensor, groups: tuple[int, int, int, int] | None = None) -> torch.Tensor:
     """gdl_conv2d_nhwc_wgrad: accumulates into fp32 dw.  dw 2-D [Cout][R*S*Ctot] (row stride = stride(0)), or
-    3-D [N][Cout][Ctot] = batched: one independent product per image (attention dV = P^T dO, dK = dS^T q)."""
+    3-D [N][Cout][Ctot] = batched: one independent product per image (attention dV = P^T dO, dK = dS^T q).
+    groups = (G, source channel stride, dy channel stride, dw column stride): G such products per image in one launch (all
+    heads); srcs[0] / dy / dw are the views of group 0."""
     d = L.ConvWgrad()
     _fill_srcs(d, srcs)
     d.Cout = dy.shape[3]
@@ -216,12 +220,14 @@ def conv2d_wgrad(srcs: Sequence[torch.Tensor], dy: torch.Tensor, r: int, s: int,
         d.batched, d.dw_img_stride, d.dw_ld = 1, dw.stride(0), dw.stride(1)
     else:
         d.batched, d.dw_img_stride, d.dw_ld = 0, 0, dw.stride(0)
+    if groups is not None and groups[0] > 1:
+        d.groups, d.g_src_stride, d.g_dy_stride, d.g_dw_stride = groups
     e0 = _PROFILER.begin() if _PROFILER is not None else None
     L.check(L.load().gdl_conv2d_nhwc_wgrad(C.byref(d), L.stream_ptr()))
     _count()
     if e0 is not None:
         ctot = sum(t.shape[3] for t in srcs)
-        _PROFILER.end("conv_wgrad_kernel", 2.0 * dy.shape[0] * dy.shape[1] * dy.shape[2] * dy.shape[3] * r * s * ctot, e0,
+        _PROFILER.end("conv_wgrad_kernel", 2.0 * (d.groups or 1) * dy.shape[0] * dy.shape[1] * dy.shape[2] * dy.shape[3] * r * s * ctot, e0,
                       f"N{dy.shape[0]} {dy.shape[1]}x{dy.shape[2]} src{[t.shape[3] for t in srcs]} -> {dy.shape[3]} k{r}")
     return dw
 

@@ -127,6 +127,13 @@ typedef struct {
   int dw_ld;
   long long dw_img_stride;
   int batched;
+  /* optional, batched 1x1 only (0 or 1 = not grouped): `groups` independent products per image in one launch — group g reads the
+   * source channels shifted by g*g_src_stride, the dy channels shifted by g*g_dy_stride and adds into dw + g*g_dw_stride
+   * (all attention heads of dV = P^T dO / dK = dS^T q at once). */
+  int groups;
+  int g_src_stride;
+  int g_dy_stride;
+  int g_dw_stride;
 } gdl_conv_wgrad_t;
 int gdl_conv2d_nhwc_wgrad(const gdl_conv_wgrad_t* d, void* stream);
 

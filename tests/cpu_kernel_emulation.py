@@ -95,7 +95,18 @@ def conv2d_fwd(srcs, weight, cout, r, s, pad_h, pad_w, *, out=None, out_dtype=No
     return y.contiguous()
 
 
-def conv2d_wgrad(srcs, dy, r, s, pad_h, pad_w, dw):
+def conv2d_wgrad(srcs, dy, r, s, pad_h, pad_w, dw, groups=None):
+    if groups is not None and groups[0] > 1:
+        # all heads in one launch: group g = the same call on views shifted by the per-group strides
+        ng, sx, sdy, sdw = groups
+        x0, c0, k0 = srcs[0], srcs[0].shape[3], dy.shape[3]
+        xfull = torch.as_strided(x0, x0.shape[:3] + (c0 + (ng - 1) * sx,), x0.stride(), x0.storage_offset())
+        dyfull = torch.as_strided(dy, dy.shape[:3] + (k0 + (ng - 1) * sdy,), dy.stride(), dy.storage_offset())
+        dwfull = torch.as_strided(dw, dw.shape[:2] + (dw.shape[2] + (ng - 1) * sdw,), dw.stride(), dw.storage_offset())
+        for g in range(ng):
+            conv2d_wgrad([xfull[..., g * sx:g * sx + c0]], dyfull[..., g * sdy:g * sdy + k0], r, s, pad_h, pad_w,
+                         dwfull[..., g * sdw:g * sdw + dw.shape[2]])
+        return dw
     x = torch.cat(list(srcs), 3).to(_WORK)
     cout, ctot = dy.shape[3], x.shape[3]
     if dw.dim() == 3:  # batched: dw[n] += dy[n]^T x[n]

@@ -44,3 +44,32 @@ def test_grouped_attention_gemms(cuda, b, n, nk, heads, d, dtype):
     vf = kv[:, c:].float().view(b, nk, heads, d)
     ref_o = torch.einsum("bnhk,bkhd->bnhd", p.view(b, n, heads, lp)[..., :nk].float(), vf).reshape(b, 1, n, c)
     assert ((o_grp.float() - ref_o).abs().max() / ref_o.abs().max()).item() < 6e-3
+
+
+@pytest.mark.parametrize("b,n,nk,heads,d,dtype", [
+    (3, 300, 256, 5, 64, torch.bfloat16),    # SegFormer stage 3
+    (2, 256, 64, 2, 32, torch.float16),      # MiT-B0 head dim
+    (2, 200, 200, 3, 64, torch.bfloat16),    # DOFA-like: keys = queries, key rows padded to 64
+])
+def test_grouped_attention_wgrads(cuda, b, n, nk, heads, d, dtype):
+    """dV = P^T.dO and dK = dS^T.q of all heads as ONE grouped batched-wgrad launch each: same sums as the per-head launches
+    (fp32 atomics: compared with a tolerance) and as torch"""
+    from gdl_b200 import ops
+    g = torch.Generator().manual_seed(n * 3 + nk)
+    c = heads * d
+    lp = (nk + 63) // 64 * 64 if nk == n else (nk + 15) // 16 * 16
+    do = (torch.randn(b, 1, n, c, generator=g) * 0.3).to(dtype).cuda()
+    p = torch.zeros(b, 1, n, heads * lp, dtype=dtype).cuda()
+    p.view(b, n, heads, lp)[..., :nk] = torch.rand(b, n, heads, nk, generator=g).to(dtype).cuda()
+    dkv_loop = torch.zeros(b, lp, 2 * c, device="cuda")
+    dkv_grp = torch.zeros_like(dkv_loop)
+    for hd in range(heads):
+        ops.conv2d_wgrad([do[..., hd * d:(hd + 1) * d]], p[..., hd * lp:(hd + 1) * lp], 1, 1, 0, 0, dkv_loop[:, :, c + hd * d:c + (hd + 1) * d])
+    ops.conv2d_wgrad([do[..., 0:d]], p[..., 0:lp], 1, 1, 0, 0, dkv_grp[:, :, c:c + d], groups=(heads, d, lp, d))
+    torch.cuda.synchronize()
+    ref = torch.einsum("bnhk,bnhd->bkhd", p.view(b, n, heads, lp).float(), do.view(b, n, heads, d).float()).reshape(b, lp, c)
+    assert ((dkv_grp[:, :, c:] - ref).abs().max() / ref.abs().max()).item() < 2e-3
+    assert ((dkv_grp - dkv_loop).abs().max() / ref.abs().max()).item() < 1e-5
+    assert not dkv_grp[:, :, :c].any()  # the K half was not touched
+    with pytest.raises(ValueError):  # grouped products are batched 1x1 only
+        ops.conv2d_wgrad([do[..., 0:d]], p[..., 0:lp], 1, 1, 0, 0, dkv_grp[0, :, c:c + d], groups=(heads, d, lp, d))

@@ -144,3 +144,43 @@ def test_hbm_kernels_random_shapes(monkeypatch, seed):
     ops.bn_stats(xs, sums, pivot)
     d = xs.float().reshape(-1, c) - pivot
     assert torch.allclose(sums[:c], d.sum(0), rtol=1e-4, atol=1e-3) and torch.allclose(sums[c:], (d * d).sum(0), rtol=1e-4, atol=1e-3)
+
+
+@pytest.mark.parametrize("seed", range(CASES))
+def test_fused_attention_random_shapes(monkeypatch, seed):
+    """gdl_mha_flash_fwd / gdl_sra_attention_fwd on the functional model: token counts around the 128-query / 128-key block edges,
+    few long CTAs (ring wrap, K / V reload), both dtypes"""
+    hostemu.install(monkeypatch, torch_convs=False)
+    from gdl_b200 import ops
+    rng = random.Random(4000 + seed)
+    g = torch.Generator().manual_seed(300 + seed)
+    dt = rng.choice([torch.bfloat16, torch.float16])
+    ulp = 2.0 ** -8 if dt == torch.bfloat16 else 2.0 ** -11
+    b, heads = rng.choice([1, 2]), rng.choice([1, 2, 3])
+    c = 64 * heads
+    ops.set_option("sra_max_ctas", rng.choice([0, 0, 1, 2, 5]))
+    try:
+        if rng.random() < 0.6:
+            n = rng.choice([1, 15, 16, 17, 127, 128, 129, 255, 256, 257, 383, 385, rng.randint(1, 700)])
+            qkv = torch.randn(b * n, 3 * c, generator=g).to(dt)
+            qkv[:, :c] *= rng.choice([1.0, 3.0])
+            o = ops.mha_flash_fwd(qkv, b, n, heads, 0.125)
+            q, k, v = (qkv[:, i * c:(i + 1) * c].float().view(b, n, heads, 64) for i in range(3))
+            p = (torch.einsum("bnhd,bkhd->bhnk", q, k) * 0.125).softmax(-1)
+            ref = torch.einsum("bhnk,bkhd->bnhd", p, v).reshape(b * n, c)
+            assert (o.float() - ref).abs().max() <= 3 * ulp * ref.abs().max(), (b, n, heads, dt)
+        else:
+            n, nk = 128 * rng.randint(1, 4), 64 * rng.randint(1, 4)
+            q = torch.randn(b, n, c, generator=g).to(dt)
+            kv2 = torch.randn(b * nk, 2 * c, generator=g).to(dt)
+            save = rng.random() < 0.7
+            o, p = ops.sra_attention_fwd(q, kv2, heads, nk, 0.125, save_p=save)
+            k = kv2[:, :c].float().view(b, nk, heads, 64)
+            v = kv2[:, c:].float().view(b, nk, heads, 64)
+            pr = (torch.einsum("bnhd,bkhd->bhnk", q.float().view(b, n, heads, 64), k) * 0.125).softmax(-1)
+            ref = torch.einsum("bhnk,bkhd->bnhd", pr, v).reshape(b, n, c)
+            assert (o.float() - ref).abs().max() <= 3 * ulp * ref.abs().max(), (b, n, nk, heads, dt)
+            if save:
+                assert (p.float() - pr.permute(0, 2, 1, 3).reshape(b, n, heads * nk)).abs().max() <= 3 * ulp
+    finally:
+        ops.set_option("sra_max_ctas", 0)

@@ -24,6 +24,7 @@ for f in 0 1; do
   GDL_SRA_FUSED=$f timeout 600 python bench.py --workload segformer_b2 --steps 8 --warmup 3 --no-cpu-baseline 2>>gpurun_out/bench.err | tee gpurun_out/bench_sf_b2_fused$f.json | python -c "$show"
   GDL_SRA_FUSED=$f timeout 600 python bench.py --workload segformer_b5_infer --raster 4096 --steps 3 --warmup 1 --no-cpu-baseline 2>>gpurun_out/bench.err | tee gpurun_out/bench_infer_4096_fused$f.json | cut -c1-300
 done
+GDL_ATTN_WGRAD_GROUPED=1 timeout 600 python bench.py --workload segformer_b2 --steps 8 --warmup 3 --no-cpu-baseline 2>>gpurun_out/bench.err | tee gpurun_out/bench_sf_b2_wgrad_grouped.json | python -c "$show"
 for f in 0 1; do
   GDL_MHA_FLASH=$f timeout 600 python bench.py --workload dofa_base --steps 8 --warmup 3 --no-cpu-baseline 2>>gpurun_out/bench.err | tee gpurun_out/bench_dofa_flash$f.json | python -c "$show"
 done
