@@ -37,6 +37,8 @@ int g_opt_sra_max_ctas = 0;  // gdl_set_option("sra_max_ctas", n): cap the persi
 
 struct SraParams {
   CUtensorMap tmQ, tmK, tmV, tmO, tmP;
+  CUtensorMap tmPin;                // backward: the saved probabilities (load side)
+  float scale;                      // backward: dS = scale * P * (dP - delta)
   int B, heads, qtiles, nk;
   int kb, nblocks;                  // keys per block, blocks per query tile (1: K / V resident per (image, head))
   int lp;                           // columns per head of the saved probabilities
@@ -55,14 +57,18 @@ GDL_DEVINL float2 sra_unpack2(uint32_t u) {
   return __half22float2(*reinterpret_cast<__half2*>(&u));
 }
 
-template <int FMT>
-__global__ void __launch_bounds__(kSraThreads, 1) sra_attention_fwd_kernel(const __grid_constant__ SraParams p) {
+// BWD = false: forward (above).  BWD = true: the query-tile-local half of the backward with the same pipeline — the roles are
+//   Q -> dO,  K -> V (first MMA: dP = dO.V^T),  softmax -> dS = scale * P * (dP - rowsum(P * dP)) written IN PLACE over the P tile that
+//   TMA loaded,  V -> K (second MMA: dQ = dS.K),  O -> dQ,  saved P -> dS (stored for the dK = dS^T.q wgrad).  One key block only.
+template <int FMT, bool BWD>
+__global__ void __launch_bounds__(kSraThreads, 1) sra_attention_kernel(const __grid_constant__ SraParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = align_smem_1024(smem_raw);
 
   __shared__ __align__(8) uint64_t kv_full[2], kv_empty[2];
   __shared__ __align__(8) uint64_t q_full[2], q_empty[2];
   __shared__ __align__(8) uint64_t s_full, p_full, o_full;
+  __shared__ __align__(8) uint64_t pin_full, p_free;  // backward: P tile landed / P tile may be overwritten
   __shared__ uint32_t tmem_base_smem;
 
   const int warp = threadIdx.x >> 5;
@@ -90,6 +96,8 @@ __global__ void __launch_bounds__(kSraThreads, 1) sra_attention_fwd_kernel(const
       mbar_init(&s_full, 1);
       mbar_init(&p_full, 128);
       mbar_init(&o_full, 1);
+      mbar_init(&pin_full, 1);
+      mbar_init(&p_free, 1);
       fence_mbar_init();
     }
     __syncwarp();
@@ -113,6 +121,13 @@ __global__ void __launch_bounds__(kSraThreads, 1) sra_attention_fwd_kernel(const
         mbar_wait(&q_empty[s], ((it >> 1) & 1) ^ 1);
         mbar_expect_tx(&q_full[s], (uint32_t)kSraTileBytes);
         tma_load_4d(smem + kSraOffQ + s * kSraTileBytes, &p.tmQ, &q_full[s], g * kSraD, qt * 128, 0, b);
+        if (BWD) {
+          // the P tile is single buffered: wait until the previous tile's dS stores have read it and its second MMA is done
+          mbar_wait(&p_free, it & 1);
+          mbar_expect_tx(&pin_full, (uint32_t)(p.nk * 256));
+          for (int ch = 0; ch < p.nk; ch += 64)
+            tma_load_4d(smem + kSraOffP + (ch >> 6) * kSraTileBytes, &p.tmPin, &pin_full, g * p.lp + ch, qt * 128, 0, b);
+        }
         if (resident) {
           if (bg != cur_bg) {
             mbar_wait(&kv_empty[0], (kc & 1) ^ 1);  // every MMA that read the previous K / V has completed
@@ -202,10 +217,72 @@ __global__ void __launch_bounds__(kSraThreads, 1) sra_attention_fwd_kernel(const
       const int b = bg / p.heads, g = bg - b * p.heads;
       float m_run = -INFINITY, l_run = 0.f;
       float o_run[kSraD];
+      if (BWD && issuer) {
+        bulk_wait_group_read<0>();  // the dS / dQ stores of the previous tile have finished reading shared memory
+        mbar_arrive(&p_free);
+      }
       for (int j = 0; j < p.nblocks; ++j, ++sb) {
         const int valid = min(p.kb, p.nk - j * p.kb);  // keys of this block that exist (the rest is TMA zero fill)
         mbar_wait(&s_full, sb & 1);
         tc_fence_after();
+        if (BWD) {
+          mbar_wait(&pin_full, sb & 1);  // this tile's P (TMA writes are visible after the wait)
+          // pass 1: delta = sum_j P_j * dP_j  (own row: P from the swizzled tile, dP from TMEM)
+          float delta = 0.f;
+          for (int cb = 0; cb < p.nk; cb += 16) {
+            uint32_t v[16];
+            tmem_ld_32x32b_x16(t_row + cb, v);
+            tmem_ld_wait();
+            const uint8_t* chunk = p_smem + (cb >> 6) * kSraTileBytes + row * 128;
+            const uint32_t u0 = (uint32_t)((cb & 63) >> 3);
+            const uint4 w0 = *reinterpret_cast<const uint4*>(chunk + ((u0 ^ rsw) << 4));
+            const uint4 w1 = *reinterpret_cast<const uint4*>(chunk + (((u0 + 1) ^ rsw) << 4));
+            const uint32_t pw[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float2 pp = sra_unpack2<FMT>(pw[i]);
+              delta = fmaf(pp.x, __uint_as_float(v[2 * i]), delta);
+              delta = fmaf(pp.y, __uint_as_float(v[2 * i + 1]), delta);
+            }
+          }
+          // pass 2: dS in place
+          for (int cb = 0; cb < p.nk; cb += 16) {
+            uint32_t v[16];
+            tmem_ld_32x32b_x16(t_row + cb, v);
+            tmem_ld_wait();
+            uint8_t* chunk = p_smem + (cb >> 6) * kSraTileBytes + row * 128;
+            const uint32_t u0 = (uint32_t)((cb & 63) >> 3);
+            uint4* q0 = reinterpret_cast<uint4*>(chunk + ((u0 ^ rsw) << 4));
+            uint4* q1 = reinterpret_cast<uint4*>(chunk + (((u0 + 1) ^ rsw) << 4));
+            const uint4 w0 = *q0, w1 = *q1;
+            const uint32_t pw[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+            uint32_t dw[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float2 pp = sra_unpack2<FMT>(pw[i]);
+              dw[i] = sra_pack2<FMT>(p.scale * pp.x * (__uint_as_float(v[2 * i]) - delta),
+                                     p.scale * pp.y * (__uint_as_float(v[2 * i + 1]) - delta));
+            }
+            *q0 = make_uint4(dw[0], dw[1], dw[2], dw[3]);
+            *q1 = make_uint4(dw[4], dw[5], dw[6], dw[7]);
+          }
+          l_run = 1.f;
+          tc_fence_before();
+          fence_proxy_async_smem();
+          mbar_arrive(&p_full);
+          mbar_wait(&o_full, sb & 1);
+          tc_fence_after();
+#pragma unroll
+          for (int cb = 0; cb < kSraD; cb += 16) {
+            uint32_t v2[16];
+            tmem_ld_32x32b_x16(t_row + kSraColO + cb, v2);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) o_run[cb + i] = __uint_as_float(v2[i]);
+          }
+          tc_fence_before();
+          continue;
+        }
         // pass 1: block maximum
         float mx = m_run;
         for (int cb = 0; cb < valid; cb += 16) {
@@ -265,7 +342,7 @@ __global__ void __launch_bounds__(kSraThreads, 1) sra_attention_fwd_kernel(const
         }
         tc_fence_before();  // O_blk has been read: the next second MMA (issued after the next p_full) may overwrite it
       }
-      const float inv = 1.f / l_run;
+      const float inv = 1.f / l_run;  // backward: l_run = 1
       uint8_t* orow = o_smem + row * 128;
 #pragma unroll
       for (int cb = 0; cb < kSraD; cb += 16) {
@@ -277,7 +354,7 @@ __global__ void __launch_bounds__(kSraThreads, 1) sra_attention_fwd_kernel(const
             make_uint4(sra_pack2<FMT>(o_run[cb + 8] * inv, o_run[cb + 9] * inv), sra_pack2<FMT>(o_run[cb + 10] * inv, o_run[cb + 11] * inv),
                        sra_pack2<FMT>(o_run[cb + 12] * inv, o_run[cb + 13] * inv), sra_pack2<FMT>(o_run[cb + 14] * inv, o_run[cb + 15] * inv));
       }
-      if (p.save_p) {
+      if (p.save_p && !BWD) {
         // one key block: normalise this thread's own row of P~ in place (the second MMA has completed: o_full) — the saved
         // probabilities of the backward
         for (int ch = 0; ch < p.nk; ch += 64) {
@@ -299,7 +376,7 @@ __global__ void __launch_bounds__(kSraThreads, 1) sra_attention_fwd_kernel(const
       named_bar_sync(1, 128);
       if (issuer) {
         tma_store_4d(&p.tmO, o_smem, g * kSraD, qt * 128, 0, b);  // rows past the image's last query are clipped
-        if (p.save_p)
+        if (p.save_p || BWD)  // forward: normalised P; backward: dS
           for (int ch = 0; ch < p.nk; ch += 64)
             tma_store_4d(&p.tmP, p_smem + (ch >> 6) * kSraTileBytes, g * p.lp + ch, qt * 128, 0, b);
         bulk_commit_group();
@@ -320,7 +397,7 @@ __global__ void __launch_bounds__(kSraThreads, 1) sra_attention_fwd_kernel(const
 // apart; head g sits 64*g columns to the right.  cols_* = columns of the tensor from that pointer on (the TMA bound of the maps).
 static int sra_launch(const void* q, long long ldq, int cols_q, const void* k, long long ldk, const void* v, long long ldv, int cols_kv,
                       void* o, long long ldo, void* p_out, long long ldp, int B, int nq, int nk, int heads, float scale, int dtype,
-                      cudaStream_t s) {
+                      cudaStream_t s, const void* pin = nullptr, long long ldpin = 0) {
   SraParams p;
   memset(&p, 0, sizeof(p));
   p.B = B;
@@ -353,17 +430,25 @@ static int sra_launch(const void* q, long long ldq, int cols_q, const void* k, l
     st = make_tmap_nhwc(&p.tmP, p_out, dtype, (long long)heads * nk, nq, 1, B, ldp, 64, 128, 1, 128);
     if (st) return st;
   }
+  if (pin != nullptr) {
+    st = make_tmap_nhwc(&p.tmPin, pin, dtype, (long long)heads * nk, nq, 1, B, ldpin, 64, 128, 1, 128);
+    if (st) return st;
+    p.scale = scale;
+  }
   const int smem = kSraSmem + 1024;
   // trailing CTAs may have no item (per_cta rounding): they only allocate and free their TMEM columns
-  if (dtype == GDL_BF16) {
-    static PerDeviceOnce once;
-    GDL_CHECK_CUDA(set_max_dyn_smem_once(once, sra_attention_fwd_kernel<1>, smem));
-    sra_attention_fwd_kernel<1><<<grid, kSraThreads, smem, s>>>(p);
+#define GDL_SRA_LAUNCH(FMT, BWD)                                                            \
+  do {                                                                                      \
+    static PerDeviceOnce once;                                                              \
+    GDL_CHECK_CUDA(set_max_dyn_smem_once(once, sra_attention_kernel<FMT, BWD>, smem));      \
+    sra_attention_kernel<FMT, BWD><<<grid, kSraThreads, smem, s>>>(p);                      \
+  } while (0)
+  if (pin != nullptr) {
+    if (dtype == GDL_BF16) GDL_SRA_LAUNCH(1, true); else GDL_SRA_LAUNCH(0, true);
   } else {
-    static PerDeviceOnce once;
-    GDL_CHECK_CUDA(set_max_dyn_smem_once(once, sra_attention_fwd_kernel<0>, smem));
-    sra_attention_fwd_kernel<0><<<grid, kSraThreads, smem, s>>>(p);
+    if (dtype == GDL_BF16) GDL_SRA_LAUNCH(1, false); else GDL_SRA_LAUNCH(0, false);
   }
+#undef GDL_SRA_LAUNCH
   GDL_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -378,9 +463,12 @@ extern "C" int gdl_sra_attention_fwd(const void* q, long long ldq, const void* k
   GDL_REQUIRE(q && kv && o && B > 0 && N > 0 && heads > 0 && nk > 0, GDL_ERR_INVALID, "sra_attention: bad args");
   GDL_REQUIRE(dtype == GDL_BF16 || dtype == GDL_F16, GDL_ERR_INVALID, "sra_attention: 16-bit dtype expected");
   GDL_REQUIRE(c == heads * kSraD, GDL_ERR_UNSUPPORTED, "sra_attention: head dim %d (64 expected)", heads ? c / heads : 0);
-  GDL_REQUIRE(nk % 64 == 0 && nk <= kSraMaxKeys, GDL_ERR_UNSUPPORTED,
-              "sra_attention: %d keys (a multiple of 64, at most %d: use the three-kernel path otherwise)", nk, kSraMaxKeys);
-  GDL_REQUIRE(N % 128 == 0, GDL_ERR_UNSUPPORTED, "sra_attention: %d queries per image (a multiple of 128 expected)", N);
+  // saving the probabilities needs the whole key range in one block and whole 64-key / 128-query store boxes; without them
+  // (inference) any shape goes: ragged tiles are zero-filled / clipped, more than 256 keys are streamed
+  GDL_REQUIRE(p_out == nullptr || (nk % 64 == 0 && nk <= kSraMaxKeys), GDL_ERR_UNSUPPORTED,
+              "sra_attention: %d keys (saving P needs a multiple of 64, at most %d: use the three-kernel path otherwise)", nk, kSraMaxKeys);
+  GDL_REQUIRE(p_out == nullptr || N % 128 == 0, GDL_ERR_UNSUPPORTED,
+              "sra_attention: %d queries per image (saving P needs a multiple of 128)", N);
   GDL_REQUIRE(ldq >= c && ldo >= c && ldkv >= 2 * c && (p_out == nullptr || ldp >= (long long)heads * nk), GDL_ERR_INVALID,
               "sra_attention: leading dimensions too small");
   const char* kvp = reinterpret_cast<const char*>(kv);
@@ -395,4 +483,21 @@ extern "C" int gdl_mha_flash_fwd(const void* q, long long ldq, const void* k, lo
   const int c = heads * kSraD;
   GDL_REQUIRE(ldq >= c && ldk >= c && ldv >= c && ldo >= c, GDL_ERR_INVALID, "mha_flash: leading dimensions too small (head dim 64)");
   return sra_launch(q, ldq, c, k, ldk, v, ldv, c, o, ldo, nullptr, 0, B, N, N, heads, scale, dtype, (cudaStream_t)stream);
+}
+
+extern "C" int gdl_sra_attention_bwd(const void* d_o, long long lddo, const void* kv, long long ldkv, const void* p_saved, long long ldp,
+                                     void* dq, long long lddq, void* ds, long long ldds, int B, int N, int heads, int nk, int c,
+                                     float scale, int dtype, void* stream) {
+  GDL_REQUIRE(d_o && kv && p_saved && dq && ds && B > 0 && N > 0 && heads > 0 && nk > 0, GDL_ERR_INVALID, "sra_attention_bwd: bad args");
+  GDL_REQUIRE(dtype == GDL_BF16 || dtype == GDL_F16, GDL_ERR_INVALID, "sra_attention_bwd: 16-bit dtype expected");
+  GDL_REQUIRE(c == heads * kSraD, GDL_ERR_UNSUPPORTED, "sra_attention_bwd: head dim %d (64 expected)", heads ? c / heads : 0);
+  GDL_REQUIRE(nk % 64 == 0 && nk <= kSraMaxKeys && N % 128 == 0, GDL_ERR_UNSUPPORTED,
+              "sra_attention_bwd: %d keys / %d queries (keys: a multiple of 64 up to %d, queries: a multiple of 128)", nk, N, kSraMaxKeys);
+  GDL_REQUIRE(lddo >= c && lddq >= c && ldkv >= 2 * c && ldp >= (long long)heads * nk && ldds >= (long long)heads * nk, GDL_ERR_INVALID,
+              "sra_attention_bwd: leading dimensions too small");
+  GDL_REQUIRE(p_saved != ds, GDL_ERR_INVALID, "sra_attention_bwd: dS must not alias P (dV = P^T.dO still reads P)");
+  const char* kvp = reinterpret_cast<const char*>(kv);
+  // roles: Q <- dO, first-MMA operand <- V, second-MMA operand <- K, O <- dQ, stored tile <- dS
+  return sra_launch(d_o, lddo, c, kvp + (size_t)c * 2, ldkv, kvp, ldkv, c, dq, lddq, ds, ldds, B, N, nk, heads, scale, dtype,
+                    (cudaStream_t)stream, p_saved, ldp);
 }

@@ -136,6 +136,7 @@ _SIGS = {
     "gdl_softmax_fwd": [_VP, _LL, _F, _VP, _LL, _I, _LL, _I, _I, _VP],
     "gdl_softmax_bwd": [_VP, _LL, _VP, _LL, _F, _VP, _LL, _I, _LL, _I, _I, _VP],
     "gdl_sra_attention_fwd": [_VP, _LL, _VP, _LL, _VP, _LL, _VP, _LL, _I, _I, _I, _I, _I, _F, _I, _VP],
+    "gdl_sra_attention_bwd": [_VP, _LL, _VP, _LL, _VP, _LL, _VP, _LL, _VP, _LL, _I, _I, _I, _I, _I, _F, _I, _VP],
     "gdl_mha_flash_fwd": [_VP, _LL, _VP, _LL, _VP, _LL, _VP, _LL, _I, _I, _I, _F, _I, _VP],
     "gdl_dwconv3x3_gelu_fwd": [_VP, _I, _VP, _VP, _VP, _VP, _I, _I, _I, _I, _I, _VP],
     "gdl_dwconv3x3_gelu_bwd": [_VP, _VP, _VP, _I, _VP, _VP, _VP, _I, _VP, _I, _I, _I, _I, _I, _VP],

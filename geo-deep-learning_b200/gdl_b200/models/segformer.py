@@ -264,7 +264,7 @@ class SegFormer(nn.Module):
         lp = (nk + 15) // 16 * 16
         kv2 = kv.view(b * nk, 2 * c)
         q4 = q.view(b, 1, n, c)
-        if ops.option("sra_fused") and ops.sra_attention_supported(n, nk, d):
+        if ops.option("sra_fused") and ops.sra_attention_supported(n, nk, d, save_p=eng.training):
             # ONE kernel: q.k^T in TMEM -> softmax in registers -> P~ through shared memory -> P.V (csrc/sra_attention.cu); the
             # normalised probabilities are written only when a backward will read them
             o3, p3 = ops.sra_attention_fwd(q.view(b, n, c), kv2, heads, nk, d ** -0.5, save_p=eng.training)
@@ -487,15 +487,20 @@ class SegFormer(nn.Module):
         n = h * w
         dt = eng.dtype
         do4 = do.view(b, 1, n, c)
-        dp = torch.empty((b, 1, n, heads * lp), dtype=dt, device=do.device)
-        ops.conv2d_fwd([do4[..., 0:d]], sv.kv2[:, c:c + d], nk, 1, 1, 0, 0, out=dp[..., 0:nk], w_rows_per_img=nk,
-                       groups=(heads, d, d, lp))
-        ds = ops.softmax_bwd(sv.p4.view(b, n, heads, lp), dp.view(b, n, heads, lp), d ** -0.5, nk)
-        ds4 = ds.view(b, 1, n, heads * lp)
-        dq = torch.empty((b, 1, n, c), dtype=dt, device=do.device)
         dkv32 = torch.zeros((b, lp, 2 * c), dtype=eng.acc_dtype, device=do.device)
-        ops.conv2d_fwd([ds4[..., 0:lp]], sv.kv2[:, 0:d], d, 1, 1, 0, 0, out=dq[..., 0:d], w_rows_per_img=nk,
-                       w_mn_major=True, groups=(heads, lp, d, d))
+        if ops.option("sra_fused") and ops.sra_attention_supported(n, nk, d, save_p=True):
+            # ONE kernel: dP = dO.V^T in TMEM -> dS over the loaded P tile -> dQ = dS.K (csrc/sra_attention.cu); dP never reaches HBM
+            dq3, ds3 = ops.sra_attention_bwd(do.view(b, n, c), sv.kv2, sv.p4.view(b, n, heads * lp), heads, nk, d ** -0.5)
+            dq, ds4 = dq3.view(b, 1, n, c), ds3.view(b, 1, n, heads * lp)
+        else:
+            dp = torch.empty((b, 1, n, heads * lp), dtype=dt, device=do.device)
+            ops.conv2d_fwd([do4[..., 0:d]], sv.kv2[:, c:c + d], nk, 1, 1, 0, 0, out=dp[..., 0:nk], w_rows_per_img=nk,
+                           groups=(heads, d, d, lp))
+            ds = ops.softmax_bwd(sv.p4.view(b, n, heads, lp), dp.view(b, n, heads, lp), d ** -0.5, nk)
+            ds4 = ds.view(b, 1, n, heads * lp)
+            dq = torch.empty((b, 1, n, c), dtype=dt, device=do.device)
+            ops.conv2d_fwd([ds4[..., 0:lp]], sv.kv2[:, 0:d], d, 1, 1, 0, 0, out=dq[..., 0:d], w_rows_per_img=nk,
+                           w_mn_major=True, groups=(heads, lp, d, d))
         # dV[b] = P^T dO,  dK[b] = dS^T q   (one independent product per image and head)
         if ops.option("attn_wgrad_grouped") and heads > 1:
             # all heads in one launch each: head g reads the dO / q columns shifted by g*d, the P / dS columns by g*lp

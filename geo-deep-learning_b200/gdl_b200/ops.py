@@ -560,9 +560,12 @@ def softmax_fwd(s, scale, length, p=None):
     return p
 
 
-def sra_attention_supported(n: int, nk: int, d: int) -> bool:
-    """shapes gdl_sra_attention_fwd covers (one 128-query tile x all keys in TMEM): every MiT stage of a 512x512 tile"""
-    return d == 64 and nk % 64 == 0 and 0 < nk <= 256 and n % 128 == 0
+def sra_attention_supported(n: int, nk: int, d: int, save_p: bool = True) -> bool:
+    """shapes gdl_sra_attention_fwd covers.  Training (probabilities saved for the backward): one 128-query tile x all keys in
+    TMEM — every MiT stage of a 512x512 tile.  Inference: any token counts (ragged tiles, streamed keys)."""
+    if d != 64:
+        return False
+    return not save_p or (nk % 64 == 0 and 0 < nk <= 256 and n % 128 == 0)
 
 
 def sra_attention_fwd(q, kv2, heads, nk, scale, save_p=True):
@@ -577,6 +580,19 @@ def sra_attention_fwd(q, kv2, heads, nk, scale, save_p=True):
                                        p.stride(1) if p is not None else 0, b, n, heads, nk, c, float(scale),
                                        L.dt_code(q.dtype), L.stream_ptr()))
     return o, p
+
+
+def sra_attention_bwd(do, kv2, p, heads, nk, scale):
+    """Fused dP -> dS -> dQ.  do: (B, N, c) gradient of the attention output; kv2: (B*nk, 2c); p: (B, N, heads*nk) saved
+    probabilities.  Returns (dq (B, N, c), ds (B, N, heads*nk))."""
+    b, n, c = do.shape
+    if do.stride(2) != 1 or p.stride(2) != 1 or kv2.stride(1) != 1 or do.stride(0) != n * do.stride(1) or p.stride(0) != n * p.stride(1):
+        raise ValueError("sra_attention_bwd: token rows with a contiguous channel dim expected")
+    dq = torch.empty((b, n, c), dtype=do.dtype, device=do.device)
+    ds = torch.empty((b, n, heads * nk), dtype=do.dtype, device=do.device)
+    _ck(L.load().gdl_sra_attention_bwd(L.ptr(do), do.stride(1), L.ptr(kv2), kv2.stride(0), L.ptr(p), p.stride(1), L.ptr(dq), dq.stride(1),
+                                       L.ptr(ds), ds.stride(1), b, n, heads, nk, c, float(scale), L.dt_code(do.dtype), L.stream_ptr()))
+    return dq, ds
 
 
 def mha_flash_fwd(qkv, b, n, heads, scale):

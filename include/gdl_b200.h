@@ -324,11 +324,21 @@ int gdl_softmax_bwd(const void* p, long long ldp, const void* dp, long long lddp
  * in ONE kernel (scores stay in TMEM / shared memory).  q: (B, N, c) tokens, row stride ldq; kv: (B*nk, 2c) rows = reduced
  * tokens, K in columns [0, c), V in [c, 2c), row stride ldkv; o: (B, N, c), row stride ldo.  p_out (optional, training):
  * (B, N, heads*nk) normalised probabilities of head g in columns [g*nk, (g+1)*nk) — what the backward's dV = P^T.dO and
- * softmax_bwd read.  Covers head dim 64 (c == 64*heads), nk a multiple of 64 up to 256, N a multiple of 128; anything else
- * returns GDL_ERR_UNSUPPORTED and the caller uses gdl_conv2d_nhwc_fwd + gdl_softmax_fwd + gdl_conv2d_nhwc_fwd. */
+ * softmax_bwd read.  Head dim 64 (c == 64*heads).  With p_out: nk a multiple of 64 up to 256 and N a multiple of 128 (every MiT
+ * stage of a 512x512 tile); without (inference): any N and nk.  Anything else returns GDL_ERR_UNSUPPORTED and the caller uses
+ * gdl_conv2d_nhwc_fwd + gdl_softmax_fwd + gdl_conv2d_nhwc_fwd. */
 int gdl_sra_attention_fwd(const void* q, long long ldq, const void* kv, long long ldkv, void* o, long long ldo,
                           void* p_out, long long ldp, int B, int N, int heads, int nk, int c, float scale, int dtype,
                           void* stream);
+
+/* The query-tile-local half of the attention backward in one kernel (same pipeline, roles swapped): dP = dO.V^T in TMEM ->
+ * dS = scale * P * (dP - rowsum(P * dP)) written over the TMA-loaded P tile in shared memory -> dQ = dS.K.  Outputs dq (B, N, c) and
+ * ds (B, N, heads*nk) 16-bit (ds feeds the dK = dS^T.q weight-gradient launch; dV = P^T.dO reads the saved P): replaces
+ * gdl_conv2d_nhwc_fwd (dP) + gdl_softmax_bwd + gdl_conv2d_nhwc_fwd (dQ); dP never reaches HBM.  Same shape limits as the forward
+ * with p_out. */
+int gdl_sra_attention_bwd(const void* d_o, long long lddo, const void* kv, long long ldkv, const void* p_saved, long long ldp,
+                          void* dq, long long lddq, void* ds, long long ldds, int B, int N, int heads, int nk, int c, float scale,
+                          int dtype, void* stream);
 
 /* The same kernel for plain multi-head self-attention with many keys (timm's Attention inside the DOFA ViT blocks,
  * dofa_v2.py:445-487 -> timm vision_transformer.Block): keys are streamed in blocks of 128 with the online-softmax recurrence, so

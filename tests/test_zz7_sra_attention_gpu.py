@@ -123,6 +123,49 @@ def test_dofa_encoder_with_flash_attention_equals_three_kernel_encoder(cuda):
         assert ((f1 - f0).norm() / f0.norm()).item() < 1e-2
 
 
+@pytest.mark.parametrize("b,n,heads,nk,dtype,ctas", [
+    (2, 256, 1, 256, torch.bfloat16, 0),
+    (1, 384, 2, 64, torch.bfloat16, 1),      # one long CTA: P tile reuse handshake, K / V reload between heads
+    (2, 128, 5, 128, torch.float16, 3),
+])
+def test_fused_attention_backward_matches_fp32(cuda, b, n, heads, nk, dtype, ctas):
+    """gdl_sra_attention_bwd: dS = scale * P * (dP - rowsum(P * dP)), dQ = dS.K against torch fp32 on the same 16-bit operands and
+    against the three launches it replaces"""
+    from gdl_b200 import ops
+    g = torch.Generator().manual_seed(13)
+    c = 64 * heads
+    do = torch.randn(b, n, c, generator=g).to(dtype).cuda()
+    kv2 = torch.randn(b * nk, 2 * c, generator=g).to(dtype).cuda()
+    p = (torch.randn(b, n, heads, nk, generator=g) * 2).softmax(-1).reshape(b, n, heads * nk).to(dtype).cuda()
+    scale = 0.125
+    ops.set_option("sra_max_ctas", ctas)
+    try:
+        dq, ds = ops.sra_attention_bwd(do, kv2, p, heads, nk, scale)
+        torch.cuda.synchronize()
+    finally:
+        ops.set_option("sra_max_ctas", 0)
+    k = kv2[:, :c].float().view(b, nk, heads, 64)
+    v = kv2[:, c:].float().view(b, nk, heads, 64)
+    pf = p.float().view(b, n, heads, nk)
+    dp = torch.einsum("bnhd,bkhd->bnhk", do.float().view(b, n, heads, 64), v)
+    ds_ref = scale * pf * (dp - (pf * dp).sum(-1, keepdim=True))
+    ulp = 2.0 ** -8 if dtype == torch.bfloat16 else 2.0 ** -11
+    assert (ds.float().view(b, n, heads, nk) - ds_ref).abs().max() <= 3 * ulp * ds_ref.abs().max()
+    dq_ref = torch.einsum("bnhk,bkhd->bnhd", ds.float().view(b, n, heads, nk), k).reshape(b, n, c)  # from the 16-bit dS the kernel used
+    assert (dq.float() - dq_ref).abs().max() <= 3 * ulp * dq_ref.abs().max()
+    # the three launches of models/segformer.py
+    do4 = do.view(b, 1, n, c)
+    dp3 = torch.empty((b, 1, n, heads * nk), dtype=dtype, device=do.device)
+    ops.conv2d_fwd([do4[..., 0:64]], kv2[:, c:c + 64], nk, 1, 1, 0, 0, out=dp3[..., 0:nk], w_rows_per_img=nk, groups=(heads, 64, 64, nk))
+    ds3 = ops.softmax_bwd(p.view(b, n, heads, nk), dp3.view(b, n, heads, nk), scale, nk)
+    dq3 = torch.empty((b, 1, n, c), dtype=dtype, device=do.device)
+    ops.conv2d_fwd([ds3.view(b, 1, n, heads * nk)[..., 0:nk]], kv2[:, 0:64], 64, 1, 1, 0, 0, out=dq3[..., 0:64], w_rows_per_img=nk,
+                   w_mn_major=True, groups=(heads, nk, 64, 64))
+    torch.cuda.synchronize()
+    assert (ds.float() - ds3.view(b, n, heads * nk).float()).abs().max() <= 2.0 ** -5 * ds_ref.abs().max()
+    assert (dq.float() - dq3.view(b, n, c).float()).abs().max() <= 2.0 ** -5 * dq_ref.abs().max()
+
+
 def test_fused_attention_equals_three_kernel_path_and_rejects_other_shapes(cuda):
     from gdl_b200 import ops
     g = torch.Generator().manual_seed(8)
@@ -148,11 +191,17 @@ def test_fused_attention_equals_three_kernel_path_and_rejects_other_shapes(cuda)
         ops.sra_attention_fwd(q[:, :200].contiguous(), kv2, heads, nk, 0.125)
     with pytest.raises(NotImplementedError):
         ops.sra_attention_fwd(q, kv2[: b * 48].contiguous(), heads, 48, 0.125)
+    # without saved probabilities (inference) ragged query tiles and any key count are fine
+    assert ops.sra_attention_supported(200, 48, 64, save_p=False)
+    o_r, none = ops.sra_attention_fwd(q[:, :200].contiguous(), kv2[: b * 48].contiguous(), heads, 48, 0.125, save_p=False)
+    torch.cuda.synchronize()
+    o_ref, _ = _ref(q[:, :200], kv2[: b * 48], heads, 48, 0.125)
+    assert none is None and (o_r.float() - o_ref).abs().max() <= 3 * 2.0 ** -8 * o_ref.abs().max()
 
 
 def test_segformer_with_fused_attention_equals_three_kernel_model(cuda):
-    """whole model (MiT-B1: head dim 64), 256x256 tile (64 keys per image: stages 1-3 take the fused kernel, stage 4 with its 64
-    queries the three-kernel path): eval logits and a training step (loss + parameter gradients) with the option on and off"""
+    """whole model (MiT-B1: head dim 64), 256x256 tile (64 keys per image: in training stages 1-3 take the fused kernels, stage 4 with
+    its 64 queries the three-kernel path): eval logits and a training step (loss + parameter gradients) with the option on and off"""
     from test_segformer_gpu import _rel, _setup
     import torch.nn.functional as F
     from gdl_b200 import ops
@@ -186,7 +235,9 @@ def test_segformer_with_fused_attention_equals_three_kernel_model(cuda):
         ops.set_option("sra_fused", 0)
         ops.sra_attention_fwd = real
     torch.cuda.synchronize()
-    assert calls["n"] == 2 * 6  # eval + train forward, 2 blocks in each of the stages 1-3
+    # eval forward: all 4 stages x 2 blocks (no P to save: any shape); train forward: stages 1-3 (stage 4 has 64 queries); the
+    # backward of those 6 blocks takes gdl_sra_attention_bwd
+    assert calls["n"] == 8 + 6
     (e0, l0, g0), (e1, l1, g1) = res[0], res[1]
     # the two routes differ by 16-bit roundings of the scores / probabilities only
     flat = lambda gr: torch.cat([v.flatten() for v in gr.values()])  # noqa: E731
