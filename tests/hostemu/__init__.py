@@ -43,13 +43,19 @@ def load_lib():
     return _lib
 
 
-def install(monkeypatch, torch_convs: bool = False) -> None:
+def install(monkeypatch, torch_convs: bool = False, async_seed: int | None = None) -> None:
     """torch_convs: take the tensor-core entry points from the torch emulation instead of running the tcgen05 / TMA kernels on
-    the functional model of hostemu_tc.cpp (faster for whole-model steps)."""
+    the functional model of hostemu_tc.cpp (faster for whole-model steps).
+    async_seed: None = GDL_HOSTEMU_ASYNC from the environment (unset: synchronous completion); otherwise the asynchronous mode
+    of the model with that seed — TMA copies / MMAs / commits complete at random later points (even seed: operands read at issue,
+    odd: at completion), which exposes missing waits and premature reuse of stages, accumulators and staging tiles."""
     import cpu_kernel_emulation as emu
     from gdl_b200 import _lib as L
     from gdl_b200 import ops
     lib = load_lib()
+    if async_seed is None:
+        async_seed = int(os.environ.get("GDL_HOSTEMU_ASYNC", "-1") or -1)
+    lib.hostemu_set_async(int(async_seed))
     monkeypatch.setattr(L, "_lib", lib)
     monkeypatch.setattr(L, "stream_ptr", lambda: C.c_void_p(0))
     monkeypatch.setattr(L, "ptr", lambda t: C.c_void_p(0 if t is None else t.data_ptr()))

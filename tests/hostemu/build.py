@@ -23,8 +23,11 @@ SOURCES = ["runtime.cu", "elementwise.cu", "transformer.cu", "loss_optim.cu", "a
 # PTX wrappers of common.cuh whose bodies are forwarded to the functional model in hostemu_tc.cpp
 TC_FORWARD = ["smem_u32", "elect_one", "mbar_init", "mbar_expect_tx", "mbar_arrive", "mbar_try_wait", "tma_load_2d", "tma_load_4d",
               "tma_store_4d", "named_bar_sync", "tmem_alloc", "tmem_dealloc", "umma_f16", "umma_commit", "tmem_ld_32x32b_x16"]
-TC_NOP = ["fence_mbar_init", "fence_proxy_async_smem", "tma_prefetch_desc", "bulk_commit_group", "bulk_wait_group_read",
-          "bulk_wait_group", "tmem_relinquish", "tc_fence_before", "tc_fence_after", "tmem_ld_wait"]
+TC_NOP = ["fence_mbar_init", "fence_proxy_async_smem", "tma_prefetch_desc", "tmem_relinquish", "tc_fence_before", "tc_fence_after",
+          "tmem_ld_wait"]
+# bulk-group bookkeeping of the TMA stores (template <int N> wait_group[.read] N)
+TC_BULK = {"bulk_commit_group": "hostemu::tc::bulk_commit_group()", "bulk_wait_group_read": "hostemu::tc::bulk_wait_group(N)",
+           "bulk_wait_group": "hostemu::tc::bulk_wait_group(N)"}
 HEADERS = ["common.cuh", "tmap.cuh"]
 CUDA_INC = "/usr/local/cuda/include"
 
@@ -130,7 +133,7 @@ def rewrite_asm(src: str) -> str:
 
 def forward_wrappers(src: str) -> str:
     """common.cuh: replace the inline-PTX body of each wrapper by a call into the functional model"""
-    for name in TC_FORWARD + TC_NOP:
+    for name in TC_FORWARD + TC_NOP + list(TC_BULK):
         m = re.search(rf"GDL_DEVINL\s+[\w \*&:]+?\b{name}\s*\(", src)
         if not m:
             raise RuntimeError(f"wrapper {name} not found in common.cuh")
@@ -139,7 +142,7 @@ def forward_wrappers(src: str) -> str:
         names = [re.findall(r"[A-Za-z_]\w*", re.sub(r"\[[^\]]*\]", "", q))[-1] for q in params]
         b0 = src.index("{", p1)
         b1 = _match_fwd(src, b0, "{", "}")
-        call = f"hostemu::tc::{name}({', '.join(names)})" if name in TC_FORWARD else "hostemu::tc::nop()"
+        call = (f"hostemu::tc::{name}({', '.join(names)})" if name in TC_FORWARD else TC_BULK.get(name, "hostemu::tc::nop()"))
         src = src[:b0] + "{ return " + call + "; }" + src[b1 + 1:]
     return src
 

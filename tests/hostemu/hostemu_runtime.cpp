@@ -56,6 +56,7 @@ void yield_spin() {
 int warp_index() { return g_cur->warp; }
 int thread_linear() { return g_cur->warp * 32 + g_cur->lane; }
 namespace tc {
+bool async_tick(bool stuck);
 void* encode_entry_point();
 void block_begin();
 void block_end(unsigned bx, unsigned by, unsigned bz);
@@ -157,8 +158,11 @@ void launch(dim3 grid, dim3 block, size_t smem, const std::function<void()>& bod
             }
           }
           if (released) ++g_progress;
+          // asynchronous mode: complete some of the queued TMA / tensor-core operations (all fibers are blocked or polling now)
+          const bool pending = tc::async_tick(g_progress == progress0);
           idle_passes = (g_progress == progress0) ? idle_passes + 1 : 0;
-          if ((!released && spinning == 0) || idle_passes > 4) {
+          if (pending && idle_passes <= 64 && (released || spinning > 0 || g_progress != progress0)) continue;
+          if ((!released && spinning == 0 && g_progress == progress0) || idle_passes > 4) {
             fprintf(stderr, "hostemu: block (%u,%u,%u) stuck (%s): %d live fibers, %d at __syncthreads, %d polling an mbarrier\n",
                     bx, by, bz, spinning ? "mbarrier deadlock" : (ran ? "divergent barrier" : "nothing runnable"), live, at_block, spinning);
             for (int t = 0; t < nthreads; ++t)

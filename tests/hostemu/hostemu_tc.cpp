@@ -2,6 +2,10 @@
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 
+#include <deque>
+#include <functional>
+#include <memory>
+#include <random>
 #include <vector>
 
 #include "cuda_hostemu.h"
@@ -48,6 +52,112 @@ bool elect_one() { return hostemu::lane() == 0; }
 // ---------------------------------------------------------------------------------------------------------------------
 enum { kCtrTmaLoadBytes, kCtrTmaStoreBytes, kCtrTmaLoads, kCtrMmaIssued, kCtrMmaMacs, kCtrTmemLd, kCtrMbarWaitsFailed, kCtrRedAdds, kNumCtr };
 static unsigned long long g_ctr[kNumCtr];
+
+// ---------------------------------------------------------------------------------------------------------------------
+// asynchronous mode (GDL_HOSTEMU_ASYNC=<seed>): TMA copies, tensor-core operations and commits do NOT complete at issue.  They
+// are queued and completed later, at random scheduler passes: TMA loads in any order, tcgen05 operations in issue order
+// (commit after the MMAs before it), TMA stores in order.  Operands are read and results written AT COMPLETION, so a missing
+// mbarrier wait / fence-less reuse of a shared-memory stage, a TMEM accumulator or a staging tile computes with stale or
+// clobbered data — the class of bug the synchronous model cannot see.
+// ---------------------------------------------------------------------------------------------------------------------
+static int g_async = -1;
+static bool g_early_read = false;  // even seeds: MMAs / TMA stores read shared memory at issue; odd seeds: at completion
+static std::mt19937 g_rng;
+static std::vector<std::function<void()>> g_q_tma;   // completes in any order
+static std::deque<std::function<void()>> g_q_tc;     // in order
+static std::deque<std::function<void()>> g_q_store;  // in order; entries of one bulk group end with a marker (empty function)
+static int g_store_groups = 0;                        // committed bulk groups still pending
+static size_t g_max_tma = 0, g_max_tc = 0, g_max_store = 0, g_deferred = 0;  // GDL_HOSTEMU_ASYNC_STATS=1: printed at exit
+struct AsyncStats {
+  ~AsyncStats() {
+    if (getenv("GDL_HOSTEMU_ASYNC_STATS"))
+      fprintf(stderr, "hostemu async: %zu deferred operations, deepest queues: %zu TMA loads, %zu tensor-core ops, %zu store entries\n",
+              g_deferred, g_max_tma, g_max_tc, g_max_store);
+  }
+} g_async_stats;
+static bool async_on() {
+  if (g_async < 0) {
+    const char* e = getenv("GDL_HOSTEMU_ASYNC");
+    g_async = (e && *e && atoi(e) >= 0) ? 1 : 0;
+    g_rng.seed(e ? (unsigned)atoi(e) : 0u);
+    g_early_read = e && (atoi(e) % 2 == 0);
+  }
+  return g_async == 1;
+}
+static void run_store_front() {
+  auto fn = std::move(g_q_store.front());
+  g_q_store.pop_front();
+  if (fn) fn(); else --g_store_groups;
+}
+// called by the fiber scheduler after every pass; `stuck`: no fiber could make progress on its own
+bool async_tick(bool stuck) {
+  if (!async_on()) return false;
+  bool did = false;
+  g_max_tma = std::max(g_max_tma, g_q_tma.size());
+  g_max_tc = std::max(g_max_tc, g_q_tc.size());
+  g_max_store = std::max(g_max_store, g_q_store.size());
+  g_deferred += g_q_tma.size() + g_q_tc.size() + g_q_store.size();
+  auto run_tma = [&](size_t i) {
+    auto fn = std::move(g_q_tma[i]);
+    g_q_tma[i] = std::move(g_q_tma.back());
+    g_q_tma.pop_back();
+    fn();
+    did = true;
+  };
+  auto run_tc = [&]() {
+    auto fn = std::move(g_q_tc.front());
+    g_q_tc.pop_front();
+    fn();
+    did = true;
+  };
+  for (size_t i = 0; i < g_q_tma.size();) {
+    if ((g_rng() & 7) == 0) run_tma(i); else ++i;
+  }
+  while (!g_q_tc.empty() && (g_rng() & 3) == 0) run_tc();
+  while (!g_q_store.empty() && (g_rng() & 3) == 0) {
+    run_store_front();
+    did = true;
+  }
+  if (stuck && !did) {
+    // nothing can move on its own: complete ONE pending operation, chosen at random (not the oldest: completion order is free)
+    const int nq = (!g_q_tma.empty()) + (!g_q_tc.empty()) + (!g_q_store.empty());
+    if (nq > 0) {
+      int pick = (int)(g_rng() % (unsigned)nq);
+      if (!g_q_tma.empty() && pick-- == 0) {
+        run_tma(g_rng() % g_q_tma.size());
+      } else if (!g_q_tc.empty() && pick-- == 0) {
+        run_tc();
+      } else {
+        run_store_front();
+        did = true;
+      }
+    }
+  }
+  if (did) hostemu::note_progress();
+  return did || !g_q_tma.empty() || !g_q_tc.empty() || !g_q_store.empty();
+}
+static void async_drain_all() {
+  while (!g_q_tma.empty() || !g_q_tc.empty() || !g_q_store.empty()) {
+    for (auto& fn : g_q_tma) fn();
+    g_q_tma.clear();
+    while (!g_q_tc.empty()) {
+      auto fn = std::move(g_q_tc.front());
+      g_q_tc.pop_front();
+      fn();
+    }
+    while (!g_q_store.empty()) run_store_front();
+  }
+}
+// cp.async.bulk.commit_group / wait_group[.read] N (executed by the thread that issued the stores)
+void bulk_commit_group() {
+  if (!async_on()) return;
+  g_q_store.emplace_back();  // group marker
+  ++g_store_groups;
+}
+void bulk_wait_group(int n) {
+  if (!async_on()) return;
+  while (g_store_groups > n) run_store_front();
+}
 
 // ---------------------------------------------------------------------------------------------------------------------
 // mbarrier: the 8-byte object itself holds the state
@@ -196,27 +306,40 @@ static void tma_copy(const TMap& t, uint32_t saddr, const int* c, bool load) {
 void tma_load_2d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1) {
   const TMap& t = tmap(m);
   if (t.rank != 2) TC_FAIL("tma_load_2d with a rank-%u map", t.rank);
-  const int c[5] = {c0, c1, 0, 0, 0};
-  tma_copy(t, smem_u32(smem_dst), c, true);
   g_ctr[kCtrTmaLoadBytes] += t.box[0] * t.box[1] * t.esz;
   ++g_ctr[kCtrTmaLoads];
-  mbar_complete_tx(bar, t.box[0] * t.box[1] * t.esz);
+  const uint32_t saddr = smem_u32(smem_dst), bytes = t.box[0] * t.box[1] * t.esz;
+  auto fn = [t, saddr, c0, c1, bar, bytes]() {
+    const int c[5] = {c0, c1, 0, 0, 0};
+    tma_copy(t, saddr, c, true);
+    mbar_complete_tx(bar, bytes);
+  };
+  if (async_on()) g_q_tma.emplace_back(fn); else fn();
 }
 void tma_load_4d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2, int c3) {
   const TMap& t = tmap(m);
   if (t.rank != 4) TC_FAIL("tma_load_4d with a rank-%u map", t.rank);
-  const int c[5] = {c0, c1, c2, c3, 0};
-  tma_copy(t, smem_u32(smem_dst), c, true);
   g_ctr[kCtrTmaLoadBytes] += t.box[0] * t.box[1] * t.box[2] * t.box[3] * t.esz;
   ++g_ctr[kCtrTmaLoads];
-  mbar_complete_tx(bar, t.box[0] * t.box[1] * t.box[2] * t.box[3] * t.esz);
+  const uint32_t saddr = smem_u32(smem_dst), bytes = t.box[0] * t.box[1] * t.box[2] * t.box[3] * t.esz;
+  auto fn = [t, saddr, c0, c1, c2, c3, bar, bytes]() {
+    const int c[5] = {c0, c1, c2, c3, 0};
+    tma_copy(t, saddr, c, true);
+    mbar_complete_tx(bar, bytes);
+  };
+  if (async_on()) g_q_tma.emplace_back(fn); else fn();
 }
 void tma_store_4d(const CUtensorMap* m, const void* smem_src, int c0, int c1, int c2, int c3) {
   const TMap& t = tmap(m);
   if (t.rank != 4) TC_FAIL("tma_store_4d with a rank-%u map", t.rank);
-  const int c[5] = {c0, c1, c2, c3, 0};
-  tma_copy(t, smem_u32(smem_src), c, false);
   g_ctr[kCtrTmaStoreBytes] += t.box[0] * t.box[1] * t.box[2] * t.box[3] * t.esz;
+  const uint32_t saddr = smem_u32(smem_src);
+  auto fn = [t, saddr, c0, c1, c2, c3]() {
+    const int c[5] = {c0, c1, c2, c3, 0};
+    tma_copy(t, saddr, c, false);
+  };
+  // asynchronous mode, odd seeds: the tile is read at completion (a staging tile rewritten before wait_group.read shows)
+  if (async_on() && !g_early_read) g_q_store.emplace_back(fn); else fn();
   hostemu::note_progress();
 }
 
@@ -238,6 +361,7 @@ void block_begin() {
     for (float& v : row) v = __builtin_nanf("");  // reading an accumulator nobody wrote is a bug
 }
 void block_end(unsigned bx, unsigned by, unsigned bz) {
+  async_drain_all();  // a CTA's outstanding bulk operations complete before its resources are released
   if (g_tmem_live != 0) TC_FAIL("block (%u,%u,%u) exits with %u TMEM columns still allocated", bx, by, bz, g_tmem_live);
 }
 
@@ -307,7 +431,13 @@ static inline uint32_t elem_addr(const Desc& d, int mn_major, int r, int k) {
   return swizzle(d.start + off, d.span);
 }
 
-void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+// operands gathered from shared memory (through the descriptors) into dense tiles; the product accumulated into TMEM
+struct MmaTiles {
+  int M, N;
+  uint32_t col0, accumulate;
+  std::vector<float> A, B;  // [M][16], [N][16]
+};
+static void umma_gather(MmaTiles& t, uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
   const int N = (int)((idesc >> 17) & 0x3f) << 3, M = (int)((idesc >> 24) & 0x1f) << 4;
   const int afmt = (idesc >> 7) & 7, bfmt = (idesc >> 10) & 7, a_mn = (idesc >> 15) & 1, b_mn = (idesc >> 16) & 1;
   if (((idesc >> 4) & 3) != 1) TC_FAIL("tcgen05.mma: accumulator format %u (f32 expected)", (idesc >> 4) & 3);
@@ -317,33 +447,67 @@ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
   if (M != 128) TC_FAIL("tcgen05.mma: M = %d accumulator layout not modelled", M);
   const uint32_t lane0 = tmem_d >> 16, col0 = tmem_d & 0xffff;
   if (lane0 != 0 || col0 + (uint32_t)N > 512) TC_FAIL("tcgen05.mma: accumulator at lane %u, columns %u..%u", lane0, col0, col0 + N - 1);
-  ++g_ctr[kCtrMmaIssued];
-  g_ctr[kCtrMmaMacs] += (unsigned long long)M * N * 16;
   const Desc da = decode_desc(desc_a, "A"), db = decode_desc(desc_b, "B");
-  static float A[128][16], B[256][16];
+  t.M = M;
+  t.N = N;
+  t.col0 = col0;
+  t.accumulate = accumulate;
+  t.A.resize((size_t)M * 16);
+  t.B.resize((size_t)N * 16);
   for (int m = 0; m < M; ++m)
     for (int k = 0; k < 16; ++k) {
       const uint32_t ad = elem_addr(da, a_mn, m, k);
       if (ad + 2 > kArenaBytes) TC_FAIL("tcgen05.mma: A operand reads shared address %u", ad);
-      A[m][k] = load16(ad, afmt);
+      t.A[(size_t)m * 16 + k] = load16(ad, afmt);
     }
   for (int n = 0; n < N; ++n)
     for (int k = 0; k < 16; ++k) {
       const uint32_t ad = elem_addr(db, b_mn, n, k);
       if (ad + 2 > kArenaBytes) TC_FAIL("tcgen05.mma: B operand reads shared address %u", ad);
-      B[n][k] = load16(ad, bfmt);
+      t.B[(size_t)n * 16 + k] = load16(ad, bfmt);
     }
-  for (int m = 0; m < M; ++m) {
-    float* drow = &g_tmem[m][col0];
-    for (int n = 0; n < N; ++n) {
+}
+static void umma_accumulate(const MmaTiles& t) {
+  for (int m = 0; m < t.M; ++m) {
+    float* drow = &g_tmem[m][t.col0];
+    const float* a = &t.A[(size_t)m * 16];
+    for (int n = 0; n < t.N; ++n) {
+      const float* b = &t.B[(size_t)n * 16];
       float acc = 0.f;
-      for (int k = 0; k < 16; ++k) acc += A[m][k] * B[n][k];
-      drow[n] = accumulate ? drow[n] + acc : acc;
+      for (int k = 0; k < 16; ++k) acc += a[k] * b[k];
+      drow[n] = t.accumulate ? drow[n] + acc : acc;
     }
   }
   hostemu::note_progress();
 }
-void umma_commit(uint64_t* bar) { mbar_arrive(bar); }  // every MMA issued so far has completed (they complete at issue)
+void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  ++g_ctr[kCtrMmaIssued];
+  g_ctr[kCtrMmaMacs] += (unsigned long long)(((idesc >> 24) & 0x1f) << 4) * (((idesc >> 17) & 0x3f) << 3) * 16;
+  if (!async_on()) {
+    static MmaTiles t;
+    umma_gather(t, tmem_d, desc_a, desc_b, idesc, accumulate);
+    umma_accumulate(t);
+  } else if (g_early_read) {
+    // operands read AT ISSUE (a missing wait for the TMA load / the P~ writes shows), accumulator written at completion
+    auto t = std::make_shared<MmaTiles>();
+    umma_gather(*t, tmem_d, desc_a, desc_b, idesc, accumulate);
+    g_q_tc.emplace_back([t]() { umma_accumulate(*t); });
+  } else {
+    // operands read AT COMPLETION (a stage / tile reused before the commit was observed shows)
+    g_q_tc.emplace_back([=]() {
+      MmaTiles t;
+      umma_gather(t, tmem_d, desc_a, desc_b, idesc, accumulate);
+      umma_accumulate(t);
+    });
+  }
+}
+// arrives when every tensor-core operation issued before it has completed (in-order queue; synchronous mode: at once)
+void umma_commit(uint64_t* bar) {
+  if (async_on())
+    g_q_tc.emplace_back([bar]() { mbar_arrive(bar); });
+  else
+    mbar_arrive(bar);
+}
 
 void red_add_f32(float* dst, float v) {
   ++g_ctr[kCtrRedAdds];
@@ -360,3 +524,9 @@ extern "C" void hostemu_counters_reset(void) { memset(hostemu::tc::g_ctr, 0, siz
 // out[8]: TMA load bytes, TMA store bytes, TMA load instructions, tcgen05.mma issued, MACs, tcgen05.ld (per warp), failed mbarrier polls,
 // fp32 global reductions
 extern "C" void hostemu_counters_get(unsigned long long* out) { memcpy(out, hostemu::tc::g_ctr, sizeof(hostemu::tc::g_ctr)); }
+// seed < 0: synchronous completion; even seed: asynchronous, operands read at issue; odd seed: asynchronous, operands read at completion
+extern "C" void hostemu_set_async(int seed) {
+  hostemu::tc::g_async = seed >= 0 ? 1 : 0;
+  hostemu::tc::g_rng.seed((unsigned)(seed >= 0 ? seed : 0));
+  hostemu::tc::g_early_read = seed >= 0 && seed % 2 == 0;
+}

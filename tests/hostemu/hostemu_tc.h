@@ -32,6 +32,9 @@ void umma_commit(uint64_t* bar);
 void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t (&v)[16]);
 void red_add_f32(float* dst, float v);
 void check_align(const void* p, unsigned bytes, const char* what);
+void bulk_commit_group();
+void bulk_wait_group(int n);
+bool async_tick(bool stuck);
 inline void nop() {}
 }  // namespace tc
 }  // namespace hostemu

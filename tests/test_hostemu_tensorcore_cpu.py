@@ -54,3 +54,14 @@ def _params():
 def test_tensor_core_kernel_on_functional_model(monkeypatch, tmp_path, file, fname, kw):
     hostemu.install(monkeypatch, torch_convs=False)
     hostemu.run_case(file, fname, kw, tmp_path)
+
+
+# The same cases with ASYNCHRONOUS completion of TMA copies, MMAs and commits (random completion points; seed 2: operands read at
+# issue, seed 3: at completion).  The synchronous model cannot see a missing mbarrier wait or a stage / accumulator / staging tile
+# reused too early; this mode does (checked by removing such waits from csrc/sra_attention.cu: the tests then fail here and
+# only here).  The kernels that are green on a B200 must stay green (no false alarms); the ones that never ran there get the scrutiny.
+@pytest.mark.parametrize("seed", [2, 3])
+@pytest.mark.parametrize("file,fname,kw", _params())
+def test_tensor_core_kernel_with_asynchronous_completion(monkeypatch, tmp_path, file, fname, kw, seed):
+    hostemu.install(monkeypatch, torch_convs=False, async_seed=seed)
+    hostemu.run_case(file, fname, kw, tmp_path)
