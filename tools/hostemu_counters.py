@@ -108,6 +108,23 @@ def main() -> None:
         rows.append({"kernel": label, "shape": f"B{b} heads{heads} N{n} keys{nk} d64", **cc, "useful_macs": useful,
                      "mma_efficiency": round(useful / max(cc["mma_macs"], 1), 3), "score_tensor_hbm_bytes": hbm})
 
+    # DOFA-like self-attention (keys streamed in blocks of 128): three launches vs the flash kernel
+    n2, heads2 = 1297, 1
+    qkv = torch.randn(n2, 3 * 64 * heads2, generator=g).to(bf)
+
+    def three_mha():
+        from gdl_b200.models.dofa import _mha
+        ops.set_option("mha_flash", 0)
+        _mha(qkv, 1, n2, heads2, 64 * heads2, bf)
+
+    lp2 = (n2 + 63) // 64 * 64
+    for label, fn, hbm in (("ViT self-attention fwd: q.k^T GEMM + softmax + P.V GEMM", three_mha, 4 * n2 * lp2 * 2),
+                           ("sra_attention_kernel, streamed keys (gdl_mha_flash_fwd)", lambda: ops.mha_flash_fwd(qkv, 1, n2, heads2, 0.125), 0)):
+        cc = counted(fn)
+        useful2 = 2 * heads2 * n2 * n2 * 64
+        rows.append({"kernel": label, "shape": f"B1 heads{heads2} N{n2} d64", **cc, "useful_macs": useful2,
+                     "mma_efficiency": round(useful2 / max(cc["mma_macs"], 1), 3), "score_tensor_hbm_bytes": hbm})
+
     out = {"note": "static counters from the CPU functional model of TMA / tcgen05 (tests/hostemu): algorithmic work per launch, not timings; "
                    "tma_load_bytes = L2 -> shared-memory traffic the kernel requests, mma_efficiency = useful MACs / MACs issued",
            "rows": rows}
