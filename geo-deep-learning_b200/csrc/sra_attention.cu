@@ -463,12 +463,12 @@ extern "C" int gdl_sra_attention_fwd(const void* q, long long ldq, const void* k
   GDL_REQUIRE(q && kv && o && B > 0 && N > 0 && heads > 0 && nk > 0, GDL_ERR_INVALID, "sra_attention: bad args");
   GDL_REQUIRE(dtype == GDL_BF16 || dtype == GDL_F16, GDL_ERR_INVALID, "sra_attention: 16-bit dtype expected");
   GDL_REQUIRE(c == heads * kSraD, GDL_ERR_UNSUPPORTED, "sra_attention: head dim %d (64 expected)", heads ? c / heads : 0);
-  // saving the probabilities needs the whole key range in one block and whole 64-key / 128-query store boxes; without them
-  // (inference) any shape goes: ragged tiles are zero-filled / clipped, more than 256 keys are streamed
+  // saving the probabilities needs the whole key range in one block and whole 64-key store boxes (a box must not spill into the
+  // next head's columns); ragged query tiles are zero-filled / clipped by the TMA unit.  Without P (inference) any shape goes: more
+  // than 256 keys are streamed
   GDL_REQUIRE(p_out == nullptr || (nk % 64 == 0 && nk <= kSraMaxKeys), GDL_ERR_UNSUPPORTED,
               "sra_attention: %d keys (saving P needs a multiple of 64, at most %d: use the three-kernel path otherwise)", nk, kSraMaxKeys);
-  GDL_REQUIRE(p_out == nullptr || N % 128 == 0, GDL_ERR_UNSUPPORTED,
-              "sra_attention: %d queries per image (saving P needs a multiple of 128)", N);
+
   GDL_REQUIRE(ldq >= c && ldo >= c && ldkv >= 2 * c && (p_out == nullptr || ldp >= (long long)heads * nk), GDL_ERR_INVALID,
               "sra_attention: leading dimensions too small");
   const char* kvp = reinterpret_cast<const char*>(kv);
@@ -491,8 +491,8 @@ extern "C" int gdl_sra_attention_bwd(const void* d_o, long long lddo, const void
   GDL_REQUIRE(d_o && kv && p_saved && dq && ds && B > 0 && N > 0 && heads > 0 && nk > 0, GDL_ERR_INVALID, "sra_attention_bwd: bad args");
   GDL_REQUIRE(dtype == GDL_BF16 || dtype == GDL_F16, GDL_ERR_INVALID, "sra_attention_bwd: 16-bit dtype expected");
   GDL_REQUIRE(c == heads * kSraD, GDL_ERR_UNSUPPORTED, "sra_attention_bwd: head dim %d (64 expected)", heads ? c / heads : 0);
-  GDL_REQUIRE(nk % 64 == 0 && nk <= kSraMaxKeys && N % 128 == 0, GDL_ERR_UNSUPPORTED,
-              "sra_attention_bwd: %d keys / %d queries (keys: a multiple of 64 up to %d, queries: a multiple of 128)", nk, N, kSraMaxKeys);
+  GDL_REQUIRE(nk % 64 == 0 && nk <= kSraMaxKeys, GDL_ERR_UNSUPPORTED, "sra_attention_bwd: %d keys (a multiple of 64 up to %d)", nk,
+              kSraMaxKeys);
   GDL_REQUIRE(lddo >= c && lddq >= c && ldkv >= 2 * c && ldp >= (long long)heads * nk && ldds >= (long long)heads * nk, GDL_ERR_INVALID,
               "sra_attention_bwd: leading dimensions too small");
   GDL_REQUIRE(p_saved != ds, GDL_ERR_INVALID, "sra_attention_bwd: dS must not alias P (dV = P^T.dO still reads P)");

@@ -561,11 +561,11 @@ def softmax_fwd(s, scale, length, p=None):
 
 
 def sra_attention_supported(n: int, nk: int, d: int, save_p: bool = True) -> bool:
-    """shapes gdl_sra_attention_fwd covers.  Training (probabilities saved for the backward): one 128-query tile x all keys in
-    TMEM — every MiT stage of a 512x512 tile.  Inference: any token counts (ragged tiles, streamed keys)."""
-    if d != 64:
+    """shapes gdl_sra_attention_fwd / _bwd cover.  Training (probabilities saved for the backward): all keys of a head in one TMEM
+    tile, whole 64-key store boxes — every MiT stage of a 256x256 or 512x512 tile.  Inference: any token counts (streamed keys)."""
+    if d != 64 or n <= 0:
         return False
-    return not save_p or (nk % 64 == 0 and 0 < nk <= 256 and n % 128 == 0)
+    return not save_p or (nk % 64 == 0 and 0 < nk <= 256)
 
 
 def sra_attention_fwd(q, kv2, heads, nk, scale, save_p=True):

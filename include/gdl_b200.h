@@ -324,8 +324,8 @@ int gdl_softmax_bwd(const void* p, long long ldp, const void* dp, long long lddp
  * in ONE kernel (scores stay in TMEM / shared memory).  q: (B, N, c) tokens, row stride ldq; kv: (B*nk, 2c) rows = reduced
  * tokens, K in columns [0, c), V in [c, 2c), row stride ldkv; o: (B, N, c), row stride ldo.  p_out (optional, training):
  * (B, N, heads*nk) normalised probabilities of head g in columns [g*nk, (g+1)*nk) — what the backward's dV = P^T.dO and
- * softmax_bwd read.  Head dim 64 (c == 64*heads).  With p_out: nk a multiple of 64 up to 256 and N a multiple of 128 (every MiT
- * stage of a 512x512 tile); without (inference): any N and nk.  Anything else returns GDL_ERR_UNSUPPORTED and the caller uses
+ * softmax_bwd read.  Head dim 64 (c == 64*heads).  With p_out: nk a multiple of 64 up to 256 (every MiT stage of a 256x256 or
+ * 512x512 tile), any N; without (inference): any N and nk.  Anything else returns GDL_ERR_UNSUPPORTED and the caller uses
  * gdl_conv2d_nhwc_fwd + gdl_softmax_fwd + gdl_conv2d_nhwc_fwd. */
 int gdl_sra_attention_fwd(const void* q, long long ldq, const void* kv, long long ldkv, void* o, long long ldo,
                           void* p_out, long long ldp, int B, int N, int heads, int nk, int c, float scale, int dtype,

@@ -28,6 +28,8 @@ def _ref(q, kv2, heads, nk, scale):
     (1, 128, 2, 64, torch.bfloat16, True),     # 256x256 tile: 64 keys
     (3, 128, 5, 128, torch.float16, True),     # 5 heads (stage 3), fp16, K/V reload between heads
     (1, 384, 2, 192, torch.bfloat16, False),   # inference: no probabilities written; 192 keys
+    (2, 64, 8, 64, torch.bfloat16, True),      # MiT stage 4 of a 256x256 tile: 64 queries — half a query tile, rows clipped
+    (1, 200, 2, 128, torch.bfloat16, True),    # ragged second query tile with saved probabilities
 ])
 def test_fused_attention_matches_fp32(cuda, b, n, heads, nk, dtype, save_p):
     from gdl_b200 import ops
@@ -127,6 +129,7 @@ def test_dofa_encoder_with_flash_attention_equals_three_kernel_encoder(cuda):
     (2, 256, 1, 256, torch.bfloat16, 0),
     (1, 384, 2, 64, torch.bfloat16, 1),      # one long CTA: P tile reuse handshake, K / V reload between heads
     (2, 128, 5, 128, torch.float16, 3),
+    (2, 200, 2, 64, torch.bfloat16, 2),      # ragged query tiles: zero-filled loads, clipped stores
 ])
 def test_fused_attention_backward_matches_fp32(cuda, b, n, heads, nk, dtype, ctas):
     """gdl_sra_attention_bwd: dS = scale * P * (dP - rowsum(P * dP)), dQ = dS.K against torch fp32 on the same 16-bit operands and
@@ -186,9 +189,7 @@ def test_fused_attention_equals_three_kernel_path_and_rejects_other_shapes(cuda)
     # the three-kernel path rounds the scores to 16 bits before the softmax; the fused one keeps them in fp32
     assert (o.float() - o3.view(b, n, c).float()).abs().max() <= 2.0 ** -6 * o3.float().abs().max()
     assert (p.float() - p3.view(b, n, heads * nk).float()).abs().max() <= 2.0 ** -5 * p3.float().abs().max()
-    assert not ops.sra_attention_supported(n, 144, 64) and not ops.sra_attention_supported(200, nk, 64)
-    with pytest.raises(NotImplementedError):
-        ops.sra_attention_fwd(q[:, :200].contiguous(), kv2, heads, nk, 0.125)
+    assert not ops.sra_attention_supported(n, 144, 64) and not ops.sra_attention_supported(n, nk, 32)
     with pytest.raises(NotImplementedError):
         ops.sra_attention_fwd(q, kv2[: b * 48].contiguous(), heads, 48, 0.125)
     # without saved probabilities (inference) ragged query tiles and any key count are fine
@@ -200,8 +201,8 @@ def test_fused_attention_equals_three_kernel_path_and_rejects_other_shapes(cuda)
 
 
 def test_segformer_with_fused_attention_equals_three_kernel_model(cuda):
-    """whole model (MiT-B1: head dim 64), 256x256 tile (64 keys per image: in training stages 1-3 take the fused kernels, stage 4 with
-    its 64 queries the three-kernel path): eval logits and a training step (loss + parameter gradients) with the option on and off"""
+    """whole model (MiT-B1: head dim 64), 256x256 tile (64 keys per image at every stage): eval logits and a training step (loss +
+    parameter gradients) with the option on and off"""
     from test_segformer_gpu import _rel, _setup
     import torch.nn.functional as F
     from gdl_b200 import ops
@@ -235,9 +236,9 @@ def test_segformer_with_fused_attention_equals_three_kernel_model(cuda):
         ops.set_option("sra_fused", 0)
         ops.sra_attention_fwd = real
     torch.cuda.synchronize()
-    # eval forward: all 4 stages x 2 blocks (no P to save: any shape); train forward: stages 1-3 (stage 4 has 64 queries); the
-    # backward of those 6 blocks takes gdl_sra_attention_bwd
-    assert calls["n"] == 8 + 6
+    # eval and train forward: all 4 stages x 2 blocks (stage 4's 64 queries are half a query tile); the backward of the 8 blocks
+    # takes gdl_sra_attention_bwd
+    assert calls["n"] == 8 + 8
     (e0, l0, g0), (e1, l1, g1) = res[0], res[1]
     # the two routes differ by 16-bit roundings of the scores / probabilities only
     flat = lambda gr: torch.cat([v.flatten() for v in gr.values()])  # noqa: E731
