@@ -16,8 +16,9 @@ from pathlib import Path
 
 HERE = Path(__file__).resolve().parent
 ROOT = HERE.parent.parent
-CSRC = ROOT / "geo-deep-learning_b200" / "csrc"
-OUT = HERE / "_build"
+# GDL_HOSTEMU_CSRC / GDL_HOSTEMU_OUT: build from another copy of the sources into another directory (tools/hostemu_mutation_check.py)
+CSRC = Path(os.environ.get("GDL_HOSTEMU_CSRC", ROOT / "geo-deep-learning_b200" / "csrc"))
+OUT = Path(os.environ.get("GDL_HOSTEMU_OUT", HERE / "_build"))
 SOURCES = ["runtime.cu", "elementwise.cu", "transformer.cu", "loss_optim.cu", "augment_metrics.cu",
            "igemm_conv.cu", "conv3x3_rows.cu", "wgrad3x3_rows.cu", "debug_probe.cu", "sra_attention.cu"]
 # PTX wrappers of common.cuh whose bodies are forwarded to the functional model in hostemu_tc.cpp
