@@ -167,6 +167,18 @@ def lib_path() -> Path:
 
 
 def build(verbose: bool = False) -> Path:
+    """(re)build the host library if any input changed; safe under pytest-xdist (one builder at a time, the others wait)"""
+    import fcntl
+    OUT.mkdir(parents=True, exist_ok=True)
+    with open(OUT / "lock", "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            return _build_locked(verbose)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+
+
+def _build_locked(verbose: bool) -> Path:
     OUT.mkdir(exist_ok=True)
     h = hashlib.sha256()
     inputs = [CSRC / f for f in SOURCES + HEADERS] + [HERE / "cuda_hostemu.h", HERE / "hostemu_runtime.cpp", HERE / "hostemu_tc.h", HERE / "hostemu_tc.cpp", Path(__file__),
@@ -195,12 +207,13 @@ def build(verbose: bool = False) -> Path:
         dst.write_text(text)
         cpps.append(dst)
     cmd = ["g++", "-std=c++20", "-O1", "-g", "-fPIC", "-shared", "-Wl,-Bsymbolic", "-Wno-unknown-pragmas", "-Wno-attributes", "-fno-strict-aliasing", "-fsanitize=alignment", "-fno-sanitize-recover=alignment", *(["-fsanitize=address"] if ASAN else []),
-           f"-I{HERE}", f"-I{CUDA_INC}", *map(str, cpps), str(HERE / "hostemu_runtime.cpp"), str(HERE / "hostemu_tc.cpp"), "-o", str(lib_path())]
+           f"-I{HERE}", f"-I{CUDA_INC}", *map(str, cpps), str(HERE / "hostemu_runtime.cpp"), str(HERE / "hostemu_tc.cpp"), "-o", str(lib_path()) + ".tmp"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0 or verbose:
         print(r.stdout[-4000:], r.stderr[-12000:])
     if r.returncode != 0:
         raise RuntimeError("hostemu build failed")
+    os.replace(str(lib_path()) + ".tmp", lib_path())
     stamp.write_text(h.hexdigest())
     return lib_path()
 

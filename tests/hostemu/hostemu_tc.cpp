@@ -114,7 +114,7 @@ bool async_tick(bool stuck) {
     if ((g_rng() & 7) == 0) run_tma(i); else ++i;
   }
   while (!g_q_tc.empty() && (g_rng() & 3) == 0) run_tc();
-  while (!g_q_store.empty() && (g_rng() & 3) == 0) {
+  while (!g_q_store.empty() && (g_rng() & 31) == 0) {  // stores linger: only wait_group[.read] (or luck) completes them early
     run_store_front();
     did = true;
   }
