@@ -184,3 +184,34 @@ def test_fused_attention_random_shapes(monkeypatch, seed):
                 assert (p.float() - pr.permute(0, 2, 1, 3).reshape(b, n, heads * nk)).abs().max() <= 3 * ulp
     finally:
         ops.set_option("sra_max_ctas", 0)
+
+
+@pytest.mark.parametrize("seed", range(max(4, CASES // 3)))
+def test_fused_attention_backward_random_shapes(monkeypatch, seed):
+    """gdl_sra_attention_bwd on the functional model (asynchronous completion, both operand-read modes): ragged query counts, 1-4 key
+    chunks, few long CTAs"""
+    hostemu.install(monkeypatch, torch_convs=False, async_seed=seed)
+    from gdl_b200 import ops
+    rng = random.Random(5000 + seed)
+    g = torch.Generator().manual_seed(400 + seed)
+    dt = rng.choice([torch.bfloat16, torch.float16])
+    ulp = 2.0 ** -8 if dt == torch.bfloat16 else 2.0 ** -11
+    b, heads = rng.choice([1, 2]), rng.choice([1, 2, 3])
+    n, nk = rng.choice([64, 128, 200, 256, 300, 384]), 64 * rng.randint(1, 4)
+    c = 64 * heads
+    do = torch.randn(b, n, c, generator=g).to(dt)
+    kv2 = torch.randn(b * nk, 2 * c, generator=g).to(dt)
+    p = (torch.randn(b, n, heads, nk, generator=g) * 2).softmax(-1).reshape(b, n, heads * nk).to(dt)
+    ops.set_option("sra_max_ctas", rng.choice([0, 1, 2, 5]))
+    try:
+        dq, ds = ops.sra_attention_bwd(do, kv2, p, heads, nk, 0.125)
+    finally:
+        ops.set_option("sra_max_ctas", 0)
+    k = kv2[:, :c].float().view(b, nk, heads, 64)
+    v = kv2[:, c:].float().view(b, nk, heads, 64)
+    pf = p.float().view(b, n, heads, nk)
+    dp = torch.einsum("bnhd,bkhd->bnhk", do.float().view(b, n, heads, 64), v)
+    ds_ref = 0.125 * pf * (dp - (pf * dp).sum(-1, keepdim=True))
+    assert (ds.float().view(b, n, heads, nk) - ds_ref).abs().max() <= 3 * ulp * ds_ref.abs().max(), (b, n, nk, heads, dt)
+    dq_ref = torch.einsum("bnhk,bkhd->bnhd", ds.float().view(b, n, heads, nk), k).reshape(b, n, c)
+    assert (dq.float() - dq_ref).abs().max() <= 3 * ulp * dq_ref.abs().max(), (b, n, nk, heads, dt)
