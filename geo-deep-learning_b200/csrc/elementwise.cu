@@ -9,6 +9,7 @@
 
 #include "../../include/gdl_b200.h"
 #include "common.cuh"
+#include "det_reduce.cuh"
 
 namespace gdl {
 
@@ -261,7 +262,7 @@ __global__ void col2im_vec8_kernel(const T* __restrict__ dcol, T* __restrict__ d
 template <typename T>
 __global__ void bn_stats_kernel(const T* __restrict__ x, long long M, int C, int ld,
                                 float* __restrict__ sums /* [2][C], pre-zeroed */,
-                                const float* __restrict__ pivot /* [C] or null */) {
+                                const float* __restrict__ pivot /* [C] or null */, const DetCtx det) {
   const int cv = C / 8;
   const int tpr = cv < (int)blockDim.x ? cv : blockDim.x;  // threads spanning the channel dim
   const int rows_per_block = blockDim.x / tpr;
@@ -331,11 +332,17 @@ __global__ void bn_stats_kernel(const T* __restrict__ x, long long M, int C, int
           a += red[((r * tpr + tc) * 8 + j) * 2 + 0];
           b += red[((r * tpr + tc) * 8 + j) * 2 + 1];
         }
-        atomicAdd(&sums[c8 * 8 + j], a);
-        atomicAdd(&sums[C + c8 * 8 + j], b);
+        if (det.s0 != nullptr) {  // ordered reduction: this block's slot, summed in block order by det_finish
+          det_put(det, 2 * C, c8 * 8 + j, a);
+          det_put(det, 2 * C, C + c8 * 8 + j, b);
+        } else {
+          atomicAdd(&sums[c8 * 8 + j], a);
+          atomicAdd(&sums[C + c8 * 8 + j], b);
+        }
       }
     }
   }
+  if (det.s0 != nullptr) det_finish(det, 2 * C, sums);
 }
 
 // finalize: mean/var -> (scale, shift) for the apply kernel, saved (mean, invstd) for backward,
@@ -463,7 +470,7 @@ __global__ void __launch_bounds__(256) grad_gather_kernel(GatherSrcs srcs, const
                                                           const float* __restrict__ mean,
                                                           const float* __restrict__ invstd, T* __restrict__ g, int ldg,
                                                           float* __restrict__ sums /* [2][C] or null */, int N, int H,
-                                                          int W, int C) {
+                                                          int W, int C, const DetCtx det) {
   constexpr int PIX = NS <= 2 ? 2 : 1;
   const int cv = C / 8;
   const int tpr = cv < (int)blockDim.x ? cv : blockDim.x;
@@ -586,12 +593,18 @@ __global__ void __launch_bounds__(256) grad_gather_kernel(GatherSrcs srcs, const
             a += red[((r * tpr + tc) * 8 + j) * 2 + 0];
             b += red[((r * tpr + tc) * 8 + j) * 2 + 1];
           }
-          atomicAdd(&sums[c0 + j], a);
-          atomicAdd(&sums[C + c0 + j], b);
+          if (det.s0 != nullptr) {
+            det_put(det, 2 * C, c0 + j, a);
+            det_put(det, 2 * C, C + c0 + j, b);
+          } else {
+            atomicAdd(&sums[c0 + j], a);
+            atomicAdd(&sums[C + c0 + j], b);
+          }
         }
       }
     }
   }
+  if (sums != nullptr && det.s0 != nullptr) det_finish(det, 2 * C, sums);
 }
 
 // BN backward, elementwise part:  dx = gamma*invstd * (g - sum_g/M - xhat * sum_gxhat/M)
@@ -870,7 +883,13 @@ extern "C" int gdl_bn_stats(const void* x, int dtype, long long M, int C, int ld
   long long blocks = (M + rpb * 16 - 1) / (rpb * 16);  // >= 16 rows per thread
   if (blocks > 2 * kNumSMsB200) blocks = 2 * kNumSMsB200;
   if (blocks < 1) blocks = 1;
-  GDL_DISPATCH_16(dtype, { bn_stats_kernel<T><<<(int)blocks, threads, smem, st>>>((const T*)x, M, C, ld, sums, pivot); });
+  const DetWs ws = det_workspace();
+  DetCtx det = det_none();
+  if (const int g = det_grid(ws, blocks, 2 * C)) {
+    blocks = g;
+    det = det_ctx(ws, g, 2 * C);
+  }
+  GDL_DISPATCH_16(dtype, { bn_stats_kernel<T><<<(int)blocks, threads, smem, st>>>((const T*)x, M, C, ld, sums, pivot, det); });
   GDL_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -943,10 +962,18 @@ extern "C" int gdl_grad_gather(int num_src, const void* const* src_ptr, const in
   if (blocks > 8 * kNumSMsB200) blocks = 8 * kNumSMsB200;
   if (blocks < 1) blocks = 1;
   GDL_REQUIRE(M < (1ll << 31), GDL_ERR_UNSUPPORTED, "grad_gather: too many pixels");
+  DetCtx det = det_none();
+  if (sums) {
+    const DetWs ws = det_workspace();
+    if (const int gd = det_grid(ws, blocks, 2 * C)) {
+      blocks = gd;
+      det = det_ctx(ws, gd, 2 * C);
+    }
+  }
 #define GDL_GG_LAUNCH(NSV)                                                                                             \
   GDL_DISPATCH_16(dtype, {                                                                                             \
     grad_gather_kernel<T, NSV><<<(int)blocks, threads, smem, st>>>(gs, (const T*)y, ldy, (const T*)x, ldx, mean,        \
-                                                                   invstd, (T*)g, ldg, sums, N, H, W, C);              \
+                                                                   invstd, (T*)g, ldg, sums, N, H, W, C, det);         \
   })
   switch (num_src) {
     case 1: GDL_GG_LAUNCH(1); break;

@@ -20,6 +20,7 @@
 
 #include "../../include/gdl_b200.h"
 #include "tmap.cuh"
+#include "det_reduce.cuh"
 
 namespace gdl {
 
@@ -666,6 +667,7 @@ static int validate_srcs(int num_src, const gdl_src_t* src, int* ctot) {
 }
 
 extern int g_opt_sra_max_ctas;  // sra_attention.cu
+extern int g_opt_deterministic;  // runtime.cu
 }  // namespace gdl
 
 using namespace gdl;
@@ -678,6 +680,7 @@ extern "C" int gdl_set_option(const char* name, long long value) {
   else if (!strcmp(name, "wgrad_l2_mb")) g_opt_wgrad_l2_mb = value;
   else if (!strcmp(name, "conv_rows")) g_opt_conv_rows = (int)value;
   else if (!strcmp(name, "wgrad_rows")) g_opt_wgrad_rows = (int)value;
+  else if (!strcmp(name, "deterministic")) g_opt_deterministic = (int)value;  // 1 (default): ordered reductions when a workspace is registered
   else if (!strcmp(name, "sra_max_ctas")) g_opt_sra_max_ctas = (int)value;  // 0 = one CTA per SM (tests: fewer, longer CTAs)
   else {
     set_last_error("set_option: unknown option '%s'", name);
@@ -905,6 +908,9 @@ struct ConvWgradKParams {
   int nacc;        // TMEM accumulator sets in flight (2 = double buffered, 1 = single)
   int unit_taps;   // units along the tap axis (R*S, or 3 filter rows in halo mode)
   int b_atom_bytes;  // bytes of one X atom in a stage (64 px, or 66 px padded to 9 KiB in halo mode)
+  // ordered pixel-split accumulation (det_reduce.cuh): the ksplit units of one output tile add in split order
+  unsigned* turnstile;  // null: arrival order (fp32 atomics)
+  int Nimg;             // batched: images (tile index)
 };
 
 __global__ void __launch_bounds__(kConvThreads, 1)
@@ -1080,6 +1086,16 @@ conv_wgrad_kernel(const __grid_constant__ ConvWgradKParams p) {
       const bool nonempty = pb0 < pb1;
       mbar_wait(&tfull_bar[acc], aphase);
       tc_fence_after();
+      unsigned* ts = nullptr;
+      unsigned turn = 0;
+      if (p.turnstile != nullptr) {
+        const int sp = p.batched ? ks - uimg * p.ksplit : ks;
+        const long long tile = ((((long long)grp * p.Nimg + uimg) * p.m_tiles + mt) * p.n_ntiles + nt) * taps + tap;
+        ts = p.turnstile + tile;
+        turn = (unsigned)sp;
+        if (warp == 2 && lane == 0) turnstile_wait(ts, turn);
+        named_bar_sync(1, 128);
+      }
       for (int s3 = 0; s3 < p.nsub; ++s3) {
         const int tap_idx = p.halo ? tap * 3 + s3 : tap;
         float* dst = p.dw + (long long)uimg * p.dw_img_stride + (long long)m * p.dw_ld + (long long)tap_idx * p.Ctot +
@@ -1104,6 +1120,11 @@ conv_wgrad_kernel(const __grid_constant__ ConvWgradKParams p) {
       }
       tc_fence_before();
       mbar_arrive(&tempty_bar[acc]);
+      if (ts != nullptr) {
+        __threadfence();
+        named_bar_sync(1, 128);
+        if (warp == 2 && lane == 0) turnstile_pass(ts, turn, (int)turn == p.ksplit - 1);
+      }
     }
   }
 
@@ -1272,6 +1293,13 @@ extern "C" int gdl_conv2d_nhwc_wgrad(const gdl_conv_wgrad_t* d, void* stream_) {
   p.upg = p.num_units;
   GDL_REQUIRE((long long)p.num_units * G < (1ll << 31), GDL_ERR_UNSUPPORTED, "too many work units");
   p.num_units *= G;
+  p.Nimg = d->batched ? N : 1;
+  if (p.ksplit > 1) {
+    // several units add into the same dW tile: order them (split 0, 1, ...) when a workspace is registered
+    const DetWs ws = det_workspace();
+    const long long tiles = (long long)G * p.Nimg * base_units;
+    if (ws.ok() && tiles <= kDetTurnstiles) p.turnstile = ws.turnstiles();
+  }
 
   p.a_bytes = kWgPix * 128 * 2;
   const int b_bytes = p.halo ? ((bn_max + p.caB - 1) / p.caB) * p.b_atom_bytes : kWgPix * bn_max * 2;

@@ -13,6 +13,7 @@
 
 #include "../../include/gdl_b200.h"
 #include "common.cuh"
+#include "det_reduce.cuh"
 
 namespace gdl {
 
@@ -40,11 +41,10 @@ GDL_DEVINL long long load_target(const TT* t, long long i) {
 
 template <int KMAX, typename TT>
 __global__ void seg_loss_stats_kernel(const float* __restrict__ logits, int ld, const TT* __restrict__ target,
-                                      long long M, LossCfg cfg, float* __restrict__ stats) {
+                                      long long M, LossCfg cfg, float* __restrict__ stats, const DetCtx det) {
   const int K = cfg.K;
-  __shared__ float sh[4 + 3 * kLossMaxK];
-  for (int i = threadIdx.x; i < 4 + 3 * K; i += blockDim.x) sh[i] = 0.f;
-  __syncthreads();
+  // per-warp partials, added in warp order (no shared-memory atomics: their arrival order is not reproducible)
+  __shared__ float shw[8][4 + 3 * kLossMaxK];  // blockDim.x == 256
   float nll = 0.f, smooth = 0.f, valid = 0.f, total = 0.f;
   float inter[KMAX], card[KMAX], tsum[KMAX];
 #pragma unroll
@@ -99,30 +99,38 @@ __global__ void seg_loss_stats_kernel(const float* __restrict__ logits, int ld, 
       }
     }
   }
-  // block reduction: warp shuffles then shared atomics
+  // block reduction: warp shuffles (fixed tree), then the 8 warps' partials in warp order
+  const int wid = threadIdx.x >> 5;
   nll = warp_sum(nll);
   smooth = warp_sum(smooth);
   valid = warp_sum(valid);
   total = warp_sum(total);
   if ((threadIdx.x & 31) == 0) {
-    atomicAdd(&sh[0], nll);
-    atomicAdd(&sh[1], smooth);
-    atomicAdd(&sh[2], valid);
-    atomicAdd(&sh[3], total);
+    shw[wid][0] = nll;
+    shw[wid][1] = smooth;
+    shw[wid][2] = valid;
+    shw[wid][3] = total;
   }
 #pragma unroll
   for (int c = 0; c < KMAX; ++c) {
     if (c < K) {
       const float a = warp_sum(inter[c]), b = warp_sum(card[c]), d = warp_sum(tsum[c]);
       if ((threadIdx.x & 31) == 0) {
-        atomicAdd(&sh[4 + c], a);
-        atomicAdd(&sh[4 + K + c], b);
-        atomicAdd(&sh[4 + 2 * K + c], d);
+        shw[wid][4 + c] = a;
+        shw[wid][4 + K + c] = b;
+        shw[wid][4 + 2 * K + c] = d;
       }
     }
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < 4 + 3 * K; i += blockDim.x) atomicAdd(&stats[i], sh[i]);
+  const int nvals = 4 + 3 * K;
+  for (int i = threadIdx.x; i < nvals; i += blockDim.x) {
+    float v = 0.f;
+    for (int w = 0; w < 8; ++w) v += shw[w][i];
+    if (det.s0 != nullptr) det_put(det, nvals, i, v);
+    else atomicAdd(&stats[i], v);
+  }
+  if (det.s0 != nullptr) det_finish(det, nvals, stats);
 }
 
 __global__ void seg_loss_finalize_kernel(const float* __restrict__ stats, LossCfg cfg, float* __restrict__ coeff) {
@@ -310,18 +318,22 @@ __global__ void adam_dev_kernel(float* __restrict__ p, const float* __restrict__
 }
 
 // sum of squares of a flat fp32 buffer (for clip_grad_norm_); result accumulated into out[0]
-__global__ void sumsq_kernel(const float* __restrict__ g, long long n, float* __restrict__ out) {
+__global__ void sumsq_kernel(const float* __restrict__ g, long long n, float* __restrict__ out, const DetCtx det) {
   float s = 0.f;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
        i += (long long)gridDim.x * blockDim.x)
     s = fmaf(g[i], g[i], s);
   s = warp_sum(s);
-  __shared__ float sh;
-  if (threadIdx.x == 0) sh = 0.f;
+  __shared__ float shw[8];  // blockDim.x == 256: warp partials added in warp order
+  if ((threadIdx.x & 31) == 0) shw[threadIdx.x >> 5] = s;
   __syncthreads();
-  if ((threadIdx.x & 31) == 0) atomicAdd(&sh, s);
-  __syncthreads();
-  if (threadIdx.x == 0) atomicAdd(out, sh);
+  if (threadIdx.x == 0) {
+    float v = 0.f;
+    for (int w = 0; w < 8; ++w) v += shw[w];
+    if (det.s0 != nullptr) det_put(det, 1, 0, v);
+    else atomicAdd(out, v);
+  }
+  if (det.s0 != nullptr) det_finish(det, 1, out);
 }
 
 // scale[0] = min(1, max_norm / (sqrt(sumsq) + 1e-6))  (torch.nn.utils.clip_grad_norm_)
@@ -369,13 +381,21 @@ extern "C" int gdl_seg_loss_fwd(const float* logits, int ld, const void* target,
   if (st) return st;
   cudaStream_t s = (cudaStream_t)stream;
   GDL_CHECK_CUDA(cudaMemsetAsync(stats, 0, (4 + 3 * (size_t)K) * sizeof(float), s));
-  const int blocks = loss_blocks(M);
+  int blocks = loss_blocks(M);
+  DetCtx det = det_none();
+  {
+    const DetWs ws = det_workspace();
+    if (const int gd = det_grid(ws, blocks, 4 + 3 * K)) {
+      blocks = gd;
+      det = det_ctx(ws, gd, 4 + 3 * K);
+    }
+  }
 #define LAUNCH_STATS(KMAX)                                                                                  \
   do {                                                                                                      \
     if (target_kind == 0)                                                                                   \
-      seg_loss_stats_kernel<KMAX, long long><<<blocks, 256, 0, s>>>(logits, ld, (const long long*)target, M, cfg, stats); \
+      seg_loss_stats_kernel<KMAX, long long><<<blocks, 256, 0, s>>>(logits, ld, (const long long*)target, M, cfg, stats, det); \
     else                                                                                                    \
-      seg_loss_stats_kernel<KMAX, uint8_t><<<blocks, 256, 0, s>>>(logits, ld, (const uint8_t*)target, M, cfg, stats);     \
+      seg_loss_stats_kernel<KMAX, uint8_t><<<blocks, 256, 0, s>>>(logits, ld, (const uint8_t*)target, M, cfg, stats, det); \
   } while (0)
   if (K <= 2) LAUNCH_STATS(2);
   else if (K <= 8) LAUNCH_STATS(8);
@@ -465,7 +485,15 @@ extern "C" int gdl_grad_clip_coef(const float* g, long long n, float max_norm, f
   GDL_CHECK_CUDA(cudaMemsetAsync(sumsq_scratch, 0, sizeof(float), s));
   long long b = (n + 255) / 256;
   if (b > 4 * kNumSMsB200) b = 4 * kNumSMsB200;
-  sumsq_kernel<<<(int)b, 256, 0, s>>>(g, n, sumsq_scratch);
+  DetCtx det = det_none();
+  {
+    const DetWs ws = det_workspace();
+    if (const int gd = det_grid(ws, b, 1)) {
+      b = gd;
+      det = det_ctx(ws, gd, 1);
+    }
+  }
+  sumsq_kernel<<<(int)b, 256, 0, s>>>(g, n, sumsq_scratch, det);
   clip_coef_kernel<<<1, 1, 0, s>>>(sumsq_scratch, max_norm, scale);
   GDL_CHECK_CUDA(cudaGetLastError());
   return 0;

@@ -7,6 +7,7 @@
 
 #include "../../include/gdl_b200.h"
 #include "tmap.cuh"
+#include "det_reduce.cuh"
 
 namespace gdl {
 
@@ -100,9 +101,50 @@ int make_tmap_2d(CUtensorMap* out, const void* base, int dtype, long long cols, 
   return encode(out, base, dtype, 2, dims, str, box, swizzle_bytes);
 }
 
+// ---- deterministic-reduction workspace (det_reduce.cuh): registered per device by the caller -----------------------
+struct WsEntry {
+  void* ptr;
+  long long bytes;
+};
+static WsEntry g_ws[64];
+int g_opt_deterministic = 1;  // gdl_set_option("deterministic", 0/1); only effective with a registered workspace
+
+DetWs det_workspace() {
+  DetWs w;
+  w.ctr = nullptr;
+  w.slots = nullptr;
+  w.slot_floats = 0;
+  int dev = 0;
+  if (!g_opt_deterministic || cudaGetDevice(&dev) != cudaSuccess) return w;
+  const WsEntry e = g_ws[dev & 63];
+  if (e.ptr == nullptr || e.bytes <= kDetCtrBytes) return w;
+  w.ctr = reinterpret_cast<unsigned*>(e.ptr);
+  w.slots = reinterpret_cast<float*>(reinterpret_cast<char*>(e.ptr) + kDetCtrBytes);
+  w.slot_floats = (e.bytes - kDetCtrBytes) / 4;
+  return w;
+}
+
 }  // namespace gdl
 
 extern "C" {
+
+long long gdl_query_workspace_bytes(void) { return gdl::kDetCtrBytes + 32ll * 1024 * 1024; }
+
+int gdl_set_workspace(void* ptr, long long bytes, void* stream) {
+  int dev = 0;
+  GDL_CHECK_CUDA(cudaGetDevice(&dev));
+  if (ptr == nullptr) {
+    gdl::g_ws[dev & 63] = gdl::WsEntry{nullptr, 0};
+    return 0;
+  }
+  GDL_REQUIRE((reinterpret_cast<uintptr_t>(ptr) & 255) == 0 && bytes >= gdl::kDetCtrBytes + (1ll << 20), GDL_ERR_INVALID,
+              "set_workspace: need a 256-byte aligned buffer of at least %lld bytes (gdl_query_workspace_bytes() recommends %lld)",
+              gdl::kDetCtrBytes + (1ll << 20), gdl_query_workspace_bytes());
+  // tickets and turnstiles are zero at rest; every kernel that uses them leaves them at zero
+  GDL_CHECK_CUDA(cudaMemsetAsync(ptr, 0, (size_t)gdl::kDetCtrBytes, (cudaStream_t)stream));
+  gdl::g_ws[dev & 63] = gdl::WsEntry{ptr, bytes};
+  return 0;
+}
 
 const char* gdl_last_error(void) { return gdl::g_err; }
 

@@ -13,6 +13,7 @@
 
 #include "../../include/gdl_b200.h"
 #include "common.cuh"
+#include "det_reduce.cuh"
 
 namespace gdl {
 
@@ -91,7 +92,7 @@ __global__ void layernorm_bwd_kernel(const TG* __restrict__ g, long long ldg, co
                                      const float* __restrict__ mean, const float* __restrict__ rstd,
                                      const float* __restrict__ gamma, const float* __restrict__ add, long long lda,
                                      float* __restrict__ dx32, long long ld32, void* __restrict__ dx16, long long ld16,
-                                     int dx16_is_half, float* __restrict__ pgrads, long long M, int C) {
+                                     int dx16_is_half, float* __restrict__ pgrads, long long M, int C, const DetCtx det) {
   extern __shared__ float sh[];  // [2][C]
   for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sh[i] = 0.f;
   __syncthreads();
@@ -139,16 +140,25 @@ __global__ void layernorm_bwd_kernel(const TG* __restrict__ g, long long ldg, co
     }
   }
   if (pgrads != nullptr) {
+    // the block's warps add their partials in warp order (shared-memory atomics would land in arrival order)
+    for (int w = 0; w < wpb; ++w) {
+      if ((int)(threadIdx.x >> 5) == w) {
 #pragma unroll 4
-    for (int i = 0; i < per; ++i) {
-      const int c = lane + 32 * i;
-      if (c < C) {
-        atomicAdd(&sh[c], dga[i]);
-        atomicAdd(&sh[C + c], dbe[i]);
+        for (int i = 0; i < per; ++i) {
+          const int c = lane + 32 * i;
+          if (c < C) {
+            sh[c] += dga[i];
+            sh[C + c] += dbe[i];
+          }
+        }
       }
+      __syncthreads();
     }
-    __syncthreads();
-    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) atomicAdd(&pgrads[i], sh[i]);
+    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) {
+      if (det.s0 != nullptr) det_put(det, 2 * C, i, sh[i]);
+      else atomicAdd(&pgrads[i], sh[i]);
+    }
+    if (det.s0 != nullptr) det_finish(det, 2 * C, pgrads);
   }
 }
 
@@ -490,7 +500,8 @@ __global__ void gelu_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ 
 // shared memory before the atomics.
 template <typename T>
 __global__ void __launch_bounds__(kDwThreads) dwconv_bwd_dw_kernel(const T* __restrict__ dpre, const T* __restrict__ x, int ldx,
-                                                            float* __restrict__ pgrads, int N, int H, int W, int C) {
+                                                            float* __restrict__ pgrads, int N, int H, int W, int C,
+                                                            const DetCtx det) {
   const int cv = C / 8;
   const int tpr = cv < (int)blockDim.x ? cv : blockDim.x;
   const int rows_per_block = blockDim.x / tpr;
@@ -575,11 +586,13 @@ __global__ void __launch_bounds__(kDwThreads) dwconv_bwd_dw_kernel(const T* __re
         for (int k = 0; k < 10; ++k) {
           float a = 0.f;
           for (int r2 = 0; r2 < rows_per_block; ++r2) a += red[r2 * tpr + tc][k];
-          atomicAdd(&pgrads[(long long)(c0 + j) * 10 + k], a);
+          if (det.s0 != nullptr) det_put(det, 10 * C, (c0 + j) * 10 + k, a);
+          else atomicAdd(&pgrads[(long long)(c0 + j) * 10 + k], a);
         }
       }
     }
   }
+  if (det.s0 != nullptr) det_finish(det, 10 * C, pgrads);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -891,34 +904,49 @@ __global__ void layerscale_add_kernel(const float* __restrict__ res, const T* __
 template <typename T>
 __global__ void layerscale_bwd_kernel(const float* __restrict__ g, const T* __restrict__ u, const float* __restrict__ gamma,
                                       const float* __restrict__ sscale, long long rows_per_sample, T* __restrict__ du,
-                                      float* __restrict__ dgamma, long long M, int C) {
+                                      float* __restrict__ dgamma, long long M, int C, const DetCtx det) {
   const int tpr = C / 8;
   const int rpb = blockDim.x / tpr;
   const int rl = threadIdx.x / tpr, v = threadIdx.x - rl * tpr;
-  if (rl >= rpb) return;
+  const bool act = rl < rpb;
   const int c = v * 8;
   float gm[8], acc[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    gm[j] = gamma[c + j];
+    gm[j] = act ? gamma[c + j] : 0.f;
     acc[j] = 0.f;
   }
-  for (long long r = (long long)blockIdx.x * rpb + rl; r < M; r += (long long)gridDim.x * rpb) {
-    const float s = sscale != nullptr ? sscale[r / rows_per_sample] : 1.f;
-    float uu[8], o[8];
-    ld8(u + r * C + c, uu);
-    const float4 g0 = *reinterpret_cast<const float4*>(g + r * C + c), g1 = *reinterpret_cast<const float4*>(g + r * C + c + 4);
-    const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+  if (act) {
+    for (long long r = (long long)blockIdx.x * rpb + rl; r < M; r += (long long)gridDim.x * rpb) {
+      const float s = sscale != nullptr ? sscale[r / rows_per_sample] : 1.f;
+      float uu[8], o[8];
+      ld8(u + r * C + c, uu);
+      const float4 g0 = *reinterpret_cast<const float4*>(g + r * C + c), g1 = *reinterpret_cast<const float4*>(g + r * C + c + 4);
+      const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      o[j] = s * gm[j] * gg[j];
-      acc[j] += s * gg[j] * uu[j];
+      for (int j = 0; j < 8; ++j) {
+        o[j] = s * gm[j] * gg[j];
+        acc[j] += s * gg[j] * uu[j];
+      }
+      st8(du + r * C + c, o);
     }
-    st8(du + r * C + c, o);
   }
   if (dgamma != nullptr) {
+    // rows of the block in row order per channel (no atomics inside the block), then block partials -> dgamma
+    __shared__ float red[256][8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) atomicAdd(dgamma + c + j, acc[j]);
+    for (int j = 0; j < 8; ++j) red[threadIdx.x][j] = acc[j];
+    __syncthreads();
+    if (rl == 0) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float a = 0.f;
+        for (int r2 = 0; r2 < rpb; ++r2) a += red[r2 * tpr + v][j];
+        if (det.s0 != nullptr) det_put(det, C, c + j, a);
+        else atomicAdd(dgamma + c + j, a);
+      }
+    }
+    if (det.s0 != nullptr) det_finish(det, C, dgamma);
   }
 }
 
@@ -1108,12 +1136,20 @@ extern "C" int gdl_layernorm_bwd(const void* g, int g_dtype, long long ldg, cons
   GDL_REQUIRE(g && x && mean && rstd && gamma && (dx32 || dx16) && M > 0 && C > 0 && C <= 32 * kLnMaxPerLane,
               GDL_ERR_INVALID, "layernorm_bwd: bad args");
   cudaStream_t st = (cudaStream_t)stream;
-  const int blocks = row_blocks(M, 8, 4);
+  int blocks = row_blocks(M, 8, 4);
   const int smem = 2 * C * (int)sizeof(float);
   const int is_half = dx16_dtype == GDL_F16;
+  DetCtx det = det_none();
+  if (pgrads) {
+    const DetWs ws = det_workspace();
+    if (const int gd = det_grid(ws, blocks, 2 * C)) {
+      blocks = gd;
+      det = det_ctx(ws, gd, 2 * C);
+    }
+  }
 #define LN_BWD(TI, TG)                                                                                          \
   layernorm_bwd_kernel<TI, TG><<<blocks, 256, smem, st>>>((const TG*)g, ldg, (const TI*)x, ldx, mean, rstd, gamma, add, \
-                                                         lda, dx32, ld32, dx16, ld16, is_half, pgrads, M, C)
+                                                         lda, dx32, ld32, dx16, ld16, is_half, pgrads, M, C, det)
   if (x_dtype == GDL_F32) {
     if (g_dtype == GDL_F32) LN_BWD(float, float);
     else if (g_dtype == GDL_BF16) LN_BWD(float, __nv_bfloat16);
@@ -1248,17 +1284,25 @@ extern "C" int gdl_dwconv3x3_gelu_bwd(const void* dy, const void* pre, const voi
   if (b1 > 16 * kNumSMsB200) b1 = 16 * kNumSMsB200;
   const long long nstrips = (long long)N * H * ((W + kDwStrip - 1) / kDwStrip);
   const int g_dx = chan_row_grid(nstrips, C, 1, kDwThreads);
-  const int g_dw = chan_row_grid(nstrips, C, 4, kDwThreads);  // a few strips per thread: one block-reduced set of atomics per block
+  int g_dw = chan_row_grid(nstrips, C, 4, kDwThreads);  // a few strips per thread: one block-reduced set of sums per block
+  DetCtx det = det_none();
+  if (pgrads) {
+    const DetWs ws = det_workspace();
+    if (const int gd = det_grid(ws, g_dw, 10 * C)) {
+      g_dw = gd;
+      det = det_ctx(ws, gd, 10 * C);
+    }
+  }
   if (dtype == GDL_BF16) {
     using T = __nv_bfloat16;
     gelu_bwd_kernel<T><<<(int)b1, 256, 0, st>>>((const T*)dy, (const T*)pre, (T*)dpre_scratch, n8);
     dwconv_strip_kernel<T, false, true><<<g_dx, kDwThreads, 0, st>>>((const T*)dpre_scratch, C, w, nullptr, nullptr, (T*)dx, lddx, N, H, W, C);
-    if (pgrads) dwconv_bwd_dw_kernel<T><<<g_dw, kDwThreads, 0, st>>>((const T*)dpre_scratch, (const T*)x, ldx, pgrads, N, H, W, C);
+    if (pgrads) dwconv_bwd_dw_kernel<T><<<g_dw, kDwThreads, 0, st>>>((const T*)dpre_scratch, (const T*)x, ldx, pgrads, N, H, W, C, det);
   } else {
     using T = __half;
     gelu_bwd_kernel<T><<<(int)b1, 256, 0, st>>>((const T*)dy, (const T*)pre, (T*)dpre_scratch, n8);
     dwconv_strip_kernel<T, false, true><<<g_dx, kDwThreads, 0, st>>>((const T*)dpre_scratch, C, w, nullptr, nullptr, (T*)dx, lddx, N, H, W, C);
-    if (pgrads) dwconv_bwd_dw_kernel<T><<<g_dw, kDwThreads, 0, st>>>((const T*)dpre_scratch, (const T*)x, ldx, pgrads, N, H, W, C);
+    if (pgrads) dwconv_bwd_dw_kernel<T><<<g_dw, kDwThreads, 0, st>>>((const T*)dpre_scratch, (const T*)x, ldx, pgrads, N, H, W, C, det);
   }
   GDL_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -1443,9 +1487,17 @@ extern "C" int gdl_layerscale_bwd(const float* g, const void* u, int dtype, cons
   long long b = (M + (long long)rpb * 8 - 1) / ((long long)rpb * 8);  // >= 8 rows per thread: few atomics per channel
   if (b > 2 * kNumSMsB200) b = 2 * kNumSMsB200;
   if (b < 1) b = 1;
+  DetCtx det = det_none();
+  if (dgamma) {
+    const DetWs ws = det_workspace();
+    if (const int gd = det_grid(ws, b, C)) {
+      b = gd;
+      det = det_ctx(ws, gd, C);
+    }
+  }
   GDL_DISPATCH_T16(dtype, {
     layerscale_bwd_kernel<T><<<(int)b, 256, 0, (cudaStream_t)stream>>>(g, (const T*)u, gamma, sscale,
-                                                                      rows_per_sample > 0 ? rows_per_sample : 1, (T*)du, dgamma, M, C);
+                                                                      rows_per_sample > 0 ? rows_per_sample : 1, (T*)du, dgamma, M, C, det);
   });
   GDL_CHECK_CUDA(cudaGetLastError());
   return 0;

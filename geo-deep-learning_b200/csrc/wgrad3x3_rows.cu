@@ -10,8 +10,12 @@
 // so one MMA chain produces TWO horizontal taps (rows 0-63 / 64-127 of the accumulator) and a second chain the third
 // tap: 3 useful half-tiles out of 4 instead of 1 out of 2.  A unit = (one 64-channel slab of one source, one block of
 // Hb image rows of one 128-pixel column): it streams the Hb + 2 input rows ONCE (each against the dY rows above, at and
-// below it: filter rows 2, 1, 0), keeps the 3 dY rows it needs in a ring, and owns 6 TMEM accumulators
-// (3 filter rows x {taps 0|1, tap 2}) that are added to the fp32 gradient with coalesced red.global.add at the end.
+// below it: filter rows 2, 1, 0) and keeps the 3 dY rows it needs in a ring.
+//
+// Slab-stationary CTAs (round 2): CTA c owns slab c % num_slabs for its whole life and walks the pixel blocks
+// c / num_slabs, + ctas_per_slab, ...; its 6 TMEM accumulators (3 filter rows x {taps 0|1, tap 2}) keep accumulating
+// across all of them, so there is ONE epilogue per CTA (coalesced red.global.add into the fp32 gradient) instead of
+// one per unit — and the CTAs of a slab can add in a fixed order (turnstile, det_reduce.cuh): bit-reproducible.
 //
 // The two 64-channel MN atoms of the paired A operand are two TMA boxes of the same input row (130 pixels starting at
 // w0-1 and at w0) placed kXAtomBytes apart, addressed through the descriptor's leading-dimension byte offset.
@@ -21,6 +25,7 @@
 #include "../../include/gdl_b200.h"
 #include "common.cuh"
 #include "tmap.cuh"
+#include "det_reduce.cuh"
 
 namespace gdl {
 
@@ -37,7 +42,9 @@ struct WgradRowsKParams {
   int Ctot, Cout;
   int Nimg, H, W;
   int tiles_w, Hb, hblocks;
-  long long num_units;
+  int nblk;           // pixel blocks (image x column x row block); a unit = (slab, pixel block)
+  int ctas_per_slab;  // gridDim.x = num_slabs * ctas_per_slab
+  unsigned* turnstile;  // [num_slabs] ordered epilogues (null: arrival order)
   int dy_stage_bytes, dy_row_bytes;  // 128 px x Cout x 2 B (1024-aligned), Cout x 2 B
   int ab_fmt;
   float* dw;
@@ -87,14 +94,15 @@ __global__ void __launch_bounds__(kWrThreads, 1) wgrad3x3_rows_kernel(const __gr
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
 
-  // unit -> (slab fastest: co-resident CTAs share the dY rows of one pixel range in L2; then row block, column, image)
-  auto decode = [&](long long u, int& slab, int& img, int& w0, int& h0, int& rows) {
-    slab = (int)(u % p.num_slabs);
-    long long t = u / p.num_slabs;
-    const int hb = (int)(t % p.hblocks);
+  // CTA -> (slab, first pixel block); pixel block t -> (row block fastest, column, image).  CTAs with the same
+  // blockIdx.x / num_slabs stream the same dY rows at the same time (shared in L2).
+  const int slab = blockIdx.x % p.num_slabs;
+  const int blk0 = blockIdx.x / p.num_slabs;
+  auto decode = [&](int t, int& img, int& w0, int& h0, int& rows) {
+    const int hb = t % p.hblocks;
     t /= p.hblocks;
-    const int wt = (int)(t % p.tiles_w);
-    img = (int)(t / p.tiles_w);
+    const int wt = t % p.tiles_w;
+    img = t / p.tiles_w;
     w0 = wt * 128;
     h0 = hb * p.Hb;
     rows = min(p.Hb, p.H - h0);
@@ -105,10 +113,10 @@ __global__ void __launch_bounds__(kWrThreads, 1) wgrad3x3_rows_kernel(const __gr
     if (lane == 0) {
       int xs = 0, ds = 0;
       uint32_t xph = 0, dph = 0;
-      for (long long u = blockIdx.x; u < p.num_units; u += gridDim.x) {
-        int slab, img, w0, h0, rows;
-        decode(u, slab, img, w0, h0, rows);
-        const int src = p.slab_src[slab], c0 = p.slab_c0[slab];
+      const int src = p.slab_src[slab], c0 = p.slab_c0[slab];
+      for (int t = blk0; t < p.nblk; t += p.ctas_per_slab) {
+        int img, w0, h0, rows;
+        decode(t, img, w0, h0, rows);
         for (int i = h0 - 1; i <= h0 + rows; ++i) {
           if (i + 1 < h0 + rows) {  // dY row i+1 (filter row 0 of input row i) — first use of that row
             mbar_wait(&dy_empty[ds], dph ^ 1);
@@ -140,14 +148,11 @@ __global__ void __launch_bounds__(kWrThreads, 1) wgrad3x3_rows_kernel(const __gr
       const uint32_t kstepA = 16u * 128u, kstepB = 16u * (uint32_t)p.dy_row_bytes;  // 16 pixel rows
       int xs = 0, ds = 0;
       uint32_t xph = 0, dph = 0;
-      int it = 0;
-      for (long long u = blockIdx.x; u < p.num_units; u += gridDim.x, ++it) {
-        int slab, img, w0, h0, rows;
-        decode(u, slab, img, w0, h0, rows);
-        mbar_wait(&tempty_bar, (it & 1) ^ 1);
-        tc_fence_after();
+      uint32_t started = 0;     // bit ky: accumulators of filter row ky already hold data (kept across pixel blocks)
+      for (int t = blk0; t < p.nblk; t += p.ctas_per_slab) {
+        int img, w0, h0, rows;
+        decode(t, img, w0, h0, rows);
         const int ds_first = ds;  // ring slot of dY row h0; row h lives in (ds_first + h - h0) % kWrDYStages
-        uint32_t started = 0;     // bit ky: accumulators of filter row ky already hold data
         for (int i = h0 - 1; i <= h0 + rows; ++i) {
           if (i + 1 < h0 + rows) {
             mbar_wait(&dy_full[ds], dph);
@@ -187,8 +192,8 @@ __global__ void __launch_bounds__(kWrThreads, 1) wgrad3x3_rows_kernel(const __gr
           // dY row i-1 was last used by this input row (filter row 2)
           if (i - 1 >= h0) umma_commit(&dy_empty[(ds_first + i - 1 - h0) % kWrDYStages]);
         }
-        umma_commit(&tfull_bar);
       }
+      umma_commit(&tfull_bar);  // all pixel blocks of this CTA accumulated
     }
   } else {
     // ===================== epilogue: thread = one accumulator row = one input channel (two taps) =====================
@@ -196,34 +201,38 @@ __global__ void __launch_bounds__(kWrThreads, 1) wgrad3x3_rows_kernel(const __gr
     const int row = q * 32 + lane;
     const int cin_row = row & 63;      // channel inside the slab
     const int kx_pair = row >> 6;      // rows 0-63: tap kx = 0, rows 64-127: tap kx = 1
-    int it = 0;
-    for (long long u = blockIdx.x; u < p.num_units; u += gridDim.x, ++it) {
-      int slab, img, w0, h0, rows;
-      decode(u, slab, img, w0, h0, rows);
-      const long long col0 = p.slab_coff[slab] + cin_row;
-      mbar_wait(&tfull_bar, it & 1);
-      tc_fence_after();
-      for (int ky = 0; ky < 3; ++ky) {
-        const uint32_t t_pair = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ky * 128);
-        for (int sel = 0; sel < 2; ++sel) {  // 0: paired accumulator (taps 0|1), 1: tap 2 (rows 0-63 only)
-          const int kx = sel == 0 ? kx_pair : 2;
-          float* dst = p.dw + (long long)((ky * 3 + kx) * p.Ctot) + col0;
-          for (int j = 0; j < p.Cout; j += 16) {
-            uint32_t v[16];
-            tmem_ld_32x32b_x16(t_pair + (uint32_t)(sel * 64 + j), v);
-            tmem_ld_wait();
-            if (sel == 1 && row >= 64) continue;
-            // lanes = consecutive input channels: every red below is one coalesced 128-byte request per warp
+    const long long col0 = p.slab_coff[slab] + cin_row;
+    mbar_wait(&tfull_bar, 0);
+    tc_fence_after();
+    // ordered mode: the CTAs of a slab add in the order of their first pixel block
+    unsigned* ts = p.turnstile ? p.turnstile + slab : nullptr;
+    if (ts != nullptr) {
+      if (warp == 2 && lane == 0) turnstile_wait(ts, (unsigned)blk0);
+      named_bar_sync(1, 128);
+    }
+    for (int ky = 0; ky < 3; ++ky) {
+      const uint32_t t_pair = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ky * 128);
+      for (int sel = 0; sel < 2; ++sel) {  // 0: paired accumulator (taps 0|1), 1: tap 2 (rows 0-63 only)
+        const int kx = sel == 0 ? kx_pair : 2;
+        float* dst = p.dw + (long long)((ky * 3 + kx) * p.Ctot) + col0;
+        for (int j = 0; j < p.Cout; j += 16) {
+          uint32_t v[16];
+          tmem_ld_32x32b_x16(t_pair + (uint32_t)(sel * 64 + j), v);
+          tmem_ld_wait();
+          if (sel == 1 && row >= 64) continue;
+          // lanes = consecutive input channels: every red below is one coalesced 128-byte request per warp
 #pragma unroll
-            for (int o = 0; o < 16; ++o)
-              asm volatile("red.global.add.f32 [%0], %1;" ::"l"(dst + (long long)(j + o) * p.dw_ld),
-                           "f"(__uint_as_float(v[o]))
-                           : "memory");
-          }
+          for (int o = 0; o < 16; ++o)
+            asm volatile("red.global.add.f32 [%0], %1;" ::"l"(dst + (long long)(j + o) * p.dw_ld),
+                         "f"(__uint_as_float(v[o]))
+                         : "memory");
         }
       }
-      tc_fence_before();
-      mbar_arrive(&tempty_bar);
+    }
+    if (ts != nullptr) {
+      __threadfence();
+      named_bar_sync(1, 128);
+      if (warp == 2 && lane == 0) turnstile_pass(ts, (unsigned)blk0, blk0 == p.ctas_per_slab - 1);
     }
   }
 
@@ -266,12 +275,22 @@ int wgrad3x3_rows_try(const gdl_conv_wgrad_t* d, cudaStream_t stream, int* statu
   if (cudaGetDevice(&dev) != cudaSuccess ||
       cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0)
     sms = kNumSMsB200;
+  const int cps_max = sms / p.num_slabs;
+  if (cps_max < 1) return 0;  // more slabs than SMs: the generic kernel
+  // rows per unit: long units amortise the 2 halo rows per block; keep >= ~4 pixel blocks per CTA for balance
   int Hb = 32;
-  while (Hb > 8 && (long long)p.num_slabs * d->N * p.tiles_w * ((d->H + Hb - 1) / Hb) < 4ll * sms) Hb >>= 1;
+  while (Hb > 8 && (long long)d->N * p.tiles_w * ((d->H + Hb - 1) / Hb) < 4ll * cps_max) Hb >>= 1;
   if (Hb > d->H) Hb = d->H;
   p.Hb = Hb;
   p.hblocks = (d->H + Hb - 1) / Hb;
-  p.num_units = (long long)p.num_slabs * d->N * p.tiles_w * p.hblocks;
+  const long long nblk = (long long)d->N * p.tiles_w * p.hblocks;
+  if (nblk >= (1ll << 31)) return 0;
+  p.nblk = (int)nblk;
+  p.ctas_per_slab = nblk < cps_max ? (int)nblk : cps_max;
+  {
+    const DetWs ws = det_workspace();
+    p.turnstile = (ws.ok() && p.ctas_per_slab > 1 && p.num_slabs <= kDetTurnstiles) ? ws.turnstiles() : nullptr;
+  }
   p.dy_row_bytes = d->Cout * 2;
   p.dy_stage_bytes = 128 * p.dy_row_bytes;  // 4 / 8 / 16 KB
   p.ab_fmt = d->dtype == GDL_BF16 ? 1 : 0;
@@ -293,7 +312,7 @@ int wgrad3x3_rows_try(const gdl_conv_wgrad_t* d, cudaStream_t stream, int* statu
                                              kWrXStages * 2 * kWrXAtomBytes + kWrDYStages * 16 * 1024 + 1024),
                        "cudaFuncSetAttribute(wgrad3x3_rows_kernel)");
   if (*status) return 1;
-  const int grid = p.num_units < sms ? (int)p.num_units : sms;
+  const int grid = p.num_slabs * p.ctas_per_slab;
   wgrad3x3_rows_kernel<<<grid, kWrThreads, smem, stream>>>(p);
   *status = check_cuda(cudaGetLastError(), "wgrad3x3_rows_kernel launch");
   return 1;

@@ -92,6 +92,7 @@ def load():
     lib = C.CDLL(str(_LIB_PATH))
     lib.gdl_last_error.restype = C.c_char_p
     lib.gdl_version.restype = C.c_int
+    lib.gdl_query_workspace_bytes.restype = C.c_longlong
     _declare(lib)
     _lib = lib
     return lib
@@ -157,11 +158,12 @@ _SIGS = {
     "gdl_adaptive_avgpool_bwd": [_VP, _VP, _I, _I, _I, _I, _I, _I, _VP],
     "gdl_add_nhwc": [_VP, _LL, _VP, _LL, _VP, _LL, _I, _LL, _I, _VP],
     "gdl_debug_shift_probe": [_VP, _VP, _VP, _I, _I, _I, _VP],
+    "gdl_set_workspace": [_VP, _LL, _VP],
 }
 
 
 def exported_symbols() -> list[str]:
-    return ["gdl_last_error", "gdl_version", *_SIGS.keys()]
+    return ["gdl_last_error", "gdl_version", "gdl_query_workspace_bytes", *_SIGS.keys()]
 
 
 def _declare(lib) -> None:
@@ -182,7 +184,38 @@ def check(status: int) -> None:
     raise GdlError(msg)
 
 
+# ---- deterministic-reduction workspace (include/gdl_b200.h: gdl_set_workspace) ------------------------------------
+# One caller-owned scratch buffer per device, registered before the first launch on that device: with it every
+# cross-block sum of the library is formed in a fixed order (bit-reproducible steps; a CUDA-graph replay equals the
+# eager launch).  GDL_DETERMINISTIC=0 leaves it unregistered (fp32 atomics, arrival order).
+_WORKSPACES: dict[int, torch.Tensor] = {}
+
+
+def _register_workspace(dev: int) -> None:
+    import os
+    if os.environ.get("GDL_DETERMINISTIC", "1") == "0":
+        _WORKSPACES[dev] = None
+        return
+    if torch.cuda.is_current_stream_capturing():
+        raise GdlError("the reduction workspace must be registered before CUDA-graph capture: run one eager call first")
+    lib = load()
+    nbytes = int(lib.gdl_query_workspace_bytes())
+    buf = torch.empty(nbytes, dtype=torch.uint8, device=torch.device("cuda", dev))
+    check(lib.gdl_set_workspace(C.c_void_p(buf.data_ptr()), nbytes, C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+    _WORKSPACES[dev] = buf
+
+
+def deterministic() -> bool:
+    """True when the current device has a registered reduction workspace (ordered sums instead of fp32 atomics)."""
+    return _WORKSPACES.get(torch.cuda.current_device()) is not None
+
+
 def stream_ptr() -> C.c_void_p:
+    """current torch stream as a cudaStream_t; every kernel wrapper passes through here, so this is also where the
+    per-device workspace is registered (once)"""
+    dev = torch.cuda.current_device()
+    if dev not in _WORKSPACES:
+        _register_workspace(dev)
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 

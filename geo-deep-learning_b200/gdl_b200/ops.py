@@ -118,6 +118,12 @@ def set_option(name: str, value: int) -> None:
     L.check(L.load().gdl_set_option(name.encode(), int(value)))
 
 
+def deterministic() -> bool:
+    """ordered (bit-reproducible) reductions are active on the current device (see _lib.stream_ptr)"""
+    L.stream_ptr()
+    return L.deterministic()
+
+
 def require_cuda(t: torch.Tensor, what: str) -> None:
     """the hot path has no CPU implementation: refuse host tensors loudly, before any kernel wrapper is reached"""
     if not t.is_cuda:

@@ -49,6 +49,20 @@ int gdl_device_info(int* sm_count, int* cc_major, int* cc_minor, unsigned long l
  * paired-tap row-streaming weight-gradient kernel). */
 int gdl_set_option(const char* name, long long value);
 
+/* ---- deterministic reductions: caller-owned scratch workspace ------------------------------------------------------
+ * SURVEY.md 8(b) `gdl_query_workspace_bytes`; reference behaviour being matched: torch's BatchNorm / cuDNN wgrad are
+ * run-to-run reproducible under torch.use_deterministic_algorithms, which the parity tests of the fused step rely on
+ * (tasks_with_models/segmentation_unetplus.py:223-248 replayed from a CUDA graph must equal the eager step bit for bit).
+ * With a workspace registered for the current device (and option "deterministic" != 0, the default) every cross-block
+ * sum — BatchNorm statistics, BN/LN/bias/LayerScale parameter gradients, loss statistics, gradient norms, the pixel
+ * split of the weight-gradient kernels — is formed in a fixed order (per-block slots + ordered tree, or an ordered
+ * turnstile per output tile) instead of with fp32 atomics.  Without one the atomic paths are used.
+ * The ONE exception to "the library keeps no pointer": the registered buffer must stay valid until it is replaced or
+ * cleared (ptr = NULL), and every launch that uses it must be stream-ordered with the others on that device.
+ * gdl_set_workspace zeroes the first 256 KiB (tickets) on `stream`. */
+long long gdl_query_workspace_bytes(void);
+int gdl_set_workspace(void* ptr, long long bytes, void* stream);
+
 /* One member of a "virtual concat": a conv reads its input channels from up to GDL_MAX_SRC
  * NHWC tensors of identical N,H,W (replaces torch.cat([...], dim=1) in smp UnetPlusPlus'
  * DecoderBlock, segformer_mlp.py:127, upernet.py:145 — the concat is never materialised). */

@@ -87,7 +87,7 @@ def dynamic_channel_embed(sd, x, p="encoder.dynamic_patch_embed1"):
     per-band channel weights from the band's position code, channel attention over the bands, projection + LayerNorm."""
     b, c, hh, ww = x.shape
     pos_dim = sd[p + ".weight_gen.0.weight"].shape[1]
-    pe = channel_position_encoding(c, pos_dim, x.dtype)
+    pe = channel_position_encoding(c, pos_dim, x.dtype).to(x.device)
     cw = torch.tanh(F.linear(F.relu(F.linear(pe, sd[p + ".weight_gen.0.weight"], sd[p + ".weight_gen.0.bias"])),
                              sd[p + ".weight_gen.2.weight"], sd[p + ".weight_gen.2.bias"]))            # (C, E)
     xc = F.conv2d(x.reshape(b * c, 1, hh, ww), sd[p + ".spatial_conv.weight"], sd[p + ".spatial_conv.bias"], stride=4, padding=3)

@@ -29,7 +29,7 @@ TC_NOP = ["fence_mbar_init", "fence_proxy_async_smem", "tma_prefetch_desc", "tme
 # bulk-group bookkeeping of the TMA stores (template <int N> wait_group[.read] N)
 TC_BULK = {"bulk_commit_group": "hostemu::tc::bulk_commit_group()", "bulk_wait_group_read": "hostemu::tc::bulk_wait_group(N)",
            "bulk_wait_group": "hostemu::tc::bulk_wait_group(N)"}
-HEADERS = ["common.cuh", "tmap.cuh"]
+HEADERS = ["common.cuh", "tmap.cuh", "det_reduce.cuh"]
 CUDA_INC = "/usr/local/cuda/include"
 
 

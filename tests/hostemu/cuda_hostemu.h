@@ -167,6 +167,9 @@ inline T __ldg(const T* p) { return *p; }
 template <typename T>
 inline T __ldcs(const T* p) { return *p; }
 template <typename T>
+inline T __ldcg(const T* p) { return *p; }
+inline void __threadfence() {}
+template <typename T>
 inline void __stcs(T* p, T v) { *p = v; }
 
 // CUDA's mixed-type min / max overloads

@@ -105,3 +105,32 @@ def test_fused_trainer_reduces_loss(cuda):
     losses = [tr.step(raw, t).item() for _ in range(15)]
     print("losses", [round(v, 4) for v in losses])
     assert losses[-1] < 0.7 * losses[0]
+
+
+@pytest.mark.parametrize("fused", [0, 1])
+def test_cuda_graph_step_equals_eager_step_bitwise(cuda, fused):
+    """SegFormer's fused step (attention three-kernel path or the single fused kernel, LayerNorm / DWConv parameter
+    gradients, batched dK / dV weight gradients, gradient clipping): the CUDA-graph replay, a second eager run and the
+    first agree bit for bit — every cross-block sum is ordered (gdl_set_workspace)."""
+    from gdl_b200 import ops
+    from gdl_b200.ops import LossSpec
+    from gdl_b200.trainer import FusedTrainer
+    assert ops.deterministic()
+    g = torch.Generator().manual_seed(6)
+    t = torch.randint(0, 5, (4, 4, 4), generator=g).repeat_interleave(32, 1).repeat_interleave(32, 2).cuda()
+    raw = (t.unsqueeze(-1) * 50 + torch.randint(0, 30, (4, 128, 128, 3), generator=g).cuda()).to(torch.uint8)
+    old = ops.option("sra_fused")
+    ops.set_option("sra_fused", fused)
+    try:
+        losses, flats = {}, {}
+        for mode in ("eager", "eager2", "graph"):
+            prod = _setup("mit_b1", 3, 5, seed=3).train()
+            tr = FusedTrainer(prod, LossSpec(1.0, 0.0, ignore_index=-100), lr=1e-3, mean=[0.5] * 3, std=[0.2] * 3,
+                              clip_grad_norm=1.0, cuda_graph=mode == "graph")
+            losses[mode] = [tr.step(raw, t).item() for _ in range(5)]
+            flats[mode] = tr.flat.clone()
+    finally:
+        ops.set_option("sra_fused", old)
+    print("eager", losses["eager"], "graph", losses["graph"])
+    assert losses["eager"] == losses["eager2"] and torch.equal(flats["eager"], flats["eager2"])
+    assert losses["eager"] == losses["graph"] and torch.equal(flats["eager"], flats["graph"])

@@ -211,24 +211,30 @@ def test_training_reduces_loss(cuda):
 
 
 def test_cuda_graph_step_equals_eager_step(cuda):
-    """The captured step (normalise .. Adam in one CUDA graph) must follow the same trajectory as eager launches."""
+    """The captured step (normalise .. Adam in one CUDA graph — what bench.py times) is the SAME arithmetic as eager launches:
+    with the ordered reductions (gdl_set_workspace) the trajectories agree bit for bit, losses and every parameter.
+    (Round 1 compared them at a 5 % tolerance and failed at step 3: tools/diag_graph_vs_eager.py measured 12-26 % run-to-run
+    noise in the flat gradient between two EAGER steps from the fp32 atomics of that version — reduction order, not capture.)"""
+    from gdl_b200 import ops
     from gdl_b200.ops import LossSpec
     from gdl_b200.trainer import FusedTrainer
+    assert ops.deterministic()
     g = torch.Generator().manual_seed(6)
     t = torch.randint(0, 5, (4, 2, 2), generator=g).repeat_interleave(32, 1).repeat_interleave(32, 2).cuda()
     raw = [(t.unsqueeze(-1) * 50 + torch.randint(0, 30, (4, 64, 64, 3), generator=g).cuda()).to(torch.uint8) for _ in range(3)]
-    losses = {}
-    for mode in (False, True):
+    losses, flats = {}, {}
+    for mode in ("eager", "eager2", "graph"):
         _, prod = _models("resnet18", 3, 5, seed=5)
         prod.train()
         tr = FusedTrainer(prod, LossSpec(1.0, 0.0, ignore_index=-100), lr=2e-3, mean=[0.5] * 3, std=[0.2] * 3,
-                          cuda_graph=mode)
+                          cuda_graph=mode == "graph")
         losses[mode] = [tr.step(raw[i % 3], t).item() for i in range(8)]
-        if mode:
+        flats[mode] = tr.flat.clone()
+        if mode == "graph":
             assert tr._graph is not None and tr.launches_per_step > 100
-    print("eager", [round(v, 4) for v in losses[False]])
-    print("graph", [round(v, 4) for v in losses[True]])
-    assert losses[True][-1] < 0.8 * losses[True][0]
-    # identical arithmetic; only fp32 atomics ordering differs -> early steps agree closely
-    for a, b in zip(losses[False][:3], losses[True][:3]):
-        assert abs(a - b) < 0.05 * max(abs(a), 1e-3)
+    print("eager", [round(v, 4) for v in losses["eager"]])
+    print("graph", [round(v, 4) for v in losses["graph"]])
+    assert losses["graph"][-1] < 0.8 * losses["graph"][0]
+    assert losses["eager"] == losses["eager2"] and torch.equal(flats["eager"], flats["eager2"])  # run-to-run
+    assert losses["eager"] == losses["graph"]
+    assert torch.equal(flats["eager"], flats["graph"])
