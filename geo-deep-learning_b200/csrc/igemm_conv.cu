@@ -908,9 +908,12 @@ struct ConvWgradKParams {
   int nacc;        // TMEM accumulator sets in flight (2 = double buffered, 1 = single)
   int unit_taps;   // units along the tap axis (R*S, or 3 filter rows in halo mode)
   int b_atom_bytes;  // bytes of one X atom in a stage (64 px, or 66 px padded to 9 KiB in halo mode)
-  // ordered pixel-split accumulation (det_reduce.cuh): the ksplit units of one output tile add in split order
-  unsigned* turnstile;  // null: arrival order (fp32 atomics)
-  int Nimg;             // batched: images (tile index)
+  // ordered pixel-split accumulation (det_reduce.cuh): with `partials` every unit stores its accumulator tile
+  // ([nsub][128 rows][bn_max] floats at partials + unit * tile_floats) instead of adding it to dw with fp32 atomics;
+  // wgrad_reduce_kernel then adds the ksplit partial tiles of each output tile in split order.
+  float* partials;      // null: red.global.add in arrival order
+  long long tile_floats;
+  int Nimg;             // batched: images
 };
 
 __global__ void __launch_bounds__(kConvThreads, 1)
@@ -1086,16 +1089,6 @@ conv_wgrad_kernel(const __grid_constant__ ConvWgradKParams p) {
       const bool nonempty = pb0 < pb1;
       mbar_wait(&tfull_bar[acc], aphase);
       tc_fence_after();
-      unsigned* ts = nullptr;
-      unsigned turn = 0;
-      if (p.turnstile != nullptr) {
-        const int sp = p.batched ? ks - uimg * p.ksplit : ks;
-        const long long tile = ((((long long)grp * p.Nimg + uimg) * p.m_tiles + mt) * p.n_ntiles + nt) * taps + tap;
-        ts = p.turnstile + tile;
-        turn = (unsigned)sp;
-        if (warp == 2 && lane == 0) turnstile_wait(ts, turn);
-        named_bar_sync(1, 128);
-      }
       for (int s3 = 0; s3 < p.nsub; ++s3) {
         const int tap_idx = p.halo ? tap * 3 + s3 : tap;
         float* dst = p.dw + (long long)uimg * p.dw_img_stride + (long long)m * p.dw_ld + (long long)tap_idx * p.Ctot +
@@ -1106,7 +1099,16 @@ conv_wgrad_kernel(const __grid_constant__ ConvWgradKParams p) {
           uint32_t v[16];
           tmem_ld_32x32b_x16(t_addr + j * 16, v);
           tmem_ld_wait();
-          if (m < p.Cout && nonempty) {
+          if (p.partials != nullptr) {
+            // ordered mode: plain 128-bit stores of this unit's partial tile (every row, empty units store zeros)
+            float4* d4 = reinterpret_cast<float4*>(p.partials + (long long)u * p.tile_floats +
+                                                   ((long long)s3 * 128 + row) * p.bn_max + j * 16);
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              d4[i] = nonempty ? make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]),
+                                             __uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3]))
+                               : make_float4(0.f, 0.f, 0.f, 0.f);
+          } else if (m < p.Cout && nonempty) {
             // 4 x red.global.add.v4.f32 (16-byte aligned: Ctot, channel offsets and j*16 are multiples of 16)
             float* d = dst + j * 16;
 #pragma unroll
@@ -1120,11 +1122,6 @@ conv_wgrad_kernel(const __grid_constant__ ConvWgradKParams p) {
       }
       tc_fence_before();
       mbar_arrive(&tempty_bar[acc]);
-      if (ts != nullptr) {
-        __threadfence();
-        named_bar_sync(1, 128);
-        if (warp == 2 && lane == 0) turnstile_pass(ts, turn, (int)turn == p.ksplit - 1);
-      }
     }
   }
 
@@ -1133,6 +1130,59 @@ conv_wgrad_kernel(const __grid_constant__ ConvWgradKParams p) {
   if (warp == 1) {
     __syncwarp();
     tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+  }
+}
+
+// dw[tile] += partial(split 0) + partial(split 1) + ... (fixed order): one thread per float4 of an output tile.
+struct WgradReduceParams {
+  const float* partials;
+  long long tile_floats;
+  float* dw;
+  long long dw_ld, dw_img_stride, g_dw;
+  int Ctot, Cout, bn_max, nsub, halo;
+  int taps, n_ntiles, m_tiles, ksplit, Nimg, groups, upg;
+  int nt_w[kMaxNTiles], nt_coff[kMaxNTiles];
+};
+
+__global__ void __launch_bounds__(256) wgrad_reduce_kernel(const __grid_constant__ WgradReduceParams p) {
+  const int vec_per_row = p.bn_max / 4;
+  const long long per_tile = (long long)p.nsub * 128 * vec_per_row;
+  const long long base_tiles = (long long)p.taps * p.n_ntiles * p.m_tiles;
+  const long long total = (long long)p.groups * p.Nimg * base_tiles * per_tile;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    long long t = i;
+    const int v4 = (int)(t % vec_per_row);
+    t /= vec_per_row;
+    const int row = (int)(t % 128);
+    t /= 128;
+    const int s3 = (int)(t % p.nsub);
+    t /= p.nsub;
+    const int tap = (int)(t % p.taps);
+    t /= p.taps;
+    const int nt = (int)(t % p.n_ntiles);
+    t /= p.n_ntiles;
+    const int mt = (int)(t % p.m_tiles);
+    t /= p.m_tiles;
+    const int img = (int)(t % p.Nimg);
+    const int grp = (int)(t / p.Nimg);
+    const int m = mt * 128 + row;
+    const int col = v4 * 4;
+    if (m >= p.Cout || col >= p.nt_w[nt]) continue;
+    // unit index of (tile, split): tap fastest, then n-tile, m-tile, split (decode() of conv_wgrad_kernel)
+    const long long u0 = (long long)grp * p.upg + (((long long)img * p.ksplit * p.m_tiles + mt) * p.n_ntiles + nt) * p.taps + tap;
+    const long long ustride = base_tiles;
+    const float* src = p.partials + u0 * p.tile_floats + ((long long)s3 * 128 + row) * p.bn_max + col;
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int sp = 0; sp < p.ksplit; ++sp) {
+      const float4 x = __ldcg(reinterpret_cast<const float4*>(src + (long long)sp * ustride * p.tile_floats));
+      a.x += x.x; a.y += x.y; a.z += x.z; a.w += x.w;
+    }
+    const int tap_idx = p.halo ? tap * 3 + s3 : tap;
+    float4* d = reinterpret_cast<float4*>(p.dw + (long long)img * p.dw_img_stride + (long long)m * p.dw_ld +
+                                          (long long)tap_idx * p.Ctot + p.nt_coff[nt] + col + (long long)grp * p.g_dw);
+    float4 o = *d;
+    o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w;
+    *d = o;
   }
 }
 
@@ -1294,12 +1344,6 @@ extern "C" int gdl_conv2d_nhwc_wgrad(const gdl_conv_wgrad_t* d, void* stream_) {
   GDL_REQUIRE((long long)p.num_units * G < (1ll << 31), GDL_ERR_UNSUPPORTED, "too many work units");
   p.num_units *= G;
   p.Nimg = d->batched ? N : 1;
-  if (p.ksplit > 1) {
-    // several units add into the same dW tile: order them (split 0, 1, ...) when a workspace is registered
-    const DetWs ws = det_workspace();
-    const long long tiles = (long long)G * p.Nimg * base_units;
-    if (ws.ok() && tiles <= kDetTurnstiles) p.turnstile = ws.turnstiles();
-  }
 
   p.a_bytes = kWgPix * 128 * 2;
   const int b_bytes = p.halo ? ((bn_max + p.caB - 1) / p.caB) * p.b_atom_bytes : kWgPix * bn_max * 2;
@@ -1313,6 +1357,13 @@ extern "C" int gdl_conv2d_nhwc_wgrad(const gdl_conv_wgrad_t* d, void* stream_) {
   p.ab_fmt = d->dtype == GDL_BF16 ? 1 : 0;
   p.dw = d->dw;
 
+  const DetWs ws = det_workspace();
+  if (p.ksplit > 1 && ws.ok()) {
+    // several units add into the same dW tile: give every unit a partial tile and add them in split order afterwards
+    p.tile_floats = (long long)p.nsub * 128 * bn_max;
+    if ((long long)p.num_units * p.tile_floats <= ws.slot_floats) p.partials = ws.slots;
+  }
+
   int smem = p.stages * p.stage_bytes + 1024;
   if (smem < kMinSmemRequest) smem = kMinSmemRequest;
   static PerDeviceOnce attr_once;
@@ -1320,6 +1371,37 @@ extern "C" int gdl_conv2d_nhwc_wgrad(const gdl_conv_wgrad_t* d, void* stream_) {
   int grid = p.num_units < sm_count() ? p.num_units : sm_count();
   conv_wgrad_kernel<<<grid, kConvThreads, smem, stream>>>(p);
   GDL_CHECK_CUDA(cudaGetLastError());
+  if (p.partials != nullptr) {
+    WgradReduceParams r;
+    memset(&r, 0, sizeof(r));
+    r.partials = p.partials;
+    r.tile_floats = p.tile_floats;
+    r.dw = p.dw;
+    r.dw_ld = p.dw_ld;
+    r.dw_img_stride = p.dw_img_stride;
+    r.g_dw = p.g_dw;
+    r.Ctot = p.Ctot;
+    r.Cout = p.Cout;
+    r.bn_max = bn_max;
+    r.nsub = p.nsub;
+    r.halo = p.halo;
+    r.taps = p.unit_taps;
+    r.n_ntiles = p.n_ntiles;
+    r.m_tiles = p.m_tiles;
+    r.ksplit = p.ksplit;
+    r.Nimg = p.Nimg;
+    r.groups = G;
+    r.upg = p.upg;
+    for (int i = 0; i < p.n_ntiles; ++i) {
+      r.nt_w[i] = p.nt_w[i];
+      r.nt_coff[i] = p.nt_coff[i];
+    }
+    const long long total = (long long)G * p.Nimg * p.unit_taps * p.n_ntiles * p.m_tiles * p.nsub * 128 * (bn_max / 4);
+    long long rb = (total + 255) / 256;
+    if (rb > 8ll * sm_count()) rb = 8ll * sm_count();
+    wgrad_reduce_kernel<<<(int)rb, 256, 0, stream>>>(r);
+    GDL_CHECK_CUDA(cudaGetLastError());
+  }
   return 0;
 }
 

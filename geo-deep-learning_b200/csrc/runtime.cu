@@ -128,7 +128,7 @@ DetWs det_workspace() {
 
 extern "C" {
 
-long long gdl_query_workspace_bytes(void) { return gdl::kDetCtrBytes + 32ll * 1024 * 1024; }
+long long gdl_query_workspace_bytes(void) { return gdl::kDetCtrBytes + 192ll * 1024 * 1024; }
 
 int gdl_set_workspace(void* ptr, long long bytes, void* stream) {
   int dev = 0;

@@ -14,8 +14,9 @@
 //
 // Slab-stationary CTAs (round 2): CTA c owns slab c % num_slabs for its whole life and walks the pixel blocks
 // c / num_slabs, + ctas_per_slab, ...; its 6 TMEM accumulators (3 filter rows x {taps 0|1, tap 2}) keep accumulating
-// across all of them, so there is ONE epilogue per CTA (coalesced red.global.add into the fp32 gradient) instead of
-// one per unit — and the CTAs of a slab can add in a fixed order (turnstile, det_reduce.cuh): bit-reproducible.
+// across all of them, so there is ONE epilogue per CTA instead of one per unit: coalesced red.global.add into the fp32
+// gradient, or — ordered mode (det_reduce.cuh) — a plain store of the CTA's partial gradient, after which
+// wgrad_rows_reduce_kernel adds the partials of a slab in CTA order: bit-reproducible.
 //
 // The two 64-channel MN atoms of the paired A operand are two TMA boxes of the same input row (130 pixels starting at
 // w0-1 and at w0) placed kXAtomBytes apart, addressed through the descriptor's leading-dimension byte offset.
@@ -35,6 +36,9 @@ constexpr int kWrXStages = 3;             // input-row stages (2 atoms each)
 constexpr int kWrDYStages = 4;            // dY rows: 3 in use + 1 in flight
 
 struct WgradRowsKParams {
+  struct SlabOffsets {
+    int coff[64];
+  };
   CUtensorMap tmX[GDL_MAX_SRC];
   CUtensorMap tmDY;
   int num_slabs;
@@ -44,7 +48,7 @@ struct WgradRowsKParams {
   int tiles_w, Hb, hblocks;
   int nblk;           // pixel blocks (image x column x row block); a unit = (slab, pixel block)
   int ctas_per_slab;  // gridDim.x = num_slabs * ctas_per_slab
-  unsigned* turnstile;  // [num_slabs] ordered epilogues (null: arrival order)
+  float* partials;    // ordered mode: [gridDim.x][3][3][Cout][64] per-CTA partial gradients (null: red.global.add)
   int dy_stage_bytes, dy_row_bytes;  // 128 px x Cout x 2 B (1024-aligned), Cout x 2 B
   int ab_fmt;
   float* dw;
@@ -204,12 +208,7 @@ __global__ void __launch_bounds__(kWrThreads, 1) wgrad3x3_rows_kernel(const __gr
     const long long col0 = p.slab_coff[slab] + cin_row;
     mbar_wait(&tfull_bar, 0);
     tc_fence_after();
-    // ordered mode: the CTAs of a slab add in the order of their first pixel block
-    unsigned* ts = p.turnstile ? p.turnstile + slab : nullptr;
-    if (ts != nullptr) {
-      if (warp == 2 && lane == 0) turnstile_wait(ts, (unsigned)blk0);
-      named_bar_sync(1, 128);
-    }
+    float* part = p.partials ? p.partials + (long long)blockIdx.x * (9ll * p.Cout * 64) : nullptr;
     for (int ky = 0; ky < 3; ++ky) {
       const uint32_t t_pair = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ky * 128);
       for (int sel = 0; sel < 2; ++sel) {  // 0: paired accumulator (taps 0|1), 1: tap 2 (rows 0-63 only)
@@ -220,19 +219,20 @@ __global__ void __launch_bounds__(kWrThreads, 1) wgrad3x3_rows_kernel(const __gr
           tmem_ld_32x32b_x16(t_pair + (uint32_t)(sel * 64 + j), v);
           tmem_ld_wait();
           if (sel == 1 && row >= 64) continue;
-          // lanes = consecutive input channels: every red below is one coalesced 128-byte request per warp
+          // lanes = consecutive input channels: every access below is one coalesced 128-byte request per warp
+          if (part != nullptr) {
+            float* pd = part + ((long long)(ky * 3 + kx) * p.Cout + j) * 64 + cin_row;
 #pragma unroll
-          for (int o = 0; o < 16; ++o)
-            asm volatile("red.global.add.f32 [%0], %1;" ::"l"(dst + (long long)(j + o) * p.dw_ld),
-                         "f"(__uint_as_float(v[o]))
-                         : "memory");
+            for (int o = 0; o < 16; ++o) pd[o * 64] = __uint_as_float(v[o]);
+          } else {
+#pragma unroll
+            for (int o = 0; o < 16; ++o)
+              asm volatile("red.global.add.f32 [%0], %1;" ::"l"(dst + (long long)(j + o) * p.dw_ld),
+                           "f"(__uint_as_float(v[o]))
+                           : "memory");
+          }
         }
       }
-    }
-    if (ts != nullptr) {
-      __threadfence();
-      named_bar_sync(1, 128);
-      if (warp == 2 && lane == 0) turnstile_pass(ts, (unsigned)blk0, blk0 == p.ctas_per_slab - 1);
     }
   }
 
@@ -241,6 +241,24 @@ __global__ void __launch_bounds__(kWrThreads, 1) wgrad3x3_rows_kernel(const __gr
   if (warp == 1) {
     __syncwarp();
     tmem_dealloc(tmem_base, 512u);
+  }
+}
+
+// ordered mode: dw[cout][(ky,kx)][slab channels] += partial(CTA 0 of the slab) + partial(CTA 1) + ... in CTA order
+__global__ void __launch_bounds__(256) wgrad_rows_reduce_kernel(const float* __restrict__ partials, int num_slabs, int cps,
+                                                                 int Cout, int Ctot, float* __restrict__ dw, long long dw_ld,
+                                                                 const __grid_constant__ WgradRowsKParams::SlabOffsets so) {
+  const long long per_cta = 9ll * Cout * 64;
+  const long long total = (long long)num_slabs * per_cta;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int slab = (int)(i / per_cta);
+    const long long e = i - (long long)slab * per_cta;
+    const int cin = (int)(e & 63);
+    const int cout = (int)((e >> 6) % Cout);
+    const int tap = (int)((e >> 6) / Cout);
+    float a = 0.f;
+    for (int j = 0; j < cps; ++j) a += __ldcg(partials + ((long long)j * num_slabs + slab) * per_cta + e);
+    dw[(long long)cout * dw_ld + (long long)tap * Ctot + so.coff[slab] + cin] += a;
   }
 }
 
@@ -289,7 +307,8 @@ int wgrad3x3_rows_try(const gdl_conv_wgrad_t* d, cudaStream_t stream, int* statu
   p.ctas_per_slab = nblk < cps_max ? (int)nblk : cps_max;
   {
     const DetWs ws = det_workspace();
-    p.turnstile = (ws.ok() && p.ctas_per_slab > 1 && p.num_slabs <= kDetTurnstiles) ? ws.turnstiles() : nullptr;
+    const long long need = (long long)p.num_slabs * p.ctas_per_slab * 9 * d->Cout * 64;
+    p.partials = (ws.ok() && p.ctas_per_slab > 1 && need <= ws.slot_floats) ? ws.slots : nullptr;
   }
   p.dy_row_bytes = d->Cout * 2;
   p.dy_stage_bytes = 128 * p.dy_row_bytes;  // 4 / 8 / 16 KB
@@ -315,6 +334,17 @@ int wgrad3x3_rows_try(const gdl_conv_wgrad_t* d, cudaStream_t stream, int* statu
   const int grid = p.num_slabs * p.ctas_per_slab;
   wgrad3x3_rows_kernel<<<grid, kWrThreads, smem, stream>>>(p);
   *status = check_cuda(cudaGetLastError(), "wgrad3x3_rows_kernel launch");
+  if (*status == 0 && p.partials != nullptr) {
+    WgradRowsKParams::SlabOffsets so;
+    memset(&so, 0, sizeof(so));
+    for (int i = 0; i < p.num_slabs; ++i) so.coff[i] = p.slab_coff[i];
+    const long long total = (long long)p.num_slabs * 9 * d->Cout * 64;
+    long long rb = (total + 255) / 256;
+    if (rb > 4ll * sms) rb = 4ll * sms;
+    wgrad_rows_reduce_kernel<<<(int)rb, 256, 0, stream>>>(p.partials, p.num_slabs, p.ctas_per_slab, d->Cout, p.Ctot, p.dw,
+                                                        p.dw_ld, so);
+    *status = check_cuda(cudaGetLastError(), "wgrad_rows_reduce_kernel launch");
+  }
   return 1;
 }
 

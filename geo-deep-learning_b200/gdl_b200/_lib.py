@@ -205,9 +205,14 @@ def _register_workspace(dev: int) -> None:
     _WORKSPACES[dev] = buf
 
 
+def workspace_tensor():
+    """the reduction workspace registered for the current device (uint8 tensor), or None"""
+    return _WORKSPACES.get(torch.cuda.current_device())
+
+
 def deterministic() -> bool:
     """True when the current device has a registered reduction workspace (ordered sums instead of fp32 atomics)."""
-    return _WORKSPACES.get(torch.cuda.current_device()) is not None
+    return workspace_tensor() is not None
 
 
 def stream_ptr() -> C.c_void_p:

@@ -100,10 +100,10 @@ def set_conv_profiler(p: ConvProfiler | None) -> None:
 # host-side switches (the library's own are in gdl_set_option); pixel_pack: run 16/32-channel 3x3 convs pixel-packed
 # sra_fused: SegFormer attention forward as ONE kernel (gdl_sra_attention_fwd) where its shape limits allow
 # mha_flash: the DOFA encoder's (forward-only) self-attention as ONE kernel (gdl_mha_flash_fwd, keys streamed)
-_HOST_OPTS = {"pixel_pack": int(os.environ.get("GDL_PIXEL_PACK", "1")), "sra_fused": int(os.environ.get("GDL_SRA_FUSED", "0")),
-              "mha_flash": int(os.environ.get("GDL_MHA_FLASH", "0")),
+_HOST_OPTS = {"pixel_pack": int(os.environ.get("GDL_PIXEL_PACK", "1")), "sra_fused": int(os.environ.get("GDL_SRA_FUSED", "1")),
+              "mha_flash": int(os.environ.get("GDL_MHA_FLASH", "1")),
               # attn_wgrad_grouped: dV / dK of all attention heads as one grouped wgrad launch each (instead of 2 x heads launches)
-              "attn_wgrad_grouped": int(os.environ.get("GDL_ATTN_WGRAD_GROUPED", "0"))}
+              "attn_wgrad_grouped": int(os.environ.get("GDL_ATTN_WGRAD_GROUPED", "1"))}
 
 
 def option(name: str) -> int:

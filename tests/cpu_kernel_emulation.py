@@ -637,6 +637,10 @@ def install(monkeypatch):
         if hasattr(ops, n):
             monkeypatch.setattr(ops, n, globals()[n])
     monkeypatch.setattr(trainer, "LossSpec", LossSpec, raising=False)
+    # the single-kernel attention paths have no torch emulation (their CUDA source runs in tests/hostemu instead): the
+    # host logic checked here is the three-kernel route
+    monkeypatch.setitem(ops._HOST_OPTS, "sra_fused", 0)
+    monkeypatch.setitem(ops._HOST_OPTS, "mha_flash", 0)
 
 
 def install_global():
@@ -647,3 +651,5 @@ def install_global():
         if callable(v) and not n.startswith("_") and n not in ("install", "install_global", "set_work_dtype") and hasattr(ops, n):
             setattr(ops, n, v)
     trainer.LossSpec = LossSpec
+    ops._HOST_OPTS["sra_fused"] = 0
+    ops._HOST_OPTS["mha_flash"] = 0

@@ -24,6 +24,7 @@ TESTS = HERE.parent
 TENSOR_CORE_OPS = ("conv2d_fwd", "conv2d_wgrad", "pack_conv_weight", "unpack_conv_wgrad", "widen_conv_weight", "fold_widened_wgrad")
 
 _lib = None
+_ws = None  # host copy of the reduction workspace (gdl_set_workspace): the ordered-reduction paths run on the CPU too
 
 
 def load_lib():
@@ -60,6 +61,15 @@ def install(monkeypatch, torch_convs: bool = False, async_seed: int | None = Non
     monkeypatch.setattr(L, "stream_ptr", lambda: C.c_void_p(0))
     monkeypatch.setattr(L, "ptr", lambda t: C.c_void_p(0 if t is None else t.data_ptr()))
     monkeypatch.setattr(ops, "require_cuda", lambda t, what: None)
+    global _ws
+    if _ws is None and os.environ.get("GDL_HOSTEMU_DET", "1") != "0":
+        lib.gdl_query_workspace_bytes.restype = C.c_longlong
+        n = int(lib.gdl_query_workspace_bytes())
+        _ws = torch.zeros(n + 512, dtype=torch.uint8)
+        off = (-_ws.data_ptr()) % 256
+        _ws = _ws[off:off + n]
+        L.check(lib.gdl_set_workspace(C.c_void_p(_ws.data_ptr()), n, C.c_void_p(0)))
+    monkeypatch.setattr(L, "workspace_tensor", lambda: _ws)
     monkeypatch.setattr(torch.cuda, "synchronize", lambda *a, **k: None)
     if torch_convs:
         for n in TENSOR_CORE_OPS:

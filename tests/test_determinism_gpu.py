@@ -19,7 +19,7 @@ def _twice(fn):
 
 def _tickets_at_rest():
     from gdl_b200 import _lib
-    ws = _lib._WORKSPACES[torch.cuda.current_device()]
+    ws = _lib.workspace_tensor()
     torch.cuda.synchronize()
     return int(ws[:256 * 1024].view(torch.int32).abs().sum().item()) == 0
 
@@ -163,6 +163,19 @@ WGRAD_CASES = [
     (16, 64, 64, [256], 64, 1),
     (4, 32, 32, [512, 256, 64], 256, 3),
 ]
+
+
+# small shapes that still split the pixel range (also executed on the CPU functional model, tests/hostemu)
+WGRAD_CASES_SMALL = [
+    (2, 32, 64, [64], 128, 3),      # halo variant, 3 accumulators per unit
+    (2, 16, 128, [64, 64], 32, 3),  # row-streaming kernel, two slabs
+    (2, 48, 48, [32], 48, 1),       # pointwise
+]
+
+
+@pytest.mark.parametrize("n,h,w,cins,cout,r", WGRAD_CASES_SMALL)
+def test_wgrad_reproducible_small(cuda, n, h, w, cins, cout, r):
+    test_wgrad_reproducible(cuda, n, h, w, cins, cout, r)
 
 
 @pytest.mark.parametrize("n,h,w,cins,cout,r", WGRAD_CASES)

@@ -160,10 +160,23 @@ def test_loss_modules_and_fused_trainer_agree_with_autograd_route(cuda):
     raw = torch.randint(0, 256, (4, 128, 128, 3), generator=g, dtype=torch.uint8).cuda()
     t = torch.randint(0, 5, (4, 128, 128), generator=g).cuda()
     mean, std = [0.4, 0.5, 0.6], [0.2, 0.25, 0.3]
-    # route A: reference-style batch (float NCHW standardised) -> module forward -> loss module -> autograd
+    # the first kernel of the two routes: a reference-style batch (float NCHW, standardised by the reference's own
+    # utils/tensors.py arithmetic) cast to the 16-bit NHWC operand vs the raw uint8 tile normalised by the kernel itself.
+    # They agree up to ONE 16-bit rounding on a fraction of a percent of the values (fp32 operation order).
     from oracle import tensors as ot
-    img = ot.standardization(ot.normalization(raw.permute(0, 3, 1, 2).float()), torch.tensor(mean).view(3, 1).cuda(),
-                             torch.tensor(std).view(3, 1).cuda())
+    img_ref = ot.standardization(ot.normalization(raw.permute(0, 3, 1, 2).float()), torch.tensor(mean).view(3, 1).cuda(),
+                                 torch.tensor(std).view(3, 1).cuda())
+    x_a = ops_mod.normalize_to_nhwc(img_ref.contiguous(), True, torch.bfloat16, 8)
+    x_b = ops_mod.normalize_to_nhwc(raw, False, torch.bfloat16, 8, torch.tensor(mean).cuda(), torch.tensor(std).cuda(), 255.0)
+    mism = x_a != x_b
+    print("input mismatch elements:", int(mism.sum()), "of", x_a.numel())
+    assert mism.float().mean() < 0.01
+    assert ((x_a.float() - x_b.float()).abs() <= 2.0 ** -7 * x_b.float().abs() + 1e-6).all()
+    # Through a randomly initialised UNet++ in 16-bit arithmetic those few roundings move sensitive first-layer gradients
+    # by tens of percent (round 2 measured 49 % on encoder.layer1.0.bn1.bias), so the two ROUTES are compared on
+    # bit-identical operands: route A is fed the 16-bit values route B's kernel produces (exact in fp32).
+    img = x_b[..., :3].permute(0, 3, 1, 2).float().contiguous()
+    # route A: float NCHW batch -> module forward -> loss module -> autograd
     prod.train()
     loss_a = CrossEntropyLoss()(prod(img), t)
     loss_a.backward()
@@ -171,20 +184,17 @@ def test_loss_modules_and_fused_trainer_agree_with_autograd_route(cuda):
     prod2.train()
     tr = FusedTrainer(prod2, LossSpec(1.0, 0.0, ignore_index=-100), lr=1e-3, mean=mean, std=std)
     loss_b = tr.forward_backward(raw, t)
-    # run-to-run noise of the same route (fp32 atomics in wgrad / BN sums are order-dependent)
+    # run-to-run: the same route twice is bit-identical (ordered reductions)
     _, prod3 = _models("resnet18", 3, 5)
     prod3.train()
     tr3 = FusedTrainer(prod3, LossSpec(1.0, 0.0, ignore_index=-100), lr=1e-3, mean=mean, std=std)
     tr3.forward_backward(raw, t)
-    noise = max(_rel(p3.grad, p2.grad) for p3, p2 in zip(prod3.parameters(), prod2.parameters()))
-    # identical inputs after the first kernel?
-    x_a = ops_mod.normalize_to_nhwc(img.contiguous(), True, torch.bfloat16, 8)
-    x_b = ops_mod.normalize_to_nhwc(raw, False, torch.bfloat16, 8, torch.tensor(mean).cuda(), torch.tensor(std).cuda(), 255.0)
-    print("input mismatch elements:", int((x_a != x_b).sum()), "run-to-run grad noise:", noise)
-    assert abs(loss_a.item() - loss_b.item()) < 1e-3
+    assert torch.equal(tr3.gflat, tr.gflat)
+    assert abs(loss_a.item() - loss_b.item()) < 1e-5
     worst = max((_rel(pb.grad, pa.grad), n) for (n, pa), (_, pb) in zip(prod.named_parameters(), prod2.named_parameters()))
     print("worst route A vs B:", worst)
-    assert worst[0] < max(20 * noise, 2e-2), worst
+    # identical forward; the backward is linear in d(logits), which the two routes round to 16 bits at different points
+    assert worst[0] < 2e-2, worst
     before = tr.flat.clone()
     tr.optimizer_step()
     assert (tr.flat - before).abs().max() > 0
