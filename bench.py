@@ -285,15 +285,93 @@ def main_reference(args) -> None:
 
 
 # =================================================================================================
+# library baseline: the reference's own modules (oracle restatements, pinned to them) as a user of the reference runs
+# them on this GPU — stock PyTorch eager, torch.autocast(bf16), cuDNN / cuBLAS kernels, torch.optim.Adam(fused=True).
+# BASELINE.md §3 calls this "the real bar"; it is reported beside the product arm, never used by it.
+# =================================================================================================
+def library_baseline_steps(w: dict, dev, batch: int, steps: int = 5, warmup: int = 2) -> dict:
+    import torch
+    import torch.nn.functional as F
+
+    torch.backends.cudnn.benchmark = True
+    nb, T, K = w["bands"], w["tile"], w["classes"]
+    g = torch.Generator().manual_seed(4321)
+    infer = w["family"] == "infer"
+    # what the reference's DataLoader hands over: a float32 NCHW batch, already normalised + standardised (resident in HBM)
+    x = torch.randn(batch, nb, T, T, generator=g).to(dev)
+    mask = torch.randint(0, K, (batch, T // 32, T // 32), generator=g).repeat_interleave(32, 1).repeat_interleave(32, 2).to(dev)
+    torch.manual_seed(0)
+    if w["family"] == "unetpp":
+        from oracle.unetpp import UnetPlusPlusOracle
+        model = UnetPlusPlusOracle(w["encoder"], nb, K).to(dev).train()
+        params = list(model.parameters())
+
+        def fwd(inp):
+            return model(inp)
+    elif w["family"] == "dofa":
+        from oracle import dofa as od, upernet as ou
+        enc_sd = {k: v.to(dev) for k, v in od.init_state_dict(768, 12, T).items()}
+        sd = {k: v.to(dev) for k, v in ou.init_state_dict(768, 256, K).items()}
+        sd = {k: (v.requires_grad_(True) if v.is_floating_point() and "running" not in k else v) for k, v in sd.items()}
+        params = [v for v in sd.values() if v.requires_grad]
+        wl = torch.tensor(w["wavelengths"], device=dev)
+
+        def fwd(inp):
+            with torch.no_grad():
+                feats = od.dofa_forward(enc_sd, inp, wl)
+            return ou.upernet_forward(sd, feats, (T, T), training=True)
+    else:
+        from oracle import segformer as osf
+        sd = {k: v.to(dev) for k, v in osf.init_state_dict(w["encoder"], nb, K).items()}
+        if not infer:
+            sd = {k: (v.requires_grad_(True) if v.is_floating_point() and "running" not in k else v) for k, v in sd.items()}
+        params = [v for v in sd.values() if v.requires_grad]
+
+        def fwd(inp):
+            return osf.segformer_forward(sd, inp, w["encoder"], training=not infer)
+    opt = torch.optim.Adam(params, lr=1e-4, fused=True) if params else None
+
+    def step() -> None:
+        if infer:
+            with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+                fwd(x).softmax(dim=1).argmax(dim=1)
+            return
+        opt.zero_grad(set_to_none=True)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            out = fwd(x)
+        loss = (F.cross_entropy(out[0].float(), mask) + 0.4 * F.cross_entropy(out[1].float(), mask)) if isinstance(out, tuple) \
+            else F.cross_entropy(out.float(), mask)
+        loss.backward()
+        if w["family"] in ("segformer", "dofa"):
+            torch.nn.utils.clip_grad_norm_(params, 1.0)
+        opt.step()
+
+    for _ in range(warmup):
+        step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    out = {"value": batch / (ms / 1e3), "unit": "tiles/s", "ms_per_step": ms, "batch": batch, "steps": steps,
+           "what": ("the reference's module stack (oracle restatement pinned to it) on the SAME GPU: stock PyTorch eager, "
+                    "torch.autocast(bf16), cuDNN benchmark mode, " + ("no_grad forward + softmax/argmax" if infer else
+                    "fwd + CE + bwd + fused Adam") + "; inputs resident in HBM as float32 NCHW")}
+    del opt, params
+    return out
+
+
+# =================================================================================================
 # product arm
 # =================================================================================================
 def main_product(args) -> None:
     import torch
     import torch.distributed as dist
 
-    from gdl_b200 import _lib, ops
-    from gdl_b200.models.unetpp import UnetPlusPlus
-    from gdl_b200.trainer import FusedTrainer
+    from gdl_b200 import _lib
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -305,12 +383,56 @@ def main_product(args) -> None:
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     _lib.load()
+    ctx = (world, rank, local, dev)
 
+    head_key = args.workload
+    line = _run_workload(args, head_key, ctx, steps=args.steps, warmup=args.warmup, headline=True)
+    # the other BASELINE.json configurations ride along in the same line: configs[2]
+    # SegFormer-B2 training, configs[3] DOFA-base + UperNet training, configs[4] SegFormer-B5 sliding-window inference
+    extra = {}
+    if args.workloads == "all" and head_key == "unetpp_r50":
+        for key in ("segformer_b2", "dofa_base", "segformer_b5_infer"):
+            sub_steps = max(1, min(args.steps, 2 if key == "segformer_b5_infer" else 6))
+            sub = _run_workload(args, key, ctx, steps=sub_steps, warmup=min(args.warmup, 3) if key != "segformer_b5_infer" else 1,
+                                headline=False)
+            if sub is not None:
+                extra[key] = sub
+    if rank == 0:
+        if extra:
+            line["workloads"] = extra
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def _run_workload(args, key: str, ctx, *, steps: int, warmup: int, headline: bool):
+    import gc
+
+    import torch
+    _select_workload(key)
+    try:
+        if WORKLOAD["family"] == "infer":
+            return _run_infer(args, ctx, steps, warmup, headline)
+        return _run_train(args, ctx, steps, warmup, headline)
+    finally:
+        gc.collect()
+        torch.cuda.empty_cache()
+        _select_workload(args.workload)
+
+
+def _run_train(args, ctx, steps: int, warmup: int, headline: bool):
+    import torch
+    import torch.distributed as dist
+
+    from gdl_b200 import ops
+    from gdl_b200.models.unetpp import UnetPlusPlus
+    from gdl_b200.trainer import FusedTrainer
+
+    world, rank, local, dev = ctx
     w = WORKLOAD
-    B, C, T, K = args.batch or w["batch_per_gpu"], w["bands"], w["tile"], w["classes"]
+    B, C, T, K = (args.batch if headline and args.batch else w["batch_per_gpu"]), w["bands"], w["tile"], w["classes"]
     torch.manual_seed(0)  # identical initial weights on every rank (what DDP's broadcast gives)
-    if w["family"] == "infer":
-        return main_infer(args, world, rank, local, dev)
+    cuda_graph = args.cuda_graph
     if w["family"] == "unetpp":
         model = UnetPlusPlus(w["encoder"], in_channels=C, classes=K, compute_dtype=torch.bfloat16).to(dev).train()
     elif w["family"] == "dofa":
@@ -318,15 +440,15 @@ def main_product(args) -> None:
         model = DOFASegmentationModel(w["encoder"], (T, T), None if w.get("unfrozen") else ["encoder"], K,
                                       compute_dtype=torch.bfloat16).to(dev).train()
         if w.get("unfrozen"):
-            args.cuda_graph = 0
+            cuda_graph = 0
         model.wavelengths = torch.tensor(w["wavelengths"], device=dev)
     else:
         from gdl_b200.models.segformer import SegFormer
         model = SegFormer(w["encoder"], in_channels=C, num_classes=K, compute_dtype=torch.bfloat16).to(dev).train()
+    use_graph = bool(cuda_graph) and (world == 1 or cuda_graph >= 2)
     trainer = FusedTrainer(model, ops.LossSpec(1.0, 0.0, ignore_index=-100), lr=1e-4, mean=MEAN[:C], std=STD[:C],
                            image_max=255.0, sync_bn=bool(args.sync_bn),
-                           clip_grad_norm=1.0 if w["family"] in ("segformer", "dofa") else None,
-                           cuda_graph=bool(args.cuda_graph) and (world == 1 or args.cuda_graph >= 2))
+                           clip_grad_norm=1.0 if w["family"] in ("segformer", "dofa") else None, cuda_graph=use_graph)
 
     # synthetic tiles: NBUF distinct batches so consecutive steps never re-read the same input (and the
     # per-step working set, tens of GB of activations, is far larger than the 126 MB L2 anyway)
@@ -345,11 +467,11 @@ def main_product(args) -> None:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps: int) -> float:
+    def timed(fn, nsteps: int) -> float:
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        for i in range(steps):
+        for i in range(nsteps):
             fn(i)
         e1.record()
         barrier()
@@ -371,75 +493,90 @@ def main_product(args) -> None:
         torch.cuda.current_stream().synchronize()  # the caller gets the loss value every step
         return loss_host
 
-    for i in range(args.warmup):
+    for i in range(max(warmup, 2)):  # >= 2: the second step captures the graph
         step_resident(i)
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
-    ms = timed(step_resident, args.steps)
-    launches = trainer.launches_per_step * args.steps  # kernels of libgdlb200.so per step (counted at capture)
+    ms = timed(step_resident, steps)
+    launches = trainer.launches_per_step * steps  # kernels of libgdlb200.so per step (counted at capture)
     clk = clocks.stop() if rank == 0 else None
 
     for i in range(2):
         step_e2e(i)
-    ms_e2e = timed(step_e2e, args.steps)
+    ms_e2e = timed(step_e2e, steps)
 
     # ---- roofline of the dominant kernels: per-launch CUDA events around every tensor-core conv launch
     # (eager launches: events cannot be read back from inside a replayed graph)
     trainer.cuda_graph = False
     prof = ops.ConvProfiler()
     ops.set_conv_profiler(prof)
-    nprof = max(1, min(3, args.steps))
+    nprof = max(1, min(3, steps)) if headline else 1
     for i in range(nprof):
         step_resident(i)
     torch.cuda.synchronize()
     ops.set_conv_profiler(None)
     roof = prof.summary(nprof)
-    if args.table and rank == 0:
+    if headline and args.table and rank == 0:
         prof.dump_table(args.table, nprof)
+    deterministic = ops.deterministic()
+    del trainer, model, dev_img, dev_msk
+    import gc
+    gc.collect()
+    torch.cuda.empty_cache()
 
-    cpu = None
-    if rank == 0 and not args.no_cpu_baseline:
+    cpu = lib = None
+    if rank == 0 and headline and not args.no_cpu_baseline:
         cpu = cpu_reference_steps(steps=3, warmup=1, tiles_per_step=1, budget_s=20.0)
+    if rank == 0 and world == 1 and not args.no_library_baseline:
+        try:
+            lib = library_baseline_steps(w, dev, B, steps=5 if headline else 3, warmup=2)
+        except Exception as e:  # noqa: BLE001  (a baseline that cannot run must not take the product's line with it)
+            lib = {"unavailable": f"{type(e).__name__}: {e}"[:300]}
 
-    if rank == 0:
-        peaks = _peaks()
-        peak_tf = float(peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"]))
-        tiles = B * world * args.steps
-        value = tiles / (ms / 1e3)
-        fwd = roof["conv_fwd_kernel"]
-        traffic, traffic_src = _dram_traffic({"unetpp": "unetpp", "segformer": "segformer", "dofa": "dofa"}[w["family"]])
-        line = {
-            "metric": "512x512 multi-band tiles/sec (train fwd+bwd)", "value": value, "unit": "tiles/s",
-            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": w["name"], "global_batch": B * world, "parallelism": f"dp{world}",
-                       "loss": "cross_entropy", "optimizer": "adam", "sync_bn": bool(args.sync_bn and world > 1), "cuda_graph": bool(args.cuda_graph) and (world == 1 or args.cuda_graph >= 2),
-                       "sra_fused": bool(ops.option("sra_fused")), "mha_flash": bool(ops.option("mha_flash")),
-                       "l2": f"{NBUF} rotating input batches; per-step working set >> 126 MB L2"},
-            "clocks": clk,
-            "e2e": {"value": tiles / (ms_e2e / 1e3), "unit": "tiles/s",
-                    "h2d_bytes_per_step": B * T * T * C + B * T * T, "d2h_bytes_per_step": 4,
-                    "ms_per_step": ms_e2e / args.steps},
-            "gpu_launches": launches,
-            "model_tflops": TRAIN_GFLOP_PER_TILE * value / world / 1e3,
-            "roofline": {"bound": "tensor", "kernel": "conv_fwd_kernel + conv3x3_rows_kernel (forward + dgrad launches)",
-                         "achieved": fwd["tflops"], "peak": peak_tf, "unit": "TFLOP/s",
-                         "frac": fwd["tflops"] / peak_tf, "traffic": traffic, "traffic_unit": "DRAM bytes per launch",
-                         "traffic_source": traffic_src, "peak_source":
-                         f"{peaks['source']} bf16_tflops_sustained", "launches_per_step": fwd["launches_per_step"],
-                         "share_of_step": fwd["ms_per_step"] / (ms / args.steps),
-                         "wgrad": {"kernel": "conv_wgrad_kernel", "achieved": roof["conv_wgrad_kernel"]["tflops"],
-                                   "frac": roof["conv_wgrad_kernel"]["tflops"] / peak_tf,
-                                   "share_of_step": roof["conv_wgrad_kernel"]["ms_per_step"] / (ms / args.steps)}},
-            "cpu_baseline": ({k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")} if cpu else None),
-        }
-        print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    if rank != 0:
+        return None
+    peaks = _peaks()
+    peak_tf = float(peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"]))
+    tiles = B * world * steps
+    value = tiles / (ms / 1e3)
+    fwd = roof["conv_fwd_kernel"]
+    traffic, traffic_src = _dram_traffic({"unetpp": "unetpp", "segformer": "segformer", "dofa": "dofa"}[w["family"]])
+    line = {
+        "metric": "512x512 multi-band tiles/sec (train fwd+bwd)", "value": value, "unit": "tiles/s",
+        "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": ms / steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": w["name"], "global_batch": B * world, "parallelism": f"dp{world}",
+                   "loss": "cross_entropy", "optimizer": "adam", "sync_bn": bool(args.sync_bn and world > 1), "cuda_graph": use_graph,
+                   "sra_fused": bool(ops.option("sra_fused")), "mha_flash": bool(ops.option("mha_flash")),
+                   "deterministic_reductions": deterministic,
+                   "l2": f"{NBUF} rotating input batches; per-step working set >> 126 MB L2"},
+        "clocks": clk,
+        "e2e": {"value": tiles / (ms_e2e / 1e3), "unit": "tiles/s",
+                "h2d_bytes_per_step": B * T * T * C + B * T * T, "d2h_bytes_per_step": 4,
+                "ms_per_step": ms_e2e / steps},
+        "gpu_launches": launches,
+        "model_tflops": TRAIN_GFLOP_PER_TILE * value / world / 1e3,
+        "roofline": {"bound": "tensor", "kernel": "conv_fwd_kernel + conv3x3_rows_kernel (forward + dgrad launches)",
+                     "achieved": fwd["tflops"], "peak": peak_tf, "unit": "TFLOP/s",
+                     "frac": fwd["tflops"] / peak_tf, "flops": "algorithmic (pixel-packed / channel-padded launches count their unpadded shapes)",
+                     "traffic": traffic, "traffic_unit": "DRAM bytes per launch",
+                     "traffic_source": traffic_src, "peak_source":
+                     f"{peaks['source']} bf16_tflops_sustained", "launches_per_step": fwd["launches_per_step"],
+                     "share_of_step": fwd["ms_per_step"] / (ms / steps),
+                     "wgrad": {"kernel": "conv_wgrad_kernel + wgrad3x3_rows_kernel (+ their ordered-reduce passes)",
+                               "achieved": roof["conv_wgrad_kernel"]["tflops"],
+                               "frac": roof["conv_wgrad_kernel"]["tflops"] / peak_tf,
+                               "share_of_step": roof["conv_wgrad_kernel"]["ms_per_step"] / (ms / steps)},
+                     "whole_step": {"achieved": TRAIN_GFLOP_PER_TILE * value / world / 1e3, "frac":
+                                    TRAIN_GFLOP_PER_TILE * value / world / 1e3 / peak_tf}},
+        "cpu_baseline": ({k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")} if cpu else None),
+        "library_baseline": lib,
+    }
+    return line
 
 
-def main_infer(args, world: int, rank: int, local: int, dev) -> None:
+def _run_infer(args, ctx, steps: int, warmup: int, headline: bool):
     """Sliding-window inference over one synthetic raster, windows dealt round-robin to the ranks (strong scaling)."""
     import torch
     import torch.distributed as dist
@@ -448,9 +585,11 @@ def main_infer(args, world: int, rank: int, local: int, dev) -> None:
     from gdl_b200.inference import SlidingWindowSegmenter, window_origins
     from gdl_b200.models.segformer import SegFormer
 
+    world, rank, local, dev = ctx
     w = WORKLOAD
-    B, C, T, K = args.batch or w["batch_per_gpu"], w["bands"], w["tile"], w["classes"]
+    B, C, T, K = (args.batch if headline and args.batch else w["batch_per_gpu"]), w["bands"], w["tile"], w["classes"]
     R = args.raster or w["raster"]
+    torch.manual_seed(0)
     model = SegFormer(w["encoder"], in_channels=C, num_classes=K, compute_dtype=torch.bfloat16).to(dev).eval()
     # --cuda-graph 2 replays the window-batch forward from a CUDA graph (default: eager launches, as validated)
     seg = SlidingWindowSegmenter(model, tile=T, stride=T // 2, batch=B, mean=MEAN[:C], std=STD[:C],
@@ -466,11 +605,11 @@ def main_infer(args, world: int, rank: int, local: int, dev) -> None:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps: int) -> float:
+    def timed(fn, nsteps: int) -> float:
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        for i in range(steps):
+        for i in range(nsteps):
             fn(i)
         e1.record()
         barrier()
@@ -487,53 +626,62 @@ def main_infer(args, world: int, rank: int, local: int, dev) -> None:
         torch.cuda.current_stream().synchronize()
 
     n0 = ops.launch_count()
-    for i in range(max(1, args.warmup)):
+    for i in range(max(1, warmup)):
         step_resident(i)
-    launches_per_step = (ops.launch_count() - n0) // max(1, args.warmup)
+    launches_per_step = (ops.launch_count() - n0) // max(1, warmup)
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
-    ms = timed(step_resident, args.steps)
+    ms = timed(step_resident, steps)
     clk = clocks.stop() if rank == 0 else None
     step_e2e(0)
-    ms_e2e = timed(step_e2e, args.steps)
+    ms_e2e = timed(step_e2e, steps)
     prof = ops.ConvProfiler()
     ops.set_conv_profiler(prof)
     step_resident(0)
     torch.cuda.synchronize()
     ops.set_conv_profiler(None)
     roof = prof.summary(1)
-    cpu = None
-    if rank == 0 and not args.no_cpu_baseline:
+    del seg, model, resident
+    import gc
+    gc.collect()
+    torch.cuda.empty_cache()
+    cpu = lib = None
+    if rank == 0 and headline and not args.no_cpu_baseline:
         cpu = cpu_reference_steps(steps=3, warmup=1, tiles_per_step=1, budget_s=20.0)
-    if rank == 0:
-        peaks = _peaks()
-        peak_tf = float(peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"]))
-        value = nwin * args.steps / (ms / 1e3)
-        fwd = roof["conv_fwd_kernel"]
-        line = {
-            "metric": "512x512 multi-band tiles/sec (inference fwd, sliding window)", "value": value, "unit": "tiles/s",
-            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
-            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": w["name"], "raster": [R, R, C], "windows": nwin, "window_batch": B,
-                       "parallelism": f"windows round-robin over {world} rank(s) + one all-reduce of the logit sums",
-                       "cuda_graph": args.cuda_graph >= 2, "sra_fused": bool(ops.option("sra_fused")),
-                       "l2": f"raster {R * R * C / 1e6:.0f} MB and activations >> 126 MB L2"},
-            "clocks": clk,
-            "e2e": {"value": nwin * args.steps / (ms_e2e / 1e3), "unit": "tiles/s", "h2d_bytes_per_step": R * R * C,
-                    "d2h_bytes_per_step": R * R, "ms_per_step": ms_e2e / args.steps},
-            "gpu_launches": launches_per_step * args.steps,
-            "model_tflops": w["train_gflop_per_tile"] * value / world / 1e3,
-            "roofline": {"bound": "tensor", "kernel": "conv_fwd_kernel (every GEMM / conv of the forward)",
-                         "achieved": fwd["tflops"], "peak": peak_tf, "unit": "TFLOP/s", "frac": fwd["tflops"] / peak_tf,
-                         "traffic": None, "peak_source": f"{peaks['source']} bf16_tflops_sustained",
-                         "launches_per_step": fwd["launches_per_step"],
-                         "share_of_step": fwd["ms_per_step"] / (ms / args.steps)},
-            "cpu_baseline": ({k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")} if cpu else None),
-        }
-        print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    if rank == 0 and world == 1 and not args.no_library_baseline:
+        try:
+            lib = library_baseline_steps(w, dev, B, steps=3, warmup=2)
+        except Exception as e:  # noqa: BLE001
+            lib = {"unavailable": f"{type(e).__name__}: {e}"[:300]}
+    if rank != 0:
+        return None
+    peaks = _peaks()
+    peak_tf = float(peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"]))
+    value = nwin * steps / (ms / 1e3)
+    fwd = roof["conv_fwd_kernel"]
+    line = {
+        "metric": "512x512 multi-band tiles/sec (inference fwd, sliding window)", "value": value, "unit": "tiles/s",
+        "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": ms / steps,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": w["name"], "raster": [R, R, C], "windows": nwin, "window_batch": B,
+                   "parallelism": f"windows round-robin over {world} rank(s) + one all-reduce of the logit sums",
+                   "cuda_graph": args.cuda_graph >= 2, "sra_fused": bool(ops.option("sra_fused")),
+                   "l2": f"raster {R * R * C / 1e6:.0f} MB and activations >> 126 MB L2"},
+        "clocks": clk,
+        "e2e": {"value": nwin * steps / (ms_e2e / 1e3), "unit": "tiles/s", "h2d_bytes_per_step": R * R * C,
+                "d2h_bytes_per_step": R * R, "ms_per_step": ms_e2e / steps},
+        "gpu_launches": launches_per_step * steps,
+        "model_tflops": w["train_gflop_per_tile"] * value / world / 1e3,
+        "roofline": {"bound": "tensor", "kernel": "conv_fwd_kernel (every GEMM / conv of the forward)",
+                     "achieved": fwd["tflops"], "peak": peak_tf, "unit": "TFLOP/s", "frac": fwd["tflops"] / peak_tf,
+                     "traffic": None, "peak_source": f"{peaks['source']} bf16_tflops_sustained",
+                     "launches_per_step": fwd["launches_per_step"],
+                     "share_of_step": fwd["ms_per_step"] / (ms / steps)},
+        "cpu_baseline": ({k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")} if cpu else None),
+        "library_baseline": lib,
+    }
+    return line
 
 
 def main() -> None:
@@ -549,6 +697,10 @@ def main() -> None:
     ap.add_argument("--raster", type=int, default=0, help="segformer_b5_infer: raster side in pixels (default 10000)")
     ap.add_argument("--table", default="", help="write the per-launch conv profile (shape, ms, TFLOP/s) to this JSON file")
     ap.add_argument("--workload", default="unetpp_r50", choices=sorted(WORKLOADS))
+    ap.add_argument("--workloads", default="all", choices=["all", "headline"],
+                    help="all: after the headline (default workload only) also run BASELINE configs[2..4] and attach them as `workloads`")
+    ap.add_argument("--no-library-baseline", action="store_true",
+                    help="skip the stock-PyTorch eager bf16 run of the reference's modules on the same GPU")
     args = ap.parse_args()
     _select_workload(args.workload)
     if args.impl == "reference":

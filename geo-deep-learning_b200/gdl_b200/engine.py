@@ -175,7 +175,7 @@ class Engine:
             f = 64 // cin
             x = ops.conv2d_fwd([a.t.view(n, h, wd // f, f * cin)], self.packed_wide(weight, 0, f, wshape), f * cout,
                                r, s, pad, pad, out_dtype=out_dtype, relu=relu,
-                               bias=self._tiled_bias(bias, f) if bias is not None else None)
+                               bias=self._tiled_bias(bias, f) if bias is not None else None, alg_scale=1.0 / f)
             return RawConv(x.view(n, h, wd, cout), srcs, weight, stride, pad, cin_store=stored, wshape=wshape, bias=bias,
                            pixel_packed=True)
         if direct:
@@ -190,7 +190,8 @@ class Engine:
         kpad = (k + 63) // 64 * 64
         col = ops.im2col(a.t, cin, r, s, stride, pad, kpad)
         wp = self.packed(weight, 0, kpad, wshape)
-        x = ops.conv2d_fwd([col], wp, cout, 1, 1, 0, 0, out_dtype=out_dtype, bias=bias, relu=relu, residual=residual)
+        x = ops.conv2d_fwd([col], wp, cout, 1, 1, 0, 0, out_dtype=out_dtype, bias=bias, relu=relu, residual=residual,
+                           alg_scale=k / kpad)
         return RawConv(x, srcs, weight, stride, pad, col=col if self.training else None, kpad=kpad, cin_store=stored,
                        wshape=wshape, bias=bias)
 
@@ -214,12 +215,12 @@ class Engine:
                 f = 64 // max(cin, coutp)
                 dw = torch.zeros((f * coutp, r * s * f * cin), dtype=self.acc_dtype, device=dev)
                 ops.conv2d_wgrad([a.t.view(n, h, wd // f, f * cin)], dx.view(n, h, wd // f, f * coutp), r, s, rc.pad,
-                                 rc.pad, dw)
+                                 rc.pad, dw, alg_scale=cout / (f * coutp))
                 ops.fold_widened_wgrad(dw, self.grad_buffer(w, False).view(cout, cin, r, s), f)
             if a.needs_grad:
                 f = 64 // coutp
                 dcat = ops.conv2d_fwd([dx.view(n, h, wd // f, f * coutp)], self.packed_wide(w, 1, f, rc.wshape, coutp),
-                                      f * cin, r, s, r - 1 - rc.pad, s - 1 - rc.pad)
+                                      f * cin, r, s, r - 1 - rc.pad, s - 1 - rc.pad, alg_scale=cout / (f * coutp))
                 a.gsrcs.append((dcat.view(n, h, wd, cin), 0))
             return
         if rc.col is None:
@@ -229,11 +230,12 @@ class Engine:
                     ops.conv2d_wgrad([a.t for a in rc.srcs], dx, 1, 1, 0, 0, self.grad_buffer(w, True).view(cout, cin))
                 else:
                     dw = torch.zeros((coutp, r * s * cin), dtype=self.acc_dtype, device=dev)
-                    ops.conv2d_wgrad([a.t for a in rc.srcs], dx, r, s, rc.pad, rc.pad, dw)
+                    ops.conv2d_wgrad([a.t for a in rc.srcs], dx, r, s, rc.pad, rc.pad, dw, alg_scale=cout / coutp)
                     ops.unpack_conv_wgrad(dw, self.grad_buffer(w, False).view(cout, cin, r, s), r * s * cin)
             if any(a.needs_grad for a in rc.srcs):
                 wt = self._dgrad_weight(w, coutp, rc.wshape)
-                dcat = ops.conv2d_fwd([dx], wt, cin, r, s, r - 1 - rc.pad, s - 1 - rc.pad, residual=dgrad_residual)
+                dcat = ops.conv2d_fwd([dx], wt, cin, r, s, r - 1 - rc.pad, s - 1 - rc.pad, residual=dgrad_residual,
+                                      alg_scale=cout / coutp)
                 off = 0
                 for a in rc.srcs:
                     c = a.t.shape[3]
@@ -244,13 +246,13 @@ class Engine:
             a = rc.srcs[0]
             if w.requires_grad:
                 dw = torch.zeros((coutp, rc.kpad), dtype=self.acc_dtype, device=dev)
-                ops.conv2d_wgrad([rc.col], dx, 1, 1, 0, 0, dw)
+                ops.conv2d_wgrad([rc.col], dx, 1, 1, 0, 0, dw, alg_scale=(cout * r * s * cin) / (coutp * rc.kpad))
                 ops.unpack_conv_wgrad(dw, self.grad_buffer(w, False).view(cout, cin, r, s), rc.kpad)
             if a.needs_grad:
                 if coutp != cout:
                     raise NotImplementedError("padded-output dgrad through im2col")
                 wt = self.packed(w, 2, 0, rc.wshape)  # [(r,s,c)][Cout]
-                dcol = ops.conv2d_fwd([dx], wt, r * s * cin, 1, 1, 0, 0)
+                dcol = ops.conv2d_fwd([dx], wt, r * s * cin, 1, 1, 0, 0)  # (stored channels == cin here)
                 n, h, wd, c = a.t.shape
                 a.gsrcs.append((ops.col2im(dcol, n, h, wd, c, r, s, rc.stride, rc.pad), 0))
 

@@ -165,9 +165,12 @@ def conv2d_fwd(srcs: Sequence[torch.Tensor], weight: torch.Tensor, cout: int, r:
                out_dtype: torch.dtype | None = None, bias: torch.Tensor | None = None,
                relu: bool = False, residual: torch.Tensor | None = None, w_ld: int = 0, w_rows: int = 0,
                w_rows_per_img: int = 0, w_mn_major: bool = False, gelu: bool = False,
-               oscale: torch.Tensor | None = None, groups: tuple[int, int, int, int] | None = None) -> torch.Tensor:
+               oscale: torch.Tensor | None = None, groups: tuple[int, int, int, int] | None = None,
+               alg_scale: float = 1.0) -> torch.Tensor:
     """gdl_conv2d_nhwc_fwd. `weight` is the packed [Cout][R][S][Ctot] 16-bit operand (or, with the w_*
-    options, a slice of an activation tensor used as the B operand of an attention GEMM)."""
+    options, a slice of an activation tensor used as the B operand of an attention GEMM).
+    alg_scale: ALGORITHMIC / executed FLOPs of this launch (profiler only): < 1 for pixel-packed (block-Toeplitz) and
+    channel-padded launches, whose zeros are not work the reference does."""
     d = L.ConvFwd()
     n, h, w = _fill_srcs(d, srcs)
     dt = srcs[0].dtype
@@ -201,13 +204,14 @@ def conv2d_fwd(srcs: Sequence[torch.Tensor], weight: torch.Tensor, cout: int, r:
     _count()
     if e0 is not None:
         ctot = sum(t.shape[3] for t in srcs)
-        _PROFILER.end("conv_fwd_kernel", 2.0 * ng * n * ho * wo * cout * r * s * ctot, e0,
+        _PROFILER.end("conv_fwd_kernel", 2.0 * alg_scale * ng * n * ho * wo * cout * r * s * ctot, e0,
                       f"N{n} {ho}x{wo} src{[t.shape[3] for t in srcs]} -> {cout} k{r}" + (f" x{ng} groups" if ng > 1 else ""))
     return out
 
 
 def conv2d_wgrad(srcs: Sequence[torch.Tensor], dy: torch.Tensor, r: int, s: int, pad_h: int,
-                 pad_w: int, dw: torch.Tensor, groups: tuple[int, int, int, int] | None = None) -> torch.Tensor:
+                 pad_w: int, dw: torch.Tensor, groups: tuple[int, int, int, int] | None = None,
+                 alg_scale: float = 1.0) -> torch.Tensor:
     """gdl_conv2d_nhwc_wgrad: accumulates into fp32 dw.  dw 2-D [Cout][R*S*Ctot] (row stride = stride(0)), or
     3-D [N][Cout][Ctot] = batched: one independent product per image (attention dV = P^T dO, dK = dS^T q).
     groups = (G, source channel stride, dy channel stride, dw column stride): G such products per image in one launch (all
@@ -233,7 +237,7 @@ def conv2d_wgrad(srcs: Sequence[torch.Tensor], dy: torch.Tensor, r: int, s: int,
     _count()
     if e0 is not None:
         ctot = sum(t.shape[3] for t in srcs)
-        _PROFILER.end("conv_wgrad_kernel", 2.0 * (d.groups or 1) * dy.shape[0] * dy.shape[1] * dy.shape[2] * dy.shape[3] * r * s * ctot, e0,
+        _PROFILER.end("conv_wgrad_kernel", 2.0 * alg_scale * (d.groups or 1) * dy.shape[0] * dy.shape[1] * dy.shape[2] * dy.shape[3] * r * s * ctot, e0,
                       f"N{dy.shape[0]} {dy.shape[1]}x{dy.shape[2]} src{[t.shape[3] for t in srcs]} -> {dy.shape[3]} k{r}")
     return dw
 

@@ -42,7 +42,7 @@ def pack_conv_weight(w, dtype, mode=0, ld=0, out=None):
 
 
 def conv2d_fwd(srcs, weight, cout, r, s, pad_h, pad_w, *, out=None, out_dtype=None, bias=None, relu=False,
-               residual=None, w_ld=0, w_rows=0, w_rows_per_img=0, w_mn_major=False, gelu=False, oscale=None, groups=None):
+               residual=None, w_ld=0, w_rows=0, w_rows_per_img=0, w_mn_major=False, gelu=False, oscale=None, groups=None, alg_scale=1.0):
     if groups is not None and groups[0] > 1:
         # all heads in one launch: group g = the same call on views shifted by the per-group strides
         ng, sa, sw, so = groups
@@ -95,7 +95,7 @@ def conv2d_fwd(srcs, weight, cout, r, s, pad_h, pad_w, *, out=None, out_dtype=No
     return y.contiguous()
 
 
-def conv2d_wgrad(srcs, dy, r, s, pad_h, pad_w, dw, groups=None):
+def conv2d_wgrad(srcs, dy, r, s, pad_h, pad_w, dw, groups=None, alg_scale=1.0):
     if groups is not None and groups[0] > 1:
         # all heads in one launch: group g = the same call on views shifted by the per-group strides
         ng, sx, sdy, sdw = groups
