@@ -14,123 +14,24 @@
 #include "../../include/gdl_b200.h"
 #include "common.cuh"
 #include "det_reduce.cuh"
+#include "loss_cfg.cuh"
 
 namespace gdl {
-
-constexpr int kLossMaxK = 32;
-
-// stats layout (floats): [0] nll_sum [1] smooth_sum [2] valid_count [3] total_count
-//                        [4 + c] inter_c   [4 + K + c] card_c   [4 + 2K + c] tsum_c
-// coeff layout (floats): [0] loss  [1] ce_denominator  [2 + c] dice_a_c (dL/dp_c for t=0)
-//                        [2 + K + c] dice_b_c (dL/dp_c for t=1)
-struct LossCfg {
-  int K;
-  int binary;         // K == 1: sigmoid instead of softmax
-  long long ignore_index;
-  int has_ignore;
-  float w_ce, w_dice;
-  float label_smoothing;
-  int ce_mean_over_all;  // smp SoftCrossEntropyLoss: mean over all pixels
-  float dice_smooth, dice_eps;
-};
-
-template <typename TT>
-GDL_DEVINL long long load_target(const TT* t, long long i) {
-  return (long long)t[i];
-}
 
 template <int KMAX, typename TT>
 __global__ void seg_loss_stats_kernel(const float* __restrict__ logits, int ld, const TT* __restrict__ target,
                                       long long M, LossCfg cfg, float* __restrict__ stats, const DetCtx det) {
   const int K = cfg.K;
-  // per-warp partials, added in warp order (no shared-memory atomics: their arrival order is not reproducible)
-  __shared__ float shw[8][4 + 3 * kLossMaxK];  // blockDim.x == 256
-  float nll = 0.f, smooth = 0.f, valid = 0.f, total = 0.f;
-  float inter[KMAX], card[KMAX], tsum[KMAX];
-#pragma unroll
-  for (int c = 0; c < KMAX; ++c) inter[c] = card[c] = tsum[c] = 0.f;
-
+  LossAcc<KMAX> acc;
+  acc.init();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < M;
        i += (long long)gridDim.x * blockDim.x) {
-    const long long t = load_target(target, i);
-    const bool ign = cfg.has_ignore && t == cfg.ignore_index;
     float z[KMAX];
 #pragma unroll
     for (int c = 0; c < KMAX; ++c) z[c] = c < K ? logits[i * ld + c] : -INFINITY;
-    total += 1.f;
-    if (cfg.binary) {
-      // p = sigmoid(z) computed as exp(logsigmoid(z)) like smp
-      const float ls = fminf(z[0], 0.f) - log1pf(expf(-fabsf(z[0])));
-      const float p = expf(ls);
-      if (!ign) {
-        const float tt = t != 0 ? 1.f : 0.f;
-        inter[0] += p * tt;
-        card[0] += p + tt;
-        tsum[0] += tt;
-        // BCE-with-logits as the "ce" term
-        nll += -(tt * ls + (1.f - tt) * (ls - z[0]));
-        valid += 1.f;
-      }
-    } else {
-      float mx = z[0];
-#pragma unroll
-      for (int c = 1; c < KMAX; ++c) mx = fmaxf(mx, z[c]);
-      float se = 0.f;
-#pragma unroll
-      for (int c = 0; c < KMAX; ++c) se += c < K ? expf(z[c] - mx) : 0.f;
-      const float lse = mx + logf(se);
-      if (!ign) {
-        float sl = 0.f;
-#pragma unroll
-        for (int c = 0; c < KMAX; ++c) {
-          if (c < K) {
-            const float lp = z[c] - lse;
-            const float p = expf(lp);
-            const float tt = (t == c) ? 1.f : 0.f;
-            inter[c] += p * tt;
-            card[c] += p + tt;
-            tsum[c] += tt;
-            sl += -lp;
-            if (t == c) nll += -lp;
-          }
-        }
-        smooth += sl;
-        valid += 1.f;
-      }
-    }
+    acc.add(z, load_target(target, i), cfg);
   }
-  // block reduction: warp shuffles (fixed tree), then the 8 warps' partials in warp order
-  const int wid = threadIdx.x >> 5;
-  nll = warp_sum(nll);
-  smooth = warp_sum(smooth);
-  valid = warp_sum(valid);
-  total = warp_sum(total);
-  if ((threadIdx.x & 31) == 0) {
-    shw[wid][0] = nll;
-    shw[wid][1] = smooth;
-    shw[wid][2] = valid;
-    shw[wid][3] = total;
-  }
-#pragma unroll
-  for (int c = 0; c < KMAX; ++c) {
-    if (c < K) {
-      const float a = warp_sum(inter[c]), b = warp_sum(card[c]), d = warp_sum(tsum[c]);
-      if ((threadIdx.x & 31) == 0) {
-        shw[wid][4 + c] = a;
-        shw[wid][4 + K + c] = b;
-        shw[wid][4 + 2 * K + c] = d;
-      }
-    }
-  }
-  __syncthreads();
-  const int nvals = 4 + 3 * K;
-  for (int i = threadIdx.x; i < nvals; i += blockDim.x) {
-    float v = 0.f;
-    for (int w = 0; w < 8; ++w) v += shw[w][i];
-    if (det.s0 != nullptr) det_put(det, nvals, i, v);
-    else atomicAdd(&stats[i], v);
-  }
-  if (det.s0 != nullptr) det_finish(det, nvals, stats);
+  acc.commit(cfg, stats, det);
 }
 
 __global__ void seg_loss_finalize_kernel(const float* __restrict__ stats, LossCfg cfg, float* __restrict__ coeff) {
@@ -178,57 +79,8 @@ __global__ void seg_loss_bwd_kernel(const float* __restrict__ logits, int ld, co
     const bool ign = cfg.has_ignore && t == cfg.ignore_index;
     float z[KMAX], d[KMAX];
 #pragma unroll
-    for (int c = 0; c < KMAX; ++c) {
-      z[c] = c < K ? logits[i * ld + c] : -INFINITY;
-      d[c] = 0.f;
-    }
-    if (!ign) {
-      if (cfg.binary) {
-        const float p = 1.f / (1.f + expf(-z[0]));
-        const float tt = t != 0 ? 1.f : 0.f;
-        float g = 0.f;
-        if (cfg.w_ce != 0.f) g += cfg.w_ce * (p - tt) * inv_denom;
-        if (cfg.w_dice != 0.f) g += cfg.w_dice * (tt > 0.f ? coeff[2 + K] : coeff[2]) * p * (1.f - p);
-        d[0] = g;
-      } else {
-        float mx = z[0];
-#pragma unroll
-        for (int c = 1; c < KMAX; ++c) mx = fmaxf(mx, z[c]);
-        float p[KMAX];
-        float se = 0.f;
-#pragma unroll
-        for (int c = 0; c < KMAX; ++c) {
-          p[c] = c < K ? expf(z[c] - mx) : 0.f;
-          se += p[c];
-        }
-        const float inv = 1.f / se;
-        float dot = 0.f;
-        float dldp[KMAX];
-#pragma unroll
-        for (int c = 0; c < KMAX; ++c) {
-          p[c] *= inv;
-          dldp[c] = 0.f;
-          if (c < K && cfg.w_dice != 0.f) {
-            dldp[c] = cfg.w_dice * ((t == c) ? coeff[2 + K + c] : coeff[2 + c]);
-            dot += dldp[c] * p[c];
-          }
-        }
-        const float eps = cfg.label_smoothing;
-#pragma unroll
-        for (int c = 0; c < KMAX; ++c) {
-          if (c < K) {
-            float g = 0.f;
-            if (cfg.w_ce != 0.f) {
-              // d/dz [ (1-eps) * nll + eps/K * sum_c(-log p_c) ] = p - (1-eps) onehot - eps/K
-              const float tt = (t == c) ? 1.f : 0.f;
-              g += cfg.w_ce * (p[c] - (1.f - eps) * tt - eps / (float)K) * inv_denom;
-            }
-            if (cfg.w_dice != 0.f) g += p[c] * (dldp[c] - dot);
-            d[c] = g;
-          }
-        }
-      }
-    }
+    for (int c = 0; c < KMAX; ++c) z[c] = c < K ? logits[i * ld + c] : -INFINITY;
+    loss_pixel_grad<KMAX>(z, t, ign, cfg, coeff, inv_denom, d);
 #pragma unroll
     for (int c = 0; c < KMAX; ++c) {
       if (c < K) {
@@ -343,18 +195,18 @@ __global__ void clip_coef_kernel(const float* __restrict__ sumsq, float max_norm
   scale[0] = c < 1.f ? c : 1.f;
 }
 
-}  // namespace gdl
-
-using namespace gdl;
-
-static int loss_blocks(long long M) {
+int loss_blocks(long long M) {
   long long b = (M + 255) / 256;
   if (b > 4 * kNumSMsB200) b = 4 * kNumSMsB200;
   return (int)(b < 1 ? 1 : b);
 }
 
-static int make_cfg(LossCfg* c, int K, long long ignore_index, int has_ignore, float w_ce, float w_dice,
-                    float label_smoothing, int ce_mean_over_all, float dice_smooth, float dice_eps) {
+void launch_loss_finalize(const float* stats, const LossCfg& cfg, float* coeff, cudaStream_t s) {
+  seg_loss_finalize_kernel<<<1, 32, 0, s>>>(stats, cfg, coeff);
+}
+
+int make_cfg(LossCfg* c, int K, long long ignore_index, int has_ignore, float w_ce, float w_dice,
+             float label_smoothing, int ce_mean_over_all, float dice_smooth, float dice_eps) {
   GDL_REQUIRE(K >= 1 && K <= kLossMaxK, GDL_ERR_UNSUPPORTED, "loss: number of classes %d outside [1,%d]", K, kLossMaxK);
   c->K = K;
   c->binary = K == 1;
@@ -368,6 +220,10 @@ static int make_cfg(LossCfg* c, int K, long long ignore_index, int has_ignore, f
   c->dice_eps = dice_eps;
   return 0;
 }
+
+}  // namespace gdl
+
+using namespace gdl;
 
 // target_kind: 0 = int64, 1 = uint8
 extern "C" int gdl_seg_loss_fwd(const float* logits, int ld, const void* target, int target_kind, long long M,

@@ -14,6 +14,7 @@
 #include "../../include/gdl_b200.h"
 #include "common.cuh"
 #include "det_reduce.cuh"
+#include "bilinear.cuh"
 
 namespace gdl {
 
@@ -599,16 +600,6 @@ __global__ void __launch_bounds__(kDwThreads) dwconv_bwd_dw_kernel(const T* __re
 // bilinear resize, align_corners=False (F.interpolate(mode="bilinear"), segformer.py:51-57,
 // segformer_mlp.py:88-119).  Source index rule of ATen: src = scale*(dst+0.5)-0.5, clamped at 0.
 // ------------------------------------------------------------------------------------------
-GDL_DEVINL void bil_src(int dst, float scale, int in_size, int& i0, int& i1, float& l0, float& l1) {
-  float src = scale * ((float)dst + 0.5f) - 0.5f;
-  if (src < 0.f) src = 0.f;
-  i0 = (int)src;
-  if (i0 > in_size - 1) i0 = in_size - 1;
-  i1 = i0 < in_size - 1 ? i0 + 1 : i0;
-  l1 = src - (float)i0;
-  l0 = 1.f - l1;
-}
-
 template <typename T>
 __global__ void bilinear_fwd_kernel(const T* __restrict__ x, long long ldx, T* __restrict__ y, long long ldy, int N,
                                     int Hi, int Wi, int Ho, int Wo, int C, float sh, float sw) {
@@ -626,8 +617,8 @@ __global__ void bilinear_fwd_kernel(const T* __restrict__ x, long long ldx, T* _
     bil_src(ho, sh, Hi, h0, h1, a0, a1);
     bil_src(wo, sw, Wi, w0, w1, b0, b1);
     const T* base = x + n * Hi * Wi * ldx + c;
-    const float v = a0 * (b0 * to_f<T>(base[((long long)h0 * Wi + w0) * ldx]) + b1 * to_f<T>(base[((long long)h0 * Wi + w1) * ldx])) +
-                    a1 * (b0 * to_f<T>(base[((long long)h1 * Wi + w0) * ldx]) + b1 * to_f<T>(base[((long long)h1 * Wi + w1) * ldx]));
+    const float v = bil_mix(a0, a1, b0, b1, to_f<T>(base[((long long)h0 * Wi + w0) * ldx]), to_f<T>(base[((long long)h0 * Wi + w1) * ldx]),
+                            to_f<T>(base[((long long)h1 * Wi + w0) * ldx]), to_f<T>(base[((long long)h1 * Wi + w1) * ldx]));
     y[((n * Ho + ho) * Wo + wo) * ldy + c] = from_f<T>(v);
   }
 }
@@ -657,21 +648,12 @@ __global__ void bilinear_fwd_vec8_kernel(const T* __restrict__ x, long long ldx,
     ld8(base + ((long long)h1 * Wi + w0) * ldx, f10);
     ld8(base + ((long long)h1 * Wi + w1) * ldx, f11);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) o[j] = a0 * (b0 * f00[j] + b1 * f01[j]) + a1 * (b0 * f10[j] + b1 * f11[j]);
+    for (int j = 0; j < 8; ++j) o[j] = bil_mix(a0, a1, b0, b1, f00[j], f01[j], f10[j], f11[j]);
     st8(y + ((n * Ho + ho) * Wo + wo) * ldy + c0, o);
   }
 }
 
 // gather-form adjoint: dx[n,hi,wi,c] = sum over output pixels whose taps touch (hi,wi)
-GDL_DEVINL void bil_range(int i, float scale, int out_size, int& lo, int& hi) {
-  // outputs d with floor(src(d)) in {i-1, i}: src(d) in [i-1, i+1)  ->  d in [(i-0.5)/scale-0.5, (i+1.5)/scale-0.5)
-  float a = ((float)i - 0.5f) / scale - 0.5f, b = ((float)i + 1.5f) / scale - 0.5f;
-  lo = (int)floorf(a) - 1;
-  hi = (int)ceilf(b) + 1;
-  if (lo < 0) lo = 0;
-  if (hi > out_size - 1) hi = out_size - 1;
-}
-
 template <typename T>
 __global__ void bilinear_bwd_kernel(const T* __restrict__ dy, long long ldy, T* __restrict__ dx, long long ldx, int N,
                                     int Hi, int Wi, int Ho, int Wo, int C, float sh, float sw) {

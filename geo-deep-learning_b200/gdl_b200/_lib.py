@@ -126,6 +126,9 @@ _SIGS = {
     "gdl_seg_loss_fwd": [_VP, _I, _VP, _I, _LL, _I, _LL, _I, _F, _F, _F, _I, _F, _F, _VP, _VP, _VP],
     "gdl_seg_loss_bwd": [_VP, _I, _VP, _I, _LL, _I, _LL, _I, _F, _F, _F, _I, _F, _F, _VP, _VP, _VP, _I, _I, _VP],
     "gdl_argmax_classes": [_VP, _I, _LL, _I, _F, _VP, _VP],
+    "gdl_upsample_ce_fwd": [_VP, _I, _I, _I, _I, _I, _I, _VP, _I, _I, _LL, _I, _F, _F, _F, _I, _F, _F, _VP, _VP, _VP],
+    "gdl_upsample_ce_bwd": [_VP, _I, _I, _I, _I, _I, _I, _VP, _I, _I, _LL, _I, _F, _F, _F, _I, _F, _F, _VP, _VP, _VP, _I, _I, _VP],
+    "gdl_upsample_argmax": [_VP, _I, _I, _I, _I, _I, _I, _I, _F, _VP, _VP],
     "gdl_argmax_confusion": [_VP, _I, _LL, _LL, _I, _F, _VP, _I, _LL, _I, _VP, _VP, _VP],
     "gdl_adam_step": [_VP, _VP, _VP, _VP, _LL, _F, _F, _F, _F, _F, _I, _VP, _VP],
     "gdl_adam_step_dev": [_VP, _VP, _VP, _VP, _LL, _F, _F, _F, _F, _F, _VP, _VP, _VP],

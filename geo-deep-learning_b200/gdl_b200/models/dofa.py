@@ -564,17 +564,30 @@ class DOFASegmentationModel(UperNetSegmentor):
         else:
             feats = [Act(f, needs_grad=False) for f in self.encoder._features_nhwc(x16, c, self.wavelengths)]
         image_size = tuple(x16.shape[1:3])
-        o, a = self.run(eng, feats, image_size)
+        fused = bool(ops.option("fused_head"))
+        o, a = self.run(eng, feats, image_size, upsample=not fused)
         if getattr(self, "_aux_w", None) is None or self._aux_w.device != o.device:
             self._aux_w = torch.full((1,), 0.4, dtype=torch.float32, device=o.device)
-        co, _ = ops.seg_loss_fwd(o, target, spec)
-        ca, _ = ops.seg_loss_fwd(a, target, spec)
-        d_o, d_a = torch.empty_like(o), torch.empty_like(a)
         # grad_scale: the trainer's fp16 loss scale S (device scalar): d(out) *= S, d(aux) *= 0.4 S
-        ops.seg_loss_bwd(o, target, spec, co, grad_scale, d_o)
         aux_scale = self._aux_w if grad_scale is None else self._aux_w * grad_scale.to(self._aux_w.dtype)
-        ops.seg_loss_bwd(a, target, spec, ca, aux_scale, d_a)
-        self.backward(eng, d_o, d_a)
+        if fused:
+            # the two bilinear resizes to the image size (models/segmentation/dofa.py:90-105) are fused with the loss:
+            # neither (N,H,W,K) map nor its gradient is materialised
+            co, _ = ops.upsample_ce_fwd(o, target, spec)
+            ca, _ = ops.upsample_ce_fwd(a, target, spec)
+            kp = (o.shape[3] + 15) // 16 * 16
+            d_o = torch.zeros((*o.shape[:3], kp), dtype=eng.dtype, device=o.device)
+            d_a = torch.zeros((*a.shape[:3], kp), dtype=eng.dtype, device=a.device)
+            ops.upsample_ce_bwd(o, target, spec, co, grad_scale, d_o)
+            ops.upsample_ce_bwd(a, target, spec, ca, aux_scale, d_a)
+            self.backward(eng, d_o, d_a, lowres16=True)
+        else:
+            co, _ = ops.seg_loss_fwd(o, target, spec)
+            ca, _ = ops.seg_loss_fwd(a, target, spec)
+            d_o, d_a = torch.empty_like(o), torch.empty_like(a)
+            ops.seg_loss_bwd(o, target, spec, co, grad_scale, d_o)
+            ops.seg_loss_bwd(a, target, spec, ca, aux_scale, d_a)
+            self.backward(eng, d_o, d_a)
         if train_enc:
             self.encoder.backward(eng)
         return co[0] + 0.4 * ca[0]

@@ -379,9 +379,10 @@ class SegFormer(nn.Module):
                 if g_ is not None:
                     eng.grad_buffer(p_, False).copy_(g_)
 
-    def run(self, eng: Engine, x: Act, bands: int | None = None) -> torch.Tensor:
+    def run(self, eng: Engine, x: Act, bands: int | None = None, upsample: bool = True) -> torch.Tensor:
         """x: NHWC 16-bit image (channels possibly zero padded; `bands` = the real channel count, needed by the dynamic
-        encoder).  Returns fp32 logits (N,H,W,K)."""
+        encoder).  Returns fp32 logits (N,H,W,K); with upsample=False the decoder's own (N,H/4,W/4,K) map, for the fused
+        upsample + loss / argmax head (ops.upsample_ce_*, ops.upsample_argmax)."""
         enc, dec = self.encoder, self.decoder
         dims, heads, depths, emb = MIT_CFG[self.name]
         dt = eng.dtype
@@ -436,7 +437,7 @@ class SegFormer(nn.Module):
         z = eng.bn_act(rc_fuse, bn_state, relu=True)  # registers its own backward on the tape
         z = eng.dropout2d(z, self.dropout_ratio, self.dropout_mask)  # nn.Dropout2d before linear_pred (train mode only)
         rc_pred = eng.conv_raw([z], dec.linear_pred.weight, 1, 0, bias=dec.linear_pred.bias, out_dtype=acc)
-        logits = ops.bilinear_fwd(rc_pred.x, hh, ww)
+        logits = ops.bilinear_fwd(rc_pred.x, hh, ww) if upsample else rc_pred.x
         eng.named = {f"c{s + 1}": stages[s].feat for s in range(4)}
         self._saved = _Saved(stages=stages, projs=projs, rc_pred=rc_pred, z=z, h1=h1, w1=w1, hh=hh, ww=ww)
         return logits
@@ -526,13 +527,46 @@ class SegFormer(nn.Module):
         eng.conv_backward(sv.rc_q, dq.view(b, h, w, c), dgrad_residual=other)
         return self._take(sv.act_a)
 
-    def backward(self, eng: Engine, dlogits: torch.Tensor) -> None:
-        """dlogits: fp32 (N,H,W,K) gradient of the loss w.r.t. the logits returned by run()."""
+    def fused_train(self, eng: Engine, x16: torch.Tensor, bands: int, target: torch.Tensor, spec,
+                    grad_scale: torch.Tensor | None = None) -> torch.Tensor:
+        """FusedTrainer hook: normalised NHWC tiles -> loss, gradients left in the engine's destination buffers.  The final
+        bilinear x4 (segformer.py:47-57) is fused with the loss: the (N,H,W,K) logits and their gradient never exist."""
+        lr = self.run(eng, Act(x16, needs_grad=False), bands, upsample=not ops.option("fused_head"))
+        n, h, w, k = lr.shape
+        if not ops.option("fused_head"):
+            coeff, _ = ops.seg_loss_fwd(lr, target, spec)
+            d = torch.empty_like(lr)
+            ops.seg_loss_bwd(lr, target, spec, coeff, grad_scale, d)
+            self.backward(eng, d)
+            return coeff[0]
+        coeff, _ = ops.upsample_ce_fwd(lr, target, spec)
+        d16 = torch.zeros((n, h, w, (k + 15) // 16 * 16), dtype=eng.dtype, device=lr.device)
+        ops.upsample_ce_bwd(lr, target, spec, coeff, grad_scale, d16)
+        self.backward(eng, None, d16_lowres=d16)
+        return coeff[0]
+
+    @torch.no_grad()
+    def predict_classes(self, img: torch.Tensor, threshold: float = 0.5) -> torch.Tensor:
+        """Eval post-processing of the reference's validation / test steps (segmentation_segformer.py:268-271,288-291):
+        softmax(dim=1).argmax(dim=1) (K == 1: sigmoid > threshold) of forward(img), as ONE pass over the low-resolution
+        logits — (N,H,W) int64 class map."""
+        ops.require_cuda(img, "gdl_b200.SegFormer")
+        eng = Engine(self.compute_dtype, training=False, wcache=self._wcache)
+        lr = self.run(eng, self._input(img), img.shape[1], upsample=False)
+        self._saved = None
+        return ops.upsample_argmax(lr, img.shape[2], img.shape[3], threshold)
+
+    def backward(self, eng: Engine, dlogits: torch.Tensor | None, d16_lowres: torch.Tensor | None = None) -> None:
+        """dlogits: fp32 (N,H,W,K) gradient of the loss w.r.t. the logits returned by run(); or d16_lowres: the 16-bit,
+        16-channel-padded gradient w.r.t. the low-resolution logits (fused head)."""
         S = self._saved
         dt = eng.dtype
-        k = dlogits.shape[3]
-        d128 = ops.bilinear_bwd(dlogits, S.h1, S.w1)
-        d16 = ops.normalize_to_nhwc(d128, False, dt, (k + 15) // 16 * 16)
+        if d16_lowres is not None:
+            d16 = d16_lowres
+        else:
+            k = dlogits.shape[3]
+            d128 = ops.bilinear_bwd(dlogits, S.h1, S.w1)
+            d16 = ops.normalize_to_nhwc(d128, False, dt, (k + 15) // 16 * 16)
         eng.conv_backward(S.rc_pred, d16)
         eng.backward()  # linear_fuse BN/ReLU + the fuse GEMM: registers gradients on the 4 projections
         feat_grads: list[list[torch.Tensor]] = [[] for _ in range(4)]

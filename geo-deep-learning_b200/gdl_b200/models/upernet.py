@@ -93,8 +93,9 @@ class UperNetSegmentor(nn.Module):
         self._wcache: dict = {}
         self.sync_bn_group = None
 
-    def run(self, eng: Engine, feats: list[Act], image_size: tuple[int, int]):
-        """feats: 4 NHWC 16-bit encoder maps. Returns fp32 logits (out, aux), both (N, H, W, K)."""
+    def run(self, eng: Engine, feats: list[Act], image_size: tuple[int, int], upsample: bool = True):
+        """feats: 4 NHWC 16-bit encoder maps. Returns fp32 logits (out, aux), both (N, H, W, K); with upsample=False the two
+        heads' own low-resolution maps (for the fused upsample + loss / argmax head)."""
         if len(feats) != len(self.neck.in_channels):
             raise ValueError(f"len(inputs) must be equal to len(in_channels), but got {len(feats)} and {len(self.neck.in_channels)}")
         cb = eng.conv_bn_relu
@@ -129,13 +130,19 @@ class UperNetSegmentor(nn.Module):
         rc_aux = eng.conv_raw([a], self.aux_head.cls_seg.weight, 1, 0, bias=self.aux_head.cls_seg.bias, out_dtype=acc)
         self._saved = (rc_out, rc_aux)
         eng.named = {f"neck{i}": nf[i] for i in range(4)} | {"fpn": y}
+        if not upsample:
+            return rc_out.x, rc_aux.x
         return ops.bilinear_fwd(rc_out.x, *image_size), ops.bilinear_fwd(rc_aux.x, *image_size)
 
-    def backward(self, eng: Engine, d_out: torch.Tensor, d_aux: torch.Tensor | None) -> None:
-        """d_out / d_aux: fp32 (N,H,W,K) gradients of the loss w.r.t. the two logit maps."""
+    def backward(self, eng: Engine, d_out: torch.Tensor | None, d_aux: torch.Tensor | None, lowres16: bool = False) -> None:
+        """d_out / d_aux: fp32 (N,H,W,K) gradients of the loss w.r.t. the two logit maps; with lowres16 they are the 16-bit,
+        16-channel-padded gradients w.r.t. the heads' low-resolution maps (fused head)."""
         rc_out, rc_aux = self._saved
         for rc, d in ((rc_out, d_out), (rc_aux, d_aux)):
             if d is None:
+                continue
+            if lowres16:
+                eng.conv_backward(rc, d)
                 continue
             k = d.shape[3]
             dl = ops.bilinear_bwd(d, rc.x.shape[1], rc.x.shape[2])

@@ -103,7 +103,10 @@ def set_conv_profiler(p: ConvProfiler | None) -> None:
 _HOST_OPTS = {"pixel_pack": int(os.environ.get("GDL_PIXEL_PACK", "1")), "sra_fused": int(os.environ.get("GDL_SRA_FUSED", "1")),
               "mha_flash": int(os.environ.get("GDL_MHA_FLASH", "1")),
               # attn_wgrad_grouped: dV / dK of all attention heads as one grouped wgrad launch each (instead of 2 x heads launches)
-              "attn_wgrad_grouped": int(os.environ.get("GDL_ATTN_WGRAD_GROUPED", "1"))}
+              "attn_wgrad_grouped": int(os.environ.get("GDL_ATTN_WGRAD_GROUPED", "1")),
+              # fused_head: the fused trainer never materialises the upsampled (N,H,W,K) logits of SegFormer / UperNet heads:
+              # gdl_upsample_ce_fwd / _bwd interpolate them on the fly (training); eval masks come from gdl_upsample_argmax
+              "fused_head": int(os.environ.get("GDL_FUSED_HEAD", "1"))}
 
 
 def option(name: str) -> int:
@@ -482,6 +485,36 @@ def seg_loss_bwd(logits, target, spec: LossSpec, coeff, grad_scale, dlogits) -> 
     _ck(L.load().gdl_seg_loss_bwd(L.ptr(logits), logits.stride(2), L.ptr(target), _target_kind(target),
                                       _rows(logits), k, *spec.args(), L.ptr(coeff), L.ptr(grad_scale), L.ptr(dlogits),
                                       dlogits.stride(2), L.dt_code(dlogits.dtype), L.stream_ptr()))
+
+
+def upsample_ce_fwd(logits_lr: torch.Tensor, target: torch.Tensor, spec: LossSpec):
+    """Loss of bilinear(logits_lr -> target's H x W) against target without materialising the upsampled logits.
+    logits_lr fp32 (N,h,w,K) NHWC; target (N,H,W) int64 / uint8.  Returns (coeff, stats) as seg_loss_fwd."""
+    n, h, w, k = logits_lr.shape
+    hh, ww = target.shape[1:3]
+    stats = torch.empty(4 + 3 * k, dtype=torch.float32, device=logits_lr.device)
+    coeff = torch.empty(2 + 2 * k, dtype=torch.float32, device=logits_lr.device)
+    _ck(L.load().gdl_upsample_ce_fwd(L.ptr(logits_lr), logits_lr.stride(2), n, h, w, hh, ww, L.ptr(target),
+                                     _target_kind(target), k, *spec.args(), L.ptr(stats), L.ptr(coeff), L.stream_ptr()))
+    return coeff, stats
+
+
+def upsample_ce_bwd(logits_lr, target, spec: LossSpec, coeff, grad_scale, dlogits_lr) -> None:
+    """dlogits_lr (N,h,w,>=K) fp32 or 16-bit: d(loss)/d(logits_lr) [* grad_scale]; channels >= K are not written."""
+    n, h, w, k = logits_lr.shape
+    hh, ww = target.shape[1:3]
+    _ck(L.load().gdl_upsample_ce_bwd(L.ptr(logits_lr), logits_lr.stride(2), n, h, w, hh, ww, L.ptr(target),
+                                     _target_kind(target), k, *spec.args(), L.ptr(coeff), L.ptr(grad_scale),
+                                     L.ptr(dlogits_lr), dlogits_lr.stride(2), L.dt_code(dlogits_lr.dtype), L.stream_ptr()))
+
+
+def upsample_argmax(logits_lr: torch.Tensor, hh: int, ww: int, threshold: float = 0.5) -> torch.Tensor:
+    """argmax over classes (K == 1: sigmoid > threshold) of bilinear(logits_lr -> hh x ww): (N,hh,ww) int64."""
+    n, h, w, k = logits_lr.shape
+    out = torch.empty((n, hh, ww), dtype=torch.int64, device=logits_lr.device)
+    _ck(L.load().gdl_upsample_argmax(L.ptr(logits_lr), logits_lr.stride(2), n, h, w, hh, ww, k, float(threshold),
+                                     L.ptr(out), L.stream_ptr()))
+    return out
 
 
 def argmax_classes(logits: torch.Tensor, threshold: float = 0.5) -> torch.Tensor:

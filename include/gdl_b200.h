@@ -286,6 +286,27 @@ int gdl_seg_loss_bwd(const float* logits, int ld, const void* target, int target
 int gdl_argmax_classes(const float* logits, int ld, long long M, int K, float threshold, long long* out,
                        void* stream);
 
+/* ---- fused head: bilinear upsample (align_corners=False) + loss / argmax, SURVEY.md 8(b) gdl_upsample_ce_* ----------
+ * Replaces  F.interpolate(logits, size=image.shape[2:], mode="bilinear", align_corners=False)
+ * (models/segmentation/segformer.py:47-57, models/segmentation/dofa.py:90-105) FOLLOWED BY the loss of training_step
+ * (tasks_with_models/segmentation_segformer.py:218-243; CrossEntropy / smp Dice / SoftCE as gdl_seg_loss_*) or by
+ * softmax(dim=1).argmax(dim=1) | sigmoid > threshold (segmentation_segformer.py:268-271,288-291).  The (N,K,H,W) fp32
+ * logits are never materialised: each full-resolution pixel is interpolated from its 4 low-resolution taps in registers.
+ * logits_lr: fp32 NHWC [N][h][w][ld] (ld >= K); target [N][H][W] (target_kind 0 = int64, 1 = uint8); stats / coeff as
+ * gdl_seg_loss_fwd (coeff[0] = loss).  _bwd writes d(loss)/d(logits_lr) * grad_scale[0] as [N][h][w][ldd] of
+ * out_dtype (channels >= K are left untouched: pre-zero a padded operand); gather form, no atomics. */
+int gdl_upsample_ce_fwd(const float* logits_lr, int ld, int N, int h, int w, int H, int W, const void* target,
+                        int target_kind, int K, long long ignore_index, int has_ignore, float w_ce, float w_dice,
+                        float label_smoothing, int ce_mean_over_all, float dice_smooth, float dice_eps, float* stats,
+                        float* coeff, void* stream);
+int gdl_upsample_ce_bwd(const float* logits_lr, int ld, int N, int h, int w, int H, int W, const void* target,
+                        int target_kind, int K, long long ignore_index, int has_ignore, float w_ce, float w_dice,
+                        float label_smoothing, int ce_mean_over_all, float dice_smooth, float dice_eps,
+                        const float* coeff, const float* grad_scale, void* dlogits_lr, int ldd, int out_dtype,
+                        void* stream);
+int gdl_upsample_argmax(const float* logits_lr, int ld, int N, int h, int w, int H, int W, int K, float threshold,
+                        long long* out, void* stream);
+
 /* The same post-processing fused with the confusion counts of the evaluation metric: torchmetrics
  * `MeanIoU(num_classes, per_class=True, input_format="index")` as used by the three tasks' test_step
  * (segmentation_segformer.py:78-92,283-296) reduces per-SAMPLE intersection / union counts, so the counts are kept per

@@ -407,6 +407,25 @@ def argmax_classes(logits, threshold=0.5):
     return logits.argmax(3) if logits.shape[3] > 1 else (logits[..., 0].sigmoid() > threshold).long()
 
 
+# fused head (upsample_head.cu): bilinear upsample + loss / argmax = the unfused emulations composed
+def upsample_ce_fwd(logits_lr, target, spec):
+    up = bilinear_fwd(logits_lr, *target.shape[1:3])
+    coeff, _ = seg_loss_fwd(up, target, spec)
+    _LOSS_GRADS[id(coeff)] = (up, _LOSS_GRADS.pop(id(coeff)))
+    return coeff, None
+
+
+def upsample_ce_bwd(logits_lr, target, spec, coeff, grad_scale, dlogits_lr):
+    up, grad = _LOSS_GRADS.pop(id(coeff))
+    n, h, w, k = logits_lr.shape
+    s = grad_scale[0] if grad_scale is not None else 1.0
+    dlogits_lr[..., :k] = bilinear_bwd(grad * s, h, w).to(dlogits_lr.dtype)
+
+
+def upsample_argmax(logits_lr, hh, ww, threshold=0.5):
+    return argmax_classes(bilinear_fwd(logits_lr, hh, ww), threshold)
+
+
 def argmax_confusion(logits, target, threshold=0.5, ignore_index=None, want_classes=True):
     n, h, w, k = logits.shape
     kc = 2 if k == 1 else k

@@ -20,7 +20,7 @@ ROOT = HERE.parent.parent
 CSRC = Path(os.environ.get("GDL_HOSTEMU_CSRC", ROOT / "geo-deep-learning_b200" / "csrc"))
 OUT = Path(os.environ.get("GDL_HOSTEMU_OUT", HERE / "_build"))
 SOURCES = ["runtime.cu", "elementwise.cu", "transformer.cu", "loss_optim.cu", "augment_metrics.cu",
-           "igemm_conv.cu", "conv3x3_rows.cu", "wgrad3x3_rows.cu", "debug_probe.cu", "sra_attention.cu"]
+           "igemm_conv.cu", "conv3x3_rows.cu", "wgrad3x3_rows.cu", "debug_probe.cu", "sra_attention.cu", "upsample_head.cu"]
 # PTX wrappers of common.cuh whose bodies are forwarded to the functional model in hostemu_tc.cpp
 TC_FORWARD = ["smem_u32", "elect_one", "mbar_init", "mbar_expect_tx", "mbar_arrive", "mbar_try_wait", "tma_load_2d", "tma_load_4d",
               "tma_store_4d", "named_bar_sync", "tmem_alloc", "tmem_dealloc", "umma_f16", "umma_commit", "tmem_ld_32x32b_x16"]
@@ -29,7 +29,7 @@ TC_NOP = ["fence_mbar_init", "fence_proxy_async_smem", "tma_prefetch_desc", "tme
 # bulk-group bookkeeping of the TMA stores (template <int N> wait_group[.read] N)
 TC_BULK = {"bulk_commit_group": "hostemu::tc::bulk_commit_group()", "bulk_wait_group_read": "hostemu::tc::bulk_wait_group(N)",
            "bulk_wait_group": "hostemu::tc::bulk_wait_group(N)"}
-HEADERS = ["common.cuh", "tmap.cuh", "det_reduce.cuh"]
+HEADERS = ["common.cuh", "tmap.cuh", "det_reduce.cuh", "bilinear.cuh", "loss_cfg.cuh"]
 CUDA_INC = "/usr/local/cuda/include"
 
 

@@ -79,8 +79,8 @@ def test_grad_gather_sums_reproducible(cuda, n, h, w, c, nsrc, up):
 def test_loss_statistics_reproducible(cuda, k, binary):
     from gdl_b200 import ops
     g = torch.Generator().manual_seed(k)
-    logits = torch.randn(4, 96, 96, k, generator=g).cuda()
-    t = torch.randint(0, max(k, 2), (4, 96, 96), generator=g).cuda()
+    logits = torch.randn(2, 64, 48, k, generator=g).cuda()
+    t = torch.randint(0, max(k, 2), (2, 64, 48), generator=g).cuda()
     spec = ops.LossSpec(1.0, 0.5, label_smoothing=0.1, ignore_index=-100)
     (c1, s1), (c2, s2) = _twice(lambda: ops.seg_loss_fwd(logits, t, spec))
     assert torch.equal(c1, c2) and torch.equal(s1, s2)
@@ -101,7 +101,7 @@ def test_grad_norm_reproducible(cuda):
     assert _tickets_at_rest()
 
 
-@pytest.mark.parametrize("m,c", [(16 * 1024, 64), (4 * 256, 512), (5000, 320)])
+@pytest.mark.parametrize("m,c", [(4 * 1024, 64), (4 * 256, 512), (1500, 320)])
 def test_layernorm_param_grads_reproducible(cuda, m, c):
     from gdl_b200 import ops
     g = torch.Generator().manual_seed(m)
