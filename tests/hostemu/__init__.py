@@ -132,8 +132,8 @@ def run_case(name: str, fname: str, kw: dict, tmp_path=None) -> None:
         kwargs["tmp_path"] = tmp_path
     # module-level pytest fixtures (option switches with a teardown) are driven by hand
     mod, teardown = load_test_module(name), []
-    for pname in sig.parameters:
-        if pname in kwargs:
+    for pname, par in sig.parameters.items():
+        if pname in kwargs or par.default is not inspect.Parameter.empty:
             continue
         fx = getattr(mod, pname, None)
         raw = getattr(fx, "_get_wrapped_function", None)

@@ -115,12 +115,12 @@ def test_vit_token_kernels(cuda):
     assert torch.equal(feat, tok[:, 1:].bfloat16())
 
 
-def test_dofa_segmentation_train_step(cuda):
+def test_dofa_segmentation_train_step(cuda, img=224, bands=3, batch=4, wavelengths=(0.665, 0.56, 0.49)):
     """DOFASegmentationModel (frozen encoder) forward + backward through autograd vs the oracle on the same maps."""
     from gdl_b200.models.dofa import DOFASegmentationModel
     from oracle import dofa as od, upernet as ou
     torch.manual_seed(0)
-    k, img = 5, 224
+    k = 5
     m = DOFASegmentationModel("dofa_base", (img, img), ["encoder"], k).cuda().train()
     with torch.no_grad():
         for n_, p in m.named_parameters():
@@ -130,9 +130,9 @@ def test_dofa_segmentation_train_step(cuda):
                 p.add_(0.1 * torch.randn_like(p))
     assert not any(p.requires_grad for p in m.encoder.parameters())
     gen = torch.Generator().manual_seed(3)
-    x = torch.randn(4, 3, img, img, generator=gen).cuda()
-    wl = torch.tensor([0.665, 0.56, 0.49]).cuda()
-    t = torch.randint(0, k, (4, img, img), generator=gen).cuda()
+    x = torch.randn(batch, bands, img, img, generator=gen).cuda()
+    wl = torch.tensor(list(wavelengths)).cuda()
+    t = torch.randint(0, k, (batch, img, img), generator=gen).cuda()
 
     def sd_copy():
         return {n: (v.detach().clone().requires_grad_(True)
@@ -170,4 +170,4 @@ def test_dofa_segmentation_train_step(cuda):
     m.eval()
     with torch.no_grad():
         ev = m(x, wl)
-    assert ev.out.shape == (4, k, img, img) and ev.aux.shape == (4, k, img, img)
+    assert ev.out.shape == (batch, k, img, img) and ev.aux.shape == (batch, k, img, img)
