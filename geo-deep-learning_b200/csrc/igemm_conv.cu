@@ -28,7 +28,7 @@ namespace gdl {
 static int g_opt_conv_halo = -1, g_opt_wgrad_halo = -1, g_opt_conv_epilogue = -1, g_opt_conv_rows = -1;
 int conv3x3_rows_try(const gdl_conv_fwd_t* d, cudaStream_t stream, int* status);  // conv3x3_rows.cu
 int wgrad3x3_rows_try(const gdl_conv_wgrad_t* d, cudaStream_t stream, int* status);  // wgrad3x3_rows.cu
-static int g_opt_wgrad_rows = -1;
+static int g_opt_wgrad_rows = -1, g_opt_wgrad_sched = -1;
 static long long g_opt_wgrad_l2_mb = -1;
 static int opt_int(int& slot, const char* env, int dflt) {
   if (slot < 0) {
@@ -680,6 +680,7 @@ extern "C" int gdl_set_option(const char* name, long long value) {
   else if (!strcmp(name, "wgrad_l2_mb")) g_opt_wgrad_l2_mb = value;
   else if (!strcmp(name, "conv_rows")) g_opt_conv_rows = (int)value;
   else if (!strcmp(name, "wgrad_rows")) g_opt_wgrad_rows = (int)value;
+  else if (!strcmp(name, "wgrad_sched")) g_opt_wgrad_sched = (int)value;  // 1: few long units (one epilogue per CTA); 0: round-1 rule
   else if (!strcmp(name, "deterministic")) g_opt_deterministic = (int)value;  // 1 (default): ordered reductions when a workspace is registered
   else if (!strcmp(name, "sra_max_ctas")) g_opt_sra_max_ctas = (int)value;  // 0 = one CTA per SM (tests: fewer, longer CTAs)
   else {
@@ -1295,6 +1296,9 @@ extern "C" int gdl_conv2d_nhwc_wgrad(const gdl_conv_wgrad_t* d, void* stream_) {
   p.pb_per_img = p.tiles_w * p.tiles_h;
   p.dw_ld = d->dw_ld > 0 ? d->dw_ld : (long long)d->R * d->S * Ctot;
   p.dw_img_stride = d->dw_img_stride;
+  const DetWs ws = det_workspace();
+  p.tile_floats = (long long)p.nsub * 128 * bn_max;  // one partial accumulator tile (ordered mode)
+  const long long max_units_ws = ws.ok() ? ws.slot_floats / p.tile_floats : (1ll << 40);
   if (d->batched) {
     // one independent product per image: split each image's pixel blocks on its own
     GDL_REQUIRE(!(d->R == 1 && d->S == 1 && d->pad_h == 0 && d->pad_w == 0) || N == d->N, GDL_ERR_INVALID, "batched wgrad");
@@ -1303,6 +1307,7 @@ extern "C" int gdl_conv2d_nhwc_wgrad(const gdl_conv_wgrad_t* d, void* stream_) {
     int max_ks = p.pb_per_img / 8;
     if (max_ks < 1) max_ks = 1;
     if (ks > max_ks) ks = max_ks;
+    while (ks > 1 && bu * ks * G > max_units_ws) --ks;  // ordered mode: the partial tiles must fit the workspace
     if (ks < 1) ks = 1;
     p.pb_per_split = (p.pb_per_img + ks - 1) / ks;
     p.ksplit = (p.pb_per_img + p.pb_per_split - 1) / p.pb_per_split;
@@ -1311,12 +1316,32 @@ extern "C" int gdl_conv2d_nhwc_wgrad(const gdl_conv_wgrad_t* d, void* stream_) {
     p.num_units = (int)units;
   }
   long long base_units = (long long)p.m_tiles * nn * taps;
-  // Split the pixel range: (a) the grid should see >= ~3 waves; (b) the pixels one wave of co-resident
-  // units streams (dY + X rows of one split) should stay L2-resident so the 9 taps / channel tiles that
-  // share them hit in L2 (budget GDL_WGRAD_L2_MB, default 8 MB: measured best of 8/24/64 on B200); (c) keep >= 32 stages of MMA work per
-  // unit so the red.global epilogue stays a small fraction.
-  int ks = (int)((3ll * sm_count() + base_units - 1) / base_units);
-  {
+  int ks = 1;
+  if (opt_int(g_opt_wgrad_sched, "GDL_WGRAD_SCHED", 1) > 0) {
+    // Round 2: few LONG units.  Split the pixel range into as few pieces as keep every SM busy: with base_units * ks <= #SM
+    // each CTA owns one (tile, pixel range) for the whole launch and accumulates it in TMEM — ONE epilogue per CTA instead of
+    // one per ~64-pixel-block unit (the round-1 rule below produced up to ~4600 units per launch: as many bytes of fp32
+    // reductions as operand bytes, and, in ordered mode, that many partial tiles).  CTAs of one pixel range run in lockstep
+    // (equal work per pixel block), so the range is still read from HBM once and shared through L2.  When base_units
+    // exceeds the SM count, ks is the split with the smallest makespan  ceil(base_units * ks / #SM) / ks.
+    const int sms = sm_count();
+    int max_ks = p.pix_blocks / 16;
+    if (max_ks > 64) max_ks = 64;
+    if (max_ks < 1) max_ks = 1;
+    double best = 1e30;
+    for (int g = 1; g <= max_ks; ++g) {
+      const long long units = base_units * g;
+      if (g > 1 && units > max_units_ws) break;
+      const double cost = (double)((units + sms - 1) / sms) / g;
+      if (cost < best * 0.97) {
+        best = cost;
+        ks = g;
+      }
+    }
+  } else {
+    // Round-1 rule: (a) the grid should see >= ~3 waves; (b) the pixels one wave of co-resident units streams (dY + X rows
+    // of one split) should stay L2-resident (budget GDL_WGRAD_L2_MB, default 8 MB); (c) keep >= 32 stages of MMA work per unit.
+    ks = (int)((3ll * sm_count() + base_units - 1) / base_units);
     if (g_opt_wgrad_l2_mb < 0) {
       const char* e = getenv("GDL_WGRAD_L2_MB");
       g_opt_wgrad_l2_mb = e ? atoll(e) : 8;
@@ -1327,10 +1352,11 @@ extern "C" int gdl_conv2d_nhwc_wgrad(const gdl_conv_wgrad_t* d, void* stream_) {
     if (pb_budget < 32) pb_budget = 32;
     int ks_l2 = (int)((p.pix_blocks + pb_budget - 1) / pb_budget);
     if (ks_l2 > ks) ks = ks_l2;
+    int max_ks = p.pix_blocks / 32;
+    if (max_ks < 1) max_ks = 1;
+    if (ks > max_ks) ks = max_ks;
+    while (ks > 1 && base_units * ks > max_units_ws) --ks;  // ordered mode: the partial tiles must fit the workspace
   }
-  int max_ks = p.pix_blocks / 32;
-  if (max_ks < 1) max_ks = 1;
-  if (ks > max_ks) ks = max_ks;
   if (ks < 1) ks = 1;
   if (!d->batched) {
     p.pb_per_split = (p.pix_blocks + ks - 1) / ks;
@@ -1357,11 +1383,12 @@ extern "C" int gdl_conv2d_nhwc_wgrad(const gdl_conv_wgrad_t* d, void* stream_) {
   p.ab_fmt = d->dtype == GDL_BF16 ? 1 : 0;
   p.dw = d->dw;
 
-  const DetWs ws = det_workspace();
   if (p.ksplit > 1 && ws.ok()) {
     // several units add into the same dW tile: give every unit a partial tile and add them in split order afterwards
-    p.tile_floats = (long long)p.nsub * 128 * bn_max;
-    if ((long long)p.num_units * p.tile_floats <= ws.slot_floats) p.partials = ws.slots;
+    GDL_REQUIRE((long long)p.num_units * p.tile_floats <= ws.slot_floats, GDL_ERR_UNSUPPORTED,
+                "wgrad: %d partial tiles of %lld floats exceed the registered workspace (gdl_query_workspace_bytes)",
+                p.num_units, p.tile_floats);
+    p.partials = ws.slots;
   }
 
   int smem = p.stages * p.stage_bytes + 1024;
@@ -1445,6 +1472,61 @@ __global__ void pack_weight_kernel(const float* __restrict__ src, T* __restrict_
         r = t / S;
       }
       v = src[(((long long)k * Cin + c) * R + r) * S + s];
+    }
+    if constexpr (std::is_same<T, __nv_bfloat16>::value)
+      dst[i] = __float2bfloat16_rn(v);
+    else
+      dst[i] = __float2half_rn(v);
+  }
+}
+
+// All packed operands of a model in ONE launch (after the optimizer step of the fused trainer: the fp32 masters changed,
+// the cached 16-bit operands are refreshed in place).  Entry e covers chunks [chunk0[e], chunk0[e+1]) of kRepackChunk
+// elements; a block finds its entry by binary search.
+constexpr int kRepackChunk = 4096;
+template <typename T>
+__global__ void __launch_bounds__(256) repack_weights_kernel(const gdl_repack_t* __restrict__ table, const int* __restrict__ chunk0,
+                                                              int n_entries) {
+  int lo = 0, hi = n_entries;  // last entry with chunk0[e] <= blockIdx.x
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (chunk0[mid] <= (int)blockIdx.x) lo = mid;
+    else hi = mid;
+  }
+  const gdl_repack_t e = table[lo];
+  const int Cout = e.Cout, Cin = e.Cin, R = e.R, S = e.S, mode = e.mode, dst_ld = e.dst_ld;
+  const int rows = mode == 0 ? Cout : (mode == 1 ? Cin : R * S * Cin);
+  const int cols = mode == 0 ? R * S * Cin : (mode == 1 ? R * S * Cout : Cout);
+  const long long total = (long long)rows * dst_ld;
+  const long long base = (long long)((int)blockIdx.x - chunk0[lo]) * kRepackChunk;
+  const float* __restrict__ src = e.src;
+  T* __restrict__ dst = reinterpret_cast<T*>(e.dst);
+  for (long long i = base + threadIdx.x; i < base + kRepackChunk && i < total; i += blockDim.x) {
+    const int row = (int)(i / dst_ld);
+    const int col = (int)(i - (long long)row * dst_ld);
+    float v = 0.f;
+    if (col < cols) {
+      int k, c, r, s2;
+      if (mode == 0) {
+        k = row;
+        c = col % Cin;
+        const int t = col / Cin;
+        s2 = t % S;
+        r = t / S;
+      } else if (mode == 1) {
+        c = row;
+        k = col % Cout;
+        const int t = col / Cout;
+        s2 = S - 1 - (t % S);
+        r = R - 1 - (t / S);
+      } else {
+        k = col;
+        c = row % Cin;
+        const int t = row / Cin;
+        s2 = t % S;
+        r = t / S;
+      }
+      v = src[(((long long)k * Cin + c) * R + r) * S + s2];
     }
     if constexpr (std::is_same<T, __nv_bfloat16>::value)
       dst[i] = __float2bfloat16_rn(v);
@@ -1574,6 +1656,18 @@ extern "C" int gdl_pack_conv_weight(const float* src, void* dst, int Cout, int C
   else
     pack_weight_kernel<__half><<<blocks, 256, 0, (cudaStream_t)stream>>>(src, (__half*)dst, Cout, Cin, R, S,
                                                                         mode, rows, cols, dst_ld);
+  GDL_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int gdl_repack_weights(const gdl_repack_t* table_dev, const int* chunk0_dev, int n_entries, int total_chunks,
+                                  int dtype, void* stream) {
+  GDL_REQUIRE(table_dev && chunk0_dev && n_entries > 0 && total_chunks > 0, GDL_ERR_INVALID, "repack_weights: bad args");
+  GDL_REQUIRE(dtype == GDL_BF16 || dtype == GDL_F16, GDL_ERR_INVALID, "repack_weights: dtype");
+  if (dtype == GDL_BF16)
+    repack_weights_kernel<__nv_bfloat16><<<total_chunks, 256, 0, (cudaStream_t)stream>>>(table_dev, chunk0_dev, n_entries);
+  else
+    repack_weights_kernel<__half><<<total_chunks, 256, 0, (cudaStream_t)stream>>>(table_dev, chunk0_dev, n_entries);
   GDL_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

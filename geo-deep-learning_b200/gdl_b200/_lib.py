@@ -76,6 +76,12 @@ class ConvWgrad(C.Structure):
     ]
 
 
+class Repack(C.Structure):
+    """gdl_repack_t: one packed operand of the batched refresh (gdl_repack_weights)"""
+    _fields_ = [("src", C.c_void_p), ("dst", C.c_void_p), ("Cout", C.c_int), ("Cin", C.c_int), ("R", C.c_int),
+                ("S", C.c_int), ("mode", C.c_int), ("dst_ld", C.c_int)]
+
+
 def lib_path() -> Path:
     return _LIB_PATH
 
@@ -162,6 +168,7 @@ _SIGS = {
     "gdl_add_nhwc": [_VP, _LL, _VP, _LL, _VP, _LL, _I, _LL, _I, _VP],
     "gdl_debug_shift_probe": [_VP, _VP, _VP, _I, _I, _I, _VP],
     "gdl_set_workspace": [_VP, _LL, _VP],
+    "gdl_repack_weights": [_VP, _VP, _I, _I, _I, _VP],
 }
 
 

@@ -78,6 +78,43 @@ class BNState:
     count: int = 0
 
 
+def refresh_packed_weights(wcache: dict) -> bool:
+    """The owner of `wcache` changed parameters in place BEHIND torch's version counters (the fused trainer's flat-buffer
+    Adam): bring every cached 16-bit operand up to date in place — one gdl_repack_weights launch for the plain packings,
+    then the few derived operands (zero-padded dgrad weights, block-Toeplitz widenings, tiled biases) — instead of dropping
+    the cache and re-packing ~150-200 weights one launch at a time at the start of the next step.  Cached tensors keep their
+    addresses, so a captured CUDA graph stays valid.  Returns False when the cache holds nothing refreshable."""
+    items = [(k, v) for k, v in wcache.items() if isinstance(k, tuple) and isinstance(v, tuple) and len(v) == 3]
+    if not items:
+        return False
+    plain = [(v[2][1], v[1], *v[2][1].shape, v[2][2], v[2][3]) for _, v in items if v[2][0] == "plain"]
+    # plain entries of one cache share the engine's dtype; group defensively
+    by_dtype: dict = {}
+    for e in plain:
+        by_dtype.setdefault(e[1].dtype, []).append(e)
+    for dt, entries in by_dtype.items():
+        sig = tuple((e[0].data_ptr(), e[1].data_ptr()) for e in entries)
+        pk = ("__repack_plan__", dt)
+        old = wcache.get(pk)
+        plan = old[1] if old is not None and old[0] == sig else None
+        plan = ops.repack_weights(entries, plan)
+        wcache[pk] = (sig, plan)
+    with torch.no_grad():
+        for _, v in items:  # padded dgrad weights first: widenings may read them
+            if v[2][0] == "dgrad_pad":
+                _, wv, wpad, cout = v[2]
+                wpad[:cout].copy_(wv)
+                ops.pack_conv_weight(wpad, v[1].dtype, 1, out=v[1])
+        for _, v in items:
+            if v[2][0] == "wide":
+                _, src, co, ci, r, f = v[2]
+                ops.widen_conv_weight(src, co, ci, r, f, out=v[1])
+            elif v[2][0] == "tiled_bias":
+                _, bias, f = v[2]
+                v[1].copy_(bias.detach().to(v[1].dtype).repeat(f))
+    return True
+
+
 class Engine:
     def __init__(self, dtype: torch.dtype = torch.bfloat16, training: bool = True, wcache: dict | None = None,
                  grad_dst: dict[int, torch.Tensor] | None = None, sync_bn_group=None,
@@ -98,7 +135,8 @@ class Engine:
 
     # ------------------------------------------------------------------ parameters
     def packed(self, w: torch.Tensor, mode: int, ld: int = 0, wshape: tuple | None = None) -> torch.Tensor:
-        """16-bit operand of a weight, cached until the parameter is modified in place."""
+        """16-bit operand of a weight, cached until the parameter is modified in place (torch's version counter) — or
+        refreshed in place by refresh_packed_weights() when the owner updates parameters behind that counter."""
         key = (w.data_ptr(), mode, ld, self.dtype)
         ver = w._version
         hit = self._wcache.get(key)
@@ -108,7 +146,7 @@ class Engine:
         if wshape is not None:
             wv = wv.view(wshape)
         out = ops.pack_conv_weight(wv, self.dtype, mode, ld)
-        self._wcache[key] = (ver, out)
+        self._wcache[key] = (ver, out, ("plain", wv, mode, out.stride(0)))
         return out
 
     def packed_wide(self, w: torch.Tensor, mode: int, f: int, wshape: tuple, coutp: int = 0) -> torch.Tensor:
@@ -120,10 +158,11 @@ class Engine:
             return hit[1]
         cout, cin, r, _ = wshape
         if mode == 0:
-            out = ops.widen_conv_weight(self.packed(w, 0, 0, wshape), cout, cin, r, f)
+            src, co, ci = self.packed(w, 0, 0, wshape), cout, cin
         else:
-            out = ops.widen_conv_weight(self._dgrad_weight(w, coutp or cout, wshape), cin, coutp or cout, r, f)
-        self._wcache[key] = (w._version, out)
+            src, co, ci = self._dgrad_weight(w, coutp or cout, wshape), cin, coutp or cout
+        out = ops.widen_conv_weight(src, co, ci, r, f)
+        self._wcache[key] = (w._version, out, ("wide", src, co, ci, r, f))
         return out
 
     def _tiled_bias(self, bias: torch.Tensor, f: int) -> torch.Tensor:
@@ -132,7 +171,7 @@ class Engine:
         if hit is not None and hit[0] == bias._version:
             return hit[1]
         out = bias.detach().to(self.acc_dtype).repeat(f)
-        self._wcache[key] = (bias._version, out)
+        self._wcache[key] = (bias._version, out, ("tiled_bias", bias, f))
         return out
 
     @staticmethod
@@ -267,7 +306,7 @@ class Engine:
         wpad = torch.zeros((coutp, *wshape[1:]), dtype=self.acc_dtype, device=w.device)
         wpad[:cout] = w.detach().view(wshape)
         out = ops.pack_conv_weight(wpad, self.dtype, 1)
-        self._wcache[key] = (w._version, out)
+        self._wcache[key] = (w._version, out, ("dgrad_pad", w.detach().view(wshape), wpad, cout))
         return out
 
     # ------------------------------------------------------------------ batch norm

@@ -270,11 +270,37 @@ def unpack_conv_wgrad(dw: torch.Tensor, out_oihw: torch.Tensor, src_ld: int = 0,
     return out_oihw
 
 
-def widen_conv_weight(wp: torch.Tensor, co: int, ci: int, r: int, f: int) -> torch.Tensor:
+REPACK_CHUNK = 4096  # kRepackChunk of igemm_conv.cu
+
+
+def repack_weights(entries: list[tuple[torch.Tensor, torch.Tensor, int, int, int, int, int, int]], plan=None):
+    """Refresh every packed 16-bit operand in `entries` = [(fp32 OIHW master, packed out, Cout, Cin, R, S, mode, dst_ld)] from
+    its master in ONE launch (gdl_repack_weights).  Returns the device-side plan; pass it back while `entries` is unchanged."""
+    if not entries:
+        return plan
+    if plan is None:
+        tab = (L.Repack * len(entries))()
+        chunk0 = [0]
+        for i, (w, out, co, ci, r, s_, mode, ld) in enumerate(entries):
+            tab[i].src, tab[i].dst = w.data_ptr(), out.data_ptr()
+            tab[i].Cout, tab[i].Cin, tab[i].R, tab[i].S, tab[i].mode, tab[i].dst_ld = co, ci, r, s_, mode, ld
+            rows = co if mode == 0 else (ci if mode == 1 else r * s_ * ci)
+            chunk0.append(chunk0[-1] + (rows * ld + REPACK_CHUNK - 1) // REPACK_CHUNK)
+        dev = entries[0][1].device
+        raw = torch.frombuffer(bytearray(bytes(tab)), dtype=torch.uint8).to(dev)
+        plan = (raw, torch.tensor(chunk0, dtype=torch.int32, device=dev), len(entries), chunk0[-1],
+                L.dt_code(entries[0][1].dtype))
+    raw, chunk0_dev, n, total, dtc = plan
+    _ck(L.load().gdl_repack_weights(L.ptr(raw), L.ptr(chunk0_dev), n, total, dtc, L.stream_ptr()))
+    return plan
+
+
+def widen_conv_weight(wp: torch.Tensor, co: int, ci: int, r: int, f: int, out: torch.Tensor | None = None) -> torch.Tensor:
     """packed 16-bit [Co][R][3][Ci] -> block-Toeplitz [f*Co][R][3][f*Ci]: the same conv on (N,H,W/f,f*Ci) pixels"""
     if wp.shape != (co, r * 3 * ci) or not wp.is_contiguous():
         raise ValueError("widen_conv_weight: dense packed [Co][R*3*Ci] operand expected")
-    out = torch.empty((f * co, r * 3 * f * ci), dtype=wp.dtype, device=wp.device)
+    if out is None:
+        out = torch.empty((f * co, r * 3 * f * ci), dtype=wp.dtype, device=wp.device)
     _ck(L.load().gdl_widen_conv_weight(L.ptr(wp), L.ptr(out), co, ci, r, f, L.dt_code(wp.dtype), L.stream_ptr()))
     return out
 

@@ -11,7 +11,7 @@ import torch
 import torch.distributed as dist
 
 from . import ops
-from .engine import Act, Engine
+from .engine import Act, Engine, refresh_packed_weights
 from .ops import LossSpec
 
 
@@ -76,6 +76,7 @@ class FusedTrainer:
         # CUDA graph of the whole step (normalise .. Adam): removes the ~10 us/launch host cost of the
         # ~800-2000 launches of a step.  Captured lazily on the first step() with a given input shape.
         self.cuda_graph = cuda_graph
+        self.repack_in_place = True  # False: drop the packed-weight cache after every step (round-1 behaviour)
         self._graph = None
         self._static = None
         self._static_aug = None
@@ -155,7 +156,9 @@ class FusedTrainer:
         self.step_count += 1
         ops.adam_step_dev(self.flat, self.gflat, self.m, self.v, self.lr, self.betas[0], self.betas[1], self.eps,
                           self.weight_decay, self.adam_state, gs)
-        self.model._wcache.clear()  # parameters changed behind torch's version counters
+        # parameters changed behind torch's version counters: refresh the cached 16-bit operands in place (one launch)
+        if not self.repack_in_place or not refresh_packed_weights(self.model._wcache):
+            self.model._wcache.clear()
 
     def _eager_step(self, image_u8: torch.Tensor, target: torch.Tensor,
                     aug_params: torch.Tensor | None = None) -> torch.Tensor:

@@ -162,6 +162,20 @@ int gdl_conv2d_nhwc_wgrad(const gdl_conv_wgrad_t* d, void* stream);
  * dst is 16-bit (dtype); dst_ld = row stride in elements (0 = dense), pad columns are zeroed. */
 int gdl_pack_conv_weight(const float* src, void* dst, int Cout, int Cin, int R, int S, int mode,
                          int dst_ld, int dtype, void* stream);
+
+/* Every packed operand of a model refreshed in ONE launch (the fused trainer calls it after its Adam step instead of
+ * ~150-200 gdl_pack_conv_weight launches at the start of the next step; same element mapping as gdl_pack_conv_weight).
+ * table_dev: DEVICE array of n_entries descriptors; chunk0_dev: DEVICE int[n_entries + 1], chunk0[e] = first 4096-element
+ * chunk of entry e (prefix sums of ceil(rows * dst_ld / 4096)), chunk0[n_entries] = total_chunks. */
+typedef struct {
+  const float* src; /* fp32 OIHW master                                  */
+  void* dst;        /* 16-bit packed operand, rows x dst_ld              */
+  int Cout, Cin, R, S;
+  int mode;         /* 0 / 1 / 2 as gdl_pack_conv_weight                 */
+  int dst_ld;       /* row stride of dst (>= columns, zero padded)       */
+} gdl_repack_t;
+int gdl_repack_weights(const gdl_repack_t* table_dev, const int* chunk0_dev, int n_entries, int total_chunks, int dtype,
+                       void* stream);
 /* grad fp32 [Cout][src_ld] (columns (r,s,c), from wgrad) -> fp32 OIHW; dst = (accumulate? dst:0)+src */
 int gdl_unpack_conv_wgrad(const float* src, float* dst, int Cout, int Cin, int R, int S, int src_ld,
                           int accumulate, void* stream);

@@ -38,7 +38,17 @@ def pack_conv_weight(w, dtype, mode=0, ld=0, out=None):
     ld = ld or m.shape[1]
     o = torch.zeros(m.shape[0], ld, dtype=dtype)
     o[:, :m.shape[1]] = m.to(dtype)
+    if out is not None:
+        out.copy_(o)
+        return out
     return o
+
+
+def repack_weights(entries, plan=None):
+    """gdl_repack_weights: every cached packed operand refreshed in place from its fp32 master"""
+    for w, out, co, ci, r, s, mode, ld in entries:
+        pack_conv_weight(w, out.dtype, mode, ld, out=out)
+    return plan
 
 
 def conv2d_fwd(srcs, weight, cout, r, s, pad_h, pad_w, *, out=None, out_dtype=None, bias=None, relu=False,
@@ -128,7 +138,8 @@ def unpack_conv_wgrad(dw, out_oihw, src_ld=0, accumulate=False):
     return out_oihw
 
 
-def widen_conv_weight(wp, co, ci, r, f):
+def widen_conv_weight(wp, co, ci, r, f, out=None):
+    dst = out
     w = wp.reshape(co, r, 3, ci)
     out = torch.zeros(f, co, r, 3, f, ci, dtype=wp.dtype)
     for j in range(f):
@@ -137,7 +148,11 @@ def widen_conv_weight(wp, co, ci, r, f):
                 kx = f * (sx - 1) + jp - j + 1
                 if 0 <= kx < 3:
                     out[j, :, :, sx, jp, :] = w[:, :, kx, :]
-    return out.reshape(f * co, r * 3 * f * ci)
+    out = out.reshape(f * co, r * 3 * f * ci)
+    if dst is not None:
+        dst.copy_(out)
+        return dst
+    return out
 
 
 def fold_widened_wgrad(dw, out_oihw, f, accumulate=False):
