@@ -104,6 +104,9 @@ class ClockSampler:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
                                           "-i", str(self.gpu), "-lms", "100"], stdout=subprocess.PIPE, text=True)
             threading.Thread(target=self._read, daemon=True).start()
+            t0 = time.perf_counter()
+            while not self.rows and time.perf_counter() - t0 < 2.0:  # first sample in hand before the timed region starts
+                time.sleep(0.02)
         except OSError:
             self.proc = None
 
@@ -495,6 +498,11 @@ def _run_train(args, ctx, steps: int, warmup: int, headline: bool):
 
     for i in range(max(warmup, 2)):  # >= 2: the second step captures the graph
         step_resident(i)
+    if not headline:
+        # ride-along workloads: enough steps for ~1.5 s of timed work (nvidia-smi samples clocks every 100 ms); the
+        # headline times EXACTLY the --steps the driver asked for
+        t_one = timed(step_resident, 1)
+        steps = int(max(steps, min(60, 1500.0 / max(t_one, 1.0) + 1)))
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
