@@ -599,9 +599,9 @@ def _run_infer(args, ctx, steps: int, warmup: int, headline: bool):
     R = args.raster or w["raster"]
     torch.manual_seed(0)
     model = SegFormer(w["encoder"], in_channels=C, num_classes=K, compute_dtype=torch.bfloat16).to(dev).eval()
-    # --cuda-graph 2 replays the window-batch forward from a CUDA graph (default: eager launches, as validated)
+    # --cuda-graph 3 replays the window-batch forward from a CUDA graph (default: eager launches, as validated)
     seg = SlidingWindowSegmenter(model, tile=T, stride=T // 2, batch=B, mean=MEAN[:C], std=STD[:C],
-                                 cuda_graph=args.cuda_graph >= 2)
+                                 cuda_graph=args.cuda_graph >= 3)
     nwin = len(window_origins(R, T, T // 2)) ** 2
     g = torch.Generator().manual_seed(1234)  # the same raster on every rank
     host = torch.randint(0, 256, (R, R, C), generator=g, dtype=torch.uint8).pin_memory()
@@ -674,7 +674,7 @@ def _run_infer(args, ctx, steps: int, warmup: int, headline: bool):
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": {"workload": w["name"], "raster": [R, R, C], "windows": nwin, "window_batch": B,
                    "parallelism": f"windows round-robin over {world} rank(s) + one all-reduce of the logit sums",
-                   "cuda_graph": args.cuda_graph >= 2, "sra_fused": bool(ops.option("sra_fused")),
+                   "cuda_graph": args.cuda_graph >= 3, "sra_fused": bool(ops.option("sra_fused")),
                    "l2": f"raster {R * R * C / 1e6:.0f} MB and activations >> 126 MB L2"},
         "clocks": clk,
         "e2e": {"value": nwin * steps / (ms_e2e / 1e3), "unit": "tiles/s", "h2d_bytes_per_step": R * R * C,
@@ -701,7 +701,10 @@ def main() -> None:
     ap.add_argument("--batch", type=int, default=0, help="tiles per GPU (default: the workload's 32)")
     ap.add_argument("--sync-bn", type=int, default=1, help="SyncBatchNorm statistics when N > 1 (reference YAMLs: true)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cuda-graph", type=int, default=1, help="1: capture the whole step in a CUDA graph at N=1; 2: also at N>1 (NCCL collectives captured)")
+    ap.add_argument("--cuda-graph", type=int, default=2,
+                    help="0: eager launches; 1: capture the whole step in a CUDA graph at N=1 only; 2 (default): also at N>1, the NCCL "
+                         "collectives (SyncBN sums, flat-gradient all-reduce) captured with the kernels (validated at N=2: "
+                         "profiles/r02_run6_*)")
     ap.add_argument("--raster", type=int, default=0, help="segformer_b5_infer: raster side in pixels (default 10000)")
     ap.add_argument("--table", default="", help="write the per-launch conv profile (shape, ms, TFLOP/s) to this JSON file")
     ap.add_argument("--workload", default="unetpp_r50", choices=sorted(WORKLOADS))

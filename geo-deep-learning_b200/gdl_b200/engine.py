@@ -66,6 +66,8 @@ class RawConv:
     wshape: tuple | None = None  # (Cout, Cin, R, S) view of the parameter (nn.Linear weights are (Cout, Cin))
     bias: torch.Tensor | None = None
     pixel_packed: bool = False  # narrow 3x3 conv run as its pixel-packed (block-Toeplitz) equivalent
+    groups: int = 1             # grouped conv (ResNeXt): run as Cout / 64 dense 64 -> 64 convs over channel slices
+    cols: list | None = None    # grouped + strided: the im2col matrix of every 64-channel slice
 
 
 @dataclass
@@ -87,6 +89,11 @@ def refresh_packed_weights(wcache: dict) -> bool:
     items = [(k, v) for k, v in wcache.items() if isinstance(k, tuple) and isinstance(v, tuple) and len(v) == 3]
     if not items:
         return False
+    with torch.no_grad():
+        for _, v in items:  # slice-dense masters of grouped convs: rebuilt from the parameter before anything is packed from them
+            if v[2][0] == "slice_dense":
+                _, w, rows, idx = v[2]
+                v[1][rows, idx] = w.detach().to(v[1].dtype)
     plain = [(v[2][1], v[1], *v[2][1].shape, v[2][2], v[2][3]) for _, v in items if v[2][0] == "plain"]
     # plain entries of one cache share the engine's dtype; group defensively
     by_dtype: dict = {}
@@ -99,6 +106,9 @@ def refresh_packed_weights(wcache: dict) -> bool:
         plan = old[1] if old is not None and old[0] == sig else None
         plan = ops.repack_weights(entries, plan)
         wcache[pk] = (sig, plan)
+    for k, v in items:  # up to date with their masters as they are NOW (slice-dense masters were just rewritten in place)
+        if v[2][0] == "plain":
+            wcache[k] = (v[2][1]._version, v[1], v[2])
     with torch.no_grad():
         for _, v in items:  # padded dgrad weights first: widenings may read them
             if v[2][0] == "dgrad_pad":
@@ -239,6 +249,8 @@ class Engine:
         Weight (and bias) gradients go to grad_buffer; input gradients are registered as gradient sources on
         the source activations.  `dgrad_residual` is added to the (single-source) input gradient in the dgrad
         GEMM epilogue (sum of two gradient paths without an extra pass)."""
+        if rc.groups > 1:
+            return self._grouped_backward(rc, dx)
         w = rc.weight
         cout, cin, r, s = rc.wshape
         coutp = dx.shape[3]
@@ -308,6 +320,100 @@ class Engine:
         out = ops.pack_conv_weight(wpad, self.dtype, 1)
         self._wcache[key] = (w._version, out, ("dgrad_pad", w.detach().view(wshape), wpad, cout))
         return out
+
+    # ------------------------------------------------------------------ grouped convolution (ResNeXt)
+    GROUP_SLICE = 64  # channels per dense slice: 64 / (channels per group) groups side by side, block-diagonal weights
+
+    def _slice_dense(self, w: torch.Tensor, groups: int):
+        """Grouped weight (C, C/groups, R, S) -> fp32 "slice-dense" master (C, 64, R, S): output channel o reads the 64 input
+        channels of ITS 64-channel slice; entries outside o's group are zero.  Rows [64 j, 64 j + 64) are then the ordinary
+        dense OIHW weight of slice j (so the existing packers, kernels and the batched refresh apply unchanged)."""
+        key = (w.data_ptr(), "slice_dense", groups)
+        hit = self._wcache.get(key)
+        if hit is not None and hit[0] == w._version:
+            return hit[1], hit[2][2], hit[2][3]
+        c, cg, r, s = w.shape
+        sl = self.GROUP_SLICE
+        if c != cg * groups or c % sl or sl % cg:
+            raise NotImplementedError(f"grouped conv: {c} channels in {groups} groups of {cg} (needs C % 64 == 0, 64 % (C / groups) == 0, C_in == C_out)")
+        if hit is not None:
+            ws, rows, idx = hit[1], hit[2][2], hit[2][3]
+        else:
+            ws = torch.zeros((c, sl, r, s), dtype=self.acc_dtype, device=w.device)
+            o = torch.arange(c, device=w.device)
+            rows = o.view(c, 1)
+            idx = ((o % sl) // cg * cg).view(c, 1) + torch.arange(cg, device=w.device).view(1, cg)
+        with torch.no_grad():
+            ws[rows, idx] = w.detach().to(ws.dtype)  # in place: packed operands cached against ws._version are re-packed
+        self._wcache[key] = (w._version, ws, ("slice_dense", w, rows, idx))
+        return ws, rows, idx
+
+    def conv_raw_grouped(self, a: Act, weight: torch.nn.Parameter, groups: int, stride: int, pad: int) -> RawConv:
+        """nn.Conv2d(C, C, 3, stride, padding=1, groups=groups, bias=False) (torchvision ResNeXt Bottleneck.conv2) as C / 64
+        dense 64 -> 64 convolutions over channel slices of the NHWC tensors (block-diagonal inside a slice: a factor
+        64 / (C / groups) of padded MMA work, none for 32x8d's layer4)."""
+        c, cg, r, s = weight.shape
+        ws, _, _ = self._slice_dense(weight, groups)
+        sl = self.GROUP_SLICE
+        n, h, wd, cs = a.t.shape
+        if cs != c:
+            raise ValueError("grouped conv: input channel count mismatch")
+        ho, wo = (h + 2 * pad - r) // stride + 1, (wd + 2 * pad - s) // stride + 1
+        x = torch.empty((n, ho, wo, c), dtype=self.dtype, device=a.t.device)
+        scale = cg / sl
+        cols = None
+        if stride == 1:
+            wp = self.packed(ws, 0)  # [C][R*S*64]: rows of slice j = its dense operand
+            for j in range(c // sl):
+                ops.conv2d_fwd([a.t[..., j * sl:(j + 1) * sl]], wp[j * sl:(j + 1) * sl], sl, r, s, pad, pad,
+                               out=x[..., j * sl:(j + 1) * sl], alg_scale=scale)
+        else:
+            k = r * s * sl
+            wp = self.packed(ws, 0, k)
+            cols = []
+            for j in range(c // sl):
+                col = ops.im2col(a.t[..., j * sl:(j + 1) * sl], sl, r, s, stride, pad, k)
+                ops.conv2d_fwd([col], wp[j * sl:(j + 1) * sl], sl, 1, 1, 0, 0, out=x[..., j * sl:(j + 1) * sl], alg_scale=scale)
+                if self.training:
+                    cols.append(col)
+        return RawConv(x, [a], weight, stride, pad, cin_store=c, wshape=(c, cg, r, s), groups=groups, cols=cols, kpad=r * s * sl)
+
+    def _grouped_backward(self, rc: RawConv, dx: torch.Tensor) -> None:
+        w = rc.weight
+        c, cg, r, s = rc.wshape
+        sl = self.GROUP_SLICE
+        a = rc.srcs[0]
+        ws, rows, idx = self._slice_dense(w, rc.groups)
+        nsl = c // sl
+        dev = dx.device
+        scale = cg / sl
+        n, h, wd, _ = a.t.shape
+        if w.requires_grad:
+            dws = torch.zeros((c, r * s * sl), dtype=self.acc_dtype, device=dev)
+            for j in range(nsl):
+                sj = slice(j * sl, (j + 1) * sl)
+                if rc.cols is None:
+                    ops.conv2d_wgrad([a.t[..., sj]], dx[..., sj], r, s, rc.pad, rc.pad, dws[sj], alg_scale=scale)
+                else:
+                    ops.conv2d_wgrad([rc.cols[j]], dx[..., sj], 1, 1, 0, 0, dws[sj], alg_scale=scale)
+            dense = torch.empty((c, sl, r, s), dtype=self.acc_dtype, device=dev)
+            ops.unpack_conv_wgrad(dws, dense, r * s * sl)
+            self.grad_buffer(w, False).copy_(dense[rows, idx])  # the diagonal blocks = the grouped weight's gradient
+        if a.needs_grad:
+            dcat = torch.empty((n, h, wd, c), dtype=self.dtype, device=dev)
+            if rc.cols is None:
+                for j in range(nsl):
+                    sj = slice(j * sl, (j + 1) * sl)
+                    wt = self.packed(ws[sj], 1)  # [64][(R-1-r,S-1-s,k)] of slice j
+                    ops.conv2d_fwd([dx[..., sj]], wt, sl, r, s, r - 1 - rc.pad, s - 1 - rc.pad, out=dcat[..., sj], alg_scale=scale)
+            else:
+                for j in range(nsl):
+                    sj = slice(j * sl, (j + 1) * sl)
+                    wt = self.packed(ws[sj], 2)  # [(r,s,c)][64]
+                    dcol = ops.conv2d_fwd([dx[..., sj]], wt, r * s * sl, 1, 1, 0, 0, alg_scale=scale)
+                    dslice = ops.col2im(dcol, n, h, wd, sl, r, s, rc.stride, rc.pad)
+                    dcat[..., sj].copy_(dslice)
+            a.gsrcs.append((dcat, 0))
 
     # ------------------------------------------------------------------ batch norm
     def _allreduce(self, t: torch.Tensor) -> None:

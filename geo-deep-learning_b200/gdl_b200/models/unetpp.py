@@ -25,6 +25,11 @@ _RESNETS = {
     "resnet50": ("bottleneck", (3, 4, 6, 3), (64, 256, 512, 1024, 2048)),
     "resnet101": ("bottleneck", (3, 4, 23, 3), (64, 256, 512, 1024, 2048)),
     "resnet152": ("bottleneck", (3, 8, 36, 3), (64, 256, 512, 1024, 2048)),
+    # grouped 3x3 convolutions (torchvision ResNeXt: groups, width_per_group) — the encoder of the reference's shipped
+    # UNet++ YAML (configs/unetplus_config_RGB.yaml:37 `encoder: resnext101_32x8d`)
+    "resnext50_32x4d": ("bottleneck", (3, 4, 6, 3), (64, 256, 512, 1024, 2048), 32, 4),
+    "resnext101_32x4d": ("bottleneck", (3, 4, 23, 3), (64, 256, 512, 1024, 2048), 32, 4),
+    "resnext101_32x8d": ("bottleneck", (3, 4, 23, 3), (64, 256, 512, 1024, 2048), 32, 8),
 }
 DECODER_CHANNELS = (256, 128, 64, 32, 16)
 
@@ -51,13 +56,16 @@ class _BasicBlock(nn.Module):
 class _Bottleneck(nn.Module):
     expansion = 4
 
-    def __init__(self, inplanes: int, planes: int, stride: int) -> None:
+    def __init__(self, inplanes: int, planes: int, stride: int, groups: int = 1, base_width: int = 64) -> None:
         super().__init__()
-        self.conv1 = _conv(inplanes, planes, 1)
-        self.bn1 = nn.BatchNorm2d(planes)
-        self.conv2 = _conv(planes, planes, 3, stride, 1)  # torchvision "v1.5": stride on the 3x3
-        self.bn2 = nn.BatchNorm2d(planes)
-        self.conv3 = _conv(planes, planes * 4, 1)
+        width = int(planes * (base_width / 64.0)) * groups  # torchvision.models.resnet.Bottleneck
+        self.groups = groups
+        self.conv1 = _conv(inplanes, width, 1)
+        self.bn1 = nn.BatchNorm2d(width)
+        # torchvision "v1.5": stride on the 3x3; ResNeXt: `groups` independent 3x3 convs over width / groups channels each
+        self.conv2 = nn.Conv2d(width, width, 3, stride=stride, padding=1, groups=groups, bias=False)
+        self.bn2 = nn.BatchNorm2d(width)
+        self.conv3 = _conv(width, planes * 4, 1)
         self.bn3 = nn.BatchNorm2d(planes * 4)
         self.downsample = None
         if stride != 1 or inplanes != planes * 4:
@@ -72,9 +80,15 @@ class ResNetEncoder(nn.Module):
         super().__init__()
         if name not in _RESNETS:
             raise KeyError(f"Wrong encoder name `{name}`, supported encoders: {list(_RESNETS)}")
-        kind, layers, self.out_channels = _RESNETS[name]
+        kind, layers, self.out_channels = _RESNETS[name][:3]
+        groups, wpg = (_RESNETS[name][3:] + (1, 64))[:2] if len(_RESNETS[name]) > 3 else (1, 64)
         self.in_channels = in_channels
-        block = _BasicBlock if kind == "basic" else _Bottleneck
+        if kind == "basic":
+            block = _BasicBlock
+        else:
+            def block(inplanes: int, planes: int, stride: int) -> _Bottleneck:
+                return _Bottleneck(inplanes, planes, stride, groups, wpg)
+            block.expansion = _Bottleneck.expansion
         self.conv1 = _conv(in_channels, 64, 7, 2, 3)
         self.bn1 = nn.BatchNorm2d(64)
         inplanes = 64
@@ -166,7 +180,8 @@ class UnetPlusPlus(nn.Module):
         else:
             r1 = eng.conv_raw([x], blk.conv1.weight, 1, 0)
             a1 = eng.bn_act(r1, eng.bn_prepare(r1, _bnp(blk.bn1)))
-            r2 = eng.conv_raw([a1], blk.conv2.weight, blk.stride, 1)
+            r2 = (eng.conv_raw([a1], blk.conv2.weight, blk.stride, 1) if blk.groups == 1
+                  else eng.conv_raw_grouped(a1, blk.conv2.weight, blk.groups, blk.stride, 1))
             a2 = eng.bn_act(r2, eng.bn_prepare(r2, _bnp(blk.bn2)))
             last = eng.conv_raw([a2], blk.conv3.weight, 1, 0)
             last_bn = _bnp(blk.bn3)

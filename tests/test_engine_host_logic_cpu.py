@@ -34,7 +34,7 @@ def f64(monkeypatch):
     emu.set_work_dtype(torch.float32)
 
 
-@pytest.mark.parametrize("enc,cin,k", [("resnet18", 3, 5), ("resnet50", 4, 3)])
+@pytest.mark.parametrize("enc,cin,k", [("resnet18", 3, 5), ("resnet50", 4, 3), ("resnext50_32x4d", 3, 2)])
 def test_engine_backward_equals_oracle_autograd(monkeypatch, f64, enc, cin, k):
     from gdl_b200.engine import Act, Engine
     emu.install(monkeypatch)

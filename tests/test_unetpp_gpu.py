@@ -42,6 +42,8 @@ def _rel(a, b):
     ("resnet18", 3, 5, 128, torch.float16),
     ("resnet50", 4, 5, 128, torch.bfloat16),
     ("resnet34", 6, 2, 96, torch.bfloat16),
+    ("resnext50_32x4d", 3, 5, 128, torch.bfloat16),   # grouped 3x3 convs (32 groups of 4 / 8 / 16 / 32 channels)
+    ("resnext101_32x8d", 3, 5, 128, torch.bfloat16),  # the encoder of the reference's shipped YAML (unetplus_config_RGB.yaml:37)
 ])
 def test_train_step_parity(cuda, enc, cin, k, hw, dtype):
     ora, prod = _models(enc, cin, k, dtype=dtype)
