@@ -152,9 +152,10 @@ __global__ void adam_advance_kernel(float* __restrict__ state, float beta1, floa
 __global__ void adam_dev_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                                 float* __restrict__ v, long long n, float lr, float beta1, float beta2, float eps,
                                 float weight_decay, const float* __restrict__ state,
-                                const float* __restrict__ grad_scale) {
+                                const float* __restrict__ grad_scale, const float* __restrict__ lr_scale) {
   const float gsc = grad_scale ? grad_scale[0] : 1.f;
   const float bc1 = state[1], bc2_sqrt = state[2];
+  if (lr_scale != nullptr) lr *= lr_scale[0];  // learning-rate schedule as a device value: a captured graph follows it
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
        i += (long long)gridDim.x * blockDim.x) {
     float gi = g[i] * gsc;
@@ -323,13 +324,13 @@ extern "C" int gdl_adam_step(float* p, const float* g, float* m, float* v, long 
 
 extern "C" int gdl_adam_step_dev(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1,
                                  float beta2, float eps, float weight_decay, float* state /* 3 floats */,
-                                 const float* grad_scale, void* stream) {
+                                 const float* grad_scale, const float* lr_scale, void* stream) {
   GDL_REQUIRE(p && g && m && v && state && n > 0, GDL_ERR_INVALID, "adam_dev: bad args");
   cudaStream_t st = (cudaStream_t)stream;
   adam_advance_kernel<<<1, 1, 0, st>>>(state, beta1, beta2);
   long long b = (n + 255) / 256;
   if (b > 8 * kNumSMsB200) b = 8 * kNumSMsB200;
-  adam_dev_kernel<<<(int)b, 256, 0, st>>>(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, state, grad_scale);
+  adam_dev_kernel<<<(int)b, 256, 0, st>>>(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, state, grad_scale, lr_scale);
   GDL_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

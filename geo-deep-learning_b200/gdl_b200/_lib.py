@@ -137,7 +137,7 @@ _SIGS = {
     "gdl_upsample_argmax": [_VP, _I, _I, _I, _I, _I, _I, _I, _F, _VP, _VP],
     "gdl_argmax_confusion": [_VP, _I, _LL, _LL, _I, _F, _VP, _I, _LL, _I, _VP, _VP, _VP],
     "gdl_adam_step": [_VP, _VP, _VP, _VP, _LL, _F, _F, _F, _F, _F, _I, _VP, _VP],
-    "gdl_adam_step_dev": [_VP, _VP, _VP, _VP, _LL, _F, _F, _F, _F, _F, _VP, _VP, _VP],
+    "gdl_adam_step_dev": [_VP, _VP, _VP, _VP, _LL, _F, _F, _F, _F, _F, _VP, _VP, _VP, _VP],
     "gdl_grad_clip_coef": [_VP, _LL, _F, _VP, _VP, _VP],
     "gdl_device_info": [_VP, _VP, _VP, _VP],
     "gdl_set_option": [C.c_char_p, _LL],

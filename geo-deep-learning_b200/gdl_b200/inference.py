@@ -3,7 +3,8 @@
 The reference ships no such driver (`tools/script_model.py` only exports a traced model); the per-tile computation is
 exactly its eval path: `normalization` / `standardization` (utils/tensors.py:10-35) -> `model(x)` -> `softmax(dim=1)
 .argmax(dim=1)` (segmentation_segformer.py:268-271).  Overlapping windows are blended by summing the fp32 logits of every
-window that covers a pixel (argmax is invariant to the per-pixel window count, so no division is needed).
+window that covers a pixel (argmax is invariant to the per-pixel window count; a single-logit model is blended with the
+mean logit, so that `sigmoid > threshold` means the same for every threshold).
 
 Everything on the device runs on the kernels of libgdlb200.so: uint8 HWC -> 16-bit NHWC normalisation, the model's eval
 forward (`model.run` on an Engine with training=False), and the argmax kernel.  Host-side torch is used for the crop /
@@ -114,6 +115,13 @@ class SlidingWindowSegmenter:
             acc = torch.zeros((hp, wp, k), dtype=torch.float32, device=self.dev)
         if self.world > 1:
             dist.all_reduce(acc, group=self.group)
+        if acc.shape[2] == 1:
+            # one logit: sigmoid(sum) > threshold equals sigmoid(mean) > threshold only at threshold 0.5, so blend with
+            # the MEAN logit (divide by the number of windows covering the pixel); argmax (K > 1) is invariant to it
+            cnt = torch.zeros((hp, wp, 1), dtype=torch.float32, device=self.dev)
+            for y, x in wins:
+                cnt[y:y + t, x:x + t] += 1.0
+            acc = acc / cnt.clamp_(min=1.0)
         return acc[:h, :w]
 
     @torch.no_grad()

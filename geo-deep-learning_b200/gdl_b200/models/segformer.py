@@ -193,9 +193,12 @@ class SegFormer(nn.Module):
         self._wcache: dict = {}
         self.sync_bn_group = None
         self.last_engine: Engine | None = None
-        if freeze_layers:  # BaseSegmentationModel._freeze_layers (models/segmentation/base.py:29-44)
-            for n, p in self.named_parameters():
-                if any(layer in n for layer in freeze_layers):
+        if freeze_layers:
+            # BaseSegmentationModel._freeze_layers (models/segmentation/base.py:40-44), called by the reference BEFORE the
+            # decoder exists (models/segmentation/segformer.py:42-45): only encoder parameters can match — a pattern such as
+            # "proj" or "norm" must not freeze decoder.linear_c*.proj / linear_fuse / linear_pred
+            for n, p in self.encoder.named_parameters():
+                if any(layer in f"encoder.{n}" for layer in freeze_layers):
                     p.requires_grad = False
 
     # ====================================================================================== forward

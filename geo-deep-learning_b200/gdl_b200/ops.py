@@ -576,11 +576,12 @@ def adam_step(p, g, m, v, lr, beta1, beta2, eps, weight_decay, step, grad_scale=
                                    L.stream_ptr()))
 
 
-def adam_step_dev(p, g, m, v, lr, beta1, beta2, eps, weight_decay, state, grad_scale=None) -> None:
-    """Adam with the step counter / bias corrections kept on the device (`state`: 3 floats)."""
+def adam_step_dev(p, g, m, v, lr, beta1, beta2, eps, weight_decay, state, grad_scale=None, lr_scale=None) -> None:
+    """Adam with the step counter / bias corrections kept on the device (`state`: 3 floats); lr_scale: optional device
+    scalar multiplying lr (a scheduler's factor: read at run time, so a captured CUDA graph follows it)."""
     _ck(L.load().gdl_adam_step_dev(L.ptr(p), L.ptr(g), L.ptr(m), L.ptr(v), p.numel(), float(lr), float(beta1),
                                    float(beta2), float(eps), float(weight_decay), L.ptr(state), L.ptr(grad_scale),
-                                   L.stream_ptr()))
+                                   L.ptr(lr_scale), L.stream_ptr()))
 
 
 def grad_clip_coef(g, max_norm, scratch, scale) -> None:

@@ -11,6 +11,7 @@ import torch
 from torch import Tensor
 
 from ..models.dofa import DOFASegmentationModel, SegmentationOutput
+from . import _common
 from ._hooks import GpuSideHooks
 from .segmentation_segformer import SegmentationSegformer
 from .segmentation_unetplus import _Base, _strip_model_prefix
@@ -44,8 +45,9 @@ class SegmentationDOFA(GpuSideHooks, _Base):
                                            pretrained=self.pretrained, compute_dtype=self.compute_dtype,
                                            aux_dropout_ratio=0.1)  # FCNHead's Dropout2d default (fcn_head.py:24)
         if self.weights_from_checkpoint_path:
-            ckpt = torch.load(self.weights_from_checkpoint_path, map_location="cpu", weights_only=False)
-            self.model.load_state_dict(_strip_model_prefix(ckpt.get("state_dict", ckpt)))
+            _common.load_weights_from_checkpoint(self.model, self.weights_from_checkpoint_path,
+                                                 _common.hparam(self, "load_parts"),
+                                                 trust_pickle=bool(_common.hparam(self, "trust_checkpoint_pickle", False)))
 
     configure_optimizers = SegmentationSegformer.configure_optimizers
     _predict = SegmentationSegformer._predict

@@ -12,6 +12,7 @@ from torch import Tensor
 
 from .. import ops
 from ..models.segformer import SegFormer
+from . import _common
 from ._hooks import GpuSideHooks
 from .segmentation_unetplus import _Base, _strip_model_prefix
 
@@ -42,19 +43,22 @@ class SegmentationSegformer(GpuSideHooks, _Base):
     def configure_model(self) -> None:
         if self.model is not None:
             return
+        # `weights` reaches the model exactly as in the reference (segmentation_segformer.py:129-137): a pretrained request
+        # is refused loudly there instead of being dropped here
+        _common.check_pretrained_request(self.weights, "SegmentationSegformer")
         # the reference's train-mode regularisation: DropPath 0.1 in every MiT variant (mix_transformer.py:614-705) and
         # Dropout2d(0.1) in the MLP decoder (segformer_mlp.py:32,73)
-        self.model = SegFormer(self.encoder, self.in_channels, None, self.freeze_layers, self.num_classes,
+        self.model = SegFormer(self.encoder, self.in_channels, self.weights, self.freeze_layers, self.num_classes,
                                use_dynamic_encoder=self.use_dynamic_encoder, compute_dtype=self.compute_dtype,
                                drop_path_rate=0.1, dropout_ratio=0.1)
         if self.weights_from_checkpoint_path:
-            ckpt = torch.load(self.weights_from_checkpoint_path, map_location="cpu", weights_only=False)
-            self.model.load_state_dict(_strip_model_prefix(ckpt.get("state_dict", ckpt)))
+            _common.load_weights_from_checkpoint(self.model, self.weights_from_checkpoint_path,
+                                                 _common.hparam(self, "load_parts"),
+                                                 trust_pickle=bool(_common.hparam(self, "trust_checkpoint_pickle", False)))
 
     def configure_optimizers(self):
-        opt = self.optimizer(self.parameters())
-        sched = self.scheduler(opt) if callable(self.scheduler) else None
-        return [opt] if sched is None else ([opt], [{"scheduler": sched, **self.scheduler_config}])
+        """segmentation_segformer.py:150-199 (OneCycleLR horizon from the trainer; tasks/_common.py)"""
+        return _common.configure_optimizers(self)
 
     def forward(self, image: Tensor) -> Tensor:
         return self.model(image)

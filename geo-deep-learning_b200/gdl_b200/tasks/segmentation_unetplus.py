@@ -43,6 +43,7 @@ def _strip_model_prefix(sd: dict[str, Tensor]) -> dict[str, Tensor]:
     return {(k[len("model."):] if k.startswith("model.") else k): v for k, v in sd.items()}
 
 
+from . import _common  # noqa: E402
 from ._hooks import GpuSideHooks  # noqa: E402  (after _Base: the stand-in must exist first)
 
 
@@ -71,48 +72,17 @@ class SegmentationUnetPlus(GpuSideHooks, _Base):
     def configure_model(self) -> None:
         if self.model is not None:
             return
+        _common.check_pretrained_request(self.weights, "SegmentationUnetPlus")  # smp downloads `encoder_weights` here (:126-131)
         self.model = UnetPlusPlus(encoder_name=self.encoder, in_channels=self.in_channels, encoder_weights=None,
                                   classes=self.num_classes, compute_dtype=self.compute_dtype)
         if self.weights_from_checkpoint_path:
-            ckpt = torch.load(self.weights_from_checkpoint_path, map_location="cpu", weights_only=False)
-            sd = _strip_model_prefix(ckpt.get("state_dict", ckpt))
-            parts = self.hparams.get("load_parts") if isinstance(self.hparams, dict) else None
-            if parts:
-                parts = [parts] if isinstance(parts, str) else list(parts)
-                sd = {k: v for k, v in sd.items() if any(k.startswith(f"{p}.") for p in parts)}
-                self.model.load_state_dict(sd, strict=False)
-            else:
-                self.model.load_state_dict(sd)
+            _common.load_weights_from_checkpoint(self.model, self.weights_from_checkpoint_path,
+                                                 _common.hparam(self, "load_parts"),
+                                                 trust_pickle=bool(_common.hparam(self, "trust_checkpoint_pickle", False)))
 
     def configure_optimizers(self):
-        """segmentation_unetplus.py:146-205.  Without a LightningCLI scheduler dictionary in the hyper-parameters the
-        scheduler callable is applied as is; with one, OneCycleLR gets its horizon from the trainer (estimated stepping
-        batches, else the datamodule's epoch_size / batch_size, else the configured total_steps) and any other class is
-        built by the callable."""
-        import math
-        opt = self.optimizer(self.parameters())
-        hp = self.hparams if isinstance(self.hparams, dict) else dict(self.hparams)
-        cfg = hp.get("scheduler")
-        if not cfg or not isinstance(cfg, dict):
-            sched = self.scheduler(opt) if callable(self.scheduler) else None
-            return ([opt], [{"scheduler": sched, **self.scheduler_config}]) if sched else [opt]
-        if cfg.get("class_path", "") == "torch.optim.lr_scheduler.OneCycleLR":
-            init = cfg.get("init_args", {})
-            max_lr = init.get("max_lr")
-            stepping = self.trainer.estimated_stepping_batches
-            dm = getattr(self.trainer, "datamodule", None)
-            if stepping > -1:
-                sched = torch.optim.lr_scheduler.OneCycleLR(opt, max_lr=max_lr, total_steps=stepping)
-            elif getattr(dm, "epoch_size", None) is not None:
-                accum = self.trainer.accumulate_grad_batches
-                per_epoch = math.ceil(dm.epoch_size / (dm.batch_size * accum))
-                sched = torch.optim.lr_scheduler.OneCycleLR(opt, max_lr=max_lr, steps_per_epoch=per_epoch + int(per_epoch * accum),
-                                                            epochs=self.trainer.max_epochs)
-            else:
-                sched = torch.optim.lr_scheduler.OneCycleLR(opt, max_lr=max_lr, total_steps=init.get("total_steps"))
-        else:
-            sched = self.scheduler(opt)
-        return ([opt], [{"scheduler": sched, **self.scheduler_config}]) if sched else [opt]
+        """segmentation_unetplus.py:146-205 (shared with the SegFormer / DOFA mirrors: tasks/_common.py)"""
+        return _common.configure_optimizers(self)
 
     def forward(self, image: Tensor) -> Tensor:
         return self.model(image)

@@ -72,6 +72,9 @@ class FusedTrainer:
                            torch.full((1,), 65536.0 if loss_scale == "dynamic" else float(loss_scale), dtype=acc_dtype, device=dev))
         self.scratch = torch.zeros(2, dtype=acc_dtype, device=dev)
         self.adam_state = torch.zeros(3, dtype=acc_dtype, device=dev)  # step, 1-b1^t, sqrt(1-b2^t) (device side)
+        # the learning rate the step uses is lr0 * lr_scale[0], read on the device: set_lr() also reaches a captured graph
+        self.lr0 = float(lr)
+        self.lr_scale = torch.ones(1, dtype=acc_dtype, device=dev)
         self.last_engine: Engine | None = None
         # CUDA graph of the whole step (normalise .. Adam): removes the ~10 us/launch host cost of the
         # ~800-2000 launches of a step.  Captured lazily on the first step() with a given input shape.
@@ -154,11 +157,17 @@ class FusedTrainer:
             else:
                 gs.fill_(scale_by)
         self.step_count += 1
-        ops.adam_step_dev(self.flat, self.gflat, self.m, self.v, self.lr, self.betas[0], self.betas[1], self.eps,
-                          self.weight_decay, self.adam_state, gs)
+        ops.adam_step_dev(self.flat, self.gflat, self.m, self.v, self.lr0, self.betas[0], self.betas[1], self.eps,
+                          self.weight_decay, self.adam_state, gs, self.lr_scale)
         # parameters changed behind torch's version counters: refresh the cached 16-bit operands in place (one launch)
         if not self.repack_in_place or not refresh_packed_weights(self.model._wcache):
             self.model._wcache.clear()
+
+    def set_lr(self, lr: float) -> None:
+        """Learning rate of the following steps (a scheduler's hook: ReduceLROnPlateau / OneCycleLR in the reference's
+        YAMLs).  Stored on the device, so eager steps and replays of an already captured graph both use it."""
+        self.lr = float(lr)
+        self.lr_scale.fill_(self.lr / self.lr0 if self.lr0 != 0.0 else 0.0)
 
     def _eager_step(self, image_u8: torch.Tensor, target: torch.Tensor,
                     aug_params: torch.Tensor | None = None) -> torch.Tensor:

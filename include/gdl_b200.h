@@ -336,9 +336,12 @@ int gdl_argmax_confusion(const float* logits, int ld, long long N, long long HW,
 int gdl_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
                   float eps, float weight_decay, int step, const float* grad_scale, void* stream);
 /* same update with the step counter on the device: state[0] = step, state[1..2] = bias corrections, advanced
- * by the call itself (nothing step-dependent in kernel parameters: the step can live in a CUDA graph). */
+ * by the call itself (nothing step-dependent in kernel parameters: the step can live in a CUDA graph).
+ * lr_scale (device, may be NULL): the step uses lr * lr_scale[0] — how a learning-rate scheduler (the reference
+ * configures ReduceLROnPlateau / OneCycleLR, configs/*.yaml) reaches a step that is replayed from a captured graph. */
 int gdl_adam_step_dev(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
-                      float eps, float weight_decay, float* state, const float* grad_scale, void* stream);
+                      float eps, float weight_decay, float* state, const float* grad_scale, const float* lr_scale,
+                      void* stream);
 int gdl_grad_clip_coef(const float* g, long long n, float max_norm, float* sumsq_scratch, float* scale,
                        void* stream);
 

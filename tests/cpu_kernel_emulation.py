@@ -468,7 +468,9 @@ def adam_step(p, g, m, v, lr, beta1, beta2, eps, weight_decay, step, grad_scale=
     p.sub_((lr / bc1) * m / (v.sqrt() / bc2 ** 0.5 + eps))
 
 
-def adam_step_dev(p, g, m, v, lr, beta1, beta2, eps, weight_decay, state, grad_scale=None):
+def adam_step_dev(p, g, m, v, lr, beta1, beta2, eps, weight_decay, state, grad_scale=None, lr_scale=None):
+    if lr_scale is not None:
+        lr = lr * float(lr_scale[0])
     state[0] += 1
     step = int(state[0].item())
     state[1] = 1 - beta1 ** step

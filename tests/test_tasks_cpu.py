@@ -181,3 +181,58 @@ def test_unetplus_onecycle_from_cli_hyperparameters(monkeypatch):
     task.trainer = SimpleNamespace(estimated_stepping_batches=-1, datamodule=None, accumulate_grad_batches=1, max_epochs=3)
     _, (s3,) = task.configure_optimizers()
     assert s3["scheduler"].total_steps == 77
+
+
+def test_segformer_and_dofa_mirrors_share_checkpoint_and_scheduler_logic(monkeypatch, tmp_path):
+    """the SegFormer / DOFA mirrors must (a) honour `load_parts` (utils/models.py:31-66: filter + strict=False),
+    (b) size OneCycleLR from the trainer like the reference's configure_optimizers (segmentation_segformer.py:150-199),
+    (c) refuse a pretrained-weights request loudly instead of training from random initialisation, (d) load checkpoints
+    with torch.load's default weights_only=True."""
+    from types import SimpleNamespace
+
+    from gdl_b200.tasks.segmentation_segformer import SegmentationSegformer
+    from gdl_b200.tasks.segmentation_unetplus import SegmentationUnetPlus
+    emu.install(monkeypatch)
+
+    def make(**kw):
+        return SegmentationSegformer("mit_b0", image_size=(64, 64), in_channels=3, num_classes=3, max_samples=1,
+                                     loss=torch.nn.CrossEntropyLoss(), optimizer=lambda p: torch.optim.Adam(p, lr=1e-3),
+                                     compute_dtype=torch.float32, **kw)
+    torch.manual_seed(0)
+    src = make()
+    src.configure_model()
+    ckpt = tmp_path / "ckpt.pt"
+    torch.save({"state_dict": {f"model.{k}": v for k, v in src.model.state_dict().items()}}, ckpt)
+    # (a) only the encoder is taken from the checkpoint; the decoder keeps its own initialisation
+    torch.manual_seed(1)
+    dst = make(weights_from_checkpoint_path=str(ckpt))
+    dst.hparams = {"load_parts": ["encoder"]}
+    dst.configure_model()
+    a, b = src.model.state_dict(), dst.model.state_dict()
+    assert all(torch.equal(a[k], b[k]) for k in a if k.startswith("encoder."))
+    assert any(not torch.equal(a[k], b[k]) for k in a if k.startswith("decoder.") and a[k].is_floating_point() and a[k].dim() > 1)
+    # full load: everything
+    full = make(weights_from_checkpoint_path=str(ckpt))
+    full.configure_model()
+    assert all(torch.equal(a[k], v) for k, v in full.model.state_dict().items())
+    # (d) a checkpoint with arbitrary pickled objects is rejected unless explicitly trusted
+    bad = tmp_path / "bad.pt"
+    torch.save({"state_dict": a, "callback": SimpleNamespace(x=1)}, bad)
+    risky = make(weights_from_checkpoint_path=str(bad))
+    with pytest.raises(Exception):
+        risky.configure_model()
+    # (b) OneCycleLR horizon from the trainer
+    cfg = {"class_path": "torch.optim.lr_scheduler.OneCycleLR", "init_args": {"max_lr": 0.01, "total_steps": 55}}
+    full.hparams = {"scheduler": cfg}
+    full.trainer = SimpleNamespace(estimated_stepping_batches=90, datamodule=None, accumulate_grad_batches=1, max_epochs=2)
+    _, (s1,) = full.configure_optimizers()
+    assert isinstance(s1["scheduler"], torch.optim.lr_scheduler.OneCycleLR) and s1["scheduler"].total_steps == 90
+    full.trainer = SimpleNamespace(estimated_stepping_batches=-1, datamodule=None, accumulate_grad_batches=1, max_epochs=2)
+    _, (s2,) = full.configure_optimizers()
+    assert s2["scheduler"].total_steps == 55
+    # (c) `weights: imagenet` (the shipped YAMLs) must not be dropped silently
+    for task in (make(weights="imagenet"),
+                 SegmentationUnetPlus("resnet18", (32, 32), 3, 2, max_samples=1, loss=torch.nn.CrossEntropyLoss(),
+                                      weights="imagenet", compute_dtype=torch.float32)):
+        with pytest.raises(ValueError, match="pretrained"):
+            task.configure_model()

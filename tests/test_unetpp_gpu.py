@@ -299,3 +299,29 @@ def test_packed_weight_cache_is_refreshed_in_place(cuda):
             assert torch.equal(cache[(head_w.data_ptr(), "dgrad_pad", 16, prod.compute_dtype)][1],
                                fresh._dgrad_weight(head_w, 16, tuple(head_w.shape)))
     assert torch.equal(flats[True], flats[False])
+
+
+def test_set_lr_reaches_a_captured_graph(cuda):
+    """the learning rate is a device value (lr0 * lr_scale[0]), so a scheduler's set_lr() changes what a replayed
+    CUDA graph does — lr = 0 freezes the parameters, restoring it resumes training; eager and graph agree bit for bit."""
+    from gdl_b200.ops import LossSpec
+    from gdl_b200.trainer import FusedTrainer
+    g = torch.Generator().manual_seed(6)
+    t = torch.randint(0, 5, (4, 2, 2), generator=g).repeat_interleave(32, 1).repeat_interleave(32, 2).cuda()
+    raw = (t.unsqueeze(-1) * 50 + torch.randint(0, 30, (4, 64, 64, 3), generator=g).cuda()).to(torch.uint8)
+    flats = {}
+    for graph in (False, True):
+        _, prod = _models("resnet18", 3, 5, seed=5)
+        prod.train()
+        tr = FusedTrainer(prod, LossSpec(1.0, 0.0, ignore_index=-100), lr=2e-3, mean=[0.5] * 3, std=[0.2] * 3, cuda_graph=graph)
+        for _ in range(3):
+            tr.step(raw, t)
+        before = tr.flat.clone()
+        tr.set_lr(0.0)
+        tr.step(raw, t)
+        assert torch.equal(tr.flat, before)
+        tr.set_lr(1e-3)
+        tr.step(raw, t)
+        assert not torch.equal(tr.flat, before)
+        flats[graph] = tr.flat.clone()
+    assert torch.equal(flats[False], flats[True])
