@@ -21,6 +21,7 @@
 #include "../../include/gdl_b200.h"
 #include "common.cuh"
 #include "tmap.cuh"
+#include "det_reduce.cuh"
 
 namespace gdl {
 
@@ -58,6 +59,11 @@ struct ConvRowsKParams {
   const void* residual;
   int res_dtype;
   long long ldr;
+  // BatchNorm statistics of the rounded output, read back from the staged 64-channel tiles (tma_store, BN == 64)
+  int bn_on, bn_smem_off;  // dynamic-smem offset of the 4 x [2][64] float accumulators
+  float* bn_sums;
+  const float* bn_pivot;
+  DetCtx bn_det;
 };
 
 struct RowsJob {
@@ -237,6 +243,12 @@ __global__ void __launch_bounds__(kRowsThreads, 1) conv3x3_rows_kernel(const __g
       const int pitch = p.BN * 2;
       int st = 0;
       int it = 0;
+      float* bn_all = reinterpret_cast<float*>(smem + p.bn_smem_off);  // [4 warps][2][64]
+      float* bn_acc = bn_all + q * 128;
+      if (p.bn_on) {
+        for (int i = lane; i < 128; i += 32) bn_acc[i] = 0.f;
+        __syncwarp();
+      }
       for (long long job = blockIdx.x; job < p.num_jobs; job += gridDim.x, ++it) {
         const int buf = it & 1;
         const RowsJob j = rows_job(p, job);
@@ -301,10 +313,54 @@ __global__ void __launch_bounds__(kRowsThreads, 1) conv3x3_rows_kernel(const __g
             tma_store_4d(&p.tmO, stg, j.n0, j.w0, j.h0 + g, j.img);
             bulk_commit_group();
           }
+          if (p.bn_on && 2 * lane < p.Cout) {
+            // the staged tile (128 pixels of one image row x 64 channels) is complete: lane = one channel pair (a 32-bit
+            // word per pixel, conflict free), warp q = pixels q, q+4, ...; pixels beyond the image width are skipped
+            const int c = 2 * lane;
+            const float pv0 = p.bn_pivot ? __ldg(p.bn_pivot + c) : 0.f;
+            const float pv1 = (p.bn_pivot && c + 1 < p.Cout) ? __ldg(p.bn_pivot + c + 1) : 0.f;
+            float s1a = 0.f, s1b = 0.f, s2a = 0.f, s2b = 0.f;
+#pragma unroll 8
+            for (int k = 0; k < 32; ++k) {
+              const int r = q + 4 * k;
+              const uint32_t off = (uint32_t)(r * pitch + lane * 4);
+              const uint32_t u = *reinterpret_cast<const uint32_t*>(stg + (off ^ (((off >> 7) & (uint32_t)p.o_swz_mask) << 4)));
+              float x0, x1;
+              if (p.out_dtype == GDL_BF16) {
+                x0 = bf16_lo(u);
+                x1 = bf16_hi(u);
+              } else {
+                const __half2 h2 = *reinterpret_cast<const __half2*>(&u);
+                x0 = __low2float(h2);
+                x1 = __high2float(h2);
+              }
+              if (j.w0 + r < p.Wo) {
+                x0 -= pv0;
+                x1 -= pv1;
+                s1a += x0;
+                s1b += x1;
+                s2a = fmaf(x0, x0, s2a);
+                s2b = fmaf(x1, x1, s2b);
+              }
+            }
+            bn_acc[c] += s1a;
+            bn_acc[c + 1] += s1b;
+            bn_acc[64 + c] += s2a;
+            bn_acc[64 + c + 1] += s2b;
+          }
           st ^= 1;
         }
       }
       if (issuer) bulk_wait_group<0>();
+      if (p.bn_on) {
+        named_bar_sync(1, 128);
+        const int i = (int)threadIdx.x - 64;  // 0..127: [2][64]
+        const int c = i & 63;
+        if (c < p.Cout) {
+          const float v = ((bn_all[i] + bn_all[128 + i]) + bn_all[256 + i]) + bn_all[384 + i];
+          det_put(p.bn_det, 2 * p.Cout, i < 64 ? c : p.Cout + c, v);
+        }
+      }
     } else {
     int it = 0;
     for (long long job = blockIdx.x; job < p.num_jobs; job += gridDim.x, ++it) {
@@ -385,7 +441,10 @@ __global__ void __launch_bounds__(kRowsThreads, 1) conv3x3_rows_kernel(const __g
     __syncwarp();
     tmem_dealloc(tmem_base, 512u);
   }
+  if (p.bn_on) det_finish(p.bn_det, 2 * p.Cout, p.bn_sums);
 }
+
+static int rows_sm_count();
 
 static int rows_sm_count() { return device_sm_count(); }
 
@@ -436,7 +495,13 @@ int conv3x3_rows_try(const gdl_conv_fwd_t* d, cudaStream_t stream, int* status) 
   p.tma_store = opt_tma_store && d->out_dtype != GDL_F32 && p.vec_ok && d->residual == nullptr && d->Cout % 8 == 0;
   p.o_stage_bytes = p.tma_store ? 128 * BN * 2 : 0;  // 4 / 8 / 12 / 16 KB
   p.o_swz_mask = BN == 64 ? 7 : (BN == 32 ? 3 : (BN == 16 ? 1 : 0));
-  const int fixed = 1024 + 2 * p.o_stage_bytes;
+  // fused BatchNorm statistics: needs the staged 64-channel tile and a workspace slot per CTA (decided before the
+  // pipeline depth: the 4 x [2][64] float accumulators come out of the dynamic shared-memory budget)
+  const int sms_bn = rows_sm_count();
+  const int grid_bn = p.num_jobs < sms_bn ? (int)p.num_jobs : sms_bn;
+  const DetWs ws = det_workspace();
+  const bool bn_fused = d->bn_sums != nullptr && p.tma_store && BN == 64 && det_grid(ws, grid_bn, 2 * d->Cout) == grid_bn;
+  const int fixed = 1024 + 2 * p.o_stage_bytes + (bn_fused ? 2048 : 0);
   p.a_stages = 4;
   p.b_stages = (kRowsSmemBudget - fixed - p.a_stages * kRowsAStage) / p.b_stage_bytes;
   if (p.b_stages > kRowsMaxBStages) p.b_stages = kRowsMaxBStages;
@@ -473,7 +538,17 @@ int conv3x3_rows_try(const gdl_conv_fwd_t* d, cudaStream_t stream, int* status) 
     *status = make_tmap_nhwc(&p.tmO, d->out, d->out_dtype, d->Cout, d->W, d->H, d->N, d->ldo, BN, 128, 1, swz);
     if (*status) return 1;
   }
-  const int smem = p.a_stages * kRowsAStage + p.b_stages * p.b_stage_bytes + 2 * p.o_stage_bytes + 1024;
+  int smem = p.a_stages * kRowsAStage + p.b_stages * p.b_stage_bytes + 2 * p.o_stage_bytes + 1024;
+  if (bn_fused) {
+    p.bn_on = 1;
+    p.bn_smem_off = p.a_stages * kRowsAStage + p.b_stages * p.b_stage_bytes + 2 * p.o_stage_bytes;  // after the staging tiles
+    smem += 2048;
+    p.bn_sums = d->bn_sums;
+    p.bn_pivot = d->bn_pivot;
+    p.bn_det = det_ctx(ws, grid_bn, 2 * d->Cout);
+    *status = check_cuda(cudaMemsetAsync(d->bn_sums, 0, 2 * (size_t)d->Cout * sizeof(float), stream), "cudaMemsetAsync(bn_sums)");
+    if (*status) return 1;
+  }
   static PerDeviceOnce attr_once;
   *status = check_cuda(set_max_dyn_smem_once(attr_once, conv3x3_rows_kernel, kRowsSmemBudget + 1024),
                        "cudaFuncSetAttribute(conv3x3_rows_kernel)");
@@ -482,6 +557,9 @@ int conv3x3_rows_try(const gdl_conv_fwd_t* d, cudaStream_t stream, int* status) 
   const int grid = p.num_jobs < sms ? (int)p.num_jobs : sms;
   conv3x3_rows_kernel<<<grid, kRowsThreads, smem, stream>>>(p);
   *status = check_cuda(cudaGetLastError(), "conv3x3_rows_kernel launch");
+  if (*status == 0 && d->bn_sums != nullptr && !bn_fused)  // the statistics kernel on the stored output
+    *status = gdl_bn_stats(d->out, d->out_dtype, (long long)d->N * d->H * d->W, d->Cout, d->ldo, d->bn_sums, d->bn_pivot,
+                           (void*)stream);
   return 1;
 }
 

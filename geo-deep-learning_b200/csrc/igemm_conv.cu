@@ -82,6 +82,12 @@ struct ConvFwdKParams {
   int halo;
   int halo_bo;           // set the descriptor base_offset field for the shifted start (probe-determined)
   int b_slot;            // bytes between the 3 per-tap weight tiles of a stage
+  // BatchNorm statistics fused into the TMA-store epilogue (epi_mode 2, 64-channel 16-bit slabs, one n-tile): per-channel
+  // sum(x - pivot) / sum((x - pivot)^2) of the ROUNDED output, read back from the staged slab; per-CTA partials -> det_finish
+  int bn_on, log2_tw;
+  float* bn_sums;
+  const float* bn_pivot;
+  DetCtx bn_det;
 };
 
 __global__ void __launch_bounds__(kConvThreads, 1)
@@ -272,6 +278,11 @@ conv_fwd_kernel(const __grid_constant__ ConvFwdKParams p) {
       const int th = row / p.TW, tw = row - th * p.TW;
       int st = 0;
       int it = 0;
+      float* bn_acc = &stage_buf[q][0];  // [2][BN] running sums of this warp's rows (the transpose tile is unused in this mode)
+      if (p.bn_on) {
+        for (int i = lane; i < 2 * p.BN; i += 32) bn_acc[i] = 0.f;
+        __syncwarp();
+      }
       for (int tile_g = blockIdx.x; tile_g < p.num_tiles; tile_g += gridDim.x, ++it) {
         const int acc = it & 1;
         const uint32_t aphase = (it >> 1) & 1;
@@ -381,10 +392,57 @@ conv_fwd_kernel(const __grid_constant__ ConvFwdKParams p) {
             tma_store_4d(&p.tmO, stg, n0 + cb0 + go, w0, h0, img);
             bulk_commit_group();
           }
+          if (p.bn_on && cb0 + 2 * lane < p.Cout) {
+            // the slab (128 pixels x 64 channels, 16-bit, swizzled) is complete in shared memory: lane = one channel pair
+            // (one 32-bit word per row: conflict free), warp q = rows q, q+4, ...; rows outside the image are skipped
+            const int c = cb0 + 2 * lane;
+            const float pv0 = p.bn_pivot ? __ldg(p.bn_pivot + c) : 0.f;
+            const float pv1 = (p.bn_pivot && c + 1 < p.Cout) ? __ldg(p.bn_pivot + c + 1) : 0.f;
+            float s1a = 0.f, s1b = 0.f, s2a = 0.f, s2b = 0.f;
+#pragma unroll 8
+            for (int k = 0; k < 32; ++k) {
+              const int r = q + 4 * k;
+              const bool vr = (h0 + (r >> p.log2_tw) < p.Ho) && (w0 + (r & (p.TW - 1)) < p.Wo);
+              const uint32_t off = (uint32_t)(r * pitch + lane * 4);
+              const uint32_t u = *reinterpret_cast<const uint32_t*>(stg + (off ^ (((off >> 7) & (uint32_t)p.o_swz_mask) << 4)));
+              float x0, x1;
+              if (p.out_dtype == GDL_BF16) {
+                x0 = bf16_lo(u);
+                x1 = bf16_hi(u);
+              } else {
+                const __half2 h2 = *reinterpret_cast<const __half2*>(&u);
+                x0 = __low2float(h2);
+                x1 = __high2float(h2);
+              }
+              if (vr) {
+                x0 -= pv0;
+                x1 -= pv1;
+                s1a += x0;
+                s1b += x1;
+                s2a = fmaf(x0, x0, s2a);
+                s2b = fmaf(x1, x1, s2b);
+              }
+            }
+            bn_acc[c] += s1a;
+            bn_acc[c + 1] += s1b;
+            bn_acc[p.BN + c] += s2a;
+            bn_acc[p.BN + c + 1] += s2b;
+          }
           st ^= 1;
         }
       }
       if (issuer) bulk_wait_group<0>();
+      if (p.bn_on) {
+        // this CTA's partial = the 4 warps' sums in warp order -> its slot; det_finish (below) adds the CTAs in order
+        named_bar_sync(1, 128);
+        for (int i = (int)threadIdx.x - 64; i < 2 * p.BN; i += 128) {
+          const int c = i < p.BN ? i : i - p.BN;
+          if (c < p.Cout) {
+            const float v = ((stage_buf[0][i] + stage_buf[1][i]) + stage_buf[2][i]) + stage_buf[3][i];
+            det_put(p.bn_det, 2 * p.Cout, i < p.BN ? c : p.Cout + c, v);
+          }
+        }
+      }
     } else if (p.epi_mode == 0) {
       // direct variant: every thread stores its own accumulator row (16-byte vectors, 32 lines per warp store)
       int it = 0;
@@ -612,6 +670,7 @@ conv_fwd_kernel(const __grid_constant__ ConvFwdKParams p) {
     __syncwarp();
     tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
   }
+  if (p.bn_on) det_finish(p.bn_det, 2 * p.Cout, p.bn_sums);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -866,8 +925,24 @@ extern "C" int gdl_conv2d_nhwc_fwd(const gdl_conv_fwd_t* d, void* stream_) {
   static PerDeviceOnce attr_once;
   GDL_CHECK_CUDA(set_max_dyn_smem_once(attr_once, conv_fwd_kernel, kSmemBudget + 4096));
   int grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();
+  bool bn_fused = false;
+  if (d->bn_sums != nullptr && p.epi_mode == 2 && p.o_slab == 64 && d->out_dtype != GDL_F32 && p.n_tiles == 1 && G == 1) {
+    const DetWs ws = det_workspace();
+    if (det_grid(ws, grid, 2 * d->Cout) == grid) {
+      bn_fused = true;
+      p.bn_on = 1;
+      p.log2_tw = 0;
+      while ((1 << p.log2_tw) < p.TW) ++p.log2_tw;
+      p.bn_sums = d->bn_sums;
+      p.bn_pivot = d->bn_pivot;
+      p.bn_det = det_ctx(ws, grid, 2 * d->Cout);
+      GDL_CHECK_CUDA(cudaMemsetAsync(d->bn_sums, 0, 2 * (size_t)d->Cout * sizeof(float), stream));
+    }
+  }
   conv_fwd_kernel<<<grid, kConvThreads, smem, stream>>>(p);
   GDL_CHECK_CUDA(cudaGetLastError());
+  if (d->bn_sums != nullptr && !bn_fused)  // shapes the epilogue cannot cover: the statistics kernel on the stored output
+    return gdl_bn_stats(d->out, d->out_dtype, (long long)N * oH * oW, d->Cout, d->ldo, d->bn_sums, d->bn_pivot, stream_);
   return 0;
 }
 

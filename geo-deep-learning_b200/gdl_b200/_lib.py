@@ -52,6 +52,8 @@ class ConvFwd(C.Structure):
         ("g_src_stride", C.c_int),
         ("g_w_stride", C.c_int),
         ("g_out_stride", C.c_int),
+        ("bn_sums", C.c_void_p),
+        ("bn_pivot", C.c_void_p),
     ]
 
 

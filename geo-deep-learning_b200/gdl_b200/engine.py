@@ -66,6 +66,7 @@ class RawConv:
     wshape: tuple | None = None  # (Cout, Cin, R, S) view of the parameter (nn.Linear weights are (Cout, Cin))
     bias: torch.Tensor | None = None
     pixel_packed: bool = False  # narrow 3x3 conv run as its pixel-packed (block-Toeplitz) equivalent
+    stats: torch.Tensor | None = None  # BatchNorm sums [2C] (pivoted on the running mean) produced by the conv itself
     groups: int = 1             # grouped conv (ResNeXt): run as Cout / 64 dense 64 -> 64 convs over channel slices
     cols: list | None = None    # grouped + strided: the im2col matrix of every 64-channel slice
 
@@ -211,27 +212,41 @@ class Engine:
     # ------------------------------------------------------------------ convolution
     def conv_raw(self, srcs: list[Act], weight: torch.nn.Parameter, stride: int, pad: int,
                  bias: torch.Tensor | None = None, out_dtype: torch.dtype | None = None,
-                 relu: bool = False, wshape: tuple | None = None, residual: torch.Tensor | None = None) -> RawConv:
+                 relu: bool = False, wshape: tuple | None = None, residual: torch.Tensor | None = None,
+                 stats_for: "BNParams | None" = None) -> RawConv:
         """Convolution / linear layer.  `wshape` views the parameter as (Cout, Cin, R, S) (nn.Linear);
-        `residual` (N,H,W,Cout) is added in the GEMM epilogue (fp32 residual stream)."""
+        `residual` (N,H,W,Cout) is added in the GEMM epilogue (fp32 residual stream).
+        stats_for: the BatchNorm that follows (training mode): the conv then also produces that layer's batch sums
+        (pivoted on its running mean) — from its epilogue where the kernel can — and bn_prepare skips the statistics pass."""
         wshape = tuple(wshape) if wshape is not None else tuple(weight.shape)
         cout, cin, r, s = wshape
+        sums = pivot = None
+        if stats_for is not None and self.training and ops.option("bn_fused"):
+            sums = torch.empty(2 * cout, dtype=self.acc_dtype, device=srcs[0].t.device)
+            pivot = stats_for.running_mean
         stored = sum(a.t.shape[3] for a in srcs)
         direct = stride == 1 and all(a.t.shape[3] % 16 == 0 for a in srcs) and stored == cin
         if direct and residual is None and self._pixel_packable(srcs, wshape, stride, pad):
             a = srcs[0]
             n, h, wd, _ = a.t.shape
             f = 64 // cin
+            wide_sums = wide_piv = None
+            if sums is not None:  # the packed conv has f * Cout pseudo-channels: f copies of every real channel
+                wide_sums = torch.empty(2 * f * cout, dtype=self.acc_dtype, device=a.t.device)
+                wide_piv = pivot.repeat(f)
             x = ops.conv2d_fwd([a.t.view(n, h, wd // f, f * cin)], self.packed_wide(weight, 0, f, wshape), f * cout,
                                r, s, pad, pad, out_dtype=out_dtype, relu=relu,
-                               bias=self._tiled_bias(bias, f) if bias is not None else None, alg_scale=1.0 / f)
+                               bias=self._tiled_bias(bias, f) if bias is not None else None, alg_scale=1.0 / f,
+                               bn_sums=wide_sums, bn_pivot=wide_piv)
+            if sums is not None:
+                torch.sum(wide_sums.view(2, f, cout), dim=1, out=sums.view(2, cout))  # fixed order: reproducible
             return RawConv(x.view(n, h, wd, cout), srcs, weight, stride, pad, cin_store=stored, wshape=wshape, bias=bias,
-                           pixel_packed=True)
+                           pixel_packed=True, stats=sums)
         if direct:
             wp = self.packed(weight, 0, 0, wshape)
             x = ops.conv2d_fwd([a.t for a in srcs], wp, cout, r, s, pad, pad, out_dtype=out_dtype, bias=bias,
-                               relu=relu, residual=residual)
-            return RawConv(x, srcs, weight, stride, pad, cin_store=stored, wshape=wshape, bias=bias)
+                               relu=relu, residual=residual, bn_sums=sums, bn_pivot=pivot)
+            return RawConv(x, srcs, weight, stride, pad, cin_store=stored, wshape=wshape, bias=bias, stats=sums)
         if len(srcs) != 1:
             raise NotImplementedError("strided / narrow-input convs take a single source")
         a = srcs[0]
@@ -240,9 +255,9 @@ class Engine:
         col = ops.im2col(a.t, cin, r, s, stride, pad, kpad)
         wp = self.packed(weight, 0, kpad, wshape)
         x = ops.conv2d_fwd([col], wp, cout, 1, 1, 0, 0, out_dtype=out_dtype, bias=bias, relu=relu, residual=residual,
-                           alg_scale=k / kpad)
+                           alg_scale=k / kpad, bn_sums=sums, bn_pivot=pivot)
         return RawConv(x, srcs, weight, stride, pad, col=col if self.training else None, kpad=kpad, cin_store=stored,
-                       wshape=wshape, bias=bias)
+                       wshape=wshape, bias=bias, stats=sums)
 
     def conv_backward(self, rc: RawConv, dx: torch.Tensor, dgrad_residual: torch.Tensor | None = None) -> None:
         """dx = gradient w.r.t. the raw conv output (N,Ho,Wo,Cout'), Cout' >= Cout zero padded.
@@ -426,9 +441,12 @@ class Engine:
         buf = torch.empty((4, c), dtype=self.acc_dtype, device=dev)
         scale, shift, mean, invstd = buf[0], buf[1], buf[2], buf[3]
         if self.training:
-            sums = torch.empty(2 * c, dtype=self.acc_dtype, device=dev)
-            # pivot = running mean: the same on every rank, so partial sums add up across ranks
-            ops.bn_stats(rc.x, sums, p.running_mean)
+            if rc.stats is not None:
+                sums = rc.stats  # produced by the conv (its epilogue, or the statistics pass the library ran itself)
+            else:
+                sums = torch.empty(2 * c, dtype=self.acc_dtype, device=dev)
+                # pivot = running mean: the same on every rank, so partial sums add up across ranks
+                ops.bn_stats(rc.x, sums, p.running_mean)
             count = ops._rows(rc.x)
             if self.sync_bn_group is not None:
                 self._allreduce(sums)
@@ -602,9 +620,10 @@ class Engine:
     def conv_bn_relu(self, srcs: list[Act], conv: torch.nn.Conv2d, bn: torch.nn.BatchNorm2d, *, want_up: bool = False) -> Act:
         """ConvModule: conv (stride 1, optional bias) + BatchNorm2d + ReLU"""
         pad = conv.padding[0]
-        rc = self.conv_raw(srcs, conv.weight, conv.stride[0], pad, bias=conv.bias)
-        st = self.bn_prepare(rc, BNParams(bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.num_batches_tracked,
-                                          bn.eps, bn.momentum if bn.momentum is not None else 0.1))
+        bnp = BNParams(bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.num_batches_tracked, bn.eps,
+                       bn.momentum if bn.momentum is not None else 0.1)
+        rc = self.conv_raw(srcs, conv.weight, conv.stride[0], pad, bias=conv.bias, stats_for=bnp)
+        st = self.bn_prepare(rc, bnp)
         return self.bn_act(rc, st, relu=True, want_up=want_up)
 
     # ------------------------------------------------------------------ head

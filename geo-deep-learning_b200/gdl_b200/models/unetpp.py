@@ -173,22 +173,25 @@ class UnetPlusPlus(nn.Module):
     # ------------------------------------------------------------------ engine graph
     def _block(self, eng: Engine, blk: nn.Module, x: Act, want_up: bool) -> Act:
         if isinstance(blk, _BasicBlock):
-            r1 = eng.conv_raw([x], blk.conv1.weight, blk.stride, 1)
-            a1 = eng.bn_act(r1, eng.bn_prepare(r1, _bnp(blk.bn1)))
-            r2 = eng.conv_raw([a1], blk.conv2.weight, 1, 1)
-            last, last_bn = r2, _bnp(blk.bn2)
+            b1, b2 = _bnp(blk.bn1), _bnp(blk.bn2)
+            r1 = eng.conv_raw([x], blk.conv1.weight, blk.stride, 1, stats_for=b1)
+            a1 = eng.bn_act(r1, eng.bn_prepare(r1, b1))
+            r2 = eng.conv_raw([a1], blk.conv2.weight, 1, 1, stats_for=b2)
+            last, last_bn = r2, b2
         else:
-            r1 = eng.conv_raw([x], blk.conv1.weight, 1, 0)
-            a1 = eng.bn_act(r1, eng.bn_prepare(r1, _bnp(blk.bn1)))
-            r2 = (eng.conv_raw([a1], blk.conv2.weight, blk.stride, 1) if blk.groups == 1
+            b1, b2, b3 = _bnp(blk.bn1), _bnp(blk.bn2), _bnp(blk.bn3)
+            r1 = eng.conv_raw([x], blk.conv1.weight, 1, 0, stats_for=b1)
+            a1 = eng.bn_act(r1, eng.bn_prepare(r1, b1))
+            r2 = (eng.conv_raw([a1], blk.conv2.weight, blk.stride, 1, stats_for=b2) if blk.groups == 1
                   else eng.conv_raw_grouped(a1, blk.conv2.weight, blk.groups, blk.stride, 1))
-            a2 = eng.bn_act(r2, eng.bn_prepare(r2, _bnp(blk.bn2)))
-            last = eng.conv_raw([a2], blk.conv3.weight, 1, 0)
-            last_bn = _bnp(blk.bn3)
+            a2 = eng.bn_act(r2, eng.bn_prepare(r2, b2))
+            last = eng.conv_raw([a2], blk.conv3.weight, 1, 0, stats_for=b3)
+            last_bn = b3
         bn_last = eng.bn_prepare(last, last_bn)
         if blk.downsample is not None:
-            rd = eng.conv_raw([x], blk.downsample[0].weight, blk.stride, 0)
-            bnd = eng.bn_prepare(rd, _bnp(blk.downsample[1]))
+            bd = _bnp(blk.downsample[1])
+            rd = eng.conv_raw([x], blk.downsample[0].weight, blk.stride, 0, stats_for=bd)
+            bnd = eng.bn_prepare(rd, bd)
             return eng.bn_act(last, bn_last, res_branch=(rd, bnd), want_up=want_up)
         return eng.bn_act(last, bn_last, residual=x, want_up=want_up)
 
@@ -202,10 +205,11 @@ class UnetPlusPlus(nn.Module):
         blk = self.decoder.blocks[name]
         if x.up is None:
             raise RuntimeError(f"{name}: producer did not emit an upsampled copy")
-        r1 = eng.conv_raw([x.up, *skips], blk.conv1[0].weight, 1, 1)
-        a1 = eng.bn_act(r1, eng.bn_prepare(r1, _bnp(blk.conv1[1])))
-        r2 = eng.conv_raw([a1], blk.conv2[0].weight, 1, 1)
-        return eng.bn_act(r2, eng.bn_prepare(r2, _bnp(blk.conv2[1])), want_up=want_up)
+        b1, b2 = _bnp(blk.conv1[1]), _bnp(blk.conv2[1])
+        r1 = eng.conv_raw([x.up, *skips], blk.conv1[0].weight, 1, 1, stats_for=b1)
+        a1 = eng.bn_act(r1, eng.bn_prepare(r1, b1))
+        r2 = eng.conv_raw([a1], blk.conv2[0].weight, 1, 1, stats_for=b2)
+        return eng.bn_act(r2, eng.bn_prepare(r2, b2), want_up=want_up)
 
     def run(self, eng: Engine, x: Act) -> torch.Tensor:
         """x: NHWC 16-bit input (channels possibly zero-padded). Returns fp32 logits (N,H,W,K)."""
@@ -213,8 +217,9 @@ class UnetPlusPlus(nn.Module):
         _, h, w, _ = x.t.shape
         if h % 32 or w % 32:
             raise RuntimeError(f"Wrong input shape height={h}, width={w}. Expected image height and width divisible by 32.")
-        r = eng.conv_raw([x], enc.conv1.weight, 2, 3)
-        e1 = eng.bn_act(r, eng.bn_prepare(r, _bnp(enc.bn1)))  # 64 @ H/2
+        bn1 = _bnp(enc.bn1)
+        r = eng.conv_raw([x], enc.conv1.weight, 2, 3, stats_for=bn1)
+        e1 = eng.bn_act(r, eng.bn_prepare(r, bn1))  # 64 @ H/2
         p = eng.maxpool3x3s2(e1)
         e2 = self._layer(eng, enc.layer1, p, True)
         e3 = self._layer(eng, enc.layer2, e2, True)

@@ -106,7 +106,10 @@ _HOST_OPTS = {"pixel_pack": int(os.environ.get("GDL_PIXEL_PACK", "1")), "sra_fus
               "attn_wgrad_grouped": int(os.environ.get("GDL_ATTN_WGRAD_GROUPED", "1")),
               # fused_head: the fused trainer never materialises the upsampled (N,H,W,K) logits of SegFormer / UperNet heads:
               # gdl_upsample_ce_fwd / _bwd interpolate them on the fly (training); eval masks come from gdl_upsample_argmax
-              "fused_head": int(os.environ.get("GDL_FUSED_HEAD", "1"))}
+              "fused_head": int(os.environ.get("GDL_FUSED_HEAD", "1")),
+              # bn_fused: a conv followed by a training-mode BatchNorm produces that layer's batch sums itself (from the
+              # epilogue's staged tile) instead of a separate pass over its output (gdl_conv_fwd_t.bn_sums)
+              "bn_fused": int(os.environ.get("GDL_BN_FUSED", "1"))}
 
 
 def option(name: str) -> int:
@@ -169,11 +172,14 @@ def conv2d_fwd(srcs: Sequence[torch.Tensor], weight: torch.Tensor, cout: int, r:
                relu: bool = False, residual: torch.Tensor | None = None, w_ld: int = 0, w_rows: int = 0,
                w_rows_per_img: int = 0, w_mn_major: bool = False, gelu: bool = False,
                oscale: torch.Tensor | None = None, groups: tuple[int, int, int, int] | None = None,
-               alg_scale: float = 1.0) -> torch.Tensor:
+               alg_scale: float = 1.0, bn_sums: torch.Tensor | None = None,
+               bn_pivot: torch.Tensor | None = None) -> torch.Tensor:
     """gdl_conv2d_nhwc_fwd. `weight` is the packed [Cout][R][S][Ctot] 16-bit operand (or, with the w_*
     options, a slice of an activation tensor used as the B operand of an attention GEMM).
     alg_scale: ALGORITHMIC / executed FLOPs of this launch (profiler only): < 1 for pixel-packed (block-Toeplitz) and
-    channel-padded launches, whose zeros are not work the reference does."""
+    channel-padded launches, whose zeros are not work the reference does.
+    bn_sums (fp32 [2*Cout]) / bn_pivot (fp32 [Cout] or None): the conv also produces the BatchNorm statistics of its
+    rounded output, sum(out - pivot) and sum((out - pivot)^2) per channel — from the epilogue's staged tile where possible."""
     d = L.ConvFwd()
     n, h, w = _fill_srcs(d, srcs)
     dt = srcs[0].dtype
@@ -196,6 +202,11 @@ def conv2d_fwd(srcs: Sequence[torch.Tensor], weight: torch.Tensor, cout: int, r:
     if w_rows_per_img or w_mn_major:  # `weight` is a 2-D view [rows][cols] of an activation tensor
         w_ld, w_rows = weight.stride(0), weight.shape[0]
     d.w_ld, d.w_rows, d.w_rows_per_img, d.w_mn_major = w_ld, w_rows, w_rows_per_img, int(w_mn_major)
+    if bn_sums is not None:
+        if bn_sums.dtype != torch.float32 or bn_sums.numel() < 2 * cout:
+            raise ValueError("bn_sums: fp32 tensor of 2 * Cout elements expected")
+        d.bn_sums = bn_sums.data_ptr()
+        d.bn_pivot = bn_pivot.data_ptr() if bn_pivot is not None else None
     ng = 1
     if groups is not None:
         # (G, source channel stride, weight stride along its contiguous dim, output channel stride): all heads at once;

@@ -119,6 +119,14 @@ typedef struct {
   int g_src_stride;
   int g_w_stride;
   int g_out_stride;
+  /* optional: BatchNorm batch statistics of the (16-bit rounded) output, produced by the conv itself — the training-mode
+   * half of ConvModule's Conv2d -> BatchNorm2d (models/utils.py:10-52, smp Conv2dReLU):
+   *   bn_sums[c] = sum(out[..., c] - bn_pivot[c]),  bn_sums[Cout + c] = sum((out[..., c] - bn_pivot[c])^2)
+   * exactly what gdl_bn_stats computes from the stored tensor (bn_pivot may be NULL = 0).  Where the epilogue stages its
+   * tile in shared memory for a TMA store the sums are taken from that tile (no second pass over the tensor in HBM);
+   * otherwise the library runs the statistics kernel after the convolution.  NULL = not wanted. */
+  float* bn_sums;
+  const float* bn_pivot;
 } gdl_conv_fwd_t;
 int gdl_conv2d_nhwc_fwd(const gdl_conv_fwd_t* d, void* stream);
 
@@ -338,7 +346,7 @@ int gdl_adam_step(float* p, const float* g, float* m, float* v, long long n, flo
 /* same update with the step counter on the device: state[0] = step, state[1..2] = bias corrections, advanced
  * by the call itself (nothing step-dependent in kernel parameters: the step can live in a CUDA graph).
  * lr_scale (device, may be NULL): the step uses lr * lr_scale[0] — how a learning-rate scheduler (the reference
- * configures ReduceLROnPlateau / OneCycleLR, configs/*.yaml) reaches a step that is replayed from a captured graph. */
+ * configures ReduceLROnPlateau / OneCycleLR in its YAML files) reaches a step that is replayed from a captured graph. */
 int gdl_adam_step_dev(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
                       float eps, float weight_decay, float* state, const float* grad_scale, const float* lr_scale,
                       void* stream);

@@ -52,7 +52,8 @@ def repack_weights(entries, plan=None):
 
 
 def conv2d_fwd(srcs, weight, cout, r, s, pad_h, pad_w, *, out=None, out_dtype=None, bias=None, relu=False,
-               residual=None, w_ld=0, w_rows=0, w_rows_per_img=0, w_mn_major=False, gelu=False, oscale=None, groups=None, alg_scale=1.0):
+               residual=None, w_ld=0, w_rows=0, w_rows_per_img=0, w_mn_major=False, gelu=False, oscale=None, groups=None, alg_scale=1.0,
+               bn_sums=None, bn_pivot=None):
     if groups is not None and groups[0] > 1:
         # all heads in one launch: group g = the same call on views shifted by the per-group strides
         ng, sa, sw, so = groups
@@ -99,6 +100,10 @@ def conv2d_fwd(srcs, weight, cout, r, s, pad_h, pad_w, *, out=None, out_dtype=No
     if gelu:
         y = F.gelu(y)
     y = y.to(out_dtype or (out.dtype if out is not None else srcs[0].dtype))
+    if bn_sums is not None:  # BatchNorm sums of the rounded output, pivoted (gdl_conv_fwd_t.bn_sums)
+        d = y.reshape(-1, cout).to(_WORK) - (bn_pivot.to(_WORK) if bn_pivot is not None else 0)
+        bn_sums[:cout] = d.sum(0).to(bn_sums.dtype)
+        bn_sums[cout:2 * cout] = (d * d).sum(0).to(bn_sums.dtype)
     if out is not None:
         out.copy_(y)
         return out

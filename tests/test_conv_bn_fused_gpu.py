@@ -1,0 +1,86 @@
+"""GPU: BatchNorm batch statistics produced by the convolution itself (gdl_conv_fwd_t.bn_sums) — the training-mode half
+of Conv2d -> BatchNorm2d in ConvModule (models/utils.py:10-52) / smp Conv2dReLU.  The sums are taken from the 16-bit
+ROUNDED output staged in shared memory for the TMA store, so they must agree with the separate statistics kernel run on
+the stored tensor (same values, different summation order), be bit-reproducible, skip the pixels a ragged tile pads, and
+fall back to the statistics kernel where the epilogue cannot produce them."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+# (N, H, W, [source channels], Cout, R, expected route)
+CASES = [
+    (2, 16, 128, [64], 128, 3, "implicit-GEMM kernel, halo tiles"),
+    (2, 24, 40, [64, 32], 256, 3, "implicit-GEMM kernel, ragged 2-D tiles"),
+    (3, 10, 13, [128], 64, 1, "pointwise GEMM over 390 flattened pixels (ragged last tile)"),
+    (2, 8, 192, [64], 64, 3, "row-streaming kernel, ragged width"),
+    (2, 16, 128, [128, 64], 64, 3, "row-streaming kernel, virtual concat"),
+    (2, 16, 64, [64], 768, 1, "three n-tiles: statistics kernel fallback"),
+    (2, 16, 64, [64], 48, 3, "48 channels (32-channel slabs): statistics kernel fallback"),
+]
+
+
+@pytest.mark.parametrize("n,h,w,cins,cout,r,route", CASES)
+def test_conv_produces_batchnorm_sums(cuda, n, h, w, cins, cout, r, route):
+    from gdl_b200 import ops
+    g = torch.Generator().manual_seed(h * w + cout)
+    srcs = [torch.randn(n, h, w, c, generator=g).to(torch.bfloat16).cuda() for c in cins]
+    ctot, pad = sum(cins), r // 2
+    wt = (torch.randn(cout, ctot, r, r, generator=g) / (ctot * r * r) ** 0.5).cuda()
+    wp = ops.pack_conv_weight(wt, torch.bfloat16)
+    pivot = (torch.randn(cout, generator=g) * 0.2).cuda()
+
+    def run():
+        sums = torch.full((2 * cout,), float("nan"), device="cuda")
+        y = ops.conv2d_fwd(srcs, wp, cout, r, r, pad, pad, bn_sums=sums, bn_pivot=pivot)
+        return y, sums
+    y, s1 = run()
+    y2, s2 = run()
+    assert torch.equal(y, y2) and torch.equal(s1, s2)                    # bit-reproducible
+    y_plain = ops.conv2d_fwd(srcs, wp, cout, r, r, pad, pad)
+    assert torch.equal(y, y_plain)                                        # the output itself is unchanged
+    ref = torch.empty(2 * cout, device="cuda")
+    ops.bn_stats(y, ref, pivot)
+    d = y.double().view(-1, cout) - pivot.double()
+    exact = torch.cat([d.sum(0), (d * d).sum(0)])
+    m = n * h * w
+    tol = 2e-5 * exact.abs() + 1e-3 * m ** 0.5
+    print(f"{route}: max |fused - exact| {(s1.double() - exact).abs().max().item():.3e}, "
+          f"max |stats kernel - exact| {(ref.double() - exact).abs().max().item():.3e}")
+    assert ((s1.double() - exact).abs() <= tol).all()
+    # no pivot
+    s0 = torch.empty(2 * cout, device="cuda")
+    ops.conv2d_fwd(srcs, wp, cout, r, r, pad, pad, bn_sums=s0)
+    d0 = y.double().view(-1, cout)
+    assert ((s0.double() - torch.cat([d0.sum(0), (d0 * d0).sum(0)])).abs() <= tol + 2e-5 * (d0 * d0).sum(0).repeat(2)).all()
+
+
+def test_engine_conv_bn_uses_the_conv_sums(cuda):
+    """Engine.conv_raw(stats_for=...) + bn_prepare: same scale / shift / running statistics as the separate pass, for a
+    plain conv, a pixel-packed 16 -> 16 conv (f = 4 pseudo-channel copies folded) and a strided (im2col) conv."""
+    from gdl_b200 import ops
+    from gdl_b200.engine import Act, BNParams, Engine
+    g = torch.Generator().manual_seed(4)
+    for cin, cout, stride, hw in ((64, 128, 1, 32), (16, 16, 1, 64), (64, 64, 2, 32)):
+        x = torch.randn(2, hw, hw, cin, generator=g).to(torch.bfloat16).cuda()
+        conv = torch.nn.Conv2d(cin, cout, 3, stride=stride, padding=1, bias=False).cuda()
+        res = {}
+        old = ops.option("bn_fused")
+        try:
+            for fused in (1, 0):
+                ops.set_option("bn_fused", fused)
+                bn = torch.nn.BatchNorm2d(cout).cuda()
+                with torch.no_grad():
+                    bn.running_mean.fill_(0.05)
+                eng = Engine(torch.bfloat16, training=True)
+                bnp = BNParams(bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.num_batches_tracked)
+                with torch.no_grad():
+                    rc = eng.conv_raw([Act(x, needs_grad=False)], conv.weight, stride, 1, stats_for=bnp)
+                    assert (rc.stats is not None) == bool(fused)
+                    st = eng.bn_prepare(rc, bnp)
+                res[fused] = (rc.x.clone(), st.scale.clone(), st.shift.clone(), bn.running_mean.clone(), bn.running_var.clone())
+        finally:
+            ops.set_option("bn_fused", old)
+        assert torch.equal(res[1][0], res[0][0])
+        for a, b in zip(res[1][1:], res[0][1:]):
+            assert torch.allclose(a, b, rtol=2e-4, atol=2e-5), (cin, cout, stride)
