@@ -1,6 +1,7 @@
 """CPU: the parts of bench.py that run without a GPU — the reference arm's JSON line (the driver parses it), workload
 table consistency with BASELINE.json / SURVEY §8d, the ncu-traffic lookup, and the clocks parser."""
 import json
+import re
 import subprocess
 import sys
 from pathlib import Path
@@ -54,7 +55,8 @@ def test_dram_traffic_lookup_uses_the_newest_committed_pass():
     import bench
     for fam in ("unetpp", "segformer", "dofa"):
         per_launch, src = bench._dram_traffic(fam)
-        assert per_launch and per_launch > 1e6 and src.startswith("profiles/r01_run") and (ROOT / src).exists()
+        assert per_launch and per_launch > 1e6 and re.match(r"profiles/r0\d_run\d+_dram_traffic_", src) and (ROOT / src).exists()
+    assert bench._dram_traffic("unetpp")[1].startswith("profiles/r02_")  # the newest round wins
     assert bench._dram_traffic("no_such_family") == (None, None)
 
 

@@ -1,4 +1,4 @@
-"""GPU: the fp32-accurate mode of the tensor-core convolutions (3 x bf16 split, ops.conv2d_*_split3) meets the tolerance
+"""GPU: the fp32-accurate mode of the tensor-core convolutions (two bf16 planes per operand, ops.conv2d_*_bf16x2) meets the tolerance
 north_star states for fp32 — 1e-5 — against torch's fp32 convolution (TF32 off) on the same fp32 operands: forward, data
 gradient and weight gradient, implicit-GEMM / row-streaming / pointwise kernels, virtual concat.  (The 16-bit training path
 is compared with the autocast reference instead: one bf16 rounding is 2^-9.)"""
@@ -22,7 +22,7 @@ def _err(a, b):
 
 
 @pytest.mark.parametrize("n,h,w,cins,cout,r", CASES)
-def test_split3_convolution_meets_1e5(cuda, n, h, w, cins, cout, r):
+def test_bf16x2_convolution_meets_1e5(cuda, n, h, w, cins, cout, r):
     from gdl_b200 import ops
     g = torch.Generator().manual_seed(h * w + cout)
     srcs = [torch.randn(n, h, w, c, generator=g).cuda() for c in cins]
@@ -35,18 +35,18 @@ def test_split3_convolution_meets_1e5(cuda, n, h, w, cins, cout, r):
     ref = F.conv2d(x, wr, bias, padding=pad)
     ref.backward(dy.permute(0, 3, 1, 2))
     # forward
-    y = ops.conv2d_fwd_split3(srcs, wt, pad, pad, bias=bias)
+    y = ops.conv2d_fwd_bf16x2(srcs, wt, pad, pad, bias=bias)
     e_f = _err(y.permute(0, 3, 1, 2), ref)
     # one bf16 product for comparison
     wp = ops.pack_conv_weight(wt, torch.bfloat16)
     y16 = ops.conv2d_fwd([s.to(torch.bfloat16) for s in srcs], wp, cout, r, r, pad, pad, out_dtype=torch.float32, bias=bias)
     e_16 = _err(y16.permute(0, 3, 1, 2), ref)
     # data gradient
-    dx = ops.conv2d_fwd_split3([dy], wt, r - 1 - pad, r - 1 - pad, mode=1)
+    dx = ops.conv2d_fwd_bf16x2([dy], wt, r - 1 - pad, r - 1 - pad, mode=1)
     e_d = _err(dx.permute(0, 3, 1, 2), x.grad)
     # weight gradient
-    dw = ops.conv2d_wgrad_split3(srcs, dy, r, r, pad, pad)
+    dw = ops.conv2d_wgrad_bf16x2(srcs, dy, r, r, pad, pad)
     e_w = _err(dw.view(cout, r, r, ctot).permute(0, 3, 1, 2), wr.grad)
-    print(f"{cins}->{cout} k{r} @{h}x{w}: split3 fwd {e_f:.2e} dgrad {e_d:.2e} wgrad {e_w:.2e}   (one bf16 product: {e_16:.2e})")
+    print(f"{cins}->{cout} k{r} @{h}x{w}: bf16x2 fwd {e_f:.2e} dgrad {e_d:.2e} wgrad {e_w:.2e}   (one bf16 product: {e_16:.2e})")
     assert e_f < 1e-5 and e_d < 1e-5 and e_w < 1e-5
     assert e_16 > 20 * e_f  # the split really buys the accuracy
