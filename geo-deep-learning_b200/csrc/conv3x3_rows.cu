@@ -320,13 +320,15 @@ __global__ void __launch_bounds__(kRowsThreads, 1) conv3x3_rows_kernel(const __g
             const float pv0 = p.bn_pivot ? __ldg(p.bn_pivot + c) : 0.f;
             const float pv1 = (p.bn_pivot && c + 1 < p.Cout) ? __ldg(p.bn_pivot + c + 1) : 0.f;
             float s1a = 0.f, s1b = 0.f, s2a = 0.f, s2b = 0.f;
+            const bool full = j.w0 + 128 <= p.Wo;
+            const uint32_t xo[2] = {(uint32_t)(lane * 4) ^ ((uint32_t)q << 4), (uint32_t)(lane * 4) ^ ((uint32_t)(q + 4) << 4)};
+            const bool is_bf16 = p.out_dtype == GDL_BF16;
 #pragma unroll 8
             for (int k = 0; k < 32; ++k) {
-              const int r = q + 4 * k;
-              const uint32_t off = (uint32_t)(r * pitch + lane * 4);
-              const uint32_t u = *reinterpret_cast<const uint32_t*>(stg + (off ^ (((off >> 7) & (uint32_t)p.o_swz_mask) << 4)));
+              const int r = q + 4 * k;  // 128-byte rows, chunk XOR mask r & 7: two masks per warp
+              const uint32_t u = *reinterpret_cast<const uint32_t*>(stg + r * 128 + xo[k & 1]);
               float x0, x1;
-              if (p.out_dtype == GDL_BF16) {
+              if (is_bf16) {
                 x0 = bf16_lo(u);
                 x1 = bf16_hi(u);
               } else {
@@ -334,7 +336,7 @@ __global__ void __launch_bounds__(kRowsThreads, 1) conv3x3_rows_kernel(const __g
                 x0 = __low2float(h2);
                 x1 = __high2float(h2);
               }
-              if (j.w0 + r < p.Wo) {
+              if (full || j.w0 + r < p.Wo) {
                 x0 -= pv0;
                 x1 -= pv1;
                 s1a += x0;

@@ -399,14 +399,17 @@ conv_fwd_kernel(const __grid_constant__ ConvFwdKParams p) {
             const float pv0 = p.bn_pivot ? __ldg(p.bn_pivot + c) : 0.f;
             const float pv1 = (p.bn_pivot && c + 1 < p.Cout) ? __ldg(p.bn_pivot + c + 1) : 0.f;
             float s1a = 0.f, s1b = 0.f, s2a = 0.f, s2b = 0.f;
+            // slab rows are 128 bytes (64 channels x 2 B): row r starts at r * 128 and its 16-byte chunks are XOR-ed with
+            // (r & 7); this warp's rows r = q + 4k alternate between two chunk masks
+            const bool full = (h0 + p.TH <= p.Ho) && (w0 + p.TW <= p.Wo);
+            const uint32_t xo[2] = {(uint32_t)(lane * 4) ^ ((uint32_t)q << 4), (uint32_t)(lane * 4) ^ ((uint32_t)(q + 4) << 4)};
+            const bool is_bf16 = p.out_dtype == GDL_BF16;
 #pragma unroll 8
             for (int k = 0; k < 32; ++k) {
               const int r = q + 4 * k;
-              const bool vr = (h0 + (r >> p.log2_tw) < p.Ho) && (w0 + (r & (p.TW - 1)) < p.Wo);
-              const uint32_t off = (uint32_t)(r * pitch + lane * 4);
-              const uint32_t u = *reinterpret_cast<const uint32_t*>(stg + (off ^ (((off >> 7) & (uint32_t)p.o_swz_mask) << 4)));
+              const uint32_t u = *reinterpret_cast<const uint32_t*>(stg + r * 128 + xo[k & 1]);
               float x0, x1;
-              if (p.out_dtype == GDL_BF16) {
+              if (is_bf16) {
                 x0 = bf16_lo(u);
                 x1 = bf16_hi(u);
               } else {
@@ -414,7 +417,7 @@ conv_fwd_kernel(const __grid_constant__ ConvFwdKParams p) {
                 x0 = __low2float(h2);
                 x1 = __high2float(h2);
               }
-              if (vr) {
+              if (full || ((h0 + (r >> p.log2_tw) < p.Ho) && (w0 + (r & (p.TW - 1)) < p.Wo))) {
                 x0 -= pv0;
                 x1 -= pv1;
                 s1a += x0;
@@ -926,7 +929,16 @@ extern "C" int gdl_conv2d_nhwc_fwd(const gdl_conv_fwd_t* d, void* stream_) {
   GDL_CHECK_CUDA(set_max_dyn_smem_once(attr_once, conv_fwd_kernel, kSmemBudget + 4096));
   int grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();
   bool bn_fused = false;
-  if (d->bn_sums != nullptr && p.epi_mode == 2 && p.o_slab == 64 && d->out_dtype != GDL_F32 && p.n_tiles == 1 && G == 1) {
+  // Fuse only where the epilogue hides behind the MMAs of the next tile: the statistics triple the epilogue's instruction
+  // count, and on short-K GEMMs (1x1 convs with K = 64..256) that cost as much as the separate pass (measured, run 8:
+  // 64 -> 256 pointwise at 128^2: +0.13 ms per launch either way; 256 -> 256 3x3: +0.02 ms fused vs 0.13 ms separate).
+  static int bn_min_k = -1;
+  if (bn_min_k < 0) {
+    const char* e = getenv("GDL_BN_FUSE_MIN_K");
+    bn_min_k = e ? atoi(e) : 512;
+  }
+  if (d->bn_sums != nullptr && p.epi_mode == 2 && p.o_slab == 64 && d->out_dtype != GDL_F32 && p.n_tiles == 1 && G == 1 &&
+      (long long)d->R * d->S * Ctot >= bn_min_k) {
     const DetWs ws = det_workspace();
     if (det_grid(ws, grid, 2 * d->Cout) == grid) {
       bn_fused = true;

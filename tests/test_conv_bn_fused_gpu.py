@@ -12,7 +12,8 @@ pytestmark = pytest.mark.gpu
 CASES = [
     (2, 16, 128, [64], 128, 3, "implicit-GEMM kernel, halo tiles"),
     (2, 24, 40, [64, 32], 256, 3, "implicit-GEMM kernel, ragged 2-D tiles"),
-    (3, 10, 13, [128], 64, 1, "pointwise GEMM over 390 flattened pixels (ragged last tile)"),
+    (3, 10, 13, [512], 64, 1, "pointwise GEMM over 390 flattened pixels (ragged last tile)"),
+    (3, 10, 13, [128], 64, 1, "short-K pointwise GEMM: statistics kernel after the conv (the epilogue would not hide it)"),
     (2, 8, 192, [64], 64, 3, "row-streaming kernel, ragged width"),
     (2, 16, 128, [128, 64], 64, 3, "row-streaming kernel, virtual concat"),
     (2, 16, 64, [64], 768, 1, "three n-tiles: statistics kernel fallback"),
