@@ -452,7 +452,8 @@ static int rows_sm_count() { return device_sm_count(); }
 
 // Returns 1 when the descriptor is a case this kernel covers (then *status holds the launch status), 0 otherwise.
 // Called by gdl_conv2d_nhwc_fwd after it validated the descriptor.
-int conv3x3_rows_try(const gdl_conv_fwd_t* d, cudaStream_t stream, int* status) {
+// dry != nullptr: launch nothing, report in *dry whether the BatchNorm statistics would come out of the epilogue
+int conv3x3_rows_try(const gdl_conv_fwd_t* d, cudaStream_t stream, int* status, int* dry) {
   *status = 0;
   if (d->R != 3 || d->S != 3 || d->pad_h != 1 || d->pad_w != 1 || d->w_mn_major || d->w_rows_per_img) return 0;
   if (d->Cout > 64 || d->W < 64) return 0;
@@ -505,6 +506,12 @@ int conv3x3_rows_try(const gdl_conv_fwd_t* d, cudaStream_t stream, int* status) 
   const bool bn_fused = d->bn_sums != nullptr && p.tma_store && BN == 64 && det_grid(ws, grid_bn, 2 * d->Cout) == grid_bn;
   const int fixed = 1024 + 2 * p.o_stage_bytes + (bn_fused ? 2048 : 0);
   p.a_stages = 4;
+  if (dry != nullptr) {
+    const int bst = (kRowsSmemBudget - fixed - p.a_stages * kRowsAStage) / (3 * BN * kRowsBK * 2);
+    if (bst < 4) return 0;  // (the same test as below: the generic kernel takes this shape)
+    *dry = bn_fused ? 1 : 0;
+    return 1;
+  }
   p.b_stages = (kRowsSmemBudget - fixed - p.a_stages * kRowsAStage) / p.b_stage_bytes;
   if (p.b_stages > kRowsMaxBStages) p.b_stages = kRowsMaxBStages;
   if (p.b_stages < 4) return 0;

@@ -26,7 +26,7 @@ namespace gdl {
 
 // runtime options (gdl_set_option); env vars GDL_CONV_HALO / GDL_WGRAD_HALO / GDL_WGRAD_L2_MB seed them
 static int g_opt_conv_halo = -1, g_opt_wgrad_halo = -1, g_opt_conv_epilogue = -1, g_opt_conv_rows = -1;
-int conv3x3_rows_try(const gdl_conv_fwd_t* d, cudaStream_t stream, int* status);  // conv3x3_rows.cu
+int conv3x3_rows_try(const gdl_conv_fwd_t* d, cudaStream_t stream, int* status, int* dry);  // conv3x3_rows.cu
 int wgrad3x3_rows_try(const gdl_conv_wgrad_t* d, cudaStream_t stream, int* status);  // wgrad3x3_rows.cu
 static int g_opt_wgrad_rows = -1, g_opt_wgrad_sched = -1;
 static long long g_opt_wgrad_l2_mb = -1;
@@ -752,7 +752,9 @@ extern "C" int gdl_set_option(const char* name, long long value) {
   return 0;
 }
 
-extern "C" int gdl_conv2d_nhwc_fwd(const gdl_conv_fwd_t* d, void* stream_) {
+// dry != nullptr: validate and plan only (nothing is launched); *dry = 1 when the BatchNorm statistics (d->bn_sums) would be
+// produced by the conv's own epilogue, 0 when the statistics kernel would run after it
+static int conv_fwd_impl(const gdl_conv_fwd_t* d, void* stream_, int* dry) {
   GDL_REQUIRE(d != nullptr, GDL_ERR_INVALID, "null descriptor");
   cudaStream_t stream = (cudaStream_t)stream_;
   int Ctot = 0;
@@ -775,7 +777,7 @@ extern "C" int gdl_conv2d_nhwc_fwd(const gdl_conv_fwd_t* d, void* stream_) {
   if (opt_int(g_opt_conv_rows, "GDL_CONV_ROWS", 1) > 0) {
     // narrow 3x3 convs: weight-stationary row-rolling kernel (conv3x3_rows.cu)
     int st_rows = 0;
-    if (conv3x3_rows_try(d, stream, &st_rows)) return st_rows;
+    if (conv3x3_rows_try(d, stream, &st_rows, dry)) return st_rows;
   }
 
   ConvFwdKParams p;
@@ -948,14 +950,27 @@ extern "C" int gdl_conv2d_nhwc_fwd(const gdl_conv_fwd_t* d, void* stream_) {
       p.bn_sums = d->bn_sums;
       p.bn_pivot = d->bn_pivot;
       p.bn_det = det_ctx(ws, grid, 2 * d->Cout);
-      GDL_CHECK_CUDA(cudaMemsetAsync(d->bn_sums, 0, 2 * (size_t)d->Cout * sizeof(float), stream));
+      if (dry == nullptr) GDL_CHECK_CUDA(cudaMemsetAsync(d->bn_sums, 0, 2 * (size_t)d->Cout * sizeof(float), stream));
     }
+  }
+  if (dry != nullptr) {
+    *dry = bn_fused ? 1 : 0;
+    return 0;
   }
   conv_fwd_kernel<<<grid, kConvThreads, smem, stream>>>(p);
   GDL_CHECK_CUDA(cudaGetLastError());
   if (d->bn_sums != nullptr && !bn_fused)  // shapes the epilogue cannot cover: the statistics kernel on the stored output
     return gdl_bn_stats(d->out, d->out_dtype, (long long)N * oH * oW, d->Cout, d->ldo, d->bn_sums, d->bn_pivot, stream_);
   return 0;
+}
+
+extern "C" int gdl_conv2d_nhwc_fwd(const gdl_conv_fwd_t* d, void* stream_) { return conv_fwd_impl(d, stream_, nullptr); }
+
+extern "C" int gdl_conv2d_bn_fusable(const gdl_conv_fwd_t* d, int* fused) {
+  GDL_REQUIRE(fused != nullptr, GDL_ERR_INVALID, "conv2d_bn_fusable: null result pointer");
+  *fused = 0;
+  if (d == nullptr || d->bn_sums == nullptr) return 0;
+  return conv_fwd_impl(d, nullptr, fused);
 }
 
 // ==========================================================================================

@@ -113,6 +113,7 @@ _VP, _I, _LL, _F = C.c_void_p, C.c_int, C.c_longlong, C.c_float
 _SIGS = {
     "gdl_conv2d_nhwc_fwd": [_VP, _VP],
     "gdl_conv2d_nhwc_wgrad": [_VP, _VP],
+    "gdl_conv2d_bn_fusable": [_VP, _VP],
     "gdl_pack_conv_weight": [_VP, _VP, _I, _I, _I, _I, _I, _I, _I, _VP],
     "gdl_unpack_conv_wgrad": [_VP, _VP, _I, _I, _I, _I, _I, _I, _VP],
     "gdl_widen_conv_weight": [_VP, _VP, _I, _I, _I, _I, _I, _VP],

@@ -213,6 +213,14 @@ def conv2d_fwd(srcs: Sequence[torch.Tensor], weight: torch.Tensor, cout: int, r:
         # srcs[0] / weight / out are the views of group 0
         ng, d.g_src_stride, d.g_w_stride, d.g_out_stride = groups
         d.groups = ng
+    stats_after = False
+    if bn_sums is not None and _PROFILER is not None:
+        # per-launch timing of the convolution alone: where the epilogue cannot produce the statistics, run the statistics
+        # kernel here (outside the timed bracket) instead of inside the library call — same kernels, same results
+        fused = C.c_int(0)
+        L.check(L.load().gdl_conv2d_bn_fusable(C.byref(d), C.byref(fused)))
+        if not fused.value:
+            d.bn_sums, d.bn_pivot, stats_after = None, None, True
     e0 = _PROFILER.begin() if _PROFILER is not None else None
     L.check(L.load().gdl_conv2d_nhwc_fwd(C.byref(d), L.stream_ptr()))
     _count()
@@ -220,6 +228,8 @@ def conv2d_fwd(srcs: Sequence[torch.Tensor], weight: torch.Tensor, cout: int, r:
         ctot = sum(t.shape[3] for t in srcs)
         _PROFILER.end("conv_fwd_kernel", 2.0 * alg_scale * ng * n * ho * wo * cout * r * s * ctot, e0,
                       f"N{n} {ho}x{wo} src{[t.shape[3] for t in srcs]} -> {cout} k{r}" + (f" x{ng} groups" if ng > 1 else ""))
+    if stats_after:
+        bn_stats(out, bn_sums, bn_pivot)
     return out
 
 

@@ -129,6 +129,9 @@ typedef struct {
   const float* bn_pivot;
 } gdl_conv_fwd_t;
 int gdl_conv2d_nhwc_fwd(const gdl_conv_fwd_t* d, void* stream);
+/* Plans the same launch without running it: *fused = 1 when d->bn_sums would come out of the conv's own epilogue, 0 when
+ * the statistics kernel would run after the conv (a caller that times the convolution alone then runs gdl_bn_stats itself). */
+int gdl_conv2d_bn_fusable(const gdl_conv_fwd_t* d, int* fused);
 
 /* ---- weight gradient ------------------------------------------------------------------------
  * dw[k,r,s,c] += sum_{n,ho,wo} dy[n,ho,wo,k] * in[n,ho+r-pad_h,wo+s-pad_w,c]
