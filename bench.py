@@ -528,6 +528,7 @@ def _run_train(args, ctx, steps: int, warmup: int, headline: bool):
     if headline and args.table and rank == 0:
         prof.dump_table(args.table, nprof)
     deterministic = ops.deterministic()
+    bn_exchange_kind = trainer.bn_exchange_kind
     del trainer, model, dev_img, dev_msk
     import gc
     gc.collect()
@@ -557,7 +558,7 @@ def _run_train(args, ctx, steps: int, warmup: int, headline: bool):
         "config": {"workload": w["name"], "global_batch": B * world, "parallelism": f"dp{world}",
                    "loss": "cross_entropy", "optimizer": "adam", "sync_bn": bool(args.sync_bn and world > 1), "cuda_graph": use_graph,
                    "sra_fused": bool(ops.option("sra_fused")), "mha_flash": bool(ops.option("mha_flash")),
-                   "deterministic_reductions": deterministic,
+                   "deterministic_reductions": deterministic, "syncbn_exchange": bn_exchange_kind,
                    "l2": f"{NBUF} rotating input batches; per-step working set >> 126 MB L2"},
         "clocks": clk,
         "e2e": {"value": tiles / (ms_e2e / 1e3), "unit": "tiles/s",

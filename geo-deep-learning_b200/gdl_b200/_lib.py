@@ -101,6 +101,8 @@ def load():
     lib.gdl_last_error.restype = C.c_char_p
     lib.gdl_version.restype = C.c_int
     lib.gdl_query_workspace_bytes.restype = C.c_longlong
+    lib.gdl_p2p_exchange_bytes.restype = C.c_longlong
+    lib.gdl_p2p_exchange_bytes.argtypes = [C.c_int, C.c_int]
     _declare(lib)
     _lib = lib
     return lib
@@ -172,11 +174,12 @@ _SIGS = {
     "gdl_debug_shift_probe": [_VP, _VP, _VP, _I, _I, _I, _VP],
     "gdl_set_workspace": [_VP, _LL, _VP],
     "gdl_repack_weights": [_VP, _VP, _I, _I, _I, _VP],
+    "gdl_p2p_allreduce_sums": [_VP, _I, _VP, _I, _I, _I, _VP, _VP],
 }
 
 
 def exported_symbols() -> list[str]:
-    return ["gdl_last_error", "gdl_version", "gdl_query_workspace_bytes", *_SIGS.keys()]
+    return ["gdl_last_error", "gdl_version", "gdl_query_workspace_bytes", "gdl_p2p_exchange_bytes", *_SIGS.keys()]
 
 
 def _declare(lib) -> None:

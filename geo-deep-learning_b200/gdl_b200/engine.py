@@ -129,7 +129,7 @@ def refresh_packed_weights(wcache: dict) -> bool:
 class Engine:
     def __init__(self, dtype: torch.dtype = torch.bfloat16, training: bool = True, wcache: dict | None = None,
                  grad_dst: dict[int, torch.Tensor] | None = None, sync_bn_group=None,
-                 acc_dtype: torch.dtype = torch.float32) -> None:
+                 acc_dtype: torch.dtype = torch.float32, sync_bn_exchange=None) -> None:
         """wcache: persistent dict for packed 16-bit weights (owner clears it when it updates parameters
         behind torch's back); grad_dst: id(param) -> pre-zeroed fp32 tensor the gradient is written into
         (e.g. a view of a flat gradient buffer); sync_bn_group: torch.distributed process group for
@@ -141,6 +141,7 @@ class Engine:
         self._wcache: dict = wcache if wcache is not None else {}
         self.grad_dst = grad_dst or {}
         self.sync_bn_group = sync_bn_group
+        self.sync_bn_exchange = sync_bn_exchange  # ops.P2PExchange: the statistics travel over NVLink peer memory instead of NCCL
         self.param_grads: dict[int, torch.Tensor] = {}
         self._head = None
 
@@ -432,6 +433,9 @@ class Engine:
 
     # ------------------------------------------------------------------ batch norm
     def _allreduce(self, t: torch.Tensor) -> None:
+        if self.sync_bn_exchange is not None:
+            self.sync_bn_exchange.all_reduce_(t)
+            return
         import torch.distributed as dist
         dist.all_reduce(t, group=self.sync_bn_group)
 

@@ -109,7 +109,9 @@ _HOST_OPTS = {"pixel_pack": int(os.environ.get("GDL_PIXEL_PACK", "1")), "sra_fus
               "fused_head": int(os.environ.get("GDL_FUSED_HEAD", "1")),
               # bn_fused: a conv followed by a training-mode BatchNorm produces that layer's batch sums itself (from the
               # epilogue's staged tile) instead of a separate pass over its output (gdl_conv_fwd_t.bn_sums)
-              "bn_fused": int(os.environ.get("GDL_BN_FUSED", "1"))}
+              "bn_fused": int(os.environ.get("GDL_BN_FUSED", "1")),
+              # p2p_syncbn: SyncBN statistics exchanged over NVLink peer memory (gdl_p2p_allreduce_sums) instead of NCCL
+              "p2p_syncbn": int(os.environ.get("GDL_P2P_SYNCBN", "1"))}
 
 
 def option(name: str) -> int:
@@ -122,6 +124,41 @@ def set_option(name: str, value: int) -> None:
         _HOST_OPTS[name] = int(value)
         return
     L.check(L.load().gdl_set_option(name.encode(), int(value)))
+
+
+class P2PExchange:
+    """SyncBatchNorm statistics over NVLink peer memory (gdl_p2p_allreduce_sums): one symmetric exchange buffer per rank,
+    mapped by every peer through torch.distributed._symmetric_memory.  Construct on every rank of `group` (collective)."""
+
+    SLOT_FLOATS = 8192  # 2 x 4096 channels
+
+    def __init__(self, group, device: torch.device) -> None:
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm_mem
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        lib = L.load()
+        nbytes = int(lib.gdl_p2p_exchange_bytes(self.world, self.SLOT_FLOATS))
+        self.buf = symm_mem.empty((nbytes + 3) // 4, dtype=torch.float32, device=device)
+        self.buf.zero_()
+        self.handle = symm_mem.rendezvous(self.buf, group)
+        ptrs = [int(v) for v in self.handle.buffer_ptrs]
+        if len(ptrs) != self.world or any(v == 0 for v in ptrs):
+            raise RuntimeError("symmetric memory rendezvous returned no peer pointers")
+        off = self.buf.data_ptr() - ptrs[self.rank]  # the tensor's offset inside its symmetric allocation (same on every rank)
+        if off < 0 or off > (1 << 30):
+            raise RuntimeError("symmetric memory: the local buffer is not inside the local allocation")
+        ptrs = [v + off for v in ptrs]
+        self.peer_ptrs = (C.c_void_p * self.world)(*ptrs)
+        self.counter = torch.zeros(1, dtype=torch.int32, device=device)
+        torch.cuda.synchronize(device)
+        dist.barrier(group=group)  # every rank's buffer is zeroed before anybody signals
+
+    def all_reduce_(self, sums: torch.Tensor) -> torch.Tensor:
+        if sums.dtype != torch.float32 or not sums.is_contiguous() or sums.numel() > self.SLOT_FLOATS:
+            raise ValueError("P2PExchange: contiguous fp32 vector of at most %d values expected" % self.SLOT_FLOATS)
+        _ck(L.load().gdl_p2p_allreduce_sums(L.ptr(sums), sums.numel(), self.peer_ptrs, self.rank, self.world, self.SLOT_FLOATS,
+                                            L.ptr(self.counter), L.stream_ptr()))
+        return sums
 
 
 def deterministic() -> bool:

@@ -42,6 +42,10 @@ class FusedTrainer:
         if self.world > 1 and self.group is None:
             self.group = dist.group.WORLD
         self.sync_bn = sync_bn and self.world > 1
+        # SyncBN statistics over NVLink peer memory (one small kernel per layer) where torch's symmetric memory is available;
+        # otherwise NCCL all-reduces.  Every rank takes the same decision (the outcome is agreed on with an all-reduce).
+        self.bn_exchange = None
+        self.bn_exchange_kind = "nccl" if self.sync_bn else None
         self.acc_dtype = acc_dtype  # fp32 on the GPU; float64 only in CPU host-logic tests
         self.step_count = 0
         dev = next(model.parameters()).device
@@ -75,6 +79,19 @@ class FusedTrainer:
         # the learning rate the step uses is lr0 * lr_scale[0], read on the device: set_lr() also reaches a captured graph
         self.lr0 = float(lr)
         self.lr_scale = torch.ones(1, dtype=acc_dtype, device=dev)
+        if self.sync_bn and ops.option("p2p_syncbn") and self.acc_dtype == torch.float32 and dev.type == "cuda":
+            ok = 1
+            try:
+                ex = ops.P2PExchange(self.group, dev)
+            except Exception as e:  # noqa: BLE001 - no VMM / fabric support on this box, old torch, ...
+                import sys
+                print(f"gdl_b200: NVLink peer exchange unavailable ({type(e).__name__}: {e}); SyncBN statistics go through NCCL",
+                      file=sys.stderr)
+                ok, ex = 0, None
+            flag = torch.tensor([ok], dtype=torch.int32, device=dev)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
+            if int(flag.item()) == 1:
+                self.bn_exchange, self.bn_exchange_kind = ex, "nvlink_p2p"
         self.last_engine: Engine | None = None
         # CUDA graph of the whole step (normalise .. Adam): removes the ~10 us/launch host cost of the
         # ~800-2000 launches of a step.  Captured lazily on the first step() with a given input shape.
@@ -94,7 +111,8 @@ class FusedTrainer:
         model = self.model
         self.gflat.zero_()
         eng = Engine(model.compute_dtype, training=True, wcache=model._wcache, grad_dst=self.grad_dst,
-                     sync_bn_group=self.group if self.sync_bn else None, acc_dtype=self.acc_dtype)
+                     sync_bn_group=self.group if self.sync_bn else None, acc_dtype=self.acc_dtype,
+                     sync_bn_exchange=self.bn_exchange)
         chw = self.input_chw
         c = image_u8.shape[1 if chw else 3]
         if aug_params is not None:

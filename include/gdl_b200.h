@@ -247,6 +247,17 @@ int gdl_im2col_nhwc(const void* x, void* col, int dtype, int N, int H, int W, in
 int gdl_col2im_nhwc(const void* dcol, void* dx, int dtype, int N, int H, int W, int C, int ld, int R, int S,
                     int stride, int pad, int Kpad, void* stream);
 
+/* ---- SyncBatchNorm statistics over NVLink peer memory ------------------------------------------------------------
+ * Replaces the per-layer statistics collectives of torch SyncBatchNorm (every shipped YAML: `sync_batchnorm: true`,
+ * configs/segformer_config_RGB.yaml:6-14): sums[0..n) := sum over ranks of sums[0..n), added in RANK order (bit-identical on
+ * every rank).  peer_bufs (HOST array of `world` device pointers): rank r's exchange buffer of gdl_p2p_exchange_bytes()
+ * bytes, zero-initialised, mapped for peer access in this process (torch.distributed._symmetric_memory); counter: one
+ * zero-initialised device word per process (the call counter).  One small kernel: store own sums, signal the peers, wait for
+ * theirs, read them over NVLink.  Every rank must make the same sequence of calls (as with any collective). */
+int gdl_p2p_allreduce_sums(float* sums, int n, const void* const* peer_bufs, int rank, int world, int slot_floats,
+                           unsigned* counter, void* stream);
+long long gdl_p2p_exchange_bytes(int world, int slot_floats);
+
 /* BatchNorm2d, training mode (nn.BatchNorm2d inside models/utils.py:10-52 ConvModule,
  * segformer_mlp.py:63-72, smp Conv2dReLU, torchvision ResNet): split into
  *   stats    sums[0:C] = sum(x - pivot), sums[C:2C] = sum((x - pivot)^2)   (fp32, zeroed inside)

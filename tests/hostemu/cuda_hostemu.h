@@ -169,6 +169,7 @@ inline T __ldcs(const T* p) { return *p; }
 template <typename T>
 inline T __ldcg(const T* p) { return *p; }
 inline void __threadfence() {}
+inline void __threadfence_system() {}
 template <typename T>
 inline void __stcs(T* p, T v) { *p = v; }
 
