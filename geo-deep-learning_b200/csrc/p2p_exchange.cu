@@ -38,7 +38,12 @@ GDL_DEVINL unsigned ld_acquire_sys(const unsigned* p) {
 }
 GDL_DEVINL float ld_relaxed_sys(const float* p) {
   float v;
-  asm volatile("ld.relaxed.sys.global.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
+  asm volatile("ld.relaxed.sys.global.f32 %0, [%1];" : "=f"(v) : "l"(p));
+  return v;
+}
+GDL_DEVINL float4 ld_relaxed_sys_v4(const float* p) {
+  float4 v;
+  asm volatile("ld.relaxed.sys.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
   return v;
 }
 
@@ -54,7 +59,7 @@ __global__ void __launch_bounds__(256) p2p_allreduce_kernel(float* __restrict__ 
   const int slot = (int)(seq & 1u);
   float* mine = peers.buf[rank] + (long long)slot * slot_floats;
   for (int i = threadIdx.x; i < n; i += blockDim.x) mine[i] = sums[i];
-  __threadfence_system();
+  __threadfence_system();  // the own slot is written before anybody is told so
   __syncthreads();
   if ((int)threadIdx.x < world) {
     const int r = threadIdx.x;
@@ -70,9 +75,29 @@ __global__ void __launch_bounds__(256) p2p_allreduce_kernel(float* __restrict__ 
     }
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+  // every peer's values of one 4-float group are requested before the first is used: ONE NVLink round trip per group
+  // (a dependent `a += load` chain serialised world x n/256 remote loads: 43 us per 4096-float exchange at N = 2, run 11)
+  const long long base = (long long)slot * slot_floats;
+  const int n4 = n >> 2;
+  for (int i = threadIdx.x; i < n4; i += blockDim.x) {
+    float4 v[kP2PMaxWorld];
+#pragma unroll
+    for (int r = 0; r < kP2PMaxWorld; ++r)
+      if (r < world) v[r] = ld_relaxed_sys_v4(peers.buf[r] + base + 4 * i);
+    float4 a = v[0];
+#pragma unroll
+    for (int r = 1; r < kP2PMaxWorld; ++r)
+      if (r < world) {
+        a.x += v[r].x;
+        a.y += v[r].y;
+        a.z += v[r].z;
+        a.w += v[r].w;
+      }
+    *reinterpret_cast<float4*>(sums + 4 * i) = a;
+  }
+  for (int i = 4 * n4 + threadIdx.x; i < n; i += blockDim.x) {
     float a = 0.f;
-    for (int r = 0; r < world; ++r) a += ld_relaxed_sys(peers.buf[r] + (long long)slot * slot_floats + i);
+    for (int r = 0; r < world; ++r) a += ld_relaxed_sys(peers.buf[r] + base + i);
     sums[i] = a;
   }
 }
@@ -85,6 +110,7 @@ extern "C" int gdl_p2p_allreduce_sums(float* sums, int n, const void* const* pee
                                       int slot_floats, unsigned* counter, void* stream) {
   GDL_REQUIRE(sums && peer_bufs_host && counter && n > 0 && world >= 1 && world <= kP2PMaxWorld && rank >= 0 && rank < world,
               GDL_ERR_INVALID, "p2p_allreduce_sums: bad args (world <= %d)", kP2PMaxWorld);
+  GDL_REQUIRE((reinterpret_cast<uintptr_t>(sums) & 15) == 0, GDL_ERR_INVALID, "p2p_allreduce_sums: sums must be 16-byte aligned");
   GDL_REQUIRE(n <= slot_floats && slot_floats % 4 == 0, GDL_ERR_INVALID, "p2p_allreduce_sums: %d values exceed the %d-float slots", n,
               slot_floats);
   P2PPeers peers;
