@@ -106,8 +106,43 @@ def main() -> None:
     report("channel_pool_bwd (4 bands x 64)", px * (e * 2 + bands * e * 2 + 64 + bands * e * 2 + 32),
            lambda: ops.channel_pool_bwd(pooled, xw, attn, bands))
     report("relu_bwd (bf16)", xw.numel() * 6, lambda: ops.relu_bwd(xw, xw))
+    # ---- the HBM-bound kernels of the UNet++ step at the bench batch: 32 x 256 x 256 x 64 and 32 x 128 x 128 x 256
+    del x, h, dh, xw, sc, pooled, attn, logits
+    torch.cuda.empty_cache()
+    for (nn_, hh, ww, cc) in ((32, 256, 256, 64), (32, 128, 128, 256)):
+        xa = torch.randn(nn_, hh, ww, cc, device=dev, generator=g).bfloat16()
+        ya = torch.randn(nn_, hh, ww, cc, device=dev, generator=g).bfloat16()
+        el = xa.numel()
+        piv = torch.zeros(cc, device=dev)
+        sums = torch.empty(2 * cc, device=dev)
+        tag = f"{nn_}x{hh}x{ww}x{cc}"
+        report(f"bn_stats {tag} (bf16 in, 2C sums, ordered)", el * 2, lambda: ops.bn_stats(xa, sums, piv))
+        scale, shift = torch.rand(cc, device=dev) + 0.5, torch.randn(cc, device=dev)
+        yo = torch.empty_like(xa)
+        report(f"bn_apply + ReLU {tag}", el * 4, lambda: ops.bn_apply(xa, scale, shift, relu=True, y=yo))
+        yu = torch.empty(nn_, 2 * hh, 2 * ww, cc, dtype=torch.bfloat16, device=dev)
+        report(f"bn_apply + ReLU + nearest x2 copy {tag}", el * (2 + 2 + 8), lambda: ops.bn_apply(xa, scale, shift, relu=True, y=yo, y_up=yu))
+        del yu
+        mean_, inv_ = torch.randn(cc, device=dev) * 0.1, torch.rand(cc, device=dev) + 0.5
+        go = torch.empty_like(xa)
+        for ns in (1, 2, 4):
+            srcs = [(torch.randn(nn_, hh, ww, cc, device=dev, generator=g).bfloat16(), 0) for _ in range(ns)]
+            report(f"grad_gather {ns} source(s) + ReLU mask + BN-backward sums {tag}", el * 2 * (ns + 3),
+                   lambda srcs=srcs: ops.grad_gather(srcs, xa.shape, torch.bfloat16, y=ya, x=xa, mean=mean_, invstd=inv_, g=go, sums=sums))
+            del srcs
+        dxo = torch.empty_like(xa)
+        gam_ = torch.rand(cc, device=dev)
+        report(f"bn_bwd_apply {tag}", el * 6, lambda: ops.bn_bwd_apply(go, xa, mean_, inv_, gam_, sums, dxo, None, None, False))
+        del xa, ya, yo, go, dxo
+        torch.cuda.empty_cache()
     if args.out:
-        Path(args.out).write_text(json.dumps({"hbm_peak_GBps": peak, "rows": rows}, indent=1))
+        import subprocess
+        try:
+            clk = subprocess.run(["nvidia-smi", "--query-gpu=clocks.sm,clocks.max.sm,clocks_event_reasons.active", "--format=csv,noheader"],
+                                 capture_output=True, text=True, timeout=10).stdout.strip()
+        except Exception:  # noqa: BLE001
+            clk = None
+        Path(args.out).write_text(json.dumps({"hbm_peak_GBps": peak, "clocks_after_run": clk, "rows": rows}, indent=1))
 
 
 if __name__ == "__main__":
