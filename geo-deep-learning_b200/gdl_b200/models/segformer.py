@@ -442,7 +442,9 @@ class SegFormer(nn.Module):
         rc_pred = eng.conv_raw([z], dec.linear_pred.weight, 1, 0, bias=dec.linear_pred.bias, out_dtype=acc)
         logits = ops.bilinear_fwd(rc_pred.x, hh, ww) if upsample else rc_pred.x
         eng.named = {f"c{s + 1}": stages[s].feat for s in range(4)}
-        self._saved = _Saved(stages=stages, projs=projs, rc_pred=rc_pred, z=z, h1=h1, w1=w1, hh=hh, ww=ww)
+        # the saved activations belong to THIS forward (its engine), not to the module: two training forwards before a
+        # backward, or an eval forward in between, must not overwrite each other's graph
+        eng.saved_segformer = _Saved(stages=stages, projs=projs, rc_pred=rc_pred, z=z, h1=h1, w1=w1, hh=hh, ww=ww)
         return logits
 
     # ====================================================================================== backward
@@ -556,13 +558,12 @@ class SegFormer(nn.Module):
         ops.require_cuda(img, "gdl_b200.SegFormer")
         eng = Engine(self.compute_dtype, training=False, wcache=self._wcache)
         lr = self.run(eng, self._input(img), img.shape[1], upsample=False)
-        self._saved = None
         return ops.upsample_argmax(lr, img.shape[2], img.shape[3], threshold)
 
     def backward(self, eng: Engine, dlogits: torch.Tensor | None, d16_lowres: torch.Tensor | None = None) -> None:
         """dlogits: fp32 (N,H,W,K) gradient of the loss w.r.t. the logits returned by run(); or d16_lowres: the 16-bit,
         16-channel-padded gradient w.r.t. the low-resolution logits (fused head)."""
-        S = self._saved
+        S = eng.saved_segformer
         dt = eng.dtype
         if d16_lowres is not None:
             d16 = d16_lowres
@@ -611,7 +612,7 @@ class SegFormer(nn.Module):
             eng.conv_backward(st.rc_pe, dpe)
             if s > 0:
                 feat_grads[s - 1].append(self._take(S.stages[s - 1].feat))
-        self._saved = None
+        eng.saved_segformer = None
 
     # ====================================================================================== nn.Module surface
     def _input(self, image: torch.Tensor) -> Act:
@@ -627,7 +628,6 @@ class SegFormer(nn.Module):
         with torch.no_grad():
             eng = Engine(self.compute_dtype, training=False, wcache=self._wcache)
             logits = self.run(eng, self._input(img), img.shape[1])
-            self._saved = None
         return logits.permute(0, 3, 1, 2)
 
 

@@ -128,7 +128,7 @@ class UperNetSegmentor(nn.Module):
         a = cb([nf[-1]], self.aux_head.convs[0].conv, self.aux_head.convs[0].norm)
         a = eng.dropout2d(a, self.aux_dropout_ratio, self.aux_dropout_mask)
         rc_aux = eng.conv_raw([a], self.aux_head.cls_seg.weight, 1, 0, bias=self.aux_head.cls_seg.bias, out_dtype=acc)
-        self._saved = (rc_out, rc_aux)
+        eng.saved_upernet = (rc_out, rc_aux)  # per forward (engine), not per module
         eng.named = {f"neck{i}": nf[i] for i in range(4)} | {"fpn": y}
         if not upsample:
             return rc_out.x, rc_aux.x
@@ -137,7 +137,7 @@ class UperNetSegmentor(nn.Module):
     def backward(self, eng: Engine, d_out: torch.Tensor | None, d_aux: torch.Tensor | None, lowres16: bool = False) -> None:
         """d_out / d_aux: fp32 (N,H,W,K) gradients of the loss w.r.t. the two logit maps; with lowres16 they are the 16-bit,
         16-channel-padded gradients w.r.t. the heads' low-resolution maps (fused head)."""
-        rc_out, rc_aux = self._saved
+        rc_out, rc_aux = eng.saved_upernet
         for rc, d in ((rc_out, d_out), (rc_aux, d_aux)):
             if d is None:
                 continue
@@ -148,7 +148,7 @@ class UperNetSegmentor(nn.Module):
             dl = ops.bilinear_bwd(d, rc.x.shape[1], rc.x.shape[2])
             eng.conv_backward(rc, ops.normalize_to_nhwc(dl, False, eng.dtype, (k + 15) // 16 * 16))
         eng.backward()
-        self._saved = None
+        eng.saved_upernet = None
 
     def forward(self, enc_feats: list[torch.Tensor], image_size: tuple[int, int]):
         """enc_feats: 4 x (N, C, h, w) float tensors (what DOFAv2.forward returns)."""
@@ -160,7 +160,6 @@ class UperNetSegmentor(nn.Module):
         with torch.no_grad():
             eng = Engine(self.compute_dtype, training=False, wcache=self._wcache)
             o, a = self.run(eng, [self._feat(f, False) for f in enc_feats], image_size)
-            self._saved = None
         return o.permute(0, 3, 1, 2), a.permute(0, 3, 1, 2)
 
     def _feat(self, f: torch.Tensor, needs_grad: bool) -> Act:
