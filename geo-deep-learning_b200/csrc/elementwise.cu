@@ -465,13 +465,22 @@ struct GatherSrcs {
 // NS = number of gradient sources (compile time: the loads of one iteration are all issued before the first use,
 // 2..20 independent 16-byte loads in flight per thread — run 8 measured the previous sequential version at 2.1 TB/s,
 // a third of what bn_apply reaches).  Narrow gathers (NS <= 2) take two pixels per iteration.
-template <typename T, int NS>
+// NUP (round 2): how the sources are laid out.  0 / 1 = the first NS - NUP sources are plain (mode 0) and the LAST one is
+// the gradient of the nearest-x2 copy (mode 1, a 2x2 sum: four loads) — every gather of a UNet++ / UperNet step has this
+// form — so the staging registers are 1 vector per plain source instead of 4 for every source: 155 -> ~90 registers at
+// NS = 2 (one resident block of 256 threads per SM -> two or three; the round-1 kernel ran at 0.55 of the copy peak with
+// 2+ sources, 0.75 with one).  -1 = any mix of modes (4 vectors staged per source).
+template <typename T, int NS, int NUP>
 __global__ void __launch_bounds__(256) grad_gather_kernel(GatherSrcs srcs, const T* __restrict__ y, int ldy,
                                                           const T* __restrict__ x, int ldx,
                                                           const float* __restrict__ mean,
                                                           const float* __restrict__ invstd, T* __restrict__ g, int ldg,
                                                           float* __restrict__ sums /* [2][C] or null */, int N, int H,
                                                           int W, int C, const DetCtx det) {
+  constexpr bool kGeneric = NUP < 0;
+  constexpr int N0 = kGeneric ? NS : NS - NUP;        // plain sources (generic: every source, staged with 4 vectors)
+  constexpr int NU = kGeneric ? 0 : NUP;              // trailing 2x2-pooled sources
+  constexpr int V0 = kGeneric ? 4 : 1;
   constexpr int PIX = NS <= 2 ? 2 : 1;
   const int cv = C / 8;
   const int tpr = cv < (int)blockDim.x ? cv : blockDim.x;
@@ -480,9 +489,11 @@ __global__ void __launch_bounds__(256) grad_gather_kernel(GatherSrcs srcs, const
   const int tr = threadIdx.x / tpr;
   const long long M = (long long)N * H * W;
   extern __shared__ float red[];
-  bool any_up = false;
+  bool any_up = NU > 0;
+  if (kGeneric) {
 #pragma unroll
-  for (int k = 0; k < NS; ++k) any_up |= srcs.mode[k] != 0;
+    for (int k = 0; k < NS; ++k) any_up |= srcs.mode[k] != 0;
+  }
   for (int cbase = 0; cbase < cv; cbase += tpr) {  // uniform trip count (barriers inside)
     const int c8 = cbase + tc;
     const bool active = (c8 < cv) && (tr < rows_per_block);
@@ -501,7 +512,8 @@ __global__ void __launch_bounds__(256) grad_gather_kernel(GatherSrcs srcs, const
       const long long stride = rows_per_block;
       for (long long pix0 = (long long)blockIdx.x * PIX * rows_per_block + tr; pix0 < M;
            pix0 += (long long)gridDim.x * PIX * rows_per_block) {
-        uint4 raw[PIX][NS][4];
+        uint4 raw[PIX][N0 > 0 ? N0 : 1][V0];
+        uint4 rawu[PIX][NU > 0 ? NU : 1][4];
         uint4 yv[PIX], xv[PIX];
         // ---- issue every load of this iteration ----
 #pragma unroll
@@ -516,18 +528,28 @@ __global__ void __launch_bounds__(256) grad_gather_kernel(GatherSrcs srcs, const
             up_off = ((long long)(n * 2 * H + 2 * h)) * (2ll * W) + 2 * w;
           }
 #pragma unroll
-          for (int k = 0; k < NS; ++k) {
+          for (int k = 0; k < N0; ++k) {
             const T* sp = reinterpret_cast<const T*>(srcs.ptr[k]);
             const long long ld = srcs.ld[k];
-            if (srcs.mode[k] == 0) {
+            if (!kGeneric || srcs.mode[k] == 0) {
               raw[pp][k][0] = *reinterpret_cast<const uint4*>(sp + pix * ld + c0);
             } else {
               const T* b = sp + up_off * ld + c0;
               raw[pp][k][0] = *reinterpret_cast<const uint4*>(b);
-              raw[pp][k][1] = *reinterpret_cast<const uint4*>(b + ld);
-              raw[pp][k][2] = *reinterpret_cast<const uint4*>(b + 2ll * W * ld);
-              raw[pp][k][3] = *reinterpret_cast<const uint4*>(b + (2ll * W + 1) * ld);
+              raw[pp][k][V0 > 1 ? 1 : 0] = *reinterpret_cast<const uint4*>(b + ld);
+              raw[pp][k][V0 > 2 ? 2 : 0] = *reinterpret_cast<const uint4*>(b + 2ll * W * ld);
+              raw[pp][k][V0 > 3 ? 3 : 0] = *reinterpret_cast<const uint4*>(b + (2ll * W + 1) * ld);
             }
+          }
+#pragma unroll
+          for (int k = 0; k < NU; ++k) {
+            const T* sp = reinterpret_cast<const T*>(srcs.ptr[N0 + k]);
+            const long long ld = srcs.ld[N0 + k];
+            const T* b = sp + up_off * ld + c0;
+            rawu[pp][k][0] = *reinterpret_cast<const uint4*>(b);
+            rawu[pp][k][1] = *reinterpret_cast<const uint4*>(b + ld);
+            rawu[pp][k][2] = *reinterpret_cast<const uint4*>(b + 2ll * W * ld);
+            rawu[pp][k][3] = *reinterpret_cast<const uint4*>(b + (2ll * W + 1) * ld);
           }
           if (y != nullptr) yv[pp] = *reinterpret_cast<const uint4*>(y + pix * ldy + c0);
           if (sums != nullptr) xv[pp] = *reinterpret_cast<const uint4*>(x + pix * ldx + c0);
@@ -539,20 +561,30 @@ __global__ void __launch_bounds__(256) grad_gather_kernel(GatherSrcs srcs, const
           if (pix >= M) continue;
           float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 #pragma unroll
-          for (int k = 0; k < NS; ++k) {
+          for (int k = 0; k < N0; ++k) {
             float f[8];
             Vec8<T>::unpack(raw[pp][k][0], f);
-            if (srcs.mode[k] == 0) {
+            if (!kGeneric || srcs.mode[k] == 0) {
 #pragma unroll
               for (int j = 0; j < 8; ++j) acc[j] += f[j];
             } else {
               float f1[8], f2[8], f3[8];
-              Vec8<T>::unpack(raw[pp][k][1], f1);
-              Vec8<T>::unpack(raw[pp][k][2], f2);
-              Vec8<T>::unpack(raw[pp][k][3], f3);
+              Vec8<T>::unpack(raw[pp][k][V0 > 1 ? 1 : 0], f1);
+              Vec8<T>::unpack(raw[pp][k][V0 > 2 ? 2 : 0], f2);
+              Vec8<T>::unpack(raw[pp][k][V0 > 3 ? 3 : 0], f3);
 #pragma unroll
               for (int j = 0; j < 8; ++j) acc[j] += ((f[j] + f1[j]) + f2[j]) + f3[j];
             }
+          }
+#pragma unroll
+          for (int k = 0; k < NU; ++k) {
+            float f[8], f1[8], f2[8], f3[8];
+            Vec8<T>::unpack(rawu[pp][k][0], f);
+            Vec8<T>::unpack(rawu[pp][k][1], f1);
+            Vec8<T>::unpack(rawu[pp][k][2], f2);
+            Vec8<T>::unpack(rawu[pp][k][3], f3);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[j] += ((f[j] + f1[j]) + f2[j]) + f3[j];
           }
           if (y != nullptr) {
             float yy[8];
@@ -971,11 +1003,21 @@ extern "C" int gdl_grad_gather(int num_src, const void* const* src_ptr, const in
       det = det_ctx(ws, gd, 2 * C);
     }
   }
-#define GDL_GG_LAUNCH(NSV)                                                                                             \
+  // source layout: plain sources first, at most one 2x2-pooled (mode 1) source, last -> the lean kernel; anything else -> generic
+  int nup = 0;
+  for (int i = 0; i < num_src; ++i) nup += src_mode[i] != 0;
+  const bool lean = nup == 0 || (nup == 1 && src_mode[num_src - 1] != 0);
+#define GDL_GG_LAUNCH2(NSV, NUPV)                                                                                      \
   GDL_DISPATCH_16(dtype, {                                                                                             \
-    grad_gather_kernel<T, NSV><<<(int)blocks, threads, smem, st>>>(gs, (const T*)y, ldy, (const T*)x, ldx, mean,        \
-                                                                   invstd, (T*)g, ldg, sums, N, H, W, C, det);         \
+    grad_gather_kernel<T, NSV, NUPV><<<(int)blocks, threads, smem, st>>>(gs, (const T*)y, ldy, (const T*)x, ldx, mean, \
+                                                                         invstd, (T*)g, ldg, sums, N, H, W, C, det);   \
   })
+#define GDL_GG_LAUNCH(NSV)                          \
+  do {                                              \
+    if (!lean) GDL_GG_LAUNCH2(NSV, -1);             \
+    else if (nup == 0) GDL_GG_LAUNCH2(NSV, 0);      \
+    else GDL_GG_LAUNCH2(NSV, 1);                    \
+  } while (0)
   switch (num_src) {
     case 1: GDL_GG_LAUNCH(1); break;
     case 2: GDL_GG_LAUNCH(2); break;
@@ -984,6 +1026,7 @@ extern "C" int gdl_grad_gather(int num_src, const void* const* src_ptr, const in
     case 5: GDL_GG_LAUNCH(5); break;
     default: GDL_GG_LAUNCH(6); break;
   }
+#undef GDL_GG_LAUNCH2
 #undef GDL_GG_LAUNCH
   GDL_CHECK_CUDA(cudaGetLastError());
   return 0;

@@ -50,13 +50,15 @@ def test_bn_stats_reproducible(cuda, m, c):
 
 
 @pytest.mark.parametrize("n,h,w,c,nsrc,up", [(4, 32, 32, 64, 3, True), (2, 17, 9, 16, 1, False), (8, 64, 64, 128, 2, False),
-                                             (32, 16, 16, 1024, 6, False)])
+                                             (32, 16, 16, 1024, 6, False), (2, 12, 20, 32, 2, "first")])
 def test_grad_gather_sums_reproducible(cuda, n, h, w, c, nsrc, up):
     from gdl_b200 import ops
     g = torch.Generator().manual_seed(n * h + c)
     srcs = [(torch.randn(n, h, w, c, generator=g).to(torch.bfloat16).cuda(), 0) for _ in range(nsrc)]
     if up:
         srcs.append((torch.randn(n, 2 * h, 2 * w, c, generator=g).to(torch.bfloat16).cuda(), 1))
+    if up == "first":  # a 2x2-pooled source that is not the last one: the generic kernel variant
+        srcs.insert(0, (torch.randn(n, 2 * h, 2 * w, c, generator=g).to(torch.bfloat16).cuda(), 1))
     x = torch.randn(n, h, w, c, generator=g).to(torch.bfloat16).cuda()
     y = torch.randn(n, h, w, c, generator=g).to(torch.bfloat16).cuda()
     mean, invstd = torch.randn(c, generator=g).cuda() * 0.1, (torch.rand(c, generator=g) + 0.5).cuda()
@@ -68,6 +70,11 @@ def test_grad_gather_sums_reproducible(cuda, n, h, w, c, nsrc, up):
         return gg, s
     (g1, s1), (g2, s2) = _twice(run)
     assert torch.equal(g1, g2) and torch.equal(s1, s2)
+    want = torch.zeros(n, h, w, c, dtype=torch.float32, device="cuda")
+    for t_, mode in srcs:
+        want += t_.float() if mode == 0 else t_.float().view(n, h, 2, w, 2, c).sum(dim=(2, 4))
+    want = torch.where(y.float() > 0, want, torch.zeros_like(want))
+    assert (g1.float() - want).abs().max() <= 0.02 * want.abs().max() + 1e-3  # one 16-bit rounding of the sum
     gd = g1.double().view(-1, c)
     xh = (x.double().view(-1, c) - mean.double()) * invstd.double()
     ref = torch.cat([gd.sum(0), (gd * xh).sum(0)])
