@@ -143,6 +143,7 @@ class Engine:
         self.sync_bn_group = sync_bn_group
         self.sync_bn_exchange = sync_bn_exchange  # ops.P2PExchange: the statistics travel over NVLink peer memory instead of NCCL
         self.param_grads: dict[int, torch.Tensor] = {}
+        self.on_progress = None  # optional callback(engine) after every backward closure
         self._head = None
 
     # ------------------------------------------------------------------ parameters
@@ -647,4 +648,6 @@ class Engine:
         # pop as we go so each layer's saved activations are released as soon as it is done
         while self.tape:
             self.tape.pop()()
+            if self.on_progress is not None:  # the trainer starts the all-reduce of finished gradient buckets here
+                self.on_progress(self)
         self._head = None

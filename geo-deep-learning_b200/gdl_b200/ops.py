@@ -111,7 +111,10 @@ _HOST_OPTS = {"pixel_pack": int(os.environ.get("GDL_PIXEL_PACK", "1")), "sra_fus
               # epilogue's staged tile) instead of a separate pass over its output (gdl_conv_fwd_t.bn_sums)
               "bn_fused": int(os.environ.get("GDL_BN_FUSED", "1")),
               # p2p_syncbn: SyncBN statistics exchanged over NVLink peer memory (gdl_p2p_allreduce_sums) instead of NCCL
-              "p2p_syncbn": int(os.environ.get("GDL_P2P_SYNCBN", "1"))}
+              "p2p_syncbn": int(os.environ.get("GDL_P2P_SYNCBN", "1")),
+              # overlap_allreduce: the flat gradient is all-reduced in 3 buckets, each started as soon as its layers' backward
+              # is done (UNet++ route of the fused trainer); 0 = one all-reduce after the backward
+              "overlap_allreduce": int(os.environ.get("GDL_OVERLAP_ALLREDUCE", "1"))}
 
 
 def option(name: str) -> int:

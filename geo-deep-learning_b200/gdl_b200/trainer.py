@@ -70,6 +70,29 @@ class FusedTrainer:
                 g = self.gflat[off:off + n].view(p.shape)
                 p.grad = g
                 self.grad_dst[id(p)] = g
+        # gradient buckets for the overlapped all-reduce (DDP's bucketed reduction, configs/segformer_config_RGB.yaml:6-14):
+        # contiguous ranges of the flat buffer in BACKWARD order (the tail of the flat buffer = the layers whose gradients are
+        # complete first).  A bucket is all-reduced on NCCL's stream as soon as every parameter in it has its gradient, while
+        # the backward of the earlier layers keeps the GPU busy; what is left is reduced in optimizer_step.
+        self.overlap_allreduce = self.world > 1 and ops.option("overlap_allreduce") != 0
+        self._buckets: list[tuple[int, int, frozenset]] = []
+        if self.overlap_allreduce and self.params:
+            nb = 3
+            bounds = [total * (i + 1) // nb for i in range(nb)]
+            start, ids, bi = 0, [], 0
+            for p, off in zip(self.params, offsets):
+                ids.append(id(p))
+                end = off + (p.numel() + 3) // 4 * 4
+                if end >= bounds[bi]:
+                    self._buckets.append((start, end, frozenset(ids)))
+                    start, ids, bi = end, [], bi + 1
+                    if bi >= nb:
+                        break
+            if ids:
+                self._buckets.append((start, total, frozenset(ids)))
+            self._buckets.reverse()  # backward order: tail of the flat buffer first
+        self._pending: list = []
+        self._next_bucket = 0
         self.mean = torch.as_tensor(mean, dtype=acc_dtype, device=dev) if mean is not None else None
         self.std = torch.as_tensor(std, dtype=acc_dtype, device=dev) if std is not None else None
         self.loss_scale = (None if loss_scale is None else
@@ -109,6 +132,9 @@ class FusedTrainer:
         with d(loss)/d(params) left in the flat gradient buffer.  aug_params: optional int32 (N,6) device table of
         gdl_b200.augment.BatchAugmenter.sample(): the augmentation is then applied by the normalisation pass itself."""
         model = self.model
+        for work in self._pending:  # bucket all-reduces of a backward whose optimizer_step was never called
+            work.wait()
+        self._pending = []
         self.gflat.zero_()
         eng = Engine(model.compute_dtype, training=True, wcache=model._wcache, grad_dst=self.grad_dst,
                      sync_bn_group=self.group if self.sync_bn else None, acc_dtype=self.acc_dtype,
@@ -141,14 +167,34 @@ class FusedTrainer:
             d16 = torch.zeros((n, h, w, (k + 15) // 16 * 16), dtype=model.compute_dtype, device=logits.device)
             ops.seg_loss_bwd(logits, target, self.loss, coeff, self.loss_scale, d16)
             eng.head_backward(d16)
+            if self.overlap_allreduce:
+                self._next_bucket, self._pending = 0, []
+                eng.on_progress = self._reduce_finished_buckets
             eng.backward()
         self.last_engine = eng
         return coeff[0]
 
+    def _reduce_finished_buckets(self, eng: Engine) -> None:
+        """after a backward closure: start the all-reduce of every bucket (in backward order) whose parameters all have their
+        gradient — the kernels that wrote it are already enqueued on this stream, NCCL's stream waits for them"""
+        while self._next_bucket < len(self._buckets):
+            a, b, ids = self._buckets[self._next_bucket]
+            if not ids <= eng.param_grads.keys():
+                return
+            self._pending.append(dist.all_reduce(self.gflat[a:b], group=self.group, async_op=True))
+            self._next_bucket += 1
+
     @torch.no_grad()
     def optimizer_step(self) -> None:
         if self.world > 1:
-            dist.all_reduce(self.gflat, group=self.group)
+            if self.overlap_allreduce and self._buckets:
+                for work in self._pending:
+                    work.wait()  # the current stream waits for NCCL's
+                for a, b, _ in self._buckets[self._next_bucket:]:  # whatever the backward did not finish early
+                    dist.all_reduce(self.gflat[a:b], group=self.group)
+                self._pending, self._next_bucket = [], len(self._buckets)
+            else:
+                dist.all_reduce(self.gflat, group=self.group)
             scale_by = 1.0 / self.world
         else:
             scale_by = None
