@@ -227,6 +227,15 @@ class FusedTrainer:
         if not self.repack_in_place or not refresh_packed_weights(self.model._wcache):
             self.model._wcache.clear()
 
+    def close(self) -> None:
+        """Drop what lives in the process group (the NVLink exchange buffers, pending collectives).  Call it — or delete the
+        trainer — BEFORE torch.distributed.destroy_process_group(): symmetric memory torn down after the group is gone blocks."""
+        for work in self._pending:
+            work.wait()
+        self._pending = []
+        self.bn_exchange = None
+        self._graph = None
+
     def set_lr(self, lr: float) -> None:
         """Learning rate of the following steps (a scheduler's hook: ReduceLROnPlateau / OneCycleLR in the reference's
         YAMLs).  Stored on the device, so eager steps and replays of an already captured graph both use it."""

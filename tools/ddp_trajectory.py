@@ -32,6 +32,13 @@ def main() -> None:
     if rank == 0:
         print(f"overlap={ops.option('overlap_allreduce')} exchange={tr.bn_exchange_kind} losses {losses} param checksum {chk:.9f} "
               f"ranks identical: {len(set(allchk)) == 1}")
+    # release the symmetric-memory exchange (and everything else that lives in the process group) BEFORE the group goes away:
+    # torn down at interpreter exit, after destroy_process_group, it blocked until the launcher's timeout (round 2, run 16)
+    del tr, m
+    import gc
+    gc.collect()
+    torch.cuda.synchronize()
+    dist.barrier()
     dist.destroy_process_group()
 
 
