@@ -171,7 +171,6 @@ _SIGS = {
     "gdl_adaptive_avgpool_fwd": [_VP, _LL, _VP, _I, _I, _I, _I, _I, _I, _VP],
     "gdl_adaptive_avgpool_bwd": [_VP, _VP, _I, _I, _I, _I, _I, _I, _VP],
     "gdl_add_nhwc": [_VP, _LL, _VP, _LL, _VP, _LL, _I, _LL, _I, _VP],
-    "gdl_debug_shift_probe": [_VP, _VP, _VP, _I, _I, _I, _VP],
     "gdl_set_workspace": [_VP, _LL, _VP],
     "gdl_repack_weights": [_VP, _VP, _I, _I, _I, _VP],
     "gdl_p2p_allreduce_sums": [_VP, _I, _VP, _I, _I, _I, _VP, _VP],

@@ -491,10 +491,6 @@ int gdl_relu_bwd(const void* dy, const void* y, void* dx, int dtype, long long n
 /* fp32 -> dtype cast of a flat buffer (residual-stream gradient -> 16-bit GEMM operand) */
 int gdl_cast_f32(const float* x, void* y, int dtype, long long n, void* stream);
 
-/* Development probe (csrc/debug_probe.cu): UMMA descriptor with a start address inside the 1024-byte
- * swizzle repeat (halo-tile reuse across filter taps).  Not used by the product path. */
-int gdl_debug_shift_probe(const void* a, const void* b, float* out, int mode, int shift, int bo_mode, void* stream);
-
 #ifdef __cplusplus
 }
 #endif

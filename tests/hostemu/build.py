@@ -20,7 +20,7 @@ ROOT = HERE.parent.parent
 CSRC = Path(os.environ.get("GDL_HOSTEMU_CSRC", ROOT / "geo-deep-learning_b200" / "csrc"))
 OUT = Path(os.environ.get("GDL_HOSTEMU_OUT", HERE / "_build"))
 SOURCES = ["runtime.cu", "elementwise.cu", "transformer.cu", "loss_optim.cu", "augment_metrics.cu",
-           "igemm_conv.cu", "conv3x3_rows.cu", "wgrad3x3_rows.cu", "debug_probe.cu", "sra_attention.cu", "upsample_head.cu", "p2p_exchange.cu"]
+           "igemm_conv.cu", "conv3x3_rows.cu", "wgrad3x3_rows.cu", "sra_attention.cu", "upsample_head.cu", "p2p_exchange.cu"]
 # PTX wrappers of common.cuh whose bodies are forwarded to the functional model in hostemu_tc.cpp
 TC_FORWARD = ["smem_u32", "elect_one", "mbar_init", "mbar_expect_tx", "mbar_arrive", "mbar_try_wait", "tma_load_2d", "tma_load_4d",
               "tma_store_4d", "named_bar_sync", "tmem_alloc", "tmem_dealloc", "umma_f16", "umma_commit", "tmem_ld_32x32b_x16"]

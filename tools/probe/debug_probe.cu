@@ -1,11 +1,13 @@
-// debug_probe.cu — development probe (not on the product path): does a UMMA shared-memory descriptor whose
+// debug_probe.cu — development probe, built by tools/probe_shift.py into its own library (NOT part of libgdlb200.so): does a UMMA shared-memory descriptor whose
 // start address is NOT aligned to the 1024-byte swizzle repeat address the rows one expects?  If it does,
 // a conv tile loaded once with its halo can serve several filter taps by shifting the descriptor start.
 //   mode 0: K-major SW128 A operand [rows = pixels][64 ch]; start = base + shift*128 B
 //   mode 1: MN-major SW128 A operand [K rows = pixels][2 atoms x 64 ch]; start = base + shift*128 B
 // bo_mode 1 sets the descriptor's base_offset field (bits 49..51) to (start >> 7) & 7.
 #include "../../include/gdl_b200.h"
-#include "tmap.cuh"
+#include "../../geo-deep-learning_b200/csrc/tmap.cuh"
+
+extern "C" int gdl_debug_shift_probe(const void* a, const void* b, float* out, int mode, int shift, int bo_mode, void* stream);
 
 namespace gdl {
 

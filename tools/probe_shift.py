@@ -1,5 +1,8 @@
-"""GPU probe: shifted UMMA descriptor start inside a swizzle atom (see csrc/debug_probe.cu)."""
+"""GPU probe: shifted UMMA descriptor start inside a swizzle atom (tools/probe/debug_probe.cu, built here into its own
+library together with the product's runtime.cu — the probe is not part of libgdlb200.so)."""
+import ctypes
 import json
+import subprocess
 import sys
 from pathlib import Path
 
@@ -9,7 +12,14 @@ ROOT = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT / "geo-deep-learning_b200"))
 from gdl_b200 import _lib as L  # noqa: E402
 
-lib = L.load()
+L.load()
+_so = ROOT / "tools" / "probe" / "libgdlprobe.so"
+subprocess.run(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-Xcompiler", "-fPIC", "-shared",
+                "-I", str(ROOT / "include"), str(ROOT / "tools" / "probe" / "debug_probe.cu"),
+                str(ROOT / "geo-deep-learning_b200" / "csrc" / "runtime.cu"), "-o", str(_so)], check=True)
+lib = ctypes.CDLL(str(_so))
+lib.gdl_debug_shift_probe.argtypes = [ctypes.c_void_p] * 3 + [ctypes.c_int] * 3 + [ctypes.c_void_p]
+lib.gdl_debug_shift_probe.restype = ctypes.c_int
 g = torch.Generator().manual_seed(0)
 res = []
 for mode in (0, 1):
