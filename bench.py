@@ -1,13 +1,17 @@
 #!/usr/bin/env python
-"""bench.py — tiles/sec of the UNet++ training hot path on B200.
+"""bench.py — tiles/sec of the segmentation training / inference hot path on B200.
 
   python bench.py [--gpus N] [--steps K] [--warmup W]            # product arm (sm_100a kernels)
   python bench.py --impl reference [--gpus N] --steps K --warmup W   # the reference's CPU path (oracle port)
 
-Workload (BASELINE.json configs[1]): UNet++-ResNet50, 4-band 512x512 synthetic uint8 tiles, 5 classes,
-bf16 compute, batch 32 per GPU, train step = normalise + forward + CE loss + backward + Adam.
-One JSON line on stdout (rank 0).  `value` = tiles/s with inputs resident in HBM; `e2e` = the same
-step fed from pinned host memory (H2D inside the timed region) with the loss read back (D2H).
+Headline workload (BASELINE.json configs[1]): UNet++-ResNet50, 4-band 512x512 synthetic uint8 tiles, 5 classes,
+bf16 compute, batch 32 per GPU, train step = normalise + forward + CE loss + backward + (all-reduce) + Adam, replayed
+from one CUDA graph at every N.  One JSON line on stdout (rank 0).  `value` = tiles/s with inputs resident in HBM;
+`e2e` = the same step fed from pinned host memory (H2D inside the timed region) with the loss read back (D2H);
+`roofline` = algorithmic FLOPs / measured kernel time of the forward + dgrad (and weight-gradient) convolutions;
+`cpu_baseline` = the reference's CPU path on the box's cores; `library_baseline` = the reference's module stack in eager
+bf16 autocast on the same GPU; `workloads` = BASELINE configs[2] SegFormer-B2, [3] DOFA-base + UperNet, [4] SegFormer-B5
+sliding-window inference, each with the same keys (`--workloads headline` skips them, `--workload X` makes X the headline).
 """
 from __future__ import annotations
 
