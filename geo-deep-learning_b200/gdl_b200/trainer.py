@@ -15,6 +15,31 @@ from .engine import Act, Engine, refresh_packed_weights
 from .ops import LossSpec
 
 
+def gradient_buckets(numels: list[int], keys: list, nb: int = 3) -> list[tuple[int, int, frozenset]]:
+    """Contiguous [start, end) ranges of the flat gradient buffer (parameters in `numels` order, each slot rounded up to 4
+    elements as FusedTrainer lays them out), about `nb` of equal size, returned in BACKWARD order: the tail of the buffer —
+    the head / decoder, whose gradients are complete first — comes first.  Every element and every key belongs to exactly
+    one bucket."""
+    offsets, total = [], 0
+    for n in numels:
+        offsets.append(total)
+        total += (n + 3) // 4 * 4
+    bounds = [total * (i + 1) // nb for i in range(nb)]
+    buckets, start, ids, bi = [], 0, [], 0
+    for n, off, key in zip(numels, offsets, keys):
+        ids.append(key)
+        end = off + (n + 3) // 4 * 4
+        if bi < nb - 1 and end >= bounds[bi]:
+            buckets.append((start, end, frozenset(ids)))
+            start, ids = end, []
+            while bi < nb - 1 and end >= bounds[bi]:
+                bi += 1
+    if ids:
+        buckets.append((start, total, frozenset(ids)))
+    buckets.reverse()
+    return buckets
+
+
 class FusedTrainer:
     def __init__(self, model: torch.nn.Module, loss: LossSpec, *, lr: float = 1e-4, betas=(0.9, 0.999),
                  eps: float = 1e-8, weight_decay: float = 0.0, mean=None, std=None, image_max: float = 255.0,
@@ -75,22 +100,8 @@ class FusedTrainer:
         # complete first).  A bucket is all-reduced on NCCL's stream as soon as every parameter in it has its gradient, while
         # the backward of the earlier layers keeps the GPU busy; what is left is reduced in optimizer_step.
         self.overlap_allreduce = self.world > 1 and ops.option("overlap_allreduce") != 0
-        self._buckets: list[tuple[int, int, frozenset]] = []
-        if self.overlap_allreduce and self.params:
-            nb = 3
-            bounds = [total * (i + 1) // nb for i in range(nb)]
-            start, ids, bi = 0, [], 0
-            for p, off in zip(self.params, offsets):
-                ids.append(id(p))
-                end = off + (p.numel() + 3) // 4 * 4
-                if end >= bounds[bi]:
-                    self._buckets.append((start, end, frozenset(ids)))
-                    start, ids, bi = end, [], bi + 1
-                    if bi >= nb:
-                        break
-            if ids:
-                self._buckets.append((start, total, frozenset(ids)))
-            self._buckets.reverse()  # backward order: tail of the flat buffer first
+        self._buckets = gradient_buckets([p.numel() for p in self.params], [id(p) for p in self.params]) \
+            if self.overlap_allreduce else []
         self._pending: list = []
         self._next_bucket = 0
         self.mean = torch.as_tensor(mean, dtype=acc_dtype, device=dev) if mean is not None else None
@@ -135,6 +146,7 @@ class FusedTrainer:
         for work in self._pending:  # bucket all-reduces of a backward whose optimizer_step was never called
             work.wait()
         self._pending = []
+        self._next_bucket = 0  # every route: optimizer_step reduces the buckets the backward has not started itself
         self.gflat.zero_()
         eng = Engine(model.compute_dtype, training=True, wcache=model._wcache, grad_dst=self.grad_dst,
                      sync_bn_group=self.group if self.sync_bn else None, acc_dtype=self.acc_dtype,
@@ -168,7 +180,6 @@ class FusedTrainer:
             ops.seg_loss_bwd(logits, target, self.loss, coeff, self.loss_scale, d16)
             eng.head_backward(d16)
             if self.overlap_allreduce:
-                self._next_bucket, self._pending = 0, []
                 eng.on_progress = self._reduce_finished_buckets
             eng.backward()
         self.last_engine = eng

@@ -644,32 +644,29 @@ def test_trainer_gradient_buckets_cover_the_flat_buffer_once(monkeypatch):
     """The overlapped all-reduce (FusedTrainer.overlap_allreduce) reduces contiguous buckets of the flat gradient buffer in
     backward order: together they must cover every element exactly once, each parameter must belong to exactly one bucket,
     and the first bucket must hold the layers whose backward runs first (the head / decoder = the tail of the buffer)."""
-    from gdl_b200.trainer import FusedTrainer
+    from gdl_b200.trainer import FusedTrainer, gradient_buckets
     emu.install(monkeypatch)
     _, prod = _pair("resnet18", 3, 4)
     tr = FusedTrainer(prod, emu.LossSpec(1.0, 0.0, ignore_index=-100), lr=1e-2, mean=[0.5] * 3, std=[0.25] * 3)
     assert tr._buckets == [] and not tr.overlap_allreduce  # single process: nothing to reduce
-    tr.world, tr.overlap_allreduce = 2, True
-    # rebuild the buckets the way __init__ does for world > 1
     total = tr.flat.numel()
-    offsets, off = [], 0
-    for p in tr.params:
-        offsets.append(off)
-        off += (p.numel() + 3) // 4 * 4
-    nb, buckets = 3, []
-    bounds = [total * (i + 1) // nb for i in range(nb)]
-    start, ids, bi = 0, [], 0
-    for p, o in zip(tr.params, offsets):
-        ids.append(id(p))
-        end = o + (p.numel() + 3) // 4 * 4
-        if end >= bounds[bi]:
-            buckets.append((start, end, frozenset(ids)))
-            start, ids, bi = end, [], bi + 1
-    buckets.reverse()
-    assert [b[0] for b in buckets] == sorted((b[0] for b in buckets), reverse=True)       # backward order
-    assert buckets[-1][0] == 0 and buckets[0][1] == total                                 # covers the whole buffer ...
-    assert all(buckets[i][0] == buckets[i + 1][1] for i in range(len(buckets) - 1))       # ... contiguously, no overlap
-    all_ids = [i for b in buckets for i in b[2]]
-    assert sorted(all_ids) == sorted(id(p) for p in tr.params)                            # every parameter exactly once
-    assert id(prod.segmentation_head[0].weight) in buckets[0][2]                          # head: first to finish its backward
-    assert id(prod.encoder.conv1.weight) in buckets[-1][2]                                # stem: last
+    for nb in (1, 2, 3, 7):
+        buckets = gradient_buckets([p.numel() for p in tr.params], [id(p) for p in tr.params], nb)
+        assert 1 <= len(buckets) <= nb
+        assert [b[0] for b in buckets] == sorted((b[0] for b in buckets), reverse=True)       # backward order
+        assert buckets[-1][0] == 0 and buckets[0][1] == total                                 # covers the whole buffer ...
+        assert all(buckets[i][0] == buckets[i + 1][1] for i in range(len(buckets) - 1))       # ... contiguously, no overlap
+        all_ids = [i for b in buckets for i in b[2]]
+        assert sorted(all_ids) == sorted(id(p) for p in tr.params)                            # every parameter exactly once
+        assert id(prod.segmentation_head[0].weight) in buckets[0][2]                          # head: first to finish its backward
+        assert id(prod.encoder.conv1.weight) in buckets[-1][2]                                # stem: last
+        # a parameter's slot lies inside its bucket
+        off = 0
+        for p in tr.params:
+            b = next(b for b in buckets if id(p) in b[2])
+            assert b[0] <= off and off + p.numel() <= b[1]
+            off += (p.numel() + 3) // 4 * 4
+    # one parameter larger than a whole share: it closes its bucket, the walk skips the bounds it ran over
+    bs = gradient_buckets([4, 100, 4, 4], list("abcd"), 3)
+    assert [(a, b, sorted(k)) for a, b, k in bs] == [(104, 112, ["c", "d"]), (0, 104, ["a", "b"])]
+    assert gradient_buckets([], [], 3) == []

@@ -47,6 +47,7 @@ def _worker(rank, world, port, out):
     for p in (ROOT, ROOT / "geo-deep-learning_b200", ROOT / "tests"):
         sys.path.insert(0, str(p))
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.set_num_threads(2)  # two workers on one host: full-width OpenMP teams spin against each other
     dist.init_process_group("gloo", rank=rank, world_size=world)
     tr = _make_trainer(sync_bn=True)
     assert tr.world == 2 and tr.sync_bn
@@ -84,6 +85,61 @@ def test_two_ranks_equal_one_process_on_the_union(tmp_path, monkeypatch, f64_wor
 
 
 # ---------------------------------------------------------------------------------------------
+# models that own their backward (SegFormer: `model.backward`, no per-closure progress hook): the bucketed all-reduce must
+# still reduce EVERY bucket in EVERY step — three steps, so a bucket cursor left at the end of step 1 would show
+# ---------------------------------------------------------------------------------------------
+def _segformer_trainer(monkeypatch=None):
+    import cpu_kernel_emulation as emu
+    from gdl_b200.models.segformer import SegFormer
+    from gdl_b200.trainer import FusedTrainer
+    if monkeypatch is None:
+        emu.install_global()
+    else:
+        emu.install(monkeypatch)
+    emu.set_work_dtype(torch.float64)
+    torch.manual_seed(0)
+    model = SegFormer("mit_b0", in_channels=3, num_classes=4, compute_dtype=torch.float64).double().train()
+    return FusedTrainer(model, emu.LossSpec(1.0, 0.0, ignore_index=-100), lr=1e-3, mean=[0.5] * 3, std=[0.25] * 3,
+                        sync_bn=True, acc_dtype=torch.float64)
+
+
+def _segformer_data():
+    g = torch.Generator().manual_seed(5)
+    t = torch.randint(0, 4, (4, 2, 2), generator=g).repeat_interleave(16, 1).repeat_interleave(16, 2)
+    raw = (t.unsqueeze(-1) * 60 + torch.randint(0, 20, (4, 32, 32, 3), generator=g)).to(torch.uint8)
+    return raw, t
+
+
+def _segformer_worker(rank, world, port, out):
+    for p in (ROOT, ROOT / "geo-deep-learning_b200", ROOT / "tests"):
+        sys.path.insert(0, str(p))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.set_num_threads(2)  # two workers on one host: full-width OpenMP teams spin against each other
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    tr = _segformer_trainer()
+    assert tr.world == 2 and tr.overlap_allreduce and len(tr._buckets) >= 2
+    raw, t = _segformer_data()
+    lo, hi = rank * 2, rank * 2 + 2
+    losses = [float(tr.step(raw[lo:hi], t[lo:hi])) for _ in range(3)]
+    torch.save({"flat": tr.flat.clone(), "losses": losses}, f"{out}/sf{rank}.pt")
+    dist.destroy_process_group()
+
+
+def test_segformer_route_reduces_every_bucket_in_every_step(tmp_path, monkeypatch, f64_work_dtype):
+    port = _free_port()
+    mp.spawn(_segformer_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    r0, r1 = torch.load(tmp_path / "sf0.pt"), torch.load(tmp_path / "sf1.pt")
+    assert torch.equal(r0["flat"], r1["flat"])  # ranks that skipped an all-reduce would drift apart from step 2 on
+    sys.path.insert(0, str(ROOT / "tests"))
+    tr = _segformer_trainer(monkeypatch)
+    raw, t = _segformer_data()
+    losses = [float(tr.step(raw, t)) for _ in range(3)]
+    assert torch.allclose(tr.flat, r0["flat"], atol=1e-9, rtol=1e-6)
+    for i in range(3):
+        assert abs(losses[i] - 0.5 * (r0["losses"][i] + r1["losses"][i])) < 1e-8
+
+
+# ---------------------------------------------------------------------------------------------
 # tile-sharded sliding-window inference (BASELINE configs[4]): windows dealt round-robin to the ranks, one all-reduce
 # ---------------------------------------------------------------------------------------------
 def _infer_model():
@@ -108,6 +164,7 @@ def _infer_worker(rank, world, port, out):
     for p in (ROOT, ROOT / "geo-deep-learning_b200", ROOT / "tests"):
         sys.path.insert(0, str(p))
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.set_num_threads(2)  # two workers on one host: full-width OpenMP teams spin against each other
     dist.init_process_group("gloo", rank=rank, world_size=world)
     import cpu_kernel_emulation as emu
     from gdl_b200.inference import SlidingWindowSegmenter
