@@ -563,6 +563,7 @@ def _run_train(args, ctx, steps: int, warmup: int, headline: bool):
                    "loss": "cross_entropy", "optimizer": "adam", "sync_bn": bool(args.sync_bn and world > 1), "cuda_graph": use_graph,
                    "sra_fused": bool(ops.option("sra_fused")), "mha_flash": bool(ops.option("mha_flash")),
                    "deterministic_reductions": deterministic, "syncbn_exchange": bn_exchange_kind,
+                   "pdl": bool(ops.option("pdl")),
                    "l2": f"{NBUF} rotating input batches; per-step working set >> 126 MB L2"},
         "clocks": clk,
         "e2e": {"value": tiles / (ms_e2e / 1e3), "unit": "tiles/s",
@@ -681,6 +682,7 @@ def _run_infer(args, ctx, steps: int, warmup: int, headline: bool):
         "config": {"workload": w["name"], "raster": [R, R, C], "windows": nwin, "window_batch": B,
                    "parallelism": f"windows round-robin over {world} rank(s) + one all-reduce of the logit sums",
                    "cuda_graph": args.cuda_graph >= 2, "sra_fused": bool(ops.option("sra_fused")),
+                   "pdl": bool(ops.option("pdl")),
                    "l2": f"raster {R * R * C / 1e6:.0f} MB and activations >> 126 MB L2"},
         "clocks": clk,
         "e2e": {"value": nwin * steps / (ms_e2e / 1e3), "unit": "tiles/s", "h2d_bytes_per_step": R * R * C,

@@ -96,6 +96,7 @@ __global__ void augment_kernel(const TIn* __restrict__ x, const TM* __restrict__
                                void* __restrict__ yv, TM* __restrict__ mask_out, long long N, int H, int W, int C, int ld,
                                const float* __restrict__ mean, const float* __restrict__ stdv, float image_max,
                                int in_chw) {
+  GDL_PDL_ENTRY();
   const long long hw = (long long)H * W, total = N * hw;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -150,10 +151,10 @@ static void launch_augment(const void* x, const void* mask, int mask_kind, const
                            float image_max, int in_chw, cudaStream_t st) {
   const int blocks = am_blocks(N * H * W, 256, 16);
   if (mask_kind == 0)
-    augment_kernel<T, TIn, long long, OUT_F32><<<blocks, 256, 0, st>>>(
+    GDL_LAUNCH((augment_kernel<T, TIn, long long, OUT_F32>), blocks, 256, 0, st, 
         (const TIn*)x, (const long long*)mask, params, y, (long long*)mask_out, N, H, W, C, ld, mean, stdv, image_max, in_chw);
   else
-    augment_kernel<T, TIn, uint8_t, OUT_F32><<<blocks, 256, 0, st>>>(
+    GDL_LAUNCH((augment_kernel<T, TIn, uint8_t, OUT_F32>), blocks, 256, 0, st, 
         (const TIn*)x, (const uint8_t*)mask, params, y, (uint8_t*)mask_out, N, H, W, C, ld, mean, stdv, image_max, in_chw);
 }
 
@@ -167,6 +168,7 @@ template <typename TT>
 __global__ void argmax_confusion_kernel(const float* __restrict__ logits, int ld, long long hw, int K, float threshold,
                                         const TT* __restrict__ target, long long ignore_index, int has_ignore,
                                         long long* __restrict__ classes, unsigned long long* __restrict__ conf) {
+  GDL_PDL_ENTRY();
   extern __shared__ unsigned int hist[];
   const int Kc = K == 1 ? 2 : K;
   const int bins = target != nullptr ? Kc * Kc : 0;  // no histogram (and no shared memory) for a classes-only call
@@ -264,10 +266,10 @@ extern "C" int gdl_argmax_confusion(const float* logits, int ld, long long N, lo
   const size_t smem = conf != nullptr ? (size_t)Kc * Kc * sizeof(unsigned int) : 0;
   cudaStream_t st = (cudaStream_t)stream;
   if (target_kind == 0)
-    argmax_confusion_kernel<long long><<<grid, 256, smem, st>>>(logits, ld, HW, K, threshold, (const long long*)target,
+    GDL_LAUNCH(argmax_confusion_kernel<long long>, grid, 256, smem, st, logits, ld, HW, K, threshold, (const long long*)target,
                                                                ignore_index, has_ignore, classes, (unsigned long long*)conf);
   else
-    argmax_confusion_kernel<uint8_t><<<grid, 256, smem, st>>>(logits, ld, HW, K, threshold, (const uint8_t*)target,
+    GDL_LAUNCH(argmax_confusion_kernel<uint8_t>, grid, 256, smem, st, logits, ld, HW, K, threshold, (const uint8_t*)target,
                                                              ignore_index, has_ignore, classes, (unsigned long long*)conf);
   GDL_CHECK_CUDA(cudaGetLastError());
   return 0;

@@ -71,6 +71,51 @@ inline int device_sm_count() {
 }
 
 // ----------------------------------------------------------------------------------------
+// kernel launches: programmatic dependent launch (PDL).
+// Every kernel of the library is launched through GDL_LAUNCH and begins with GDL_PDL_ENTRY().  With the "pdl" option on
+// (gdl_set_option("pdl", 1); the Python host sets it from GDL_PDL) a launch carries cudaLaunchAttributeProgrammaticStreamSerialization: the grid may
+// become resident while its predecessor in the stream (or in the captured graph) is still running, and every thread then
+// blocks in griddepcontrol.wait until that predecessor has COMPLETED and its memory is visible — nothing is read or
+// written before it, so the stream's semantics are unchanged; only the launch latency between two dependent kernels
+// (a model step is 700..6000 of them) is hidden.  griddepcontrol.launch_dependents right after the wait lets the NEXT
+// kernel do the same.  Both instructions are no-ops in a grid launched without the attribute.  The rule "first
+// statement of every __global__ function" is enforced by tests/test_boundary_cpu.py.
+// ----------------------------------------------------------------------------------------
+extern int g_opt_pdl;  // runtime.cu
+
+GDL_DEVINL void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+GDL_DEVINL void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+#define GDL_PDL_ENTRY()    \
+  do {                     \
+    ::gdl::pdl_wait();     \
+    ::gdl::pdl_trigger();  \
+  } while (0)
+
+#ifdef GDL_HOSTEMU
+// tests/hostemu: the kernel body runs thread by thread on the host
+#define GDL_LAUNCH(kern, grid, block, smem, stream, ...) \
+  hostemu::launch(dim3(grid), dim3(block), (size_t)(smem), [=]() { kern(__VA_ARGS__); })
+#else
+template <typename... KArgs, typename... Args>
+inline void launch_kernel(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = g_opt_pdl ? 1u : 0u;
+  // a failed launch is picked up by the cudaGetLastError() that follows every launch site
+  (void)cudaLaunchKernelEx(&cfg, kern, static_cast<Args&&>(args)...);
+}
+#define GDL_LAUNCH(kern, grid, block, smem, stream, ...) \
+  ::gdl::launch_kernel(kern, dim3(grid), dim3(block), (size_t)(smem), (cudaStream_t)(stream), __VA_ARGS__)
+#endif
+
+// ----------------------------------------------------------------------------------------
 // shared-memory address helpers
 // ----------------------------------------------------------------------------------------
 GDL_DEVINL uint32_t smem_u32(const void* p) {

@@ -85,6 +85,7 @@ GDL_DEVINL RowsJob rows_job(const ConvRowsKParams& p, long long job) {
 }
 
 __global__ void __launch_bounds__(kRowsThreads, 1) conv3x3_rows_kernel(const __grid_constant__ ConvRowsKParams p) {
+  GDL_PDL_ENTRY();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = align_smem_1024(smem_raw);
   uint8_t* smem_b = smem + (size_t)p.a_stages * kRowsAStage;
@@ -564,7 +565,7 @@ int conv3x3_rows_try(const gdl_conv_fwd_t* d, cudaStream_t stream, int* status, 
   if (*status) return 1;
   const int sms = rows_sm_count();
   const int grid = p.num_jobs < sms ? (int)p.num_jobs : sms;
-  conv3x3_rows_kernel<<<grid, kRowsThreads, smem, stream>>>(p);
+  GDL_LAUNCH(conv3x3_rows_kernel, grid, kRowsThreads, smem, stream, p);
   *status = check_cuda(cudaGetLastError(), "conv3x3_rows_kernel launch");
   if (*status == 0 && d->bn_sums != nullptr && !bn_fused)  // the statistics kernel on the stored output
     *status = gdl_bn_stats(d->out, d->out_dtype, (long long)d->N * d->H * d->W, d->Cout, d->ldo, d->bn_sums, d->bn_pivot,

@@ -107,6 +107,7 @@ template <typename T, typename TIn>
 __global__ void normalize_kernel(const TIn* __restrict__ x, T* __restrict__ y, long long npix, int C,
                                  int ld, const float* __restrict__ mean, const float* __restrict__ stdv,
                                  float image_max, int in_is_chw, long long hw) {
+  GDL_PDL_ENTRY();
   const long long total = npix * ld;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -137,6 +138,7 @@ template <typename T>
 __global__ void im2col_vec8_kernel(const T* __restrict__ x, T* __restrict__ col, int N, int H, int W,
                                    int C, int ld, int R, int S, int stride, int pad, int Ho, int Wo,
                                    int Kpad) {
+  GDL_PDL_ENTRY();
   const int cv = C / 8;
   const int kchunks = Kpad / 8;
   const long long total = (long long)N * Ho * Wo * kchunks;
@@ -164,6 +166,7 @@ __global__ void im2col_vec8_kernel(const T* __restrict__ x, T* __restrict__ col,
 template <typename T>
 __global__ void im2col_c4_kernel(const T* __restrict__ x, T* __restrict__ col, int N, int H, int W, int ld, int R,
                                  int S, int stride, int pad, int Ho, int Wo, int Kpad) {
+  GDL_PDL_ENTRY();
   const int pairs = Kpad / 8;  // 8 elements = 2 taps per thread
   const int taps = R * S;
   const long long total = (long long)N * Ho * Wo * pairs;
@@ -196,6 +199,7 @@ template <typename T>
 __global__ void im2col_scalar_kernel(const T* __restrict__ x, T* __restrict__ col, int N, int H, int W,
                                      int C, int ld, int R, int S, int stride, int pad, int Ho, int Wo,
                                      int Kpad) {
+  GDL_PDL_ENTRY();
   const long long total = (long long)N * Ho * Wo * Kpad;
   const int K = R * S * C;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
@@ -222,6 +226,7 @@ template <typename T>
 __global__ void col2im_vec8_kernel(const T* __restrict__ dcol, T* __restrict__ dx, int N, int H, int W,
                                    int C, int ld, int R, int S, int stride, int pad, int Ho, int Wo,
                                    int Kpad) {
+  GDL_PDL_ENTRY();
   const int cv = C / 8;
   const long long total = (long long)N * H * W * cv;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
@@ -263,6 +268,7 @@ template <typename T>
 __global__ void bn_stats_kernel(const T* __restrict__ x, long long M, int C, int ld,
                                 float* __restrict__ sums /* [2][C], pre-zeroed */,
                                 const float* __restrict__ pivot /* [C] or null */, const DetCtx det) {
+  GDL_PDL_ENTRY();
   const int cv = C / 8;
   const int tpr = cv < (int)blockDim.x ? cv : blockDim.x;  // threads spanning the channel dim
   const int rows_per_block = blockDim.x / tpr;
@@ -354,6 +360,7 @@ __global__ void bn_finalize_kernel(const float* pivot /* may alias running_mean 
                                    float* __restrict__ running_var, float* __restrict__ scale,
                                    float* __restrict__ shift, float* __restrict__ save_mean,
                                    float* __restrict__ save_invstd) {
+  GDL_PDL_ENTRY();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   const float piv = pivot ? pivot[c] : 0.f;
@@ -379,6 +386,7 @@ __global__ void bn_finalize_kernel(const float* pivot /* may alias running_mean 
 __global__ void bn_eval_coeffs_kernel(int C, const float* __restrict__ gamma, const float* __restrict__ beta,
                                       const float* __restrict__ rm, const float* __restrict__ rv, float eps,
                                       float* __restrict__ scale, float* __restrict__ shift) {
+  GDL_PDL_ENTRY();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   const float invstd = rsqrtf(rv[c] + eps);
@@ -397,6 +405,7 @@ __global__ void bn_apply_kernel(const T* __restrict__ x, int ldx, const float* _
                                 const float* __restrict__ rscale, const float* __restrict__ rshift,
                                 int relu, T* __restrict__ y, int ldy, T* __restrict__ y_up, int ldu,
                                 int N, int H, int W, int C) {
+  GDL_PDL_ENTRY();
   // each thread owns one 8-channel vector (coefficients live in registers) and strides over pixels
   const int cv = C / 8;
   const int tpr = cv < (int)blockDim.x ? cv : blockDim.x;
@@ -477,6 +486,7 @@ __global__ void __launch_bounds__(256) grad_gather_kernel(GatherSrcs srcs, const
                                                           const float* __restrict__ invstd, T* __restrict__ g, int ldg,
                                                           float* __restrict__ sums /* [2][C] or null */, int N, int H,
                                                           int W, int C, const DetCtx det) {
+  GDL_PDL_ENTRY();
   constexpr bool kGeneric = NUP < 0;
   constexpr int N0 = kGeneric ? NS : NS - NUP;        // plain sources (generic: every source, staged with 4 vectors)
   constexpr int NU = kGeneric ? 0 : NUP;              // trailing 2x2-pooled sources
@@ -647,6 +657,7 @@ __global__ void bn_bwd_apply_kernel(const T* __restrict__ g, int ldg, const T* _
                                     const float* __restrict__ mean, const float* __restrict__ invstd,
                                     const float* __restrict__ gamma, const float* __restrict__ sums,
                                     T* __restrict__ dx, int ldd, long long M, long long count, int C) {
+  GDL_PDL_ENTRY();
   // dx = a*g + b*x + c with per-channel a = gamma*invstd, b = -a*invstd*s2/M, c = a*(mean*invstd*s2/M - s1/M)
   const int cv = C / 8;
   const int tpr = cv < (int)blockDim.x ? cv : blockDim.x;
@@ -697,6 +708,7 @@ __global__ void bn_bwd_apply_kernel(const T* __restrict__ g, int ldg, const T* _
 
 __global__ void bn_param_grads_kernel(const float* __restrict__ sums, int C, float* __restrict__ dgamma,
                                       float* __restrict__ dbeta, int accumulate) {
+  GDL_PDL_ENTRY();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   if (dgamma) dgamma[c] = (accumulate ? dgamma[c] : 0.f) + sums[C + c];
@@ -710,6 +722,7 @@ __global__ void bn_param_grads_kernel(const float* __restrict__ sums, int C, flo
 template <typename T>
 __global__ void maxpool3x3s2_fwd_kernel(const T* __restrict__ x, int ldx, T* __restrict__ y, int ldy,
                                         uint8_t* __restrict__ idx, int N, int H, int W, int C, int Ho, int Wo) {
+  GDL_PDL_ENTRY();
   const int cv = C / 8;
   const long long total = (long long)N * Ho * Wo * cv;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
@@ -760,6 +773,7 @@ template <typename T>
 __global__ void maxpool3x3s2_bwd_kernel(const T* __restrict__ dy, int ldy, const uint8_t* __restrict__ idx,
                                         T* __restrict__ dx, int ldx, int N, int H, int W, int C, int Ho,
                                         int Wo) {
+  GDL_PDL_ENTRY();
   const int cv = C / 8;
   const long long total = (long long)N * H * W * cv;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
@@ -806,6 +820,7 @@ __global__ void maxpool3x3s2_bwd_kernel(const T* __restrict__ dy, int ldy, const
 template <typename T>
 __global__ void scale_nc_kernel(const T* __restrict__ x, long long ldx, const float* __restrict__ m, T* __restrict__ y,
                                 long long ldy, long long N, long long HW, int C) {
+  GDL_PDL_ENTRY();
   const int cv = C / 8;
   const long long total = N * HW * cv;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
@@ -840,13 +855,13 @@ extern "C" int gdl_normalize_to_nhwc(const void* x, int in_kind, void* y, int ou
   // in_kind: 0 = uint8 NHWC, 1 = f32 NHWC, 2 = f32 NCHW, 3 = uint8 NCHW
   GDL_DISPATCH_16(out_dtype, {
     if (in_kind == 0)
-      normalize_kernel<T, uint8_t><<<blocks, 256, 0, st>>>((const uint8_t*)x, (T*)y, npix, C, ld, mean, stdv, image_max, 0, H * W);
+      GDL_LAUNCH((normalize_kernel<T, uint8_t>), blocks, 256, 0, st, (const uint8_t*)x, (T*)y, npix, C, ld, mean, stdv, image_max, 0, H * W);
     else if (in_kind == 1)
-      normalize_kernel<T, float><<<blocks, 256, 0, st>>>((const float*)x, (T*)y, npix, C, ld, mean, stdv, image_max, 0, H * W);
+      GDL_LAUNCH((normalize_kernel<T, float>), blocks, 256, 0, st, (const float*)x, (T*)y, npix, C, ld, mean, stdv, image_max, 0, H * W);
     else if (in_kind == 2)
-      normalize_kernel<T, float><<<blocks, 256, 0, st>>>((const float*)x, (T*)y, npix, C, ld, mean, stdv, image_max, 1, H * W);
+      GDL_LAUNCH((normalize_kernel<T, float>), blocks, 256, 0, st, (const float*)x, (T*)y, npix, C, ld, mean, stdv, image_max, 1, H * W);
     else if (in_kind == 3)
-      normalize_kernel<T, uint8_t><<<blocks, 256, 0, st>>>((const uint8_t*)x, (T*)y, npix, C, ld, mean, stdv, image_max, 1, H * W);
+      GDL_LAUNCH((normalize_kernel<T, uint8_t>), blocks, 256, 0, st, (const uint8_t*)x, (T*)y, npix, C, ld, mean, stdv, image_max, 1, H * W);
     else {
       set_last_error("normalize: unknown in_kind %d", in_kind);
       return GDL_ERR_INVALID;
@@ -867,13 +882,13 @@ extern "C" int gdl_im2col_nhwc(const void* x, void* col, int dtype, int N, int H
   GDL_DISPATCH_16(dtype, {
     if (C == 4 && ld % 4 == 0 && ((reinterpret_cast<uintptr_t>(x) & 7) == 0)) {
       const long long total = (long long)N * Ho * Wo * (Kpad / 8);
-      im2col_c4_kernel<T><<<ew_blocks(total, 256, 16), 256, 0, st>>>((const T*)x, (T*)col, N, H, W, ld, R, S, stride, pad, Ho, Wo, Kpad);
+      GDL_LAUNCH(im2col_c4_kernel<T>, ew_blocks(total, 256, 16), 256, 0, st, (const T*)x, (T*)col, N, H, W, ld, R, S, stride, pad, Ho, Wo, Kpad);
     } else if (vec) {
       const long long total = (long long)N * Ho * Wo * (Kpad / 8);
-      im2col_vec8_kernel<T><<<ew_blocks(total, 256, 16), 256, 0, st>>>((const T*)x, (T*)col, N, H, W, C, ld, R, S, stride, pad, Ho, Wo, Kpad);
+      GDL_LAUNCH(im2col_vec8_kernel<T>, ew_blocks(total, 256, 16), 256, 0, st, (const T*)x, (T*)col, N, H, W, C, ld, R, S, stride, pad, Ho, Wo, Kpad);
     } else {
       const long long total = (long long)N * Ho * Wo * Kpad;
-      im2col_scalar_kernel<T><<<ew_blocks(total, 256, 32), 256, 0, st>>>((const T*)x, (T*)col, N, H, W, C, ld, R, S, stride, pad, Ho, Wo, Kpad);
+      GDL_LAUNCH(im2col_scalar_kernel<T>, ew_blocks(total, 256, 32), 256, 0, st, (const T*)x, (T*)col, N, H, W, C, ld, R, S, stride, pad, Ho, Wo, Kpad);
     }
   });
   GDL_CHECK_CUDA(cudaGetLastError());
@@ -889,7 +904,7 @@ extern "C" int gdl_col2im_nhwc(const void* dcol, void* dx, int dtype, int N, int
   const long long total = (long long)N * H * W * (C / 8);
   cudaStream_t st = (cudaStream_t)stream;
   GDL_DISPATCH_16(dtype, {
-    col2im_vec8_kernel<T><<<ew_blocks(total, 256, 16), 256, 0, st>>>((const T*)dcol, (T*)dx, N, H, W, C, ld, R, S, stride, pad, Ho, Wo, Kpad);
+    GDL_LAUNCH(col2im_vec8_kernel<T>, ew_blocks(total, 256, 16), 256, 0, st, (const T*)dcol, (T*)dx, N, H, W, C, ld, R, S, stride, pad, Ho, Wo, Kpad);
   });
   GDL_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -922,7 +937,7 @@ extern "C" int gdl_bn_stats(const void* x, int dtype, long long M, int C, int ld
     blocks = g;
     det = det_ctx(ws, g, 2 * C);
   }
-  GDL_DISPATCH_16(dtype, { bn_stats_kernel<T><<<(int)blocks, threads, smem, st>>>((const T*)x, M, C, ld, sums, pivot, det); });
+  GDL_DISPATCH_16(dtype, { GDL_LAUNCH(bn_stats_kernel<T>, (int)blocks, threads, smem, st, (const T*)x, M, C, ld, sums, pivot, det); });
   GDL_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -933,7 +948,7 @@ extern "C" int gdl_bn_finalize(const float* pivot, const float* sums, long long 
                                float* save_invstd, void* stream) {
   GDL_REQUIRE(sums && scale && shift && save_mean && save_invstd && M > 0 && C > 0, GDL_ERR_INVALID,
               "bn_finalize: bad args");
-  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, (cudaStream_t)stream>>>(pivot, sums, M, C, gamma, beta, eps,
+  GDL_LAUNCH(bn_finalize_kernel, (C + 127) / 128, 128, 0, (cudaStream_t)stream, pivot, sums, M, C, gamma, beta, eps,
                                                                        momentum, running_mean, running_var, scale,
                                                                        shift, save_mean, save_invstd);
   GDL_CHECK_CUDA(cudaGetLastError());
@@ -943,7 +958,7 @@ extern "C" int gdl_bn_finalize(const float* pivot, const float* sums, long long 
 extern "C" int gdl_bn_eval_coeffs(int C, const float* gamma, const float* beta, const float* running_mean,
                                   const float* running_var, float eps, float* scale, float* shift, void* stream) {
   GDL_REQUIRE(C > 0 && running_mean && running_var && scale && shift, GDL_ERR_INVALID, "bn_eval_coeffs: bad args");
-  bn_eval_coeffs_kernel<<<(C + 127) / 128, 128, 0, (cudaStream_t)stream>>>(C, gamma, beta, running_mean,
+  GDL_LAUNCH(bn_eval_coeffs_kernel, (C + 127) / 128, 128, 0, (cudaStream_t)stream, C, gamma, beta, running_mean,
                                                                           running_var, eps, scale, shift);
   GDL_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -960,7 +975,7 @@ extern "C" int gdl_bn_apply(const void* x, int ldx, const float* scale, const fl
   const long long total = (long long)N * H * W * (C / 8);
   cudaStream_t st = (cudaStream_t)stream;
   GDL_DISPATCH_16(dtype, {
-    bn_apply_kernel<T><<<row_grid(total / (C / 8), C), 256, 0, st>>>((const T*)x, ldx, scale, shift, (const T*)res, ldr,
+    GDL_LAUNCH(bn_apply_kernel<T>, row_grid(total / (C / 8), C), 256, 0, st, (const T*)x, ldx, scale, shift, (const T*)res, ldr,
                                                                   rscale, rshift, relu, (T*)y, ldy, (T*)y_up, ldu,
                                                                   N, H, W, C);
   });
@@ -1009,7 +1024,7 @@ extern "C" int gdl_grad_gather(int num_src, const void* const* src_ptr, const in
   const bool lean = nup == 0 || (nup == 1 && src_mode[num_src - 1] != 0);
 #define GDL_GG_LAUNCH2(NSV, NUPV)                                                                                      \
   GDL_DISPATCH_16(dtype, {                                                                                             \
-    grad_gather_kernel<T, NSV, NUPV><<<(int)blocks, threads, smem, st>>>(gs, (const T*)y, ldy, (const T*)x, ldx, mean, \
+    GDL_LAUNCH((grad_gather_kernel<T, NSV, NUPV>), (int)blocks, threads, smem, st, gs, (const T*)y, ldy, (const T*)x, ldx, mean, \
                                                                          invstd, (T*)g, ldg, sums, N, H, W, C, det);   \
   })
 #define GDL_GG_LAUNCH(NSV)                          \
@@ -1040,12 +1055,12 @@ extern "C" int gdl_bn_bwd_apply(const void* g, int ldg, const void* x, int ldx, 
               "bn_bwd_apply: bad args");
   cudaStream_t st = (cudaStream_t)stream;
   GDL_DISPATCH_16(dtype, {
-    bn_bwd_apply_kernel<T><<<row_grid(M, C), 256, 0, st>>>((const T*)g, ldg, (const T*)x, ldx, mean,
+    GDL_LAUNCH(bn_bwd_apply_kernel<T>, row_grid(M, C), 256, 0, st, (const T*)g, ldg, (const T*)x, ldx, mean,
                                                                            invstd, gamma, sums, (T*)dx, ldd, M, count > 0 ? count : M, C);
   });
   GDL_CHECK_CUDA(cudaGetLastError());
   if (dgamma || dbeta) {
-    bn_param_grads_kernel<<<(C + 127) / 128, 128, 0, st>>>(sums, C, dgamma, dbeta, accumulate_param_grads);
+    GDL_LAUNCH(bn_param_grads_kernel, (C + 127) / 128, 128, 0, st, sums, C, dgamma, dbeta, accumulate_param_grads);
     GDL_CHECK_CUDA(cudaGetLastError());
   }
   return 0;
@@ -1055,7 +1070,7 @@ extern "C" int gdl_bn_param_grads(const float* sums, int C, float* dgamma, float
                                   void* stream) {
   GDL_REQUIRE(sums && C > 0, GDL_ERR_INVALID, "bn_param_grads: bad args");
   if (dgamma || dbeta) {
-    bn_param_grads_kernel<<<(C + 127) / 128, 128, 0, (cudaStream_t)stream>>>(sums, C, dgamma, dbeta, accumulate);
+    GDL_LAUNCH(bn_param_grads_kernel, (C + 127) / 128, 128, 0, (cudaStream_t)stream, sums, C, dgamma, dbeta, accumulate);
     GDL_CHECK_CUDA(cudaGetLastError());
   }
   return 0;
@@ -1069,7 +1084,7 @@ extern "C" int gdl_maxpool3x3s2_fwd(const void* x, int ldx, void* y, int ldy, un
   const long long total = (long long)N * Ho * Wo * (C / 8);
   cudaStream_t st = (cudaStream_t)stream;
   GDL_DISPATCH_16(dtype, {
-    maxpool3x3s2_fwd_kernel<T><<<ew_blocks(total, 256, 16), 256, 0, st>>>((const T*)x, ldx, (T*)y, ldy, idx, N, H, W, C, Ho, Wo);
+    GDL_LAUNCH(maxpool3x3s2_fwd_kernel<T>, ew_blocks(total, 256, 16), 256, 0, st, (const T*)x, ldx, (T*)y, ldy, idx, N, H, W, C, Ho, Wo);
   });
   GDL_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -1082,7 +1097,7 @@ extern "C" int gdl_maxpool3x3s2_bwd(const void* dy, int ldy, const unsigned char
   const long long total = (long long)N * H * W * (C / 8);
   cudaStream_t st = (cudaStream_t)stream;
   GDL_DISPATCH_16(dtype, {
-    maxpool3x3s2_bwd_kernel<T><<<ew_blocks(total, 256, 16), 256, 0, st>>>((const T*)dy, ldy, idx, (T*)dx, ldx, N, H, W, C, Ho, Wo);
+    GDL_LAUNCH(maxpool3x3s2_bwd_kernel<T>, ew_blocks(total, 256, 16), 256, 0, st, (const T*)dy, ldy, idx, (T*)dx, ldx, N, H, W, C, Ho, Wo);
   });
   GDL_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -1096,7 +1111,7 @@ extern "C" int gdl_dropout2d_apply(const void* x, long long ldx, const float* ma
               "dropout2d: 16-byte aligned buffers expected");
   const int blocks = ew_blocks(N * HW * (C / 8), 256, 16);
   GDL_DISPATCH_16(dtype, {
-    scale_nc_kernel<T><<<blocks, 256, 0, (cudaStream_t)stream>>>((const T*)x, ldx, mask, (T*)y, ldy, N, HW, C);
+    GDL_LAUNCH(scale_nc_kernel<T>, blocks, 256, 0, (cudaStream_t)stream, (const T*)x, ldx, mask, (T*)y, ldy, N, HW, C);
   });
   GDL_CHECK_CUDA(cudaGetLastError());
   return 0;

@@ -92,6 +92,7 @@ struct ConvFwdKParams {
 
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv_fwd_kernel(const __grid_constant__ ConvFwdKParams p) {
+  GDL_PDL_ENTRY();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = align_smem_1024(smem_raw);
 
@@ -745,6 +746,7 @@ extern "C" int gdl_set_option(const char* name, long long value) {
   else if (!strcmp(name, "wgrad_sched")) g_opt_wgrad_sched = (int)value;  // 1: few long units (one epilogue per CTA); 0: round-1 rule
   else if (!strcmp(name, "deterministic")) g_opt_deterministic = (int)value;  // 1 (default): ordered reductions when a workspace is registered
   else if (!strcmp(name, "sra_max_ctas")) g_opt_sra_max_ctas = (int)value;  // 0 = one CTA per SM (tests: fewer, longer CTAs)
+  else if (!strcmp(name, "pdl")) g_opt_pdl = value != 0;  // programmatic dependent launch of every kernel (common.cuh)
   else {
     set_last_error("set_option: unknown option '%s'", name);
     return GDL_ERR_INVALID;
@@ -957,7 +959,7 @@ static int conv_fwd_impl(const gdl_conv_fwd_t* d, void* stream_, int* dry) {
     *dry = bn_fused ? 1 : 0;
     return 0;
   }
-  conv_fwd_kernel<<<grid, kConvThreads, smem, stream>>>(p);
+  GDL_LAUNCH(conv_fwd_kernel, grid, kConvThreads, smem, stream, p);
   GDL_CHECK_CUDA(cudaGetLastError());
   if (d->bn_sums != nullptr && !bn_fused)  // shapes the epilogue cannot cover: the statistics kernel on the stored output
     return gdl_bn_stats(d->out, d->out_dtype, (long long)N * oH * oW, d->Cout, d->ldo, d->bn_sums, d->bn_pivot, stream_);
@@ -1021,6 +1023,7 @@ struct ConvWgradKParams {
 
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv_wgrad_kernel(const __grid_constant__ ConvWgradKParams p) {
+  GDL_PDL_ENTRY();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = align_smem_1024(smem_raw);
 
@@ -1248,6 +1251,7 @@ struct WgradReduceParams {
 };
 
 __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const __grid_constant__ WgradReduceParams p) {
+  GDL_PDL_ENTRY();
   const int vec_per_row = p.bn_max / 4;
   const long long per_tile = (long long)p.nsub * 128 * vec_per_row;
   const long long base_tiles = (long long)p.taps * p.n_ntiles * p.m_tiles;
@@ -1498,7 +1502,7 @@ extern "C" int gdl_conv2d_nhwc_wgrad(const gdl_conv_wgrad_t* d, void* stream_) {
   static PerDeviceOnce attr_once;
   GDL_CHECK_CUDA(set_max_dyn_smem_once(attr_once, conv_wgrad_kernel, kSmemBudget + 4096));
   int grid = p.num_units < sm_count() ? p.num_units : sm_count();
-  conv_wgrad_kernel<<<grid, kConvThreads, smem, stream>>>(p);
+  GDL_LAUNCH(conv_wgrad_kernel, grid, kConvThreads, smem, stream, p);
   GDL_CHECK_CUDA(cudaGetLastError());
   if (p.partials != nullptr) {
     WgradReduceParams r;
@@ -1528,7 +1532,7 @@ extern "C" int gdl_conv2d_nhwc_wgrad(const gdl_conv_wgrad_t* d, void* stream_) {
     const long long total = (long long)G * p.Nimg * p.unit_taps * p.n_ntiles * p.m_tiles * p.nsub * 128 * (bn_max / 4);
     long long rb = (total + 255) / 256;
     if (rb > 8ll * sm_count()) rb = 8ll * sm_count();
-    wgrad_reduce_kernel<<<(int)rb, 256, 0, stream>>>(r);
+    GDL_LAUNCH(wgrad_reduce_kernel, (int)rb, 256, 0, stream, r);
     GDL_CHECK_CUDA(cudaGetLastError());
   }
   return 0;
@@ -1546,6 +1550,7 @@ namespace gdl {
 template <typename T>
 __global__ void pack_weight_kernel(const float* __restrict__ src, T* __restrict__ dst, int Cout, int Cin,
                                    int R, int S, int mode, int rows, int cols, int dst_ld) {
+  GDL_PDL_ENTRY();
   const long long total = (long long)rows * dst_ld;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -1589,6 +1594,7 @@ constexpr int kRepackChunk = 4096;
 template <typename T>
 __global__ void __launch_bounds__(256) repack_weights_kernel(const gdl_repack_t* __restrict__ table, const int* __restrict__ chunk0,
                                                               int n_entries) {
+  GDL_PDL_ENTRY();
   int lo = 0, hi = n_entries;  // last entry with chunk0[e] <= blockIdx.x
   while (hi - lo > 1) {
     const int mid = (lo + hi) >> 1;
@@ -1640,6 +1646,7 @@ __global__ void __launch_bounds__(256) repack_weights_kernel(const gdl_repack_t*
 // grad fp32 [Cout][src_ld] with columns (r,s,c) -> fp32 OIHW
 __global__ void unpack_wgrad_kernel(const float* __restrict__ src, float* __restrict__ dst, int Cout,
                                     int Cin, int R, int S, int src_ld, int accumulate) {
+  GDL_PDL_ENTRY();
   const long long total = (long long)Cout * Cin * R * S;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -1662,6 +1669,7 @@ __global__ void unpack_wgrad_kernel(const float* __restrict__ src, float* __rest
 //   dst[(j,o)][ky][sx][(j',c)] = src[o][ky][kx][c],  kx = f*(sx-1) + j' - j + 1  (zero when kx is outside 0..2)
 template <typename T>
 __global__ void widen_weight_kernel(const T* __restrict__ src, T* __restrict__ dst, int Co, int Ci, int R, int f) {
+  GDL_PDL_ENTRY();
   const long long total = (long long)f * Co * R * 3 * f * Ci;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -1684,6 +1692,7 @@ __global__ void widen_weight_kernel(const T* __restrict__ src, T* __restrict__ d
 // fp32 gradient of the widened weights [f*Co][src_ld] (columns (ky,sx,(j',c))) -> fp32 OIHW of the real conv
 __global__ void fold_widened_wgrad_kernel(const float* __restrict__ src, int src_ld, int src_co,
                                           float* __restrict__ dst, int Co, int Ci, int R, int f, int accumulate) {
+  GDL_PDL_ENTRY();
   const long long total = (long long)Co * Ci * R * 3;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -1715,10 +1724,10 @@ extern "C" int gdl_widen_conv_weight(const void* src, void* dst, int Co, int Ci,
   int blocks = (int)((total + 255) / 256);
   if (blocks > 148 * 16) blocks = 148 * 16;
   if (dtype == GDL_BF16)
-    gdl::widen_weight_kernel<__nv_bfloat16><<<blocks, 256, 0, (cudaStream_t)stream>>>(
+    GDL_LAUNCH(gdl::widen_weight_kernel<__nv_bfloat16>, blocks, 256, 0, (cudaStream_t)stream, 
         (const __nv_bfloat16*)src, (__nv_bfloat16*)dst, Co, Ci, R, f);
   else
-    gdl::widen_weight_kernel<__half><<<blocks, 256, 0, (cudaStream_t)stream>>>((const __half*)src, (__half*)dst, Co, Ci,
+    GDL_LAUNCH(gdl::widen_weight_kernel<__half>, blocks, 256, 0, (cudaStream_t)stream, (const __half*)src, (__half*)dst, Co, Ci,
                                                                             R, f);
   GDL_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -1734,7 +1743,7 @@ extern "C" int gdl_fold_widened_wgrad(const float* src, int src_ld, int src_co, 
   const long long total = (long long)Co * Ci * R * 3;
   int blocks = (int)((total + 255) / 256);
   if (blocks > 148 * 16) blocks = 148 * 16;
-  gdl::fold_widened_wgrad_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(src, src_ld, src_co, dst, Co, Ci, R, f,
+  GDL_LAUNCH(gdl::fold_widened_wgrad_kernel, blocks, 256, 0, (cudaStream_t)stream, src, src_ld, src_co, dst, Co, Ci, R, f,
                                                                            accumulate);
   GDL_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -1753,10 +1762,10 @@ extern "C" int gdl_pack_conv_weight(const float* src, void* dst, int Cout, int C
   int blocks = (int)((total + 255) / 256);
   if (blocks > 148 * 16) blocks = 148 * 16;
   if (dtype == GDL_BF16)
-    pack_weight_kernel<__nv_bfloat16><<<blocks, 256, 0, (cudaStream_t)stream>>>(
+    GDL_LAUNCH(pack_weight_kernel<__nv_bfloat16>, blocks, 256, 0, (cudaStream_t)stream, 
         src, (__nv_bfloat16*)dst, Cout, Cin, R, S, mode, rows, cols, dst_ld);
   else
-    pack_weight_kernel<__half><<<blocks, 256, 0, (cudaStream_t)stream>>>(src, (__half*)dst, Cout, Cin, R, S,
+    GDL_LAUNCH(pack_weight_kernel<__half>, blocks, 256, 0, (cudaStream_t)stream, src, (__half*)dst, Cout, Cin, R, S,
                                                                         mode, rows, cols, dst_ld);
   GDL_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -1767,9 +1776,9 @@ extern "C" int gdl_repack_weights(const gdl_repack_t* table_dev, const int* chun
   GDL_REQUIRE(table_dev && chunk0_dev && n_entries > 0 && total_chunks > 0, GDL_ERR_INVALID, "repack_weights: bad args");
   GDL_REQUIRE(dtype == GDL_BF16 || dtype == GDL_F16, GDL_ERR_INVALID, "repack_weights: dtype");
   if (dtype == GDL_BF16)
-    repack_weights_kernel<__nv_bfloat16><<<total_chunks, 256, 0, (cudaStream_t)stream>>>(table_dev, chunk0_dev, n_entries);
+    GDL_LAUNCH(repack_weights_kernel<__nv_bfloat16>, total_chunks, 256, 0, (cudaStream_t)stream, table_dev, chunk0_dev, n_entries);
   else
-    repack_weights_kernel<__half><<<total_chunks, 256, 0, (cudaStream_t)stream>>>(table_dev, chunk0_dev, n_entries);
+    GDL_LAUNCH(repack_weights_kernel<__half>, total_chunks, 256, 0, (cudaStream_t)stream, table_dev, chunk0_dev, n_entries);
   GDL_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -1782,7 +1791,7 @@ extern "C" int gdl_unpack_conv_wgrad(const float* src, float* dst, int Cout, int
   const long long total = (long long)Cout * Cin * R * S;
   int blocks = (int)((total + 255) / 256);
   if (blocks > 148 * 16) blocks = 148 * 16;
-  unpack_wgrad_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(src, dst, Cout, Cin, R, S, src_ld, accumulate);
+  GDL_LAUNCH(unpack_wgrad_kernel, blocks, 256, 0, (cudaStream_t)stream, src, dst, Cout, Cin, R, S, src_ld, accumulate);
   GDL_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -21,6 +21,7 @@ namespace gdl {
 template <int KMAX, typename TT>
 __global__ void seg_loss_stats_kernel(const float* __restrict__ logits, int ld, const TT* __restrict__ target,
                                       long long M, LossCfg cfg, float* __restrict__ stats, const DetCtx det) {
+  GDL_PDL_ENTRY();
   const int K = cfg.K;
   LossAcc<KMAX> acc;
   acc.init();
@@ -35,6 +36,7 @@ __global__ void seg_loss_stats_kernel(const float* __restrict__ logits, int ld, 
 }
 
 __global__ void seg_loss_finalize_kernel(const float* __restrict__ stats, LossCfg cfg, float* __restrict__ coeff) {
+  GDL_PDL_ENTRY();
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   const int K = cfg.K;
   float loss = 0.f;
@@ -70,6 +72,7 @@ template <int KMAX, typename TT, typename TO>
 __global__ void seg_loss_bwd_kernel(const float* __restrict__ logits, int ld, const TT* __restrict__ target,
                                     long long M, LossCfg cfg, const float* __restrict__ coeff,
                                     const float* __restrict__ grad_scale, TO* __restrict__ dlogits, int ldd) {
+  GDL_PDL_ENTRY();
   const int K = cfg.K;
   const float gs = grad_scale ? grad_scale[0] : 1.f;
   const float inv_denom = 1.f / coeff[1];
@@ -99,6 +102,7 @@ __global__ void seg_loss_bwd_kernel(const float* __restrict__ logits, int ld, co
 // softmax is monotone, so argmax(logits) == argmax(softmax(logits)); first maximum wins (torch).
 __global__ void argmax_kernel(const float* __restrict__ logits, int ld, long long M, int K, float threshold,
                               long long* __restrict__ out) {
+  GDL_PDL_ENTRY();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < M;
        i += (long long)gridDim.x * blockDim.x) {
     if (K == 1) {
@@ -125,6 +129,7 @@ __global__ void argmax_kernel(const float* __restrict__ logits, int ld, long lon
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                             float* __restrict__ v, long long n, float lr, float beta1, float beta2, float eps,
                             float weight_decay, float bc1, float bc2_sqrt, const float* __restrict__ grad_scale) {
+  GDL_PDL_ENTRY();
   const float gsc = grad_scale ? grad_scale[0] : 1.f;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
        i += (long long)gridDim.x * blockDim.x) {
@@ -143,6 +148,7 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
 // device-side step counter variant (CUDA-graph friendly: nothing step-dependent is baked into kernel
 // parameters).  state[0] = step (as float), state[1] = 1 - beta1^step, state[2] = sqrt(1 - beta2^step)
 __global__ void adam_advance_kernel(float* __restrict__ state, float beta1, float beta2) {
+  GDL_PDL_ENTRY();
   const float step = state[0] + 1.f;
   state[0] = step;
   state[1] = 1.f - powf(beta1, step);
@@ -153,6 +159,7 @@ __global__ void adam_dev_kernel(float* __restrict__ p, const float* __restrict__
                                 float* __restrict__ v, long long n, float lr, float beta1, float beta2, float eps,
                                 float weight_decay, const float* __restrict__ state,
                                 const float* __restrict__ grad_scale, const float* __restrict__ lr_scale) {
+  GDL_PDL_ENTRY();
   const float gsc = grad_scale ? grad_scale[0] : 1.f;
   const float bc1 = state[1], bc2_sqrt = state[2];
   if (lr_scale != nullptr) lr *= lr_scale[0];  // learning-rate schedule as a device value: a captured graph follows it
@@ -172,6 +179,7 @@ __global__ void adam_dev_kernel(float* __restrict__ p, const float* __restrict__
 
 // sum of squares of a flat fp32 buffer (for clip_grad_norm_); result accumulated into out[0]
 __global__ void sumsq_kernel(const float* __restrict__ g, long long n, float* __restrict__ out, const DetCtx det) {
+  GDL_PDL_ENTRY();
   float s = 0.f;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
        i += (long long)gridDim.x * blockDim.x)
@@ -191,6 +199,7 @@ __global__ void sumsq_kernel(const float* __restrict__ g, long long n, float* __
 
 // scale[0] = min(1, max_norm / (sqrt(sumsq) + 1e-6))  (torch.nn.utils.clip_grad_norm_)
 __global__ void clip_coef_kernel(const float* __restrict__ sumsq, float max_norm, float* __restrict__ scale) {
+  GDL_PDL_ENTRY();
   const float nrm = sqrtf(sumsq[0]);
   const float c = max_norm / (nrm + 1e-6f);
   scale[0] = c < 1.f ? c : 1.f;
@@ -203,7 +212,7 @@ int loss_blocks(long long M) {
 }
 
 void launch_loss_finalize(const float* stats, const LossCfg& cfg, float* coeff, cudaStream_t s) {
-  seg_loss_finalize_kernel<<<1, 32, 0, s>>>(stats, cfg, coeff);
+  GDL_LAUNCH(seg_loss_finalize_kernel, 1, 32, 0, s, stats, cfg, coeff);
 }
 
 int make_cfg(LossCfg* c, int K, long long ignore_index, int has_ignore, float w_ce, float w_dice,
@@ -250,16 +259,16 @@ extern "C" int gdl_seg_loss_fwd(const float* logits, int ld, const void* target,
 #define LAUNCH_STATS(KMAX)                                                                                  \
   do {                                                                                                      \
     if (target_kind == 0)                                                                                   \
-      seg_loss_stats_kernel<KMAX, long long><<<blocks, 256, 0, s>>>(logits, ld, (const long long*)target, M, cfg, stats, det); \
+      GDL_LAUNCH((seg_loss_stats_kernel<KMAX, long long>), blocks, 256, 0, s, logits, ld, (const long long*)target, M, cfg, stats, det); \
     else                                                                                                    \
-      seg_loss_stats_kernel<KMAX, uint8_t><<<blocks, 256, 0, s>>>(logits, ld, (const uint8_t*)target, M, cfg, stats, det); \
+      GDL_LAUNCH((seg_loss_stats_kernel<KMAX, uint8_t>), blocks, 256, 0, s, logits, ld, (const uint8_t*)target, M, cfg, stats, det); \
   } while (0)
   if (K <= 2) LAUNCH_STATS(2);
   else if (K <= 8) LAUNCH_STATS(8);
   else LAUNCH_STATS(32);
 #undef LAUNCH_STATS
   GDL_CHECK_CUDA(cudaGetLastError());
-  seg_loss_finalize_kernel<<<1, 32, 0, s>>>(stats, cfg, coeff);
+  GDL_LAUNCH(seg_loss_finalize_kernel, 1, 32, 0, s, stats, cfg, coeff);
   GDL_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -278,7 +287,7 @@ extern "C" int gdl_seg_loss_bwd(const float* logits, int ld, const void* target,
   cudaStream_t s = (cudaStream_t)stream;
   const int blocks = loss_blocks(M);
 #define LAUNCH_BWD2(KMAX, TT, TO) \
-  seg_loss_bwd_kernel<KMAX, TT, TO><<<blocks, 256, 0, s>>>(logits, ld, (const TT*)target, M, cfg, coeff, grad_scale, (TO*)dlogits, ldd)
+  GDL_LAUNCH((seg_loss_bwd_kernel<KMAX, TT, TO>), blocks, 256, 0, s, logits, ld, (const TT*)target, M, cfg, coeff, grad_scale, (TO*)dlogits, ldd)
 #define LAUNCH_BWD1(KMAX, TT)                                     \
   do {                                                            \
     if (out_dtype == GDL_F32) LAUNCH_BWD2(KMAX, TT, float);       \
@@ -303,7 +312,7 @@ extern "C" int gdl_seg_loss_bwd(const float* logits, int ld, const void* target,
 extern "C" int gdl_argmax_classes(const float* logits, int ld, long long M, int K, float threshold, long long* out,
                                   void* stream) {
   GDL_REQUIRE(logits && out && M > 0 && K >= 1 && ld >= K, GDL_ERR_INVALID, "argmax: bad args");
-  argmax_kernel<<<loss_blocks(M), 256, 0, (cudaStream_t)stream>>>(logits, ld, M, K, threshold, out);
+  GDL_LAUNCH(argmax_kernel, loss_blocks(M), 256, 0, (cudaStream_t)stream, logits, ld, M, K, threshold, out);
   GDL_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -316,7 +325,7 @@ extern "C" int gdl_adam_step(float* p, const float* g, float* m, float* v, long 
   const double bc2 = 1.0 - pow((double)beta2, (double)step);
   long long b = (n + 255) / 256;
   if (b > 8 * kNumSMsB200) b = 8 * kNumSMsB200;
-  adam_kernel<<<(int)b, 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay,
+  GDL_LAUNCH(adam_kernel, (int)b, 256, 0, (cudaStream_t)stream, p, g, m, v, n, lr, beta1, beta2, eps, weight_decay,
                                                        (float)bc1, (float)sqrt(bc2), grad_scale);
   GDL_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -327,10 +336,10 @@ extern "C" int gdl_adam_step_dev(float* p, const float* g, float* m, float* v, l
                                  const float* grad_scale, const float* lr_scale, void* stream) {
   GDL_REQUIRE(p && g && m && v && state && n > 0, GDL_ERR_INVALID, "adam_dev: bad args");
   cudaStream_t st = (cudaStream_t)stream;
-  adam_advance_kernel<<<1, 1, 0, st>>>(state, beta1, beta2);
+  GDL_LAUNCH(adam_advance_kernel, 1, 1, 0, st, state, beta1, beta2);
   long long b = (n + 255) / 256;
   if (b > 8 * kNumSMsB200) b = 8 * kNumSMsB200;
-  adam_dev_kernel<<<(int)b, 256, 0, st>>>(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, state, grad_scale, lr_scale);
+  GDL_LAUNCH(adam_dev_kernel, (int)b, 256, 0, st, p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, state, grad_scale, lr_scale);
   GDL_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -350,8 +359,8 @@ extern "C" int gdl_grad_clip_coef(const float* g, long long n, float max_norm, f
       det = det_ctx(ws, gd, 1);
     }
   }
-  sumsq_kernel<<<(int)b, 256, 0, s>>>(g, n, sumsq_scratch, det);
-  clip_coef_kernel<<<1, 1, 0, s>>>(sumsq_scratch, max_norm, scale);
+  GDL_LAUNCH(sumsq_kernel, (int)b, 256, 0, s, g, n, sumsq_scratch, det);
+  GDL_LAUNCH(clip_coef_kernel, 1, 1, 0, s, sumsq_scratch, max_norm, scale);
   GDL_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -49,6 +49,7 @@ GDL_DEVINL float4 ld_relaxed_sys_v4(const float* p) {
 
 __global__ void __launch_bounds__(256) p2p_allreduce_kernel(float* __restrict__ sums, int n, const __grid_constant__ P2PPeers peers,
                                                              unsigned* __restrict__ counter, int rank, int world, int slot_floats) {
+  GDL_PDL_ENTRY();
   __shared__ unsigned s_seq;
   if (threadIdx.x == 0) {
     s_seq = *counter + 1u;
@@ -123,7 +124,7 @@ extern "C" int gdl_p2p_allreduce_sums(float* sums, int n, const void* const* pee
     peers.buf[r] = nullptr;
     peers.flags[r] = nullptr;
   }
-  p2p_allreduce_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(sums, n, peers, counter, rank, world, slot_floats);
+  GDL_LAUNCH(p2p_allreduce_kernel, 1, 256, 0, (cudaStream_t)stream, sums, n, peers, counter, rank, world, slot_floats);
   GDL_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -107,6 +107,7 @@ struct WsEntry {
   long long bytes;
 };
 static WsEntry g_ws[64];
+int g_opt_pdl = 0;  // gdl_set_option("pdl", 0/1): launches carry the programmatic-stream-serialization attribute (common.cuh)
 int g_opt_deterministic = 1;  // gdl_set_option("deterministic", 0/1); only effective with a registered workspace
 
 DetWs det_workspace() {

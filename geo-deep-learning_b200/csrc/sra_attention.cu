@@ -62,6 +62,7 @@ GDL_DEVINL float2 sra_unpack2(uint32_t u) {
 //   TMA loaded,  V -> K (second MMA: dQ = dS.K),  O -> dQ,  saved P -> dS (stored for the dK = dS^T.q wgrad).  One key block only.
 template <int FMT, bool BWD>
 __global__ void __launch_bounds__(kSraThreads, 1) sra_attention_kernel(const __grid_constant__ SraParams p) {
+  GDL_PDL_ENTRY();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = align_smem_1024(smem_raw);
 
@@ -441,7 +442,7 @@ static int sra_launch(const void* q, long long ldq, int cols_q, const void* k, l
   do {                                                                                      \
     static PerDeviceOnce once;                                                              \
     GDL_CHECK_CUDA(set_max_dyn_smem_once(once, sra_attention_kernel<FMT, BWD>, smem));      \
-    sra_attention_kernel<FMT, BWD><<<grid, kSraThreads, smem, s>>>(p);                      \
+    GDL_LAUNCH((sra_attention_kernel<FMT, BWD>), grid, kSraThreads, smem, s, p);                      \
   } while (0)
   if (pin != nullptr) {
     if (dtype == GDL_BF16) GDL_SRA_LAUNCH(1, true); else GDL_SRA_LAUNCH(0, true);

@@ -52,6 +52,7 @@ template <typename TI, typename TO>
 __global__ void layernorm_fwd_kernel(const TI* __restrict__ x, long long ldx, const float* __restrict__ gamma,
                                      const float* __restrict__ beta, float eps, TO* __restrict__ y, long long ldy,
                                      float* __restrict__ mean_out, float* __restrict__ rstd_out, long long M, int C) {
+  GDL_PDL_ENTRY();
   const int lane = threadIdx.x & 31;
   const int wpb = blockDim.x >> 5;
   const int per = (C + 31) / 32;
@@ -94,6 +95,7 @@ __global__ void layernorm_bwd_kernel(const TG* __restrict__ g, long long ldg, co
                                      const float* __restrict__ gamma, const float* __restrict__ add, long long lda,
                                      float* __restrict__ dx32, long long ld32, void* __restrict__ dx16, long long ld16,
                                      int dx16_is_half, float* __restrict__ pgrads, long long M, int C, const DetCtx det) {
+  GDL_PDL_ENTRY();
   extern __shared__ float sh[];  // [2][C]
   for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sh[i] = 0.f;
   __syncthreads();
@@ -175,6 +177,7 @@ constexpr int kSmMaxPerLane = 48;  // L <= 1536 (DOFA: 1297 tokens)
 template <typename T, int PER>
 __global__ void softmax_fwd_kernel(const T* __restrict__ s, long long lds, float scale, T* __restrict__ p,
                                    long long ldp, long long M, int L, int Lpad) {
+  GDL_PDL_ENTRY();
   const int lane = threadIdx.x & 31;
   const int wpb = blockDim.x >> 5;
   for (long long row = (long long)blockIdx.x * wpb + (threadIdx.x >> 5); row < M; row += (long long)gridDim.x * wpb) {
@@ -207,6 +210,7 @@ __global__ void softmax_fwd_kernel(const T* __restrict__ s, long long lds, float
 template <typename T, int PER>
 __global__ void softmax_bwd_kernel(const T* __restrict__ p, long long ldp, const T* __restrict__ dp, long long lddp,
                                    float scale, T* __restrict__ ds, long long ldds, long long M, int L, int Lpad) {
+  GDL_PDL_ENTRY();
   const int lane = threadIdx.x & 31;
   const int wpb = blockDim.x >> 5;
   for (long long row = (long long)blockIdx.x * wpb + (threadIdx.x >> 5); row < M; row += (long long)gridDim.x * wpb) {
@@ -302,6 +306,7 @@ GDL_DEVINL void unpack8<__half>(const uint4& u, float (&f)[8]) {
 template <typename T, int PV>
 __global__ void softmax_fwd_vec_kernel(const T* __restrict__ s, long long lds, float scale, T* __restrict__ p,
                                        long long ldp, long long M, int L, int Lpad) {
+  GDL_PDL_ENTRY();
   const int lane = threadIdx.x & 31;
   const int wpb = blockDim.x >> 5;
   for (long long row = (long long)blockIdx.x * wpb + (threadIdx.x >> 5); row < M; row += (long long)gridDim.x * wpb) {
@@ -351,6 +356,7 @@ __global__ void softmax_fwd_vec_kernel(const T* __restrict__ s, long long lds, f
 template <typename T, int PV>
 __global__ void softmax_bwd_vec_kernel(const T* __restrict__ p, long long ldp, const T* __restrict__ dp, long long lddp,
                                        float scale, T* __restrict__ ds, long long ldds, long long M, int L, int Lpad) {
+  GDL_PDL_ENTRY();
   const int lane = threadIdx.x & 31;
   const int wpb = blockDim.x >> 5;
   for (long long row = (long long)blockIdx.x * wpb + (threadIdx.x >> 5); row < M; row += (long long)gridDim.x * wpb) {
@@ -398,6 +404,7 @@ template <typename T, bool GELU, bool FLIP>
 __global__ void __launch_bounds__(kDwThreads) dwconv_strip_kernel(const T* __restrict__ x, int ldx, const float* __restrict__ w,
                                                            const float* __restrict__ bias, T* __restrict__ pre,
                                                            T* __restrict__ y, int ldy, int N, int H, int W, int C) {
+  GDL_PDL_ENTRY();
   const int cv = C / 8;
   const int tpr = cv < (int)blockDim.x ? cv : blockDim.x;
   const int rows_per_block = blockDim.x / tpr;
@@ -485,6 +492,7 @@ __global__ void __launch_bounds__(kDwThreads) dwconv_strip_kernel(const T* __res
 template <typename T>
 __global__ void gelu_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ pre, T* __restrict__ dpre,
                                 long long n8) {
+  GDL_PDL_ENTRY();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n8;
        i += (long long)gridDim.x * blockDim.x) {
     float a[8], b[8], o[8];
@@ -503,6 +511,7 @@ template <typename T>
 __global__ void __launch_bounds__(kDwThreads) dwconv_bwd_dw_kernel(const T* __restrict__ dpre, const T* __restrict__ x, int ldx,
                                                             float* __restrict__ pgrads, int N, int H, int W, int C,
                                                             const DetCtx det) {
+  GDL_PDL_ENTRY();
   const int cv = C / 8;
   const int tpr = cv < (int)blockDim.x ? cv : blockDim.x;
   const int rows_per_block = blockDim.x / tpr;
@@ -603,6 +612,7 @@ __global__ void __launch_bounds__(kDwThreads) dwconv_bwd_dw_kernel(const T* __re
 template <typename T>
 __global__ void bilinear_fwd_kernel(const T* __restrict__ x, long long ldx, T* __restrict__ y, long long ldy, int N,
                                     int Hi, int Wi, int Ho, int Wo, int C, float sh, float sw) {
+  GDL_PDL_ENTRY();
   const long long total = (long long)N * Ho * Wo * C;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -627,6 +637,7 @@ __global__ void bilinear_fwd_kernel(const T* __restrict__ x, long long ldx, T* _
 template <typename T>
 __global__ void bilinear_fwd_vec8_kernel(const T* __restrict__ x, long long ldx, T* __restrict__ y, long long ldy, int N,
                                          int Hi, int Wi, int Ho, int Wo, int C, float sh, float sw) {
+  GDL_PDL_ENTRY();
   const int cv = C / 8;
   const long long total = (long long)N * Ho * Wo * cv;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
@@ -657,6 +668,7 @@ __global__ void bilinear_fwd_vec8_kernel(const T* __restrict__ x, long long ldx,
 template <typename T>
 __global__ void bilinear_bwd_kernel(const T* __restrict__ dy, long long ldy, T* __restrict__ dx, long long ldx, int N,
                                     int Hi, int Wi, int Ho, int Wo, int C, float sh, float sw) {
+  GDL_PDL_ENTRY();
   const long long total = (long long)N * Hi * Wi * C;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -692,6 +704,7 @@ __global__ void bilinear_bwd_kernel(const T* __restrict__ dy, long long ldy, T* 
 template <typename T>
 __global__ void bilinear_bwd_vec8_kernel(const T* __restrict__ dy, long long ldy, T* __restrict__ dx, long long ldx,
                                          int N, int Hi, int Wi, int Ho, int Wo, int C, float sh, float sw) {
+  GDL_PDL_ENTRY();
   const int cv = C / 8;
   const long long total = (long long)N * Hi * Wi * cv;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
@@ -735,6 +748,7 @@ __global__ void bilinear_bwd_vec8_kernel(const T* __restrict__ dy, long long ldy
 template <typename T>
 __global__ void adaptive_avgpool_fwd_kernel(const T* __restrict__ x, long long ldx, T* __restrict__ y, int N, int H,
                                             int W, int C, int S) {
+  GDL_PDL_ENTRY();
   const long long total = (long long)N * S * S * C;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -756,6 +770,7 @@ __global__ void adaptive_avgpool_fwd_kernel(const T* __restrict__ x, long long l
 template <typename T>
 __global__ void adaptive_avgpool_bwd_kernel(const T* __restrict__ dy, T* __restrict__ dx, int N, int H, int W, int C,
                                             int S) {
+  GDL_PDL_ENTRY();
   const long long total = (long long)N * H * W * C;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -783,6 +798,7 @@ __global__ void adaptive_avgpool_bwd_kernel(const T* __restrict__ dy, T* __restr
 template <typename T>
 __global__ void add_kernel(const T* __restrict__ a, long long lda, const T* __restrict__ b, long long ldb,
                            T* __restrict__ y, long long ldy, long long M, int C) {
+  GDL_PDL_ENTRY();
   const long long total = M * C;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -799,6 +815,7 @@ __global__ void add_kernel(const T* __restrict__ a, long long lda, const T* __re
 template <typename TP>
 __global__ void vit_assemble_tokens_kernel(const TP* __restrict__ patch, const float* __restrict__ pos,
                                            const float* __restrict__ cls, float* __restrict__ tokens, int B, int P, int C) {
+  GDL_PDL_ENTRY();
   const long long total = (long long)B * (P + 1) * C;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -812,6 +829,7 @@ __global__ void vit_assemble_tokens_kernel(const TP* __restrict__ patch, const f
 
 template <typename TO>
 __global__ void vit_extract_feature_kernel(const float* __restrict__ tokens, TO* __restrict__ feat, int B, int P, int C) {
+  GDL_PDL_ENTRY();
   const long long total = (long long)B * P * C;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -826,6 +844,7 @@ __global__ void vit_extract_feature_kernel(const float* __restrict__ tokens, TO*
 // elementwise helpers for the fp32 residual stream
 template <typename T>
 __global__ void cast_f32_kernel(const float* __restrict__ x, T* __restrict__ y, long long n) {
+  GDL_PDL_ENTRY();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
     y[i] = from_f<T>(x[i]);
 }
@@ -838,6 +857,7 @@ __global__ void cast_f32_kernel(const float* __restrict__ x, T* __restrict__ y, 
 // y = gelu(x), exact (erf) as nn.GELU
 template <typename T>
 __global__ void gelu_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, long long n8) {
+  GDL_PDL_ENTRY();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n8;
        i += (long long)gridDim.x * blockDim.x) {
     float a[8], o[8];
@@ -854,6 +874,7 @@ template <typename T>
 __global__ void layerscale_add_kernel(const float* __restrict__ res, const T* __restrict__ u,
                                       const float* __restrict__ gamma, const float* __restrict__ sscale,
                                       long long rows_per_sample, float* __restrict__ out, long long M, int C) {
+  GDL_PDL_ENTRY();
   const int cv = C / 8;
   const long long total = M * cv;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
@@ -887,6 +908,7 @@ template <typename T>
 __global__ void layerscale_bwd_kernel(const float* __restrict__ g, const T* __restrict__ u, const float* __restrict__ gamma,
                                       const float* __restrict__ sscale, long long rows_per_sample, T* __restrict__ du,
                                       float* __restrict__ dgamma, long long M, int C, const DetCtx det) {
+  GDL_PDL_ENTRY();
   const int tpr = C / 8;
   const int rpb = blockDim.x / tpr;
   const int rl = threadIdx.x / tpr, v = threadIdx.x - rl * tpr;
@@ -937,6 +959,7 @@ __global__ void layerscale_bwd_kernel(const float* __restrict__ g, const T* __re
 // init == 0: g[b][1+p] += dfeat[b][p]
 template <typename T>
 __global__ void vit_feature_grad_kernel(const T* __restrict__ dfeat, float* __restrict__ g, int B, int P, int C, int init) {
+  GDL_PDL_ENTRY();
   const long long total = (long long)B * (P + 1) * C;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -967,6 +990,7 @@ constexpr int kMaxBands = 16;
 template <typename T>
 __global__ void channel_pool_fwd_kernel(const T* __restrict__ xw, const float* __restrict__ scores, T* __restrict__ out,
                                         float* __restrict__ attn, long long P, int C, int E) {
+  GDL_PDL_ENTRY();
   const int tpp = E / 8;
   const long long total = P * tpp;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
@@ -1003,6 +1027,7 @@ __global__ void channel_pool_fwd_kernel(const T* __restrict__ xw, const float* _
 template <typename T>
 __global__ void channel_pool_bwd_kernel(const T* __restrict__ dout, const T* __restrict__ xw, const float* __restrict__ attn,
                                         T* __restrict__ dxw, T* __restrict__ dscores, long long P, int C, int E) {
+  GDL_PDL_ENTRY();
   const int tpp = E / 8;
   // whole pixels per block iteration so that the lanes of a pixel stay together and every lane of a warp takes the same
   // number of trips through the loop (the shuffles below need all 32 lanes)
@@ -1051,6 +1076,7 @@ __global__ void channel_pool_bwd_kernel(const T* __restrict__ dout, const T* __r
 // dx = dy * (y > 0)  (ReLU backward from the activation; 16-bit, n % 8 == 0)
 template <typename T>
 __global__ void relu_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ y, T* __restrict__ dx, long long n8) {
+  GDL_PDL_ENTRY();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n8;
        i += (long long)gridDim.x * blockDim.x) {
     float a[8], b[8], o[8];
@@ -1091,7 +1117,7 @@ extern "C" int gdl_layernorm_fwd(const void* x, int x_dtype, long long ldx, cons
   cudaStream_t st = (cudaStream_t)stream;
   const int blocks = row_blocks(M, 8);
 #define LN_FWD(TI, TO) \
-  layernorm_fwd_kernel<TI, TO><<<blocks, 256, 0, st>>>((const TI*)x, ldx, gamma, beta, eps, (TO*)y, ldy, mean, rstd, M, C)
+  GDL_LAUNCH((layernorm_fwd_kernel<TI, TO>), blocks, 256, 0, st, (const TI*)x, ldx, gamma, beta, eps, (TO*)y, ldy, mean, rstd, M, C)
   if (x_dtype == GDL_F32) {
     if (y_dtype == GDL_F32) LN_FWD(float, float);
     else if (y_dtype == GDL_BF16) LN_FWD(float, __nv_bfloat16);
@@ -1130,7 +1156,7 @@ extern "C" int gdl_layernorm_bwd(const void* g, int g_dtype, long long ldg, cons
     }
   }
 #define LN_BWD(TI, TG)                                                                                          \
-  layernorm_bwd_kernel<TI, TG><<<blocks, 256, smem, st>>>((const TG*)g, ldg, (const TI*)x, ldx, mean, rstd, gamma, add, \
+  GDL_LAUNCH((layernorm_bwd_kernel<TI, TG>), blocks, 256, smem, st, (const TG*)g, ldg, (const TI*)x, ldx, mean, rstd, gamma, add, \
                                                          lda, dx32, ld32, dx16, ld16, is_half, pgrads, M, C, det)
   if (x_dtype == GDL_F32) {
     if (g_dtype == GDL_F32) LN_BWD(float, float);
@@ -1161,10 +1187,10 @@ extern "C" int gdl_softmax_fwd(const void* s, long long lds, float scale, void* 
 #define GDL_SMV_FWD(PVV)                                                                                            \
   do {                                                                                                              \
     if (dtype == GDL_BF16)                                                                                          \
-      softmax_fwd_vec_kernel<__nv_bfloat16, PVV><<<row_blocks(M, 8), 256, 0, st>>>(                                 \
+      GDL_LAUNCH((softmax_fwd_vec_kernel<__nv_bfloat16, PVV>), row_blocks(M, 8), 256, 0, st,                                  \
           (const __nv_bfloat16*)s, lds, scale, (__nv_bfloat16*)p, ldp, M, L, Lpad);                                 \
     else                                                                                                            \
-      softmax_fwd_vec_kernel<__half, PVV><<<row_blocks(M, 8), 256, 0, st>>>((const __half*)s, lds, scale, (__half*)p, \
+      GDL_LAUNCH((softmax_fwd_vec_kernel<__half, PVV>), row_blocks(M, 8), 256, 0, st, (const __half*)s, lds, scale, (__half*)p, \
                                                                             ldp, M, L, Lpad);                       \
   } while (0)
     if (pv <= 1) GDL_SMV_FWD(1);
@@ -1177,7 +1203,7 @@ extern "C" int gdl_softmax_fwd(const void* s, long long lds, float scale, void* 
   }
   const int per = (Lpad + 31) / 32;
 #define GDL_SM_FWD(PERV) \
-  GDL_DISPATCH_T(dtype, { softmax_fwd_kernel<T, PERV><<<row_blocks(M, 8), 256, 0, st>>>((const T*)s, lds, scale, (T*)p, ldp, M, L, Lpad); })
+  GDL_DISPATCH_T(dtype, { GDL_LAUNCH((softmax_fwd_kernel<T, PERV>), row_blocks(M, 8), 256, 0, st, (const T*)s, lds, scale, (T*)p, ldp, M, L, Lpad); })
   if (per <= 8) GDL_SM_FWD(8);
   else if (per <= 16) GDL_SM_FWD(16);
   else if (per <= 32) GDL_SM_FWD(32);
@@ -1198,10 +1224,10 @@ extern "C" int gdl_softmax_bwd(const void* p, long long ldp, const void* dp, lon
 #define GDL_SMV_BWD(PVV)                                                                                             \
   do {                                                                                                               \
     if (dtype == GDL_BF16)                                                                                           \
-      softmax_bwd_vec_kernel<__nv_bfloat16, PVV><<<row_blocks(M, 8), 256, 0, st>>>(                                  \
+      GDL_LAUNCH((softmax_bwd_vec_kernel<__nv_bfloat16, PVV>), row_blocks(M, 8), 256, 0, st,                                   \
           (const __nv_bfloat16*)p, ldp, (const __nv_bfloat16*)dp, lddp, scale, (__nv_bfloat16*)ds, ldds, M, L, Lpad); \
     else                                                                                                             \
-      softmax_bwd_vec_kernel<__half, PVV><<<row_blocks(M, 8), 256, 0, st>>>((const __half*)p, ldp, (const __half*)dp, \
+      GDL_LAUNCH((softmax_bwd_vec_kernel<__half, PVV>), row_blocks(M, 8), 256, 0, st, (const __half*)p, ldp, (const __half*)dp, \
                                                                             lddp, scale, (__half*)ds, ldds, M, L, Lpad); \
   } while (0)
     if (pv <= 1) GDL_SMV_BWD(1);
@@ -1215,13 +1241,13 @@ extern "C" int gdl_softmax_bwd(const void* p, long long ldp, const void* dp, lon
   GDL_DISPATCH_T(dtype, {
     const int per = (Lpad + 31) / 32;
     if (per <= 8)
-      softmax_bwd_kernel<T, 8><<<row_blocks(M, 8), 256, 0, st>>>((const T*)p, ldp, (const T*)dp, lddp, scale, (T*)ds, ldds, M, L, Lpad);
+      GDL_LAUNCH((softmax_bwd_kernel<T, 8>), row_blocks(M, 8), 256, 0, st, (const T*)p, ldp, (const T*)dp, lddp, scale, (T*)ds, ldds, M, L, Lpad);
     else if (per <= 16)
-      softmax_bwd_kernel<T, 16><<<row_blocks(M, 8), 256, 0, st>>>((const T*)p, ldp, (const T*)dp, lddp, scale, (T*)ds, ldds, M, L, Lpad);
+      GDL_LAUNCH((softmax_bwd_kernel<T, 16>), row_blocks(M, 8), 256, 0, st, (const T*)p, ldp, (const T*)dp, lddp, scale, (T*)ds, ldds, M, L, Lpad);
     else if (per <= 32)
-      softmax_bwd_kernel<T, 32><<<row_blocks(M, 8), 256, 0, st>>>((const T*)p, ldp, (const T*)dp, lddp, scale, (T*)ds, ldds, M, L, Lpad);
+      GDL_LAUNCH((softmax_bwd_kernel<T, 32>), row_blocks(M, 8), 256, 0, st, (const T*)p, ldp, (const T*)dp, lddp, scale, (T*)ds, ldds, M, L, Lpad);
     else
-      softmax_bwd_kernel<T, kSmMaxPerLane><<<row_blocks(M, 8), 256, 0, st>>>((const T*)p, ldp, (const T*)dp, lddp, scale, (T*)ds, ldds, M, L, Lpad);
+      GDL_LAUNCH((softmax_bwd_kernel<T, kSmMaxPerLane>), row_blocks(M, 8), 256, 0, st, (const T*)p, ldp, (const T*)dp, lddp, scale, (T*)ds, ldds, M, L, Lpad);
   });
   GDL_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -1246,9 +1272,9 @@ extern "C" int gdl_dwconv3x3_gelu_fwd(const void* x, int ldx, const float* w, co
   const long long nstrips = (long long)N * H * ((W + kDwStrip - 1) / kDwStrip);
   const int grid = chan_row_grid(nstrips, C, 1, kDwThreads);
   if (dtype == GDL_BF16)
-    dwconv_strip_kernel<__nv_bfloat16, true, false><<<grid, kDwThreads, 0, st>>>((const __nv_bfloat16*)x, ldx, w, bias, (__nv_bfloat16*)pre, (__nv_bfloat16*)y, C, N, H, W, C);
+    GDL_LAUNCH((dwconv_strip_kernel<__nv_bfloat16, true, false>), grid, kDwThreads, 0, st, (const __nv_bfloat16*)x, ldx, w, bias, (__nv_bfloat16*)pre, (__nv_bfloat16*)y, C, N, H, W, C);
   else
-    dwconv_strip_kernel<__half, true, false><<<grid, kDwThreads, 0, st>>>((const __half*)x, ldx, w, bias, (__half*)pre, (__half*)y, C, N, H, W, C);
+    GDL_LAUNCH((dwconv_strip_kernel<__half, true, false>), grid, kDwThreads, 0, st, (const __half*)x, ldx, w, bias, (__half*)pre, (__half*)y, C, N, H, W, C);
   GDL_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -1277,14 +1303,14 @@ extern "C" int gdl_dwconv3x3_gelu_bwd(const void* dy, const void* pre, const voi
   }
   if (dtype == GDL_BF16) {
     using T = __nv_bfloat16;
-    gelu_bwd_kernel<T><<<(int)b1, 256, 0, st>>>((const T*)dy, (const T*)pre, (T*)dpre_scratch, n8);
-    dwconv_strip_kernel<T, false, true><<<g_dx, kDwThreads, 0, st>>>((const T*)dpre_scratch, C, w, nullptr, nullptr, (T*)dx, lddx, N, H, W, C);
-    if (pgrads) dwconv_bwd_dw_kernel<T><<<g_dw, kDwThreads, 0, st>>>((const T*)dpre_scratch, (const T*)x, ldx, pgrads, N, H, W, C, det);
+    GDL_LAUNCH(gelu_bwd_kernel<T>, (int)b1, 256, 0, st, (const T*)dy, (const T*)pre, (T*)dpre_scratch, n8);
+    GDL_LAUNCH((dwconv_strip_kernel<T, false, true>), g_dx, kDwThreads, 0, st, (const T*)dpre_scratch, C, w, nullptr, nullptr, (T*)dx, lddx, N, H, W, C);
+    if (pgrads) GDL_LAUNCH(dwconv_bwd_dw_kernel<T>, g_dw, kDwThreads, 0, st, (const T*)dpre_scratch, (const T*)x, ldx, pgrads, N, H, W, C, det);
   } else {
     using T = __half;
-    gelu_bwd_kernel<T><<<(int)b1, 256, 0, st>>>((const T*)dy, (const T*)pre, (T*)dpre_scratch, n8);
-    dwconv_strip_kernel<T, false, true><<<g_dx, kDwThreads, 0, st>>>((const T*)dpre_scratch, C, w, nullptr, nullptr, (T*)dx, lddx, N, H, W, C);
-    if (pgrads) dwconv_bwd_dw_kernel<T><<<g_dw, kDwThreads, 0, st>>>((const T*)dpre_scratch, (const T*)x, ldx, pgrads, N, H, W, C, det);
+    GDL_LAUNCH(gelu_bwd_kernel<T>, (int)b1, 256, 0, st, (const T*)dy, (const T*)pre, (T*)dpre_scratch, n8);
+    GDL_LAUNCH((dwconv_strip_kernel<T, false, true>), g_dx, kDwThreads, 0, st, (const T*)dpre_scratch, C, w, nullptr, nullptr, (T*)dx, lddx, N, H, W, C);
+    if (pgrads) GDL_LAUNCH(dwconv_bwd_dw_kernel<T>, g_dw, kDwThreads, 0, st, (const T*)dpre_scratch, (const T*)x, ldx, pgrads, N, H, W, C, det);
   }
   GDL_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -1304,13 +1330,13 @@ extern "C" int gdl_bilinear_fwd(const void* x, long long ldx, void* y, long long
     if (bv > 16 * kNumSMsB200) bv = 16 * kNumSMsB200;
     if (bv < 1) bv = 1;
     if (dtype == GDL_BF16)
-      bilinear_fwd_vec8_kernel<__nv_bfloat16><<<(int)bv, 256, 0, st>>>((const __nv_bfloat16*)x, ldx, (__nv_bfloat16*)y, ldy, N, Hi, Wi, Ho, Wo, C, sh, sw);
+      GDL_LAUNCH(bilinear_fwd_vec8_kernel<__nv_bfloat16>, (int)bv, 256, 0, st, (const __nv_bfloat16*)x, ldx, (__nv_bfloat16*)y, ldy, N, Hi, Wi, Ho, Wo, C, sh, sw);
     else
-      bilinear_fwd_vec8_kernel<__half><<<(int)bv, 256, 0, st>>>((const __half*)x, ldx, (__half*)y, ldy, N, Hi, Wi, Ho, Wo, C, sh, sw);
+      GDL_LAUNCH(bilinear_fwd_vec8_kernel<__half>, (int)bv, 256, 0, st, (const __half*)x, ldx, (__half*)y, ldy, N, Hi, Wi, Ho, Wo, C, sh, sw);
     GDL_CHECK_CUDA(cudaGetLastError());
     return 0;
   }
-  GDL_DISPATCH_T(dtype, { bilinear_fwd_kernel<T><<<(int)b, 256, 0, st>>>((const T*)x, ldx, (T*)y, ldy, N, Hi, Wi, Ho, Wo, C, sh, sw); });
+  GDL_DISPATCH_T(dtype, { GDL_LAUNCH(bilinear_fwd_kernel<T>, (int)b, 256, 0, st, (const T*)x, ldx, (T*)y, ldy, N, Hi, Wi, Ho, Wo, C, sh, sw); });
   GDL_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -1328,13 +1354,13 @@ extern "C" int gdl_bilinear_bwd(const void* dy, long long ldy, void* dx, long lo
     if (bv > 16 * kNumSMsB200) bv = 16 * kNumSMsB200;
     if (bv < 1) bv = 1;
     if (dtype == GDL_BF16)
-      bilinear_bwd_vec8_kernel<__nv_bfloat16><<<(int)bv, 128, 0, st>>>((const __nv_bfloat16*)dy, ldy, (__nv_bfloat16*)dx, ldx, N, Hi, Wi, Ho, Wo, C, sh, sw);
+      GDL_LAUNCH(bilinear_bwd_vec8_kernel<__nv_bfloat16>, (int)bv, 128, 0, st, (const __nv_bfloat16*)dy, ldy, (__nv_bfloat16*)dx, ldx, N, Hi, Wi, Ho, Wo, C, sh, sw);
     else
-      bilinear_bwd_vec8_kernel<__half><<<(int)bv, 128, 0, st>>>((const __half*)dy, ldy, (__half*)dx, ldx, N, Hi, Wi, Ho, Wo, C, sh, sw);
+      GDL_LAUNCH(bilinear_bwd_vec8_kernel<__half>, (int)bv, 128, 0, st, (const __half*)dy, ldy, (__half*)dx, ldx, N, Hi, Wi, Ho, Wo, C, sh, sw);
     GDL_CHECK_CUDA(cudaGetLastError());
     return 0;
   }
-  GDL_DISPATCH_T(dtype, { bilinear_bwd_kernel<T><<<(int)b, 256, 0, st>>>((const T*)dy, ldy, (T*)dx, ldx, N, Hi, Wi, Ho, Wo, C, sh, sw); });
+  GDL_DISPATCH_T(dtype, { GDL_LAUNCH(bilinear_bwd_kernel<T>, (int)b, 256, 0, st, (const T*)dy, ldy, (T*)dx, ldx, N, Hi, Wi, Ho, Wo, C, sh, sw); });
   GDL_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -1347,7 +1373,7 @@ extern "C" int gdl_adaptive_avgpool_fwd(const void* x, long long ldx, void* y, i
   const long long total = (long long)N * S * S * C;
   long long b = (total + 255) / 256;
   if (b > 8 * kNumSMsB200) b = 8 * kNumSMsB200;
-  GDL_DISPATCH_T(dtype, { adaptive_avgpool_fwd_kernel<T><<<(int)b, 256, 0, st>>>((const T*)x, ldx, (T*)y, N, H, W, C, S); });
+  GDL_DISPATCH_T(dtype, { GDL_LAUNCH(adaptive_avgpool_fwd_kernel<T>, (int)b, 256, 0, st, (const T*)x, ldx, (T*)y, N, H, W, C, S); });
   GDL_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -1359,7 +1385,7 @@ extern "C" int gdl_adaptive_avgpool_bwd(const void* dy, void* dx, int dtype, int
   const long long total = (long long)N * H * W * C;
   long long b = (total + 255) / 256;
   if (b > 8 * kNumSMsB200) b = 8 * kNumSMsB200;
-  GDL_DISPATCH_T(dtype, { adaptive_avgpool_bwd_kernel<T><<<(int)b, 256, 0, st>>>((const T*)dy, (T*)dx, N, H, W, C, S); });
+  GDL_DISPATCH_T(dtype, { GDL_LAUNCH(adaptive_avgpool_bwd_kernel<T>, (int)b, 256, 0, st, (const T*)dy, (T*)dx, N, H, W, C, S); });
   GDL_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -1370,7 +1396,7 @@ extern "C" int gdl_add_nhwc(const void* a, long long lda, const void* b, long lo
   cudaStream_t st = (cudaStream_t)stream;
   long long blk = (M * C + 255) / 256;
   if (blk > 16 * kNumSMsB200) blk = 16 * kNumSMsB200;
-  GDL_DISPATCH_T(dtype, { add_kernel<T><<<(int)blk, 256, 0, st>>>((const T*)a, lda, (const T*)b, ldb, (T*)y, ldy, M, C); });
+  GDL_DISPATCH_T(dtype, { GDL_LAUNCH(add_kernel<T>, (int)blk, 256, 0, st, (const T*)a, lda, (const T*)b, ldb, (T*)y, ldy, M, C); });
   GDL_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -1381,7 +1407,7 @@ extern "C" int gdl_vit_assemble_tokens(const void* patch, int patch_dtype, const
   cudaStream_t st = (cudaStream_t)stream;
   long long b = ((long long)B * (P + 1) * C + 255) / 256;
   if (b > 16 * kNumSMsB200) b = 16 * kNumSMsB200;
-  GDL_DISPATCH_T(patch_dtype, { vit_assemble_tokens_kernel<T><<<(int)b, 256, 0, st>>>((const T*)patch, pos, cls, tokens, B, P, C); });
+  GDL_DISPATCH_T(patch_dtype, { GDL_LAUNCH(vit_assemble_tokens_kernel<T>, (int)b, 256, 0, st, (const T*)patch, pos, cls, tokens, B, P, C); });
   GDL_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -1391,7 +1417,7 @@ extern "C" int gdl_vit_extract_feature(const float* tokens, void* feat, int feat
   cudaStream_t st = (cudaStream_t)stream;
   long long b = ((long long)B * P * C + 255) / 256;
   if (b > 16 * kNumSMsB200) b = 16 * kNumSMsB200;
-  GDL_DISPATCH_T(feat_dtype, { vit_extract_feature_kernel<T><<<(int)b, 256, 0, st>>>(tokens, (T*)feat, B, P, C); });
+  GDL_DISPATCH_T(feat_dtype, { GDL_LAUNCH(vit_extract_feature_kernel<T>, (int)b, 256, 0, st, tokens, (T*)feat, B, P, C); });
   GDL_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -1401,7 +1427,7 @@ extern "C" int gdl_cast_f32(const float* x, void* y, int dtype, long long n, voi
   cudaStream_t st = (cudaStream_t)stream;
   long long b = (n + 255) / 256;
   if (b > 16 * kNumSMsB200) b = 16 * kNumSMsB200;
-  GDL_DISPATCH_T(dtype, { cast_f32_kernel<T><<<(int)b, 256, 0, st>>>(x, (T*)y, n); });
+  GDL_DISPATCH_T(dtype, { GDL_LAUNCH(cast_f32_kernel<T>, (int)b, 256, 0, st, x, (T*)y, n); });
   GDL_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -1426,7 +1452,7 @@ extern "C" int gdl_gelu_fwd(const void* x, void* y, int dtype, long long n, void
               "gelu_fwd: 16-byte aligned buffers expected");
   long long b = (n / 8 + 255) / 256;
   if (b > 16 * kNumSMsB200) b = 16 * kNumSMsB200;
-  GDL_DISPATCH_T16(dtype, { gelu_fwd_kernel<T><<<(int)b, 256, 0, (cudaStream_t)stream>>>((const T*)x, (T*)y, n / 8); });
+  GDL_DISPATCH_T16(dtype, { GDL_LAUNCH(gelu_fwd_kernel<T>, (int)b, 256, 0, (cudaStream_t)stream, (const T*)x, (T*)y, n / 8); });
   GDL_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -1437,7 +1463,7 @@ extern "C" int gdl_gelu_bwd(const void* dy, const void* pre, void* dpre, int dty
               GDL_ERR_INVALID, "gelu_bwd: 16-byte aligned buffers expected");
   long long b = (n / 8 + 255) / 256;
   if (b > 16 * kNumSMsB200) b = 16 * kNumSMsB200;
-  GDL_DISPATCH_T16(dtype, { gelu_bwd_kernel<T><<<(int)b, 256, 0, (cudaStream_t)stream>>>((const T*)dy, (const T*)pre, (T*)dpre, n / 8); });
+  GDL_DISPATCH_T16(dtype, { GDL_LAUNCH(gelu_bwd_kernel<T>, (int)b, 256, 0, (cudaStream_t)stream, (const T*)dy, (const T*)pre, (T*)dpre, n / 8); });
   GDL_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -1451,7 +1477,7 @@ extern "C" int gdl_layerscale_add(const float* res, const void* u, int dtype, co
   long long b = (M * (C / 8) + 255) / 256;
   if (b > 16 * kNumSMsB200) b = 16 * kNumSMsB200;
   GDL_DISPATCH_T16(dtype, {
-    layerscale_add_kernel<T><<<(int)b, 256, 0, (cudaStream_t)stream>>>(res, (const T*)u, gamma, sscale,
+    GDL_LAUNCH(layerscale_add_kernel<T>, (int)b, 256, 0, (cudaStream_t)stream, res, (const T*)u, gamma, sscale,
                                                                       rows_per_sample > 0 ? rows_per_sample : 1, out, M, C);
   });
   GDL_CHECK_CUDA(cudaGetLastError());
@@ -1478,7 +1504,7 @@ extern "C" int gdl_layerscale_bwd(const float* g, const void* u, int dtype, cons
     }
   }
   GDL_DISPATCH_T16(dtype, {
-    layerscale_bwd_kernel<T><<<(int)b, 256, 0, (cudaStream_t)stream>>>(g, (const T*)u, gamma, sscale,
+    GDL_LAUNCH(layerscale_bwd_kernel<T>, (int)b, 256, 0, (cudaStream_t)stream, g, (const T*)u, gamma, sscale,
                                                                       rows_per_sample > 0 ? rows_per_sample : 1, (T*)du, dgamma, M, C, det);
   });
   GDL_CHECK_CUDA(cudaGetLastError());
@@ -1489,7 +1515,7 @@ extern "C" int gdl_vit_feature_grad(const void* dfeat, int dtype, float* g, int 
   GDL_REQUIRE(dfeat && g && B > 0 && P > 0 && C > 0, GDL_ERR_INVALID, "vit_feature_grad: bad args");
   long long b = ((long long)B * (P + 1) * C + 255) / 256;
   if (b > 16 * kNumSMsB200) b = 16 * kNumSMsB200;
-  GDL_DISPATCH_T(dtype, { vit_feature_grad_kernel<T><<<(int)b, 256, 0, (cudaStream_t)stream>>>((const T*)dfeat, g, B, P, C, init); });
+  GDL_DISPATCH_T(dtype, { GDL_LAUNCH(vit_feature_grad_kernel<T>, (int)b, 256, 0, (cudaStream_t)stream, (const T*)dfeat, g, B, P, C, init); });
   GDL_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -1505,7 +1531,7 @@ extern "C" int gdl_channel_pool_fwd(const void* xw, const float* scores, void* o
   long long b = (P * (E / 8) + 255) / 256;
   if (b > 16 * kNumSMsB200) b = 16 * kNumSMsB200;
   GDL_DISPATCH_T16(dtype, {
-    channel_pool_fwd_kernel<T><<<(int)b, 256, 0, (cudaStream_t)stream>>>((const T*)xw, scores, (T*)out, attn, P, C, E);
+    GDL_LAUNCH(channel_pool_fwd_kernel<T>, (int)b, 256, 0, (cudaStream_t)stream, (const T*)xw, scores, (T*)out, attn, P, C, E);
   });
   GDL_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -1520,7 +1546,7 @@ extern "C" int gdl_channel_pool_bwd(const void* dout, const void* xw, const floa
   long long b = (P * (E / 8) + 255) / 256;
   if (b > 16 * kNumSMsB200) b = 16 * kNumSMsB200;
   GDL_DISPATCH_T16(dtype, {
-    channel_pool_bwd_kernel<T><<<(int)b, 256, 0, (cudaStream_t)stream>>>((const T*)dout, (const T*)xw, attn, (T*)dxw,
+    GDL_LAUNCH(channel_pool_bwd_kernel<T>, (int)b, 256, 0, (cudaStream_t)stream, (const T*)dout, (const T*)xw, attn, (T*)dxw,
                                                                         (T*)dscores, P, C, E);
   });
   GDL_CHECK_CUDA(cudaGetLastError());
@@ -1533,7 +1559,7 @@ extern "C" int gdl_relu_bwd(const void* dy, const void* y, void* dx, int dtype, 
               GDL_ERR_INVALID, "relu_bwd: 16-byte aligned buffers expected");
   long long b = (n / 8 + 255) / 256;
   if (b > 16 * kNumSMsB200) b = 16 * kNumSMsB200;
-  GDL_DISPATCH_T16(dtype, { relu_bwd_kernel<T><<<(int)b, 256, 0, (cudaStream_t)stream>>>((const T*)dy, (const T*)y, (T*)dx, n / 8); });
+  GDL_DISPATCH_T16(dtype, { GDL_LAUNCH(relu_bwd_kernel<T>, (int)b, 256, 0, (cudaStream_t)stream, (const T*)dy, (const T*)y, (T*)dx, n / 8); });
   GDL_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

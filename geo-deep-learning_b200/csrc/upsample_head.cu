@@ -49,6 +49,7 @@ template <int KMAX, typename TT>
 __global__ void __launch_bounds__(256) upsample_ce_stats_kernel(const float* __restrict__ lr, UpGeom g,
                                                                  const TT* __restrict__ target, LossCfg cfg,
                                                                  float* __restrict__ stats, const DetCtx det) {
+  GDL_PDL_ENTRY();
   const long long M = (long long)g.N * g.H * g.W;
   LossAcc<KMAX> acc;
   acc.init();
@@ -69,6 +70,7 @@ __global__ void __launch_bounds__(256) upsample_ce_bwd_kernel(const float* __res
                                                                const TT* __restrict__ target, LossCfg cfg,
                                                                const float* __restrict__ coeff,
                                                                const float* __restrict__ grad_scale, TO* __restrict__ dlr, int ldd) {
+  GDL_PDL_ENTRY();
   const int K = cfg.K;
   const float gs = grad_scale ? grad_scale[0] : 1.f;
   const float inv_denom = 1.f / coeff[1];
@@ -129,6 +131,7 @@ __global__ void __launch_bounds__(256) upsample_ce_bwd_kernel(const float* __res
 template <int KMAX>
 __global__ void __launch_bounds__(256) upsample_argmax_kernel(const float* __restrict__ lr, UpGeom g, int K, float threshold,
                                                                long long* __restrict__ out) {
+  GDL_PDL_ENTRY();
   const long long M = (long long)g.N * g.H * g.W;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < M; i += (long long)gridDim.x * blockDim.x) {
     const int X = (int)(i % g.W);
@@ -196,9 +199,9 @@ extern "C" int gdl_upsample_ce_fwd(const float* logits_lr, int ld, int N, int h,
 #define LAUNCH_STATS(KMAX)                                                                                              \
   do {                                                                                                                  \
     if (target_kind == 0)                                                                                               \
-      upsample_ce_stats_kernel<KMAX, long long><<<blocks, 256, 0, s>>>(logits_lr, g, (const long long*)target, cfg, stats, det); \
+      GDL_LAUNCH((upsample_ce_stats_kernel<KMAX, long long>), blocks, 256, 0, s, logits_lr, g, (const long long*)target, cfg, stats, det); \
     else                                                                                                                \
-      upsample_ce_stats_kernel<KMAX, uint8_t><<<blocks, 256, 0, s>>>(logits_lr, g, (const uint8_t*)target, cfg, stats, det);     \
+      GDL_LAUNCH((upsample_ce_stats_kernel<KMAX, uint8_t>), blocks, 256, 0, s, logits_lr, g, (const uint8_t*)target, cfg, stats, det);     \
   } while (0)
   if (K <= 2) LAUNCH_STATS(2);
   else if (K <= 8) LAUNCH_STATS(8);
@@ -227,7 +230,7 @@ extern "C" int gdl_upsample_ce_bwd(const float* logits_lr, int ld, int N, int h,
   long long blocks = (npix + 7) / 8;  // 8 warps per block, one low-resolution pixel per warp and iteration
   if (blocks > 32ll * kNumSMsB200) blocks = 32ll * kNumSMsB200;
 #define LAUNCH_BWD(KMAX, TT, TO)                                                                                        \
-  upsample_ce_bwd_kernel<KMAX, TT, TO><<<(int)blocks, 256, 0, s>>>(logits_lr, g, (const TT*)target, cfg, coeff, grad_scale, \
+  GDL_LAUNCH((upsample_ce_bwd_kernel<KMAX, TT, TO>), (int)blocks, 256, 0, s, logits_lr, g, (const TT*)target, cfg, coeff, grad_scale, \
                                                                    (TO*)dlogits_lr, ldd)
 #define DISPATCH_TO(KMAX, TT)                                            \
   do {                                                                   \
@@ -259,9 +262,9 @@ extern "C" int gdl_upsample_argmax(const float* logits_lr, int ld, int N, int h,
   if (st) return st;
   const int blocks = loss_blocks((long long)N * H * W);
   cudaStream_t s = (cudaStream_t)stream;
-  if (K <= 2) upsample_argmax_kernel<2><<<blocks, 256, 0, s>>>(logits_lr, g, K, threshold, out);
-  else if (K <= 8) upsample_argmax_kernel<8><<<blocks, 256, 0, s>>>(logits_lr, g, K, threshold, out);
-  else upsample_argmax_kernel<32><<<blocks, 256, 0, s>>>(logits_lr, g, K, threshold, out);
+  if (K <= 2) GDL_LAUNCH(upsample_argmax_kernel<2>, blocks, 256, 0, s, logits_lr, g, K, threshold, out);
+  else if (K <= 8) GDL_LAUNCH(upsample_argmax_kernel<8>, blocks, 256, 0, s, logits_lr, g, K, threshold, out);
+  else GDL_LAUNCH(upsample_argmax_kernel<32>, blocks, 256, 0, s, logits_lr, g, K, threshold, out);
   GDL_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

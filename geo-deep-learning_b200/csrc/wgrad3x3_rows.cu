@@ -56,6 +56,7 @@ struct WgradRowsKParams {
 };
 
 __global__ void __launch_bounds__(kWrThreads, 1) wgrad3x3_rows_kernel(const __grid_constant__ WgradRowsKParams p) {
+  GDL_PDL_ENTRY();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = align_smem_1024(smem_raw);
   uint8_t* smem_dy = smem + (size_t)kWrXStages * 2 * kWrXAtomBytes;
@@ -248,6 +249,7 @@ __global__ void __launch_bounds__(kWrThreads, 1) wgrad3x3_rows_kernel(const __gr
 __global__ void __launch_bounds__(256) wgrad_rows_reduce_kernel(const float* __restrict__ partials, int num_slabs, int cps,
                                                                  int Cout, int Ctot, float* __restrict__ dw, long long dw_ld,
                                                                  const __grid_constant__ WgradRowsKParams::SlabOffsets so) {
+  GDL_PDL_ENTRY();
   const long long per_cta = 9ll * Cout * 64;
   const long long total = (long long)num_slabs * per_cta;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -332,7 +334,7 @@ int wgrad3x3_rows_try(const gdl_conv_wgrad_t* d, cudaStream_t stream, int* statu
                        "cudaFuncSetAttribute(wgrad3x3_rows_kernel)");
   if (*status) return 1;
   const int grid = p.num_slabs * p.ctas_per_slab;
-  wgrad3x3_rows_kernel<<<grid, kWrThreads, smem, stream>>>(p);
+  GDL_LAUNCH(wgrad3x3_rows_kernel, grid, kWrThreads, smem, stream, p);
   *status = check_cuda(cudaGetLastError(), "wgrad3x3_rows_kernel launch");
   if (*status == 0 && p.partials != nullptr) {
     WgradRowsKParams::SlabOffsets so;
@@ -341,7 +343,7 @@ int wgrad3x3_rows_try(const gdl_conv_wgrad_t* d, cudaStream_t stream, int* statu
     const long long total = (long long)p.num_slabs * 9 * d->Cout * 64;
     long long rb = (total + 255) / 256;
     if (rb > 4ll * sms) rb = 4ll * sms;
-    wgrad_rows_reduce_kernel<<<(int)rb, 256, 0, stream>>>(p.partials, p.num_slabs, p.ctas_per_slab, d->Cout, p.Ctot, p.dw,
+    GDL_LAUNCH(wgrad_rows_reduce_kernel, (int)rb, 256, 0, stream, p.partials, p.num_slabs, p.ctas_per_slab, d->Cout, p.Ctot, p.dw,
                                                         p.dw_ld, so);
     *status = check_cuda(cudaGetLastError(), "wgrad_rows_reduce_kernel launch");
   }

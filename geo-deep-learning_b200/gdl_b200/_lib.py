@@ -6,6 +6,7 @@ product path raises.  (oracle/ is test infrastructure and is never imported from
 from __future__ import annotations
 
 import ctypes as C
+import os
 from pathlib import Path
 
 import torch
@@ -104,8 +105,20 @@ def load():
     lib.gdl_p2p_exchange_bytes.restype = C.c_longlong
     lib.gdl_p2p_exchange_bytes.argtypes = [C.c_int, C.c_int]
     _declare(lib)
+    lib.gdl_set_option(b"pdl", PDL)
     _lib = lib
     return lib
+
+
+# Programmatic dependent launch of every kernel (include/gdl_b200.h, option "pdl"; csrc/common.cuh): the host owns the
+# switch so that what ran can be reported (bench.py config.pdl).  GDL_PDL=0/1 overrides the default.
+PDL = int(os.environ.get("GDL_PDL", "0") != "0")
+
+
+def set_pdl(on: bool) -> None:
+    global PDL
+    PDL = int(bool(on))
+    load().gdl_set_option(b"pdl", PDL)
 
 
 _VP, _I, _LL, _F = C.c_void_p, C.c_int, C.c_longlong, C.c_float

@@ -118,6 +118,8 @@ _HOST_OPTS = {"pixel_pack": int(os.environ.get("GDL_PIXEL_PACK", "1")), "sra_fus
 
 
 def option(name: str) -> int:
+    if name == "pdl":
+        return L.PDL
     return _HOST_OPTS[name]
 
 
@@ -125,6 +127,9 @@ def set_option(name: str, value: int) -> None:
     """runtime tuning switch of the library (see gdl_set_option in include/gdl_b200.h) or of the host engine"""
     if name in _HOST_OPTS:
         _HOST_OPTS[name] = int(value)
+        return
+    if name == "pdl":
+        L.set_pdl(bool(value))
         return
     L.check(L.load().gdl_set_option(name.encode(), int(value)))
 

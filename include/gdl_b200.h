@@ -46,7 +46,9 @@ int gdl_device_info(int* sm_count, int* cc_major, int* cc_minor, unsigned long l
 /* tuning switches: "conv_halo" / "wgrad_halo" (0/1: 3x3 convs reuse one halo row tile for the 3 horizontal
  * taps), "wgrad_l2_mb" (L2 budget of the wgrad pixel split), "conv_epilogue" (0 direct row stores / 1 smem-transposed),
  * "conv_rows" / "wgrad_rows" (0/1: 3x3 convs with Cout <= 64 use the weight-stationary row-rolling forward kernel / the
- * paired-tap row-streaming weight-gradient kernel). */
+ * paired-tap row-streaming weight-gradient kernel), "pdl" (0/1: every kernel is launched with the programmatic-stream-
+ * serialization attribute and begins with griddepcontrol.wait — the launch latency between dependent kernels of a stream
+ * or a captured graph is hidden, results are unchanged; off until set). */
 int gdl_set_option(const char* name, long long value);
 
 /* ---- deterministic reductions: caller-owned scratch workspace ------------------------------------------------------

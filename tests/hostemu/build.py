@@ -24,7 +24,7 @@ SOURCES = ["runtime.cu", "elementwise.cu", "transformer.cu", "loss_optim.cu", "a
 # PTX wrappers of common.cuh whose bodies are forwarded to the functional model in hostemu_tc.cpp
 TC_FORWARD = ["smem_u32", "elect_one", "mbar_init", "mbar_expect_tx", "mbar_arrive", "mbar_try_wait", "tma_load_2d", "tma_load_4d",
               "tma_store_4d", "named_bar_sync", "tmem_alloc", "tmem_dealloc", "umma_f16", "umma_commit", "tmem_ld_32x32b_x16"]
-TC_NOP = ["fence_mbar_init", "fence_proxy_async_smem", "tma_prefetch_desc", "tmem_relinquish", "tc_fence_before", "tc_fence_after",
+TC_NOP = ["pdl_wait", "pdl_trigger", "fence_mbar_init", "fence_proxy_async_smem", "tma_prefetch_desc", "tmem_relinquish", "tc_fence_before", "tc_fence_after",
           "tmem_ld_wait"]
 # bulk-group bookkeeping of the TMA stores (template <int N> wait_group[.read] N)
 TC_BULK = {"bulk_commit_group": "hostemu::tc::bulk_commit_group()", "bulk_wait_group_read": "hostemu::tc::bulk_wait_group(N)",

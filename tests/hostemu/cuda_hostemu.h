@@ -29,6 +29,8 @@
 
 #include "hostemu_tc.h"
 
+#define GDL_HOSTEMU 1  // common.cuh: GDL_LAUNCH runs the kernel body on the host (hostemu::launch)
+
 #ifndef __grid_constant__
 #define __grid_constant__
 #endif

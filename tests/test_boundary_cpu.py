@@ -155,3 +155,39 @@ def test_reference_patch_first_conv_works_on_the_product_models(monkeypatch):
     x6 = torch.randn(1, 6, 32, 32)
     with torch.no_grad():
         assert torch.allclose(s(x6), osf.segformer_forward(s.state_dict(), x6, "mit_b0"), atol=1e-4, rtol=1e-4)
+
+
+def test_every_kernel_waits_for_its_predecessor_before_touching_memory():
+    """Programmatic dependent launch (csrc/common.cuh): with the "pdl" option every launch may become resident before the
+    previous kernel of the stream has finished, so EVERY __global__ function must block in griddepcontrol.wait
+    (GDL_PDL_ENTRY) before its first statement, and every launch must go through GDL_LAUNCH (the one place that attaches
+    the attribute).  A kernel that skipped the wait would race with its producer; a raw <<< >>> launch is harmless but
+    would silently opt out."""
+    csrc = ROOT / "geo-deep-learning_b200" / "csrc"
+    kernels = 0
+    for f in sorted(csrc.glob("*.cu")) + sorted(csrc.glob("*.cuh")):
+        text = f.read_text()
+        code = re.sub(r"//[^\n]*", "", text)
+        assert "<<<" not in code, f"{f.name}: raw <<< >>> launch (use GDL_LAUNCH)"
+        for m in re.finditer(r"\b__global__\b", code):
+            depth, i = 0, m.end()
+            while True:  # the function body's opening brace: the first '{' outside parentheses
+                c = code[i]
+                if c == "(":
+                    depth += 1
+                elif c == ")":
+                    depth -= 1
+                elif c == "{" and depth == 0:
+                    break
+                elif c == ";" and depth == 0:
+                    i = -1  # a declaration without body
+                    break
+                i += 1
+            if i < 0:
+                continue
+            kernels += 1
+            name = re.findall(r"(\w+)\s*\(", code[m.end():i])[-1]
+            assert re.match(r"\s*GDL_PDL_ENTRY\(\);", code[i + 1:]), f"{f.name}: kernel {name} does not begin with GDL_PDL_ENTRY()"
+    assert kernels >= 60
+    common = (csrc / "common.cuh").read_text()
+    assert "griddepcontrol.wait" in common and "cudaLaunchAttributeProgrammaticStreamSerialization" in common
