@@ -564,6 +564,7 @@ def _run_train(args, ctx, steps: int, warmup: int, headline: bool):
                    "sra_fused": bool(ops.option("sra_fused")), "mha_flash": bool(ops.option("mha_flash")),
                    "deterministic_reductions": deterministic, "syncbn_exchange": bn_exchange_kind,
                    "pdl": bool(ops.option("pdl")),
+                   **({"decoder_folded": bool(ops.option("decoder_folded"))} if w["family"] == "segformer" else {}),
                    "l2": f"{NBUF} rotating input batches; per-step working set >> 126 MB L2"},
         "clocks": clk,
         "e2e": {"value": tiles / (ms_e2e / 1e3), "unit": "tiles/s",
@@ -571,6 +572,9 @@ def _run_train(args, ctx, steps: int, warmup: int, headline: bool):
                 "ms_per_step": ms_e2e / steps},
         "gpu_launches": launches,
         "model_tflops": TRAIN_GFLOP_PER_TILE * value / world / 1e3,
+        **({"flops_note": "model_tflops and roofline.whole_step count the reference topology's 363.1 GFLOP per tile; with "
+            "decoder_folded the 4*emb -> emb fuse product (3 x 77.3 GFLOP per tile) runs in front of the resizes at each level's "
+            "own resolution and 131.2 GFLOP per tile are executed"} if w["family"] == "segformer" and ops.option("decoder_folded") else {}),
         "roofline": {"bound": "tensor", "kernel": "conv_fwd_kernel + conv3x3_rows_kernel (forward + dgrad launches)",
                      "achieved": fwd["tflops"], "peak": peak_tf, "unit": "TFLOP/s",
                      "frac": fwd["tflops"] / peak_tf, "flops": "algorithmic (pixel-packed / channel-padded launches count their unpadded shapes)",
@@ -682,7 +686,7 @@ def _run_infer(args, ctx, steps: int, warmup: int, headline: bool):
         "config": {"workload": w["name"], "raster": [R, R, C], "windows": nwin, "window_batch": B,
                    "parallelism": f"windows round-robin over {world} rank(s) + one all-reduce of the logit sums",
                    "cuda_graph": args.cuda_graph >= 2, "sra_fused": bool(ops.option("sra_fused")),
-                   "pdl": bool(ops.option("pdl")),
+                   "pdl": bool(ops.option("pdl")), "decoder_folded": bool(ops.option("decoder_folded")),
                    "l2": f"raster {R * R * C / 1e6:.0f} MB and activations >> 126 MB L2"},
         "clocks": clk,
         "e2e": {"value": nwin * steps / (ms_e2e / 1e3), "unit": "tiles/s", "h2d_bytes_per_step": R * R * C,

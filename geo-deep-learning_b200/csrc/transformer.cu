@@ -664,6 +664,64 @@ __global__ void bilinear_fwd_vec8_kernel(const T* __restrict__ x, long long ldx,
   }
 }
 
+// out = base + sum_i bilinear(src_i -> (Ho, Wo)): the SegFormer decoder's fuse layer after the 1x1 conv has been moved in
+// front of the (linear) resizes (segformer_mlp.py:77-128; gdl_bilinear_sum_fwd).  8 channels per thread, fp32 sum in a
+// fixed order (base, src 0, 1, 2), ONE rounding to 16 bits; every tap uses bil_mix, so one term equals bilinear_fwd's value
+// before its rounding.
+struct BilinearSumSrc {
+  const void* ptr;
+  long long ld;
+  int H, W;
+  float sh, sw;
+};
+struct BilinearSumParams {
+  BilinearSumSrc src[3];
+  int num_src;
+};
+template <typename T>
+__global__ void bilinear_sum_vec8_kernel(const T* __restrict__ base, long long ldb, const BilinearSumParams p,
+                                         T* __restrict__ y, long long ldy, int N, int Ho, int Wo, int C) {
+  GDL_PDL_ENTRY();
+  const int cv = C / 8;
+  const long long total = (long long)N * Ho * Wo * cv;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c0 = (int)(i % cv) * 8;
+    long long t = i / cv;
+    const int wo = (int)(t % Wo);
+    t /= Wo;
+    const int ho = (int)(t % Ho);
+    const long long n = t / Ho;
+    const long long pix = (n * Ho + ho) * Wo + wo;
+    float o[8];
+    if (base != nullptr) {
+      ld8(base + pix * ldb + c0, o);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = 0.f;
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      if (k < p.num_src) {
+        const BilinearSumSrc& s = p.src[k];
+        int h0, h1, w0, w1;
+        float a0, a1, b0, b1;
+        bil_src(ho, s.sh, s.H, h0, h1, a0, a1);
+        bil_src(wo, s.sw, s.W, w0, w1, b0, b1);
+        const T* x = reinterpret_cast<const T*>(s.ptr) + n * s.H * s.W * s.ld + c0;
+        float f00[8], f01[8], f10[8], f11[8];
+        ld8(x + ((long long)h0 * s.W + w0) * s.ld, f00);
+        ld8(x + ((long long)h0 * s.W + w1) * s.ld, f01);
+        ld8(x + ((long long)h1 * s.W + w0) * s.ld, f10);
+        ld8(x + ((long long)h1 * s.W + w1) * s.ld, f11);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = __fadd_rn(o[j], bil_mix(a0, a1, b0, b1, f00[j], f01[j], f10[j], f11[j]));
+      }
+    }
+    st8(y + pix * ldy + c0, o);
+  }
+}
+
 // gather-form adjoint: dx[n,hi,wi,c] = sum over output pixels whose taps touch (hi,wi)
 template <typename T>
 __global__ void bilinear_bwd_kernel(const T* __restrict__ dy, long long ldy, T* __restrict__ dx, long long ldx, int N,
@@ -1337,6 +1395,37 @@ extern "C" int gdl_bilinear_fwd(const void* x, long long ldx, void* y, long long
     return 0;
   }
   GDL_DISPATCH_T(dtype, { GDL_LAUNCH(bilinear_fwd_kernel<T>, (int)b, 256, 0, st, (const T*)x, ldx, (T*)y, ldy, N, Hi, Wi, Ho, Wo, C, sh, sw); });
+  GDL_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int gdl_bilinear_sum_fwd(const void* base, long long ld_base, int num_src, const gdl_lowres_t* src, void* out,
+                                    long long ld_out, int dtype, int N, int Ho, int Wo, int C, void* stream) {
+  GDL_REQUIRE(out && N > 0 && Ho > 0 && Wo > 0 && C > 0 && ld_out >= C && num_src >= 0 && num_src <= 3 &&
+                  (num_src == 0 || src != nullptr) && (base != nullptr || num_src > 0),
+              GDL_ERR_INVALID, "bilinear_sum: bad args (at most 3 resized sources)");
+  GDL_REQUIRE(dtype == GDL_BF16 || dtype == GDL_F16, GDL_ERR_UNSUPPORTED, "bilinear_sum: 16-bit features only");
+  GDL_REQUIRE(C % 8 == 0 && ld_out % 8 == 0 && ((uintptr_t)out & 15) == 0 &&
+                  (base == nullptr || (ld_base % 8 == 0 && ld_base >= C && ((uintptr_t)base & 15) == 0)),
+              GDL_ERR_UNSUPPORTED, "bilinear_sum: channels and row strides must be multiples of 8, pointers 16-byte aligned");
+  BilinearSumParams p;
+  p.num_src = num_src;
+  for (int k = 0; k < 3; ++k) {
+    p.src[k] = BilinearSumSrc{nullptr, 0, 1, 1, 1.f, 1.f};
+    if (k >= num_src) continue;
+    GDL_REQUIRE(src[k].ptr && src[k].H > 0 && src[k].W > 0 && src[k].ld >= C && src[k].ld % 8 == 0 &&
+                    ((uintptr_t)src[k].ptr & 15) == 0,
+                GDL_ERR_INVALID, "bilinear_sum: bad source %d", k);
+    p.src[k] = BilinearSumSrc{src[k].ptr, src[k].ld, src[k].H, src[k].W, (float)src[k].H / (float)Ho, (float)src[k].W / (float)Wo};
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long total = (long long)N * Ho * Wo * (C / 8);
+  long long b = (total + 255) / 256;
+  if (b > 16 * kNumSMsB200) b = 16 * kNumSMsB200;
+  if (dtype == GDL_BF16)
+    GDL_LAUNCH(bilinear_sum_vec8_kernel<__nv_bfloat16>, (int)b, 256, 0, st, (const __nv_bfloat16*)base, ld_base, p, (__nv_bfloat16*)out, ld_out, N, Ho, Wo, C);
+  else
+    GDL_LAUNCH(bilinear_sum_vec8_kernel<__half>, (int)b, 256, 0, st, (const __half*)base, ld_base, p, (__half*)out, ld_out, N, Ho, Wo, C);
   GDL_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -85,6 +85,11 @@ class Repack(C.Structure):
                 ("S", C.c_int), ("mode", C.c_int), ("dst_ld", C.c_int)]
 
 
+class Lowres(C.Structure):
+    """gdl_lowres_t: one low-resolution source of gdl_bilinear_sum_fwd"""
+    _fields_ = [("ptr", C.c_void_p), ("H", C.c_int), ("W", C.c_int), ("ld", C.c_longlong)]
+
+
 def lib_path() -> Path:
     return _LIB_PATH
 
@@ -170,6 +175,7 @@ _SIGS = {
     "gdl_dwconv3x3_gelu_bwd": [_VP, _VP, _VP, _I, _VP, _VP, _VP, _I, _VP, _I, _I, _I, _I, _I, _VP],
     "gdl_bilinear_fwd": [_VP, _LL, _VP, _LL, _I, _I, _I, _I, _I, _I, _I, _VP],
     "gdl_bilinear_bwd": [_VP, _LL, _VP, _LL, _I, _I, _I, _I, _I, _I, _I, _VP],
+    "gdl_bilinear_sum_fwd": [_VP, _LL, _I, _VP, _VP, _LL, _I, _I, _I, _I, _I, _VP],
     "gdl_cast_f32": [_VP, _VP, _I, _LL, _VP],
     "gdl_vit_assemble_tokens": [_VP, _I, _VP, _VP, _VP, _I, _I, _I, _VP],
     "gdl_vit_extract_feature": [_VP, _VP, _I, _I, _I, _I, _VP],

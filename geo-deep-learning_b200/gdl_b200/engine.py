@@ -69,6 +69,7 @@ class RawConv:
     stats: torch.Tensor | None = None  # BatchNorm sums [2C] (pivoted on the running mean) produced by the conv itself
     groups: int = 1             # grouped conv (ResNeXt): run as Cout / 64 dense 64 -> 64 convs over channel slices
     cols: list | None = None    # grouped + strided: the im2col matrix of every 64-channel slice
+    custom_backward: Callable | None = None  # the producer of x is not one conv of `weight`: it owns the backward of d(x)
 
 
 @dataclass
@@ -266,6 +267,8 @@ class Engine:
         Weight (and bias) gradients go to grad_buffer; input gradients are registered as gradient sources on
         the source activations.  `dgrad_residual` is added to the (single-source) input gradient in the dgrad
         GEMM epilogue (sum of two gradient paths without an extra pass)."""
+        if rc.custom_backward is not None:
+            return rc.custom_backward(dx)
         if rc.groups > 1:
             return self._grouped_backward(rc, dx)
         w = rc.weight

@@ -29,7 +29,7 @@ import torch
 import torch.nn as nn
 
 from .. import ops
-from ..engine import Act, BNParams, Engine
+from ..engine import Act, BNParams, Engine, RawConv
 
 MIT_CFG = {
     # name: (embed_dims, heads, depths, decoder embedding dim)
@@ -426,14 +426,18 @@ class SegFormer(nn.Module):
             cur = feat_act
         # ---- decoder (segformer_mlp.py:77-130)
         h1, w1 = stages[0].feat.t.shape[1:3]
-        projs = []
-        for lvl in (4, 3, 2, 1):
-            f = stages[lvl - 1].feat
-            lin = getattr(dec, f"linear_c{lvl}").proj
-            rc = eng.conv_raw([f], lin.weight, 1, 0, bias=lin.bias, wshape=_lin_shape(lin.weight))
-            up = Act(ops.bilinear_fwd(rc.x, h1, w1)) if lvl != 1 else Act(rc.x)
-            projs.append(_Saved(lvl=lvl, rc=rc, up=up))
-        rc_fuse = eng.conv_raw([p.up for p in projs], dec.linear_fuse[0].weight, 1, 0)
+        projs = None
+        if ops.option("decoder_folded"):
+            rc_fuse = self._decoder_folded_fwd(eng, stages)
+        else:
+            projs = []
+            for lvl in (4, 3, 2, 1):
+                f = stages[lvl - 1].feat
+                lin = getattr(dec, f"linear_c{lvl}").proj
+                rc = eng.conv_raw([f], lin.weight, 1, 0, bias=lin.bias, wshape=_lin_shape(lin.weight))
+                up = Act(ops.bilinear_fwd(rc.x, h1, w1)) if lvl != 1 else Act(rc.x)
+                projs.append(_Saved(lvl=lvl, rc=rc, up=up))
+            rc_fuse = eng.conv_raw([p.up for p in projs], dec.linear_fuse[0].weight, 1, 0)
         bn = dec.linear_fuse[1]
         bn_state = eng.bn_prepare(rc_fuse, BNParams(bn.weight, bn.bias, bn.running_mean, bn.running_var,
                                                     bn.num_batches_tracked, bn.eps, bn.momentum or 0.1))
@@ -446,6 +450,66 @@ class SegFormer(nn.Module):
         # backward, or an eval forward in between, must not overwrite each other's graph
         eng.saved_segformer = _Saved(stages=stages, projs=projs, rc_pred=rc_pred, z=z, h1=h1, w1=w1, hh=hh, ww=ww)
         return logits
+
+    # ---- decoder with linear_fuse's 1x1 conv moved in front of the resizes (option "decoder_folded") -----------------------
+    # segformer_mlp.py:77-128 computes  Z = W . concat_l(resize(P_l c_l + b_l))  with W = linear_fuse[0] (no bias) split into
+    # four (emb x emb) blocks W_l, P_l / b_l = linear_c{l}.proj, resize = bilinear to the stride-4 grid (identity for l = 1).
+    # The resize is linear with taps that sum to 1 and acts per channel, so it commutes with the channel mix:
+    #     Z = sum_l resize((W_l P_l) c_l) + sum_l W_l b_l .
+    # M_l = W_l P_l (emb x C_l) is formed from the fp32 masters every step (0.6 GFLOP for B2, parameter space); the big
+    # products then run at each level's own resolution with K = C_l instead of one 4*emb -> emb product on the stride-4
+    # grid (B2, 512^2 tiles: 50 instead of 1290 GFLOP forward per 16 tiles), and the three resized emb-channel maps are
+    # never written: gdl_bilinear_sum_fwd reads the low-resolution products and writes Z once.  Same parameters, same
+    # state_dict, same function; gradients by the chain rule:  dM_l = dY_l^T c_l,  dP_l = W_l^T dM_l,
+    # dW_l = dM_l P_l^T + s b_l^T,  db_l = W_l^T s  with  dY_l = resize^T(dZ),  s = column sums of dZ.
+    def _decoder_folded_fwd(self, eng: Engine, stages) -> RawConv:
+        dec = self.decoder
+        emb, acc = dec.embedding_dim, eng.acc_dtype
+        fuse_w = dec.linear_fuse[0].weight
+        wf = fuse_w.detach().view(emb, 4 * emb).to(acc)
+        levels, cbias = [], None
+        for slot, lvl in enumerate((4, 3, 2, 1)):  # concat order of the reference: [_c4, _c3, _c2, _c1]
+            lin = getattr(dec, f"linear_c{lvl}").proj
+            wl = wf[:, slot * emb:(slot + 1) * emb]
+            m = torch.matmul(wl, lin.weight.detach().to(acc)).contiguous()
+            cb = torch.mv(wl, lin.bias.detach().to(acc))
+            cbias = cb if cbias is None else cbias + cb
+            levels.append(_Saved(lvl=lvl, lin=lin, wl=wl, m=m, feat=stages[lvl - 1].feat))
+        ys = {}
+        for lv in levels:
+            cin = lv.m.shape[1]
+            wp = ops.pack_conv_weight(lv.m.view(emb, cin, 1, 1), eng.dtype, 0)
+            ys[lv.lvl] = ops.conv2d_fwd([lv.feat.t], wp, emb, 1, 1, 0, 0, bias=cbias if lv.lvl == 1 else None)
+        z = ops.bilinear_sum_fwd(ys[1], [ys[4], ys[3], ys[2]])
+        return RawConv(z, [], fuse_w, 1, 0, wshape=tuple(fuse_w.shape),
+                       custom_backward=(lambda dz: self._decoder_folded_bwd(eng, levels, dz)) if eng.training else None)
+
+    def _decoder_folded_bwd(self, eng: Engine, levels, dz: torch.Tensor) -> None:
+        dec = self.decoder
+        emb, acc = dec.embedding_dim, eng.acc_dtype
+        fuse_w = dec.linear_fuse[0].weight
+        sums = torch.empty(2 * emb, dtype=acc, device=dz.device)
+        ops.bn_stats(dz, sums)  # column sums of dZ (no pivot): the gradient of the constant term sum_l W_l b_l
+        colsum = sums[:emb]
+        gwf = torch.empty((emb, 4 * emb), dtype=acc, device=dz.device) if fuse_w.requires_grad else None
+        for slot, lv in enumerate(levels):
+            f, lin = lv.feat, lv.lin
+            cin = lv.m.shape[1]
+            dy = dz if lv.lvl == 1 else ops.bilinear_bwd(dz, f.t.shape[1], f.t.shape[2])
+            dm = torch.zeros((emb, cin), dtype=acc, device=dz.device)
+            ops.conv2d_wgrad([f.t], dy, 1, 1, 0, 0, dm)
+            if f.needs_grad:
+                wt = ops.pack_conv_weight(lv.m.view(emb, cin, 1, 1), eng.dtype, 1)
+                f.gsrcs.append((ops.conv2d_fwd([dy], wt, cin, 1, 1, 0, 0), 0))
+            if lin.weight.requires_grad:
+                eng.grad_buffer(lin.weight, False).copy_(torch.matmul(lv.wl.t(), dm))
+            if lin.bias.requires_grad:
+                eng.grad_buffer(lin.bias, False).copy_(torch.mv(lv.wl.t(), colsum))
+            if gwf is not None:
+                gwf[:, slot * emb:(slot + 1) * emb] = torch.addmm(torch.outer(colsum, lin.bias.detach().to(acc)), dm,
+                                                                   lin.weight.detach().to(acc).t())
+        if gwf is not None:
+            eng.grad_buffer(fuse_w, False).view(emb, 4 * emb).copy_(gwf)
 
     # ====================================================================================== backward
     def _pgrads_ln(self, eng: Engine, ln: nn.LayerNorm):
@@ -574,12 +638,16 @@ class SegFormer(nn.Module):
         eng.conv_backward(S.rc_pred, d16)
         eng.backward()  # linear_fuse BN/ReLU + the fuse GEMM: registers gradients on the 4 projections
         feat_grads: list[list[torch.Tensor]] = [[] for _ in range(4)]
-        for p in S.projs:
-            g = self._take(p.up)
-            if p.lvl != 1:
-                g = ops.bilinear_bwd(g, p.rc.x.shape[1], p.rc.x.shape[2])
-            eng.conv_backward(p.rc, g)
-            feat_grads[p.lvl - 1].append(self._take(S.stages[p.lvl - 1].feat))
+        if S.projs is None:  # folded decoder: its backward (run from the tape) already registered d(feature) of every level
+            for lvl in (4, 3, 2, 1):
+                feat_grads[lvl - 1].append(self._take(S.stages[lvl - 1].feat))
+        else:
+            for p in S.projs:
+                g = self._take(p.up)
+                if p.lvl != 1:
+                    g = ops.bilinear_bwd(g, p.rc.x.shape[1], p.rc.x.shape[2])
+                eng.conv_backward(p.rc, g)
+                feat_grads[p.lvl - 1].append(self._take(S.stages[p.lvl - 1].feat))
         for s in (3, 2, 1, 0):
             st = S.stages[s]
             gs = feat_grads[s]

@@ -114,7 +114,11 @@ _HOST_OPTS = {"pixel_pack": int(os.environ.get("GDL_PIXEL_PACK", "1")), "sra_fus
               "p2p_syncbn": int(os.environ.get("GDL_P2P_SYNCBN", "1")),
               # overlap_allreduce: the flat gradient is all-reduced in 3 buckets, each started as soon as its layers' backward
               # is done (UNet++ route of the fused trainer); 0 = one all-reduce after the backward
-              "overlap_allreduce": int(os.environ.get("GDL_OVERLAP_ALLREDUCE", "1"))}
+              "overlap_allreduce": int(os.environ.get("GDL_OVERLAP_ALLREDUCE", "1")),
+              # decoder_folded: SegFormer's linear_fuse 1x1 conv is applied in front of the (linear) bilinear resizes — per
+              # level at its own resolution, composed with linear_c{l} — instead of on the concatenated resized maps
+              # (models/segformer.py: _decoder_folded_fwd); 0 = the reference's op order
+              "decoder_folded": int(os.environ.get("GDL_DECODER_FOLDED", "1"))}
 
 
 def option(name: str) -> int:
@@ -823,6 +827,24 @@ def bilinear_fwd(x, ho, wo, out=None):
         out = torch.empty((n, ho, wo, c), dtype=x.dtype, device=x.device)
     _ck(L.load().gdl_bilinear_fwd(L.ptr(x), x.stride(2), L.ptr(out), out.stride(2), L.dt_code(x.dtype), n, hi, wi, ho,
                                   wo, c, L.stream_ptr()))
+    return out
+
+
+def bilinear_sum_fwd(base, srcs, out=None):
+    """base (N,Ho,Wo,C) + sum of the (N,h_i,w_i,C) maps in `srcs` (<= 3), each resized bilinearly (align_corners=False) to
+    (Ho,Wo): fp32 sum in the given order, one rounding (gdl_bilinear_sum_fwd).  16-bit NHWC, channel slices allowed."""
+    import ctypes as C
+    n, ho, wo, c = base.shape
+    require_cuda(base, "bilinear_sum_fwd")
+    if out is None:
+        out = torch.empty((n, ho, wo, c), dtype=base.dtype, device=base.device)
+    arr = (L.Lowres * max(1, len(srcs)))()
+    for i, t in enumerate(srcs):
+        if t.shape[0] != n or t.shape[3] != c or t.dtype != base.dtype:
+            raise ValueError("bilinear_sum_fwd: sources must share batch, channels and dtype with the base")
+        arr[i].ptr, arr[i].H, arr[i].W, arr[i].ld = t.data_ptr(), t.shape[1], t.shape[2], t.stride(2)
+    _ck(L.load().gdl_bilinear_sum_fwd(L.ptr(base), base.stride(2), len(srcs), C.cast(arr, C.c_void_p), L.ptr(out),
+                                      out.stride(2), L.dt_code(base.dtype), n, ho, wo, c, L.stream_ptr()))
     return out
 
 

@@ -441,6 +441,20 @@ int gdl_bilinear_fwd(const void* x, long long ldx, void* y, long long ldy, int d
 int gdl_bilinear_bwd(const void* dy, long long ldy, void* dx, long long ldx, int dtype, int N, int Hi, int Wi,
                      int Ho, int Wo, int C, void* stream);
 
+/* out = base + sum_i resize_i(src_i): `num_src` (<= 3) low-resolution maps, each bilinearly resized (align_corners=False)
+ * to (Ho, Wo), added to the optional full-resolution `base` in fp32 in a fixed order and rounded once (16-bit NHWC, C % 8 ==
+ * 0).  The SegFormer decoder's fuse layer (segformer_mlp.py:77-128: four projections, three resizes to the stride-4 grid,
+ * concat, 1x1 conv without bias) with the 1x1 conv moved in front of the resizes — both are linear, so
+ * conv1x1(concat_i resize(y_i)) == sum_i resize(conv1x1_i(y_i)) — which never writes the three resized 768-channel maps
+ * and runs the 3072 -> 768 product at each map's own resolution.  Adjoint: gdl_bilinear_bwd per source. */
+typedef struct {
+  const void* ptr; /* (N, H, W, C) 16-bit */
+  int H, W;
+  long long ld;    /* elements between pixels */
+} gdl_lowres_t;
+int gdl_bilinear_sum_fwd(const void* base, long long ld_base, int num_src, const gdl_lowres_t* src, void* out,
+                         long long ld_out, int dtype, int N, int Ho, int Wo, int C, void* stream);
+
 /* nn.AdaptiveAvgPool2d(S) of the UperNet pyramid pooling module (models/utils.py:55-93) and its adjoint;
  * y/dy are dense [N][S][S][C]. */
 int gdl_adaptive_avgpool_fwd(const void* x, long long ldx, void* y, int dtype, int N, int H, int W, int C, int S,

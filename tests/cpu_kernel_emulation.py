@@ -557,6 +557,18 @@ def bilinear_fwd(x, ho, wo, out=None):
     return y.contiguous()
 
 
+def bilinear_sum_fwd(base, srcs, out=None):
+    n, ho, wo, c = base.shape
+    acc = base.to(_WORK)
+    for t in srcs:
+        acc = acc + _nhwc(F.interpolate(_nchw(t.to(_WORK)), size=(ho, wo), mode="bilinear", align_corners=False))
+    y = acc.to(base.dtype)
+    if out is not None:
+        out.copy_(y)
+        return out
+    return y.contiguous()
+
+
 def bilinear_bwd(dy, hi, wi):
     n, ho, wo, c = dy.shape
     xr = torch.zeros(n, c, hi, wi, dtype=_WORK, requires_grad=True)

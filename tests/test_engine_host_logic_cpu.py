@@ -156,14 +156,19 @@ def test_trainer_loss_scaling(monkeypatch, f64):
         trainer(loss_scale="auto")
 
 
-@pytest.mark.parametrize("name,cin,hw", [("mit_b0", 3, 64), ("mit_b1", 4, 128)])
-def test_segformer_backward_equals_oracle_autograd(monkeypatch, f64, name, cin, hw):
+@pytest.mark.parametrize("name,cin,hw,folded", [("mit_b0", 3, 64, 1), ("mit_b1", 4, 128, 1), ("mit_b0", 3, 64, 0)])
+def test_segformer_backward_equals_oracle_autograd(monkeypatch, f64, name, cin, hw, folded):
     """SegFormer graph wiring (attention GEMM operand slicing, fp32 residual stream, LayerNorm chain,
-    virtual-concat decoder, bilinear heads) against the reference-pinned functional oracle, in float64."""
+    virtual-concat decoder, bilinear heads) against the reference-pinned functional oracle, in float64.
+    folded = 1 (the default): the decoder applies linear_fuse's 1x1 conv in front of the resizes, composed with the four
+    projections (SegFormer._decoder_folded_fwd) — the same function and the same parameter gradients as the reference's
+    op order (folded = 0), to float64 rounding."""
+    from gdl_b200 import ops as _ops
     from gdl_b200.engine import Act, Engine
     from gdl_b200.models.segformer import SegFormer
     from oracle import segformer as osf
     emu.install(monkeypatch)
+    monkeypatch.setitem(_ops._HOST_OPTS, "decoder_folded", folded)
     k = 5
     torch.manual_seed(0)
     prod = SegFormer(name, in_channels=cin, num_classes=k, compute_dtype=torch.float64).double().train()
@@ -183,6 +188,7 @@ def test_segformer_backward_equals_oracle_autograd(monkeypatch, f64, name, cin, 
     with torch.no_grad():
         xin = emu.normalize_to_nhwc(x, True, torch.float64, 8)
         logits = prod.run(eng, Act(xin, needs_grad=False))
+    assert (eng.saved_segformer.projs is None) == bool(folded)  # the route under test really ran
     assert torch.allclose(logits.permute(0, 3, 1, 2), ref, atol=1e-9, rtol=1e-9)
     d = logits.detach().permute(0, 3, 1, 2).clone().requires_grad_(True)
     F.cross_entropy(d, t).backward()

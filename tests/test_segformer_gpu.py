@@ -30,14 +30,28 @@ def _oracle_sd(prod):
             for n, v in prod.state_dict().items()}
 
 
-@pytest.mark.parametrize("name,cin,k,hw,dtype", [
-    ("mit_b0", 3, 5, 128, torch.bfloat16),
-    ("mit_b0", 3, 5, 64, torch.bfloat16),      # 4 keys per image: exercises the key padding to 16
-    ("mit_b2", 4, 5, 128, torch.bfloat16),
-    ("mit_b1", 6, 2, 128, torch.float16),
+@pytest.fixture
+def decoder_route():
+    """set the "decoder_folded" host option for one test, restore it afterwards"""
+    from gdl_b200 import ops
+    old = ops.option("decoder_folded")
+    yield lambda v: ops.set_option("decoder_folded", v)
+    ops.set_option("decoder_folded", old)
+
+
+@pytest.mark.parametrize("name,cin,k,hw,dtype,folded", [
+    ("mit_b0", 3, 5, 128, torch.bfloat16, 1),
+    ("mit_b0", 3, 5, 64, torch.bfloat16, 1),      # 4 keys per image: exercises the key padding to 16
+    ("mit_b2", 4, 5, 128, torch.bfloat16, 1),
+    ("mit_b1", 6, 2, 128, torch.float16, 1),
+    ("mit_b0", 3, 5, 128, torch.bfloat16, 0),     # the reference's op order in the decoder (resize, concat, 4*emb -> emb conv)
+    ("mit_b2", 4, 5, 128, torch.bfloat16, 0),
 ])
-def test_train_step_parity(cuda, name, cin, k, hw, dtype):
+def test_train_step_parity(cuda, decoder_route, name, cin, k, hw, dtype, folded):
+    """folded = 1 (default): linear_fuse's 1x1 conv runs in front of the resizes, composed with linear_c1..4
+    (SegFormer._decoder_folded_fwd); both routes meet the same bar against the fp32 oracle."""
     from oracle import segformer as osf
+    decoder_route(folded)
     prod = _setup(name, cin, k, dtype)
     g = torch.Generator().manual_seed(1)
     x = torch.randn(4, cin, hw, hw, generator=g).cuda()

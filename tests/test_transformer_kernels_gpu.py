@@ -103,6 +103,48 @@ def test_bilinear_fwd_bwd(cuda, hi, wi, ho, wo, c, dt):
     assert _relerr(dx, xr.grad.permute(0, 2, 3, 1)) < (1e-5 if dt == torch.float32 else 2 ** -7)
 
 
+@pytest.mark.parametrize("n,ho,wo,c,lows,dt", [
+    (2, 32, 32, 64, [(4, 4), (8, 8), (16, 16)], torch.bfloat16),     # the SegFormer decoder: strides 32 / 16 / 8 onto 4
+    (1, 24, 40, 16, [(3, 5), (12, 20)], torch.bfloat16),             # two sources, non-square
+    (3, 16, 16, 8, [(5, 7)], torch.float16),                         # one source, non-integer scale
+    (2, 8, 8, 32, [], torch.bfloat16),                               # no resized source: a copy of the base
+])
+def test_bilinear_sum_fwd(cuda, n, ho, wo, c, lows, dt):
+    """out = base + sum_i resize(src_i) (gdl_bilinear_sum_fwd): fp32 sum in the given order, ONE rounding — against
+    F.interpolate in fp32 on the same 16-bit operands; channel slices of wider tensors (row stride > C) as inputs and output;
+    and the identity that makes the folded SegFormer decoder valid: a channel mix applied before the resizes equals the
+    mix applied to the concatenated resized maps."""
+    from gdl_b200 import ops
+    g = torch.Generator().manual_seed(ho * 3 + c)
+    wide = torch.randn(n, ho, wo, c + 8, generator=g).to(dt).cuda()
+    base = wide[..., 8:]                                             # row stride c + 8
+    srcs = [torch.randn(n, h, w, c, generator=g).to(dt).cuda() for h, w in lows]
+    want = base.float()
+    for t in srcs:
+        want = want + F.interpolate(t.float().permute(0, 3, 1, 2), size=(ho, wo), mode="bilinear",
+                                    align_corners=False).permute(0, 2, 3, 1)
+    y = ops.bilinear_sum_fwd(base, srcs)
+    ulp = 2 ** -8 if dt == torch.bfloat16 else 2 ** -11
+    assert (y.float() - want).abs().max() <= ulp * want.abs().max() + 1e-6      # one rounding of the fp32 sum
+    out_wide = torch.zeros(n, ho, wo, c + 16, dtype=dt, device="cuda")
+    ops.bilinear_sum_fwd(base, srcs, out=out_wide[..., 16:])
+    assert torch.equal(out_wide[..., 16:], y) and not out_wide[..., :16].any()
+    if not srcs:
+        assert torch.equal(y, base)
+        return
+    # linearity: mix(concat(resize(s_i))) == sum_i resize(mix_i(s_i))   (mix = a 1x1 conv without bias)
+    k = len(srcs)
+    w = torch.randn(c, k * c, generator=g).cuda() / (k * c) ** 0.5
+    ups = [F.interpolate(t.float().permute(0, 3, 1, 2), size=(ho, wo), mode="bilinear", align_corners=False) for t in srcs]
+    ref = F.conv2d(torch.cat(ups, 1), w.view(c, k * c, 1, 1)).permute(0, 2, 3, 1)
+    mixed = [F.conv2d(t.float().permute(0, 3, 1, 2), w[:, i * c:(i + 1) * c].reshape(c, c, 1, 1)).permute(0, 2, 3, 1)
+             .contiguous().to(dt) for i, t in enumerate(srcs)]
+    got = ops.bilinear_sum_fwd(torch.zeros(n, ho, wo, c, dtype=dt, device="cuda"), mixed)
+    assert _relerr(got, ref) < 4 * ulp
+    with pytest.raises(ValueError):
+        ops.bilinear_sum_fwd(base, [srcs[0][..., :c - 8].contiguous()] if c > 8 else [srcs[0].float()])
+
+
 def test_cast_f32(cuda):
     from gdl_b200 import ops
     x = torch.randn(1000, 7, device="cuda")
