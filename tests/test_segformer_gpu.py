@@ -50,8 +50,15 @@ def decoder_route():
 def test_train_step_parity(cuda, decoder_route, name, cin, k, hw, dtype, folded):
     """folded = 1 (default): linear_fuse's 1x1 conv runs in front of the resizes, composed with linear_c1..4
     (SegFormer._decoder_folded_fwd); both routes meet the same bar against the fp32 oracle."""
-    from oracle import segformer as osf
     decoder_route(folded)
+    train_step_parity(name, cin, k, hw, dtype)
+
+
+def train_step_parity(name, cin, k, hw, dtype):
+    """one training step (forward, CE, backward) through the nn.Module surface against the fp32 oracle; the bar is what the
+    reference stack itself deviates under torch.autocast on the same tiles (also used at the BASELINE shapes:
+    tests/test_baseline_shapes_gpu.py)"""
+    from oracle import segformer as osf
     prod = _setup(name, cin, k, dtype)
     g = torch.Generator().manual_seed(1)
     x = torch.randn(4, cin, hw, hw, generator=g).cuda()
