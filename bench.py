@@ -400,8 +400,13 @@ def main_product(args) -> None:
     if args.workloads == "all" and head_key == "unetpp_r50":
         for key in ("segformer_b2", "dofa_base", "segformer_b5_infer"):
             sub_steps = max(1, min(args.steps, 2 if key == "segformer_b5_infer" else 6))
-            sub = _run_workload(args, key, ctx, steps=sub_steps, warmup=min(args.warmup, 3) if key != "segformer_b5_infer" else 1,
-                                headline=False)
+            try:
+                sub = _run_workload(args, key, ctx, steps=sub_steps, warmup=min(args.warmup, 3) if key != "segformer_b5_infer" else 1,
+                                    headline=False)
+            except Exception as e:  # noqa: BLE001  (a ride-along workload must not take the headline's line with it)
+                import traceback
+                traceback.print_exc()
+                sub = {"error": f"{type(e).__name__}: {e}"[:300]} if rank == 0 else None
             if sub is not None:
                 extra[key] = sub
     if rank == 0:
