@@ -179,3 +179,28 @@ def test_confusion_skips_ignored_and_out_of_range_targets():
     target[1, 0] = 7
     _, conf = emu.argmax_confusion(logits, target, ignore_index=255)
     assert conf.sum() == 2 * 64 - 16 - 8
+
+
+def test_mean_iou_restatement_agrees_with_sklearn_per_sample():
+    """Independent cross-check of oracle.metrics (torchmetrics itself is un-vendored: parity stays unpinned): its per-sample,
+    per-class score is the Jaccard index, which scikit-learn computes from its own confusion-matrix code; the metric is the
+    mean of those scores over the samples in which the class occurs (in the prediction or the target)."""
+    skm = pytest.importorskip("sklearn.metrics")
+    k, n = 5, 6
+    g = torch.Generator().manual_seed(11)
+    target = torch.randint(0, k, (n, 24, 24), generator=g)
+    pred = torch.where(torch.rand(n, 24, 24, generator=g) < 0.7, target, torch.randint(0, k, (n, 24, 24), generator=g))
+    target[0][target[0] == 3] = 1  # class 3 absent from sample 0's target ...
+    pred[0][pred[0] == 3] = 1      # ... and prediction: not a valid sample for that class
+    score_sum, valid = omet.mean_iou_update(pred, target, k)
+    want_sum, want_valid = torch.zeros(k, dtype=torch.float64), torch.zeros(k, dtype=torch.long)
+    for i in range(n):
+        t_, p_ = target[i].reshape(-1).numpy(), pred[i].reshape(-1).numpy()
+        j = skm.jaccard_score(t_, p_, labels=list(range(k)), average=None, zero_division=0.0)
+        present = torch.tensor([(t_ == c).any() or (p_ == c).any() for c in range(k)])
+        want_sum += torch.tensor(j, dtype=torch.float64) * present
+        want_valid += present.long()
+    assert want_valid[3] == n - 1
+    assert torch.equal(valid, want_valid)
+    assert torch.allclose(score_sum, want_sum, atol=1e-12)
+    assert torch.allclose(omet.mean_iou_compute(score_sum, valid), want_sum / want_valid, atol=1e-12)

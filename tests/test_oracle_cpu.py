@@ -106,6 +106,32 @@ def test_soft_ce_reduces_to_ce_without_smoothing():
                           torch.nn.functional.cross_entropy(x, t, label_smoothing=0.1), atol=1e-6)
 
 
+def test_dice_restatement_agrees_with_an_independent_implementation():
+    """Independent cross-check (smp itself is un-vendored: parity stays unpinned): HuggingFace MaskFormer's dice_loss is
+    1 - (2 sum(p t) + 1) / (sum(p) + sum(t) + 1) per mask — smp's binary DiceLoss with smooth = 1 over one mask; and the
+    multiclass loss is the mean over the present classes of the same expression on the softmax probabilities."""
+    pytest.importorskip("transformers")
+    from transformers.models.maskformer.modeling_maskformer import dice_loss as hf_dice
+    g = torch.Generator().manual_seed(4)
+    x = torch.randn(1, 1, 12, 10, generator=g, dtype=torch.float64)
+    t = (torch.rand(1, 12, 10, generator=g) < 0.4).long()
+    want = hf_dice(x.view(1, -1), t.view(1, -1).double(), 1)
+    assert torch.allclose(olosses.dice_loss(x, t, "binary", smooth=1.0), want, atol=1e-12)
+    k = 4
+    xm = torch.randn(2, k, 9, 7, generator=g, dtype=torch.float64)
+    tm = torch.randint(0, k - 1, (2, 9, 7), generator=g)          # class k-1 never occurs: it must not count
+    probs = xm.softmax(1)
+    per_class = []
+    for c in range(k):
+        tc = (tm == c).double()
+        if tc.sum() > 0:
+            pc = probs[:, c]
+            per_class.append(1 - (2 * (pc * tc).sum() + 1) / (pc.sum() + tc.sum() + 1))
+        else:
+            per_class.append(torch.zeros((), dtype=torch.float64))
+    assert torch.allclose(olosses.dice_loss(xm, tm, "multiclass", smooth=1.0), torch.stack(per_class).mean(), atol=1e-12)
+
+
 # --- SegFormer restatement: pinned to the reference's own modules ------------------------------------
 def _close(a, b, rel=5e-6):
     """max |a-b| <= rel * max |b|  (fp32 re-association noise between two summation orders)"""
@@ -240,3 +266,57 @@ def test_dofa_convert_patch_to_16_matches_reference_import():
         want = ref(x, wl)
     for a, b in zip(od.dofa_forward(sd, x, wl, 96, 2, 3, out_indices=(0, 1), convert_to_16=True), want):
         assert a.shape == b.shape == (1, 96, 4, 4) and _close(a, b, 2e-5)
+
+
+# ---------------------------------------------------------------------------------------------
+# Independent cross-checks of the restatements whose sources are not vendored (parity stays "unpinned" for them: these are
+# other implementations of the same published definitions, not the reference's dependency itself)
+# ---------------------------------------------------------------------------------------------
+def test_vit_block_restatement_agrees_with_an_independent_implementation():
+    """oracle.dofa.vit_block restates timm's vision_transformer.Block (pre-norm attention + MLP, LayerScale, exact GELU) from
+    its published definition; timm is not installable here.  HuggingFace's Dinov2Layer is an independently written
+    implementation of the same block ("This corresponds to the Block class in the original implementation"): separate q / k /
+    v Linears instead of timm's fused qkv (rows [q; k; v]), `lambda1` instead of `gamma`.  Forward and every parameter
+    gradient must agree in float64."""
+    transformers = pytest.importorskip("transformers")
+    from transformers.models.dinov2.modeling_dinov2 import Dinov2Config, Dinov2Layer
+    from oracle import dofa as od
+    c, heads, n, b = 48, 4, 19, 3
+    cfg = Dinov2Config(hidden_size=c, num_attention_heads=heads, mlp_ratio=4, hidden_act="gelu", layer_norm_eps=1e-5,
+                       layerscale_value=1.0, drop_path_rate=0.0, attention_probs_dropout_prob=0.0, hidden_dropout_prob=0.0,
+                       qkv_bias=True, use_swiglu_ffn=False)
+    cfg._attn_implementation = "eager"
+    torch.manual_seed(0)
+    layer = Dinov2Layer(cfg).double().eval()
+    with torch.no_grad():
+        for p_ in layer.parameters():
+            p_.copy_(torch.randn_like(p_) * (0.3 if p_.dim() > 1 else 0.5))
+    hf = dict(layer.named_parameters())
+    att = "attention.attention."
+    p = "blocks.0."
+    sd = {
+        p + "norm1.weight": hf["norm1.weight"], p + "norm1.bias": hf["norm1.bias"],
+        p + "attn.qkv.weight": torch.cat([hf[att + "query.weight"], hf[att + "key.weight"], hf[att + "value.weight"]]),
+        p + "attn.qkv.bias": torch.cat([hf[att + "query.bias"], hf[att + "key.bias"], hf[att + "value.bias"]]),
+        p + "attn.proj.weight": hf["attention.output.dense.weight"], p + "attn.proj.bias": hf["attention.output.dense.bias"],
+        p + "ls1.gamma": hf["layer_scale1.lambda1"],
+        p + "norm2.weight": hf["norm2.weight"], p + "norm2.bias": hf["norm2.bias"],
+        p + "mlp.fc1.weight": hf["mlp.fc1.weight"], p + "mlp.fc1.bias": hf["mlp.fc1.bias"],
+        p + "mlp.fc2.weight": hf["mlp.fc2.weight"], p + "mlp.fc2.bias": hf["mlp.fc2.bias"],
+        p + "ls2.gamma": hf["layer_scale2.lambda1"],
+    }
+    sd = {k: v.detach().clone().requires_grad_(True) for k, v in sd.items()}
+    x = torch.randn(b, n, c, dtype=torch.float64, generator=torch.Generator().manual_seed(1))
+    want = layer(x)
+    want = want[0] if isinstance(want, tuple) else want
+    got = od.vit_block(sd, x, p, heads)
+    assert torch.allclose(got, want, atol=1e-11, rtol=1e-11)
+    probe = torch.randn(want.shape, dtype=torch.float64, generator=torch.Generator().manual_seed(2))
+    (want * probe).sum().backward()
+    (got * probe).sum().backward()
+    qkv_w = torch.cat([hf[att + "query.weight"].grad, hf[att + "key.weight"].grad, hf[att + "value.weight"].grad])
+    assert torch.allclose(sd[p + "attn.qkv.weight"].grad, qkv_w, atol=1e-10, rtol=1e-9)
+    for mine, theirs in [("attn.proj.weight", "attention.output.dense.weight"), ("ls1.gamma", "layer_scale1.lambda1"),
+                         ("ls2.gamma", "layer_scale2.lambda1"), ("mlp.fc1.weight", "mlp.fc1.weight"),
+                         ("mlp.fc2.bias", "mlp.fc2.bias"), ("norm1.weight", "norm1.weight"), ("norm2.bias", "norm2.bias")]:
+        assert torch.allclose(sd[p + mine].grad, hf[theirs].grad, atol=1e-10, rtol=1e-9), mine
