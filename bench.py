@@ -560,6 +560,10 @@ def _run_train(args, ctx, steps: int, warmup: int, headline: bool):
     value = tiles / (ms / 1e3)
     fwd = roof["conv_fwd_kernel"]
     traffic, traffic_src = _dram_traffic({"unetpp": "unetpp", "segformer": "segformer", "dofa": "dofa"}[w["family"]])
+    if w["family"] == "segformer" and ops.option("decoder_folded"):
+        # the committed SegFormer ncu pass predates the folded decoder (its launch list contains the 4*emb -> emb fuse
+        # product): no per-launch DRAM figure for the launches that run now
+        traffic, traffic_src = None, None
     line = {
         "metric": "512x512 multi-band tiles/sec (train fwd+bwd)", "value": value, "unit": "tiles/s",
         "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": ms / steps,
