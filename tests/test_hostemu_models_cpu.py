@@ -34,7 +34,7 @@ SLOW = {
 
 # CUDA-graph capture / stream behaviour has no CPU counterpart
 EXCLUDE = ("test_sliding_window_cuda_graph_replay_equals_eager", "test_cuda_graph_step_equals_eager_step",
-           "test_cuda_graph_step_equals_eager_step_bitwise")
+           "test_cuda_graph_step_equals_eager_step_bitwise", "test_set_lr_reaches_a_captured_graph")
 
 
 def _params(table, slow):
